@@ -1,0 +1,709 @@
+/*
+ * hb_oracle.c -- CPU restatement of the HomerHEVC ME + interpolation + T/Q hot path.
+ * TEST INFRASTRUCTURE ONLY (see hb_oracle.h).  Plain C99, scalar, single-threaded.
+ *
+ * Citations are to /root/reference/src/homer_lib/<file>:<line>.
+ */
+#include "hb_oracle.h"
+
+#include <limits.h>
+#include <stdlib.h>
+#include <string.h>
+
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* ------------------------------------------------------------------------------------------
+ * Pixel primitives.  hmr_motion_intra.c:51-186.  The SSE4.2 twins (hmr_sse42_functions_pixel.c:462,
+ * :728, :817, :919) give the same values on the reachable sample ranges.
+ * ------------------------------------------------------------------------------------------ */
+uint32_t orc_sad(const int16_t *src, int src_stride, const int16_t *pred, int pred_stride, int size)
+{
+    int acc = 0;
+    for (int y = 0; y < size; y++, src += src_stride, pred += pred_stride)
+        for (int x = 0; x < size; x++)
+            acc += abs(src[x] - pred[x]);
+    return (uint32_t)acc;
+}
+
+uint32_t orc_ssd16b(const int16_t *src, int src_stride, const int16_t *pred, int pred_stride, int size)
+{
+    uint32_t acc = 0;
+    for (int y = 0; y < size; y++, src += src_stride, pred += pred_stride)
+        for (int x = 0; x < size; x++) {
+            int d = src[x] - pred[x];
+            acc += (uint32_t)(d * d);
+        }
+    return acc;
+}
+
+void orc_predict(const int16_t *orig, int orig_stride, const int16_t *pred, int pred_stride,
+                 int16_t *resid, int resid_stride, int size)
+{
+    for (int y = 0; y < size; y++, orig += orig_stride, pred += pred_stride, resid += resid_stride)
+        for (int x = 0; x < size; x++)
+            resid[x] = (int16_t)(orig[x] - pred[x]);
+}
+
+void orc_reconst(const int16_t *pred, int pred_stride, const int16_t *resid, int resid_stride,
+                 int16_t *dec, int dec_stride, int size)
+{
+    for (int y = 0; y < size; y++, pred += pred_stride, resid += resid_stride, dec += dec_stride)
+        for (int x = 0; x < size; x++)
+            dec[x] = (int16_t)clampi(resid[x] + pred[x], 0, 255);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Interpolation.  Taps: hmr_motion_inter.c:240-258.  One pass = one call with (is_first,is_last):
+ *   (1,0) 8-bit -> 14-bit minus 8192      (1,1) 8-bit -> 8-bit, rounded and clipped
+ *   (0,1) 14-bit -> 8-bit, clipped        (0,0) 14-bit -> 14-bit
+ * Every result goes through an int16 before the clip, as in the reference ("short val").
+ * ------------------------------------------------------------------------------------------ */
+static const int8_t k_luma_taps[4][8] = {
+    { 0, 0,   0, 64,  0,   0, 0,  0 },
+    {-1, 4, -10, 58, 17,  -5, 1,  0 },
+    {-1, 4, -11, 40, 40, -11, 4, -1 },
+    { 0, 1,  -5, 17, 58, -10, 4, -1 },
+};
+static const int8_t k_chroma_taps[8][4] = {
+    { 0, 64,  0,  0 }, {-2, 58, 10, -2 }, {-4, 54, 16, -2 }, {-6, 46, 28, -4 },
+    {-4, 36, 36, -4 }, {-4, 28, 46, -6 }, {-2, 16, 54, -4 }, {-2, 10, 58, -2 },
+};
+
+/* fraction 0 of the luma path: hmr_motion_inter.c:261 (filter_copy) */
+static void copy_pass(const int16_t *src, int src_stride, int16_t *dst, int dst_stride,
+                      int width, int height, int is_first, int is_last)
+{
+    const int shift = 14 - 8;
+    for (int y = 0; y < height; y++, src += src_stride, dst += dst_stride) {
+        for (int x = 0; x < width; x++) {
+            if (is_first == is_last) {
+                dst[x] = src[x];
+            } else if (is_first) {
+                int16_t v = (int16_t)(src[x] << shift);
+                dst[x] = (int16_t)(v - (int16_t)8192);
+            } else {
+                int16_t v = src[x];
+                v = (int16_t)((v + (int16_t)(8192 + (1 << (shift - 1)))) >> shift);
+                dst[x] = (int16_t)clampi(v, 0, 255);
+            }
+        }
+    }
+}
+
+/* hmr_motion_inter.c:312 (8 taps) and :878 (4 taps) share this shape */
+static void filter_pass(const int16_t *src, int src_stride, int16_t *dst, int dst_stride,
+                        const int8_t *taps, int ntaps, int width, int height,
+                        int is_vertical, int is_first, int is_last)
+{
+    const int head_room = 14 - 8;
+    const int step = is_vertical ? src_stride : 1;
+    int shift = 6, offset;
+    if (is_last) {
+        shift += is_first ? 0 : head_room;
+        offset = 1 << (shift - 1);
+        offset += is_first ? 0 : (8192 << 6);
+    } else {
+        shift -= is_first ? head_room : 0;
+        offset = is_first ? -(8192 << shift) : 0;
+    }
+    src -= (ntaps / 2 - 1) * step;
+    for (int y = 0; y < height; y++, src += src_stride, dst += dst_stride) {
+        for (int x = 0; x < width; x++) {
+            int sum = 0;
+            for (int k = 0; k < ntaps; k++)
+                sum += src[x + k * step] * taps[k];
+            int16_t v = (int16_t)((sum + offset) >> shift);
+            if (is_last)
+                v = (int16_t)clampi(v, 0, 255);
+            dst[x] = v;
+        }
+    }
+}
+
+void orc_interpolate_luma(const int16_t *src, int src_stride, int16_t *dst, int dst_stride,
+                          int fraction, int width, int height, int is_vertical, int is_first, int is_last)
+{
+    if (fraction == 0)
+        copy_pass(src, src_stride, dst, dst_stride, width, height, is_first, is_last);
+    else
+        filter_pass(src, src_stride, dst, dst_stride, k_luma_taps[fraction], 8, width, height,
+                    is_vertical, is_first, is_last);
+}
+
+void orc_interpolate_chroma(const int16_t *src, int src_stride, int16_t *dst, int dst_stride,
+                            int fraction, int width, int height, int is_vertical, int is_first, int is_last)
+{
+    /* the plain-C reference runs the {0,64,0,0} filter for fraction 0 (hmr_motion_inter.c:878) */
+    filter_pass(src, src_stride, dst, dst_stride, k_chroma_taps[fraction], 4, width, height,
+                is_vertical, is_first, is_last);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Transforms.  hmr_transform.c:514/:553 are HM's partial butterflies; a butterfly is an exact
+ * refactoring of the integer matrix product, so the restatement is the matrix product itself with
+ * the same stage shifts, int16 truncation (forward) and int16 clipping (inverse).
+ * The HEVC core matrix is generated from its 32 distinct magnitudes (first column of the 32-point
+ * matrix, hmr_transform.c:91-128); smaller sizes are its row-subsampled top-left corners.
+ * ------------------------------------------------------------------------------------------ */
+static const int8_t k_dct_mag[33] = { 64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67,
+                                      64, 61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13,  9,  4, 0 };
+static const int8_t k_dst4[4][4] = { { 29, 55, 74, 84 }, { 74, 74, 0, -74 }, { 84, -29, -74, 55 }, { 55, -84, 74, -29 } };
+
+static int dct_coef(int n, int k, int j)          /* T_n[k][j] */
+{
+    int m = (k * (32 / n) * (2 * j + 1)) & 127;    /* angle index: cos(m*pi/64) */
+    if (m > 64) m = 128 - m;
+    return m <= 32 ? k_dct_mag[m] : -k_dct_mag[64 - m];
+}
+static int tr_coef(int n, int is_dst, int k, int j) { return is_dst ? k_dst4[k][j] : dct_coef(n, k, j); }
+
+static int ilog2(int n) { int l = 0; while ((1 << l) < n) l++; return l; }
+
+void orc_transform(int bit_depth, const int16_t *block, int block_stride, int16_t *coeff, int n, int is_dst)
+{
+    int16_t tmp[32 * 32];
+    const int lg = ilog2(n);
+    const int shift1 = lg - 2 + 1 + bit_depth - 8, shift2 = lg - 2 + 8;
+    /* stage 1: rows of the residual -> tmp[k][row] */
+    for (int r = 0; r < n; r++)
+        for (int k = 0; k < n; k++) {
+            int s = 0;
+            for (int j = 0; j < n; j++) s += tr_coef(n, is_dst, k, j) * block[r * block_stride + j];
+            tmp[k * n + r] = (int16_t)((s + (1 << (shift1 - 1))) >> shift1);
+        }
+    /* stage 2: rows of tmp -> coeff[k][row] */
+    for (int r = 0; r < n; r++)
+        for (int k = 0; k < n; k++) {
+            int s = 0;
+            for (int j = 0; j < n; j++) s += tr_coef(n, is_dst, k, j) * tmp[r * n + j];
+            coeff[k * n + r] = (int16_t)((s + (1 << (shift2 - 1))) >> shift2);
+        }
+}
+
+void orc_itransform(int bit_depth, int16_t *block, int block_stride, const int16_t *coeff, int n, int is_dst)
+{
+    int16_t tmp[32 * 32];
+    const int shift1 = 7, shift2 = 12 - (bit_depth - 8);
+    /* stage 1: columns of coeff -> rows of tmp */
+    for (int c = 0; c < n; c++)
+        for (int j = 0; j < n; j++) {
+            int s = 0;
+            for (int k = 0; k < n; k++) s += tr_coef(n, is_dst, k, j) * coeff[k * n + c];
+            tmp[c * n + j] = (int16_t)clampi((s + (1 << (shift1 - 1))) >> shift1, -32768, 32767);
+        }
+    for (int c = 0; c < n; c++)
+        for (int j = 0; j < n; j++) {
+            int s = 0;
+            for (int k = 0; k < n; k++) s += tr_coef(n, is_dst, k, j) * tmp[k * n + c];
+            block[c * block_stride + j] = (int16_t)clampi((s + (1 << (shift2 - 1))) >> shift2, -32768, 32767);
+        }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Tables.  Scans: hmr_tables.c:62-196.  Quant pyramids from the default HEVC scaling lists:
+ * hmr_tables.c:199-250, hmr_tables.h:53-85, wiring hmr_encoder_lib.c:103-140.
+ * ------------------------------------------------------------------------------------------ */
+static const uint8_t k_sl_intra8[64] = {
+    16, 16, 16, 16, 17, 18, 21, 24, 16, 16, 16, 16, 17, 19, 22, 25, 16, 16, 17, 18, 20, 22, 25, 29,
+    16, 16, 18, 21, 24, 27, 31, 36, 17, 17, 20, 24, 30, 35, 41, 47, 18, 19, 22, 27, 35, 44, 54, 65,
+    21, 22, 25, 31, 41, 54, 70, 88, 24, 25, 29, 36, 47, 65, 88, 115 };
+static const uint8_t k_sl_inter8[64] = {
+    16, 16, 16, 16, 17, 18, 20, 24, 16, 16, 16, 17, 18, 20, 24, 25, 16, 16, 17, 18, 20, 24, 25, 28,
+    16, 17, 18, 20, 24, 25, 28, 33, 17, 18, 20, 24, 25, 28, 33, 41, 18, 20, 24, 25, 28, 33, 41, 54,
+    20, 24, 25, 28, 33, 41, 54, 71, 24, 25, 28, 33, 41, 54, 71, 91 };
+static const int k_qscale[6] = { 26214, 23302, 20560, 18396, 16384, 14564 };
+static const int k_iqscale[6] = { 40, 45, 51, 57, 64, 72 };
+
+const uint8_t orc_chroma_qp_table[58] = {
+    0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29,
+    29, 30, 31, 32, 33, 33, 34, 34, 35, 35, 36, 36, 37, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51 };
+
+/* up-right diagonal order of a w x w grid, entries are row*w+col */
+static void simple_diag(uint32_t *out, int w)
+{
+    int pos = 0;
+    for (int line = 0; pos < w * w; line++) {
+        int row = line, col = 0;
+        while (row >= w) { row--; col++; }
+        for (; row >= 0 && col < w; row--, col++)
+            out[pos++] = (uint32_t)(row * w + col);
+    }
+}
+
+static void build_scans(orc_tables *t)
+{
+    uint32_t diag8[64];
+    simple_diag(diag8, 8);
+    for (int lv = 0; lv < 5; lv++) {                 /* sizes 2,4,8,16,32 */
+        const int w = 2 << lv, cgs = w >> 2;
+        for (int m = 0; m < 4; m++) t->scan[m][lv] = (uint32_t *)calloc((size_t)w * w, sizeof(uint32_t));
+        uint32_t *hor = t->scan[1][lv], *ver = t->scan[2][lv], *diag = t->scan[3][lv];
+        if (w <= 4) {
+            simple_diag(diag, w);
+        } else {
+            uint32_t cg_order[64], in_cg[16];
+            if (w == 32) memcpy(cg_order, diag8, sizeof diag8); else simple_diag(cg_order, cgs);
+            simple_diag(in_cg, 4);
+            for (int b = 0; b < cgs * cgs; b++) {
+                const int by = cg_order[b] / cgs, bx = cg_order[b] % cgs;
+                for (int i = 0; i < 16; i++)
+                    diag[16 * b + i] = (uint32_t)((4 * by + in_cg[i] / 4) * w + 4 * bx + in_cg[i] % 4);
+            }
+        }
+        if (w > 2) {
+            int n = 0;
+            for (int by = 0; by < cgs; by++) for (int bx = 0; bx < cgs; bx++)
+                for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++)
+                    hor[n++] = (uint32_t)((4 * by + y) * w + 4 * bx + x);
+            n = 0;
+            for (int bx = 0; bx < cgs; bx++) for (int by = 0; by < cgs; by++)
+                for (int x = 0; x < 4; x++) for (int y = 0; y < 4; y++)
+                    ver[n++] = (uint32_t)((4 * by + y) * w + 4 * bx + x);
+        } else {
+            int n = 0;
+            for (int y = 0; y < w; y++) for (int x = 0; x < w; x++) hor[n++] = (uint32_t)(y * w + x);
+            n = 0;
+            for (int x = 0; x < w; x++) for (int y = 0; y < w; y++) ver[n++] = (uint32_t)(y * w + x);
+        }
+    }
+}
+
+static void build_quant(orc_tables *t)
+{
+    static const int n_lists[4] = { 6, 6, 6, 2 };
+    for (int sm = 0; sm < 4; sm++) {
+        const int w = 4 << sm, side = w < 8 ? w : 8, ratio = w / side;
+        for (int list = 0; list < n_lists[sm]; list++) {
+            const int inter = (sm == 3) ? (list >= 1) : (list >= 3);
+            for (int rem = 0; rem < 6; rem++) {
+                int32_t *q = (int32_t *)malloc(sizeof(int32_t) * (size_t)w * w);
+                int32_t *dq = (int32_t *)malloc(sizeof(int32_t) * (size_t)w * w);
+                for (int y = 0; y < w; y++)
+                    for (int x = 0; x < w; x++) {
+                        int m = 16;
+                        if (sm > 0) m = (inter ? k_sl_inter8 : k_sl_intra8)[8 * (y / ratio) + x / ratio];
+                        q[y * w + x] = (k_qscale[rem] << 4) / m;
+                        dq[y * w + x] = k_iqscale[rem] * m;
+                    }
+                if (ratio > 1) { q[0] = (k_qscale[rem] << 4) / 16; dq[0] = k_iqscale[rem] * 16; }
+                t->quant[sm][list][rem] = q;
+                t->dequant[sm][list][rem] = dq;
+            }
+        }
+    }
+    for (int rem = 0; rem < 6; rem++) {              /* hmr_encoder_lib.c:135-140: 32x32 list 3 aliases list 1 */
+        t->quant[3][3][rem] = t->quant[3][1][rem];
+        t->dequant[3][3][rem] = t->dequant[3][1][rem];
+    }
+}
+
+orc_tables *orc_tables_create(void)
+{
+    orc_tables *t = (orc_tables *)calloc(1, sizeof *t);
+    build_scans(t);
+    build_quant(t);
+    return t;
+}
+
+void orc_tables_destroy(orc_tables *t)
+{
+    if (!t) return;
+    for (int m = 0; m < 4; m++) for (int lv = 0; lv < 7; lv++) free(t->scan[m][lv]);
+    for (int sm = 0; sm < 4; sm++) for (int l = 0; l < 6; l++) for (int r = 0; r < 6; r++) {
+        if (sm == 3 && l == 3) continue;
+        free(t->quant[sm][l][r]); free(t->dequant[sm][l][r]);
+    }
+    free(t);
+}
+
+const uint32_t *orc_tables_scan(const orc_tables *t, int mode, int log2n) { return t->scan[mode][log2n - 1]; }
+const int32_t *orc_tables_quant(const orc_tables *t, int log2n, int list, int rem) { return t->quant[log2n - 2][list][rem]; }
+const int32_t *orc_tables_dequant(const orc_tables *t, int log2n, int list, int rem) { return t->dequant[log2n - 2][list][rem]; }
+
+/* ------------------------------------------------------------------------------------------
+ * Quantisation.  Target = the SSE4.2 function the reference selects on x86
+ * (hmr_sse42_functions_quant.c:34-133): rounding offset 171 on I slices and 85 otherwise (:47),
+ * |level| saturated to int16 by a signed pack before the sign is put back (:69), deltaU saturated
+ * likewise (:70), ac_sum = sum of unsaturated levels, then sign-data hiding when enabled and sum >= 2.
+ * ------------------------------------------------------------------------------------------ */
+static inline int16_t sat16(int32_t v) { return (int16_t)clampi(v, -32768, 32767); }
+
+void orc_quant(const orc_tables *t, const int16_t *src, int16_t *dst, int16_t *delta_u,
+               int scan_mode, int log2n, int comp, int is_intra, int is_islice, int sign_hiding,
+               int per, int rem, int *ac_sum)
+{
+    const int n = 1 << log2n;
+    const int32_t *q = orc_tables_quant(t, log2n, (is_intra ? 0 : 3) + comp, rem);
+    const int qbits = 14 + per + (15 - 8 - log2n);
+    const int32_t add = (int32_t)((uint32_t)(is_islice ? 171 : 85) << (qbits - 9));
+    int32_t sum = 0;
+    for (int i = 0; i < n * n; i++) {
+        const int32_t a = src[i] < 0 ? -(int32_t)src[i] : src[i];
+        const int32_t prod = (int32_t)((uint32_t)a * (uint32_t)q[i]);
+        const int32_t level = (int32_t)((uint32_t)prod + (uint32_t)add) >> qbits;
+        const int32_t delta = (int32_t)((uint32_t)prod - ((uint32_t)level << qbits)) >> (qbits - 8);
+        const int sgn = src[i] > 0 ? 1 : (src[i] < 0 ? -1 : 0);
+        sum += level;
+        dst[i] = (int16_t)(sgn * sat16(level));
+        delta_u[i] = sat16(delta);
+    }
+    *ac_sum = sum;
+    if (sign_hiding && sum >= 2)
+        orc_sign_bit_hiding(dst, src, orc_tables_scan(t, scan_mode, log2n), delta_u, n);
+}
+
+/* hmr_quant.c:61-169.  Coefficient groups of 16 in scan order, from the last to the first.  The first group
+ * (from the end) that holds a non-zero level is "the last CG": only there the adjustment search starts at the
+ * last non-zero position instead of position 15. */
+void orc_sign_bit_hiding(int16_t *dst, const int16_t *src, const uint32_t *scan, const int16_t *delta_u, int n)
+{
+    int seen_last_cg = 0;
+    for (int cg = (n * n - 1) >> 4; cg >= 0; cg--) {
+        const uint32_t *sc = scan + 16 * cg;
+        int first = 16, last = -1, abs_sum = 0;
+        for (int i = 15; i >= 0; i--) if (dst[sc[i]]) { last = i; break; }
+        for (int i = 0; i < 16; i++) if (dst[sc[i]]) { first = i; break; }
+        for (int i = first; i <= last; i++) abs_sum += dst[sc[i]];
+        const int is_last_cg = (last >= 0 && !seen_last_cg);
+        if (last >= 0) seen_last_cg = 1;
+        if (last - first < 4) continue;
+        const unsigned sign_bit = dst[sc[first]] > 0 ? 0u : 1u;
+        if (sign_bit == (unsigned)(abs_sum & 1)) continue;
+
+        int min_cost = INT_MAX, min_pos = -1, final_change = 0, cur_cost = INT_MAX, cur_change = 0;
+        for (int i = is_last_cg ? last : 15; i >= 0; i--) {
+            const uint32_t p = sc[i];
+            if (dst[p] != 0) {
+                if (delta_u[p] > 0) { cur_cost = -delta_u[p]; cur_change = 1; }
+                else if (i == first && abs(dst[p]) == 1) cur_cost = INT_MAX;
+                else { cur_cost = delta_u[p]; cur_change = -1; }
+            } else if (i < first) {
+                const unsigned this_sign = src[p] >= 0 ? 0u : 1u;
+                if (this_sign != sign_bit) cur_cost = INT_MAX;
+                else { cur_cost = -delta_u[p]; cur_change = 1; }
+            } else {
+                cur_cost = -delta_u[p]; cur_change = 1;
+            }
+            if (cur_cost < min_cost) { min_cost = cur_cost; final_change = cur_change; min_pos = (int)p; }
+        }
+        if (dst[min_pos] == 32767 || dst[min_pos] == -32768) final_change = -1;
+        if (src[min_pos] >= 0) dst[min_pos] = (int16_t)(dst[min_pos] + final_change);
+        else                   dst[min_pos] = (int16_t)(dst[min_pos] - final_change);
+    }
+}
+
+/* hmr_sse42_functions_quant.c:135-245 (== hmr_quant.c:224 on the default tables).  The SSE version picks
+ * the table with `is_intra?0:3+comp` (:138), i.e. list 0 for every intra block. */
+void orc_inv_quant(const orc_tables *t, const int16_t *src, int16_t *dst,
+                   int log2n, int comp, int is_intra, int per, int rem)
+{
+    const int n = 1 << log2n;
+    const int32_t *dq = orc_tables_dequant(t, log2n, is_intra ? 0 : 3 + comp, rem);
+    const int iq_shift = 20 - 14 - (15 - 8 - log2n) + 4;
+    if (iq_shift > per) {
+        const int sh = iq_shift - per;
+        const int32_t add = 1 << (sh - 1);
+        for (int i = 0; i < n * n; i++)
+            dst[i] = sat16((int32_t)((uint32_t)(int32_t)src[i] * (uint32_t)dq[i] + (uint32_t)add) >> sh);
+    } else {
+        const int sh = per - iq_shift;
+        for (int i = 0; i < n * n; i++)
+            dst[i] = sat16((int32_t)(((uint32_t)(int32_t)src[i] * (uint32_t)dq[i]) << sh));
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Motion search.  hmr_motion_inter.c:1404-1774.
+ * ------------------------------------------------------------------------------------------ */
+/* select_mv_candidate_fast, hmr_motion_inter.c:1004; calc_mv_correction hmr_common.h:53 */
+uint32_t orc_mv_cost(const orc_mv *cands, int n, int qp, double avg_dist, int mvx, int mvy, int *best_idx)
+{
+    uint32_t best = INT_MAX;
+    int bi = 0;
+    for (int i = 0; i < n; i++) {
+        double w = avg_dist / 2000.;
+        w = w < .15 ? .15 : (w > 1.4 ? 1.4 : w);
+        const double corr = (uint32_t)qp * w;
+        const double cx = corr * ((float)abs(cands[i].x - mvx));
+        const double cy = corr * ((float)abs(cands[i].y - mvy));
+        const uint32_t c = (uint32_t)(cx + cy + .5);
+        if (best > c) { best = c; bi = i; }
+    }
+    if (best_idx) *best_idx = bi;
+    return best;
+}
+
+typedef struct me_state {
+    const orc_me_in *in;
+    int xlo, xhi, ylo, yhi;
+    int bx, by;                 /* running best ("curr_best") */
+    uint32_t bsad, brd;
+    uint32_t n_sads;
+} me_state;
+
+static int me_inside(const me_state *s, int x, int y) { return x >= s->xlo && x <= s->xhi && y >= s->ylo && y <= s->yhi; }
+
+static uint32_t me_sad_at(me_state *s, int x, int y)
+{
+    const orc_me_in *in = s->in;
+    s->n_sads++;
+    return orc_sad(in->orig, in->orig_stride, in->ref + y * in->ref_stride + x, in->ref_stride, in->size);
+}
+
+/* probe one integer position; returns 1 when it became the running best */
+static int me_probe(me_state *s, int x, int y)
+{
+    const orc_me_in *in = s->in;
+    if (!me_inside(s, x, y)) return 0;
+    const uint32_t sad = me_sad_at(s, x, y);
+    const uint32_t rd = sad + orc_mv_cost(in->amvp, in->n_amvp, in->qp, in->avg_dist, x << 2, y << 2, NULL);
+    if (rd < s->brd) { s->bsad = sad; s->brd = rd; s->bx = x; s->by = y; return 1; }
+    return 0;
+}
+
+static const int8_t k_small[4][2] = { {-1, 0}, {0, -1}, {1, 0}, {0, 1} };                                   /* :1079 */
+static const int8_t k_big[8][2] = { {-2, 0}, {-1, -1}, {0, -2}, {1, -1}, {2, 0}, {1, 1}, {0, 2}, {-1, 1} }; /* :1080 */
+static const int8_t k_half_order[9][2] = { {0,0}, {0,-1}, {0,1}, {-1,0}, {1,0}, {-1,-1}, {1,-1}, {-1,1}, {1,1} };    /* :1035 */
+static const int8_t k_quarter_order[9][2] = { {0,0}, {0,-1}, {0,1}, {-1,-1}, {1,-1}, {-1,0}, {1,0}, {-1,1}, {1,1} }; /* :1062 */
+
+#define PL_STRIDE 80
+#define PL_ROWS   76
+typedef struct subpel_planes {
+    int16_t tmp[4][PL_STRIDE * PL_ROWS];        /* H-pass results, 14 bit, by x fraction */
+    int16_t pl[4][4][PL_STRIDE * PL_ROWS];      /* [y fraction][x fraction] 8-bit planes */
+} subpel_planes;
+
+/* hmr_motion_inter.c:395 */
+static void build_half_planes(subpel_planes *p, const int16_t *ref, int rs, int n)
+{
+    const int16_t *src = ref - 4 * rs - 1;
+    orc_interpolate_luma(src, rs, p->tmp[0], PL_STRIDE, 0, n + 1, n + 8, 0, 1, 0);
+    orc_interpolate_luma(src, rs, p->tmp[2], PL_STRIDE, 2, n + 1, n + 8, 0, 1, 0);
+    orc_interpolate_luma(p->tmp[0] + 4 * PL_STRIDE + 1, PL_STRIDE, p->pl[0][0], PL_STRIDE, 0, n, n, 1, 0, 1);
+    orc_interpolate_luma(p->tmp[0] + 3 * PL_STRIDE + 1, PL_STRIDE, p->pl[2][0], PL_STRIDE, 2, n, n + 1, 1, 0, 1);
+    orc_interpolate_luma(p->tmp[2] + 4 * PL_STRIDE, PL_STRIDE, p->pl[0][2], PL_STRIDE, 0, n + 1, n, 1, 0, 1);
+    orc_interpolate_luma(p->tmp[2] + 3 * PL_STRIDE, PL_STRIDE, p->pl[2][2], PL_STRIDE, 2, n + 1, n + 1, 1, 0, 1);
+}
+
+/* hmr_motion_inter.c:442; (hx,hy) is the half-pel winner in half-pel steps, each in {-1,0,1} */
+static void build_quarter_planes(subpel_planes *p, const int16_t *ref, int rs, int n, int hx, int hy)
+{
+    const int ext_h = (hy == 0) ? n + 8 : n + 7;
+    const int T = PL_STRIDE;
+    const int16_t *base = ref - 4 * rs - 1 + (hy > 0 ? rs : 0);
+    orc_interpolate_luma(base + (hx >= 0 ? 1 : 0), rs, p->tmp[1], T, 1, n, ext_h, 0, 1, 0);
+    orc_interpolate_luma(base + (hx > 0 ? 1 : 0), rs, p->tmp[3], T, 3, n, ext_h, 0, 1, 0);
+
+    const int row0 = 3 * T;                                  /* (half_filter_size-1) rows down */
+    const int vz = (hy == 0) ? T : 0;
+    orc_interpolate_luma(p->tmp[1] + row0 + vz, T, p->pl[1][1], T, 1, n, n, 1, 0, 1);
+    orc_interpolate_luma(p->tmp[1] + row0, T, p->pl[3][1], T, 3, n, n, 1, 0, 1);
+    if (hy != 0) {
+        orc_interpolate_luma(p->tmp[1] + row0, T, p->pl[2][1], T, 2, n, n, 1, 0, 1);
+        orc_interpolate_luma(p->tmp[3] + row0, T, p->pl[2][3], T, 2, n, n, 1, 0, 1);
+    } else {
+        orc_interpolate_luma(p->tmp[1] + 4 * T, T, p->pl[0][1], T, 0, n, n, 1, 0, 1);
+        orc_interpolate_luma(p->tmp[3] + 4 * T, T, p->pl[0][3], T, 0, n, n, 1, 0, 1);
+    }
+    if (hx != 0) {
+        const int16_t *s2 = p->tmp[2] + row0 + (hx > 0 ? 1 : 0);
+        orc_interpolate_luma(s2 + (hy >= 0 ? T : 0), T, p->pl[1][2], T, 1, n, n, 1, 0, 1);
+        orc_interpolate_luma(s2 + (hy > 0 ? T : 0), T, p->pl[3][2], T, 3, n, n, 1, 0, 1);
+    } else {
+        const int16_t *s0 = p->tmp[0] + row0 + 1;
+        orc_interpolate_luma(s0 + (hy >= 0 ? T : 0), T, p->pl[1][0], T, 1, n, n, 1, 0, 1);
+        orc_interpolate_luma(s0 + (hy > 0 ? T : 0), T, p->pl[3][0], T, 3, n, n, 1, 0, 1);
+    }
+    orc_interpolate_luma(p->tmp[3] + row0 + vz, T, p->pl[1][3], T, 1, n, n, 1, 0, 1);
+    orc_interpolate_luma(p->tmp[3] + row0, T, p->pl[3][3], T, 3, n, n, 1, 0, 1);
+}
+
+/* plane + offset selection shared by both sub-pel stages, hmr_motion_inter.c:1700-1710 / :1745-1755 */
+static const int16_t *subpel_plane_at(const subpel_planes *p, int cx, int cy)
+{
+    const int16_t *s = p->pl[cy & 3][cx & 3];
+    if (cx == 2 && (cy & 1) == 0) s += 1;
+    if ((cx & 1) == 0 && cy == 2) s += PL_STRIDE;
+    return s;
+}
+
+void orc_motion_estimation(const orc_me_in *in, orc_me_out *out)
+{
+    me_state s;
+    memset(&s, 0, sizeof s);
+    s.in = in;
+    const int n = in->size;
+    s.xlo = (in->gx - in->range_x < 0) ? -in->gx : -in->range_x;
+    s.xhi = (in->gx + in->range_x > in->frame_w - n) ? in->frame_w - in->gx - n : in->range_x;
+    s.ylo = (in->gy - in->range_y < 0) ? -in->gy : -in->range_y;
+    s.yhi = (in->gy + in->range_y > in->frame_h - n) ? in->frame_h - in->gy - n : in->range_y;
+
+    orc_mv mv = { 0, 0 }, sub = { 0, 0 };
+    uint32_t best_sad = UINT_MAX / 8;
+    int cx0 = 0, cy0 = 0;             /* "best_x/best_y": centre of the pattern being scanned */
+
+    if (in->action & 1) {
+        s.bx = clampi(0, s.xlo, s.xhi);
+        s.by = clampi(0, s.ylo, s.yhi);
+        s.bsad = me_sad_at(&s, s.bx, s.by);
+        s.brd = s.bsad + orc_mv_cost(in->amvp, in->n_amvp, in->qp, in->avg_dist, s.bx << 2, s.by << 2, NULL);
+        best_sad = s.bsad; cx0 = s.bx; cy0 = s.by;
+        if (best_sad <= 0) goto refine;
+
+        for (int i = 0; i < in->n_start; i++) {                      /* :1465-1490 */
+            const int x = in->start[i].x >> 2, y = in->start[i].y >> 2;
+            if (x == 0 && y == 0) continue;
+            me_probe(&s, x, y);
+        }
+        best_sad = s.bsad; cx0 = s.bx; cy0 = s.by;
+        if (best_sad <= 0) goto refine;
+
+        for (int i = 0; i < 4; i++)                                  /* :1501-1523, centre stays put */
+            me_probe(&s, cx0 + k_small[i][0], cy0 + k_small[i][1]);
+        if (best_sad <= 0) goto refine;
+
+        {                                                            /* :1528-1599, only l == 0 runs */
+            int dist = 2;
+            const int end = (cx0 != 0 && cy0 != 0) ? 4 : 8;
+            int next_start = 0, span = 8;
+            cx0 = s.bx; cy0 = s.by;
+            while (dist < end) {
+                for (int i = next_start; i < next_start + span; i++) {
+                    const int idx = i % 8;
+                    if (me_probe(&s, cx0 + k_big[idx][0] * dist, cy0 + k_big[idx][1] * dist)) {
+                        next_start = (idx - 2 + 8) % 8;
+                        span = 8 - 3;
+                    }
+                }
+                dist *= 2;
+            }
+        }
+refine:                                                              /* :1601-1663 */
+        cx0 = s.bx; cy0 = s.by;
+        {
+            int next_start = 0, span = 4;
+            for (;;) {
+                for (int i = next_start; i < next_start + span; i++) {
+                    const int idx = i % 4;
+                    if (me_probe(&s, cx0 + k_small[idx][0], cy0 + k_small[idx][1])) {
+                        next_start = (idx - 1 + 4) % 4;
+                        span = 4 - 1;
+                    }
+                }
+                if (cx0 == s.bx && cy0 == s.by) break;
+                cx0 = s.bx; cy0 = s.by;
+            }
+        }
+        best_sad = s.bsad;
+        mv.x = s.bx << 2; mv.y = s.by << 2;
+    }
+
+    if (in->action & 2) {                                            /* :1675-1767 */
+        subpel_planes *p = (subpel_planes *)malloc(sizeof *p);
+        const int ix = mv.x >> 2, iy = mv.y >> 2;
+        const int16_t *ref = in->ref + iy * in->ref_stride + ix;
+        uint32_t cur = s.bsad;
+        if (!(in->action & 1))
+            cur = orc_sad(in->orig, in->orig_stride, ref, in->ref_stride, n);
+        build_half_planes(p, ref, in->ref_stride, n);
+        int bx = 0, by = 0, bidx = 0;
+        for (int i = 0; i < 9; i++) {
+            const int cx = k_half_order[i][0] * 2, cy = k_half_order[i][1] * 2;
+            const uint32_t v = orc_sad(in->orig, in->orig_stride, subpel_plane_at(p, cx, cy), PL_STRIDE, n);
+            if (v < cur) { cur = v; bx = cx; by = cy; bidx = i; }
+        }
+        mv.x = (ix << 2) + bx; mv.y = (iy << 2) + by;
+        sub.x = bx; sub.y = by;
+        best_sad = cur;
+        if (in->action & 4) {
+            const int hx = k_half_order[bidx][0], hy = k_half_order[bidx][1];
+            build_quarter_planes(p, ref, in->ref_stride, n, hx, hy);
+            bx = hx * 2; by = hy * 2;
+            for (int i = 0; i < 9; i++) {
+                const int cx = hx * 2 + k_quarter_order[i][0], cy = hy * 2 + k_quarter_order[i][1];
+                const uint32_t v = orc_sad(in->orig, in->orig_stride, subpel_plane_at(p, cx, cy), PL_STRIDE, n);
+                if (v < cur) { cur = v; bx = cx; by = cy; }
+            }
+            best_sad = cur;
+            mv.x = (ix << 2) + bx; mv.y = (iy << 2) + by;
+            sub.x = bx; sub.y = by;
+        }
+        free(p);
+    }
+    out->mv = mv; out->subpix = sub; out->sad = best_sad; out->n_int_sads = s.n_sads;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Motion compensation (uni-prediction).  hmr_motion_inter.c:1779 and :1860.
+ * ------------------------------------------------------------------------------------------ */
+void orc_mc_luma(const int16_t *ref, int ref_stride, int16_t *pred, int pred_stride, int size, orc_mv mv)
+{
+    const int fx = mv.x & 3, fy = mv.y & 3;
+    const int16_t *src = ref + (mv.y >> 2) * ref_stride + (mv.x >> 2);
+    if (fx == 0) {
+        orc_interpolate_luma(src, ref_stride, pred, pred_stride, fy, size, size, 1, 1, 1);
+    } else if (fy == 0) {
+        orc_interpolate_luma(src, ref_stride, pred, pred_stride, fx, size, size, 0, 1, 1);
+    } else {
+        int16_t tmp[PL_STRIDE * PL_ROWS];
+        orc_interpolate_luma(src - 3 * ref_stride, ref_stride, tmp, PL_STRIDE, fx, size, size + 7, 0, 1, 0);
+        orc_interpolate_luma(tmp + 3 * PL_STRIDE, PL_STRIDE, pred, pred_stride, fy, size, size, 1, 0, 1);
+    }
+}
+
+void orc_mc_chroma(const int16_t *ref, int ref_stride, int16_t *pred, int pred_stride, int size, orc_mv mv)
+{
+    const int fx = mv.x & 7, fy = mv.y & 7;
+    const int16_t *src = ref + (mv.y >> 3) * ref_stride + (mv.x >> 3);
+    if (fx == 0) {
+        orc_interpolate_chroma(src, ref_stride, pred, pred_stride, fy, size, size, 1, 1, 1);
+    } else if (fy == 0) {
+        orc_interpolate_chroma(src, ref_stride, pred, pred_stride, fx, size, size, 0, 1, 1);
+    } else {
+        int16_t tmp[PL_STRIDE * PL_ROWS];
+        orc_interpolate_chroma(src - ref_stride, ref_stride, tmp, PL_STRIDE, fx, size, size + 4 + 1, 0, 1, 0);
+        orc_interpolate_chroma(tmp + PL_STRIDE, PL_STRIDE, pred, pred_stride, fy, size, size, 1, 0, 1);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * T/Q chain of one inter TU.  hmr_motion_inter.c:40-131 (luma) and :133-228 (chroma):
+ * predict -> transform -> quant -> [ssd(resid,0), inv_quant, itransform, ssd(resid,dec_resid), zero-out test] -> reconst.
+ * The value handed back as `ssd` is the one the reference returns: it is NOT replaced by ssd_zero when the TU is
+ * zeroed out (:106-113).
+ * ------------------------------------------------------------------------------------------ */
+void orc_encode_inter_tu(const orc_tables *t, const int16_t *orig, int orig_stride,
+                         const int16_t *pred, int pred_stride,
+                         int16_t *coeff, int16_t *dec, int dec_stride,
+                         int n, int comp, int qp, int is_islice, int sign_hiding,
+                         double avg_dist, double weight, orc_tu_out *out)
+{
+    int16_t resid[32 * 32], tc[32 * 32], dq[32 * 32], rdec[32 * 32], du[32 * 32];
+    static const int16_t zeros[32] = { 0 };
+    const int lg = ilog2(n), per = qp / 6, rem = qp % 6;
+    int sum = 0;
+    orc_predict(orig, orig_stride, pred, pred_stride, resid, n, n);
+    orc_transform(8, resid, n, tc, n, 0);
+    orc_quant(t, tc, coeff, du, 3 /* DIAG_SCAN */, lg, comp, 0, is_islice, sign_hiding, per, rem, &sum);
+    out->zeroed = 0; out->ssd_zero = 0;
+    if (sum > 0) {
+        const uint32_t ssd_zero = (uint32_t)(weight * orc_ssd16b(resid, n, zeros, 0, n));
+        orc_inv_quant(t, coeff, dq, lg, comp, 0, per, rem);
+        orc_itransform(8, rdec, n, dq, n, 0);
+        const uint32_t ssd = (uint32_t)(weight * orc_ssd16b(resid, n, rdec, n, n));
+        double k = avg_dist / 2.5 - 5.;
+        k = k < 1. ? 1. : (k > 20000. ? 20000. : k);
+        out->ssd_zero = ssd_zero; out->ssd = ssd;
+        if (comp == 0 ? ((double)ssd_zero <= (double)(int)ssd + k * sum) : ((double)ssd_zero <= (double)ssd + k * sum)) {
+            memset(coeff, 0, sizeof(int16_t) * (size_t)n * n);
+            sum = 0; out->zeroed = 1;
+            orc_reconst(pred, pred_stride, zeros, 0, dec, dec_stride, n);
+        } else {
+            orc_reconst(pred, pred_stride, rdec, n, dec, dec_stride, n);
+        }
+    } else {
+        out->ssd = (uint32_t)(weight * orc_ssd16b(resid, n, zeros, 0, n));
+        orc_reconst(pred, pred_stride, zeros, 0, dec, dec_stride, n);
+    }
+    out->sum = sum;
+}

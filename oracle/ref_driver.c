@@ -1,0 +1,299 @@
+/*
+ * ref_driver.c -- thin harness around the UNMODIFIED reference (HomerHEVC), compiled against the headers
+ * where they lie under /root/reference/src/homer_lib and linked with oracle/_ref/libhomer_ref.so.
+ * TEST INFRASTRUCTURE ONLY: it exists so that tests (and bench.py --impl reference) can call the reference's
+ * own functions that need a live henc_thread_t (quant, inv_quant, motion estimation, motion compensation,
+ * the inter T/Q chain) and so that a whole-encode golden can be produced in lock step.
+ * The simple kernels (sse_aligned_sad, sse_transform, ...) are called straight from libhomer_ref.so via ctypes.
+ *
+ * Build: see oracle/Makefile (outputs only into oracle/_ref/).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+#include <fcntl.h>
+#include <time.h>
+
+#include "hmr_private.h"
+#include "hmr_common.h"
+#include "hmr_sse42_functions.h"
+
+/* reference functions without a prototype in its headers */
+int encode_inter_cu(henc_thread_t *et, ctu_info_t *ctu, cu_partition_info_t *curr_cu_info, int depth, PartSize part_size_type, int *curr_sum, int gcnt);
+int encode_inter_cu_chroma(henc_thread_t *et, ctu_info_t *ctu, cu_partition_info_t *curr_cu_info, int component, int depth, PartSize part_size_type, int *curr_sum, int gcnt);
+uint32_t hmr_motion_estimation(henc_thread_t *et, ctu_info_t *ctu, cu_partition_info_t *curr_cu_info, int16_t *orig_buff, int orig_buff_stride, int16_t *reference_buff, int reference_buff_stride, int curr_part_global_x,
+                               int curr_part_global_y, int init_x, int init_y, int curr_part_size, int curr_part_size_shift, int search_range_x, int search_range_y, int frame_size_x, int frame_size_y, motion_vector_t *mv, motion_vector_t *subpix_mv, mv_candiate_list_t *amvp_candidate_list, uint32_t threshold, unsigned int action);
+void hmr_motion_compensation_luma(henc_thread_t *et, cu_partition_info_t *curr_cu_info, int16_t *reference_buff, int reference_buff_stride, int16_t *pred_buff, int pred_buff_stride, int width, int height, int curr_part_size_shift, motion_vector_t *mv, int is_bi_predict);
+void hmr_motion_compensation_chroma(henc_thread_t *et, int16_t *reference_buff, int reference_buff_stride, int16_t *pred_buff, int pred_buff_stride, int curr_part_size, int curr_part_size_shift, motion_vector_t *mv, int is_bi_predict);
+
+typedef struct refdrv {
+    void *handle;
+    hvenc_enc_t *enc;
+    hvenc_engine_t *eng;
+    henc_thread_t *et;
+    HVENC_Cfg cfg;
+} refdrv;
+
+static int g_quiet_fd = -1;
+static void hush(void)   { fflush(stdout); g_quiet_fd = dup(1); int n = open("/dev/null", 1); dup2(n, 1); close(n); }
+static void unhush(void) { fflush(stdout); if (g_quiet_fd >= 0) { dup2(g_quiet_fd, 1); close(g_quiet_fd); g_quiet_fd = -1; } }
+
+static void default_cfg(HVENC_Cfg *cfg, int width, int height, int qp, int sign_hiding)
+{
+    memset(cfg, 0, sizeof *cfg);
+    cfg->size = sizeof *cfg;
+    cfg->width = width; cfg->height = height;
+    cfg->profile = 1;
+    cfg->intra_period = 100; cfg->gop_size = 1; cfg->num_b = 0;
+    cfg->motion_estimation_precision = QUARTER_PEL;
+    cfg->qp = qp; cfg->frame_rate = 25; cfg->num_ref_frames = 1; cfg->cu_size = 64;
+    cfg->max_pred_partition_depth = 4; cfg->max_intra_tr_depth = 2; cfg->max_inter_tr_depth = 1;
+    cfg->num_enc_engines = 1; cfg->wfpp_enable = 0; cfg->wfpp_num_threads = 1;
+    cfg->sign_hiding = sign_hiding; cfg->sample_adaptive_offset = 1;
+    cfg->rd_mode = RD_FAST; cfg->bitrate_mode = BR_FIXED_QP; cfg->bitrate = 1250;
+    cfg->vbv_size = 1250; cfg->vbv_init = 437; cfg->chroma_qp_offset = 2;
+    cfg->reinit_gop_on_scene_change = 1; cfg->performance_mode = PERF_FASTER_COMPUTATION;
+}
+
+refdrv *refdrv_open(int width, int height, int qp, int sign_hiding)
+{
+    refdrv *d = (refdrv *)calloc(1, sizeof *d);
+    hush();
+    d->handle = HOMER_enc_init();
+    default_cfg(&d->cfg, width, height, qp, sign_hiding);
+    int ok = HOMER_enc_control(d->handle, HOMER_SETCFG, &d->cfg);
+    unhush();
+    if (!ok) { free(d); return NULL; }
+    d->enc = (hvenc_enc_t *)d->handle;
+    d->eng = d->enc->encoder_engines[0];
+    d->et = d->eng->thread[0];
+    return d;
+}
+
+void refdrv_close(refdrv *d)
+{
+    if (!d) return;
+    hush();
+    HOMER_enc_close(d->handle);
+    unhush();
+    free(d);
+}
+
+/* 1 when the CPUID branch picked the SSE4.2 table (hmr_encoder_lib.c:155-186) */
+int refdrv_sse_selected(refdrv *d) { return d->enc->funcs.sad == sse_aligned_sad; }
+
+const uint32_t *refdrv_scan(refdrv *d, int mode, int log2n) { return d->enc->scan_pyramid[mode][log2n - 1]; }
+const int32_t *refdrv_quant_table(refdrv *d, int log2n, int list, int rem) { return d->enc->quant_pyramid[log2n - 2][list][rem]; }
+const int32_t *refdrv_dequant_table(refdrv *d, int log2n, int list, int rem) { return d->enc->dequant_pyramid[log2n - 2][list][rem]; }
+
+static void set_slice(refdrv *d, int is_islice, int sign_hiding)
+{
+    d->eng->current_pict.slice.slice_type = is_islice ? I_SLICE : P_SLICE;
+    d->et->pps->sign_data_hiding_flag = sign_hiding;
+}
+
+/* src/dst must be 16-byte aligned (aligned SSE loads, hmr_sse42_functions_quant.c:59-82) */
+void refdrv_quant(refdrv *d, int16_t *src, int16_t *dst, int16_t *delta_u_out, int scan_mode, int log2n, int comp,
+                  int is_intra, int is_islice, int sign_hiding, int per, int rem, int *ac_sum)
+{
+    const int n = 1 << log2n;
+    const int depth = d->et->max_cu_size_shift - log2n - (comp != Y_COMP);
+    set_slice(d, is_islice, sign_hiding);
+    d->enc->funcs.quant(d->et, src, dst, scan_mode, depth, comp, REG_DCT, is_intra, ac_sum, n, per, rem);
+    if (delta_u_out) memcpy(delta_u_out, d->et->aux_buff, sizeof(int16_t) * n * n);
+}
+
+void refdrv_inv_quant(refdrv *d, int16_t *src, int16_t *dst, int log2n, int comp, int is_intra, int per, int rem)
+{
+    const int n = 1 << log2n;
+    const int depth = d->et->max_cu_size_shift - log2n - (comp != Y_COMP);
+    d->enc->funcs.inv_quant(d->et, src, dst, depth, comp, is_intra, n, per, rem);
+}
+
+/* the plain-C twins, to document where C and SSE4.2 differ */
+void refdrv_quant_plainc(refdrv *d, int16_t *src, int16_t *dst, int scan_mode, int log2n, int comp,
+                         int is_intra, int is_islice, int sign_hiding, int per, int rem, int *ac_sum)
+{
+    const int n = 1 << log2n;
+    const int depth = d->et->max_cu_size_shift - log2n - (comp != Y_COMP);
+    set_slice(d, is_islice, sign_hiding);
+    quant(d->et, src, dst, scan_mode, depth, comp, REG_DCT, is_intra, ac_sum, n, per, rem);
+}
+
+/* out[0..3] = mv.x, mv.y, subpix.x, subpix.y; returns best SAD.  cands are (x,y) pairs in quarter-pel units. */
+uint32_t refdrv_motion_estimation(refdrv *d, int16_t *orig, int orig_stride, int16_t *ref, int ref_stride,
+                                  int gx, int gy, int size, int frame_w, int frame_h,
+                                  int n_amvp, const int32_t *amvp, int n_start, const int32_t *start,
+                                  int qp, double avg_dist, unsigned action, int32_t *out)
+{
+    henc_thread_t *et = d->et;
+    cu_partition_info_t cu;
+    ctu_info_t ctu;
+    mv_candiate_list_t amvp_list;
+    motion_vector_t mv = { 0, 0 }, sub = { 0, 0 };
+    int shift = 0;
+    memset(&cu, 0, sizeof cu); memset(&ctu, 0, sizeof ctu); memset(&amvp_list, 0, sizeof amvp_list);
+    while ((1 << shift) < size) shift++;
+    cu.size = (uint16_t)size; cu.qp = (uint32_t)qp;
+    cu.x_position = (uint16_t)(gx & 63); cu.y_position = (uint16_t)(gy & 63);
+    if (cu.x_position + size > 64) cu.x_position = 0;
+    if (cu.y_position + size > 64) cu.y_position = 0;
+    amvp_list.num_mv_candidates = n_amvp;
+    for (int i = 0; i < n_amvp; i++) { amvp_list.mv_candidates[i].mv.hor_vector = amvp[2 * i]; amvp_list.mv_candidates[i].mv.ver_vector = amvp[2 * i + 1]; }
+    et->mv_search_candidates.num_mv_candidates = n_start;
+    for (int i = 0; i < n_start; i++) { et->mv_search_candidates.mv_candidates[i].mv.hor_vector = start[2 * i]; et->mv_search_candidates.mv_candidates[i].mv.ver_vector = start[2 * i + 1]; }
+    d->eng->avg_dist = avg_dist;
+    uint32_t best = hmr_motion_estimation(et, &ctu, &cu, orig, orig_stride, ref, ref_stride, gx, gy, 0, 0, size, shift,
+                                          MOTION_SEARCH_RANGE_X, MOTION_SEARCH_RANGE_Y, frame_w, frame_h, &mv, &sub, &amvp_list, 0, action);
+    out[0] = mv.hor_vector; out[1] = mv.ver_vector; out[2] = sub.hor_vector; out[3] = sub.ver_vector;
+    return best;
+}
+
+void refdrv_mc_luma(refdrv *d, int16_t *ref, int ref_stride, int16_t *pred, int pred_stride, int size, int mvx, int mvy)
+{
+    motion_vector_t mv = { mvx, mvy };
+    cu_partition_info_t cu;
+    int shift = 0;
+    memset(&cu, 0, sizeof cu);
+    while ((1 << shift) < size) shift++;
+    hmr_motion_compensation_luma(d->et, &cu, ref, ref_stride, pred, pred_stride, size, size, shift, &mv, 0);
+}
+
+void refdrv_mc_chroma(refdrv *d, int16_t *ref, int ref_stride, int16_t *pred, int pred_stride, int size, int mvx, int mvy)
+{
+    motion_vector_t mv = { mvx, mvy };
+    int shift = 0;
+    while ((1 << shift) < size) shift++;
+    hmr_motion_compensation_chroma(d->et, ref, ref_stride, pred, pred_stride, size, shift, &mv, 0);
+}
+
+/* One inter TU through the reference's own chain (hmr_motion_inter.c:40 / :133).
+ * orig/pred: n x n samples, row stride n.  depth: CU depth (1 -> 32x32 ... 4 -> 4x4 luma); part: index inside that depth.
+ * comp 0 luma, 1 U, 2 V (chroma TU is n/2, taken from the same CU; a 4x4 luma CU has no chroma TU of its own).
+ * Returns the function's return value (ssd); coeff_out n*n levels, dec_out n*n samples. */
+int refdrv_encode_inter_tu(refdrv *d, const int16_t *orig, const int16_t *pred, int depth, int part, int comp, int qp,
+                           int is_islice, int sign_hiding, double avg_dist, int16_t *coeff_out, int16_t *dec_out, int *sum_out)
+{
+    henc_thread_t *et = d->et;
+    ctu_info_t *ctu = &d->eng->ctu_info[0];
+    cu_partition_info_t *cu = &ctu->partition_list[et->partition_depth_start[depth]] + part;
+    const int n = comp == Y_COMP ? cu->size : cu->size_chroma;
+    const int px = comp == Y_COMP ? cu->x_position : cu->x_position_chroma;
+    const int py = comp == Y_COMP ? cu->y_position : cu->y_position_chroma;
+    int sum = 0, ret;
+    wnd_t *quant_wnd = et->transform_quant_wnd[depth + 1];
+    wnd_t *dec_wnd = et->decoded_mbs_wnd[depth + 1];
+
+    set_slice(d, is_islice, sign_hiding);
+    d->eng->current_pict.slice.qp = qp;
+    d->eng->avg_dist = avg_dist;
+    cu->qp = (uint32_t)qp;
+
+    int16_t *o = WND_POSITION_2D(int16_t *, et->curr_mbs_wnd, comp, px, py, 0, et->ctu_width);
+    int16_t *p = WND_POSITION_2D(int16_t *, et->prediction_wnd[0], comp, px, py, 0, et->ctu_width);
+    int16_t *r = WND_POSITION_2D(int16_t *, et->residual_wnd, comp, px, py, 0, et->ctu_width);
+    const int os = WND_STRIDE_2D(et->curr_mbs_wnd, comp), ps = WND_STRIDE_2D(et->prediction_wnd[0], comp), rs = WND_STRIDE_2D(et->residual_wnd, comp);
+    for (int y = 0; y < n; y++) {
+        memcpy(o + y * os, orig + y * n, sizeof(int16_t) * n);
+        memcpy(p + y * ps, pred + y * n, sizeof(int16_t) * n);
+    }
+    et->funcs->predict(o, os, p, ps, r, rs, n);            /* predict_inter, hmr_motion_inter.c:3059-3061 */
+    if (comp == Y_COMP)
+        ret = encode_inter_cu(et, ctu, cu, depth, SIZE_2Nx2N, &sum, 0);
+    else
+        ret = encode_inter_cu_chroma(et, ctu, cu, comp, depth, SIZE_2Nx2N, &sum, 0);
+
+    int16_t *q = comp == Y_COMP
+        ? WND_POSITION_1D(int16_t *, *quant_wnd, comp, 0, et->ctu_width, (cu->abs_index << et->num_partitions_in_cu_shift))
+        : WND_POSITION_1D(int16_t *, *quant_wnd, comp, 0, et->ctu_width, (cu->abs_index << et->num_partitions_in_cu_shift) >> 2);
+    memcpy(coeff_out, q, sizeof(int16_t) * n * n);
+    int16_t *dd = WND_POSITION_2D(int16_t *, *dec_wnd, comp, px, py, 0, et->ctu_width);
+    const int ds = WND_STRIDE_2D(*dec_wnd, comp);
+    for (int y = 0; y < n; y++) memcpy(dec_out + y * n, dd + y * ds, sizeof(int16_t) * n);
+    *sum_out = sum;
+    return ret;
+}
+
+int refdrv_chroma_qp(refdrv *d, int qp)
+{
+    extern const uint8_t chroma_scale_conversion_table[];
+    int v = qp + d->eng->chroma_qp_offset;
+    return chroma_scale_conversion_table[v < 0 ? 0 : (v > 57 ? 57 : v)];
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Lock-step whole-encode driver: feed one frame, spin until its NAL units arrive, append them,
+ * repeat; then HOMER_END and drain.  yuv: planar 4:2:0 8-bit frames back to back.  Returns bytes written to
+ * `bitstream` (capacity cap) or -1.  recon (optional) receives the reconstructed frames, same layout as yuv.
+ * force_intra != 0 sets image_type = IMAGE_I on every frame (the only way to get all-intra, hmr_encoder_lib.c:311).
+ * hook (optional) is called once after SETCFG with the address of the encoder's low_level_funcs_t so that a
+ * replacement table can be installed (this is the drop-in boundary, hmr_private.h:1063 / :1443).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef void (*refdrv_table_hook)(void *funcs_table, void *user);
+
+long refdrv_encode_lockstep(int width, int height, int n_frames, const uint8_t *yuv, int qp, int sign_hiding,
+                            int force_intra, int performance_mode, uint8_t *bitstream, long cap, uint8_t *recon,
+                            refdrv_table_hook hook, void *hook_user, double *seconds_out)
+{
+    HVENC_Cfg cfg;
+    encoder_in_out_t in, out_frame, out_stream;
+    nalu_t *nalus[8];
+    uint32_t n_nalus = 0;
+    long written = 0;
+    const long ysz = (long)width * height, csz = ysz >> 2, fsz = ysz + 2 * csz;
+    int got = 0;
+
+    hush();
+    void *h = HOMER_enc_init();
+    default_cfg(&cfg, width, height, qp, sign_hiding);
+    if (performance_mode >= 0) cfg.performance_mode = performance_mode;
+    if (!HOMER_enc_control(h, HOMER_SETCFG, &cfg)) { unhush(); return -1; }
+    if (hook) hook(&((hvenc_enc_t *)h)->funcs, hook_user);
+
+    memset(&in, 0, sizeof in); memset(&out_frame, 0, sizeof out_frame); memset(&out_stream, 0, sizeof out_stream);
+    out_stream.stream.streams[0] = (uint8_t *)malloc(0x2000000);
+    if (recon) for (int c = 0; c < 3; c++) out_frame.stream.streams[c] = (uint8_t *)malloc(c ? csz : ysz);
+
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int f = 0; f <= n_frames; f++) {
+        if (f < n_frames) {
+            const uint8_t *fr = yuv + f * fsz;
+            in.stream.streams[0] = (uint8_t *)fr; in.stream.streams[1] = (uint8_t *)fr + ysz; in.stream.streams[2] = (uint8_t *)fr + ysz + csz;
+            in.stream.data_stride[0] = width; in.stream.data_stride[1] = in.stream.data_stride[2] = width / 2;
+            in.pts = f; in.image_type = force_intra ? IMAGE_I : IMAGE_AUTO;
+            HOMER_enc_encode(h, &in);
+        } else {
+            HOMER_enc_control(h, HOMER_END, NULL);
+        }
+        /* spin until this frame's output set is there */
+        for (long spins = 0; got < (f < n_frames ? f + 1 : n_frames) && spins < 200000000L; spins++) {
+            n_nalus = 8;
+            HOMER_enc_get_coded_frame(h, &out_frame, nalus, &n_nalus);
+            if (n_nalus > 0) {
+                HOMER_enc_write_annex_b_output(nalus, n_nalus, &out_stream);
+                const long sz = out_stream.stream.data_size[0];
+                if (written + sz > cap) { unhush(); return -1; }
+                memcpy(bitstream + written, out_stream.stream.streams[0], sz);
+                written += sz;
+                if (recon) {
+                    uint8_t *r = recon + got * fsz;
+                    memcpy(r, out_frame.stream.streams[0], ysz);
+                    memcpy(r + ysz, out_frame.stream.streams[1], csz);
+                    memcpy(r + ysz + csz, out_frame.stream.streams[2], csz);
+                }
+                got++;
+            } else {
+                usleep(50);
+            }
+        }
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (seconds_out) *seconds_out = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    HOMER_enc_close(h);
+    unhush();
+    free(out_stream.stream.streams[0]);
+    if (recon) for (int c = 0; c < 3; c++) free(out_frame.stream.streams[c]);
+    return got == n_frames ? written : -1;
+}

@@ -1,0 +1,162 @@
+"""ctypes access to the checker: oracle/liboracle.so (C restatement) and, when it was built, the compiled
+UNMODIFIED reference under oracle/_ref/ (libhomer_ref.so + librefdrv.so).  Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+i16p = C.POINTER(C.c_int16)
+i32p = C.POINTER(C.c_int32)
+u8p = C.POINTER(C.c_uint8)
+
+
+def ptr(a, off=0):
+    """int16 pointer `off` elements into a C-contiguous int16 array."""
+    assert a.dtype == np.int16 and a.flags["C_CONTIGUOUS"]
+    return C.cast(a.ctypes.data + 2 * off, i16p)
+
+
+def aligned_i16(n, align=64):
+    raw = np.zeros(n + align, dtype=np.int16)
+    off = (-raw.ctypes.data % align) // 2
+    return raw[off:off + n]
+
+
+def build_oracle():
+    if not os.path.exists(os.path.join(ORACLE_DIR, "liboracle.so")) or (
+            os.path.isdir("/root/reference") and not os.path.exists(os.path.join(ORACLE_DIR, "_ref", "librefdrv.so"))):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
+
+
+class OrcMv(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32)]
+
+
+class OrcMeIn(C.Structure):
+    _fields_ = [("orig", i16p), ("orig_stride", C.c_int), ("ref", i16p), ("ref_stride", C.c_int),
+                ("gx", C.c_int), ("gy", C.c_int), ("size", C.c_int), ("frame_w", C.c_int), ("frame_h", C.c_int),
+                ("range_x", C.c_int), ("range_y", C.c_int),
+                ("n_amvp", C.c_int), ("amvp", OrcMv * 2), ("n_start", C.c_int), ("start", OrcMv * 3),
+                ("qp", C.c_int), ("avg_dist", C.c_double), ("action", C.c_int)]
+
+
+class OrcMeOut(C.Structure):
+    _fields_ = [("mv", OrcMv), ("subpix", OrcMv), ("sad", C.c_uint32), ("n_int_sads", C.c_uint32)]
+
+
+class OrcTuOut(C.Structure):
+    _fields_ = [("sum", C.c_int32), ("ssd", C.c_uint32), ("ssd_zero", C.c_uint32), ("zeroed", C.c_int32)]
+
+
+_oracle = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        build_oracle()
+        L = C.CDLL(os.path.join(ORACLE_DIR, "liboracle.so"))
+        L.orc_sad.restype = C.c_uint32
+        L.orc_ssd16b.restype = C.c_uint32
+        L.orc_tables_create.restype = C.c_void_p
+        L.orc_tables_destroy.argtypes = [C.c_void_p]
+        for f in ("orc_tables_scan",):
+            getattr(L, f).restype = C.POINTER(C.c_uint32)
+            getattr(L, f).argtypes = [C.c_void_p, C.c_int, C.c_int]
+        for f in ("orc_tables_quant", "orc_tables_dequant"):
+            getattr(L, f).restype = i32p
+            getattr(L, f).argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_quant.argtypes = [C.c_void_p, i16p, i16p, i16p] + [C.c_int] * 8 + [C.POINTER(C.c_int)]
+        L.orc_inv_quant.argtypes = [C.c_void_p, i16p, i16p] + [C.c_int] * 5
+        L.orc_mv_cost.restype = C.c_uint32
+        L.orc_mv_cost.argtypes = [C.POINTER(OrcMv), C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.orc_motion_estimation.argtypes = [C.POINTER(OrcMeIn), C.POINTER(OrcMeOut)]
+        L.orc_mc_luma.argtypes = [i16p, C.c_int, i16p, C.c_int, C.c_int, OrcMv]
+        L.orc_mc_chroma.argtypes = [i16p, C.c_int, i16p, C.c_int, C.c_int, OrcMv]
+        L.orc_encode_inter_tu.argtypes = [C.c_void_p, i16p, C.c_int, i16p, C.c_int, i16p, i16p, C.c_int,
+                                          C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                          C.POINTER(OrcTuOut)]
+        L.tables = L.orc_tables_create()
+        _oracle = L
+    return _oracle
+
+
+_ref = None
+
+
+def have_ref():
+    build_oracle()
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "librefdrv.so"))
+
+
+def ref():
+    """(libhomer_ref, librefdrv) -- the compiled reference.  Only call when have_ref()."""
+    global _ref
+    if _ref is None:
+        R = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libhomer_ref.so"), mode=C.RTLD_GLOBAL)
+        D = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "librefdrv.so"))
+        R.sse_aligned_sad.restype = C.c_uint32
+        R.sse_aligned_ssd16b.restype = C.c_uint32
+        R.sad.restype = C.c_uint32
+        R.ssd16b.restype = C.c_uint32
+        D.refdrv_open.restype = C.c_void_p
+        D.refdrv_open.argtypes = [C.c_int] * 4
+        D.refdrv_close.argtypes = [C.c_void_p]
+        D.refdrv_sse_selected.argtypes = [C.c_void_p]
+        D.refdrv_scan.restype = C.POINTER(C.c_uint32)
+        D.refdrv_scan.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        for f in ("refdrv_quant_table", "refdrv_dequant_table"):
+            getattr(D, f).restype = i32p
+            getattr(D, f).argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        D.refdrv_quant.argtypes = [C.c_void_p, i16p, i16p, i16p] + [C.c_int] * 8 + [C.POINTER(C.c_int)]
+        D.refdrv_quant_plainc.argtypes = [C.c_void_p, i16p, i16p] + [C.c_int] * 8 + [C.POINTER(C.c_int)]
+        D.refdrv_inv_quant.argtypes = [C.c_void_p, i16p, i16p] + [C.c_int] * 5
+        D.refdrv_motion_estimation.restype = C.c_uint32
+        D.refdrv_motion_estimation.argtypes = [C.c_void_p, i16p, C.c_int, i16p, C.c_int] + [C.c_int] * 5 + [
+            C.c_int, i32p, C.c_int, i32p, C.c_int, C.c_double, C.c_uint, i32p]
+        D.refdrv_mc_luma.argtypes = [C.c_void_p, i16p, C.c_int, i16p, C.c_int, C.c_int, C.c_int, C.c_int]
+        D.refdrv_mc_chroma.argtypes = [C.c_void_p, i16p, C.c_int, i16p, C.c_int, C.c_int, C.c_int, C.c_int]
+        D.refdrv_encode_inter_tu.argtypes = [C.c_void_p, i16p, i16p] + [C.c_int] * 6 + [C.c_double, i16p, i16p,
+                                                                                       C.POINTER(C.c_int)]
+        D.refdrv_chroma_qp.argtypes = [C.c_void_p, C.c_int]
+        D.refdrv_encode_lockstep.restype = C.c_long
+        D.refdrv_encode_lockstep.argtypes = [C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             u8p, C.c_long, u8p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        _ref = (R, D)
+    return _ref
+
+
+_drv = {}
+
+
+def refdrv(width=416, height=240, qp=32, sign_hiding=1):
+    """a live reference encoder (its henc_thread_t is what quant / ME / the TQ chain need)"""
+    key = (width, height, qp, sign_hiding)
+    if key not in _drv:
+        _, D = ref()
+        h = D.refdrv_open(width, height, qp, sign_hiding)
+        assert h, "reference SETCFG failed"
+        _drv[key] = h
+    return _drv[key]
+
+
+def make_frame_pair(rng, w, h, pad, shift=(3, 2), noise=3.0):
+    """Synthetic current / reference luma pair: block texture, blurred, panned, plus noise.
+    Returns int16 planes of (h+2*pad) x (w+2*pad), reference border-replicated."""
+    tex = rng.integers(0, 256, size=((h + 96) // 8 + 2, (w + 96) // 8 + 2)).astype(np.float64)
+    tex = np.kron(tex, np.ones((8, 8)))
+    k = np.ones(9) / 9.0
+    tex = np.apply_along_axis(lambda r: np.convolve(r, k, mode="same"), 1, tex)
+    tex = np.apply_along_axis(lambda r: np.convolve(r, k, mode="same"), 0, tex)
+
+    def crop(ox, oy):
+        f = tex[16 + oy:16 + oy + h, 16 + ox:16 + ox + w] + rng.normal(0, noise, size=(h, w))
+        return np.clip(np.rint(f), 0, 255).astype(np.int16)
+
+    cur = crop(shift[0], shift[1])
+    ref_ = crop(0, 0)
+    return np.pad(cur, pad, mode="edge"), np.pad(ref_, pad, mode="edge")
