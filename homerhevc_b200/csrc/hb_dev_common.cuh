@@ -1,0 +1,54 @@
+// hb_dev_common.cuh -- device helpers shared by all kernels (sm_100a).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define HB_FULL_MASK 0xffffffffu
+
+// unaligned 4-byte read of 8-bit samples: two aligned words + funnel shift (read-only path)
+__device__ __forceinline__ uint32_t hb_ld_u8x4(const uint8_t *p)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+    const uint32_t lo = __ldg(q), hi = __ldg(q + 1);
+    return __funnelshift_r(lo, hi, static_cast<uint32_t>(a & 3) * 8u);
+}
+
+__device__ __forceinline__ int hb_clip255(int v) { return min(max(v, 0), 255); }
+__device__ __forceinline__ int hb_sat16(int v) { return min(max(v, -32768), 32767); }
+
+__device__ __forceinline__ uint32_t hb_pack4(int a, int b, int c, int d)
+{
+    return static_cast<uint32_t>(a) | (static_cast<uint32_t>(b) << 8) | (static_cast<uint32_t>(c) << 16) | (static_cast<uint32_t>(d) << 24);
+}
+
+// HEVC interpolation taps (hmr_motion_inter.c:240-258) as compile-time immediates
+template <int F> __device__ __forceinline__ int hb_luma8(int a0, int a1, int a2, int a3, int a4, int a5, int a6, int a7)
+{
+    if (F == 1) return -a0 + 4 * a1 - 10 * a2 + 58 * a3 + 17 * a4 - 5 * a5 + a6;
+    if (F == 2) return -a0 + 4 * a1 - 11 * a2 + 40 * a3 + 40 * a4 - 11 * a5 + 4 * a6 - a7;
+    if (F == 3) return a1 - 5 * a2 + 17 * a3 + 58 * a4 - 10 * a5 + 4 * a6 - a7;
+    return 64 * a3;
+}
+__device__ __forceinline__ int hb_luma8_dyn(int f, int a0, int a1, int a2, int a3, int a4, int a5, int a6, int a7)
+{
+    switch (f) {
+    case 1: return hb_luma8<1>(a0, a1, a2, a3, a4, a5, a6, a7);
+    case 2: return hb_luma8<2>(a0, a1, a2, a3, a4, a5, a6, a7);
+    case 3: return hb_luma8<3>(a0, a1, a2, a3, a4, a5, a6, a7);
+    default: return 64 * a3;
+    }
+}
+__device__ __forceinline__ int hb_chroma4_dyn(int f, int a0, int a1, int a2, int a3)
+{
+    switch (f) {
+    case 1: return -2 * a0 + 58 * a1 + 10 * a2 - 2 * a3;
+    case 2: return -4 * a0 + 54 * a1 + 16 * a2 - 2 * a3;
+    case 3: return -6 * a0 + 46 * a1 + 28 * a2 - 4 * a3;
+    case 4: return -4 * a0 + 36 * a1 + 36 * a2 - 4 * a3;
+    case 5: return -4 * a0 + 28 * a1 + 46 * a2 - 6 * a3;
+    case 6: return -2 * a0 + 16 * a1 + 54 * a2 - 4 * a3;
+    case 7: return -2 * a0 + 10 * a1 + 58 * a2 - 2 * a3;
+    default: return 64 * a1;
+    }
+}

@@ -1,0 +1,557 @@
+/*
+ * hb_host.c -- C99 host layer of libhomer_b200: contexts, HEVC tables, resident frames, the per-call drop-ins of
+ * low_level_funcs_t and the batched job API.  All GPU work goes through the thin C shim in hb_shim.h; there is no
+ * CPU implementation of any operator in this file -- without a CUDA device every entry point fails.
+ *
+ * Reference citations are to /root/reference/src/homer_lib/<file>:<line>.
+ */
+#define _POSIX_C_SOURCE 200809L
+#include "hb_host.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ errors */
+static __thread char t_err[256];
+
+const char *hb_last_error(void) { return t_err; }
+
+int hb_fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof t_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int hb_cuda_fail(int cuda_code, const char *what)
+{
+    return hb_fail(HB_ERR_CUDA, "%s: %s", what, hbc_error_string(cuda_code));
+}
+
+/* ------------------------------------------------------------------ HEVC tables (host build, device resident)
+ * Scans: hmr_tables.c:62-196.  Quant/dequant pyramids from the default scaling lists: hmr_tables.c:199-250,
+ * hmr_tables.h:53-85, wiring hmr_encoder_lib.c:103-140. */
+static const uint8_t k_list_intra[64] = {
+    16, 16, 16, 16, 17, 18, 21, 24,  16, 16, 16, 16, 17, 19, 22, 25,  16, 16, 17, 18, 20, 22, 25, 29,  16, 16, 18, 21, 24, 27, 31, 36,
+    17, 17, 20, 24, 30, 35, 41, 47,  18, 19, 22, 27, 35, 44, 54, 65,  21, 22, 25, 31, 41, 54, 70, 88,  24, 25, 29, 36, 47, 65, 88, 115 };
+static const uint8_t k_list_inter[64] = {
+    16, 16, 16, 16, 17, 18, 20, 24,  16, 16, 16, 17, 18, 20, 24, 25,  16, 16, 17, 18, 20, 24, 25, 28,  16, 17, 18, 20, 24, 25, 28, 33,
+    17, 18, 20, 24, 25, 28, 33, 41,  18, 20, 24, 25, 28, 33, 41, 54,  20, 24, 25, 28, 33, 41, 54, 71,  24, 25, 28, 33, 41, 54, 71, 91 };
+static const int32_t k_fwd_scale[6] = { 26214, 23302, 20560, 18396, 16384, 14564 };
+static const int32_t k_inv_scale[6] = { 40, 45, 51, 57, 64, 72 };
+static const uint8_t k_chroma_qp[58] = {            /* hmr_encoder_lib.c:2245 */
+    0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29,
+    29, 30, 31, 32, 33, 33, 34, 34, 35, 35, 36, 36, 37, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51 };
+
+int hb_chroma_qp(int qp, int offset)
+{
+    int v = qp + offset;
+    v = v < 0 ? 0 : (v > 57 ? 57 : v);
+    return k_chroma_qp[v];
+}
+
+/* anti-diagonal walk of a w x w grid starting bottom-left of each diagonal; emits row*w+col */
+static void diag_walk(uint16_t *out, int w)
+{
+    int n = 0;
+    for (int d = 0; d <= 2 * (w - 1); d++)
+        for (int col = (d < w ? 0 : d - w + 1); col < w && col <= d; col++)
+            out[n++] = (uint16_t)((d - col) * w + col);
+}
+
+static void build_scan(uint16_t *out, int mode, int lg)
+{
+    const int w = 1 << lg, g = w >> 2;
+    int n = 0;
+    if (mode == HB_SCAN_DIAG) {
+        if (w == 4) { diag_walk(out, 4); return; }
+        uint16_t group_order[64], inner[16];
+        diag_walk(group_order, g);
+        diag_walk(inner, 4);
+        for (int b = 0; b < g * g; b++) {
+            const int gy = group_order[b] / g, gx = group_order[b] % g;
+            for (int i = 0; i < 16; i++)
+                out[n++] = (uint16_t)((4 * gy + inner[i] / 4) * w + 4 * gx + inner[i] % 4);
+        }
+    } else if (mode == HB_SCAN_HOR) {
+        for (int gy = 0; gy < g; gy++) for (int gx = 0; gx < g; gx++)
+            for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++)
+                out[n++] = (uint16_t)((4 * gy + y) * w + 4 * gx + x);
+    } else {
+        for (int gx = 0; gx < g; gx++) for (int gy = 0; gy < g; gy++)
+            for (int x = 0; x < 4; x++) for (int y = 0; y < 4; y++)
+                out[n++] = (uint16_t)((4 * gy + y) * w + 4 * gx + x);
+    }
+}
+
+static void build_qtables(int32_t *q, int32_t *dq, int lg, int list, int rem)
+{
+    const int w = 1 << lg, up = w > 8 ? w / 8 : 1;
+    const int inter = (lg == 5) ? (list >= 1) : (list >= 3);
+    const uint8_t *m8 = inter ? k_list_inter : k_list_intra;
+    for (int y = 0; y < w; y++)
+        for (int x = 0; x < w; x++) {
+            const int m = (lg == 2) ? 16 : m8[8 * (y / up) + x / up];
+            q[y * w + x] = (k_fwd_scale[rem] << 4) / m;
+            dq[y * w + x] = k_inv_scale[rem] * m;
+        }
+    if (up > 1) { q[0] = (k_fwd_scale[rem] << 4) / 16; dq[0] = k_inv_scale[rem] * 16; }   /* DC of 16x16 / 32x32 lists */
+}
+
+size_t hb_tab_scan_off(int mode, int lg)      /* in uint16 elements; mode 1..3, lg 2..5 */
+{
+    size_t off = 0;
+    for (int m = 1; m <= 3; m++)
+        for (int l = 2; l <= 5; l++) {
+            if (m == mode && l == lg) return off;
+            off += (size_t)1 << (2 * l);
+        }
+    return 0;
+}
+size_t hb_tab_q_off(int lg, int list, int rem) /* in int32 elements */
+{
+    size_t off = 0;
+    for (int l = 2; l <= 5; l++)
+        for (int li = 0; li < 6; li++)
+            for (int r = 0; r < 6; r++) {
+                if (l == lg && li == list && r == rem) return off;
+                off += (size_t)1 << (2 * l);
+            }
+    return 0;
+}
+
+static int tables_upload(hb_ctx *ctx)
+{
+    const size_t n_scan = 3 * (16 + 64 + 256 + 1024);
+    const size_t n_q = 36 * (16 + 64 + 256 + 1024);
+    uint16_t *scan = (uint16_t *)malloc(n_scan * sizeof *scan);
+    int32_t *q = (int32_t *)malloc(n_q * sizeof *q), *dq = (int32_t *)malloc(n_q * sizeof *dq);
+    int rc;
+    if (!scan || !q || !dq) { free(scan); free(q); free(dq); return hb_fail(HB_ERR_NOMEM, "tables: out of host memory"); }
+    for (int m = 1; m <= 3; m++) for (int l = 2; l <= 5; l++) build_scan(scan + hb_tab_scan_off(m, l), m, l);
+    for (int l = 2; l <= 5; l++) for (int li = 0; li < 6; li++) for (int r = 0; r < 6; r++) {
+        /* 32x32 has the two lists 0 (intra) and 1 (inter); index 3 aliases 1 (hmr_encoder_lib.c:135-140), the rest is never used */
+        const int src_list = (l == 5 && li >= 1) ? 1 : li;
+        build_qtables(q + hb_tab_q_off(l, li, r), dq + hb_tab_q_off(l, li, r), l, src_list, r);
+    }
+    if ((rc = hbc_malloc((void **)&ctx->d_scan, n_scan * sizeof *scan)) || (rc = hbc_malloc((void **)&ctx->d_q, n_q * sizeof *q)) ||
+        (rc = hbc_malloc((void **)&ctx->d_dq, n_q * sizeof *dq))) { free(scan); free(q); free(dq); return hb_cuda_fail(rc, "tables: cudaMalloc"); }
+    rc = hbc_h2d_async(ctx->d_scan, scan, n_scan * sizeof *scan, ctx->stream);
+    if (!rc) rc = hbc_h2d_async(ctx->d_q, q, n_q * sizeof *q, ctx->stream);
+    if (!rc) rc = hbc_h2d_async(ctx->d_dq, dq, n_q * sizeof *dq, ctx->stream);
+    if (!rc) rc = hbc_stream_sync(ctx->stream);
+    free(scan); free(q); free(dq);
+    return rc ? hb_cuda_fail(rc, "tables: upload") : HB_OK;
+}
+
+/* ------------------------------------------------------------------ contexts */
+int hb_device_count(void) { return hbc_device_count(); }
+
+int hb_ctx_create(hb_ctx **out, int device)
+{
+    int rc;
+    if (!out) return hb_fail(HB_ERR_ARG, "hb_ctx_create: out is NULL");
+    *out = NULL;
+    if (hbc_device_count() <= 0) return hb_fail(HB_ERR_CUDA, "hb_ctx_create: no CUDA device visible (there is no CPU fallback)");
+    if (device < 0 || device >= hbc_device_count()) return hb_fail(HB_ERR_ARG, "hb_ctx_create: device %d out of range", device);
+    hb_ctx *ctx = (hb_ctx *)calloc(1, sizeof *ctx);
+    if (!ctx) return hb_fail(HB_ERR_NOMEM, "hb_ctx_create: out of memory");
+    ctx->device = device;
+    if ((rc = hbc_set_device(device)) || (rc = hbc_stream_create(&ctx->stream)) ||
+        (rc = hbc_event_create(&ctx->ev[0])) || (rc = hbc_event_create(&ctx->ev[1]))) {
+        free(ctx);
+        return hb_cuda_fail(rc, "hb_ctx_create");
+    }
+    pthread_mutex_init(&ctx->lock, NULL);
+    if ((rc = tables_upload(ctx)) != HB_OK) { hb_ctx_destroy(ctx); return rc; }
+    if ((rc = hbc_malloc((void **)&ctx->d_flag, 256))) { hb_ctx_destroy(ctx); return hb_cuda_fail(rc, "hb_ctx_create: flag"); }
+    hbc_memset_async(ctx->d_flag, 0, 256, ctx->stream);
+    *out = ctx;
+    return HB_OK;
+}
+
+void hb_ctx_destroy(hb_ctx *ctx)
+{
+    if (!ctx) return;
+    hbc_set_device(ctx->device);
+    if (ctx->stream) hbc_stream_sync(ctx->stream);
+    for (int i = 0; i < HB_N_SCRATCH; i++) { if (ctx->d_scratch[i]) hbc_free(ctx->d_scratch[i]); if (ctx->h_scratch[i]) hbc_host_free(ctx->h_scratch[i]); }
+    if (ctx->d_scan) hbc_free(ctx->d_scan);
+    if (ctx->d_q) hbc_free(ctx->d_q);
+    if (ctx->d_dq) hbc_free(ctx->d_dq);
+    if (ctx->d_flag) hbc_free(ctx->d_flag);
+    if (ctx->ev[0]) hbc_event_destroy(ctx->ev[0]);
+    if (ctx->ev[1]) hbc_event_destroy(ctx->ev[1]);
+    if (ctx->stream) hbc_stream_destroy(ctx->stream);
+    pthread_mutex_destroy(&ctx->lock);
+    free(ctx);
+}
+
+int hb_ctx_sync(hb_ctx *ctx)
+{
+    if (!ctx) return hb_fail(HB_ERR_ARG, "hb_ctx_sync: NULL context");
+    const int rc = hbc_stream_sync(ctx->stream);
+    return rc ? hb_cuda_fail(rc, "hb_ctx_sync") : HB_OK;
+}
+void *hb_ctx_stream(hb_ctx *ctx) { return ctx ? ctx->stream : NULL; }
+uint64_t hb_ctx_launch_count(hb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int hb_timer_begin(hb_ctx *ctx)
+{
+    const int rc = hbc_event_record(ctx->ev[0], ctx->stream);
+    return rc ? hb_cuda_fail(rc, "hb_timer_begin") : HB_OK;
+}
+int hb_timer_end(hb_ctx *ctx, float *ms_out)
+{
+    int rc = hbc_event_record(ctx->ev[1], ctx->stream);
+    if (!rc) rc = hbc_event_elapsed(ctx->ev[0], ctx->ev[1], ms_out);
+    return rc ? hb_cuda_fail(rc, "hb_timer_end") : HB_OK;
+}
+
+void *hb_pinned_alloc(size_t bytes)
+{
+    void *p = NULL;
+    const int rc = hbc_host_alloc(&p, bytes);
+    if (rc) { hb_cuda_fail(rc, "hb_pinned_alloc"); return NULL; }
+    return p;
+}
+void hb_pinned_free(void *p) { if (p) hbc_host_free(p); }
+
+/* grow-only scratch: device buffer i and its pinned host twin */
+int hb_scratch(hb_ctx *ctx, int i, size_t bytes, void **dev, void **host)
+{
+    int rc;
+    if (ctx->scratch_bytes[i] < bytes) {
+        size_t cap = ctx->scratch_bytes[i] ? ctx->scratch_bytes[i] : 4096;
+        while (cap < bytes) cap *= 2;
+        if ((rc = hbc_stream_sync(ctx->stream))) return hb_cuda_fail(rc, "scratch: sync");
+        if (ctx->d_scratch[i]) hbc_free(ctx->d_scratch[i]);
+        if (ctx->h_scratch[i]) hbc_host_free(ctx->h_scratch[i]);
+        ctx->d_scratch[i] = ctx->h_scratch[i] = NULL; ctx->scratch_bytes[i] = 0;
+        if ((rc = hbc_malloc(&ctx->d_scratch[i], cap))) return hb_cuda_fail(rc, "scratch: cudaMalloc");
+        if ((rc = hbc_host_alloc(&ctx->h_scratch[i], cap))) return hb_cuda_fail(rc, "scratch: cudaHostAlloc");
+        ctx->scratch_bytes[i] = cap;
+    }
+    if (dev) *dev = ctx->d_scratch[i];
+    if (host) *host = ctx->h_scratch[i];
+    return HB_OK;
+}
+
+/* ------------------------------------------------------------------ resident frames */
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int hb_frame_create(hb_ctx *ctx, int width, int height, hb_frame **out)
+{
+    if (!ctx || !out) return hb_fail(HB_ERR_ARG, "hb_frame_create: NULL argument");
+    if (width < 16 || height < 16 || (width & 7) || (height & 7)) return hb_fail(HB_ERR_ARG, "hb_frame_create: %dx%d must be multiples of 8, at least 16", width, height);
+    hb_frame *f = (hb_frame *)calloc(1, sizeof *f);
+    if (!f) return hb_fail(HB_ERR_NOMEM, "hb_frame_create: out of memory");
+    f->ctx = ctx; f->w = width; f->h = height;
+    hbc_set_device(ctx->device);
+    for (int c = 0; c < 3; c++) {
+        hbd_plane *p = &f->d.p[c];
+        p->w = c ? width / 2 : width; p->h = c ? height / 2 : height;
+        p->pad = c ? HB_PAD_LUMA / 2 : HB_PAD_LUMA;
+        p->pitch = (int32_t)align_up((size_t)p->w + 2 * (size_t)p->pad, 128);
+        const size_t bytes = (size_t)p->pitch * ((size_t)p->h + 2 * (size_t)p->pad) + 256;
+        const int rc = hbc_malloc((void **)&p->base, bytes);
+        if (rc) { hb_frame_destroy(f); return hb_cuda_fail(rc, "hb_frame_create: cudaMalloc"); }
+        hbc_memset_async(p->base, 0, bytes, ctx->stream);
+        p->org = p->base + (size_t)p->pad * p->pitch + p->pad;
+    }
+    *out = f;
+    return HB_OK;
+}
+
+void hb_frame_destroy(hb_frame *f)
+{
+    if (!f) return;
+    hbc_set_device(f->ctx->device);
+    hbc_stream_sync(f->ctx->stream);
+    for (int c = 0; c < 3; c++) if (f->d.p[c].base) hbc_free(f->d.p[c].base);
+    free(f);
+}
+int hb_frame_width(const hb_frame *f) { return f ? f->w : 0; }
+int hb_frame_height(const hb_frame *f) { return f ? f->h : 0; }
+
+int hb_frame_upload_u8(hb_ctx *ctx, hb_frame *f, const uint8_t *y, int ys, const uint8_t *u, int us, const uint8_t *v, int vs)
+{
+    const uint8_t *src[3] = { y, u, v };
+    const int st[3] = { ys, us, vs };
+    int rc = 0;
+    if (!ctx || !f || !y || !u || !v) return hb_fail(HB_ERR_ARG, "hb_frame_upload_u8: NULL argument");
+    hbc_set_device(ctx->device);
+    for (int c = 0; c < 3 && !rc; c++) {
+        const hbd_plane *p = &f->d.p[c];
+        rc = hbc_h2d_2d_async(p->org, (size_t)p->pitch, src[c], (size_t)st[c], (size_t)p->w, (size_t)p->h, ctx->stream);
+    }
+    if (!rc) { rc = hbk_pad_frame(&f->d, ctx->stream); ctx->launches += 3; }
+    return rc ? hb_cuda_fail(rc, "hb_frame_upload_u8") : HB_OK;
+}
+
+int hb_frame_upload_i16(hb_ctx *ctx, hb_frame *f, const int16_t *y, int ys, const int16_t *u, int us, const int16_t *v, int vs)
+{
+    const int16_t *src[3] = { y, u, v };
+    const int st[3] = { ys, us, vs };
+    int rc = 0;
+    void *dev = NULL, *host = NULL;
+    if (!ctx || !f || !y || !u || !v) return hb_fail(HB_ERR_ARG, "hb_frame_upload_i16: NULL argument");
+    hbc_set_device(ctx->device);
+    pthread_mutex_lock(&ctx->lock);
+    const size_t luma = (size_t)f->w * f->h;
+    if ((rc = hb_scratch(ctx, 0, 2 * (luma + luma / 2) + 64, &dev, &host)) != HB_OK) { pthread_mutex_unlock(&ctx->lock); return rc; }
+    size_t off = 0;
+    uint32_t *flag_h = (uint32_t *)((char *)host);        /* reuse the first word of the pinned twin for the read-back */
+    for (int c = 0; c < 3 && !rc; c++) {
+        const hbd_plane *p = &f->d.p[c];
+        int16_t *d = (int16_t *)dev + off;
+        rc = hbc_h2d_2d_async(d, (size_t)p->w * 2, src[c], (size_t)st[c] * 2, (size_t)p->w * 2, (size_t)p->h, ctx->stream);
+        if (!rc) { rc = hbk_narrow_plane(d, p->w, *p, ctx->d_flag, ctx->stream); ctx->launches++; }
+        off += (size_t)p->w * p->h;
+    }
+    if (!rc) { rc = hbk_pad_frame(&f->d, ctx->stream); ctx->launches += 3; }
+    if (!rc) rc = hbc_d2h_async(flag_h, ctx->d_flag, 4, ctx->stream);
+    if (!rc) rc = hbc_memset_async(ctx->d_flag, 0, 4, ctx->stream);
+    if (!rc) rc = hbc_stream_sync(ctx->stream);
+    const uint32_t flag = rc ? 0 : *flag_h;
+    pthread_mutex_unlock(&ctx->lock);
+    if (rc) return hb_cuda_fail(rc, "hb_frame_upload_i16");
+    if (flag) return hb_fail(HB_ERR_ARG, "hb_frame_upload_i16: samples outside 0..255 (8-bit video only)");
+    return HB_OK;
+}
+
+int hb_frame_download_u8(hb_ctx *ctx, const hb_frame *f, uint8_t *y, int ys, uint8_t *u, int us, uint8_t *v, int vs)
+{
+    uint8_t *dst[3] = { y, u, v };
+    const int st[3] = { ys, us, vs };
+    int rc = 0;
+    if (!ctx || !f || !y || !u || !v) return hb_fail(HB_ERR_ARG, "hb_frame_download_u8: NULL argument");
+    hbc_set_device(ctx->device);
+    for (int c = 0; c < 3 && !rc; c++) {
+        const hbd_plane *p = &f->d.p[c];
+        rc = hbc_d2h_2d_async(dst[c], (size_t)st[c], p->org, (size_t)p->pitch, (size_t)p->w, (size_t)p->h, ctx->stream);
+    }
+    if (!rc) rc = hbc_stream_sync(ctx->stream);
+    return rc ? hb_cuda_fail(rc, "hb_frame_download_u8") : HB_OK;
+}
+
+/* ------------------------------------------------------------------ batched jobs (host arrays in, host arrays out) */
+static double mv_cost_weight(int qp, double avg_dist)     /* calc_mv_correction, hmr_common.h:53 */
+{
+    double w = avg_dist / 2000.;
+    w = w < .15 ? .15 : (w > 1.4 ? 1.4 : w);
+    return (uint32_t)qp * w;
+}
+double hb_zero_out_k(double avg_dist)                     /* hmr_motion_inter.c:106 */
+{
+    double k = avg_dist / 2.5 - 5.;
+    return k < 1. ? 1. : (k > 20000. ? 20000. : k);
+}
+
+int hb_me_search(hb_ctx *ctx, const hb_frame *cur, const hb_frame *ref, const hb_me_job *jobs, int n_jobs,
+                 const hb_me_result *parent_results, int n_parent, double avg_dist, int action, hb_me_result *results)
+{
+    static const int sizes[4] = { 64, 32, 16, 8 };
+    int rc = HB_OK, crc = 0;
+    void *d_jobs, *h_jobs, *d_res, *h_res, *d_par = NULL, *h_par = NULL;
+    if (!ctx || !cur || !ref || !jobs || !results || n_jobs < 0) return hb_fail(HB_ERR_ARG, "hb_me_search: bad argument");
+    if (cur->w != ref->w || cur->h != ref->h) return hb_fail(HB_ERR_ARG, "hb_me_search: frame sizes differ");
+    if (n_jobs == 0) return HB_OK;
+    for (int i = 0; i < n_jobs; i++) {
+        const hb_me_job *j = &jobs[i];
+        if ((j->size != 8 && j->size != 16 && j->size != 32 && j->size != 64) || j->x < 0 || j->y < 0 || j->x + j->size > cur->w ||
+            j->y + j->size > cur->h || j->n_amvp < 0 || j->n_amvp > 2 || j->n_start < 0 || j->n_start > 3 || j->parent >= n_parent)
+            return hb_fail(HB_ERR_ARG, "hb_me_search: job %d is invalid", i);
+    }
+    hbc_set_device(ctx->device);
+    pthread_mutex_lock(&ctx->lock);
+    if ((rc = hb_scratch(ctx, 0, sizeof(hbd_me_job) * (size_t)n_jobs, &d_jobs, &h_jobs)) != HB_OK) goto done;
+    if ((rc = hb_scratch(ctx, 1, sizeof(hb_me_result) * (size_t)n_jobs, &d_res, &h_res)) != HB_OK) goto done;
+    if (n_parent > 0 && parent_results) {
+        if ((rc = hb_scratch(ctx, 2, sizeof(hb_me_result) * (size_t)n_parent, &d_par, &h_par)) != HB_OK) goto done;
+        memcpy(h_par, parent_results, sizeof(hb_me_result) * (size_t)n_parent);
+        if ((crc = hbc_h2d_async(d_par, h_par, sizeof(hb_me_result) * (size_t)n_parent, ctx->stream))) goto done;
+    }
+    /* group by size, keep the caller's index in `out` */
+    hbd_me_job *hj = (hbd_me_job *)h_jobs;
+    int n = 0, start_of[5];
+    for (int s = 0; s < 4; s++) {
+        start_of[s] = n;
+        for (int i = 0; i < n_jobs; i++) {
+            const hb_me_job *j = &jobs[i];
+            if (j->size != sizes[s]) continue;
+            hbd_me_job *d = &hj[n++];
+            memset(d, 0, sizeof *d);
+            d->x = j->x; d->y = j->y; d->n_amvp = j->n_amvp; d->n_start = j->n_start;
+            for (int k = 0; k < 2; k++) { d->amvp[2 * k] = j->amvp[k].x; d->amvp[2 * k + 1] = j->amvp[k].y; }
+            for (int k = 0; k < 3; k++) { d->start[2 * k] = j->start[k].x; d->start[2 * k + 1] = j->start[k].y; }
+            d->parent = (d_par && j->parent >= 0) ? j->parent : -1;
+            d->out = i;
+            d->corr = mv_cost_weight(j->qp, avg_dist);
+        }
+    }
+    start_of[4] = n;
+    if ((crc = hbc_h2d_async(d_jobs, h_jobs, sizeof(hbd_me_job) * (size_t)n_jobs, ctx->stream))) goto done;
+    for (int s = 0; s < 4 && !crc; s++) {
+        const int cnt = start_of[s + 1] - start_of[s];
+        if (!cnt) continue;
+        crc = hbk_me_search(&cur->d, &ref->d, sizes[s], (const hbd_me_job *)d_jobs + start_of[s], cnt, (const hb_me_result *)d_par,
+                            (hb_me_result *)d_res, action, NULL, ctx->stream);
+        ctx->launches++;
+    }
+    if (!crc) crc = hbc_d2h_async(h_res, d_res, sizeof(hb_me_result) * (size_t)n_jobs, ctx->stream);
+    if (!crc) crc = hbc_stream_sync(ctx->stream);
+    if (!crc) memcpy(results, h_res, sizeof(hb_me_result) * (size_t)n_jobs);
+done:
+    pthread_mutex_unlock(&ctx->lock);
+    if (crc) return hb_cuda_fail(crc, "hb_me_search");
+    return rc;
+}
+
+int hb_mc_predict(hb_ctx *ctx, const hb_frame *ref, hb_frame *pred, const hb_mc_job *jobs, int n_jobs)
+{
+    static const int sizes[4] = { 64, 32, 16, 8 };
+    int rc = HB_OK, crc = 0;
+    void *d_pus, *h_pus, *d_mv, *h_mv;
+    if (!ctx || !ref || !pred || !jobs || n_jobs < 0) return hb_fail(HB_ERR_ARG, "hb_mc_predict: bad argument");
+    if (pred->w != ref->w || pred->h != ref->h) return hb_fail(HB_ERR_ARG, "hb_mc_predict: frame sizes differ");
+    if (n_jobs == 0) return HB_OK;
+    const int reach = HB_PAD_LUMA - 16;                    /* how far outside the picture a predicted block may reach */
+    for (int i = 0; i < n_jobs; i++) {
+        const hb_mc_job *j = &jobs[i];
+        const int x0 = j->x + (j->mv.x >> 2), y0 = j->y + (j->mv.y >> 2);
+        if ((j->size != 8 && j->size != 16 && j->size != 32 && j->size != 64) || j->x < 0 || j->y < 0 || j->x + j->size > ref->w ||
+            j->y + j->size > ref->h || x0 < -reach || y0 < -reach || x0 + j->size > ref->w + reach || y0 + j->size > ref->h + reach)
+            return hb_fail(HB_ERR_ARG, "hb_mc_predict: job %d is invalid or points further than %d samples outside the picture", i, reach);
+    }
+    hbc_set_device(ctx->device);
+    pthread_mutex_lock(&ctx->lock);
+    if ((rc = hb_scratch(ctx, 0, sizeof(hbd_mc_pu) * (size_t)n_jobs, &d_pus, &h_pus)) != HB_OK) goto done;
+    if ((rc = hb_scratch(ctx, 1, sizeof(hb_me_result) * (size_t)n_jobs, &d_mv, &h_mv)) != HB_OK) goto done;
+    hbd_mc_pu *hp = (hbd_mc_pu *)h_pus;
+    hb_me_result *hm = (hb_me_result *)h_mv;
+    int n = 0, start_of[5];
+    memset(hm, 0, sizeof(hb_me_result) * (size_t)n_jobs);
+    for (int s = 0; s < 4; s++) {
+        start_of[s] = n;
+        for (int i = 0; i < n_jobs; i++) {
+            if (jobs[i].size != sizes[s]) continue;
+            hp[n].x = jobs[i].x; hp[n].y = jobs[i].y; hp[n].mv_idx = i;
+            hm[i].mv = jobs[i].mv;
+            n++;
+        }
+    }
+    start_of[4] = n;
+    crc = hbc_h2d_async(d_pus, h_pus, sizeof(hbd_mc_pu) * (size_t)n_jobs, ctx->stream);
+    if (!crc) crc = hbc_h2d_async(d_mv, h_mv, sizeof(hb_me_result) * (size_t)n_jobs, ctx->stream);
+    for (int s = 0; s < 4 && !crc; s++) {
+        const int cnt = start_of[s + 1] - start_of[s];
+        if (!cnt) continue;
+        crc = hbk_mc_predict(&ref->d, &pred->d, sizes[s], (const hbd_mc_pu *)d_pus + start_of[s], cnt, (const hb_me_result *)d_mv, ctx->stream);
+        ctx->launches++;
+    }
+    if (!crc) crc = hbc_stream_sync(ctx->stream);
+done:
+    pthread_mutex_unlock(&ctx->lock);
+    if (crc) return hb_cuda_fail(crc, "hb_mc_predict");
+    return rc;
+}
+
+/* fill the launch-invariant part of a T/Q launch: tables and shifts of (component, size, qp) -- inter lists 3+comp */
+void hb_tq_setup(hb_ctx *ctx, hbd_tq_args *a, int comp, int n, int qp, int is_islice, int sign_hiding)
+{
+    int lg = 2;
+    while ((1 << lg) < n) lg++;
+    const int per = qp / 6, rem = qp % 6;
+    a->n = n;
+    a->qtab = ctx->d_q + hb_tab_q_off(lg, 3 + comp, rem);
+    a->dqtab = ctx->d_dq + hb_tab_q_off(lg, 3 + comp, rem);
+    a->scan = ctx->d_scan + hb_tab_scan_off(HB_SCAN_DIAG, lg);
+    a->qbits = 14 + per + (15 - 8 - lg);
+    a->add = (int32_t)((uint32_t)(is_islice ? 171 : 85) << (a->qbits - 9));    /* hmr_sse42_functions_quant.c:47 */
+    a->per = per;
+    a->sign_hiding = sign_hiding;
+    a->is_luma = comp == 0;
+}
+
+int hb_tq_encode(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_frame *recon, const hb_tu_job *jobs, int n_jobs,
+                 const hb_tq_params *params, int16_t *coeffs, hb_tu_result *results)
+{
+    int rc = HB_OK, crc = 0;
+    if (!ctx || !cur || !pred || !recon || !jobs || !params || !coeffs || !results || n_jobs < 0) return hb_fail(HB_ERR_ARG, "hb_tq_encode: bad argument");
+    if (n_jobs == 0) return HB_OK;
+    size_t total = 0;
+    for (int i = 0; i < n_jobs; i++) {
+        const hb_tu_job *j = &jobs[i];
+        if (j->comp < 0 || j->comp > 2 || (j->size != 4 && j->size != 8 && j->size != 16 && j->size != 32) || j->qp < 0 || j->qp > 51 ||
+            j->x < 0 || j->y < 0 || j->x + j->size > cur->d.p[j->comp].w || j->y + j->size > cur->d.p[j->comp].h ||
+            (j->comp && j->size == 32))
+            return hb_fail(HB_ERR_ARG, "hb_tq_encode: job %d is invalid", i);
+        total += (size_t)j->size * j->size;
+    }
+    hbc_set_device(ctx->device);
+    pthread_mutex_lock(&ctx->lock);
+    void *d_xy, *h_xy, *d_co, *h_co, *d_rs, *h_rs;
+    int *order = (int *)malloc(sizeof(int) * (size_t)n_jobs);
+    char *done_flag = (char *)calloc((size_t)n_jobs, 1);
+    size_t *coeff_off = (size_t *)malloc(sizeof(size_t) * (size_t)n_jobs);
+    if (!order || !done_flag || !coeff_off) { rc = hb_fail(HB_ERR_NOMEM, "hb_tq_encode: out of memory"); goto done; }
+    if ((rc = hb_scratch(ctx, 0, sizeof(int32_t) * 2 * (size_t)n_jobs, &d_xy, &h_xy)) != HB_OK) goto done;
+    if ((rc = hb_scratch(ctx, 1, sizeof(int16_t) * total, &d_co, &h_co)) != HB_OK) goto done;
+    if ((rc = hb_scratch(ctx, 2, sizeof(hb_tu_result) * (size_t)n_jobs, &d_rs, &h_rs)) != HB_OK) goto done;
+    { size_t o = 0; for (int i = 0; i < n_jobs; i++) { coeff_off[i] = o; o += (size_t)jobs[i].size * jobs[i].size; } }
+    /* launch one group per distinct (comp, size, qp); jobs of a group are packed in caller order */
+    int packed = 0;
+    size_t packed_coeff = 0;
+    for (int i = 0; i < n_jobs && !crc; i++) {
+        if (done_flag[i]) continue;
+        const hb_tu_job key = jobs[i];
+        const int g0 = packed;
+        const size_t c0 = packed_coeff;
+        int32_t *xy = (int32_t *)h_xy;
+        for (int k = i; k < n_jobs; k++) {
+            if (done_flag[k] || jobs[k].comp != key.comp || jobs[k].size != key.size || jobs[k].qp != key.qp) continue;
+            done_flag[k] = 1; order[packed] = k;
+            xy[2 * packed] = jobs[k].x; xy[2 * packed + 1] = jobs[k].y;
+            packed++; packed_coeff += (size_t)key.size * key.size;
+        }
+        const int cnt = packed - g0;
+        crc = hbc_h2d_async((int32_t *)d_xy + 2 * g0, xy + 2 * g0, sizeof(int32_t) * 2 * (size_t)cnt, ctx->stream);
+        if (crc) break;
+        hbd_tq_args a;
+        memset(&a, 0, sizeof a);
+        hb_tq_setup(ctx, &a, key.comp, key.size, key.qp, params->is_islice, params->sign_hiding);
+        a.cur = cur->d.p[key.comp]; a.pred = pred->d.p[key.comp]; a.rec = recon->d.p[key.comp];
+        a.jobs_xy = (const int32_t *)d_xy + 2 * g0; a.n_jobs = cnt;
+        a.thr_k = hb_zero_out_k(params->avg_dist);
+        a.weight = key.comp ? params->chroma_weight : 1.0;
+        a.dyn = NULL;
+        a.coeff_out = (int16_t *)d_co + c0;
+        a.res_out = (hb_tu_result *)d_rs + g0;
+        crc = hbk_tq_encode(&a, ctx->stream);
+        ctx->launches++;
+    }
+    if (!crc) crc = hbc_d2h_async(h_co, d_co, sizeof(int16_t) * total, ctx->stream);
+    if (!crc) crc = hbc_d2h_async(h_rs, d_rs, sizeof(hb_tu_result) * (size_t)n_jobs, ctx->stream);
+    if (!crc) crc = hbc_stream_sync(ctx->stream);
+    if (!crc) {
+        size_t o = 0;
+        for (int p = 0; p < n_jobs; p++) {
+            const int k = order[p];
+            const size_t nn = (size_t)jobs[k].size * jobs[k].size;
+            memcpy(coeffs + coeff_off[k], (int16_t *)h_co + o, sizeof(int16_t) * nn);
+            results[k] = ((hb_tu_result *)h_rs)[p];
+            o += nn;
+        }
+    }
+done:
+    free(order); free(done_flag); free(coeff_off);
+    pthread_mutex_unlock(&ctx->lock);
+    if (crc) return hb_cuda_fail(crc, "hb_tq_encode");
+    return rc;
+}

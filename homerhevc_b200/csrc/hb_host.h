@@ -1,0 +1,42 @@
+/* hb_host.h -- internal definitions of the C99 host layer (hb_host.c, hb_percall.c, hb_prepass.c). */
+#ifndef HB_HOST_H
+#define HB_HOST_H
+
+#include <pthread.h>
+#include "hb_shim.h"
+
+#define HB_SCAN_HOR  1      /* hmr_private.h:92-96 */
+#define HB_SCAN_VER  2
+#define HB_SCAN_DIAG 3
+#define HB_N_SCRATCH 4
+
+struct hb_ctx {
+    int device;
+    void *stream;
+    void *ev[2];
+    pthread_mutex_t lock;             /* serialises users of the scratch buffers */
+    uint16_t *d_scan;                 /* device tables, see hb_tab_*_off */
+    int32_t *d_q, *d_dq;
+    uint32_t *d_flag;
+    void *d_scratch[HB_N_SCRATCH], *h_scratch[HB_N_SCRATCH];
+    size_t scratch_bytes[HB_N_SCRATCH];
+    uint64_t launches;
+};
+
+struct hb_frame {
+    hb_ctx *ctx;
+    int w, h;
+    hbd_frame d;
+};
+
+hb_ctx *hb_default_ctx(void);
+int hb_fail(int code, const char *fmt, ...);
+int hb_cuda_fail(int cuda_code, const char *what);
+int hb_scratch(hb_ctx *ctx, int i, size_t bytes, void **dev, void **host);
+size_t hb_tab_scan_off(int mode, int lg);
+size_t hb_tab_q_off(int lg, int list, int rem);
+int hb_chroma_qp(int qp, int offset);
+double hb_zero_out_k(double avg_dist);
+void hb_tq_setup(hb_ctx *ctx, hbd_tq_args *a, int comp, int n, int qp, int is_islice, int sign_hiding);
+
+#endif

@@ -1,0 +1,182 @@
+// hb_kernels_mc.cu -- motion compensation (hmr_motion_compensation_luma / _chroma, hmr_motion_inter.c:1779/:1860,
+// uni-prediction) on resident u8 planes, plus frame maintenance (border replication, int16 -> u8 narrowing).
+//
+// k_mc<T>: one warp predicts one T x T luma tile (T = 16, or 8 for 8x8 PUs) and the two (T/2)x(T/2) chroma tiles of
+// a PU.  The (T+7)x(T+8) reference patch is staged in the warp's shared memory; the horizontal pass writes 14-bit
+// intermediates (value - 8192) next to it and the vertical pass finishes -- or a single pass when one fraction is 0,
+// exactly the three branches of the reference.  No block-level synchronisation.
+#include "hb_shim.h"
+#include "hb_dev_common.cuh"
+
+namespace {
+
+constexpr int kMcWarps = 8;
+
+struct McArgs {
+    hbd_frame ref, pred;
+    const hbd_mc_pu *pus;
+    int n_pus;
+    int tiles_per_pu;      // (size/T)^2
+    int tiles_per_row;     // size/T
+    const hb_me_result *mvsrc;
+};
+
+// generic separable prediction of a W x W tile at (x,y) of `ref` displaced by (ix,iy) whole samples with fractions
+// (fx,fy); NT taps (8 luma / 4 chroma); patch/tmp are per-warp shared memory.
+template <int W, int NT>
+__device__ __forceinline__ void mc_tile(const hbd_plane &ref, const hbd_plane &dst, int x, int y, int ix, int iy, int fx, int fy,
+                                        uint8_t *patch, int16_t *tmp, int lane)
+{
+    constexpr int HALF = NT / 2 - 1;           // taps before the sample: 3 luma, 1 chroma
+    constexpr int PR = W + NT - 1;             // patch rows/cols actually needed
+    constexpr int PSB = ((W + NT - 1 + 3) / 4) * 4 + 4;  // patch stride (bytes), whole words
+    const uint8_t *src = ref.org + (y + iy - HALF) * ref.pitch + (x + ix - HALF);
+    for (int w = lane; w < PR * (PSB / 4); w += 32) {
+        const int r = w / (PSB / 4), c = (w % (PSB / 4)) * 4;
+        *reinterpret_cast<uint32_t *>(patch + r * PSB + c) = hb_ld_u8x4(src + r * ref.pitch + c);
+    }
+    __syncwarp();
+    uint8_t *out = dst.org + y * dst.pitch + x;
+    if (fx == 0 && fy == 0) {
+        for (int e = lane; e < W * W; e += 32) out[(e / W) * dst.pitch + e % W] = patch[(e / W + HALF) * PSB + e % W + HALF];
+    } else if (fx == 0) {                      // vertical only, 8 bit -> 8 bit
+        for (int e = lane; e < W * W; e += 32) {
+            const int r = e / W, c = e % W;
+            int t[NT];
+#pragma unroll
+            for (int k = 0; k < NT; k++) t[k] = patch[(r + k) * PSB + c + HALF];
+            int s;
+            if constexpr (NT == 8) s = hb_luma8_dyn(fy, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
+            else s = hb_chroma4_dyn(fy, t[0], t[1], t[2], t[3]);
+            out[r * dst.pitch + c] = static_cast<uint8_t>(hb_clip255((s + 32) >> 6));
+        }
+    } else if (fy == 0) {                      // horizontal only
+        for (int e = lane; e < W * W; e += 32) {
+            const int r = e / W, c = e % W;
+            int t[NT];
+#pragma unroll
+            for (int k = 0; k < NT; k++) t[k] = patch[(r + HALF) * PSB + c + k];
+            int s;
+            if constexpr (NT == 8) s = hb_luma8_dyn(fx, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
+            else s = hb_chroma4_dyn(fx, t[0], t[1], t[2], t[3]);
+            out[r * dst.pitch + c] = static_cast<uint8_t>(hb_clip255((s + 32) >> 6));
+        }
+    } else {                                   // horizontal to 14 bit, then vertical
+        for (int e = lane; e < PR * W; e += 32) {
+            const int r = e / W, c = e % W;
+            int t[NT];
+#pragma unroll
+            for (int k = 0; k < NT; k++) t[k] = patch[r * PSB + c + k];
+            int s;
+            if constexpr (NT == 8) s = hb_luma8_dyn(fx, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
+            else s = hb_chroma4_dyn(fx, t[0], t[1], t[2], t[3]);
+            tmp[r * W + c] = static_cast<int16_t>(s - 8192);
+        }
+        __syncwarp();
+        for (int e = lane; e < W * W; e += 32) {
+            const int r = e / W, c = e % W;
+            int t[NT];
+#pragma unroll
+            for (int k = 0; k < NT; k++) t[k] = tmp[(r + k) * W + c];
+            int s;
+            if constexpr (NT == 8) s = hb_luma8_dyn(fy, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
+            else s = hb_chroma4_dyn(fy, t[0], t[1], t[2], t[3]);
+            out[r * dst.pitch + c] = static_cast<uint8_t>(hb_clip255((s + 2048 + (8192 << 6)) >> 12));
+        }
+    }
+    __syncwarp();
+}
+
+template <int T>
+__global__ void __launch_bounds__(kMcWarps * 32) k_mc(const McArgs a)
+{
+    constexpr int PSB = ((T + 7 + 3) / 4) * 4 + 4;
+    __shared__ __align__(16) uint8_t s_patch[kMcWarps][(T + 7) * PSB];
+    __shared__ __align__(16) int16_t s_tmp[kMcWarps][(T + 7) * T];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * kMcWarps + warp;
+    if (tile >= a.n_pus * a.tiles_per_pu) return;
+    const int pu_i = tile / a.tiles_per_pu, ti = tile % a.tiles_per_pu;
+    const hbd_mc_pu pu = a.pus[pu_i];
+    const hb_mv mv = a.mvsrc[pu.mv_idx].mv;
+    const int x = pu.x + (ti % a.tiles_per_row) * T, y = pu.y + (ti / a.tiles_per_row) * T;
+
+    mc_tile<T, 8>(a.ref.p[0], a.pred.p[0], x, y, mv.x >> 2, mv.y >> 2, mv.x & 3, mv.y & 3, s_patch[warp], s_tmp[warp], lane);
+    // chroma: eighth-sample units (hmr_motion_inter.c:1863-1867)
+    mc_tile<T / 2, 4>(a.ref.p[1], a.pred.p[1], x >> 1, y >> 1, mv.x >> 3, mv.y >> 3, mv.x & 7, mv.y & 7, s_patch[warp], s_tmp[warp], lane);
+    mc_tile<T / 2, 4>(a.ref.p[2], a.pred.p[2], x >> 1, y >> 1, mv.x >> 3, mv.y >> 3, mv.x & 7, mv.y & 7, s_patch[warp], s_tmp[warp], lane);
+}
+
+// ---- border replication of one plane (reference_picture_border_padding_ctu, hmr_encoder_lib.c:1723): every sample
+// outside the picture takes the nearest picture sample.
+__global__ void k_pad_plane(hbd_plane p)
+{
+    const int W = p.w + 2 * p.pad, H = p.h + 2 * p.pad;
+    const int n_side = 2 * p.pad * p.h;                 // left+right strips of the picture rows
+    const int n_tb = 2 * p.pad * W;                     // top+bottom bands, full padded width
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_side + n_tb; i += gridDim.x * blockDim.x) {
+        int px, py;                                     // padded coordinates
+        if (i < n_side) {
+            const int r = i / (2 * p.pad), c = i % (2 * p.pad);
+            py = p.pad + r;
+            px = c < p.pad ? c : p.w + c;               // c-pad+pad+w
+        } else {
+            const int j = i - n_side, r = j / W;
+            px = j % W;
+            py = r < p.pad ? r : p.h + r;
+        }
+        const int sx = min(max(px - p.pad, 0), p.w - 1), sy = min(max(py - p.pad, 0), p.h - 1);
+        (void)H;
+        p.org[(py - p.pad) * p.pitch + (px - p.pad)] = p.org[sy * p.pitch + sx];
+    }
+}
+
+__global__ void k_narrow_plane(const int16_t *src, int src_stride, hbd_plane dst, uint32_t *range_flag)
+{
+    bool bad = false;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dst.w * dst.h; i += gridDim.x * blockDim.x) {
+        const int r = i / dst.w, c = i % dst.w;
+        const int v = src[r * src_stride + c];
+        bad |= (v < 0 || v > 255);
+        dst.org[r * dst.pitch + c] = static_cast<uint8_t>(v);
+    }
+    if (__any_sync(HB_FULL_MASK, bad) && (threadIdx.x & 31) == 0) atomicOr(range_flag, 1u);
+}
+
+}  // namespace
+
+extern "C" int hbk_mc_predict(const hbd_frame *ref, const hbd_frame *pred, int size, const hbd_mc_pu *pus, int n_pus,
+                              const hb_me_result *mvsrc, void *stream)
+{
+    if (n_pus <= 0) return 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    McArgs a;
+    a.ref = *ref; a.pred = *pred; a.pus = pus; a.n_pus = n_pus; a.mvsrc = mvsrc;
+    const int T = size >= 16 ? 16 : 8;
+    if (size != 8 && size != 16 && size != 32 && size != 64) return static_cast<int>(cudaErrorInvalidValue);
+    a.tiles_per_row = size / T; a.tiles_per_pu = a.tiles_per_row * a.tiles_per_row;
+    const long tiles = static_cast<long>(n_pus) * a.tiles_per_pu;
+    const int grid = static_cast<int>((tiles + kMcWarps - 1) / kMcWarps);
+    if (T == 16) k_mc<16><<<grid, kMcWarps * 32, 0, s>>>(a);
+    else k_mc<8><<<grid, kMcWarps * 32, 0, s>>>(a);
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int hbk_pad_frame(const hbd_frame *f, void *stream)
+{
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    for (int c = 0; c < 3; c++) {
+        const hbd_plane &p = f->p[c];
+        const int n = 2 * p.pad * p.h + 2 * p.pad * (p.w + 2 * p.pad);
+        k_pad_plane<<<(n + 255) / 256, 256, 0, s>>>(p);
+    }
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int hbk_narrow_plane(const int16_t *src, int src_stride, hbd_plane dst, uint32_t *range_flag, void *stream)
+{
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int n = dst.w * dst.h;
+    k_narrow_plane<<<min((n + 255) / 256, 148 * 8), 256, 0, s>>>(src, src_stride, dst, range_flag);
+    return static_cast<int>(cudaGetLastError());
+}

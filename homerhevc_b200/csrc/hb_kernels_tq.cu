@@ -1,0 +1,257 @@
+// hb_kernels_tq.cu -- fused inter T/Q chain (encode_inter_cu / encode_inter_cu_chroma, hmr_motion_inter.c:40/:133)
+// and the per-call transform / quant kernels built from the same warp routines.
+//
+// k_tq<N>: one warp = 32/N transform units, 4 warps per CTA, no block-level synchronisation at all.
+// Per unit: residual = cur - pred (u8 planes) -> 2-D DCT -> quant (+ sign hiding) -> if any level:
+// dequant -> inverse DCT -> SSD(resid, decoded resid), SSD(resid, 0), the reference's zero-out test in
+// IEEE double without contraction -> reconstruction (u8) + levels (int16) + {sum, ssd, ssd_zero, zeroed}.
+// HBM traffic per sample: 2 B read (cur, pred) + 1 B recon + 2 B levels; everything else stays in shared memory.
+#include "hb_shim.h"
+#include "hb_tq_core.cuh"
+
+namespace {
+
+constexpr int kWarpsPerCta = 4;
+
+template <int N>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) k_tq(const hbd_tq_args a)
+{
+    using Q = HbTq<N>;
+    constexpr int S = Q::S, TPW = Q::TPW;
+    __shared__ __align__(16) int16_t smem[kWarpsPerCta][5][Q::ELEMS];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int first_job = (blockIdx.x * kWarpsPerCta + warp) * TPW;
+    if (first_job >= a.n_jobs) return;
+    const double thr_k = a.dyn ? a.dyn->thr_k : a.thr_k;
+    int16_t *X = smem[warp][0], *T = smem[warp][1], *C = smem[warp][2], *L = smem[warp][3], *U = smem[warp][4];
+
+    // ---- residual of every unit of the stack (element-wise, coalesced inside a row)
+    int jx[TPW], jy[TPW];
+#pragma unroll
+    for (int u = 0; u < TPW; u++) {
+        const int j = min(first_job + u, a.n_jobs - 1);
+        jx[u] = __ldg(a.jobs_xy + 2 * j);
+        jy[u] = __ldg(a.jobs_xy + 2 * j + 1);
+    }
+    for (int it = 0; it < N; it++) {
+        const int e = it * 32 + lane;
+        const int row = e / N, col = e % N, unit = row / N, r = row % N;
+        int x = 0, y = 0;
+#pragma unroll
+        for (int u = 0; u < TPW; u++) if (u == unit) { x = jx[u]; y = jy[u]; }
+        const int o = a.cur.org[(y + r) * a.cur.pitch + x + col];
+        const int p = a.pred.org[(y + r) * a.pred.pitch + x + col];
+        X[row * S + col] = static_cast<int16_t>(o - p);
+    }
+    __syncwarp();
+
+    Q::template forward<false>(X, T, C, lane);
+
+    int unit_sum[TPW];
+    Q::quantise(C, L, U, a.qtab, a.qbits, a.add, lane, unit_sum);
+    if (a.sign_hiding) Q::sign_hide(L, C, U, a.scan, lane, unit_sum);
+
+    bool any = false;
+#pragma unroll
+    for (int u = 0; u < TPW; u++) any |= unit_sum[u] > 0;
+    if (any) {                                            // warp-uniform
+        Q::dequantise(L, T, a.dqtab, a.per, lane);        // T = dequantised coefficients
+        Q::template inverse<false>(T, U, C, lane);        // U scratch, C = decoded residual
+    }
+
+    // ---- per-unit SSDs
+    uint32_t ssd_dec[TPW], ssd_zero[TPW];
+#pragma unroll
+    for (int u = 0; u < TPW; u++) { ssd_dec[u] = 0; ssd_zero[u] = 0; }
+    {
+        constexpr int IT_PER_UNIT = (N * N) / 32;
+        for (int it = 0; it < N; it++) {
+            const int e = it * 32 + lane;
+            const int off = Q::elem_off(e);
+            const int r = X[off];
+            const int d = r - (any ? static_cast<int>(C[off]) : 0);
+            uint32_t z = static_cast<uint32_t>(r) * static_cast<uint32_t>(r), s = static_cast<uint32_t>(d) * static_cast<uint32_t>(d);
+            if constexpr (N == 4) {
+                const uint32_t m = lane < 16 ? 0x0000ffffu : 0xffff0000u;
+                z = __reduce_add_sync(m, z); s = __reduce_add_sync(m, s);
+                const uint32_t z0 = __shfl_sync(HB_FULL_MASK, z, 0), z1 = __shfl_sync(HB_FULL_MASK, z, 16);
+                const uint32_t s0 = __shfl_sync(HB_FULL_MASK, s, 0), s1 = __shfl_sync(HB_FULL_MASK, s, 16);
+#pragma unroll
+                for (int u = 0; u < TPW; u++) {
+                    if (u == 2 * it) { ssd_zero[u] = z0; ssd_dec[u] = s0; }
+                    if (u == 2 * it + 1) { ssd_zero[u] = z1; ssd_dec[u] = s1; }
+                }
+            } else {
+                z = __reduce_add_sync(HB_FULL_MASK, z); s = __reduce_add_sync(HB_FULL_MASK, s);
+#pragma unroll
+                for (int u = 0; u < TPW; u++) if (u == it / IT_PER_UNIT) { ssd_zero[u] += z; ssd_dec[u] += s; }
+            }
+        }
+    }
+
+    // ---- decision per unit (hmr_motion_inter.c:90-121 / :186-224), uniform across the warp
+    bool keep[TPW];
+#pragma unroll
+    for (int u = 0; u < TPW; u++) {
+        hb_tu_result r;
+        r.sum = unit_sum[u]; r.zeroed = 0; r.ssd_zero = 0;
+        keep[u] = false;
+        uint32_t zw = ssd_zero[u], dw = ssd_dec[u];
+        if (!a.is_luma) {
+            zw = __double2uint_rz(__dmul_rn(a.weight, static_cast<double>(zw)));
+            dw = __double2uint_rz(__dmul_rn(a.weight, static_cast<double>(dw)));
+        }
+        if (unit_sum[u] > 0) {
+            const double lhs = static_cast<double>(zw);
+            const double base = a.is_luma ? static_cast<double>(static_cast<int32_t>(dw)) : static_cast<double>(dw);
+            const double rhs = __dadd_rn(base, __dmul_rn(thr_k, static_cast<double>(unit_sum[u])));
+            r.ssd = dw; r.ssd_zero = zw;
+            if (lhs <= rhs) { r.zeroed = 1; r.sum = 0; }
+            else keep[u] = true;
+        } else {
+            r.ssd = zw;                                   // ssd16b(residual, zeros)
+        }
+        if (lane == 0 && first_job + u < a.n_jobs) a.res_out[first_job + u] = r;
+    }
+
+    // ---- outputs: levels and reconstruction
+    for (int it = 0; it < N; it++) {
+        const int e = it * 32 + lane;
+        const int row = e / N, col = e % N, unit = row / N, r = row % N;
+        int x = 0, y = 0; bool k = false;
+#pragma unroll
+        for (int u = 0; u < TPW; u++) if (u == unit) { x = jx[u]; y = jy[u]; k = keep[u]; }
+        if (first_job + unit >= a.n_jobs) continue;
+        const int off = row * S + col;
+        a.coeff_out[static_cast<size_t>(first_job + unit) * (N * N) + r * N + col] = k ? L[off] : int16_t(0);
+        const int p = a.pred.org[(y + r) * a.pred.pitch + x + col];
+        a.rec.org[(y + r) * a.rec.pitch + x + col] = static_cast<uint8_t>(hb_clip255(p + (k ? static_cast<int>(C[off]) : 0)));
+    }
+}
+
+// ------------------------------------------------------------------ per-call kernels (one warp, one unit)
+template <int N, bool DST>
+__global__ void __launch_bounds__(32) k_pc_transform(const int16_t *block, int bs, int16_t *coeff)
+{
+    using Q = HbTq<N>;
+    __shared__ __align__(16) int16_t sm[3][Q::ELEMS];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < Q::ELEMS; i += 32) sm[0][i] = 0;
+    __syncwarp();
+    for (int e = lane; e < N * N; e += 32) sm[0][(e / N) * Q::S + e % N] = block[(e / N) * bs + e % N];
+    __syncwarp();
+    Q::template forward<DST>(sm[0], sm[1], sm[2], lane);
+    for (int e = lane; e < N * N; e += 32) coeff[e] = sm[2][(e / N) * Q::S + e % N];
+}
+
+template <int N, bool DST>
+__global__ void __launch_bounds__(32) k_pc_itransform(int16_t *block, int bs, const int16_t *coeff)
+{
+    using Q = HbTq<N>;
+    __shared__ __align__(16) int16_t sm[3][Q::ELEMS];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < Q::ELEMS; i += 32) sm[0][i] = 0;
+    __syncwarp();
+    for (int e = lane; e < N * N; e += 32) sm[0][(e / N) * Q::S + e % N] = coeff[e];
+    __syncwarp();
+    Q::template inverse<DST>(sm[0], sm[1], sm[2], lane);
+    for (int e = lane; e < N * N; e += 32) block[(e / N) * bs + e % N] = sm[2][(e / N) * Q::S + e % N];
+}
+
+template <int N>
+__global__ void __launch_bounds__(32) k_pc_quant(const int16_t *src, int16_t *dst, int16_t *delta_u, int32_t *sum,
+                                                 const int32_t *qtab, const uint16_t *scan, int qbits, int add, int sign_hiding)
+{
+    using Q = HbTq<N>;
+    __shared__ __align__(16) int16_t sm[3][Q::ELEMS];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < Q::ELEMS; i += 32) sm[0][i] = 0;
+    __syncwarp();
+    for (int e = lane; e < N * N; e += 32) sm[0][(e / N) * Q::S + e % N] = src[e];
+    __syncwarp();
+    int unit_sum[Q::TPW];
+    Q::quantise(sm[0], sm[1], sm[2], qtab, qbits, add, lane, unit_sum);
+    if (sign_hiding) Q::sign_hide(sm[1], sm[0], sm[2], scan, lane, unit_sum);
+    for (int e = lane; e < N * N; e += 32) {
+        dst[e] = sm[1][(e / N) * Q::S + e % N];
+        if (delta_u) delta_u[e] = sm[2][(e / N) * Q::S + e % N];
+    }
+    if (lane == 0) *sum = unit_sum[0];
+}
+
+template <int N>
+__global__ void __launch_bounds__(32) k_pc_inv_quant(const int16_t *src, int16_t *dst, const int32_t *dqtab, int per)
+{
+    using Q = HbTq<N>;
+    __shared__ __align__(16) int16_t sm[2][Q::ELEMS];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < Q::ELEMS; i += 32) sm[0][i] = 0;
+    __syncwarp();
+    for (int e = lane; e < N * N; e += 32) sm[0][(e / N) * Q::S + e % N] = src[e];
+    __syncwarp();
+    Q::dequantise(sm[0], sm[1], dqtab, per, lane);
+    for (int e = lane; e < N * N; e += 32) dst[e] = sm[1][(e / N) * Q::S + e % N];
+}
+
+template <int N> int launch_tq(const hbd_tq_args *a, cudaStream_t s)
+{
+    const int per_cta = kWarpsPerCta * HbTq<N>::TPW;
+    const int grid = (a->n_jobs + per_cta - 1) / per_cta;
+    k_tq<N><<<grid, kWarpsPerCta * 32, 0, s>>>(*a);
+    return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace
+
+extern "C" int hbk_tq_encode(const hbd_tq_args *a, void *stream)
+{
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (a->n_jobs <= 0) return 0;
+    switch (a->n) {
+    case 4: return launch_tq<4>(a, s);
+    case 8: return launch_tq<8>(a, s);
+    case 16: return launch_tq<16>(a, s);
+    case 32: return launch_tq<32>(a, s);
+    default: return static_cast<int>(cudaErrorInvalidValue);
+    }
+}
+
+#define HB_DISPATCH_N(n, ...)                                 \
+    switch (n) {                                              \
+    case 4: { constexpr int N = 4; __VA_ARGS__; } break;      \
+    case 8: { constexpr int N = 8; __VA_ARGS__; } break;      \
+    case 16: { constexpr int N = 16; __VA_ARGS__; } break;    \
+    case 32: { constexpr int N = 32; __VA_ARGS__; } break;    \
+    default: return static_cast<int>(cudaErrorInvalidValue); }
+
+extern "C" int hbk_pc_transform(const int16_t *block, int bs, int16_t *coeff, int n, int dst4, void *stream)
+{
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (n == 4 && dst4) k_pc_transform<4, true><<<1, 32, 0, s>>>(block, bs, coeff);
+    else HB_DISPATCH_N(n, k_pc_transform<N, false><<<1, 32, 0, s>>>(block, bs, coeff))
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int hbk_pc_itransform(int16_t *block, int bs, const int16_t *coeff, int n, int dst4, void *stream)
+{
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (n == 4 && dst4) k_pc_itransform<4, true><<<1, 32, 0, s>>>(block, bs, coeff);
+    else HB_DISPATCH_N(n, k_pc_itransform<N, false><<<1, 32, 0, s>>>(block, bs, coeff))
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int hbk_pc_quant(const int16_t *src, int16_t *dst, int16_t *delta_u, int32_t *sum, int n, const int32_t *qtab,
+                            const uint16_t *scan, int qbits, int add, int sign_hiding, void *stream)
+{
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    HB_DISPATCH_N(n, k_pc_quant<N><<<1, 32, 0, s>>>(src, dst, delta_u, sum, qtab, scan, qbits, add, sign_hiding))
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int hbk_pc_inv_quant(const int16_t *src, int16_t *dst, int n, const int32_t *dqtab, int per, void *stream)
+{
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    HB_DISPATCH_N(n, k_pc_inv_quant<N><<<1, 32, 0, s>>>(src, dst, dqtab, per))
+    return static_cast<int>(cudaGetLastError());
+}

@@ -1,0 +1,366 @@
+/*
+ * hb_prepass.c -- frame-level batched pre-pass (section D of include/homer_b200.h).
+ *
+ * One plan per (frame size, QP, band).  Static job lists for every PU size 64/32/16/8 and every TU pass live in
+ * HBM; a frame is one replay of: ME(d) -> MC(d) for d = 0..3 (children read their parent's vector from the result
+ * table of depth d-1, hmr_motion_inter.c:2613), then the inter T/Q chain per pass for Y, U, V.  With use_graph the
+ * whole sequence is captured once per (cur, ref) frame pair and replayed as a single CUDA graph launch; the only
+ * per-frame scalars (MV-cost weight, zero-out threshold -- both functions of avg_dist) are read by the kernels
+ * from a small device block refreshed before each replay.
+ */
+#define _POSIX_C_SOURCE 200809L
+#include "hb_host.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define N_DEPTH HB_PREPASS_DEPTHS
+#define N_PASS  HB_PREPASS_TQ_PASSES
+#define MAX_GRAPHS 8
+
+typedef struct pass_comp {
+    int n_tus, tu;                 /* TU count and size (0 = component not coded in this pass) */
+    int32_t *d_xy;                 /* job coordinates */
+    int16_t *d_coeff;
+    hb_tu_result *d_res;
+} pass_comp;
+
+struct hb_prepass {
+    hb_ctx *ctx;
+    hb_prepass_cfg cfg;
+    int w, h, ctu_cols, ctu_rows, row0, rows;
+    int qp_c;
+    double weight_c;
+    /* motion search / compensation */
+    int grid_w[N_DEPTH], grid_h[N_DEPTH];      /* PU raster grid per depth (covers whole CTUs) */
+    int n_valid[N_DEPTH];
+    hbd_me_job *d_jobs[N_DEPTH];
+    hbd_mc_pu *d_pus[N_DEPTH];
+    hb_me_result *d_me[N_DEPTH];
+    hb_frame *pred[N_DEPTH];
+    /* T/Q */
+    pass_comp pc[N_PASS][3];
+    hb_frame *recon[N_PASS];
+    /* per-frame scalars */
+    hbd_dyn_params *d_dyn;
+    /* captured replays */
+    struct { const hb_frame *cur, *ref; void *exec; } graphs[MAX_GRAPHS];
+    int n_graphs;
+    int launches_per_frame;
+};
+
+static int pass_depth(int pass) { return pass < N_DEPTH ? pass : N_DEPTH - 1; }
+static int pass_luma_tu(int pass) { static const int t[N_PASS] = { 32, 32, 16, 8, 4 }; return t[pass]; }
+
+static int pu_valid(const hb_prepass *pp, int x, int y, int s)
+{
+    const int ctu_row = y / 64;
+    return x + s <= pp->w && y + s <= pp->h && ctu_row >= pp->row0 && ctu_row < pp->row0 + pp->rows;
+}
+
+static int upload(hb_ctx *ctx, void **dev, const void *host, size_t bytes)
+{
+    int rc = hbc_malloc(dev, bytes ? bytes : 16);
+    if (rc) return hb_cuda_fail(rc, "prepass: cudaMalloc");
+    if (bytes) {
+        rc = hbc_h2d_async(*dev, host, bytes, ctx->stream);
+        if (!rc) rc = hbc_stream_sync(ctx->stream);      /* host staging is pageable and freed by the caller */
+        if (rc) return hb_cuda_fail(rc, "prepass: upload");
+    }
+    return HB_OK;
+}
+
+int hb_prepass_create(hb_ctx *ctx, int width, int height, const hb_prepass_cfg *cfg, hb_prepass **out)
+{
+    int rc = HB_OK;
+    if (!ctx || !cfg || !out) return hb_fail(HB_ERR_ARG, "hb_prepass_create: NULL argument");
+    if (cfg->qp < 0 || cfg->qp > 51) return hb_fail(HB_ERR_ARG, "hb_prepass_create: qp %d", cfg->qp);
+    *out = NULL;
+    hb_prepass *pp = (hb_prepass *)calloc(1, sizeof *pp);
+    if (!pp) return hb_fail(HB_ERR_NOMEM, "hb_prepass_create: out of memory");
+    pp->ctx = ctx; pp->cfg = *cfg; pp->w = width; pp->h = height;
+    pp->ctu_cols = (width + 63) / 64; pp->ctu_rows = (height + 63) / 64;
+    pp->row0 = cfg->band_ctu_rows > 0 ? cfg->band_ctu_row0 : 0;
+    pp->rows = cfg->band_ctu_rows > 0 ? cfg->band_ctu_rows : pp->ctu_rows;
+    if (pp->row0 < 0 || pp->row0 + pp->rows > pp->ctu_rows) { free(pp); return hb_fail(HB_ERR_ARG, "hb_prepass_create: band outside the frame"); }
+    pp->qp_c = hb_chroma_qp(cfg->qp, cfg->chroma_qp_offset);
+    pp->weight_c = pow(2.0, (cfg->qp - pp->qp_c) / 3.0);           /* hmr_motion_inter.c:155 */
+    hbc_set_device(ctx->device);
+
+    /* ---- PU job lists */
+    for (int d = 0; d < N_DEPTH && rc == HB_OK; d++) {
+        const int s = 64 >> d;
+        const int gw = pp->ctu_cols * (64 / s), gh = pp->ctu_rows * (64 / s);
+        pp->grid_w[d] = gw; pp->grid_h[d] = gh;
+        hbd_me_job *jobs = (hbd_me_job *)calloc((size_t)gw * gh, sizeof *jobs);
+        hbd_mc_pu *pus = (hbd_mc_pu *)calloc((size_t)gw * gh, sizeof *pus);
+        hb_me_result *init = (hb_me_result *)calloc((size_t)gw * gh, sizeof *init);
+        if (!jobs || !pus || !init) { free(jobs); free(pus); free(init); rc = hb_fail(HB_ERR_NOMEM, "hb_prepass_create: out of memory"); break; }
+        int n = 0;
+        for (int py = 0; py < gh; py++)
+            for (int px = 0; px < gw; px++) {
+                const int idx = py * gw + px;
+                init[idx].sad = 0xffffffffu;
+                if (!pu_valid(pp, px * s, py * s, s)) continue;
+                hbd_me_job *j = &jobs[n];
+                j->x = px * s; j->y = py * s;
+                j->n_amvp = 2;                               /* zero predictors: the AMVP list always holds two entries */
+                j->n_start = 0;
+                j->parent = -1;
+                if (d > 0 && pu_valid(pp, (px / 2) * 2 * s, (py / 2) * 2 * s, 2 * s)) j->parent = (py / 2) * pp->grid_w[d - 1] + px / 2;
+                j->out = idx;
+                j->corr = 0.;                                /* taken from the per-frame block */
+                pus[n].x = j->x; pus[n].y = j->y; pus[n].mv_idx = idx;
+                n++;
+            }
+        pp->n_valid[d] = n;
+        rc = upload(ctx, (void **)&pp->d_jobs[d], jobs, sizeof *jobs * (size_t)n);
+        if (rc == HB_OK) rc = upload(ctx, (void **)&pp->d_pus[d], pus, sizeof *pus * (size_t)n);
+        if (rc == HB_OK) rc = upload(ctx, (void **)&pp->d_me[d], init, sizeof *init * (size_t)gw * gh);
+        free(jobs); free(pus); free(init);
+        if (rc == HB_OK) rc = hb_frame_create(ctx, width, height, &pp->pred[d]);
+    }
+    /* ---- TU job lists: a TU is coded when the PU it belongs to is valid */
+    for (int p = 0; p < N_PASS && rc == HB_OK; p++) {
+        const int d = pass_depth(p), s = 64 >> d;
+        rc = hb_frame_create(ctx, width, height, &pp->recon[p]);
+        for (int c = 0; c < 3 && rc == HB_OK; c++) {
+            pass_comp *pc = &pp->pc[p][c];
+            const int tu = c == 0 ? pass_luma_tu(p) : pass_luma_tu(p) / 2;
+            if (c > 0 && p == N_PASS - 1) { pc->tu = 0; continue; }   /* 8x8 CUs code chroma as one 4x4 (pass 3) */
+            pc->tu = tu;
+            const int pw = c ? width / 2 : width, ph = c ? height / 2 : height, sc = c ? s / 2 : s;
+            const int tw = (pp->ctu_cols * (c ? 32 : 64)) / tu, th = (pp->ctu_rows * (c ? 32 : 64)) / tu;
+            int32_t *xy = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)tw * th);
+            if (!xy) { rc = hb_fail(HB_ERR_NOMEM, "hb_prepass_create: out of memory"); break; }
+            int n = 0;
+            for (int ty = 0; ty < th; ty++)
+                for (int tx = 0; tx < tw; tx++) {
+                    const int x = tx * tu, y = ty * tu;
+                    if (x + tu > pw || y + tu > ph) continue;
+                    const int pux = (x / sc) * s, puy = (y / sc) * s;     /* owning PU in luma samples */
+                    if (!pu_valid(pp, pux, puy, s)) continue;
+                    xy[2 * n] = x; xy[2 * n + 1] = y; n++;
+                }
+            pc->n_tus = n;
+            rc = upload(ctx, (void **)&pc->d_xy, xy, sizeof(int32_t) * 2 * (size_t)n);
+            free(xy);
+            int crc = 0;
+            if (rc == HB_OK && (crc = hbc_malloc((void **)&pc->d_coeff, sizeof(int16_t) * (size_t)(n ? n : 1) * tu * tu))) rc = hb_cuda_fail(crc, "prepass: coeff");
+            if (rc == HB_OK && (crc = hbc_malloc((void **)&pc->d_res, sizeof(hb_tu_result) * (size_t)(n ? n : 1)))) rc = hb_cuda_fail(crc, "prepass: results");
+        }
+    }
+    if (rc == HB_OK) {
+        const int crc = hbc_malloc((void **)&pp->d_dyn, sizeof *pp->d_dyn);
+        if (crc) rc = hb_cuda_fail(crc, "prepass: dyn block");
+    }
+    if (rc != HB_OK) { hb_prepass_destroy(pp); return rc; }
+    *out = pp;
+    return HB_OK;
+}
+
+void hb_prepass_destroy(hb_prepass *pp)
+{
+    if (!pp) return;
+    hbc_set_device(pp->ctx->device);
+    hbc_stream_sync(pp->ctx->stream);
+    for (int i = 0; i < pp->n_graphs; i++) hbc_graph_destroy(pp->graphs[i].exec);
+    for (int d = 0; d < N_DEPTH; d++) {
+        if (pp->d_jobs[d]) hbc_free(pp->d_jobs[d]);
+        if (pp->d_pus[d]) hbc_free(pp->d_pus[d]);
+        if (pp->d_me[d]) hbc_free(pp->d_me[d]);
+        hb_frame_destroy(pp->pred[d]);
+    }
+    for (int p = 0; p < N_PASS; p++) {
+        for (int c = 0; c < 3; c++) {
+            if (pp->pc[p][c].d_xy) hbc_free(pp->pc[p][c].d_xy);
+            if (pp->pc[p][c].d_coeff) hbc_free(pp->pc[p][c].d_coeff);
+            if (pp->pc[p][c].d_res) hbc_free(pp->pc[p][c].d_res);
+        }
+        hb_frame_destroy(pp->recon[p]);
+    }
+    if (pp->d_dyn) hbc_free(pp->d_dyn);
+    free(pp);
+}
+
+/* queue the kernels of one frame on the context's stream; returns a cudaError_t value */
+static int enqueue(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, int *n_launches)
+{
+    hb_ctx *ctx = pp->ctx;
+    int crc = 0, n = 0;
+    for (int d = 0; d < N_DEPTH && !crc; d++) {
+        if (!pp->n_valid[d]) continue;
+        crc = hbk_me_search(&cur->d, &ref->d, 64 >> d, pp->d_jobs[d], pp->n_valid[d], d ? pp->d_me[d - 1] : NULL, pp->d_me[d],
+                            pp->cfg.me_action, pp->d_dyn, ctx->stream);
+        n++;
+        if (!crc) { crc = hbk_mc_predict(&ref->d, &pp->pred[d]->d, 64 >> d, pp->d_pus[d], pp->n_valid[d], pp->d_me[d], ctx->stream); n++; }
+    }
+    for (int p = 0; p < N_PASS && !crc; p++) {
+        const hb_frame *pred = pp->pred[pass_depth(p)];
+        for (int c = 0; c < 3 && !crc; c++) {
+            pass_comp *pc = &pp->pc[p][c];
+            if (!pc->tu || !pc->n_tus) continue;
+            hbd_tq_args a;
+            memset(&a, 0, sizeof a);
+            hb_tq_setup(ctx, &a, c, pc->tu, c ? pp->qp_c : pp->cfg.qp, pp->cfg.is_islice, pp->cfg.sign_hiding);
+            a.cur = cur->d.p[c]; a.pred = pred->d.p[c]; a.rec = pp->recon[p]->d.p[c];
+            a.jobs_xy = pc->d_xy; a.n_jobs = pc->n_tus;
+            a.thr_k = 1.; a.weight = c ? pp->weight_c : 1.; a.dyn = pp->d_dyn;
+            a.coeff_out = pc->d_coeff; a.res_out = pc->d_res;
+            crc = hbk_tq_encode(&a, ctx->stream);
+            n++;
+        }
+    }
+    *n_launches = n;
+    return crc;
+}
+
+int hb_prepass_run(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, double avg_dist)
+{
+    int crc = 0, n = 0;
+    if (!pp || !cur || !ref) return hb_fail(HB_ERR_ARG, "hb_prepass_run: NULL argument");
+    if (cur->w != pp->w || cur->h != pp->h || ref->w != pp->w || ref->h != pp->h) return hb_fail(HB_ERR_ARG, "hb_prepass_run: frame size differs from the plan");
+    hb_ctx *ctx = pp->ctx;
+    hbc_set_device(ctx->device);
+    /* per-frame scalars: same expressions, same host libm as the reference (hmr_common.h:53, hmr_motion_inter.c:106) */
+    double w = avg_dist / 2000.;
+    w = w < .15 ? .15 : (w > 1.4 ? 1.4 : w);
+    /* pageable source on purpose: the runtime stages it before returning, so the block can be rebuilt every frame
+     * without waiting for the previous replay */
+    hbd_dyn_params dyn;
+    dyn.corr = (uint32_t)pp->cfg.qp * w;
+    dyn.thr_k = hb_zero_out_k(avg_dist);
+    if ((crc = hbc_h2d_async(pp->d_dyn, &dyn, sizeof dyn, ctx->stream))) return hb_cuda_fail(crc, "hb_prepass_run: params");
+
+    if (!pp->cfg.use_graph) {
+        crc = enqueue(pp, cur, ref, &n);
+    } else {
+        void *exec = NULL;
+        for (int i = 0; i < pp->n_graphs; i++) if (pp->graphs[i].cur == cur && pp->graphs[i].ref == ref) exec = pp->graphs[i].exec;
+        if (!exec) {
+            if (pp->n_graphs == MAX_GRAPHS) { hbc_graph_destroy(pp->graphs[0].exec); memmove(&pp->graphs[0], &pp->graphs[1], sizeof pp->graphs[0] * (MAX_GRAPHS - 1)); pp->n_graphs--; }
+            if ((crc = hbc_graph_begin(ctx->stream))) return hb_cuda_fail(crc, "hb_prepass_run: begin capture");
+            crc = enqueue(pp, cur, ref, &n);
+            const int erc = hbc_graph_end(ctx->stream, &exec);
+            if (crc || erc) return hb_cuda_fail(crc ? crc : erc, "hb_prepass_run: capture");
+            pp->graphs[pp->n_graphs].cur = cur; pp->graphs[pp->n_graphs].ref = ref; pp->graphs[pp->n_graphs].exec = exec;
+            pp->n_graphs++;
+            pp->launches_per_frame = n;
+        }
+        n = pp->launches_per_frame;
+        crc = hbc_graph_launch(exec, ctx->stream);
+    }
+    if (crc) return hb_cuda_fail(crc, "hb_prepass_run");
+    pp->launches_per_frame = n;
+    ctx->launches += (uint64_t)n;
+    return HB_OK;
+}
+
+int hb_prepass_num_pus(const hb_prepass *pp, int depth) { return (pp && depth >= 0 && depth < N_DEPTH) ? pp->grid_w[depth] * pp->grid_h[depth] : 0; }
+int hb_prepass_num_tus(const hb_prepass *pp, int pass, int comp)
+{
+    return (pp && pass >= 0 && pass < N_PASS && comp >= 0 && comp < 3) ? pp->pc[pass][comp].n_tus : 0;
+}
+const hb_frame *hb_prepass_pred(const hb_prepass *pp, int depth) { return (pp && depth >= 0 && depth < N_DEPTH) ? pp->pred[depth] : NULL; }
+const hb_frame *hb_prepass_recon(const hb_prepass *pp, int pass) { return (pp && pass >= 0 && pass < N_PASS) ? pp->recon[pass] : NULL; }
+
+static int fetch(hb_prepass *pp, void *dst, const void *dev, size_t bytes, const char *what)
+{
+    void *h = NULL;
+    int rc, crc;
+    hb_ctx *ctx = pp->ctx;
+    if (!bytes) return HB_OK;
+    hbc_set_device(ctx->device);
+    pthread_mutex_lock(&ctx->lock);
+    if ((rc = hb_scratch(ctx, 3, bytes, NULL, &h)) != HB_OK) { pthread_mutex_unlock(&ctx->lock); return rc; }
+    crc = hbc_d2h_async(h, dev, bytes, ctx->stream);
+    if (!crc) crc = hbc_stream_sync(ctx->stream);
+    if (!crc) memcpy(dst, h, bytes);
+    pthread_mutex_unlock(&ctx->lock);
+    return crc ? hb_cuda_fail(crc, what) : HB_OK;
+}
+
+int hb_prepass_fetch_me(hb_prepass *pp, int depth, hb_me_result *out)
+{
+    if (!pp || !out || depth < 0 || depth >= N_DEPTH) return hb_fail(HB_ERR_ARG, "hb_prepass_fetch_me: bad argument");
+    return fetch(pp, out, pp->d_me[depth], sizeof(hb_me_result) * (size_t)hb_prepass_num_pus(pp, depth), "hb_prepass_fetch_me");
+}
+int hb_prepass_fetch_tu(hb_prepass *pp, int pass, int comp, hb_tu_result *out)
+{
+    if (!pp || !out || pass < 0 || pass >= N_PASS || comp < 0 || comp > 2) return hb_fail(HB_ERR_ARG, "hb_prepass_fetch_tu: bad argument");
+    return fetch(pp, out, pp->pc[pass][comp].d_res, sizeof(hb_tu_result) * (size_t)pp->pc[pass][comp].n_tus, "hb_prepass_fetch_tu");
+}
+int hb_prepass_fetch_coeffs(hb_prepass *pp, int pass, int comp, int16_t *out)
+{
+    if (!pp || !out || pass < 0 || pass >= N_PASS || comp < 0 || comp > 2) return hb_fail(HB_ERR_ARG, "hb_prepass_fetch_coeffs: bad argument");
+    const pass_comp *pc = &pp->pc[pass][comp];
+    return fetch(pp, out, pc->d_coeff, sizeof(int16_t) * (size_t)pc->n_tus * pc->tu * pc->tu, "hb_prepass_fetch_coeffs");
+}
+int hb_prepass_tu_xy(hb_prepass *pp, int pass, int comp, int32_t *xy_out)
+{
+    if (!pp || !xy_out || pass < 0 || pass >= N_PASS || comp < 0 || comp > 2) return hb_fail(HB_ERR_ARG, "hb_prepass_tu_xy: bad argument");
+    return fetch(pp, xy_out, pp->pc[pass][comp].d_xy, sizeof(int32_t) * 2 * (size_t)pp->pc[pass][comp].n_tus, "hb_prepass_tu_xy");
+}
+int hb_prepass_tu_size(const hb_prepass *pp, int pass, int comp)
+{
+    return (pp && pass >= 0 && pass < N_PASS && comp >= 0 && comp < 3) ? pp->pc[pass][comp].tu : 0;
+}
+int hb_prepass_fetch_recon(hb_prepass *pp, int pass, uint8_t *y, int ys, uint8_t *u, int us, uint8_t *v, int vs)
+{
+    if (!pp || pass < 0 || pass >= N_PASS) return hb_fail(HB_ERR_ARG, "hb_prepass_fetch_recon: bad argument");
+    return hb_frame_download_u8(pp->ctx, pp->recon[pass], y, ys, u, us, v, vs);
+}
+
+size_t hb_prepass_output_bytes(const hb_prepass *pp)
+{
+    size_t n = 0;
+    if (!pp) return 0;
+    for (int d = 0; d < N_DEPTH; d++) n += sizeof(hb_me_result) * (size_t)hb_prepass_num_pus(pp, d);
+    for (int p = 0; p < N_PASS; p++) {
+        for (int c = 0; c < 3; c++) {
+            const pass_comp *pc = &pp->pc[p][c];
+            n += sizeof(hb_tu_result) * (size_t)pc->n_tus + sizeof(int16_t) * (size_t)pc->n_tus * pc->tu * pc->tu;
+        }
+        n += (size_t)pp->w * pp->h * 3 / 2;
+    }
+    return n;
+}
+
+/* everything the host side consumes, packed in the order of hb_prepass_output_bytes: ME tables d0..d3, then per pass
+ * {TU results Y,U,V; levels Y,U,V; reconstruction Y,U,V (tight pitch)}.  dst should be pinned. */
+int hb_prepass_fetch_all(hb_prepass *pp, void *pinned_dst, size_t cap, size_t *bytes_out)
+{
+    if (!pp || !pinned_dst) return hb_fail(HB_ERR_ARG, "hb_prepass_fetch_all: NULL argument");
+    const size_t need = hb_prepass_output_bytes(pp);
+    if (cap < need) return hb_fail(HB_ERR_ARG, "hb_prepass_fetch_all: need %zu bytes, got %zu", need, cap);
+    hb_ctx *ctx = pp->ctx;
+    char *o = (char *)pinned_dst;
+    int crc = 0;
+    hbc_set_device(ctx->device);
+    for (int d = 0; d < N_DEPTH && !crc; d++) {
+        const size_t b = sizeof(hb_me_result) * (size_t)hb_prepass_num_pus(pp, d);
+        crc = hbc_d2h_async(o, pp->d_me[d], b, ctx->stream); o += b;
+    }
+    for (int p = 0; p < N_PASS && !crc; p++) {
+        for (int c = 0; c < 3 && !crc; c++) {
+            const pass_comp *pc = &pp->pc[p][c];
+            const size_t b = sizeof(hb_tu_result) * (size_t)pc->n_tus;
+            if (b) { crc = hbc_d2h_async(o, pc->d_res, b, ctx->stream); o += b; }
+        }
+        for (int c = 0; c < 3 && !crc; c++) {
+            const pass_comp *pc = &pp->pc[p][c];
+            const size_t b = sizeof(int16_t) * (size_t)pc->n_tus * pc->tu * pc->tu;
+            if (b) { crc = hbc_d2h_async(o, pc->d_coeff, b, ctx->stream); o += b; }
+        }
+        for (int c = 0; c < 3 && !crc; c++) {
+            const hbd_plane *pl = &pp->recon[p]->d.p[c];
+            crc = hbc_d2h_2d_async(o, (size_t)pl->w, pl->org, (size_t)pl->pitch, (size_t)pl->w, (size_t)pl->h, ctx->stream);
+            o += (size_t)pl->w * pl->h;
+        }
+    }
+    if (!crc) crc = hbc_stream_sync(ctx->stream);
+    if (crc) return hb_cuda_fail(crc, "hb_prepass_fetch_all");
+    if (bytes_out) *bytes_out = (size_t)(o - (char *)pinned_dst);
+    return HB_OK;
+}

@@ -1,0 +1,162 @@
+// hb_shim.cu -- CUDA runtime wrappers and the small per-call kernels (int16 operands, reference semantics of
+// hmr_motion_intra.c:51-186 and hmr_motion_inter.c:261-391, :878-936).  See hb_shim.h.
+#include "hb_shim.h"
+#include "hb_dev_common.cuh"
+
+// ------------------------------------------------------------------ runtime wrappers
+extern "C" int hbc_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" int hbc_set_device(int dev) { return static_cast<int>(cudaSetDevice(dev)); }
+extern "C" int hbc_stream_create(void **stream)
+{
+    cudaStream_t s;
+    const cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    *stream = s;
+    return static_cast<int>(e);
+}
+extern "C" int hbc_stream_destroy(void *stream) { return static_cast<int>(cudaStreamDestroy(static_cast<cudaStream_t>(stream))); }
+extern "C" int hbc_stream_sync(void *stream) { return static_cast<int>(cudaStreamSynchronize(static_cast<cudaStream_t>(stream))); }
+extern "C" int hbc_malloc(void **p, size_t bytes) { return static_cast<int>(cudaMalloc(p, bytes)); }
+extern "C" int hbc_free(void *p) { return static_cast<int>(cudaFree(p)); }
+extern "C" int hbc_host_alloc(void **p, size_t bytes) { return static_cast<int>(cudaHostAlloc(p, bytes, cudaHostAllocMapped | cudaHostAllocPortable)); }
+extern "C" int hbc_host_free(void *p) { return static_cast<int>(cudaFreeHost(p)); }
+extern "C" int hbc_host_devptr(void *host, void **dev) { return static_cast<int>(cudaHostGetDevicePointer(dev, host, 0)); }
+extern "C" int hbc_memset_async(void *p, int v, size_t bytes, void *stream) { return static_cast<int>(cudaMemsetAsync(p, v, bytes, static_cast<cudaStream_t>(stream))); }
+extern "C" int hbc_h2d_async(void *dst, const void *src, size_t bytes, void *stream)
+{
+    return static_cast<int>(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+}
+extern "C" int hbc_d2h_async(void *dst, const void *src, size_t bytes, void *stream)
+{
+    return static_cast<int>(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+}
+extern "C" int hbc_h2d_2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t rows, void *stream)
+{
+    return static_cast<int>(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, rows, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+}
+extern "C" int hbc_d2h_2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t rows, void *stream)
+{
+    return static_cast<int>(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, rows, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+}
+extern "C" int hbc_event_create(void **ev)
+{
+    cudaEvent_t e;
+    const cudaError_t r = cudaEventCreate(&e);
+    *ev = e;
+    return static_cast<int>(r);
+}
+extern "C" int hbc_event_destroy(void *ev) { return static_cast<int>(cudaEventDestroy(static_cast<cudaEvent_t>(ev))); }
+extern "C" int hbc_event_record(void *ev, void *stream) { return static_cast<int>(cudaEventRecord(static_cast<cudaEvent_t>(ev), static_cast<cudaStream_t>(stream))); }
+extern "C" int hbc_event_elapsed(void *a, void *b, float *ms)
+{
+    cudaError_t e = cudaEventSynchronize(static_cast<cudaEvent_t>(b));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    return static_cast<int>(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(a), static_cast<cudaEvent_t>(b)));
+}
+extern "C" int hbc_graph_begin(void *stream)
+{
+    return static_cast<int>(cudaStreamBeginCapture(static_cast<cudaStream_t>(stream), cudaStreamCaptureModeThreadLocal));
+}
+extern "C" int hbc_graph_end(void *stream, void **exec)
+{
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(static_cast<cudaStream_t>(stream), &g);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    cudaGraphExec_t x = nullptr;
+    e = cudaGraphInstantiate(&x, g, 0);
+    cudaGraphDestroy(g);
+    *exec = x;
+    return static_cast<int>(e);
+}
+extern "C" int hbc_graph_launch(void *exec, void *stream) { return static_cast<int>(cudaGraphLaunch(static_cast<cudaGraphExec_t>(exec), static_cast<cudaStream_t>(stream))); }
+extern "C" int hbc_graph_destroy(void *exec) { return static_cast<int>(cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(exec))); }
+extern "C" const char *hbc_error_string(int code) { return cudaGetErrorString(static_cast<cudaError_t>(code)); }
+
+// ------------------------------------------------------------------ per-call pixel kernels
+namespace {
+
+__global__ void __launch_bounds__(256) k_pc_sad(const int16_t *a, int as, const int16_t *b, int bs, int n, int squared, uint32_t *out)
+{
+    __shared__ uint32_t red[8];
+    uint32_t acc = 0;
+    for (int e = threadIdx.x; e < n * n; e += 256) {
+        const int d = static_cast<int>(a[(e / n) * as + e % n]) - static_cast<int>(b[(e / n) * bs + e % n]);
+        acc += squared ? static_cast<uint32_t>(d) * static_cast<uint32_t>(d) : static_cast<uint32_t>(abs(d));
+    }
+    acc = __reduce_add_sync(HB_FULL_MASK, acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (int i = 0; i < 8; i++) s += red[i];
+        *out = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pc_predict(const int16_t *orig, int os, const int16_t *pred, int ps, int16_t *res, int rs, int n)
+{
+    for (int e = threadIdx.x; e < n * n; e += 256)
+        res[(e / n) * rs + e % n] = static_cast<int16_t>(orig[(e / n) * os + e % n] - pred[(e / n) * ps + e % n]);
+}
+
+__global__ void __launch_bounds__(256) k_pc_reconst(const int16_t *pred, int ps, const int16_t *res, int rs, int16_t *dec, int ds, int n)
+{
+    for (int e = threadIdx.x; e < n * n; e += 256)
+        dec[(e / n) * ds + e % n] = static_cast<int16_t>(hb_clip255(static_cast<int>(res[(e / n) * rs + e % n]) + pred[(e / n) * ps + e % n]));
+}
+
+// one interpolation pass with the reference's four (is_first, is_last) roundings; every value passes through an int16
+__global__ void __launch_bounds__(256) k_pc_interp(const int16_t *src, int ss, int org_off, int16_t *dst, int ds, int chroma, int fraction,
+                                                   int w, int h, int vertical, int first, int last)
+{
+    const int16_t *org = src + org_off;
+    const int step = vertical ? ss : 1;
+    for (int e = threadIdx.x; e < w * h; e += 256) {
+        const int r = e / w, c = e % w;
+        const int16_t *p = org + r * ss + c;
+        int v;
+        if (!chroma && fraction == 0) {                         // filter_copy, hmr_motion_inter.c:261
+            if (first == last) v = p[0];
+            else if (first) v = static_cast<int16_t>(static_cast<int16_t>(p[0] << 6) - 8192);
+            else v = hb_clip255(static_cast<int16_t>((p[0] + 8224) >> 6));
+        } else {
+            int shift = 6, offset;
+            if (last) { shift += first ? 0 : 6; offset = (1 << (shift - 1)) + (first ? 0 : (8192 << 6)); }
+            else { shift -= first ? 6 : 0; offset = first ? -(8192 << shift) : 0; }
+            int sum;
+            if (chroma) sum = hb_chroma4_dyn(fraction, p[-step], p[0], p[step], p[2 * step]);
+            else sum = hb_luma8_dyn(fraction, p[-3 * step], p[-2 * step], p[-step], p[0], p[step], p[2 * step], p[3 * step], p[4 * step]);
+            v = static_cast<int16_t>((sum + offset) >> shift);
+            if (last) v = hb_clip255(v);
+        }
+        dst[r * ds + c] = static_cast<int16_t>(v);
+    }
+}
+
+}  // namespace
+
+extern "C" int hbk_pc_sad(const int16_t *a, int as, const int16_t *b, int bs, int n, int squared, uint32_t *out, void *stream)
+{
+    k_pc_sad<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, as, b, bs, n, squared, out);
+    return static_cast<int>(cudaGetLastError());
+}
+extern "C" int hbk_pc_predict(const int16_t *orig, int os, const int16_t *pred, int ps, int16_t *res, int rs, int n, void *stream)
+{
+    k_pc_predict<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(orig, os, pred, ps, res, rs, n);
+    return static_cast<int>(cudaGetLastError());
+}
+extern "C" int hbk_pc_reconst(const int16_t *pred, int ps, const int16_t *res, int rs, int16_t *dec, int ds, int n, void *stream)
+{
+    k_pc_reconst<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(pred, ps, res, rs, dec, ds, n);
+    return static_cast<int>(cudaGetLastError());
+}
+extern "C" int hbk_pc_interp(const int16_t *src, int ss, int org_off, int16_t *dst, int ds, int chroma, int fraction, int w, int h,
+                             int vertical, int first, int last, void *stream)
+{
+    k_pc_interp<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, ss, org_off, dst, ds, chroma, fraction, w, h, vertical, first, last);
+    return static_cast<int>(cudaGetLastError());
+}

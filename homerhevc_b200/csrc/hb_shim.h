@@ -1,0 +1,114 @@
+/*
+ * hb_shim.h -- the thin C ABI between the C99 host layer (hb_host.c) and CUDA (hb_*.cu).
+ * Internal: not installed, not part of include/.  Everything here is plain C.
+ * Every launcher queues work on `stream` and returns 0 or a cudaError_t value.
+ */
+#ifndef HB_SHIM_H
+#define HB_SHIM_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "../../include/homer_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- device-side picture: three 8-bit planes, each with its own replicated border */
+typedef struct hbd_plane {
+    uint8_t *base;      /* allocation start */
+    uint8_t *org;       /* first real sample */
+    int32_t pitch;      /* bytes per row */
+    int32_t w, h;       /* real samples */
+    int32_t pad;        /* border on each side */
+} hbd_plane;
+typedef struct hbd_frame { hbd_plane p[3]; } hbd_frame;
+
+/* ---- CUDA runtime wrappers */
+int  hbc_device_count(void);
+int  hbc_set_device(int dev);
+int  hbc_stream_create(void **stream);
+int  hbc_stream_destroy(void *stream);
+int  hbc_stream_sync(void *stream);
+int  hbc_malloc(void **p, size_t bytes);
+int  hbc_free(void *p);
+int  hbc_host_alloc(void **p, size_t bytes);          /* pinned + mapped */
+int  hbc_host_free(void *p);
+int  hbc_host_devptr(void *host, void **dev);         /* device alias of mapped pinned memory */
+int  hbc_memset_async(void *p, int v, size_t bytes, void *stream);
+int  hbc_h2d_async(void *dst, const void *src, size_t bytes, void *stream);
+int  hbc_d2h_async(void *dst, const void *src, size_t bytes, void *stream);
+int  hbc_h2d_2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t rows, void *stream);
+int  hbc_d2h_2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t rows, void *stream);
+int  hbc_event_create(void **ev);
+int  hbc_event_destroy(void *ev);
+int  hbc_event_record(void *ev, void *stream);
+int  hbc_event_elapsed(void *a, void *b, float *ms);   /* synchronises on b */
+int  hbc_graph_begin(void *stream);
+int  hbc_graph_end(void *stream, void **exec);
+int  hbc_graph_launch(void *exec, void *stream);
+int  hbc_graph_destroy(void *exec);
+const char *hbc_error_string(int code);
+
+/* ---- frame maintenance */
+int hbk_pad_frame(const hbd_frame *f, void *stream);                                   /* replicate borders of all planes */
+int hbk_narrow_plane(const int16_t *src, int src_stride, hbd_plane dst, uint32_t *range_flag, void *stream);
+
+/* ---- per-call kernels: operands live in mapped pinned staging, strides in samples */
+int hbk_pc_sad(const int16_t *a, int as, const int16_t *b, int bs, int n, int squared, uint32_t *out, void *stream);
+int hbk_pc_predict(const int16_t *orig, int os, const int16_t *pred, int ps, int16_t *res, int rs, int n, void *stream);
+int hbk_pc_reconst(const int16_t *pred, int ps, const int16_t *res, int rs, int16_t *dec, int ds, int n, void *stream);
+/* src points at the first needed sample (margins included), org_off = offset of sample (0,0) */
+int hbk_pc_interp(const int16_t *src, int ss, int org_off, int16_t *dst, int ds, int chroma, int fraction, int w, int h,
+                  int vertical, int first, int last, void *stream);
+int hbk_pc_transform(const int16_t *block, int bs, int16_t *coeff, int n, int dst4, void *stream);
+int hbk_pc_itransform(int16_t *block, int bs, const int16_t *coeff, int n, int dst4, void *stream);
+int hbk_pc_quant(const int16_t *src, int16_t *dst, int16_t *delta_u, int32_t *sum, int n, const int32_t *qtab,
+                 const uint16_t *scan, int qbits, int add, int sign_hiding, void *stream);
+int hbk_pc_inv_quant(const int16_t *src, int16_t *dst, int n, const int32_t *dqtab, int per, void *stream);
+
+/* ---- batched jobs on resident frames */
+/* per-frame scalars that change between replays of a captured launch sequence; kernels read them from device
+ * memory when the pointer is non-NULL, otherwise the per-job / per-launch values are used */
+typedef struct hbd_dyn_params {
+    double corr;                  /* qp * clip(avg_dist/2000, .15, 1.4) */
+    double thr_k;                 /* clip(avg_dist/2.5-5, 1, 20000) */
+} hbd_dyn_params;
+typedef struct hbd_me_job {       /* one PU, device layout */
+    int32_t x, y;
+    int32_t n_amvp; int32_t amvp[4];
+    int32_t n_start; int32_t start[6];
+    int32_t parent;               /* index into parent results or -1 */
+    int32_t out;                  /* index into results */
+    int32_t pad_;
+    double  corr;                 /* qp * clip(avg_dist/2000, .15, 1.4), hmr_common.h:53 */
+} hbd_me_job;
+int hbk_me_search(const hbd_frame *cur, const hbd_frame *ref, int size, const hbd_me_job *jobs, int n_jobs,
+                  const hb_me_result *parent, hb_me_result *out, int action, const hbd_dyn_params *dyn, void *stream);
+
+typedef struct hbd_mc_pu { int32_t x, y; int32_t mv_idx; } hbd_mc_pu;   /* luma position; mv = mvsrc[mv_idx].mv */
+int hbk_mc_predict(const hbd_frame *ref, const hbd_frame *pred, int size, const hbd_mc_pu *pus, int n_pus,
+                   const hb_me_result *mvsrc, void *stream);
+
+typedef struct hbd_tq_args {
+    hbd_plane cur, pred, rec;     /* planes of the component being coded */
+    const int32_t *jobs_xy;       /* n_jobs pairs (x,y) in samples of that plane */
+    int32_t n_jobs;
+    int32_t n;                    /* TU size 4..32 */
+    const int32_t *qtab, *dqtab;  /* N*N tables of (list, qp%6) */
+    const uint16_t *scan;         /* diagonal scan, N*N */
+    int32_t qbits, add, per;
+    int32_t sign_hiding;
+    int32_t is_luma;
+    double  thr_k;                /* clip(avg_dist/2.5-5, 1, 20000) */
+    double  weight;               /* chroma SSD weight, 1 for luma */
+    const hbd_dyn_params *dyn;    /* overrides thr_k when non-NULL */
+    int16_t *coeff_out;           /* n_jobs * N*N */
+    hb_tu_result *res_out;        /* n_jobs */
+} hbd_tq_args;
+int hbk_tq_encode(const hbd_tq_args *a, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,395 @@
+"""ctypes bindings of libhomer_b200.so (see include/homer_b200.h).  Host-side mirror only -- no computation here."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ME_PEL, ME_HALF, ME_QUARTER = 1, 2, 4
+REG_DCT = 65535
+
+i16p = C.POINTER(C.c_int16)
+u8p = C.POINTER(C.c_uint8)
+i32p = C.POINTER(C.c_int32)
+
+
+class HbError(RuntimeError):
+    pass
+
+
+class Mv(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32)]
+
+
+class MeJob(C.Structure):
+    """one hmr_motion_estimation call (hmr_motion_inter.c:1404)"""
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("size", C.c_int32), ("qp", C.c_int32),
+                ("n_amvp", C.c_int32), ("amvp", Mv * 2), ("n_start", C.c_int32), ("start", Mv * 3),
+                ("parent", C.c_int32)]
+
+
+class MeResult(C.Structure):
+    _fields_ = [("mv", Mv), ("subpix", Mv), ("sad", C.c_uint32), ("n_probes", C.c_uint32)]
+
+
+class McJob(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("size", C.c_int32), ("mv", Mv)]
+
+
+class TuJob(C.Structure):
+    _fields_ = [("comp", C.c_int32), ("x", C.c_int32), ("y", C.c_int32), ("size", C.c_int32), ("qp", C.c_int32)]
+
+
+class TuResult(C.Structure):
+    _fields_ = [("sum", C.c_int32), ("ssd", C.c_uint32), ("ssd_zero", C.c_uint32), ("zeroed", C.c_int32)]
+
+
+class TqParams(C.Structure):
+    _fields_ = [("is_islice", C.c_int32), ("sign_hiding", C.c_int32), ("avg_dist", C.c_double),
+                ("chroma_weight", C.c_double)]
+
+
+class QuantEnv(C.Structure):
+    _fields_ = [("is_islice", C.c_int32), ("sign_hiding", C.c_int32), ("max_cu_size_shift", C.c_int32),
+                ("bit_depth", C.c_int32), ("delta_u", i16p)]
+
+
+class PrepassCfg(C.Structure):
+    _fields_ = [("qp", C.c_int32), ("chroma_qp_offset", C.c_int32), ("sign_hiding", C.c_int32),
+                ("is_islice", C.c_int32), ("me_action", C.c_int32), ("use_graph", C.c_int32),
+                ("band_ctu_row0", C.c_int32), ("band_ctu_rows", C.c_int32)]
+
+
+class LowLevelFuncs(C.Structure):
+    """member-for-member image of low_level_funcs_t (19 pointers, hmr_private.h:1063-1092)"""
+    _fields_ = [(n, C.c_void_p) for n in (
+        "sse_copy_16_16", "sse_copy_16_8", "sse_copy_8_16", "sad", "ssd16b", "predict", "reconst",
+        "modified_variance", "create_intra_planar_prediction", "create_intra_angular_prediction",
+        "interpolate_luma_m_compensation", "interpolate_chroma_m_compensation", "interpolate_luma_m_estimation",
+        "weighted_average_motion", "quant", "inv_quant", "transform", "itransform", "get_sao_stats")]
+
+
+def library_path():
+    return os.path.join(_HERE, "libhomer_b200.so")
+
+
+def build_library(verbose=False):
+    """compile every CUDA/C source for sm_100a into libhomer_b200.so (nvcc cross-compiles without a GPU)"""
+    out = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j8"], capture_output=True, text=True)
+    if verbose or out.returncode:
+        print(out.stdout[-4000:], out.stderr[-4000:])
+    if out.returncode:
+        raise HbError("building libhomer_b200.so failed")
+    return library_path()
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the CUDA library.  Fails loudly when it has not been built -- there is nothing to fall back to."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise HbError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(the hot path is CUDA only, there is no CPU fallback)")
+    L = C.CDLL(path)
+    L.hb_last_error.restype = C.c_char_p
+    L.hb_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    L.hb_ctx_destroy.argtypes = [C.c_void_p]
+    L.hb_ctx_sync.argtypes = [C.c_void_p]
+    L.hb_ctx_stream.restype = C.c_void_p
+    L.hb_ctx_stream.argtypes = [C.c_void_p]
+    L.hb_ctx_launch_count.restype = C.c_uint64
+    L.hb_ctx_launch_count.argtypes = [C.c_void_p]
+    L.hb_timer_begin.argtypes = [C.c_void_p]
+    L.hb_timer_end.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.hb_pinned_alloc.restype = C.c_void_p
+    L.hb_pinned_alloc.argtypes = [C.c_size_t]
+    L.hb_pinned_free.argtypes = [C.c_void_p]
+    # section A
+    L.hb_sad.restype = C.c_uint32
+    L.hb_sad.argtypes = [i16p, C.c_uint32, i16p, C.c_uint32, C.c_int]
+    L.hb_ssd16b.restype = C.c_uint32
+    L.hb_ssd16b.argtypes = [i16p, C.c_uint32, i16p, C.c_uint32, C.c_int]
+    L.hb_predict.restype = None
+    L.hb_predict.argtypes = [i16p, C.c_int, i16p, C.c_int, i16p, C.c_int, C.c_int]
+    L.hb_reconst.restype = None
+    L.hb_reconst.argtypes = [i16p, C.c_int, i16p, C.c_int, i16p, C.c_int, C.c_int]
+    for f in (L.hb_interpolate_luma, L.hb_interpolate_chroma):
+        f.restype = None
+        f.argtypes = [i16p, C.c_int, i16p, C.c_int] + [C.c_int] * 6
+    L.hb_transform.restype = None
+    L.hb_transform.argtypes = [C.c_int, i16p, i16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint16, i16p]
+    L.hb_itransform.restype = None
+    L.hb_itransform.argtypes = [C.c_int, i16p, i16p, C.c_int, C.c_int, C.c_int, C.c_uint, i16p]
+    L.hb_quant.restype = None
+    L.hb_quant.argtypes = [C.POINTER(QuantEnv), i16p, i16p] + [C.c_int] * 5 + [C.POINTER(C.c_int)] + [C.c_int] * 3
+    L.hb_inv_quant.restype = None
+    L.hb_inv_quant.argtypes = [C.POINTER(QuantEnv), i16p, i16p] + [C.c_int] * 6
+    L.hb_fill_low_level_funcs.restype = None
+    L.hb_fill_low_level_funcs.argtypes = [C.POINTER(LowLevelFuncs)]
+    # section B
+    L.hb_frame_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.hb_frame_destroy.argtypes = [C.c_void_p]
+    L.hb_frame_upload_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.hb_frame_upload_i16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.hb_frame_download_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    # section C
+    L.hb_me_search.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(MeJob), C.c_int, C.POINTER(MeResult), C.c_int,
+                               C.c_double, C.c_int, C.POINTER(MeResult)]
+    L.hb_mc_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(McJob), C.c_int]
+    L.hb_tq_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TuJob), C.c_int,
+                               C.POINTER(TqParams), i16p, C.POINTER(TuResult)]
+    # section D
+    L.hb_prepass_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(PrepassCfg), C.POINTER(C.c_void_p)]
+    L.hb_prepass_destroy.argtypes = [C.c_void_p]
+    L.hb_prepass_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
+    L.hb_prepass_num_pus.argtypes = [C.c_void_p, C.c_int]
+    L.hb_prepass_num_tus.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.hb_prepass_tu_size.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.hb_prepass_tu_xy.argtypes = [C.c_void_p, C.c_int, C.c_int, i32p]
+    L.hb_prepass_fetch_me.argtypes = [C.c_void_p, C.c_int, C.POINTER(MeResult)]
+    L.hb_prepass_fetch_tu.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(TuResult)]
+    L.hb_prepass_fetch_coeffs.argtypes = [C.c_void_p, C.c_int, C.c_int, i16p]
+    L.hb_prepass_fetch_recon.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.hb_prepass_fetch_all.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.hb_prepass_output_bytes.restype = C.c_size_t
+    L.hb_prepass_output_bytes.argtypes = [C.c_void_p]
+    L.hb_prepass_pred.restype = C.c_void_p
+    L.hb_prepass_pred.argtypes = [C.c_void_p, C.c_int]
+    L.hb_prepass_recon.restype = C.c_void_p
+    L.hb_prepass_recon.argtypes = [C.c_void_p, C.c_int]
+    _lib = L
+    return L
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise HbError(f"{what}: rc={rc}: {load_library().hb_last_error().decode(errors='replace')}")
+
+
+def _p16(a, off=0):
+    assert a.dtype == np.int16 and a.flags["C_CONTIGUOUS"]
+    return C.cast(a.ctypes.data + 2 * off, i16p)
+
+
+class _LowLevel:
+    """the per-call drop-ins under the reference's own member names (low_level_funcs_t); numpy int16 in/out,
+    `off` arguments are element offsets into flat arrays so callers can address the interior of padded windows"""
+
+    def sad(self, src, src_stride, pred, pred_stride, size, src_off=0, pred_off=0):
+        return load_library().hb_sad(_p16(src, src_off), src_stride, _p16(pred, pred_off), pred_stride, size)
+
+    def ssd16b(self, src, src_stride, pred, pred_stride, size, src_off=0, pred_off=0):
+        return load_library().hb_ssd16b(_p16(src, src_off), src_stride, _p16(pred, pred_off), pred_stride, size)
+
+    def predict(self, orig, orig_stride, pred, pred_stride, residual, residual_stride, size):
+        load_library().hb_predict(_p16(orig), orig_stride, _p16(pred), pred_stride, _p16(residual), residual_stride, size)
+
+    def reconst(self, pred, pred_stride, residual, residual_stride, decoded, decoded_stride, size):
+        load_library().hb_reconst(_p16(pred), pred_stride, _p16(residual), residual_stride, _p16(decoded), decoded_stride, size)
+
+    def interpolate_luma(self, ref, ref_stride, dst, dst_stride, fraction, width, height, is_vertical, is_first, is_last,
+                         ref_off=0):
+        load_library().hb_interpolate_luma(_p16(ref, ref_off), ref_stride, _p16(dst), dst_stride, fraction, width, height,
+                                           is_vertical, is_first, is_last)
+
+    def interpolate_chroma(self, ref, ref_stride, dst, dst_stride, fraction, width, height, is_vertical, is_first, is_last,
+                           ref_off=0):
+        load_library().hb_interpolate_chroma(_p16(ref, ref_off), ref_stride, _p16(dst), dst_stride, fraction, width, height,
+                                             is_vertical, is_first, is_last)
+
+    def transform(self, bit_depth, block, coeff, block_stride, n, mode=REG_DCT):
+        lg = int(n).bit_length() - 1
+        load_library().hb_transform(bit_depth, _p16(block), _p16(coeff), block_stride, n, n, lg, lg, mode, None)
+
+    def itransform(self, bit_depth, block, coeff, block_stride, n, mode=REG_DCT):
+        load_library().hb_itransform(bit_depth, _p16(block), _p16(coeff), block_stride, n, n, mode, None)
+
+    def quant(self, env, src, dst, scan_mode, depth, comp, cu_mode, is_intra, cu_size, per, rem):
+        s = C.c_int(0)
+        load_library().hb_quant(C.byref(env), _p16(src), _p16(dst), scan_mode, depth, comp, cu_mode, is_intra, C.byref(s),
+                                cu_size, per, rem)
+        return s.value
+
+    def inv_quant(self, env, src, dst, depth, comp, is_intra, cu_size, per, rem):
+        load_library().hb_inv_quant(C.byref(env), _p16(src), _p16(dst), depth, comp, is_intra, cu_size, per, rem)
+
+
+lowlevel = _LowLevel()
+
+
+class Context:
+    def __init__(self, device=0):
+        self.L = load_library()
+        h = C.c_void_p()
+        _check(self.L.hb_ctx_create(C.byref(h), device), "hb_ctx_create")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            self.L.hb_ctx_destroy(self.h)
+            self.h = None
+
+    def sync(self):
+        _check(self.L.hb_ctx_sync(self.h), "hb_ctx_sync")
+
+    def launch_count(self):
+        return int(self.L.hb_ctx_launch_count(self.h))
+
+    def timer_begin(self):
+        _check(self.L.hb_timer_begin(self.h), "hb_timer_begin")
+
+    def timer_end(self):
+        ms = C.c_float(0)
+        _check(self.L.hb_timer_end(self.h, C.byref(ms)), "hb_timer_end")
+        return ms.value
+
+    def pinned(self, nbytes):
+        """numpy uint8 view of pinned host memory (freed with the process)"""
+        p = self.L.hb_pinned_alloc(nbytes)
+        if not p:
+            raise HbError("hb_pinned_alloc failed: " + self.L.hb_last_error().decode())
+        return np.ctypeslib.as_array(C.cast(p, u8p), shape=(nbytes,))
+
+    # ---- section C
+    def me_search(self, cur, ref, jobs, avg_dist, action=7, parent_results=None):
+        n = len(jobs)
+        arr = (MeJob * n)(*jobs)
+        out = (MeResult * n)()
+        npar = len(parent_results) if parent_results is not None else 0
+        par = (MeResult * npar)(*parent_results) if npar else None
+        _check(self.L.hb_me_search(self.h, cur.h, ref.h, arr, n, par, npar, avg_dist, action, out), "hb_me_search")
+        return list(out)
+
+    def mc_predict(self, ref, pred, jobs):
+        n = len(jobs)
+        arr = (McJob * n)(*jobs)
+        _check(self.L.hb_mc_predict(self.h, ref.h, pred.h, arr, n), "hb_mc_predict")
+
+    def tq_encode(self, cur, pred, recon, jobs, params):
+        n = len(jobs)
+        arr = (TuJob * n)(*jobs)
+        total = sum(j.size * j.size for j in jobs)
+        coeffs = np.zeros(total, dtype=np.int16)
+        res = (TuResult * n)()
+        _check(self.L.hb_tq_encode(self.h, cur.h, pred.h, recon.h, arr, n, C.byref(params), _p16(coeffs), res), "hb_tq_encode")
+        return coeffs, list(res)
+
+
+class Frame:
+    def __init__(self, ctx, width, height):
+        self.ctx, self.w, self.h_px = ctx, width, height
+        h = C.c_void_p()
+        _check(ctx.L.hb_frame_create(ctx.h, width, height, C.byref(h)), "hb_frame_create")
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.ctx.L.hb_frame_destroy(self.h)
+            self.h = None
+
+    def upload_u8(self, y, u, v):
+        for a in (y, u, v):
+            assert a.dtype == np.uint8 and a.ndim == 2 and a.strides[1] == 1
+        _check(self.ctx.L.hb_frame_upload_u8(self.ctx.h, self.h, y.ctypes.data, y.strides[0], u.ctypes.data, u.strides[0],
+                                             v.ctypes.data, v.strides[0]), "hb_frame_upload_u8")
+
+    def upload_i16(self, y, u, v):
+        for a in (y, u, v):
+            assert a.dtype == np.int16 and a.ndim == 2 and a.strides[1] == 2
+        _check(self.ctx.L.hb_frame_upload_i16(self.ctx.h, self.h, y.ctypes.data, y.strides[0] // 2, u.ctypes.data,
+                                              u.strides[0] // 2, v.ctypes.data, v.strides[0] // 2), "hb_frame_upload_i16")
+
+    def download(self):
+        y = np.zeros((self.h_px, self.w), np.uint8)
+        u = np.zeros((self.h_px // 2, self.w // 2), np.uint8)
+        v = np.zeros_like(u)
+        _check(self.ctx.L.hb_frame_download_u8(self.ctx.h, self.h, y.ctypes.data, self.w, u.ctypes.data, self.w // 2,
+                                               v.ctypes.data, self.w // 2), "hb_frame_download_u8")
+        return y, u, v
+
+
+class _BorrowedFrame(Frame):
+    def __init__(self, ctx, handle, width, height):
+        self.ctx, self.w, self.h_px, self.h = ctx, width, height, C.c_void_p(handle)
+
+    def close(self):
+        self.h = None
+
+
+class Prepass:
+    """frame-level pre-pass: every CTU, PU sizes 64..8, TU sizes 32..4 in one replay (include/homer_b200.h section D)"""
+    DEPTHS, PASSES = 4, 5
+
+    def __init__(self, ctx, width, height, qp=32, chroma_qp_offset=2, sign_hiding=1, is_islice=0, me_action=7,
+                 use_graph=1, band=(0, 0)):
+        self.ctx, self.w, self.h_px = ctx, width, height
+        self.cfg = PrepassCfg(qp, chroma_qp_offset, sign_hiding, is_islice, me_action, use_graph, band[0], band[1])
+        h = C.c_void_p()
+        _check(ctx.L.hb_prepass_create(ctx.h, width, height, C.byref(self.cfg), C.byref(h)), "hb_prepass_create")
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.ctx.L.hb_prepass_destroy(self.h)
+            self.h = None
+
+    def run(self, cur, ref, avg_dist):
+        _check(self.ctx.L.hb_prepass_run(self.h, cur.h, ref.h, avg_dist), "hb_prepass_run")
+
+    def num_pus(self, depth):
+        return self.ctx.L.hb_prepass_num_pus(self.h, depth)
+
+    def num_tus(self, p, comp):
+        return self.ctx.L.hb_prepass_num_tus(self.h, p, comp)
+
+    def tu_size(self, p, comp):
+        return self.ctx.L.hb_prepass_tu_size(self.h, p, comp)
+
+    def tu_xy(self, p, comp):
+        n = self.num_tus(p, comp)
+        xy = np.zeros((n, 2), np.int32)
+        if n:
+            _check(self.ctx.L.hb_prepass_tu_xy(self.h, p, comp, xy.ctypes.data_as(i32p)), "hb_prepass_tu_xy")
+        return xy
+
+    def fetch_me(self, depth):
+        n = self.num_pus(depth)
+        out = (MeResult * n)()
+        _check(self.ctx.L.hb_prepass_fetch_me(self.h, depth, out), "hb_prepass_fetch_me")
+        return np.frombuffer(out, dtype=np.dtype([("mvx", "<i4"), ("mvy", "<i4"), ("subx", "<i4"), ("suby", "<i4"),
+                                                  ("sad", "<u4"), ("n_probes", "<u4")])).copy()
+
+    def fetch_tu(self, p, comp):
+        n = self.num_tus(p, comp)
+        out = (TuResult * max(n, 1))()
+        if n:
+            _check(self.ctx.L.hb_prepass_fetch_tu(self.h, p, comp, out), "hb_prepass_fetch_tu")
+        return np.frombuffer(out, dtype=np.dtype([("sum", "<i4"), ("ssd", "<u4"), ("ssd_zero", "<u4"), ("zeroed", "<i4")]))[:n].copy()
+
+    def fetch_coeffs(self, p, comp):
+        n, t = self.num_tus(p, comp), self.tu_size(p, comp)
+        out = np.zeros((n, t, t), np.int16)
+        if n:
+            _check(self.ctx.L.hb_prepass_fetch_coeffs(self.h, p, comp, _p16(out.reshape(-1))), "hb_prepass_fetch_coeffs")
+        return out
+
+    def pred(self, depth):
+        return _BorrowedFrame(self.ctx, self.ctx.L.hb_prepass_pred(self.h, depth), self.w, self.h_px)
+
+    def recon(self, p):
+        return _BorrowedFrame(self.ctx, self.ctx.L.hb_prepass_recon(self.h, p), self.w, self.h_px)
+
+    def output_bytes(self):
+        return int(self.ctx.L.hb_prepass_output_bytes(self.h))
+
+    def fetch_all(self, pinned):
+        n = C.c_size_t(0)
+        _check(self.ctx.L.hb_prepass_fetch_all(self.h, pinned.ctypes.data, pinned.nbytes, C.byref(n)), "hb_prepass_fetch_all")
+        return n.value

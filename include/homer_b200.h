@@ -1,0 +1,211 @@
+/*
+ * homer_b200.h -- C ABI of the B200 (sm_100a) implementation of HomerHEVC's data-parallel hot path:
+ * SAD/SSD motion search, luma/chroma interpolation with sub-pel refinement, motion compensation,
+ * forward/inverse DCT/DST with quantisation (incl. sign-data hiding), dequantisation and reconstruction.
+ *
+ * Plain C: pointers, sizes and PODs only.  The library is libhomer_b200.so (homerhevc_b200/csrc).
+ * There is NO CPU fallback: every entry point computes on the GPU and fails loudly when CUDA is unavailable
+ * (status-returning calls give HB_ERR_CUDA; the void/value-returning drop-ins of section A print and abort()).
+ *
+ * Reference interfaces replaced (paths under /root/reference/src/homer_lib/):
+ *   section A -- the members of struct low_level_funcs_t, hmr_private.h:1063-1092, same prototypes;
+ *   section B -- frame residency: the int16 wnd_t frames of hmr_private.h:660 / hmr_encoder_lib.c:1512-1516
+ *                and reference_picture_border_padding_ctu hmr_encoder_lib.c:1723;
+ *   section C -- batched forms of hmr_motion_estimation hmr_motion_inter.c:1404,
+ *                hmr_motion_compensation_luma/_chroma :1779/:1860, encode_inter_cu/_chroma :40/:133;
+ *   section D -- the frame-level pre-pass the north star asks for (no counterpart in the reference; it is the
+ *                batched composition of section C over every CTU and every partition size).
+ */
+#ifndef HOMER_B200_H
+#define HOMER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_OK         0
+#define HB_ERR_CUDA  -1     /* no device / CUDA runtime error (message in hb_last_error) */
+#define HB_ERR_ARG   -2
+#define HB_ERR_NOMEM -3
+
+typedef struct hb_ctx hb_ctx;         /* one per GPU: stream, scratch, tables */
+typedef struct hb_frame hb_frame;     /* one YUV 4:2:0 8-bit picture resident in HBM, border-padded */
+typedef struct hb_prepass hb_prepass; /* plan + resident outputs of the frame-level pre-pass */
+
+/* ------------------------------------------------------------------ lifecycle ------------------------------ */
+int         hb_device_count(void);
+int         hb_ctx_create(hb_ctx **out, int device);
+void        hb_ctx_destroy(hb_ctx *ctx);
+const char *hb_last_error(void);                       /* thread-local text of the last failure */
+int         hb_ctx_sync(hb_ctx *ctx);                  /* wait for everything queued on the context's stream */
+void       *hb_ctx_stream(hb_ctx *ctx);                /* the cudaStream_t work is queued on (for interop/timing) */
+uint64_t    hb_ctx_launch_count(hb_ctx *ctx);          /* kernels launched so far through this context */
+/* device-side stopwatch on the context's stream (CUDA events): begin, ..., end -> milliseconds */
+int         hb_timer_begin(hb_ctx *ctx);
+int         hb_timer_end(hb_ctx *ctx, float *ms_out);  /* synchronises */
+/* pinned host memory for async uploads/downloads */
+void       *hb_pinned_alloc(size_t bytes);
+void        hb_pinned_free(void *p);
+
+/* ------------------------------------------------------------------ A. per-call drop-ins -------------------
+ * Exactly the prototypes of low_level_funcs_t (hmr_private.h:1069-1088).  Buffers are HOST memory owned by the
+ * caller, as in the reference; each call stages them through pinned memory and runs one kernel on the calling
+ * thread's stream of the default context (device $HB_DEVICE, default 0).  Thread-safe and re-entrant.
+ * They exist so the library is a literal drop-in and so per-call parity can be tested; throughput comes from
+ * sections C and D.  Semantics: the reference's plain-C definitions (== its SSE4.2 functions on 8-bit video),
+ * quant with the SSE4.2 rounding rule (hmr_sse42_functions_quant.c:47). */
+uint32_t hb_sad(int16_t *src, uint32_t src_stride, int16_t *pred, uint32_t pred_stride, int size);
+uint32_t hb_ssd16b(int16_t *src, uint32_t src_stride, int16_t *pred, uint32_t pred_stride, int size);
+void hb_predict(int16_t *orig, int orig_stride, int16_t *pred, int pred_stride, int16_t *residual, int residual_stride, int size);
+void hb_reconst(int16_t *pred, int pred_stride, int16_t *residual, int residual_stride, int16_t *decoded, int decoded_stride, int size);
+void hb_interpolate_luma(int16_t *reference_buff, int reference_buff_stride, int16_t *pred_buff, int pred_buff_stride,
+                         int fraction, int width, int height, int is_vertical, int is_first, int is_last);
+void hb_interpolate_chroma(int16_t *reference_buff, int reference_buff_stride, int16_t *pred_buff, int pred_buff_stride,
+                           int fraction, int width, int height, int is_vertical, int is_first, int is_last);
+void hb_transform(int bit_depth, int16_t *block, int16_t *coeff, int block_size, int iWidth, int iHeight,
+                  int width_shift, int height_shift, uint16_t uiMode, int16_t *aux);
+void hb_itransform(int bit_depth, int16_t *block, int16_t *coeff, int block_size, int iWidth, int iHeight,
+                   unsigned int uiMode, int16_t *aux);
+#define HB_REG_DCT 65535              /* hmr_private.h:217; any other uiMode selects the 4x4 DST */
+
+/* quant / inv_quant take a henc_thread_t* in the reference only to reach these five values
+ * (hmr_sse42_functions_quant.c:36-48, :137-142); the drop-in takes them directly.  See INTEGRATION.md for the
+ * two-line adapter on the reference side. */
+typedef struct hb_quant_env {
+    int32_t is_islice;            /* currslice->slice_type == I_SLICE */
+    int32_t sign_hiding;          /* et->pps->sign_data_hiding_flag */
+    int32_t max_cu_size_shift;    /* et->max_cu_size_shift (6) */
+    int32_t bit_depth;            /* et->bit_depth (8) */
+    int16_t *delta_u;             /* et->aux_buff, receives deltaU (may be NULL) */
+} hb_quant_env;
+void hb_quant(const hb_quant_env *env, int16_t *src, int16_t *dst, int scan_mode, int depth, int comp, int cu_mode,
+              int is_intra, int *ac_sum, int cu_size, int per, int rem);
+void hb_inv_quant(const hb_quant_env *env, int16_t *src, int16_t *dst, int depth, int comp, int is_intra,
+                  int cu_size, int per, int rem);
+
+/* The table itself, laid out member for member like low_level_funcs_t (19 pointers, hmr_private.h:1063-1092).
+ * hb_fill_low_level_funcs overwrites the 10 members this library implements and leaves the rest (copies,
+ * variance, intra predictors, weighted average, SAO stats -- out of scope) untouched. */
+typedef struct hb_low_level_funcs {
+    void *sse_copy_16_16, *sse_copy_16_8, *sse_copy_8_16;
+    uint32_t (*sad)(int16_t *, uint32_t, int16_t *, uint32_t, int);
+    uint32_t (*ssd16b)(int16_t *, uint32_t, int16_t *, uint32_t, int);
+    void (*predict)(int16_t *, int, int16_t *, int, int16_t *, int, int);
+    void (*reconst)(int16_t *, int, int16_t *, int, int16_t *, int, int);
+    void *modified_variance, *create_intra_planar_prediction, *create_intra_angular_prediction;
+    void (*interpolate_luma_m_compensation)(int16_t *, int, int16_t *, int, int, int, int, int, int, int);
+    void (*interpolate_chroma_m_compensation)(int16_t *, int, int16_t *, int, int, int, int, int, int, int);
+    void (*interpolate_luma_m_estimation)(int16_t *, int, int16_t *, int, int, int, int, int, int, int);
+    void *weighted_average_motion;
+    void *quant, *inv_quant;      /* need the henc_thread_t adapter, see INTEGRATION.md */
+    void (*transform)(int, int16_t *, int16_t *, int, int, int, int, int, uint16_t, int16_t *);
+    void (*itransform)(int, int16_t *, int16_t *, int, int, int, unsigned int, int16_t *);
+    void *get_sao_stats;
+} hb_low_level_funcs;
+void hb_fill_low_level_funcs(hb_low_level_funcs *table);
+
+/* ------------------------------------------------------------------ B. resident frames ---------------------
+ * 8-bit planes with a replicated border of HB_PAD_LUMA (luma) / HB_PAD_LUMA/2 (chroma) samples on every side.
+ * The reference keeps int16 frames with an 80-sample border; all its samples are 0..255, so u8 is lossless and
+ * halves HBM/PCIe traffic.  hb_frame_upload_i16 accepts the reference's own wnd_t planes (int16) and narrows on
+ * the device; it reports HB_ERR_ARG (after the copy) if a sample was outside 0..255. */
+#define HB_PAD_LUMA 96
+int  hb_frame_create(hb_ctx *ctx, int width, int height, hb_frame **out);
+void hb_frame_destroy(hb_frame *f);
+int  hb_frame_width(const hb_frame *f);
+int  hb_frame_height(const hb_frame *f);
+/* async on the context's stream; host planes should be pinned (hb_pinned_alloc) for true async copies.
+ * Uploads finish with the border replication (hmr_encoder_lib.c:1723). */
+int  hb_frame_upload_u8(hb_ctx *ctx, hb_frame *f, const uint8_t *y, int y_stride, const uint8_t *u, int u_stride,
+                        const uint8_t *v, int v_stride);
+int  hb_frame_upload_i16(hb_ctx *ctx, hb_frame *f, const int16_t *y, int y_stride, const int16_t *u, int u_stride,
+                         const int16_t *v, int v_stride);
+int  hb_frame_download_u8(hb_ctx *ctx, const hb_frame *f, uint8_t *y, int y_stride, uint8_t *u, int u_stride,
+                          uint8_t *v, int v_stride);
+
+/* ------------------------------------------------------------------ C. batched jobs on resident frames ----- */
+typedef struct hb_mv { int32_t x, y; } hb_mv;                 /* quarter-pel units (motion_vector_t, hmr_private.h:712) */
+
+/* one hmr_motion_estimation call (hmr_motion_inter.c:1404) */
+typedef struct hb_me_job {
+    int32_t x, y;               /* luma position of the PU in the frame (curr_part_global_x/y) */
+    int32_t size;               /* 8, 16, 32 or 64; the PU must lie inside the frame */
+    int32_t qp;                 /* curr_cu_info->qp, weights the MV cost (hmr_common.h:53) */
+    int32_t n_amvp;             /* 0..2 AMVP candidates the MV cost is measured against */
+    hb_mv   amvp[2];
+    int32_t n_start;            /* 0..3 extra start points (et->mv_search_candidates) */
+    hb_mv   start[3];
+    int32_t parent;             /* >= 0: index into `parent_results`; that MV is appended to the start points when
+                                   both its components are non-zero (hmr_motion_inter.c:2613).  -1: none */
+} hb_me_job;
+typedef struct hb_me_result {
+    hb_mv    mv;                /* best MV, quarter-pel */
+    hb_mv    subpix;            /* its sub-pel part as the reference reports it */
+    uint32_t sad;               /* SAD at mv (return value of hmr_motion_estimation) */
+    uint32_t n_probes;          /* integer positions evaluated (diagnostic) */
+} hb_me_result;
+#define HB_ME_PEL 1
+#define HB_ME_HALF 2
+#define HB_ME_QUARTER 4
+/* jobs/results/parent_results are HOST arrays; search range is the reference's +-128 x +-64 (hmr_private.h:76). */
+int hb_me_search(hb_ctx *ctx, const hb_frame *cur, const hb_frame *ref, const hb_me_job *jobs, int n_jobs,
+                 const hb_me_result *parent_results, int n_parent, double avg_dist, int action, hb_me_result *results);
+
+/* one hmr_motion_compensation_luma + two _chroma calls (uni-prediction) */
+typedef struct hb_mc_job { int32_t x, y, size; hb_mv mv; } hb_mc_job;     /* size: luma 8..64 (chroma size/2) */
+int hb_mc_predict(hb_ctx *ctx, const hb_frame *ref, hb_frame *pred, const hb_mc_job *jobs, int n_jobs);
+
+/* one encode_inter_cu (comp 0) or encode_inter_cu_chroma (comp 1,2) call: T -> Q -> [IQ -> IT -> SSD -> zero-out] -> recon */
+typedef struct hb_tu_job { int32_t comp; int32_t x, y; int32_t size; int32_t qp; } hb_tu_job; /* x,y,size in samples of that plane; qp already chroma-mapped */
+typedef struct hb_tu_result { int32_t sum; uint32_t ssd; uint32_t ssd_zero; int32_t zeroed; } hb_tu_result;
+typedef struct hb_tq_params {
+    int32_t is_islice;          /* rounding 171 vs 85 (hmr_sse42_functions_quant.c:47) */
+    int32_t sign_hiding;
+    double  avg_dist;           /* zero-out threshold input (hmr_motion_inter.c:106) */
+    double  chroma_weight;      /* pow(2,(qp-qp_c)/3) of hmr_motion_inter.c:155; luma uses 1 */
+} hb_tq_params;
+/* coeffs: host array receiving size*size levels per job, jobs back to back in job order. recon gets the decoded samples. */
+int hb_tq_encode(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_frame *recon, const hb_tu_job *jobs, int n_jobs,
+                 const hb_tq_params *params, int16_t *coeffs, hb_tu_result *results);
+
+/* ------------------------------------------------------------------ D. frame-level pre-pass ----------------
+ * For every CTU and every inter PU size 64/32/16/8 at once: motion search chained parent -> child exactly as
+ * hmr_cu_motion_estimation does (zero AMVP predictors, parent MV as extra start), motion compensation of
+ * luma + chroma with the MVs found, and the inter T/Q chain over TU sizes 32/32/16/8 (+4x4 for the 8x8 level),
+ * chroma at half size.  Everything stays in HBM; the host fetches cost tables, coefficients and reconstructions. */
+typedef struct hb_prepass_cfg {
+    int32_t qp;                 /* fixed slice QP */
+    int32_t chroma_qp_offset;   /* HVENC_Cfg.chroma_qp_offset (reference default 2) */
+    int32_t sign_hiding;
+    int32_t is_islice;          /* 0 for the P-slice pre-pass */
+    int32_t me_action;          /* HB_ME_PEL|HB_ME_HALF|HB_ME_QUARTER */
+    int32_t use_graph;          /* replay the launch sequence as one CUDA graph */
+    /* CTU-row band of the frame this GPU works on: rows [band_ctu_row0, band_ctu_row0+band_ctu_rows); 0,0 = all */
+    int32_t band_ctu_row0, band_ctu_rows;
+} hb_prepass_cfg;
+#define HB_PREPASS_DEPTHS 4     /* PU 64,32,16,8 */
+#define HB_PREPASS_TQ_PASSES 5  /* luma TU 32(d0),32(d1),16(d2),8(d3),4(d3) */
+int  hb_prepass_create(hb_ctx *ctx, int width, int height, const hb_prepass_cfg *cfg, hb_prepass **out);
+void hb_prepass_destroy(hb_prepass *pp);
+/* queue one frame (async); results become valid after hb_ctx_sync or a fetch */
+int  hb_prepass_run(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, double avg_dist);
+int  hb_prepass_num_pus(const hb_prepass *pp, int depth);            /* PUs per frame at that depth (raster order) */
+int  hb_prepass_num_tus(const hb_prepass *pp, int pass, int comp);   /* coded TUs of that pass and plane (raster order of the coded ones) */
+int  hb_prepass_tu_size(const hb_prepass *pp, int pass, int comp);   /* TU side in samples of that plane, 0 = plane not coded in this pass */
+int  hb_prepass_tu_xy(hb_prepass *pp, int pass, int comp, int32_t *xy_out); /* num_tus (x,y) pairs, samples of that plane */
+int  hb_prepass_fetch_me(hb_prepass *pp, int depth, hb_me_result *out);                 /* PU raster order; sad = UINT32_MAX outside the frame/band */
+int  hb_prepass_fetch_tu(hb_prepass *pp, int pass, int comp, hb_tu_result *out);        /* TU raster order */
+int  hb_prepass_fetch_coeffs(hb_prepass *pp, int pass, int comp, int16_t *out);         /* num_tus * n*n levels, TU raster order, row-major inside */
+int  hb_prepass_fetch_recon(hb_prepass *pp, int pass, uint8_t *y, int y_stride, uint8_t *u, int u_stride, uint8_t *v, int v_stride);
+int  hb_prepass_fetch_all(hb_prepass *pp, void *pinned_dst, size_t cap, size_t *bytes_out); /* everything above, packed, one async burst + sync */
+size_t hb_prepass_output_bytes(const hb_prepass *pp);
+const hb_frame *hb_prepass_pred(const hb_prepass *pp, int depth);     /* resident prediction of that depth */
+const hb_frame *hb_prepass_recon(const hb_prepass *pp, int pass);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

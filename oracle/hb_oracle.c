@@ -31,7 +31,7 @@ uint32_t orc_ssd16b(const int16_t *src, int src_stride, const int16_t *pred, int
     for (int y = 0; y < size; y++, src += src_stride, pred += pred_stride)
         for (int x = 0; x < size; x++) {
             int d = src[x] - pred[x];
-            acc += (uint32_t)(d * d);
+            acc += (uint32_t)d * (uint32_t)d;
         }
     return acc;
 }

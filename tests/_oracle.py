@@ -160,3 +160,9 @@ def make_frame_pair(rng, w, h, pad, shift=(3, 2), noise=3.0):
     cur = crop(shift[0], shift[1])
     ref_ = crop(0, 0)
     return np.pad(cur, pad, mode="edge"), np.pad(ref_, pad, mode="edge")
+
+
+def chroma_qp(qp, offset=2):
+    """chroma QP of a luma QP (chroma_scale_conversion_table, hmr_encoder_lib.c:2245)"""
+    t = (C.c_uint8 * 58).in_dll(oracle(), "orc_chroma_qp_table")
+    return int(t[min(max(qp + offset, 0), 57)])

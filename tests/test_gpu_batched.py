@@ -1,0 +1,141 @@
+"""Batched jobs on resident frames (include/homer_b200.h section C) against the oracle: motion search
+(hmr_motion_estimation), motion compensation, the inter T/Q chain.  Bit-exact."""
+import numpy as np
+import pytest
+
+import homerhevc_b200 as hb
+from homerhevc_b200.lib import Mv
+from _frames import HostFrame, clip_pair, oracle_mc, oracle_me, oracle_tu, upload
+from _oracle import chroma_qp
+
+pytestmark = pytest.mark.gpu
+W, H = 416, 240
+
+
+def _me_job(x, y, size, qp, amvp, starts, parent=-1):
+    j = hb.MeJob()
+    j.x, j.y, j.size, j.qp, j.parent = x, y, size, qp, parent
+    j.n_amvp = len(amvp)
+    for i, (ax, ay) in enumerate(amvp):
+        j.amvp[i] = Mv(ax, ay)
+    j.n_start = len(starts)
+    for i, (sx, sy) in enumerate(starts):
+        j.start[i] = Mv(sx, sy)
+    return j
+
+
+@pytest.mark.parametrize("noise,avg_dist,action", [(3.0, 700.0, 7), (0.0, 0.0, 7), (8.0, 5000.0, 7), (3.0, 100.0, 3), (1.0, 2500.0, 1)])
+def test_me_search(ctx, noise, avg_dist, action):
+    rng = np.random.default_rng(int(noise * 10 + avg_dist))
+    cur, ref = clip_pair(W, H, n=3, noise=noise, seed=5)
+    fc, fr = upload(ctx, cur, W, H), upload(ctx, ref, W, H)
+    jobs, meta = [], []
+    for size in (64, 32, 16, 8):
+        for _ in range(40 if size > 8 else 80):
+            x = int(rng.integers(0, (W - size) // size + 1)) * size
+            y = int(rng.integers(0, (H - size) // size + 1)) * size
+            qp = int(rng.integers(20, 45))
+            amvp = [(0, 0), (0, 0)] if rng.random() < 0.4 else [tuple(int(v) for v in rng.integers(-40, 41, 2)) for _ in range(2)]
+            starts = [tuple(int(v) for v in rng.integers(-60, 61, 2)) for _ in range(int(rng.integers(0, 4)))]
+            jobs.append(_me_job(x, y, size, qp, amvp, starts))
+            meta.append((x, y, size, qp, amvp, starts))
+    res = ctx.me_search(fc, fr, jobs, avg_dist, action)
+    bad = []
+    for r, (x, y, size, qp, amvp, starts) in zip(res, meta):
+        o = oracle_me(cur, ref, W, H, x, y, size, qp, amvp, starts, avg_dist, action)
+        got = (r.mv.x, r.mv.y, r.subpix.x, r.subpix.y, r.sad, r.n_probes)
+        exp = (o.mv.x, o.mv.y, o.subpix.x, o.subpix.y, o.sad, o.n_int_sads)
+        if got != exp:
+            bad.append(((x, y, size), got, exp))
+    assert not bad, bad[:5]
+    fc.close(); fr.close()
+
+
+def test_me_parent_chain(ctx):
+    """children take the parent's vector as an extra start only when both components are non-zero (hmr_motion_inter.c:2613)"""
+    cur, ref = clip_pair(W, H, n=5, noise=2.0, seed=9)
+    fc, fr = upload(ctx, cur, W, H), upload(ctx, ref, W, H)
+    parents = [_me_job(x, y, 64, 30, [(0, 0), (0, 0)], []) for y in (0, 64, 128) for x in range(0, 384, 64)]
+    pres = ctx.me_search(fc, fr, parents, 700.0)
+    kids, meta = [], []
+    for i, p in enumerate(parents):
+        for (dx, dy) in ((0, 0), (32, 0), (0, 32), (32, 32)):
+            kids.append(_me_job(p.x + dx, p.y + dy, 32, 30, [(0, 0), (0, 0)], [], parent=i))
+            meta.append((p.x + dx, p.y + dy, i))
+    kres = ctx.me_search(fc, fr, kids, 700.0, parent_results=pres)
+    for r, (x, y, i) in zip(kres, meta):
+        pm = pres[i].mv
+        starts = [(pm.x, pm.y)] if (pm.x != 0 and pm.y != 0) else []
+        o = oracle_me(cur, ref, W, H, x, y, 32, 30, [(0, 0), (0, 0)], starts, 700.0)
+        assert (r.mv.x, r.mv.y, r.sad, r.n_probes) == (o.mv.x, o.mv.y, o.sad, o.n_int_sads)
+    fc.close(); fr.close()
+
+
+def test_mc_predict(ctx):
+    rng = np.random.default_rng(21)
+    cur, ref = clip_pair(W, H, n=2, noise=3.0, seed=6)
+    fr = upload(ctx, ref, W, H)
+    pred = hb.Frame(ctx, W, H)
+    # non-overlapping PUs on a 64 grid, each cell holds one PU of a random size
+    jobs, meta = [], []
+    for cy in range(0, H - 63, 64):
+        for cx in range(0, W - 63, 64):
+            size = int(rng.choice([64, 32, 16, 8]))
+            for oy in range(0, 64, size):
+                for ox in range(0, 64, size):
+                    mvx, mvy = (int(v) for v in rng.integers(-70, 71, 2))
+                    if rng.random() < 0.15:
+                        mvx &= ~3
+                    if rng.random() < 0.15:
+                        mvy &= ~3
+                    j = hb.McJob(cx + ox, cy + oy, size, Mv(mvx, mvy))
+                    jobs.append(j); meta.append((cx + ox, cy + oy, size, mvx, mvy))
+    ctx.mc_predict(fr, pred, jobs)
+    py, pu, pv = pred.download()
+    for (x, y, size, mvx, mvy) in meta:
+        assert np.array_equal(py[y:y + size, x:x + size], oracle_mc(ref, 0, x, y, size, mvx, mvy)), ("luma", x, y, size, mvx, mvy)
+        c = size // 2
+        assert np.array_equal(pu[y // 2:y // 2 + c, x // 2:x // 2 + c], oracle_mc(ref, 1, x // 2, y // 2, c, mvx, mvy)), ("U", x, y, size, mvx, mvy)
+        assert np.array_equal(pv[y // 2:y // 2 + c, x // 2:x // 2 + c], oracle_mc(ref, 2, x // 2, y // 2, c, mvx, mvy)), ("V", x, y, size, mvx, mvy)
+    fr.close(); pred.close()
+
+
+@pytest.mark.parametrize("qp,isl,sh,avg_dist", [(32, 0, 1, 700.0), (22, 0, 1, 30.0), (40, 0, 0, 3000.0), (27, 1, 1, 0.0), (36, 0, 1, 200.0)])
+def test_tq_encode(ctx, qp, isl, sh, avg_dist):
+    rng = np.random.default_rng(qp * 7 + isl)
+    cur, ref = clip_pair(W, H, n=4, noise=4.0, seed=8)
+    # prediction = reference with a little extra noise, so that some TUs keep levels and some are zeroed out
+    noisy = [np.clip(pl.astype(np.int32) + np.rint(rng.normal(0, 2.0, pl.shape)).astype(np.int32), 0, 255).astype(np.uint8)
+             for pl in (ref.y, ref.u, ref.v)]
+    pred_h = HostFrame(*noisy)
+    fc, fp = upload(ctx, cur, W, H), upload(ctx, pred_h, W, H)
+    rec = hb.Frame(ctx, W, H)
+    qp_c = chroma_qp(qp, 2)
+    weight = 2.0 ** ((qp - qp_c) / 3.0)
+    jobs, meta = [], []
+    # disjoint regions per size so the reconstruction plane can be checked afterwards
+    for comp in (0, 1, 2):
+        pw, ph = (W, H) if comp == 0 else (W // 2, H // 2)
+        bands = [(32, 0), (16, 64), (8, 128), (4, 160)] if comp == 0 else [(16, 0), (8, 48), (4, 80)]
+        for size, y0 in bands:
+            for y in range(y0, min(y0 + (64 if comp == 0 else 32), ph - size + 1), size):
+                for x in range(0, pw - size + 1, size):
+                    if rng.random() < 0.5:
+                        continue
+                    jobs.append(hb.TuJob(comp, x, y, size, qp if comp == 0 else qp_c)); meta.append((comp, x, y, size))
+    params = hb.TqParams(isl, sh, avg_dist, weight)
+    coeffs, res = ctx.tq_encode(fc, fp, rec, jobs, params)
+    ry, ru, rv = rec.download()
+    recs = (ry, ru, rv)
+    off = 0
+    n_keep = n_zeroed = 0
+    for r, (comp, x, y, size) in zip(res, meta):
+        eco, ede, eo = oracle_tu(cur.block(comp, x, y, size), pred_h.block(comp, x, y, size), size, comp,
+                                 qp if comp == 0 else qp_c, isl, sh, avg_dist, 1.0 if comp == 0 else weight)
+        got = coeffs[off:off + size * size].reshape(size, size); off += size * size
+        assert (r.sum, r.ssd, r.zeroed) == (eo.sum, eo.ssd, eo.zeroed), (comp, x, y, size, (r.sum, r.ssd, r.ssd_zero, r.zeroed), (eo.sum, eo.ssd, eo.ssd_zero, eo.zeroed))
+        assert np.array_equal(got, eco), ("levels", comp, x, y, size)
+        assert np.array_equal(recs[comp][y:y + size, x:x + size], ede), ("recon", comp, x, y, size)
+        n_keep += r.sum > 0; n_zeroed += r.zeroed
+    assert n_keep > 10, "test input never produced coded TUs"
+    fc.close(); fp.close(); rec.close()

@@ -1,0 +1,156 @@
+"""Frame-level pre-pass (include/homer_b200.h section D) against the oracle chain on a small frame, and
+size-independent properties at the benchmark's frame size."""
+import numpy as np
+import pytest
+
+import homerhevc_b200 as hb
+from _frames import clip_pair, oracle_mc, oracle_me, oracle_tu, upload
+from _oracle import chroma_qp
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_prepass_me(cur, ref, w, h, qp, avg_dist):
+    """depth by depth, parent vector as extra start when both components are non-zero"""
+    out = []
+    for d in range(4):
+        s = 64 >> d
+        gw, gh = ((w + 63) // 64) * (64 // s), ((h + 63) // 64) * (64 // s)
+        tab = {}
+        for py in range(gh):
+            for px in range(gw):
+                x, y = px * s, py * s
+                if x + s > w or y + s > h:
+                    continue
+                starts = []
+                if d > 0:
+                    par = out[d - 1].get((px // 2, py // 2))
+                    if par is not None and par.mv.x != 0 and par.mv.y != 0:
+                        starts = [(par.mv.x, par.mv.y)]
+                tab[(px, py)] = oracle_me(cur, ref, w, h, x, y, s, qp, [(0, 0), (0, 0)], starts, avg_dist)
+        out.append(tab)
+    return out
+
+
+@pytest.mark.parametrize("w,h,use_graph", [(192, 136, 0), (256, 128, 1)])
+def test_prepass_matches_oracle(ctx, w, h, use_graph):
+    qp, avg_dist = 32, 650.0
+    cur, ref = clip_pair(w, h, n=2, noise=3.0, seed=3)
+    fc, fr = upload(ctx, cur, w, h), upload(ctx, ref, w, h)
+    pp = hb.Prepass(ctx, w, h, qp=qp, use_graph=use_graph)
+    for rep in range(2):                       # twice: the second run replays the captured graph
+        pp.run(fc, fr, avg_dist)
+    ctx.sync()
+    exp_me = _oracle_prepass_me(cur, ref, w, h, qp, avg_dist)
+    qp_c = chroma_qp(qp, 2)
+    weight = 2.0 ** ((qp - qp_c) / 3.0)
+    preds = []
+    for d in range(4):
+        s = 64 >> d
+        got = pp.fetch_me(d)
+        gw = ((w + 63) // 64) * (64 // s)
+        py_, pu_, pv_ = pp.pred(d).download()
+        for idx, r in enumerate(got):
+            px, py = idx % gw, idx // gw
+            e = exp_me[d].get((px, py))
+            if e is None:
+                assert r["sad"] == 0xFFFFFFFF
+                continue
+            assert (r["mvx"], r["mvy"], r["subx"], r["suby"], r["sad"], r["n_probes"]) == (e.mv.x, e.mv.y, e.subpix.x, e.subpix.y, e.sad, e.n_int_sads), (d, px, py)
+            x, y = px * s, py * s
+            assert np.array_equal(py_[y:y + s, x:x + s], oracle_mc(ref, 0, x, y, s, e.mv.x, e.mv.y)), ("pred Y", d, px, py)
+            assert np.array_equal(pu_[y // 2:(y + s) // 2, x // 2:(x + s) // 2], oracle_mc(ref, 1, x // 2, y // 2, s // 2, e.mv.x, e.mv.y)), ("pred U", d, px, py)
+            assert np.array_equal(pv_[y // 2:(y + s) // 2, x // 2:(x + s) // 2], oracle_mc(ref, 2, x // 2, y // 2, s // 2, e.mv.x, e.mv.y)), ("pred V", d, px, py)
+        preds.append((py_, pu_, pv_))
+    n_coded = 0
+    for p in range(5):
+        d = min(p, 3)
+        rec = pp.recon(p).download()
+        for comp in range(3):
+            t = pp.tu_size(p, comp)
+            if not t:
+                assert p == 4 and comp > 0
+                continue
+            xy = pp.tu_xy(p, comp)
+            res = pp.fetch_tu(p, comp)
+            co = pp.fetch_coeffs(p, comp)
+            assert len(xy) == len(res) == len(co) > 0
+            for (x, y), r, c in zip(xy, res, co):
+                eco, ede, eo = oracle_tu(cur.block(comp, x, y, t), preds[d][comp][y:y + t, x:x + t], t, comp,
+                                         qp if comp == 0 else qp_c, 0, 1, avg_dist, 1.0 if comp == 0 else weight)
+                assert (r["sum"], r["ssd"], r["zeroed"]) == (eo.sum, eo.ssd, eo.zeroed), (p, comp, x, y)
+                assert np.array_equal(c, eco), ("levels", p, comp, x, y)
+                assert np.array_equal(rec[comp][y:y + t, x:x + t], ede), ("recon", p, comp, x, y)
+                n_coded += r["sum"] > 0
+    assert n_coded > 0
+    # the packed fetch carries the same bytes as the individual ones
+    pin = ctx.pinned(pp.output_bytes())
+    assert pp.fetch_all(pin) == pp.output_bytes()
+    me0 = pp.fetch_me(0)
+    assert bytes(pin[:me0.nbytes]) == me0.tobytes()
+    pp.close(); fc.close(); fr.close()
+
+
+def test_prepass_band_union_equals_whole(ctx):
+    """CTU-row bands (the multi-GPU partition) produce exactly the rows of the whole-frame run"""
+    w, h = 256, 256
+    cur, ref = clip_pair(w, h, n=1, noise=3.0, seed=4)
+    fc, fr = upload(ctx, cur, w, h), upload(ctx, ref, w, h)
+    whole = hb.Prepass(ctx, w, h, use_graph=0)
+    whole.run(fc, fr, 500.0)
+    full = [whole.fetch_me(d) for d in range(4)]
+    for (r0, rows) in ((0, 1), (1, 2), (3, 1)):
+        band = hb.Prepass(ctx, w, h, use_graph=0, band=(r0, rows))
+        band.run(fc, fr, 500.0)
+        for d in range(4):
+            s = 64 >> d
+            gw = (w // 64) * (64 // s)
+            got = band.fetch_me(d)
+            for idx, r in enumerate(got):
+                ctu_row = (idx // gw) * s // 64
+                if r0 <= ctu_row < r0 + rows:
+                    assert r == full[d][idx], (d, idx)
+                else:
+                    assert r["sad"] == 0xFFFFFFFF
+        band.close()
+    whole.close(); fc.close(); fr.close()
+
+
+def test_prepass_1080p_properties(ctx):
+    """At the benchmark size the oracle is too slow for every PU: check properties instead --
+    (1) identical frames give zero vectors, zero SAD and no coded levels; (2) a spot sample of PUs matches the oracle;
+    (3) every reconstruction equals prediction + decoded residual implied by sum == 0 TUs (recon == pred there)."""
+    w, h = 1920, 1080
+    cur, ref = clip_pair(w, h, n=1, noise=3.0)
+    fc, fr = upload(ctx, cur, w, h), upload(ctx, ref, w, h)
+    pp = hb.Prepass(ctx, w, h)
+    pp.run(fc, fc, 650.0)
+    for d in range(4):
+        r = pp.fetch_me(d)
+        ok = r["sad"] != 0xFFFFFFFF
+        assert ok.sum() == (w // (64 >> d)) * (h // (64 >> d))
+        assert not r["sad"][ok].any() and not r["mvx"][ok].any() and not r["mvy"][ok].any()
+    for p in range(5):
+        assert not pp.fetch_tu(p, 0)["sum"].any()
+    pp.run(fc, fr, 650.0)
+    rng = np.random.default_rng(0)
+    r3 = pp.fetch_me(3)
+    gw = ((w + 63) // 64) * 8
+    for idx in rng.choice(len(r3), 40, replace=False):
+        px, py = int(idx % gw), int(idx // gw)
+        if r3[idx]["sad"] == 0xFFFFFFFF:
+            continue
+        par = pp.fetch_me(2)[(py // 2) * (gw // 2) + px // 2]
+        starts = [(int(par["mvx"]), int(par["mvy"]))] if par["mvx"] != 0 and par["mvy"] != 0 else []
+        e = oracle_me(cur, ref, w, h, px * 8, py * 8, 8, 32, [(0, 0), (0, 0)], starts, 650.0)
+        assert (r3[idx]["mvx"], r3[idx]["mvy"], r3[idx]["sad"]) == (e.mv.x, e.mv.y, e.sad)
+    for p in (0, 3):
+        t = pp.tu_size(p, 0)
+        xy, res = pp.tu_xy(p, 0), pp.fetch_tu(p, 0)
+        rec = pp.recon(p).download()[0]
+        prd = pp.pred(min(p, 3)).download()[0]
+        for i in rng.choice(len(xy), 200, replace=False):
+            x, y = xy[i]
+            if res[i]["sum"] == 0:
+                assert np.array_equal(rec[y:y + t, x:x + t], prd[y:y + t, x:x + t])
+    pp.close(); fc.close(); fr.close()
