@@ -116,7 +116,7 @@ def test_tq_encode(ctx, qp, isl, sh, avg_dist):
     # disjoint regions per size so the reconstruction plane can be checked afterwards
     for comp in (0, 1, 2):
         pw, ph = (W, H) if comp == 0 else (W // 2, H // 2)
-        bands = [(32, 0), (16, 64), (8, 128), (4, 160)] if comp == 0 else [(16, 0), (8, 48), (4, 80)]
+        bands = [(32, 0), (16, 64), (8, 128), (4, 192)] if comp == 0 else [(16, 0), (8, 48), (4, 80)]
         for size, y0 in bands:
             for y in range(y0, min(y0 + (64 if comp == 0 else 32), ph - size + 1), size):
                 for x in range(0, pw - size + 1, size):
