@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- ME+TQ frames/s of the frame-level pre-pass (BASELINE.json metric) on N B200s.
+
+A step = one pass of the hot path over one frame pair: motion search of every PU 64/32/16/8 (parent -> child chain,
+integer walk + half + quarter pel), motion compensation luma + chroma at each size, and the inter T/Q chain over TU
+32/32/16/8/4 (+ chroma) with reconstruction.  Workload: synthetic YUV 4:2:0 of SURVEY.md 8(d), IPPP quarter-pel, fixed QP 32.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 720p|1080p|2160p] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU); every rank processes its own independent stream of frames
+(GOP-per-GPU batching, BASELINE.json configs[4]; no data-path collective), value = frames of all ranks / max time.
+`--impl reference` times the reference's own CPU functions (oracle/_ref, compiled from /root/reference) over the same
+pre-pass on the host cores of the box; rank 0 only.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {"720p": (1280, 720), "1080p": (1920, 1080), "2160p": (3840, 2160)}
+QP, AVG_DIST = 32, 650.0
+N_RESIDENT = 16           # distinct frames cycled through so that no step finds its inputs in L2
+L2_BYTES = 126 * 2 ** 20
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(pp, w, h):
+    """per-launch algorithmic HBM bytes of every pre-pass kernel: each input plane read once,
+    each output written once, for the PUs / TUs that launch covers."""
+    out = {}
+    luma = w * h
+    for d in range(4):
+        s = 64 >> d
+        n_pu = (w // s) * (h // s)
+        out[f"me{s}"] = 2 * luma + 24 * n_pu                    # cur + ref luma (u8) in, one result record per PU out
+        out[f"mc{s}"] = int(1.5 * n_pu * s * s) * 2 + 8 * n_pu  # ref in, pred out (luma + chroma), mv in
+    for p in range(5):
+        for c in range(3):
+            t = pp.tu_size(p, c)
+            if not t:
+                continue
+            n = pp.num_tus(p, c)
+            out[f"tq{p}{'yuv'[c]}{t}"] = n * t * t * (1 + 1 + 1 + 2) + n * (8 + 16)   # cur, pred in; recon, levels out; job, result
+    return out
+
+
+def run_reference(args, w, h, rank, world):
+    """the reference's own CPU functions over the same pre-pass, all host threads; a step = `sample` frames"""
+    from homerhevc_b200 import synth
+    from _oracle import have_ref, ref_prepass
+    if rank != 0:
+        return
+    if not have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (compiled reference) is not in this tree"}))
+        return
+    cores = len(os.sched_getaffinity(0))
+    tex = synth.make_texture(w, h)
+    frames = [synth.make_frame(tex, w, h, n) for n in range(5)]
+    sample = 1 if (w, h) == WORKLOADS["2160p"] else (2 if (w, h) == WORKLOADS["1080p"] else 4)
+    def step(i):
+        t = 0.0
+        for k in range(sample):
+            j = (i * sample + k) % 4
+            s, _ = ref_prepass(frames[j + 1], frames[j], w, h, QP, AVG_DIST, n_threads=cores, want_pred=False)
+            t += s
+        return t
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    secs = time.perf_counter() - t0
+    fps = args.steps * sample / secs
+    line = {"impl": "reference", "metric": "ME+TQ frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/int16/int32", "data": "synthetic",
+            "config": {"workload": workload_name(args, w, h), "frames_per_step": sample, "qp": QP, "avg_dist": AVG_DIST},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference",
+                             "sample": f"{sample} frame(s) per step, reference functions via oracle/_ref, {cores} threads, CTUs dealt round-robin"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_name(args, w, h):
+    return f"{w}x{h} IPPP quarter-pel ME (PU 64/32/16/8) + MC + inter T/Q (TU 32/32/16/8/4), fixed QP {QP}, synthetic YUV420"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    w, h = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if args.steps > 20:
+            args.steps, args.warmup = 5, 1
+        run_reference(args, w, h, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import homerhevc_b200 as hb
+    from homerhevc_b200 import synth
+
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = hb.Context(local)
+    tex = synth.make_texture(w, h)
+    # every rank works on its own stream of frames (its own GOP): same texture, different pan phase
+    host = [synth.make_frame(tex, w, h, n + 5 * rank, seed=rank) for n in range(N_RESIDENT + 1)]
+    frame_bytes = w * h * 3 // 2
+    pin = ctx.pinned(frame_bytes * (N_RESIDENT + 1))
+    pinned = []
+    for i, (y, u, v) in enumerate(host):
+        base = pin[i * frame_bytes:(i + 1) * frame_bytes]
+        py = base[:w * h].reshape(h, w); pu = base[w * h:w * h * 5 // 4].reshape(h // 2, w // 2); pv = base[w * h * 5 // 4:].reshape(h // 2, w // 2)
+        py[:], pu[:], pv[:] = y, u, v
+        pinned.append((py, pu, pv))
+    resident = [hb.Frame(ctx, w, h) for _ in range(N_RESIDENT + 1)]
+    for f, p in zip(resident, pinned):
+        f.upload_u8(*p)
+    pp = hb.Prepass(ctx, w, h, qp=QP, use_graph=1)
+    out_bytes = pp.output_bytes()
+    out_pin = ctx.pinned(out_bytes)
+    ctx.sync()
+
+    def step_resident(i):
+        j = i % N_RESIDENT
+        pp.run(resident[j + 1], resident[j], AVG_DIST)
+
+    # ---- value: inputs resident in HBM, device time of exactly K steps on the launching stream
+    for i in range(args.warmup):
+        step_resident(i)
+    ctx.sync()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ctx.launch_count()
+    ctx.timer_begin()
+    for i in range(args.steps):
+        step_resident(i)
+    ms = ctx.timer_end()
+    launches = ctx.launch_count() - l0
+    barrier()
+    clocks = sampler.stop()
+
+    # ---- e2e: the same call sequence a host encoder makes, with host buffers: upload cur + ref (pinned, async),
+    # pre-pass, fetch every table / level / reconstruction back to pinned memory.  Timed with the same stream events.
+    e2e_cur, e2e_ref = hb.Frame(ctx, w, h), hb.Frame(ctx, w, h)
+    def step_e2e(i):
+        j = i % N_RESIDENT
+        e2e_cur.upload_u8(*pinned[j + 1])
+        e2e_ref.upload_u8(*pinned[j])
+        pp.run(e2e_cur, e2e_ref, AVG_DIST)
+        pp.fetch_all(out_pin)
+    e2e_steps = max(10, min(args.steps, 60))
+    for i in range(3):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    ctx.timer_begin()
+    for i in range(e2e_steps):
+        step_e2e(i)
+    e2e_ms = ctx.timer_end()
+    e2e_wall = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e2e_ms, e2e_wall)        # the host is in the loop here: whichever clock saw more
+    barrier()
+
+    # ---- per-kernel device times (CUDA events between launches, same stream) for the roofline
+    prof = {}
+    for rep in range(5):
+        for name, t in pp.run_profiled(resident[rep + 1], resident[rep], AVG_DIST):
+            prof.setdefault(name, []).append(t)
+    prof = {k: statistics.mean(v[1:]) for k, v in prof.items()}
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = t.tolist()
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        abytes = algorithmic_bytes(pp, w, h)
+        top = max(prof, key=prof.get)
+        achieved = abytes[top] / (prof[top] * 1e-3) / 1e9
+        step_bytes = sum(abytes.values())
+        total_prof = sum(prof.values())
+        line = {
+            "metric": "ME+TQ frames/s", "value": world * args.steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8 samples, int16 residual/levels, int32 accumulate",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args, w, h), "frames_per_step_per_gpu": 1, "qp": QP, "avg_dist": AVG_DIST,
+                       "parallelism": f"gop-per-gpu x{world}" if world > 1 else "single gpu",
+                       "l2": f"inputs rotate over {N_RESIDENT} resident frame pairs; a step touches ~{step_bytes / 2**20:.0f} MiB, "
+                             f"{N_RESIDENT} steps > {L2_BYTES / 2**20:.0f} MiB L2 before any input is reused",
+                       "cuda_graph": True},
+            "e2e": {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 2 * frame_bytes,
+                    "d2h_bytes_per_step": out_bytes, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                         "kernel_ms": prof[top], "kernel_share_of_step": prof[top] / total_prof,
+                         "step_algorithmic_bytes": step_bytes,
+                         "step_frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+            "kernels_ms": {k: round(v, 5) for k, v in prof.items()},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                from _oracle import have_ref, ref_prepass
+                if have_ref():
+                    cores = len(os.sched_getaffinity(0))
+                    ref_prepass(host[1], host[0], w, h, QP, AVG_DIST, n_threads=cores, want_pred=False)     # warm
+                    n_cpu, secs = 0, 0.0
+                    while secs < 8.0 and n_cpu < 64:
+                        s, _ = ref_prepass(host[n_cpu % N_RESIDENT + 1], host[n_cpu % N_RESIDENT], w, h, QP, AVG_DIST, n_threads=cores, want_pred=False)
+                        secs += s; n_cpu += 1
+                    line["cpu_baseline"] = {"value": n_cpu / secs, "unit": "frames/s", "cores": cores, "kind": "reference",
+                                            "sample": f"{n_cpu} frames of the same workload through the reference's own functions (oracle/_ref), {cores} threads"}
+                else:
+                    line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
+            except Exception as e:  # the baseline is a reported figure; never lose the GPU line over it
+                line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

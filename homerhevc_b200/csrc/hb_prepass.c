@@ -12,12 +12,13 @@
 #include "hb_host.h"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #define N_DEPTH HB_PREPASS_DEPTHS
 #define N_PASS  HB_PREPASS_TQ_PASSES
-#define MAX_GRAPHS 8
+#define MAX_GRAPHS 64
 
 typedef struct pass_comp {
     int n_tus, tu;                 /* TU count and size (0 = component not coded in this pass) */
@@ -48,6 +49,8 @@ struct hb_prepass {
     struct { const hb_frame *cur, *ref; void *exec; } graphs[MAX_GRAPHS];
     int n_graphs;
     int launches_per_frame;
+    void *prof_ev[HB_PREPASS_MAX_KERNELS + 1];
+    char prof_name[HB_PREPASS_MAX_KERNELS][16];
 };
 
 static int pass_depth(int pass) { return pass < N_DEPTH ? pass : N_DEPTH - 1; }
@@ -181,19 +184,23 @@ void hb_prepass_destroy(hb_prepass *pp)
         hb_frame_destroy(pp->recon[p]);
     }
     if (pp->d_dyn) hbc_free(pp->d_dyn);
+    for (int i = 0; i <= HB_PREPASS_MAX_KERNELS; i++) if (pp->prof_ev[i]) hbc_event_destroy(pp->prof_ev[i]);
     free(pp);
 }
 
 /* queue the kernels of one frame on the context's stream; returns a cudaError_t value */
-static int enqueue(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, int *n_launches)
+#define PROF_MARK(...) do { if (prof && !crc) { snprintf(pp->prof_name[n], sizeof pp->prof_name[n], __VA_ARGS__); crc = hbc_event_record(pp->prof_ev[n], ctx->stream); } } while (0)
+static int enqueue(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, int *n_launches, int prof)
 {
     hb_ctx *ctx = pp->ctx;
     int crc = 0, n = 0;
     for (int d = 0; d < N_DEPTH && !crc; d++) {
         if (!pp->n_valid[d]) continue;
-        crc = hbk_me_search(&cur->d, &ref->d, 64 >> d, pp->d_jobs[d], pp->n_valid[d], d ? pp->d_me[d - 1] : NULL, pp->d_me[d],
+        PROF_MARK("me%d", 64 >> d);
+        if (!crc) crc = hbk_me_search(&cur->d, &ref->d, 64 >> d, pp->d_jobs[d], pp->n_valid[d], d ? pp->d_me[d - 1] : NULL, pp->d_me[d],
                             pp->cfg.me_action, pp->d_dyn, ctx->stream);
         n++;
+        PROF_MARK("mc%d", 64 >> d);
         if (!crc) { crc = hbk_mc_predict(&ref->d, &pp->pred[d]->d, 64 >> d, pp->d_pus[d], pp->n_valid[d], pp->d_me[d], ctx->stream); n++; }
     }
     for (int p = 0; p < N_PASS && !crc; p++) {
@@ -208,10 +215,12 @@ static int enqueue(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, int
             a.jobs_xy = pc->d_xy; a.n_jobs = pc->n_tus;
             a.thr_k = 1.; a.weight = c ? pp->weight_c : 1.; a.dyn = pp->d_dyn;
             a.coeff_out = pc->d_coeff; a.res_out = pc->d_res;
-            crc = hbk_tq_encode(&a, ctx->stream);
+            PROF_MARK("tq%d%c%d", p, "yuv"[c], pc->tu);
+            if (!crc) crc = hbk_tq_encode(&a, ctx->stream);
             n++;
         }
     }
+    if (prof && !crc) crc = hbc_event_record(pp->prof_ev[n], ctx->stream);
     *n_launches = n;
     return crc;
 }
@@ -234,14 +243,14 @@ int hb_prepass_run(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, dou
     if ((crc = hbc_h2d_async(pp->d_dyn, &dyn, sizeof dyn, ctx->stream))) return hb_cuda_fail(crc, "hb_prepass_run: params");
 
     if (!pp->cfg.use_graph) {
-        crc = enqueue(pp, cur, ref, &n);
+        crc = enqueue(pp, cur, ref, &n, 0);
     } else {
         void *exec = NULL;
         for (int i = 0; i < pp->n_graphs; i++) if (pp->graphs[i].cur == cur && pp->graphs[i].ref == ref) exec = pp->graphs[i].exec;
         if (!exec) {
             if (pp->n_graphs == MAX_GRAPHS) { hbc_graph_destroy(pp->graphs[0].exec); memmove(&pp->graphs[0], &pp->graphs[1], sizeof pp->graphs[0] * (MAX_GRAPHS - 1)); pp->n_graphs--; }
             if ((crc = hbc_graph_begin(ctx->stream))) return hb_cuda_fail(crc, "hb_prepass_run: begin capture");
-            crc = enqueue(pp, cur, ref, &n);
+            crc = enqueue(pp, cur, ref, &n, 0);
             const int erc = hbc_graph_end(ctx->stream, &exec);
             if (crc || erc) return hb_cuda_fail(crc ? crc : erc, "hb_prepass_run: capture");
             pp->graphs[pp->n_graphs].cur = cur; pp->graphs[pp->n_graphs].ref = ref; pp->graphs[pp->n_graphs].exec = exec;
@@ -256,6 +265,32 @@ int hb_prepass_run(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, dou
     ctx->launches += (uint64_t)n;
     return HB_OK;
 }
+
+/* same work as hb_prepass_run without the graph, with a CUDA event between consecutive launches: ms[i] is the device
+ * time of kernel i (names via hb_prepass_kernel_name).  Synchronises.  Returns the number of kernels or < 0. */
+int hb_prepass_run_profiled(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, double avg_dist, float *ms, int cap)
+{
+    int crc = 0, n = 0;
+    if (!pp || !cur || !ref || !ms) return hb_fail(HB_ERR_ARG, "hb_prepass_run_profiled: NULL argument");
+    hb_ctx *ctx = pp->ctx;
+    hbc_set_device(ctx->device);
+    for (int i = 0; i <= HB_PREPASS_MAX_KERNELS && !crc; i++) if (!pp->prof_ev[i]) crc = hbc_event_create(&pp->prof_ev[i]);
+    if (crc) return hb_cuda_fail(crc, "hb_prepass_run_profiled: events");
+    double w = avg_dist / 2000.;
+    w = w < .15 ? .15 : (w > 1.4 ? 1.4 : w);
+    hbd_dyn_params dyn;
+    dyn.corr = (uint32_t)pp->cfg.qp * w;
+    dyn.thr_k = hb_zero_out_k(avg_dist);
+    if ((crc = hbc_h2d_async(pp->d_dyn, &dyn, sizeof dyn, ctx->stream))) return hb_cuda_fail(crc, "hb_prepass_run_profiled: params");
+    crc = enqueue(pp, cur, ref, &n, 1);
+    if (crc) return hb_cuda_fail(crc, "hb_prepass_run_profiled");
+    ctx->launches += (uint64_t)n;
+    if (n > cap) return hb_fail(HB_ERR_ARG, "hb_prepass_run_profiled: %d kernels, room for %d", n, cap);
+    for (int i = 0; i < n && !crc; i++) crc = hbc_event_elapsed(pp->prof_ev[i], pp->prof_ev[i + 1], &ms[i]);
+    if (crc) return hb_cuda_fail(crc, "hb_prepass_run_profiled: elapsed");
+    return n;
+}
+const char *hb_prepass_kernel_name(const hb_prepass *pp, int i) { return (pp && i >= 0 && i < HB_PREPASS_MAX_KERNELS) ? pp->prof_name[i] : ""; }
 
 int hb_prepass_num_pus(const hb_prepass *pp, int depth) { return (pp && depth >= 0 && depth < N_DEPTH) ? pp->grid_w[depth] * pp->grid_h[depth] : 0; }
 int hb_prepass_num_tus(const hb_prepass *pp, int pass, int comp)

@@ -149,6 +149,9 @@ def load_library():
     L.hb_prepass_destroy.argtypes = [C.c_void_p]
     L.hb_prepass_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
     L.hb_prepass_num_pus.argtypes = [C.c_void_p, C.c_int]
+    L.hb_prepass_run_profiled.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_float), C.c_int]
+    L.hb_prepass_kernel_name.restype = C.c_char_p
+    L.hb_prepass_kernel_name.argtypes = [C.c_void_p, C.c_int]
     L.hb_prepass_num_tus.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.hb_prepass_tu_size.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.hb_prepass_tu_xy.argtypes = [C.c_void_p, C.c_int, C.c_int, i32p]
@@ -342,6 +345,14 @@ class Prepass:
 
     def run(self, cur, ref, avg_dist):
         _check(self.ctx.L.hb_prepass_run(self.h, cur.h, ref.h, avg_dist), "hb_prepass_run")
+
+    def run_profiled(self, cur, ref, avg_dist):
+        """[(kernel name, device ms)] of one frame, launch by launch (no graph)"""
+        ms = (C.c_float * 24)()
+        n = self.ctx.L.hb_prepass_run_profiled(self.h, cur.h, ref.h, avg_dist, ms, 24)
+        if n < 0:
+            _check(n, "hb_prepass_run_profiled")
+        return [(self.ctx.L.hb_prepass_kernel_name(self.h, i).decode(), ms[i]) for i in range(n)]
 
     def num_pus(self, depth):
         return self.ctx.L.hb_prepass_num_pus(self.h, depth)

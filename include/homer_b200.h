@@ -192,6 +192,11 @@ int  hb_prepass_create(hb_ctx *ctx, int width, int height, const hb_prepass_cfg 
 void hb_prepass_destroy(hb_prepass *pp);
 /* queue one frame (async); results become valid after hb_ctx_sync or a fetch */
 int  hb_prepass_run(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, double avg_dist);
+/* the same frame without the graph and with a CUDA event between consecutive launches: ms[i] = device time of kernel i.
+ * Synchronises; returns the number of kernels (<= HB_PREPASS_MAX_KERNELS) or a negative error. */
+#define HB_PREPASS_MAX_KERNELS 24
+int  hb_prepass_run_profiled(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, double avg_dist, float *ms, int cap);
+const char *hb_prepass_kernel_name(const hb_prepass *pp, int i);  /* "me64", "mc16", "tq2y16", ... valid after a profiled run */
 int  hb_prepass_num_pus(const hb_prepass *pp, int depth);            /* PUs per frame at that depth (raster order) */
 int  hb_prepass_num_tus(const hb_prepass *pp, int pass, int comp);   /* coded TUs of that pass and plane (raster order of the coded ones) */
 int  hb_prepass_tu_size(const hb_prepass *pp, int pass, int comp);   /* TU side in samples of that plane, 0 = plane not coded in this pass */

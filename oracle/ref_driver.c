@@ -297,3 +297,235 @@ long refdrv_encode_lockstep(int width, int height, int n_frames, const uint8_t *
     if (recon) for (int c = 0; c < 3; c++) free(out_frame.stream.streams[c]);
     return got == n_frames ? written : -1;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * The frame-level pre-pass of include/homer_b200.h section D computed with the reference's OWN functions
+ * (hmr_motion_estimation, hmr_motion_compensation_luma/_chroma, predict, encode_inter_cu/_chroma) on host threads:
+ * the CPU arm of bench.py (--impl reference, cpu_baseline) and the strongest parity check of the GPU pre-pass.
+ * One encoder instance per thread (each owns its henc_thread_t scratch); CTUs are dealt round-robin.
+ * Output layouts equal the GPU library's: ME tables in PU raster order per depth, TU tables / levels in raster
+ * order of the coded TUs per (pass, plane), reconstructions and predictions as tight 8-bit planes.
+ * ------------------------------------------------------------------------------------------------------------ */
+#include <pthread.h>
+
+typedef struct rp_me { int32_t mvx, mvy, subx, suby; uint32_t sad, n_probes; } rp_me;
+typedef struct rp_tu { int32_t sum; uint32_t ssd, ssd_zero; int32_t zeroed; } rp_tu;
+typedef struct refdrv_prepass_out {
+    rp_me   *me[4];
+    rp_tu   *tu[5][3];
+    int16_t *coeff[5][3];
+    uint8_t *recon[5][3];
+    uint8_t *pred[4][3];
+} refdrv_prepass_out;
+
+typedef struct rp_shared {
+    int w, h, qp, ctu_cols, ctu_rows, row0, rows, n_threads;
+    double avg_dist;
+    int16_t *cur[3], *ref[3];           /* padded int16 planes (origin pointers) */
+    int stride[3];
+    int *tu_index[5][3];                /* raster position -> index among coded TUs, or -1 */
+    int tu_grid_w[5][3];
+    refdrv_prepass_out *out;
+} rp_shared;
+typedef struct rp_worker { rp_shared *sh; refdrv *drv; int tid; pthread_t th; } rp_worker;
+
+static const int rp_pass_tu[5] = { 32, 32, 16, 8, 4 };
+static int rp_pass_depth(int p) { return p < 4 ? p : 3; }
+static int rp_pu_valid(const rp_shared *sh, int x, int y, int s)
+{
+    const int row = y / 64;
+    return x + s <= sh->w && y + s <= sh->h && row >= sh->row0 && row < sh->row0 + sh->rows;
+}
+
+static int16_t *rp_make_plane(const uint8_t *src, int w, int h, int pad, int *stride_out, int16_t **alloc_out)
+{
+    const int stride = w + 2 * pad;
+    int16_t *a = (int16_t *)malloc(sizeof(int16_t) * (size_t)stride * (h + 2 * pad));
+    for (int y = -pad; y < h + pad; y++) {
+        const int sy = y < 0 ? 0 : (y >= h ? h - 1 : y);
+        int16_t *row = a + (size_t)(y + pad) * stride + pad;
+        for (int x = -pad; x < w + pad; x++) row[x] = src[(size_t)sy * w + (x < 0 ? 0 : (x >= w ? w - 1 : x))];
+    }
+    *stride_out = stride; *alloc_out = a;
+    return a + (size_t)pad * stride + pad;
+}
+
+static cu_partition_info_t *rp_find_cu(henc_thread_t *et, ctu_info_t *ctu, int depth, int x, int y)
+{
+    const int n = 1 << (2 * depth);
+    cu_partition_info_t *c = &ctu->partition_list[et->partition_depth_start[depth]];
+    for (int i = 0; i < n; i++) if (c[i].x_position == x && c[i].y_position == y) return &c[i];
+    return NULL;
+}
+
+static void *rp_thread(void *arg)
+{
+    rp_worker *wk = (rp_worker *)arg;
+    rp_shared *sh = wk->sh;
+    refdrv *d = wk->drv;
+    henc_thread_t *et = d->et;
+    ctu_info_t *ctu = &d->eng->ctu_info[0];
+    refdrv_prepass_out *out = sh->out;
+    d->eng->avg_dist = sh->avg_dist;
+    d->eng->current_pict.slice.slice_type = P_SLICE;
+    d->eng->current_pict.slice.qp = sh->qp;
+
+    for (int ci = sh->row0 * sh->ctu_cols + wk->tid; ci < (sh->row0 + sh->rows) * sh->ctu_cols; ci += sh->n_threads) {
+        const int x0 = (ci % sh->ctu_cols) * 64, y0 = (ci / sh->ctu_cols) * 64;
+        /* frame -> CTU window (mem_transfer_move_curr_ctu_group, hmr_mem_transfer.c:284) */
+        for (int c = 0; c < 3; c++) {
+            const int cs = c ? 32 : 64, cx = c ? x0 / 2 : x0, cy = c ? y0 / 2 : y0;
+            int16_t *dst = WND_DATA_PTR(int16_t *, et->curr_mbs_wnd, c);
+            const int ds = WND_STRIDE_2D(et->curr_mbs_wnd, c);
+            for (int r = 0; r < cs; r++) memcpy(dst + r * ds, sh->cur[c] + (size_t)(cy + r) * sh->stride[c] + cx, sizeof(int16_t) * cs);
+        }
+        motion_vector_t mvs[4][64];
+        int valid[4][64];
+        for (int dp = 0; dp < 4; dp++) {
+            const int s = 64 >> dp, per = 64 / s, gw = sh->ctu_cols * per;
+            /* ---- motion search of every PU of this depth (hmr_cu_motion_estimation, hmr_motion_inter.c:2471) */
+            for (int py = 0; py < per; py++) for (int px = 0; px < per; px++) {
+                const int gx = x0 + px * s, gy = y0 + py * s, li = py * per + px;
+                valid[dp][li] = rp_pu_valid(sh, gx, gy, s);
+                if (!valid[dp][li]) continue;
+                cu_partition_info_t cu;
+                mv_candiate_list_t amvp;
+                motion_vector_t mv = { 0, 0 }, sub = { 0, 0 };
+                memset(&cu, 0, sizeof cu); memset(&amvp, 0, sizeof amvp);
+                cu.size = (uint16_t)s; cu.qp = (uint32_t)sh->qp; cu.x_position = (uint16_t)(px * s); cu.y_position = (uint16_t)(py * s);
+                amvp.num_mv_candidates = 2;
+                et->mv_search_candidates.num_mv_candidates = 0;
+                if (dp > 0) {
+                    const int pl = (py / 2) * (per / 2) + px / 2;
+                    if (valid[dp - 1][pl] && mvs[dp - 1][pl].hor_vector != 0 && mvs[dp - 1][pl].ver_vector != 0)
+                        et->mv_search_candidates.mv_candidates[et->mv_search_candidates.num_mv_candidates++].mv = mvs[dp - 1][pl];
+                }
+                int16_t *orig = WND_POSITION_2D(int16_t *, et->curr_mbs_wnd, Y_COMP, px * s, py * s, 0, et->ctu_width);
+                int16_t *rf = sh->ref[0] + (size_t)gy * sh->stride[0] + gx;
+                const uint32_t sad_ = hmr_motion_estimation(et, ctu, &cu, orig, WND_STRIDE_2D(et->curr_mbs_wnd, Y_COMP), rf, sh->stride[0], gx, gy, 0, 0, s, 6 - dp,
+                                                            MOTION_SEARCH_RANGE_X, MOTION_SEARCH_RANGE_Y, sh->w, sh->h, &mv, &sub, &amvp, 0,
+                                                            MOTION_PEL_MASK | MOTION_HALF_PEL_MASK | MOTION_QUARTER_PEL_MASK);
+                mvs[dp][li] = mv;
+                if (out->me[dp]) {
+                    rp_me *m = &out->me[dp][(gy / s) * gw + gx / s];
+                    m->mvx = mv.hor_vector; m->mvy = mv.ver_vector; m->subx = sub.hor_vector; m->suby = sub.ver_vector; m->sad = sad_; m->n_probes = 0;
+                }
+                /* ---- motion compensation into the CTU prediction window (predict_inter, hmr_motion_inter.c:3047-3049) */
+                hmr_motion_compensation_luma(et, &cu, rf, sh->stride[0], WND_POSITION_2D(int16_t *, et->prediction_wnd[0], Y_COMP, px * s, py * s, 0, et->ctu_width),
+                                             WND_STRIDE_2D(et->prediction_wnd[0], Y_COMP), s, s, 6 - dp, &mv, 0);
+                for (int c = 1; c < 3; c++)
+                    hmr_motion_compensation_chroma(et, sh->ref[c] + (size_t)(gy / 2) * sh->stride[c] + gx / 2, sh->stride[c],
+                                                   WND_POSITION_2D(int16_t *, et->prediction_wnd[0], c, px * s / 2, py * s / 2, 0, et->ctu_width),
+                                                   WND_STRIDE_2D(et->prediction_wnd[0], c), s / 2, 5 - dp, &mv, 0);
+                if (out->pred[dp][0]) for (int c = 0; c < 3; c++) {
+                    const int n = c ? s / 2 : s, ox = c ? gx / 2 : gx, oy = c ? gy / 2 : gy, pw = c ? sh->w / 2 : sh->w;
+                    int16_t *p = WND_POSITION_2D(int16_t *, et->prediction_wnd[0], c, c ? px * s / 2 : px * s, c ? py * s / 2 : py * s, 0, et->ctu_width);
+                    const int ps = WND_STRIDE_2D(et->prediction_wnd[0], c);
+                    for (int r = 0; r < n; r++) for (int q = 0; q < n; q++) out->pred[dp][c][(size_t)(oy + r) * pw + ox + q] = (uint8_t)p[r * ps + q];
+                }
+            }
+            /* ---- T/Q passes that use this depth's prediction */
+            for (int p = 0; p < 5; p++) {
+                if (rp_pass_depth(p) != dp) continue;
+                const int node_depth = p == 0 ? 1 : (p == 4 ? 4 : dp);      /* 64x64 CUs are coded as four 32x32 TUs */
+                const int ns = 64 >> node_depth;                              /* luma size of the coded node */
+                for (int c = 0; c < 3; c++) {
+                    if (c > 0 && p == 4) continue;
+                    const int tu = c ? rp_pass_tu[p] / 2 : rp_pass_tu[p];
+                    const int pw = c ? sh->w / 2 : sh->w;
+                    for (int ny = 0; ny < 64 / ns; ny++) for (int nx = 0; nx < 64 / ns; nx++) {
+                        const int lx = nx * ns, ly = ny * ns;                 /* luma position inside the CTU */
+                        if (!rp_pu_valid(sh, x0 + (lx / s) * s, y0 + (ly / s) * s, s)) continue;
+                        if (x0 + lx + ns > sh->w || y0 + ly + ns > sh->h) continue;
+                        cu_partition_info_t *cu = rp_find_cu(et, ctu, node_depth, lx, ly);
+                        const int tx = c ? lx / 2 : lx, ty = c ? ly / 2 : ly;
+                        int sum = 0, ssd;
+                        cu->qp = (uint32_t)sh->qp;
+                        et->funcs->predict(WND_POSITION_2D(int16_t *, et->curr_mbs_wnd, c, tx, ty, 0, et->ctu_width), WND_STRIDE_2D(et->curr_mbs_wnd, c),
+                                           WND_POSITION_2D(int16_t *, et->prediction_wnd[0], c, tx, ty, 0, et->ctu_width), WND_STRIDE_2D(et->prediction_wnd[0], c),
+                                           WND_POSITION_2D(int16_t *, et->residual_wnd, c, tx, ty, 0, et->ctu_width), WND_STRIDE_2D(et->residual_wnd, c), tu);
+                        if (c == 0) ssd = encode_inter_cu(et, ctu, cu, node_depth, SIZE_2Nx2N, &sum, 0);
+                        else ssd = encode_inter_cu_chroma(et, ctu, cu, c, node_depth, SIZE_2Nx2N, &sum, 0);
+                        const int gxp = (c ? x0 / 2 : x0) + tx, gyp = (c ? y0 / 2 : y0) + ty;
+                        const int ti = sh->tu_index[p][c][(gyp / tu) * sh->tu_grid_w[p][c] + gxp / tu];
+                        if (out->tu[p][c]) { rp_tu *t = &out->tu[p][c][ti]; t->sum = sum; t->ssd = (uint32_t)ssd; t->ssd_zero = 0; t->zeroed = 0; }
+                        if (out->coeff[p][c]) {
+                            wnd_t *qw = et->transform_quant_wnd[node_depth + 1];
+                            int16_t *q = c == 0 ? WND_POSITION_1D(int16_t *, *qw, c, 0, et->ctu_width, (cu->abs_index << et->num_partitions_in_cu_shift))
+                                                : WND_POSITION_1D(int16_t *, *qw, c, 0, et->ctu_width, (cu->abs_index << et->num_partitions_in_cu_shift) >> 2);
+                            memcpy(out->coeff[p][c] + (size_t)ti * tu * tu, q, sizeof(int16_t) * tu * tu);
+                        }
+                        if (out->recon[p][c]) {
+                            wnd_t *dw = et->decoded_mbs_wnd[node_depth + 1];
+                            int16_t *dd = WND_POSITION_2D(int16_t *, *dw, c, tx, ty, 0, et->ctu_width);
+                            const int ds = WND_STRIDE_2D(*dw, c);
+                            for (int r = 0; r < tu; r++) for (int q = 0; q < tu; q++) out->recon[p][c][(size_t)(gyp + r) * pw + gxp + q] = (uint8_t)dd[r * ds + q];
+                        }
+                    }
+                }
+            }
+        }
+    }
+    return NULL;
+}
+
+/* number of coded TUs of (pass, plane) for a frame / band: the sizes the caller must allocate */
+int refdrv_prepass_num_tus(int w, int h, int ctu_row0, int ctu_rows, int pass, int comp)
+{
+    rp_shared sh; memset(&sh, 0, sizeof sh);
+    sh.w = w; sh.h = h; sh.ctu_cols = (w + 63) / 64; sh.ctu_rows = (h + 63) / 64;
+    sh.row0 = ctu_rows > 0 ? ctu_row0 : 0; sh.rows = ctu_rows > 0 ? ctu_rows : sh.ctu_rows;
+    if (comp > 0 && pass == 4) return 0;
+    const int s = 64 >> rp_pass_depth(pass), tu = comp ? rp_pass_tu[pass] / 2 : rp_pass_tu[pass], sc = comp ? s / 2 : s;
+    const int pw = comp ? w / 2 : w, ph = comp ? h / 2 : h;
+    const int tw = sh.ctu_cols * (comp ? 32 : 64) / tu, th = sh.ctu_rows * (comp ? 32 : 64) / tu;
+    int n = 0;
+    for (int ty = 0; ty < th; ty++) for (int tx = 0; tx < tw; tx++) {
+        const int x = tx * tu, y = ty * tu;
+        if (x + tu > pw || y + tu > ph) continue;
+        if (!rp_pu_valid(&sh, (x / sc) * s, (y / sc) * s, s)) continue;
+        n++;
+    }
+    return n;
+}
+
+/* returns the seconds spent (conversion of the 8-bit planes to the reference's int16 frames included) or < 0 */
+double refdrv_prepass(refdrv **drv, int n_threads, const uint8_t *const cur[3], const uint8_t *const ref[3], int w, int h, int qp,
+                      double avg_dist, int ctu_row0, int ctu_rows, refdrv_prepass_out *out)
+{
+    rp_shared sh;
+    rp_worker *wk = (rp_worker *)calloc((size_t)n_threads, sizeof *wk);
+    int16_t *alloc[6];
+    struct timespec t0, t1;
+    memset(&sh, 0, sizeof sh);
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    sh.w = w; sh.h = h; sh.qp = qp; sh.avg_dist = avg_dist; sh.n_threads = n_threads; sh.out = out;
+    sh.ctu_cols = (w + 63) / 64; sh.ctu_rows = (h + 63) / 64;
+    sh.row0 = ctu_rows > 0 ? ctu_row0 : 0; sh.rows = ctu_rows > 0 ? ctu_rows : sh.ctu_rows;
+    for (int c = 0; c < 3; c++) {
+        const int pw = c ? w / 2 : w, ph = c ? h / 2 : h, pad = c ? 72 : 144;      /* room for partial CTUs at the bottom/right edge */
+        sh.cur[c] = rp_make_plane(cur[c], pw, ph, pad, &sh.stride[c], &alloc[c]);
+        sh.ref[c] = rp_make_plane(ref[c], pw, ph, pad, &sh.stride[c], &alloc[3 + c]);
+    }
+    for (int p = 0; p < 5; p++) for (int c = 0; c < 3; c++) {
+        if (c > 0 && p == 4) continue;
+        const int s = 64 >> rp_pass_depth(p), tu = c ? rp_pass_tu[p] / 2 : rp_pass_tu[p], sc = c ? s / 2 : s;
+        const int pw = c ? w / 2 : w, ph = c ? h / 2 : h;
+        const int tw = sh.ctu_cols * (c ? 32 : 64) / tu, th = sh.ctu_rows * (c ? 32 : 64) / tu;
+        int n = 0;
+        sh.tu_grid_w[p][c] = tw;
+        sh.tu_index[p][c] = (int *)malloc(sizeof(int) * (size_t)tw * th);
+        for (int ty = 0; ty < th; ty++) for (int tx = 0; tx < tw; tx++) {
+            const int x = tx * tu, y = ty * tu;
+            int ok = !(x + tu > pw || y + tu > ph) && rp_pu_valid(&sh, (x / sc) * s, (y / sc) * s, s);
+            sh.tu_index[p][c][ty * tw + tx] = ok ? n++ : -1;
+        }
+    }
+    for (int t = 0; t < n_threads; t++) { wk[t].sh = &sh; wk[t].drv = drv[t]; wk[t].tid = t; pthread_create(&wk[t].th, NULL, rp_thread, &wk[t]); }
+    for (int t = 0; t < n_threads; t++) pthread_join(wk[t].th, NULL);
+    for (int i = 0; i < 6; i++) free(alloc[i]);
+    for (int p = 0; p < 5; p++) for (int c = 0; c < 3; c++) free(sh.tu_index[p][c]);
+    free(wk);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}

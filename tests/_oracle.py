@@ -166,3 +166,64 @@ def chroma_qp(qp, offset=2):
     """chroma QP of a luma QP (chroma_scale_conversion_table, hmr_encoder_lib.c:2245)"""
     t = (C.c_uint8 * 58).in_dll(oracle(), "orc_chroma_qp_table")
     return int(t[min(max(qp + offset, 0), 57)])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the frame-level pre-pass computed by the compiled reference's own functions (oracle/ref_driver.c: refdrv_prepass)
+class _RpOut(C.Structure):
+    _fields_ = [("me", C.c_void_p * 4), ("tu", (C.c_void_p * 3) * 5), ("coeff", (C.c_void_p * 3) * 5),
+                ("recon", (C.c_void_p * 3) * 5), ("pred", (C.c_void_p * 3) * 4)]
+
+
+ME_DT = np.dtype([("mvx", "<i4"), ("mvy", "<i4"), ("subx", "<i4"), ("suby", "<i4"), ("sad", "<u4"), ("n_probes", "<u4")])
+TU_DT = np.dtype([("sum", "<i4"), ("ssd", "<u4"), ("ssd_zero", "<u4"), ("zeroed", "<i4")])
+PASS_TU = (32, 32, 16, 8, 4)
+_rp_handles = {}
+
+
+def ref_prepass(cur, ref_planes, w, h, qp=32, avg_dist=650.0, n_threads=1, band=(0, 0), sign_hiding=1, want_pred=True):
+    """cur / ref_planes: (y, u, v) uint8 planes.  Returns (seconds, dict) with the GPU library's output layouts."""
+    _, D = ref()
+    D.refdrv_prepass.restype = C.c_double
+    D.refdrv_prepass.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                 C.c_int, C.c_double, C.c_int, C.c_int, C.POINTER(_RpOut)]
+    D.refdrv_prepass_num_tus.argtypes = [C.c_int] * 6
+    key = (qp, sign_hiding)
+    hs = _rp_handles.setdefault(key, [])
+    while len(hs) < n_threads:
+        hh = D.refdrv_open(128, 128, qp, sign_hiding)      # per-thread scratch is CTU sized; the picture size is irrelevant
+        assert hh
+        hs.append(hh)
+    handles = (C.c_void_p * n_threads)(*hs[:n_threads])
+    cur = [np.ascontiguousarray(p) for p in cur]
+    ref_planes = [np.ascontiguousarray(p) for p in ref_planes]
+    cp = (C.c_void_p * 3)(*[p.ctypes.data for p in cur])
+    rp = (C.c_void_p * 3)(*[p.ctypes.data for p in ref_planes])
+    out = _RpOut()
+    res = {"me": [], "tu": {}, "coeff": {}, "recon": [], "pred": []}
+    cc, cr = (w + 63) // 64, (h + 63) // 64
+    for d in range(4):
+        s = 64 >> d
+        a = np.zeros(cc * (64 // s) * cr * (64 // s), ME_DT)
+        a["sad"] = 0xFFFFFFFF
+        res["me"].append(a)
+        out.me[d] = a.ctypes.data
+        if want_pred:
+            pl = [np.zeros((h, w), np.uint8), np.zeros((h // 2, w // 2), np.uint8), np.zeros((h // 2, w // 2), np.uint8)]
+            res["pred"].append(pl)
+            for c in range(3):
+                out.pred[d][c] = pl[c].ctypes.data
+    for p in range(5):
+        pl = [np.zeros((h, w), np.uint8), np.zeros((h // 2, w // 2), np.uint8), np.zeros((h // 2, w // 2), np.uint8)]
+        res["recon"].append(pl)
+        for c in range(3):
+            out.recon[p][c] = pl[c].ctypes.data
+            n = D.refdrv_prepass_num_tus(w, h, band[0], band[1], p, c)
+            t = PASS_TU[p] // (2 if c else 1)
+            res["tu"][(p, c)] = np.zeros(n, TU_DT)
+            res["coeff"][(p, c)] = np.zeros((n, t, t), np.int16)
+            if n:
+                out.tu[p][c] = res["tu"][(p, c)].ctypes.data
+                out.coeff[p][c] = res["coeff"][(p, c)].ctypes.data
+    secs = D.refdrv_prepass(handles, n_threads, cp, rp, w, h, qp, avg_dist, band[0], band[1], C.byref(out))
+    return secs, res

@@ -154,3 +154,41 @@ def test_prepass_1080p_properties(ctx):
             if res[i]["sum"] == 0:
                 assert np.array_equal(rec[y:y + t, x:x + t], prd[y:y + t, x:x + t])
     pp.close(); fc.close(); fr.close()
+
+
+def test_prepass_1080p_vs_compiled_reference(ctx):
+    """The whole 1080p pre-pass against the UNMODIFIED reference's own functions (oracle/_ref: hmr_motion_estimation,
+    hmr_motion_compensation_*, encode_inter_cu*), every PU, every TU, every level and reconstructed sample."""
+    from _oracle import have_ref, ref_prepass
+    if not have_ref():
+        pytest.skip("oracle/_ref was not built (needs /root/reference at build time)")
+    w, h, qp, avg = 1920, 1080, 32, 650.0
+    cur, ref = clip_pair(w, h, n=3, noise=3.0)
+    fc, fr = upload(ctx, cur, w, h), upload(ctx, ref, w, h)
+    pp = hb.Prepass(ctx, w, h, qp=qp)
+    pp.run(fc, fr, avg)
+    _, exp = ref_prepass((cur.y, cur.u, cur.v), (ref.y, ref.u, ref.v), w, h, qp, avg, n_threads=8)
+    for d in range(4):
+        got = pp.fetch_me(d)
+        for k in ("mvx", "mvy", "subx", "suby", "sad"):
+            assert np.array_equal(got[k], exp["me"][d][k]), (d, k, int((got[k] != exp["me"][d][k]).sum()))
+        for c, pl in enumerate(pp.pred(d).download()):
+            s = 64 >> d
+            hh, ww = (h // s) * s // (2 if c else 1), (w // s) * s // (2 if c else 1)
+            assert np.array_equal(pl[:hh, :ww], exp["pred"][d][c][:hh, :ww]), ("pred", d, c)
+    coded = 0
+    for p in range(5):
+        rec = pp.recon(p).download()
+        for c in range(3):
+            if not pp.tu_size(p, c):
+                continue
+            got = pp.fetch_tu(p, c)
+            assert np.array_equal(got["sum"], exp["tu"][(p, c)]["sum"]), ("sum", p, c)
+            assert np.array_equal(got["ssd"], exp["tu"][(p, c)]["ssd"]), ("ssd", p, c)
+            assert np.array_equal(pp.fetch_coeffs(p, c), exp["coeff"][(p, c)]), ("levels", p, c)
+            s = 64 >> min(p, 3)
+            hh, ww = (h // s) * s // (2 if c else 1), (w // s) * s // (2 if c else 1)
+            assert np.array_equal(rec[c][:hh, :ww], exp["recon"][p][c][:hh, :ww]), ("recon", p, c)
+            coded += int((got["sum"] > 0).sum())
+    assert coded > 1000
+    pp.close(); fc.close(); fr.close()
