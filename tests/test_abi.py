@@ -1,0 +1,59 @@
+"""The drop-in boundary: libhomer_b200.so builds for sm_100a without a GPU, loads, and exports every function that
+include/homer_b200.h declares; and the host-side mirror refuses to compute without the CUDA library (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import homerhevc_b200 as hb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "homer_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hb_[a-z0-9_]+)\s*\(", src)) - {"hb_low_level_funcs"})
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = hb.build_library()
+    assert os.path.exists(path)
+    L = C.CDLL(path)
+    names = _declared()
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_sm100a_code_is_embedded():
+    out = subprocess.run(["cuobjdump", "--list-elf", hb.library_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_struct_layouts_match_header():
+    # sizes the C side relies on (hb_me_job 17 int32, hb_me_result 6, hb_tu_result 4, 19 function pointers)
+    assert C.sizeof(hb.MeJob) == 68 and C.sizeof(hb.MeResult) == 24 and C.sizeof(hb.TuResult) == 16
+    assert C.sizeof(hb.McJob) == 20 and C.sizeof(hb.TuJob) == 20 and C.sizeof(hb.LowLevelFuncs) == 19 * C.sizeof(C.c_void_p)
+    assert C.sizeof(hb.PrepassCfg) == 32 and C.sizeof(hb.TqParams) == 24
+
+
+def test_no_cpu_fallback_without_a_device():
+    L = hb.load_library()
+    if L.hb_device_count() > 0:
+        pytest.skip("a GPU is visible here")
+    with pytest.raises(hb.HbError) as e:
+        hb.Context(0)
+    assert "no CUDA device" in str(e.value)
+
+
+def test_product_never_touches_the_oracle():
+    """only tests/, __graft_entry__.smoke() and bench.py's baseline legs may use oracle/"""
+    pkg = os.path.join(ROOT, "homerhevc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".c", ".h", ".cu", ".cuh")) or f == "Makefile":
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle/" not in txt.replace("no oracle", "") and "hb_oracle" not in txt and "liboracle" not in txt, os.path.join(dirpath, f)

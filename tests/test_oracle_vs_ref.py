@@ -1,0 +1,138 @@
+"""The oracle against the compiled reference run live (oracle/_ref, built from /root/reference by oracle/Makefile):
+wider randomised coverage than the committed golden vectors.  Skipped where oracle/_ref does not exist."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from _oracle import (OrcMeIn, OrcMeOut, OrcMv, aligned_i16, have_ref, i32p, make_frame_pair, oracle, ptr, ref, refdrv)
+
+pytestmark = pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+
+
+def test_reference_selects_sse42_table():
+    _, D = ref()
+    assert D.refdrv_sse_selected(refdrv()) == 1
+
+
+def test_pixel_interp_transform_random():
+    O = oracle(); R, _ = ref()
+    rng = np.random.default_rng(100)
+    for it in range(200):
+        n = int(rng.choice([4, 8, 16, 32, 64]))
+        a = aligned_i16(64 * 64); b = aligned_i16(80 * 80)
+        a[:] = rng.integers(0, 256, a.size); b[:] = rng.integers(0, 256, b.size)
+        off = int(rng.integers(0, 8))
+        assert R.sse_aligned_sad(ptr(a), 64, ptr(b, off), 80, n) == O.orc_sad(ptr(a), 64, ptr(b, off), 80, n)
+        assert R.sse_aligned_ssd16b(ptr(a), 64, ptr(b, off), 80, n) == O.orc_ssd16b(ptr(a), 64, ptr(b, off), 80, n)
+        # the plain-C twins agree too on 8-bit data
+        assert R.sad(ptr(a), 64, ptr(b, off), 80, n) == O.orc_sad(ptr(a), 64, ptr(b, off), 80, n)
+    for it in range(800):
+        w = int(rng.choice([4, 8, 16, 32, 64])); h = int(rng.choice([4, 8, 9, 16, 17, 32, 64, 72]))
+        first, last = [(1, 0), (0, 1), (1, 1), (0, 0)][it % 4]
+        vert = int(rng.integers(0, 2))
+        src = aligned_i16(96 * 96)
+        src[:] = rng.integers(0, 256, src.size) if first else rng.integers(-8192, 8129, src.size)
+        for chroma in (0, 1):
+            if chroma and w == 64:
+                continue
+            frac = int(rng.integers(0, 8 if chroma else 4))
+            d1 = aligned_i16(80 * 80); d2 = aligned_i16(80 * 80)
+            f = (R.sse_interpolate_chroma, O.orc_interpolate_chroma) if chroma else (R.sse_interpolate_luma, O.orc_interpolate_luma)
+            f[0](ptr(src, 96 * 8 + 8), 96, ptr(d1), 80, frac, w, h, vert, first, last)
+            f[1](ptr(src, 96 * 8 + 8), 96, ptr(d2), 80, frac, w, h, vert, first, last)
+            assert np.array_equal(d1.reshape(80, 80)[:h, :w], d2.reshape(80, 80)[:h, :w]), (chroma, frac, w, h, vert, first, last)
+    for it in range(300):
+        n = int(rng.choice([4, 8, 16, 32])); dst = int(n == 4 and rng.integers(0, 2))
+        amp = int(rng.choice([8, 40, 255]))
+        blk = aligned_i16(64 * 64); blk[:] = rng.integers(-amp, amp + 1, blk.size)
+        c1 = aligned_i16(1024); c2 = aligned_i16(1024); aux = aligned_i16(1024)
+        lg = n.bit_length() - 1
+        R.sse_transform(8, ptr(blk), ptr(c1), 64, n, n, lg, lg, C.c_uint16(0 if dst else 65535), ptr(aux))
+        O.orc_transform(8, ptr(blk), 64, ptr(c2), n, dst)
+        assert np.array_equal(c1[:n * n], c2[:n * n])
+        co = aligned_i16(1024); co[:n * n] = rng.integers(-32768, 32768, n * n)
+        b1 = aligned_i16(64 * 64); b2 = aligned_i16(64 * 64)
+        R.sse_itransform(8, ptr(b1), ptr(co), 64, n, n, C.c_uint(0 if dst else 65535), ptr(aux))
+        O.orc_itransform(8, ptr(b2), 64, ptr(co), n, dst)
+        assert np.array_equal(b1.reshape(64, 64)[:n, :n], b2.reshape(64, 64)[:n, :n])
+
+
+def test_quant_random_and_c_vs_sse_difference():
+    O = oracle(); _, D = ref()
+    h = refdrv()
+    rng = np.random.default_rng(101)
+    differs = 0
+    for it in range(1000):
+        lg = int(rng.choice([2, 3, 4, 5])); n = 1 << lg
+        comp = int(rng.integers(0, 3)) if lg < 5 else 0
+        is_intra, isl, sh = (int(v) for v in rng.integers(0, 2, 3))
+        qp = int(rng.integers(0, 52)); per, rem = qp // 6, qp % 6
+        scan = int(rng.choice([1, 2, 3])) if lg <= 3 else 3
+        src = aligned_i16(1024)
+        src[:n * n] = rng.laplace(0, [60, 400, 4000][it % 3], n * n).clip(-32768, 32767).astype(np.int16)
+        d1 = aligned_i16(1024); d2 = aligned_i16(1024); d3 = aligned_i16(1024); u1 = aligned_i16(1024); u2 = aligned_i16(1024)
+        s1 = C.c_int(0); s2 = C.c_int(0); s3 = C.c_int(0)
+        D.refdrv_quant(h, ptr(src), ptr(d1), ptr(u1), scan, lg, comp, is_intra, isl, sh, per, rem, C.byref(s1))
+        O.orc_quant(O.tables, ptr(src), ptr(d2), ptr(u2), scan, lg, comp, is_intra, isl, sh, per, rem, C.byref(s2))
+        assert s1.value == s2.value and np.array_equal(d1[:n * n], d2[:n * n]) and np.array_equal(u1[:n * n], u2[:n * n])
+        if not isl:       # the plain-C quant always rounds with 171: it is NOT the target on P slices
+            D.refdrv_quant_plainc(h, ptr(src), ptr(d3), scan, lg, comp, is_intra, isl, sh, per, rem, C.byref(s3))
+            differs += int(not np.array_equal(d1[:n * n], d3[:n * n]))
+        q1 = aligned_i16(1024); q2 = aligned_i16(1024)
+        D.refdrv_inv_quant(h, ptr(d1), ptr(q1), lg, comp, is_intra, per, rem)
+        O.orc_inv_quant(O.tables, ptr(d1), ptr(q2), lg, comp, is_intra, per, rem)
+        assert np.array_equal(q1[:n * n], q2[:n * n])
+    assert differs > 50
+
+
+def test_motion_estimation_random():
+    O = oracle(); _, D = ref()
+    h = refdrv()
+    rng = np.random.default_rng(102)
+    W, H, PAD = 416, 240, 80
+    S = W + 2 * PAD
+    for it in range(300):
+        if it % 30 == 0:
+            cur, rf = make_frame_pair(rng, W, H, PAD, shift=(int(rng.integers(0, 21)), int(rng.integers(0, 13))), noise=float(rng.choice([0, 1, 3, 8])))
+            cur = np.ascontiguousarray(cur); rf = np.ascontiguousarray(rf)
+        n = int(rng.choice([8, 16, 32, 64]))
+        gx = int(rng.integers(0, (W - n) // n + 1)) * n; gy = int(rng.integers(0, (H - n) // n + 1)) * n
+        ob = aligned_i16(64 * 64); ob.reshape(64, 64)[:n, :n] = cur[PAD + gy:PAD + gy + n, PAD + gx:PAD + gx + n]
+        amvp = np.array(rng.integers(-40, 41, 4) if it % 3 else [0, 0, 0, 0], np.int32)
+        ns = int(rng.integers(0, 4)); st = np.array(rng.integers(-60, 61, 6), np.int32)
+        qp = int(rng.integers(20, 45)); avg = float(rng.choice([0., 100., 700., 2500., 5000.])); action = int(rng.choice([7, 7, 7, 3, 1]))
+        out = np.zeros(4, np.int32)
+        off = (PAD + gy) * S + PAD + gx
+        r = D.refdrv_motion_estimation(h, ptr(ob), 64, ptr(rf.reshape(-1), off), S, gx, gy, n, W, H, 2, amvp.ctypes.data_as(i32p), ns,
+                                       st.ctypes.data_as(i32p), qp, avg, action, out.ctypes.data_as(i32p))
+        mi = OrcMeIn()
+        mi.orig = ptr(ob); mi.orig_stride = 64; mi.ref = ptr(rf.reshape(-1), off); mi.ref_stride = S
+        mi.gx, mi.gy, mi.size, mi.frame_w, mi.frame_h, mi.range_x, mi.range_y = gx, gy, n, W, H, 128, 64
+        mi.n_amvp = 2
+        for i in range(2):
+            mi.amvp[i] = OrcMv(int(amvp[2 * i]), int(amvp[2 * i + 1]))
+        mi.n_start = ns
+        for i in range(3):
+            mi.start[i] = OrcMv(int(st[2 * i]), int(st[2 * i + 1]))
+        mi.qp, mi.avg_dist, mi.action = qp, avg, action
+        mo = OrcMeOut()
+        O.orc_motion_estimation(C.byref(mi), C.byref(mo))
+        assert (r, out[0], out[1], out[2], out[3]) == (mo.sad, mo.mv.x, mo.mv.y, mo.subpix.x, mo.subpix.y), (it, n, gx, gy, action)
+
+
+def test_lockstep_encode_is_deterministic():
+    """the whole-encode golden of SURVEY.md 8c: two lock-step runs give identical bytes and reconstructions"""
+    from homerhevc_b200 import synth
+    _, D = ref()
+    w, h, nf = 192, 128, 3
+    clip = synth.make_clip(w, h, nf, seed=11)
+    yuv = np.concatenate([np.concatenate([p.reshape(-1) for p in f]) for f in clip])
+    outs = []
+    for rep in range(2):
+        bs = np.zeros(1 << 20, np.uint8); rec = np.zeros(yuv.size, np.uint8); secs = C.c_double(0)
+        n = D.refdrv_encode_lockstep(w, h, nf, yuv.ctypes.data_as(C.POINTER(C.c_uint8)), 32, 1, 0, -1, bs.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                     bs.size, rec.ctypes.data_as(C.POINTER(C.c_uint8)), None, None, C.byref(secs))
+        assert n > 0
+        outs.append((bytes(bs[:n]), rec.copy()))
+    assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1])
