@@ -168,6 +168,7 @@ int hb_ctx_create(hb_ctx **out, int device)
         return hb_cuda_fail(rc, "hb_ctx_create");
     }
     pthread_mutex_init(&ctx->lock, NULL);
+    if ((rc = hbk_me_configure())) { hb_ctx_destroy(ctx); return hb_cuda_fail(rc, "hb_ctx_create: kernel attributes"); }
     if ((rc = tables_upload(ctx)) != HB_OK) { hb_ctx_destroy(ctx); return rc; }
     if ((rc = hbc_malloc((void **)&ctx->d_flag, 256))) { hb_ctx_destroy(ctx); return hb_cuda_fail(rc, "hb_ctx_create: flag"); }
     hbc_memset_async(ctx->d_flag, 0, 256, ctx->stream);

@@ -2,14 +2,20 @@
 // (hmr_motion_inter.c:1404-1774) exactly: integer walk (start points, small diamond, rotating big diamond,
 // iterated small diamond) with the reference's double-precision MV cost, then the 8+8 half/quarter-pel probes.
 //
-// Mapping: CTA = 256 threads; a PU is searched by GW warps (64x64: 8, 32x32: 2, 16x16 and 8x8: 1), so the
-// CTA holds 8/GW PUs.  The current block lives in registers as packed u8x4 words; a candidate SAD is
-// __vsadu4 over unaligned 4-sample reads of the resident reference plane (L2/L1 resident, funnel-shifted),
-// reduced with redux.sync and, across warps of a group, one shared-memory exchange + named barrier.
-// Sub-pel: the (N+8)x(N+12) reference patch around the integer winner is staged in shared memory once,
-// the three horizontal 14-bit planes (fractions 1,2,3) are built from it, and each candidate's prediction
-// is the vertical pass over those planes -- the same two-stage arithmetic as the reference's plane builders
-// (:395, :442), sample for sample.
+// The reference probes one position after the other, but every probe of a stage lies on a pattern around a centre
+// that is fixed for that stage, and a probe's SAD/cost does not depend on the order.  So each stage is computed as
+// ROUNDS OF FOUR CANDIDATES IN PARALLEL (all lanes busy, one reduction + one cost evaluation per round) and the
+// reference's sequential compare/rotate logic is then replayed on the four (or eight) results in registers --
+// including which probes it would have skipped, so even the probe count matches.
+//
+// Mapping: CTA = 256 threads; a PU is searched by G lanes (8x8, 16x16: one warp; 32x32: two warps; 64x64: the CTA),
+// split into four candidate slots of L = G/4 lanes.  The current block lives in registers as packed u8x4 words;
+// a candidate SAD is __vsadu4 over unaligned 4-sample reads of the resident reference plane (L1/L2 hits, funnel
+// shifted), reduced with redux.sync inside a slot and exchanged through shared memory.
+// Sub-pel: the (N+8)x(N+12) patch around the integer winner is staged in shared memory once, the four horizontal
+// 14-bit planes (fractions 0..3) are built from it with vector loads/stores, and every candidate is a vertical
+// sliding-window pass (one shared load per output sample, taps in registers) over a column strip per lane --
+// the same two-stage arithmetic as the reference's plane builders (:395, :442), sample for sample.
 #include "hb_shim.h"
 #include "hb_dev_common.cuh"
 
@@ -19,6 +25,7 @@ __constant__ int8_t c_small[4][2] = { {-1, 0}, {0, -1}, {1, 0}, {0, 1} };
 __constant__ int8_t c_big[8][2] = { {-2, 0}, {-1, -1}, {0, -2}, {1, -1}, {2, 0}, {1, 1}, {0, 2}, {-1, 1} };
 __constant__ int8_t c_half[9][2] = { {0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {1, -1}, {-1, 1}, {1, 1} };
 __constant__ int8_t c_quarter[9][2] = { {0, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {1, 1} };
+__constant__ int8_t c_taps[4][8] = { {0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1} };
 
 struct MeArgs {
     hbd_plane cur, ref;
@@ -30,163 +37,245 @@ struct MeArgs {
     const hbd_dyn_params *dyn;
 };
 
-template <int N, int GW> struct MeCfg {
-    static constexpr int GT = GW * 32;                 // threads per PU
-    static constexpr int PUS = 8 / GW;                 // PUs per CTA
+template <int N> struct MeCfg {
+    static constexpr int G = (N == 64) ? 256 : (N == 32) ? 64 : 32;   // lanes per PU
+    static constexpr int L = G / 4;                    // lanes per candidate slot
+    static constexpr int SEG = L < 32 ? L : 32;        // lanes that reduce together with one redux
+    static constexpr int NSEG = G / SEG;               // partial sums exchanged per round
+    static constexpr int SEG_PER_SLOT = L / SEG;
+    static constexpr int PUS = 256 / G;                // PUs per CTA
     static constexpr int WPR = N / 4;                  // packed words per row
     static constexpr int NW = N * N / 4;               // packed words per PU
-    static constexpr int WPL = (NW + GT - 1) / GT;     // words per lane
+    static constexpr int WPL = NW / L;                 // words per lane (of its slot's candidate)
+    static constexpr int CPL = N / L;                  // sub-pel: columns per lane
     static constexpr int PROWS = N + 8;                // patch rows: iy-4 .. iy+N+3
     static constexpr int PS = N + 12;                  // patch row stride in bytes: ix-4 .. ix+N+7
     static constexpr int TS = N + 4;                   // plane row stride in int16: column j <-> x = ix-1+j (+f/4)
     static constexpr int PATCH_BYTES = PROWS * PS;
     static constexpr int PLANE_ELEMS = PROWS * TS;
-    static constexpr int SMEM_PER_PU = PATCH_BYTES + 3 * PLANE_ELEMS * 2;
+    static constexpr int SMEM_PER_PU = PATCH_BYTES + 4 * PLANE_ELEMS * 2;
+    static constexpr int SMEM_TOTAL = PUS * SMEM_PER_PU;
 };
 
-template <int GW> __device__ __forceinline__ void group_barrier(int group)
+template <int G> __device__ __forceinline__ void group_barrier(int group)
 {
-    if (GW == 1) __syncwarp();
-    else if (GW == 8) __syncthreads();
-    else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(GW * 32) : "memory");
+    if (G == 32) __syncwarp();
+    else if (G == 256) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(G) : "memory");
 }
 
-template <int N, int GW>
+template <int K> __device__ __forceinline__ uint32_t pick(const uint32_t (&a)[K], int i)
+{
+    uint32_t v = a[0];
+#pragma unroll
+    for (int k = 1; k < K; k++) v = (i == k) ? a[k] : v;
+    return v;
+}
+
+template <int N>
 __global__ void __launch_bounds__(256) k_me(const MeArgs a)
 {
-    using Cfg = MeCfg<N, GW>;
-    constexpr int GT = Cfg::GT, PUS = Cfg::PUS, WPR = Cfg::WPR, NW = Cfg::NW, WPL = Cfg::WPL;
-    constexpr int PS = Cfg::PS, TS = Cfg::TS, PROWS = Cfg::PROWS;
+    using Cfg = MeCfg<N>;
+    constexpr int G = Cfg::G, L = Cfg::L, SEG = Cfg::SEG, NSEG = Cfg::NSEG, SPS = Cfg::SEG_PER_SLOT, PUS = Cfg::PUS;
+    constexpr int WPR = Cfg::WPR, WPL = Cfg::WPL, CPL = Cfg::CPL, PS = Cfg::PS, TS = Cfg::TS, PROWS = Cfg::PROWS;
 
-    __shared__ __align__(16) uint8_t s_raw[PUS * Cfg::SMEM_PER_PU];
-    __shared__ uint32_t s_red[PUS][2][GW];
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    __shared__ uint32_t s_x[PUS][2][NSEG][2];          // [phase][segment]{partial SAD, cost of the segment's slot}
 
-    const int group = threadIdx.x / GT, gl = threadIdx.x % GT, lane = threadIdx.x & 31, gwarp = gl >> 5;
+    const int group = threadIdx.x / G, gl = threadIdx.x % G, lane = threadIdx.x & 31;
+    const int slot = gl / L, l = gl % L, seg = gl / SEG;
     const int job_idx = blockIdx.x * PUS + group;
-    if (job_idx >= a.n_jobs) return;                   // whole group leaves together (GW == 8 -> whole CTA)
-    hbd_me_job job = a.jobs[job_idx];
-    if (a.dyn) job.corr = a.dyn->corr;
+    if (job_idx >= a.n_jobs) return;                   // the whole group leaves together
+    const hbd_me_job *jp = a.jobs + job_idx;
+    const int jx = jp->x, jy = jp->y;
+    const double corr = a.dyn ? a.dyn->corr : jp->corr;
+    const int n_amvp = jp->n_amvp;
+    const int a0x = jp->amvp[0], a0y = jp->amvp[1], a1x = jp->amvp[2], a1y = jp->amvp[3];
+    const bool two_costs = n_amvp > 1 && (a0x != a1x || a0y != a1y);
 
     uint8_t *s_patch = s_raw + group * Cfg::SMEM_PER_PU;
-    int16_t *s_plane = reinterpret_cast<int16_t *>(s_patch + Cfg::PATCH_BYTES);   // [3][PROWS][TS], fraction f -> plane f-1
-    int red_phase = 0;
+    int16_t *s_plane = reinterpret_cast<int16_t *>(s_patch + Cfg::PATCH_BYTES);   // [4][PROWS][TS] by x fraction
+    int phase = 0;
+    const uint32_t seg_mask = (SEG == 32) ? HB_FULL_MASK : (((1u << SEG) - 1u) << (lane & ~(SEG - 1)));
 
-    // ---- current block -> registers
+    // ---- current block -> registers: lane l of every slot holds words l, l+L, ...
     uint32_t cur[WPL];
-    int wrow[WPL], wcol[WPL];
+    int ref_off[WPL];                                  // byte offset of each word from the PU's co-located sample
+    const int rpitch = a.ref.pitch;
+    const uint8_t *ref_pu = a.ref.org + jy * rpitch + jx;
 #pragma unroll
     for (int k = 0; k < WPL; k++) {
-        const int w = gl + k * GT;
-        wrow[k] = w / WPR; wcol[k] = (w % WPR) * 4;
-        cur[k] = 0;
-        if (w < NW) cur[k] = hb_ld_u8x4(a.cur.org + (job.y + wrow[k]) * a.cur.pitch + job.x + wcol[k]);
+        const int w = l + k * L, row = w / WPR, col = (w % WPR) * 4;
+        cur[k] = hb_ld_u8x4(a.cur.org + (jy + row) * a.cur.pitch + jx + col);
+        ref_off[k] = row * rpitch + col;
     }
-    const uint8_t *ref_pu = a.ref.org + job.y * a.ref.pitch + job.x;
-    const int rpitch = a.ref.pitch;
 
-    auto group_sum = [&](uint32_t v) -> uint32_t {
-        v = __reduce_add_sync(HB_FULL_MASK, v);
-        if (GW == 1) return v;
-        if (lane == 0) s_red[group][red_phase][gwarp] = v;
-        group_barrier<GW>(group);
-        uint32_t s = 0;
-#pragma unroll
-        for (int i = 0; i < GW; i++) s += s_red[group][red_phase][i];
-        red_phase ^= 1;
-        return s;
-    };
-    auto sad_at = [&](int dx, int dy) -> uint32_t {
-        uint32_t acc = 0;
-#pragma unroll
-        for (int k = 0; k < WPL; k++) {
-            if (gl + k * GT < NW) {
-                const uint32_t r = hb_ld_u8x4(ref_pu + (dy + wrow[k]) * rpitch + dx + wcol[k]);
-                acc = __vsadu4(cur[k], r) + acc;
-            }
-        }
-        return group_sum(acc);
-    };
     // select_mv_candidate_fast (hmr_motion_inter.c:1004): IEEE double, products and sums rounded separately
     auto mv_cost = [&](int mvx, int mvy) -> uint32_t {
-        uint32_t best = 0x7fffffffu;
-        for (int i = 0; i < job.n_amvp; i++) {
-            const double cx = __dmul_rn(job.corr, static_cast<double>(static_cast<float>(abs(job.amvp[2 * i] - mvx))));
-            const double cy = __dmul_rn(job.corr, static_cast<double>(static_cast<float>(abs(job.amvp[2 * i + 1] - mvy))));
-            const uint32_t c = __double2uint_rz(__dadd_rn(__dadd_rn(cx, cy), 0.5));
-            if (best > c) best = c;
+        if (n_amvp <= 0) return 0x7fffffffu;
+        const double c0 = __dadd_rn(__dadd_rn(__dmul_rn(corr, static_cast<double>(static_cast<float>(abs(a0x - mvx)))),
+                                              __dmul_rn(corr, static_cast<double>(static_cast<float>(abs(a0y - mvy))))), 0.5);
+        uint32_t best = min(0x7fffffffu, __double2uint_rz(c0));
+        if (two_costs) {
+            const double c1 = __dadd_rn(__dadd_rn(__dmul_rn(corr, static_cast<double>(static_cast<float>(abs(a1x - mvx)))),
+                                                  __dmul_rn(corr, static_cast<double>(static_cast<float>(abs(a1y - mvy))))), 0.5);
+            best = min(best, __double2uint_rz(c1));
         }
         return best;
     };
 
     const int fw = a.cur.w, fh = a.cur.h;
-    const int xlo = (job.x - 128 < 0) ? -job.x : -128;
-    const int xhi = (job.x + 128 > fw - N) ? fw - job.x - N : 128;
-    const int ylo = (job.y - 64 < 0) ? -job.y : -64;
-    const int yhi = (job.y + 64 > fh - N) ? fh - job.y - N : 64;
+    const int xlo = (jx - 128 < 0) ? -jx : -128;
+    const int xhi = (jx + 128 > fw - N) ? fw - jx - N : 128;
+    const int ylo = (jy - 64 < 0) ? -jy : -64;
+    const int yhi = (jy + 64 > fh - N) ? fh - jy - N : 64;
+    auto inside = [&](int x, int y) { return x >= xlo && x <= xhi && y >= ylo && y <= yhi; };
+
+    // exchange this lane's partial value: every lane gets the four slot totals (and the four slot costs)
+    auto exchange = [&](uint32_t part, uint32_t cost, uint32_t (&tot)[4], uint32_t (&cst)[4]) {
+        part = __reduce_add_sync(seg_mask, part);
+        if ((gl & (SEG - 1)) == 0) { s_x[group][phase][seg][0] = part; s_x[group][phase][seg][1] = cost; }
+        group_barrier<G>(group);
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int q = 0; q < SPS; q++) t += s_x[group][phase][s * SPS + q][0];
+            tot[s] = t;
+            cst[s] = s_x[group][phase][s * SPS][1];
+        }
+        phase ^= 1;
+    };
+    // one round: SAD + cost of up to four integer positions (cx[s], cy[s]); invalid slots give garbage that is never read
+    auto round4 = [&](const int (&cx)[4], const int (&cy)[4], const bool (&cv)[4], uint32_t (&sad)[4], uint32_t (&rd)[4]) {
+        int mx = cx[0], my = cy[0]; bool mv = cv[0];
+#pragma unroll
+        for (int s = 1; s < 4; s++) if (slot == s) { mx = cx[s]; my = cy[s]; mv = cv[s]; }
+        uint32_t acc = 0;
+        if (mv) {
+            const int disp = my * rpitch + mx;
+#pragma unroll
+            for (int k = 0; k < WPL; k++) acc = __vsadu4(cur[k], hb_ld_u8x4(ref_pu + (disp + ref_off[k]))) + acc;
+        }
+        uint32_t cst[4];
+        exchange(acc, mv_cost(mx << 2, my << 2), sad, cst);
+#pragma unroll
+        for (int s = 0; s < 4; s++) rd[s] = sad[s] + cst[s];
+    };
 
     int bx = 0, by = 0;
     uint32_t bsad = 0, brd = 0, n_probes = 0;
-    auto probe = [&](int x, int y) -> bool {
-        if (x < xlo || x > xhi || y < ylo || y > yhi) return false;
-        const uint32_t sad = sad_at(x, y);
-        const uint32_t rd = sad + mv_cost(x << 2, y << 2);
-        n_probes++;
-        if (rd < brd) { bsad = sad; brd = rd; bx = x; by = y; return true; }
-        return false;
-    };
-
     int mvx = 0, mvy = 0, subx = 0, suby = 0;
     uint32_t best_sad = 0xffffffffu / 8;
 
     if (a.action & HB_ME_PEL) {
-        bx = min(max(0, xlo), xhi); by = min(max(0, ylo), yhi);
-        bsad = sad_at(bx, by); n_probes++;
-        brd = bsad + mv_cost(bx << 2, by << 2);
-        int cx0 = bx, cy0 = by;
+        // ---- origin + extra start points (caller's list, then the parent PU's vector when both components are non-zero)
+        int sx[5], sy[5]; bool sv[5];
+        sx[0] = min(max(0, xlo), xhi); sy[0] = min(max(0, ylo), yhi); sv[0] = true;
+        const int n_start = jp->n_start;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const int x = jp->start[2 * i] >> 2, y = jp->start[2 * i + 1] >> 2;
+            sx[1 + i] = x; sy[1 + i] = y;
+            sv[1 + i] = i < n_start && !(x == 0 && y == 0) && inside(x, y);
+        }
+        sx[4] = 0; sy[4] = 0; sv[4] = false;
+        if (jp->parent >= 0) {
+            const hb_mv pmv = a.parent[jp->parent].mv;
+            const int x = pmv.x >> 2, y = pmv.y >> 2;
+            sx[4] = x; sy[4] = y;
+            sv[4] = pmv.x != 0 && pmv.y != 0 && !(x == 0 && y == 0) && inside(x, y);
+        }
+        uint32_t ssad[5], srd[5];
+        {
+            const int cx[4] = { sx[0], sx[1], sx[2], sx[3] }, cy[4] = { sy[0], sy[1], sy[2], sy[3] };
+            const bool cv[4] = { sv[0], sv[1], sv[2], sv[3] };
+            uint32_t sad[4], rd[4];
+            round4(cx, cy, cv, sad, rd);
+#pragma unroll
+            for (int s = 0; s < 4; s++) { ssad[s] = sad[s]; srd[s] = rd[s]; }
+        }
+        ssad[4] = 0; srd[4] = 0;
+        if (sv[4]) {                                   // uniform
+            const int cx[4] = { sx[4], 0, 0, 0 }, cy[4] = { sy[4], 0, 0, 0 };
+            const bool cv[4] = { true, false, false, false };
+            uint32_t sad[4], rd[4];
+            round4(cx, cy, cv, sad, rd);
+            ssad[4] = sad[0]; srd[4] = rd[0];
+        }
+        bx = sx[0]; by = sy[0]; bsad = ssad[0]; brd = srd[0]; n_probes = 1;
         bool skip = bsad == 0;
         if (!skip) {
-            // extra start points: caller's list, then the parent PU's vector when both components are non-zero
-            for (int i = 0; i < job.n_start; i++) {
-                const int x = job.start[2 * i] >> 2, y = job.start[2 * i + 1] >> 2;
-                if (x == 0 && y == 0) continue;
-                probe(x, y);
-            }
-            if (job.parent >= 0) {
-                const hb_mv pmv = a.parent[job.parent].mv;
-                if (pmv.x != 0 && pmv.y != 0) {
-                    const int x = pmv.x >> 2, y = pmv.y >> 2;
-                    if (!(x == 0 && y == 0)) probe(x, y);
-                }
-            }
-            cx0 = bx; cy0 = by;
+#pragma unroll
+            for (int i = 1; i < 5; i++)
+                if (sv[i]) { n_probes++; if (srd[i] < brd) { bsad = ssad[i]; brd = srd[i]; bx = sx[i]; by = sy[i]; } }
             skip = bsad == 0;
         }
+        int cx0 = bx, cy0 = by;
         if (!skip) {
-            for (int i = 0; i < 4; i++) probe(cx0 + c_small[i][0], cy0 + c_small[i][1]);
-            int dist = 2;
+            {   // first small diamond, fixed order, centre stays put (:1501-1523)
+                int cx[4], cy[4]; bool cv[4]; uint32_t sad[4], rd[4];
+#pragma unroll
+                for (int s = 0; s < 4; s++) { cx[s] = cx0 + c_small[s][0]; cy[s] = cy0 + c_small[s][1]; cv[s] = inside(cx[s], cy[s]); }
+                round4(cx, cy, cv, sad, rd);
+#pragma unroll
+                for (int s = 0; s < 4; s++)
+                    if (cv[s]) { n_probes++; if (rd[s] < brd) { bsad = sad[s]; brd = rd[s]; bx = cx[s]; by = cy[s]; } }
+            }
+            // rotating big diamond (:1528-1599): dist 2, and 4 when the old centre sat on an axis
             const int end = (cx0 != 0 && cy0 != 0) ? 4 : 8;
             int next_start = 0, span = 8;
             cx0 = bx; cy0 = by;
-            while (dist < end) {
+            for (int dist = 2; dist < end; dist *= 2) {
+                uint32_t sad8[8], rd8[8]; bool v8[8];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    int cx[4], cy[4]; bool cv[4]; uint32_t sad[4], rd[4];
+#pragma unroll
+                    for (int s = 0; s < 4; s++) {
+                        cx[s] = cx0 + c_big[4 * h + s][0] * dist; cy[s] = cy0 + c_big[4 * h + s][1] * dist; cv[s] = inside(cx[s], cy[s]);
+                    }
+                    round4(cx, cy, cv, sad, rd);
+#pragma unroll
+                    for (int s = 0; s < 4; s++) { sad8[4 * h + s] = sad[s]; rd8[4 * h + s] = rd[s]; v8[4 * h + s] = cv[s]; }
+                }
+                uint32_t vmask = 0;
+#pragma unroll
+                for (int s = 0; s < 8; s++) vmask |= v8[s] ? (1u << s) : 0u;
                 for (int i = next_start; i < next_start + span; i++) {
                     const int idx = i & 7;
-                    if (probe(cx0 + c_big[idx][0] * dist, cy0 + c_big[idx][1] * dist)) {
-                        next_start = (idx - 2 + 8) & 7;
-                        span = 5;
+                    if (!((vmask >> idx) & 1u)) continue;
+                    n_probes++;
+                    const uint32_t rd = pick<8>(rd8, idx);
+                    if (rd < brd) {
+                        bsad = pick<8>(sad8, idx); brd = rd;
+                        bx = cx0 + c_big[idx][0] * dist; by = cy0 + c_big[idx][1] * dist;
+                        next_start = (idx - 2 + 8) & 7; span = 5;
                     }
                 }
-                dist *= 2;
             }
         }
+        // iterated small diamond with rotation until the centre stops moving (:1601-1663)
         cx0 = bx; cy0 = by;
         {
             int next_start = 0, span = 4;
             for (;;) {
+                int cx[4], cy[4]; bool cv[4]; uint32_t sad[4], rd[4];
+#pragma unroll
+                for (int s = 0; s < 4; s++) { cx[s] = cx0 + c_small[s][0]; cy[s] = cy0 + c_small[s][1]; cv[s] = inside(cx[s], cy[s]); }
+                round4(cx, cy, cv, sad, rd);
+                uint32_t vmask = 0;
+#pragma unroll
+                for (int s = 0; s < 4; s++) vmask |= cv[s] ? (1u << s) : 0u;
                 for (int i = next_start; i < next_start + span; i++) {
                     const int idx = i & 3;
-                    if (probe(cx0 + c_small[idx][0], cy0 + c_small[idx][1])) {
-                        next_start = (idx - 1 + 4) & 3;
-                        span = 3;
+                    if (!((vmask >> idx) & 1u)) continue;
+                    n_probes++;
+                    const uint32_t r = pick<4>(rd, idx);
+                    if (r < brd) {
+                        bsad = pick<4>(sad, idx); brd = r;
+                        bx = cx0 + c_small[idx][0]; by = cy0 + c_small[idx][1];
+                        next_start = (idx - 1 + 4) & 3; span = 3;
                     }
                 }
                 if (cx0 == bx && cy0 == by) break;
@@ -199,77 +288,111 @@ __global__ void __launch_bounds__(256) k_me(const MeArgs a)
 
     if (a.action & HB_ME_HALF) {
         const int ix = mvx >> 2, iy = mvy >> 2;
-        const uint8_t *ref_i = ref_pu + iy * rpitch + ix;
-        uint32_t cur_best = (a.action & HB_ME_PEL) ? bsad : sad_at(ix, iy);
-
-        // ---- stage the patch: rows iy-4.., columns ix-4..
-        for (int w = gl; w < PROWS * (PS / 4); w += GT) {
-            const int r = w / (PS / 4), c = (w % (PS / 4)) * 4;
-            *reinterpret_cast<uint32_t *>(s_patch + r * PS + c) = hb_ld_u8x4(ref_i + (r - 4) * rpitch + (c - 4));
+        uint32_t cur_best = bsad;
+        if (!(a.action & HB_ME_PEL)) {
+            const int cx[4] = { ix, 0, 0, 0 }, cy[4] = { iy, 0, 0, 0 };
+            const bool cv[4] = { true, false, false, false };
+            uint32_t sad[4], rd[4];
+            round4(cx, cy, cv, sad, rd);
+            cur_best = sad[0];
         }
-        group_barrier<GW>(group);
-        // ---- horizontal 14-bit planes for fractions 1,2,3 : T_f[r][j] = sum taps_f[k] * P[r][j+k] - 8192
-        for (int w = gl; w < PROWS * (TS / 4); w += GT) {
+        // ---- stage the patch: rows iy-4.., columns ix-4..
+        const uint8_t *ref_i = a.ref.org + (jy + iy - 4) * rpitch + jx + ix - 4;
+        for (int w = gl; w < PROWS * (PS / 4); w += G) {
+            const int r = w / (PS / 4), c = (w % (PS / 4)) * 4;
+            *reinterpret_cast<uint32_t *>(s_patch + r * PS + c) = hb_ld_u8x4(ref_i + r * rpitch + c);
+        }
+        group_barrier<G>(group);
+        // ---- horizontal 14-bit planes, fractions 0..3: T_f[r][j] = sum_k taps_f[k] * P[r][j+k] - 8192 (T_0 = P[r][j+3]*64 - 8192)
+        for (int w = gl; w < PROWS * (TS / 4); w += G) {
             const int r = w / (TS / 4), j0 = (w % (TS / 4)) * 4;
+            const uint32_t *pw = reinterpret_cast<const uint32_t *>(s_patch + r * PS + j0);
+            const uint32_t w0 = pw[0], w1 = pw[1], w2 = pw[2];
             int p[11];
 #pragma unroll
-            for (int k = 0; k < 11; k++) p[k] = s_patch[r * PS + j0 + k];
+            for (int k = 0; k < 4; k++) { p[k] = (w0 >> (8 * k)) & 255; p[4 + k] = (w1 >> (8 * k)) & 255; }
+#pragma unroll
+            for (int k = 0; k < 3; k++) p[8 + k] = (w2 >> (8 * k)) & 255;
+            int o[4][4];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                s_plane[0 * Cfg::PLANE_ELEMS + r * TS + j0 + q] = static_cast<int16_t>(hb_luma8<1>(p[q], p[q + 1], p[q + 2], p[q + 3], p[q + 4], p[q + 5], p[q + 6], p[q + 7]) - 8192);
-                s_plane[1 * Cfg::PLANE_ELEMS + r * TS + j0 + q] = static_cast<int16_t>(hb_luma8<2>(p[q], p[q + 1], p[q + 2], p[q + 3], p[q + 4], p[q + 5], p[q + 6], p[q + 7]) - 8192);
-                s_plane[2 * Cfg::PLANE_ELEMS + r * TS + j0 + q] = static_cast<int16_t>(hb_luma8<3>(p[q], p[q + 1], p[q + 2], p[q + 3], p[q + 4], p[q + 5], p[q + 6], p[q + 7]) - 8192);
+                o[0][q] = (p[q + 3] << 6) - 8192;
+                o[1][q] = hb_luma8<1>(p[q], p[q + 1], p[q + 2], p[q + 3], p[q + 4], p[q + 5], p[q + 6], p[q + 7]) - 8192;
+                o[2][q] = hb_luma8<2>(p[q], p[q + 1], p[q + 2], p[q + 3], p[q + 4], p[q + 5], p[q + 6], p[q + 7]) - 8192;
+                o[3][q] = hb_luma8<3>(p[q], p[q + 1], p[q + 2], p[q + 3], p[q + 4], p[q + 5], p[q + 6], p[q + 7]) - 8192;
+            }
+#pragma unroll
+            for (int f = 0; f < 4; f++) {
+                uint2 v;
+                v.x = (static_cast<uint32_t>(o[f][0]) & 0xffffu) | (static_cast<uint32_t>(o[f][1]) << 16);
+                v.y = (static_cast<uint32_t>(o[f][2]) & 0xffffu) | (static_cast<uint32_t>(o[f][3]) << 16);
+                *reinterpret_cast<uint2 *>(s_plane + f * Cfg::PLANE_ELEMS + r * TS + j0) = v;
             }
         }
-        group_barrier<GW>(group);
+        group_barrier<G>(group);
+        // ---- the current block as bytes, over the patch area (no longer needed)
+        uint8_t *s_cur = s_patch;
+#pragma unroll
+        for (int k = 0; k < WPL; k++) {
+            const int w = l + k * L;
+            if (slot == 0) *reinterpret_cast<uint32_t *>(s_cur + (w / WPR) * N + (w % WPR) * 4) = cur[k];
+        }
+        group_barrier<G>(group);
 
-        // SAD of the current block against the prediction at quarter-pel offset (cx,cy) in [-3,3]^2 from (ix,iy)
-        auto subpel_sad = [&](int cx, int cy) -> uint32_t {
-            const int fx = cx & 3, fy = cy & 3;
-            const int cb = cx >> 2, rb = cy >> 2;              // -1 or 0
+        // one round: SADs of four sub-pel candidates at quarter-pel offsets (qx[s], qy[s]) in [-3,3]^2 from (ix,iy)
+        auto subpel4 = [&](const int (&qx)[4], const int (&qy)[4], uint32_t (&sad)[4]) {
+            int cx = qx[0], cy = qy[0];
+#pragma unroll
+            for (int s = 1; s < 4; s++) if (slot == s) { cx = qx[s]; cy = qy[s]; }
+            const int fx = cx & 3, fy = cy & 3, cb = cx >> 2, rb = cy >> 2;
+            int t[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) t[k] = c_taps[fy][k];
+            const int c0 = l * CPL;
+            const int16_t *pl = s_plane + fx * Cfg::PLANE_ELEMS + (rb + 1) * TS + c0 + cb + 1;   // first tap row of output row 0
             uint32_t acc = 0;
 #pragma unroll
-            for (int k = 0; k < WPL; k++) {
-                if (gl + k * GT < NW) {
-                    const int j = wcol[k] + cb + 1;            // plane column of the first of 4 samples
-                    const int r0 = wrow[k] + rb + 4;           // plane row of the sample itself
-                    int px[4];
+            for (int cc = 0; cc < CPL; cc++) {
+                int win[8];
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        int t[8];
-                        if (fy == 0) {
-                            const int v = fx ? static_cast<int>(s_plane[(fx - 1) * Cfg::PLANE_ELEMS + r0 * TS + j + q])
-                                             : (static_cast<int>(s_patch[r0 * PS + j + q + 3]) << 6) - 8192;
-                            px[q] = hb_clip255((v + 8192 + 32) >> 6);
-                        } else {
+                for (int k = 0; k < 7; k++) win[k] = pl[k * TS + cc];
+                for (int r8 = 0; r8 < N; r8 += 8) {
 #pragma unroll
-                            for (int m = 0; m < 8; m++) {
-                                const int rr = r0 - 3 + m;
-                                t[m] = fx ? static_cast<int>(s_plane[(fx - 1) * Cfg::PLANE_ELEMS + rr * TS + j + q])
-                                          : (static_cast<int>(s_patch[rr * PS + j + q + 3]) << 6) - 8192;
-                            }
-                            const int s = hb_luma8_dyn(fy, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
-                            px[q] = hb_clip255((s + 2048 + (8192 << 6)) >> 12);
-                        }
+                    for (int rr = 0; rr < 8; rr++) {
+                        const int r = r8 + rr;
+                        win[(rr + 7) & 7] = pl[(r + 7) * TS + cc];
+                        int s = 0;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) s += t[k] * win[(rr + k) & 7];
+                        const int px = hb_clip255((s + 2048 + (8192 << 6)) >> 12);
+                        acc += static_cast<uint32_t>(abs(px - static_cast<int>(s_cur[r * N + c0 + cc])));
                     }
-                    acc = __vsadu4(cur[k], hb_pack4(px[0], px[1], px[2], px[3])) + acc;
                 }
             }
-            return group_sum(acc);
+            uint32_t cst[4];
+            exchange(acc, 0u, sad, cst);
         };
 
         int sbx = 0, sby = 0, bidx = 0;
-        for (int i = 1; i < 9; i++) {                      // candidate 0 is the integer position itself: never smaller
-            const int cx = c_half[i][0] * 2, cy = c_half[i][1] * 2;
-            const uint32_t v = subpel_sad(cx, cy);
-            if (v < cur_best) { cur_best = v; sbx = cx; sby = cy; bidx = i; }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {                  // candidate 0 is the integer position itself: never smaller
+            int qx[4], qy[4]; uint32_t sad[4];
+#pragma unroll
+            for (int s = 0; s < 4; s++) { qx[s] = c_half[1 + 4 * h + s][0] * 2; qy[s] = c_half[1 + 4 * h + s][1] * 2; }
+            subpel4(qx, qy, sad);
+#pragma unroll
+            for (int s = 0; s < 4; s++) if (sad[s] < cur_best) { cur_best = sad[s]; sbx = qx[s]; sby = qy[s]; bidx = 1 + 4 * h + s; }
         }
         if (a.action & HB_ME_QUARTER) {
             const int hx = c_half[bidx][0], hy = c_half[bidx][1];
-            for (int i = 1; i < 9; i++) {                  // candidate 0 repeats the half-pel winner
-                const int cx = hx * 2 + c_quarter[i][0], cy = hy * 2 + c_quarter[i][1];
-                const uint32_t v = subpel_sad(cx, cy);
-                if (v < cur_best) { cur_best = v; sbx = cx; sby = cy; }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {              // candidate 0 repeats the half-pel winner
+                int qx[4], qy[4]; uint32_t sad[4];
+#pragma unroll
+                for (int s = 0; s < 4; s++) { qx[s] = hx * 2 + c_quarter[1 + 4 * h + s][0]; qy[s] = hy * 2 + c_quarter[1 + 4 * h + s][1]; }
+                subpel4(qx, qy, sad);
+#pragma unroll
+                for (int s = 0; s < 4; s++) if (sad[s] < cur_best) { cur_best = sad[s]; sbx = qx[s]; sby = qy[s]; }
             }
         }
         best_sad = cur_best;
@@ -280,18 +403,33 @@ __global__ void __launch_bounds__(256) k_me(const MeArgs a)
     if (gl == 0) {
         hb_me_result r;
         r.mv.x = mvx; r.mv.y = mvy; r.subpix.x = subx; r.subpix.y = suby; r.sad = best_sad; r.n_probes = n_probes;
-        a.out[job.out] = r;
+        a.out[jp->out] = r;
     }
 }
 
-template <int N, int GW> int launch_me(const MeArgs &a, cudaStream_t s)
+template <int N> int configure_me()
 {
-    const int grid = (a.n_jobs + MeCfg<N, GW>::PUS - 1) / MeCfg<N, GW>::PUS;
-    k_me<N, GW><<<grid, 256, 0, s>>>(a);
+    return static_cast<int>(cudaFuncSetAttribute(k_me<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, MeCfg<N>::SMEM_TOTAL));
+}
+
+template <int N> int launch_me(const MeArgs &a, cudaStream_t s)
+{
+    const int grid = (a.n_jobs + MeCfg<N>::PUS - 1) / MeCfg<N>::PUS;
+    k_me<N><<<grid, 256, MeCfg<N>::SMEM_TOTAL, s>>>(a);
     return static_cast<int>(cudaGetLastError());
 }
 
 }  // namespace
+
+// opt in to the dynamic shared memory the search kernels need; once per device, outside any stream capture
+extern "C" int hbk_me_configure(void)
+{
+    int e = configure_me<64>();
+    if (!e) e = configure_me<32>();
+    if (!e) e = configure_me<16>();
+    if (!e) e = configure_me<8>();
+    return e;
+}
 
 extern "C" int hbk_me_search(const hbd_frame *cur, const hbd_frame *ref, int size, const hbd_me_job *jobs, int n_jobs,
                              const hb_me_result *parent, hb_me_result *out, int action, const hbd_dyn_params *dyn, void *stream)
@@ -301,10 +439,10 @@ extern "C" int hbk_me_search(const hbd_frame *cur, const hbd_frame *ref, int siz
     a.cur = cur->p[0]; a.ref = ref->p[0]; a.jobs = jobs; a.n_jobs = n_jobs; a.parent = parent; a.out = out; a.action = action; a.dyn = dyn;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     switch (size) {
-    case 64: return launch_me<64, 8>(a, s);
-    case 32: return launch_me<32, 2>(a, s);
-    case 16: return launch_me<16, 1>(a, s);
-    case 8: return launch_me<8, 1>(a, s);
+    case 64: return launch_me<64>(a, s);
+    case 32: return launch_me<32>(a, s);
+    case 16: return launch_me<16>(a, s);
+    case 8: return launch_me<8>(a, s);
     default: return static_cast<int>(cudaErrorInvalidValue);
     }
 }

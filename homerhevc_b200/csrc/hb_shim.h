@@ -83,6 +83,7 @@ typedef struct hbd_me_job {       /* one PU, device layout */
     int32_t pad_;
     double  corr;                 /* qp * clip(avg_dist/2000, .15, 1.4), hmr_common.h:53 */
 } hbd_me_job;
+int hbk_me_configure(void);   /* once per device, before the first search launch */
 int hbk_me_search(const hbd_frame *cur, const hbd_frame *ref, int size, const hbd_me_job *jobs, int n_jobs,
                   const hb_me_result *parent, hb_me_result *out, int action, const hbd_dyn_params *dyn, void *stream);
 
