@@ -130,6 +130,7 @@ def load_library():
     L.hb_quant.argtypes = [C.POINTER(QuantEnv), i16p, i16p] + [C.c_int] * 5 + [C.POINTER(C.c_int)] + [C.c_int] * 3
     L.hb_inv_quant.restype = None
     L.hb_inv_quant.argtypes = [C.POINTER(QuantEnv), i16p, i16p] + [C.c_int] * 6
+    L.hb_default_ctx.restype = C.c_void_p
     L.hb_fill_low_level_funcs.restype = None
     L.hb_fill_low_level_funcs.argtypes = [C.POINTER(LowLevelFuncs)]
     # section B

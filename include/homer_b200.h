@@ -57,6 +57,7 @@ void        hb_pinned_free(void *p);
  * They exist so the library is a literal drop-in and so per-call parity can be tested; throughput comes from
  * sections C and D.  Semantics: the reference's plain-C definitions (== its SSE4.2 functions on 8-bit video),
  * quant with the SSE4.2 rounding rule (hmr_sse42_functions_quant.c:47). */
+hb_ctx  *hb_default_ctx(void);          /* the lazily created context (device $HB_DEVICE) the drop-ins run on */
 uint32_t hb_sad(int16_t *src, uint32_t src_stride, int16_t *pred, uint32_t pred_stride, int size);
 uint32_t hb_ssd16b(int16_t *src, uint32_t src_stride, int16_t *pred, uint32_t pred_stride, int size);
 void hb_predict(int16_t *orig, int orig_stride, int16_t *pred, int pred_stride, int16_t *residual, int residual_stride, int size);

@@ -529,3 +529,54 @@ double refdrv_prepass(refdrv **drv, int n_threads, const uint8_t *const cur[3], 
     clock_gettime(CLOCK_MONOTONIC, &t1);
     return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * The INTEGRATION.md section 1 adapter, compiled: installs libhomer_b200's per-call drop-ins into the reference
+ * encoder's own function table.  Used by the whole-encode parity test: the UNMODIFIED reference host code
+ * (mode decision, CABAC, deblocking, SAO, rate control) runs on the CPU and every SAD / SSD / predict / reconst /
+ * interpolation / transform / quant / inv_quant call it makes through the table is computed on the GPU.
+ * `lib` is a dlopen() handle of libhomer_b200.so.  Usable as the `hook` of refdrv_encode_lockstep.
+ * ------------------------------------------------------------------------------------------------------------ */
+#include <dlfcn.h>
+
+typedef struct gpu_quant_env { int32_t is_islice, sign_hiding, max_cu_size_shift, bit_depth; int16_t *delta_u; } gpu_quant_env;
+static void (*p_hb_quant)(const gpu_quant_env *, int16_t *, int16_t *, int, int, int, int, int, int *, int, int, int);
+static void (*p_hb_inv_quant)(const gpu_quant_env *, int16_t *, int16_t *, int, int, int, int, int, int);
+static long g_gpu_calls;
+
+static void gpu_quant(henc_thread_t *et, int16_t *src, int16_t *dst, int scan_mode, int depth, int comp, int cu_mode,
+                      int is_intra, int *ac_sum, int cu_size, int per, int rem)
+{
+    gpu_quant_env env = { et->enc_engine->current_pict.slice.slice_type == I_SLICE, (int32_t)et->pps->sign_data_hiding_flag,
+                          et->max_cu_size_shift, et->bit_depth, et->aux_buff };
+    g_gpu_calls++;
+    p_hb_quant(&env, src, dst, scan_mode, depth, comp, cu_mode, is_intra, ac_sum, cu_size, per, rem);
+}
+static void gpu_inv_quant(henc_thread_t *et, short *src, short *dst, int depth, int comp, int is_intra, int cu_size, int per, int rem)
+{
+    gpu_quant_env env = { 0, 0, et->max_cu_size_shift, et->bit_depth, NULL };
+    g_gpu_calls++;
+    p_hb_inv_quant(&env, src, dst, depth, comp, is_intra, cu_size, per, rem);
+}
+
+/* which = bit mask of what to route to the GPU: 1 sad/ssd, 2 predict/reconst, 4 interpolation, 8 transforms, 16 quant */
+void refdrv_install_gpu_table(void *funcs_table, void *user)
+{
+    struct { void *lib; int which; } *u = user;
+    low_level_funcs_t *f = (low_level_funcs_t *)funcs_table;
+    void *lib = u->lib;
+    if (u->which & 1) { f->sad = dlsym(lib, "hb_sad"); f->ssd16b = dlsym(lib, "hb_ssd16b"); }
+    if (u->which & 2) { f->predict = dlsym(lib, "hb_predict"); f->reconst = dlsym(lib, "hb_reconst"); }
+    if (u->which & 4) {
+        f->interpolate_luma_m_compensation = dlsym(lib, "hb_interpolate_luma");
+        f->interpolate_chroma_m_compensation = dlsym(lib, "hb_interpolate_chroma");
+        f->interpolate_luma_m_estimation = dlsym(lib, "hb_interpolate_luma");
+    }
+    if (u->which & 8) { f->transform = dlsym(lib, "hb_transform"); f->itransform = dlsym(lib, "hb_itransform"); }
+    if (u->which & 16) {
+        p_hb_quant = dlsym(lib, "hb_quant"); p_hb_inv_quant = dlsym(lib, "hb_inv_quant");
+        f->quant = gpu_quant; f->inv_quant = gpu_inv_quant;
+    }
+}
+long refdrv_gpu_quant_calls(void) { return g_gpu_calls; }
+void *refdrv_install_gpu_table_addr(void) { return (void *)refdrv_install_gpu_table; }
