@@ -1,0 +1,94 @@
+// hb_kernels_gather.cu -- after the host has chosen a partition depth per CTU from the cost tables, pack what the
+// host-side entropy coder and in-loop filters need of that choice: the reconstruction of the chosen depth (tight
+// 8-bit planes) and the levels of the CODED transform units only, as one contiguous stream per CTU.
+//
+// One CTA per CTU.  Stream of a CTU (int16 units, starting at ctu_off[ctu]): for plane Y, U, V in turn, for every coded
+// TU in raster order inside the CTU: { header_lo, header_hi, N*N levels }, header = plane << 28 | tu_size << 16 | TU
+// raster position inside the CTU.  The host computed ctu_off from the sums it already fetched, so the launch needs no
+// global scan and the total size is known before the copy is queued.
+#include "hb_shim.h"
+#include "hb_dev_common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256) k_gather(const hbd_gather_args a)
+{
+    __shared__ int s_scan[256];
+    __shared__ int s_base;
+    const int ctu = blockIdx.x, tid = threadIdx.x;
+    const int cx = ctu % a.ctu_cols, cy = ctu / a.ctu_cols;
+    const int sel = a.sel[ctu];
+    if (tid == 0) s_base = 0;
+
+    // ---- reconstruction of the chosen depth
+    for (int c = 0; c < 3; c++) {
+        const int pass = c ? min(sel, 3) : sel;
+        const hbd_plane src = a.recon[pass].p[c];
+        const int cs = c ? 32 : 64, x0 = cx * cs, y0 = cy * cs;
+        uint8_t *dst = a.out_recon[c];
+        const int w = src.w, h = src.h;
+        for (int e = tid; e < cs * cs / 4; e += 256) {
+            const int r = e / (cs / 4), q = (e % (cs / 4)) * 4;
+            if (y0 + r < h && x0 + q < w)
+                *reinterpret_cast<uint32_t *>(dst + static_cast<size_t>(y0 + r) * w + x0 + q) =
+                    *reinterpret_cast<const uint32_t *>(src.org + (y0 + r) * src.pitch + x0 + q);
+        }
+    }
+    __syncthreads();
+
+    // ---- levels of the coded TUs
+    int16_t *out = a.out_levels + a.ctu_off[ctu];
+    for (int c = 0; c < 3; c++) {
+        const int pass = c ? min(sel, 3) : sel;
+        const hbd_gather_pc pc = a.pc[pass][c];
+        const int cs = c ? 32 : 64, tpr = cs / pc.tu, n = tpr * tpr, nn = pc.tu * pc.tu;
+        int idx = -1, len = 0;
+        if (tid < n) {
+            const int tx = cx * tpr + tid % tpr, ty = cy * tpr + tid / tpr;
+            if (tx < pc.grid_w && ty < pc.grid_h) idx = pc.tu_index[ty * pc.grid_w + tx];
+            if (idx >= 0 && pc.res[idx].sum > 0) len = 2 + nn; else idx = -1;
+        }
+        // exclusive scan of len over the 256 threads
+        s_scan[tid] = len;
+        __syncthreads();
+        for (int d = 1; d < 256; d <<= 1) {
+            const int v = tid >= d ? s_scan[tid - d] : 0;
+            __syncthreads();
+            s_scan[tid] += v;
+            __syncthreads();
+        }
+        const int base = s_base;
+        const int my_off = base + s_scan[tid] - len;
+        if (idx >= 0) {
+            const uint32_t hdr = (static_cast<uint32_t>(c) << 28) | (static_cast<uint32_t>(pc.tu) << 16) | static_cast<uint32_t>(tid);
+            out[my_off] = static_cast<int16_t>(hdr & 0xffffu);
+            out[my_off + 1] = static_cast<int16_t>(hdr >> 16);
+        }
+        // publish (offset, idx) so that warps can copy cooperatively
+        const int total = s_scan[255];
+        __syncthreads();                                   // everyone has read the scan before it is overwritten
+        s_scan[tid] = idx >= 0 ? my_off : -1;
+        __shared__ int s_idx[256];
+        s_idx[tid] = idx;
+        __syncthreads();
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int t = warp; t < n; t += 8) {
+            const int o = s_scan[t];
+            if (o < 0) continue;
+            const int16_t *src = pc.coeff + static_cast<size_t>(s_idx[t]) * nn;
+            for (int e = lane; e < nn; e += 32) out[o + 2 + e] = src[e];
+        }
+        __syncthreads();
+        if (tid == 0) s_base = base + total;
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+extern "C" int hbk_gather(const hbd_gather_args *a, int n_ctus, void *stream)
+{
+    if (n_ctus <= 0) return 0;
+    k_gather<<<n_ctus, 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+    return static_cast<int>(cudaGetLastError());
+}

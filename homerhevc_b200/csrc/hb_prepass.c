@@ -25,6 +25,9 @@ typedef struct pass_comp {
     int32_t *d_xy;                 /* job coordinates */
     int16_t *d_coeff;
     hb_tu_result *d_res;
+    int grid_w, grid_h;            /* TU grid of the frame (whole CTUs) */
+    int32_t *d_index;              /* grid position -> index among coded TUs or -1 (device) */
+    int32_t *h_ctu;                /* coded TU -> CTU number (host) */
 } pass_comp;
 
 struct hb_prepass {
@@ -49,6 +52,10 @@ struct hb_prepass {
     struct { const hb_frame *cur, *ref; void *exec; } graphs[MAX_GRAPHS];
     int n_graphs;
     int launches_per_frame;
+    /* gather of the host's selection */
+    uint8_t *d_sel; int32_t *d_ctu_off; uint8_t *d_sel_recon; int16_t *d_sel_levels; size_t sel_levels_cap;
+    void *side[N_DEPTH];                       /* one side stream per depth: MC + T/Q of depth d overlap the search of depth d+1 */
+    void *ev_fork[N_DEPTH], *ev_join[N_DEPTH];
     void *prof_ev[HB_PREPASS_MAX_KERNELS + 1];
     char prof_name[HB_PREPASS_MAX_KERNELS][16];
 };
@@ -136,23 +143,36 @@ int hb_prepass_create(hb_ctx *ctx, int width, int height, const hb_prepass_cfg *
             const int pw = c ? width / 2 : width, ph = c ? height / 2 : height, sc = c ? s / 2 : s;
             const int tw = (pp->ctu_cols * (c ? 32 : 64)) / tu, th = (pp->ctu_rows * (c ? 32 : 64)) / tu;
             int32_t *xy = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)tw * th);
-            if (!xy) { rc = hb_fail(HB_ERR_NOMEM, "hb_prepass_create: out of memory"); break; }
+            int32_t *index = (int32_t *)malloc(sizeof(int32_t) * (size_t)tw * th);
+            pc->h_ctu = (int32_t *)malloc(sizeof(int32_t) * (size_t)tw * th);
+            pc->grid_w = tw; pc->grid_h = th;
+            if (!xy || !index || !pc->h_ctu) { free(xy); free(index); rc = hb_fail(HB_ERR_NOMEM, "hb_prepass_create: out of memory"); break; }
             int n = 0;
             for (int ty = 0; ty < th; ty++)
                 for (int tx = 0; tx < tw; tx++) {
                     const int x = tx * tu, y = ty * tu;
+                    index[ty * tw + tx] = -1;
                     if (x + tu > pw || y + tu > ph) continue;
                     const int pux = (x / sc) * s, puy = (y / sc) * s;     /* owning PU in luma samples */
                     if (!pu_valid(pp, pux, puy, s)) continue;
+                    index[ty * tw + tx] = n;
+                    pc->h_ctu[n] = (puy / 64) * pp->ctu_cols + pux / 64;
                     xy[2 * n] = x; xy[2 * n + 1] = y; n++;
                 }
             pc->n_tus = n;
             rc = upload(ctx, (void **)&pc->d_xy, xy, sizeof(int32_t) * 2 * (size_t)n);
-            free(xy);
+            if (rc == HB_OK) rc = upload(ctx, (void **)&pc->d_index, index, sizeof(int32_t) * (size_t)tw * th);
+            free(xy); free(index);
             int crc = 0;
             if (rc == HB_OK && (crc = hbc_malloc((void **)&pc->d_coeff, sizeof(int16_t) * (size_t)(n ? n : 1) * tu * tu))) rc = hb_cuda_fail(crc, "prepass: coeff");
             if (rc == HB_OK && (crc = hbc_malloc((void **)&pc->d_res, sizeof(hb_tu_result) * (size_t)(n ? n : 1)))) rc = hb_cuda_fail(crc, "prepass: results");
         }
+    }
+    for (int d = 0; d < N_DEPTH && rc == HB_OK; d++) {
+        int crc = hbc_stream_create(&pp->side[d]);
+        if (!crc) crc = hbc_event_create_notiming(&pp->ev_fork[d]);
+        if (!crc) crc = hbc_event_create_notiming(&pp->ev_join[d]);
+        if (crc) rc = hb_cuda_fail(crc, "prepass: side streams");
     }
     if (rc == HB_OK) {
         const int crc = hbc_malloc((void **)&pp->d_dyn, sizeof *pp->d_dyn);
@@ -180,47 +200,84 @@ void hb_prepass_destroy(hb_prepass *pp)
             if (pp->pc[p][c].d_xy) hbc_free(pp->pc[p][c].d_xy);
             if (pp->pc[p][c].d_coeff) hbc_free(pp->pc[p][c].d_coeff);
             if (pp->pc[p][c].d_res) hbc_free(pp->pc[p][c].d_res);
+            if (pp->pc[p][c].d_index) hbc_free(pp->pc[p][c].d_index);
+            free(pp->pc[p][c].h_ctu);
         }
         hb_frame_destroy(pp->recon[p]);
     }
     if (pp->d_dyn) hbc_free(pp->d_dyn);
+    if (pp->d_sel) hbc_free(pp->d_sel);
+    if (pp->d_ctu_off) hbc_free(pp->d_ctu_off);
+    if (pp->d_sel_recon) hbc_free(pp->d_sel_recon);
+    if (pp->d_sel_levels) hbc_free(pp->d_sel_levels);
+    for (int d = 0; d < N_DEPTH; d++) {
+        if (pp->side[d]) { hbc_stream_sync(pp->side[d]); hbc_stream_destroy(pp->side[d]); }
+        if (pp->ev_fork[d]) hbc_event_destroy(pp->ev_fork[d]);
+        if (pp->ev_join[d]) hbc_event_destroy(pp->ev_join[d]);
+    }
     for (int i = 0; i <= HB_PREPASS_MAX_KERNELS; i++) if (pp->prof_ev[i]) hbc_event_destroy(pp->prof_ev[i]);
     free(pp);
 }
 
 /* queue the kernels of one frame on the context's stream; returns a cudaError_t value */
-#define PROF_MARK(...) do { if (prof && !crc) { snprintf(pp->prof_name[n], sizeof pp->prof_name[n], __VA_ARGS__); crc = hbc_event_record(pp->prof_ev[n], ctx->stream); } } while (0)
+#define PROF_MARK(...) do { if (prof && !crc) { snprintf(pp->prof_name[n], sizeof pp->prof_name[n], __VA_ARGS__); crc = hbc_event_record(pp->prof_ev[n], st); } } while (0)
+/* T/Q launches of one pass on stream st */
+static int enqueue_tq(hb_prepass *pp, const hb_frame *cur, int p, void *st, int *n_io, int prof)
+{
+    hb_ctx *ctx = pp->ctx;
+    int crc = 0, n = *n_io;
+    const hb_frame *pred = pp->pred[pass_depth(p)];
+    for (int c = 0; c < 3 && !crc; c++) {
+        pass_comp *pc = &pp->pc[p][c];
+        if (!pc->tu || !pc->n_tus) continue;
+        hbd_tq_args a;
+        memset(&a, 0, sizeof a);
+        hb_tq_setup(ctx, &a, c, pc->tu, c ? pp->qp_c : pp->cfg.qp, pp->cfg.is_islice, pp->cfg.sign_hiding);
+        a.cur = cur->d.p[c]; a.pred = pred->d.p[c]; a.rec = pp->recon[p]->d.p[c];
+        a.jobs_xy = pc->d_xy; a.n_jobs = pc->n_tus;
+        a.thr_k = 1.; a.weight = c ? pp->weight_c : 1.; a.dyn = pp->d_dyn;
+        a.coeff_out = pc->d_coeff; a.res_out = pc->d_res;
+        PROF_MARK("tq%d%c%d", p, "yuv"[c], pc->tu);
+        if (!crc) crc = hbk_tq_encode(&a, st);
+        n++;
+    }
+    *n_io = n;
+    return crc;
+}
+
+/* queue the kernels of one frame; returns a cudaError_t value.  prof != 0: everything on the context's stream with an
+ * event before each launch.  Otherwise the search chain ME(64) -> ME(32) -> ME(16) -> ME(8) runs on the context's stream
+ * and, after each ME(d), a side stream takes MC(d) and the T/Q passes of that depth, so they overlap the next search. */
 static int enqueue(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, int *n_launches, int prof)
 {
     hb_ctx *ctx = pp->ctx;
+    void *main_st = ctx->stream;
     int crc = 0, n = 0;
     for (int d = 0; d < N_DEPTH && !crc; d++) {
         if (!pp->n_valid[d]) continue;
+        void *st = main_st;
         PROF_MARK("me%d", 64 >> d);
         if (!crc) crc = hbk_me_search(&cur->d, &ref->d, 64 >> d, pp->d_jobs[d], pp->n_valid[d], d ? pp->d_me[d - 1] : NULL, pp->d_me[d],
-                            pp->cfg.me_action, pp->d_dyn, ctx->stream);
+                                      pp->cfg.me_action, pp->d_dyn, main_st);
         n++;
-        PROF_MARK("mc%d", 64 >> d);
-        if (!crc) { crc = hbk_mc_predict(&ref->d, &pp->pred[d]->d, 64 >> d, pp->d_pus[d], pp->n_valid[d], pp->d_me[d], ctx->stream); n++; }
-    }
-    for (int p = 0; p < N_PASS && !crc; p++) {
-        const hb_frame *pred = pp->pred[pass_depth(p)];
-        for (int c = 0; c < 3 && !crc; c++) {
-            pass_comp *pc = &pp->pc[p][c];
-            if (!pc->tu || !pc->n_tus) continue;
-            hbd_tq_args a;
-            memset(&a, 0, sizeof a);
-            hb_tq_setup(ctx, &a, c, pc->tu, c ? pp->qp_c : pp->cfg.qp, pp->cfg.is_islice, pp->cfg.sign_hiding);
-            a.cur = cur->d.p[c]; a.pred = pred->d.p[c]; a.rec = pp->recon[p]->d.p[c];
-            a.jobs_xy = pc->d_xy; a.n_jobs = pc->n_tus;
-            a.thr_k = 1.; a.weight = c ? pp->weight_c : 1.; a.dyn = pp->d_dyn;
-            a.coeff_out = pc->d_coeff; a.res_out = pc->d_res;
-            PROF_MARK("tq%d%c%d", p, "yuv"[c], pc->tu);
-            if (!crc) crc = hbk_tq_encode(&a, ctx->stream);
-            n++;
+        if (!prof && !crc) {
+            st = pp->side[d];
+            crc = hbc_event_record(pp->ev_fork[d], main_st);
+            if (!crc) crc = hbc_stream_wait_event(st, pp->ev_fork[d]);
         }
+        PROF_MARK("mc%d", 64 >> d);
+        if (!crc) { crc = hbk_mc_predict(&ref->d, &pp->pred[d]->d, 64 >> d, pp->d_pus[d], pp->n_valid[d], pp->d_me[d], st); n++; }
+        for (int p = 0; p < N_PASS && !crc; p++)
+            if (pass_depth(p) == d) crc = enqueue_tq(pp, cur, p, st, &n, prof);
+        if (!prof && !crc) crc = hbc_event_record(pp->ev_join[d], st);
     }
-    if (prof && !crc) crc = hbc_event_record(pp->prof_ev[n], ctx->stream);
+    if (!prof)
+        for (int d = 0; d < N_DEPTH && !crc; d++)
+            if (pp->n_valid[d]) crc = hbc_stream_wait_event(main_st, pp->ev_join[d]);
+    {
+        void *st = main_st;
+        if (prof && !crc) crc = hbc_event_record(pp->prof_ev[n], st);
+    }
     *n_launches = n;
     return crc;
 }
@@ -397,5 +454,137 @@ int hb_prepass_fetch_all(hb_prepass *pp, void *pinned_dst, size_t cap, size_t *b
     if (!crc) crc = hbc_stream_sync(ctx->stream);
     if (crc) return hb_cuda_fail(crc, "hb_prepass_fetch_all");
     if (bytes_out) *bytes_out = (size_t)(o - (char *)pinned_dst);
+    return HB_OK;
+}
+
+/* ------------------------------------------------------------------ cost tables -> host decision -> gather
+ * The host's mode decision reads the cost tables (ME results and per-TU {sum, ssd}), picks a partition depth per CTU,
+ * and only then asks for what entropy coding and the in-loop filters need of that choice. */
+size_t hb_prepass_tables_bytes(const hb_prepass *pp)
+{
+    size_t n = 0;
+    if (!pp) return 0;
+    for (int d = 0; d < N_DEPTH; d++) n += sizeof(hb_me_result) * (size_t)hb_prepass_num_pus(pp, d);
+    for (int p = 0; p < N_PASS; p++) for (int c = 0; c < 3; c++) n += sizeof(hb_tu_result) * (size_t)pp->pc[p][c].n_tus;
+    return n;
+}
+
+/* ME tables d0..d3, then TU tables pass 0..4 x (Y,U,V), packed; dst should be pinned.  Asynchronous: hb_ctx_sync before reading. */
+int hb_prepass_fetch_tables(hb_prepass *pp, void *pinned_dst, size_t cap)
+{
+    if (!pp || !pinned_dst) return hb_fail(HB_ERR_ARG, "hb_prepass_fetch_tables: NULL argument");
+    if (cap < hb_prepass_tables_bytes(pp)) return hb_fail(HB_ERR_ARG, "hb_prepass_fetch_tables: buffer too small");
+    hb_ctx *ctx = pp->ctx;
+    char *o = (char *)pinned_dst;
+    int crc = 0;
+    hbc_set_device(ctx->device);
+    for (int d = 0; d < N_DEPTH && !crc; d++) {
+        const size_t b = sizeof(hb_me_result) * (size_t)hb_prepass_num_pus(pp, d);
+        crc = hbc_d2h_async(o, pp->d_me[d], b, ctx->stream); o += b;
+    }
+    for (int p = 0; p < N_PASS && !crc; p++)
+        for (int c = 0; c < 3 && !crc; c++) {
+            const size_t b = sizeof(hb_tu_result) * (size_t)pp->pc[p][c].n_tus;
+            if (b) { crc = hbc_d2h_async(o, pp->pc[p][c].d_res, b, ctx->stream); o += b; }
+        }
+    return crc ? hb_cuda_fail(crc, "hb_prepass_fetch_tables") : HB_OK;
+}
+
+int hb_prepass_num_ctus(const hb_prepass *pp) { return pp ? pp->ctu_cols * pp->ctu_rows : 0; }
+
+/* A stand-in for the host's mode decision (which stays on the host): per CTU the pass p in 0..4
+ * (PU 64/32/16/8, and 8 with 4x4 luma TUs) that minimises sum(ssd) + lambda * sum(|levels|) over its luma TUs and the chroma
+ * TUs of pass min(p,3).  Also lays out the gather stream: ctu_off[i] = start of CTU i's levels (int16 units), ctu_off[n] = total.
+ * `tables` is what hb_prepass_fetch_tables delivered.  Pure host code. */
+int hb_prepass_select(const hb_prepass *pp, const void *tables, int lambda, uint8_t *sel, int32_t *ctu_off)
+{
+    if (!pp || !tables || !sel || !ctu_off) return hb_fail(HB_ERR_ARG, "hb_prepass_select: NULL argument");
+    const int n_ctus = hb_prepass_num_ctus(pp);
+    const char *t = (const char *)tables;
+    for (int d = 0; d < N_DEPTH; d++) t += sizeof(hb_me_result) * (size_t)hb_prepass_num_pus(pp, d);
+    const hb_tu_result *res[N_PASS][3];
+    for (int p = 0; p < N_PASS; p++) for (int c = 0; c < 3; c++) { res[p][c] = (const hb_tu_result *)t; t += sizeof(hb_tu_result) * (size_t)pp->pc[p][c].n_tus; }
+    uint64_t *cost = (uint64_t *)calloc((size_t)n_ctus * 8, sizeof *cost);       /* [ctu][0..3 luma+chroma of pass p, 4 luma of pass 4] */
+    int32_t *len = (int32_t *)calloc((size_t)n_ctus * 8, sizeof *len);            /* stream length of the same pieces */
+    if (!cost || !len) { free(cost); free(len); return hb_fail(HB_ERR_NOMEM, "hb_prepass_select: out of memory"); }
+    for (int p = 0; p < N_PASS; p++)
+        for (int c = 0; c < 3; c++) {
+            const pass_comp *pc = &pp->pc[p][c];
+            const int slot = (p == 4) ? 4 : p, piece = (p == 3 && c > 0) ? 5 : slot;   /* chroma of pass 3 is shared by choices 3 and 4 */
+            const int nn = pc->tu * pc->tu;
+            for (int i = 0; i < pc->n_tus; i++) {
+                const hb_tu_result *r = &res[p][c][i];
+                const int ctu = pc->h_ctu[i];
+                cost[ctu * 8 + piece] += (uint64_t)r->ssd + (uint64_t)lambda * (uint64_t)r->sum;
+                if (r->sum > 0) len[ctu * 8 + piece] += 2 + nn;
+            }
+        }
+    int32_t off = 0;
+    for (int i = 0; i < n_ctus; i++) {
+        uint64_t best = ~(uint64_t)0; int bp = 0;
+        for (int p = 0; p < N_PASS; p++) {
+            uint64_t v = cost[i * 8 + (p == 4 ? 4 : p)];
+            if (p >= 3) v += cost[i * 8 + 5];
+            if (v < best) { best = v; bp = p; }
+        }
+        sel[i] = (uint8_t)bp;
+        ctu_off[i] = off;
+        off += len[i * 8 + (bp == 4 ? 4 : bp)] + (bp >= 3 ? len[i * 8 + 5] : 0);
+    }
+    ctu_off[n_ctus] = off;
+    free(cost); free(len);
+    return HB_OK;
+}
+
+size_t hb_prepass_gather_bytes(const hb_prepass *pp, const int32_t *ctu_off)
+{
+    if (!pp || !ctu_off) return 0;
+    return (size_t)pp->w * pp->h * 3 / 2 + sizeof(int16_t) * (size_t)ctu_off[hb_prepass_num_ctus(pp)];
+}
+
+/* Queue the gather of the host's choice and its copy to pinned_dst: reconstruction Y,U,V (tight planes) followed by the level
+ * streams of all CTUs (layout in hb_kernels_gather.cu).  Asynchronous: hb_ctx_sync before reading. */
+int hb_prepass_gather(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_off, void *pinned_dst, size_t cap, size_t *bytes_out)
+{
+    if (!pp || !sel || !ctu_off || !pinned_dst) return hb_fail(HB_ERR_ARG, "hb_prepass_gather: NULL argument");
+    hb_ctx *ctx = pp->ctx;
+    const int n_ctus = hb_prepass_num_ctus(pp);
+    const size_t recon_bytes = (size_t)pp->w * pp->h * 3 / 2, lev = (size_t)ctu_off[n_ctus];
+    const size_t need = recon_bytes + sizeof(int16_t) * lev;
+    int crc = 0;
+    if (cap < need) return hb_fail(HB_ERR_ARG, "hb_prepass_gather: need %zu bytes, got %zu", need, cap);
+    for (int i = 0; i < n_ctus; i++) if (sel[i] > 4) return hb_fail(HB_ERR_ARG, "hb_prepass_gather: sel[%d] = %d", i, sel[i]);
+    hbc_set_device(ctx->device);
+    if (!pp->d_sel) {
+        if ((crc = hbc_malloc((void **)&pp->d_sel, (size_t)n_ctus)) || (crc = hbc_malloc((void **)&pp->d_ctu_off, sizeof(int32_t) * ((size_t)n_ctus + 1))) ||
+            (crc = hbc_malloc((void **)&pp->d_sel_recon, recon_bytes))) return hb_cuda_fail(crc, "hb_prepass_gather: cudaMalloc");
+    }
+    if (pp->sel_levels_cap < lev + 8) {
+        if ((crc = hbc_stream_sync(ctx->stream))) return hb_cuda_fail(crc, "hb_prepass_gather: sync");
+        if (pp->d_sel_levels) hbc_free(pp->d_sel_levels);
+        pp->sel_levels_cap = (lev + 8) * 2;
+        if ((crc = hbc_malloc((void **)&pp->d_sel_levels, sizeof(int16_t) * pp->sel_levels_cap))) { pp->sel_levels_cap = 0; pp->d_sel_levels = NULL; return hb_cuda_fail(crc, "hb_prepass_gather: cudaMalloc"); }
+    }
+    /* sel / ctu_off are pageable: staged by the runtime before the call returns */
+    crc = hbc_h2d_async(pp->d_sel, sel, (size_t)n_ctus, ctx->stream);
+    if (!crc) crc = hbc_h2d_async(pp->d_ctu_off, ctu_off, sizeof(int32_t) * ((size_t)n_ctus + 1), ctx->stream);
+    hbd_gather_args a;
+    memset(&a, 0, sizeof a);
+    a.sel = pp->d_sel; a.ctu_off = pp->d_ctu_off; a.ctu_cols = pp->ctu_cols;
+    for (int p = 0; p < N_PASS; p++) {
+        a.recon[p] = pp->recon[p]->d;
+        for (int c = 0; c < 3; c++) {
+            const pass_comp *pc = &pp->pc[p][c];
+            a.pc[p][c].tu_index = pc->d_index; a.pc[p][c].grid_w = pc->grid_w; a.pc[p][c].grid_h = pc->grid_h; a.pc[p][c].tu = pc->tu;
+            a.pc[p][c].res = pc->d_res; a.pc[p][c].coeff = pc->d_coeff;
+        }
+    }
+    a.out_recon[0] = pp->d_sel_recon; a.out_recon[1] = pp->d_sel_recon + (size_t)pp->w * pp->h; a.out_recon[2] = a.out_recon[1] + (size_t)pp->w * pp->h / 4;
+    a.out_levels = pp->d_sel_levels;
+    if (!crc) { crc = hbk_gather(&a, n_ctus, ctx->stream); ctx->launches++; }
+    if (!crc) crc = hbc_d2h_async(pinned_dst, pp->d_sel_recon, recon_bytes, ctx->stream);
+    if (!crc && lev) crc = hbc_d2h_async((char *)pinned_dst + recon_bytes, pp->d_sel_levels, sizeof(int16_t) * lev, ctx->stream);
+    if (crc) return hb_cuda_fail(crc, "hb_prepass_gather");
+    if (bytes_out) *bytes_out = need;
     return HB_OK;
 }

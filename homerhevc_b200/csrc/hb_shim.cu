@@ -57,6 +57,17 @@ extern "C" int hbc_event_elapsed(void *a, void *b, float *ms)
     if (e != cudaSuccess) return static_cast<int>(e);
     return static_cast<int>(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(a), static_cast<cudaEvent_t>(b)));
 }
+extern "C" int hbc_event_create_notiming(void **ev)
+{
+    cudaEvent_t e;
+    const cudaError_t r = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    *ev = e;
+    return static_cast<int>(r);
+}
+extern "C" int hbc_stream_wait_event(void *stream, void *ev)
+{
+    return static_cast<int>(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), static_cast<cudaEvent_t>(ev), 0));
+}
 extern "C" int hbc_graph_begin(void *stream)
 {
     return static_cast<int>(cudaStreamBeginCapture(static_cast<cudaStream_t>(stream), cudaStreamCaptureModeThreadLocal));

@@ -44,6 +44,8 @@ int  hbc_event_create(void **ev);
 int  hbc_event_destroy(void *ev);
 int  hbc_event_record(void *ev, void *stream);
 int  hbc_event_elapsed(void *a, void *b, float *ms);   /* synchronises on b */
+int  hbc_event_create_notiming(void **ev);
+int  hbc_stream_wait_event(void *stream, void *ev);
 int  hbc_graph_begin(void *stream);
 int  hbc_graph_end(void *stream, void **exec);
 int  hbc_graph_launch(void *exec, void *stream);
@@ -108,6 +110,25 @@ typedef struct hbd_tq_args {
     hb_tu_result *res_out;        /* n_jobs */
 } hbd_tq_args;
 int hbk_tq_encode(const hbd_tq_args *a, void *stream);
+
+/* ---- gather of the host's selection (hb_kernels_gather.cu) */
+typedef struct hbd_gather_pc {
+    const int32_t *tu_index;      /* TU raster position (frame grid) -> index among the coded TUs of this (pass, plane), or -1 */
+    int32_t grid_w, grid_h;       /* TU grid of the frame */
+    int32_t tu;                   /* TU side, 0 when the plane is not coded in this pass */
+    const hb_tu_result *res;
+    const int16_t *coeff;
+} hbd_gather_pc;
+typedef struct hbd_gather_args {
+    const uint8_t *sel;           /* chosen pass (0..4) per CTU */
+    const int32_t *ctu_off;       /* start of each CTU's level stream, int16 units */
+    int32_t ctu_cols;
+    hbd_frame recon[5];
+    hbd_gather_pc pc[5][3];
+    uint8_t *out_recon[3];        /* tight planes w*h, (w/2)*(h/2) x2 */
+    int16_t *out_levels;
+} hbd_gather_args;
+int hbk_gather(const hbd_gather_args *a, int n_ctus, void *stream);
 
 #ifdef __cplusplus
 }

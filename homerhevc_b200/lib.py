@@ -163,6 +163,14 @@ def load_library():
     L.hb_prepass_fetch_all.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.hb_prepass_output_bytes.restype = C.c_size_t
     L.hb_prepass_output_bytes.argtypes = [C.c_void_p]
+    L.hb_prepass_tables_bytes.restype = C.c_size_t
+    L.hb_prepass_tables_bytes.argtypes = [C.c_void_p]
+    L.hb_prepass_fetch_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.hb_prepass_num_ctus.argtypes = [C.c_void_p]
+    L.hb_prepass_select.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.hb_prepass_gather_bytes.restype = C.c_size_t
+    L.hb_prepass_gather_bytes.argtypes = [C.c_void_p, C.c_void_p]
+    L.hb_prepass_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.hb_prepass_pred.restype = C.c_void_p
     L.hb_prepass_pred.argtypes = [C.c_void_p, C.c_int]
     L.hb_prepass_recon.restype = C.c_void_p
@@ -397,6 +405,26 @@ class Prepass:
 
     def recon(self, p):
         return _BorrowedFrame(self.ctx, self.ctx.L.hb_prepass_recon(self.h, p), self.w, self.h_px)
+
+    # ---- host-decision flow
+    def tables_bytes(self):
+        return int(self.ctx.L.hb_prepass_tables_bytes(self.h))
+
+    def fetch_tables(self, pinned):
+        """async copy of the cost tables (ME + TU records) into pinned memory; ctx.sync() before reading"""
+        _check(self.ctx.L.hb_prepass_fetch_tables(self.h, pinned.ctypes.data, pinned.nbytes), "hb_prepass_fetch_tables")
+
+    def num_ctus(self):
+        return self.ctx.L.hb_prepass_num_ctus(self.h)
+
+    def select(self, tables, lam, sel, ctu_off):
+        _check(self.ctx.L.hb_prepass_select(self.h, tables.ctypes.data, lam, sel.ctypes.data, ctu_off.ctypes.data), "hb_prepass_select")
+
+    def gather(self, sel, ctu_off, pinned):
+        n = C.c_size_t(0)
+        _check(self.ctx.L.hb_prepass_gather(self.h, sel.ctypes.data, ctu_off.ctypes.data, pinned.ctypes.data, pinned.nbytes, C.byref(n)),
+               "hb_prepass_gather")
+        return n.value
 
     def output_bytes(self):
         return int(self.ctx.L.hb_prepass_output_bytes(self.h))

@@ -208,6 +208,18 @@ int  hb_prepass_fetch_coeffs(hb_prepass *pp, int pass, int comp, int16_t *out); 
 int  hb_prepass_fetch_recon(hb_prepass *pp, int pass, uint8_t *y, int y_stride, uint8_t *u, int u_stride, uint8_t *v, int v_stride);
 int  hb_prepass_fetch_all(hb_prepass *pp, void *pinned_dst, size_t cap, size_t *bytes_out); /* everything above, packed, one async burst + sync */
 size_t hb_prepass_output_bytes(const hb_prepass *pp);
+/* The host-decision flow (mode decision stays on the host and reads GPU cost tables): fetch the small cost tables, let the
+ * host choose a depth per CTU, then gather only the reconstruction of that choice and the levels of its CODED TUs.
+ * fetch_tables / gather are asynchronous on the context's stream (hb_ctx_sync before reading the pinned buffer). */
+size_t hb_prepass_tables_bytes(const hb_prepass *pp);
+int  hb_prepass_fetch_tables(hb_prepass *pp, void *pinned_dst, size_t cap);   /* ME tables d0..3, then TU tables pass 0..4 x Y,U,V */
+int  hb_prepass_num_ctus(const hb_prepass *pp);
+/* stand-in for the host's decision: per CTU the pass (0..4) minimising sum(ssd) + lambda*sum(|level|); also lays out the stream */
+int  hb_prepass_select(const hb_prepass *pp, const void *tables, int lambda, uint8_t *sel, int32_t *ctu_off /* num_ctus + 1 */);
+size_t hb_prepass_gather_bytes(const hb_prepass *pp, const int32_t *ctu_off);
+/* out: recon Y,U,V tight planes, then per CTU (from ctu_off[i], int16 units) for Y,U,V the coded TUs in raster order:
+ * { hdr_lo, hdr_hi, N*N levels }, hdr = plane << 28 | N << 16 | TU raster position inside the CTU */
+int  hb_prepass_gather(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_off, void *pinned_dst, size_t cap, size_t *bytes_out);
 const hb_frame *hb_prepass_pred(const hb_prepass *pp, int depth);     /* resident prediction of that depth */
 const hb_frame *hb_prepass_recon(const hb_prepass *pp, int pass);
 
