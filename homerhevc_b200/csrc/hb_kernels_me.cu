@@ -38,7 +38,7 @@ struct MeArgs {
 };
 
 template <int N> struct MeCfg {
-    static constexpr int G = (N == 64) ? 256 : (N == 32) ? 64 : 32;   // lanes per PU
+    static constexpr int G = (N == 64) ? 256 : (N == 32) ? 64 : N;    // lanes per PU (8x8: 8, 16x16: 16 -> several PUs per warp)
     static constexpr int L = G / 4;                    // lanes per candidate slot
     static constexpr int SEG = L < 32 ? L : 32;        // lanes that reduce together with one redux
     static constexpr int NSEG = G / SEG;               // partial sums exchanged per round
@@ -57,9 +57,11 @@ template <int N> struct MeCfg {
     static constexpr int SMEM_TOTAL = PUS * SMEM_PER_PU;
 };
 
-template <int G> __device__ __forceinline__ void group_barrier(int group)
+// barrier over the lanes that search one PU.  Sub-warp groups use their own lane mask, so the PUs sharing a warp may sit in
+// different iterations of the (data-dependent) search loops: the hardware runs them in lock step where their paths agree.
+template <int G> __device__ __forceinline__ void group_barrier(int group, uint32_t gmask)
 {
-    if (G == 32) __syncwarp();
+    if (G <= 32) __syncwarp(gmask);
     else if (G == 256) __syncthreads();
     else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(G) : "memory");
 }
@@ -73,14 +75,14 @@ template <int K> __device__ __forceinline__ uint32_t pick(const uint32_t (&a)[K]
 }
 
 template <int N>
-__global__ void __launch_bounds__(256) k_me(const MeArgs a)
+__global__ void __launch_bounds__(256, (N <= 16) ? 3 : 2) k_me(const MeArgs a)
 {
     using Cfg = MeCfg<N>;
     constexpr int G = Cfg::G, L = Cfg::L, SEG = Cfg::SEG, NSEG = Cfg::NSEG, SPS = Cfg::SEG_PER_SLOT, PUS = Cfg::PUS;
     constexpr int WPR = Cfg::WPR, WPL = Cfg::WPL, CPL = Cfg::CPL, PS = Cfg::PS, TS = Cfg::TS, PROWS = Cfg::PROWS;
 
     extern __shared__ __align__(16) uint8_t s_raw[];
-    __shared__ uint32_t s_x[PUS][2][NSEG][2];          // [phase][segment]{partial SAD, cost of the segment's slot}
+    __shared__ uint32_t s_x[(G > 32) ? PUS : 1][2][NSEG][2];   // G > 32: [phase][segment]{partial SAD, cost of the segment's slot}
 
     const int group = threadIdx.x / G, gl = threadIdx.x % G, lane = threadIdx.x & 31;
     const int slot = gl / L, l = gl % L, seg = gl / SEG;
@@ -97,6 +99,8 @@ __global__ void __launch_bounds__(256) k_me(const MeArgs a)
     int16_t *s_plane = reinterpret_cast<int16_t *>(s_patch + Cfg::PATCH_BYTES);   // [4][PROWS][TS] by x fraction
     int phase = 0;
     const uint32_t seg_mask = (SEG == 32) ? HB_FULL_MASK : (((1u << SEG) - 1u) << (lane & ~(SEG - 1)));
+    const uint32_t gmask = (G >= 32) ? HB_FULL_MASK : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));
+    const int gbase = lane & ~(G - 1) & 31;               // first lane of the group inside its warp (G <= 32)
 
     // ---- current block -> registers: lane l of every slot holds words l, l+L, ...
     uint32_t cur[WPL];
@@ -134,17 +138,25 @@ __global__ void __launch_bounds__(256) k_me(const MeArgs a)
     // exchange this lane's partial value: every lane gets the four slot totals (and the four slot costs)
     auto exchange = [&](uint32_t part, uint32_t cost, uint32_t (&tot)[4], uint32_t (&cst)[4]) {
         part = __reduce_add_sync(seg_mask, part);
-        if ((gl & (SEG - 1)) == 0) { s_x[group][phase][seg][0] = part; s_x[group][phase][seg][1] = cost; }
-        group_barrier<G>(group);
+        if constexpr (G <= 32) {
 #pragma unroll
-        for (int s = 0; s < 4; s++) {
-            uint32_t t = 0;
+            for (int s = 0; s < 4; s++) {
+                tot[s] = __shfl_sync(gmask, part, gbase + s * L);
+                cst[s] = __shfl_sync(gmask, cost, gbase + s * L);
+            }
+        } else {
+            if ((gl & (SEG - 1)) == 0) { s_x[group][phase][seg][0] = part; s_x[group][phase][seg][1] = cost; }
+            group_barrier<G>(group, gmask);
 #pragma unroll
-            for (int q = 0; q < SPS; q++) t += s_x[group][phase][s * SPS + q][0];
-            tot[s] = t;
-            cst[s] = s_x[group][phase][s * SPS][1];
+            for (int s = 0; s < 4; s++) {
+                uint32_t t = 0;
+#pragma unroll
+                for (int q = 0; q < SPS; q++) t += s_x[group][phase][s * SPS + q][0];
+                tot[s] = t;
+                cst[s] = s_x[group][phase][s * SPS][1];
+            }
+            phase ^= 1;
         }
-        phase ^= 1;
     };
     // one round: SAD + cost of up to four integer positions (cx[s], cy[s]); invalid slots give garbage that is never read
     auto round4 = [&](const int (&cx)[4], const int (&cy)[4], const bool (&cv)[4], uint32_t (&sad)[4], uint32_t (&rd)[4]) {
@@ -302,7 +314,7 @@ __global__ void __launch_bounds__(256) k_me(const MeArgs a)
             const int r = w / (PS / 4), c = (w % (PS / 4)) * 4;
             *reinterpret_cast<uint32_t *>(s_patch + r * PS + c) = hb_ld_u8x4(ref_i + r * rpitch + c);
         }
-        group_barrier<G>(group);
+        group_barrier<G>(group, gmask);
         // ---- horizontal 14-bit planes, fractions 0..3: T_f[r][j] = sum_k taps_f[k] * P[r][j+k] - 8192 (T_0 = P[r][j+3]*64 - 8192)
         for (int w = gl; w < PROWS * (TS / 4); w += G) {
             const int r = w / (TS / 4), j0 = (w % (TS / 4)) * 4;
@@ -329,7 +341,7 @@ __global__ void __launch_bounds__(256) k_me(const MeArgs a)
                 *reinterpret_cast<uint2 *>(s_plane + f * Cfg::PLANE_ELEMS + r * TS + j0) = v;
             }
         }
-        group_barrier<G>(group);
+        group_barrier<G>(group, gmask);
         // ---- the current block as bytes, over the patch area (no longer needed)
         uint8_t *s_cur = s_patch;
 #pragma unroll
@@ -337,7 +349,7 @@ __global__ void __launch_bounds__(256) k_me(const MeArgs a)
             const int w = l + k * L;
             if (slot == 0) *reinterpret_cast<uint32_t *>(s_cur + (w / WPR) * N + (w % WPR) * 4) = cur[k];
         }
-        group_barrier<G>(group);
+        group_barrier<G>(group, gmask);
 
         // one round: SADs of four sub-pel candidates at quarter-pel offsets (qx[s], qy[s]) in [-3,3]^2 from (ix,iy)
         auto subpel4 = [&](const int (&qx)[4], const int (&qy)[4], uint32_t (&sad)[4]) {
