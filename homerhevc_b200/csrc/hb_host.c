@@ -490,7 +490,7 @@ int hb_tq_encode(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_fram
     for (int i = 0; i < n_jobs; i++) {
         const hb_tu_job *j = &jobs[i];
         if (j->comp < 0 || j->comp > 2 || (j->size != 4 && j->size != 8 && j->size != 16 && j->size != 32) || j->qp < 0 || j->qp > 51 ||
-            j->x < 0 || j->y < 0 || j->x + j->size > cur->d.p[j->comp].w || j->y + j->size > cur->d.p[j->comp].h ||
+            j->x < 0 || j->y < 0 || (j->x & 3) || j->x + j->size > cur->d.p[j->comp].w || j->y + j->size > cur->d.p[j->comp].h ||
             (j->comp && j->size == 32))
             return hb_fail(HB_ERR_ARG, "hb_tq_encode: job %d is invalid", i);
         total += (size_t)j->size * j->size;

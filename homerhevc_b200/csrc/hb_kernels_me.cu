@@ -137,7 +137,12 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : 2) k_me(const MeArgs a)
 
     // exchange this lane's partial value: every lane gets the four slot totals (and the four slot costs)
     auto exchange = [&](uint32_t part, uint32_t cost, uint32_t (&tot)[4], uint32_t (&cst)[4]) {
-        part = __reduce_add_sync(seg_mask, part);
+        if constexpr (SEG == 32) {
+            part = __reduce_add_sync(HB_FULL_MASK, part);
+        } else {                                           // redux.sync with a partial mask is emulated: butterfly instead
+#pragma unroll
+            for (int d = SEG / 2; d > 0; d >>= 1) part += __shfl_xor_sync(seg_mask, part, d);
+        }
         if constexpr (G <= 32) {
 #pragma unroll
             for (int s = 0; s < 4; s++) {
@@ -373,11 +378,11 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : 2) k_me(const MeArgs a)
                     for (int rr = 0; rr < 8; rr++) {
                         const int r = r8 + rr;
                         win[(rr + 7) & 7] = pl[(r + 7) * TS + cc];
-                        int s = 0;
+                        int s = 2048 + (8192 << 6);        // rounding + the 14-bit offset of the first pass
 #pragma unroll
                         for (int k = 0; k < 8; k++) s += t[k] * win[(rr + k) & 7];
-                        const int px = hb_clip255((s + 2048 + (8192 << 6)) >> 12);
-                        acc += static_cast<uint32_t>(abs(px - static_cast<int>(s_cur[r * N + c0 + cc])));
+                        const int px = __vimin_s32_relu(s >> 12, 255);                       // clip to 0..255 in one instruction
+                        acc = __sad(px, static_cast<int>(s_cur[r * N + c0 + cc]), acc);
                     }
                 }
             }

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_tq(const hbd_tq_args a)
     const double thr_k = a.dyn ? a.dyn->thr_k : a.thr_k;
     int16_t *X = smem[warp][0], *T = smem[warp][1], *C = smem[warp][2], *L = smem[warp][3], *U = smem[warp][4];
 
-    // ---- residual of every unit of the stack (element-wise, coalesced inside a row)
+    // ---- residual of every unit of the stack: four samples per lane and iteration (u8x4 loads)
     int jx[TPW], jy[TPW];
 #pragma unroll
     for (int u = 0; u < TPW; u++) {
@@ -34,15 +34,23 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_tq(const hbd_tq_args a)
         jx[u] = __ldg(a.jobs_xy + 2 * j);
         jy[u] = __ldg(a.jobs_xy + 2 * j + 1);
     }
-    for (int it = 0; it < N; it++) {
-        const int e = it * 32 + lane;
-        const int row = e / N, col = e % N, unit = row / N, r = row % N;
-        int x = 0, y = 0;
+    auto unit_xy = [&](int unit, int &x, int &y) {
+        x = jx[0]; y = jy[0];
 #pragma unroll
-        for (int u = 0; u < TPW; u++) if (u == unit) { x = jx[u]; y = jy[u]; }
-        const int o = a.cur.org[(y + r) * a.cur.pitch + x + col];
-        const int p = a.pred.org[(y + r) * a.pred.pitch + x + col];
-        X[row * S + col] = static_cast<int16_t>(o - p);
+        for (int u = 1; u < TPW; u++) if (u == unit) { x = jx[u]; y = jy[u]; }
+    };
+#pragma unroll
+    for (int it = 0; it < Q::ITERS4; it++) {
+        const typename Q::G4 g = Q::group4(it, lane);
+        int x, y;
+        unit_xy(g.unit, x, y);
+        const int r = g.row % N;
+        const uint32_t o = *reinterpret_cast<const uint32_t *>(a.cur.org + (y + r) * a.cur.pitch + x + g.col);
+        const uint32_t p = *reinterpret_cast<const uint32_t *>(a.pred.org + (y + r) * a.pred.pitch + x + g.col);
+        int d[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) d[k] = static_cast<int>((o >> (8 * k)) & 255u) - static_cast<int>((p >> (8 * k)) & 255u);
+        Q::st4(X + g.off, d);
     }
     __syncwarp();
 
@@ -64,69 +72,70 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_tq(const hbd_tq_args a)
     uint32_t ssd_dec[TPW], ssd_zero[TPW];
 #pragma unroll
     for (int u = 0; u < TPW; u++) { ssd_dec[u] = 0; ssd_zero[u] = 0; }
-    {
-        constexpr int IT_PER_UNIT = (N * N) / 32;
-        for (int it = 0; it < N; it++) {
-            const int e = it * 32 + lane;
-            const int off = Q::elem_off(e);
-            const int r = X[off];
-            const int d = r - (any ? static_cast<int>(C[off]) : 0);
-            uint32_t z = static_cast<uint32_t>(r) * static_cast<uint32_t>(r), s = static_cast<uint32_t>(d) * static_cast<uint32_t>(d);
-            if constexpr (N == 4) {
-                const uint32_t m = lane < 16 ? 0x0000ffffu : 0xffff0000u;
-                z = __reduce_add_sync(m, z); s = __reduce_add_sync(m, s);
-                const uint32_t z0 = __shfl_sync(HB_FULL_MASK, z, 0), z1 = __shfl_sync(HB_FULL_MASK, z, 16);
-                const uint32_t s0 = __shfl_sync(HB_FULL_MASK, s, 0), s1 = __shfl_sync(HB_FULL_MASK, s, 16);
 #pragma unroll
-                for (int u = 0; u < TPW; u++) {
-                    if (u == 2 * it) { ssd_zero[u] = z0; ssd_dec[u] = s0; }
-                    if (u == 2 * it + 1) { ssd_zero[u] = z1; ssd_dec[u] = s1; }
-                }
-            } else {
-                z = __reduce_add_sync(HB_FULL_MASK, z); s = __reduce_add_sync(HB_FULL_MASK, s);
+    for (int it = 0; it < Q::ITERS4; it++) {
+        const typename Q::G4 g = Q::group4(it, lane);
+        int r[4], c[4] = { 0, 0, 0, 0 };
+        Q::ld4(X + g.off, r);
+        if (any) Q::ld4(C + g.off, c);
+        uint32_t z = 0, s = 0;
 #pragma unroll
-                for (int u = 0; u < TPW; u++) if (u == it / IT_PER_UNIT) { ssd_zero[u] += z; ssd_dec[u] += s; }
-            }
+        for (int k = 0; k < 4; k++) {
+            const int d = r[k] - c[k];
+            z += static_cast<uint32_t>(r[k]) * static_cast<uint32_t>(r[k]);
+            s += static_cast<uint32_t>(d) * static_cast<uint32_t>(d);
         }
+        Q::template unit_add<uint32_t>(z, it, ssd_zero);
+        Q::template unit_add<uint32_t>(s, it, ssd_dec);
     }
 
-    // ---- decision per unit (hmr_motion_inter.c:90-121 / :186-224), uniform across the warp
-    bool keep[TPW];
+    // ---- decision (hmr_motion_inter.c:90-121 / :186-224): lane u decides unit u, the verdicts travel by ballot
+    uint32_t my_z = 0, my_d = 0; int my_sum = 0;
 #pragma unroll
-    for (int u = 0; u < TPW; u++) {
+    for (int u = 0; u < TPW; u++) if (u == lane) { my_z = ssd_zero[u]; my_d = ssd_dec[u]; my_sum = unit_sum[u]; }
+    bool my_keep = false;
+    if (lane < TPW) {
         hb_tu_result r;
-        r.sum = unit_sum[u]; r.zeroed = 0; r.ssd_zero = 0;
-        keep[u] = false;
-        uint32_t zw = ssd_zero[u], dw = ssd_dec[u];
+        r.sum = my_sum; r.zeroed = 0; r.ssd_zero = 0;
+        uint32_t zw = my_z, dw = my_d;
         if (!a.is_luma) {
             zw = __double2uint_rz(__dmul_rn(a.weight, static_cast<double>(zw)));
             dw = __double2uint_rz(__dmul_rn(a.weight, static_cast<double>(dw)));
         }
-        if (unit_sum[u] > 0) {
+        if (my_sum > 0) {
             const double lhs = static_cast<double>(zw);
             const double base = a.is_luma ? static_cast<double>(static_cast<int32_t>(dw)) : static_cast<double>(dw);
-            const double rhs = __dadd_rn(base, __dmul_rn(thr_k, static_cast<double>(unit_sum[u])));
+            const double rhs = __dadd_rn(base, __dmul_rn(thr_k, static_cast<double>(my_sum)));
             r.ssd = dw; r.ssd_zero = zw;
             if (lhs <= rhs) { r.zeroed = 1; r.sum = 0; }
-            else keep[u] = true;
+            else my_keep = true;
         } else {
             r.ssd = zw;                                   // ssd16b(residual, zeros)
         }
-        if (lane == 0 && first_job + u < a.n_jobs) a.res_out[first_job + u] = r;
+        if (first_job + lane < a.n_jobs) a.res_out[first_job + lane] = r;
     }
+    const uint32_t keep_mask = __ballot_sync(HB_FULL_MASK, my_keep);
 
-    // ---- outputs: levels and reconstruction
-    for (int it = 0; it < N; it++) {
-        const int e = it * 32 + lane;
-        const int row = e / N, col = e % N, unit = row / N, r = row % N;
-        int x = 0, y = 0; bool k = false;
+    // ---- outputs: levels (int16x4 stores) and reconstruction (u8x4 stores)
 #pragma unroll
-        for (int u = 0; u < TPW; u++) if (u == unit) { x = jx[u]; y = jy[u]; k = keep[u]; }
-        if (first_job + unit >= a.n_jobs) continue;
-        const int off = row * S + col;
-        a.coeff_out[static_cast<size_t>(first_job + unit) * (N * N) + r * N + col] = k ? L[off] : int16_t(0);
-        const int p = a.pred.org[(y + r) * a.pred.pitch + x + col];
-        a.rec.org[(y + r) * a.rec.pitch + x + col] = static_cast<uint8_t>(hb_clip255(p + (k ? static_cast<int>(C[off]) : 0)));
+    for (int it = 0; it < Q::ITERS4; it++) {
+        const typename Q::G4 g = Q::group4(it, lane);
+        if (first_job + g.unit >= a.n_jobs) continue;
+        int x, y;
+        unit_xy(g.unit, x, y);
+        const bool k = (keep_mask >> g.unit) & 1u;
+        const int r = g.row % N;
+        int lv[4] = { 0, 0, 0, 0 }, dr[4] = { 0, 0, 0, 0 };
+        if (k) { Q::ld4(L + g.off, lv); Q::ld4(C + g.off, dr); }
+        uint2 w;
+        w.x = (static_cast<uint32_t>(lv[0]) & 0xffffu) | (static_cast<uint32_t>(lv[1]) << 16);
+        w.y = (static_cast<uint32_t>(lv[2]) & 0xffffu) | (static_cast<uint32_t>(lv[3]) << 16);
+        *reinterpret_cast<uint2 *>(a.coeff_out + static_cast<size_t>(first_job + g.unit) * (N * N) + g.pos4) = w;
+        const uint32_t p = *reinterpret_cast<const uint32_t *>(a.pred.org + (y + r) * a.pred.pitch + x + g.col);
+        uint32_t out = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) out |= static_cast<uint32_t>(hb_clip255(static_cast<int>((p >> (8 * q)) & 255u) + dr[q])) << (8 * q);
+        *reinterpret_cast<uint32_t *>(a.rec.org + (y + r) * a.rec.pitch + x + g.col) = out;
     }
 }
 

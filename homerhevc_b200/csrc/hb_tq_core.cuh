@@ -146,41 +146,81 @@ template <int N> struct HbTq {
         __syncwarp();
     }
 
-    // element e of the warp's stack in (unit, row-major position) order -> smem offset
-    static __device__ __forceinline__ int elem_off(int e) { return (e / N) * S + (e % N); }
+    // ---- element-wise sweeps handle FOUR consecutive samples of a row per lane and iteration
+    static constexpr int GPU4 = N * N / 4;                        // groups of four per unit
+    static constexpr int ITERS4 = N / 4;                          // 8N groups in the stack / 32 lanes
+    static constexpr int UPI = GPU4 >= 32 ? 1 : 32 / GPU4;        // units covered by one iteration (N=4: 8, N=8: 2)
+    static constexpr int IPU = GPU4 >= 32 ? GPU4 / 32 : 1;        // iterations per unit
 
-    // Quantise C -> L with deltaU -> U; returns this lane's partial level sums per iteration through `acc`
-    // (hmr_sse42_functions_quant.c:52-118).  qtab is the N*N int32 table of this (list, qp%6).
-    // unit_sum[u] (u < TPW) receives the sum of levels of unit u, identical in every lane.
+    struct G4 { int row, col, off, pos4, unit; };                 // stack row, first column, smem offset, position inside the unit
+    static __device__ __forceinline__ G4 group4(int it, int lane)
+    {
+        G4 g;
+        const int i = it * 32 + lane;
+        g.row = i / (N / 4); g.col = (i % (N / 4)) * 4; g.off = g.row * S + g.col;
+        g.pos4 = (i % GPU4) * 4; g.unit = i / GPU4;
+        return g;
+    }
+    static __device__ __forceinline__ void ld4(const int16_t *p, int (&v)[4])
+    {
+        const uint32_t a = *reinterpret_cast<const uint32_t *>(p), b = *reinterpret_cast<const uint32_t *>(p + 2);
+        v[0] = static_cast<int16_t>(a & 0xffff); v[1] = static_cast<int32_t>(a) >> 16;
+        v[2] = static_cast<int16_t>(b & 0xffff); v[3] = static_cast<int32_t>(b) >> 16;
+    }
+    static __device__ __forceinline__ void st4(int16_t *p, const int (&v)[4])
+    {
+        *reinterpret_cast<uint32_t *>(p) = (static_cast<uint32_t>(v[0]) & 0xffffu) | (static_cast<uint32_t>(v[1]) << 16);
+        *reinterpret_cast<uint32_t *>(p + 2) = (static_cast<uint32_t>(v[2]) & 0xffffu) | (static_cast<uint32_t>(v[3]) << 16);
+    }
+    // add this iteration's per-unit totals of v into acc[] (identical in every lane)
+    template <class T> static __device__ __forceinline__ void unit_add(T v, int it, T (&acc)[TPW])
+    {
+        if constexpr (UPI == 1) {
+            v = __reduce_add_sync(HB_FULL_MASK, v);
+#pragma unroll
+            for (int u = 0; u < TPW; u++) if (u == it / IPU) acc[u] += v;
+        } else {
+            constexpr int W = 32 / UPI;                           // lanes per unit
+#pragma unroll
+            for (int d = W / 2; d > 0; d >>= 1) v += __shfl_xor_sync(HB_FULL_MASK, v, d);
+#pragma unroll
+            for (int k = 0; k < UPI; k++) {
+                const T t = __shfl_sync(HB_FULL_MASK, v, k * W);
+#pragma unroll
+                for (int u = 0; u < TPW; u++) if (u == it * UPI + k) acc[u] += t;
+            }
+        }
+    }
+
+    // Quantise C -> L with deltaU -> U (hmr_sse42_functions_quant.c:52-118).  qtab is the N*N int32 table of this
+    // (list, qp%6).  unit_sum[u] (u < TPW) receives the sum of levels of unit u, identical in every lane.
     static __device__ __forceinline__ void quantise(const int16_t *C, int16_t *L, int16_t *U, const int32_t *__restrict__ qtab,
                                                     int qbits, int add, int lane, int (&unit_sum)[TPW])
     {
 #pragma unroll
         for (int u = 0; u < TPW; u++) unit_sum[u] = 0;
-        constexpr int ITERS = N;                       // 32*N elements / 32 lanes
-        constexpr int IT_PER_UNIT = (N * N) / 32;      // 0 for N = 4 (two units per iteration)
-#pragma unroll 4
-        for (int it = 0; it < ITERS; it++) {
-            const int e = it * 32 + lane;
-            const int off = elem_off(e);
-            const int c = C[off];
-            const uint32_t a = static_cast<uint32_t>(c < 0 ? -c : c);
-            const uint32_t prod = a * static_cast<uint32_t>(__ldg(qtab + (e % (N * N))));
-            const int level = static_cast<int32_t>(prod + static_cast<uint32_t>(add)) >> qbits;
-            const int delta = static_cast<int32_t>(prod - (static_cast<uint32_t>(level) << qbits)) >> (qbits - 8);
-            const int sgn = (c > 0) - (c < 0);
-            L[off] = static_cast<int16_t>(sgn * hb_sat16(level));
-            U[off] = static_cast<int16_t>(hb_sat16(delta));
-            if constexpr (N == 4) {
-                const int s = __reduce_add_sync(lane < 16 ? 0x0000ffffu : 0xffff0000u, level);
-                const int s_lo = __shfl_sync(HB_FULL_MASK, s, 0), s_hi = __shfl_sync(HB_FULL_MASK, s, 16);
 #pragma unroll
-                for (int u = 0; u < TPW; u++) { if (u == 2 * it) unit_sum[u] = s_lo; if (u == 2 * it + 1) unit_sum[u] = s_hi; }
-            } else {
-                const int s = __reduce_add_sync(HB_FULL_MASK, level);
+        for (int it = 0; it < ITERS4; it++) {
+            const G4 g = group4(it, lane);
+            int c[4], lv[4], du[4];
+            ld4(C + g.off, c);
+            const int4 q = __ldg(reinterpret_cast<const int4 *>(qtab + g.pos4));
+            const int qq[4] = { q.x, q.y, q.z, q.w };
+            int sum = 0;
 #pragma unroll
-                for (int u = 0; u < TPW; u++) if (u == it / IT_PER_UNIT) unit_sum[u] += s;
+            for (int k = 0; k < 4; k++) {
+                const uint32_t a = static_cast<uint32_t>(c[k] < 0 ? -c[k] : c[k]);
+                const uint32_t prod = a * static_cast<uint32_t>(qq[k]);
+                const int level = static_cast<int32_t>(prod + static_cast<uint32_t>(add)) >> qbits;
+                const int delta = static_cast<int32_t>(prod - (static_cast<uint32_t>(level) << qbits)) >> (qbits - 8);
+                const int sat = hb_sat16(level);
+                lv[k] = c[k] > 0 ? sat : (c[k] < 0 ? -sat : 0);
+                du[k] = hb_sat16(delta);
+                sum += level;
             }
+            st4(L + g.off, lv);
+            st4(U + g.off, du);
+            unit_add<int>(sum, it, unit_sum);
         }
         __syncwarp();
     }
@@ -193,6 +233,10 @@ template <int N> struct HbTq {
         constexpr int CG_PER_UNIT = N * N / 16;
         constexpr int CGS = TPW * CG_PER_UNIT;         // 2N groups in the stack
         constexpr int ROUNDS = (CGS + 31) / 32;
+        bool any_unit = false;
+#pragma unroll
+        for (int u = 0; u < TPW; u++) any_unit |= unit_sum[u] >= 2;
+        if (!any_unit) return;                            // warp-uniform: nothing to hide anywhere in the stack
         // non-zero map of the coefficient groups, so that each group knows whether it is the last significant one of its unit
         uint32_t nz[ROUNDS];
         int first[ROUNDS], last[ROUNDS], asum[ROUNDS];
@@ -200,7 +244,10 @@ template <int N> struct HbTq {
         for (int r = 0; r < ROUNDS; r++) {
             const int cg = r * 32 + lane;
             first[r] = 16; last[r] = -1; asum[r] = 0;
-            if (cg < CGS) {
+            int my_sum = 0;
+#pragma unroll
+            for (int u = 0; u < TPW; u++) if (u == cg / CG_PER_UNIT) my_sum = unit_sum[u];
+            if (cg < CGS && my_sum >= 2) {
                 const int unit = cg / CG_PER_UNIT, sub = cg % CG_PER_UNIT;
                 const int16_t *Lu = L + unit * N * S;
                 const uint16_t *sc = scan + 16 * sub;
@@ -269,15 +316,22 @@ template <int N> struct HbTq {
     static __device__ __forceinline__ void dequantise(const int16_t *L, int16_t *D, const int32_t *__restrict__ dqtab, int per, int lane)
     {
         const int iq_shift = LOG2 + 3;
-#pragma unroll 4
-        for (int it = 0; it < N; it++) {
-            const int e = it * 32 + lane;
-            const int off = elem_off(e);
-            const uint32_t prod = static_cast<uint32_t>(static_cast<int32_t>(L[off])) * static_cast<uint32_t>(__ldg(dqtab + (e % (N * N))));
-            int v;
-            if (iq_shift > per) v = static_cast<int32_t>(prod + (1u << (iq_shift - per - 1))) >> (iq_shift - per);
-            else v = static_cast<int32_t>(prod << (per - iq_shift));
-            D[off] = static_cast<int16_t>(hb_sat16(v));
+#pragma unroll
+        for (int it = 0; it < ITERS4; it++) {
+            const G4 g = group4(it, lane);
+            int lv[4], d[4];
+            ld4(L + g.off, lv);
+            const int4 q = __ldg(reinterpret_cast<const int4 *>(dqtab + g.pos4));
+            const int qq[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t prod = static_cast<uint32_t>(lv[k]) * static_cast<uint32_t>(qq[k]);
+                int v;
+                if (iq_shift > per) v = static_cast<int32_t>(prod + (1u << (iq_shift - per - 1))) >> (iq_shift - per);
+                else v = static_cast<int32_t>(prod << (per - iq_shift));
+                d[k] = hb_sat16(v);
+            }
+            st4(D + g.off, d);
         }
         __syncwarp();
     }
