@@ -227,60 +227,47 @@ def main():
     #   upload cur + ref (pinned, async) -> pre-pass -> fetch the cost tables -> host picks a depth per CTU (hb_prepass_select,
     #   the stand-in for the host's mode decision) -> gather + fetch the reconstruction and coded levels of that choice.
     # N_SLOTS independent streams of frames (GOPs) are in flight per GPU so that copies, kernels and the host step overlap.
-    N_SLOTS, LAMBDA = 3, 60
+    N_SLOTS, LAMBDA = 4, 60
     slots = []
     for k in range(N_SLOTS):
         c = hb.Context(local)
         spp = hb.Prepass(c, w, h, qp=QP, use_graph=1)
         n_ctus = spp.num_ctus()
         slots.append({"ctx": c, "cur": hb.Frame(c, w, h), "ref": hb.Frame(c, w, h), "pp": spp, "tables": c.pinned(spp.tables_bytes()),
-                      "out": c.pinned(frame_bytes + 4 * w * h), "sel": np.zeros(n_ctus, np.uint8), "off": np.zeros(n_ctus + 1, np.int32),
-                      "stage": 0, "d2h": 0})
-    d2h_total = [0]
+                      "out": c.pinned(frame_bytes + 4 * w * h), "sel": np.zeros(n_ctus, np.uint8), "off": np.zeros(n_ctus + 1, np.int32), "d2h": 0})
 
-    def stage_a(sl, i):
+    def one_frame(sl, i):
         j = i % N_RESIDENT
         sl["cur"].upload_u8(*pinned[j + 1]); sl["ref"].upload_u8(*pinned[j])
         sl["pp"].run(sl["cur"], sl["ref"], AVG_DIST)
         sl["pp"].fetch_tables(sl["tables"])
-        sl["stage"] = 1
-
-    def stage_b(sl):
         sl["ctx"].sync()
-        sl["pp"].select(sl["tables"], LAMBDA, sl["sel"], sl["off"])
-        sl["d2h"] = sl["pp"].gather(sl["sel"], sl["off"], sl["out"])
-        sl["stage"] = 2
-
-    def stage_c(sl):
+        sl["pp"].select(sl["tables"], LAMBDA, sl["sel"], sl["off"])          # host: depth per CTU from the cost tables
+        sl["d2h"] += sl["pp"].gather(sl["sel"], sl["off"], sl["out"]) + sl["tables"].nbytes
         sl["ctx"].sync()
-        d2h_total[0] += sl["d2h"] + sl["tables"].nbytes
-        sl["stage"] = 0
 
     def run_e2e(n):
-        # iteration i: queue frame i first, then finish the host step of frame i-1 and consume frame i-2,
-        # so the GPU always has the next frame queued while the host synchronises and decides
-        for i in range(n + 2):
-            if i < n:
-                stage_a(slots[i % N_SLOTS], i)
-            if i >= 1 and slots[(i - 1) % N_SLOTS]["stage"] == 1:
-                stage_b(slots[(i - 1) % N_SLOTS])
-            if i >= 2 and slots[(i - 2) % N_SLOTS]["stage"] == 2:
-                stage_c(slots[(i - 2) % N_SLOTS])
-        for sl in slots:
-            if sl["stage"] == 1:
-                stage_b(sl)
-            if sl["stage"] == 2:
-                stage_c(sl)
+        # one host thread per in-flight stream (the reference runs one pthread per encoder engine, hmr_encoder_lib.c:1647):
+        # the C calls release the GIL, so uploads, kernels, downloads and the host decision of different streams overlap
+        def worker(k):
+            for i in range(k, n, N_SLOTS):
+                one_frame(slots[k], i)
+        ths = [threading.Thread(target=worker, args=(k,)) for k in range(N_SLOTS)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
 
-    e2e_steps = max(30, min(args.steps, 120))
-    run_e2e(6)
+    e2e_steps = max(32, min(args.steps, 160))
+    run_e2e(2 * N_SLOTS)
     barrier()
-    d2h_total[0] = 0
+    for sl in slots:
+        sl["d2h"] = 0
     t0 = time.perf_counter()
     run_e2e(e2e_steps)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3          # the host is in this loop: wall clock around fully synchronised ends
-    d2h_per_step = d2h_total[0] // e2e_steps
+    d2h_per_step = sum(sl["d2h"] for sl in slots) // e2e_steps
     barrier()
     # the unfiltered variant for reference: one stream, every table / level / reconstruction of all five passes fetched
     e2e_cur, e2e_ref = hb.Frame(ctx, w, h), hb.Frame(ctx, w, h)

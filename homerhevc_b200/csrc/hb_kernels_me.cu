@@ -75,7 +75,7 @@ template <int K> __device__ __forceinline__ uint32_t pick(const uint32_t (&a)[K]
 }
 
 template <int N>
-__global__ void __launch_bounds__(256, (N <= 16) ? 3 : 2) k_me(const MeArgs a)
+__global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(const MeArgs a)
 {
     using Cfg = MeCfg<N>;
     constexpr int G = Cfg::G, L = Cfg::L, SEG = Cfg::SEG, NSEG = Cfg::NSEG, SPS = Cfg::SEG_PER_SLOT, PUS = Cfg::PUS;

@@ -54,8 +54,9 @@ struct hb_prepass {
     int launches_per_frame;
     /* gather of the host's selection */
     uint8_t *d_sel; int32_t *d_ctu_off; uint8_t *d_sel_recon; int16_t *d_sel_levels; size_t sel_levels_cap;
-    void *side[N_DEPTH];                       /* one side stream per depth: MC + T/Q of depth d overlap the search of depth d+1 */
-    void *ev_fork[N_DEPTH], *ev_join[N_DEPTH];
+    /* side streams per depth: [0] MC then luma T/Q, [1] chroma T/Q, [2] the 4x4 luma pass of depth 3.  They overlap the search of depth d+1 */
+    void *side[N_DEPTH][3];
+    void *ev_fork[N_DEPTH], *ev_mc[N_DEPTH], *ev_join[N_DEPTH][3];
     void *prof_ev[HB_PREPASS_MAX_KERNELS + 1];
     char prof_name[HB_PREPASS_MAX_KERNELS][16];
 };
@@ -169,9 +170,12 @@ int hb_prepass_create(hb_ctx *ctx, int width, int height, const hb_prepass_cfg *
         }
     }
     for (int d = 0; d < N_DEPTH && rc == HB_OK; d++) {
-        int crc = hbc_stream_create(&pp->side[d]);
-        if (!crc) crc = hbc_event_create_notiming(&pp->ev_fork[d]);
-        if (!crc) crc = hbc_event_create_notiming(&pp->ev_join[d]);
+        int crc = hbc_event_create_notiming(&pp->ev_fork[d]);
+        if (!crc) crc = hbc_event_create_notiming(&pp->ev_mc[d]);
+        for (int k = 0; k < 3 && !crc; k++) {
+            crc = hbc_stream_create(&pp->side[d][k]);
+            if (!crc) crc = hbc_event_create_notiming(&pp->ev_join[d][k]);
+        }
         if (crc) rc = hb_cuda_fail(crc, "prepass: side streams");
     }
     if (rc == HB_OK) {
@@ -211,9 +215,12 @@ void hb_prepass_destroy(hb_prepass *pp)
     if (pp->d_sel_recon) hbc_free(pp->d_sel_recon);
     if (pp->d_sel_levels) hbc_free(pp->d_sel_levels);
     for (int d = 0; d < N_DEPTH; d++) {
-        if (pp->side[d]) { hbc_stream_sync(pp->side[d]); hbc_stream_destroy(pp->side[d]); }
+        for (int k = 0; k < 3; k++) {
+            if (pp->side[d][k]) { hbc_stream_sync(pp->side[d][k]); hbc_stream_destroy(pp->side[d][k]); }
+            if (pp->ev_join[d][k]) hbc_event_destroy(pp->ev_join[d][k]);
+        }
         if (pp->ev_fork[d]) hbc_event_destroy(pp->ev_fork[d]);
-        if (pp->ev_join[d]) hbc_event_destroy(pp->ev_join[d]);
+        if (pp->ev_mc[d]) hbc_event_destroy(pp->ev_mc[d]);
     }
     for (int i = 0; i <= HB_PREPASS_MAX_KERNELS; i++) if (pp->prof_ev[i]) hbc_event_destroy(pp->prof_ev[i]);
     free(pp);
@@ -221,13 +228,13 @@ void hb_prepass_destroy(hb_prepass *pp)
 
 /* queue the kernels of one frame on the context's stream; returns a cudaError_t value */
 #define PROF_MARK(...) do { if (prof && !crc) { snprintf(pp->prof_name[n], sizeof pp->prof_name[n], __VA_ARGS__); crc = hbc_event_record(pp->prof_ev[n], st); } } while (0)
-/* T/Q launches of one pass on stream st */
-static int enqueue_tq(hb_prepass *pp, const hb_frame *cur, int p, void *st, int *n_io, int prof)
+/* T/Q launches of one pass: planes c0..c1 on stream st */
+static int enqueue_tq(hb_prepass *pp, const hb_frame *cur, int p, int c0, int c1, void *st, int *n_io, int prof)
 {
     hb_ctx *ctx = pp->ctx;
     int crc = 0, n = *n_io;
     const hb_frame *pred = pp->pred[pass_depth(p)];
-    for (int c = 0; c < 3 && !crc; c++) {
+    for (int c = c0; c <= c1 && !crc; c++) {
         pass_comp *pc = &pp->pc[p][c];
         if (!pc->tu || !pc->n_tus) continue;
         hbd_tq_args a;
@@ -247,7 +254,8 @@ static int enqueue_tq(hb_prepass *pp, const hb_frame *cur, int p, void *st, int 
 
 /* queue the kernels of one frame; returns a cudaError_t value.  prof != 0: everything on the context's stream with an
  * event before each launch.  Otherwise the search chain ME(64) -> ME(32) -> ME(16) -> ME(8) runs on the context's stream
- * and, after each ME(d), a side stream takes MC(d) and the T/Q passes of that depth, so they overlap the next search. */
+ * and, after each ME(d), side streams take MC(d) and then, in parallel, the luma and chroma T/Q passes of that depth
+ * (and the 4x4 luma pass after depth 3), so that they overlap the next search and each other. */
 static int enqueue(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, int *n_launches, int prof)
 {
     hb_ctx *ctx = pp->ctx;
@@ -255,25 +263,41 @@ static int enqueue(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, int
     int crc = 0, n = 0;
     for (int d = 0; d < N_DEPTH && !crc; d++) {
         if (!pp->n_valid[d]) continue;
-        void *st = main_st;
+        void *st = main_st;                      /* name used by PROF_MARK */
         PROF_MARK("me%d", 64 >> d);
         if (!crc) crc = hbk_me_search(&cur->d, &ref->d, 64 >> d, pp->d_jobs[d], pp->n_valid[d], d ? pp->d_me[d - 1] : NULL, pp->d_me[d],
                                       pp->cfg.me_action, pp->d_dyn, main_st);
         n++;
-        if (!prof && !crc) {
-            st = pp->side[d];
-            crc = hbc_event_record(pp->ev_fork[d], main_st);
-            if (!crc) crc = hbc_stream_wait_event(st, pp->ev_fork[d]);
+        if (prof) {
+            PROF_MARK("mc%d", 64 >> d);
+            if (!crc) { crc = hbk_mc_predict(&ref->d, &pp->pred[d]->d, 64 >> d, pp->d_pus[d], pp->n_valid[d], pp->d_me[d], st); n++; }
+            for (int p = 0; p < N_PASS && !crc; p++)
+                if (pass_depth(p) == d) crc = enqueue_tq(pp, cur, p, 0, 2, st, &n, prof);
+            continue;
         }
-        PROF_MARK("mc%d", 64 >> d);
-        if (!crc) { crc = hbk_mc_predict(&ref->d, &pp->pred[d]->d, 64 >> d, pp->d_pus[d], pp->n_valid[d], pp->d_me[d], st); n++; }
-        for (int p = 0; p < N_PASS && !crc; p++)
-            if (pass_depth(p) == d) crc = enqueue_tq(pp, cur, p, st, &n, prof);
-        if (!prof && !crc) crc = hbc_event_record(pp->ev_join[d], st);
+        void *s0 = pp->side[d][0], *s1 = pp->side[d][1], *s2 = pp->side[d][2];
+        crc = hbc_event_record(pp->ev_fork[d], main_st);
+        if (!crc) crc = hbc_stream_wait_event(s0, pp->ev_fork[d]);
+        if (!crc) { crc = hbk_mc_predict(&ref->d, &pp->pred[d]->d, 64 >> d, pp->d_pus[d], pp->n_valid[d], pp->d_me[d], s0); n++; }
+        if (!crc) crc = hbc_event_record(pp->ev_mc[d], s0);
+        if (!crc) crc = hbc_stream_wait_event(s1, pp->ev_mc[d]);
+        if (!crc) crc = enqueue_tq(pp, cur, d, 0, 0, s0, &n, 0);
+        if (!crc) crc = enqueue_tq(pp, cur, d, 1, 2, s1, &n, 0);
+        if (d == N_DEPTH - 1 && !crc) {
+            crc = hbc_stream_wait_event(s2, pp->ev_mc[d]);
+            if (!crc) crc = enqueue_tq(pp, cur, N_PASS - 1, 0, 0, s2, &n, 0);
+            if (!crc) crc = hbc_event_record(pp->ev_join[d][2], s2);
+        }
+        if (!crc) crc = hbc_event_record(pp->ev_join[d][0], s0);
+        if (!crc) crc = hbc_event_record(pp->ev_join[d][1], s1);
     }
     if (!prof)
-        for (int d = 0; d < N_DEPTH && !crc; d++)
-            if (pp->n_valid[d]) crc = hbc_stream_wait_event(main_st, pp->ev_join[d]);
+        for (int d = 0; d < N_DEPTH && !crc; d++) {
+            if (!pp->n_valid[d]) continue;
+            crc = hbc_stream_wait_event(main_st, pp->ev_join[d][0]);
+            if (!crc) crc = hbc_stream_wait_event(main_st, pp->ev_join[d][1]);
+            if (!crc && d == N_DEPTH - 1) crc = hbc_stream_wait_event(main_st, pp->ev_join[d][2]);
+        }
     {
         void *st = main_st;
         if (prof && !crc) crc = hbc_event_record(pp->prof_ev[n], st);
@@ -511,12 +535,20 @@ int hb_prepass_select(const hb_prepass *pp, const void *tables, int lambda, uint
         for (int c = 0; c < 3; c++) {
             const pass_comp *pc = &pp->pc[p][c];
             const int slot = (p == 4) ? 4 : p, piece = (p == 3 && c > 0) ? 5 : slot;   /* chroma of pass 3 is shared by choices 3 and 4 */
-            const int nn = pc->tu * pc->tu;
-            for (int i = 0; i < pc->n_tus; i++) {
-                const hb_tu_result *r = &res[p][c][i];
-                const int ctu = pc->h_ctu[i];
-                cost[ctu * 8 + piece] += (uint64_t)r->ssd + (uint64_t)lambda * (uint64_t)r->sum;
-                if (r->sum > 0) len[ctu * 8 + piece] += 2 + nn;
+            const int rec_len = 2 + pc->tu * pc->tu;
+            const hb_tu_result *r = res[p][c];
+            const int32_t *ctu_of = pc->h_ctu;
+            /* TUs arrive in raster order: runs of consecutive TUs share a CTU, so accumulate in registers and flush per run */
+            int i = 0;
+            while (i < pc->n_tus) {
+                const int ctu = ctu_of[i];
+                uint64_t acc = 0; int32_t l = 0;
+                for (; i < pc->n_tus && ctu_of[i] == ctu; i++) {
+                    acc += (uint64_t)r[i].ssd + (uint64_t)((int64_t)lambda * r[i].sum);
+                    l += r[i].sum > 0 ? rec_len : 0;
+                }
+                cost[ctu * 8 + piece] += acc;
+                len[ctu * 8 + piece] += l;
             }
         }
     int32_t off = 0;
