@@ -402,7 +402,7 @@ int hb_me_search(hb_ctx *ctx, const hb_frame *cur, const hb_frame *ref, const hb
         const int cnt = start_of[s + 1] - start_of[s];
         if (!cnt) continue;
         crc = hbk_me_search(&cur->d, &ref->d, sizes[s], (const hbd_me_job *)d_jobs + start_of[s], cnt, (const hb_me_result *)d_par,
-                            (hb_me_result *)d_res, action, NULL, ctx->stream);
+                            (hb_me_result *)d_res, action, NULL, NULL, ctx->stream);
         ctx->launches++;
     }
     if (!crc) crc = hbc_d2h_async(h_res, d_res, sizeof(hb_me_result) * (size_t)n_jobs, ctx->stream);
@@ -453,7 +453,7 @@ int hb_mc_predict(hb_ctx *ctx, const hb_frame *ref, hb_frame *pred, const hb_mc_
     for (int s = 0; s < 4 && !crc; s++) {
         const int cnt = start_of[s + 1] - start_of[s];
         if (!cnt) continue;
-        crc = hbk_mc_predict(&ref->d, &pred->d, sizes[s], (const hbd_mc_pu *)d_pus + start_of[s], cnt, (const hb_me_result *)d_mv, ctx->stream);
+        crc = hbk_mc_predict(&ref->d, &pred->d, sizes[s], (const hbd_mc_pu *)d_pus + start_of[s], cnt, (const hb_me_result *)d_mv, 3, ctx->stream);
         ctx->launches++;
     }
     if (!crc) crc = hbc_stream_sync(ctx->stream);

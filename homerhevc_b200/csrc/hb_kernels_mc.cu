@@ -19,6 +19,7 @@ struct McArgs {
     int tiles_per_pu;      // (size/T)^2
     int tiles_per_row;     // size/T
     const hb_me_result *mvsrc;
+    int planes;            // bit 0 luma, bit 1 chroma
 };
 
 // generic separable prediction of a W x W tile at (x,y) of `ref` displaced by (ix,iy) whole samples with fractions
@@ -101,7 +102,9 @@ __global__ void __launch_bounds__(kMcWarps * 32) k_mc(const McArgs a)
     const hb_mv mv = a.mvsrc[pu.mv_idx].mv;
     const int x = pu.x + (ti % a.tiles_per_row) * T, y = pu.y + (ti / a.tiles_per_row) * T;
 
-    mc_tile<T, 8>(a.ref.p[0], a.pred.p[0], x, y, mv.x >> 2, mv.y >> 2, mv.x & 3, mv.y & 3, s_patch[warp], s_tmp[warp], lane);
+    if (a.planes & 1)
+        mc_tile<T, 8>(a.ref.p[0], a.pred.p[0], x, y, mv.x >> 2, mv.y >> 2, mv.x & 3, mv.y & 3, s_patch[warp], s_tmp[warp], lane);
+    if (!(a.planes & 2)) return;
     // chroma: eighth-sample units (hmr_motion_inter.c:1863-1867)
     mc_tile<T / 2, 4>(a.ref.p[1], a.pred.p[1], x >> 1, y >> 1, mv.x >> 3, mv.y >> 3, mv.x & 7, mv.y & 7, s_patch[warp], s_tmp[warp], lane);
     mc_tile<T / 2, 4>(a.ref.p[2], a.pred.p[2], x >> 1, y >> 1, mv.x >> 3, mv.y >> 3, mv.x & 7, mv.y & 7, s_patch[warp], s_tmp[warp], lane);
@@ -146,12 +149,12 @@ __global__ void k_narrow_plane(const int16_t *src, int src_stride, hbd_plane dst
 }  // namespace
 
 extern "C" int hbk_mc_predict(const hbd_frame *ref, const hbd_frame *pred, int size, const hbd_mc_pu *pus, int n_pus,
-                              const hb_me_result *mvsrc, void *stream)
+                              const hb_me_result *mvsrc, int planes, void *stream)
 {
     if (n_pus <= 0) return 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     McArgs a;
-    a.ref = *ref; a.pred = *pred; a.pus = pus; a.n_pus = n_pus; a.mvsrc = mvsrc;
+    a.ref = *ref; a.pred = *pred; a.pus = pus; a.n_pus = n_pus; a.mvsrc = mvsrc; a.planes = planes;
     const int T = size >= 16 ? 16 : 8;
     if (size != 8 && size != 16 && size != 32 && size != 64) return static_cast<int>(cudaErrorInvalidValue);
     a.tiles_per_row = size / T; a.tiles_per_pu = a.tiles_per_row * a.tiles_per_row;

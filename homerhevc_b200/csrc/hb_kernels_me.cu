@@ -16,6 +16,7 @@
 // 14-bit planes (fractions 0..3) are built from it with vector loads/stores, and every candidate is a vertical
 // sliding-window pass (one shared load per output sample, taps in registers) over a column strip per lane --
 // the same two-stage arithmetic as the reference's plane builders (:395, :442), sample for sample.
+#include <cstring>
 #include "hb_shim.h"
 #include "hb_dev_common.cuh"
 
@@ -35,6 +36,7 @@ struct MeArgs {
     hb_me_result *out;
     int action;
     const hbd_dyn_params *dyn;
+    hbd_plane pred;             // luma plane receiving the prediction of the winning vector (org == nullptr: not wanted)
 };
 
 template <int N> struct MeCfg {
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
 
     extern __shared__ __align__(16) uint8_t s_raw[];
     __shared__ uint32_t s_x[(G > 32) ? PUS : 1][2][NSEG][2];   // G > 32: [phase][segment]{partial SAD, cost of the segment's slot}
+    __shared__ uint32_t s_half[PUS][8];                        // SADs of the eight half-pel candidates (c_half order 1..8)
 
     const int group = threadIdx.x / G, gl = threadIdx.x % G, lane = threadIdx.x & 31;
     const int slot = gl / L, l = gl % L, seg = gl / SEG;
@@ -354,6 +357,7 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
             const int w = l + k * L;
             if (slot == 0) *reinterpret_cast<uint32_t *>(s_cur + (w / WPR) * N + (w % WPR) * 4) = cur[k];
         }
+        if (gl < 8) s_half[group][gl] = 0;
         group_barrier<G>(group, gmask);
 
         // one round: SADs of four sub-pel candidates at quarter-pel offsets (qx[s], qy[s]) in [-3,3]^2 from (ix,iy)
@@ -390,15 +394,64 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
             exchange(acc, 0u, sad, cst);
         };
 
+        // ---- half-pel stage.  The reference builds three planes ((0,2), (2,0), (2,2), :395-438) and reads each of them for
+        // two or four candidates shifted by one sample; here a lane walks one COLUMN of the horizontal plane T_0 or T_2 with an
+        // 8-row sliding window and feeds every filtered sample to all the candidates it belongs to:
+        //   T_0 column (N strips):   v = V2(T_0)            -> candidates (0,-2) and (0,+2)
+        //   T_2 column (N+1 strips): v = V2(T_2), u = round(T_2) -> (-2,-2) (+2,-2) (-2,+2) (+2,+2) and (-2,0) (+2,0)
+        // Partial SADs go to eight shared counters.
+        for (int strip = gl; strip < 2 * N + 1; strip += G) {
+            const bool t2 = strip >= N;
+            const int j = t2 ? strip - N : strip + 1;                 // plane column: x = ix - 1 + j (+ 1/2 for T_2)
+            const int16_t *pl = s_plane + (t2 ? 2 : 0) * Cfg::PLANE_ELEMS + j;
+            const bool use_l = j >= 1, use_r = t2 && j < N;           // block column j-1 (candidate x >= 0) / column j (x = -2)
+            uint32_t acc[6] = { 0, 0, 0, 0, 0, 0 };                   // {minus,L} {minus,R} {plus,L} {plus,R} {u,L} {u,R}
+            int win[8];
+#pragma unroll
+            for (int k = 0; k < 7; k++) win[k] = pl[k * TS];
+            int pcl = 0, pcr = 0;                                     // current samples of the previous block row
+            auto row_step = [&](int rho, int rr, bool has_row) {      // rho = plane row of the filtered sample (position rho - 1/2)
+                win[(rr + 7) & 7] = pl[(rho + 7) * TS];
+                const int s = hb_luma8<2>(win[rr & 7], win[(rr + 1) & 7], win[(rr + 2) & 7], win[(rr + 3) & 7], win[(rr + 4) & 7],
+                                          win[(rr + 5) & 7], win[(rr + 6) & 7], win[(rr + 7) & 7]);
+                const int v = __vimin_s32_relu((s + 2048 + (8192 << 6)) >> 12, 255);
+                int cl = 0, cr = 0;
+                if (has_row) {
+                    if (use_l) cl = s_cur[rho * N + j - 1];
+                    if (use_r) cr = s_cur[rho * N + j];
+                    if (use_l) acc[0] = __sad(v, cl, acc[0]);
+                    if (use_r) acc[1] = __sad(v, cr, acc[1]);
+                    if (t2) {
+                        const int u = __vimin_s32_relu((win[(rr + 4) & 7] + 8192 + 32) >> 6, 255);
+                        if (use_l) acc[4] = __sad(u, cl, acc[4]);
+                        if (use_r) acc[5] = __sad(u, cr, acc[5]);
+                    }
+                }
+                if (rho >= 1) {
+                    if (use_l) acc[2] = __sad(v, pcl, acc[2]);
+                    if (use_r) acc[3] = __sad(v, pcr, acc[3]);
+                }
+                pcl = cl; pcr = cr;
+            };
+            for (int r8 = 0; r8 < N; r8 += 8) {
+#pragma unroll
+                for (int rr = 0; rr < 8; rr++) row_step(r8 + rr, rr, true);
+            }
+            row_step(N, 0, false);                                    // the extra row only feeds the +2 candidates
+            // c_half order: 1 (0,-1) 2 (0,1) 3 (-1,0) 4 (1,0) 5 (-1,-1) 6 (1,-1) 7 (-1,1) 8 (1,1)
+            if (t2) {
+                if (use_l) { atomicAdd(&s_half[group][5], acc[0]); atomicAdd(&s_half[group][7], acc[2]); atomicAdd(&s_half[group][3], acc[4]); }
+                if (use_r) { atomicAdd(&s_half[group][4], acc[1]); atomicAdd(&s_half[group][6], acc[3]); atomicAdd(&s_half[group][2], acc[5]); }
+            } else {
+                atomicAdd(&s_half[group][0], acc[0]); atomicAdd(&s_half[group][1], acc[2]);
+            }
+        }
+        group_barrier<G>(group, gmask);
         int sbx = 0, sby = 0, bidx = 0;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {                  // candidate 0 is the integer position itself: never smaller
-            int qx[4], qy[4]; uint32_t sad[4];
-#pragma unroll
-            for (int s = 0; s < 4; s++) { qx[s] = c_half[1 + 4 * h + s][0] * 2; qy[s] = c_half[1 + 4 * h + s][1] * 2; }
-            subpel4(qx, qy, sad);
-#pragma unroll
-            for (int s = 0; s < 4; s++) if (sad[s] < cur_best) { cur_best = sad[s]; sbx = qx[s]; sby = qy[s]; bidx = 1 + 4 * h + s; }
+        for (int i = 1; i < 9; i++) {                      // candidate 0 is the integer position itself: never smaller
+            const uint32_t v = s_half[group][i - 1];
+            if (v < cur_best) { cur_best = v; sbx = c_half[i][0] * 2; sby = c_half[i][1] * 2; bidx = i; }
         }
         if (a.action & HB_ME_QUARTER) {
             const int hx = c_half[bidx][0], hy = c_half[bidx][1];
@@ -415,6 +468,33 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
         best_sad = cur_best;
         mvx = (ix << 2) + sbx; mvy = (iy << 2) + sby;
         subx = sbx; suby = sby;
+
+        // ---- optionally leave the luma prediction of the winner in the prediction plane: same two-stage samples that
+        // hmr_motion_compensation_luma (:1779) produces for this vector, taken from the planes already in shared memory
+        if (a.pred.org != nullptr) {
+            constexpr int SEGS = G / N, RPS = N / SEGS;            // row segments per column, rows per segment
+            const int fx = sbx & 3, fy = sby & 3, cb = sbx >> 2, rb = sby >> 2;
+            int t[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) t[k] = c_taps[fy][k];
+            const int c = gl % N, r0 = (gl / N) * RPS;
+            const int16_t *pl = s_plane + fx * Cfg::PLANE_ELEMS + (rb + 1 + r0) * TS + c + cb + 1;
+            uint8_t *dst = a.pred.org + (jy + r0) * a.pred.pitch + jx + c;
+            int win[8];
+#pragma unroll
+            for (int k = 0; k < 7; k++) win[k] = pl[k * TS];
+            for (int r8 = 0; r8 < RPS; r8 += 8) {
+#pragma unroll
+                for (int rr = 0; rr < 8; rr++) {
+                    const int r = r8 + rr;
+                    win[(rr + 7) & 7] = pl[(r + 7) * TS];
+                    int s2 = 2048 + (8192 << 6);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) s2 += t[k] * win[(rr + k) & 7];
+                    dst[r * a.pred.pitch] = static_cast<uint8_t>(__vimin_s32_relu(s2 >> 12, 255));
+                }
+            }
+        }
     }
 
     if (gl == 0) {
@@ -449,10 +529,12 @@ extern "C" int hbk_me_configure(void)
 }
 
 extern "C" int hbk_me_search(const hbd_frame *cur, const hbd_frame *ref, int size, const hbd_me_job *jobs, int n_jobs,
-                             const hb_me_result *parent, hb_me_result *out, int action, const hbd_dyn_params *dyn, void *stream)
+                             const hb_me_result *parent, hb_me_result *out, int action, const hbd_dyn_params *dyn, const hbd_frame *pred_out, void *stream)
 {
     if (n_jobs <= 0) return 0;
     MeArgs a;
+    memset(&a.pred, 0, sizeof a.pred);
+    if (pred_out && (action & HB_ME_HALF)) a.pred = pred_out->p[0];
     a.cur = cur->p[0]; a.ref = ref->p[0]; a.jobs = jobs; a.n_jobs = n_jobs; a.parent = parent; a.out = out; a.action = action; a.dyn = dyn;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     switch (size) {

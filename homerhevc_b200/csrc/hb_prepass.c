@@ -261,16 +261,18 @@ static int enqueue(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, int
     hb_ctx *ctx = pp->ctx;
     void *main_st = ctx->stream;
     int crc = 0, n = 0;
+    /* with sub-pel refinement on, the search kernel leaves the luma prediction of its winner itself; MC then does chroma only */
+    const int fused = (pp->cfg.me_action & HB_ME_HALF) != 0;
     for (int d = 0; d < N_DEPTH && !crc; d++) {
         if (!pp->n_valid[d]) continue;
         void *st = main_st;                      /* name used by PROF_MARK */
         PROF_MARK("me%d", 64 >> d);
         if (!crc) crc = hbk_me_search(&cur->d, &ref->d, 64 >> d, pp->d_jobs[d], pp->n_valid[d], d ? pp->d_me[d - 1] : NULL, pp->d_me[d],
-                                      pp->cfg.me_action, pp->d_dyn, main_st);
+                                      pp->cfg.me_action, pp->d_dyn, fused ? &pp->pred[d]->d : NULL, main_st);
         n++;
         if (prof) {
             PROF_MARK("mc%d", 64 >> d);
-            if (!crc) { crc = hbk_mc_predict(&ref->d, &pp->pred[d]->d, 64 >> d, pp->d_pus[d], pp->n_valid[d], pp->d_me[d], st); n++; }
+            if (!crc) { crc = hbk_mc_predict(&ref->d, &pp->pred[d]->d, 64 >> d, pp->d_pus[d], pp->n_valid[d], pp->d_me[d], fused ? 2 : 3, st); n++; }
             for (int p = 0; p < N_PASS && !crc; p++)
                 if (pass_depth(p) == d) crc = enqueue_tq(pp, cur, p, 0, 2, st, &n, prof);
             continue;
@@ -278,7 +280,7 @@ static int enqueue(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, int
         void *s0 = pp->side[d][0], *s1 = pp->side[d][1], *s2 = pp->side[d][2];
         crc = hbc_event_record(pp->ev_fork[d], main_st);
         if (!crc) crc = hbc_stream_wait_event(s0, pp->ev_fork[d]);
-        if (!crc) { crc = hbk_mc_predict(&ref->d, &pp->pred[d]->d, 64 >> d, pp->d_pus[d], pp->n_valid[d], pp->d_me[d], s0); n++; }
+        if (!crc) { crc = hbk_mc_predict(&ref->d, &pp->pred[d]->d, 64 >> d, pp->d_pus[d], pp->n_valid[d], pp->d_me[d], fused ? 2 : 3, s0); n++; }
         if (!crc) crc = hbc_event_record(pp->ev_mc[d], s0);
         if (!crc) crc = hbc_stream_wait_event(s1, pp->ev_mc[d]);
         if (!crc) crc = enqueue_tq(pp, cur, d, 0, 0, s0, &n, 0);

@@ -87,11 +87,12 @@ typedef struct hbd_me_job {       /* one PU, device layout */
 } hbd_me_job;
 int hbk_me_configure(void);   /* once per device, before the first search launch */
 int hbk_me_search(const hbd_frame *cur, const hbd_frame *ref, int size, const hbd_me_job *jobs, int n_jobs,
-                  const hb_me_result *parent, hb_me_result *out, int action, const hbd_dyn_params *dyn, void *stream);
+                  const hb_me_result *parent, hb_me_result *out, int action, const hbd_dyn_params *dyn,
+                  const hbd_frame *pred_out /* NULL, or receives the luma prediction of every winner (needs HB_ME_HALF) */, void *stream);
 
 typedef struct hbd_mc_pu { int32_t x, y; int32_t mv_idx; } hbd_mc_pu;   /* luma position; mv = mvsrc[mv_idx].mv */
 int hbk_mc_predict(const hbd_frame *ref, const hbd_frame *pred, int size, const hbd_mc_pu *pus, int n_pus,
-                   const hb_me_result *mvsrc, void *stream);
+                   const hb_me_result *mvsrc, int planes /* bit 0 luma, bit 1 chroma */, void *stream);
 
 typedef struct hbd_tq_args {
     hbd_plane cur, pred, rec;     /* planes of the component being coded */
