@@ -188,6 +188,7 @@ void hb_ctx_destroy(hb_ctx *ctx)
     if (ctx->d_flag) hbc_free(ctx->d_flag);
     if (ctx->ev[0]) hbc_event_destroy(ctx->ev[0]);
     if (ctx->ev[1]) hbc_event_destroy(ctx->ev[1]);
+    if (ctx->ev_sync) hbc_event_destroy(ctx->ev_sync);
     if (ctx->stream) hbc_stream_destroy(ctx->stream);
     pthread_mutex_destroy(&ctx->lock);
     free(ctx);
@@ -200,6 +201,17 @@ int hb_ctx_sync(hb_ctx *ctx)
     return rc ? hb_cuda_fail(rc, "hb_ctx_sync") : HB_OK;
 }
 void *hb_ctx_stream(hb_ctx *ctx) { return ctx ? ctx->stream : NULL; }
+
+/* everything queued on `waiter` after this call starts only when everything queued so far on `signaler` has finished */
+int hb_ctx_wait(hb_ctx *waiter, hb_ctx *signaler)
+{
+    int rc;
+    if (!waiter || !signaler) return hb_fail(HB_ERR_ARG, "hb_ctx_wait: NULL context");
+    if (!signaler->ev_sync && (rc = hbc_event_create_notiming(&signaler->ev_sync))) return hb_cuda_fail(rc, "hb_ctx_wait: event");
+    if ((rc = hbc_event_record(signaler->ev_sync, signaler->stream)) || (rc = hbc_stream_wait_event(waiter->stream, signaler->ev_sync)))
+        return hb_cuda_fail(rc, "hb_ctx_wait");
+    return HB_OK;
+}
 uint64_t hb_ctx_launch_count(hb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int hb_timer_begin(hb_ctx *ctx)

@@ -14,6 +14,7 @@ struct hb_ctx {
     int device;
     void *stream;
     void *ev[2];
+    void *ev_sync;                    /* hb_ctx_wait */
     pthread_mutex_t lock;             /* serialises users of the scratch buffers */
     uint16_t *d_scan;                 /* device tables, see hb_tab_*_off */
     int32_t *d_q, *d_dq;

@@ -101,6 +101,7 @@ def load_library():
     L.hb_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
     L.hb_ctx_destroy.argtypes = [C.c_void_p]
     L.hb_ctx_sync.argtypes = [C.c_void_p]
+    L.hb_ctx_wait.argtypes = [C.c_void_p, C.c_void_p]
     L.hb_ctx_stream.restype = C.c_void_p
     L.hb_ctx_stream.argtypes = [C.c_void_p]
     L.hb_ctx_launch_count.restype = C.c_uint64
@@ -250,6 +251,10 @@ class Context:
 
     def sync(self):
         _check(self.L.hb_ctx_sync(self.h), "hb_ctx_sync")
+
+    def wait(self, other):
+        """work queued on this context from now on starts after everything queued so far on `other`"""
+        _check(self.L.hb_ctx_wait(self.h, other.h), "hb_ctx_wait")
 
     def launch_count(self):
         return int(self.L.hb_ctx_launch_count(self.h))

@@ -42,6 +42,7 @@ void        hb_ctx_destroy(hb_ctx *ctx);
 const char *hb_last_error(void);                       /* thread-local text of the last failure */
 int         hb_ctx_sync(hb_ctx *ctx);                  /* wait for everything queued on the context's stream */
 void       *hb_ctx_stream(hb_ctx *ctx);                /* the cudaStream_t work is queued on (for interop/timing) */
+int         hb_ctx_wait(hb_ctx *waiter, hb_ctx *signaler); /* order two contexts' streams on the device (no host wait) */
 uint64_t    hb_ctx_launch_count(hb_ctx *ctx);          /* kernels launched so far through this context */
 /* device-side stopwatch on the context's stream (CUDA events): begin, ..., end -> milliseconds */
 int         hb_timer_begin(hb_ctx *ctx);
