@@ -142,6 +142,52 @@ def run_reference(args, w, h, rank, world):
     print(json.dumps(line))
 
 
+def run_bands(args, w, h, rank, world, local, torch, dist, hb, synth, barrier):
+    """strong scaling of ONE stream of frames: every GPU owns a CTU-row band; per frame the reference rows a band needs from
+    its neighbours (68 luma / 36 chroma rows per side) are exchanged over NCCL, then the band's pre-pass runs"""
+    from homerhevc_b200 import bands
+    ctx = hb.Context(local)
+    tex = synth.make_texture(w, h)
+    n_pairs = 4
+    host = [synth.make_frame(tex, w, h, n) for n in range(n_pairs + 1)]
+    frames = [hb.Frame(ctx, w, h) for _ in range(n_pairs + 1)]
+    for f, p in zip(frames, host):
+        f.upload_u8(*p)
+    ctu_rows = (h + 63) // 64
+    row0, nrows = bands.band_ctu_rows(ctu_rows, world, rank)
+    pp = hb.Prepass(ctx, w, h, qp=QP, use_graph=1, band=(row0, nrows))
+    ex = bands.FrameHaloExchanger(torch, dist, ctx, w, h, world, rank, torch.device("cuda", local)) if world > 1 else None
+
+    def step(i):
+        j = i % n_pairs
+        if ex:
+            ex.exchange(frames[j])            # the reference of this frame: halos from the neighbours over NVLink
+        pp.run(frames[j + 1], frames[j], AVG_DIST)
+
+    for i in range(max(args.warmup, n_pairs)):
+        step(i)
+    ctx.sync()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    ctx.sync()
+    barrier()
+    ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    if rank == 0:
+        print(json.dumps({"metric": "ME+TQ frames/s", "value": args.steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "u8 samples, int16 residual/levels, int32 accumulate", "data": "synthetic",
+                          "config": {"workload": workload_name(args, w, h), "parallelism": f"ctu-row bands x{world}, NCCL halo exchange",
+                                     "halo_rows": {"luma": bands.HALO_LUMA, "chroma": bands.HALO_CHROMA},
+                                     "halo_bytes_sent_per_frame_rank0": ex.bytes_per_exchange if ex else 0,
+                                     "timing": "wall clock between device-synchronised barriers (host drives the NCCL exchange)"}}))
+
+
 def workload_name(args, w, h):
     return f"{w}x{h} IPPP quarter-pel ME (PU 64/32/16/8) + MC + inter T/Q (TU 32/32/16/8/4), fixed QP {QP}, synthetic YUV420"
 
@@ -154,6 +200,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="gops", choices=["gops", "bands"],
+                    help="gops: independent GOP streams per GPU (default, weak scaling); bands: one frame split into CTU-row bands "
+                         "across the GPUs with an NCCL halo exchange of the reference (BASELINE.json configs[3], strong scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w, h = WORKLOADS[args.workload]
@@ -180,6 +229,12 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.mode == "bands":
+        run_bands(args, w, h, rank, world, local, torch, dist, hb, synth, barrier)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     ctx = hb.Context(local)
     tex = synth.make_texture(w, h)

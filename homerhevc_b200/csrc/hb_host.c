@@ -353,6 +353,38 @@ int hb_frame_download_u8(hb_ctx *ctx, const hb_frame *f, uint8_t *y, int ys, uin
     return rc ? hb_cuda_fail(rc, "hb_frame_download_u8") : HB_OK;
 }
 
+/* Rows [row0, row0+n_rows) of one plane <-> a tight device buffer (width bytes per row), on the context's stream.  This is
+ * what a CTU-row band exchanges with its neighbours: the caller moves the tight buffer between GPUs (NCCL send/recv or a peer
+ * copy) and imports it on the other side; hb_frame_pad then refreshes the replicated border. */
+int hb_frame_export_rows(hb_ctx *ctx, const hb_frame *f, int plane, int row0, int n_rows, void *dev_dst)
+{
+    if (!ctx || !f || !dev_dst || plane < 0 || plane > 2) return hb_fail(HB_ERR_ARG, "hb_frame_export_rows: bad argument");
+    const hbd_plane *p = &f->d.p[plane];
+    if (row0 < 0 || n_rows < 0 || row0 + n_rows > p->h) return hb_fail(HB_ERR_ARG, "hb_frame_export_rows: rows %d..%d outside the plane", row0, row0 + n_rows);
+    if (!n_rows) return HB_OK;
+    hbc_set_device(ctx->device);
+    const int rc = hbc_d2d_2d_async(dev_dst, (size_t)p->w, p->org + (size_t)row0 * p->pitch, (size_t)p->pitch, (size_t)p->w, (size_t)n_rows, ctx->stream);
+    return rc ? hb_cuda_fail(rc, "hb_frame_export_rows") : HB_OK;
+}
+int hb_frame_import_rows(hb_ctx *ctx, hb_frame *f, int plane, int row0, int n_rows, const void *dev_src)
+{
+    if (!ctx || !f || !dev_src || plane < 0 || plane > 2) return hb_fail(HB_ERR_ARG, "hb_frame_import_rows: bad argument");
+    const hbd_plane *p = &f->d.p[plane];
+    if (row0 < 0 || n_rows < 0 || row0 + n_rows > p->h) return hb_fail(HB_ERR_ARG, "hb_frame_import_rows: rows %d..%d outside the plane", row0, row0 + n_rows);
+    if (!n_rows) return HB_OK;
+    hbc_set_device(ctx->device);
+    const int rc = hbc_d2d_2d_async(p->org + (size_t)row0 * p->pitch, (size_t)p->pitch, dev_src, (size_t)p->w, (size_t)p->w, (size_t)n_rows, ctx->stream);
+    return rc ? hb_cuda_fail(rc, "hb_frame_import_rows") : HB_OK;
+}
+int hb_frame_pad(hb_ctx *ctx, hb_frame *f)
+{
+    if (!ctx || !f) return hb_fail(HB_ERR_ARG, "hb_frame_pad: NULL argument");
+    hbc_set_device(ctx->device);
+    const int rc = hbk_pad_frame(&f->d, ctx->stream);
+    ctx->launches += 3;
+    return rc ? hb_cuda_fail(rc, "hb_frame_pad") : HB_OK;
+}
+
 /* ------------------------------------------------------------------ batched jobs (host arrays in, host arrays out) */
 static double mv_cost_weight(int qp, double avg_dist)     /* calc_mv_correction, hmr_common.h:53 */
 {

@@ -38,6 +38,10 @@ extern "C" int hbc_h2d_2d_async(void *dst, size_t dpitch, const void *src, size_
 {
     return static_cast<int>(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, rows, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
 }
+extern "C" int hbc_d2d_2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t rows, void *stream)
+{
+    return static_cast<int>(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, rows, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+}
 extern "C" int hbc_d2h_2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t rows, void *stream)
 {
     return static_cast<int>(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, rows, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));

@@ -38,6 +38,7 @@ int  hbc_host_devptr(void *host, void **dev);         /* device alias of mapped 
 int  hbc_memset_async(void *p, int v, size_t bytes, void *stream);
 int  hbc_h2d_async(void *dst, const void *src, size_t bytes, void *stream);
 int  hbc_d2h_async(void *dst, const void *src, size_t bytes, void *stream);
+int  hbc_d2d_2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t rows, void *stream);
 int  hbc_h2d_2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t rows, void *stream);
 int  hbc_d2h_2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t rows, void *stream);
 int  hbc_event_create(void **ev);

@@ -140,6 +140,9 @@ def load_library():
     L.hb_frame_upload_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     L.hb_frame_upload_i16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     L.hb_frame_download_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.hb_frame_export_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.hb_frame_import_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.hb_frame_pad.argtypes = [C.c_void_p, C.c_void_p]
     # section C
     L.hb_me_search.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(MeJob), C.c_int, C.POINTER(MeResult), C.c_int,
                                C.c_double, C.c_int, C.POINTER(MeResult)]
@@ -322,6 +325,15 @@ class Frame:
             assert a.dtype == np.int16 and a.ndim == 2 and a.strides[1] == 2
         _check(self.ctx.L.hb_frame_upload_i16(self.ctx.h, self.h, y.ctypes.data, y.strides[0] // 2, u.ctypes.data,
                                               u.strides[0] // 2, v.ctypes.data, v.strides[0] // 2), "hb_frame_upload_i16")
+
+    def export_rows(self, plane, row0, n_rows, dev_ptr):
+        _check(self.ctx.L.hb_frame_export_rows(self.ctx.h, self.h, plane, row0, n_rows, dev_ptr), "hb_frame_export_rows")
+
+    def import_rows(self, plane, row0, n_rows, dev_ptr):
+        _check(self.ctx.L.hb_frame_import_rows(self.ctx.h, self.h, plane, row0, n_rows, dev_ptr), "hb_frame_import_rows")
+
+    def pad(self):
+        _check(self.ctx.L.hb_frame_pad(self.ctx.h, self.h), "hb_frame_pad")
 
     def download(self):
         y = np.zeros((self.h_px, self.w), np.uint8)

@@ -128,6 +128,15 @@ int  hb_frame_upload_i16(hb_ctx *ctx, hb_frame *f, const int16_t *y, int y_strid
 int  hb_frame_download_u8(hb_ctx *ctx, const hb_frame *f, uint8_t *y, int y_stride, uint8_t *u, int u_stride,
                           uint8_t *v, int v_stride);
 
+/* CTU-row bands on several GPUs: rows [row0, row0+n_rows) of a plane <-> a tight device buffer (plane width bytes per row).
+ * The caller moves that buffer to the neighbour GPU (NCCL send/recv, peer copy) and imports it there; hb_frame_pad
+ * refreshes the replicated border afterwards.  A band needs 64 (search) + 4 (8-tap) luma rows and 36 chroma rows per side. */
+#define HB_HALO_LUMA 68
+#define HB_HALO_CHROMA 36
+int  hb_frame_export_rows(hb_ctx *ctx, const hb_frame *f, int plane, int row0, int n_rows, void *dev_dst);
+int  hb_frame_import_rows(hb_ctx *ctx, hb_frame *f, int plane, int row0, int n_rows, const void *dev_src);
+int  hb_frame_pad(hb_ctx *ctx, hb_frame *f);
+
 /* ------------------------------------------------------------------ C. batched jobs on resident frames ----- */
 typedef struct hb_mv { int32_t x, y; } hb_mv;                 /* quarter-pel units (motion_vector_t, hmr_private.h:712) */
 

@@ -265,3 +265,19 @@ def test_host_decision_flow_gather(ctx):
             assert np.array_equal(sel2, sel) and np.array_equal(off2, off)
     assert used == {0, 1, 2, 3, 4}
     pp.close(); fc.close(); fr.close()
+
+
+def test_bands_across_gpus_with_nccl_halo_exchange(ctx):
+    """configs[3]: CTU-row bands on two GPUs, reference halos swapped over NCCL; needs >= 2 devices (skipped on one)"""
+    import os
+    import subprocess
+    import sys
+    L = hb.load_library()
+    if L.hb_device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29641", os.path.join(root, "tools", "band_check.py"), "1280", "720"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
+    assert "mismatches=0" in out.stdout

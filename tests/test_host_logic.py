@@ -42,3 +42,53 @@ def test_multi_rank_timing_reduction_gloo(tmp_path):
                           "--master-port", "29617", str(script)], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "MAX [15.0, 20.0]" in out.stdout and "VALUE 13333.3" in out.stdout
+
+
+_BAND_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["HB_ROOT"])
+from homerhevc_b200 import bands
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+w, h = 256, 512 + 40                      # 9 CTU rows, the last one partial
+ctu_rows = (h + 63) // 64
+rng = np.random.default_rng(5)
+truth = [rng.integers(0, 256, (h, w), dtype=np.uint8), rng.integers(0, 256, (h // 2, w // 2), dtype=np.uint8),
+         rng.integers(0, 256, (h // 2, w // 2), dtype=np.uint8)]
+planes = []
+for c, t in enumerate(truth):
+    y0, y1 = bands.band_sample_rows(h, ctu_rows, world, rank, chroma=c > 0)
+    m = np.zeros_like(t); m[y0:y1] = t[y0:y1]
+    planes.append(torch.from_numpy(m))
+n_ops = bands.exchange_halos(dist, planes, h, ctu_rows, world, rank)
+ok = True
+for c, t in enumerate(truth):
+    halo = bands.HALO_CHROMA if c else bands.HALO_LUMA
+    y0, y1 = bands.band_sample_rows(h, ctu_rows, world, rank, chroma=c > 0)
+    lo, hi = max(0, y0 - halo), min(t.shape[0], y1 + halo)
+    ok &= bool(np.array_equal(planes[c].numpy()[lo:hi], t[lo:hi]))
+    # every CTU row belongs to exactly one band
+cover = sum(bands.band_ctu_rows(ctu_rows, world, r)[1] for r in range(world))
+res = torch.tensor([int(ok), n_ops, cover])
+out = [torch.zeros_like(res) for _ in range(world)]
+dist.all_gather(out, res)
+if rank == 0:
+    print("BANDS", [o.tolist() for o in out], ctu_rows)
+dist.destroy_process_group()
+'''
+
+
+def test_band_halo_exchange_gloo(tmp_path):
+    """the CTU-row band plan and neighbour halo exchange (the N>1 data path of configs[3]) over gloo, world sizes 2 and 3"""
+    script = tmp_path / "b.py"
+    script.write_text(_BAND_WORKER)
+    for world, port in ((2, 29631), (3, 29633)):
+        env = dict(os.environ, HB_ROOT=ROOT)
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
+                              "127.0.0.1", "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+        assert out.returncode == 0, out.stderr[-2000:]
+        line = [l for l in out.stdout.splitlines() if l.startswith("BANDS")][0]
+        oks = eval(line[len("BANDS "):line.rindex("]") + 1])
+        assert all(o[0] == 1 for o in oks), line
+        assert all(o[2] == 9 for o in oks), line
+        assert oks[0][1] == 3 * 2 and (world == 2 or oks[1][1] == 3 * 4), line          # edge ranks: send+recv per plane; inner: both sides
