@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=8, help="independent GOP streams in flight per GPU")
     ap.add_argument("--mode", default="gops", choices=["gops", "bands"],
                     help="gops: independent GOP streams per GPU (default, weak scaling); bands: one frame split into CTU-row bands "
                          "across the GPUs with an NCCL halo exchange of the reference (BASELINE.json configs[3], strong scaling)")
@@ -258,7 +259,7 @@ def main():
 
     # N_SLOTS independent streams of frames (GOPs, BASELINE.json configs[4]) are in flight per GPU: each has its own context
     # (CUDA stream), pre-pass plan and output buffers, so the search chain of one frame overlaps the T/Q tail of another
-    N_SLOTS, LAMBDA = 4, 60
+    N_SLOTS, LAMBDA = max(1, args.streams), 60
     slots = []
     for k in range(N_SLOTS):
         c = hb.Context(local)
@@ -307,13 +308,8 @@ def main():
     # N_SLOTS independent streams of frames (GOPs) are in flight per GPU so that copies, kernels and the host step overlap.
     def one_frame(sl, i):
         j = i % N_RESIDENT
-        sl["cur"].upload_u8(*pinned[j + 1]); sl["ref"].upload_u8(*pinned[j])
-        sl["pp"].run(sl["cur"], sl["ref"], AVG_DIST)
-        sl["pp"].fetch_tables(sl["tables"])
-        sl["ctx"].sync()
-        sl["pp"].select(sl["tables"], LAMBDA, sl["sel"], sl["off"])          # host: depth per CTU from the cost tables
-        sl["d2h"] += sl["pp"].gather(sl["sel"], sl["off"], sl["out"]) + sl["tables"].nbytes
-        sl["ctx"].sync()
+        sl["d2h"] += sl["pp"].process_frame(sl["cur"], sl["ref"], pinned[j + 1], pinned[j], AVG_DIST, LAMBDA, sl["tables"], sl["sel"],
+                                            sl["off"], sl["out"]) + sl["tables"].nbytes
 
     def run_e2e(n):
         # one host thread per in-flight stream (the reference runs one pthread per encoder engine, hmr_encoder_lib.c:1647):
@@ -371,6 +367,26 @@ def main():
         achieved = abytes[top] / (prof[top] * 1e-3) / 1e9
         step_bytes = sum(abytes.values())
         total_prof = sum(prof.values())
+        # instruction-issue roofline (the governing one): warp instructions per frame counted by ncu
+        # (profiles/inst_r01_v10.json, 1080p; scaled by the pixel count for the other sizes) against SMs x 4 schedulers x clock
+        issue, traffic = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "inst_r01_v10.json")) as f:
+                prof_counts = json.load(f)
+            scale = (w * h) / (1920 * 1080)
+            inst_per_frame = prof_counts["total_warp_inst"] * scale
+            sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+            peak_issue = 148 * 4 * sm_hz
+            fps_gpu = N_SLOTS * args.steps / (ms * 1e-3)
+            issue = {"bound": "warp-instruction issue", "achieved": inst_per_frame * fps_gpu, "peak": peak_issue, "unit": "warp-inst/s",
+                     "frac": inst_per_frame * fps_gpu / peak_issue, "warp_inst_per_frame": inst_per_frame,
+                     "source": "ncu smsp__inst_executed.sum per kernel, profiles/inst_r01_v10.json" + ("" if scale == 1 else " (scaled by pixel count)")}
+            if scale == 1:
+                for kk in prof_counts["kernels"]:
+                    if kk["kernel"].startswith("MeArgs") and kk["grid"].startswith("(1013") and top == "me8":
+                        traffic = kk["dram_read_bytes"] + kk["dram_write_bytes"]
+        except Exception:
+            pass
         line = {
             "metric": "ME+TQ frames/s", "value": world * N_SLOTS * args.steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -388,10 +404,11 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms": prof[top], "kernel_share_of_step": prof[top] / total_prof,
                          "step_algorithmic_bytes": step_bytes,
                          "step_frac": N_SLOTS * step_bytes / (ms / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+            "issue_roofline": issue,
             "kernels_ms": {k: round(v, 5) for k, v in prof.items()},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -622,3 +622,25 @@ int hb_prepass_gather(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_off
     if (bytes_out) *bytes_out = need;
     return HB_OK;
 }
+
+/* The whole per-frame host flow in one blocking call (what one encoder thread does per frame): upload cur and ref from
+ * (pinned) host planes, run the pre-pass, fetch the cost tables, let the stand-in decision pick a depth per CTU, gather and
+ * fetch the reconstruction + coded levels of that choice.  tables / out must be pinned; sel has num_ctus bytes, ctu_off
+ * num_ctus + 1 entries.  Tight plane pitches (width, width/2). */
+int hb_prepass_process_frame(hb_prepass *pp, hb_frame *cur, hb_frame *ref, const uint8_t *const cur_planes[3], const uint8_t *const ref_planes[3],
+                             double avg_dist, int lambda, void *tables, size_t tables_cap, uint8_t *sel, int32_t *ctu_off,
+                             void *out, size_t out_cap, size_t *out_bytes)
+{
+    int rc;
+    if (!pp || !cur || !ref || !cur_planes || !ref_planes) return hb_fail(HB_ERR_ARG, "hb_prepass_process_frame: NULL argument");
+    hb_ctx *ctx = pp->ctx;
+    const int w = pp->w;
+    if ((rc = hb_frame_upload_u8(ctx, cur, cur_planes[0], w, cur_planes[1], w / 2, cur_planes[2], w / 2)) != HB_OK) return rc;
+    if ((rc = hb_frame_upload_u8(ctx, ref, ref_planes[0], w, ref_planes[1], w / 2, ref_planes[2], w / 2)) != HB_OK) return rc;
+    if ((rc = hb_prepass_run(pp, cur, ref, avg_dist)) != HB_OK) return rc;
+    if ((rc = hb_prepass_fetch_tables(pp, tables, tables_cap)) != HB_OK) return rc;
+    if ((rc = hb_ctx_sync(ctx)) != HB_OK) return rc;
+    if ((rc = hb_prepass_select(pp, tables, lambda, sel, ctu_off)) != HB_OK) return rc;
+    if ((rc = hb_prepass_gather(pp, sel, ctu_off, out, out_cap, out_bytes)) != HB_OK) return rc;
+    return hb_ctx_sync(ctx);
+}

@@ -175,6 +175,8 @@ def load_library():
     L.hb_prepass_gather_bytes.restype = C.c_size_t
     L.hb_prepass_gather_bytes.argtypes = [C.c_void_p, C.c_void_p]
     L.hb_prepass_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.hb_prepass_process_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_double, C.c_int,
+                                           C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.hb_prepass_pred.restype = C.c_void_p
     L.hb_prepass_pred.argtypes = [C.c_void_p, C.c_int]
     L.hb_prepass_recon.restype = C.c_void_p
@@ -441,6 +443,16 @@ class Prepass:
         n = C.c_size_t(0)
         _check(self.ctx.L.hb_prepass_gather(self.h, sel.ctypes.data, ctu_off.ctypes.data, pinned.ctypes.data, pinned.nbytes, C.byref(n)),
                "hb_prepass_gather")
+        return n.value
+
+    def process_frame(self, cur, ref, cur_planes, ref_planes, avg_dist, lam, tables, sel, ctu_off, out):
+        """upload -> pre-pass -> tables -> select -> gather as ONE blocking C call (releases the GIL for its whole duration)"""
+        cp = (C.c_void_p * 3)(*[p.ctypes.data for p in cur_planes])
+        rp = (C.c_void_p * 3)(*[p.ctypes.data for p in ref_planes])
+        n = C.c_size_t(0)
+        _check(self.ctx.L.hb_prepass_process_frame(self.h, cur.h, ref.h, cp, rp, avg_dist, lam, tables.ctypes.data, tables.nbytes,
+                                                   sel.ctypes.data, ctu_off.ctypes.data, out.ctypes.data, out.nbytes, C.byref(n)),
+               "hb_prepass_process_frame")
         return n.value
 
     def output_bytes(self):

@@ -230,6 +230,11 @@ size_t hb_prepass_gather_bytes(const hb_prepass *pp, const int32_t *ctu_off);
 /* out: recon Y,U,V tight planes, then per CTU (from ctu_off[i], int16 units) for Y,U,V the coded TUs in raster order:
  * { hdr_lo, hdr_hi, N*N levels }, hdr = plane << 28 | N << 16 | TU raster position inside the CTU */
 int  hb_prepass_gather(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_off, void *pinned_dst, size_t cap, size_t *bytes_out);
+/* the whole per-frame host flow as one blocking call: upload cur + ref (tight, pinned host planes) -> pre-pass -> cost tables ->
+ * hb_prepass_select -> gather -> results in `out` (pinned).  One encoder thread per in-flight stream calls this per frame. */
+int  hb_prepass_process_frame(hb_prepass *pp, hb_frame *cur, hb_frame *ref, const uint8_t *const cur_planes[3], const uint8_t *const ref_planes[3],
+                              double avg_dist, int lambda, void *tables, size_t tables_cap, uint8_t *sel, int32_t *ctu_off,
+                              void *out, size_t out_cap, size_t *out_bytes);
 const hb_frame *hb_prepass_pred(const hb_prepass *pp, int depth);     /* resident prediction of that depth */
 const hb_frame *hb_prepass_recon(const hb_prepass *pp, int pass);
 
