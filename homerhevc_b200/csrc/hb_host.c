@@ -292,7 +292,15 @@ void hb_frame_destroy(hb_frame *f)
 int hb_frame_width(const hb_frame *f) { return f ? f->w : 0; }
 int hb_frame_height(const hb_frame *f) { return f ? f->h : 0; }
 
+int hb_frame_upload_u8_ex(hb_ctx *ctx, hb_frame *f, const uint8_t *y, int ys, const uint8_t *u, int us, const uint8_t *v, int vs, int flags);
 int hb_frame_upload_u8(hb_ctx *ctx, hb_frame *f, const uint8_t *y, int ys, const uint8_t *u, int us, const uint8_t *v, int vs)
+{
+    return hb_frame_upload_u8_ex(ctx, f, y, ys, u, us, v, vs, 0);
+}
+
+/* flags: HB_UPLOAD_NO_BORDER skips the border replication -- enough for a CURRENT frame, whose samples are only ever read
+ * inside the picture (the search reads the border of the REFERENCE frame only) */
+int hb_frame_upload_u8_ex(hb_ctx *ctx, hb_frame *f, const uint8_t *y, int ys, const uint8_t *u, int us, const uint8_t *v, int vs, int flags)
 {
     const uint8_t *src[3] = { y, u, v };
     const int st[3] = { ys, us, vs };
@@ -303,7 +311,7 @@ int hb_frame_upload_u8(hb_ctx *ctx, hb_frame *f, const uint8_t *y, int ys, const
         const hbd_plane *p = &f->d.p[c];
         rc = hbc_h2d_2d_async(p->org, (size_t)p->pitch, src[c], (size_t)st[c], (size_t)p->w, (size_t)p->h, ctx->stream);
     }
-    if (!rc) { rc = hbk_pad_frame(&f->d, ctx->stream); ctx->launches += 3; }
+    if (!rc && !(flags & HB_UPLOAD_NO_BORDER)) { rc = hbk_pad_frame(&f->d, ctx->stream); ctx->launches += 1; }
     return rc ? hb_cuda_fail(rc, "hb_frame_upload_u8") : HB_OK;
 }
 
@@ -327,7 +335,7 @@ int hb_frame_upload_i16(hb_ctx *ctx, hb_frame *f, const int16_t *y, int ys, cons
         if (!rc) { rc = hbk_narrow_plane(d, p->w, *p, ctx->d_flag, ctx->stream); ctx->launches++; }
         off += (size_t)p->w * p->h;
     }
-    if (!rc) { rc = hbk_pad_frame(&f->d, ctx->stream); ctx->launches += 3; }
+    if (!rc) { rc = hbk_pad_frame(&f->d, ctx->stream); ctx->launches += 1; }
     if (!rc) rc = hbc_d2h_async(flag_h, ctx->d_flag, 4, ctx->stream);
     if (!rc) rc = hbc_memset_async(ctx->d_flag, 0, 4, ctx->stream);
     if (!rc) rc = hbc_stream_sync(ctx->stream);
@@ -381,7 +389,7 @@ int hb_frame_pad(hb_ctx *ctx, hb_frame *f)
     if (!ctx || !f) return hb_fail(HB_ERR_ARG, "hb_frame_pad: NULL argument");
     hbc_set_device(ctx->device);
     const int rc = hbk_pad_frame(&f->d, ctx->stream);
-    ctx->launches += 3;
+    ctx->launches += 1;
     return rc ? hb_cuda_fail(rc, "hb_frame_pad") : HB_OK;
 }
 

@@ -112,9 +112,10 @@ __global__ void __launch_bounds__(kMcWarps * 32) k_mc(const McArgs a)
 
 // ---- border replication of one plane (reference_picture_border_padding_ctu, hmr_encoder_lib.c:1723): every sample
 // outside the picture takes the nearest picture sample.
-__global__ void k_pad_plane(hbd_plane p)
+__global__ void k_pad_frame(hbd_frame f)
 {
-    const int W = p.w + 2 * p.pad, H = p.h + 2 * p.pad;
+    const hbd_plane p = f.p[blockIdx.y];                // one grid row per plane: a single launch pads Y, U and V
+    const int W = p.w + 2 * p.pad;
     const int n_side = 2 * p.pad * p.h;                 // left+right strips of the picture rows
     const int n_tb = 2 * p.pad * W;                     // top+bottom bands, full padded width
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_side + n_tb; i += gridDim.x * blockDim.x) {
@@ -122,14 +123,13 @@ __global__ void k_pad_plane(hbd_plane p)
         if (i < n_side) {
             const int r = i / (2 * p.pad), c = i % (2 * p.pad);
             py = p.pad + r;
-            px = c < p.pad ? c : p.w + c;               // c-pad+pad+w
+            px = c < p.pad ? c : p.w + c;
         } else {
             const int j = i - n_side, r = j / W;
             px = j % W;
             py = r < p.pad ? r : p.h + r;
         }
         const int sx = min(max(px - p.pad, 0), p.w - 1), sy = min(max(py - p.pad, 0), p.h - 1);
-        (void)H;
         p.org[(py - p.pad) * p.pitch + (px - p.pad)] = p.org[sy * p.pitch + sx];
     }
 }
@@ -168,11 +168,9 @@ extern "C" int hbk_mc_predict(const hbd_frame *ref, const hbd_frame *pred, int s
 extern "C" int hbk_pad_frame(const hbd_frame *f, void *stream)
 {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    for (int c = 0; c < 3; c++) {
-        const hbd_plane &p = f->p[c];
-        const int n = 2 * p.pad * p.h + 2 * p.pad * (p.w + 2 * p.pad);
-        k_pad_plane<<<(n + 255) / 256, 256, 0, s>>>(p);
-    }
+    const hbd_plane &p = f->p[0];
+    const int n = 2 * p.pad * p.h + 2 * p.pad * (p.w + 2 * p.pad);
+    k_pad_frame<<<dim3((n + 255) / 256, 3), 256, 0, s>>>(*f);
     return static_cast<int>(cudaGetLastError());
 }
 

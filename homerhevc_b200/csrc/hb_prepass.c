@@ -228,6 +228,12 @@ void hb_prepass_destroy(hb_prepass *pp)
 
 /* queue the kernels of one frame on the context's stream; returns a cudaError_t value */
 #define PROF_MARK(...) do { if (prof && !crc) { snprintf(pp->prof_name[n], sizeof pp->prof_name[n], __VA_ARGS__); crc = hbc_event_record(pp->prof_ev[n], st); } } while (0)
+/* motion compensation of depth d: chroma only when the search kernel already left the luma prediction */
+static int enqueue_mc(hb_prepass *pp, const hb_frame *ref, int d, int fused, void *st)
+{
+    return hbk_mc_predict(&ref->d, &pp->pred[d]->d, 64 >> d, pp->d_pus[d], pp->n_valid[d], pp->d_me[d], fused ? 2 : 3, st);
+}
+
 /* T/Q launches of one pass: planes c0..c1 on stream st */
 static int enqueue_tq(hb_prepass *pp, const hb_frame *cur, int p, int c0, int c1, void *st, int *n_io, int prof)
 {
@@ -272,7 +278,7 @@ static int enqueue(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, int
         n++;
         if (prof) {
             PROF_MARK("mc%d", 64 >> d);
-            if (!crc) { crc = hbk_mc_predict(&ref->d, &pp->pred[d]->d, 64 >> d, pp->d_pus[d], pp->n_valid[d], pp->d_me[d], fused ? 2 : 3, st); n++; }
+            if (!crc) { crc = enqueue_mc(pp, ref, d, fused, st); n++; }
             for (int p = 0; p < N_PASS && !crc; p++)
                 if (pass_depth(p) == d) crc = enqueue_tq(pp, cur, p, 0, 2, st, &n, prof);
             continue;
@@ -280,7 +286,7 @@ static int enqueue(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, int
         void *s0 = pp->side[d][0], *s1 = pp->side[d][1], *s2 = pp->side[d][2];
         crc = hbc_event_record(pp->ev_fork[d], main_st);
         if (!crc) crc = hbc_stream_wait_event(s0, pp->ev_fork[d]);
-        if (!crc) { crc = hbk_mc_predict(&ref->d, &pp->pred[d]->d, 64 >> d, pp->d_pus[d], pp->n_valid[d], pp->d_me[d], fused ? 2 : 3, s0); n++; }
+        if (!crc) { crc = enqueue_mc(pp, ref, d, fused, s0); n++; }
         if (!crc) crc = hbc_event_record(pp->ev_mc[d], s0);
         if (!crc) crc = hbc_stream_wait_event(s1, pp->ev_mc[d]);
         if (!crc) crc = enqueue_tq(pp, cur, d, 0, 0, s0, &n, 0);
@@ -635,7 +641,7 @@ int hb_prepass_process_frame(hb_prepass *pp, hb_frame *cur, hb_frame *ref, const
     if (!pp || !cur || !ref || !cur_planes || !ref_planes) return hb_fail(HB_ERR_ARG, "hb_prepass_process_frame: NULL argument");
     hb_ctx *ctx = pp->ctx;
     const int w = pp->w;
-    if ((rc = hb_frame_upload_u8(ctx, cur, cur_planes[0], w, cur_planes[1], w / 2, cur_planes[2], w / 2)) != HB_OK) return rc;
+    if ((rc = hb_frame_upload_u8_ex(ctx, cur, cur_planes[0], w, cur_planes[1], w / 2, cur_planes[2], w / 2, HB_UPLOAD_NO_BORDER)) != HB_OK) return rc;
     if ((rc = hb_frame_upload_u8(ctx, ref, ref_planes[0], w, ref_planes[1], w / 2, ref_planes[2], w / 2)) != HB_OK) return rc;
     if ((rc = hb_prepass_run(pp, cur, ref, avg_dist)) != HB_OK) return rc;
     if ((rc = hb_prepass_fetch_tables(pp, tables, tables_cap)) != HB_OK) return rc;

@@ -123,6 +123,9 @@ int  hb_frame_height(const hb_frame *f);
  * Uploads finish with the border replication (hmr_encoder_lib.c:1723). */
 int  hb_frame_upload_u8(hb_ctx *ctx, hb_frame *f, const uint8_t *y, int y_stride, const uint8_t *u, int u_stride,
                         const uint8_t *v, int v_stride);
+#define HB_UPLOAD_NO_BORDER 1   /* a current frame is only read inside the picture: skip the border replication */
+int  hb_frame_upload_u8_ex(hb_ctx *ctx, hb_frame *f, const uint8_t *y, int y_stride, const uint8_t *u, int u_stride,
+                           const uint8_t *v, int v_stride, int flags);
 int  hb_frame_upload_i16(hb_ctx *ctx, hb_frame *f, const int16_t *y, int y_stride, const int16_t *u, int u_stride,
                          const int16_t *v, int v_stride);
 int  hb_frame_download_u8(hb_ctx *ctx, const hb_frame *f, uint8_t *y, int y_stride, uint8_t *u, int u_stride,
