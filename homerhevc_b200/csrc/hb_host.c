@@ -608,3 +608,86 @@ done:
     if (crc) return hb_cuda_fail(crc, "hb_tq_encode");
     return rc;
 }
+
+/* Intra TUs once their prediction exists: encode_intra_cu after the prediction step (hmr_motion_intra.c:1023-1069) and its
+ * chroma counterpart (hmr_motion_intra_chroma.c:340-365).  `pred` holds the intra prediction (from the host, whose intra
+ * predictors walk reconstructed neighbours); everything after it runs here. */
+int hb_tq_encode_intra(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_frame *recon, const hb_intra_tu_job *jobs, int n_jobs,
+                       int is_islice, int sign_hiding, double chroma_weight, int16_t *coeffs, hb_tu_result *results)
+{
+    int rc = HB_OK, crc = 0;
+    if (!ctx || !cur || !pred || !recon || !jobs || !coeffs || !results || n_jobs < 0) return hb_fail(HB_ERR_ARG, "hb_tq_encode_intra: bad argument");
+    if (n_jobs == 0) return HB_OK;
+    size_t total = 0;
+    for (int i = 0; i < n_jobs; i++) {
+        const hb_intra_tu_job *j = &jobs[i];
+        if (j->comp < 0 || j->comp > 2 || (j->size != 4 && j->size != 8 && j->size != 16 && j->size != 32) || j->qp < 0 || j->qp > 51 ||
+            j->x < 0 || j->y < 0 || (j->x & 3) || j->x + j->size > cur->d.p[j->comp].w || j->y + j->size > cur->d.p[j->comp].h ||
+            (j->comp && j->size == 32) || j->scan_mode < HB_SCAN_HOR || j->scan_mode > HB_SCAN_DIAG || (j->size > 8 && j->scan_mode != HB_SCAN_DIAG))
+            return hb_fail(HB_ERR_ARG, "hb_tq_encode_intra: job %d is invalid", i);
+        total += (size_t)j->size * j->size;
+    }
+    hbc_set_device(ctx->device);
+    pthread_mutex_lock(&ctx->lock);
+    void *d_xy, *h_xy, *d_co, *h_co, *d_rs, *h_rs;
+    int *order = (int *)malloc(sizeof(int) * (size_t)n_jobs);
+    char *done_flag = (char *)calloc((size_t)n_jobs, 1);
+    size_t *coeff_off = (size_t *)malloc(sizeof(size_t) * (size_t)n_jobs);
+    if (!order || !done_flag || !coeff_off) { rc = hb_fail(HB_ERR_NOMEM, "hb_tq_encode_intra: out of memory"); goto done; }
+    if ((rc = hb_scratch(ctx, 0, sizeof(int32_t) * 2 * (size_t)n_jobs, &d_xy, &h_xy)) != HB_OK) goto done;
+    if ((rc = hb_scratch(ctx, 1, sizeof(int16_t) * total, &d_co, &h_co)) != HB_OK) goto done;
+    if ((rc = hb_scratch(ctx, 2, sizeof(hb_tu_result) * (size_t)n_jobs, &d_rs, &h_rs)) != HB_OK) goto done;
+    { size_t o = 0; for (int i = 0; i < n_jobs; i++) { coeff_off[i] = o; o += (size_t)jobs[i].size * jobs[i].size; } }
+    int packed = 0;
+    size_t packed_coeff = 0;
+    for (int i = 0; i < n_jobs && !crc; i++) {
+        if (done_flag[i]) continue;
+        const hb_intra_tu_job key = jobs[i];
+        const int g0 = packed;
+        const size_t c0 = packed_coeff;
+        int32_t *xy = (int32_t *)h_xy;
+        for (int k = i; k < n_jobs; k++) {
+            if (done_flag[k] || jobs[k].comp != key.comp || jobs[k].size != key.size || jobs[k].qp != key.qp || jobs[k].scan_mode != key.scan_mode) continue;
+            done_flag[k] = 1; order[packed] = k;
+            xy[2 * packed] = jobs[k].x; xy[2 * packed + 1] = jobs[k].y;
+            packed++; packed_coeff += (size_t)key.size * key.size;
+        }
+        const int cnt = packed - g0;
+        crc = hbc_h2d_async((int32_t *)d_xy + 2 * g0, xy + 2 * g0, sizeof(int32_t) * 2 * (size_t)cnt, ctx->stream);
+        if (crc) break;
+        hbd_tq_args a;
+        memset(&a, 0, sizeof a);
+        hb_tq_setup(ctx, &a, key.comp, key.size, key.qp, is_islice, sign_hiding);
+        int lg = 2;
+        while ((1 << lg) < key.size) lg++;
+        a.qtab = ctx->d_q + hb_tab_q_off(lg, key.comp, key.qp % 6);        /* intra lists: (is_intra ? 0 : 3) + comp */
+        a.dqtab = ctx->d_dq + hb_tab_q_off(lg, 0, key.qp % 6);             /* SSE4.2 inv_quant: is_intra -> list 0 (:138) */
+        a.scan = ctx->d_scan + hb_tab_scan_off(key.scan_mode, lg);
+        a.intra = 1;
+        a.cur = cur->d.p[key.comp]; a.pred = pred->d.p[key.comp]; a.rec = recon->d.p[key.comp];
+        a.jobs_xy = (const int32_t *)d_xy + 2 * g0; a.n_jobs = cnt;
+        a.weight = key.comp ? chroma_weight : 1.0;
+        a.coeff_out = (int16_t *)d_co + c0;
+        a.res_out = (hb_tu_result *)d_rs + g0;
+        crc = hbk_tq_encode(&a, ctx->stream);
+        ctx->launches++;
+    }
+    if (!crc) crc = hbc_d2h_async(h_co, d_co, sizeof(int16_t) * total, ctx->stream);
+    if (!crc) crc = hbc_d2h_async(h_rs, d_rs, sizeof(hb_tu_result) * (size_t)n_jobs, ctx->stream);
+    if (!crc) crc = hbc_stream_sync(ctx->stream);
+    if (!crc) {
+        size_t o = 0;
+        for (int p = 0; p < n_jobs; p++) {
+            const int k = order[p];
+            const size_t nn = (size_t)jobs[k].size * jobs[k].size;
+            memcpy(coeffs + coeff_off[k], (int16_t *)h_co + o, sizeof(int16_t) * nn);
+            results[k] = ((hb_tu_result *)h_rs)[p];
+            o += nn;
+        }
+    }
+done:
+    free(order); free(done_flag); free(coeff_off);
+    pthread_mutex_unlock(&ctx->lock);
+    if (crc) return hb_cuda_fail(crc, "hb_tq_encode_intra");
+    return rc;
+}

@@ -139,6 +139,104 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_tq(const hbd_tq_args a)
     }
 }
 
+// ------------------------------------------------------------------ intra T/Q chain after prediction
+// encode_intra_cu (hmr_motion_intra.c:1023-1069) and the chroma loop of hmr_motion_intra_chroma.c:340-365: residual ->
+// DST-VII (4x4 luma) or DCT -> quant (intra lists, scan from the intra mode, sign hiding) -> if any level: dequant -> inverse
+// -> reconstruction; distortion = SSD(original, reconstruction) (chroma weighted).  No zero-out heuristic on this path.
+template <int N>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) k_tq_intra(const hbd_tq_args a)
+{
+    using Q = HbTq<N>;
+    constexpr int TPW = Q::TPW;
+    __shared__ __align__(16) int16_t smem[kWarpsPerCta][5][Q::ELEMS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int first_job = (blockIdx.x * kWarpsPerCta + warp) * TPW;
+    if (first_job >= a.n_jobs) return;
+    int16_t *X = smem[warp][0], *T = smem[warp][1], *C = smem[warp][2], *L = smem[warp][3], *U = smem[warp][4];
+    const bool dst = (N == 4) && a.is_luma;
+    int jx[TPW], jy[TPW];
+#pragma unroll
+    for (int u = 0; u < TPW; u++) {
+        const int j = min(first_job + u, a.n_jobs - 1);
+        jx[u] = __ldg(a.jobs_xy + 2 * j);
+        jy[u] = __ldg(a.jobs_xy + 2 * j + 1);
+    }
+    auto unit_xy = [&](int unit, int &x, int &y) {
+        x = jx[0]; y = jy[0];
+#pragma unroll
+        for (int u = 1; u < TPW; u++) if (u == unit) { x = jx[u]; y = jy[u]; }
+    };
+#pragma unroll
+    for (int it = 0; it < Q::ITERS4; it++) {
+        const typename Q::G4 g = Q::group4(it, lane);
+        int x, y;
+        unit_xy(g.unit, x, y);
+        const int r = g.row % N;
+        const uint32_t o = *reinterpret_cast<const uint32_t *>(a.cur.org + (y + r) * a.cur.pitch + x + g.col);
+        const uint32_t p = *reinterpret_cast<const uint32_t *>(a.pred.org + (y + r) * a.pred.pitch + x + g.col);
+        int d[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) d[k] = static_cast<int>((o >> (8 * k)) & 255u) - static_cast<int>((p >> (8 * k)) & 255u);
+        Q::st4(X + g.off, d);
+    }
+    __syncwarp();
+    if (dst) Q::template forward<true>(X, T, C, lane); else Q::template forward<false>(X, T, C, lane);
+    int unit_sum[TPW];
+    Q::quantise(C, L, U, a.qtab, a.qbits, a.add, lane, unit_sum);
+    if (a.sign_hiding) Q::sign_hide(L, C, U, a.scan, lane, unit_sum);
+    bool any = false;
+#pragma unroll
+    for (int u = 0; u < TPW; u++) any |= unit_sum[u] != 0;
+    if (any) {
+        Q::dequantise(L, T, a.dqtab, a.per, lane);
+        if (dst) Q::template inverse<true>(T, U, C, lane); else Q::template inverse<false>(T, U, C, lane);
+    }
+    uint32_t ssd[TPW];
+#pragma unroll
+    for (int u = 0; u < TPW; u++) ssd[u] = 0;
+#pragma unroll
+    for (int it = 0; it < Q::ITERS4; it++) {
+        const typename Q::G4 g = Q::group4(it, lane);
+        int x, y;
+        unit_xy(g.unit, x, y);
+        int usum = 0;
+#pragma unroll
+        for (int u = 0; u < TPW; u++) if (u == g.unit) usum = unit_sum[u];
+        const bool valid = first_job + g.unit < a.n_jobs;
+        const int r = g.row % N;
+        int lv[4], dr[4] = { 0, 0, 0, 0 };
+        Q::ld4(L + g.off, lv);
+        if (usum != 0) Q::ld4(C + g.off, dr);
+        const uint32_t o = *reinterpret_cast<const uint32_t *>(a.cur.org + (y + r) * a.cur.pitch + x + g.col);
+        const uint32_t p = *reinterpret_cast<const uint32_t *>(a.pred.org + (y + r) * a.pred.pitch + x + g.col);
+        uint32_t out = 0, s = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int rec = hb_clip255(static_cast<int>((p >> (8 * q)) & 255u) + dr[q]);
+            const int e = static_cast<int>((o >> (8 * q)) & 255u) - rec;
+            s += static_cast<uint32_t>(e * e);
+            out |= static_cast<uint32_t>(rec) << (8 * q);
+        }
+        Q::template unit_add<uint32_t>(s, it, ssd);
+        if (valid) {
+            uint2 w;
+            w.x = (static_cast<uint32_t>(lv[0]) & 0xffffu) | (static_cast<uint32_t>(lv[1]) << 16);
+            w.y = (static_cast<uint32_t>(lv[2]) & 0xffffu) | (static_cast<uint32_t>(lv[3]) << 16);
+            *reinterpret_cast<uint2 *>(a.coeff_out + static_cast<size_t>(first_job + g.unit) * (N * N) + g.pos4) = w;
+            *reinterpret_cast<uint32_t *>(a.rec.org + (y + r) * a.rec.pitch + x + g.col) = out;
+        }
+    }
+    uint32_t my_ssd = 0; int my_sum = 0;
+#pragma unroll
+    for (int u = 0; u < TPW; u++) if (u == lane) { my_ssd = ssd[u]; my_sum = unit_sum[u]; }
+    if (lane < TPW && first_job + lane < a.n_jobs) {
+        hb_tu_result r;
+        r.sum = my_sum; r.zeroed = 0; r.ssd_zero = 0;
+        r.ssd = a.is_luma ? my_ssd : static_cast<uint32_t>(__double2int_rz(__dmul_rn(a.weight, static_cast<double>(my_ssd))));
+        a.res_out[first_job + lane] = r;
+    }
+}
+
 // ------------------------------------------------------------------ per-call kernels (one warp, one unit)
 template <int N, bool DST>
 __global__ void __launch_bounds__(32) k_pc_transform(const int16_t *block, int bs, int16_t *coeff)
@@ -207,7 +305,8 @@ template <int N> int launch_tq(const hbd_tq_args *a, cudaStream_t s)
 {
     const int per_cta = kWarpsPerCta * HbTq<N>::TPW;
     const int grid = (a->n_jobs + per_cta - 1) / per_cta;
-    k_tq<N><<<grid, kWarpsPerCta * 32, 0, s>>>(*a);
+    if (a->intra) k_tq_intra<N><<<grid, kWarpsPerCta * 32, 0, s>>>(*a);
+    else k_tq<N><<<grid, kWarpsPerCta * 32, 0, s>>>(*a);
     return static_cast<int>(cudaGetLastError());
 }
 

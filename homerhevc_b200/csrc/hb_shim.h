@@ -105,6 +105,7 @@ typedef struct hbd_tq_args {
     int32_t qbits, add, per;
     int32_t sign_hiding;
     int32_t is_luma;
+    int32_t intra;                /* 1: the intra chain (DST for 4x4 luma, no zero-out test, ssd against the reconstruction) */
     double  thr_k;                /* clip(avg_dist/2.5-5, 1, 20000) */
     double  weight;               /* chroma SSD weight, 1 for luma */
     const hbd_dyn_params *dyn;    /* overrides thr_k when non-NULL */

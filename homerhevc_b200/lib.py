@@ -41,6 +41,10 @@ class TuJob(C.Structure):
     _fields_ = [("comp", C.c_int32), ("x", C.c_int32), ("y", C.c_int32), ("size", C.c_int32), ("qp", C.c_int32)]
 
 
+class IntraTuJob(C.Structure):
+    _fields_ = [("comp", C.c_int32), ("x", C.c_int32), ("y", C.c_int32), ("size", C.c_int32), ("qp", C.c_int32), ("scan_mode", C.c_int32)]
+
+
 class TuResult(C.Structure):
     _fields_ = [("sum", C.c_int32), ("ssd", C.c_uint32), ("ssd_zero", C.c_uint32), ("zeroed", C.c_int32)]
 
@@ -149,6 +153,8 @@ def load_library():
     L.hb_mc_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(McJob), C.c_int]
     L.hb_tq_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TuJob), C.c_int,
                                C.POINTER(TqParams), i16p, C.POINTER(TuResult)]
+    L.hb_tq_encode_intra.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(IntraTuJob), C.c_int, C.c_int, C.c_int, C.c_double,
+                                     i16p, C.POINTER(TuResult)]
     # section D
     L.hb_prepass_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(PrepassCfg), C.POINTER(C.c_void_p)]
     L.hb_prepass_destroy.argtypes = [C.c_void_p]
@@ -302,6 +308,19 @@ class Context:
         res = (TuResult * n)()
         _check(self.L.hb_tq_encode(self.h, cur.h, pred.h, recon.h, arr, n, C.byref(params), _p16(coeffs), res), "hb_tq_encode")
         return coeffs, list(res)
+
+
+def _tq_encode_intra(self, cur, pred, recon, jobs, is_islice, sign_hiding, chroma_weight):
+    n = len(jobs)
+    arr = (IntraTuJob * n)(*jobs)
+    coeffs = np.zeros(sum(j.size * j.size for j in jobs), dtype=np.int16)
+    res = (TuResult * n)()
+    _check(self.L.hb_tq_encode_intra(self.h, cur.h, pred.h, recon.h, arr, n, is_islice, sign_hiding, chroma_weight, _p16(coeffs), res),
+           "hb_tq_encode_intra")
+    return coeffs, list(res)
+
+
+Context.tq_encode_intra = _tq_encode_intra
 
 
 class Frame:

@@ -185,6 +185,15 @@ typedef struct hb_tq_params {
 int hb_tq_encode(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_frame *recon, const hb_tu_job *jobs, int n_jobs,
                  const hb_tq_params *params, int16_t *coeffs, hb_tu_result *results);
 
+/* the intra chain once the prediction exists: encode_intra_cu after its prediction step (hmr_motion_intra.c:1023-1069) and the
+ * chroma loop of hmr_motion_intra_chroma.c:340-365.  `pred` holds the intra prediction (built by the host's predictors, which
+ * walk reconstructed neighbours).  4x4 luma uses the DST; scan_mode is find_scan_mode()'s value for the intra mode
+ * (1 horizontal, 2 vertical, 3 diagonal; sizes above 8 are always diagonal); result.ssd = ssd16b(original, reconstruction),
+ * chroma weighted by chroma_weight and truncated like the reference's (int) cast. */
+typedef struct hb_intra_tu_job { int32_t comp; int32_t x, y; int32_t size; int32_t qp; int32_t scan_mode; } hb_intra_tu_job;
+int hb_tq_encode_intra(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_frame *recon, const hb_intra_tu_job *jobs, int n_jobs,
+                       int is_islice, int sign_hiding, double chroma_weight, int16_t *coeffs, hb_tu_result *results);
+
 /* ------------------------------------------------------------------ D. frame-level pre-pass ----------------
  * For every CTU and every inter PU size 64/32/16/8 at once: motion search chained parent -> child exactly as
  * hmr_cu_motion_estimation does (zero AMVP predictors, parent MV as extra start), motion compensation of

@@ -707,3 +707,31 @@ void orc_encode_inter_tu(const orc_tables *t, const int16_t *orig, int orig_stri
     }
     out->sum = sum;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * T/Q chain of one INTRA TU once its prediction exists.  hmr_motion_intra.c:1023-1069 (luma: DST-VII for 4x4 because the
+ * intra mode is handed to transform() as uiMode != REG_DCT, scan chosen from the mode, quant/inv_quant with is_intra = 1,
+ * distortion = ssd16b(orig, decoded)) and hmr_motion_intra_chroma.c:340-365 (chroma: DCT, distortion weighted).
+ * ------------------------------------------------------------------------------------------ */
+void orc_encode_intra_tu(const orc_tables *t, const int16_t *orig, int orig_stride, const int16_t *pred, int pred_stride,
+                         int16_t *coeff, int16_t *dec, int dec_stride, int n, int comp, int qp, int scan_mode,
+                         int is_islice, int sign_hiding, double weight, orc_tu_out *out)
+{
+    int16_t resid[32 * 32], tc[32 * 32], dq[32 * 32], du[32 * 32];
+    static const int16_t zeros[32] = { 0 };
+    const int lg = ilog2(n), per = qp / 6, rem = qp % 6, is_dst = (comp == 0 && n == 4);
+    int sum = 0;
+    orc_predict(orig, orig_stride, pred, pred_stride, resid, n, n);
+    orc_transform(8, resid, n, tc, n, is_dst);
+    orc_quant(t, tc, coeff, du, scan_mode, lg, comp, 1, is_islice, sign_hiding, per, rem, &sum);
+    if (sum) {
+        orc_inv_quant(t, coeff, dq, lg, comp, 1, per, rem);
+        orc_itransform(8, resid, n, dq, n, is_dst);
+        orc_reconst(pred, pred_stride, resid, n, dec, dec_stride, n);
+    } else {
+        orc_reconst(pred, pred_stride, zeros, 0, dec, dec_stride, n);
+    }
+    const uint32_t ssd = orc_ssd16b(orig, orig_stride, dec, dec_stride, n);
+    out->sum = sum; out->zeroed = 0; out->ssd_zero = 0;
+    out->ssd = comp == 0 ? ssd : (uint32_t)(int)(weight * ssd);
+}

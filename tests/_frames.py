@@ -78,3 +78,13 @@ def oracle_tu(cur_block, pred_block, n, comp, qp_eff, isl, sh, avg_dist, weight)
     to = OrcTuOut()
     O.orc_encode_inter_tu(O.tables, ptr(o), n, ptr(p), n, ptr(co), ptr(de), n, n, comp, qp_eff, isl, sh, avg_dist, weight, C.byref(to))
     return co.reshape(n, n), de.reshape(n, n).astype(np.uint8), to
+
+
+def oracle_intra_tu(cur_block, pred_block, n, comp, qp_eff, scan_mode, isl, sh, weight):
+    O = oracle()
+    o = np.ascontiguousarray(cur_block.astype(np.int16)).reshape(-1)
+    p = np.ascontiguousarray(pred_block.astype(np.int16)).reshape(-1)
+    co = np.zeros(n * n, np.int16); de = np.zeros(n * n, np.int16)
+    to = OrcTuOut()
+    O.orc_encode_intra_tu(O.tables, ptr(o), n, ptr(p), n, ptr(co), ptr(de), n, n, comp, qp_eff, scan_mode, isl, sh, weight, C.byref(to))
+    return co.reshape(n, n), de.reshape(n, n).astype(np.uint8), to

@@ -80,6 +80,8 @@ def oracle():
         L.orc_encode_inter_tu.argtypes = [C.c_void_p, i16p, C.c_int, i16p, C.c_int, i16p, i16p, C.c_int,
                                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                           C.POINTER(OrcTuOut)]
+        L.orc_encode_intra_tu.argtypes = [C.c_void_p, i16p, C.c_int, i16p, C.c_int, i16p, i16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_int, C.c_double, C.POINTER(OrcTuOut)]
         L.tables = L.orc_tables_create()
         _oracle = L
     return _oracle

@@ -139,3 +139,45 @@ def test_tq_encode(ctx, qp, isl, sh, avg_dist):
         n_keep += r.sum > 0; n_zeroed += r.zeroed
     assert n_keep > 10, "test input never produced coded TUs"
     fc.close(); fp.close(); rec.close()
+
+
+@pytest.mark.parametrize("qp,isl,sh", [(30, 1, 1), (24, 1, 0), (38, 0, 1)])
+def test_tq_encode_intra(ctx, qp, isl, sh):
+    """the intra T/Q chain after prediction (encode_intra_cu, hmr_motion_intra.c:1023-1069, and the chroma loop): DST for 4x4
+    luma, intra quant lists, mode-dependent scans, ssd against the reconstruction"""
+    from _frames import oracle_intra_tu
+    rng = np.random.default_rng(qp + 100 * isl)
+    cur, ref = clip_pair(W, H, n=6, noise=4.0, seed=15)
+    # a stand-in intra prediction: the current frame blurred a little (the host's predictors produce the real one)
+    blur = [np.clip((pl.astype(np.int32) + np.roll(pl, 1, 0) + np.roll(pl, 1, 1) + np.roll(pl, -1, 1)) // 4 + rng.integers(-12, 13, pl.shape), 0, 255).astype(np.uint8)
+            for pl in (cur.y, cur.u, cur.v)]
+    pred_h = HostFrame(*blur)
+    fc, fp = upload(ctx, cur, W, H), upload(ctx, pred_h, W, H)
+    rec = hb.Frame(ctx, W, H)
+    qp_c = chroma_qp(qp, 2)
+    weight = 2.0 ** ((qp - qp_c) / 3.0)
+    jobs, meta = [], []
+    for comp in (0, 1, 2):
+        pw, ph = (W, H) if comp == 0 else (W // 2, H // 2)
+        bands = [(32, 0), (16, 64), (8, 128), (4, 192)] if comp == 0 else [(16, 0), (8, 48), (4, 80)]
+        for size, y0 in bands:
+            for y in range(y0, min(y0 + (64 if comp == 0 else 32), ph - size + 1), size):
+                for x in range(0, pw - size + 1, size):
+                    if rng.random() < 0.5:
+                        continue
+                    scan = int(rng.choice([1, 2, 3])) if size <= 8 else 3
+                    jobs.append(hb.IntraTuJob(comp, x, y, size, qp if comp == 0 else qp_c, scan)); meta.append((comp, x, y, size, scan))
+    coeffs, res = ctx.tq_encode_intra(fc, fp, rec, jobs, isl, sh, weight)
+    recs = rec.download()
+    off = 0
+    coded = 0
+    for r, (comp, x, y, size, scan) in zip(res, meta):
+        eco, ede, eo = oracle_intra_tu(cur.block(comp, x, y, size), pred_h.block(comp, x, y, size), size, comp,
+                                       qp if comp == 0 else qp_c, scan, isl, sh, 1.0 if comp == 0 else weight)
+        got = coeffs[off:off + size * size].reshape(size, size); off += size * size
+        assert (r.sum, r.ssd) == (eo.sum, eo.ssd), (comp, x, y, size, scan, (r.sum, r.ssd), (eo.sum, eo.ssd))
+        assert np.array_equal(got, eco), ("levels", comp, x, y, size, scan)
+        assert np.array_equal(recs[comp][y:y + size, x:x + size], ede), ("recon", comp, x, y, size)
+        coded += r.sum > 0
+    assert coded > 5
+    fc.close(); fp.close(); rec.close()

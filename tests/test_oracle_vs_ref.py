@@ -136,3 +136,45 @@ def test_lockstep_encode_is_deterministic():
         assert n > 0
         outs.append((bytes(bs[:n]), rec.copy()))
     assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_intra_tq_chain_against_reference_calls():
+    """orc_encode_intra_tu against the reference's own functions called in the order of encode_intra_cu
+    (hmr_motion_intra.c:1037-1069) / the chroma loop (hmr_motion_intra_chroma.c:340-365)"""
+    from _oracle import OrcTuOut
+    O = oracle(); R, D = ref()
+    h = refdrv()
+    rng = np.random.default_rng(103)
+    coded = 0
+    for it in range(400):
+        comp = int(rng.integers(0, 3))
+        n = int(rng.choice([4, 8, 16, 32] if comp == 0 else [4, 8, 16])); lg = n.bit_length() - 1
+        qp = int(rng.integers(15, 45)); isl, sh = (int(v) for v in rng.integers(0, 2, 2))
+        scan = int(rng.choice([1, 2, 3])) if n <= 8 else 3
+        weight = 1.0 if comp == 0 else float(rng.choice([1.0, 1.2599210498948732, 0.7937005259840998]))
+        orig = aligned_i16(n * n); pred = aligned_i16(n * n)
+        orig[:] = rng.integers(0, 256, n * n)
+        pred[:] = np.clip(orig + np.rint(rng.normal(0, float(rng.choice([1, 4, 15, 50])), n * n)), 0, 255)
+        # ---- reference call sequence
+        res = aligned_i16(n * n); tc = aligned_i16(1024); lev = aligned_i16(1024); dq = aligned_i16(1024); aux = aligned_i16(1024)
+        dec = aligned_i16(n * n); zeros = aligned_i16(64); s = C.c_int(0)
+        mode = 10 if comp == 0 else 65535                      # luma hands the intra mode (!= REG_DCT), chroma REG_DCT
+        R.sse_aligned_predict(ptr(orig), n, ptr(pred), n, ptr(res), n, n)
+        R.sse_transform(8, ptr(res), ptr(tc), n, n, n, lg, lg, C.c_uint16(mode), ptr(aux))
+        D.refdrv_quant(h, ptr(tc), ptr(lev), None, scan, lg, comp, 1, isl, sh, qp // 6, qp % 6, C.byref(s))
+        if s.value:
+            D.refdrv_inv_quant(h, ptr(lev), ptr(dq), lg, comp, 1, qp // 6, qp % 6)
+            R.sse_itransform(8, ptr(res), ptr(dq), n, n, n, C.c_uint(mode), ptr(aux))
+            R.sse_aligned_reconst(ptr(pred), n, ptr(res), n, ptr(dec), n, n)
+        else:
+            R.sse_aligned_reconst(ptr(pred), n, ptr(zeros), 0, ptr(dec), n, n)
+        ssd = R.sse_aligned_ssd16b(ptr(orig), n, ptr(dec), n, n)
+        if comp:
+            ssd = int(weight * ssd)
+        # ---- oracle
+        co2 = aligned_i16(1024); de2 = aligned_i16(n * n); to = OrcTuOut()
+        O.orc_encode_intra_tu(O.tables, ptr(orig), n, ptr(pred), n, ptr(co2), ptr(de2), n, n, comp, qp, scan, isl, sh, weight, C.byref(to))
+        assert (to.sum, to.ssd) == (s.value, ssd), (comp, n, qp, scan)
+        assert np.array_equal(co2[:n * n], lev[:n * n]) and np.array_equal(de2, dec), (comp, n, qp, scan)
+        coded += s.value > 0
+    assert coded > 50
