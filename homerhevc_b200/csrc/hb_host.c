@@ -19,7 +19,7 @@ static __thread char t_err[256];
 
 const char *hb_last_error(void) { return t_err; }
 
-int hb_fail(int code, const char *fmt, ...)
+int hbi_fail(int code, const char *fmt, ...)
 {
     va_list ap;
     va_start(ap, fmt);
@@ -28,9 +28,9 @@ int hb_fail(int code, const char *fmt, ...)
     return code;
 }
 
-int hb_cuda_fail(int cuda_code, const char *what)
+int hbi_cuda_fail(int cuda_code, const char *what)
 {
-    return hb_fail(HB_ERR_CUDA, "%s: %s", what, hbc_error_string(cuda_code));
+    return hbi_fail(HB_ERR_CUDA, "%s: %s", what, hbc_error_string(cuda_code));
 }
 
 /* ------------------------------------------------------------------ HEVC tables (host build, device resident)
@@ -48,7 +48,7 @@ static const uint8_t k_chroma_qp[58] = {            /* hmr_encoder_lib.c:2245 */
     0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29,
     29, 30, 31, 32, 33, 33, 34, 34, 35, 35, 36, 36, 37, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51 };
 
-int hb_chroma_qp(int qp, int offset)
+int hbi_chroma_qp(int qp, int offset)
 {
     int v = qp + offset;
     v = v < 0 ? 0 : (v > 57 ? 57 : v);
@@ -103,7 +103,7 @@ static void build_qtables(int32_t *q, int32_t *dq, int lg, int list, int rem)
     if (up > 1) { q[0] = (k_fwd_scale[rem] << 4) / 16; dq[0] = k_inv_scale[rem] * 16; }   /* DC of 16x16 / 32x32 lists */
 }
 
-size_t hb_tab_scan_off(int mode, int lg)      /* in uint16 elements; mode 1..3, lg 2..5 */
+size_t hbi_tab_scan_off(int mode, int lg)      /* in uint16 elements; mode 1..3, lg 2..5 */
 {
     size_t off = 0;
     for (int m = 1; m <= 3; m++)
@@ -113,7 +113,7 @@ size_t hb_tab_scan_off(int mode, int lg)      /* in uint16 elements; mode 1..3, 
         }
     return 0;
 }
-size_t hb_tab_q_off(int lg, int list, int rem) /* in int32 elements */
+size_t hbi_tab_q_off(int lg, int list, int rem) /* in int32 elements */
 {
     size_t off = 0;
     for (int l = 2; l <= 5; l++)
@@ -132,21 +132,21 @@ static int tables_upload(hb_ctx *ctx)
     uint16_t *scan = (uint16_t *)malloc(n_scan * sizeof *scan);
     int32_t *q = (int32_t *)malloc(n_q * sizeof *q), *dq = (int32_t *)malloc(n_q * sizeof *dq);
     int rc;
-    if (!scan || !q || !dq) { free(scan); free(q); free(dq); return hb_fail(HB_ERR_NOMEM, "tables: out of host memory"); }
-    for (int m = 1; m <= 3; m++) for (int l = 2; l <= 5; l++) build_scan(scan + hb_tab_scan_off(m, l), m, l);
+    if (!scan || !q || !dq) { free(scan); free(q); free(dq); return hbi_fail(HB_ERR_NOMEM, "tables: out of host memory"); }
+    for (int m = 1; m <= 3; m++) for (int l = 2; l <= 5; l++) build_scan(scan + hbi_tab_scan_off(m, l), m, l);
     for (int l = 2; l <= 5; l++) for (int li = 0; li < 6; li++) for (int r = 0; r < 6; r++) {
         /* 32x32 has the two lists 0 (intra) and 1 (inter); index 3 aliases 1 (hmr_encoder_lib.c:135-140), the rest is never used */
         const int src_list = (l == 5 && li >= 1) ? 1 : li;
-        build_qtables(q + hb_tab_q_off(l, li, r), dq + hb_tab_q_off(l, li, r), l, src_list, r);
+        build_qtables(q + hbi_tab_q_off(l, li, r), dq + hbi_tab_q_off(l, li, r), l, src_list, r);
     }
     if ((rc = hbc_malloc((void **)&ctx->d_scan, n_scan * sizeof *scan)) || (rc = hbc_malloc((void **)&ctx->d_q, n_q * sizeof *q)) ||
-        (rc = hbc_malloc((void **)&ctx->d_dq, n_q * sizeof *dq))) { free(scan); free(q); free(dq); return hb_cuda_fail(rc, "tables: cudaMalloc"); }
+        (rc = hbc_malloc((void **)&ctx->d_dq, n_q * sizeof *dq))) { free(scan); free(q); free(dq); return hbi_cuda_fail(rc, "tables: cudaMalloc"); }
     rc = hbc_h2d_async(ctx->d_scan, scan, n_scan * sizeof *scan, ctx->stream);
     if (!rc) rc = hbc_h2d_async(ctx->d_q, q, n_q * sizeof *q, ctx->stream);
     if (!rc) rc = hbc_h2d_async(ctx->d_dq, dq, n_q * sizeof *dq, ctx->stream);
     if (!rc) rc = hbc_stream_sync(ctx->stream);
     free(scan); free(q); free(dq);
-    return rc ? hb_cuda_fail(rc, "tables: upload") : HB_OK;
+    return rc ? hbi_cuda_fail(rc, "tables: upload") : HB_OK;
 }
 
 /* ------------------------------------------------------------------ contexts */
@@ -155,22 +155,22 @@ int hb_device_count(void) { return hbc_device_count(); }
 int hb_ctx_create(hb_ctx **out, int device)
 {
     int rc;
-    if (!out) return hb_fail(HB_ERR_ARG, "hb_ctx_create: out is NULL");
+    if (!out) return hbi_fail(HB_ERR_ARG, "hb_ctx_create: out is NULL");
     *out = NULL;
-    if (hbc_device_count() <= 0) return hb_fail(HB_ERR_CUDA, "hb_ctx_create: no CUDA device visible (there is no CPU fallback)");
-    if (device < 0 || device >= hbc_device_count()) return hb_fail(HB_ERR_ARG, "hb_ctx_create: device %d out of range", device);
+    if (hbc_device_count() <= 0) return hbi_fail(HB_ERR_CUDA, "hb_ctx_create: no CUDA device visible (there is no CPU fallback)");
+    if (device < 0 || device >= hbc_device_count()) return hbi_fail(HB_ERR_ARG, "hb_ctx_create: device %d out of range", device);
     hb_ctx *ctx = (hb_ctx *)calloc(1, sizeof *ctx);
-    if (!ctx) return hb_fail(HB_ERR_NOMEM, "hb_ctx_create: out of memory");
+    if (!ctx) return hbi_fail(HB_ERR_NOMEM, "hb_ctx_create: out of memory");
     ctx->device = device;
     if ((rc = hbc_set_device(device)) || (rc = hbc_stream_create(&ctx->stream)) ||
         (rc = hbc_event_create(&ctx->ev[0])) || (rc = hbc_event_create(&ctx->ev[1]))) {
         free(ctx);
-        return hb_cuda_fail(rc, "hb_ctx_create");
+        return hbi_cuda_fail(rc, "hb_ctx_create");
     }
     pthread_mutex_init(&ctx->lock, NULL);
-    if ((rc = hbk_me_configure())) { hb_ctx_destroy(ctx); return hb_cuda_fail(rc, "hb_ctx_create: kernel attributes"); }
+    if ((rc = hbk_me_configure())) { hb_ctx_destroy(ctx); return hbi_cuda_fail(rc, "hb_ctx_create: kernel attributes"); }
     if ((rc = tables_upload(ctx)) != HB_OK) { hb_ctx_destroy(ctx); return rc; }
-    if ((rc = hbc_malloc((void **)&ctx->d_flag, 256))) { hb_ctx_destroy(ctx); return hb_cuda_fail(rc, "hb_ctx_create: flag"); }
+    if ((rc = hbc_malloc((void **)&ctx->d_flag, 256))) { hb_ctx_destroy(ctx); return hbi_cuda_fail(rc, "hb_ctx_create: flag"); }
     hbc_memset_async(ctx->d_flag, 0, 256, ctx->stream);
     *out = ctx;
     return HB_OK;
@@ -196,9 +196,9 @@ void hb_ctx_destroy(hb_ctx *ctx)
 
 int hb_ctx_sync(hb_ctx *ctx)
 {
-    if (!ctx) return hb_fail(HB_ERR_ARG, "hb_ctx_sync: NULL context");
+    if (!ctx) return hbi_fail(HB_ERR_ARG, "hb_ctx_sync: NULL context");
     const int rc = hbc_stream_sync(ctx->stream);
-    return rc ? hb_cuda_fail(rc, "hb_ctx_sync") : HB_OK;
+    return rc ? hbi_cuda_fail(rc, "hb_ctx_sync") : HB_OK;
 }
 void *hb_ctx_stream(hb_ctx *ctx) { return ctx ? ctx->stream : NULL; }
 
@@ -206,10 +206,10 @@ void *hb_ctx_stream(hb_ctx *ctx) { return ctx ? ctx->stream : NULL; }
 int hb_ctx_wait(hb_ctx *waiter, hb_ctx *signaler)
 {
     int rc;
-    if (!waiter || !signaler) return hb_fail(HB_ERR_ARG, "hb_ctx_wait: NULL context");
-    if (!signaler->ev_sync && (rc = hbc_event_create_notiming(&signaler->ev_sync))) return hb_cuda_fail(rc, "hb_ctx_wait: event");
+    if (!waiter || !signaler) return hbi_fail(HB_ERR_ARG, "hb_ctx_wait: NULL context");
+    if (!signaler->ev_sync && (rc = hbc_event_create_notiming(&signaler->ev_sync))) return hbi_cuda_fail(rc, "hb_ctx_wait: event");
     if ((rc = hbc_event_record(signaler->ev_sync, signaler->stream)) || (rc = hbc_stream_wait_event(waiter->stream, signaler->ev_sync)))
-        return hb_cuda_fail(rc, "hb_ctx_wait");
+        return hbi_cuda_fail(rc, "hb_ctx_wait");
     return HB_OK;
 }
 uint64_t hb_ctx_launch_count(hb_ctx *ctx) { return ctx ? ctx->launches : 0; }
@@ -217,37 +217,37 @@ uint64_t hb_ctx_launch_count(hb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int hb_timer_begin(hb_ctx *ctx)
 {
     const int rc = hbc_event_record(ctx->ev[0], ctx->stream);
-    return rc ? hb_cuda_fail(rc, "hb_timer_begin") : HB_OK;
+    return rc ? hbi_cuda_fail(rc, "hb_timer_begin") : HB_OK;
 }
 int hb_timer_end(hb_ctx *ctx, float *ms_out)
 {
     int rc = hbc_event_record(ctx->ev[1], ctx->stream);
     if (!rc) rc = hbc_event_elapsed(ctx->ev[0], ctx->ev[1], ms_out);
-    return rc ? hb_cuda_fail(rc, "hb_timer_end") : HB_OK;
+    return rc ? hbi_cuda_fail(rc, "hb_timer_end") : HB_OK;
 }
 
 void *hb_pinned_alloc(size_t bytes)
 {
     void *p = NULL;
     const int rc = hbc_host_alloc(&p, bytes);
-    if (rc) { hb_cuda_fail(rc, "hb_pinned_alloc"); return NULL; }
+    if (rc) { hbi_cuda_fail(rc, "hb_pinned_alloc"); return NULL; }
     return p;
 }
 void hb_pinned_free(void *p) { if (p) hbc_host_free(p); }
 
 /* grow-only scratch: device buffer i and its pinned host twin */
-int hb_scratch(hb_ctx *ctx, int i, size_t bytes, void **dev, void **host)
+int hbi_scratch(hb_ctx *ctx, int i, size_t bytes, void **dev, void **host)
 {
     int rc;
     if (ctx->scratch_bytes[i] < bytes) {
         size_t cap = ctx->scratch_bytes[i] ? ctx->scratch_bytes[i] : 4096;
         while (cap < bytes) cap *= 2;
-        if ((rc = hbc_stream_sync(ctx->stream))) return hb_cuda_fail(rc, "scratch: sync");
+        if ((rc = hbc_stream_sync(ctx->stream))) return hbi_cuda_fail(rc, "scratch: sync");
         if (ctx->d_scratch[i]) hbc_free(ctx->d_scratch[i]);
         if (ctx->h_scratch[i]) hbc_host_free(ctx->h_scratch[i]);
         ctx->d_scratch[i] = ctx->h_scratch[i] = NULL; ctx->scratch_bytes[i] = 0;
-        if ((rc = hbc_malloc(&ctx->d_scratch[i], cap))) return hb_cuda_fail(rc, "scratch: cudaMalloc");
-        if ((rc = hbc_host_alloc(&ctx->h_scratch[i], cap))) return hb_cuda_fail(rc, "scratch: cudaHostAlloc");
+        if ((rc = hbc_malloc(&ctx->d_scratch[i], cap))) return hbi_cuda_fail(rc, "scratch: cudaMalloc");
+        if ((rc = hbc_host_alloc(&ctx->h_scratch[i], cap))) return hbi_cuda_fail(rc, "scratch: cudaHostAlloc");
         ctx->scratch_bytes[i] = cap;
     }
     if (dev) *dev = ctx->d_scratch[i];
@@ -260,10 +260,10 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int hb_frame_create(hb_ctx *ctx, int width, int height, hb_frame **out)
 {
-    if (!ctx || !out) return hb_fail(HB_ERR_ARG, "hb_frame_create: NULL argument");
-    if (width < 16 || height < 16 || (width & 7) || (height & 7)) return hb_fail(HB_ERR_ARG, "hb_frame_create: %dx%d must be multiples of 8, at least 16", width, height);
+    if (!ctx || !out) return hbi_fail(HB_ERR_ARG, "hb_frame_create: NULL argument");
+    if (width < 16 || height < 16 || (width & 7) || (height & 7)) return hbi_fail(HB_ERR_ARG, "hb_frame_create: %dx%d must be multiples of 8, at least 16", width, height);
     hb_frame *f = (hb_frame *)calloc(1, sizeof *f);
-    if (!f) return hb_fail(HB_ERR_NOMEM, "hb_frame_create: out of memory");
+    if (!f) return hbi_fail(HB_ERR_NOMEM, "hb_frame_create: out of memory");
     f->ctx = ctx; f->w = width; f->h = height;
     hbc_set_device(ctx->device);
     for (int c = 0; c < 3; c++) {
@@ -273,7 +273,7 @@ int hb_frame_create(hb_ctx *ctx, int width, int height, hb_frame **out)
         p->pitch = (int32_t)align_up((size_t)p->w + 2 * (size_t)p->pad, 128);
         const size_t bytes = (size_t)p->pitch * ((size_t)p->h + 2 * (size_t)p->pad) + 256;
         const int rc = hbc_malloc((void **)&p->base, bytes);
-        if (rc) { hb_frame_destroy(f); return hb_cuda_fail(rc, "hb_frame_create: cudaMalloc"); }
+        if (rc) { hb_frame_destroy(f); return hbi_cuda_fail(rc, "hb_frame_create: cudaMalloc"); }
         hbc_memset_async(p->base, 0, bytes, ctx->stream);
         p->org = p->base + (size_t)p->pad * p->pitch + p->pad;
     }
@@ -305,14 +305,14 @@ int hb_frame_upload_u8_ex(hb_ctx *ctx, hb_frame *f, const uint8_t *y, int ys, co
     const uint8_t *src[3] = { y, u, v };
     const int st[3] = { ys, us, vs };
     int rc = 0;
-    if (!ctx || !f || !y || !u || !v) return hb_fail(HB_ERR_ARG, "hb_frame_upload_u8: NULL argument");
+    if (!ctx || !f || !y || !u || !v) return hbi_fail(HB_ERR_ARG, "hb_frame_upload_u8: NULL argument");
     hbc_set_device(ctx->device);
     for (int c = 0; c < 3 && !rc; c++) {
         const hbd_plane *p = &f->d.p[c];
         rc = hbc_h2d_2d_async(p->org, (size_t)p->pitch, src[c], (size_t)st[c], (size_t)p->w, (size_t)p->h, ctx->stream);
     }
     if (!rc && !(flags & HB_UPLOAD_NO_BORDER)) { rc = hbk_pad_frame(&f->d, ctx->stream); ctx->launches += 1; }
-    return rc ? hb_cuda_fail(rc, "hb_frame_upload_u8") : HB_OK;
+    return rc ? hbi_cuda_fail(rc, "hb_frame_upload_u8") : HB_OK;
 }
 
 int hb_frame_upload_i16(hb_ctx *ctx, hb_frame *f, const int16_t *y, int ys, const int16_t *u, int us, const int16_t *v, int vs)
@@ -321,11 +321,11 @@ int hb_frame_upload_i16(hb_ctx *ctx, hb_frame *f, const int16_t *y, int ys, cons
     const int st[3] = { ys, us, vs };
     int rc = 0;
     void *dev = NULL, *host = NULL;
-    if (!ctx || !f || !y || !u || !v) return hb_fail(HB_ERR_ARG, "hb_frame_upload_i16: NULL argument");
+    if (!ctx || !f || !y || !u || !v) return hbi_fail(HB_ERR_ARG, "hb_frame_upload_i16: NULL argument");
     hbc_set_device(ctx->device);
     pthread_mutex_lock(&ctx->lock);
     const size_t luma = (size_t)f->w * f->h;
-    if ((rc = hb_scratch(ctx, 0, 2 * (luma + luma / 2) + 64, &dev, &host)) != HB_OK) { pthread_mutex_unlock(&ctx->lock); return rc; }
+    if ((rc = hbi_scratch(ctx, 0, 2 * (luma + luma / 2) + 64, &dev, &host)) != HB_OK) { pthread_mutex_unlock(&ctx->lock); return rc; }
     size_t off = 0;
     uint32_t *flag_h = (uint32_t *)((char *)host);        /* reuse the first word of the pinned twin for the read-back */
     for (int c = 0; c < 3 && !rc; c++) {
@@ -341,8 +341,8 @@ int hb_frame_upload_i16(hb_ctx *ctx, hb_frame *f, const int16_t *y, int ys, cons
     if (!rc) rc = hbc_stream_sync(ctx->stream);
     const uint32_t flag = rc ? 0 : *flag_h;
     pthread_mutex_unlock(&ctx->lock);
-    if (rc) return hb_cuda_fail(rc, "hb_frame_upload_i16");
-    if (flag) return hb_fail(HB_ERR_ARG, "hb_frame_upload_i16: samples outside 0..255 (8-bit video only)");
+    if (rc) return hbi_cuda_fail(rc, "hb_frame_upload_i16");
+    if (flag) return hbi_fail(HB_ERR_ARG, "hb_frame_upload_i16: samples outside 0..255 (8-bit video only)");
     return HB_OK;
 }
 
@@ -351,14 +351,14 @@ int hb_frame_download_u8(hb_ctx *ctx, const hb_frame *f, uint8_t *y, int ys, uin
     uint8_t *dst[3] = { y, u, v };
     const int st[3] = { ys, us, vs };
     int rc = 0;
-    if (!ctx || !f || !y || !u || !v) return hb_fail(HB_ERR_ARG, "hb_frame_download_u8: NULL argument");
+    if (!ctx || !f || !y || !u || !v) return hbi_fail(HB_ERR_ARG, "hb_frame_download_u8: NULL argument");
     hbc_set_device(ctx->device);
     for (int c = 0; c < 3 && !rc; c++) {
         const hbd_plane *p = &f->d.p[c];
         rc = hbc_d2h_2d_async(dst[c], (size_t)st[c], p->org, (size_t)p->pitch, (size_t)p->w, (size_t)p->h, ctx->stream);
     }
     if (!rc) rc = hbc_stream_sync(ctx->stream);
-    return rc ? hb_cuda_fail(rc, "hb_frame_download_u8") : HB_OK;
+    return rc ? hbi_cuda_fail(rc, "hb_frame_download_u8") : HB_OK;
 }
 
 /* Rows [row0, row0+n_rows) of one plane <-> a tight device buffer (width bytes per row), on the context's stream.  This is
@@ -366,31 +366,31 @@ int hb_frame_download_u8(hb_ctx *ctx, const hb_frame *f, uint8_t *y, int ys, uin
  * copy) and imports it on the other side; hb_frame_pad then refreshes the replicated border. */
 int hb_frame_export_rows(hb_ctx *ctx, const hb_frame *f, int plane, int row0, int n_rows, void *dev_dst)
 {
-    if (!ctx || !f || !dev_dst || plane < 0 || plane > 2) return hb_fail(HB_ERR_ARG, "hb_frame_export_rows: bad argument");
+    if (!ctx || !f || !dev_dst || plane < 0 || plane > 2) return hbi_fail(HB_ERR_ARG, "hb_frame_export_rows: bad argument");
     const hbd_plane *p = &f->d.p[plane];
-    if (row0 < 0 || n_rows < 0 || row0 + n_rows > p->h) return hb_fail(HB_ERR_ARG, "hb_frame_export_rows: rows %d..%d outside the plane", row0, row0 + n_rows);
+    if (row0 < 0 || n_rows < 0 || row0 + n_rows > p->h) return hbi_fail(HB_ERR_ARG, "hb_frame_export_rows: rows %d..%d outside the plane", row0, row0 + n_rows);
     if (!n_rows) return HB_OK;
     hbc_set_device(ctx->device);
     const int rc = hbc_d2d_2d_async(dev_dst, (size_t)p->w, p->org + (size_t)row0 * p->pitch, (size_t)p->pitch, (size_t)p->w, (size_t)n_rows, ctx->stream);
-    return rc ? hb_cuda_fail(rc, "hb_frame_export_rows") : HB_OK;
+    return rc ? hbi_cuda_fail(rc, "hb_frame_export_rows") : HB_OK;
 }
 int hb_frame_import_rows(hb_ctx *ctx, hb_frame *f, int plane, int row0, int n_rows, const void *dev_src)
 {
-    if (!ctx || !f || !dev_src || plane < 0 || plane > 2) return hb_fail(HB_ERR_ARG, "hb_frame_import_rows: bad argument");
+    if (!ctx || !f || !dev_src || plane < 0 || plane > 2) return hbi_fail(HB_ERR_ARG, "hb_frame_import_rows: bad argument");
     const hbd_plane *p = &f->d.p[plane];
-    if (row0 < 0 || n_rows < 0 || row0 + n_rows > p->h) return hb_fail(HB_ERR_ARG, "hb_frame_import_rows: rows %d..%d outside the plane", row0, row0 + n_rows);
+    if (row0 < 0 || n_rows < 0 || row0 + n_rows > p->h) return hbi_fail(HB_ERR_ARG, "hb_frame_import_rows: rows %d..%d outside the plane", row0, row0 + n_rows);
     if (!n_rows) return HB_OK;
     hbc_set_device(ctx->device);
     const int rc = hbc_d2d_2d_async(p->org + (size_t)row0 * p->pitch, (size_t)p->pitch, dev_src, (size_t)p->w, (size_t)p->w, (size_t)n_rows, ctx->stream);
-    return rc ? hb_cuda_fail(rc, "hb_frame_import_rows") : HB_OK;
+    return rc ? hbi_cuda_fail(rc, "hb_frame_import_rows") : HB_OK;
 }
 int hb_frame_pad(hb_ctx *ctx, hb_frame *f)
 {
-    if (!ctx || !f) return hb_fail(HB_ERR_ARG, "hb_frame_pad: NULL argument");
+    if (!ctx || !f) return hbi_fail(HB_ERR_ARG, "hb_frame_pad: NULL argument");
     hbc_set_device(ctx->device);
     const int rc = hbk_pad_frame(&f->d, ctx->stream);
     ctx->launches += 1;
-    return rc ? hb_cuda_fail(rc, "hb_frame_pad") : HB_OK;
+    return rc ? hbi_cuda_fail(rc, "hb_frame_pad") : HB_OK;
 }
 
 /* ------------------------------------------------------------------ batched jobs (host arrays in, host arrays out) */
@@ -400,7 +400,7 @@ static double mv_cost_weight(int qp, double avg_dist)     /* calc_mv_correction,
     w = w < .15 ? .15 : (w > 1.4 ? 1.4 : w);
     return (uint32_t)qp * w;
 }
-double hb_zero_out_k(double avg_dist)                     /* hmr_motion_inter.c:106 */
+double hbi_zero_out_k(double avg_dist)                     /* hmr_motion_inter.c:106 */
 {
     double k = avg_dist / 2.5 - 5.;
     return k < 1. ? 1. : (k > 20000. ? 20000. : k);
@@ -412,21 +412,21 @@ int hb_me_search(hb_ctx *ctx, const hb_frame *cur, const hb_frame *ref, const hb
     static const int sizes[4] = { 64, 32, 16, 8 };
     int rc = HB_OK, crc = 0;
     void *d_jobs, *h_jobs, *d_res, *h_res, *d_par = NULL, *h_par = NULL;
-    if (!ctx || !cur || !ref || !jobs || !results || n_jobs < 0) return hb_fail(HB_ERR_ARG, "hb_me_search: bad argument");
-    if (cur->w != ref->w || cur->h != ref->h) return hb_fail(HB_ERR_ARG, "hb_me_search: frame sizes differ");
+    if (!ctx || !cur || !ref || !jobs || !results || n_jobs < 0) return hbi_fail(HB_ERR_ARG, "hb_me_search: bad argument");
+    if (cur->w != ref->w || cur->h != ref->h) return hbi_fail(HB_ERR_ARG, "hb_me_search: frame sizes differ");
     if (n_jobs == 0) return HB_OK;
     for (int i = 0; i < n_jobs; i++) {
         const hb_me_job *j = &jobs[i];
         if ((j->size != 8 && j->size != 16 && j->size != 32 && j->size != 64) || j->x < 0 || j->y < 0 || j->x + j->size > cur->w ||
             j->y + j->size > cur->h || j->n_amvp < 0 || j->n_amvp > 2 || j->n_start < 0 || j->n_start > 3 || j->parent >= n_parent)
-            return hb_fail(HB_ERR_ARG, "hb_me_search: job %d is invalid", i);
+            return hbi_fail(HB_ERR_ARG, "hb_me_search: job %d is invalid", i);
     }
     hbc_set_device(ctx->device);
     pthread_mutex_lock(&ctx->lock);
-    if ((rc = hb_scratch(ctx, 0, sizeof(hbd_me_job) * (size_t)n_jobs, &d_jobs, &h_jobs)) != HB_OK) goto done;
-    if ((rc = hb_scratch(ctx, 1, sizeof(hb_me_result) * (size_t)n_jobs, &d_res, &h_res)) != HB_OK) goto done;
+    if ((rc = hbi_scratch(ctx, 0, sizeof(hbd_me_job) * (size_t)n_jobs, &d_jobs, &h_jobs)) != HB_OK) goto done;
+    if ((rc = hbi_scratch(ctx, 1, sizeof(hb_me_result) * (size_t)n_jobs, &d_res, &h_res)) != HB_OK) goto done;
     if (n_parent > 0 && parent_results) {
-        if ((rc = hb_scratch(ctx, 2, sizeof(hb_me_result) * (size_t)n_parent, &d_par, &h_par)) != HB_OK) goto done;
+        if ((rc = hbi_scratch(ctx, 2, sizeof(hb_me_result) * (size_t)n_parent, &d_par, &h_par)) != HB_OK) goto done;
         memcpy(h_par, parent_results, sizeof(hb_me_result) * (size_t)n_parent);
         if ((crc = hbc_h2d_async(d_par, h_par, sizeof(hb_me_result) * (size_t)n_parent, ctx->stream))) goto done;
     }
@@ -462,7 +462,7 @@ int hb_me_search(hb_ctx *ctx, const hb_frame *cur, const hb_frame *ref, const hb
     if (!crc) memcpy(results, h_res, sizeof(hb_me_result) * (size_t)n_jobs);
 done:
     pthread_mutex_unlock(&ctx->lock);
-    if (crc) return hb_cuda_fail(crc, "hb_me_search");
+    if (crc) return hbi_cuda_fail(crc, "hb_me_search");
     return rc;
 }
 
@@ -471,8 +471,8 @@ int hb_mc_predict(hb_ctx *ctx, const hb_frame *ref, hb_frame *pred, const hb_mc_
     static const int sizes[4] = { 64, 32, 16, 8 };
     int rc = HB_OK, crc = 0;
     void *d_pus, *h_pus, *d_mv, *h_mv;
-    if (!ctx || !ref || !pred || !jobs || n_jobs < 0) return hb_fail(HB_ERR_ARG, "hb_mc_predict: bad argument");
-    if (pred->w != ref->w || pred->h != ref->h) return hb_fail(HB_ERR_ARG, "hb_mc_predict: frame sizes differ");
+    if (!ctx || !ref || !pred || !jobs || n_jobs < 0) return hbi_fail(HB_ERR_ARG, "hb_mc_predict: bad argument");
+    if (pred->w != ref->w || pred->h != ref->h) return hbi_fail(HB_ERR_ARG, "hb_mc_predict: frame sizes differ");
     if (n_jobs == 0) return HB_OK;
     const int reach = HB_PAD_LUMA - 16;                    /* how far outside the picture a predicted block may reach */
     for (int i = 0; i < n_jobs; i++) {
@@ -480,12 +480,12 @@ int hb_mc_predict(hb_ctx *ctx, const hb_frame *ref, hb_frame *pred, const hb_mc_
         const int x0 = j->x + (j->mv.x >> 2), y0 = j->y + (j->mv.y >> 2);
         if ((j->size != 8 && j->size != 16 && j->size != 32 && j->size != 64) || j->x < 0 || j->y < 0 || j->x + j->size > ref->w ||
             j->y + j->size > ref->h || x0 < -reach || y0 < -reach || x0 + j->size > ref->w + reach || y0 + j->size > ref->h + reach)
-            return hb_fail(HB_ERR_ARG, "hb_mc_predict: job %d is invalid or points further than %d samples outside the picture", i, reach);
+            return hbi_fail(HB_ERR_ARG, "hb_mc_predict: job %d is invalid or points further than %d samples outside the picture", i, reach);
     }
     hbc_set_device(ctx->device);
     pthread_mutex_lock(&ctx->lock);
-    if ((rc = hb_scratch(ctx, 0, sizeof(hbd_mc_pu) * (size_t)n_jobs, &d_pus, &h_pus)) != HB_OK) goto done;
-    if ((rc = hb_scratch(ctx, 1, sizeof(hb_me_result) * (size_t)n_jobs, &d_mv, &h_mv)) != HB_OK) goto done;
+    if ((rc = hbi_scratch(ctx, 0, sizeof(hbd_mc_pu) * (size_t)n_jobs, &d_pus, &h_pus)) != HB_OK) goto done;
+    if ((rc = hbi_scratch(ctx, 1, sizeof(hb_me_result) * (size_t)n_jobs, &d_mv, &h_mv)) != HB_OK) goto done;
     hbd_mc_pu *hp = (hbd_mc_pu *)h_pus;
     hb_me_result *hm = (hb_me_result *)h_mv;
     int n = 0, start_of[5];
@@ -511,20 +511,20 @@ int hb_mc_predict(hb_ctx *ctx, const hb_frame *ref, hb_frame *pred, const hb_mc_
     if (!crc) crc = hbc_stream_sync(ctx->stream);
 done:
     pthread_mutex_unlock(&ctx->lock);
-    if (crc) return hb_cuda_fail(crc, "hb_mc_predict");
+    if (crc) return hbi_cuda_fail(crc, "hb_mc_predict");
     return rc;
 }
 
 /* fill the launch-invariant part of a T/Q launch: tables and shifts of (component, size, qp) -- inter lists 3+comp */
-void hb_tq_setup(hb_ctx *ctx, hbd_tq_args *a, int comp, int n, int qp, int is_islice, int sign_hiding)
+void hbi_tq_setup(hb_ctx *ctx, hbd_tq_args *a, int comp, int n, int qp, int is_islice, int sign_hiding)
 {
     int lg = 2;
     while ((1 << lg) < n) lg++;
     const int per = qp / 6, rem = qp % 6;
     a->n = n;
-    a->qtab = ctx->d_q + hb_tab_q_off(lg, 3 + comp, rem);
-    a->dqtab = ctx->d_dq + hb_tab_q_off(lg, 3 + comp, rem);
-    a->scan = ctx->d_scan + hb_tab_scan_off(HB_SCAN_DIAG, lg);
+    a->qtab = ctx->d_q + hbi_tab_q_off(lg, 3 + comp, rem);
+    a->dqtab = ctx->d_dq + hbi_tab_q_off(lg, 3 + comp, rem);
+    a->scan = ctx->d_scan + hbi_tab_scan_off(HB_SCAN_DIAG, lg);
     a->qbits = 14 + per + (15 - 8 - lg);
     a->add = (int32_t)((uint32_t)(is_islice ? 171 : 85) << (a->qbits - 9));    /* hmr_sse42_functions_quant.c:47 */
     a->per = per;
@@ -536,7 +536,7 @@ int hb_tq_encode(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_fram
                  const hb_tq_params *params, int16_t *coeffs, hb_tu_result *results)
 {
     int rc = HB_OK, crc = 0;
-    if (!ctx || !cur || !pred || !recon || !jobs || !params || !coeffs || !results || n_jobs < 0) return hb_fail(HB_ERR_ARG, "hb_tq_encode: bad argument");
+    if (!ctx || !cur || !pred || !recon || !jobs || !params || !coeffs || !results || n_jobs < 0) return hbi_fail(HB_ERR_ARG, "hb_tq_encode: bad argument");
     if (n_jobs == 0) return HB_OK;
     size_t total = 0;
     for (int i = 0; i < n_jobs; i++) {
@@ -544,7 +544,7 @@ int hb_tq_encode(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_fram
         if (j->comp < 0 || j->comp > 2 || (j->size != 4 && j->size != 8 && j->size != 16 && j->size != 32) || j->qp < 0 || j->qp > 51 ||
             j->x < 0 || j->y < 0 || (j->x & 3) || j->x + j->size > cur->d.p[j->comp].w || j->y + j->size > cur->d.p[j->comp].h ||
             (j->comp && j->size == 32))
-            return hb_fail(HB_ERR_ARG, "hb_tq_encode: job %d is invalid", i);
+            return hbi_fail(HB_ERR_ARG, "hb_tq_encode: job %d is invalid", i);
         total += (size_t)j->size * j->size;
     }
     hbc_set_device(ctx->device);
@@ -553,10 +553,10 @@ int hb_tq_encode(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_fram
     int *order = (int *)malloc(sizeof(int) * (size_t)n_jobs);
     char *done_flag = (char *)calloc((size_t)n_jobs, 1);
     size_t *coeff_off = (size_t *)malloc(sizeof(size_t) * (size_t)n_jobs);
-    if (!order || !done_flag || !coeff_off) { rc = hb_fail(HB_ERR_NOMEM, "hb_tq_encode: out of memory"); goto done; }
-    if ((rc = hb_scratch(ctx, 0, sizeof(int32_t) * 2 * (size_t)n_jobs, &d_xy, &h_xy)) != HB_OK) goto done;
-    if ((rc = hb_scratch(ctx, 1, sizeof(int16_t) * total, &d_co, &h_co)) != HB_OK) goto done;
-    if ((rc = hb_scratch(ctx, 2, sizeof(hb_tu_result) * (size_t)n_jobs, &d_rs, &h_rs)) != HB_OK) goto done;
+    if (!order || !done_flag || !coeff_off) { rc = hbi_fail(HB_ERR_NOMEM, "hb_tq_encode: out of memory"); goto done; }
+    if ((rc = hbi_scratch(ctx, 0, sizeof(int32_t) * 2 * (size_t)n_jobs, &d_xy, &h_xy)) != HB_OK) goto done;
+    if ((rc = hbi_scratch(ctx, 1, sizeof(int16_t) * total, &d_co, &h_co)) != HB_OK) goto done;
+    if ((rc = hbi_scratch(ctx, 2, sizeof(hb_tu_result) * (size_t)n_jobs, &d_rs, &h_rs)) != HB_OK) goto done;
     { size_t o = 0; for (int i = 0; i < n_jobs; i++) { coeff_off[i] = o; o += (size_t)jobs[i].size * jobs[i].size; } }
     /* launch one group per distinct (comp, size, qp); jobs of a group are packed in caller order */
     int packed = 0;
@@ -578,10 +578,10 @@ int hb_tq_encode(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_fram
         if (crc) break;
         hbd_tq_args a;
         memset(&a, 0, sizeof a);
-        hb_tq_setup(ctx, &a, key.comp, key.size, key.qp, params->is_islice, params->sign_hiding);
+        hbi_tq_setup(ctx, &a, key.comp, key.size, key.qp, params->is_islice, params->sign_hiding);
         a.cur = cur->d.p[key.comp]; a.pred = pred->d.p[key.comp]; a.rec = recon->d.p[key.comp];
         a.jobs_xy = (const int32_t *)d_xy + 2 * g0; a.n_jobs = cnt;
-        a.thr_k = hb_zero_out_k(params->avg_dist);
+        a.thr_k = hbi_zero_out_k(params->avg_dist);
         a.weight = key.comp ? params->chroma_weight : 1.0;
         a.dyn = NULL;
         a.coeff_out = (int16_t *)d_co + c0;
@@ -605,7 +605,7 @@ int hb_tq_encode(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_fram
 done:
     free(order); free(done_flag); free(coeff_off);
     pthread_mutex_unlock(&ctx->lock);
-    if (crc) return hb_cuda_fail(crc, "hb_tq_encode");
+    if (crc) return hbi_cuda_fail(crc, "hb_tq_encode");
     return rc;
 }
 
@@ -616,7 +616,7 @@ int hb_tq_encode_intra(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, h
                        int is_islice, int sign_hiding, double chroma_weight, int16_t *coeffs, hb_tu_result *results)
 {
     int rc = HB_OK, crc = 0;
-    if (!ctx || !cur || !pred || !recon || !jobs || !coeffs || !results || n_jobs < 0) return hb_fail(HB_ERR_ARG, "hb_tq_encode_intra: bad argument");
+    if (!ctx || !cur || !pred || !recon || !jobs || !coeffs || !results || n_jobs < 0) return hbi_fail(HB_ERR_ARG, "hb_tq_encode_intra: bad argument");
     if (n_jobs == 0) return HB_OK;
     size_t total = 0;
     for (int i = 0; i < n_jobs; i++) {
@@ -624,7 +624,7 @@ int hb_tq_encode_intra(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, h
         if (j->comp < 0 || j->comp > 2 || (j->size != 4 && j->size != 8 && j->size != 16 && j->size != 32) || j->qp < 0 || j->qp > 51 ||
             j->x < 0 || j->y < 0 || (j->x & 3) || j->x + j->size > cur->d.p[j->comp].w || j->y + j->size > cur->d.p[j->comp].h ||
             (j->comp && j->size == 32) || j->scan_mode < HB_SCAN_HOR || j->scan_mode > HB_SCAN_DIAG || (j->size > 8 && j->scan_mode != HB_SCAN_DIAG))
-            return hb_fail(HB_ERR_ARG, "hb_tq_encode_intra: job %d is invalid", i);
+            return hbi_fail(HB_ERR_ARG, "hb_tq_encode_intra: job %d is invalid", i);
         total += (size_t)j->size * j->size;
     }
     hbc_set_device(ctx->device);
@@ -633,10 +633,10 @@ int hb_tq_encode_intra(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, h
     int *order = (int *)malloc(sizeof(int) * (size_t)n_jobs);
     char *done_flag = (char *)calloc((size_t)n_jobs, 1);
     size_t *coeff_off = (size_t *)malloc(sizeof(size_t) * (size_t)n_jobs);
-    if (!order || !done_flag || !coeff_off) { rc = hb_fail(HB_ERR_NOMEM, "hb_tq_encode_intra: out of memory"); goto done; }
-    if ((rc = hb_scratch(ctx, 0, sizeof(int32_t) * 2 * (size_t)n_jobs, &d_xy, &h_xy)) != HB_OK) goto done;
-    if ((rc = hb_scratch(ctx, 1, sizeof(int16_t) * total, &d_co, &h_co)) != HB_OK) goto done;
-    if ((rc = hb_scratch(ctx, 2, sizeof(hb_tu_result) * (size_t)n_jobs, &d_rs, &h_rs)) != HB_OK) goto done;
+    if (!order || !done_flag || !coeff_off) { rc = hbi_fail(HB_ERR_NOMEM, "hb_tq_encode_intra: out of memory"); goto done; }
+    if ((rc = hbi_scratch(ctx, 0, sizeof(int32_t) * 2 * (size_t)n_jobs, &d_xy, &h_xy)) != HB_OK) goto done;
+    if ((rc = hbi_scratch(ctx, 1, sizeof(int16_t) * total, &d_co, &h_co)) != HB_OK) goto done;
+    if ((rc = hbi_scratch(ctx, 2, sizeof(hb_tu_result) * (size_t)n_jobs, &d_rs, &h_rs)) != HB_OK) goto done;
     { size_t o = 0; for (int i = 0; i < n_jobs; i++) { coeff_off[i] = o; o += (size_t)jobs[i].size * jobs[i].size; } }
     int packed = 0;
     size_t packed_coeff = 0;
@@ -657,12 +657,12 @@ int hb_tq_encode_intra(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, h
         if (crc) break;
         hbd_tq_args a;
         memset(&a, 0, sizeof a);
-        hb_tq_setup(ctx, &a, key.comp, key.size, key.qp, is_islice, sign_hiding);
+        hbi_tq_setup(ctx, &a, key.comp, key.size, key.qp, is_islice, sign_hiding);
         int lg = 2;
         while ((1 << lg) < key.size) lg++;
-        a.qtab = ctx->d_q + hb_tab_q_off(lg, key.comp, key.qp % 6);        /* intra lists: (is_intra ? 0 : 3) + comp */
-        a.dqtab = ctx->d_dq + hb_tab_q_off(lg, 0, key.qp % 6);             /* SSE4.2 inv_quant: is_intra -> list 0 (:138) */
-        a.scan = ctx->d_scan + hb_tab_scan_off(key.scan_mode, lg);
+        a.qtab = ctx->d_q + hbi_tab_q_off(lg, key.comp, key.qp % 6);        /* intra lists: (is_intra ? 0 : 3) + comp */
+        a.dqtab = ctx->d_dq + hbi_tab_q_off(lg, 0, key.qp % 6);             /* SSE4.2 inv_quant: is_intra -> list 0 (:138) */
+        a.scan = ctx->d_scan + hbi_tab_scan_off(key.scan_mode, lg);
         a.intra = 1;
         a.cur = cur->d.p[key.comp]; a.pred = pred->d.p[key.comp]; a.rec = recon->d.p[key.comp];
         a.jobs_xy = (const int32_t *)d_xy + 2 * g0; a.n_jobs = cnt;
@@ -688,6 +688,6 @@ int hb_tq_encode_intra(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, h
 done:
     free(order); free(done_flag); free(coeff_off);
     pthread_mutex_unlock(&ctx->lock);
-    if (crc) return hb_cuda_fail(crc, "hb_tq_encode_intra");
+    if (crc) return hbi_cuda_fail(crc, "hb_tq_encode_intra");
     return rc;
 }

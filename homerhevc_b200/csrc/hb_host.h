@@ -31,13 +31,13 @@ struct hb_frame {
 };
 
 hb_ctx *hb_default_ctx(void);
-int hb_fail(int code, const char *fmt, ...);
-int hb_cuda_fail(int cuda_code, const char *what);
-int hb_scratch(hb_ctx *ctx, int i, size_t bytes, void **dev, void **host);
-size_t hb_tab_scan_off(int mode, int lg);
-size_t hb_tab_q_off(int lg, int list, int rem);
-int hb_chroma_qp(int qp, int offset);
-double hb_zero_out_k(double avg_dist);
-void hb_tq_setup(hb_ctx *ctx, hbd_tq_args *a, int comp, int n, int qp, int is_islice, int sign_hiding);
+int hbi_fail(int code, const char *fmt, ...);
+int hbi_cuda_fail(int cuda_code, const char *what);
+int hbi_scratch(hb_ctx *ctx, int i, size_t bytes, void **dev, void **host);
+size_t hbi_tab_scan_off(int mode, int lg);
+size_t hbi_tab_q_off(int lg, int list, int rem);
+int hbi_chroma_qp(int qp, int offset);
+double hbi_zero_out_k(double avg_dist);
+void hbi_tq_setup(hb_ctx *ctx, hbd_tq_args *a, int comp, int n, int qp, int is_islice, int sign_hiding);
 
 #endif

@@ -52,7 +52,7 @@ static pc_slot *slot(void)
         int rc;
         hbc_set_device(ctx->device);
         if ((rc = hbc_stream_create(&t_slot.stream)) || (rc = hbc_host_alloc((void **)&t_slot.host, STAGE_BYTES)) ||
-            (rc = hbc_host_devptr(t_slot.host, (void **)&t_slot.dev))) { hb_cuda_fail(rc, "per-thread slot"); die("per-call setup"); }
+            (rc = hbc_host_devptr(t_slot.host, (void **)&t_slot.dev))) { hbi_cuda_fail(rc, "per-thread slot"); die("per-call setup"); }
     }
     return &t_slot;
 }
@@ -61,7 +61,7 @@ static void finish(pc_slot *s, int launch_rc, const char *what)
 {
     int rc = launch_rc;
     if (!rc) rc = hbc_stream_sync(s->stream);
-    if (rc) { hb_cuda_fail(rc, what); die(what); }
+    if (rc) { hbi_cuda_fail(rc, what); die(what); }
     __atomic_add_fetch(&g_ctx->launches, 1, __ATOMIC_RELAXED);
 }
 
@@ -158,7 +158,7 @@ void hb_transform(int bit_depth, int16_t *block, int16_t *coeff, int block_size,
     pc_slot *s = slot();
     (void)width_shift; (void)height_shift; (void)aux;
     if (!tu_ok(iWidth, iHeight)) return;                    /* as the reference: other shapes do nothing (hmr_transform.c:519-546) */
-    if (bit_depth != 8) { hb_fail(HB_ERR_ARG, "bit depth %d (8-bit video only)", bit_depth); die("transform"); }
+    if (bit_depth != 8) { hbi_fail(HB_ERR_ARG, "bit depth %d (8-bit video only)", bit_depth); die("transform"); }
     const int n = iWidth;
     int16_t *a = (int16_t *)s->host, *c = a + 32 * 32;
     pack(a, n, block, block_size, n, n);
@@ -172,7 +172,7 @@ void hb_itransform(int bit_depth, int16_t *block, int16_t *coeff, int block_size
     pc_slot *s = slot();
     (void)aux;
     if (!tu_ok(iWidth, iHeight)) return;
-    if (bit_depth != 8) { hb_fail(HB_ERR_ARG, "bit depth %d (8-bit video only)", bit_depth); die("itransform"); }
+    if (bit_depth != 8) { hbi_fail(HB_ERR_ARG, "bit depth %d (8-bit video only)", bit_depth); die("itransform"); }
     const int n = iWidth;
     int16_t *c = (int16_t *)s->host, *b = c + 32 * 32;
     memcpy(c, coeff, sizeof(int16_t) * (size_t)n * n);
@@ -188,15 +188,15 @@ void hb_quant(const hb_quant_env *env, int16_t *src, int16_t *dst, int scan_mode
     (void)cu_mode;
     const int lg = env->max_cu_size_shift - (depth + (comp != 0));      /* inv_depth, hmr_sse42_functions_quant.c:39 */
     if (lg < 2 || lg > 5 || cu_size != (1 << lg) || scan_mode < HB_SCAN_HOR || scan_mode > HB_SCAN_DIAG || rem < 0 || rem > 5 ||
-        env->bit_depth != 8) { hb_fail(HB_ERR_ARG, "quant: unsupported shape (size %d, depth %d, comp %d, scan %d)", cu_size, depth, comp, scan_mode); die("quant"); }
+        env->bit_depth != 8) { hbi_fail(HB_ERR_ARG, "quant: unsupported shape (size %d, depth %d, comp %d, scan %d)", cu_size, depth, comp, scan_mode); die("quant"); }
     const int n = cu_size, list = (is_intra ? 0 : 3) + comp;
     const int qbits = 14 + per + (15 - env->bit_depth - lg);
     const int add = (int)((uint32_t)(env->is_islice ? 171 : 85) << (qbits - 9));
     int16_t *a = (int16_t *)s->host, *l = a + 32 * 32, *u = l + 32 * 32;
     int32_t *sum = (int32_t *)(u + 32 * 32);
     memcpy(a, src, sizeof(int16_t) * (size_t)n * n);
-    finish(s, hbk_pc_quant(D(s, a), D(s, l), D(s, u), D(s, sum), n, ctx->d_q + hb_tab_q_off(lg, list, rem),
-                           ctx->d_scan + hb_tab_scan_off(scan_mode, lg), qbits, add, env->sign_hiding, s->stream), "quant");
+    finish(s, hbk_pc_quant(D(s, a), D(s, l), D(s, u), D(s, sum), n, ctx->d_q + hbi_tab_q_off(lg, list, rem),
+                           ctx->d_scan + hbi_tab_scan_off(scan_mode, lg), qbits, add, env->sign_hiding, s->stream), "quant");
     memcpy(dst, l, sizeof(int16_t) * (size_t)n * n);
     if (env->delta_u) memcpy(env->delta_u, u, sizeof(int16_t) * (size_t)n * n);
     *ac_sum = *sum;
@@ -208,12 +208,12 @@ void hb_inv_quant(const hb_quant_env *env, int16_t *src, int16_t *dst, int depth
     hb_ctx *ctx = hb_default_ctx();
     const int lg = env->max_cu_size_shift - (depth + (comp != 0));
     if (lg < 2 || lg > 5 || cu_size != (1 << lg) || rem < 0 || rem > 5 || env->bit_depth != 8) {
-        hb_fail(HB_ERR_ARG, "inv_quant: unsupported shape (size %d, depth %d, comp %d)", cu_size, depth, comp); die("inv_quant");
+        hbi_fail(HB_ERR_ARG, "inv_quant: unsupported shape (size %d, depth %d, comp %d)", cu_size, depth, comp); die("inv_quant");
     }
     const int n = cu_size, list = is_intra ? 0 : 3 + comp;  /* the SSE4.2 precedence quirk, hmr_sse42_functions_quant.c:138 */
     int16_t *a = (int16_t *)s->host, *d = a + 32 * 32;
     memcpy(a, src, sizeof(int16_t) * (size_t)n * n);
-    finish(s, hbk_pc_inv_quant(D(s, a), D(s, d), n, ctx->d_dq + hb_tab_q_off(lg, list, rem), per, s->stream), "inv_quant");
+    finish(s, hbk_pc_inv_quant(D(s, a), D(s, d), n, ctx->d_dq + hbi_tab_q_off(lg, list, rem), per, s->stream), "inv_quant");
     memcpy(dst, d, sizeof(int16_t) * (size_t)n * n);
 }
 

@@ -73,11 +73,11 @@ static int pu_valid(const hb_prepass *pp, int x, int y, int s)
 static int upload(hb_ctx *ctx, void **dev, const void *host, size_t bytes)
 {
     int rc = hbc_malloc(dev, bytes ? bytes : 16);
-    if (rc) return hb_cuda_fail(rc, "prepass: cudaMalloc");
+    if (rc) return hbi_cuda_fail(rc, "prepass: cudaMalloc");
     if (bytes) {
         rc = hbc_h2d_async(*dev, host, bytes, ctx->stream);
         if (!rc) rc = hbc_stream_sync(ctx->stream);      /* host staging is pageable and freed by the caller */
-        if (rc) return hb_cuda_fail(rc, "prepass: upload");
+        if (rc) return hbi_cuda_fail(rc, "prepass: upload");
     }
     return HB_OK;
 }
@@ -85,17 +85,17 @@ static int upload(hb_ctx *ctx, void **dev, const void *host, size_t bytes)
 int hb_prepass_create(hb_ctx *ctx, int width, int height, const hb_prepass_cfg *cfg, hb_prepass **out)
 {
     int rc = HB_OK;
-    if (!ctx || !cfg || !out) return hb_fail(HB_ERR_ARG, "hb_prepass_create: NULL argument");
-    if (cfg->qp < 0 || cfg->qp > 51) return hb_fail(HB_ERR_ARG, "hb_prepass_create: qp %d", cfg->qp);
+    if (!ctx || !cfg || !out) return hbi_fail(HB_ERR_ARG, "hb_prepass_create: NULL argument");
+    if (cfg->qp < 0 || cfg->qp > 51) return hbi_fail(HB_ERR_ARG, "hb_prepass_create: qp %d", cfg->qp);
     *out = NULL;
     hb_prepass *pp = (hb_prepass *)calloc(1, sizeof *pp);
-    if (!pp) return hb_fail(HB_ERR_NOMEM, "hb_prepass_create: out of memory");
+    if (!pp) return hbi_fail(HB_ERR_NOMEM, "hb_prepass_create: out of memory");
     pp->ctx = ctx; pp->cfg = *cfg; pp->w = width; pp->h = height;
     pp->ctu_cols = (width + 63) / 64; pp->ctu_rows = (height + 63) / 64;
     pp->row0 = cfg->band_ctu_rows > 0 ? cfg->band_ctu_row0 : 0;
     pp->rows = cfg->band_ctu_rows > 0 ? cfg->band_ctu_rows : pp->ctu_rows;
-    if (pp->row0 < 0 || pp->row0 + pp->rows > pp->ctu_rows) { free(pp); return hb_fail(HB_ERR_ARG, "hb_prepass_create: band outside the frame"); }
-    pp->qp_c = hb_chroma_qp(cfg->qp, cfg->chroma_qp_offset);
+    if (pp->row0 < 0 || pp->row0 + pp->rows > pp->ctu_rows) { free(pp); return hbi_fail(HB_ERR_ARG, "hb_prepass_create: band outside the frame"); }
+    pp->qp_c = hbi_chroma_qp(cfg->qp, cfg->chroma_qp_offset);
     pp->weight_c = pow(2.0, (cfg->qp - pp->qp_c) / 3.0);           /* hmr_motion_inter.c:155 */
     hbc_set_device(ctx->device);
 
@@ -107,7 +107,7 @@ int hb_prepass_create(hb_ctx *ctx, int width, int height, const hb_prepass_cfg *
         hbd_me_job *jobs = (hbd_me_job *)calloc((size_t)gw * gh, sizeof *jobs);
         hbd_mc_pu *pus = (hbd_mc_pu *)calloc((size_t)gw * gh, sizeof *pus);
         hb_me_result *init = (hb_me_result *)calloc((size_t)gw * gh, sizeof *init);
-        if (!jobs || !pus || !init) { free(jobs); free(pus); free(init); rc = hb_fail(HB_ERR_NOMEM, "hb_prepass_create: out of memory"); break; }
+        if (!jobs || !pus || !init) { free(jobs); free(pus); free(init); rc = hbi_fail(HB_ERR_NOMEM, "hb_prepass_create: out of memory"); break; }
         int n = 0;
         for (int py = 0; py < gh; py++)
             for (int px = 0; px < gw; px++) {
@@ -147,7 +147,7 @@ int hb_prepass_create(hb_ctx *ctx, int width, int height, const hb_prepass_cfg *
             int32_t *index = (int32_t *)malloc(sizeof(int32_t) * (size_t)tw * th);
             pc->h_ctu = (int32_t *)malloc(sizeof(int32_t) * (size_t)tw * th);
             pc->grid_w = tw; pc->grid_h = th;
-            if (!xy || !index || !pc->h_ctu) { free(xy); free(index); rc = hb_fail(HB_ERR_NOMEM, "hb_prepass_create: out of memory"); break; }
+            if (!xy || !index || !pc->h_ctu) { free(xy); free(index); rc = hbi_fail(HB_ERR_NOMEM, "hb_prepass_create: out of memory"); break; }
             int n = 0;
             for (int ty = 0; ty < th; ty++)
                 for (int tx = 0; tx < tw; tx++) {
@@ -165,8 +165,8 @@ int hb_prepass_create(hb_ctx *ctx, int width, int height, const hb_prepass_cfg *
             if (rc == HB_OK) rc = upload(ctx, (void **)&pc->d_index, index, sizeof(int32_t) * (size_t)tw * th);
             free(xy); free(index);
             int crc = 0;
-            if (rc == HB_OK && (crc = hbc_malloc((void **)&pc->d_coeff, sizeof(int16_t) * (size_t)(n ? n : 1) * tu * tu))) rc = hb_cuda_fail(crc, "prepass: coeff");
-            if (rc == HB_OK && (crc = hbc_malloc((void **)&pc->d_res, sizeof(hb_tu_result) * (size_t)(n ? n : 1)))) rc = hb_cuda_fail(crc, "prepass: results");
+            if (rc == HB_OK && (crc = hbc_malloc((void **)&pc->d_coeff, sizeof(int16_t) * (size_t)(n ? n : 1) * tu * tu))) rc = hbi_cuda_fail(crc, "prepass: coeff");
+            if (rc == HB_OK && (crc = hbc_malloc((void **)&pc->d_res, sizeof(hb_tu_result) * (size_t)(n ? n : 1)))) rc = hbi_cuda_fail(crc, "prepass: results");
         }
     }
     for (int d = 0; d < N_DEPTH && rc == HB_OK; d++) {
@@ -176,11 +176,11 @@ int hb_prepass_create(hb_ctx *ctx, int width, int height, const hb_prepass_cfg *
             crc = hbc_stream_create(&pp->side[d][k]);
             if (!crc) crc = hbc_event_create_notiming(&pp->ev_join[d][k]);
         }
-        if (crc) rc = hb_cuda_fail(crc, "prepass: side streams");
+        if (crc) rc = hbi_cuda_fail(crc, "prepass: side streams");
     }
     if (rc == HB_OK) {
         const int crc = hbc_malloc((void **)&pp->d_dyn, sizeof *pp->d_dyn);
-        if (crc) rc = hb_cuda_fail(crc, "prepass: dyn block");
+        if (crc) rc = hbi_cuda_fail(crc, "prepass: dyn block");
     }
     if (rc != HB_OK) { hb_prepass_destroy(pp); return rc; }
     *out = pp;
@@ -245,7 +245,7 @@ static int enqueue_tq(hb_prepass *pp, const hb_frame *cur, int p, int c0, int c1
         if (!pc->tu || !pc->n_tus) continue;
         hbd_tq_args a;
         memset(&a, 0, sizeof a);
-        hb_tq_setup(ctx, &a, c, pc->tu, c ? pp->qp_c : pp->cfg.qp, pp->cfg.is_islice, pp->cfg.sign_hiding);
+        hbi_tq_setup(ctx, &a, c, pc->tu, c ? pp->qp_c : pp->cfg.qp, pp->cfg.is_islice, pp->cfg.sign_hiding);
         a.cur = cur->d.p[c]; a.pred = pred->d.p[c]; a.rec = pp->recon[p]->d.p[c];
         a.jobs_xy = pc->d_xy; a.n_jobs = pc->n_tus;
         a.thr_k = 1.; a.weight = c ? pp->weight_c : 1.; a.dyn = pp->d_dyn;
@@ -317,8 +317,8 @@ static int enqueue(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, int
 int hb_prepass_run(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, double avg_dist)
 {
     int crc = 0, n = 0;
-    if (!pp || !cur || !ref) return hb_fail(HB_ERR_ARG, "hb_prepass_run: NULL argument");
-    if (cur->w != pp->w || cur->h != pp->h || ref->w != pp->w || ref->h != pp->h) return hb_fail(HB_ERR_ARG, "hb_prepass_run: frame size differs from the plan");
+    if (!pp || !cur || !ref) return hbi_fail(HB_ERR_ARG, "hb_prepass_run: NULL argument");
+    if (cur->w != pp->w || cur->h != pp->h || ref->w != pp->w || ref->h != pp->h) return hbi_fail(HB_ERR_ARG, "hb_prepass_run: frame size differs from the plan");
     hb_ctx *ctx = pp->ctx;
     hbc_set_device(ctx->device);
     /* per-frame scalars: same expressions, same host libm as the reference (hmr_common.h:53, hmr_motion_inter.c:106) */
@@ -328,8 +328,8 @@ int hb_prepass_run(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, dou
      * without waiting for the previous replay */
     hbd_dyn_params dyn;
     dyn.corr = (uint32_t)pp->cfg.qp * w;
-    dyn.thr_k = hb_zero_out_k(avg_dist);
-    if ((crc = hbc_h2d_async(pp->d_dyn, &dyn, sizeof dyn, ctx->stream))) return hb_cuda_fail(crc, "hb_prepass_run: params");
+    dyn.thr_k = hbi_zero_out_k(avg_dist);
+    if ((crc = hbc_h2d_async(pp->d_dyn, &dyn, sizeof dyn, ctx->stream))) return hbi_cuda_fail(crc, "hb_prepass_run: params");
 
     if (!pp->cfg.use_graph) {
         crc = enqueue(pp, cur, ref, &n, 0);
@@ -338,10 +338,10 @@ int hb_prepass_run(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, dou
         for (int i = 0; i < pp->n_graphs; i++) if (pp->graphs[i].cur == cur && pp->graphs[i].ref == ref) exec = pp->graphs[i].exec;
         if (!exec) {
             if (pp->n_graphs == MAX_GRAPHS) { hbc_graph_destroy(pp->graphs[0].exec); memmove(&pp->graphs[0], &pp->graphs[1], sizeof pp->graphs[0] * (MAX_GRAPHS - 1)); pp->n_graphs--; }
-            if ((crc = hbc_graph_begin(ctx->stream))) return hb_cuda_fail(crc, "hb_prepass_run: begin capture");
+            if ((crc = hbc_graph_begin(ctx->stream))) return hbi_cuda_fail(crc, "hb_prepass_run: begin capture");
             crc = enqueue(pp, cur, ref, &n, 0);
             const int erc = hbc_graph_end(ctx->stream, &exec);
-            if (crc || erc) return hb_cuda_fail(crc ? crc : erc, "hb_prepass_run: capture");
+            if (crc || erc) return hbi_cuda_fail(crc ? crc : erc, "hb_prepass_run: capture");
             pp->graphs[pp->n_graphs].cur = cur; pp->graphs[pp->n_graphs].ref = ref; pp->graphs[pp->n_graphs].exec = exec;
             pp->n_graphs++;
             pp->launches_per_frame = n;
@@ -349,7 +349,7 @@ int hb_prepass_run(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, dou
         n = pp->launches_per_frame;
         crc = hbc_graph_launch(exec, ctx->stream);
     }
-    if (crc) return hb_cuda_fail(crc, "hb_prepass_run");
+    if (crc) return hbi_cuda_fail(crc, "hb_prepass_run");
     pp->launches_per_frame = n;
     ctx->launches += (uint64_t)n;
     return HB_OK;
@@ -360,23 +360,23 @@ int hb_prepass_run(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, dou
 int hb_prepass_run_profiled(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, double avg_dist, float *ms, int cap)
 {
     int crc = 0, n = 0;
-    if (!pp || !cur || !ref || !ms) return hb_fail(HB_ERR_ARG, "hb_prepass_run_profiled: NULL argument");
+    if (!pp || !cur || !ref || !ms) return hbi_fail(HB_ERR_ARG, "hb_prepass_run_profiled: NULL argument");
     hb_ctx *ctx = pp->ctx;
     hbc_set_device(ctx->device);
     for (int i = 0; i <= HB_PREPASS_MAX_KERNELS && !crc; i++) if (!pp->prof_ev[i]) crc = hbc_event_create(&pp->prof_ev[i]);
-    if (crc) return hb_cuda_fail(crc, "hb_prepass_run_profiled: events");
+    if (crc) return hbi_cuda_fail(crc, "hb_prepass_run_profiled: events");
     double w = avg_dist / 2000.;
     w = w < .15 ? .15 : (w > 1.4 ? 1.4 : w);
     hbd_dyn_params dyn;
     dyn.corr = (uint32_t)pp->cfg.qp * w;
-    dyn.thr_k = hb_zero_out_k(avg_dist);
-    if ((crc = hbc_h2d_async(pp->d_dyn, &dyn, sizeof dyn, ctx->stream))) return hb_cuda_fail(crc, "hb_prepass_run_profiled: params");
+    dyn.thr_k = hbi_zero_out_k(avg_dist);
+    if ((crc = hbc_h2d_async(pp->d_dyn, &dyn, sizeof dyn, ctx->stream))) return hbi_cuda_fail(crc, "hb_prepass_run_profiled: params");
     crc = enqueue(pp, cur, ref, &n, 1);
-    if (crc) return hb_cuda_fail(crc, "hb_prepass_run_profiled");
+    if (crc) return hbi_cuda_fail(crc, "hb_prepass_run_profiled");
     ctx->launches += (uint64_t)n;
-    if (n > cap) return hb_fail(HB_ERR_ARG, "hb_prepass_run_profiled: %d kernels, room for %d", n, cap);
+    if (n > cap) return hbi_fail(HB_ERR_ARG, "hb_prepass_run_profiled: %d kernels, room for %d", n, cap);
     for (int i = 0; i < n && !crc; i++) crc = hbc_event_elapsed(pp->prof_ev[i], pp->prof_ev[i + 1], &ms[i]);
-    if (crc) return hb_cuda_fail(crc, "hb_prepass_run_profiled: elapsed");
+    if (crc) return hbi_cuda_fail(crc, "hb_prepass_run_profiled: elapsed");
     return n;
 }
 const char *hb_prepass_kernel_name(const hb_prepass *pp, int i) { return (pp && i >= 0 && i < HB_PREPASS_MAX_KERNELS) ? pp->prof_name[i] : ""; }
@@ -397,33 +397,33 @@ static int fetch(hb_prepass *pp, void *dst, const void *dev, size_t bytes, const
     if (!bytes) return HB_OK;
     hbc_set_device(ctx->device);
     pthread_mutex_lock(&ctx->lock);
-    if ((rc = hb_scratch(ctx, 3, bytes, NULL, &h)) != HB_OK) { pthread_mutex_unlock(&ctx->lock); return rc; }
+    if ((rc = hbi_scratch(ctx, 3, bytes, NULL, &h)) != HB_OK) { pthread_mutex_unlock(&ctx->lock); return rc; }
     crc = hbc_d2h_async(h, dev, bytes, ctx->stream);
     if (!crc) crc = hbc_stream_sync(ctx->stream);
     if (!crc) memcpy(dst, h, bytes);
     pthread_mutex_unlock(&ctx->lock);
-    return crc ? hb_cuda_fail(crc, what) : HB_OK;
+    return crc ? hbi_cuda_fail(crc, what) : HB_OK;
 }
 
 int hb_prepass_fetch_me(hb_prepass *pp, int depth, hb_me_result *out)
 {
-    if (!pp || !out || depth < 0 || depth >= N_DEPTH) return hb_fail(HB_ERR_ARG, "hb_prepass_fetch_me: bad argument");
+    if (!pp || !out || depth < 0 || depth >= N_DEPTH) return hbi_fail(HB_ERR_ARG, "hb_prepass_fetch_me: bad argument");
     return fetch(pp, out, pp->d_me[depth], sizeof(hb_me_result) * (size_t)hb_prepass_num_pus(pp, depth), "hb_prepass_fetch_me");
 }
 int hb_prepass_fetch_tu(hb_prepass *pp, int pass, int comp, hb_tu_result *out)
 {
-    if (!pp || !out || pass < 0 || pass >= N_PASS || comp < 0 || comp > 2) return hb_fail(HB_ERR_ARG, "hb_prepass_fetch_tu: bad argument");
+    if (!pp || !out || pass < 0 || pass >= N_PASS || comp < 0 || comp > 2) return hbi_fail(HB_ERR_ARG, "hb_prepass_fetch_tu: bad argument");
     return fetch(pp, out, pp->pc[pass][comp].d_res, sizeof(hb_tu_result) * (size_t)pp->pc[pass][comp].n_tus, "hb_prepass_fetch_tu");
 }
 int hb_prepass_fetch_coeffs(hb_prepass *pp, int pass, int comp, int16_t *out)
 {
-    if (!pp || !out || pass < 0 || pass >= N_PASS || comp < 0 || comp > 2) return hb_fail(HB_ERR_ARG, "hb_prepass_fetch_coeffs: bad argument");
+    if (!pp || !out || pass < 0 || pass >= N_PASS || comp < 0 || comp > 2) return hbi_fail(HB_ERR_ARG, "hb_prepass_fetch_coeffs: bad argument");
     const pass_comp *pc = &pp->pc[pass][comp];
     return fetch(pp, out, pc->d_coeff, sizeof(int16_t) * (size_t)pc->n_tus * pc->tu * pc->tu, "hb_prepass_fetch_coeffs");
 }
 int hb_prepass_tu_xy(hb_prepass *pp, int pass, int comp, int32_t *xy_out)
 {
-    if (!pp || !xy_out || pass < 0 || pass >= N_PASS || comp < 0 || comp > 2) return hb_fail(HB_ERR_ARG, "hb_prepass_tu_xy: bad argument");
+    if (!pp || !xy_out || pass < 0 || pass >= N_PASS || comp < 0 || comp > 2) return hbi_fail(HB_ERR_ARG, "hb_prepass_tu_xy: bad argument");
     return fetch(pp, xy_out, pp->pc[pass][comp].d_xy, sizeof(int32_t) * 2 * (size_t)pp->pc[pass][comp].n_tus, "hb_prepass_tu_xy");
 }
 int hb_prepass_tu_size(const hb_prepass *pp, int pass, int comp)
@@ -432,7 +432,7 @@ int hb_prepass_tu_size(const hb_prepass *pp, int pass, int comp)
 }
 int hb_prepass_fetch_recon(hb_prepass *pp, int pass, uint8_t *y, int ys, uint8_t *u, int us, uint8_t *v, int vs)
 {
-    if (!pp || pass < 0 || pass >= N_PASS) return hb_fail(HB_ERR_ARG, "hb_prepass_fetch_recon: bad argument");
+    if (!pp || pass < 0 || pass >= N_PASS) return hbi_fail(HB_ERR_ARG, "hb_prepass_fetch_recon: bad argument");
     return hb_frame_download_u8(pp->ctx, pp->recon[pass], y, ys, u, us, v, vs);
 }
 
@@ -455,9 +455,9 @@ size_t hb_prepass_output_bytes(const hb_prepass *pp)
  * {TU results Y,U,V; levels Y,U,V; reconstruction Y,U,V (tight pitch)}.  dst should be pinned. */
 int hb_prepass_fetch_all(hb_prepass *pp, void *pinned_dst, size_t cap, size_t *bytes_out)
 {
-    if (!pp || !pinned_dst) return hb_fail(HB_ERR_ARG, "hb_prepass_fetch_all: NULL argument");
+    if (!pp || !pinned_dst) return hbi_fail(HB_ERR_ARG, "hb_prepass_fetch_all: NULL argument");
     const size_t need = hb_prepass_output_bytes(pp);
-    if (cap < need) return hb_fail(HB_ERR_ARG, "hb_prepass_fetch_all: need %zu bytes, got %zu", need, cap);
+    if (cap < need) return hbi_fail(HB_ERR_ARG, "hb_prepass_fetch_all: need %zu bytes, got %zu", need, cap);
     hb_ctx *ctx = pp->ctx;
     char *o = (char *)pinned_dst;
     int crc = 0;
@@ -484,7 +484,7 @@ int hb_prepass_fetch_all(hb_prepass *pp, void *pinned_dst, size_t cap, size_t *b
         }
     }
     if (!crc) crc = hbc_stream_sync(ctx->stream);
-    if (crc) return hb_cuda_fail(crc, "hb_prepass_fetch_all");
+    if (crc) return hbi_cuda_fail(crc, "hb_prepass_fetch_all");
     if (bytes_out) *bytes_out = (size_t)(o - (char *)pinned_dst);
     return HB_OK;
 }
@@ -504,8 +504,8 @@ size_t hb_prepass_tables_bytes(const hb_prepass *pp)
 /* ME tables d0..d3, then TU tables pass 0..4 x (Y,U,V), packed; dst should be pinned.  Asynchronous: hb_ctx_sync before reading. */
 int hb_prepass_fetch_tables(hb_prepass *pp, void *pinned_dst, size_t cap)
 {
-    if (!pp || !pinned_dst) return hb_fail(HB_ERR_ARG, "hb_prepass_fetch_tables: NULL argument");
-    if (cap < hb_prepass_tables_bytes(pp)) return hb_fail(HB_ERR_ARG, "hb_prepass_fetch_tables: buffer too small");
+    if (!pp || !pinned_dst) return hbi_fail(HB_ERR_ARG, "hb_prepass_fetch_tables: NULL argument");
+    if (cap < hb_prepass_tables_bytes(pp)) return hbi_fail(HB_ERR_ARG, "hb_prepass_fetch_tables: buffer too small");
     hb_ctx *ctx = pp->ctx;
     char *o = (char *)pinned_dst;
     int crc = 0;
@@ -519,7 +519,7 @@ int hb_prepass_fetch_tables(hb_prepass *pp, void *pinned_dst, size_t cap)
             const size_t b = sizeof(hb_tu_result) * (size_t)pp->pc[p][c].n_tus;
             if (b) { crc = hbc_d2h_async(o, pp->pc[p][c].d_res, b, ctx->stream); o += b; }
         }
-    return crc ? hb_cuda_fail(crc, "hb_prepass_fetch_tables") : HB_OK;
+    return crc ? hbi_cuda_fail(crc, "hb_prepass_fetch_tables") : HB_OK;
 }
 
 int hb_prepass_num_ctus(const hb_prepass *pp) { return pp ? pp->ctu_cols * pp->ctu_rows : 0; }
@@ -530,7 +530,7 @@ int hb_prepass_num_ctus(const hb_prepass *pp) { return pp ? pp->ctu_cols * pp->c
  * `tables` is what hb_prepass_fetch_tables delivered.  Pure host code. */
 int hb_prepass_select(const hb_prepass *pp, const void *tables, int lambda, uint8_t *sel, int32_t *ctu_off)
 {
-    if (!pp || !tables || !sel || !ctu_off) return hb_fail(HB_ERR_ARG, "hb_prepass_select: NULL argument");
+    if (!pp || !tables || !sel || !ctu_off) return hbi_fail(HB_ERR_ARG, "hb_prepass_select: NULL argument");
     const int n_ctus = hb_prepass_num_ctus(pp);
     const char *t = (const char *)tables;
     for (int d = 0; d < N_DEPTH; d++) t += sizeof(hb_me_result) * (size_t)hb_prepass_num_pus(pp, d);
@@ -538,7 +538,7 @@ int hb_prepass_select(const hb_prepass *pp, const void *tables, int lambda, uint
     for (int p = 0; p < N_PASS; p++) for (int c = 0; c < 3; c++) { res[p][c] = (const hb_tu_result *)t; t += sizeof(hb_tu_result) * (size_t)pp->pc[p][c].n_tus; }
     uint64_t *cost = (uint64_t *)calloc((size_t)n_ctus * 8, sizeof *cost);       /* [ctu][0..3 luma+chroma of pass p, 4 luma of pass 4] */
     int32_t *len = (int32_t *)calloc((size_t)n_ctus * 8, sizeof *len);            /* stream length of the same pieces */
-    if (!cost || !len) { free(cost); free(len); return hb_fail(HB_ERR_NOMEM, "hb_prepass_select: out of memory"); }
+    if (!cost || !len) { free(cost); free(len); return hbi_fail(HB_ERR_NOMEM, "hb_prepass_select: out of memory"); }
     for (int p = 0; p < N_PASS; p++)
         for (int c = 0; c < 3; c++) {
             const pass_comp *pc = &pp->pc[p][c];
@@ -586,24 +586,24 @@ size_t hb_prepass_gather_bytes(const hb_prepass *pp, const int32_t *ctu_off)
  * streams of all CTUs (layout in hb_kernels_gather.cu).  Asynchronous: hb_ctx_sync before reading. */
 int hb_prepass_gather(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_off, void *pinned_dst, size_t cap, size_t *bytes_out)
 {
-    if (!pp || !sel || !ctu_off || !pinned_dst) return hb_fail(HB_ERR_ARG, "hb_prepass_gather: NULL argument");
+    if (!pp || !sel || !ctu_off || !pinned_dst) return hbi_fail(HB_ERR_ARG, "hb_prepass_gather: NULL argument");
     hb_ctx *ctx = pp->ctx;
     const int n_ctus = hb_prepass_num_ctus(pp);
     const size_t recon_bytes = (size_t)pp->w * pp->h * 3 / 2, lev = (size_t)ctu_off[n_ctus];
     const size_t need = recon_bytes + sizeof(int16_t) * lev;
     int crc = 0;
-    if (cap < need) return hb_fail(HB_ERR_ARG, "hb_prepass_gather: need %zu bytes, got %zu", need, cap);
-    for (int i = 0; i < n_ctus; i++) if (sel[i] > 4) return hb_fail(HB_ERR_ARG, "hb_prepass_gather: sel[%d] = %d", i, sel[i]);
+    if (cap < need) return hbi_fail(HB_ERR_ARG, "hb_prepass_gather: need %zu bytes, got %zu", need, cap);
+    for (int i = 0; i < n_ctus; i++) if (sel[i] > 4) return hbi_fail(HB_ERR_ARG, "hb_prepass_gather: sel[%d] = %d", i, sel[i]);
     hbc_set_device(ctx->device);
     if (!pp->d_sel) {
         if ((crc = hbc_malloc((void **)&pp->d_sel, (size_t)n_ctus)) || (crc = hbc_malloc((void **)&pp->d_ctu_off, sizeof(int32_t) * ((size_t)n_ctus + 1))) ||
-            (crc = hbc_malloc((void **)&pp->d_sel_recon, recon_bytes))) return hb_cuda_fail(crc, "hb_prepass_gather: cudaMalloc");
+            (crc = hbc_malloc((void **)&pp->d_sel_recon, recon_bytes))) return hbi_cuda_fail(crc, "hb_prepass_gather: cudaMalloc");
     }
     if (pp->sel_levels_cap < lev + 8) {
-        if ((crc = hbc_stream_sync(ctx->stream))) return hb_cuda_fail(crc, "hb_prepass_gather: sync");
+        if ((crc = hbc_stream_sync(ctx->stream))) return hbi_cuda_fail(crc, "hb_prepass_gather: sync");
         if (pp->d_sel_levels) hbc_free(pp->d_sel_levels);
         pp->sel_levels_cap = (lev + 8) * 2;
-        if ((crc = hbc_malloc((void **)&pp->d_sel_levels, sizeof(int16_t) * pp->sel_levels_cap))) { pp->sel_levels_cap = 0; pp->d_sel_levels = NULL; return hb_cuda_fail(crc, "hb_prepass_gather: cudaMalloc"); }
+        if ((crc = hbc_malloc((void **)&pp->d_sel_levels, sizeof(int16_t) * pp->sel_levels_cap))) { pp->sel_levels_cap = 0; pp->d_sel_levels = NULL; return hbi_cuda_fail(crc, "hb_prepass_gather: cudaMalloc"); }
     }
     /* sel / ctu_off are pageable: staged by the runtime before the call returns */
     crc = hbc_h2d_async(pp->d_sel, sel, (size_t)n_ctus, ctx->stream);
@@ -624,7 +624,7 @@ int hb_prepass_gather(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_off
     if (!crc) { crc = hbk_gather(&a, n_ctus, ctx->stream); ctx->launches++; }
     if (!crc) crc = hbc_d2h_async(pinned_dst, pp->d_sel_recon, recon_bytes, ctx->stream);
     if (!crc && lev) crc = hbc_d2h_async((char *)pinned_dst + recon_bytes, pp->d_sel_levels, sizeof(int16_t) * lev, ctx->stream);
-    if (crc) return hb_cuda_fail(crc, "hb_prepass_gather");
+    if (crc) return hbi_cuda_fail(crc, "hb_prepass_gather");
     if (bytes_out) *bytes_out = need;
     return HB_OK;
 }
@@ -638,7 +638,7 @@ int hb_prepass_process_frame(hb_prepass *pp, hb_frame *cur, hb_frame *ref, const
                              void *out, size_t out_cap, size_t *out_bytes)
 {
     int rc;
-    if (!pp || !cur || !ref || !cur_planes || !ref_planes) return hb_fail(HB_ERR_ARG, "hb_prepass_process_frame: NULL argument");
+    if (!pp || !cur || !ref || !cur_planes || !ref_planes) return hbi_fail(HB_ERR_ARG, "hb_prepass_process_frame: NULL argument");
     hb_ctx *ctx = pp->ctx;
     const int w = pp->w;
     if ((rc = hb_frame_upload_u8_ex(ctx, cur, cur_planes[0], w, cur_planes[1], w / 2, cur_planes[2], w / 2, HB_UPLOAD_NO_BORDER)) != HB_OK) return rc;

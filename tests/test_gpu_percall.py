@@ -157,3 +157,65 @@ def test_function_table(ctx):
     assert filled == {"sad", "ssd16b", "predict", "reconst", "interpolate_luma_m_compensation",
                       "interpolate_chroma_m_compensation", "interpolate_luma_m_estimation", "transform", "itransform"}
     assert t.sad == C.cast(L.hb_sad, C.c_void_p).value
+
+
+def test_percall_is_thread_safe(ctx):
+    """the table is shared by all encoder threads without locks (hmr_encoder_lib.c:1262): concurrent callers, each with its own
+    stream and staging area, must get the same answers as a single thread"""
+    import threading
+    O = oracle()
+    rng = np.random.default_rng(17)
+    cases = []
+    for _ in range(64):
+        n = int(rng.choice([4, 8, 16, 32]))
+        a = aligned_i16(64 * 64); b = aligned_i16(64 * 64)
+        a[:] = rng.integers(0, 256, a.size); b[:] = rng.integers(0, 256, b.size)
+        cases.append((n, a, b, O.orc_sad(ptr(a), 64, ptr(b), 64, n), O.orc_ssd16b(ptr(a), 64, ptr(b), 64, n)))
+    errors = []
+
+    def worker(k):
+        for rep in range(4):
+            for i in range(k, len(cases), 8):
+                n, a, b, esad, essd = cases[i]
+                if ll.sad(a, 64, b, 64, n) != esad or ll.ssd16b(a, 64, b, 64, n) != essd:
+                    errors.append((k, i))
+                blk = aligned_i16(64 * 64); blk[:] = a - b
+                c1 = np.zeros(1024, np.int16); c2 = np.zeros(1024, np.int16)
+                ll.transform(8, blk, c1, 64, n)
+                O.orc_transform(8, ptr(blk), 64, ptr(c2), n, 0)
+                if not np.array_equal(c1, c2):
+                    errors.append((k, i, "tx"))
+
+    ths = [threading.Thread(target=worker, args=(k,)) for k in range(8)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errors, errors[:5]
+
+
+def test_batched_api_rejects_bad_arguments(ctx):
+    """status-returning entry points validate their jobs instead of launching on garbage"""
+    w, h = 128, 64
+    f = hb.Frame(ctx, w, h)
+    y = np.zeros((h, w), np.uint8); u = np.zeros((h // 2, w // 2), np.uint8)
+    f.upload_u8(y, u, u)
+    bad_me = hb.MeJob(); bad_me.x, bad_me.y, bad_me.size, bad_me.qp, bad_me.parent = 96, 0, 64, 30, -1      # sticks out of the frame
+    with pytest.raises(hb.HbError):
+        ctx.me_search(f, f, [bad_me], 100.0)
+    odd = hb.MeJob(); odd.x, odd.y, odd.size, odd.qp, odd.parent = 0, 0, 24, 30, -1                            # not a PU size
+    with pytest.raises(hb.HbError):
+        ctx.me_search(f, f, [odd], 100.0)
+    with pytest.raises(hb.HbError):
+        ctx.tq_encode(f, f, f, [hb.TuJob(1, 0, 0, 32, 30)], hb.TqParams(0, 1, 0.0, 1.0))                       # no 32x32 chroma TU
+    with pytest.raises(hb.HbError):
+        hb.Frame(ctx, 100, 60)                                                                                 # not a multiple of 8
+    with pytest.raises(hb.HbError):
+        hb.Prepass(ctx, w, h, qp=77)
+    i16 = np.full((h, w), 300, np.int16); c16 = np.zeros((h // 2, w // 2), np.int16)
+    with pytest.raises(hb.HbError):
+        f.upload_i16(i16, c16, c16)                                                                            # 8-bit video only
+    ok = np.full((h, w), 200, np.int16)
+    f.upload_i16(ok, c16, c16)
+    assert int(f.download()[0][5, 7]) == 200
+    f.close()
