@@ -691,3 +691,53 @@ done:
     if (crc) return hbi_cuda_fail(crc, "hb_tq_encode_intra");
     return rc;
 }
+
+/* ------------------------------------------------------------------ intra prediction
+ * adi: per job 4*size+1 reference samples (index 2*size = top-left corner, +i above, -i left), jobs back to back.
+ * mode >= 0: the prediction goes to `pred` (then hb_tq_encode_intra); mode < 0: sads[35*i + m] = SAD of luma mode m. */
+int hb_intra_run(hb_ctx *ctx, const hb_frame *cur, hb_frame *pred, const hb_intra_job *jobs, int n_jobs, const int16_t *adi, uint32_t *sads)
+{
+    int rc = HB_OK, crc = 0, need_sads = 0;
+    if (!ctx || !jobs || !adi || n_jobs < 0) return hbi_fail(HB_ERR_ARG, "hb_intra_run: bad argument");
+    if (n_jobs == 0) return HB_OK;
+    size_t n_adi = 0;
+    for (int i = 0; i < n_jobs; i++) {
+        const hb_intra_job *j = &jobs[i];
+        const hb_frame *f = j->mode < 0 ? cur : pred;
+        if (!f || j->comp < 0 || j->comp > 2 || (j->size != 4 && j->size != 8 && j->size != 16 && j->size != 32) || j->mode > 34 ||
+            (j->mode < 0 && j->comp != 0) || j->x < 0 || j->y < 0 || j->x + j->size > f->d.p[j->comp].w || j->y + j->size > f->d.p[j->comp].h)
+            return hbi_fail(HB_ERR_ARG, "hb_intra_run: job %d is invalid", i);
+        need_sads |= j->mode < 0;
+        n_adi += 4 * (size_t)j->size + 1;
+    }
+    if (need_sads && !sads) return hbi_fail(HB_ERR_ARG, "hb_intra_run: sads is NULL");
+    hbc_set_device(ctx->device);
+    pthread_mutex_lock(&ctx->lock);
+    void *d_jobs, *h_jobs, *d_adi, *h_adi, *d_sad, *h_sad;
+    if ((rc = hbi_scratch(ctx, 0, sizeof(hbd_intra_job) * (size_t)n_jobs, &d_jobs, &h_jobs)) != HB_OK) goto done;
+    if ((rc = hbi_scratch(ctx, 1, sizeof(int16_t) * n_adi, &d_adi, &h_adi)) != HB_OK) goto done;
+    if ((rc = hbi_scratch(ctx, 2, sizeof(uint32_t) * 35 * (size_t)n_jobs, &d_sad, &h_sad)) != HB_OK) goto done;
+    hbd_intra_job *hj = (hbd_intra_job *)h_jobs;
+    size_t off = 0;
+    for (int i = 0; i < n_jobs; i++) {
+        hj[i].comp = jobs[i].comp; hj[i].x = jobs[i].x; hj[i].y = jobs[i].y; hj[i].size = jobs[i].size; hj[i].mode = jobs[i].mode;
+        hj[i].filtered = jobs[i].filtered; hj[i].adi_off = (int32_t)off; hj[i].pad_ = 0;
+        off += 4 * (size_t)jobs[i].size + 1;
+    }
+    memcpy(h_adi, adi, sizeof(int16_t) * n_adi);
+    crc = hbc_h2d_async(d_jobs, h_jobs, sizeof(hbd_intra_job) * (size_t)n_jobs, ctx->stream);
+    if (!crc) crc = hbc_h2d_async(d_adi, h_adi, sizeof(int16_t) * n_adi, ctx->stream);
+    hbd_intra_args a;
+    memset(&a, 0, sizeof a);
+    if (cur) a.cur = cur->d.p[0];
+    if (pred) a.pred = pred->d;
+    a.jobs = (const hbd_intra_job *)d_jobs; a.n_jobs = n_jobs; a.adi = (const int16_t *)d_adi; a.sads = (uint32_t *)d_sad;
+    if (!crc) { crc = hbk_intra(&a, ctx->stream); ctx->launches++; }
+    if (!crc && need_sads) crc = hbc_d2h_async(h_sad, d_sad, sizeof(uint32_t) * 35 * (size_t)n_jobs, ctx->stream);
+    if (!crc) crc = hbc_stream_sync(ctx->stream);
+    if (!crc && need_sads) memcpy(sads, h_sad, sizeof(uint32_t) * 35 * (size_t)n_jobs);
+done:
+    pthread_mutex_unlock(&ctx->lock);
+    if (crc) return hbi_cuda_fail(crc, "hb_intra_run");
+    return rc;
+}

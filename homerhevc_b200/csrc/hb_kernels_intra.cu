@@ -1,0 +1,171 @@
+// hb_kernels_intra.cu -- intra prediction: planar (hmr_motion_intra.c:408), DC and the 33 angular
+// modes with their edge filters (:482), reference-sample smoothing (adi_filter, :189) and the filtered-or-not rule of the
+// mode search (:1122), as closed forms per sample -- no intermediate refMain/refSide arrays, no transposition pass:
+//   planar   ((l << s) + N + (x+1)(tr - l) + (t << s) + (y+1)(lb - t)) >> (s+1)
+//   angular  pos = (j+1)*angle, k = i + (pos >> 5) + 1, f = pos & 31, sample = f ? ((32-f) R(k) + f R(k+1) + 16) >> 5 : R(k)
+//            with R(k) = main[k] for k >= 0 and side[(128 - k*inv_angle) >> 8] for the projected part (k < 0);
+//            vertical modes read (j,i) = (y,x), horizontal modes (x,y).
+// One warp per job.  mode >= 0: the prediction is written to the prediction plane (input of the intra T/Q chain);
+// mode < 0: the SADs of all 35 luma modes against the current block (what the host's mode search probes).
+#include "hb_shim.h"
+#include "hb_dev_common.cuh"
+
+namespace {
+
+__constant__ int c_ang[9] = { 0, 2, 5, 9, 13, 17, 21, 26, 32 };
+__constant__ int c_inv_ang[9] = { 0, 4096, 1638, 910, 630, 482, 390, 315, 256 };
+__constant__ int c_flt_thr[4] = { 10, 7, 1, 0 };
+
+struct IntraMode { int kind; int hor; int angle; int inv; };      // kind 0 planar, 1 DC, 2 pure H/V, 3 angular
+
+__device__ __forceinline__ IntraMode intra_mode_info(int mode)
+{
+    IntraMode m;
+    m.hor = mode < 18; m.angle = 0; m.inv = 0;
+    if (mode == 0) { m.kind = 0; return m; }
+    if (mode == 1) { m.kind = 1; return m; }
+    const int a = m.hor ? -(mode - 10) : mode - 26;
+    const int aa = abs(a);
+    m.angle = (a < 0 ? -1 : 1) * c_ang[aa];
+    m.inv = c_inv_ang[aa];
+    m.kind = a == 0 ? 2 : 3;
+    return m;
+}
+
+// mid points at the top-left corner sample of the 4n+1 array
+__device__ __forceinline__ int intra_sample(const int16_t *mid, int n, int lg, const IntraMode &m, int dc, bool edge, int x, int y)
+{
+    if (m.kind == 0) {
+        const int l = mid[-(y + 1)], t = mid[x + 1], lb = mid[-(n + 1)], tr = mid[n + 1];
+        return ((l << lg) + n + (x + 1) * (tr - l) + (t << lg) + (y + 1) * (lb - t)) >> (lg + 1);
+    }
+    if (m.kind == 1) {
+        if (edge) {
+            if (x == 0 && y == 0) return (mid[-1] + mid[1] + 2 * dc + 2) >> 2;
+            if (y == 0) return (mid[1 + x] + 3 * dc + 2) >> 2;
+            if (x == 0) return (mid[-1 - y] + 3 * dc + 2) >> 2;
+        }
+        return dc;
+    }
+    const int j = m.hor ? x : y, i = m.hor ? y : x;
+    const int sm = m.hor ? -1 : 1;                          // main[k] = mid[sm*k], side[k] = mid[-sm*k]
+    if (m.kind == 2) {
+        int v = mid[sm * (i + 1)];
+        if (edge && i == 0) v = hb_clip255(v + ((mid[-sm * (j + 1)] - mid[0]) >> 1));   // first sample of every line along the direction
+        return v;
+    }
+    const int pos = (j + 1) * m.angle, d = pos >> 5, f = pos & 31;
+    const int k = i + d + 1;
+    auto ref = [&](int kk) -> int { return kk >= 0 ? mid[sm * kk] : mid[-sm * ((128 - kk * m.inv) >> 8)]; };
+    if (!f) return ref(k);
+    return ((32 - f) * ref(k) + f * ref(k + 1) + 16) >> 5;
+}
+
+// [1,2,1] or strong bilinear smoothing of the 4n+1 reference samples (hmr_motion_intra.c:189, strong_intra_smooth on)
+__device__ __forceinline__ void intra_filter_adi(const int16_t *adi, int16_t *flt, int n, int lg, int lane)
+{
+    const int size = 4 * n + 1;
+    const int lb = adi[0], lt = adi[2 * n], tr = adi[size - 1];
+    const bool strong = n >= 32 && abs(lb + lt - 2 * adi[n]) < 8 && abs(lt + tr - 2 * adi[3 * n]) < 8;
+    for (int i = lane; i < size; i += 32) {
+        int v;
+        if (i == 0 || i == size - 1) v = adi[i];
+        else if (strong) {
+            if (i == 2 * n) v = adi[i];
+            else if (i < 2 * n) v = ((2 * n - i) * lb + i * lt + n) >> (lg + 1);
+            else v = ((4 * n - i) * lt + (i - 2 * n) * tr + n) >> (lg + 1);
+        } else v = (adi[i - 1] + 2 * adi[i] + adi[i + 1] + 2) >> 2;
+        flt[i] = static_cast<int16_t>(v);
+    }
+}
+
+__device__ __forceinline__ bool intra_uses_filtered(int lg, int mode)
+{
+    const int d = min(abs(mode - 10), abs(mode - 26));
+    return mode != 1 && d > c_flt_thr[lg - 2];
+}
+
+__device__ __forceinline__ int intra_dc(const int16_t *mid, int n, int lane)
+{
+    int s = 0;
+    for (int i = 1 + lane; i <= n; i += 32) s += mid[i] + mid[-i];
+    s = __reduce_add_sync(HB_FULL_MASK, s);
+    return (s + n) / (2 * n);
+}
+
+constexpr int kIntraWarps = 4;
+
+__global__ void __launch_bounds__(kIntraWarps * 32) k_intra(const hbd_intra_args a)
+{
+    __shared__ int16_t s_adi[kIntraWarps][2][132];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ji = blockIdx.x * kIntraWarps + warp;
+    if (ji >= a.n_jobs) return;
+    const hbd_intra_job job = a.jobs[ji];
+    const int n = job.size;
+    int lg = 2;
+    while ((1 << lg) < n) lg++;
+    int16_t *raw = s_adi[warp][0], *flt = s_adi[warp][1];
+    for (int i = lane; i < 4 * n + 1; i += 32) raw[i] = a.adi[job.adi_off + i];
+    __syncwarp();
+    const bool is_luma = job.comp == 0;
+    if (is_luma) intra_filter_adi(raw, flt, n, lg, lane);
+    __syncwarp();
+    const bool edge = is_luma && n <= 16;
+    if (job.mode >= 0) {
+        // ---- one prediction into the plane.  The caller decides which reference array a chroma block uses (always the raw
+        // one in the reference); luma follows the search rule unless the job says otherwise
+        const bool use_flt = is_luma && (job.filtered < 0 ? intra_uses_filtered(lg, job.mode) : job.filtered != 0);
+        const int16_t *mid = (use_flt ? flt : raw) + 2 * n;
+        const IntraMode m = intra_mode_info(job.mode);
+        const int dc = m.kind == 1 ? intra_dc(mid, n, lane) : 0;
+        const hbd_plane p = a.pred.p[job.comp];
+        for (int e = lane; e < n * n; e += 32) {
+            const int x = e % n, y = e / n;
+            p.org[(job.y + y) * p.pitch + job.x + x] = static_cast<uint8_t>(intra_sample(mid, n, lg, m, dc, edge, x, y));
+        }
+        return;
+    }
+    // ---- SAD of every mode against the current block
+    for (int mode = 0; mode < 35; mode++) {
+        const int16_t *mid = (intra_uses_filtered(lg, mode) ? flt : raw) + 2 * n;
+        const IntraMode m = intra_mode_info(mode);
+        const int dc = m.kind == 1 ? intra_dc(mid, n, lane) : 0;
+        uint32_t acc = 0;
+        for (int e = lane; e < n * n; e += 32) {
+            const int x = e % n, y = e / n;
+            const int c = a.cur.org[(job.y + y) * a.cur.pitch + job.x + x];
+            acc = __sad(intra_sample(mid, n, lg, m, dc, edge, x, y), c, acc);
+        }
+        acc = __reduce_add_sync(HB_FULL_MASK, acc);
+        if (lane == 0) a.sads[static_cast<size_t>(ji) * 35 + mode] = acc;
+    }
+}
+
+// per-call form: prediction of one block as int16 into a caller buffer (the table members create_intra_*_prediction)
+__global__ void __launch_bounds__(32) k_pc_intra(const int16_t *adi, int n, int mode, int is_luma, int16_t *pred, int stride)
+{
+    const int lane = threadIdx.x;
+    int lg = 2;
+    while ((1 << lg) < n) lg++;
+    const int16_t *mid = adi + 2 * n;
+    const IntraMode m = intra_mode_info(mode);
+    const int dc = m.kind == 1 ? intra_dc(mid, n, lane) : 0;
+    const bool edge = is_luma && n <= 16;
+    for (int e = lane; e < n * n; e += 32) pred[(e / n) * stride + e % n] = static_cast<int16_t>(intra_sample(mid, n, lg, m, dc, edge, e % n, e / n));
+}
+
+}  // namespace
+
+extern "C" int hbk_intra(const hbd_intra_args *a, void *stream)
+{
+    if (a->n_jobs <= 0) return 0;
+    k_intra<<<(a->n_jobs + kIntraWarps - 1) / kIntraWarps, kIntraWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int hbk_pc_intra(const int16_t *adi, int n, int mode, int is_luma, int16_t *pred, int stride, void *stream)
+{
+    k_pc_intra<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(adi, n, mode, is_luma, pred, stride);
+    return static_cast<int>(cudaGetLastError());
+}

@@ -217,6 +217,29 @@ void hb_inv_quant(const hb_quant_env *env, int16_t *src, int16_t *dst, int depth
     memcpy(dst, d, sizeof(int16_t) * (size_t)n * n);
 }
 
+/* create_intra_planar_prediction / create_intra_angular_prediction (hmr_private.h:1076-1077) without the henc_thread_t* / ctu_info_t*
+ * the reference only uses for scratch rows and the (always set) DC neighbour flags */
+static void intra_predict(int16_t *pred, int pred_stride, int16_t *adi, int adi_size, int cu_size, int mode, int is_luma)
+{
+    pc_slot *s = slot();
+    if ((cu_size != 4 && cu_size != 8 && cu_size != 16 && cu_size != 32) || adi_size != 4 * cu_size + 1 || mode < 0 || mode > 34) {
+        hbi_fail(HB_ERR_ARG, "intra prediction: unsupported shape (size %d, adi_size %d, mode %d)", cu_size, adi_size, mode); die("intra prediction");
+    }
+    int16_t *a = (int16_t *)s->host, *p = a + 160;
+    memcpy(a, adi, sizeof(int16_t) * (size_t)adi_size);
+    finish(s, hbk_pc_intra(D(s, a), cu_size, mode, is_luma, D(s, p), cu_size, s->stream), "intra prediction");
+    pack(pred, pred_stride, p, cu_size, cu_size, cu_size);
+}
+void hb_create_intra_planar_prediction(int16_t *prediction, int pred_stride, int16_t *adi_pred_buff, int adi_size, int cu_size, int cu_size_shift)
+{
+    (void)cu_size_shift;
+    intra_predict(prediction, pred_stride, adi_pred_buff, adi_size, cu_size, 0, 1);
+}
+void hb_create_intra_angular_prediction(int16_t *prediction, int pred_stride, int16_t *adi_pred_buff, int adi_size, int cu_size, int cu_mode, int is_luma)
+{
+    intra_predict(prediction, pred_stride, adi_pred_buff, adi_size, cu_size, cu_mode, is_luma);
+}
+
 void hb_fill_low_level_funcs(hb_low_level_funcs *t)
 {
     t->sad = hb_sad;

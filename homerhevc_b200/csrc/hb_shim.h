@@ -114,6 +114,25 @@ typedef struct hbd_tq_args {
 } hbd_tq_args;
 int hbk_tq_encode(const hbd_tq_args *a, void *stream);
 
+/* ---- intra prediction (hb_kernels_intra.cu) */
+typedef struct hbd_intra_job {
+    int32_t comp, x, y, size;     /* plane, position and size (4..32) in samples of that plane */
+    int32_t mode;                 /* 0 planar, 1 DC, 2..34 angular: write the prediction; < 0: SADs of all 35 luma modes */
+    int32_t filtered;             /* luma only: 1 / 0 force the smoothed / raw reference samples, < 0 apply the search rule */
+    int32_t adi_off;              /* first of the 4*size+1 reference samples of this job inside `adi` */
+    int32_t pad_;
+} hbd_intra_job;
+typedef struct hbd_intra_args {
+    hbd_plane cur;                /* luma plane of the current frame (SAD form) */
+    hbd_frame pred;               /* receives predictions (prediction form) */
+    const hbd_intra_job *jobs;
+    int32_t n_jobs;
+    const int16_t *adi;
+    uint32_t *sads;               /* n_jobs x 35 */
+} hbd_intra_args;
+int hbk_intra(const hbd_intra_args *a, void *stream);
+int hbk_pc_intra(const int16_t *adi, int n, int mode, int is_luma, int16_t *pred, int stride, void *stream);
+
 /* ---- gather of the host's selection (hb_kernels_gather.cu) */
 typedef struct hbd_gather_pc {
     const int32_t *tu_index;      /* TU raster position (frame grid) -> index among the coded TUs of this (pass, plane), or -1 */

@@ -45,6 +45,10 @@ class IntraTuJob(C.Structure):
     _fields_ = [("comp", C.c_int32), ("x", C.c_int32), ("y", C.c_int32), ("size", C.c_int32), ("qp", C.c_int32), ("scan_mode", C.c_int32)]
 
 
+class IntraJob(C.Structure):
+    _fields_ = [("comp", C.c_int32), ("x", C.c_int32), ("y", C.c_int32), ("size", C.c_int32), ("mode", C.c_int32), ("filtered", C.c_int32)]
+
+
 class TuResult(C.Structure):
     _fields_ = [("sum", C.c_int32), ("ssd", C.c_uint32), ("ssd_zero", C.c_uint32), ("zeroed", C.c_int32)]
 
@@ -155,6 +159,11 @@ def load_library():
                                C.POINTER(TqParams), i16p, C.POINTER(TuResult)]
     L.hb_tq_encode_intra.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(IntraTuJob), C.c_int, C.c_int, C.c_int, C.c_double,
                                      i16p, C.POINTER(TuResult)]
+    L.hb_intra_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(IntraJob), C.c_int, i16p, C.POINTER(C.c_uint32)]
+    L.hb_create_intra_planar_prediction.restype = None
+    L.hb_create_intra_planar_prediction.argtypes = [i16p, C.c_int, i16p, C.c_int, C.c_int, C.c_int]
+    L.hb_create_intra_angular_prediction.restype = None
+    L.hb_create_intra_angular_prediction.argtypes = [i16p, C.c_int, i16p, C.c_int, C.c_int, C.c_int, C.c_int]
     # section D
     L.hb_prepass_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(PrepassCfg), C.POINTER(C.c_void_p)]
     L.hb_prepass_destroy.argtypes = [C.c_void_p]
@@ -321,6 +330,19 @@ def _tq_encode_intra(self, cur, pred, recon, jobs, is_islice, sign_hiding, chrom
 
 
 Context.tq_encode_intra = _tq_encode_intra
+
+
+def _intra_run(self, cur, pred, jobs, adi):
+    """adi: int16 array, the jobs' 4*size+1 reference samples back to back.  Returns (n, 35) SADs (rows of prediction jobs are 0)"""
+    n = len(jobs)
+    arr = (IntraJob * n)(*jobs)
+    sads = np.zeros((n, 35), np.uint32)
+    _check(self.L.hb_intra_run(self.h, cur.h if cur is not None else None, pred.h if pred is not None else None, arr, n, _p16(adi),
+                               sads.ctypes.data_as(C.POINTER(C.c_uint32))), "hb_intra_run")
+    return sads
+
+
+Context.intra_run = _intra_run
 
 
 class Frame:

@@ -194,6 +194,20 @@ typedef struct hb_intra_tu_job { int32_t comp; int32_t x, y; int32_t size; int32
 int hb_tq_encode_intra(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_frame *recon, const hb_intra_tu_job *jobs, int n_jobs,
                        int is_islice, int sign_hiding, double chroma_weight, int16_t *coeffs, hb_tu_result *results);
 
+/* intra prediction: planar hmr_motion_intra.c:408, DC/angular + edge filters :482, reference-sample smoothing
+ * adi_filter :189, filtered-or-not rule of the mode search :1122.  Every job brings its 4*size+1 reference samples (index 2*size =
+ * top-left corner, +i the row above, -i the left column), which the host takes from reconstructed neighbours.
+ * mode >= 0: the prediction is written into `pred`; mode < 0 (luma): sads[35*i + m] = SAD(current block, mode m) for all modes. */
+typedef struct hb_intra_job {
+    int32_t comp, x, y, size;     /* size 4..32 */
+    int32_t mode;                 /* 0 planar, 1 DC, 2..34 angular, < 0 = all-mode SADs */
+    int32_t filtered;             /* luma: 1 / 0 force smoothed / raw samples, < 0 = the reference's rule (intra_filter[] :148) */
+} hb_intra_job;
+int hb_intra_run(hb_ctx *ctx, const hb_frame *cur, hb_frame *pred, const hb_intra_job *jobs, int n_jobs, const int16_t *adi, uint32_t *sads);
+/* per-call forms of the two table members (adapter drops et / ctu) */
+void hb_create_intra_planar_prediction(int16_t *prediction, int pred_stride, int16_t *adi_pred_buff, int adi_size, int cu_size, int cu_size_shift);
+void hb_create_intra_angular_prediction(int16_t *prediction, int pred_stride, int16_t *adi_pred_buff, int adi_size, int cu_size, int cu_mode, int is_luma);
+
 /* ------------------------------------------------------------------ D. frame-level pre-pass ----------------
  * For every CTU and every inter PU size 64/32/16/8 at once: motion search chained parent -> child exactly as
  * hmr_cu_motion_estimation does (zero AMVP predictors, parent MV as extra start), motion compensation of

@@ -735,3 +735,120 @@ void orc_encode_intra_tu(const orc_tables *t, const int16_t *orig, int orig_stri
     out->sum = sum; out->zeroed = 0; out->ssd_zero = 0;
     out->ssd = comp == 0 ? ssd : (uint32_t)(int)(weight * ssd);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Intra prediction.  Reference samples ("ADI") are one array of 4N+1 values: index 2N is the
+ * top-left corner, 2N+i (i = 1..2N) the row above from left to right, 2N-i the column on the left from top to bottom.
+ *   adi_filter                       hmr_motion_intra.c:189   ([1,2,1] or the strong bilinear smoothing for N >= 32)
+ *   create_intra_planar_prediction   hmr_motion_intra.c:408
+ *   create_intra_angular_prediction  hmr_motion_intra.c:482   (modes 1 = DC, 2..34 angular; DC/H/V edge filters for luma N <= 16)
+ *   filtered-or-not per mode         hmr_motion_intra.c:1122-1123 (intra_filter[] thresholds :148)
+ * ------------------------------------------------------------------------------------------ */
+void orc_adi_filter(const int16_t *adi, int16_t *flt, int n, int strong_enabled)
+{
+    const int size = 4 * n + 1;
+    const int lb = adi[0], lt = adi[2 * n], tr = adi[size - 1];
+    const int thr = 1 << (8 - 5);
+    const int bil_l = abs(lb + lt - 2 * adi[n]) < thr, bil_a = abs(lt + tr - 2 * adi[3 * n]) < thr;
+    if (strong_enabled && n >= 32 && bil_l && bil_a) {
+        const int sh = ilog2(n) + 1;
+        flt[0] = adi[0]; flt[2 * n] = adi[2 * n]; flt[size - 1] = adi[size - 1];
+        for (int i = 1; i < 2 * n; i++) flt[i] = (int16_t)(((2 * n - i) * lb + i * lt + n) >> sh);
+        for (int i = 1; i < 2 * n; i++) flt[2 * n + i] = (int16_t)(((2 * n - i) * lt + i * tr + n) >> sh);
+    } else {
+        flt[0] = adi[0];
+        for (int i = 1; i < size - 1; i++) flt[i] = (int16_t)((adi[i - 1] + 2 * adi[i] + adi[i + 1] + 2) >> 2);
+        flt[size - 1] = adi[size - 1];
+    }
+}
+
+static const int k_ang[9] = { 0, 2, 5, 9, 13, 17, 21, 26, 32 };            /* hmr_encoder_lib.c:35 */
+static const int k_inv_ang[9] = { 0, 4096, 1638, 910, 630, 482, 390, 315, 256 };
+
+void orc_intra_predict(const int16_t *adi, int n, int mode, int is_luma, int16_t *pred, int stride)
+{
+    const int16_t *mid = adi + 2 * n;
+    const int lg = ilog2(n);
+    if (mode == 0) {                                                          /* planar */
+        int top_row[64], left_col[64], bottom[64], right[64];
+        const int lb = mid[-(n + 1)], tr = mid[n + 1];
+        for (int i = 0; i < n; i++) {
+            const int l = mid[-(i + 1)], t = mid[i + 1];
+            bottom[i] = lb - t; right[i] = tr - l; top_row[i] = t << lg; left_col[i] = l << lg;
+        }
+        for (int j = 0; j < n; j++) {
+            int hor = left_col[j] + n;
+            for (int i = 0; i < n; i++) {
+                hor += right[j];
+                top_row[i] += bottom[i];
+                pred[j * stride + i] = (int16_t)((hor + top_row[i]) >> (lg + 1));
+            }
+        }
+        return;
+    }
+    if (mode == 1) {                                                          /* DC, both neighbours always "available" (:257-258) */
+        int sum = 0;
+        for (int i = 1; i <= n; i++) sum += mid[i] + mid[-i];
+        const int dc = (uint16_t)((sum + n) / (2 * n));
+        for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) pred[j * stride + i] = (uint8_t)dc;
+        if (n <= 16 && is_luma) {
+            pred[0] = (int16_t)((mid[-1] + mid[1] + 2 * pred[0] + 2) >> 2);
+            for (int i = 1; i < n; i++) pred[i] = (int16_t)((mid[1 + i] + 3 * pred[i] + 2) >> 2);
+            for (int j = 1; j < n; j++) pred[j * stride] = (int16_t)((mid[-1 - j] + 3 * pred[j * stride] + 2) >> 2);
+        }
+        return;
+    }
+    const int hor_mode = mode < 18;
+    int angle = hor_mode ? -(mode - 10) : mode - 26;
+    const int a = abs(angle), sgn = angle < 0 ? -1 : 1;
+    const int inv = k_inv_ang[a];
+    angle = sgn * k_ang[a];
+    int16_t above[3 * 64 + 2], left[3 * 64 + 2];
+    int16_t *ref_main, *ref_side;
+    if (angle < 0) {
+        for (int i = 0; i < n + 1; i++) { above[i + n - 1] = mid[i]; left[i + n - 1] = mid[-i]; }
+        ref_main = (hor_mode ? left : above) + (n - 1);
+        ref_side = (hor_mode ? above : left) + (n - 1);
+        int inv_sum = 128;
+        for (int i = -1; i > ((n * angle) >> 5); i--) { inv_sum += inv; ref_main[i] = ref_side[inv_sum >> 8]; }
+    } else {
+        for (int i = 0; i < 2 * n + 1; i++) { above[i] = mid[i]; left[i] = mid[-i]; }
+        ref_main = hor_mode ? left : above;
+        ref_side = hor_mode ? above : left;
+    }
+    const int s1 = hor_mode ? 1 : stride, s2 = hor_mode ? stride : 1;       /* horizontal modes write transposed */
+    if (angle == 0) {
+        for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) pred[j * s1 + i * s2] = (uint8_t)ref_main[i + 1];
+        if (is_luma && n <= 16)
+            for (int i = 0; i < n; i++) pred[i * s1] = (int16_t)clampi(pred[i * s1] + ((ref_side[i + 1] - ref_side[0]) >> 1), 0, 255);
+        return;
+    }
+    int pos = 0;
+    for (int j = 0; j < n; j++) {
+        pos += angle;
+        const int d = pos >> 5, f = pos & 31;
+        for (int i = 0; i < n; i++) {
+            const int k = i + d + 1;
+            pred[j * s1 + i * s2] = f ? (uint8_t)(((32 - f) * ref_main[k] + f * ref_main[k + 1] + 16) >> 5) : (uint8_t)ref_main[k];
+        }
+    }
+}
+
+/* which reference array a luma mode reads (hmr_motion_intra.c:1122-1123) */
+int orc_intra_uses_filtered(int n, int mode)
+{
+    static const int thr[5] = { 10, 7, 1, 0, 10 };
+    const int d1 = abs(mode - 10), d2 = abs(mode - 26);
+    return mode != 1 && ((d1 < d2 ? d1 : d2) > thr[ilog2(n) - 2]);
+}
+
+/* SAD of every luma mode 0..34 against the original block: what the search loop of homer_loop1_motion_intra (:1084) probes */
+void orc_intra_mode_sads(const int16_t *orig, int orig_stride, const int16_t *adi, int n, uint32_t sads[35])
+{
+    int16_t flt[4 * 64 + 1], pred[64 * 64];
+    orc_adi_filter(adi, flt, n, 1);
+    for (int m = 0; m < 35; m++) {
+        orc_intra_predict(orc_intra_uses_filtered(n, m) ? flt : adi, n, m, 1, pred, n);
+        sads[m] = orc_sad(orig, orig_stride, pred, n, n);
+    }
+}

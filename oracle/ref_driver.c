@@ -580,3 +580,23 @@ void refdrv_install_gpu_table(void *funcs_table, void *user)
 }
 long refdrv_gpu_quant_calls(void) { return g_gpu_calls; }
 void *refdrv_install_gpu_table_addr(void) { return (void *)refdrv_install_gpu_table; }
+
+/* intra prediction through the reference's table (create_intra_planar_prediction / create_intra_angular_prediction);
+ * adi: 4n+1 samples, pred: n*n out (stride n) */
+void refdrv_intra_predict(refdrv *d, int16_t *adi, int n, int mode, int is_luma, int16_t *pred)
+{
+    henc_thread_t *et = d->et;
+    ctu_info_t ctu;
+    int shift = 0;
+    memset(&ctu, 0, sizeof ctu);
+    ctu.top = 1; ctu.left = 1;                                   /* fill_reference_samples always sets both (hmr_motion_intra.c:257) */
+    while ((1 << shift) < n) shift++;
+    if (mode == PLANAR_IDX) d->enc->funcs.create_intra_planar_prediction(et, pred, n, adi, 4 * n + 1, n, shift);
+    else d->enc->funcs.create_intra_angular_prediction(et, &ctu, pred, n, adi, 4 * n + 1, n, mode, is_luma);
+}
+void refdrv_adi_filter(refdrv *d, int16_t *adi, int16_t *flt, int n)
+{
+    int shift = 0;
+    while ((1 << shift) < n) shift++;
+    adi_filter(adi, flt, d->et->max_cu_size_shift - shift, 4 * n + 1, n, d->et->max_cu_size_shift, d->et->sps->strong_intra_smooth_enabled_flag, d->et->bit_depth);
+}

@@ -82,6 +82,10 @@ def oracle():
                                           C.POINTER(OrcTuOut)]
         L.orc_encode_intra_tu.argtypes = [C.c_void_p, i16p, C.c_int, i16p, C.c_int, i16p, i16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, C.c_double, C.POINTER(OrcTuOut)]
+        L.orc_adi_filter.argtypes = [i16p, i16p, C.c_int, C.c_int]
+        L.orc_intra_predict.argtypes = [i16p, C.c_int, C.c_int, C.c_int, i16p, C.c_int]
+        L.orc_intra_uses_filtered.argtypes = [C.c_int, C.c_int]
+        L.orc_intra_mode_sads.argtypes = [i16p, C.c_int, i16p, C.c_int, C.POINTER(C.c_uint32)]
         L.tables = L.orc_tables_create()
         _oracle = L
     return _oracle
@@ -125,6 +129,8 @@ def ref():
         D.refdrv_encode_inter_tu.argtypes = [C.c_void_p, i16p, i16p] + [C.c_int] * 6 + [C.c_double, i16p, i16p,
                                                                                        C.POINTER(C.c_int)]
         D.refdrv_chroma_qp.argtypes = [C.c_void_p, C.c_int]
+        D.refdrv_intra_predict.argtypes = [C.c_void_p, i16p, C.c_int, C.c_int, C.c_int, i16p]
+        D.refdrv_adi_filter.argtypes = [C.c_void_p, i16p, i16p, C.c_int]
         D.refdrv_encode_lockstep.restype = C.c_long
         D.refdrv_encode_lockstep.argtypes = [C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int,
                                              u8p, C.c_long, u8p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]

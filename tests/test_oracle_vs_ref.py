@@ -178,3 +178,39 @@ def test_intra_tq_chain_against_reference_calls():
         assert np.array_equal(co2[:n * n], lev[:n * n]) and np.array_equal(de2, dec), (comp, n, qp, scan)
         coded += s.value > 0
     assert coded > 50
+
+
+def _random_adi(rng, n, kind):
+    size = 4 * n + 1
+    if kind == 0:
+        return rng.integers(0, 256, size)
+    if kind == 1:
+        return np.clip(128 + np.cumsum(rng.integers(-3, 4, size)), 0, 255)
+    return np.clip(np.linspace(rng.integers(0, 256), rng.integers(0, 256), size) + rng.integers(-1, 2, size), 0, 255)   # smooth: strong filter
+
+
+def test_intra_prediction_against_reference():
+    """reference-sample smoothing and every intra mode (planar, DC, 33 angular, luma and chroma variants), sizes 4..32,
+    through the reference's own table members (create_intra_planar_prediction / create_intra_angular_prediction, adi_filter)"""
+    O = oracle(); _, D = ref()
+    h = refdrv()
+    rng = np.random.default_rng(104)
+    strong = 0
+    for it in range(240):
+        n = int(rng.choice([4, 8, 16, 32]))
+        adi = aligned_i16(4 * n + 1 + 8); adi[:4 * n + 1] = _random_adi(rng, n, it % 3)
+        f1 = aligned_i16(4 * n + 1 + 8); f2 = aligned_i16(4 * n + 1 + 8)
+        D.refdrv_adi_filter(h, ptr(adi), ptr(f1), n)
+        O.orc_adi_filter(ptr(adi), ptr(f2), n, 1)
+        assert np.array_equal(f1[:4 * n + 1], f2[:4 * n + 1]), ("filter", n, it % 3)
+        if n == 32 and it % 3 == 2:
+            plain = (adi[:-10].astype(np.int32) + 2 * adi[1:-9] + adi[2:-8] + 2) >> 2
+            strong += int(not np.array_equal(plain[:4 * n - 1], f1[1:4 * n]))
+        for mode in range(35):
+            for is_luma in (1, 0):
+                src = f1 if (is_luma and it % 2) else adi
+                p1 = aligned_i16(n * n); p2 = aligned_i16(n * n)
+                D.refdrv_intra_predict(h, ptr(src), n, mode, is_luma, ptr(p1))
+                O.orc_intra_predict(ptr(src), n, mode, is_luma, ptr(p2), n)
+                assert np.array_equal(p1, p2), (n, mode, is_luma, it % 3)
+    assert strong > 0          # the strong bilinear smoothing branch ran
