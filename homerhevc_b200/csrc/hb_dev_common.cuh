@@ -14,6 +14,14 @@ __device__ __forceinline__ uint32_t hb_ld_u8x4(const uint8_t *p)
     return __funnelshift_r(lo, hi, static_cast<uint32_t>(a & 3) * 8u);
 }
 
+// acc + sum of |a.b[i] - b.b[i]| over the four packed bytes, one instruction (VABSDIFF4.U8.ACC)
+__device__ __forceinline__ uint32_t hb_sad4_acc(uint32_t a, uint32_t b, uint32_t acc)
+{
+    uint32_t d;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc));
+    return d;
+}
+
 __device__ __forceinline__ int hb_clip255(int v) { return min(max(v, 0), 255); }
 __device__ __forceinline__ int hb_sat16(int v) { return min(max(v, -32768), 32767); }
 

@@ -105,16 +105,21 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
     const uint32_t gmask = (G >= 32) ? HB_FULL_MASK : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));
     const int gbase = lane & ~(G - 1) & 31;               // first lane of the group inside its warp (G <= 32)
 
-    // ---- current block -> registers: lane l of every slot holds words l, l+L, ...
+    // ---- current block -> registers: lane l of every slot holds the 8-sample pairs l, l+L, ... (two packed words each).
+    // Pair k sits (L/PPR) rows below pair k-1 in the same columns, so reference addresses advance by one constant.
+    constexpr int PPR = WPR / 2, PPL = WPL / 2;        // pairs per row / per lane
+    static_assert(L % PPR == 0, "pairs of a lane share their columns");
     uint32_t cur[WPL];
-    int ref_off[WPL];                                  // byte offset of each word from the PU's co-located sample
-    const int rpitch = a.ref.pitch;
-    const uint8_t *ref_pu = a.ref.org + jy * rpitch + jx;
+    const uint32_t rpitch = static_cast<uint32_t>(a.ref.pitch);
+    const int prow0 = l / PPR, pcol = (l % PPR) * 8;
+    // byte offset of this lane's first pair from the start of the reference allocation (unsigned: one uniform base + 32-bit offsets)
+    const uint32_t ref_lane = static_cast<uint32_t>(jy + a.ref.pad + prow0) * rpitch + static_cast<uint32_t>(jx + a.ref.pad + pcol);
+    const uint32_t ref_step = (L / PPR) * rpitch;
 #pragma unroll
-    for (int k = 0; k < WPL; k++) {
-        const int w = l + k * L, row = w / WPR, col = (w % WPR) * 4;
-        cur[k] = hb_ld_u8x4(a.cur.org + (jy + row) * a.cur.pitch + jx + col);
-        ref_off[k] = row * rpitch + col;
+    for (int k = 0; k < PPL; k++) {
+        const uint8_t *c = a.cur.org + (jy + prow0 + k * (L / PPR)) * a.cur.pitch + jx + pcol;
+        cur[2 * k] = hb_ld_u8x4(c);
+        cur[2 * k + 1] = hb_ld_u8x4(c + 4);
     }
 
     // select_mv_candidate_fast (hmr_motion_inter.c:1004): IEEE double, products and sums rounded separately
@@ -171,11 +176,21 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
         int mx = cx[0], my = cy[0]; bool mv = cv[0];
 #pragma unroll
         for (int s = 1; s < 4; s++) if (slot == s) { mx = cx[s]; my = cy[s]; mv = cv[s]; }
-        uint32_t acc = 0;
+        uint32_t acc = 0, acc1 = 0;
         if (mv) {
-            const int disp = my * rpitch + mx;
+            // the pitch is a multiple of 4, so every word of this candidate has the same misalignment: shift once
+            uint32_t off = ref_lane + static_cast<uint32_t>(my * static_cast<int>(rpitch) + mx);
+            const uint32_t sh = (off & 3u) * 8u;
+            off &= ~3u;
 #pragma unroll
-            for (int k = 0; k < WPL; k++) acc = __vsadu4(cur[k], hb_ld_u8x4(ref_pu + (disp + ref_off[k]))) + acc;
+            for (int k = 0; k < PPL; k++) {
+                const uint32_t *q = reinterpret_cast<const uint32_t *>(a.ref.base + off);
+                const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+                acc = hb_sad4_acc(cur[2 * k], __funnelshift_r(w0, w1, sh), acc);
+                acc1 = hb_sad4_acc(cur[2 * k + 1], __funnelshift_r(w1, w2, sh), acc1);       // two chains for ILP
+                off += ref_step;
+            }
+            acc += acc1;
         }
         uint32_t cst[4];
         exchange(acc, mv_cost(mx << 2, my << 2), sad, cst);
@@ -317,10 +332,10 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
             cur_best = sad[0];
         }
         // ---- stage the patch: rows iy-4.., columns ix-4..
-        const uint8_t *ref_i = a.ref.org + (jy + iy - 4) * rpitch + jx + ix - 4;
+        const uint8_t *ref_i = a.ref.org + (jy + iy - 4) * a.ref.pitch + jx + ix - 4;
         for (int w = gl; w < PROWS * (PS / 4); w += G) {
             const int r = w / (PS / 4), c = (w % (PS / 4)) * 4;
-            *reinterpret_cast<uint32_t *>(s_patch + r * PS + c) = hb_ld_u8x4(ref_i + r * rpitch + c);
+            *reinterpret_cast<uint32_t *>(s_patch + r * PS + c) = hb_ld_u8x4(ref_i + r * a.ref.pitch + c);
         }
         group_barrier<G>(group, gmask);
         // ---- horizontal 14-bit planes, fractions 0..3: T_f[r][j] = sum_k taps_f[k] * P[r][j+k] - 8192 (T_0 = P[r][j+3]*64 - 8192)
@@ -353,10 +368,8 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
         // ---- the current block as bytes, over the patch area (no longer needed)
         uint8_t *s_cur = s_patch;
 #pragma unroll
-        for (int k = 0; k < WPL; k++) {
-            const int w = l + k * L;
-            if (slot == 0) *reinterpret_cast<uint32_t *>(s_cur + (w / WPR) * N + (w % WPR) * 4) = cur[k];
-        }
+        for (int k = 0; k < PPL; k++)
+            if (slot == 0) *reinterpret_cast<uint2 *>(s_cur + (prow0 + k * (L / PPR)) * N + pcol) = make_uint2(cur[2 * k], cur[2 * k + 1]);
         if (gl < 8) s_half[group][gl] = 0;
         group_barrier<G>(group, gmask);
 
@@ -400,7 +413,7 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
         //   T_0 column (N strips):   v = V2(T_0)            -> candidates (0,-2) and (0,+2)
         //   T_2 column (N+1 strips): v = V2(T_2), u = round(T_2) -> (-2,-2) (+2,-2) (-2,+2) (+2,+2) and (-2,0) (+2,0)
         // Partial SADs go to eight shared counters.
-        for (int strip = gl; strip < 2 * N + 1; strip += G) {
+        for (int strip = gl; strip < 2 * N; strip += G) {
             const bool t2 = strip >= N;
             const int j = t2 ? strip - N : strip + 1;                 // plane column: x = ix - 1 + j (+ 1/2 for T_2)
             const int16_t *pl = s_plane + (t2 ? 2 : 0) * Cfg::PLANE_ELEMS + j;
@@ -444,6 +457,29 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
                 if (use_r) { atomicAdd(&s_half[group][4], acc[1]); atomicAdd(&s_half[group][6], acc[3]); atomicAdd(&s_half[group][2], acc[5]); }
             } else {
                 atomicAdd(&s_half[group][0], acc[0]); atomicAdd(&s_half[group][1], acc[2]);
+            }
+        }
+        // the last T_2 column (j = N, right edge of the x = +2 candidates) would cost a whole extra pass of the strip loop for one
+        // lane: its N+1 filtered samples are spread over the lanes instead, one direct 8-tap sum each
+        for (int rho0 = 0; rho0 <= N; rho0 += G) {
+            const int rho = rho0 + gl;
+            uint32_t am = 0, ap = 0, au = 0;
+            if (rho <= N) {
+                const int16_t *pl = s_plane + 2 * Cfg::PLANE_ELEMS + rho * TS + N;
+                const int s = hb_luma8<2>(pl[0], pl[TS], pl[2 * TS], pl[3 * TS], pl[4 * TS], pl[5 * TS], pl[6 * TS], pl[7 * TS]);
+                const int v = __vimin_s32_relu((s + 2048 + (8192 << 6)) >> 12, 255);
+                if (rho < N) {
+                    const int cl = s_cur[rho * N + N - 1];
+                    am = __sad(v, cl, 0u);
+                    au = __sad(__vimin_s32_relu((pl[4 * TS] + 8192 + 32) >> 6, 255), cl, 0u);
+                }
+                if (rho >= 1) ap = __sad(v, static_cast<int>(s_cur[(rho - 1) * N + N - 1]), 0u);
+            }
+            if constexpr (G >= 32) {
+                am = __reduce_add_sync(HB_FULL_MASK, am); ap = __reduce_add_sync(HB_FULL_MASK, ap); au = __reduce_add_sync(HB_FULL_MASK, au);
+                if (lane == 0 && (am | ap | au)) { atomicAdd(&s_half[group][5], am); atomicAdd(&s_half[group][7], ap); atomicAdd(&s_half[group][3], au); }
+            } else if (rho <= N) {
+                atomicAdd(&s_half[group][5], am); atomicAdd(&s_half[group][7], ap); atomicAdd(&s_half[group][3], au);
             }
         }
         group_barrier<G>(group, gmask);
