@@ -22,6 +22,23 @@ __device__ __forceinline__ uint32_t hb_sad4_acc(uint32_t a, uint32_t b, uint32_t
     return d;
 }
 
+// c + sum of four u8 (a) x s8 (b) products
+__device__ __forceinline__ int hb_dp4a_us(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// four ints clipped to 0..255 and packed, v0 in the low byte (two I2IP)
+__device__ __forceinline__ uint32_t hb_pack_sat_u8x4(int v0, int v1, int v2, int v3)
+{
+    uint32_t hi, d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(v3), "r"(v2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v1), "r"(v0), "r"(hi));
+    return d;
+}
+
 __device__ __forceinline__ int hb_clip255(int v) { return min(max(v, 0), 255); }
 __device__ __forceinline__ int hb_sat16(int v) { return min(max(v, -32768), 32767); }
 

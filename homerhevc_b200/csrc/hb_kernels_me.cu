@@ -55,9 +55,101 @@ template <int N> struct MeCfg {
     static constexpr int TS = N + 4;                   // plane row stride in int16: column j <-> x = ix-1+j (+f/4)
     static constexpr int PATCH_BYTES = PROWS * PS;
     static constexpr int PLANE_ELEMS = PROWS * TS;
+    static constexpr int QROWS = PROWS / 2;            // plane rows are stored in pairs: one 32-bit word = rows 2q, 2q+1 of a column
+    static constexpr int PLANE_WORDS = QROWS * TS;
+    static constexpr int CS = N + 4;                   // column stride (bytes) of the transposed current block
     static constexpr int SMEM_PER_PU = PATCH_BYTES + 4 * PLANE_ELEMS * 2;
     static constexpr int SMEM_TOTAL = PUS * SMEM_PER_PU;
 };
+
+// ---- packed filter taps.  Horizontal: u8 samples x s8 taps through dp4a, taps k..k+3 of fraction f in one word.
+__host__ __device__ constexpr int luma_tap(int f, int k)
+{
+    constexpr int t[4][8] = { {0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1} };
+    return t[f][k];
+}
+__host__ __device__ constexpr uint32_t pack_s8(int b0, int b1, int b2, int b3)
+{
+    return static_cast<uint32_t>(b0 & 255) | (static_cast<uint32_t>(b1 & 255) << 8) | (static_cast<uint32_t>(b2 & 255) << 16) | (static_cast<uint32_t>(b3 & 255) << 24);
+}
+__host__ __device__ constexpr uint32_t htap4(int f, int half)
+{
+    return pack_s8(luma_tap(f, 4 * half), luma_tap(f, 4 * half + 1), luma_tap(f, 4 * half + 2), luma_tap(f, 4 * half + 3));
+}
+// Vertical: the planes hold two rows per word, so an 8-tap column sum over rows rho0..rho0+7 is four dp2a when rho0 is even
+// (tap pairs E_i = (t2i, t2i+1)) and five when it is odd (O_i = (t(2i-1), t2i), with t(-1) = t8 = 0).  A lane produces TWO
+// consecutive output rows from the same five words W[m..m+4]: for par = 0 (first tap row even) these are E | O, for par = 1
+// O | (0, E).  vtap(f, par, i) packs the pair of the first row in the low two bytes (dp2a.lo) and of the second in the high two.
+__host__ __device__ constexpr int tap_or0(int f, int k) { return (k < 0 || k > 7) ? 0 : luma_tap(f, k); }
+__host__ __device__ constexpr uint32_t vtap(int f, int par, int i)
+{
+    // pair of row A (first tap row par + 2m): taps start at half `par` of word m; row B: one row further down
+    const int a0 = 2 * i - par, b0 = 2 * i - par - 1;
+    return pack_s8(tap_or0(f, a0), tap_or0(f, a0 + 1), tap_or0(f, b0), tap_or0(f, b0 + 1));
+}
+#define HB_VTAP5(f, p) { vtap(f, p, 0), vtap(f, p, 1), vtap(f, p, 2), vtap(f, p, 3), vtap(f, p, 4) }
+__constant__ uint32_t c_vtab[4][2][5] = { { HB_VTAP5(0, 0), HB_VTAP5(0, 1) }, { HB_VTAP5(1, 0), HB_VTAP5(1, 1) },
+                                          { HB_VTAP5(2, 0), HB_VTAP5(2, 1) }, { HB_VTAP5(3, 0), HB_VTAP5(3, 1) } };
+constexpr int kVRound = 2048 + (8192 << 6);            // second-pass rounding + the 14-bit offset of the first pass
+
+// one column of the half-pel stage: the fraction-2 filter down the N+1 positions rho - 1/2 (rho = 0..N) of plane column `pl`
+// (pair-interleaved words, row stride TS).  v[rho] is compared with current row rho ("minus" candidates, y = -2) and with
+// current row rho-1 ("plus", y = +2) of the left (block column j-1) and, for T_2, right (column j) neighbours; T_2 also gives
+// the horizontal-only half-pel sample u[rho] = round(T_2[rho+4]).  Four rows per packed compare.
+template <int N, int TS, bool T2>
+__device__ __forceinline__ void half_strip(const uint32_t *pl, const uint8_t *cur_l, const uint8_t *cur_r, uint32_t (&acc)[6])
+{
+    uint32_t win[5];
+#pragma unroll
+    for (int k = 0; k < 4; k++) win[k] = pl[k * TS];
+    uint32_t prev_v = 0, prev_l = 0, prev_r = 0;
+#pragma unroll
+    for (int k4 = 0; k4 <= N / 4; k4++) {
+        const bool last = k4 == N / 4;                 // only row N: feeds the plus candidates
+        int v[4] = { 0, 0, 0, 0 }, u[4] = { 0, 0, 0, 0 };
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int m = 2 * k4 + h;
+            if (last && h == 1) break;
+            if (!last) win[(m + 4) % 5] = pl[(m + 4) * TS];
+            int se = kVRound;
+#pragma unroll
+            for (int i = 0; i < 4; i++) se = __dp2a_lo(static_cast<int>(win[(m + i) % 5]), static_cast<int>(vtap(2, 0, i)), se);
+            v[2 * h] = se >> 12;
+            if (!last) {
+                int so = kVRound;
+#pragma unroll
+                for (int i = 0; i < 5; i++) so = __dp2a_hi(static_cast<int>(win[(m + i) % 5]), static_cast<int>(vtap(2, 0, i)), so);
+                v[2 * h + 1] = so >> 12;
+                if (T2) {
+                    const int w = static_cast<int>(win[(m + 2) % 5]);          // rows rho+4 of the two outputs
+                    u[2 * h] = __dp2a_lo(w, 0x0001, 8192 + 32) >> 6;
+                    u[2 * h + 1] = __dp2a_lo(w, 0x0100, 8192 + 32) >> 6;
+                }
+            }
+        }
+        const uint32_t pv = hb_pack_sat_u8x4(v[0], v[1], v[2], v[3]);
+        if (k4 >= 1) {
+            const uint32_t vs = __funnelshift_r(prev_v, pv, 8);               // rows 4(k4-1)+1 .. 4(k4-1)+4
+            acc[2] = hb_sad4_acc(vs, prev_l, acc[2]);
+            if (T2) acc[3] = hb_sad4_acc(vs, prev_r, acc[3]);
+        }
+        if (!last) {
+            const uint32_t l4 = *reinterpret_cast<const uint32_t *>(cur_l + 4 * k4);
+            acc[0] = hb_sad4_acc(pv, l4, acc[0]);
+            prev_l = l4;
+            if (T2) {
+                const uint32_t r4 = *reinterpret_cast<const uint32_t *>(cur_r + 4 * k4);
+                const uint32_t pu = hb_pack_sat_u8x4(u[0], u[1], u[2], u[3]);
+                acc[1] = hb_sad4_acc(pv, r4, acc[1]);
+                acc[4] = hb_sad4_acc(pu, l4, acc[4]);
+                acc[5] = hb_sad4_acc(pu, r4, acc[5]);
+                prev_r = r4;
+            }
+        }
+        prev_v = pv;
+    }
+}
 
 // barrier over the lanes that search one PU.  Sub-warp groups use their own lane mask, so the PUs sharing a warp may sit in
 // different iterations of the (data-dependent) search loops: the hardware runs them in lock step where their paths agree.
@@ -82,6 +174,7 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
     using Cfg = MeCfg<N>;
     constexpr int G = Cfg::G, L = Cfg::L, SEG = Cfg::SEG, NSEG = Cfg::NSEG, SPS = Cfg::SEG_PER_SLOT, PUS = Cfg::PUS;
     constexpr int WPR = Cfg::WPR, WPL = Cfg::WPL, CPL = Cfg::CPL, PS = Cfg::PS, TS = Cfg::TS, PROWS = Cfg::PROWS;
+    constexpr int QROWS = Cfg::QROWS, PLANE_WORDS = Cfg::PLANE_WORDS, CS = Cfg::CS;
 
     extern __shared__ __align__(16) uint8_t s_raw[];
     __shared__ uint32_t s_x[(G > 32) ? PUS : 1][2][NSEG][2];   // G > 32: [phase][segment]{partial SAD, cost of the segment's slot}
@@ -99,7 +192,7 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
     const bool two_costs = n_amvp > 1 && (a0x != a1x || a0y != a1y);
 
     uint8_t *s_patch = s_raw + group * Cfg::SMEM_PER_PU;
-    int16_t *s_plane = reinterpret_cast<int16_t *>(s_patch + Cfg::PATCH_BYTES);   // [4][PROWS][TS] by x fraction
+    uint32_t *s_plane = reinterpret_cast<uint32_t *>(s_patch + Cfg::PATCH_BYTES);  // [4][QROWS][TS] by x fraction, rows in pairs
     int phase = 0;
     const uint32_t seg_mask = (SEG == 32) ? HB_FULL_MASK : (((1u << SEG) - 1u) << (lane & ~(SEG - 1)));
     const uint32_t gmask = (G >= 32) ? HB_FULL_MASK : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));
@@ -338,69 +431,79 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
             *reinterpret_cast<uint32_t *>(s_patch + r * PS + c) = hb_ld_u8x4(ref_i + r * a.ref.pitch + c);
         }
         group_barrier<G>(group, gmask);
-        // ---- horizontal 14-bit planes, fractions 0..3: T_f[r][j] = sum_k taps_f[k] * P[r][j+k] - 8192 (T_0 = P[r][j+3]*64 - 8192)
-        for (int w = gl; w < PROWS * (TS / 4); w += G) {
-            const int r = w / (TS / 4), j0 = (w % (TS / 4)) * 4;
-            const uint32_t *pw = reinterpret_cast<const uint32_t *>(s_patch + r * PS + j0);
-            const uint32_t w0 = pw[0], w1 = pw[1], w2 = pw[2];
-            int p[11];
+        // ---- horizontal 14-bit planes, fractions 0..3: T_f[rho][j] = sum_k taps_f[k] * P[rho][j+k] - 8192 (T_0 = 64 P[rho][j+3] - 8192),
+        // stored PAIR-INTERLEAVED: word (q, j) of a plane holds T[2q][j] in its low half and T[2q+1][j] in its high half, so the
+        // vertical passes read two taps per shared load and multiply them with one dp2a.  One work item = two rows x four columns
+        // x four fractions: u8 samples x s8 taps through dp4a, one 16-byte store per fraction.
+        for (int w = gl; w < QROWS * (TS / 4); w += G) {
+            const int q = w / (TS / 4), j0 = (w % (TS / 4)) * 4;
+            int o[2][4][4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) { p[k] = (w0 >> (8 * k)) & 255; p[4 + k] = (w1 >> (8 * k)) & 255; }
+            for (int rr = 0; rr < 2; rr++) {
+                const uint32_t *pw = reinterpret_cast<const uint32_t *>(s_patch + (2 * q + rr) * PS + j0);
+                const uint32_t w0 = pw[0], w1 = pw[1], w2 = pw[2];
+                uint32_t win[8];                                       // win[c] = samples j0+c .. j0+c+3
+                win[0] = w0; win[4] = w1;
 #pragma unroll
-            for (int k = 0; k < 3; k++) p[8 + k] = (w2 >> (8 * k)) & 255;
-            int o[4][4];
+                for (int c = 1; c < 4; c++) { win[c] = __funnelshift_r(w0, w1, 8 * c); win[4 + c] = __funnelshift_r(w1, w2, 8 * c); }
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                o[0][q] = (p[q + 3] << 6) - 8192;
-                o[1][q] = hb_luma8<1>(p[q], p[q + 1], p[q + 2], p[q + 3], p[q + 4], p[q + 5], p[q + 6], p[q + 7]) - 8192;
-                o[2][q] = hb_luma8<2>(p[q], p[q + 1], p[q + 2], p[q + 3], p[q + 4], p[q + 5], p[q + 6], p[q + 7]) - 8192;
-                o[3][q] = hb_luma8<3>(p[q], p[q + 1], p[q + 2], p[q + 3], p[q + 4], p[q + 5], p[q + 6], p[q + 7]) - 8192;
+                for (int c = 0; c < 4; c++) {
+                    o[rr][0][c] = hb_dp4a_us(win[c], htap4(0, 0), -8192);
+#pragma unroll
+                    for (int f = 1; f < 4; f++) o[rr][f][c] = hb_dp4a_us(win[c + 4], htap4(f, 1), hb_dp4a_us(win[c], htap4(f, 0), -8192));
+                }
             }
 #pragma unroll
             for (int f = 0; f < 4; f++) {
-                uint2 v;
-                v.x = (static_cast<uint32_t>(o[f][0]) & 0xffffu) | (static_cast<uint32_t>(o[f][1]) << 16);
-                v.y = (static_cast<uint32_t>(o[f][2]) & 0xffffu) | (static_cast<uint32_t>(o[f][3]) << 16);
-                *reinterpret_cast<uint2 *>(s_plane + f * Cfg::PLANE_ELEMS + r * TS + j0) = v;
+                uint4 v;
+                v.x = __byte_perm(o[0][f][0], o[1][f][0], 0x5410); v.y = __byte_perm(o[0][f][1], o[1][f][1], 0x5410);
+                v.z = __byte_perm(o[0][f][2], o[1][f][2], 0x5410); v.w = __byte_perm(o[0][f][3], o[1][f][3], 0x5410);
+                *reinterpret_cast<uint4 *>(s_plane + f * PLANE_WORDS + q * TS + j0) = v;
             }
         }
         group_barrier<G>(group, gmask);
-        // ---- the current block as bytes, over the patch area (no longer needed)
+        // ---- the current block, transposed (column c at s_cur + c*CS: four vertical neighbours per word), over the patch area
         uint8_t *s_cur = s_patch;
 #pragma unroll
-        for (int k = 0; k < PPL; k++)
-            if (slot == 0) *reinterpret_cast<uint2 *>(s_cur + (prow0 + k * (L / PPR)) * N + pcol) = make_uint2(cur[2 * k], cur[2 * k + 1]);
+        for (int k = 0; k < WPL; k++) {
+            const int row = prow0 + (k / 2) * (L / PPR), col = pcol + (k & 1) * 4 + slot;     // slot s stores byte s of every word
+            s_cur[col * CS + row] = static_cast<uint8_t>(cur[k] >> (8 * slot));
+        }
         if (gl < 8) s_half[group][gl] = 0;
         group_barrier<G>(group, gmask);
 
-        // one round: SADs of four sub-pel candidates at quarter-pel offsets (qx[s], qy[s]) in [-3,3]^2 from (ix,iy)
+        // one round: SADs of four sub-pel candidates at quarter-pel offsets (qx[s], qy[s]) in [-3,3]^2 from (ix,iy).  A lane filters
+        // CPL columns of its slot's candidate top to bottom: per two output rows one shared load and ten dp2a; four clipped
+        // samples are packed and compared with four current samples in one instruction.
         auto subpel4 = [&](const int (&qx)[4], const int (&qy)[4], uint32_t (&sad)[4]) {
             int cx = qx[0], cy = qy[0];
 #pragma unroll
             for (int s = 1; s < 4; s++) if (slot == s) { cx = qx[s]; cy = qy[s]; }
-            const int fx = cx & 3, fy = cy & 3, cb = cx >> 2, rb = cy >> 2;
-            int t[8];
+            const int fx = cx & 3, fy = cy & 3, cb = cx >> 2, par = (cy >> 2) + 1;
+            uint32_t tb[5];
 #pragma unroll
-            for (int k = 0; k < 8; k++) t[k] = c_taps[fy][k];
+            for (int i = 0; i < 5; i++) tb[i] = c_vtab[fy][par][i];
             const int c0 = l * CPL;
-            const int16_t *pl = s_plane + fx * Cfg::PLANE_ELEMS + (rb + 1) * TS + c0 + cb + 1;   // first tap row of output row 0
+            const uint32_t *pl = s_plane + fx * PLANE_WORDS + c0 + cb + 1;
             uint32_t acc = 0;
 #pragma unroll
             for (int cc = 0; cc < CPL; cc++) {
-                int win[8];
+                uint32_t win[5];
 #pragma unroll
-                for (int k = 0; k < 7; k++) win[k] = pl[k * TS + cc];
-                for (int r8 = 0; r8 < N; r8 += 8) {
+                for (int k = 0; k < 4; k++) win[k] = pl[k * TS + cc];
 #pragma unroll
-                    for (int rr = 0; rr < 8; rr++) {
-                        const int r = r8 + rr;
-                        win[(rr + 7) & 7] = pl[(r + 7) * TS + cc];
-                        int s = 2048 + (8192 << 6);        // rounding + the 14-bit offset of the first pass
+                for (int m4 = 0; m4 < N / 4; m4++) {
+                    int v[4];
 #pragma unroll
-                        for (int k = 0; k < 8; k++) s += t[k] * win[(rr + k) & 7];
-                        const int px = __vimin_s32_relu(s >> 12, 255);                       // clip to 0..255 in one instruction
-                        acc = __sad(px, static_cast<int>(s_cur[r * N + c0 + cc]), acc);
+                    for (int h = 0; h < 2; h++) {
+                        const int m = 2 * m4 + h;
+                        win[(m + 4) % 5] = pl[(m + 4) * TS + cc];
+                        int sa = kVRound, sb = kVRound;
+#pragma unroll
+                        for (int i = 0; i < 5; i++) { sa = __dp2a_lo(static_cast<int>(win[(m + i) % 5]), static_cast<int>(tb[i]), sa); sb = __dp2a_hi(static_cast<int>(win[(m + i) % 5]), static_cast<int>(tb[i]), sb); }
+                        v[2 * h] = sa >> 12; v[2 * h + 1] = sb >> 12;
                     }
+                    acc = hb_sad4_acc(hb_pack_sat_u8x4(v[0], v[1], v[2], v[3]), *reinterpret_cast<const uint32_t *>(s_cur + (c0 + cc) * CS + 4 * m4), acc);
                 }
             }
             uint32_t cst[4];
@@ -408,54 +511,24 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
         };
 
         // ---- half-pel stage.  The reference builds three planes ((0,2), (2,0), (2,2), :395-438) and reads each of them for
-        // two or four candidates shifted by one sample; here a lane walks one COLUMN of the horizontal plane T_0 or T_2 with an
-        // 8-row sliding window and feeds every filtered sample to all the candidates it belongs to:
-        //   T_0 column (N strips):   v = V2(T_0)            -> candidates (0,-2) and (0,+2)
-        //   T_2 column (N+1 strips): v = V2(T_2), u = round(T_2) -> (-2,-2) (+2,-2) (-2,+2) (+2,+2) and (-2,0) (+2,0)
-        // Partial SADs go to eight shared counters.
+        // two or four candidates shifted by one sample; here a lane walks one COLUMN of the horizontal plane T_0 or T_2 and
+        // feeds every filtered sample to all the candidates it belongs to:
+        //   T_0 column (N strips): v = V2(T_0)                   -> candidates (0,-2) and (0,+2)
+        //   T_2 column (N strips): v = V2(T_2), u = round(T_2)   -> (-2,-2) (+2,-2) (-2,+2) (+2,+2) and (-2,0) (+2,0)
+        // Partial SADs go to eight shared counters.  T_0 / T_2 is uniform per warp.
         for (int strip = gl; strip < 2 * N; strip += G) {
             const bool t2 = strip >= N;
             const int j = t2 ? strip - N : strip + 1;                 // plane column: x = ix - 1 + j (+ 1/2 for T_2)
-            const int16_t *pl = s_plane + (t2 ? 2 : 0) * Cfg::PLANE_ELEMS + j;
-            const bool use_l = j >= 1, use_r = t2 && j < N;           // block column j-1 (candidate x >= 0) / column j (x = -2)
+            const bool use_l = j >= 1;                                // block column j-1 exists (j = 0: only the x = -2 candidates)
+            const uint8_t *cur_l = s_cur + max(j - 1, 0) * CS, *cur_r = s_cur + j * CS;
             uint32_t acc[6] = { 0, 0, 0, 0, 0, 0 };                   // {minus,L} {minus,R} {plus,L} {plus,R} {u,L} {u,R}
-            int win[8];
-#pragma unroll
-            for (int k = 0; k < 7; k++) win[k] = pl[k * TS];
-            int pcl = 0, pcr = 0;                                     // current samples of the previous block row
-            auto row_step = [&](int rho, int rr, bool has_row) {      // rho = plane row of the filtered sample (position rho - 1/2)
-                win[(rr + 7) & 7] = pl[(rho + 7) * TS];
-                const int s = hb_luma8<2>(win[rr & 7], win[(rr + 1) & 7], win[(rr + 2) & 7], win[(rr + 3) & 7], win[(rr + 4) & 7],
-                                          win[(rr + 5) & 7], win[(rr + 6) & 7], win[(rr + 7) & 7]);
-                const int v = __vimin_s32_relu((s + 2048 + (8192 << 6)) >> 12, 255);
-                int cl = 0, cr = 0;
-                if (has_row) {
-                    if (use_l) cl = s_cur[rho * N + j - 1];
-                    if (use_r) cr = s_cur[rho * N + j];
-                    if (use_l) acc[0] = __sad(v, cl, acc[0]);
-                    if (use_r) acc[1] = __sad(v, cr, acc[1]);
-                    if (t2) {
-                        const int u = __vimin_s32_relu((win[(rr + 4) & 7] + 8192 + 32) >> 6, 255);
-                        if (use_l) acc[4] = __sad(u, cl, acc[4]);
-                        if (use_r) acc[5] = __sad(u, cr, acc[5]);
-                    }
-                }
-                if (rho >= 1) {
-                    if (use_l) acc[2] = __sad(v, pcl, acc[2]);
-                    if (use_r) acc[3] = __sad(v, pcr, acc[3]);
-                }
-                pcl = cl; pcr = cr;
-            };
-            for (int r8 = 0; r8 < N; r8 += 8) {
-#pragma unroll
-                for (int rr = 0; rr < 8; rr++) row_step(r8 + rr, rr, true);
-            }
-            row_step(N, 0, false);                                    // the extra row only feeds the +2 candidates
             // c_half order: 1 (0,-1) 2 (0,1) 3 (-1,0) 4 (1,0) 5 (-1,-1) 6 (1,-1) 7 (-1,1) 8 (1,1)
             if (t2) {
+                half_strip<N, TS, true>(s_plane + 2 * PLANE_WORDS + j, cur_l, cur_r, acc);
                 if (use_l) { atomicAdd(&s_half[group][5], acc[0]); atomicAdd(&s_half[group][7], acc[2]); atomicAdd(&s_half[group][3], acc[4]); }
-                if (use_r) { atomicAdd(&s_half[group][4], acc[1]); atomicAdd(&s_half[group][6], acc[3]); atomicAdd(&s_half[group][2], acc[5]); }
+                atomicAdd(&s_half[group][4], acc[1]); atomicAdd(&s_half[group][6], acc[3]); atomicAdd(&s_half[group][2], acc[5]);
             } else {
+                half_strip<N, TS, false>(s_plane + j, cur_l, cur_r, acc);
                 atomicAdd(&s_half[group][0], acc[0]); atomicAdd(&s_half[group][1], acc[2]);
             }
         }
@@ -465,15 +538,15 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
             const int rho = rho0 + gl;
             uint32_t am = 0, ap = 0, au = 0;
             if (rho <= N) {
-                const int16_t *pl = s_plane + 2 * Cfg::PLANE_ELEMS + rho * TS + N;
-                const int s = hb_luma8<2>(pl[0], pl[TS], pl[2 * TS], pl[3 * TS], pl[4 * TS], pl[5 * TS], pl[6 * TS], pl[7 * TS]);
-                const int v = __vimin_s32_relu((s + 2048 + (8192 << 6)) >> 12, 255);
+                auto t2_at = [&](int r) -> int { return reinterpret_cast<const int16_t *>(s_plane + 2 * PLANE_WORDS + (r >> 1) * TS + N)[r & 1]; };
+                const int s = hb_luma8<2>(t2_at(rho), t2_at(rho + 1), t2_at(rho + 2), t2_at(rho + 3), t2_at(rho + 4), t2_at(rho + 5), t2_at(rho + 6), t2_at(rho + 7));
+                const int v = __vimin_s32_relu((s + kVRound) >> 12, 255);
                 if (rho < N) {
-                    const int cl = s_cur[rho * N + N - 1];
+                    const int cl = s_cur[(N - 1) * CS + rho];
                     am = __sad(v, cl, 0u);
-                    au = __sad(__vimin_s32_relu((pl[4 * TS] + 8192 + 32) >> 6, 255), cl, 0u);
+                    au = __sad(__vimin_s32_relu((t2_at(rho + 4) + 8192 + 32) >> 6, 255), cl, 0u);
                 }
-                if (rho >= 1) ap = __sad(v, static_cast<int>(s_cur[(rho - 1) * N + N - 1]), 0u);
+                if (rho >= 1) ap = __sad(v, static_cast<int>(s_cur[(N - 1) * CS + rho - 1]), 0u);
             }
             if constexpr (G >= 32) {
                 am = __reduce_add_sync(HB_FULL_MASK, am); ap = __reduce_add_sync(HB_FULL_MASK, ap); au = __reduce_add_sync(HB_FULL_MASK, au);
@@ -508,27 +581,25 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
         // ---- optionally leave the luma prediction of the winner in the prediction plane: same two-stage samples that
         // hmr_motion_compensation_luma (:1779) produces for this vector, taken from the planes already in shared memory
         if (a.pred.org != nullptr) {
-            constexpr int SEGS = G / N, RPS = N / SEGS;            // row segments per column, rows per segment
-            const int fx = sbx & 3, fy = sby & 3, cb = sbx >> 2, rb = sby >> 2;
-            int t[8];
+            constexpr int SEGS = G / N, RPS = N / SEGS;            // row segments per column, rows per segment (even)
+            const int fx = sbx & 3, fy = sby & 3, cb = sbx >> 2, par = (sby >> 2) + 1;
+            uint32_t tb[5];
 #pragma unroll
-            for (int k = 0; k < 8; k++) t[k] = c_taps[fy][k];
+            for (int i = 0; i < 5; i++) tb[i] = c_vtab[fy][par][i];
             const int c = gl % N, r0 = (gl / N) * RPS;
-            const int16_t *pl = s_plane + fx * Cfg::PLANE_ELEMS + (rb + 1 + r0) * TS + c + cb + 1;
+            const uint32_t *pl = s_plane + fx * PLANE_WORDS + (r0 / 2) * TS + c + cb + 1;
             uint8_t *dst = a.pred.org + (jy + r0) * a.pred.pitch + jx + c;
-            int win[8];
+            uint32_t win[5];
 #pragma unroll
-            for (int k = 0; k < 7; k++) win[k] = pl[k * TS];
-            for (int r8 = 0; r8 < RPS; r8 += 8) {
+            for (int k = 0; k < 4; k++) win[k] = pl[k * TS];
 #pragma unroll
-                for (int rr = 0; rr < 8; rr++) {
-                    const int r = r8 + rr;
-                    win[(rr + 7) & 7] = pl[(r + 7) * TS];
-                    int s2 = 2048 + (8192 << 6);
+            for (int m = 0; m < RPS / 2; m++) {
+                win[(m + 4) % 5] = pl[(m + 4) * TS];
+                int sa = kVRound, sb = kVRound;
 #pragma unroll
-                    for (int k = 0; k < 8; k++) s2 += t[k] * win[(rr + k) & 7];
-                    dst[r * a.pred.pitch] = static_cast<uint8_t>(__vimin_s32_relu(s2 >> 12, 255));
-                }
+                for (int i = 0; i < 5; i++) { sa = __dp2a_lo(static_cast<int>(win[(m + i) % 5]), static_cast<int>(tb[i]), sa); sb = __dp2a_hi(static_cast<int>(win[(m + i) % 5]), static_cast<int>(tb[i]), sb); }
+                dst[(2 * m) * a.pred.pitch] = static_cast<uint8_t>(__vimin_s32_relu(sa >> 12, 255));
+                dst[(2 * m + 1) * a.pred.pitch] = static_cast<uint8_t>(__vimin_s32_relu(sb >> 12, 255));
             }
         }
     }
