@@ -287,6 +287,7 @@ void hb_frame_destroy(hb_frame *f)
     hbc_set_device(f->ctx->device);
     hbc_stream_sync(f->ctx->stream);
     for (int c = 0; c < 3; c++) if (f->d.p[c].base) hbc_free(f->d.p[c].base);
+    if (f->stage) hbc_free(f->stage);
     free(f);
 }
 int hb_frame_width(const hb_frame *f) { return f ? f->w : 0; }
@@ -307,11 +308,23 @@ int hb_frame_upload_u8_ex(hb_ctx *ctx, hb_frame *f, const uint8_t *y, int ys, co
     int rc = 0;
     if (!ctx || !f || !y || !u || !v) return hbi_fail(HB_ERR_ARG, "hb_frame_upload_u8: NULL argument");
     hbc_set_device(ctx->device);
-    for (int c = 0; c < 3 && !rc; c++) {
-        const hbd_plane *p = &f->d.p[c];
-        rc = hbc_h2d_2d_async(p->org, (size_t)p->pitch, src[c], (size_t)st[c], (size_t)p->w, (size_t)p->h, ctx->stream);
+    /* One plain copy per plane (a single one when the caller's planes are contiguous) into a dense staging buffer -- 1-D copies
+     * run at link speed, pitched ones at about half of it -- then one kernel spreads the samples into the padded planes and
+     * replicates the borders in the same pass. */
+    const size_t luma = (size_t)f->w * f->h;
+    if (!f->stage && (rc = hbc_malloc((void **)&f->stage, luma + luma / 2 + 16))) return hbi_cuda_fail(rc, "hb_frame_upload_u8: cudaMalloc");
+    if (ys == f->w && us == f->w / 2 && vs == f->w / 2 && u == y + luma && v == u + luma / 4)
+        rc = hbc_h2d_async(f->stage, y, luma + luma / 2, ctx->stream);
+    else {
+        size_t off = 0;
+        for (int c = 0; c < 3 && !rc; c++) {
+            const hbd_plane *p = &f->d.p[c];
+            if (st[c] == p->w) rc = hbc_h2d_async(f->stage + off, src[c], (size_t)p->w * p->h, ctx->stream);
+            else rc = hbc_h2d_2d_async(f->stage + off, (size_t)p->w, src[c], (size_t)st[c], (size_t)p->w, (size_t)p->h, ctx->stream);
+            off += (size_t)p->w * p->h;
+        }
     }
-    if (!rc && !(flags & HB_UPLOAD_NO_BORDER)) { rc = hbk_pad_frame(&f->d, ctx->stream); ctx->launches += 1; }
+    if (!rc) { rc = hbk_ingest_frame(&f->d, f->stage, !(flags & HB_UPLOAD_NO_BORDER), ctx->stream); ctx->launches += 1; }
     return rc ? hbi_cuda_fail(rc, "hb_frame_upload_u8") : HB_OK;
 }
 

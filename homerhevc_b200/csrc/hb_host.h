@@ -28,6 +28,7 @@ struct hb_frame {
     hb_ctx *ctx;
     int w, h;
     hbd_frame d;
+    uint8_t *stage;            /* dense device copy of the last uploaded planes (allocated on first upload) */
 };
 
 hb_ctx *hb_default_ctx(void);

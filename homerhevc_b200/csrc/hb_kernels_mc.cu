@@ -134,6 +134,26 @@ __global__ void k_pad_frame(hbd_frame f)
     }
 }
 
+// ---- dense host layout -> padded planes.  `stage` holds the three planes back to back with tight pitches (what one plain
+// 1-D copy from the host delivers at full link speed); every 4-byte group of the padded destination is either inside the
+// picture or a replicated edge sample (widths and borders are multiples of 4).  border = 0 writes the picture only.
+__global__ void k_ingest_frame(hbd_frame f, const uint8_t *stage, int border)
+{
+    const hbd_plane p = f.p[blockIdx.y];
+    const uint8_t *src = stage + (blockIdx.y == 0 ? 0 : f.p[0].w * f.p[0].h + (blockIdx.y == 2 ? f.p[1].w * f.p[1].h : 0));
+    const int pad = border ? p.pad : 0;
+    const int ww = (p.w + 2 * pad) >> 2, rows = p.h + 2 * pad;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ww * rows; i += gridDim.x * blockDim.x) {
+        const int r = i / ww, x = (i % ww) * 4 - pad;
+        const int y = min(max(r - pad, 0), p.h - 1);
+        const uint8_t *row = src + y * p.w;
+        uint32_t v;
+        if (x >= 0 && x < p.w) v = *reinterpret_cast<const uint32_t *>(row + x);
+        else v = static_cast<uint32_t>(x < 0 ? row[0] : row[p.w - 1]) * 0x01010101u;
+        *reinterpret_cast<uint32_t *>(p.org + (r - pad) * p.pitch + x) = v;
+    }
+}
+
 __global__ void k_narrow_plane(const int16_t *src, int src_stride, hbd_plane dst, uint32_t *range_flag)
 {
     bool bad = false;
@@ -171,6 +191,16 @@ extern "C" int hbk_pad_frame(const hbd_frame *f, void *stream)
     const hbd_plane &p = f->p[0];
     const int n = 2 * p.pad * p.h + 2 * p.pad * (p.w + 2 * p.pad);
     k_pad_frame<<<dim3((n + 255) / 256, 3), 256, 0, s>>>(*f);
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int hbk_ingest_frame(const hbd_frame *f, const uint8_t *stage, int border, void *stream)
+{
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const hbd_plane &p = f->p[0];
+    const int pad = border ? p.pad : 0;
+    const int n = ((p.w + 2 * pad) / 4) * (p.h + 2 * pad);
+    k_ingest_frame<<<dim3(min((n + 255) / 256, 148 * 8), 3), 256, 0, s>>>(*f, stage, border);
     return static_cast<int>(cudaGetLastError());
 }
 

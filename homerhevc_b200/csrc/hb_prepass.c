@@ -42,6 +42,9 @@ struct hb_prepass {
     hbd_me_job *d_jobs[N_DEPTH];
     hbd_mc_pu *d_pus[N_DEPTH];
     hb_me_result *d_me[N_DEPTH];
+    char *d_tables;                                 /* one block: ME results of every depth, then TU results of every (pass, comp) --
+                                                     * exactly the layout hb_prepass_fetch_tables delivers, so the fetch is ONE copy */
+    size_t tables_bytes;
     hb_frame *pred[N_DEPTH];
     /* T/Q */
     pass_comp pc[N_PASS][3];
@@ -106,13 +109,11 @@ int hb_prepass_create(hb_ctx *ctx, int width, int height, const hb_prepass_cfg *
         pp->grid_w[d] = gw; pp->grid_h[d] = gh;
         hbd_me_job *jobs = (hbd_me_job *)calloc((size_t)gw * gh, sizeof *jobs);
         hbd_mc_pu *pus = (hbd_mc_pu *)calloc((size_t)gw * gh, sizeof *pus);
-        hb_me_result *init = (hb_me_result *)calloc((size_t)gw * gh, sizeof *init);
-        if (!jobs || !pus || !init) { free(jobs); free(pus); free(init); rc = hbi_fail(HB_ERR_NOMEM, "hb_prepass_create: out of memory"); break; }
+        if (!jobs || !pus) { free(jobs); free(pus); rc = hbi_fail(HB_ERR_NOMEM, "hb_prepass_create: out of memory"); break; }
         int n = 0;
         for (int py = 0; py < gh; py++)
             for (int px = 0; px < gw; px++) {
                 const int idx = py * gw + px;
-                init[idx].sad = 0xffffffffu;
                 if (!pu_valid(pp, px * s, py * s, s)) continue;
                 hbd_me_job *j = &jobs[n];
                 j->x = px * s; j->y = py * s;
@@ -128,8 +129,7 @@ int hb_prepass_create(hb_ctx *ctx, int width, int height, const hb_prepass_cfg *
         pp->n_valid[d] = n;
         rc = upload(ctx, (void **)&pp->d_jobs[d], jobs, sizeof *jobs * (size_t)n);
         if (rc == HB_OK) rc = upload(ctx, (void **)&pp->d_pus[d], pus, sizeof *pus * (size_t)n);
-        if (rc == HB_OK) rc = upload(ctx, (void **)&pp->d_me[d], init, sizeof *init * (size_t)gw * gh);
-        free(jobs); free(pus); free(init);
+        free(jobs); free(pus);
         if (rc == HB_OK) rc = hb_frame_create(ctx, width, height, &pp->pred[d]);
     }
     /* ---- TU job lists: a TU is coded when the PU it belongs to is valid */
@@ -166,7 +166,30 @@ int hb_prepass_create(hb_ctx *ctx, int width, int height, const hb_prepass_cfg *
             free(xy); free(index);
             int crc = 0;
             if (rc == HB_OK && (crc = hbc_malloc((void **)&pc->d_coeff, sizeof(int16_t) * (size_t)(n ? n : 1) * tu * tu))) rc = hbi_cuda_fail(crc, "prepass: coeff");
-            if (rc == HB_OK && (crc = hbc_malloc((void **)&pc->d_res, sizeof(hb_tu_result) * (size_t)(n ? n : 1)))) rc = hbi_cuda_fail(crc, "prepass: results");
+        }
+    }
+    /* ---- result tables: one device block in the layout of hb_prepass_fetch_tables */
+    if (rc == HB_OK) {
+        size_t me_bytes = 0, total;
+        for (int d = 0; d < N_DEPTH; d++) me_bytes += sizeof(hb_me_result) * (size_t)pp->grid_w[d] * pp->grid_h[d];
+        total = me_bytes;
+        for (int p = 0; p < N_PASS; p++) for (int c = 0; c < 3; c++) total += sizeof(hb_tu_result) * (size_t)pp->pc[p][c].n_tus;
+        hb_me_result *init = (hb_me_result *)calloc(me_bytes / sizeof(hb_me_result) + 1, sizeof *init);
+        if (!init) rc = hbi_fail(HB_ERR_NOMEM, "hb_prepass_create: out of memory");
+        else {
+            for (size_t i = 0; i < me_bytes / sizeof *init; i++) init[i].sad = 0xffffffffu;       /* PUs outside the band / picture */
+            int crc = hbc_malloc((void **)&pp->d_tables, total + 16);
+            if (!crc) crc = hbc_memset_async(pp->d_tables, 0, total + 16, ctx->stream);
+            if (!crc) crc = hbc_h2d_async(pp->d_tables, init, me_bytes, ctx->stream);
+            if (!crc) crc = hbc_stream_sync(ctx->stream);
+            free(init);
+            if (crc) rc = hbi_cuda_fail(crc, "prepass: result tables");
+            else {
+                char *o = pp->d_tables;
+                pp->tables_bytes = total;
+                for (int d = 0; d < N_DEPTH; d++) { pp->d_me[d] = (hb_me_result *)o; o += sizeof(hb_me_result) * (size_t)pp->grid_w[d] * pp->grid_h[d]; }
+                for (int p = 0; p < N_PASS; p++) for (int c = 0; c < 3; c++) { pp->pc[p][c].d_res = (hb_tu_result *)o; o += sizeof(hb_tu_result) * (size_t)pp->pc[p][c].n_tus; }
+            }
         }
     }
     for (int d = 0; d < N_DEPTH && rc == HB_OK; d++) {
@@ -196,19 +219,18 @@ void hb_prepass_destroy(hb_prepass *pp)
     for (int d = 0; d < N_DEPTH; d++) {
         if (pp->d_jobs[d]) hbc_free(pp->d_jobs[d]);
         if (pp->d_pus[d]) hbc_free(pp->d_pus[d]);
-        if (pp->d_me[d]) hbc_free(pp->d_me[d]);
         hb_frame_destroy(pp->pred[d]);
     }
     for (int p = 0; p < N_PASS; p++) {
         for (int c = 0; c < 3; c++) {
             if (pp->pc[p][c].d_xy) hbc_free(pp->pc[p][c].d_xy);
             if (pp->pc[p][c].d_coeff) hbc_free(pp->pc[p][c].d_coeff);
-            if (pp->pc[p][c].d_res) hbc_free(pp->pc[p][c].d_res);
             if (pp->pc[p][c].d_index) hbc_free(pp->pc[p][c].d_index);
             free(pp->pc[p][c].h_ctu);
         }
         hb_frame_destroy(pp->recon[p]);
     }
+    if (pp->d_tables) hbc_free(pp->d_tables);
     if (pp->d_dyn) hbc_free(pp->d_dyn);
     if (pp->d_sel) hbc_free(pp->d_sel);
     if (pp->d_ctu_off) hbc_free(pp->d_ctu_off);
@@ -507,18 +529,8 @@ int hb_prepass_fetch_tables(hb_prepass *pp, void *pinned_dst, size_t cap)
     if (!pp || !pinned_dst) return hbi_fail(HB_ERR_ARG, "hb_prepass_fetch_tables: NULL argument");
     if (cap < hb_prepass_tables_bytes(pp)) return hbi_fail(HB_ERR_ARG, "hb_prepass_fetch_tables: buffer too small");
     hb_ctx *ctx = pp->ctx;
-    char *o = (char *)pinned_dst;
-    int crc = 0;
     hbc_set_device(ctx->device);
-    for (int d = 0; d < N_DEPTH && !crc; d++) {
-        const size_t b = sizeof(hb_me_result) * (size_t)hb_prepass_num_pus(pp, d);
-        crc = hbc_d2h_async(o, pp->d_me[d], b, ctx->stream); o += b;
-    }
-    for (int p = 0; p < N_PASS && !crc; p++)
-        for (int c = 0; c < 3 && !crc; c++) {
-            const size_t b = sizeof(hb_tu_result) * (size_t)pp->pc[p][c].n_tus;
-            if (b) { crc = hbc_d2h_async(o, pp->pc[p][c].d_res, b, ctx->stream); o += b; }
-        }
+    const int crc = hbc_d2h_async(pinned_dst, pp->d_tables, pp->tables_bytes, ctx->stream);
     return crc ? hbi_cuda_fail(crc, "hb_prepass_fetch_tables") : HB_OK;
 }
 

@@ -55,6 +55,7 @@ const char *hbc_error_string(int code);
 
 /* ---- frame maintenance */
 int hbk_pad_frame(const hbd_frame *f, void *stream);                                   /* replicate borders of all planes */
+int hbk_ingest_frame(const hbd_frame *f, const uint8_t *stage, int border, void *stream);          /* dense planes -> padded planes (+ borders) */
 int hbk_narrow_plane(const int16_t *src, int src_stride, hbd_plane dst, uint32_t *range_flag, void *stream);
 
 /* ---- per-call kernels: operands live in mapped pinned staging, strides in samples */
