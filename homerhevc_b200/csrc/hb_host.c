@@ -491,7 +491,7 @@ int hb_mc_predict(hb_ctx *ctx, const hb_frame *ref, hb_frame *pred, const hb_mc_
     for (int i = 0; i < n_jobs; i++) {
         const hb_mc_job *j = &jobs[i];
         const int x0 = j->x + (j->mv.x >> 2), y0 = j->y + (j->mv.y >> 2);
-        if ((j->size != 8 && j->size != 16 && j->size != 32 && j->size != 64) || j->x < 0 || j->y < 0 || j->x + j->size > ref->w ||
+        if ((j->size != 8 && j->size != 16 && j->size != 32 && j->size != 64) || j->x < 0 || j->y < 0 || ((j->x | j->y) & 7) || j->x + j->size > ref->w ||
             j->y + j->size > ref->h || x0 < -reach || y0 < -reach || x0 + j->size > ref->w + reach || y0 + j->size > ref->h + reach)
             return hbi_fail(HB_ERR_ARG, "hb_mc_predict: job %d is invalid or points further than %d samples outside the picture", i, reach);
     }
@@ -519,7 +519,7 @@ int hb_mc_predict(hb_ctx *ctx, const hb_frame *ref, hb_frame *pred, const hb_mc_
         const int cnt = start_of[s + 1] - start_of[s];
         if (!cnt) continue;
         crc = hbk_mc_predict(&ref->d, &pred->d, sizes[s], (const hbd_mc_pu *)d_pus + start_of[s], cnt, (const hb_me_result *)d_mv, 3, ctx->stream);
-        ctx->launches++;
+        ctx->launches += 2;                                /* one luma, one chroma kernel */
     }
     if (!crc) crc = hbc_stream_sync(ctx->stream);
 done:

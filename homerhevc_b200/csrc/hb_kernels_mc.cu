@@ -1,10 +1,14 @@
 // hb_kernels_mc.cu -- motion compensation (hmr_motion_compensation_luma / _chroma, hmr_motion_inter.c:1779/:1860,
 // uni-prediction) on resident u8 planes, plus frame maintenance (border replication, int16 -> u8 narrowing).
 //
-// k_mc<T>: one warp predicts one T x T luma tile (T = 16, or 8 for 8x8 PUs) and the two (T/2)x(T/2) chroma tiles of
-// a PU.  The (T+7)x(T+8) reference patch is staged in the warp's shared memory; the horizontal pass writes 14-bit
-// intermediates (value - 8192) next to it and the vertical pass finishes -- or a single pass when one fraction is 0,
-// exactly the three branches of the reference.  No block-level synchronisation.
+// k_mc<T> (luma): one warp predicts one T x T tile (T = 16, or 8 for 8x8 PUs).  The (T+7)x(T+8) reference patch is staged
+// in the warp's shared memory; the horizontal pass writes 14-bit intermediates (value - 8192) next to it and the vertical
+// pass finishes -- or a single pass when one fraction is 0, exactly the three branches of the reference.
+// k_mc_chroma<RS>: one THREAD predicts a 4-wide, RS-tall strip of one chroma plane entirely in registers: the 4-tap
+// horizontal filter of four neighbours is four dp4a on funnel-shifted words of the resident reference, the vertical filter
+// runs over a rotating 4-row window, four clipped samples leave as one 32-bit store.  One arithmetic path serves the three
+// branches of the reference: with taps {0,64,0,0} for a zero fraction the two-stage result equals the single-stage one
+// ((64 s + 2048) >> 12 == (s + 32) >> 6), and the 14-bit offset cancels because the taps sum to 64.
 #include "hb_shim.h"
 #include "hb_dev_common.cuh"
 
@@ -19,7 +23,6 @@ struct McArgs {
     int tiles_per_pu;      // (size/T)^2
     int tiles_per_row;     // size/T
     const hb_me_result *mvsrc;
-    int planes;            // bit 0 luma, bit 1 chroma
 };
 
 // generic separable prediction of a W x W tile at (x,y) of `ref` displaced by (ix,iy) whole samples with fractions
@@ -102,12 +105,62 @@ __global__ void __launch_bounds__(kMcWarps * 32) k_mc(const McArgs a)
     const hb_mv mv = a.mvsrc[pu.mv_idx].mv;
     const int x = pu.x + (ti % a.tiles_per_row) * T, y = pu.y + (ti / a.tiles_per_row) * T;
 
-    if (a.planes & 1)
-        mc_tile<T, 8>(a.ref.p[0], a.pred.p[0], x, y, mv.x >> 2, mv.y >> 2, mv.x & 3, mv.y & 3, s_patch[warp], s_tmp[warp], lane);
-    if (!(a.planes & 2)) return;
-    // chroma: eighth-sample units (hmr_motion_inter.c:1863-1867)
-    mc_tile<T / 2, 4>(a.ref.p[1], a.pred.p[1], x >> 1, y >> 1, mv.x >> 3, mv.y >> 3, mv.x & 7, mv.y & 7, s_patch[warp], s_tmp[warp], lane);
-    mc_tile<T / 2, 4>(a.ref.p[2], a.pred.p[2], x >> 1, y >> 1, mv.x >> 3, mv.y >> 3, mv.x & 7, mv.y & 7, s_patch[warp], s_tmp[warp], lane);
+    mc_tile<T, 8>(a.ref.p[0], a.pred.p[0], x, y, mv.x >> 2, mv.y >> 2, mv.x & 3, mv.y & 3, s_patch[warp], s_tmp[warp], lane);
+}
+
+// ---- chroma (hmr_motion_compensation_chroma, hmr_motion_inter.c:1860; vectors in eighth-sample units :1863-1867)
+__constant__ int8_t c_ctap[8][4] = { {0, 64, 0, 0}, {-2, 58, 10, -2}, {-4, 54, 16, -2}, {-6, 46, 28, -4},
+                                     {-4, 36, 36, -4}, {-4, 28, 46, -6}, {-2, 16, 54, -4}, {-2, 10, 58, -2} };
+
+struct McCArgs {
+    hbd_plane ref[2], pred[2];
+    const hbd_mc_pu *pus;
+    const hb_me_result *mvsrc;
+    int total;             // work items: n_pus * 2 planes * segments * strips
+    int lg_strips, lg_segs;
+};
+
+template <int RS>
+__global__ void __launch_bounds__(256) k_mc_chroma(const McCArgs a)
+{
+    const int item = blockIdx.x * 256 + threadIdx.x;
+    if (item >= a.total) return;
+    // adjacent threads: adjacent strips of a row segment, then the segments, then the two planes of a PU
+    const int strip = item & ((1 << a.lg_strips) - 1);
+    int t = item >> a.lg_strips;
+    const int seg = t & ((1 << a.lg_segs) - 1);
+    t >>= a.lg_segs;
+    const int plane = t & 1;
+    const hbd_mc_pu pu = a.pus[t >> 1];
+    const hb_mv mv = a.mvsrc[pu.mv_idx].mv;
+    const int x = (pu.x >> 1) + strip * 4, y = (pu.y >> 1) + seg * RS;
+    const hbd_plane &rp = a.ref[plane], &pp = a.pred[plane];
+    const uint8_t *src = rp.org + (y + (mv.y >> 3) - 1) * rp.pitch + x + (mv.x >> 3) - 1;
+    const uint32_t sh = (static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src)) & 3u) * 8u;
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(src) & ~uintptr_t(3));
+    const int qstep = rp.pitch >> 2;
+    const int8_t *th = c_ctap[mv.x & 7], *tv = c_ctap[mv.y & 7];
+    const uint32_t htap = hb_pack4(th[0] & 255, th[1] & 255, th[2] & 255, th[3] & 255);
+    const int v0 = tv[0], v1 = tv[1], v2 = tv[2], v3 = tv[3];
+    uint8_t *dst = pp.org + y * pp.pitch + x;
+    int h[4][4];                                            // rotating window of horizontal sums: [row & 3][column]
+#pragma unroll
+    for (int r = 0; r < RS + 3; r++) {
+        const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+        q += qstep;
+        const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);     // samples x-1 .. x+6
+        h[r & 3][0] = hb_dp4a_us(x0, htap, 0);
+#pragma unroll
+        for (int c = 1; c < 4; c++) h[r & 3][c] = hb_dp4a_us(__funnelshift_r(x0, x1, 8 * c), htap, 0);
+        if (r >= 3) {
+            int o[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                o[c] = (v0 * h[(r - 3) & 3][c] + v1 * h[(r - 2) & 3][c] + v2 * h[(r - 1) & 3][c] + v3 * h[r & 3][c] + 2048) >> 12;
+            *reinterpret_cast<uint32_t *>(dst) = hb_pack_sat_u8x4(o[0], o[1], o[2], o[3]);
+            dst += pp.pitch;
+        }
+    }
 }
 
 // ---- border replication of one plane (reference_picture_border_padding_ctu, hmr_encoder_lib.c:1723): every sample
@@ -173,15 +226,29 @@ extern "C" int hbk_mc_predict(const hbd_frame *ref, const hbd_frame *pred, int s
 {
     if (n_pus <= 0) return 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    McArgs a;
-    a.ref = *ref; a.pred = *pred; a.pus = pus; a.n_pus = n_pus; a.mvsrc = mvsrc; a.planes = planes;
-    const int T = size >= 16 ? 16 : 8;
     if (size != 8 && size != 16 && size != 32 && size != 64) return static_cast<int>(cudaErrorInvalidValue);
-    a.tiles_per_row = size / T; a.tiles_per_pu = a.tiles_per_row * a.tiles_per_row;
-    const long tiles = static_cast<long>(n_pus) * a.tiles_per_pu;
-    const int grid = static_cast<int>((tiles + kMcWarps - 1) / kMcWarps);
-    if (T == 16) k_mc<16><<<grid, kMcWarps * 32, 0, s>>>(a);
-    else k_mc<8><<<grid, kMcWarps * 32, 0, s>>>(a);
+    if (planes & 1) {
+        McArgs a;
+        a.ref = *ref; a.pred = *pred; a.pus = pus; a.n_pus = n_pus; a.mvsrc = mvsrc;
+        const int T = size >= 16 ? 16 : 8;
+        a.tiles_per_row = size / T; a.tiles_per_pu = a.tiles_per_row * a.tiles_per_row;
+        const long tiles = static_cast<long>(n_pus) * a.tiles_per_pu;
+        const int grid = static_cast<int>((tiles + kMcWarps - 1) / kMcWarps);
+        if (T == 16) k_mc<16><<<grid, kMcWarps * 32, 0, s>>>(a);
+        else k_mc<8><<<grid, kMcWarps * 32, 0, s>>>(a);
+    }
+    if (planes & 2) {
+        McCArgs c;
+        const int cs = size / 2, rs = cs < 8 ? 4 : 8;      // chroma block size, rows per work item
+        c.ref[0] = ref->p[1]; c.ref[1] = ref->p[2]; c.pred[0] = pred->p[1]; c.pred[1] = pred->p[2];
+        c.pus = pus; c.mvsrc = mvsrc;
+        c.lg_strips = 0; while ((4 << c.lg_strips) < cs) c.lg_strips++;
+        c.lg_segs = 0; while ((rs << c.lg_segs) < cs) c.lg_segs++;
+        c.total = n_pus * 2 << (c.lg_strips + c.lg_segs);
+        const int grid = (c.total + 255) / 256;
+        if (rs == 4) k_mc_chroma<4><<<grid, 256, 0, s>>>(c);
+        else k_mc_chroma<8><<<grid, 256, 0, s>>>(c);
+    }
     return static_cast<int>(cudaGetLastError());
 }
 

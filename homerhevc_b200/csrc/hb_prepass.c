@@ -308,7 +308,7 @@ static int enqueue(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, int
         void *s0 = pp->side[d][0], *s1 = pp->side[d][1], *s2 = pp->side[d][2];
         crc = hbc_event_record(pp->ev_fork[d], main_st);
         if (!crc) crc = hbc_stream_wait_event(s0, pp->ev_fork[d]);
-        if (!crc) { crc = enqueue_mc(pp, ref, d, fused, s0); n++; }
+        if (!crc) { crc = enqueue_mc(pp, ref, d, fused, s0); n += fused ? 1 : 2; }   /* chroma kernel (+ luma kernel when not fused) */
         if (!crc) crc = hbc_event_record(pp->ev_mc[d], s0);
         if (!crc) crc = hbc_stream_wait_event(s1, pp->ev_mc[d]);
         if (!crc) crc = enqueue_tq(pp, cur, d, 0, 0, s0, &n, 0);
