@@ -155,7 +155,7 @@ __device__ __forceinline__ void half_strip(const uint32_t *pl, const uint8_t *cu
 // different iterations of the (data-dependent) search loops: the hardware runs them in lock step where their paths agree.
 template <int G> __device__ __forceinline__ void group_barrier(int group, uint32_t gmask)
 {
-    if (G <= 32) __syncwarp(gmask);
+    if (G <= 32) __syncwarp();
     else if (G == 256) __syncthreads();
     else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(G) : "memory");
 }
@@ -194,9 +194,12 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
     uint8_t *s_patch = s_raw + group * Cfg::SMEM_PER_PU;
     uint32_t *s_plane = reinterpret_cast<uint32_t *>(s_patch + Cfg::PATCH_BYTES);  // [4][QROWS][TS] by x fraction, rows in pairs
     int phase = 0;
-    const uint32_t seg_mask = (SEG == 32) ? HB_FULL_MASK : (((1u << SEG) - 1u) << (lane & ~(SEG - 1)));
-    const uint32_t gmask = (G >= 32) ? HB_FULL_MASK : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));
-    const int gbase = lane & ~(G - 1) & 31;               // first lane of the group inside its warp (G <= 32)
+    // G < 32: several PUs share a warp.  Their data-dependent loops are run in LOCK STEP (a PU that is finished idles through the
+    // rounds the others still need -- the hardware would serialise them anyway), so every warp primitive names the full warp
+    // and compiles to a single instruction; groups are addressed through the width argument of the shuffles.
+    constexpr bool LOCKSTEP = G < 32;
+    auto any_pu = [&](bool p) -> bool { if constexpr (LOCKSTEP) return __any_sync(HB_FULL_MASK, p); else return p; };
+    constexpr uint32_t gmask = HB_FULL_MASK;
 
     // ---- current block -> registers: lane l of every slot holds the 8-sample pairs l, l+L, ... (two packed words each).
     // Pair k sits (L/PPR) rows below pair k-1 in the same columns, so reference addresses advance by one constant.
@@ -242,13 +245,13 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
             part = __reduce_add_sync(HB_FULL_MASK, part);
         } else {                                           // redux.sync with a partial mask is emulated: butterfly instead
 #pragma unroll
-            for (int d = SEG / 2; d > 0; d >>= 1) part += __shfl_xor_sync(seg_mask, part, d);
+            for (int d = SEG / 2; d > 0; d >>= 1) part += __shfl_xor_sync(HB_FULL_MASK, part, d);
         }
         if constexpr (G <= 32) {
 #pragma unroll
             for (int s = 0; s < 4; s++) {
-                tot[s] = __shfl_sync(gmask, part, gbase + s * L);
-                cst[s] = __shfl_sync(gmask, cost, gbase + s * L);
+                tot[s] = __shfl_sync(HB_FULL_MASK, part, s * L, G);
+                cst[s] = __shfl_sync(HB_FULL_MASK, cost, s * L, G);
             }
         } else {
             if ((gl & (SEG - 1)) == 0) { s_x[group][phase][seg][0] = part; s_x[group][phase][seg][1] = cost; }
@@ -324,9 +327,9 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
             for (int s = 0; s < 4; s++) { ssad[s] = sad[s]; srd[s] = rd[s]; }
         }
         ssad[4] = 0; srd[4] = 0;
-        if (sv[4]) {                                   // uniform
+        if (any_pu(sv[4])) {                           // uniform per PU; PUs without a parent vector idle through the round
             const int cx[4] = { sx[4], 0, 0, 0 }, cy[4] = { sy[4], 0, 0, 0 };
-            const bool cv[4] = { true, false, false, false };
+            const bool cv[4] = { sv[4], false, false, false };
             uint32_t sad[4], rd[4];
             round4(cx, cy, cv, sad, rd);
             ssad[4] = sad[0]; srd[4] = rd[0];
@@ -340,34 +343,35 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
             skip = bsad == 0;
         }
         int cx0 = bx, cy0 = by;
-        if (!skip) {
+        if (any_pu(!skip)) {
             {   // first small diamond, fixed order, centre stays put (:1501-1523)
                 int cx[4], cy[4]; bool cv[4]; uint32_t sad[4], rd[4];
 #pragma unroll
-                for (int s = 0; s < 4; s++) { cx[s] = cx0 + c_small[s][0]; cy[s] = cy0 + c_small[s][1]; cv[s] = inside(cx[s], cy[s]); }
+                for (int s = 0; s < 4; s++) { cx[s] = cx0 + c_small[s][0]; cy[s] = cy0 + c_small[s][1]; cv[s] = !skip && inside(cx[s], cy[s]); }
                 round4(cx, cy, cv, sad, rd);
 #pragma unroll
                 for (int s = 0; s < 4; s++)
                     if (cv[s]) { n_probes++; if (rd[s] < brd) { bsad = sad[s]; brd = rd[s]; bx = cx[s]; by = cy[s]; } }
             }
             // rotating big diamond (:1528-1599): dist 2, and 4 when the old centre sat on an axis
-            const int end = (cx0 != 0 && cy0 != 0) ? 4 : 8;
+            const int end = skip ? 0 : (cx0 != 0 && cy0 != 0) ? 4 : 8;
             int next_start = 0, span = 8;
             cx0 = bx; cy0 = by;
-            for (int dist = 2; dist < end; dist *= 2) {
+            for (int dist = 2; any_pu(dist < end); dist *= 2) {
+                const bool act = dist < end;
                 uint32_t sad8[8], rd8[8]; bool v8[8];
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     int cx[4], cy[4]; bool cv[4]; uint32_t sad[4], rd[4];
 #pragma unroll
                     for (int s = 0; s < 4; s++) {
-                        cx[s] = cx0 + c_big[4 * h + s][0] * dist; cy[s] = cy0 + c_big[4 * h + s][1] * dist; cv[s] = inside(cx[s], cy[s]);
+                        cx[s] = cx0 + c_big[4 * h + s][0] * dist; cy[s] = cy0 + c_big[4 * h + s][1] * dist; cv[s] = act && inside(cx[s], cy[s]);
                     }
                     round4(cx, cy, cv, sad, rd);
 #pragma unroll
                     for (int s = 0; s < 4; s++) { sad8[4 * h + s] = sad[s]; rd8[4 * h + s] = rd[s]; v8[4 * h + s] = cv[s]; }
                 }
-                uint32_t vmask = 0;
+                uint32_t vmask = 0;                           // empty for a PU that only idles through this round
 #pragma unroll
                 for (int s = 0; s < 8; s++) vmask |= v8[s] ? (1u << s) : 0u;
                 for (int i = next_start; i < next_start + span; i++) {
@@ -387,10 +391,11 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
         cx0 = bx; cy0 = by;
         {
             int next_start = 0, span = 4;
+            bool done = false;
             for (;;) {
                 int cx[4], cy[4]; bool cv[4]; uint32_t sad[4], rd[4];
 #pragma unroll
-                for (int s = 0; s < 4; s++) { cx[s] = cx0 + c_small[s][0]; cy[s] = cy0 + c_small[s][1]; cv[s] = inside(cx[s], cy[s]); }
+                for (int s = 0; s < 4; s++) { cx[s] = cx0 + c_small[s][0]; cy[s] = cy0 + c_small[s][1]; cv[s] = !done && inside(cx[s], cy[s]); }
                 round4(cx, cy, cv, sad, rd);
                 uint32_t vmask = 0;
 #pragma unroll
@@ -406,8 +411,9 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
                         next_start = (idx - 1 + 4) & 3; span = 3;
                     }
                 }
-                if (cx0 == bx && cy0 == by) break;
+                if (cx0 == bx && cy0 == by) done = true;
                 cx0 = bx; cy0 = by;
+                if (!any_pu(!done)) break;
             }
         }
         best_sad = bsad;
@@ -425,10 +431,30 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
             cur_best = sad[0];
         }
         // ---- stage the patch: rows iy-4.., columns ix-4..
-        const uint8_t *ref_i = a.ref.org + (jy + iy - 4) * a.ref.pitch + jx + ix - 4;
-        for (int w = gl; w < PROWS * (PS / 4); w += G) {
-            const int r = w / (PS / 4), c = (w % (PS / 4)) * 4;
-            *reinterpret_cast<uint32_t *>(s_patch + r * PS + c) = hb_ld_u8x4(ref_i + r * a.ref.pitch + c);
+        // G/N lanes share a row, each takes a run of consecutive words: one misalignment shift per row, no index arithmetic
+        {
+            constexpr int SPLIT = G / N, WPRW = PS / 4, CH = (WPRW + SPLIT - 1) / SPLIT;
+            const int prow = gl / SPLIT, part = gl % SPLIT;
+            uint32_t off = static_cast<uint32_t>(jy + a.ref.pad + iy - 4 + prow) * rpitch + static_cast<uint32_t>(jx + a.ref.pad + ix - 4 + part * CH * 4);
+            const uint32_t sh = (off & 3u) * 8u;
+            off &= ~3u;
+#pragma unroll
+            for (int r0 = 0; r0 < PROWS; r0 += N) {
+                if (r0 + prow < PROWS) {
+                    const uint32_t *q = reinterpret_cast<const uint32_t *>(a.ref.base + off);
+                    uint32_t *d = reinterpret_cast<uint32_t *>(s_patch + (r0 + prow) * PS) + part * CH;
+                    uint32_t lo = __ldg(q);
+#pragma unroll
+                    for (int k = 0; k < CH; k++) {
+                        if (SPLIT == 1 || part * CH + k < WPRW) {
+                            const uint32_t hi = __ldg(q + k + 1);
+                            d[k] = __funnelshift_r(lo, hi, sh);
+                            lo = hi;
+                        }
+                    }
+                }
+                off += N * rpitch;
+            }
         }
         group_barrier<G>(group, gmask);
         // ---- horizontal 14-bit planes, fractions 0..3: T_f[rho][j] = sum_k taps_f[k] * P[rho][j+k] - 8192 (T_0 = 64 P[rho][j+3] - 8192),
