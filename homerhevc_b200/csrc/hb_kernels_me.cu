@@ -318,21 +318,24 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
             sv[4] = pmv.x != 0 && pmv.y != 0 && !(x == 0 && y == 0) && inside(x, y);
         }
         uint32_t ssad[5], srd[5];
+        // the parent's vector rides in the fourth slot of the first round when the caller's list leaves it free (always in the
+        // pre-pass): one round instead of two.  The compare order below is unchanged, and a probe's result does not depend on it.
+        const bool merged = !sv[3];
         {
-            const int cx[4] = { sx[0], sx[1], sx[2], sx[3] }, cy[4] = { sy[0], sy[1], sy[2], sy[3] };
-            const bool cv[4] = { sv[0], sv[1], sv[2], sv[3] };
+            const int cx[4] = { sx[0], sx[1], sx[2], merged ? sx[4] : sx[3] }, cy[4] = { sy[0], sy[1], sy[2], merged ? sy[4] : sy[3] };
+            const bool cv[4] = { sv[0], sv[1], sv[2], merged ? sv[4] : sv[3] };
             uint32_t sad[4], rd[4];
             round4(cx, cy, cv, sad, rd);
 #pragma unroll
             for (int s = 0; s < 4; s++) { ssad[s] = sad[s]; srd[s] = rd[s]; }
         }
-        ssad[4] = 0; srd[4] = 0;
-        if (any_pu(sv[4])) {                           // uniform per PU; PUs without a parent vector idle through the round
+        ssad[4] = ssad[3]; srd[4] = srd[3];
+        if (any_pu(sv[4] && !merged)) {                // uniform per PU; PUs that need no extra round idle through it
             const int cx[4] = { sx[4], 0, 0, 0 }, cy[4] = { sy[4], 0, 0, 0 };
-            const bool cv[4] = { sv[4], false, false, false };
+            const bool cv[4] = { sv[4] && !merged, false, false, false };
             uint32_t sad[4], rd[4];
             round4(cx, cy, cv, sad, rd);
-            ssad[4] = sad[0]; srd[4] = rd[0];
+            if (!merged) { ssad[4] = sad[0]; srd[4] = rd[0]; }
         }
         bx = sx[0]; by = sy[0]; bsad = ssad[0]; brd = srd[0]; n_probes = 1;
         bool skip = bsad == 0;
