@@ -200,7 +200,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=8, help="independent GOP streams in flight per GPU")
+    ap.add_argument("--streams", type=int, default=16, help="independent GOP streams in flight per GPU")
     ap.add_argument("--mode", default="gops", choices=["gops", "bands"],
                     help="gops: independent GOP streams per GPU (default, weak scaling); bands: one frame split into CTU-row bands "
                          "across the GPUs with an NCCL halo exchange of the reference (BASELINE.json configs[3], strong scaling)")
@@ -323,7 +323,8 @@ def main():
         for t in ths:
             t.join()
 
-    e2e_steps = max(32, min(args.steps, 160))
+    # long enough for a stable wall-clock figure (>= 0.1 s), the same number of frames on every in-flight stream
+    e2e_steps = max(4 * N_SLOTS, min(4 * args.steps, 960)) // N_SLOTS * N_SLOTS
     run_e2e(2 * N_SLOTS)
     barrier()
     for sl in slots:
