@@ -139,6 +139,192 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_tq(const hbd_tq_args a)
     }
 }
 
+// ------------------------------------------------------------------ 4x4 units, inter chain: one THREAD per unit
+// A 4x4 unit is 16 samples: the whole chain fits in registers, so nothing is shared, shuffled or synchronised, and every lane
+// of the warp carries a unit (the warp-stack kernel above spends most of its instructions on per-phase overhead at this size).
+// Same arithmetic, same results: stage shifts 1 / 8 forward, 7 / 12 inverse, truncation / saturation as in HbTq<4>.
+// Only sign-data hiding indexes coefficients by a run-time scan position; it reads them from a small element-major shared
+// array (s_l / s_u, [position][thread]) that is written just before it -- the port of HbTq::sign_hide for a single group.
+constexpr int kTq4Threads = 128;
+
+__global__ void __launch_bounds__(kTq4Threads) k_tq4(const hbd_tq_args a)
+{
+    __shared__ int16_t s_l[16][kTq4Threads], s_u[16][kTq4Threads];
+    const int tid = threadIdx.x;
+    const int job = blockIdx.x * kTq4Threads + tid;
+    if (job >= a.n_jobs) return;
+    const int2 xy = __ldg(reinterpret_cast<const int2 *>(a.jobs_xy) + job);
+    const double thr_k = a.dyn ? a.dyn->thr_k : a.thr_k;
+
+    // ---- residual
+    int r[16];
+    uint32_t pw[4];
+#pragma unroll
+    for (int row = 0; row < 4; row++) {
+        const uint32_t o = *reinterpret_cast<const uint32_t *>(a.cur.org + (xy.y + row) * a.cur.pitch + xy.x);
+        pw[row] = *reinterpret_cast<const uint32_t *>(a.pred.org + (xy.y + row) * a.pred.pitch + xy.x);
+#pragma unroll
+        for (int k = 0; k < 4; k++) r[4 * row + k] = static_cast<int>((o >> (8 * k)) & 255u) - static_cast<int>((pw[row] >> (8 * k)) & 255u);
+    }
+    // ---- forward: t[k][row] = (T x_row)[k], c[k'][k] = (T t_k)[k']
+    int t[16], c[16];
+#pragma unroll
+    for (int row = 0; row < 4; row++) {
+        const int x[4] = { r[4 * row], r[4 * row + 1], r[4 * row + 2], r[4 * row + 3] };
+        int y[4];
+        hb_fwd1d<4>(x, y);
+#pragma unroll
+        for (int k = 0; k < 4; k++) t[4 * k + row] = static_cast<int16_t>((y[k] + 1) >> 1);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int x[4] = { t[4 * k], t[4 * k + 1], t[4 * k + 2], t[4 * k + 3] };
+        int y[4];
+        hb_fwd1d<4>(x, y);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; k2++) c[4 * k2 + k] = static_cast<int16_t>((y[k2] + 128) >> 8);
+    }
+    // ---- quantise (hmr_sse42_functions_quant.c:52-118)
+    int lv[16], du[16], sum = 0;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const int4 q = __ldg(reinterpret_cast<const int4 *>(a.qtab) + g);
+        const int qq[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int p = 4 * g + k;
+            const uint32_t ab = static_cast<uint32_t>(c[p] < 0 ? -c[p] : c[p]);
+            const uint32_t prod = ab * static_cast<uint32_t>(qq[k]);
+            const int level = static_cast<int32_t>(prod + static_cast<uint32_t>(a.add)) >> a.qbits;
+            const int delta = static_cast<int32_t>(prod - (static_cast<uint32_t>(level) << a.qbits)) >> (a.qbits - 8);
+            const int sat = hb_sat16(level);
+            lv[p] = c[p] > 0 ? sat : (c[p] < 0 ? -sat : 0);
+            du[p] = hb_sat16(delta);
+            sum += level;
+        }
+    }
+    // ---- sign-data hiding (hmr_quant.c:61), one coefficient group
+    if (a.sign_hiding && sum >= 2) {
+        uint32_t neg_c = 0;                                 // bit p: coefficient p is negative
+#pragma unroll
+        for (int p = 0; p < 16; p++) { s_l[p][tid] = static_cast<int16_t>(lv[p]); s_u[p][tid] = static_cast<int16_t>(du[p]); neg_c |= c[p] < 0 ? (1u << p) : 0u; }
+        const uint16_t *sc = a.scan;
+        int first = 16, last = -1, asum = 0;
+        for (int i = 0; i < 16; i++) {
+            const int v = s_l[__ldg(sc + i)][tid];
+            if (v) { if (first == 16) first = i; last = i; }
+        }
+        if (last - first >= 4) {
+            for (int i = first; i <= last; i++) asum += s_l[__ldg(sc + i)][tid];
+            const unsigned sign_bit = s_l[__ldg(sc + first)][tid] > 0 ? 0u : 1u;
+            if (sign_bit != static_cast<unsigned>(asum & 1)) {
+                int min_cost = 0x7fffffff, min_pos = -1, final_change = 0, cur_cost = 0x7fffffff, cur_change = 0;
+                for (int i = last; i >= 0; i--) {
+                    const int p = __ldg(sc + i);
+                    const int l = s_l[p][tid], d = s_u[p][tid];
+                    if (l != 0) {
+                        if (d > 0) { cur_cost = -d; cur_change = 1; }
+                        else if (i == first && (l == 1 || l == -1)) cur_cost = 0x7fffffff;
+                        else { cur_cost = d; cur_change = -1; }
+                    } else if (i < first) {
+                        const unsigned this_sign = (neg_c >> p) & 1u;
+                        if (this_sign != sign_bit) cur_cost = 0x7fffffff;
+                        else { cur_cost = -d; cur_change = 1; }
+                    } else {
+                        cur_cost = -d; cur_change = 1;
+                    }
+                    if (cur_cost < min_cost) { min_cost = cur_cost; final_change = cur_change; min_pos = p; }
+                }
+                const int l = s_l[min_pos][tid];
+                if (l == 32767 || l == -32768) final_change = -1;
+                const int nv = static_cast<int16_t>(((neg_c >> min_pos) & 1u) ? l - final_change : l + final_change);
+#pragma unroll
+                for (int p = 0; p < 16; p++) if (p == min_pos) lv[p] = nv;
+            }
+        }
+    }
+    // ---- dequantise + inverse when anything is left
+    int dec[16];
+#pragma unroll
+    for (int p = 0; p < 16; p++) dec[p] = 0;
+    if (sum > 0) {
+        int d[16];
+        const int iq_shift = 2 + 3;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const int4 q = __ldg(reinterpret_cast<const int4 *>(a.dqtab) + g);
+            const int qq[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t prod = static_cast<uint32_t>(lv[4 * g + k]) * static_cast<uint32_t>(qq[k]);
+                int v;
+                if (iq_shift > a.per) v = static_cast<int32_t>(prod + (1u << (iq_shift - a.per - 1))) >> (iq_shift - a.per);
+                else v = static_cast<int32_t>(prod << (a.per - iq_shift));
+                d[4 * g + k] = hb_sat16(v);
+            }
+        }
+        int t2[16];                                         // t2[col][j] = sum_k coef[k][j] d[k][col]
+#pragma unroll
+        for (int col = 0; col < 4; col++) {
+            const int y[4] = { d[col], d[4 + col], d[8 + col], d[12 + col] };
+            int x[4];
+            hb_inv1d<4>(y, x);
+#pragma unroll
+            for (int j = 0; j < 4; j++) t2[4 * col + j] = hb_sat16((x[j] + 64) >> 7);
+        }
+#pragma unroll
+        for (int row = 0; row < 4; row++) {
+            const int y[4] = { t2[row], t2[4 + row], t2[8 + row], t2[12 + row] };
+            int x[4];
+            hb_inv1d<4>(y, x);
+#pragma unroll
+            for (int j = 0; j < 4; j++) dec[4 * row + j] = hb_sat16((x[j] + 2048) >> 12);
+        }
+    }
+    // ---- SSDs and the zero-out decision (hmr_motion_inter.c:90-121 / :186-224)
+    uint32_t z = 0, sd = 0;
+#pragma unroll
+    for (int p = 0; p < 16; p++) {
+        const int e = r[p] - dec[p];
+        z += static_cast<uint32_t>(r[p]) * static_cast<uint32_t>(r[p]);
+        sd += static_cast<uint32_t>(e) * static_cast<uint32_t>(e);
+    }
+    hb_tu_result res;
+    res.sum = sum; res.zeroed = 0; res.ssd_zero = 0;
+    uint32_t zw = z, dw = sd;
+    if (!a.is_luma) {
+        zw = __double2uint_rz(__dmul_rn(a.weight, static_cast<double>(zw)));
+        dw = __double2uint_rz(__dmul_rn(a.weight, static_cast<double>(dw)));
+    }
+    bool keep = false;
+    if (sum > 0) {
+        const double lhs = static_cast<double>(zw);
+        const double base = a.is_luma ? static_cast<double>(static_cast<int32_t>(dw)) : static_cast<double>(dw);
+        const double rhs = __dadd_rn(base, __dmul_rn(thr_k, static_cast<double>(sum)));
+        res.ssd = dw; res.ssd_zero = zw;
+        if (lhs <= rhs) { res.zeroed = 1; res.sum = 0; }
+        else keep = true;
+    } else {
+        res.ssd = zw;
+    }
+    a.res_out[job] = res;
+    // ---- outputs
+    uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;
+    if (keep) {
+        auto pk = [&](int i) { return (static_cast<uint32_t>(lv[i]) & 0xffffu) | (static_cast<uint32_t>(lv[i + 1]) << 16); };
+        w0 = make_uint4(pk(0), pk(2), pk(4), pk(6)); w1 = make_uint4(pk(8), pk(10), pk(12), pk(14));
+    }
+    uint4 *co = reinterpret_cast<uint4 *>(a.coeff_out + static_cast<size_t>(job) * 16);
+    co[0] = w0; co[1] = w1;
+#pragma unroll
+    for (int row = 0; row < 4; row++) {
+        uint32_t out = pw[row];
+        if (keep) out = hb_pack_sat_u8x4(static_cast<int>(pw[row] & 255u) + dec[4 * row], static_cast<int>((pw[row] >> 8) & 255u) + dec[4 * row + 1],
+                                         static_cast<int>((pw[row] >> 16) & 255u) + dec[4 * row + 2], static_cast<int>(pw[row] >> 24) + dec[4 * row + 3]);
+        *reinterpret_cast<uint32_t *>(a.rec.org + (xy.y + row) * a.rec.pitch + xy.x) = out;
+    }
+}
+
 // ------------------------------------------------------------------ intra T/Q chain after prediction
 // encode_intra_cu (hmr_motion_intra.c:1023-1069) and the chroma loop of hmr_motion_intra_chroma.c:340-365: residual ->
 // DST-VII (4x4 luma) or DCT -> quant (intra lists, scan from the intra mode, sign hiding) -> if any level: dequant -> inverse
@@ -306,6 +492,7 @@ template <int N> int launch_tq(const hbd_tq_args *a, cudaStream_t s)
     const int per_cta = kWarpsPerCta * HbTq<N>::TPW;
     const int grid = (a->n_jobs + per_cta - 1) / per_cta;
     if (a->intra) k_tq_intra<N><<<grid, kWarpsPerCta * 32, 0, s>>>(*a);
+    else if (N == 4) k_tq4<<<(a->n_jobs + kTq4Threads - 1) / kTq4Threads, kTq4Threads, 0, s>>>(*a);
     else k_tq<N><<<grid, kWarpsPerCta * 32, 0, s>>>(*a);
     return static_cast<int>(cudaGetLastError());
 }
