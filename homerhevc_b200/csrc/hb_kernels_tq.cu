@@ -17,87 +17,84 @@ template <int N>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_tq(const hbd_tq_args a)
 {
     using Q = HbTq<N>;
-    constexpr int S = Q::S, TPW = Q::TPW;
-    __shared__ __align__(16) int16_t smem[kWarpsPerCta][5][Q::ELEMS];
+    constexpr int TPW = Q::TPW, NW = N / 4;
+    __shared__ __align__(16) int16_t smem[kWarpsPerCta][4][Q::ELEMS];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int first_job = (blockIdx.x * kWarpsPerCta + warp) * TPW;
     if (first_job >= a.n_jobs) return;
     const double thr_k = a.dyn ? a.dyn->thr_k : a.thr_k;
-    int16_t *X = smem[warp][0], *T = smem[warp][1], *C = smem[warp][2], *L = smem[warp][3], *U = smem[warp][4];
+    int16_t *T = smem[warp][0], *C = smem[warp][1], *L = smem[warp][2], *U = smem[warp][3];
 
-    // ---- residual of every unit of the stack: four samples per lane and iteration (u8x4 loads)
-    int jx[TPW], jy[TPW];
+    // ---- a lane owns stack row `lane` = row lane%N of unit lane/N from the first load to the last store: its current and
+    // predicted samples stay in registers as packed words (the residual never goes through shared memory), it computes its
+    // part of both SSDs from the decoded row the last inverse stage leaves in registers, and writes its reconstructed row.
+    const int unit = lane / N, row = lane % N;
+    const bool valid = first_job + unit < a.n_jobs;
+    const int2 xy = __ldg(reinterpret_cast<const int2 *>(a.jobs_xy) + min(first_job + unit, a.n_jobs - 1));
+    uint32_t ow[NW], pw[NW];
+    {
+        const uint8_t *co = a.cur.org + (xy.y + row) * a.cur.pitch + xy.x, *po = a.pred.org + (xy.y + row) * a.pred.pitch + xy.x;
+        if constexpr (N == 8) {
+            const uint2 o = *reinterpret_cast<const uint2 *>(co), p = *reinterpret_cast<const uint2 *>(po);
+            ow[0] = o.x; ow[1] = o.y; pw[0] = p.x; pw[1] = p.y;
+        } else {
 #pragma unroll
-    for (int u = 0; u < TPW; u++) {
-        const int j = min(first_job + u, a.n_jobs - 1);
-        jx[u] = __ldg(a.jobs_xy + 2 * j);
-        jy[u] = __ldg(a.jobs_xy + 2 * j + 1);
+            for (int q = 0; q < NW / 4; q++) {
+                const uint4 o = reinterpret_cast<const uint4 *>(co)[q], p = reinterpret_cast<const uint4 *>(po)[q];
+                ow[4 * q] = o.x; ow[4 * q + 1] = o.y; ow[4 * q + 2] = o.z; ow[4 * q + 3] = o.w;
+                pw[4 * q] = p.x; pw[4 * q + 1] = p.y; pw[4 * q + 2] = p.z; pw[4 * q + 3] = p.w;
+            }
+        }
     }
-    auto unit_xy = [&](int unit, int &x, int &y) {
-        x = jx[0]; y = jy[0];
+    auto resid = [&](int j) -> int { return static_cast<int>((ow[j >> 2] >> (8 * (j & 3))) & 255u) - static_cast<int>((pw[j >> 2] >> (8 * (j & 3))) & 255u); };
+    {
+        int x[N];
 #pragma unroll
-        for (int u = 1; u < TPW; u++) if (u == unit) { x = jx[u]; y = jy[u]; }
-    };
-#pragma unroll
-    for (int it = 0; it < Q::ITERS4; it++) {
-        const typename Q::G4 g = Q::group4(it, lane);
-        int x, y;
-        unit_xy(g.unit, x, y);
-        const int r = g.row % N;
-        const uint32_t o = *reinterpret_cast<const uint32_t *>(a.cur.org + (y + r) * a.cur.pitch + x + g.col);
-        const uint32_t p = *reinterpret_cast<const uint32_t *>(a.pred.org + (y + r) * a.pred.pitch + x + g.col);
-        int d[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) d[k] = static_cast<int>((o >> (8 * k)) & 255u) - static_cast<int>((p >> (8 * k)) & 255u);
-        Q::st4(X + g.off, d);
+        for (int j = 0; j < N; j++) x[j] = resid(j);
+        Q::fwd_stage_regs(x, T, lane, Q::LOG2 - 1);
     }
     __syncwarp();
-
-    Q::template forward<false>(X, T, C, lane);
+    Q::template fwd_stage<false>(T, C, lane, Q::LOG2 + 6);
+    __syncwarp();
 
     int unit_sum[TPW];
     Q::quantise(C, L, U, a.qtab, a.qbits, a.add, lane, unit_sum);
     if (a.sign_hiding) Q::sign_hide(L, C, U, a.scan, lane, unit_sum);
 
     bool any = false;
+    int my_sum = 0;
 #pragma unroll
-    for (int u = 0; u < TPW; u++) any |= unit_sum[u] > 0;
+    for (int u = 0; u < TPW; u++) { any |= unit_sum[u] > 0; if (u == unit) my_sum = unit_sum[u]; }
+    int dec[N];                                           // decoded residual of this lane's row
+#pragma unroll
+    for (int j = 0; j < N; j++) dec[j] = 0;
     if (any) {                                            // warp-uniform
-        Q::dequantise(L, T, a.dqtab, a.per, lane);        // T = dequantised coefficients
-        Q::template inverse<false>(T, U, C, lane);        // U scratch, C = decoded residual
+        Q::inv_stage1_dequant(L, a.dqtab, a.per, T, lane);     // dequantisation folded into the column loads
+        __syncwarp();
+        Q::inv_stage2_regs(T, dec, lane);
     }
 
-    // ---- per-unit SSDs
-    uint32_t ssd_dec[TPW], ssd_zero[TPW];
+    // ---- per-unit SSDs: row sums, then a butterfly over the N lanes of the unit
+    uint32_t z = 0, sd = 0;
 #pragma unroll
-    for (int u = 0; u < TPW; u++) { ssd_dec[u] = 0; ssd_zero[u] = 0; }
+    for (int j = 0; j < N; j++) {
+        const int r = resid(j), e = r - dec[j];
+        z += static_cast<uint32_t>(r) * static_cast<uint32_t>(r);
+        sd += static_cast<uint32_t>(e) * static_cast<uint32_t>(e);
+    }
+    if constexpr (N == 32) { z = __reduce_add_sync(HB_FULL_MASK, z); sd = __reduce_add_sync(HB_FULL_MASK, sd); }
+    else {
 #pragma unroll
-    for (int it = 0; it < Q::ITERS4; it++) {
-        const typename Q::G4 g = Q::group4(it, lane);
-        int r[4], c[4] = { 0, 0, 0, 0 };
-        Q::ld4(X + g.off, r);
-        if (any) Q::ld4(C + g.off, c);
-        uint32_t z = 0, s = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int d = r[k] - c[k];
-            z += static_cast<uint32_t>(r[k]) * static_cast<uint32_t>(r[k]);
-            s += static_cast<uint32_t>(d) * static_cast<uint32_t>(d);
-        }
-        Q::template unit_add<uint32_t>(z, it, ssd_zero);
-        Q::template unit_add<uint32_t>(s, it, ssd_dec);
+        for (int d = N / 2; d > 0; d >>= 1) { z += __shfl_xor_sync(HB_FULL_MASK, z, d); sd += __shfl_xor_sync(HB_FULL_MASK, sd, d); }
     }
 
-    // ---- decision (hmr_motion_inter.c:90-121 / :186-224): lane u decides unit u, the verdicts travel by ballot
-    uint32_t my_z = 0, my_d = 0; int my_sum = 0;
-#pragma unroll
-    for (int u = 0; u < TPW; u++) if (u == lane) { my_z = ssd_zero[u]; my_d = ssd_dec[u]; my_sum = unit_sum[u]; }
-    bool my_keep = false;
-    if (lane < TPW) {
+    // ---- decision (hmr_motion_inter.c:90-121 / :186-224), identical in every lane of a unit
+    bool keep = false;
+    {
         hb_tu_result r;
         r.sum = my_sum; r.zeroed = 0; r.ssd_zero = 0;
-        uint32_t zw = my_z, dw = my_d;
+        uint32_t zw = z, dw = sd;
         if (!a.is_luma) {
             zw = __double2uint_rz(__dmul_rn(a.weight, static_cast<double>(zw)));
             dw = __double2uint_rz(__dmul_rn(a.weight, static_cast<double>(dw)));
@@ -108,34 +105,41 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_tq(const hbd_tq_args a)
             const double rhs = __dadd_rn(base, __dmul_rn(thr_k, static_cast<double>(my_sum)));
             r.ssd = dw; r.ssd_zero = zw;
             if (lhs <= rhs) { r.zeroed = 1; r.sum = 0; }
-            else my_keep = true;
+            else keep = true;
         } else {
             r.ssd = zw;                                   // ssd16b(residual, zeros)
         }
-        if (first_job + lane < a.n_jobs) a.res_out[first_job + lane] = r;
+        if (valid && row == 0) a.res_out[first_job + unit] = r;
     }
-    const uint32_t keep_mask = __ballot_sync(HB_FULL_MASK, my_keep);
+    const uint32_t keep_mask = __ballot_sync(HB_FULL_MASK, keep);          // bit unit*N: verdict of that unit
 
-    // ---- outputs: levels (int16x4 stores) and reconstruction (u8x4 stores)
+    // ---- reconstruction of this lane's row
+    if (valid) {
+        uint32_t out[NW];
+#pragma unroll
+        for (int q = 0; q < NW; q++) {
+            out[q] = pw[q];
+            if (keep) out[q] = hb_pack_sat_u8x4(static_cast<int>(pw[q] & 255u) + dec[4 * q], static_cast<int>((pw[q] >> 8) & 255u) + dec[4 * q + 1],
+                                                static_cast<int>((pw[q] >> 16) & 255u) + dec[4 * q + 2], static_cast<int>(pw[q] >> 24) + dec[4 * q + 3]);
+        }
+        uint8_t *ro = a.rec.org + (xy.y + row) * a.rec.pitch + xy.x;
+        if constexpr (N == 8) *reinterpret_cast<uint2 *>(ro) = make_uint2(out[0], out[1]);
+        else {
+#pragma unroll
+            for (int q = 0; q < NW / 4; q++) reinterpret_cast<uint4 *>(ro)[q] = make_uint4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+        }
+    }
+    // ---- levels (int16x4 stores), zeros for a unit that was zeroed out
 #pragma unroll
     for (int it = 0; it < Q::ITERS4; it++) {
         const typename Q::G4 g = Q::group4(it, lane);
         if (first_job + g.unit >= a.n_jobs) continue;
-        int x, y;
-        unit_xy(g.unit, x, y);
-        const bool k = (keep_mask >> g.unit) & 1u;
-        const int r = g.row % N;
-        int lv[4] = { 0, 0, 0, 0 }, dr[4] = { 0, 0, 0, 0 };
-        if (k) { Q::ld4(L + g.off, lv); Q::ld4(C + g.off, dr); }
+        int lv[4] = { 0, 0, 0, 0 };
+        if ((keep_mask >> (g.unit * N)) & 1u) Q::ld4(L + g.off, lv);
         uint2 w;
         w.x = (static_cast<uint32_t>(lv[0]) & 0xffffu) | (static_cast<uint32_t>(lv[1]) << 16);
         w.y = (static_cast<uint32_t>(lv[2]) & 0xffffu) | (static_cast<uint32_t>(lv[3]) << 16);
         *reinterpret_cast<uint2 *>(a.coeff_out + static_cast<size_t>(first_job + g.unit) * (N * N) + g.pos4) = w;
-        const uint32_t p = *reinterpret_cast<const uint32_t *>(a.pred.org + (y + r) * a.pred.pitch + x + g.col);
-        uint32_t out = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) out |= static_cast<uint32_t>(hb_clip255(static_cast<int>((p >> (8 * q)) & 255u) + dr[q])) << (8 * q);
-        *reinterpret_cast<uint32_t *>(a.rec.org + (y + r) * a.rec.pitch + x + g.col) = out;
     }
 }
 

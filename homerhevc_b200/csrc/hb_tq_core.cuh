@@ -110,6 +110,16 @@ template <int N> struct HbTq {
 #pragma unroll
         for (int k = 0; k < N; k++) col[k * S] = static_cast<int16_t>((y[k] + add) >> shift);
     }
+    // The same stage on a row that is already in registers (the residual of the fused chain)
+    static __device__ __forceinline__ void fwd_stage_regs(const int (&x)[N], int16_t *out, int lane, int shift)
+    {
+        int y[N];
+        hb_fwd1d<N>(x, y);
+        const int add = 1 << (shift - 1);
+        int16_t *col = out + (lane / N) * N * S + (lane % N);
+#pragma unroll
+        for (int k = 0; k < N; k++) col[k * S] = static_cast<int16_t>((y[k] + add) >> shift);
+    }
     // One inverse stage: lane reads column `lane%N` of its unit in `in`, writes row `lane` of `out`,
     // value = clip16((sum + add) >> shift) (hmr_transform.c:195).
     template <bool DST> static __device__ __forceinline__ void inv_stage(const int16_t *in, int16_t *out, int lane, int shift)
@@ -127,6 +137,42 @@ template <int N> struct HbTq {
             const int a = hb_sat16((x[j] + add) >> shift), b = hb_sat16((x[j + 1] + add) >> shift);
             *reinterpret_cast<uint32_t *>(row + j) = (static_cast<uint32_t>(a) & 0xffffu) | (static_cast<uint32_t>(b) << 16);
         }
+    }
+
+    // First inverse stage with the dequantisation (hmr_sse42_functions_quant.c:135, iq_shift = log2N + 3) folded into its column
+    // loads: lane reads column lane%N of the LEVELS of its unit and of the dequant table (consecutive lanes, consecutive words)
+    static __device__ __forceinline__ void inv_stage1_dequant(const int16_t *Lv, const int32_t *__restrict__ dqtab, int per, int16_t *out, int lane)
+    {
+        int y[N], x[N];
+        const int c = lane % N;
+        const int16_t *col = Lv + (lane / N) * N * S + c;
+        constexpr int iq_shift = LOG2 + 3;
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            const uint32_t prod = static_cast<uint32_t>(static_cast<int>(col[k * S])) * static_cast<uint32_t>(__ldg(dqtab + k * N + c));
+            int v;
+            if (iq_shift > per) v = static_cast<int32_t>(prod + (1u << (iq_shift - per - 1))) >> (iq_shift - per);
+            else v = static_cast<int32_t>(prod << (per - iq_shift));
+            y[k] = hb_sat16(v);
+        }
+        hb_inv1d<N>(y, x);
+        int16_t *row = out + lane * S;
+#pragma unroll
+        for (int j = 0; j < N; j += 2) {
+            const int a = hb_sat16((x[j] + 64) >> 7), b = hb_sat16((x[j + 1] + 64) >> 7);
+            *reinterpret_cast<uint32_t *>(row + j) = (static_cast<uint32_t>(a) & 0xffffu) | (static_cast<uint32_t>(b) << 16);
+        }
+    }
+    // Second inverse stage (shift 12) that leaves its row in registers
+    static __device__ __forceinline__ void inv_stage2_regs(const int16_t *in, int (&x)[N], int lane)
+    {
+        int y[N];
+        const int16_t *col = in + (lane / N) * N * S + (lane % N);
+#pragma unroll
+        for (int k = 0; k < N; k++) y[k] = col[k * S];
+        hb_inv1d<N>(y, x);
+#pragma unroll
+        for (int j = 0; j < N; j++) x[j] = hb_sat16((x[j] + 2048) >> 12);
     }
 
     // 2-D forward transform of the warp's units: X -> C (T is scratch).  8-bit video: shifts log2N-1 and log2N+6.
