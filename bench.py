@@ -306,18 +306,33 @@ def main():
     #   upload cur + ref (pinned, async) -> pre-pass -> fetch the cost tables -> host picks a depth per CTU (hb_prepass_select,
     #   the stand-in for the host's mode decision) -> gather + fetch the reconstruction and coded levels of that choice.
     # N_SLOTS independent streams of frames (GOPs) are in flight per GPU so that copies, kernels and the host step overlap.
-    def one_frame(sl, i):
+    def begin_frame(sl, i):
         j = i % N_RESIDENT
-        sl["d2h"] += sl["pp"].process_frame(sl["cur"], sl["ref"], pinned[j + 1], pinned[j], AVG_DIST, LAMBDA, sl["tables"], sl["sel"],
-                                            sl["off"], sl["out"]) + sl["tables"].nbytes
+        sl["pp"].frame_begin(sl["cur"], sl["ref"], pinned[j + 1], pinned[j], AVG_DIST, sl["tables"])
+
+    def finish_frame(sl):
+        sl["d2h"] += sl["pp"].frame_finish(LAMBDA, sl["tables"], sl["sel"], sl["off"], sl["out"]) + sl["tables"].nbytes
+
+    E2E_THREADS = max(1, N_SLOTS // 2)
 
     def run_e2e(n):
-        # one host thread per in-flight stream (the reference runs one pthread per encoder engine, hmr_encoder_lib.c:1647):
-        # the C calls release the GIL, so uploads, kernels, downloads and the host decision of different streams overlap
+        # one host thread per TWO in-flight streams (the reference runs one pthread per encoder engine, hmr_encoder_lib.c:1647):
+        # a thread queues frame n+1 on its second stream (hb_prepass_frame_begin returns at once) before it blocks in
+        # hb_prepass_frame_finish of frame n.  The C calls release the GIL, so the threads overlap as well.
         def worker(k):
-            for i in range(k, n, N_SLOTS):
-                one_frame(slots[k], i)
-        ths = [threading.Thread(target=worker, args=(k,)) for k in range(N_SLOTS)]
+            mine = [slots[k], slots[k + E2E_THREADS]] if k + E2E_THREADS < N_SLOTS else [slots[k]]
+            pending = None
+            for c, i in enumerate(range(k, n, E2E_THREADS)):
+                sl = mine[c % len(mine)]
+                if pending is sl:                       # single-stream fallback: finish before reusing the stream
+                    finish_frame(pending); pending = None
+                begin_frame(sl, i)
+                if pending is not None:
+                    finish_frame(pending)
+                pending = sl
+            if pending is not None:
+                finish_frame(pending)
+        ths = [threading.Thread(target=worker, args=(k,)) for k in range(E2E_THREADS)]
         for t in ths:
             t.start()
         for t in ths:
@@ -401,7 +416,7 @@ def main():
                              f"{N_RESIDENT} steps > {L2_BYTES / 2**20:.0f} MiB L2 before any input is reused",
                        "cuda_graph": True},
             "e2e": {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 2 * frame_bytes,
-                    "d2h_bytes_per_step": int(d2h_per_step), "steps": e2e_steps, "streams_in_flight": N_SLOTS,
+                    "d2h_bytes_per_step": int(d2h_per_step), "steps": e2e_steps, "streams_in_flight": N_SLOTS, "host_threads": E2E_THREADS,
                     "flow": "upload cur+ref -> pre-pass -> fetch cost tables -> host depth choice per CTU -> gather + fetch recon and coded levels of that choice",
                     "fetch_everything_variant": {"value": world * 20 / (full_ms * 1e-3), "unit": "frames/s", "d2h_bytes_per_step": out_bytes}},
             "gpu_launches": int(launches),

@@ -645,20 +645,38 @@ int hb_prepass_gather(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_off
  * (pinned) host planes, run the pre-pass, fetch the cost tables, let the stand-in decision pick a depth per CTU, gather and
  * fetch the reconstruction + coded levels of that choice.  tables / out must be pinned; sel has num_ctus bytes, ctu_off
  * num_ctus + 1 entries.  Tight plane pitches (width, width/2). */
-int hb_prepass_process_frame(hb_prepass *pp, hb_frame *cur, hb_frame *ref, const uint8_t *const cur_planes[3], const uint8_t *const ref_planes[3],
-                             double avg_dist, int lambda, void *tables, size_t tables_cap, uint8_t *sel, int32_t *ctu_off,
-                             void *out, size_t out_cap, size_t *out_bytes)
+/* The same flow in two halves, so that ONE host thread can keep two frames in flight (begin frame n+1 on a second plan /
+ * context before finishing frame n): begin queues the uploads, the pre-pass and the table fetch and returns at once;
+ * finish waits for the tables, decides, gathers and waits for the results. */
+int hb_prepass_frame_begin(hb_prepass *pp, hb_frame *cur, hb_frame *ref, const uint8_t *const cur_planes[3], const uint8_t *const ref_planes[3],
+                           double avg_dist, void *tables, size_t tables_cap)
 {
     int rc;
-    if (!pp || !cur || !ref || !cur_planes || !ref_planes) return hbi_fail(HB_ERR_ARG, "hb_prepass_process_frame: NULL argument");
+    if (!pp || !cur || !ref || !cur_planes || !ref_planes) return hbi_fail(HB_ERR_ARG, "hb_prepass_frame_begin: NULL argument");
     hb_ctx *ctx = pp->ctx;
     const int w = pp->w;
     if ((rc = hb_frame_upload_u8_ex(ctx, cur, cur_planes[0], w, cur_planes[1], w / 2, cur_planes[2], w / 2, HB_UPLOAD_NO_BORDER)) != HB_OK) return rc;
     if ((rc = hb_frame_upload_u8(ctx, ref, ref_planes[0], w, ref_planes[1], w / 2, ref_planes[2], w / 2)) != HB_OK) return rc;
     if ((rc = hb_prepass_run(pp, cur, ref, avg_dist)) != HB_OK) return rc;
-    if ((rc = hb_prepass_fetch_tables(pp, tables, tables_cap)) != HB_OK) return rc;
+    return hb_prepass_fetch_tables(pp, tables, tables_cap);
+}
+
+int hb_prepass_frame_finish(hb_prepass *pp, int lambda, const void *tables, uint8_t *sel, int32_t *ctu_off, void *out, size_t out_cap, size_t *out_bytes)
+{
+    int rc;
+    if (!pp) return hbi_fail(HB_ERR_ARG, "hb_prepass_frame_finish: NULL argument");
+    hb_ctx *ctx = pp->ctx;
     if ((rc = hb_ctx_sync(ctx)) != HB_OK) return rc;
     if ((rc = hb_prepass_select(pp, tables, lambda, sel, ctu_off)) != HB_OK) return rc;
     if ((rc = hb_prepass_gather(pp, sel, ctu_off, out, out_cap, out_bytes)) != HB_OK) return rc;
     return hb_ctx_sync(ctx);
+}
+
+int hb_prepass_process_frame(hb_prepass *pp, hb_frame *cur, hb_frame *ref, const uint8_t *const cur_planes[3], const uint8_t *const ref_planes[3],
+                             double avg_dist, int lambda, void *tables, size_t tables_cap, uint8_t *sel, int32_t *ctu_off,
+                             void *out, size_t out_cap, size_t *out_bytes)
+{
+    const int rc = hb_prepass_frame_begin(pp, cur, ref, cur_planes, ref_planes, avg_dist, tables, tables_cap);
+    if (rc != HB_OK) return rc;
+    return hb_prepass_frame_finish(pp, lambda, tables, sel, ctu_off, out, out_cap, out_bytes);
 }

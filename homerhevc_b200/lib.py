@@ -192,6 +192,8 @@ def load_library():
     L.hb_prepass_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.hb_prepass_process_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_double, C.c_int,
                                            C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.hb_prepass_frame_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_double, C.c_void_p, C.c_size_t]
+    L.hb_prepass_frame_finish.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.hb_prepass_pred.restype = C.c_void_p
     L.hb_prepass_pred.argtypes = [C.c_void_p, C.c_int]
     L.hb_prepass_recon.restype = C.c_void_p
@@ -494,6 +496,19 @@ class Prepass:
         _check(self.ctx.L.hb_prepass_process_frame(self.h, cur.h, ref.h, cp, rp, avg_dist, lam, tables.ctypes.data, tables.nbytes,
                                                    sel.ctypes.data, ctu_off.ctypes.data, out.ctypes.data, out.nbytes, C.byref(n)),
                "hb_prepass_process_frame")
+        return n.value
+
+    def frame_begin(self, cur, ref, cur_planes, ref_planes, avg_dist, tables):
+        """first half of process_frame: queues uploads, pre-pass and table fetch, returns immediately"""
+        cp = (C.c_void_p * 3)(*[p.ctypes.data for p in cur_planes])
+        rp = (C.c_void_p * 3)(*[p.ctypes.data for p in ref_planes])
+        _check(self.ctx.L.hb_prepass_frame_begin(self.h, cur.h, ref.h, cp, rp, avg_dist, tables.ctypes.data, tables.nbytes), "hb_prepass_frame_begin")
+
+    def frame_finish(self, lam, tables, sel, ctu_off, out):
+        """second half: waits for the tables, decides, gathers, waits for the results; returns the bytes written to `out`"""
+        n = C.c_size_t(0)
+        _check(self.ctx.L.hb_prepass_frame_finish(self.h, lam, tables.ctypes.data, sel.ctypes.data, ctu_off.ctypes.data, out.ctypes.data, out.nbytes,
+                                                  C.byref(n)), "hb_prepass_frame_finish")
         return n.value
 
     def output_bytes(self):

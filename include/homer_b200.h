@@ -261,6 +261,12 @@ int  hb_prepass_gather(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_of
 int  hb_prepass_process_frame(hb_prepass *pp, hb_frame *cur, hb_frame *ref, const uint8_t *const cur_planes[3], const uint8_t *const ref_planes[3],
                               double avg_dist, int lambda, void *tables, size_t tables_cap, uint8_t *sel, int32_t *ctu_off,
                               void *out, size_t out_cap, size_t *out_bytes);
+/* the two halves of hb_prepass_process_frame: begin only queues work (uploads, pre-pass, table fetch) and returns; finish
+ * blocks (tables -> decision -> gather -> results).  One host thread can begin frame n+1 on a second plan before it
+ * finishes frame n. */
+int  hb_prepass_frame_begin(hb_prepass *pp, hb_frame *cur, hb_frame *ref, const uint8_t *const cur_planes[3], const uint8_t *const ref_planes[3],
+                            double avg_dist, void *tables, size_t tables_cap);
+int  hb_prepass_frame_finish(hb_prepass *pp, int lambda, const void *tables, uint8_t *sel, int32_t *ctu_off, void *out, size_t out_cap, size_t *out_bytes);
 const hb_frame *hb_prepass_pred(const hb_prepass *pp, int depth);     /* resident prediction of that depth */
 const hb_frame *hb_prepass_recon(const hb_prepass *pp, int pass);
 

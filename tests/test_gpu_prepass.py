@@ -267,6 +267,63 @@ def test_host_decision_flow_gather(ctx):
     pp.close(); fc.close(); fr.close()
 
 
+def test_process_frame_and_its_two_halves(ctx):
+    """hb_prepass_process_frame, and begin/finish interleaved over two plans by one thread (frame n+1 queued before frame n
+    is finished), deliver the bytes of the step-by-step flow: upload, run, fetch_tables, select, gather"""
+    w, h, qp, avg, lam = 320, 192, 31, 420.0, 55
+    clips = [clip_pair(w, h, n=k + 2, noise=4.0, seed=40 + k) for k in range(3)]
+    fb = w * h * 3 // 2
+    pin = ctx.pinned(6 * fb)
+    def planes(i, fr):
+        b = pin[i * fb:(i + 1) * fb]
+        py = b[:w * h].reshape(h, w); pu = b[w * h:w * h * 5 // 4].reshape(h // 2, w // 2); pv = b[w * h * 5 // 4:].reshape(h // 2, w // 2)
+        py[:], pu[:], pv[:] = fr.y, fr.u, fr.v
+        return (py, pu, pv)
+    host = [(planes(2 * k, c), planes(2 * k + 1, r)) for k, (c, r) in enumerate(clips)]
+    n_ctus = 5 * 3
+    # step by step
+    exp = []
+    pp = hb.Prepass(ctx, w, h, qp=qp)
+    fc, fr = hb.Frame(ctx, w, h), hb.Frame(ctx, w, h)
+    for cur_p, ref_p in host:
+        fc.upload_u8(*cur_p); fr.upload_u8(*ref_p)
+        pp.run(fc, fr, avg)
+        tables = ctx.pinned(pp.tables_bytes()); pp.fetch_tables(tables); ctx.sync()
+        sel = np.zeros(n_ctus, np.uint8); off = np.zeros(n_ctus + 1, np.int32)
+        pp.select(tables, lam, sel, off)
+        out = ctx.pinned(fb + 4 * w * h); n = pp.gather(sel, off, out); ctx.sync()
+        exp.append((bytes(tables), sel.copy(), off.copy(), bytes(out[:n])))
+    # one call per frame
+    for k, (cur_p, ref_p) in enumerate(host):
+        tables = ctx.pinned(pp.tables_bytes()); sel = np.zeros(n_ctus, np.uint8); off = np.zeros(n_ctus + 1, np.int32); out = ctx.pinned(fb + 4 * w * h)
+        n = pp.process_frame(fc, fr, cur_p, ref_p, avg, lam, tables, sel, off, out)
+        assert (bytes(tables), bytes(out[:n])) == (exp[k][0], exp[k][3]) and np.array_equal(sel, exp[k][1]) and np.array_equal(off, exp[k][2]), k
+    # two plans on two contexts, frame k+1 begun before frame k is finished
+    ctx2 = hb.Context(0)
+    lanes = []
+    for c in (ctx, ctx2):
+        lanes.append(dict(pp=hb.Prepass(c, w, h, qp=qp), cur=hb.Frame(c, w, h), ref=hb.Frame(c, w, h), tables=c.pinned(pp.tables_bytes()),
+                          sel=np.zeros(n_ctus, np.uint8), off=np.zeros(n_ctus + 1, np.int32), out=c.pinned(fb + 4 * w * h)))
+    pending = None
+    got = {}
+    for k, (cur_p, ref_p) in enumerate(host):
+        ln = lanes[k % 2]
+        ln["pp"].frame_begin(ln["cur"], ln["ref"], cur_p, ref_p, avg, ln["tables"])
+        if pending is not None:
+            pk, pl = pending
+            n = pl["pp"].frame_finish(lam, pl["tables"], pl["sel"], pl["off"], pl["out"])
+            got[pk] = (bytes(pl["tables"]), pl["sel"].copy(), pl["off"].copy(), bytes(pl["out"][:n]))
+        pending = (k, ln)
+    pk, pl = pending
+    n = pl["pp"].frame_finish(lam, pl["tables"], pl["sel"], pl["off"], pl["out"])
+    got[pk] = (bytes(pl["tables"]), pl["sel"].copy(), pl["off"].copy(), bytes(pl["out"][:n]))
+    for k in range(len(host)):
+        assert got[k][0] == exp[k][0] and got[k][3] == exp[k][3] and np.array_equal(got[k][1], exp[k][1]) and np.array_equal(got[k][2], exp[k][2]), k
+    for ln in lanes:
+        ln["pp"].close(); ln["cur"].close(); ln["ref"].close()
+    ctx2.close(); pp.close(); fc.close(); fr.close()
+
+
 def test_bands_across_gpus_with_nccl_halo_exchange(ctx):
     """configs[3]: CTU-row bands on two GPUs, reference halos swapped over NCCL; needs >= 2 devices (skipped on one)"""
     import os
