@@ -142,6 +142,55 @@ def run_reference(args, w, h, rank, world):
     print(json.dumps(line))
 
 
+def run_intra(args, w, h, rank, world, local, hb, synth):
+    """the intra mode pre-search of one picture -- SADs of all 35 modes for every 32/16/8/4 luma block, reference
+    samples from the original picture -- through hb_intra_run (host job list and samples in, host SAD table out, copies inside
+    the timed call), next to the reference's own predictors + sad on all host cores.  Rank 0 only; not the headline metric."""
+    if rank != 0:
+        return
+    from homerhevc_b200.intra_jobs import presearch_jobs
+    ctx = hb.Context(local)
+    tex = synth.make_texture(w, h)
+    frames = [synth.make_frame(tex, w, h, n) for n in range(4)]
+    from homerhevc_b200.lib import presearch_records
+    prep = [presearch_jobs(f[0]) for f in frames]
+    rec = presearch_records(prep[0][0])                     # the block list is the same for every frame of this size
+    # samples and SAD table in pinned host memory, as an encoder would keep them
+    adi_pin = [ctx.pinned(p[1].nbytes).view(np.int16) for p in prep]
+    for a, p in zip(adi_pin, prep):
+        a[:] = p[1]
+    sad_pin = ctx.pinned(len(rec) * 35 * 4).view(np.uint32).reshape(len(rec), 35)
+    dev = [hb.Frame(ctx, w, h) for _ in frames]
+    for d, f in zip(dev, frames):
+        d.upload_u8(*f)
+    ctx.sync()
+    for i in range(max(3, args.warmup)):
+        ctx.intra_presearch(dev[i % 4], rec, adi_pin[i % 4], sad_pin)
+    steps = min(args.steps, 40)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        sads = ctx.intra_presearch(dev[i % 4], rec, adi_pin[i % 4], sad_pin)
+    secs = time.perf_counter() - t0
+    jobs, adi, off = prep[(steps - 1) % 4]
+    line = {"metric": "intra 35-mode pre-search frames/s", "value": steps / secs, "unit": "frames/s", "n_gpus": 1, "steps": steps, "warmup": max(3, args.warmup),
+            "ms_per_step": secs / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 samples, int32 accumulate",
+            "data": "synthetic", "config": {"workload": workload_name(args, w, h) + ", every 32/16/8/4 luma block, reference samples from the original picture",
+                                            "blocks": int(len(jobs)), "modes": 35, "timing": "wall clock around the blocking API call, host buffers in and out"},
+            "e2e": {"value": steps / secs, "unit": "frames/s", "h2d_bytes_per_step": int(jobs.nbytes * 2 + adi.nbytes), "d2h_bytes_per_step": int(sads.nbytes)},
+            "gpu_launches": steps}
+    try:
+        from _oracle import have_ref, ref_intra_presearch
+        if have_ref() and not args.no_cpu_baseline:
+            cores = len(os.sched_getaffinity(0))
+            ref_secs, ref_sads = ref_intra_presearch(frames[(steps - 1) % 4][0], jobs, adi, off, n_threads=cores)
+            line["cpu_baseline"] = {"value": 1.0 / ref_secs, "unit": "frames/s", "cores": cores, "kind": "reference",
+                                    "sample": "1 frame, the reference's create_intra_*_prediction + adi_filter + sad (oracle/_ref)",
+                                    "identical_to_gpu": bool((ref_sads == sads).all())}
+    except Exception as e:
+        line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+    print(json.dumps(line))
+
+
 def run_bands(args, w, h, rank, world, local, torch, dist, hb, synth, barrier):
     """strong scaling of ONE stream of frames: every GPU owns a CTU-row band; per frame the reference rows a band needs from
     its neighbours (68 luma / 36 chroma rows per side) are exchanged over NCCL, then the band's pre-pass runs"""
@@ -201,7 +250,7 @@ def main():
     ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=16, help="independent GOP streams in flight per GPU")
-    ap.add_argument("--mode", default="gops", choices=["gops", "bands"],
+    ap.add_argument("--mode", default="gops", choices=["gops", "bands", "intra"],
                     help="gops: independent GOP streams per GPU (default, weak scaling); bands: one frame split into CTU-row bands "
                          "across the GPUs with an NCCL halo exchange of the reference (BASELINE.json configs[3], strong scaling)")
     args = ap.parse_args()
@@ -231,6 +280,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.mode == "intra":
+        run_intra(args, w, h, rank, world, local, hb, synth)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.mode == "bands":
         run_bands(args, w, h, rank, world, local, torch, dist, hb, synth, barrier)
         if world > 1:

@@ -710,45 +710,59 @@ done:
  * mode >= 0: the prediction goes to `pred` (then hb_tq_encode_intra); mode < 0: sads[35*i + m] = SAD of luma mode m. */
 int hb_intra_run(hb_ctx *ctx, const hb_frame *cur, hb_frame *pred, const hb_intra_job *jobs, int n_jobs, const int16_t *adi, uint32_t *sads)
 {
-    int rc = HB_OK, crc = 0, need_sads = 0;
+    int rc = HB_OK, crc = 0;
     if (!ctx || !jobs || !adi || n_jobs < 0) return hbi_fail(HB_ERR_ARG, "hb_intra_run: bad argument");
     if (n_jobs == 0) return HB_OK;
-    size_t n_adi = 0;
-    for (int i = 0; i < n_jobs; i++) {
-        const hb_intra_job *j = &jobs[i];
-        const hb_frame *f = j->mode < 0 ? cur : pred;
-        if (!f || j->comp < 0 || j->comp > 2 || (j->size != 4 && j->size != 8 && j->size != 16 && j->size != 32) || j->mode > 34 ||
-            (j->mode < 0 && j->comp != 0) || j->x < 0 || j->y < 0 || j->x + j->size > f->d.p[j->comp].w || j->y + j->size > f->d.p[j->comp].h)
-            return hbi_fail(HB_ERR_ARG, "hb_intra_run: job %d is invalid", i);
-        need_sads |= j->mode < 0;
-        n_adi += 4 * (size_t)j->size + 1;
-    }
-    if (need_sads && !sads) return hbi_fail(HB_ERR_ARG, "hb_intra_run: sads is NULL");
     hbc_set_device(ctx->device);
     pthread_mutex_lock(&ctx->lock);
-    void *d_jobs, *h_jobs, *d_adi, *h_adi, *d_sad, *h_sad;
-    if ((rc = hbi_scratch(ctx, 0, sizeof(hbd_intra_job) * (size_t)n_jobs, &d_jobs, &h_jobs)) != HB_OK) goto done;
-    if ((rc = hbi_scratch(ctx, 1, sizeof(int16_t) * n_adi, &d_adi, &h_adi)) != HB_OK) goto done;
-    if ((rc = hbi_scratch(ctx, 2, sizeof(uint32_t) * 35 * (size_t)n_jobs, &d_sad, &h_sad)) != HB_OK) goto done;
+    void *d_jobs, *h_jobs, *d_adi, *h_adi, *d_sad = NULL, *h_sad = NULL;
+    /* scratch 0: the job records, then one index list per block size for the SAD-form jobs */
+    const size_t jobs_bytes = (sizeof(hbd_intra_job) * (size_t)n_jobs + 15) & ~(size_t)15;
+    if ((rc = hbi_scratch(ctx, 0, jobs_bytes + sizeof(int32_t) * (size_t)n_jobs, &d_jobs, &h_jobs)) != HB_OK) goto done;
     hbd_intra_job *hj = (hbd_intra_job *)h_jobs;
-    size_t off = 0;
-    for (int i = 0; i < n_jobs; i++) {
-        hj[i].comp = jobs[i].comp; hj[i].x = jobs[i].x; hj[i].y = jobs[i].y; hj[i].size = jobs[i].size; hj[i].mode = jobs[i].mode;
-        hj[i].filtered = jobs[i].filtered; hj[i].adi_off = (int32_t)off; hj[i].pad_ = 0;
-        off += 4 * (size_t)jobs[i].size + 1;
+    int32_t *hidx = (int32_t *)((char *)h_jobs + jobs_bytes);
+    const int32_t *didx = (const int32_t *)((char *)d_jobs + jobs_bytes);
+    size_t n_adi = 0;
+    int n_pred = 0, first[5] = { 0, 0, 0, 0, 0 }, fill[4];
+    for (int i = 0; i < n_jobs; i++) {                       /* one pass: validate, convert, count */
+        const hb_intra_job *j = &jobs[i];
+        const hb_frame *f = j->mode < 0 ? cur : pred;
+        const int sz = j->size == 4 ? 0 : j->size == 8 ? 1 : j->size == 16 ? 2 : j->size == 32 ? 3 : -1;
+        if (!f || sz < 0 || j->comp < 0 || j->comp > 2 || j->mode > 34 || (j->mode < 0 && j->comp != 0) || j->x < 0 || j->y < 0 ||
+            j->x + j->size > f->d.p[j->comp].w || j->y + j->size > f->d.p[j->comp].h) {
+            rc = hbi_fail(HB_ERR_ARG, "hb_intra_run: job %d is invalid", i);
+            goto done;
+        }
+        hj[i].comp = j->comp; hj[i].x = j->x; hj[i].y = j->y; hj[i].size = j->size; hj[i].mode = j->mode;
+        hj[i].filtered = j->filtered; hj[i].adi_off = (int32_t)n_adi; hj[i].pad_ = 0;
+        n_adi += 4 * (size_t)j->size + 1;
+        if (j->mode >= 0) n_pred++; else first[sz + 1]++;
     }
-    memcpy(h_adi, adi, sizeof(int16_t) * n_adi);
-    crc = hbc_h2d_async(d_jobs, h_jobs, sizeof(hbd_intra_job) * (size_t)n_jobs, ctx->stream);
-    if (!crc) crc = hbc_h2d_async(d_adi, h_adi, sizeof(int16_t) * n_adi, ctx->stream);
+    const int n_sad = n_jobs - n_pred;
+    if (n_sad && !sads) { rc = hbi_fail(HB_ERR_ARG, "hb_intra_run: sads is NULL"); goto done; }
+    for (int s = 0; s < 4; s++) { first[s + 1] += first[s]; fill[s] = first[s]; }
+    if (n_sad) for (int i = 0; i < n_jobs; i++)
+        if (jobs[i].mode < 0) hidx[fill[jobs[i].size == 4 ? 0 : jobs[i].size == 8 ? 1 : jobs[i].size == 16 ? 2 : 3]++] = i;
+    if ((rc = hbi_scratch(ctx, 1, sizeof(int16_t) * n_adi, &d_adi, &h_adi)) != HB_OK) goto done;
+    if (n_sad && (rc = hbi_scratch(ctx, 2, sizeof(uint32_t) * 35 * (size_t)n_jobs, &d_sad, &h_sad)) != HB_OK) goto done;
+    crc = hbc_h2d_async(d_jobs, h_jobs, jobs_bytes + sizeof(int32_t) * (size_t)first[4], ctx->stream);
+    /* the caller's samples go up without an extra host copy (pinned: one DMA; pageable: staged by the runtime before the call returns) */
+    if (!crc) crc = hbc_h2d_async(d_adi, adi, sizeof(int16_t) * n_adi, ctx->stream);
     hbd_intra_args a;
     memset(&a, 0, sizeof a);
     if (cur) a.cur = cur->d.p[0];
     if (pred) a.pred = pred->d;
     a.jobs = (const hbd_intra_job *)d_jobs; a.n_jobs = n_jobs; a.adi = (const int16_t *)d_adi; a.sads = (uint32_t *)d_sad;
-    if (!crc) { crc = hbk_intra(&a, ctx->stream); ctx->launches++; }
-    if (!crc && need_sads) crc = hbc_d2h_async(h_sad, d_sad, sizeof(uint32_t) * 35 * (size_t)n_jobs, ctx->stream);
+    if (!crc && n_pred) { crc = hbk_intra(&a, ctx->stream); ctx->launches++; }
+    for (int s = 0; s < 4 && !crc; s++)
+        if (first[s + 1] > first[s]) { crc = hbk_intra_sads(&a, 4 << s, didx + first[s], first[s + 1] - first[s], ctx->stream); ctx->launches++; }
+    /* rows of prediction-form jobs are written by no kernel: the caller's table is only touched for SAD-form jobs.  All SAD form
+     * (the mode search): straight into the caller's table, no staging */
+    if (!crc && n_sad) crc = n_pred ? hbc_d2h_async(h_sad, d_sad, sizeof(uint32_t) * 35 * (size_t)n_jobs, ctx->stream)
+                                    : hbc_d2h_async(sads, d_sad, sizeof(uint32_t) * 35 * (size_t)n_jobs, ctx->stream);
     if (!crc) crc = hbc_stream_sync(ctx->stream);
-    if (!crc && need_sads) memcpy(sads, h_sad, sizeof(uint32_t) * 35 * (size_t)n_jobs);
+    if (!crc && n_sad && n_pred)
+        for (int i = 0; i < n_jobs; i++) if (jobs[i].mode < 0) memcpy(sads + 35 * (size_t)i, (uint32_t *)h_sad + 35 * (size_t)i, sizeof(uint32_t) * 35);
 done:
     pthread_mutex_unlock(&ctx->lock);
     if (crc) return hbi_cuda_fail(crc, "hb_intra_run");

@@ -79,6 +79,25 @@ __device__ __forceinline__ void intra_filter_adi(const int16_t *adi, int16_t *fl
     }
 }
 
+// the same with LJ lanes per block and a compile-time size
+template <int N, int LJ> __device__ __forceinline__ void intra_filter_adi_n(const int16_t *adi, int16_t *flt, int sl)
+{
+    constexpr int size = 4 * N + 1;
+    constexpr int lg = (N == 4) ? 2 : (N == 8) ? 3 : (N == 16) ? 4 : 5;
+    const int lb = adi[0], lt = adi[2 * N], tr = adi[size - 1];
+    const bool strong = N >= 32 && abs(lb + lt - 2 * adi[N]) < 8 && abs(lt + tr - 2 * adi[3 * N]) < 8;
+    for (int i = sl; i < size; i += LJ) {
+        int v;
+        if (i == 0 || i == size - 1) v = adi[i];
+        else if (strong) {
+            if (i == 2 * N) v = adi[i];
+            else if (i < 2 * N) v = ((2 * N - i) * lb + i * lt + N) >> (lg + 1);
+            else v = ((4 * N - i) * lt + (i - 2 * N) * tr + N) >> (lg + 1);
+        } else v = (adi[i - 1] + 2 * adi[i] + adi[i + 1] + 2) >> 2;
+        flt[i] = static_cast<int16_t>(v);
+    }
+}
+
 __device__ __forceinline__ bool intra_uses_filtered(int lg, int mode)
 {
     const int d = min(abs(mode - 10), abs(mode - 26));
@@ -102,6 +121,7 @@ __global__ void __launch_bounds__(kIntraWarps * 32) k_intra(const hbd_intra_args
     const int ji = blockIdx.x * kIntraWarps + warp;
     if (ji >= a.n_jobs) return;
     const hbd_intra_job job = a.jobs[ji];
+    if (job.mode < 0) return;                          // SAD form: k_intra_sads
     const int n = job.size;
     int lg = 2;
     while ((1 << lg) < n) lg++;
@@ -126,19 +146,60 @@ __global__ void __launch_bounds__(kIntraWarps * 32) k_intra(const hbd_intra_args
         }
         return;
     }
-    // ---- SAD of every mode against the current block
+}
+
+// ---- SAD form, one launch per block size: the SADs of all 35 luma modes against the current block (what the mode search of
+// homer_loop1_motion_intra, hmr_motion_intra.c:1084, probes one call at a time).  `idx` lists the jobs of this size; a 4x4
+// block takes 16 lanes, so two of them share a warp.  A lane keeps its current samples in registers for all modes; the mode is
+// uniform per iteration, so the kind switch does not diverge.
+template <int N>
+__global__ void __launch_bounds__(kIntraWarps * 32) k_intra_sads(const hbd_intra_args a, const int32_t *idx, int n_idx)
+{
+    constexpr int LJ = (N * N < 32) ? N * N : 32;      // lanes per job
+    constexpr int JPW = 32 / LJ;                       // jobs per warp
+    constexpr int SPL = N * N / LJ;                    // samples per lane
+    constexpr int LG = (N == 4) ? 2 : (N == 8) ? 3 : (N == 16) ? 4 : 5;
+    __shared__ int16_t s_adi[kIntraWarps][JPW][2][4 * N + 4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane / LJ, sl = lane % LJ;
+    const int k = (blockIdx.x * kIntraWarps + warp) * JPW + sub;
+    if ((blockIdx.x * kIntraWarps + warp) * JPW >= n_idx) return;          // whole warp
+    const bool valid = k < n_idx;
+    const int ji = idx[min(k, n_idx - 1)];
+    const hbd_intra_job job = a.jobs[ji];
+    int16_t *raw = s_adi[warp][sub][0], *flt = s_adi[warp][sub][1];
+    for (int i = sl; i < 4 * N + 1; i += LJ) raw[i] = a.adi[job.adi_off + i];
+    __syncwarp();
+    intra_filter_adi_n<N, LJ>(raw, flt, sl);
+    __syncwarp();
+    int cur[SPL];
+#pragma unroll
+    for (int q = 0; q < SPL; q++) {
+        const int e = sl + q * LJ;
+        cur[q] = a.cur.org[(job.y + e / N) * a.cur.pitch + job.x + e % N];
+    }
+    // DC value (mode 1 always reads the raw samples)
+    int dcs = 0;
+    for (int i = 1 + sl; i <= N; i += LJ) dcs += raw[2 * N + i] + raw[2 * N - i];
+#pragma unroll
+    for (int d = LJ / 2; d > 0; d >>= 1) dcs += __shfl_xor_sync(HB_FULL_MASK, dcs, d);
+    const int dc = (dcs + N) >> (LG + 1);
+    const bool edge = N <= 16;
     for (int mode = 0; mode < 35; mode++) {
-        const int16_t *mid = (intra_uses_filtered(lg, mode) ? flt : raw) + 2 * n;
+        const int16_t *mid = (intra_uses_filtered(LG, mode) ? flt : raw) + 2 * N;
         const IntraMode m = intra_mode_info(mode);
-        const int dc = m.kind == 1 ? intra_dc(mid, n, lane) : 0;
         uint32_t acc = 0;
-        for (int e = lane; e < n * n; e += 32) {
-            const int x = e % n, y = e / n;
-            const int c = a.cur.org[(job.y + y) * a.cur.pitch + job.x + x];
-            acc = __sad(intra_sample(mid, n, lg, m, dc, edge, x, y), c, acc);
+#pragma unroll
+        for (int q = 0; q < SPL; q++) {
+            const int e = sl + q * LJ;
+            acc = __sad(intra_sample(mid, N, LG, m, dc, edge, e % N, e / N), cur[q], acc);
         }
-        acc = __reduce_add_sync(HB_FULL_MASK, acc);
-        if (lane == 0) a.sads[static_cast<size_t>(ji) * 35 + mode] = acc;
+        if constexpr (JPW == 1) {
+            acc = __reduce_add_sync(HB_FULL_MASK, acc);
+            if (lane == 0) a.sads[static_cast<size_t>(ji) * 35 + mode] = acc;
+        } else {
+            const uint32_t t0 = __reduce_add_sync(HB_FULL_MASK, sub == 0 ? acc : 0u), t1 = __reduce_add_sync(HB_FULL_MASK, sub == 1 ? acc : 0u);
+            if (sl == 0 && valid) a.sads[static_cast<size_t>(ji) * 35 + mode] = sub ? t1 : t0;
+        }
     }
 }
 
@@ -161,6 +222,22 @@ extern "C" int hbk_intra(const hbd_intra_args *a, void *stream)
 {
     if (a->n_jobs <= 0) return 0;
     k_intra<<<(a->n_jobs + kIntraWarps - 1) / kIntraWarps, kIntraWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int hbk_intra_sads(const hbd_intra_args *a, int size, const int32_t *idx, int n_idx, void *stream)
+{
+    if (n_idx <= 0) return 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int per_cta = kIntraWarps * (size == 4 ? 2 : 1);
+    const int grid = (n_idx + per_cta - 1) / per_cta;
+    switch (size) {
+    case 4: k_intra_sads<4><<<grid, kIntraWarps * 32, 0, s>>>(*a, idx, n_idx); break;
+    case 8: k_intra_sads<8><<<grid, kIntraWarps * 32, 0, s>>>(*a, idx, n_idx); break;
+    case 16: k_intra_sads<16><<<grid, kIntraWarps * 32, 0, s>>>(*a, idx, n_idx); break;
+    case 32: k_intra_sads<32><<<grid, kIntraWarps * 32, 0, s>>>(*a, idx, n_idx); break;
+    default: return static_cast<int>(cudaErrorInvalidValue);
+    }
     return static_cast<int>(cudaGetLastError());
 }
 

@@ -131,7 +131,8 @@ typedef struct hbd_intra_args {
     const int16_t *adi;
     uint32_t *sads;               /* n_jobs x 35 */
 } hbd_intra_args;
-int hbk_intra(const hbd_intra_args *a, void *stream);
+int hbk_intra(const hbd_intra_args *a, void *stream);                                  /* prediction-form jobs (mode >= 0) */
+int hbk_intra_sads(const hbd_intra_args *a, int size, const int32_t *idx, int n_idx, void *stream);   /* SAD-form jobs of one size */
 int hbk_pc_intra(const int16_t *adi, int n, int mode, int is_luma, int16_t *pred, int stride, void *stream);
 
 /* ---- gather of the host's selection (hb_kernels_gather.cu) */

@@ -347,6 +347,29 @@ def _intra_run(self, cur, pred, jobs, adi):
 Context.intra_run = _intra_run
 
 
+def presearch_records(jobs_xyn):
+    """int32 (n, 3) {x, y, size} -> the hb_intra_job records of an all-mode search (build once, reuse every frame of that size)"""
+    rec = np.zeros((len(jobs_xyn), 6), np.int32)
+    rec[:, 1:4] = jobs_xyn
+    rec[:, 4] = -1; rec[:, 5] = -1                      # mode < 0: SADs of all modes; filtered < 0: the search rule
+    return rec
+
+
+def _intra_presearch(self, cur, jobs, adi, out=None):
+    """all 35 mode SADs of many luma blocks at once.  jobs: presearch_records(...) (or the (n, 3) {x, y, size} array),
+    adi: their reference samples back to back, out: optional (n, 35) uint32 table (pinned memory avoids a staging copy)."""
+    rec = jobs if jobs.shape[1] == 6 else presearch_records(jobs)
+    n = len(rec)
+    arr = (IntraJob * n).from_buffer(rec)
+    sads = out if out is not None else np.empty((n, 35), np.uint32)
+    assert sads.dtype == np.uint32 and sads.size == n * 35 and adi.dtype == np.int16 and adi.flags.c_contiguous
+    _check(self.L.hb_intra_run(self.h, cur.h, None, arr, n, _p16(adi), sads.ctypes.data_as(C.POINTER(C.c_uint32))), "hb_intra_run")
+    return sads
+
+
+Context.intra_presearch = _intra_presearch
+
+
 class Frame:
     def __init__(self, ctx, width, height):
         self.ctx, self.w, self.h_px = ctx, width, height

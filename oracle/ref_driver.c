@@ -600,3 +600,55 @@ void refdrv_adi_filter(refdrv *d, int16_t *adi, int16_t *flt, int n)
     while ((1 << shift) < n) shift++;
     adi_filter(adi, flt, d->et->max_cu_size_shift - shift, 4 * n + 1, n, d->et->max_cu_size_shift, d->et->sps->strong_intra_smooth_enabled_flag, d->et->bit_depth);
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Intra mode pre-search with the reference's own functions (the loop of homer_loop1_motion_intra,
+ * hmr_motion_intra.c:1084-1140, without its bit-cost terms): per block smooth the reference samples (adi_filter), and for
+ * each of the 35 modes build the prediction through the function table from the raw or smoothed samples (:1122) and take
+ * its SAD against the original block through the table.  jobs: n_jobs x {x, y, size}; adi: the 4*size+1 reference samples
+ * of every job back to back (adi_off[j] = first sample of job j); sads: n_jobs x 35.  Jobs are split over n_threads.
+ * Returns the seconds spent.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct ip_shared { const uint8_t *luma; int w, h; const int32_t *jobs; int n_jobs; const int16_t *adi; const int32_t *adi_off; uint32_t *sads; int n_threads; } ip_shared;
+typedef struct ip_worker { ip_shared *sh; refdrv *drv; int tid; pthread_t th; } ip_worker;
+
+static void *ip_thread(void *arg)
+{
+    static const int thr[5] = { 10, 7, 1, 0, 10 };
+    ip_worker *wk = (ip_worker *)arg;
+    ip_shared *sh = wk->sh;
+    refdrv *d = wk->drv;
+    int16_t *orig = (int16_t *)aligned_alloc(64, 64 * 64 * 2), *pred = (int16_t *)aligned_alloc(64, 64 * 64 * 2);
+    int16_t *raw = (int16_t *)aligned_alloc(64, 272 * 2), *flt = (int16_t *)aligned_alloc(64, 272 * 2);
+    const int lo = (int)((long)sh->n_jobs * wk->tid / sh->n_threads), hi = (int)((long)sh->n_jobs * (wk->tid + 1) / sh->n_threads);
+    for (int j = lo; j < hi; j++) {
+        const int x = sh->jobs[3 * j], y = sh->jobs[3 * j + 1], n = sh->jobs[3 * j + 2];
+        int lg = 0;
+        while ((1 << lg) < n) lg++;
+        for (int r = 0; r < n; r++) for (int c = 0; c < n; c++) orig[r * n + c] = sh->luma[(size_t)(y + r) * sh->w + x + c];
+        memcpy(raw, sh->adi + sh->adi_off[j], sizeof(int16_t) * (size_t)(4 * n + 1));
+        refdrv_adi_filter(d, raw, flt, n);
+        for (int m = 0; m < 35; m++) {
+            const int d1 = abs(m - 10), d2 = abs(m - 26);
+            const int use_flt = m != 1 && ((d1 < d2 ? d1 : d2) > thr[lg - 2]);
+            refdrv_intra_predict(d, use_flt ? flt : raw, n, m, 1, pred);
+            sh->sads[(size_t)j * 35 + m] = d->enc->funcs.sad(orig, n, pred, n, n);
+        }
+    }
+    free(orig); free(pred); free(raw); free(flt);
+    return NULL;
+}
+
+double refdrv_intra_presearch(refdrv **drv, int n_threads, const uint8_t *luma, int w, int h, const int32_t *jobs, int n_jobs,
+                              const int16_t *adi, const int32_t *adi_off, uint32_t *sads)
+{
+    ip_shared sh = { luma, w, h, jobs, n_jobs, adi, adi_off, sads, n_threads };
+    ip_worker *wk = (ip_worker *)calloc((size_t)n_threads, sizeof *wk);
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = 0; t < n_threads; t++) { wk[t].sh = &sh; wk[t].drv = drv[t]; wk[t].tid = t; pthread_create(&wk[t].th, NULL, ip_thread, &wk[t]); }
+    for (int t = 0; t < n_threads; t++) pthread_join(wk[t].th, NULL);
+    free(wk);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}

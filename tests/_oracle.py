@@ -189,6 +189,25 @@ PASS_TU = (32, 32, 16, 8, 4)
 _rp_handles = {}
 
 
+def ref_intra_presearch(luma, jobs, adi, adi_off, n_threads=1):
+    """35-mode SADs of every job through the reference's own functions; returns (seconds, sads (n,35) uint32)"""
+    _, D = ref()
+    D.refdrv_intra_presearch.restype = C.c_double
+    D.refdrv_intra_presearch.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    hs = _rp_handles.setdefault((32, 1), [])
+    while len(hs) < n_threads:
+        hh = D.refdrv_open(128, 128, 32, 1)
+        assert hh
+        hs.append(hh)
+    handles = (C.c_void_p * n_threads)(*hs[:n_threads])
+    luma = np.ascontiguousarray(luma, np.uint8); jobs = np.ascontiguousarray(jobs, np.int32)
+    adi = np.ascontiguousarray(adi, np.int16); adi_off = np.ascontiguousarray(adi_off, np.int32)
+    sads = np.zeros((len(jobs), 35), np.uint32)
+    h, w = luma.shape
+    secs = D.refdrv_intra_presearch(handles, n_threads, luma.ctypes.data, w, h, jobs.ctypes.data, len(jobs), adi.ctypes.data, adi_off.ctypes.data, sads.ctypes.data)
+    return secs, sads
+
+
 def ref_prepass(cur, ref_planes, w, h, qp=32, avg_dist=650.0, n_threads=1, band=(0, 0), sign_hiding=1, want_pred=True):
     """cur / ref_planes: (y, u, v) uint8 planes.  Returns (seconds, dict) with the GPU library's output layouts."""
     _, D = ref()

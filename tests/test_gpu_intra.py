@@ -103,3 +103,23 @@ def test_percall_intra_predictors(ctx):
                 L.hb_create_intra_angular_prediction(ptr(p1), 64, ptr(adi), 4 * n + 1, n, mode, is_luma)
             O.orc_intra_predict(ptr(adi), n, mode, is_luma if mode else 1, ptr(p2), n)
             assert np.array_equal(p1.reshape(64, 64)[:n, :n], p2.reshape(n, n)), (n, mode, is_luma)
+
+
+def test_presearch_against_reference_functions(ctx):
+    """every luma block of a small picture, sizes 4..32, reference samples from the original picture: the 35 SADs per block
+    equal what the reference's own predictors + sad deliver (oracle/_ref), and the oracle agrees"""
+    from _oracle import have_ref, ref_intra_presearch
+    from homerhevc_b200.intra_jobs import presearch_jobs
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    w, h = 192, 128
+    cur, _ = clip_pair(w, h, n=1, noise=6.0, seed=23)
+    jobs, adi, off = presearch_jobs(cur.y)
+    assert len(jobs) == sum((w // n) * (h // n) for n in (32, 16, 8, 4))
+    fc = upload(ctx, cur, w, h)
+    got = ctx.intra_presearch(fc, jobs, adi)
+    assert np.array_equal(got, ctx.intra_presearch(fc, hb.lib.presearch_records(jobs), adi, ctx.pinned(len(jobs) * 140).view(np.uint32).reshape(-1, 35)))
+    _, exp = ref_intra_presearch(cur.y, jobs, adi, off, n_threads=2)
+    bad = np.argwhere(got != exp)
+    assert len(bad) == 0, (len(bad), bad[:4], jobs[bad[0][0]])
+    fc.close()
