@@ -267,32 +267,47 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
             phase ^= 1;
         }
     };
+    // SAD of this lane's words at integer displacement (mx, my)
+    auto sad_at = [&](int mx, int my) -> uint32_t {
+        uint32_t acc = 0, acc1 = 0;
+        // the pitch is a multiple of 4, so every word of this candidate has the same misalignment: shift once
+        uint32_t off = ref_lane + static_cast<uint32_t>(my * static_cast<int>(rpitch) + mx);
+        const uint32_t sh = (off & 3u) * 8u;
+        off &= ~3u;
+#pragma unroll
+        for (int k = 0; k < PPL; k++) {
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(a.ref.base + off);
+            const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+            acc = hb_sad4_acc(cur[2 * k], __funnelshift_r(w0, w1, sh), acc);
+            acc1 = hb_sad4_acc(cur[2 * k + 1], __funnelshift_r(w1, w2, sh), acc1);       // two chains for ILP
+            off += ref_step;
+        }
+        return acc + acc1;
+    };
     // one round: SAD + cost of up to four integer positions (cx[s], cy[s]); invalid slots give garbage that is never read
     auto round4 = [&](const int (&cx)[4], const int (&cy)[4], const bool (&cv)[4], uint32_t (&sad)[4], uint32_t (&rd)[4]) {
         int mx = cx[0], my = cy[0]; bool mv = cv[0];
 #pragma unroll
         for (int s = 1; s < 4; s++) if (slot == s) { mx = cx[s]; my = cy[s]; mv = cv[s]; }
-        uint32_t acc = 0, acc1 = 0;
-        if (mv) {
-            // the pitch is a multiple of 4, so every word of this candidate has the same misalignment: shift once
-            uint32_t off = ref_lane + static_cast<uint32_t>(my * static_cast<int>(rpitch) + mx);
-            const uint32_t sh = (off & 3u) * 8u;
-            off &= ~3u;
-#pragma unroll
-            for (int k = 0; k < PPL; k++) {
-                const uint32_t *q = reinterpret_cast<const uint32_t *>(a.ref.base + off);
-                const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
-                acc = hb_sad4_acc(cur[2 * k], __funnelshift_r(w0, w1, sh), acc);
-                acc1 = hb_sad4_acc(cur[2 * k + 1], __funnelshift_r(w1, w2, sh), acc1);       // two chains for ILP
-                off += ref_step;
-            }
-            acc += acc1;
-        }
+        const uint32_t acc = mv ? sad_at(mx, my) : 0u;
         uint32_t cst[4];
         exchange(acc, mv_cost(mx << 2, my << 2), sad, cst);
 #pragma unroll
         for (int s = 0; s < 4; s++) rd[s] = sad[s] + cst[s];
     };
+    // the same for the pattern stages: every lane derives ITS slot's position (mx, my) itself and tests it alone; whether the
+    // other three slots were inside the search area comes back with their cost (no cost is ever 0xffffffff)
+    auto round_own = [&](int mx, int my, bool mv, uint32_t (&sad)[4], uint32_t (&rd)[4], uint32_t &vmask) {
+        const uint32_t acc = mv ? sad_at(mx, my) : 0u;
+        uint32_t cst[4];
+        exchange(acc, mv ? mv_cost(mx << 2, my << 2) : 0xffffffffu, sad, cst);
+        vmask = 0;
+#pragma unroll
+        for (int s = 0; s < 4; s++) { rd[s] = sad[s] + cst[s]; vmask |= cst[s] != 0xffffffffu ? (1u << s) : 0u; }
+    };
+    // this lane's offsets inside the small diamond and the two halves of the big diamond (c_small / c_big rows slot, 4 + slot)
+    const int sdx = (slot & 1) ? 0 : slot - 1, sdy = (slot & 1) ? slot - 2 : 0;
+    const int bdx0 = slot - 2, bdy0 = (slot <= 2) ? -slot : -1, bdx1 = 2 - slot, bdy1 = (slot <= 2) ? slot : 1;
 
     int bx = 0, by = 0;
     uint32_t bsad = 0, brd = 0, n_probes = 0;
@@ -348,13 +363,11 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
         int cx0 = bx, cy0 = by;
         if (any_pu(!skip)) {
             {   // first small diamond, fixed order, centre stays put (:1501-1523)
-                int cx[4], cy[4]; bool cv[4]; uint32_t sad[4], rd[4];
-#pragma unroll
-                for (int s = 0; s < 4; s++) { cx[s] = cx0 + c_small[s][0]; cy[s] = cy0 + c_small[s][1]; cv[s] = !skip && inside(cx[s], cy[s]); }
-                round4(cx, cy, cv, sad, rd);
+                uint32_t sad[4], rd[4], vmask;
+                round_own(cx0 + sdx, cy0 + sdy, !skip && inside(cx0 + sdx, cy0 + sdy), sad, rd, vmask);
 #pragma unroll
                 for (int s = 0; s < 4; s++)
-                    if (cv[s]) { n_probes++; if (rd[s] < brd) { bsad = sad[s]; brd = rd[s]; bx = cx[s]; by = cy[s]; } }
+                    if ((vmask >> s) & 1u) { n_probes++; if (rd[s] < brd) { bsad = sad[s]; brd = rd[s]; bx = cx0 + c_small[s][0]; by = cy0 + c_small[s][1]; } }
             }
             // rotating big diamond (:1528-1599): dist 2, and 4 when the old centre sat on an axis
             const int end = skip ? 0 : (cx0 != 0 && cy0 != 0) ? 4 : 8;
@@ -362,21 +375,17 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
             cx0 = bx; cy0 = by;
             for (int dist = 2; any_pu(dist < end); dist *= 2) {
                 const bool act = dist < end;
-                uint32_t sad8[8], rd8[8]; bool v8[8];
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    int cx[4], cy[4]; bool cv[4]; uint32_t sad[4], rd[4];
-#pragma unroll
-                    for (int s = 0; s < 4; s++) {
-                        cx[s] = cx0 + c_big[4 * h + s][0] * dist; cy[s] = cy0 + c_big[4 * h + s][1] * dist; cv[s] = act && inside(cx[s], cy[s]);
-                    }
-                    round4(cx, cy, cv, sad, rd);
-#pragma unroll
-                    for (int s = 0; s < 4; s++) { sad8[4 * h + s] = sad[s]; rd8[4 * h + s] = rd[s]; v8[4 * h + s] = cv[s]; }
-                }
+                uint32_t sad8[8], rd8[8];
                 uint32_t vmask = 0;                           // empty for a PU that only idles through this round
 #pragma unroll
-                for (int s = 0; s < 8; s++) vmask |= v8[s] ? (1u << s) : 0u;
+                for (int h = 0; h < 2; h++) {
+                    uint32_t sad[4], rd[4], vm;
+                    const int mx = cx0 + (h ? bdx1 : bdx0) * dist, my = cy0 + (h ? bdy1 : bdy0) * dist;
+                    round_own(mx, my, act && inside(mx, my), sad, rd, vm);
+                    vmask |= vm << (4 * h);
+#pragma unroll
+                    for (int s = 0; s < 4; s++) { sad8[4 * h + s] = sad[s]; rd8[4 * h + s] = rd[s]; }
+                }
                 for (int i = next_start; i < next_start + span; i++) {
                     const int idx = i & 7;
                     if (!((vmask >> idx) & 1u)) continue;
@@ -396,13 +405,8 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
             int next_start = 0, span = 4;
             bool done = false;
             for (;;) {
-                int cx[4], cy[4]; bool cv[4]; uint32_t sad[4], rd[4];
-#pragma unroll
-                for (int s = 0; s < 4; s++) { cx[s] = cx0 + c_small[s][0]; cy[s] = cy0 + c_small[s][1]; cv[s] = !done && inside(cx[s], cy[s]); }
-                round4(cx, cy, cv, sad, rd);
-                uint32_t vmask = 0;
-#pragma unroll
-                for (int s = 0; s < 4; s++) vmask |= cv[s] ? (1u << s) : 0u;
+                uint32_t sad[4], rd[4], vmask;
+                round_own(cx0 + sdx, cy0 + sdy, !done && inside(cx0 + sdx, cy0 + sdy), sad, rd, vmask);
                 for (int i = next_start; i < next_start + span; i++) {
                     const int idx = i & 3;
                     if (!((vmask >> idx) & 1u)) continue;
@@ -545,21 +549,24 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
         //   T_0 column (N strips): v = V2(T_0)                   -> candidates (0,-2) and (0,+2)
         //   T_2 column (N strips): v = V2(T_2), u = round(T_2)   -> (-2,-2) (+2,-2) (-2,+2) (+2,+2) and (-2,0) (+2,0)
         // Partial SADs go to eight shared counters.  T_0 / T_2 is uniform per warp.
-        for (int strip = gl; strip < 2 * N; strip += G) {
-            const bool t2 = strip >= N;
-            const int j = t2 ? strip - N : strip + 1;                 // plane column: x = ix - 1 + j (+ 1/2 for T_2)
-            const bool use_l = j >= 1;                                // block column j-1 exists (j = 0: only the x = -2 candidates)
-            const uint8_t *cur_l = s_cur + max(j - 1, 0) * CS, *cur_r = s_cur + j * CS;
+        // c_half order: 1 (0,-1) 2 (0,1) 3 (-1,0) 4 (1,0) 5 (-1,-1) 6 (1,-1) 7 (-1,1) 8 (1,1)
+        auto t0_strip = [&](int j) {                                  // plane column j: x = ix - 1 + j, block column j - 1
             uint32_t acc[6] = { 0, 0, 0, 0, 0, 0 };                   // {minus,L} {minus,R} {plus,L} {plus,R} {u,L} {u,R}
-            // c_half order: 1 (0,-1) 2 (0,1) 3 (-1,0) 4 (1,0) 5 (-1,-1) 6 (1,-1) 7 (-1,1) 8 (1,1)
-            if (t2) {
-                half_strip<N, TS, true>(s_plane + 2 * PLANE_WORDS + j, cur_l, cur_r, acc);
-                if (use_l) { atomicAdd(&s_half[group][5], acc[0]); atomicAdd(&s_half[group][7], acc[2]); atomicAdd(&s_half[group][3], acc[4]); }
-                atomicAdd(&s_half[group][4], acc[1]); atomicAdd(&s_half[group][6], acc[3]); atomicAdd(&s_half[group][2], acc[5]);
-            } else {
-                half_strip<N, TS, false>(s_plane + j, cur_l, cur_r, acc);
-                atomicAdd(&s_half[group][0], acc[0]); atomicAdd(&s_half[group][1], acc[2]);
-            }
+            half_strip<N, TS, false>(s_plane + j, s_cur + (j - 1) * CS, s_cur, acc);
+            atomicAdd(&s_half[group][0], acc[0]); atomicAdd(&s_half[group][1], acc[2]);
+        };
+        auto t2_strip = [&](int j) {                                  // x = ix - 1/2 + j: block columns j - 1 (L) and j (R)
+            uint32_t acc[6] = { 0, 0, 0, 0, 0, 0 };
+            half_strip<N, TS, true>(s_plane + 2 * PLANE_WORDS + j, s_cur + max(j - 1, 0) * CS, s_cur + j * CS, acc);
+            if (j >= 1) { atomicAdd(&s_half[group][5], acc[0]); atomicAdd(&s_half[group][7], acc[2]); atomicAdd(&s_half[group][3], acc[4]); }
+            atomicAdd(&s_half[group][4], acc[1]); atomicAdd(&s_half[group][6], acc[3]); atomicAdd(&s_half[group][2], acc[5]);
+        };
+        if constexpr (G == N) {                                       // small PUs: every lane takes one column of each plane
+            t0_strip(gl + 1);
+            t2_strip(gl);
+        } else {                                                      // large PUs: whole warps take T_0 or T_2 columns (G >= 2N)
+            if (gl < N) t0_strip(gl + 1);
+            else if (gl < 2 * N) t2_strip(gl - N);
         }
         // the last T_2 column (j = N, right edge of the x = +2 candidates) would cost a whole extra pass of the strip loop for one
         // lane: its N+1 filtered samples are spread over the lanes instead, one direct 8-tap sum each

@@ -2,9 +2,9 @@
 nearest preceding instruction that maps to hb_kernels_me.cu).  usage: python tools/ncu_regions.py cuda_sass.csv "k_me<(int)8>" """
 import csv, sys, collections, bisect
 path, want = sys.argv[1], sys.argv[2]
-REG = [(0, 94, "setup/load cur"), (95, 170, "half-pel strips"), (171, 218, "setup/load cur"), (219, 239, "mv_cost"), (240, 267, "exchange"), (268, 293, "round4 (SAD)"),
-       (294, 416, "walk replay/control"), (417, 433, "patch staging"), (434, 464, "H planes"), (465, 476, "cur->smem"), (477, 512, "quarter subpel4"),
-       (513, 558, "half-pel strips"), (559, 580, "subpel decide"), (581, 606, "pred write"), (607, 700, "result")]
+REG = [(0, 94, "setup/load cur"), (95, 170, "half-pel strips"), (171, 221, "setup/load cur"), (222, 242, "mv_cost"), (243, 270, "exchange"), (271, 296, "round4 (SAD)"),
+       (297, 425, "walk replay/control"), (426, 462, "patch staging"), (463, 493, "H planes"), (494, 505, "cur->smem"), (506, 541, "quarter subpel4"),
+       (542, 587, "half-pel strips"), (588, 609, "subpel decide"), (610, 635, "pred write"), (636, 700, "result")]
 def region(line):
     for lo, hi, n in REG:
         if lo <= line <= hi: return n

@@ -14,7 +14,7 @@ for r in rows[1:]:
 ks = list(agg.values())
 # last index of k_me<64>, then everything up to the next k_me<64> / non pre-pass kernel
 starts = [i for i, k in enumerate(ks) if k["kernel"].startswith("k_me<64>")]
-pre = ("k_me<", "k_mc", "k_tq<")
+pre = ("k_me<", "k_mc", "k_tq")
 frames = []
 for s in starts:
     e = s + 1
