@@ -118,6 +118,19 @@ void hb_reconst(int16_t *pred, int pred_stride, int16_t *residual, int residual_
     pack(decoded, decoded_stride, c, size, size, size);
 }
 
+/* weighted_average_motion of the table (hmr_motion_inter.c:2903): the two 14-bit predictions of a bi-predicted block -> 8-bit samples */
+void hb_weighted_average_motion(int16_t *src0, int src0_stride, int16_t *src1, int src1_stride, int16_t *dst, int dst_stride, int height, int width, int bit_depth)
+{
+    pc_slot *s = slot();
+    (void)bit_depth;                                        /* 8-bit video only, like the rest of the library */
+    if (width <= 0 || height <= 0 || width > 64 || height > 64) return;
+    int16_t *a = (int16_t *)s->host, *b = a + 64 * 64, *c = b + 64 * 64;
+    pack(a, width, src0, src0_stride, width, height);
+    pack(b, width, src1, src1_stride, width, height);
+    finish(s, hbk_pc_wavg(D(s, a), D(s, b), D(s, c), width, height, s->stream), "weighted_average_motion");
+    pack(dst, dst_stride, c, width, width, height);
+}
+
 static void interpolate(int chroma, int16_t *ref, int ref_stride, int16_t *dst, int dst_stride, int fraction, int width, int height,
                         int is_vertical, int is_first, int is_last)
 {
@@ -246,6 +259,7 @@ void hb_fill_low_level_funcs(hb_low_level_funcs *t)
     t->ssd16b = hb_ssd16b;
     t->predict = hb_predict;
     t->reconst = hb_reconst;
+    t->weighted_average_motion = hb_weighted_average_motion;
     t->interpolate_luma_m_compensation = hb_interpolate_luma;
     t->interpolate_chroma_m_compensation = hb_interpolate_chroma;
     t->interpolate_luma_m_estimation = hb_interpolate_luma;

@@ -124,6 +124,12 @@ __global__ void __launch_bounds__(256) k_pc_reconst(const int16_t *pred, int ps,
         dec[(e / n) * ds + e % n] = static_cast<int16_t>(hb_clip255(static_cast<int>(res[(e / n) * rs + e % n]) + pred[(e / n) * ps + e % n]));
 }
 
+// bi-prediction average of two 14-bit predictions (weighted_average_motion, hmr_motion_inter.c:2903)
+__global__ void __launch_bounds__(256) k_pc_wavg(const int16_t *s0, const int16_t *s1, int16_t *dst, int w, int h)
+{
+    for (int e = threadIdx.x; e < w * h; e += 256) dst[e] = static_cast<int16_t>(hb_clip255((static_cast<int>(s0[e]) + s1[e] + 64 + 2 * 8192) >> 7));
+}
+
 // one interpolation pass with the reference's four (is_first, is_last) roundings; every value passes through an int16
 __global__ void __launch_bounds__(256) k_pc_interp(const int16_t *src, int ss, int org_off, int16_t *dst, int ds, int chroma, int fraction,
                                                    int w, int h, int vertical, int first, int last)
@@ -167,6 +173,11 @@ extern "C" int hbk_pc_predict(const int16_t *orig, int os, const int16_t *pred, 
 extern "C" int hbk_pc_reconst(const int16_t *pred, int ps, const int16_t *res, int rs, int16_t *dec, int ds, int n, void *stream)
 {
     k_pc_reconst<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(pred, ps, res, rs, dec, ds, n);
+    return static_cast<int>(cudaGetLastError());
+}
+extern "C" int hbk_pc_wavg(const int16_t *s0, const int16_t *s1, int16_t *dst, int w, int h, void *stream)
+{
+    k_pc_wavg<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(s0, s1, dst, w, h);
     return static_cast<int>(cudaGetLastError());
 }
 extern "C" int hbk_pc_interp(const int16_t *src, int ss, int org_off, int16_t *dst, int ds, int chroma, int fraction, int w, int h,

@@ -61,6 +61,7 @@ int hbk_narrow_plane(const int16_t *src, int src_stride, hbd_plane dst, uint32_t
 /* ---- per-call kernels: operands live in mapped pinned staging, strides in samples */
 int hbk_pc_sad(const int16_t *a, int as, const int16_t *b, int bs, int n, int squared, uint32_t *out, void *stream);
 int hbk_pc_predict(const int16_t *orig, int os, const int16_t *pred, int ps, int16_t *res, int rs, int n, void *stream);
+int hbk_pc_wavg(const int16_t *s0, const int16_t *s1, int16_t *dst, int w, int h, void *stream);   /* tight w-sample rows */
 int hbk_pc_reconst(const int16_t *pred, int ps, const int16_t *res, int rs, int16_t *dec, int ds, int n, void *stream);
 /* src points at the first needed sample (margins included), org_off = offset of sample (0,0) */
 int hbk_pc_interp(const int16_t *src, int ss, int org_off, int16_t *dst, int ds, int chroma, int fraction, int w, int h,

@@ -128,6 +128,8 @@ def load_library():
     L.hb_predict.argtypes = [i16p, C.c_int, i16p, C.c_int, i16p, C.c_int, C.c_int]
     L.hb_reconst.restype = None
     L.hb_reconst.argtypes = [i16p, C.c_int, i16p, C.c_int, i16p, C.c_int, C.c_int]
+    L.hb_weighted_average_motion.restype = None
+    L.hb_weighted_average_motion.argtypes = [i16p, C.c_int, i16p, C.c_int, i16p, C.c_int, C.c_int, C.c_int, C.c_int]
     for f in (L.hb_interpolate_luma, L.hb_interpolate_chroma):
         f.restype = None
         f.argtypes = [i16p, C.c_int, i16p, C.c_int] + [C.c_int] * 6

@@ -63,6 +63,8 @@ uint32_t hb_sad(int16_t *src, uint32_t src_stride, int16_t *pred, uint32_t pred_
 uint32_t hb_ssd16b(int16_t *src, uint32_t src_stride, int16_t *pred, uint32_t pred_stride, int size);
 void hb_predict(int16_t *orig, int orig_stride, int16_t *pred, int pred_stride, int16_t *residual, int residual_stride, int size);
 void hb_reconst(int16_t *pred, int pred_stride, int16_t *residual, int residual_stride, int16_t *decoded, int decoded_stride, int size);
+/* weighted_average_motion, hmr_private.h:1084 / hmr_motion_inter.c:2903: average of the two 14-bit predictions of a bi-predicted block */
+void hb_weighted_average_motion(int16_t *src0, int src0_stride, int16_t *src1, int src1_stride, int16_t *dst, int dst_stride, int height, int width, int bit_depth);
 void hb_interpolate_luma(int16_t *reference_buff, int reference_buff_stride, int16_t *pred_buff, int pred_buff_stride,
                          int fraction, int width, int height, int is_vertical, int is_first, int is_last);
 void hb_interpolate_chroma(int16_t *reference_buff, int reference_buff_stride, int16_t *pred_buff, int pred_buff_stride,
@@ -89,8 +91,9 @@ void hb_inv_quant(const hb_quant_env *env, int16_t *src, int16_t *dst, int depth
                   int cu_size, int per, int rem);
 
 /* The table itself, laid out member for member like low_level_funcs_t (19 pointers, hmr_private.h:1063-1092).
- * hb_fill_low_level_funcs overwrites the 10 members this library implements and leaves the rest (copies,
- * variance, intra predictors, weighted average, SAO stats -- out of scope) untouched. */
+ * hb_fill_low_level_funcs overwrites the 10 members with table-compatible prototypes that this library implements and leaves the
+ * rest untouched: copies, variance, SAO stats (out of scope), quant / inv_quant and the two intra predictors
+ * (implemented, but their table prototypes take henc_thread_t* / ctu_info_t*: INTEGRATION.md shows the adapters). */
 typedef struct hb_low_level_funcs {
     void *sse_copy_16_16, *sse_copy_16_8, *sse_copy_8_16;
     uint32_t (*sad)(int16_t *, uint32_t, int16_t *, uint32_t, int);
@@ -101,7 +104,7 @@ typedef struct hb_low_level_funcs {
     void (*interpolate_luma_m_compensation)(int16_t *, int, int16_t *, int, int, int, int, int, int, int);
     void (*interpolate_chroma_m_compensation)(int16_t *, int, int16_t *, int, int, int, int, int, int, int);
     void (*interpolate_luma_m_estimation)(int16_t *, int, int16_t *, int, int, int, int, int, int, int);
-    void *weighted_average_motion;
+    void (*weighted_average_motion)(int16_t *, int, int16_t *, int, int16_t *, int, int, int, int);
     void *quant, *inv_quant;      /* need the henc_thread_t adapter, see INTEGRATION.md */
     void (*transform)(int, int16_t *, int16_t *, int, int, int, int, int, uint16_t, int16_t *);
     void (*itransform)(int, int16_t *, int16_t *, int, int, int, unsigned int, int16_t *);

@@ -852,3 +852,12 @@ void orc_intra_mode_sads(const int16_t *orig, int orig_stride, const int16_t *ad
         sads[m] = orc_sad(orig, orig_stride, pred, n, n);
     }
 }
+
+/* Bi-prediction average of two 14-bit predictions (weighted_average_motion, hmr_motion_inter.c:2903; the SSE4.2 form,
+ * hmr_sse42_functions_inter_prediction.c:848-945, adds in 32 bits, packs with saturation and clips: the same values) */
+void orc_weighted_average(const int16_t *src0, int s0, const int16_t *src1, int s1, int16_t *dst, int ds, int height, int width)
+{
+    const int shift = 14 + 1 - 8, offset = (1 << (shift - 1)) + 2 * 8192;
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++) dst[y * ds + x] = (int16_t)clampi((src0[y * s0 + x] + src1[y * s1 + x] + offset) >> shift, 0, 255);
+}

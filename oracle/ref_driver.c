@@ -652,3 +652,9 @@ double refdrv_intra_presearch(refdrv **drv, int n_threads, const uint8_t *luma, 
     clock_gettime(CLOCK_MONOTONIC, &t1);
     return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
+
+/* the table's weighted_average_motion (bi-prediction average) */
+void refdrv_weighted_average(refdrv *d, int16_t *src0, int s0, int16_t *src1, int s1, int16_t *dst, int ds, int height, int width)
+{
+    d->enc->funcs.weighted_average_motion(src0, s0, src1, s1, dst, ds, height, width, 8);
+}

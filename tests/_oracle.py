@@ -86,6 +86,7 @@ def oracle():
         L.orc_intra_predict.argtypes = [i16p, C.c_int, C.c_int, C.c_int, i16p, C.c_int]
         L.orc_intra_uses_filtered.argtypes = [C.c_int, C.c_int]
         L.orc_intra_mode_sads.argtypes = [i16p, C.c_int, i16p, C.c_int, C.POINTER(C.c_uint32)]
+        L.orc_weighted_average.argtypes = [i16p, C.c_int, i16p, C.c_int, i16p, C.c_int, C.c_int, C.c_int]
         L.tables = L.orc_tables_create()
         _oracle = L
     return _oracle
@@ -129,6 +130,7 @@ def ref():
         D.refdrv_encode_inter_tu.argtypes = [C.c_void_p, i16p, i16p] + [C.c_int] * 6 + [C.c_double, i16p, i16p,
                                                                                        C.POINTER(C.c_int)]
         D.refdrv_chroma_qp.argtypes = [C.c_void_p, C.c_int]
+        D.refdrv_weighted_average.argtypes = [C.c_void_p, i16p, C.c_int, i16p, C.c_int, i16p, C.c_int, C.c_int, C.c_int]
         D.refdrv_intra_predict.argtypes = [C.c_void_p, i16p, C.c_int, C.c_int, C.c_int, i16p]
         D.refdrv_adi_filter.argtypes = [C.c_void_p, i16p, i16p, C.c_int]
         D.refdrv_encode_lockstep.restype = C.c_long

@@ -148,13 +148,27 @@ def test_quant_inv_quant(ctx):
     assert n_sbh_changed > 20          # the sign-hiding branch really ran
 
 
+def test_weighted_average(ctx):
+    O = oracle()
+    L = hb.load_library()
+    rng = np.random.default_rng(18)
+    for it in range(60):
+        w = int(rng.choice([4, 8, 16, 32, 64])); h = int(rng.choice([4, 8, 16, 32, 64]))
+        a = aligned_i16(80 * 64); b = aligned_i16(72 * 64)
+        a[:] = rng.integers(-14312, 14248, a.size); b[:] = rng.integers(-8192, 8192, b.size)
+        d1 = np.full(96 * 64, 7, np.int16); d2 = np.full(96 * 64, 7, np.int16)
+        L.hb_weighted_average_motion(ptr(a), 80, ptr(b), 72, ptr(d1), 96, h, w, 8)
+        O.orc_weighted_average(ptr(a), 80, ptr(b), 72, ptr(d2), 96, h, w)
+        assert np.array_equal(d1, d2), (w, h)
+
+
 def test_function_table(ctx):
-    """hb_fill_low_level_funcs writes exactly the 9 members it implements (quant/inv_quant need the adapter)"""
+    """hb_fill_low_level_funcs writes exactly the 10 members it implements with table prototypes (quant/inv_quant and the intra predictors need the adapter)"""
     L = hb.load_library()
     t = hb.LowLevelFuncs()
     L.hb_fill_low_level_funcs(C.byref(t))
     filled = {n for n, _ in t._fields_ if getattr(t, n)}
-    assert filled == {"sad", "ssd16b", "predict", "reconst", "interpolate_luma_m_compensation",
+    assert filled == {"sad", "ssd16b", "predict", "reconst", "interpolate_luma_m_compensation", "weighted_average_motion",
                       "interpolate_chroma_m_compensation", "interpolate_luma_m_estimation", "transform", "itransform"}
     assert t.sad == C.cast(L.hb_sad, C.c_void_p).value
 

@@ -214,3 +214,19 @@ def test_intra_prediction_against_reference():
                 O.orc_intra_predict(ptr(src), n, mode, is_luma, ptr(p2), n)
                 assert np.array_equal(p1, p2), (n, mode, is_luma, it % 3)
     assert strong > 0          # the strong bilinear smoothing branch ran
+
+
+def test_weighted_average_against_reference():
+    """bi-prediction average of two 14-bit predictions (the table's weighted_average_motion), all block shapes, extreme inputs included"""
+    O = oracle(); _, D = ref()
+    h = refdrv()
+    rng = np.random.default_rng(105)
+    for it in range(200):
+        w = int(rng.choice([4, 8, 16, 32, 64])); hh = int(rng.choice([4, 8, 16, 32, 64]))
+        lo, hi = (-8192, 8192) if it % 3 else (-14312, 14248)          # the whole range a first filter stage can produce
+        a = aligned_i16(64 * 64); b = aligned_i16(64 * 64)
+        a[:] = rng.integers(lo, hi, a.size); b[:] = rng.integers(lo, hi, b.size)
+        d1 = aligned_i16(64 * 64); d2 = aligned_i16(64 * 64)
+        D.refdrv_weighted_average(h, ptr(a), 64, ptr(b), 64, ptr(d1), 64, hh, w)
+        O.orc_weighted_average(ptr(a), 64, ptr(b), 64, ptr(d2), 64, hh, w)
+        assert np.array_equal(d1.reshape(64, 64)[:hh, :w], d2.reshape(64, 64)[:hh, :w]), (w, hh, it)
