@@ -32,7 +32,7 @@ def _oracle_prepass_me(cur, ref, w, h, qp, avg_dist):
     return out
 
 
-@pytest.mark.parametrize("w,h,use_graph", [(192, 136, 0), (256, 128, 1)])
+@pytest.mark.parametrize("w,h,use_graph", [(192, 136, 0), (256, 128, 1), (200, 104, 1)])
 def test_prepass_matches_oracle(ctx, w, h, use_graph):
     qp, avg_dist = 32, 650.0
     cur, ref = clip_pair(w, h, n=2, noise=3.0, seed=3)
