@@ -151,6 +151,30 @@ def main():
         tqin += [orig.copy(), pred.copy()]; tqout += [c1[:n * n].copy(), d1[:n * n].copy()]
     g["tq_cases"], g["tq_in"], g["tq_out"] = np.array(tqcases, np.int64), np.concatenate(tqin), np.concatenate(tqout)
 
+    # ---- 8f item 1: reference-sample smoothing + the 35 intra predictors; bi-prediction average (table members)
+    ip_adi, ip_flt, ip_pred, ip_cases = [], [], [], []
+    for n in (4, 8, 16, 32):
+        for kind in range(2):
+            adi = aligned_i16(4 * n + 1 + 8)
+            if kind == 0:
+                adi[:4 * n + 1] = rng.integers(0, 256, 4 * n + 1)
+            else:                                                        # smooth: the strong filter at 32
+                adi[:4 * n + 1] = np.clip(np.linspace(rng.integers(20, 90), rng.integers(150, 240), 4 * n + 1) + rng.integers(-1, 2, 4 * n + 1), 0, 255)
+            flt = aligned_i16(4 * n + 1 + 8)
+            D.refdrv_adi_filter(h, ptr(adi), ptr(flt), n)
+            ip_adi.append(adi[:4 * n + 1].copy()); ip_flt.append(flt[:4 * n + 1].copy())
+            for mode in range(35):
+                for is_luma in ((1, 0) if mode in (1, 10, 26) else (1,)):
+                    pr = aligned_i16(n * n)
+                    D.refdrv_intra_predict(h, ptr(flt if (kind and is_luma) else adi), n, mode, is_luma, ptr(pr))
+                    ip_cases.append((n, kind, mode, is_luma)); ip_pred.append(pr.astype(np.uint8))
+    g["ip_adi"], g["ip_flt"], g["ip_pred"], g["ip_cases"] = np.concatenate(ip_adi), np.concatenate(ip_flt), np.concatenate(ip_pred), np.array(ip_cases, np.int32)
+    wa, wb = aligned_i16(64 * 64), aligned_i16(64 * 64)
+    wa[:] = rng.integers(-14312, 14249, wa.size); wb[:] = rng.integers(-8192, 8193, wb.size)
+    wd = aligned_i16(64 * 64)
+    D.refdrv_weighted_average(h, ptr(wa), 64, ptr(wb), 64, ptr(wd), 64, 64, 64)
+    g["wavg_a"], g["wavg_b"], g["wavg_out"] = wa.copy(), wb.copy(), wd.astype(np.uint8)
+
     out = os.path.join(HERE, "ref_vectors.npz")
     np.savez_compressed(out, **g)
     print("wrote", out, os.path.getsize(out), "bytes")

@@ -139,3 +139,30 @@ def test_inter_tq_chain():
         assert np.array_equal(de[:n2], G["tq_out"][oo:oo + n2]); oo += n2
         coded += to.sum > 0; zeroed += to.zeroed
     assert coded > 20 and zeroed > 5
+
+
+def test_intra_prediction_and_weighted_average():
+    """reference-sample smoothing, all 35 predictors (luma; the chroma variants of DC / pure horizontal / vertical) and the
+    bi-prediction average against the compiled reference's outputs"""
+    O = oracle()
+    ia = io = 0
+    for k in range(8):                                   # (size, kind) blocks in generation order
+        n = (4, 8, 16, 32)[k // 2]
+        m = 4 * n + 1
+        adi = aligned_i16(m); adi[:] = G["ip_adi"][ia:ia + m]
+        flt = aligned_i16(m)
+        O.orc_adi_filter(ptr(adi), ptr(flt), n, 1)
+        assert np.array_equal(flt, G["ip_flt"][ia:ia + m]), ("filter", n, k % 2)
+        ia += m
+        for (cn, kind, mode, is_luma) in G["ip_cases"]:
+            if cn != n or kind != k % 2:
+                continue
+            pr = aligned_i16(n * n)
+            O.orc_intra_predict(ptr(flt if (kind and is_luma) else adi), n, int(mode), int(is_luma), ptr(pr), n)
+            assert np.array_equal(pr.astype(np.uint8), G["ip_pred"][io:io + n * n]) and pr.min() >= 0 and pr.max() <= 255, (n, kind, mode, is_luma)
+            io += n * n
+    assert io == len(G["ip_pred"])
+    a = aligned_i16(64 * 64); b = aligned_i16(64 * 64); d = aligned_i16(64 * 64)
+    a[:] = G["wavg_a"]; b[:] = G["wavg_b"]
+    O.orc_weighted_average(ptr(a), 64, ptr(b), 64, ptr(d), 64, 64, 64)
+    assert np.array_equal(d.astype(np.uint8), G["wavg_out"]) and d.min() >= 0 and d.max() <= 255
