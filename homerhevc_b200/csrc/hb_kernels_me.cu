@@ -8,14 +8,19 @@
 // reference's sequential compare/rotate logic is then replayed on the four (or eight) results in registers --
 // including which probes it would have skipped, so even the probe count matches.
 //
-// Mapping: CTA = 256 threads; a PU is searched by G lanes (8x8, 16x16: one warp; 32x32: two warps; 64x64: the CTA),
-// split into four candidate slots of L = G/4 lanes.  The current block lives in registers as packed u8x4 words;
-// a candidate SAD is __vsadu4 over unaligned 4-sample reads of the resident reference plane (L1/L2 hits, funnel
-// shifted), reduced with redux.sync inside a slot and exchanged through shared memory.
-// Sub-pel: the (N+8)x(N+12) patch around the integer winner is staged in shared memory once, the four horizontal
-// 14-bit planes (fractions 0..3) are built from it with vector loads/stores, and every candidate is a vertical
-// sliding-window pass (one shared load per output sample, taps in registers) over a column strip per lane --
-// the same two-stage arithmetic as the reference's plane builders (:395, :442), sample for sample.
+// Mapping: CTA = 256 threads; a PU is searched by G lanes (8x8: 8 lanes, 16x16: 16 lanes -- four / two PUs share a warp and
+// run their data-dependent loops in lock step, so every warp primitive names the full warp; 32x32: two warps; 64x64: the CTA),
+// split into four candidate slots of L = G/4 lanes.  A lane keeps 8-sample pairs of the current block in registers; a
+// candidate SAD reads the resident reference plane as three aligned words per pair (one misalignment shift per candidate,
+// 32-bit offsets from one base) into VABSDIFF4.ACC on two chains, is summed inside the slot (redux / shuffle butterfly) and
+// exchanged by shuffles (G <= 32) or through shared memory.  In the pattern stages a lane derives and range-checks only its
+// own slot's position; whether the other slots were valid comes back with their cost.
+// Sub-pel: the (N+8)x(N+12) patch around the integer winner is staged in shared memory by row runs; the four horizontal
+// 14-bit planes (fractions 0..3) are dp4a products of u8 samples and s8 taps, stored PAIR-INTERLEAVED (one word = rows 2q,
+// 2q+1 of a column) so that every vertical filter is dp2a on one shared load per two taps.  Half-pel: a lane walks one plane
+// column and feeds each filtered sample to all candidates that share it; quarter-pel: four candidates per round; four clipped
+// samples are packed (I2IP) and compared in one VABSDIFF4.  Same two-stage arithmetic as the reference's plane builders
+// (:395, :442), sample for sample; the winner's luma prediction is written from the same planes.
 #include <cstring>
 #include "hb_shim.h"
 #include "hb_dev_common.cuh"

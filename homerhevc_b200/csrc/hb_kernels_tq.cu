@@ -1,11 +1,14 @@
 // hb_kernels_tq.cu -- fused inter T/Q chain (encode_inter_cu / encode_inter_cu_chroma, hmr_motion_inter.c:40/:133)
 // and the per-call transform / quant kernels built from the same warp routines.
 //
-// k_tq<N>: one warp = 32/N transform units, 4 warps per CTA, no block-level synchronisation at all.
-// Per unit: residual = cur - pred (u8 planes) -> 2-D DCT -> quant (+ sign hiding) -> if any level:
-// dequant -> inverse DCT -> SSD(resid, decoded resid), SSD(resid, 0), the reference's zero-out test in
-// IEEE double without contraction -> reconstruction (u8) + levels (int16) + {sum, ssd, ssd_zero, zeroed}.
-// HBM traffic per sample: 2 B read (cur, pred) + 1 B recon + 2 B levels; everything else stays in shared memory.
+// k_tq<N> (N = 8, 16, 32): one warp = 32/N transform units, 4 warps per CTA, no block-level synchronisation at all.  A lane
+// owns one row of its unit from the first load to the last store: residual = cur - pred (vector loads, kept as packed
+// words) -> first forward stage in registers -> second stage -> quant (+ sign hiding) -> if any level: first inverse stage with
+// the dequantisation folded into its column loads -> second inverse stage into registers -> the lane's part of SSD(resid,
+// decoded resid) and SSD(resid, 0), butterfly over the unit's lanes, the reference's zero-out test in IEEE double without
+// contraction -> reconstructed row (vector store), levels (int16) and {sum, ssd, ssd_zero, zeroed}.
+// k_tq4: 4x4 units, one THREAD per unit, everything in registers.  k_tq_intra<N>: the intra chain (DST for 4x4 luma).
+// HBM traffic per sample: 2 B read (cur, pred) + 1 B recon + 2 B levels; everything else stays on chip.
 #include "hb_shim.h"
 #include "hb_tq_core.cuh"
 
