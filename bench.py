@@ -139,6 +139,24 @@ def run_reference(args, w, h, rank, world):
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference",
                              "sample": f"{sample} frame(s) per step, reference functions via oracle/_ref, {cores} threads, CTUs dealt round-robin"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    # for context (not the metric): the WHOLE unmodified reference encoder -- mode decision, CABAC, in-loop filters included -- on
+    # the same kind of input, one engine, WPP off, fixed QP (the configuration whose output the parity tests pin)
+    try:
+        import ctypes as C
+        import numpy as np
+        from _oracle import ref
+        _, D = ref()
+        nf = 3
+        clip = synth.make_clip(w, h, nf, seed=5)
+        yuv = np.concatenate([np.concatenate([p.reshape(-1) for p in f]) for f in clip])
+        bs = np.zeros(16 << 20, np.uint8); enc_secs = C.c_double(0)
+        n = D.refdrv_encode_lockstep(w, h, nf, yuv.ctypes.data_as(C.POINTER(C.c_uint8)), QP, 1, 0, -1, bs.ctypes.data_as(C.POINTER(C.c_uint8)), bs.size,
+                                     None, None, None, C.byref(enc_secs))
+        if n > 0 and enc_secs.value > 0:
+            line["whole_encoder"] = {"value": nf / enc_secs.value, "unit": "frames/s", "frames": nf, "bytes": int(n),
+                                     "what": "unmodified reference encoder (homer_lib), IPP, 1 engine, WPP off, fixed QP, all stages"}
+    except Exception as e:
+        line["whole_encoder"] = {"value": None, "what": f"failed: {e}"}
     print(json.dumps(line))
 
 
