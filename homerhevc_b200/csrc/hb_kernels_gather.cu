@@ -86,6 +86,37 @@ __global__ void __launch_bounds__(256) k_gather(const hbd_gather_args a)
 
 }  // namespace
 
+// ---- compact wire format of the result tables: 12-byte records instead of 24 / 16 (hb_prepass_cfg.compact_tables)
+namespace {
+__global__ void __launch_bounds__(256) k_pack_tables(const hb_me_result *me, const hb_tu_result *tu, hb_me_result_c *me_c, hb_tu_result_c *tu_c, int n_me, int n_tu)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n_me) {
+        const hb_me_result r = me[i];
+        hb_me_result_c c;
+        c.mvx = static_cast<int16_t>(r.mv.x); c.mvy = static_cast<int16_t>(r.mv.y); c.sad = r.sad;
+        c.n_probes = static_cast<uint16_t>(min(r.n_probes, 65535u)); c.subx = static_cast<int8_t>(r.subpix.x); c.suby = static_cast<int8_t>(r.subpix.y);
+        me_c[i] = c;
+    } else if (i < n_me + n_tu) {
+        const hb_tu_result r = tu[i - n_me];
+        hb_tu_result_c c;
+        c.ssd = r.ssd; c.ssd_zero = r.ssd_zero; c.sum_zeroed = (static_cast<uint32_t>(r.sum) & 0x7fffffffu) | (r.zeroed ? 0x80000000u : 0u);
+        tu_c[i - n_me] = c;
+    }
+}
+}  // namespace
+
+extern "C" int hbk_pack_tables(const void *full, void *compact, int n_me, int n_tu, void *stream)
+{
+    const int n = n_me + n_tu;
+    if (n <= 0) return 0;
+    const hb_me_result *me = static_cast<const hb_me_result *>(full);
+    hb_me_result_c *me_c = static_cast<hb_me_result_c *>(compact);
+    k_pack_tables<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(me, reinterpret_cast<const hb_tu_result *>(me + n_me), me_c,
+                                                                                 reinterpret_cast<hb_tu_result_c *>(me_c + n_me), n_me, n_tu);
+    return static_cast<int>(cudaGetLastError());
+}
+
 extern "C" int hbk_gather(const hbd_gather_args *a, int n_ctus, void *stream)
 {
     if (n_ctus <= 0) return 0;

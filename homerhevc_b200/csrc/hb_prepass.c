@@ -45,6 +45,8 @@ struct hb_prepass {
     char *d_tables;                                 /* one block: ME results of every depth, then TU results of every (pass, comp) --
                                                      * exactly the layout hb_prepass_fetch_tables delivers, so the fetch is ONE copy */
     size_t tables_bytes;
+    char *d_tables_c;                               /* compact copy (cfg.compact_tables), packed right before each fetch */
+    int n_me_total, n_tu_total;
     hb_frame *pred[N_DEPTH];
     /* T/Q */
     pass_comp pc[N_PASS][3];
@@ -187,6 +189,12 @@ int hb_prepass_create(hb_ctx *ctx, int width, int height, const hb_prepass_cfg *
             else {
                 char *o = pp->d_tables;
                 pp->tables_bytes = total;
+                pp->n_me_total = (int)(me_bytes / sizeof(hb_me_result));
+                pp->n_tu_total = (int)((total - me_bytes) / sizeof(hb_tu_result));
+                if (cfg->compact_tables) {
+                    const int c2 = hbc_malloc((void **)&pp->d_tables_c, sizeof(hb_me_result_c) * (size_t)pp->n_me_total + sizeof(hb_tu_result_c) * (size_t)pp->n_tu_total + 16);
+                    if (c2) rc = hbi_cuda_fail(c2, "prepass: compact tables");
+                }
                 for (int d = 0; d < N_DEPTH; d++) { pp->d_me[d] = (hb_me_result *)o; o += sizeof(hb_me_result) * (size_t)pp->grid_w[d] * pp->grid_h[d]; }
                 for (int p = 0; p < N_PASS; p++) for (int c = 0; c < 3; c++) { pp->pc[p][c].d_res = (hb_tu_result *)o; o += sizeof(hb_tu_result) * (size_t)pp->pc[p][c].n_tus; }
             }
@@ -231,6 +239,7 @@ void hb_prepass_destroy(hb_prepass *pp)
         hb_frame_destroy(pp->recon[p]);
     }
     if (pp->d_tables) hbc_free(pp->d_tables);
+    if (pp->d_tables_c) hbc_free(pp->d_tables_c);
     if (pp->d_dyn) hbc_free(pp->d_dyn);
     if (pp->d_sel) hbc_free(pp->d_sel);
     if (pp->d_ctu_off) hbc_free(pp->d_ctu_off);
@@ -516,21 +525,26 @@ int hb_prepass_fetch_all(hb_prepass *pp, void *pinned_dst, size_t cap, size_t *b
  * and only then asks for what entropy coding and the in-loop filters need of that choice. */
 size_t hb_prepass_tables_bytes(const hb_prepass *pp)
 {
-    size_t n = 0;
     if (!pp) return 0;
-    for (int d = 0; d < N_DEPTH; d++) n += sizeof(hb_me_result) * (size_t)hb_prepass_num_pus(pp, d);
-    for (int p = 0; p < N_PASS; p++) for (int c = 0; c < 3; c++) n += sizeof(hb_tu_result) * (size_t)pp->pc[p][c].n_tus;
-    return n;
+    if (pp->cfg.compact_tables) return sizeof(hb_me_result_c) * (size_t)pp->n_me_total + sizeof(hb_tu_result_c) * (size_t)pp->n_tu_total;
+    return pp->tables_bytes;
 }
 
-/* ME tables d0..d3, then TU tables pass 0..4 x (Y,U,V), packed; dst should be pinned.  Asynchronous: hb_ctx_sync before reading. */
+/* ME tables d0..d3, then TU tables pass 0..4 x (Y,U,V), packed; dst should be pinned.  Asynchronous: hb_ctx_sync before reading.
+ * With cfg.compact_tables the same records in their 12-byte forms (one small packing kernel, then one copy). */
 int hb_prepass_fetch_tables(hb_prepass *pp, void *pinned_dst, size_t cap)
 {
     if (!pp || !pinned_dst) return hbi_fail(HB_ERR_ARG, "hb_prepass_fetch_tables: NULL argument");
     if (cap < hb_prepass_tables_bytes(pp)) return hbi_fail(HB_ERR_ARG, "hb_prepass_fetch_tables: buffer too small");
     hb_ctx *ctx = pp->ctx;
     hbc_set_device(ctx->device);
-    const int crc = hbc_d2h_async(pinned_dst, pp->d_tables, pp->tables_bytes, ctx->stream);
+    int crc;
+    if (pp->cfg.compact_tables) {
+        crc = hbk_pack_tables(pp->d_tables, pp->d_tables_c, pp->n_me_total, pp->n_tu_total, ctx->stream);
+        ctx->launches++;
+        if (!crc) crc = hbc_d2h_async(pinned_dst, pp->d_tables_c, hb_prepass_tables_bytes(pp), ctx->stream);
+    } else
+        crc = hbc_d2h_async(pinned_dst, pp->d_tables, pp->tables_bytes, ctx->stream);
     return crc ? hbi_cuda_fail(crc, "hb_prepass_fetch_tables") : HB_OK;
 }
 
@@ -544,10 +558,11 @@ int hb_prepass_select(const hb_prepass *pp, const void *tables, int lambda, uint
 {
     if (!pp || !tables || !sel || !ctu_off) return hbi_fail(HB_ERR_ARG, "hb_prepass_select: NULL argument");
     const int n_ctus = hb_prepass_num_ctus(pp);
-    const char *t = (const char *)tables;
-    for (int d = 0; d < N_DEPTH; d++) t += sizeof(hb_me_result) * (size_t)hb_prepass_num_pus(pp, d);
-    const hb_tu_result *res[N_PASS][3];
-    for (int p = 0; p < N_PASS; p++) for (int c = 0; c < 3; c++) { res[p][c] = (const hb_tu_result *)t; t += sizeof(hb_tu_result) * (size_t)pp->pc[p][c].n_tus; }
+    const int compact = pp->cfg.compact_tables != 0;
+    const char *t = (const char *)tables + (compact ? sizeof(hb_me_result_c) : sizeof(hb_me_result)) * (size_t)pp->n_me_total;
+    const size_t rec = compact ? sizeof(hb_tu_result_c) : sizeof(hb_tu_result);
+    const char *res[N_PASS][3];
+    for (int p = 0; p < N_PASS; p++) for (int c = 0; c < 3; c++) { res[p][c] = t; t += rec * (size_t)pp->pc[p][c].n_tus; }
     uint64_t *cost = (uint64_t *)calloc((size_t)n_ctus * 8, sizeof *cost);       /* [ctu][0..3 luma+chroma of pass p, 4 luma of pass 4] */
     int32_t *len = (int32_t *)calloc((size_t)n_ctus * 8, sizeof *len);            /* stream length of the same pieces */
     if (!cost || !len) { free(cost); free(len); return hbi_fail(HB_ERR_NOMEM, "hb_prepass_select: out of memory"); }
@@ -556,7 +571,8 @@ int hb_prepass_select(const hb_prepass *pp, const void *tables, int lambda, uint
             const pass_comp *pc = &pp->pc[p][c];
             const int slot = (p == 4) ? 4 : p, piece = (p == 3 && c > 0) ? 5 : slot;   /* chroma of pass 3 is shared by choices 3 and 4 */
             const int rec_len = 2 + pc->tu * pc->tu;
-            const hb_tu_result *r = res[p][c];
+            const hb_tu_result *rf = (const hb_tu_result *)res[p][c];
+            const hb_tu_result_c *rc = (const hb_tu_result_c *)res[p][c];
             const int32_t *ctu_of = pc->h_ctu;
             /* TUs arrive in raster order: runs of consecutive TUs share a CTU, so accumulate in registers and flush per run */
             int i = 0;
@@ -564,8 +580,10 @@ int hb_prepass_select(const hb_prepass *pp, const void *tables, int lambda, uint
                 const int ctu = ctu_of[i];
                 uint64_t acc = 0; int32_t l = 0;
                 for (; i < pc->n_tus && ctu_of[i] == ctu; i++) {
-                    acc += (uint64_t)r[i].ssd + (uint64_t)((int64_t)lambda * r[i].sum);
-                    l += r[i].sum > 0 ? rec_len : 0;
+                    const uint32_t ssd = compact ? rc[i].ssd : rf[i].ssd;
+                    const int32_t sum = compact ? (int32_t)(rc[i].sum_zeroed & 0x7fffffffu) : rf[i].sum;
+                    acc += (uint64_t)ssd + (uint64_t)((int64_t)lambda * sum);
+                    l += sum > 0 ? rec_len : 0;
                 }
                 cost[ctu * 8 + piece] += acc;
                 len[ctu * 8 + piece] += l;

@@ -154,6 +154,8 @@ typedef struct hbd_gather_args {
     int16_t *out_levels;
 } hbd_gather_args;
 int hbk_gather(const hbd_gather_args *a, int n_ctus, void *stream);
+/* full result tables (n_me hb_me_result, then n_tu hb_tu_result) -> compact records (hb_me_result_c, hb_tu_result_c) */
+int hbk_pack_tables(const void *full, void *compact, int n_me, int n_tu, void *stream);
 
 #ifdef __cplusplus
 }

@@ -324,6 +324,40 @@ def test_process_frame_and_its_two_halves(ctx):
     ctx2.close(); pp.close(); fc.close(); fr.close()
 
 
+def test_compact_tables(ctx):
+    """cfg.compact_tables: the 12-byte wire records carry exactly the values of the full tables, and the host flow built on them
+    (select -> gather) ends in the same decision and the same bytes"""
+    from homerhevc_b200.lib import ME_COMPACT_DT, TU_COMPACT_DT
+    w, h, qp, avg, lam = 320, 192, 30, 380.0, 45
+    cur, ref = clip_pair(w, h, n=3, noise=5.0, seed=77)
+    fc, fr = upload(ctx, cur, w, h), upload(ctx, ref, w, h)
+    outs = []
+    for compact in (0, 1):
+        pp = hb.Prepass(ctx, w, h, qp=qp, compact_tables=compact)
+        pp.run(fc, fr, avg)
+        tables = ctx.pinned(pp.tables_bytes()); pp.fetch_tables(tables); ctx.sync()
+        n_ctus = pp.num_ctus()
+        sel = np.zeros(n_ctus, np.uint8); off = np.zeros(n_ctus + 1, np.int32)
+        pp.select(tables, lam, sel, off)
+        out = ctx.pinned(w * h * 3 // 2 + 4 * w * h); n = pp.gather(sel, off, out); ctx.sync()
+        n_me = sum(pp.num_pus(d) for d in range(4)); n_tu = sum(pp.num_tus(p, c) for p in range(5) for c in range(3))
+        outs.append((bytes(tables), sel.copy(), off.copy(), bytes(out[:n]), n_me, n_tu))
+        pp.close()
+    (tf, self_, offf, outf, n_me, n_tu), (tc, selc, offc, outc, _, _) = outs
+    assert len(tf) == 24 * n_me + 16 * n_tu and len(tc) == 12 * (n_me + n_tu)
+    mf = np.frombuffer(tf[:24 * n_me], hb.lib.ME_DT if hasattr(hb.lib, "ME_DT") else np.dtype([("mvx", "<i4"), ("mvy", "<i4"), ("subx", "<i4"), ("suby", "<i4"), ("sad", "<u4"), ("n_probes", "<u4")]))
+    mc = np.frombuffer(tc[:12 * n_me], ME_COMPACT_DT)
+    for k in ("mvx", "mvy", "subx", "suby", "sad", "n_probes"):
+        assert np.array_equal(mf[k].astype(np.int64), mc[k].astype(np.int64)), k
+    uf = np.frombuffer(tf[24 * n_me:], np.dtype([("sum", "<i4"), ("ssd", "<u4"), ("ssd_zero", "<u4"), ("zeroed", "<i4")]))
+    uc = np.frombuffer(tc[12 * n_me:], TU_COMPACT_DT)
+    assert np.array_equal(uf["ssd"], uc["ssd"]) and np.array_equal(uf["ssd_zero"], uc["ssd_zero"])
+    assert np.array_equal(uf["sum"], (uc["sum_zeroed"] & 0x7fffffff).astype(np.int32)) and np.array_equal(uf["zeroed"] != 0, (uc["sum_zeroed"] >> 31) != 0)
+    assert (uf["zeroed"] != 0).any() and (uf["sum"] > 0).any()
+    assert np.array_equal(self_, selc) and np.array_equal(offf, offc) and outf == outc
+    fc.close(); fr.close()
+
+
 def test_bands_across_gpus_with_nccl_halo_exchange(ctx):
     """configs[3]: CTU-row bands on two GPUs, reference halos swapped over NCCL; needs >= 2 devices (skipped on one)"""
     import os
