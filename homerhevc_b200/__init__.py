@@ -8,10 +8,10 @@ names and argument order follow the reference's low-level function table (``low_
 There is no CPU fallback: importing works anywhere (so the build and symbol checks can run without a GPU), but every
 compute call needs the CUDA library and a visible device and raises otherwise.
 """
-from .lib import (HbError, Context, Frame, Prepass, MeJob, MeResult, McJob, TuJob, IntraTuJob, IntraJob, TuResult, TqParams, QuantEnv,
+from .lib import (HbError, Context, Frame, Prepass, MeJob, MeResult, McJob, McBiJob, TuJob, IntraTuJob, IntraJob, TuResult, TqParams, QuantEnv,
                   PrepassCfg, LowLevelFuncs, load_library, library_path, build_library, lowlevel,
                   ME_PEL, ME_HALF, ME_QUARTER, REG_DCT)
 
-__all__ = ["HbError", "Context", "Frame", "Prepass", "MeJob", "MeResult", "McJob", "TuJob", "IntraTuJob", "IntraJob", "TuResult", "TqParams",
+__all__ = ["HbError", "Context", "Frame", "Prepass", "MeJob", "MeResult", "McJob", "McBiJob", "TuJob", "IntraTuJob", "IntraJob", "TuResult", "TqParams",
            "QuantEnv", "PrepassCfg", "LowLevelFuncs", "load_library", "library_path", "build_library", "lowlevel",
            "ME_PEL", "ME_HALF", "ME_QUARTER", "REG_DCT"]

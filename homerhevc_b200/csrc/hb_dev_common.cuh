@@ -77,3 +77,18 @@ __device__ __forceinline__ int hb_chroma4_dyn(int f, int a0, int a1, int a2, int
     default: return 64 * a1;
     }
 }
+
+// ---- packed luma filter taps (shared by the search and the compensation kernels).  Horizontal: u8 samples x s8 taps through dp4a, taps k..k+3 of fraction f in one word.
+__host__ __device__ constexpr int luma_tap(int f, int k)
+{
+    constexpr int t[4][8] = { {0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1} };
+    return t[f][k];
+}
+__host__ __device__ constexpr uint32_t pack_s8(int b0, int b1, int b2, int b3)
+{
+    return static_cast<uint32_t>(b0 & 255) | (static_cast<uint32_t>(b1 & 255) << 8) | (static_cast<uint32_t>(b2 & 255) << 16) | (static_cast<uint32_t>(b3 & 255) << 24);
+}
+__host__ __device__ constexpr uint32_t htap4(int f, int half)
+{
+    return pack_s8(luma_tap(f, 4 * half), luma_tap(f, 4 * half + 1), luma_tap(f, 4 * half + 2), luma_tap(f, 4 * half + 3));
+}

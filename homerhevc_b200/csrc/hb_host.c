@@ -528,6 +528,62 @@ done:
     return rc;
 }
 
+/* bi-prediction (B slices): both lists' hmr_motion_compensation_luma/_chroma with is_bi_predict = 1 and the weighted_average_motion
+ * of the two 14-bit predictions (predict_inter, hmr_motion_inter.c:3047-3056), fused per block */
+int hb_mc_predict_bi(hb_ctx *ctx, const hb_frame *ref0, const hb_frame *ref1, hb_frame *pred, const hb_mc_bi_job *jobs, int n_jobs)
+{
+    static const int sizes[4] = { 64, 32, 16, 8 };
+    int rc = HB_OK, crc = 0;
+    void *d_pus, *h_pus, *d_mv, *h_mv;
+    if (!ctx || !ref0 || !ref1 || !pred || !jobs || n_jobs < 0) return hbi_fail(HB_ERR_ARG, "hb_mc_predict_bi: bad argument");
+    if (pred->w != ref0->w || pred->h != ref0->h || ref1->w != ref0->w || ref1->h != ref0->h) return hbi_fail(HB_ERR_ARG, "hb_mc_predict_bi: frame sizes differ");
+    if (n_jobs == 0) return HB_OK;
+    const int reach = HB_PAD_LUMA - 16;
+    for (int i = 0; i < n_jobs; i++) {
+        const hb_mc_bi_job *j = &jobs[i];
+        int bad = (j->size != 8 && j->size != 16 && j->size != 32 && j->size != 64) || j->x < 0 || j->y < 0 || ((j->x | j->y) & 7) ||
+                  j->x + j->size > ref0->w || j->y + j->size > ref0->h;
+        for (int l = 0; l < 2 && !bad; l++) {
+            const hb_mv mv = l ? j->mv1 : j->mv0;
+            const int x0 = j->x + (mv.x >> 2), y0 = j->y + (mv.y >> 2);
+            bad = x0 < -reach || y0 < -reach || x0 + j->size > ref0->w + reach || y0 + j->size > ref0->h + reach;
+        }
+        if (bad) return hbi_fail(HB_ERR_ARG, "hb_mc_predict_bi: job %d is invalid or points further than %d samples outside the picture", i, reach);
+    }
+    hbc_set_device(ctx->device);
+    pthread_mutex_lock(&ctx->lock);
+    if ((rc = hbi_scratch(ctx, 0, sizeof(hbd_mc_pu) * (size_t)n_jobs, &d_pus, &h_pus)) != HB_OK) goto done;
+    if ((rc = hbi_scratch(ctx, 1, sizeof(hb_me_result) * 2 * (size_t)n_jobs, &d_mv, &h_mv)) != HB_OK) goto done;
+    hbd_mc_pu *hp = (hbd_mc_pu *)h_pus;
+    hb_me_result *hm = (hb_me_result *)h_mv;                /* list 0 vectors, then list 1 vectors */
+    int n = 0, start_of[5];
+    memset(hm, 0, sizeof(hb_me_result) * 2 * (size_t)n_jobs);
+    for (int s = 0; s < 4; s++) {
+        start_of[s] = n;
+        for (int i = 0; i < n_jobs; i++) {
+            if (jobs[i].size != sizes[s]) continue;
+            hp[n].x = jobs[i].x; hp[n].y = jobs[i].y; hp[n].mv_idx = i;
+            hm[i].mv = jobs[i].mv0; hm[n_jobs + i].mv = jobs[i].mv1;
+            n++;
+        }
+    }
+    start_of[4] = n;
+    crc = hbc_h2d_async(d_pus, h_pus, sizeof(hbd_mc_pu) * (size_t)n_jobs, ctx->stream);
+    if (!crc) crc = hbc_h2d_async(d_mv, h_mv, sizeof(hb_me_result) * 2 * (size_t)n_jobs, ctx->stream);
+    for (int s = 0; s < 4 && !crc; s++) {
+        const int cnt = start_of[s + 1] - start_of[s];
+        if (!cnt) continue;
+        crc = hbk_mc_predict_bi(&ref0->d, &ref1->d, &pred->d, sizes[s], (const hbd_mc_pu *)d_pus + start_of[s], cnt,
+                                (const hb_me_result *)d_mv, (const hb_me_result *)d_mv + n_jobs, ctx->stream);
+        ctx->launches += 2;
+    }
+    if (!crc) crc = hbc_stream_sync(ctx->stream);
+done:
+    pthread_mutex_unlock(&ctx->lock);
+    if (crc) return hbi_cuda_fail(crc, "hb_mc_predict_bi");
+    return rc;
+}
+
 /* fill the launch-invariant part of a T/Q launch: tables and shifts of (component, size, qp) -- inter lists 3+comp */
 void hbi_tq_setup(hb_ctx *ctx, hbd_tq_args *a, int comp, int n, int qp, int is_islice, int sign_hiding)
 {

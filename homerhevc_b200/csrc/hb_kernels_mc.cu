@@ -114,13 +114,17 @@ __constant__ int8_t c_ctap[8][4] = { {0, 64, 0, 0}, {-2, 58, 10, -2}, {-4, 54, 1
 
 struct McCArgs {
     hbd_plane ref[2], pred[2];
+    hbd_plane ref1[2];     // second list (bi-prediction)
     const hbd_mc_pu *pus;
-    const hb_me_result *mvsrc;
+    const hb_me_result *mvsrc, *mvsrc1;
     int total;             // work items: n_pus * 2 planes * segments * strips
     int lg_strips, lg_segs;
 };
 
-template <int RS>
+// BI: the block is the average of two 14-bit predictions (weighted_average_motion, hmr_motion_inter.c:2903).  With X the sum
+// of vertical taps x horizontal sums, a list's 14-bit value is (X >> 6) - 8192 in all three branches of the reference
+// (is_last = 0), so the average (a + b + 64 + 2*8192) >> 7 becomes ((X0 >> 6) + (X1 >> 6) + 64) >> 7.
+template <int RS, bool BI>
 __global__ void __launch_bounds__(256) k_mc_chroma(const McCArgs a)
 {
     const int item = blockIdx.x * 256 + threadIdx.x;
@@ -132,33 +136,117 @@ __global__ void __launch_bounds__(256) k_mc_chroma(const McCArgs a)
     t >>= a.lg_segs;
     const int plane = t & 1;
     const hbd_mc_pu pu = a.pus[t >> 1];
-    const hb_mv mv = a.mvsrc[pu.mv_idx].mv;
     const int x = (pu.x >> 1) + strip * 4, y = (pu.y >> 1) + seg * RS;
-    const hbd_plane &rp = a.ref[plane], &pp = a.pred[plane];
-    const uint8_t *src = rp.org + (y + (mv.y >> 3) - 1) * rp.pitch + x + (mv.x >> 3) - 1;
-    const uint32_t sh = (static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src)) & 3u) * 8u;
-    const uint32_t *q = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(src) & ~uintptr_t(3));
-    const int qstep = rp.pitch >> 2;
-    const int8_t *th = c_ctap[mv.x & 7], *tv = c_ctap[mv.y & 7];
-    const uint32_t htap = hb_pack4(th[0] & 255, th[1] & 255, th[2] & 255, th[3] & 255);
-    const int v0 = tv[0], v1 = tv[1], v2 = tv[2], v3 = tv[3];
+    const hbd_plane &pp = a.pred[plane];
+    constexpr int NL = BI ? 2 : 1;
+    const uint32_t *q[NL];
+    uint32_t sh[NL], htap[NL];
+    int qstep[NL], tv[NL][4];
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+        const hb_mv mv = (l ? a.mvsrc1 : a.mvsrc)[pu.mv_idx].mv;
+        const hbd_plane &rp = l ? a.ref1[plane] : a.ref[plane];
+        const uint8_t *src = rp.org + (y + (mv.y >> 3) - 1) * rp.pitch + x + (mv.x >> 3) - 1;
+        sh[l] = (static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src)) & 3u) * 8u;
+        q[l] = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(src) & ~uintptr_t(3));
+        qstep[l] = rp.pitch >> 2;
+        const int8_t *th = c_ctap[mv.x & 7], *tvp = c_ctap[mv.y & 7];
+        htap[l] = hb_pack4(th[0] & 255, th[1] & 255, th[2] & 255, th[3] & 255);
+#pragma unroll
+        for (int k = 0; k < 4; k++) tv[l][k] = tvp[k];
+    }
     uint8_t *dst = pp.org + y * pp.pitch + x;
-    int h[4][4];                                            // rotating window of horizontal sums: [row & 3][column]
+    int h[NL][4][4];                                        // rotating windows of horizontal sums: [list][row & 3][column]
 #pragma unroll
     for (int r = 0; r < RS + 3; r++) {
-        const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
-        q += qstep;
-        const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);     // samples x-1 .. x+6
-        h[r & 3][0] = hb_dp4a_us(x0, htap, 0);
 #pragma unroll
-        for (int c = 1; c < 4; c++) h[r & 3][c] = hb_dp4a_us(__funnelshift_r(x0, x1, 8 * c), htap, 0);
+        for (int l = 0; l < NL; l++) {
+            const uint32_t w0 = __ldg(q[l]), w1 = __ldg(q[l] + 1), w2 = __ldg(q[l] + 2);
+            q[l] += qstep[l];
+            const uint32_t x0 = __funnelshift_r(w0, w1, sh[l]), x1 = __funnelshift_r(w1, w2, sh[l]);     // samples x-1 .. x+6
+            h[l][r & 3][0] = hb_dp4a_us(x0, htap[l], 0);
+#pragma unroll
+            for (int c = 1; c < 4; c++) h[l][r & 3][c] = hb_dp4a_us(__funnelshift_r(x0, x1, 8 * c), htap[l], 0);
+        }
         if (r >= 3) {
             int o[4];
 #pragma unroll
-            for (int c = 0; c < 4; c++)
-                o[c] = (v0 * h[(r - 3) & 3][c] + v1 * h[(r - 2) & 3][c] + v2 * h[(r - 1) & 3][c] + v3 * h[r & 3][c] + 2048) >> 12;
+            for (int c = 0; c < 4; c++) {
+                int s[NL];
+#pragma unroll
+                for (int l = 0; l < NL; l++)
+                    s[l] = tv[l][0] * h[l][(r - 3) & 3][c] + tv[l][1] * h[l][(r - 2) & 3][c] + tv[l][2] * h[l][(r - 1) & 3][c] + tv[l][3] * h[l][r & 3][c];
+                if constexpr (BI) o[c] = ((s[0] >> 6) + (s[NL - 1] >> 6) + 64) >> 7;
+                else o[c] = (s[0] + 2048) >> 12;
+            }
             *reinterpret_cast<uint32_t *>(dst) = hb_pack_sat_u8x4(o[0], o[1], o[2], o[3]);
             dst += pp.pitch;
+        }
+    }
+}
+
+// ---- luma, bi-prediction (hmr_motion_compensation_luma with is_bi_predict = 1 for both lists + weighted_average_motion):
+// the same thread-per-strip form with the 8-tap filters -- two dp4a per horizontal sum, an 8-row rotating window per list.
+__constant__ uint32_t c_ltap4[4][2] = { { htap4(0, 0), htap4(0, 1) }, { htap4(1, 0), htap4(1, 1) }, { htap4(2, 0), htap4(2, 1) }, { htap4(3, 0), htap4(3, 1) } };
+__constant__ int8_t c_ltap[4][8] = { {0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1} };
+
+struct McLArgs {
+    hbd_plane ref0, ref1, pred;
+    const hbd_mc_pu *pus;
+    const hb_me_result *mvsrc0, *mvsrc1;
+    int total, lg_strips, lg_segs;
+};
+
+template <int RS>
+__global__ void __launch_bounds__(128) k_mc_luma_bi(const McLArgs a)
+{
+    const int item = blockIdx.x * 128 + threadIdx.x;
+    if (item >= a.total) return;
+    const int strip = item & ((1 << a.lg_strips) - 1);
+    int t = item >> a.lg_strips;
+    const int seg = t & ((1 << a.lg_segs) - 1);
+    const hbd_mc_pu pu = a.pus[t >> a.lg_segs];
+    const int x = pu.x + strip * 4, y = pu.y + seg * RS;
+    const uint32_t *q[2];
+    uint32_t sh[2], tlo[2], thi[2];
+    int qstep[2], tv[2][8];
+#pragma unroll
+    for (int l = 0; l < 2; l++) {
+        const hb_mv mv = (l ? a.mvsrc1 : a.mvsrc0)[pu.mv_idx].mv;
+        const hbd_plane &rp = l ? a.ref1 : a.ref0;
+        const uint8_t *src = rp.org + (y + (mv.y >> 2) - 3) * rp.pitch + x + (mv.x >> 2) - 3;
+        sh[l] = (static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src)) & 3u) * 8u;
+        q[l] = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(src) & ~uintptr_t(3));
+        qstep[l] = rp.pitch >> 2;
+        tlo[l] = c_ltap4[mv.x & 3][0]; thi[l] = c_ltap4[mv.x & 3][1];
+#pragma unroll
+        for (int k = 0; k < 8; k++) tv[l][k] = c_ltap[mv.y & 3][k];
+    }
+    uint8_t *dst = a.pred.org + y * a.pred.pitch + x;
+    int h[2][8][4];                                         // rotating windows: [list][row & 7][column]
+#pragma unroll
+    for (int r = 0; r < RS + 7; r++) {
+#pragma unroll
+        for (int l = 0; l < 2; l++) {
+            const uint32_t w0 = __ldg(q[l]), w1 = __ldg(q[l] + 1), w2 = __ldg(q[l] + 2), w3 = __ldg(q[l] + 3);
+            q[l] += qstep[l];
+            const uint32_t x0 = __funnelshift_r(w0, w1, sh[l]), x1 = __funnelshift_r(w1, w2, sh[l]), x2 = __funnelshift_r(w2, w3, sh[l]);   // samples x-3 .. x+8
+            h[l][r & 7][0] = hb_dp4a_us(x1, thi[l], hb_dp4a_us(x0, tlo[l], 0));
+#pragma unroll
+            for (int c = 1; c < 4; c++)
+                h[l][r & 7][c] = hb_dp4a_us(__funnelshift_r(x1, x2, 8 * c), thi[l], hb_dp4a_us(__funnelshift_r(x0, x1, 8 * c), tlo[l], 0));
+        }
+        if (r >= 7) {
+            int o[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                int s0 = 0, s1 = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) { s0 += tv[0][k] * h[0][(r - 7 + k) & 7][c]; s1 += tv[1][k] * h[1][(r - 7 + k) & 7][c]; }
+                o[c] = ((s0 >> 6) + (s1 >> 6) + 64) >> 7;
+            }
+            *reinterpret_cast<uint32_t *>(dst) = hb_pack_sat_u8x4(o[0], o[1], o[2], o[3]);
+            dst += a.pred.pitch;
         }
     }
 }
@@ -246,8 +334,40 @@ extern "C" int hbk_mc_predict(const hbd_frame *ref, const hbd_frame *pred, int s
         c.lg_segs = 0; while ((rs << c.lg_segs) < cs) c.lg_segs++;
         c.total = n_pus * 2 << (c.lg_strips + c.lg_segs);
         const int grid = (c.total + 255) / 256;
-        if (rs == 4) k_mc_chroma<4><<<grid, 256, 0, s>>>(c);
-        else k_mc_chroma<8><<<grid, 256, 0, s>>>(c);
+        c.mvsrc1 = nullptr;
+        if (rs == 4) k_mc_chroma<4, false><<<grid, 256, 0, s>>>(c);
+        else k_mc_chroma<8, false><<<grid, 256, 0, s>>>(c);
+    }
+    return static_cast<int>(cudaGetLastError());
+}
+
+// bi-prediction: pred = average of the 14-bit predictions from (ref0, mvsrc0) and (ref1, mvsrc1), luma and chroma
+extern "C" int hbk_mc_predict_bi(const hbd_frame *ref0, const hbd_frame *ref1, const hbd_frame *pred, int size, const hbd_mc_pu *pus, int n_pus,
+                                 const hb_me_result *mvsrc0, const hb_me_result *mvsrc1, void *stream)
+{
+    if (n_pus <= 0) return 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (size != 8 && size != 16 && size != 32 && size != 64) return static_cast<int>(cudaErrorInvalidValue);
+    {
+        McLArgs l;
+        const int rs = 8;
+        l.ref0 = ref0->p[0]; l.ref1 = ref1->p[0]; l.pred = pred->p[0]; l.pus = pus; l.mvsrc0 = mvsrc0; l.mvsrc1 = mvsrc1;
+        l.lg_strips = 0; while ((4 << l.lg_strips) < size) l.lg_strips++;
+        l.lg_segs = 0; while ((rs << l.lg_segs) < size) l.lg_segs++;
+        l.total = n_pus << (l.lg_strips + l.lg_segs);
+        k_mc_luma_bi<8><<<(l.total + 127) / 128, 128, 0, s>>>(l);
+    }
+    {
+        McCArgs c;
+        const int cs = size / 2, rs = cs < 8 ? 4 : 8;
+        c.ref[0] = ref0->p[1]; c.ref[1] = ref0->p[2]; c.ref1[0] = ref1->p[1]; c.ref1[1] = ref1->p[2]; c.pred[0] = pred->p[1]; c.pred[1] = pred->p[2];
+        c.pus = pus; c.mvsrc = mvsrc0; c.mvsrc1 = mvsrc1;
+        c.lg_strips = 0; while ((4 << c.lg_strips) < cs) c.lg_strips++;
+        c.lg_segs = 0; while ((rs << c.lg_segs) < cs) c.lg_segs++;
+        c.total = n_pus * 2 << (c.lg_strips + c.lg_segs);
+        const int grid = (c.total + 255) / 256;
+        if (rs == 4) k_mc_chroma<4, true><<<grid, 256, 0, s>>>(c);
+        else k_mc_chroma<8, true><<<grid, 256, 0, s>>>(c);
     }
     return static_cast<int>(cudaGetLastError());
 }

@@ -67,20 +67,6 @@ template <int N> struct MeCfg {
     static constexpr int SMEM_TOTAL = PUS * SMEM_PER_PU;
 };
 
-// ---- packed filter taps.  Horizontal: u8 samples x s8 taps through dp4a, taps k..k+3 of fraction f in one word.
-__host__ __device__ constexpr int luma_tap(int f, int k)
-{
-    constexpr int t[4][8] = { {0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1} };
-    return t[f][k];
-}
-__host__ __device__ constexpr uint32_t pack_s8(int b0, int b1, int b2, int b3)
-{
-    return static_cast<uint32_t>(b0 & 255) | (static_cast<uint32_t>(b1 & 255) << 8) | (static_cast<uint32_t>(b2 & 255) << 16) | (static_cast<uint32_t>(b3 & 255) << 24);
-}
-__host__ __device__ constexpr uint32_t htap4(int f, int half)
-{
-    return pack_s8(luma_tap(f, 4 * half), luma_tap(f, 4 * half + 1), luma_tap(f, 4 * half + 2), luma_tap(f, 4 * half + 3));
-}
 // Vertical: the planes hold two rows per word, so an 8-tap column sum over rows rho0..rho0+7 is four dp2a when rho0 is even
 // (tap pairs E_i = (t2i, t2i+1)) and five when it is odd (O_i = (t(2i-1), t2i), with t(-1) = t8 = 0).  A lane produces TWO
 // consecutive output rows from the same five words W[m..m+4]: for par = 0 (first tap row even) these are E | O, for par = 1

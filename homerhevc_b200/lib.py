@@ -37,6 +37,10 @@ class McJob(C.Structure):
     _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("size", C.c_int32), ("mv", Mv)]
 
 
+class McBiJob(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("size", C.c_int32), ("mv0", Mv), ("mv1", Mv)]
+
+
 class TuJob(C.Structure):
     _fields_ = [("comp", C.c_int32), ("x", C.c_int32), ("y", C.c_int32), ("size", C.c_int32), ("qp", C.c_int32)]
 
@@ -162,6 +166,7 @@ def load_library():
     L.hb_me_search.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(MeJob), C.c_int, C.POINTER(MeResult), C.c_int,
                                C.c_double, C.c_int, C.POINTER(MeResult)]
     L.hb_mc_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(McJob), C.c_int]
+    L.hb_mc_predict_bi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(McBiJob), C.c_int]
     L.hb_tq_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TuJob), C.c_int,
                                C.POINTER(TqParams), i16p, C.POINTER(TuResult)]
     L.hb_tq_encode_intra.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(IntraTuJob), C.c_int, C.c_int, C.c_int, C.c_double,
@@ -317,6 +322,11 @@ class Context:
         n = len(jobs)
         arr = (McJob * n)(*jobs)
         _check(self.L.hb_mc_predict(self.h, ref.h, pred.h, arr, n), "hb_mc_predict")
+
+    def mc_predict_bi(self, ref0, ref1, pred, jobs):
+        n = len(jobs)
+        arr = (McBiJob * n)(*jobs)
+        _check(self.L.hb_mc_predict_bi(self.h, ref0.h, ref1.h, pred.h, arr, n), "hb_mc_predict_bi")
 
     def tq_encode(self, cur, pred, recon, jobs, params):
         n = len(jobs)

@@ -174,6 +174,9 @@ int hb_me_search(hb_ctx *ctx, const hb_frame *cur, const hb_frame *ref, const hb
 /* one hmr_motion_compensation_luma + two _chroma calls (uni-prediction) */
 typedef struct hb_mc_job { int32_t x, y, size; hb_mv mv; } hb_mc_job;     /* size: luma 8..64 (chroma size/2) */
 int hb_mc_predict(hb_ctx *ctx, const hb_frame *ref, hb_frame *pred, const hb_mc_job *jobs, int n_jobs);
+/* bi-prediction (B slices): both lists with is_bi_predict = 1 (14-bit predictions) + weighted_average_motion, hmr_motion_inter.c:3047-3056 */
+typedef struct hb_mc_bi_job { int32_t x, y, size; hb_mv mv0, mv1; } hb_mc_bi_job;     /* mv0 into ref0 (list 0), mv1 into ref1 (list 1) */
+int hb_mc_predict_bi(hb_ctx *ctx, const hb_frame *ref0, const hb_frame *ref1, hb_frame *pred, const hb_mc_bi_job *jobs, int n_jobs);
 
 /* one encode_inter_cu (comp 0) or encode_inter_cu_chroma (comp 1,2) call: T -> Q -> [IQ -> IT -> SSD -> zero-out] -> recon */
 typedef struct hb_tu_job { int32_t comp; int32_t x, y; int32_t size; int32_t qp; } hb_tu_job; /* x,y,size in samples of that plane; qp already chroma-mapped */

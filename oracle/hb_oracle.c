@@ -636,34 +636,44 @@ refine:                                                              /* :1601-16
 /* ------------------------------------------------------------------------------------------
  * Motion compensation (uni-prediction).  hmr_motion_inter.c:1779 and :1860.
  * ------------------------------------------------------------------------------------------ */
-void orc_mc_luma(const int16_t *ref, int ref_stride, int16_t *pred, int pred_stride, int size, orc_mv mv)
+/* is_bi != 0: the 14-bit prediction of one list of a bi-predicted block (is_last = !is_bi_predict, :1797-1812), to be
+ * averaged by orc_weighted_average */
+void orc_mc_luma_ex(const int16_t *ref, int ref_stride, int16_t *pred, int pred_stride, int size, orc_mv mv, int is_bi)
 {
     const int fx = mv.x & 3, fy = mv.y & 3;
     const int16_t *src = ref + (mv.y >> 2) * ref_stride + (mv.x >> 2);
     if (fx == 0) {
-        orc_interpolate_luma(src, ref_stride, pred, pred_stride, fy, size, size, 1, 1, 1);
+        orc_interpolate_luma(src, ref_stride, pred, pred_stride, fy, size, size, 1, 1, !is_bi);
     } else if (fy == 0) {
-        orc_interpolate_luma(src, ref_stride, pred, pred_stride, fx, size, size, 0, 1, 1);
+        orc_interpolate_luma(src, ref_stride, pred, pred_stride, fx, size, size, 0, 1, !is_bi);
     } else {
         int16_t tmp[PL_STRIDE * PL_ROWS];
         orc_interpolate_luma(src - 3 * ref_stride, ref_stride, tmp, PL_STRIDE, fx, size, size + 7, 0, 1, 0);
-        orc_interpolate_luma(tmp + 3 * PL_STRIDE, PL_STRIDE, pred, pred_stride, fy, size, size, 1, 0, 1);
+        orc_interpolate_luma(tmp + 3 * PL_STRIDE, PL_STRIDE, pred, pred_stride, fy, size, size, 1, 0, !is_bi);
     }
 }
+void orc_mc_luma(const int16_t *ref, int ref_stride, int16_t *pred, int pred_stride, int size, orc_mv mv)
+{
+    orc_mc_luma_ex(ref, ref_stride, pred, pred_stride, size, mv, 0);
+}
 
-void orc_mc_chroma(const int16_t *ref, int ref_stride, int16_t *pred, int pred_stride, int size, orc_mv mv)
+void orc_mc_chroma_ex(const int16_t *ref, int ref_stride, int16_t *pred, int pred_stride, int size, orc_mv mv, int is_bi)
 {
     const int fx = mv.x & 7, fy = mv.y & 7;
     const int16_t *src = ref + (mv.y >> 3) * ref_stride + (mv.x >> 3);
     if (fx == 0) {
-        orc_interpolate_chroma(src, ref_stride, pred, pred_stride, fy, size, size, 1, 1, 1);
+        orc_interpolate_chroma(src, ref_stride, pred, pred_stride, fy, size, size, 1, 1, !is_bi);
     } else if (fy == 0) {
-        orc_interpolate_chroma(src, ref_stride, pred, pred_stride, fx, size, size, 0, 1, 1);
+        orc_interpolate_chroma(src, ref_stride, pred, pred_stride, fx, size, size, 0, 1, !is_bi);
     } else {
         int16_t tmp[PL_STRIDE * PL_ROWS];
         orc_interpolate_chroma(src - ref_stride, ref_stride, tmp, PL_STRIDE, fx, size, size + 4 + 1, 0, 1, 0);
-        orc_interpolate_chroma(tmp + PL_STRIDE, PL_STRIDE, pred, pred_stride, fy, size, size, 1, 0, 1);
+        orc_interpolate_chroma(tmp + PL_STRIDE, PL_STRIDE, pred, pred_stride, fy, size, size, 1, 0, !is_bi);
     }
+}
+void orc_mc_chroma(const int16_t *ref, int ref_stride, int16_t *pred, int pred_stride, int size, orc_mv mv)
+{
+    orc_mc_chroma_ex(ref, ref_stride, pred, pred_stride, size, mv, 0);
 }
 
 /* ------------------------------------------------------------------------------------------

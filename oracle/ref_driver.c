@@ -658,3 +658,21 @@ void refdrv_weighted_average(refdrv *d, int16_t *src0, int s0, int16_t *src1, in
 {
     d->enc->funcs.weighted_average_motion(src0, s0, src1, s1, dst, ds, height, width, 8);
 }
+
+/* one list of a bi-predicted block: the reference's motion compensation with is_bi_predict = 1 (14-bit output) */
+void refdrv_mc_luma_bi(refdrv *d, int16_t *ref, int ref_stride, int16_t *pred, int pred_stride, int size, int mvx, int mvy)
+{
+    motion_vector_t mv = { mvx, mvy };
+    cu_partition_info_t cu;
+    int shift = 0;
+    memset(&cu, 0, sizeof cu);
+    while ((1 << shift) < size) shift++;
+    hmr_motion_compensation_luma(d->et, &cu, ref, ref_stride, pred, pred_stride, size, size, shift, &mv, 1);
+}
+void refdrv_mc_chroma_bi(refdrv *d, int16_t *ref, int ref_stride, int16_t *pred, int pred_stride, int size, int mvx, int mvy)
+{
+    motion_vector_t mv = { mvx, mvy };
+    int shift = 0;
+    while ((1 << shift) < size) shift++;
+    hmr_motion_compensation_chroma(d->et, ref, ref_stride, pred, pred_stride, size, shift, &mv, 1);
+}

@@ -70,6 +70,17 @@ def oracle_mc(ref, comp, x, y, n, mvx, mvy):
     return out.astype(np.uint8)
 
 
+def oracle_mc_bi(ref0, ref1, comp, x, y, n, mv0, mv1):
+    """bi-prediction: the 14-bit predictions of the two lists, averaged (hmr_motion_inter.c:3047-3056)"""
+    O = oracle()
+    a = np.zeros((n, n), np.int16); b = np.zeros((n, n), np.int16); out = np.zeros((n, n), np.int16)
+    f = O.orc_mc_luma_ex if comp == 0 else O.orc_mc_chroma_ex
+    p, s = ref0.ptr(comp, x, y); f(p, s, ptr(a.reshape(-1)), n, n, OrcMv(*mv0), 1)
+    p, s = ref1.ptr(comp, x, y); f(p, s, ptr(b.reshape(-1)), n, n, OrcMv(*mv1), 1)
+    O.orc_weighted_average(ptr(a.reshape(-1)), n, ptr(b.reshape(-1)), n, ptr(out.reshape(-1)), n, n, n)
+    return out.astype(np.uint8)
+
+
 def oracle_tu(cur_block, pred_block, n, comp, qp_eff, isl, sh, avg_dist, weight):
     O = oracle()
     o = np.ascontiguousarray(cur_block.astype(np.int16)).reshape(-1)

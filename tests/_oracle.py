@@ -77,6 +77,8 @@ def oracle():
         L.orc_motion_estimation.argtypes = [C.POINTER(OrcMeIn), C.POINTER(OrcMeOut)]
         L.orc_mc_luma.argtypes = [i16p, C.c_int, i16p, C.c_int, C.c_int, OrcMv]
         L.orc_mc_chroma.argtypes = [i16p, C.c_int, i16p, C.c_int, C.c_int, OrcMv]
+        L.orc_mc_luma_ex.argtypes = [i16p, C.c_int, i16p, C.c_int, C.c_int, OrcMv, C.c_int]
+        L.orc_mc_chroma_ex.argtypes = [i16p, C.c_int, i16p, C.c_int, C.c_int, OrcMv, C.c_int]
         L.orc_encode_inter_tu.argtypes = [C.c_void_p, i16p, C.c_int, i16p, C.c_int, i16p, i16p, C.c_int,
                                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                           C.POINTER(OrcTuOut)]
@@ -127,6 +129,8 @@ def ref():
             C.c_int, i32p, C.c_int, i32p, C.c_int, C.c_double, C.c_uint, i32p]
         D.refdrv_mc_luma.argtypes = [C.c_void_p, i16p, C.c_int, i16p, C.c_int, C.c_int, C.c_int, C.c_int]
         D.refdrv_mc_chroma.argtypes = [C.c_void_p, i16p, C.c_int, i16p, C.c_int, C.c_int, C.c_int, C.c_int]
+        D.refdrv_mc_luma_bi.argtypes = [C.c_void_p, i16p, C.c_int, i16p, C.c_int, C.c_int, C.c_int, C.c_int]
+        D.refdrv_mc_chroma_bi.argtypes = [C.c_void_p, i16p, C.c_int, i16p, C.c_int, C.c_int, C.c_int, C.c_int]
         D.refdrv_encode_inter_tu.argtypes = [C.c_void_p, i16p, i16p] + [C.c_int] * 6 + [C.c_double, i16p, i16p,
                                                                                        C.POINTER(C.c_int)]
         D.refdrv_chroma_qp.argtypes = [C.c_void_p, C.c_int]

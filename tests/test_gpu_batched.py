@@ -181,3 +181,34 @@ def test_tq_encode_intra(ctx, qp, isl, sh):
         coded += r.sum > 0
     assert coded > 5
     fc.close(); fp.close(); rec.close()
+
+
+def test_mc_predict_bi(ctx):
+    """bi-prediction: both lists' 14-bit predictions averaged on the GPU == oracle MC (is_bi) x 2 + weighted average"""
+    from _frames import oracle_mc_bi
+    from homerhevc_b200.lib import Mv
+    rng = np.random.default_rng(9)
+    _, ref0 = clip_pair(W, H, n=2, noise=2.0, seed=5)
+    _, ref1 = clip_pair(W, H, n=5, noise=4.0, seed=6)
+    f0, f1 = upload(ctx, ref0, W, H), upload(ctx, ref1, W, H)
+    pred = hb.Frame(ctx, W, H)
+    jobs, meta = [], []
+    for cy in range(0, H - 63, 64):
+        for cx in range(0, W - 63, 64):
+            size = int(rng.choice([64, 32, 16, 8]))
+            for oy in range(0, 64, size):
+                for ox in range(0, 64, size):
+                    mv0 = [int(v) for v in rng.integers(-70, 71, 2)]; mv1 = [int(v) for v in rng.integers(-70, 71, 2)]
+                    if rng.random() < 0.2:
+                        mv0[0] &= ~3; mv1[1] &= ~3
+                    if rng.random() < 0.1:
+                        mv0 = [mv0[0] & ~7, mv0[1] & ~7]
+                    jobs.append(hb.McBiJob(cx + ox, cy + oy, size, Mv(*mv0), Mv(*mv1))); meta.append((cx + ox, cy + oy, size, tuple(mv0), tuple(mv1)))
+    ctx.mc_predict_bi(f0, f1, pred, jobs)
+    py, pu, pv = pred.download()
+    for (x, y, size, mv0, mv1) in meta:
+        assert np.array_equal(py[y:y + size, x:x + size], oracle_mc_bi(ref0, ref1, 0, x, y, size, mv0, mv1)), ("luma", x, y, size, mv0, mv1)
+        c = size // 2
+        assert np.array_equal(pu[y // 2:y // 2 + c, x // 2:x // 2 + c], oracle_mc_bi(ref0, ref1, 1, x // 2, y // 2, c, mv0, mv1)), ("U", x, y, size, mv0, mv1)
+        assert np.array_equal(pv[y // 2:y // 2 + c, x // 2:x // 2 + c], oracle_mc_bi(ref0, ref1, 2, x // 2, y // 2, c, mv0, mv1)), ("V", x, y, size, mv0, mv1)
+    f0.close(); f1.close(); pred.close()

@@ -230,3 +230,27 @@ def test_weighted_average_against_reference():
         D.refdrv_weighted_average(h, ptr(a), 64, ptr(b), 64, ptr(d1), 64, hh, w)
         O.orc_weighted_average(ptr(a), 64, ptr(b), 64, ptr(d2), 64, hh, w)
         assert np.array_equal(d1.reshape(64, 64)[:hh, :w], d2.reshape(64, 64)[:hh, :w]), (w, hh, it)
+
+
+def test_bi_prediction_mc_against_reference():
+    """motion compensation with is_bi_predict = 1 (14-bit output of one list), luma and chroma, all fraction combinations"""
+    from _oracle import OrcMv, make_frame_pair
+    O = oracle(); _, D = ref()
+    h = refdrv()
+    rng = np.random.default_rng(106)
+    plane = aligned_i16(200 * 200); plane[:] = rng.integers(0, 256, plane.size)
+    for it in range(300):
+        chroma = it % 2
+        n = int(rng.choice([4, 8, 16, 32] if chroma else [8, 16, 32, 64]))
+        x, y = int(rng.integers(70, 110 - 0)), int(rng.integers(70, 110))
+        lim = 7 if chroma else 3
+        mvx, mvy = int(rng.integers(-40, 41)), int(rng.integers(-40, 41))
+        if it % 7 == 0: mvx &= ~lim
+        if it % 5 == 0: mvy &= ~lim
+        p1 = aligned_i16(64 * 64); p2 = aligned_i16(64 * 64)
+        if x + n + 30 > 200 or y + n + 30 > 200:
+            continue
+        (D.refdrv_mc_chroma_bi if chroma else D.refdrv_mc_luma_bi)(h, ptr(plane, y * 200 + x), 200, ptr(p1), 64, n, mvx, mvy)
+        (O.orc_mc_chroma_ex if chroma else O.orc_mc_luma_ex)(ptr(plane, y * 200 + x), 200, ptr(p2), 64, n, OrcMv(mvx, mvy), 1)
+        assert np.array_equal(p1.reshape(64, 64)[:n, :n], p2.reshape(64, 64)[:n, :n]), (chroma, n, mvx, mvy)
+        assert p2.reshape(64, 64)[:n, :n].min() < 0 or p2.reshape(64, 64)[:n, :n].max() > 255      # 14-bit values, not samples
