@@ -1,112 +1,16 @@
 // hb_kernels_mc.cu -- motion compensation (hmr_motion_compensation_luma / _chroma, hmr_motion_inter.c:1779/:1860,
-// uni-prediction) on resident u8 planes, plus frame maintenance (border replication, int16 -> u8 narrowing).
+// uni- and bi-prediction) on resident u8 planes, plus frame maintenance (ingest, border replication, int16 -> u8 narrowing).
 //
-// k_mc<T> (luma): one warp predicts one T x T tile (T = 16, or 8 for 8x8 PUs).  The (T+7)x(T+8) reference patch is staged
-// in the warp's shared memory; the horizontal pass writes 14-bit intermediates (value - 8192) next to it and the vertical
-// pass finishes -- or a single pass when one fraction is 0, exactly the three branches of the reference.
-// k_mc_chroma<RS>: one THREAD predicts a 4-wide, RS-tall strip of one chroma plane entirely in registers: the 4-tap
-// horizontal filter of four neighbours is four dp4a on funnel-shifted words of the resident reference, the vertical filter
-// runs over a rotating 4-row window, four clipped samples leave as one 32-bit store.  One arithmetic path serves the three
+// k_mc_chroma<RS, BI> / k_mc_luma<RS, BI>: one THREAD predicts a 4-wide, RS-tall strip of a plane entirely in registers: the 4-tap
+// (luma: 8-tap, two dp4a per sum) horizontal filter of four neighbours is dp4a on funnel-shifted words of the resident reference,
+// the vertical filter runs over a rotating 4-row (luma: 8-row) window, four clipped samples leave as one 32-bit store.  BI: two
+// lists and their weighted average in the same pass.  One arithmetic path serves the three
 // branches of the reference: with taps {0,64,0,0} for a zero fraction the two-stage result equals the single-stage one
 // ((64 s + 2048) >> 12 == (s + 32) >> 6), and the 14-bit offset cancels because the taps sum to 64.
 #include "hb_shim.h"
 #include "hb_dev_common.cuh"
 
 namespace {
-
-constexpr int kMcWarps = 8;
-
-struct McArgs {
-    hbd_frame ref, pred;
-    const hbd_mc_pu *pus;
-    int n_pus;
-    int tiles_per_pu;      // (size/T)^2
-    int tiles_per_row;     // size/T
-    const hb_me_result *mvsrc;
-};
-
-// generic separable prediction of a W x W tile at (x,y) of `ref` displaced by (ix,iy) whole samples with fractions
-// (fx,fy); NT taps (8 luma / 4 chroma); patch/tmp are per-warp shared memory.
-template <int W, int NT>
-__device__ __forceinline__ void mc_tile(const hbd_plane &ref, const hbd_plane &dst, int x, int y, int ix, int iy, int fx, int fy,
-                                        uint8_t *patch, int16_t *tmp, int lane)
-{
-    constexpr int HALF = NT / 2 - 1;           // taps before the sample: 3 luma, 1 chroma
-    constexpr int PR = W + NT - 1;             // patch rows/cols actually needed
-    constexpr int PSB = ((W + NT - 1 + 3) / 4) * 4 + 4;  // patch stride (bytes), whole words
-    const uint8_t *src = ref.org + (y + iy - HALF) * ref.pitch + (x + ix - HALF);
-    for (int w = lane; w < PR * (PSB / 4); w += 32) {
-        const int r = w / (PSB / 4), c = (w % (PSB / 4)) * 4;
-        *reinterpret_cast<uint32_t *>(patch + r * PSB + c) = hb_ld_u8x4(src + r * ref.pitch + c);
-    }
-    __syncwarp();
-    uint8_t *out = dst.org + y * dst.pitch + x;
-    if (fx == 0 && fy == 0) {
-        for (int e = lane; e < W * W; e += 32) out[(e / W) * dst.pitch + e % W] = patch[(e / W + HALF) * PSB + e % W + HALF];
-    } else if (fx == 0) {                      // vertical only, 8 bit -> 8 bit
-        for (int e = lane; e < W * W; e += 32) {
-            const int r = e / W, c = e % W;
-            int t[NT];
-#pragma unroll
-            for (int k = 0; k < NT; k++) t[k] = patch[(r + k) * PSB + c + HALF];
-            int s;
-            if constexpr (NT == 8) s = hb_luma8_dyn(fy, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
-            else s = hb_chroma4_dyn(fy, t[0], t[1], t[2], t[3]);
-            out[r * dst.pitch + c] = static_cast<uint8_t>(hb_clip255((s + 32) >> 6));
-        }
-    } else if (fy == 0) {                      // horizontal only
-        for (int e = lane; e < W * W; e += 32) {
-            const int r = e / W, c = e % W;
-            int t[NT];
-#pragma unroll
-            for (int k = 0; k < NT; k++) t[k] = patch[(r + HALF) * PSB + c + k];
-            int s;
-            if constexpr (NT == 8) s = hb_luma8_dyn(fx, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
-            else s = hb_chroma4_dyn(fx, t[0], t[1], t[2], t[3]);
-            out[r * dst.pitch + c] = static_cast<uint8_t>(hb_clip255((s + 32) >> 6));
-        }
-    } else {                                   // horizontal to 14 bit, then vertical
-        for (int e = lane; e < PR * W; e += 32) {
-            const int r = e / W, c = e % W;
-            int t[NT];
-#pragma unroll
-            for (int k = 0; k < NT; k++) t[k] = patch[r * PSB + c + k];
-            int s;
-            if constexpr (NT == 8) s = hb_luma8_dyn(fx, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
-            else s = hb_chroma4_dyn(fx, t[0], t[1], t[2], t[3]);
-            tmp[r * W + c] = static_cast<int16_t>(s - 8192);
-        }
-        __syncwarp();
-        for (int e = lane; e < W * W; e += 32) {
-            const int r = e / W, c = e % W;
-            int t[NT];
-#pragma unroll
-            for (int k = 0; k < NT; k++) t[k] = tmp[(r + k) * W + c];
-            int s;
-            if constexpr (NT == 8) s = hb_luma8_dyn(fy, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
-            else s = hb_chroma4_dyn(fy, t[0], t[1], t[2], t[3]);
-            out[r * dst.pitch + c] = static_cast<uint8_t>(hb_clip255((s + 2048 + (8192 << 6)) >> 12));
-        }
-    }
-    __syncwarp();
-}
-
-template <int T>
-__global__ void __launch_bounds__(kMcWarps * 32) k_mc(const McArgs a)
-{
-    constexpr int PSB = ((T + 7 + 3) / 4) * 4 + 4;
-    __shared__ __align__(16) uint8_t s_patch[kMcWarps][(T + 7) * PSB];
-    __shared__ __align__(16) int16_t s_tmp[kMcWarps][(T + 7) * T];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * kMcWarps + warp;
-    if (tile >= a.n_pus * a.tiles_per_pu) return;
-    const int pu_i = tile / a.tiles_per_pu, ti = tile % a.tiles_per_pu;
-    const hbd_mc_pu pu = a.pus[pu_i];
-    const hb_mv mv = a.mvsrc[pu.mv_idx].mv;
-    const int x = pu.x + (ti % a.tiles_per_row) * T, y = pu.y + (ti / a.tiles_per_row) * T;
-
-    mc_tile<T, 8>(a.ref.p[0], a.pred.p[0], x, y, mv.x >> 2, mv.y >> 2, mv.x & 3, mv.y & 3, s_patch[warp], s_tmp[warp], lane);
-}
 
 // ---- chroma (hmr_motion_compensation_chroma, hmr_motion_inter.c:1860; vectors in eighth-sample units :1863-1867)
 __constant__ int8_t c_ctap[8][4] = { {0, 64, 0, 0}, {-2, 58, 10, -2}, {-4, 54, 16, -2}, {-6, 46, 28, -4},
@@ -185,8 +89,8 @@ __global__ void __launch_bounds__(256) k_mc_chroma(const McCArgs a)
     }
 }
 
-// ---- luma, bi-prediction (hmr_motion_compensation_luma with is_bi_predict = 1 for both lists + weighted_average_motion):
-// the same thread-per-strip form with the 8-tap filters -- two dp4a per horizontal sum, an 8-row rotating window per list.
+// ---- luma (hmr_motion_compensation_luma, hmr_motion_inter.c:1779): the same thread-per-strip form with the 8-tap filters -- two
+// dp4a per horizontal sum, an 8-row rotating window per list.  BI: is_bi_predict = 1 for both lists + weighted_average_motion.
 __constant__ uint32_t c_ltap4[4][2] = { { htap4(0, 0), htap4(0, 1) }, { htap4(1, 0), htap4(1, 1) }, { htap4(2, 0), htap4(2, 1) }, { htap4(3, 0), htap4(3, 1) } };
 __constant__ int8_t c_ltap[4][8] = { {0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1} };
 
@@ -197,9 +101,10 @@ struct McLArgs {
     int total, lg_strips, lg_segs;
 };
 
-template <int RS>
-__global__ void __launch_bounds__(128) k_mc_luma_bi(const McLArgs a)
+template <int RS, bool BI>
+__global__ void __launch_bounds__(128) k_mc_luma(const McLArgs a)
 {
+    constexpr int NL = BI ? 2 : 1;
     const int item = blockIdx.x * 128 + threadIdx.x;
     if (item >= a.total) return;
     const int strip = item & ((1 << a.lg_strips) - 1);
@@ -207,11 +112,11 @@ __global__ void __launch_bounds__(128) k_mc_luma_bi(const McLArgs a)
     const int seg = t & ((1 << a.lg_segs) - 1);
     const hbd_mc_pu pu = a.pus[t >> a.lg_segs];
     const int x = pu.x + strip * 4, y = pu.y + seg * RS;
-    const uint32_t *q[2];
-    uint32_t sh[2], tlo[2], thi[2];
-    int qstep[2], tv[2][8];
+    const uint32_t *q[NL];
+    uint32_t sh[NL], tlo[NL], thi[NL];
+    int qstep[NL], tv[NL][8];
 #pragma unroll
-    for (int l = 0; l < 2; l++) {
+    for (int l = 0; l < NL; l++) {
         const hb_mv mv = (l ? a.mvsrc1 : a.mvsrc0)[pu.mv_idx].mv;
         const hbd_plane &rp = l ? a.ref1 : a.ref0;
         const uint8_t *src = rp.org + (y + (mv.y >> 2) - 3) * rp.pitch + x + (mv.x >> 2) - 3;
@@ -223,11 +128,11 @@ __global__ void __launch_bounds__(128) k_mc_luma_bi(const McLArgs a)
         for (int k = 0; k < 8; k++) tv[l][k] = c_ltap[mv.y & 3][k];
     }
     uint8_t *dst = a.pred.org + y * a.pred.pitch + x;
-    int h[2][8][4];                                         // rotating windows: [list][row & 7][column]
+    int h[NL][8][4];                                        // rotating windows: [list][row & 7][column]
 #pragma unroll
     for (int r = 0; r < RS + 7; r++) {
 #pragma unroll
-        for (int l = 0; l < 2; l++) {
+        for (int l = 0; l < NL; l++) {
             const uint32_t w0 = __ldg(q[l]), w1 = __ldg(q[l] + 1), w2 = __ldg(q[l] + 2), w3 = __ldg(q[l] + 3);
             q[l] += qstep[l];
             const uint32_t x0 = __funnelshift_r(w0, w1, sh[l]), x1 = __funnelshift_r(w1, w2, sh[l]), x2 = __funnelshift_r(w2, w3, sh[l]);   // samples x-3 .. x+8
@@ -240,10 +145,15 @@ __global__ void __launch_bounds__(128) k_mc_luma_bi(const McLArgs a)
             int o[4];
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                int s0 = 0, s1 = 0;
+                int s[NL];
 #pragma unroll
-                for (int k = 0; k < 8; k++) { s0 += tv[0][k] * h[0][(r - 7 + k) & 7][c]; s1 += tv[1][k] * h[1][(r - 7 + k) & 7][c]; }
-                o[c] = ((s0 >> 6) + (s1 >> 6) + 64) >> 7;
+                for (int l = 0; l < NL; l++) {
+                    s[l] = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) s[l] += tv[l][k] * h[l][(r - 7 + k) & 7][c];
+                }
+                if constexpr (BI) o[c] = ((s[0] >> 6) + (s[NL - 1] >> 6) + 64) >> 7;
+                else o[c] = (s[0] + 2048) >> 12;           // two-stage == single-stage when a fraction is zero (taps {..,64,..})
             }
             *reinterpret_cast<uint32_t *>(dst) = hb_pack_sat_u8x4(o[0], o[1], o[2], o[3]);
             dst += a.pred.pitch;
@@ -316,14 +226,13 @@ extern "C" int hbk_mc_predict(const hbd_frame *ref, const hbd_frame *pred, int s
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (size != 8 && size != 16 && size != 32 && size != 64) return static_cast<int>(cudaErrorInvalidValue);
     if (planes & 1) {
-        McArgs a;
-        a.ref = *ref; a.pred = *pred; a.pus = pus; a.n_pus = n_pus; a.mvsrc = mvsrc;
-        const int T = size >= 16 ? 16 : 8;
-        a.tiles_per_row = size / T; a.tiles_per_pu = a.tiles_per_row * a.tiles_per_row;
-        const long tiles = static_cast<long>(n_pus) * a.tiles_per_pu;
-        const int grid = static_cast<int>((tiles + kMcWarps - 1) / kMcWarps);
-        if (T == 16) k_mc<16><<<grid, kMcWarps * 32, 0, s>>>(a);
-        else k_mc<8><<<grid, kMcWarps * 32, 0, s>>>(a);
+        McLArgs l;
+        const int rs = 8;
+        l.ref0 = ref->p[0]; l.ref1 = ref->p[0]; l.pred = pred->p[0]; l.pus = pus; l.mvsrc0 = mvsrc; l.mvsrc1 = mvsrc;
+        l.lg_strips = 0; while ((4 << l.lg_strips) < size) l.lg_strips++;
+        l.lg_segs = 0; while ((rs << l.lg_segs) < size) l.lg_segs++;
+        l.total = n_pus << (l.lg_strips + l.lg_segs);
+        k_mc_luma<8, false><<<(l.total + 127) / 128, 128, 0, s>>>(l);
     }
     if (planes & 2) {
         McCArgs c;
@@ -355,7 +264,7 @@ extern "C" int hbk_mc_predict_bi(const hbd_frame *ref0, const hbd_frame *ref1, c
         l.lg_strips = 0; while ((4 << l.lg_strips) < size) l.lg_strips++;
         l.lg_segs = 0; while ((rs << l.lg_segs) < size) l.lg_segs++;
         l.total = n_pus << (l.lg_strips + l.lg_segs);
-        k_mc_luma_bi<8><<<(l.total + 127) / 128, 128, 0, s>>>(l);
+        k_mc_luma<8, true><<<(l.total + 127) / 128, 128, 0, s>>>(l);
     }
     {
         McCArgs c;
