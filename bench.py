@@ -456,10 +456,10 @@ def main():
         step_bytes = sum(abytes.values())
         total_prof = sum(prof.values())
         # instruction-issue roofline (the governing one): warp instructions per frame counted by ncu
-        # (profiles/inst_r01_v23.json, 1080p; scaled by the pixel count for the other sizes) against SMs x 4 schedulers x clock
+        # (profiles/inst_r01_v26.json, 1080p; scaled by the pixel count for the other sizes) against SMs x 4 schedulers x clock
         issue, traffic = None, None
         try:
-            with open(os.path.join(ROOT, "profiles", "inst_r01_v23.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "inst_r01_v26.json")) as f:
                 prof_counts = json.load(f)
             scale = (w * h) / (1920 * 1080)
             inst_per_frame = prof_counts["total_warp_inst"] * scale
@@ -468,7 +468,7 @@ def main():
             fps_gpu = N_SLOTS * args.steps / (ms * 1e-3)
             issue = {"bound": "warp-instruction issue", "achieved": inst_per_frame * fps_gpu, "peak": peak_issue, "unit": "warp-inst/s",
                      "frac": inst_per_frame * fps_gpu / peak_issue, "warp_inst_per_frame": inst_per_frame,
-                     "source": "ncu smsp__inst_executed.sum per kernel, profiles/inst_r01_v23.json" + ("" if scale == 1 else " (scaled by pixel count)")}
+                     "source": "ncu smsp__inst_executed.sum per kernel, profiles/inst_r01_v26.json" + ("" if scale == 1 else " (scaled by pixel count)")}
             if scale == 1:
                 want = {"me": "k_me<", "mc": "k_mc", "tq": "k_tq<"}[top[:2]] + (top[2:] + ">" if top[:2] == "me" else "")
                 for kk in prof_counts["kernels"]:
