@@ -142,8 +142,8 @@ __device__ __forceinline__ void half_strip(const uint32_t *pl, const uint8_t *cu
     }
 }
 
-// barrier over the lanes that search one PU.  Sub-warp groups use their own lane mask, so the PUs sharing a warp may sit in
-// different iterations of the (data-dependent) search loops: the hardware runs them in lock step where their paths agree.
+// barrier over the lanes that search one PU.  Sub-warp groups (several PUs per warp) run in lock step, so the whole warp
+// synchronises; two-warp groups use a named barrier each, the 64x64 PU is the CTA.
 template <int G> __device__ __forceinline__ void group_barrier(int group, uint32_t gmask)
 {
     if (G <= 32) __syncwarp();

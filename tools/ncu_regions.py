@@ -2,7 +2,7 @@
 nearest preceding instruction that maps to hb_kernels_me.cu).  usage: python tools/ncu_regions.py cuda_sass.csv "k_me<(int)8>" """
 import csv, sys, collections, bisect
 path, want = sys.argv[1], sys.argv[2]
-REG = [(0, 85, "setup/load cur"), (86, 161, "half-pel strips"), (162, 212, "setup/load cur"), (213, 233, "mv_cost"), (234, 261, "exchange"), (262, 302, "round4 (SAD)"),
+REG = [(0, 85, "setup/load cur"), (86, 143, "half-pel strips"), (144, 161, "walk replay/control"), (162, 212, "setup/load cur"), (213, 233, "mv_cost"), (234, 261, "exchange"), (262, 302, "round4 (SAD)"),
        (303, 420, "walk replay/control"), (421, 457, "patch staging"), (458, 488, "H planes"), (489, 500, "cur->smem"), (501, 536, "quarter subpel4"),
        (537, 585, "half-pel strips"), (586, 607, "subpel decide"), (608, 633, "pred write"), (634, 700, "result")]
 def region(line):
