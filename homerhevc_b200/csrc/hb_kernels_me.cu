@@ -159,6 +159,21 @@ template <int K> __device__ __forceinline__ uint32_t pick(const uint32_t (&a)[K]
     return v;
 }
 
+// does any valid candidate beat the best cost so far?  (static register indexing, unlike the replay loop's pick)
+template <int K> __device__ __forceinline__ bool beats(const uint32_t (&rd)[K], uint32_t vmask, uint32_t brd)
+{
+    uint32_t mn = 0xffffffffu;
+#pragma unroll
+    for (int s = 0; s < K; s++) mn = min(mn, ((vmask >> s) & 1u) ? rd[s] : 0xffffffffu);
+    return mn < brd;
+}
+// number of valid positions among the `span` consecutive ones (mod K) that the replay loop visits from next_start
+template <int K> __device__ __forceinline__ uint32_t visited(uint32_t vmask, int next_start, int span)
+{
+    const uint32_t m = (1u << span) - 1u;
+    return __popc(vmask & ((m << next_start) | (m >> (K - next_start))) & ((1u << K) - 1u));
+}
+
 template <int N>
 __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(const MeArgs a)
 {
@@ -377,15 +392,19 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
 #pragma unroll
                     for (int s = 0; s < 4; s++) { sad8[4 * h + s] = sad[s]; rd8[4 * h + s] = rd[s]; }
                 }
-                for (int i = next_start; i < next_start + span; i++) {
-                    const int idx = i & 7;
-                    if (!((vmask >> idx) & 1u)) continue;
-                    n_probes++;
-                    const uint32_t rd = pick<8>(rd8, idx);
-                    if (rd < brd) {
-                        bsad = pick<8>(sad8, idx); brd = rd;
-                        bx = cx0 + c_big[idx][0] * dist; by = cy0 + c_big[idx][1] * dist;
-                        next_start = (idx - 2 + 8) & 7; span = 5;
+                if (!beats<8>(rd8, vmask, brd)) {             // nothing can win: the walk only counts the probes it would make
+                    n_probes += visited<8>(vmask, next_start, span);
+                } else {
+                    for (int i = next_start; i < next_start + span; i++) {
+                        const int idx = i & 7;
+                        if (!((vmask >> idx) & 1u)) continue;
+                        n_probes++;
+                        const uint32_t rd = pick<8>(rd8, idx);
+                        if (rd < brd) {
+                            bsad = pick<8>(sad8, idx); brd = rd;
+                            bx = cx0 + c_big[idx][0] * dist; by = cy0 + c_big[idx][1] * dist;
+                            next_start = (idx - 2 + 8) & 7; span = 5;
+                        }
                     }
                 }
             }
@@ -398,15 +417,19 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
             for (;;) {
                 uint32_t sad[4], rd[4], vmask;
                 round_own(cx0 + sdx, cy0 + sdy, !done && inside(cx0 + sdx, cy0 + sdy), sad, rd, vmask);
-                for (int i = next_start; i < next_start + span; i++) {
-                    const int idx = i & 3;
-                    if (!((vmask >> idx) & 1u)) continue;
-                    n_probes++;
-                    const uint32_t r = pick<4>(rd, idx);
-                    if (r < brd) {
-                        bsad = pick<4>(sad, idx); brd = r;
-                        bx = cx0 + c_small[idx][0]; by = cy0 + c_small[idx][1];
-                        next_start = (idx - 1 + 4) & 3; span = 3;
+                if (!beats<4>(rd, vmask, brd)) {              // the usual last iteration: no neighbour wins, only the probe count moves
+                    n_probes += visited<4>(vmask, next_start, span);
+                } else {
+                    for (int i = next_start; i < next_start + span; i++) {
+                        const int idx = i & 3;
+                        if (!((vmask >> idx) & 1u)) continue;
+                        n_probes++;
+                        const uint32_t r = pick<4>(rd, idx);
+                        if (r < brd) {
+                            bsad = pick<4>(sad, idx); brd = r;
+                            bx = cx0 + c_small[idx][0]; by = cy0 + c_small[idx][1];
+                            next_start = (idx - 1 + 4) & 3; span = 3;
+                        }
                     }
                 }
                 if (cx0 == bx && cy0 == by) done = true;
