@@ -31,6 +31,12 @@ __constant__ int8_t c_small[4][2] = { {-1, 0}, {0, -1}, {1, 0}, {0, 1} };
 __constant__ int8_t c_big[8][2] = { {-2, 0}, {-1, -1}, {0, -2}, {1, -1}, {2, 0}, {1, 1}, {0, 2}, {-1, 1} };
 __constant__ int8_t c_half[9][2] = { {0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {1, -1}, {-1, 1}, {1, 1} };
 __constant__ int8_t c_quarter[9][2] = { {0, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {1, 1} };
+// the same table for compile-time indices (folds to immediates)
+__host__ __device__ constexpr int quarter_off(int i, int c)
+{
+    constexpr int t[9][2] = { {0, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {1, 1} };
+    return t[i][c];
+}
 __constant__ int8_t c_taps[4][8] = { {0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1} };
 
 struct MeArgs {
@@ -184,7 +190,7 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
 
     extern __shared__ __align__(16) uint8_t s_raw[];
     __shared__ uint32_t s_x[(G > 32) ? PUS : 1][2][NSEG][2];   // G > 32: [phase][segment]{partial SAD, cost of the segment's slot}
-    __shared__ uint32_t s_half[PUS][8];                        // SADs of the eight half-pel candidates (c_half order 1..8)
+    __shared__ __align__(16) uint32_t s_half[PUS][8];                        // SADs of the eight half-pel candidates (c_half order 1..8)
 
     const int group = threadIdx.x / G, gl = threadIdx.x % G, lane = threadIdx.x & 31;
     const int slot = gl / L, l = gl % L, seg = gl / SEG;
@@ -522,10 +528,7 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
         // one round: SADs of four sub-pel candidates at quarter-pel offsets (qx[s], qy[s]) in [-3,3]^2 from (ix,iy).  A lane filters
         // CPL columns of its slot's candidate top to bottom: per two output rows one shared load and ten dp2a; four clipped
         // samples are packed and compared with four current samples in one instruction.
-        auto subpel4 = [&](const int (&qx)[4], const int (&qy)[4], uint32_t (&sad)[4]) {
-            int cx = qx[0], cy = qy[0];
-#pragma unroll
-            for (int s = 1; s < 4; s++) if (slot == s) { cx = qx[s]; cy = qy[s]; }
+        auto subpel4 = [&](int cx, int cy, uint32_t (&sad)[4]) {                // (cx, cy): this lane's slot's candidate
             const int fx = cx & 3, fy = cy & 3, cb = cx >> 2, par = (cy >> 2) + 1;
             uint32_t tb[5];
 #pragma unroll
@@ -606,22 +609,24 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
             }
         }
         group_barrier<G>(group, gmask);
-        int sbx = 0, sby = 0, bidx = 0;
+        int bidx = 0;
+        {
+            const uint4 h0 = *reinterpret_cast<const uint4 *>(&s_half[group][0]), h1 = *reinterpret_cast<const uint4 *>(&s_half[group][4]);
+            const uint32_t hv[8] = { h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w };
 #pragma unroll
-        for (int i = 1; i < 9; i++) {                      // candidate 0 is the integer position itself: never smaller
-            const uint32_t v = s_half[group][i - 1];
-            if (v < cur_best) { cur_best = v; sbx = c_half[i][0] * 2; sby = c_half[i][1] * 2; bidx = i; }
+            for (int i = 1; i < 9; i++)                    // candidate 0 is the integer position itself: never smaller
+                if (hv[i - 1] < cur_best) { cur_best = hv[i - 1]; bidx = i; }
         }
+        const int hx = c_half[bidx][0], hy = c_half[bidx][1];
+        int sbx = hx * 2, sby = hy * 2;
         if (a.action & HB_ME_QUARTER) {
-            const int hx = c_half[bidx][0], hy = c_half[bidx][1];
 #pragma unroll
             for (int h = 0; h < 2; h++) {              // candidate 0 repeats the half-pel winner
-                int qx[4], qy[4]; uint32_t sad[4];
+                uint32_t sad[4];
+                subpel4(hx * 2 + c_quarter[1 + 4 * h + slot][0], hy * 2 + c_quarter[1 + 4 * h + slot][1], sad);
 #pragma unroll
-                for (int s = 0; s < 4; s++) { qx[s] = hx * 2 + c_quarter[1 + 4 * h + s][0]; qy[s] = hy * 2 + c_quarter[1 + 4 * h + s][1]; }
-                subpel4(qx, qy, sad);
-#pragma unroll
-                for (int s = 0; s < 4; s++) if (sad[s] < cur_best) { cur_best = sad[s]; sbx = qx[s]; sby = qy[s]; }
+                for (int s = 0; s < 4; s++)
+                    if (sad[s] < cur_best) { cur_best = sad[s]; sbx = hx * 2 + quarter_off(1 + 4 * h + s, 0); sby = hy * 2 + quarter_off(1 + 4 * h + s, 1); }
             }
         }
         best_sad = cur_best;
