@@ -37,7 +37,6 @@ __host__ __device__ constexpr int quarter_off(int i, int c)
     constexpr int t[9][2] = { {0, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {1, 1} };
     return t[i][c];
 }
-__constant__ int8_t c_taps[4][8] = { {0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1} };
 
 struct MeArgs {
     hbd_plane cur, ref;
