@@ -464,9 +464,9 @@ def main():
             scale = (w * h) / (1920 * 1080)
             inst_per_frame = prof_counts["total_warp_inst"] * scale
             sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
-            peak_issue = 148 * 4 * sm_hz
+            peak_issue = 148 * 3.8 * sm_hz        # measured: 3.80 warp-inst/clk/SM when both integer pipes are fed (tools/int_peak.cu, profiles/int_peak_r01.txt)
             fps_gpu = N_SLOTS * args.steps / (ms * 1e-3)
-            issue = {"bound": "warp-instruction issue", "achieved": inst_per_frame * fps_gpu, "peak": peak_issue, "unit": "warp-inst/s",
+            issue = {"bound": "warp-instruction issue (int-op roofline)", "achieved": inst_per_frame * fps_gpu, "peak": peak_issue, "unit": "warp-inst/s",
                      "frac": inst_per_frame * fps_gpu / peak_issue, "warp_inst_per_frame": inst_per_frame,
                      "source": "ncu smsp__inst_executed.sum per kernel, profiles/inst_r01_v26.json" + ("" if scale == 1 else " (scaled by pixel count)")}
             if scale == 1:
