@@ -584,6 +584,29 @@ done:
     return rc;
 }
 
+/* SAO statistics of a whole picture: one launch, one copy back */
+int hb_sao_stats_frame(hb_ctx *ctx, const hb_frame *orig, const hb_frame *rec, hb_sao_stats *out)
+{
+    int rc = HB_OK, crc = 0;
+    void *d_out, *h_out;
+    if (!ctx || !orig || !rec || !out) return hbi_fail(HB_ERR_ARG, "hb_sao_stats_frame: NULL argument");
+    if (orig->w != rec->w || orig->h != rec->h) return hbi_fail(HB_ERR_ARG, "hb_sao_stats_frame: frame sizes differ");
+    const int cols = (rec->w + 63) / 64, n_ctus = cols * ((rec->h + 63) / 64);
+    const size_t bytes = sizeof(hb_sao_stats) * 3 * (size_t)n_ctus;
+    hbc_set_device(ctx->device);
+    pthread_mutex_lock(&ctx->lock);
+    if ((rc = hbi_scratch(ctx, 0, bytes, &d_out, &h_out)) != HB_OK) goto done;
+    crc = hbk_sao_stats(&orig->d, &rec->d, cols, n_ctus, (hb_sao_stats *)d_out, ctx->stream);
+    ctx->launches++;
+    if (!crc) crc = hbc_d2h_async(h_out, d_out, bytes, ctx->stream);
+    if (!crc) crc = hbc_stream_sync(ctx->stream);
+    if (!crc) memcpy(out, h_out, bytes);
+done:
+    pthread_mutex_unlock(&ctx->lock);
+    if (crc) return hbi_cuda_fail(crc, "hb_sao_stats_frame");
+    return rc;
+}
+
 /* fill the launch-invariant part of a T/Q launch: tables and shifts of (component, size, qp) -- inter lists 3+comp */
 void hbi_tq_setup(hb_ctx *ctx, hbd_tq_args *a, int comp, int n, int qp, int is_islice, int sign_hiding)
 {

@@ -86,6 +86,72 @@ __global__ void __launch_bounds__(256) k_gather(const hbd_gather_args a)
 
 }  // namespace
 
+// ---- SAO statistics (sao_get_ctu_stats, hmr_sao.c:75-330 / sse_sao_get_ctu_stats, hmr_sse42_sao.c:35):
+// per CTU and component, for the four edge directions the count and the sum of (source - reconstruction) of every sample by
+// edge class sign(c - a) + sign(c - b), and the same by band (c >> 3).  The reference walks rows with running sign buffers;
+// per sample this is a closed form inside a rectangle that depends on the neighbouring CTUs and on the columns / rows the
+// deblocking filter has not finished (5/3 columns, 4/2 rows).  One CTA per (CTU, component): edge classes accumulate in
+// registers and are reduced once, bands go through shared atomics.
+namespace {
+__device__ __forceinline__ int sgn3(int v) { return (v > 0) - (v < 0); }
+
+__global__ void __launch_bounds__(256) k_sao_stats(hbd_frame org, hbd_frame rec, int ctu_cols, hb_sao_stats *out)
+{
+    __shared__ int s_acc[104];                           // eo_diff[4][5], eo_count[4][5], bo_diff[32], bo_count[32]
+    const int comp = blockIdx.y, ctu = blockIdx.x;
+    const hbd_plane &pr = rec.p[comp], &po = org.p[comp];
+    const int cs = comp ? 32 : 64;
+    const int x0 = (ctu % ctu_cols) * cs, y0 = (ctu / ctu_cols) * cs;
+    const int w = min(cs, pr.w - x0), h = min(cs, pr.h - y0);
+    const bool l = x0 > 0, t = y0 > 0, r = x0 + cs < pr.w, b = y0 + cs < pr.h;
+    const int skr = comp ? 3 : 5, skb = comp ? 2 : 4;
+    for (int i = threadIdx.x; i < 104; i += 256) s_acc[i] = 0;
+    __syncthreads();
+    // the rectangles of the five types (hmr_sao.c:123-127, :154-157, :201-205, :262-264, :312-314)
+    const int ex_e = r ? w - skr : w - 1, ex_f = r ? w - skr : w;          // EO_0/135/45 stop one short of a picture edge; EO_90 and BO do not
+    const int sx_e = l ? 0 : 1, sy_v = t ? 0 : 1;
+    const int ey_all = b ? h - skb : h, ey_v = b ? h - skb : h - 1;
+    int cnt[4][5], dif[4][5];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int c = 0; c < 5; c++) { cnt[k][c] = 0; dif[k][c] = 0; }
+    for (int i = threadIdx.x; i < w * h; i += 256) {
+        const int x = i % w, y = i / w;
+        const uint8_t *p = pr.org + (y0 + y) * pr.pitch + x0 + x;
+        const int c = p[0], d = static_cast<int>(po.org[(y0 + y) * po.pitch + x0 + x]) - c;
+        const bool in_e = x >= sx_e && x < ex_e, in_f = x < ex_f;
+        const bool v0 = in_e && y < ey_all, v1 = in_f && y >= sy_v && y < ey_v, v23 = in_e && y >= sy_v && y < ey_v, vb = in_f && y < ey_all;
+        // samples outside the picture are never classified (the rectangles exclude them); the border keeps the loads legal
+        const int cls[4] = { 2 + sgn3(c - p[-1]) + sgn3(c - p[1]), 2 + sgn3(c - p[-pr.pitch]) + sgn3(c - p[pr.pitch]),
+                             2 + sgn3(c - p[-pr.pitch - 1]) + sgn3(c - p[pr.pitch + 1]), 2 + sgn3(c - p[-pr.pitch + 1]) + sgn3(c - p[pr.pitch - 1]) };
+        const bool val[4] = { v0, v1, v23, v23 };
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int q = 0; q < 5; q++) { const bool hit = val[k] && cls[k] == q; cnt[k][q] += hit; dif[k][q] += hit ? d : 0; }
+        if (vb) { atomicAdd(&s_acc[40 + (c >> 3)], d); atomicAdd(&s_acc[72 + (c >> 3)], 1); }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+            const int sd = __reduce_add_sync(HB_FULL_MASK, dif[k][q]), sc = __reduce_add_sync(HB_FULL_MASK, cnt[k][q]);
+            if ((threadIdx.x & 31) == 0 && sc) { atomicAdd(&s_acc[k * 5 + q], sd); atomicAdd(&s_acc[20 + k * 5 + q], sc); }
+        }
+    __syncthreads();
+    int *o = reinterpret_cast<int *>(out + (static_cast<size_t>(ctu) * 3 + comp));
+    for (int i = threadIdx.x; i < 104; i += 256) o[i] = s_acc[i];
+}
+}  // namespace
+
+extern "C" int hbk_sao_stats(const hbd_frame *org, const hbd_frame *rec, int ctu_cols, int n_ctus, hb_sao_stats *out, void *stream)
+{
+    if (n_ctus <= 0) return 0;
+    k_sao_stats<<<dim3(n_ctus, 3), 256, 0, static_cast<cudaStream_t>(stream)>>>(*org, *rec, ctu_cols, out);
+    return static_cast<int>(cudaGetLastError());
+}
+
 // ---- compact wire format of the result tables: 12-byte records instead of 24 / 16 (hb_prepass_cfg.compact_tables)
 namespace {
 __global__ void __launch_bounds__(256) k_pack_tables(const hb_me_result *me, const hb_tu_result *tu, hb_me_result_c *me_c, hb_tu_result_c *tu_c, int n_me, int n_tu)

@@ -167,6 +167,7 @@ def load_library():
                                C.c_double, C.c_int, C.POINTER(MeResult)]
     L.hb_mc_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(McJob), C.c_int]
     L.hb_mc_predict_bi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(McBiJob), C.c_int]
+    L.hb_sao_stats_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb_tq_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TuJob), C.c_int,
                                C.POINTER(TqParams), i16p, C.POINTER(TuResult)]
     L.hb_tq_encode_intra.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(IntraTuJob), C.c_int, C.c_int, C.c_int, C.c_double,
@@ -362,6 +363,19 @@ def _intra_run(self, cur, pred, jobs, adi):
 
 
 Context.intra_run = _intra_run
+
+SAO_DT = np.dtype([("eo_diff", "<i4", (4, 5)), ("eo_count", "<i4", (4, 5)), ("bo_diff", "<i4", (32,)), ("bo_count", "<i4", (32,))])
+
+
+def _sao_stats(self, orig, rec):
+    """SAO statistics of every CTU and component: (n_ctus, 3) array of SAO_DT (hb_sao_stats)"""
+    n = ((rec.w + 63) // 64) * ((rec.h_px + 63) // 64)
+    out = np.zeros((n, 3), SAO_DT)
+    _check(self.L.hb_sao_stats_frame(self.h, orig.h, rec.h, out.ctypes.data), "hb_sao_stats_frame")
+    return out
+
+
+Context.sao_stats = _sao_stats
 
 
 def presearch_records(jobs_xyn):

@@ -214,6 +214,13 @@ int hb_intra_run(hb_ctx *ctx, const hb_frame *cur, hb_frame *pred, const hb_intr
 void hb_create_intra_planar_prediction(int16_t *prediction, int pred_stride, int16_t *adi_pred_buff, int adi_size, int cu_size, int cu_size_shift);
 void hb_create_intra_angular_prediction(int16_t *prediction, int pred_stride, int16_t *adi_pred_buff, int adi_size, int cu_size, int cu_mode, int is_luma);
 
+/* SAO statistics (get_sao_stats of the function table, hmr_private.h:1091; sao_get_ctu_stats hmr_sao.c:75 /
+ * sse_sao_get_ctu_stats hmr_sse42_sao.c:35, calculate_preblock_stats = 0) for every CTU and component of a picture in one
+ * launch: `rec` is the deblocked reconstruction (before SAO), `orig` the source.  out[ctu * 3 + comp], CTUs in raster order.
+ * Edge classes 0..4 stand for the reference's edge types -2..2; eo_*[k]: k = 0 EO_0 (horizontal), 1 EO_90, 2 EO_135, 3 EO_45. */
+typedef struct hb_sao_stats { int32_t eo_diff[4][5], eo_count[4][5], bo_diff[32], bo_count[32]; } hb_sao_stats;   /* 416 bytes */
+int hb_sao_stats_frame(hb_ctx *ctx, const hb_frame *orig, const hb_frame *rec, hb_sao_stats *out);
+
 /* ------------------------------------------------------------------ D. frame-level pre-pass ----------------
  * For every CTU and every inter PU size 64/32/16/8 at once: motion search chained parent -> child exactly as
  * hmr_cu_motion_estimation does (zero AMVP predictors, parent MV as extra start), motion compensation of

@@ -871,3 +871,37 @@ void orc_weighted_average(const int16_t *src0, int s0, const int16_t *src1, int 
     for (int y = 0; y < height; y++)
         for (int x = 0; x < width; x++) dst[y * ds + x] = (int16_t)clampi((src0[y * s0 + x] + src1[y * s1 + x] + offset) >> shift, 0, 255);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * SAO statistics of one CTU and component: sao_get_ctu_stats, hmr_sao.c:75-330, with
+ * calculate_preblock_stats = 0 (the only value the encoder sets, hmr_encoder_lib.c:684).  The reference walks each edge class
+ * with running sign buffers; every sample it counts ends up classified by sign(c - a) + sign(c - b) of its two neighbours
+ * along the class direction, inside a rectangle that depends on which neighbouring CTUs exist and on the columns / rows the
+ * deblocking filter has not finished yet (skiped_lines_r = {5,3,3}, skiped_lines_b = {4,2,2}, :60-61).
+ * rec / org: the component's planes (deblocked reconstruction, source), (x0, y0) the CTU origin in that plane.
+ * ------------------------------------------------------------------------------------------ */
+static int sgn3(int v) { return v == 0 ? 0 : (v < 0 ? -1 : 1); }
+void orc_sao_ctu_stats(const int16_t *rec, int rec_stride, const int16_t *org, int org_stride, int comp, int x0, int y0,
+                       int pic_w, int pic_h, int ctu_size, orc_sao_stats *st)
+{
+    static const int skip_r[3] = { 5, 3, 3 }, skip_b[3] = { 4, 2, 2 };
+    static const int dx[4] = { 1, 0, 1, -1 }, dy[4] = { 0, 1, 1, 1 };      /* EO_0, EO_90, EO_135, EO_45: second neighbour; the first is its opposite */
+    const int w = x0 + ctu_size > pic_w ? pic_w - x0 : ctu_size, h = y0 + ctu_size > pic_h ? pic_h - y0 : ctu_size;
+    const int l = x0 > 0, t = y0 > 0, r = x0 + ctu_size < pic_w, b = y0 + ctu_size < pic_h;
+    memset(st, 0, sizeof *st);
+    for (int type = 0; type < 5; type++) {
+        int sx, ex, sy, ey;
+        if (type == 0)      { sx = l ? 0 : 1; ex = r ? w - skip_r[comp] : w - 1; sy = 0; ey = b ? h - skip_b[comp] : h; }
+        else if (type == 1) { sx = 0; ex = r ? w - skip_r[comp] : w; sy = t ? 0 : 1; ey = b ? h - skip_b[comp] : h - 1; }
+        else if (type < 4)  { sx = l ? 0 : 1; ex = r ? w - skip_r[comp] : w - 1; sy = t ? 0 : 1; ey = b ? h - skip_b[comp] : h - 1; }
+        else                { sx = 0; ex = r ? w - skip_r[comp] : w; sy = 0; ey = b ? h - skip_b[comp] : h; }
+        for (int y = sy; y < ey; y++)
+            for (int x = sx; x < ex; x++) {
+                const int c = rec[(y0 + y) * rec_stride + x0 + x], d = org[(y0 + y) * org_stride + x0 + x] - c;
+                if (type == 4) { st->bo_diff[c >> 3] += d; st->bo_count[c >> 3]++; continue; }
+                const int a = rec[(y0 + y - dy[type]) * rec_stride + x0 + x - dx[type]], n = rec[(y0 + y + dy[type]) * rec_stride + x0 + x + dx[type]];
+                const int k = 2 + sgn3(c - a) + sgn3(c - n);
+                st->eo_diff[type][k] += d; st->eo_count[type][k]++;
+            }
+    }
+}

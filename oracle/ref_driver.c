@@ -676,3 +676,48 @@ void refdrv_mc_chroma_bi(refdrv *d, int16_t *ref, int ref_stride, int16_t *pred,
     while ((1 << shift) < size) shift++;
     hmr_motion_compensation_chroma(d->et, ref, ref_stride, pred, pred_stride, size, shift, &mv, 1);
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * SAO statistics through the table's get_sao_stats (sse_sao_get_ctu_stats on x86): the encoder structures the function reads
+ * are filled in by hand -- the deblocked reconstruction as curr_reference_frame, the source as img2encode, the picture size in
+ * the thread, one ctu_info_t per call.  rec / org: 8-bit planes (Y, U, V) of a w x h picture.  out: per CTU (raster) and
+ * component 5 types x {diff[32], count[32]} as int64, the reference's own layout (sao_stat_data_t).  Returns the CTU count.
+ * ------------------------------------------------------------------------------------------------------------ */
+int refdrv_sao_stats(refdrv *d, const uint8_t *const rec[3], const uint8_t *const org[3], int w, int h, int64_t *out)
+{
+    henc_thread_t *et = d->et;
+    hvenc_engine_t *eng = et->enc_engine;
+    video_frame_t fr_rec, fr_org;
+    video_frame_t *save_ref = eng->curr_reference_frame, *save_in = eng->current_pict.img2encode;
+    int save_w[3], save_h[3], n = 0;
+    const int save_pre = eng->calculate_preblock_stats;
+    memset(&fr_rec, 0, sizeof fr_rec); memset(&fr_org, 0, sizeof fr_org);
+    wnd_alloc(&fr_rec.img, w, h, 80, 80, sizeof(int16_t));
+    wnd_alloc(&fr_org.img, w, h, 80, 80, sizeof(int16_t));
+    for (int c = 0; c < 3; c++) {
+        const int pw = c ? w / 2 : w, ph = c ? h / 2 : h;
+        int16_t *pr = (int16_t *)fr_rec.img.pwnd[c], *po = (int16_t *)fr_org.img.pwnd[c];
+        for (int y = 0; y < ph; y++)
+            for (int x = 0; x < pw; x++) {
+                pr[y * fr_rec.img.window_size_x[c] + x] = rec[c][y * pw + x];
+                po[y * fr_org.img.window_size_x[c] + x] = org[c][y * pw + x];
+            }
+        save_w[c] = et->pict_width[c]; save_h[c] = et->pict_height[c];
+        et->pict_width[c] = pw; et->pict_height[c] = ph;
+    }
+    eng->curr_reference_frame = &fr_rec; eng->current_pict.img2encode = &fr_org; eng->calculate_preblock_stats = 0;
+    for (int cy = 0; cy < h; cy += 64)
+        for (int cx = 0; cx < w; cx += 64) {
+            ctu_info_t ctu;
+            sao_stat_data_t stats[NUM_PICT_COMPONENTS][NUM_SAO_NEW_TYPES];
+            memset(&ctu, 0, sizeof ctu); memset(stats, 0, sizeof stats);
+            ctu.size = 64; ctu.x[0] = cx; ctu.y[0] = cy; ctu.x[1] = ctu.x[2] = cx / 2; ctu.y[1] = ctu.y[2] = cy / 2;
+            d->enc->funcs.get_sao_stats(et, &eng->current_pict.slice, &ctu, stats);
+            memcpy(out + (size_t)n * NUM_PICT_COMPONENTS * NUM_SAO_NEW_TYPES * 64, stats, sizeof stats);
+            n++;
+        }
+    eng->curr_reference_frame = save_ref; eng->current_pict.img2encode = save_in; eng->calculate_preblock_stats = save_pre;
+    for (int c = 0; c < 3; c++) { et->pict_width[c] = save_w[c]; et->pict_height[c] = save_h[c]; }
+    wnd_delete(&fr_rec.img); wnd_delete(&fr_org.img);
+    return n;
+}

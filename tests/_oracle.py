@@ -89,6 +89,7 @@ def oracle():
         L.orc_intra_uses_filtered.argtypes = [C.c_int, C.c_int]
         L.orc_intra_mode_sads.argtypes = [i16p, C.c_int, i16p, C.c_int, C.POINTER(C.c_uint32)]
         L.orc_weighted_average.argtypes = [i16p, C.c_int, i16p, C.c_int, i16p, C.c_int, C.c_int, C.c_int]
+        L.orc_sao_ctu_stats.argtypes = [i16p, C.c_int, i16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.tables = L.orc_tables_create()
         _oracle = L
     return _oracle
@@ -193,6 +194,40 @@ ME_DT = np.dtype([("mvx", "<i4"), ("mvy", "<i4"), ("subx", "<i4"), ("suby", "<i4
 TU_DT = np.dtype([("sum", "<i4"), ("ssd", "<u4"), ("ssd_zero", "<u4"), ("zeroed", "<i4")])
 PASS_TU = (32, 32, 16, 8, 4)
 _rp_handles = {}
+
+SAO_DT = np.dtype([("eo_diff", "<i4", (4, 5)), ("eo_count", "<i4", (4, 5)), ("bo_diff", "<i4", (32,)), ("bo_count", "<i4", (32,))])
+
+
+def oracle_sao_stats(rec, org, w, h):
+    """rec / org: (y, u, v) uint8 planes.  Returns SAO_DT array [n_ctus, 3] from the C restatement."""
+    O = oracle()
+    cols, rows = (w + 63) // 64, (h + 63) // 64
+    out = np.zeros((rows * cols, 3), SAO_DT)
+    for c in range(3):
+        pw, ph = (w, h) if c == 0 else (w // 2, h // 2)
+        r16 = np.ascontiguousarray(np.pad(rec[c].astype(np.int16), 2)); o16 = np.ascontiguousarray(org[c].astype(np.int16))
+        cs = 64 if c == 0 else 32
+        for i in range(rows * cols):
+            x0, y0 = (i % cols) * cs, (i // cols) * cs
+            O.orc_sao_ctu_stats(ptr(r16.reshape(-1), 2 * (pw + 4) + 2), pw + 4, ptr(o16.reshape(-1)), pw, c, x0, y0, pw, ph, cs, out[i, c:c + 1].ctypes.data)
+    return out
+
+
+def ref_sao_stats(rec, org, w, h):
+    """the same through the reference's table member get_sao_stats; returns SAO_DT array [n_ctus, 3]"""
+    _, D = ref()
+    hnd = refdrv()
+    D.refdrv_sao_stats.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]
+    rec = [np.ascontiguousarray(p) for p in rec]; org = [np.ascontiguousarray(p) for p in org]
+    rp = (C.c_void_p * 3)(*[p.ctypes.data for p in rec]); op = (C.c_void_p * 3)(*[p.ctypes.data for p in org])
+    n = ((w + 63) // 64) * ((h + 63) // 64)
+    raw = np.zeros((n, 3, 5, 2, 32), np.int64)
+    assert D.refdrv_sao_stats(hnd, rp, op, w, h, raw.ctypes.data) == n
+    out = np.zeros((n, 3), SAO_DT)
+    out["eo_diff"] = raw[:, :, 0:4, 0, 0:5]; out["eo_count"] = raw[:, :, 0:4, 1, 0:5]      # the reference offsets its pointers by 2: classes -2..2 -> 0..4
+    out["bo_diff"] = raw[:, :, 4, 0, :]; out["bo_count"] = raw[:, :, 4, 1, :]
+    assert (raw[:, :, 0:4, :, 5:] == 0).all()
+    return out
 
 
 def ref_intra_presearch(luma, jobs, adi, adi_off, n_threads=1):

@@ -175,6 +175,16 @@ def main():
     D.refdrv_weighted_average(h, ptr(wa), 64, ptr(wb), 64, ptr(wd), 64, 64, 64)
     g["wavg_a"], g["wavg_b"], g["wavg_out"] = wa.copy(), wb.copy(), wd.astype(np.uint8)
 
+    # ---- 8f item 4: SAO statistics of a small picture with partial CTUs (table member get_sao_stats)
+    from _oracle import ref_sao_stats
+    sw, shh = 200, 136
+    base = [np.clip(rng.normal(128, 40, (hh_, ww_)), 0, 255) for (ww_, hh_) in ((sw, shh), (sw // 2, shh // 2), (sw // 2, shh // 2))]
+    sao_org = [b_.astype(np.uint8) for b_ in base]
+    sao_rec = [np.clip(b_ + rng.normal(0, 3, b_.shape), 0, 255).astype(np.uint8) for b_ in base]
+    st = ref_sao_stats(sao_rec, sao_org, sw, shh)
+    g["sao_org"] = np.concatenate([p_.reshape(-1) for p_ in sao_org]); g["sao_rec"] = np.concatenate([p_.reshape(-1) for p_ in sao_rec])
+    g["sao_stats"] = np.frombuffer(st.tobytes(), np.int32).copy()
+
     out = os.path.join(HERE, "ref_vectors.npz")
     np.savez_compressed(out, **g)
     print("wrote", out, os.path.getsize(out), "bytes")

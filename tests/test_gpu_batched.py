@@ -212,3 +212,20 @@ def test_mc_predict_bi(ctx):
         assert np.array_equal(pu[y // 2:y // 2 + c, x // 2:x // 2 + c], oracle_mc_bi(ref0, ref1, 1, x // 2, y // 2, c, mv0, mv1)), ("U", x, y, size, mv0, mv1)
         assert np.array_equal(pv[y // 2:y // 2 + c, x // 2:x // 2 + c], oracle_mc_bi(ref0, ref1, 2, x // 2, y // 2, c, mv0, mv1)), ("V", x, y, size, mv0, mv1)
     f0.close(); f1.close(); pred.close()
+
+
+def test_sao_statistics(ctx):
+    """SAO statistics of every CTU and component on the GPU == the restatement of sao_get_ctu_stats (whole and partial CTUs)"""
+    from _oracle import oracle_sao_stats
+    rng = np.random.default_rng(41)
+    for (w, h) in ((320, 192), (200, 136), (64, 72)):
+        base = [np.clip(rng.normal(128, 45, (hh, ww)), 0, 255) for (ww, hh) in ((w, h), (w // 2, h // 2), (w // 2, h // 2))]
+        org = [b.astype(np.uint8) for b in base]
+        rec = [np.clip(b + rng.normal(0, 3, b.shape), 0, 255).astype(np.uint8) for b in base]
+        fo, fr = hb.Frame(ctx, w, h), hb.Frame(ctx, w, h)
+        fo.upload_u8(*org); fr.upload_u8(*rec)
+        got = ctx.sao_stats(fo, fr)
+        exp = oracle_sao_stats(rec, org, w, h)
+        for f in ("eo_diff", "eo_count", "bo_diff", "bo_count"):
+            assert np.array_equal(got[f], exp[f]), (w, h, f, np.argwhere(got[f] != exp[f])[:3])
+        fo.close(); fr.close()

@@ -166,3 +166,12 @@ def test_intra_prediction_and_weighted_average():
     a[:] = G["wavg_a"]; b[:] = G["wavg_b"]
     O.orc_weighted_average(ptr(a), 64, ptr(b), 64, ptr(d), 64, 64, 64)
     assert np.array_equal(d.astype(np.uint8), G["wavg_out"]) and d.min() >= 0 and d.max() <= 255
+
+
+def test_sao_statistics():
+    from _oracle import oracle_sao_stats
+    w, h = 200, 136
+    def planes(a):
+        return [a[:w * h].reshape(h, w), a[w * h:w * h * 5 // 4].reshape(h // 2, w // 2), a[w * h * 5 // 4:].reshape(h // 2, w // 2)]
+    got = oracle_sao_stats(planes(G["sao_rec"]), planes(G["sao_org"]), w, h)
+    assert np.array_equal(np.frombuffer(got.tobytes(), np.int32), G["sao_stats"])

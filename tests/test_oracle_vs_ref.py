@@ -254,3 +254,18 @@ def test_bi_prediction_mc_against_reference():
         (O.orc_mc_chroma_ex if chroma else O.orc_mc_luma_ex)(ptr(plane, y * 200 + x), 200, ptr(p2), 64, n, OrcMv(mvx, mvy), 1)
         assert np.array_equal(p1.reshape(64, 64)[:n, :n], p2.reshape(64, 64)[:n, :n]), (chroma, n, mvx, mvy)
         assert p2.reshape(64, 64)[:n, :n].min() < 0 or p2.reshape(64, 64)[:n, :n].max() > 255      # 14-bit values, not samples
+
+
+def test_sao_statistics_against_reference():
+    """SAO statistics (edge classes in four directions + 32 bands) of every CTU and component through the table's get_sao_stats
+    versus the restatement: whole CTUs, partial CTUs at the right / bottom edge, a one-CTU-wide picture"""
+    from _oracle import make_frame_pair, oracle_sao_stats, ref_sao_stats
+    rng = np.random.default_rng(107)
+    for (w, h) in ((192, 128), (200, 136), (64, 200), (328, 72)):
+        base = [np.clip(rng.normal(128, 40, (hh, ww)), 0, 255) for (ww, hh) in ((w, h), (w // 2, h // 2), (w // 2, h // 2))]
+        org = [b.astype(np.uint8) for b in base]
+        rec = [np.clip(b + rng.normal(0, 3, b.shape), 0, 255).astype(np.uint8) for b in base]
+        a = oracle_sao_stats(rec, org, w, h); b = ref_sao_stats(rec, org, w, h)
+        for f in ("eo_diff", "eo_count", "bo_diff", "bo_count"):
+            assert np.array_equal(a[f], b[f]), (w, h, f, np.argwhere(a[f] != b[f])[:3])
+        assert a["eo_count"].sum() > 0 and (a["eo_count"][:, :, :, 0] > 0).any() and (a["eo_count"][:, :, :, 4] > 0).any()
