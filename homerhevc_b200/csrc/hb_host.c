@@ -607,6 +607,33 @@ done:
     return rc;
 }
 
+/* SAO offset pass of a whole picture; refreshes dst's replicated border afterwards (dst is the next reference picture) */
+int hb_sao_apply_frame(hb_ctx *ctx, const hb_frame *src, hb_frame *dst, const hb_sao_param *params)
+{
+    int rc = HB_OK, crc = 0;
+    void *d_prm, *h_prm;
+    if (!ctx || !src || !dst || !params) return hbi_fail(HB_ERR_ARG, "hb_sao_apply_frame: NULL argument");
+    if (src == dst) return hbi_fail(HB_ERR_ARG, "hb_sao_apply_frame: dst must not be src (classes are taken from the untouched picture)");
+    if (src->w != dst->w || src->h != dst->h) return hbi_fail(HB_ERR_ARG, "hb_sao_apply_frame: frame sizes differ");
+    const int cols = (src->w + 63) / 64, n_ctus = cols * ((src->h + 63) / 64);
+    for (int i = 0; i < n_ctus; i++)
+        for (int c = 0; c < 3; c++)
+            if (params[i].type[c] < -1 || params[i].type[c] > 4) return hbi_fail(HB_ERR_ARG, "hb_sao_apply_frame: CTU %d component %d has type %d", i, c, params[i].type[c]);
+    const size_t bytes = sizeof(hb_sao_param) * (size_t)n_ctus;
+    hbc_set_device(ctx->device);
+    pthread_mutex_lock(&ctx->lock);
+    if ((rc = hbi_scratch(ctx, 0, bytes, &d_prm, &h_prm)) != HB_OK) goto done;
+    memcpy(h_prm, params, bytes);
+    crc = hbc_h2d_async(d_prm, h_prm, bytes, ctx->stream);
+    if (!crc) { crc = hbk_sao_apply(&src->d, &dst->d, cols, n_ctus, (const hb_sao_param *)d_prm, ctx->stream); ctx->launches++; }
+    if (!crc) { crc = hbk_pad_frame(&dst->d, ctx->stream); ctx->launches++; }
+    if (!crc) crc = hbc_stream_sync(ctx->stream);
+done:
+    pthread_mutex_unlock(&ctx->lock);
+    if (crc) return hbi_cuda_fail(crc, "hb_sao_apply_frame");
+    return rc;
+}
+
 /* fill the launch-invariant part of a T/Q launch: tables and shifts of (component, size, qp) -- inter lists 3+comp */
 void hbi_tq_setup(hb_ctx *ctx, hbd_tq_args *a, int comp, int n, int qp, int is_islice, int sign_hiding)
 {

@@ -145,6 +145,58 @@ __global__ void __launch_bounds__(256) k_sao_stats(hbd_frame org, hbd_frame rec,
 }
 }  // namespace
 
+namespace {
+// ---- SAO offset pass (offset_block, hmr_sao.c:960; sao_offset_ctu :1210): dst = clip(src + offset[class]) inside the rectangle of
+// the CTU's type, a plain copy elsewhere, so dst is a complete picture.  src is the deblocked picture; classes always come
+// from src, as the reference reads them from its untouched copy (sao_aux_wnd).  Four samples per thread along a row.
+__global__ void __launch_bounds__(256) k_sao_apply(hbd_frame src, hbd_frame dst, int ctu_cols, const hb_sao_param *prm)
+{
+    __shared__ int s_off[32];
+    const int comp = blockIdx.y, ctu = blockIdx.x;
+    const hbd_plane &ps = src.p[comp], &pd = dst.p[comp];
+    const int cs = comp ? 32 : 64;
+    const int x0 = (ctu % ctu_cols) * cs, y0 = (ctu / ctu_cols) * cs;
+    const int w = min(cs, ps.w - x0), h = min(cs, ps.h - y0);
+    const bool l = x0 > 0, t = y0 > 0, r = x0 + cs < ps.w, b = y0 + cs < ps.h;
+    const int type = prm[ctu].type[comp];
+    if (threadIdx.x < 32) s_off[threadIdx.x] = prm[ctu].offset[comp][threadIdx.x];
+    __syncthreads();
+    int sx = 0, ex = w, sy = 0, ey = h;
+    if (type == 0 || type == 2 || type == 3) { sx = l ? 0 : 1; ex = r ? w : w - 1; }
+    if (type == 1 || type == 2 || type == 3) { sy = t ? 0 : 1; ey = b ? h : h - 1; }
+    if (type < 0 || type > 4) { ex = 0; ey = 0; }
+    const int ddx = type == 3 ? -1 : (type == 1 ? 0 : 1), ddy = type == 0 ? 0 : 1;       // second neighbour; the first is its opposite
+    const int nb = ddy * ps.pitch + ddx;
+    for (int i = threadIdx.x; i < (w >> 2) * h; i += 256) {
+        const int x4 = (i % (w >> 2)) * 4, y = i / (w >> 2);
+        const uint8_t *p = ps.org + (y0 + y) * ps.pitch + x0 + x4;
+        uint32_t outw = *reinterpret_cast<const uint32_t *>(p);
+        if (y >= sy && y < ey) {
+            int o[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int c = p[k];
+                int v = c;
+                if (x4 + k >= sx && x4 + k < ex) {
+                    const int cls = type == 4 ? (c >> 3) : 2 + sgn3(c - p[k - nb]) + sgn3(c - p[k + nb]);
+                    v = c + s_off[cls];
+                }
+                o[k] = v;
+            }
+            outw = hb_pack_sat_u8x4(o[0], o[1], o[2], o[3]);
+        }
+        *reinterpret_cast<uint32_t *>(pd.org + (y0 + y) * pd.pitch + x0 + x4) = outw;
+    }
+}
+}  // namespace
+
+extern "C" int hbk_sao_apply(const hbd_frame *src, const hbd_frame *dst, int ctu_cols, int n_ctus, const hb_sao_param *prm, void *stream)
+{
+    if (n_ctus <= 0) return 0;
+    k_sao_apply<<<dim3(n_ctus, 3), 256, 0, static_cast<cudaStream_t>(stream)>>>(*src, *dst, ctu_cols, prm);
+    return static_cast<int>(cudaGetLastError());
+}
+
 extern "C" int hbk_sao_stats(const hbd_frame *org, const hbd_frame *rec, int ctu_cols, int n_ctus, hb_sao_stats *out, void *stream)
 {
     if (n_ctus <= 0) return 0;

@@ -168,6 +168,7 @@ def load_library():
     L.hb_mc_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(McJob), C.c_int]
     L.hb_mc_predict_bi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(McBiJob), C.c_int]
     L.hb_sao_stats_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hb_sao_apply_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb_tq_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TuJob), C.c_int,
                                C.POINTER(TqParams), i16p, C.POINTER(TuResult)]
     L.hb_tq_encode_intra.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(IntraTuJob), C.c_int, C.c_int, C.c_int, C.c_double,
@@ -376,6 +377,18 @@ def _sao_stats(self, orig, rec):
 
 
 Context.sao_stats = _sao_stats
+
+SAO_PARAM_DT = np.dtype([("type", "i1", (3,)), ("reserved", "i1"), ("offset", "<i2", (3, 32))])
+
+
+def _sao_apply(self, src, dst, types, offsets):
+    """SAO offset pass: types (n_ctus, 3) in -1..4, offsets (n_ctus, 3, 32) as sao_offset_t.offset holds them"""
+    prm = np.zeros(len(types), SAO_PARAM_DT)
+    prm["type"] = types; prm["offset"] = offsets
+    _check(self.L.hb_sao_apply_frame(self.h, src.h, dst.h, prm.ctypes.data), "hb_sao_apply_frame")
+
+
+Context.sao_apply = _sao_apply
 
 
 def presearch_records(jobs_xyn):

@@ -220,6 +220,11 @@ void hb_create_intra_angular_prediction(int16_t *prediction, int pred_stride, in
  * Edge classes 0..4 stand for the reference's edge types -2..2; eo_*[k]: k = 0 EO_0 (horizontal), 1 EO_90, 2 EO_135, 3 EO_45. */
 typedef struct hb_sao_stats { int32_t eo_diff[4][5], eo_count[4][5], bo_diff[32], bo_count[32]; } hb_sao_stats;   /* 416 bytes */
 int hb_sao_stats_frame(hb_ctx *ctx, const hb_frame *orig, const hb_frame *rec, hb_sao_stats *out);
+/* SAO offset pass of a whole picture (sao_offset_ctu hmr_sao.c:1210 / offset_block :960 for every CTU): dst = src (the deblocked
+ * picture) with the CTU's offsets applied.  Per CTU (raster) and component: type -1 off, 0..3 EO_0/90/135/45 (offset[0..4] for edge
+ * types -2..2), 4 band offset (offset[band], 32 entries) -- the values of sao_offset_t.offset.  dst must be another frame. */
+typedef struct hb_sao_param { int8_t type[3]; int8_t reserved; int16_t offset[3][32]; } hb_sao_param;   /* 196 bytes */
+int hb_sao_apply_frame(hb_ctx *ctx, const hb_frame *src, hb_frame *dst, const hb_sao_param *params);
 
 /* ------------------------------------------------------------------ D. frame-level pre-pass ----------------
  * For every CTU and every inter PU size 64/32/16/8 at once: motion search chained parent -> child exactly as

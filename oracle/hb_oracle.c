@@ -905,3 +905,33 @@ void orc_sao_ctu_stats(const int16_t *rec, int rec_stride, const int16_t *org, i
             }
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * SAO offset pass of one CTU and component: offset_block, hmr_sao.c:960-1208 (called by sao_offset_ctu :1210).  src: the
+ * deblocked picture (the reference keeps a copy in sao_aux_wnd), dst: the picture being finalised.  type 0..3 edge classes
+ * (offset[0..4] for edge types -2..2), 4 band offset (offset[0..31] by band), anything else: untouched.  With the
+ * availability of the diagonal neighbours being the AND of the two sides (:1224-1231) the first / last line rules collapse
+ * into one rectangle per type.
+ * ------------------------------------------------------------------------------------------ */
+void orc_sao_offset_ctu(const int16_t *src, int src_stride, int16_t *dst, int dst_stride, int x0, int y0, int pic_w, int pic_h,
+                        int ctu_size, int type, const int *offset)
+{
+    static const int dx[4] = { 1, 0, 1, -1 }, dy[4] = { 0, 1, 1, 1 };
+    const int w = x0 + ctu_size > pic_w ? pic_w - x0 : ctu_size, h = y0 + ctu_size > pic_h ? pic_h - y0 : ctu_size;
+    const int l = x0 > 0, t = y0 > 0, r = x0 + ctu_size < pic_w, b = y0 + ctu_size < pic_h;
+    if (type < 0 || type > 4) return;
+    int sx = 0, ex = w, sy = 0, ey = h;
+    if (type == 0 || type == 2 || type == 3) { sx = l ? 0 : 1; ex = r ? w : w - 1; }
+    if (type == 1 || type == 2 || type == 3) { sy = t ? 0 : 1; ey = b ? h : h - 1; }
+    for (int y = sy; y < ey; y++)
+        for (int x = sx; x < ex; x++) {
+            const int c = src[(y0 + y) * src_stride + x0 + x];
+            int k;
+            if (type == 4) k = c >> 3;
+            else {
+                const int a = src[(y0 + y - dy[type]) * src_stride + x0 + x - dx[type]], n = src[(y0 + y + dy[type]) * src_stride + x0 + x + dx[type]];
+                k = 2 + sgn3(c - a) + sgn3(c - n);
+            }
+            dst[(y0 + y) * dst_stride + x0 + x] = (int16_t)clampi(c + offset[k], 0, 255);
+        }
+}

@@ -721,3 +721,55 @@ int refdrv_sao_stats(refdrv *d, const uint8_t *const rec[3], const uint8_t *cons
     wnd_delete(&fr_rec.img); wnd_delete(&fr_org.img);
     return n;
 }
+
+/* SAO offset pass through the reference's sao_offset_ctu (hmr_sao.c:1210) for every CTU of a picture.  src: 8-bit planes of the
+ * deblocked picture; types[ctu*3+comp] in -1 (off), 0..3 (EO), 4 (BO); offsets[(ctu*3+comp)*32 ..]: per-class offsets exactly as
+ * sao_offset_t.offset holds them (EO: indices 0..4 for edge types -2..2, BO: one per band).  out: the finalised 8-bit planes. */
+void sao_offset_ctu(henc_thread_t *wpp_thread, ctu_info_t *ctu, sao_blk_param_t *sao_blk_param);
+int refdrv_sao_apply(refdrv *d, const uint8_t *const src[3], int w, int h, const int8_t *types, const int32_t *offsets, uint8_t *const out[3])
+{
+    henc_thread_t *et = d->et;
+    hvenc_engine_t *eng = et->enc_engine;
+    video_frame_t fr_rec;
+    video_frame_t *save_ref = eng->curr_reference_frame;
+    wnd_t save_aux = eng->sao_aux_wnd, aux;
+    int save_w[3], save_h[3], n = 0;
+    const int save_cu = et->max_cu_size;
+    memset(&fr_rec, 0, sizeof fr_rec); memset(&aux, 0, sizeof aux);
+    wnd_alloc(&fr_rec.img, w, h, 80, 80, sizeof(int16_t));
+    wnd_alloc(&aux, w, h, 80, 80, sizeof(int16_t));
+    for (int c = 0; c < 3; c++) {
+        const int pw = c ? w / 2 : w, ph = c ? h / 2 : h;
+        int16_t *pr = (int16_t *)fr_rec.img.pwnd[c], *pa = (int16_t *)aux.pwnd[c];
+        for (int y = 0; y < ph; y++)
+            for (int x = 0; x < pw; x++) pr[y * fr_rec.img.window_size_x[c] + x] = pa[y * aux.window_size_x[c] + x] = src[c][y * pw + x];
+        save_w[c] = et->pict_width[c]; save_h[c] = et->pict_height[c];
+        et->pict_width[c] = pw; et->pict_height[c] = ph;
+    }
+    eng->curr_reference_frame = &fr_rec; eng->sao_aux_wnd = aux; et->max_cu_size = 64;
+    for (int cy = 0; cy < h; cy += 64)
+        for (int cx = 0; cx < w; cx += 64) {
+            ctu_info_t ctu;
+            sao_blk_param_t prm;
+            memset(&ctu, 0, sizeof ctu); memset(&prm, 0, sizeof prm);
+            ctu.size = 64; ctu.ctu_number = n; ctu.x[0] = cx; ctu.y[0] = cy; ctu.x[1] = ctu.x[2] = cx / 2; ctu.y[1] = ctu.y[2] = cy / 2;
+            for (int c = 0; c < 3; c++) {
+                const int ty = types[n * 3 + c];
+                prm.offsetParam[c].modeIdc = ty < 0 ? SAO_MODE_OFF : SAO_MODE_NEW;
+                prm.offsetParam[c].typeIdc = ty < 0 ? 0 : ty;
+                for (int k = 0; k < 32; k++) prm.offsetParam[c].offset[k] = offsets[(n * 3 + c) * 32 + k];
+            }
+            sao_offset_ctu(et, &ctu, &prm);
+            n++;
+        }
+    for (int c = 0; c < 3; c++) {
+        const int pw = c ? w / 2 : w, ph = c ? h / 2 : h;
+        const int16_t *pr = (const int16_t *)fr_rec.img.pwnd[c];
+        for (int y = 0; y < ph; y++)
+            for (int x = 0; x < pw; x++) out[c][y * pw + x] = (uint8_t)pr[y * fr_rec.img.window_size_x[c] + x];
+        et->pict_width[c] = save_w[c]; et->pict_height[c] = save_h[c];
+    }
+    eng->curr_reference_frame = save_ref; eng->sao_aux_wnd = save_aux; et->max_cu_size = save_cu;
+    wnd_delete(&fr_rec.img); wnd_delete(&aux);
+    return n;
+}

@@ -90,6 +90,7 @@ def oracle():
         L.orc_intra_mode_sads.argtypes = [i16p, C.c_int, i16p, C.c_int, C.POINTER(C.c_uint32)]
         L.orc_weighted_average.argtypes = [i16p, C.c_int, i16p, C.c_int, i16p, C.c_int, C.c_int, C.c_int]
         L.orc_sao_ctu_stats.argtypes = [i16p, C.c_int, i16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orc_sao_offset_ctu.argtypes = [i16p, C.c_int, i16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.tables = L.orc_tables_create()
         _oracle = L
     return _oracle
@@ -210,6 +211,51 @@ def oracle_sao_stats(rec, org, w, h):
         for i in range(rows * cols):
             x0, y0 = (i % cols) * cs, (i // cols) * cs
             O.orc_sao_ctu_stats(ptr(r16.reshape(-1), 2 * (pw + 4) + 2), pw + 4, ptr(o16.reshape(-1)), pw, c, x0, y0, pw, ph, cs, out[i, c:c + 1].ctypes.data)
+    return out
+
+
+def random_sao_params(rng, w, h):
+    """per CTU and component a type in -1..4 and the offsets the way sao_offset_t.offset holds them"""
+    n = ((w + 63) // 64) * ((h + 63) // 64)
+    types = rng.integers(-1, 5, (n, 3)).astype(np.int8)
+    offs = np.zeros((n, 3, 32), np.int32)
+    for i in range(n):
+        for c in range(3):
+            t = types[i, c]
+            if 0 <= t < 4:
+                offs[i, c, :5] = [rng.integers(0, 8), rng.integers(0, 8), 0, -rng.integers(0, 8), -rng.integers(0, 8)]
+            elif t == 4:
+                b0 = int(rng.integers(0, 29))
+                offs[i, c, b0:b0 + 4] = rng.integers(-7, 8, 4)
+    return types, offs
+
+
+def oracle_sao_apply(src, w, h, types, offs):
+    O = oracle()
+    cols = (w + 63) // 64
+    out = []
+    for c in range(3):
+        pw, ph = (w, h) if c == 0 else (w // 2, h // 2)
+        cs = 64 if c == 0 else 32
+        s16 = np.ascontiguousarray(np.pad(src[c].astype(np.int16), 2)); d16 = s16.copy()
+        for i in range(len(types)):
+            x0, y0 = (i % cols) * cs, (i // cols) * cs
+            o = np.ascontiguousarray(offs[i, c], np.int32)
+            O.orc_sao_offset_ctu(ptr(s16.reshape(-1), 2 * (pw + 4) + 2), pw + 4, ptr(d16.reshape(-1), 2 * (pw + 4) + 2), pw + 4, x0, y0, pw, ph, cs,
+                                 int(types[i, c]), o.ctypes.data_as(C.POINTER(C.c_int)))
+        out.append(d16[2:-2, 2:-2].astype(np.uint8))
+    return out
+
+
+def ref_sao_apply(src, w, h, types, offs):
+    _, D = ref()
+    hnd = refdrv()
+    D.refdrv_sao_apply.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    src = [np.ascontiguousarray(p) for p in src]
+    out = [np.zeros_like(p) for p in src]
+    sp = (C.c_void_p * 3)(*[p.ctypes.data for p in src]); op = (C.c_void_p * 3)(*[p.ctypes.data for p in out])
+    types = np.ascontiguousarray(types, np.int8); offs = np.ascontiguousarray(offs, np.int32)
+    assert D.refdrv_sao_apply(hnd, sp, w, h, types.ctypes.data, offs.ctypes.data, op) == len(types)
     return out
 
 

@@ -229,3 +229,20 @@ def test_sao_statistics(ctx):
         for f in ("eo_diff", "eo_count", "bo_diff", "bo_count"):
             assert np.array_equal(got[f], exp[f]), (w, h, f, np.argwhere(got[f] != exp[f])[:3])
         fo.close(); fr.close()
+
+
+def test_sao_offset_pass(ctx):
+    """the SAO offset pass of a whole picture on the GPU == the restatement of offset_block per CTU, border refreshed"""
+    from _oracle import oracle_sao_apply, random_sao_params
+    rng = np.random.default_rng(42)
+    for (w, h) in ((320, 192), (200, 136), (64, 72)):
+        src = [np.clip(rng.normal(128, 50, (hh, ww)), 0, 255).astype(np.uint8) for (ww, hh) in ((w, h), (w // 2, h // 2), (w // 2, h // 2))]
+        types, offs = random_sao_params(rng, w, h)
+        fs, fd = hb.Frame(ctx, w, h), hb.Frame(ctx, w, h)
+        fs.upload_u8(*src)
+        ctx.sao_apply(fs, fd, types, offs)
+        got = fd.download()
+        exp = oracle_sao_apply(src, w, h, types, offs)
+        for c in range(3):
+            assert np.array_equal(got[c], exp[c]), (w, h, c, np.argwhere(got[c] != exp[c])[:4])
+        fs.close(); fd.close()

@@ -269,3 +269,16 @@ def test_sao_statistics_against_reference():
         for f in ("eo_diff", "eo_count", "bo_diff", "bo_count"):
             assert np.array_equal(a[f], b[f]), (w, h, f, np.argwhere(a[f] != b[f])[:3])
         assert a["eo_count"].sum() > 0 and (a["eo_count"][:, :, :, 0] > 0).any() and (a["eo_count"][:, :, :, 4] > 0).any()
+
+
+def test_sao_offset_pass_against_reference():
+    """the SAO offset pass (sao_offset_ctu / offset_block) with random per-CTU types and offsets, whole and partial CTUs"""
+    from _oracle import oracle_sao_apply, random_sao_params, ref_sao_apply
+    rng = np.random.default_rng(108)
+    for (w, h) in ((192, 128), (200, 136), (64, 200), (328, 72)):
+        src = [np.clip(rng.normal(128, 50, (hh, ww)), 0, 255).astype(np.uint8) for (ww, hh) in ((w, h), (w // 2, h // 2), (w // 2, h // 2))]
+        types, offs = random_sao_params(rng, w, h)
+        a = oracle_sao_apply(src, w, h, types, offs); b = ref_sao_apply(src, w, h, types, offs)
+        for c in range(3):
+            assert np.array_equal(a[c], b[c]), (w, h, c, np.argwhere(a[c] != b[c])[:4])
+        assert any((a[c] != src[c]).any() for c in range(3))
