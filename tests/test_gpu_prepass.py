@@ -10,7 +10,7 @@ from _oracle import chroma_qp
 pytestmark = pytest.mark.gpu
 
 
-def _oracle_prepass_me(cur, ref, w, h, qp, avg_dist):
+def _oracle_prepass_me(cur, ref, w, h, qp, avg_dist, action=7):
     """depth by depth, parent vector as extra start when both components are non-zero"""
     out = []
     for d in range(4):
@@ -27,7 +27,7 @@ def _oracle_prepass_me(cur, ref, w, h, qp, avg_dist):
                     par = out[d - 1].get((px // 2, py // 2))
                     if par is not None and par.mv.x != 0 and par.mv.y != 0:
                         starts = [(par.mv.x, par.mv.y)]
-                tab[(px, py)] = oracle_me(cur, ref, w, h, x, y, s, qp, [(0, 0), (0, 0)], starts, avg_dist)
+                tab[(px, py)] = oracle_me(cur, ref, w, h, x, y, s, qp, [(0, 0), (0, 0)], starts, avg_dist, action)
         out.append(tab)
     return out
 
@@ -88,6 +88,33 @@ def test_prepass_matches_oracle(ctx, w, h, use_graph):
     assert pp.fetch_all(pin) == pp.output_bytes()
     me0 = pp.fetch_me(0)
     assert bytes(pin[:me0.nbytes]) == me0.tobytes()
+    pp.close(); fc.close(); fr.close()
+
+
+@pytest.mark.parametrize("action", [hb.ME_PEL, hb.ME_PEL | hb.ME_HALF])
+def test_prepass_other_search_precisions(ctx, action):
+    """integer-only search (luma and chroma predictions from the compensation kernels, nothing fused) and half-pel search:
+    vectors, probe counts and predictions of every depth against the oracle"""
+    w, h, qp, avg_dist = 192, 136, 32, 650.0
+    cur, ref = clip_pair(w, h, n=2, noise=3.0, seed=8)
+    fc, fr = upload(ctx, cur, w, h), upload(ctx, ref, w, h)
+    pp = hb.Prepass(ctx, w, h, qp=qp, me_action=action)
+    pp.run(fc, fr, avg_dist); ctx.sync()
+    exp_me = _oracle_prepass_me(cur, ref, w, h, qp, avg_dist, action)
+    for d in range(4):
+        s = 64 >> d
+        got = pp.fetch_me(d)
+        gw = ((w + 63) // 64) * (64 // s)
+        py_, pu_, pv_ = pp.pred(d).download()
+        for idx, r in enumerate(got):
+            px, py = idx % gw, idx // gw
+            e = exp_me[d].get((px, py))
+            if e is None:
+                continue
+            assert (r["mvx"], r["mvy"], r["sad"], r["n_probes"]) == (e.mv.x, e.mv.y, e.sad, e.n_int_sads), (d, px, py)
+            x, y = px * s, py * s
+            assert np.array_equal(py_[y:y + s, x:x + s], oracle_mc(ref, 0, x, y, s, e.mv.x, e.mv.y)), ("pred Y", d, px, py)
+            assert np.array_equal(pu_[y // 2:(y + s) // 2, x // 2:(x + s) // 2], oracle_mc(ref, 1, x // 2, y // 2, s // 2, e.mv.x, e.mv.y)), ("pred U", d, px, py)
     pp.close(); fc.close(); fr.close()
 
 
