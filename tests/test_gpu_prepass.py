@@ -118,6 +118,36 @@ def test_prepass_other_search_precisions(ctx, action):
     pp.close(); fc.close(); fr.close()
 
 
+def test_prepass_quantiser_variants(ctx):
+    """the pre-pass T/Q with the I-slice rounding and without sign-data hiding (all unit sizes, the one-thread 4x4 kernel included)"""
+    w, h, qp, avg_dist = 128, 72, 27, 120.0
+    cur, ref = clip_pair(w, h, n=2, noise=6.0, seed=15)
+    fc, fr = upload(ctx, cur, w, h), upload(ctx, ref, w, h)
+    for (isl, sh) in ((1, 0), (1, 1), (0, 0)):
+        pp = hb.Prepass(ctx, w, h, qp=qp, sign_hiding=sh, is_islice=isl)
+        pp.run(fc, fr, avg_dist); ctx.sync()
+        qp_c = chroma_qp(qp, 2)
+        weight = 2.0 ** ((qp - qp_c) / 3.0)
+        n_coded = 0
+        for p in range(5):
+            d = min(p, 3)
+            pred = pp.pred(d).download()
+            rec = pp.recon(p).download()
+            for comp in range(3):
+                t = pp.tu_size(p, comp)
+                if not t:
+                    continue
+                for (x, y), r, c in zip(pp.tu_xy(p, comp), pp.fetch_tu(p, comp), pp.fetch_coeffs(p, comp)):
+                    eco, ede, eo = oracle_tu(cur.block(comp, x, y, t), pred[comp][y:y + t, x:x + t], t, comp, qp if comp == 0 else qp_c, isl, sh,
+                                             avg_dist, 1.0 if comp == 0 else weight)
+                    assert (r["sum"], r["ssd"], r["zeroed"]) == (eo.sum, eo.ssd, eo.zeroed), (isl, sh, p, comp, x, y)
+                    assert np.array_equal(c, eco) and np.array_equal(rec[comp][y:y + t, x:x + t], ede), (isl, sh, p, comp, x, y)
+                    n_coded += r["sum"] > 0
+        assert n_coded > 20
+        pp.close()
+    fc.close(); fr.close()
+
+
 def test_prepass_band_union_equals_whole(ctx):
     """CTU-row bands (the multi-GPU partition) produce exactly the rows of the whole-frame run"""
     w, h = 256, 256
