@@ -246,3 +246,38 @@ def test_sao_offset_pass(ctx):
         for c in range(3):
             assert np.array_equal(got[c], exp[c]), (w, h, c, np.argwhere(got[c] != exp[c])[:4])
         fs.close(); fd.close()
+
+
+def test_frame_upload_layouts_and_border(ctx):
+    """uploads from contiguous planes (one copy), separate planes and strided views (pitched copies) land identically, the
+    replicated border included (checked through a prediction that reaches outside the picture); int16 uploads agree"""
+    from homerhevc_b200.lib import Mv
+    w, h = 192, 136
+    rng = np.random.default_rng(50)
+    buf = rng.integers(0, 256, w * h * 3 // 2, dtype=np.uint8)
+    y = buf[:w * h].reshape(h, w); u = buf[w * h:w * h * 5 // 4].reshape(h // 2, w // 2); v = buf[w * h * 5 // 4:].reshape(h // 2, w // 2)
+    wide = rng.integers(0, 256, (h, w + 40), dtype=np.uint8); wide[:, 8:8 + w] = y
+    wide_c = rng.integers(0, 256, (h // 2, w // 2 + 24), dtype=np.uint8); wide_c[:, 4:4 + w // 2] = u
+    frames = []
+    for planes in ((y, u, v), (y.copy(), u.copy(), v.copy()), (wide[:, 8:8 + w], wide_c[:, 4:4 + w // 2], v)):
+        f = hb.Frame(ctx, w, h); f.upload_u8(*planes); frames.append(f)
+    f16 = hb.Frame(ctx, w, h); f16.upload_i16(y.astype(np.int16), u.astype(np.int16), v.astype(np.int16)); frames.append(f16)
+    ref_dl = frames[0].download()
+    assert np.array_equal(ref_dl[0], y) and np.array_equal(ref_dl[1], u) and np.array_equal(ref_dl[2], v)
+    # blocks at the four corners predicted from far outside the picture: only border samples contribute
+    jobs = [hb.McJob(x, yy, 16, Mv(mx, my)) for (x, yy, mx, my) in ((0, 0, -4 * 40 - 1, -4 * 30 - 2), (w - 16, 0, 4 * 50 + 3, -4 * 20 - 1),
+                                                                     (0, h - 24, -4 * 33 - 2, 4 * 45 + 1), (w - 16, h - 24, 4 * 60 + 1, 4 * 55 + 3))]
+    outs = []
+    for f in frames:
+        pred = hb.Frame(ctx, w, h)
+        ctx.mc_predict(f, pred, jobs)
+        outs.append(pred.download()); pred.close()
+    for o in outs[1:]:
+        for c in range(3):
+            assert np.array_equal(o[c], outs[0][c])
+    # and against the oracle on an explicitly edge-padded host frame
+    hf = HostFrame(y, u, v)
+    for j in jobs:
+        assert np.array_equal(outs[0][0][j.y:j.y + 16, j.x:j.x + 16], oracle_mc(hf, 0, j.x, j.y, 16, j.mv.x, j.mv.y)), (j.x, j.y)
+    for f in frames:
+        f.close()
