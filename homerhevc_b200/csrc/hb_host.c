@@ -584,6 +584,33 @@ done:
     return rc;
 }
 
+/* deblocking of a whole picture in place (pixel stage; strengths and QPs from the host) */
+int hb_deblock_frame(hb_ctx *ctx, hb_frame *frame, const uint8_t *bs_ver, const uint8_t *bs_hor, const uint8_t *qp, int units_w,
+                     const hb_deblock_params *params)
+{
+    int rc = HB_OK, crc = 0;
+    void *d_maps, *h_maps;
+    if (!ctx || !frame || !bs_ver || !bs_hor || !qp || !params) return hbi_fail(HB_ERR_ARG, "hb_deblock_frame: NULL argument");
+    if (units_w < frame->w / 4) return hbi_fail(HB_ERR_ARG, "hb_deblock_frame: units_w %d is smaller than width/4", units_w);
+    const size_t plane = (size_t)units_w * (size_t)(frame->h / 4);
+    hbc_set_device(ctx->device);
+    pthread_mutex_lock(&ctx->lock);
+    if ((rc = hbi_scratch(ctx, 0, 3 * plane, &d_maps, &h_maps)) != HB_OK) goto done;
+    memcpy(h_maps, bs_ver, plane); memcpy((char *)h_maps + plane, bs_hor, plane); memcpy((char *)h_maps + 2 * plane, qp, plane);
+    crc = hbc_h2d_async(d_maps, h_maps, 3 * plane, ctx->stream);
+    if (!crc) {
+        crc = hbk_deblock(&frame->d, (const uint8_t *)d_maps, (const uint8_t *)d_maps + plane, (const uint8_t *)d_maps + 2 * plane, units_w,
+                          params->cb_qp_offset, params->cr_qp_offset, params->beta_offset_div2, params->tc_offset_div2, ctx->stream);
+        ctx->launches += 2;
+    }
+    if (!crc) { crc = hbk_pad_frame(&frame->d, ctx->stream); ctx->launches++; }
+    if (!crc) crc = hbc_stream_sync(ctx->stream);
+done:
+    pthread_mutex_unlock(&ctx->lock);
+    if (crc) return hbi_cuda_fail(crc, "hb_deblock_frame");
+    return rc;
+}
+
 /* SAO statistics of a whole picture: one launch, one copy back */
 int hb_sao_stats_frame(hb_ctx *ctx, const hb_frame *orig, const hb_frame *rec, hb_sao_stats *out)
 {

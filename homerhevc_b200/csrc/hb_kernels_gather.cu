@@ -145,6 +145,138 @@ __global__ void __launch_bounds__(256) k_sao_stats(hbd_frame org, hbd_frame rec,
 }
 }  // namespace
 
+// ---- deblocking, pixel stage (deblock_filter_luma / _chroma, filter_luma, filter_chroma, use_strong_filter,
+// hmr_deblocking_filter.c:264-627; picture order of hmr_deblock_filter :827: one launch for every vertical edge, one for every
+// horizontal edge).  One thread per 4x4 luma unit whose left (top) side lies on the 8x8 grid and carries a non-zero boundary
+// strength: it decides on lines 0 and 3 and filters the four luma lines of its segment in place, plus -- strength 2, 8x8 chroma
+// grid -- two lines of U and V.  Segments of one direction never touch the same samples.  Strengths and QPs are inputs.
+namespace {
+__constant__ uint8_t c_dbk_tc[54] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,1,1,1,1,1,2,2,2,2,3,3,3,3,4,4,4,5,5,6,6,7,8,9,10,11,13,14,16,18,20,22,24 };
+__constant__ uint8_t c_dbk_beta[52] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,6,7,8,9,10,11,12,13,14,15,16,17,18,20,22,24,26,28,30,32,34,36,38,40,42,44,46,48,50,52,54,56,58,60,62,64 };
+__constant__ uint8_t c_dbk_chroma_qp[58] = { 0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,29,30,31,32,33,33,34,34,35,35,36,36,37,37,38,39,40,41,42,43,44,45,46,47,48,49,50,51 };
+
+struct DbkArgs {
+    hbd_frame f;
+    const uint8_t *bs, *qp;      // strengths of this direction, CU QP; per 4x4 unit, picture raster
+    int units_w, dir;
+    int cb_off, cr_off, beta_off2, tc_off2;
+};
+
+__device__ __forceinline__ int clamp3(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// one luma line across the edge: m[0..3] = p3 p2 p1 p0, m[4..7] = q0 q1 q2 q3
+__device__ __forceinline__ void dbk_luma_line(int (&m)[8], int tc, bool sw, int thr_cut, bool second_p, bool second_q)
+{
+    const int m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4], m5 = m[5], m6 = m[6], m7 = m[7];
+    if (sw) {
+        m[3] = clamp3((m1 + 2 * m2 + 2 * m3 + 2 * m4 + m5 + 4) >> 3, m3 - 2 * tc, m3 + 2 * tc);
+        m[4] = clamp3((m2 + 2 * m3 + 2 * m4 + 2 * m5 + m6 + 4) >> 3, m4 - 2 * tc, m4 + 2 * tc);
+        m[2] = clamp3((m1 + m2 + m3 + m4 + 2) >> 2, m2 - 2 * tc, m2 + 2 * tc);
+        m[5] = clamp3((m3 + m4 + m5 + m6 + 2) >> 2, m5 - 2 * tc, m5 + 2 * tc);
+        m[1] = clamp3((2 * m0 + 3 * m1 + m2 + m3 + m4 + 4) >> 3, m1 - 2 * tc, m1 + 2 * tc);
+        m[6] = clamp3((m3 + m4 + m5 + 3 * m6 + 2 * m7 + 4) >> 3, m6 - 2 * tc, m6 + 2 * tc);
+    } else {
+        int delta = (9 * (m4 - m3) - 3 * (m5 - m2) + 8) >> 4;
+        if (abs(delta) < thr_cut) {
+            const int tc2 = tc >> 1;
+            delta = clamp3(delta, -tc, tc);
+            m[3] = hb_clip255(m3 + delta);
+            m[4] = hb_clip255(m4 - delta);
+            if (second_p) m[2] = hb_clip255(m2 + clamp3((((m1 + m3 + 1) >> 1) - m2 + delta) >> 1, -tc2, tc2));
+            if (second_q) m[5] = hb_clip255(m5 + clamp3((((m6 + m4 + 1) >> 1) - m5 - delta) >> 1, -tc2, tc2));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_deblock(const DbkArgs a)
+{
+    const hbd_plane &py = a.f.p[0];
+    const int uw = py.w >> 2, uh = py.h >> 2;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= uw * uh) return;
+    const int ux = i % uw, uy = i / uw, along = a.dir ? uy : ux;
+    const int bs = a.bs[uy * a.units_w + ux];
+    if (!bs || along == 0 || (along & 1)) return;
+    const int qpq = a.qp[uy * a.units_w + ux], qpp = a.dir ? a.qp[(uy - 1) * a.units_w + ux] : a.qp[uy * a.units_w + ux - 1];
+    const int q = (qpp + qpq + 1) >> 1;
+    {
+        const int tc = c_dbk_tc[clamp3(q + 2 * (bs - 1) + 2 * a.tc_off2, 0, 53)], beta = c_dbk_beta[clamp3(q + 2 * a.beta_off2, 0, 51)];
+        const int side_thr = (beta + (beta >> 1)) >> 3, thr_cut = tc * 10;
+        uint8_t *e = py.org + (4 * uy) * py.pitch + 4 * ux;          // q0 of line 0
+        int m[4][8];
+        if (a.dir == 0) {                                            // vertical edge: a line is a row, samples x-4 .. x+3
+#pragma unroll
+            for (int l = 0; l < 4; l++) {
+                const uint32_t *rw = reinterpret_cast<const uint32_t *>(e + l * py.pitch - 4);      // 4-byte aligned, not 8
+                const uint32_t wp = rw[0], wq = rw[1];
+#pragma unroll
+                for (int k = 0; k < 4; k++) { m[l][k] = (wp >> (8 * k)) & 255; m[l][4 + k] = (wq >> (8 * k)) & 255; }
+            }
+        } else {                                                     // horizontal edge: a line is a column, rows y-4 .. y+3
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t wv = *reinterpret_cast<const uint32_t *>(e + (k - 4) * py.pitch);
+#pragma unroll
+                for (int l = 0; l < 4; l++) m[l][k] = (wv >> (8 * l)) & 255;
+            }
+        }
+        auto dp = [&](int l) { return abs(m[l][1] - 2 * m[l][2] + m[l][3]); };
+        auto dq = [&](int l) { return abs(m[l][4] - 2 * m[l][5] + m[l][6]); };
+        const int dp0 = dp(0), dq0 = dq(0), dp3 = dp(3), dq3 = dq(3);
+        const int d0 = dp0 + dq0, d3 = dp3 + dq3;
+        if (d0 + d3 < beta) {
+            auto strong = [&](int l, int d) { return abs(m[l][0] - m[l][3]) + abs(m[l][7] - m[l][4]) < (beta >> 3) && d < (beta >> 2) && abs(m[l][3] - m[l][4]) < ((tc * 5 + 1) >> 1); };
+            const bool sw = strong(0, 2 * d0) && strong(3, 2 * d3);
+#pragma unroll
+            for (int l = 0; l < 4; l++) dbk_luma_line(m[l], tc, sw, thr_cut, dp0 + dp3 < side_thr, dq0 + dq3 < side_thr);
+            if (a.dir == 0) {
+#pragma unroll
+                for (int l = 0; l < 4; l++)
+                {
+                    uint32_t *rw = reinterpret_cast<uint32_t *>(e + l * py.pitch - 4);
+                    rw[0] = hb_pack4(m[l][0], m[l][1], m[l][2], m[l][3]); rw[1] = hb_pack4(m[l][4], m[l][5], m[l][6], m[l][7]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 1; k < 7; k++)
+                    *reinterpret_cast<uint32_t *>(e + (k - 4) * py.pitch) = hb_pack4(m[0][k], m[1][k], m[2][k], m[3][k]);
+            }
+        }
+    }
+    if (bs > 1 && (along & 3) == 0) {
+#pragma unroll
+        for (int c = 1; c < 3; c++) {
+            const hbd_plane &pc = a.f.p[c];
+            const int qc = c_dbk_chroma_qp[clamp3(q + (c == 1 ? a.cb_off : a.cr_off), 0, 57)];
+            const int tc = c_dbk_tc[clamp3(qc + 2 * (bs - 1) + 2 * a.tc_off2, 0, 53)];
+            const int o = a.dir ? pc.pitch : 1, step = a.dir ? 1 : pc.pitch;
+            uint8_t *e = pc.org + (2 * uy) * pc.pitch + 2 * ux;
+#pragma unroll
+            for (int l = 0; l < 2; l++) {
+                uint8_t *s2 = e + l * step;
+                const int m2 = s2[-2 * o], m3 = s2[-o], m4 = s2[0], m5 = s2[o];
+                const int delta = clamp3((((m4 - m3) << 2) + m2 - m5 + 4) >> 3, -tc, tc);
+                s2[-o] = static_cast<uint8_t>(hb_clip255(m3 + delta));
+                s2[0] = static_cast<uint8_t>(hb_clip255(m4 - delta));
+            }
+        }
+    }
+}
+}  // namespace
+
+extern "C" int hbk_deblock(const hbd_frame *f, const uint8_t *bs_ver, const uint8_t *bs_hor, const uint8_t *qp, int units_w,
+                           int cb_off, int cr_off, int beta_off2, int tc_off2, void *stream)
+{
+    DbkArgs a;
+    a.f = *f; a.qp = qp; a.units_w = units_w; a.cb_off = cb_off; a.cr_off = cr_off; a.beta_off2 = beta_off2; a.tc_off2 = tc_off2;
+    const int n = (f->p[0].w >> 2) * (f->p[0].h >> 2);
+    a.bs = bs_ver; a.dir = 0;
+    k_deblock<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    a.bs = bs_hor; a.dir = 1;
+    k_deblock<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return static_cast<int>(cudaGetLastError());
+}
+
 namespace {
 // ---- SAO offset pass (offset_block, hmr_sao.c:960; sao_offset_ctu :1210): dst = clip(src + offset[class]) inside the rectangle of
 // the CTU's type, a plain copy elsewhere, so dst is a complete picture.  src is the deblocked picture; classes always come

@@ -159,6 +159,9 @@ typedef struct hbd_gather_args {
 int hbk_gather(const hbd_gather_args *a, int n_ctus, void *stream);
 /* SAO statistics of every CTU and component of a frame: out[ctu * 3 + comp] */
 int hbk_sao_stats(const hbd_frame *org, const hbd_frame *rec, int ctu_cols, int n_ctus, hb_sao_stats *out, void *stream);
+/* deblocking, pixel stage, in place: all vertical edges, then all horizontal ones (two launches); maps in device memory */
+int hbk_deblock(const hbd_frame *f, const uint8_t *bs_ver, const uint8_t *bs_hor, const uint8_t *qp, int units_w,
+                int cb_off, int cr_off, int beta_off2, int tc_off2, void *stream);
 /* SAO offset pass: dst = src with the per-CTU offsets applied (prm[ctu], device memory) */
 int hbk_sao_apply(const hbd_frame *src, const hbd_frame *dst, int ctu_cols, int n_ctus, const hb_sao_param *prm, void *stream);
 /* full result tables (n_me hb_me_result, then n_tu hb_tu_result) -> compact records (hb_me_result_c, hb_tu_result_c) */

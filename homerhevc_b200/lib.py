@@ -167,6 +167,7 @@ def load_library():
                                C.c_double, C.c_int, C.POINTER(MeResult)]
     L.hb_mc_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(McJob), C.c_int]
     L.hb_mc_predict_bi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(McBiJob), C.c_int]
+    L.hb_deblock_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.hb_sao_stats_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb_sao_apply_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb_tq_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TuJob), C.c_int,
@@ -377,6 +378,17 @@ def _sao_stats(self, orig, rec):
 
 
 Context.sao_stats = _sao_stats
+
+
+def _deblock(self, frame, bs_ver, bs_hor, qp, cb_qp_offset=0, cr_qp_offset=0, beta_offset_div2=0, tc_offset_div2=0):
+    """deblocking in place; bs_ver / bs_hor / qp: uint8 (rows, units_w) maps per 4x4 luma unit"""
+    bs_ver = np.ascontiguousarray(bs_ver, np.uint8); bs_hor = np.ascontiguousarray(bs_hor, np.uint8); qp = np.ascontiguousarray(qp, np.uint8)
+    assert bs_ver.shape == bs_hor.shape == qp.shape and bs_ver.shape[0] >= frame.h_px // 4
+    prm = (C.c_int32 * 4)(cb_qp_offset, cr_qp_offset, beta_offset_div2, tc_offset_div2)
+    _check(self.L.hb_deblock_frame(self.h, frame.h, bs_ver.ctypes.data, bs_hor.ctypes.data, qp.ctypes.data, bs_ver.shape[1], prm), "hb_deblock_frame")
+
+
+Context.deblock = _deblock
 
 SAO_PARAM_DT = np.dtype([("type", "i1", (3,)), ("reserved", "i1"), ("offset", "<i2", (3, 32))])
 

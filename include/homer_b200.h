@@ -214,6 +214,16 @@ int hb_intra_run(hb_ctx *ctx, const hb_frame *cur, hb_frame *pred, const hb_intr
 void hb_create_intra_planar_prediction(int16_t *prediction, int pred_stride, int16_t *adi_pred_buff, int adi_size, int cu_size, int cu_size_shift);
 void hb_create_intra_angular_prediction(int16_t *prediction, int pred_stride, int16_t *adi_pred_buff, int adi_size, int cu_size, int cu_mode, int is_luma);
 
+/* Deblocking of a whole picture, pixel stage, in place (deblock_filter_luma / _chroma hmr_deblocking_filter.c:351/:504 with
+ * filter_luma :287, filter_chroma :478, use_strong_filter :275, in the picture order of hmr_deblock_filter :827: every vertical
+ * edge, then every horizontal one).  The boundary strengths are INPUTS: bs_ver / bs_hor hold, per 4x4 luma unit in picture
+ * raster (units_w entries per row, at least width/4), the strength 0..2 of the edge on the unit's left / top side -- the
+ * values get_boundary_strength_single (:138) leaves in deblock_filter_strength_bs; entries off the 8x8 grid are ignored.
+ * qp: the QP of the CU each unit belongs to.  The replicated border is refreshed afterwards. */
+typedef struct hb_deblock_params { int32_t cb_qp_offset, cr_qp_offset, beta_offset_div2, tc_offset_div2; } hb_deblock_params;
+int hb_deblock_frame(hb_ctx *ctx, hb_frame *frame, const uint8_t *bs_ver, const uint8_t *bs_hor, const uint8_t *qp, int units_w,
+                     const hb_deblock_params *params);
+
 /* SAO statistics (get_sao_stats of the function table, hmr_private.h:1091; sao_get_ctu_stats hmr_sao.c:75 /
  * sse_sao_get_ctu_stats hmr_sse42_sao.c:35, calculate_preblock_stats = 0) for every CTU and component of a picture in one
  * launch: `rec` is the deblocked reconstruction (before SAO), `orig` the source.  out[ctu * 3 + comp], CTUs in raster order.

@@ -935,3 +935,86 @@ void orc_sao_offset_ctu(const int16_t *src, int src_stride, int16_t *dst, int ds
             dst[(y0 + y) * dst_stride + x0 + x] = (int16_t)clampi(c + offset[k], 0, 255);
         }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Deblocking of a whole picture, pixel stage: deblock_filter_luma / _chroma, filter_luma, filter_chroma,
+ * use_strong_filter, hmr_deblocking_filter.c:264-627, in the picture order of hmr_deblock_filter (:827): every vertical edge,
+ * then every horizontal edge.  The boundary strengths are an INPUT (per 4x4 luma unit, picture raster, units_w per row; the
+ * strength of the edge on the unit's left / top side): deriving them from modes, cbf and vectors is host data
+ * (get_boundary_strength_single :138).  qp: the CU's QP per unit.  Edges lie on the 8x8 luma grid (chroma: 8x8 chroma grid,
+ * strength 2 only); a unit's entry off that grid is ignored.  planes: int16 pictures, modified in place.
+ * ------------------------------------------------------------------------------------------ */
+static const uint8_t k_tc_table[54] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,1,1,1,1,1,2,2,2,2,3,3,3,3,4,4,4,5,5,6,6,7,8,9,10,11,13,14,16,18,20,22,24 };
+static const uint8_t k_beta_table[52] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,6,7,8,9,10,11,12,13,14,15,16,17,18,20,22,24,26,28,30,32,34,36,38,40,42,44,46,48,50,52,54,56,58,60,62,64 };
+
+static int dbk_strong(const int16_t *s, int o, int d, int beta, int tc)
+{
+    const int d_strong = abs(s[-4 * o] - s[-o]) + abs(s[3 * o] - s[0]);
+    return d_strong < (beta >> 3) && d < (beta >> 2) && abs(s[-o] - s[0]) < ((tc * 5 + 1) >> 1);
+}
+static void dbk_luma_line(int16_t *s, int o, int tc, int sw, int thr_cut, int second_p, int second_q)
+{
+    const int m0 = s[-4 * o], m1 = s[-3 * o], m2 = s[-2 * o], m3 = s[-o], m4 = s[0], m5 = s[o], m6 = s[2 * o], m7 = s[3 * o];
+    if (sw) {
+        s[-o] = (int16_t)clampi((m1 + 2 * m2 + 2 * m3 + 2 * m4 + m5 + 4) >> 3, m3 - 2 * tc, m3 + 2 * tc);
+        s[0] = (int16_t)clampi((m2 + 2 * m3 + 2 * m4 + 2 * m5 + m6 + 4) >> 3, m4 - 2 * tc, m4 + 2 * tc);
+        s[-2 * o] = (int16_t)clampi((m1 + m2 + m3 + m4 + 2) >> 2, m2 - 2 * tc, m2 + 2 * tc);
+        s[o] = (int16_t)clampi((m3 + m4 + m5 + m6 + 2) >> 2, m5 - 2 * tc, m5 + 2 * tc);
+        s[-3 * o] = (int16_t)clampi((2 * m0 + 3 * m1 + m2 + m3 + m4 + 4) >> 3, m1 - 2 * tc, m1 + 2 * tc);
+        s[2 * o] = (int16_t)clampi((m3 + m4 + m5 + 3 * m6 + 2 * m7 + 4) >> 3, m6 - 2 * tc, m6 + 2 * tc);
+    } else {
+        int delta = (9 * (m4 - m3) - 3 * (m5 - m2) + 8) >> 4;
+        if (abs(delta) < thr_cut) {
+            const int tc2 = tc >> 1;
+            delta = clampi(delta, -tc, tc);
+            s[-o] = (int16_t)clampi(m3 + delta, 0, 255);
+            s[0] = (int16_t)clampi(m4 - delta, 0, 255);
+            if (second_p) s[-2 * o] = (int16_t)clampi(m2 + clampi((((m1 + m3 + 1) >> 1) - m2 + delta) >> 1, -tc2, tc2), 0, 255);
+            if (second_q) s[o] = (int16_t)clampi(m5 + clampi((((m6 + m4 + 1) >> 1) - m5 - delta) >> 1, -tc2, tc2), 0, 255);
+        }
+    }
+}
+void orc_deblock_picture(int16_t *const planes[3], const int strides[3], int w, int h, const uint8_t *bs_ver, const uint8_t *bs_hor,
+                         const uint8_t *qp, int units_w, int cb_qp_offset, int cr_qp_offset, int beta_offset_div2, int tc_offset_div2)
+{
+    for (int dir = 0; dir < 2; dir++) {
+        const uint8_t *bsm = dir ? bs_hor : bs_ver;
+        for (int uy = 0; uy < h / 4; uy++)
+            for (int ux = 0; ux < w / 4; ux++) {
+                const int along = dir ? uy : ux;                       /* unit coordinate across the edge */
+                const int bs = bsm[uy * units_w + ux];
+                if (!bs || along == 0 || (along & 1)) continue;
+                const int qpq = qp[uy * units_w + ux], qpp = dir ? qp[(uy - 1) * units_w + ux] : qp[uy * units_w + ux - 1];
+                const int q = (qpp + qpq + 1) >> 1;
+                {   /* luma: four lines of the 8x8-grid edge */
+                    const int tc = k_tc_table[clampi(q + 2 * (bs - 1) + (tc_offset_div2 << 1), 0, 53)];
+                    const int beta = k_beta_table[clampi(q + (beta_offset_div2 << 1), 0, 51)];
+                    const int side_thr = (beta + (beta >> 1)) >> 3, thr_cut = tc * 10;
+                    const int o = dir ? strides[0] : 1, step = dir ? 1 : strides[0];
+                    int16_t *e = planes[0] + (4 * uy) * strides[0] + 4 * ux;
+                    const int16_t *l0 = e, *l3 = e + 3 * step;
+                    const int dp0 = abs(l0[-3 * o] - 2 * l0[-2 * o] + l0[-o]), dq0 = abs(l0[0] - 2 * l0[o] + l0[2 * o]);
+                    const int dp3 = abs(l3[-3 * o] - 2 * l3[-2 * o] + l3[-o]), dq3 = abs(l3[0] - 2 * l3[o] + l3[2 * o]);
+                    const int d0 = dp0 + dq0, d3 = dp3 + dq3, d = d0 + d3;
+                    if (d < beta) {
+                        const int sw = dbk_strong(l0, o, 2 * d0, beta, tc) && dbk_strong(l3, o, 2 * d3, beta, tc);
+                        for (int i = 0; i < 4; i++) dbk_luma_line(e + i * step, o, tc, sw, thr_cut, dp0 + dp3 < side_thr, dq0 + dq3 < side_thr);
+                    }
+                }
+                if (bs > 1 && (along & 3) == 0)                         /* chroma: 8x8 chroma grid, two lines per luma unit */
+                    for (int c = 1; c < 3; c++) {
+                        const int qc = orc_chroma_qp_table[clampi(q + (c == 1 ? cb_qp_offset : cr_qp_offset), 0, 57)];
+                        const int tc = k_tc_table[clampi(qc + 2 * (bs - 1) + (tc_offset_div2 << 1), 0, 53)];
+                        const int o = dir ? strides[c] : 1, step = dir ? 1 : strides[c];
+                        int16_t *e = planes[c] + (2 * uy) * strides[c] + 2 * ux;
+                        for (int i = 0; i < 2; i++) {
+                            int16_t *s = e + i * step;
+                            const int m2 = s[-2 * o], m3 = s[-o], m4 = s[0], m5 = s[o];
+                            const int delta = clampi((((m4 - m3) << 2) + m2 - m5 + 4) >> 3, -tc, tc);
+                            s[-o] = (int16_t)clampi(m3 + delta, 0, 255);
+                            s[0] = (int16_t)clampi(m4 - delta, 0, 255);
+                        }
+                    }
+            }
+    }
+}

@@ -773,3 +773,81 @@ int refdrv_sao_apply(refdrv *d, const uint8_t *const src[3], int w, int h, const
     wnd_delete(&fr_rec.img); wnd_delete(&aux);
     return n;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Deblocking through the reference's own per-CTU function (hmr_deblock_filter_cu, hmr_deblocking_filter.c:737), driven the way
+ * hmr_deblock_filter (:827) drives it: all vertical edges of the picture, then all horizontal ones.  `d` must have been opened
+ * with the picture size.  The CTU descriptions the function reads are filled in from per-4x4-unit maps in PICTURE raster order
+ * (units_w = 16 * CTU columns per row): CU depth, TU depth below the CU, intra flag, luma cbf byte, QP, list-0 vector.  The
+ * boundary strengths the reference derives are handed back (per unit, picture raster) so that the pixel stage of a
+ * re-implementation can be pinned on exactly the same edges.  in / out: 8-bit planes.
+ * ------------------------------------------------------------------------------------------------------------ */
+void hmr_deblock_filter_cu(henc_thread_t *et, slice_t *currslice, ctu_info_t *ctu, int dir);
+void create_partition_ctu_neighbours(henc_thread_t *et, ctu_info_t *ctu, cu_partition_info_t *curr_partition_info);
+int refdrv_deblock(refdrv *d, const uint8_t *const in[3], int w, int h, const uint8_t *cu_depth, const uint8_t *tu_depth, const uint8_t *intra,
+                   const uint8_t *cbf, const uint8_t *qp, const int16_t *mv, uint8_t *bs_ver, uint8_t *bs_hor, uint8_t *const out[3])
+{
+    henc_thread_t *et = d->et;
+    hvenc_engine_t *eng = et->enc_engine;
+    slice_t *slice = &eng->current_pict.slice;
+    video_frame_t fr, dummy_ref;
+    video_frame_t *save_ref = eng->curr_reference_frame;
+    const int cols = (w + 63) / 64, rows = (h + 63) / 64, units_w = cols * 16;
+    if (eng->pict_total_ctu != cols * rows || et->pict_width[0] != w || et->pict_height[0] != h) return -1;
+    memset(&fr, 0, sizeof fr); memset(&dummy_ref, 0, sizeof dummy_ref);
+    wnd_alloc(&fr.img, w, h, 80, 80, sizeof(int16_t));
+    for (int c = 0; c < 3; c++) {
+        const int pw = c ? w / 2 : w, ph = c ? h / 2 : h;
+        int16_t *p = (int16_t *)fr.img.pwnd[c];
+        for (int y = 0; y < ph; y++) for (int x = 0; x < pw; x++) p[y * fr.img.window_size_x[c] + x] = in[c][y * pw + x];
+    }
+    eng->curr_reference_frame = &fr;
+    slice->slice_type = P_SLICE; slice->sps = &d->enc->sps; slice->pps = &d->enc->pps;
+    slice->deblocking_filter_disabled_flag = 0; slice->slice_beta_offset_div2 = 0; slice->slice_tc_offset_div2 = 0;
+    slice->ref_pic_list[REF_PIC_LIST_0][0] = &dummy_ref;
+    for (int n = 0; n < cols * rows; n++) {
+        ctu_info_t *ctu = &eng->ctu_info[n];
+        const int cx = n % cols, cy = n / cols;
+        ctu->ctu_number = n; ctu->size = 64;
+        ctu->x[0] = cx * 64; ctu->y[0] = cy * 64; ctu->x[1] = ctu->x[2] = cx * 32; ctu->y[1] = ctu->y[2] = cy * 32;
+        ctu->ctu_left = cx ? &eng->ctu_info[n - 1] : NULL;
+        ctu->ctu_top = cy ? &eng->ctu_info[n - cols] : NULL;
+        ctu->ctu_top_left = (cx && cy) ? &eng->ctu_info[n - cols - 1] : NULL;
+        ctu->ctu_top_right = (cy && cx + 1 < cols) ? &eng->ctu_info[n - cols + 1] : NULL;
+        ctu->ctu_left_bottom = NULL;
+        for (int r = 0; r < 256; r++) {
+            const int a = eng->raster2abs_table[r];
+            const int u = (cy * 16 + r / 16) * units_w + cx * 16 + r % 16;
+            ctu->pred_depth[a] = cu_depth[u]; ctu->tr_idx[a] = tu_depth[u];
+            ctu->pred_mode[a] = intra[u] ? INTRA_MODE : INTER_MODE;
+            ctu->cbf[Y_COMP][a] = cbf[u]; ctu->cbf[U_COMP][a] = 0; ctu->cbf[V_COMP][a] = 0;
+            ctu->qp[a] = qp[u];
+            ctu->part_size_type[a] = SIZE_2Nx2N;
+            ctu->mv_ref[REF_PIC_LIST_0][a].hor_vector = mv[2 * u]; ctu->mv_ref[REF_PIC_LIST_0][a].ver_vector = mv[2 * u + 1];
+            ctu->mv_ref_idx[REF_PIC_LIST_0][a] = intra[u] ? -1 : 0;
+        }
+    }
+    memset(bs_ver, 0, (size_t)units_w * rows * 16); memset(bs_hor, 0, (size_t)units_w * rows * 16);
+    hush();
+    for (int dir = EDGE_VER; dir <= EDGE_HOR; dir++)
+        for (int n = 0; n < cols * rows; n++) {
+            ctu_info_t *ctu = &eng->ctu_info[n];
+            const int cx = n % cols, cy = n / cols;
+            create_partition_ctu_neighbours(et, ctu, ctu->partition_list);
+            hmr_deblock_filter_cu(et, slice, ctu, dir);
+            for (int r = 0; r < 256; r++) {
+                const int u = (cy * 16 + r / 16) * units_w + cx * 16 + r % 16;
+                (dir == EDGE_VER ? bs_ver : bs_hor)[u] = et->deblock_filter_strength_bs[dir][eng->raster2abs_table[r]];
+            }
+        }
+    unhush();
+    for (int c = 0; c < 3; c++) {
+        const int pw = c ? w / 2 : w, ph = c ? h / 2 : h;
+        const int16_t *p = (const int16_t *)fr.img.pwnd[c];
+        for (int y = 0; y < ph; y++) for (int x = 0; x < pw; x++) out[c][y * pw + x] = (uint8_t)p[y * fr.img.window_size_x[c] + x];
+    }
+    eng->curr_reference_frame = save_ref;
+    wnd_delete(&fr.img);
+    return cols * rows;
+}
+void refdrv_pps_qp_offsets(refdrv *d, int *cb, int *cr) { *cb = d->enc->pps.cb_qp_offset; *cr = d->enc->pps.cr_qp_offset; }

@@ -259,6 +259,76 @@ def ref_sao_apply(src, w, h, types, offs):
     return out
 
 
+def random_deblock_case(rng, w, h):
+    """a random but consistent CU/TU quadtree per CTU with modes, cbf, QP and vectors per 4x4 unit (picture raster, 16 units per CTU
+    and row), and a blocky picture so that the filters have something to do"""
+    cols, rows = (w + 63) // 64, (h + 63) // 64
+    uw, uh = cols * 16, rows * 16
+    m = dict(cu=np.zeros((uh, uw), np.uint8), tu=np.zeros((uh, uw), np.uint8), intra=np.zeros((uh, uw), np.uint8), cbf=np.zeros((uh, uw), np.uint8),
+             qp=np.full((uh, uw), 30, np.uint8), mv=np.zeros((uh, uw, 2), np.int16))
+
+    def gen(x, y, size, depth):
+        if x >= w or y >= h:
+            return
+        if size > 8 and (x + size > w or y + size > h or rng.random() < 0.55):
+            for dy in (0, size // 2):
+                for dx in (0, size // 2):
+                    gen(x + dx, y + dy, size // 2, depth + 1)
+            return
+        u0, v0, n = x // 4, y // 4, size // 4
+        m["cu"][v0:v0 + n, u0:u0 + n] = depth
+        m["tu"][v0:v0 + n, u0:u0 + n] = 1 if size == 64 else int(rng.integers(0, 2))
+        m["intra"][v0:v0 + n, u0:u0 + n] = rng.random() < 0.3
+        m["cbf"][v0:v0 + n, u0:u0 + n] = rng.integers(0, 4, (n, n))
+        m["qp"][v0:v0 + n, u0:u0 + n] = rng.integers(18, 46)
+        m["mv"][v0:v0 + n, u0:u0 + n] = rng.integers(-6, 7, 2)
+    for cy in range(rows):
+        for cx in range(cols):
+            gen(cx * 64, cy * 64, 64, 0)
+    planes = []
+    for (ww, hh, b) in ((w, h, 8), (w // 2, h // 2, 4), (w // 2, h // 2, 4)):
+        p = np.clip(rng.normal(128, 30, (hh, ww)), 0, 255)
+        mean = p.reshape(hh // b, b, ww // b, b).mean((1, 3))
+        planes.append(np.clip(np.repeat(np.repeat(mean, b, 0), b, 1) + rng.integers(-3, 4, (hh, ww)), 0, 255).astype(np.uint8))
+    return m, planes
+
+
+_dbk_handles = {}
+
+
+def ref_deblock(planes, w, h, m):
+    """the reference's own deblocking (hmr_deblock_filter_cu per CTU and direction).  Returns (planes out, bs_ver, bs_hor, (cb, cr) qp offsets)"""
+    _, D = ref()
+    D.refdrv_open.restype = C.c_void_p
+    D.refdrv_open.argtypes = [C.c_int] * 4
+    if (w, h) not in _dbk_handles:
+        _dbk_handles[(w, h)] = D.refdrv_open(w, h, 32, 1)
+    hnd = _dbk_handles[(w, h)]
+    D.refdrv_deblock.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int] + [C.c_void_p] * 8 + [C.POINTER(C.c_void_p)]
+    D.refdrv_pps_qp_offsets.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    planes = [np.ascontiguousarray(p) for p in planes]
+    out = [np.zeros_like(p) for p in planes]
+    bsv = np.zeros_like(m["cu"]); bsh = np.zeros_like(m["cu"])
+    ip = (C.c_void_p * 3)(*[p.ctypes.data for p in planes]); op = (C.c_void_p * 3)(*[p.ctypes.data for p in out])
+    a = {k: np.ascontiguousarray(v) for k, v in m.items()}
+    n = D.refdrv_deblock(hnd, ip, w, h, a["cu"].ctypes.data, a["tu"].ctypes.data, a["intra"].ctypes.data, a["cbf"].ctypes.data, a["qp"].ctypes.data,
+                         a["mv"].ctypes.data, bsv.ctypes.data, bsh.ctypes.data, op)
+    assert n == ((w + 63) // 64) * ((h + 63) // 64)
+    cb, cr = C.c_int(0), C.c_int(0)
+    D.refdrv_pps_qp_offsets(hnd, C.byref(cb), C.byref(cr))
+    return out, bsv, bsh, (cb.value, cr.value)
+
+
+def oracle_deblock(planes, w, h, bsv, bsh, qp, offs, beta_off=0, tc_off=0):
+    O = oracle()
+    O.orc_deblock_picture.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5
+    pl = [np.ascontiguousarray(p.astype(np.int16)) for p in planes]
+    pp = (C.c_void_p * 3)(*[p.ctypes.data for p in pl]); st = (C.c_int * 3)(w, w // 2, w // 2)
+    bsv = np.ascontiguousarray(bsv); bsh = np.ascontiguousarray(bsh); qp = np.ascontiguousarray(qp)
+    O.orc_deblock_picture(pp, st, w, h, bsv.ctypes.data, bsh.ctypes.data, qp.ctypes.data, bsv.shape[1], offs[0], offs[1], beta_off, tc_off)
+    return [p.astype(np.uint8) for p in pl]
+
+
 def ref_sao_stats(rec, org, w, h):
     """the same through the reference's table member get_sao_stats; returns SAO_DT array [n_ctus, 3]"""
     _, D = ref()

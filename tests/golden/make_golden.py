@@ -185,6 +185,14 @@ def main():
     g["sao_org"] = np.concatenate([p_.reshape(-1) for p_ in sao_org]); g["sao_rec"] = np.concatenate([p_.reshape(-1) for p_ in sao_rec])
     g["sao_stats"] = np.frombuffer(st.tobytes(), np.int32).copy()
 
+    # ---- 8f item 4: deblocking of a small picture by the reference's own per-CTU function, with the strengths it derived
+    from _oracle import random_deblock_case, ref_deblock
+    dw, dh = 192, 136
+    dm, dplanes = random_deblock_case(rng, dw, dh)
+    dexp, dbsv, dbsh, doffs = ref_deblock(dplanes, dw, dh, dm)
+    g["dbk_in"] = np.concatenate([p_.reshape(-1) for p_ in dplanes]); g["dbk_out"] = np.concatenate([p_.reshape(-1) for p_ in dexp])
+    g["dbk_bsv"], g["dbk_bsh"], g["dbk_qp"], g["dbk_offs"] = dbsv, dbsh, dm["qp"], np.array(doffs, np.int32)
+
     out = os.path.join(HERE, "ref_vectors.npz")
     np.savez_compressed(out, **g)
     print("wrote", out, os.path.getsize(out), "bytes")

@@ -281,3 +281,40 @@ def test_frame_upload_layouts_and_border(ctx):
         assert np.array_equal(outs[0][0][j.y:j.y + 16, j.x:j.x + 16], oracle_mc(hf, 0, j.x, j.y, 16, j.mv.x, j.mv.y)), (j.x, j.y)
     for f in frames:
         f.close()
+
+
+def test_deblocking(ctx):
+    """deblocking of a whole picture on the GPU == the restatement pinned against the reference's own deblocking (CPU suite):
+    random strengths on the 8x8 grid (0/1/2, junk off the grid that must be ignored), QPs 10..51, tc / beta offsets"""
+    from _oracle import oracle_deblock, random_deblock_case
+    rng = np.random.default_rng(43)
+    for (w, h, beta_off, tc_off) in ((320, 192, 0, 0), (200, 136, 2, -1), (64, 72, -3, 3)):
+        m, planes = random_deblock_case(rng, w, h)
+        uh, uw = m["qp"].shape
+        bsv = rng.choice([0, 1, 2], (uh, uw), p=[0.3, 0.35, 0.35]).astype(np.uint8); bsh = rng.choice([0, 1, 2], (uh, uw), p=[0.3, 0.35, 0.35]).astype(np.uint8)
+        qp = np.repeat(np.repeat(rng.integers(10, 52, (uh // 2 + 1, uw // 2 + 1)), 2, 0), 2, 1)[:uh, :uw].astype(np.uint8)
+        f = hb.Frame(ctx, w, h); f.upload_u8(*planes)
+        ctx.deblock(f, bsv, bsh, qp, 2, -1, beta_off, tc_off)
+        got = f.download()
+        exp = oracle_deblock(planes, w, h, bsv, bsh, qp, (2, -1), beta_off, tc_off)
+        for c in range(3):
+            assert np.array_equal(got[c], exp[c]), (w, h, c, np.argwhere(got[c] != exp[c])[:4])
+        assert (got[0] != planes[0]).sum() > 200
+        f.close()
+
+
+def test_deblocking_against_reference_pictures(ctx):
+    """the GPU picture equals the picture the reference's own deblocking produces, on the strengths the reference derived"""
+    from _oracle import have_ref, random_deblock_case, ref_deblock
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(44)
+    for (w, h) in ((192, 136), (128, 128)):
+        m, planes = random_deblock_case(rng, w, h)
+        exp, bsv, bsh, offs = ref_deblock(planes, w, h, m)
+        f = hb.Frame(ctx, w, h); f.upload_u8(*planes)
+        ctx.deblock(f, bsv, bsh, m["qp"], offs[0], offs[1])
+        got = f.download()
+        for c in range(3):
+            assert np.array_equal(got[c], exp[c]), (w, h, c, np.argwhere(got[c] != exp[c])[:4])
+        f.close()

@@ -175,3 +175,15 @@ def test_sao_statistics():
         return [a[:w * h].reshape(h, w), a[w * h:w * h * 5 // 4].reshape(h // 2, w // 2), a[w * h * 5 // 4:].reshape(h // 2, w // 2)]
     got = oracle_sao_stats(planes(G["sao_rec"]), planes(G["sao_org"]), w, h)
     assert np.array_equal(np.frombuffer(got.tobytes(), np.int32), G["sao_stats"])
+
+
+def test_deblocking():
+    from _oracle import oracle_deblock
+    w, h = 192, 136
+    def planes(a):
+        return [a[:w * h].reshape(h, w), a[w * h:w * h * 5 // 4].reshape(h // 2, w // 2), a[w * h * 5 // 4:].reshape(h // 2, w // 2)]
+    got = oracle_deblock(planes(G["dbk_in"]), w, h, G["dbk_bsv"], G["dbk_bsh"], G["dbk_qp"], tuple(int(v) for v in G["dbk_offs"]))
+    exp = planes(G["dbk_out"])
+    for c in range(3):
+        assert np.array_equal(got[c], exp[c]), c
+    assert (exp[0] != planes(G["dbk_in"])[0]).sum() > 1000
