@@ -611,6 +611,39 @@ done:
     return rc;
 }
 
+/* deblocking of a whole picture in place, strengths derived on the device from per-unit mode data */
+int hb_deblock_frame_units(hb_ctx *ctx, hb_frame *frame, const hb_unit_info *units, int units_w, const hb_deblock_params *params,
+                           uint8_t *bs_ver_out, uint8_t *bs_hor_out)
+{
+    int rc = HB_OK, crc = 0;
+    void *d_units, *h_units, *d_maps, *h_maps;
+    if (!ctx || !frame || !units || !params) return hbi_fail(HB_ERR_ARG, "hb_deblock_frame_units: NULL argument");
+    if (units_w < frame->w / 4) return hbi_fail(HB_ERR_ARG, "hb_deblock_frame_units: units_w %d is smaller than width/4", units_w);
+    const size_t plane = (size_t)units_w * (size_t)(frame->h / 4);
+    hbc_set_device(ctx->device);
+    pthread_mutex_lock(&ctx->lock);
+    if ((rc = hbi_scratch(ctx, 0, sizeof(hb_unit_info) * plane, &d_units, &h_units)) != HB_OK) goto done;
+    if ((rc = hbi_scratch(ctx, 1, 3 * plane, &d_maps, &h_maps)) != HB_OK) goto done;
+    memcpy(h_units, units, sizeof(hb_unit_info) * plane);
+    crc = hbc_h2d_async(d_units, h_units, sizeof(hb_unit_info) * plane, ctx->stream);
+    if (!crc) crc = hbc_memset_async(d_maps, 0, 3 * plane, ctx->stream);
+    uint8_t *bv = (uint8_t *)d_maps, *bh = bv + plane, *qp = bh + plane;
+    if (!crc) { crc = hbk_deblock_strengths((const hb_unit_info *)d_units, units_w, frame->w, frame->h, bv, bh, qp, ctx->stream); ctx->launches++; }
+    if (!crc) {
+        crc = hbk_deblock(&frame->d, bv, bh, qp, units_w, params->cb_qp_offset, params->cr_qp_offset, params->beta_offset_div2, params->tc_offset_div2, ctx->stream);
+        ctx->launches += 2;
+    }
+    if (!crc) { crc = hbk_pad_frame(&frame->d, ctx->stream); ctx->launches++; }
+    if (!crc && (bs_ver_out || bs_hor_out)) crc = hbc_d2h_async(h_maps, d_maps, 2 * plane, ctx->stream);
+    if (!crc) crc = hbc_stream_sync(ctx->stream);
+    if (!crc && bs_ver_out) memcpy(bs_ver_out, h_maps, plane);
+    if (!crc && bs_hor_out) memcpy(bs_hor_out, (char *)h_maps + plane, plane);
+done:
+    pthread_mutex_unlock(&ctx->lock);
+    if (crc) return hbi_cuda_fail(crc, "hb_deblock_frame_units");
+    return rc;
+}
+
 /* SAO statistics of a whole picture: one launch, one copy back */
 int hb_sao_stats_frame(hb_ctx *ctx, const hb_frame *orig, const hb_frame *rec, hb_sao_stats *out)
 {

@@ -264,6 +264,39 @@ __global__ void __launch_bounds__(256) k_deblock(const DbkArgs a)
 }
 }  // namespace
 
+namespace {
+// ---- boundary strengths of a P picture from per-unit mode data (hmr_deblock_filter_cu :737 edge marking, set_edge_filter_pu :692,
+// get_boundary_strength_single :138): one thread per 4x4 unit writes the strength of its left and top side and its QP
+__global__ void __launch_bounds__(256) k_deblock_strengths(const hb_unit_info *units, int units_w, int uw, int uh, uint8_t *bs_ver, uint8_t *bs_hor, uint8_t *qp)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= uw * uh) return;
+    const int ux = i % uw, uy = i / uw, qi = uy * units_w + ux;
+    const hb_unit_info q = units[qi];
+    qp[qi] = q.qp;
+    const int ts = max(64 >> (q.cu_depth + q.tu_depth), 8);
+#pragma unroll
+    for (int dir = 0; dir < 2; dir++) {
+        const int pos = 4 * (dir ? uy : ux);
+        int bs = 0;
+        if (pos != 0 && pos % ts == 0) {
+            const hb_unit_info p = units[dir ? qi - units_w : qi - 1];
+            if (p.intra || q.intra) bs = 2;
+            else if (((q.cbf_luma >> q.tu_depth) & 1) || ((p.cbf_luma >> p.tu_depth) & 1)) bs = 1;
+            else bs = (p.ref_idx != q.ref_idx) || abs(q.mvx - p.mvx) >= 4 || abs(q.mvy - p.mvy) >= 4;
+        }
+        (dir ? bs_hor : bs_ver)[qi] = static_cast<uint8_t>(bs);
+    }
+}
+}  // namespace
+
+extern "C" int hbk_deblock_strengths(const hb_unit_info *units, int units_w, int w, int h, uint8_t *bs_ver, uint8_t *bs_hor, uint8_t *qp, void *stream)
+{
+    const int uw = w >> 2, uh = h >> 2;
+    k_deblock_strengths<<<(uw * uh + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(units, units_w, uw, uh, bs_ver, bs_hor, qp);
+    return static_cast<int>(cudaGetLastError());
+}
+
 extern "C" int hbk_deblock(const hbd_frame *f, const uint8_t *bs_ver, const uint8_t *bs_hor, const uint8_t *qp, int units_w,
                            int cb_off, int cr_off, int beta_off2, int tc_off2, void *stream)
 {

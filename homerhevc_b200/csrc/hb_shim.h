@@ -159,6 +159,8 @@ typedef struct hbd_gather_args {
 int hbk_gather(const hbd_gather_args *a, int n_ctus, void *stream);
 /* SAO statistics of every CTU and component of a frame: out[ctu * 3 + comp] */
 int hbk_sao_stats(const hbd_frame *org, const hbd_frame *rec, int ctu_cols, int n_ctus, hb_sao_stats *out, void *stream);
+/* boundary strengths + QP map of a P picture from per-unit mode data (device pointers) */
+int hbk_deblock_strengths(const hb_unit_info *units, int units_w, int w, int h, uint8_t *bs_ver, uint8_t *bs_hor, uint8_t *qp, void *stream);
 /* deblocking, pixel stage, in place: all vertical edges, then all horizontal ones (two launches); maps in device memory */
 int hbk_deblock(const hbd_frame *f, const uint8_t *bs_ver, const uint8_t *bs_hor, const uint8_t *qp, int units_w,
                 int cb_off, int cr_off, int beta_off2, int tc_off2, void *stream);

@@ -168,6 +168,7 @@ def load_library():
     L.hb_mc_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(McJob), C.c_int]
     L.hb_mc_predict_bi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(McBiJob), C.c_int]
     L.hb_deblock_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.hb_deblock_frame_units.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb_sao_stats_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb_sao_apply_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb_tq_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TuJob), C.c_int,
@@ -389,6 +390,20 @@ def _deblock(self, frame, bs_ver, bs_hor, qp, cb_qp_offset=0, cr_qp_offset=0, be
 
 
 Context.deblock = _deblock
+
+UNIT_INFO_DT = np.dtype([("cu_depth", "u1"), ("tu_depth", "u1"), ("intra", "u1"), ("cbf_luma", "u1"), ("ref_idx", "i1"), ("qp", "u1"), ("mvx", "<i2"), ("mvy", "<i2")])
+
+
+def _deblock_units(self, frame, units, cb_qp_offset=0, cr_qp_offset=0, beta_offset_div2=0, tc_offset_div2=0):
+    """deblocking in place with the strengths derived on the device; units: (rows, units_w) array of UNIT_INFO_DT.  Returns (bs_ver, bs_hor)"""
+    units = np.ascontiguousarray(units, UNIT_INFO_DT)
+    bsv = np.zeros(units.shape, np.uint8); bsh = np.zeros(units.shape, np.uint8)
+    prm = (C.c_int32 * 4)(cb_qp_offset, cr_qp_offset, beta_offset_div2, tc_offset_div2)
+    _check(self.L.hb_deblock_frame_units(self.h, frame.h, units.ctypes.data, units.shape[1], prm, bsv.ctypes.data, bsh.ctypes.data), "hb_deblock_frame_units")
+    return bsv, bsh
+
+
+Context.deblock_units = _deblock_units
 
 SAO_PARAM_DT = np.dtype([("type", "i1", (3,)), ("reserved", "i1"), ("offset", "<i2", (3, 32))])
 

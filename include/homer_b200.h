@@ -224,6 +224,15 @@ typedef struct hb_deblock_params { int32_t cb_qp_offset, cr_qp_offset, beta_offs
 int hb_deblock_frame(hb_ctx *ctx, hb_frame *frame, const uint8_t *bs_ver, const uint8_t *bs_hor, const uint8_t *qp, int units_w,
                      const hb_deblock_params *params);
 
+/* The same with the strengths derived on the device from what the host's decisions left per 4x4 unit (P pictures, 2Nx2N units):
+ * transform / coding unit edges as hmr_deblock_filter_cu :737 marks them (transform leaves of at least 8x8, picture border
+ * excluded :692) and get_boundary_strength_single :138 -- 2 if either side is intra, else 1 if either side's transform unit has
+ * luma coefficients (bit tu_depth of cbf_luma), else 1 if the list-0 references differ or a vector component differs by >= 4.
+ * bs_ver_out / bs_hor_out (optional, units_w * height/4 bytes each) receive the strengths that were used. */
+typedef struct hb_unit_info { uint8_t cu_depth, tu_depth, intra, cbf_luma; int8_t ref_idx; uint8_t qp; int16_t mvx, mvy; } hb_unit_info;   /* 10 bytes */
+int hb_deblock_frame_units(hb_ctx *ctx, hb_frame *frame, const hb_unit_info *units, int units_w, const hb_deblock_params *params,
+                           uint8_t *bs_ver_out, uint8_t *bs_hor_out);
+
 /* SAO statistics (get_sao_stats of the function table, hmr_private.h:1091; sao_get_ctu_stats hmr_sao.c:75 /
  * sse_sao_get_ctu_stats hmr_sse42_sao.c:35, calculate_preblock_stats = 0) for every CTU and component of a picture in one
  * launch: `rec` is the deblocked reconstruction (before SAO), `orig` the source.  out[ctu * 3 + comp], CTUs in raster order.

@@ -1018,3 +1018,34 @@ void orc_deblock_picture(int16_t *const planes[3], const int strides[3], int w, 
             }
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Boundary strengths of a whole P picture (2Nx2N prediction units): which unit sides are transform / coding unit edges
+ * (hmr_deblock_filter_cu :737 marks the left column and top row of every transform leaf of at least 8x8, set_edge_filter_pu :692
+ * clears the picture border) and get_boundary_strength_single :138 -- 2 when either side is intra, else 1 when either side's
+ * transform unit has luma coefficients, else 1 when the list-0 references differ or a vector component differs by 4 or more.
+ * Per 4x4 unit, picture raster: cu_depth (0..3), tu_depth below the CU, intra flag, luma cbf byte (bit tu_depth), list-0
+ * reference index (< 0 none) and vector.
+ * ------------------------------------------------------------------------------------------ */
+void orc_deblock_strengths(const uint8_t *cu_depth, const uint8_t *tu_depth, const uint8_t *intra, const uint8_t *cbf, const int8_t *ref_idx,
+                           const int16_t *mv, int units_w, int w, int h, uint8_t *bs_ver, uint8_t *bs_hor)
+{
+    for (int uy = 0; uy < h / 4; uy++)
+        for (int ux = 0; ux < w / 4; ux++) {
+            const int q = uy * units_w + ux;
+            int ts = 64 >> (cu_depth[q] + tu_depth[q]);
+            if (ts < 8) ts = 8;
+            for (int dir = 0; dir < 2; dir++) {
+                const int pos = 4 * (dir ? uy : ux);
+                uint8_t *out = (dir ? bs_hor : bs_ver) + q;
+                *out = 0;
+                if (pos == 0 || pos % ts) continue;
+                const int p = dir ? q - units_w : q - 1;
+                int bs;
+                if (intra[p] || intra[q]) bs = 2;
+                else if (((cbf[q] >> tu_depth[q]) & 1) || ((cbf[p] >> tu_depth[p]) & 1)) bs = 1;
+                else bs = (ref_idx[p] != ref_idx[q]) || abs(mv[2 * q] - mv[2 * p]) >= 4 || abs(mv[2 * q + 1] - mv[2 * p + 1]) >= 4;
+                *out = (uint8_t)bs;
+            }
+        }
+}

@@ -329,6 +329,17 @@ def oracle_deblock(planes, w, h, bsv, bsh, qp, offs, beta_off=0, tc_off=0):
     return [p.astype(np.uint8) for p in pl]
 
 
+def oracle_deblock_strengths(m, w, h):
+    O = oracle()
+    O.orc_deblock_strengths.argtypes = [C.c_void_p] * 6 + [C.c_int] * 3 + [C.c_void_p] * 2
+    a = {k: np.ascontiguousarray(v) for k, v in m.items()}
+    ref_idx = np.ascontiguousarray(np.where(a["intra"] != 0, -1, 0).astype(np.int8))
+    bsv = np.zeros_like(a["cu"]); bsh = np.zeros_like(a["cu"])
+    O.orc_deblock_strengths(a["cu"].ctypes.data, a["tu"].ctypes.data, a["intra"].ctypes.data, a["cbf"].ctypes.data, ref_idx.ctypes.data,
+                            a["mv"].ctypes.data, a["cu"].shape[1], w, h, bsv.ctypes.data, bsh.ctypes.data)
+    return bsv, bsh
+
+
 def ref_sao_stats(rec, org, w, h):
     """the same through the reference's table member get_sao_stats; returns SAO_DT array [n_ctus, 3]"""
     _, D = ref()

@@ -39,7 +39,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(hb.McJob) == 20 and C.sizeof(hb.TuJob) == 20 and C.sizeof(hb.LowLevelFuncs) == 19 * C.sizeof(C.c_void_p)
     assert C.sizeof(hb.PrepassCfg) == 36 and C.sizeof(hb.TqParams) == 24
     assert hb.lib.ME_COMPACT_DT.itemsize == 12 and hb.lib.TU_COMPACT_DT.itemsize == 12
-    assert hb.lib.SAO_DT.itemsize == 416 and hb.lib.SAO_PARAM_DT.itemsize == 196
+    assert hb.lib.SAO_DT.itemsize == 416 and hb.lib.SAO_PARAM_DT.itemsize == 196 and hb.lib.UNIT_INFO_DT.itemsize == 10
 
 
 def test_no_cpu_fallback_without_a_device():

@@ -317,4 +317,14 @@ def test_deblocking_against_reference_pictures(ctx):
         got = f.download()
         for c in range(3):
             assert np.array_equal(got[c], exp[c]), (w, h, c, np.argwhere(got[c] != exp[c])[:4])
+        # strengths derived on the device from the per-unit mode data
+        units = np.zeros(m["qp"].shape, hb.lib.UNIT_INFO_DT)
+        units["cu_depth"], units["tu_depth"], units["intra"], units["cbf_luma"], units["qp"] = m["cu"], m["tu"], m["intra"], m["cbf"], m["qp"]
+        units["ref_idx"] = np.where(m["intra"] != 0, -1, 0); units["mvx"] = m["mv"][..., 0]; units["mvy"] = m["mv"][..., 1]
+        f.upload_u8(*planes)
+        gbv, gbh = ctx.deblock_units(f, units, offs[0], offs[1])
+        assert np.array_equal(gbv[:h // 4, :w // 4], bsv[:h // 4, :w // 4]) and np.array_equal(gbh[:h // 4, :w // 4], bsh[:h // 4, :w // 4])
+        got = f.download()
+        for c in range(3):
+            assert np.array_equal(got[c], exp[c]), ("units", w, h, c)
         f.close()

@@ -288,7 +288,7 @@ def test_deblocking_pixel_stage_against_reference():
     """the reference's own deblocking (its per-CTU function, vertical edges of the whole picture first) on random CU/TU trees,
     modes, cbf, QPs and vectors; the restatement gets the boundary strengths the reference derived and must produce the same
     picture: luma normal / strong filters, chroma filter, QP averaging across CU and CTU borders, partial CTUs"""
-    from _oracle import oracle_deblock, random_deblock_case, ref_deblock
+    from _oracle import oracle_deblock, oracle_deblock_strengths, random_deblock_case, ref_deblock
     rng = np.random.default_rng(109)
     strong = weak = 0
     for (w, h) in ((192, 136), (128, 128), (200, 72), (64, 200)):
@@ -296,6 +296,8 @@ def test_deblocking_pixel_stage_against_reference():
             m, planes = random_deblock_case(rng, w, h)
             exp, bsv, bsh, offs = ref_deblock(planes, w, h, m)
             assert set(np.unique(bsv)) <= {0, 1, 2} and (bsv == 2).any() and (bsv == 1).any() and (bsh == 1).any()
+            obv, obh = oracle_deblock_strengths(m, w, h)
+            assert np.array_equal(obv[:h // 4, :w // 4], bsv[:h // 4, :w // 4]) and np.array_equal(obh[:h // 4, :w // 4], bsh[:h // 4, :w // 4]), (w, h, rep)
             got = oracle_deblock(planes, w, h, bsv, bsh, m["qp"], offs)
             for c in range(3):
                 assert np.array_equal(got[c], exp[c]), (w, h, rep, c, np.argwhere(got[c] != exp[c])[:4])
