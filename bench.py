@@ -209,6 +209,60 @@ def run_intra(args, w, h, rank, world, local, hb, synth):
     print(json.dumps(line))
 
 
+def run_finalise(args, w, h, rank, world, local, hb, synth):
+    """reference-frame finalisation of one picture -- deblocking (strengths derived on the device from per-unit mode
+    data), SAO statistics, SAO offset pass, border -- through the blocking C API with host buffers, next to the reference's own
+    functions (one host thread: the reference deblocks a picture on a single thread).  Rank 0 only; not the headline metric."""
+    if rank != 0:
+        return
+    from _oracle import have_ref, random_deblock_case, random_sao_params, ref_deblock, ref_sao_apply, ref_sao_stats
+    rng = np.random.default_rng(7)
+    ctx = hb.Context(local)
+    m, planes = random_deblock_case(rng, w, h)
+    units = np.zeros(m["qp"].shape, hb.lib.UNIT_INFO_DT)
+    units["cu_depth"], units["tu_depth"], units["intra"], units["cbf_luma"], units["qp"] = m["cu"], m["tu"], m["intra"], m["cbf"], m["qp"]
+    units["ref_idx"] = np.where(m["intra"] != 0, -1, 0); units["mvx"] = m["mv"][..., 0]; units["mvy"] = m["mv"][..., 1]
+    org = [np.clip(p.astype(np.int16) + rng.integers(-4, 5, p.shape), 0, 255).astype(np.uint8) for p in planes]
+    types, offs = random_sao_params(rng, w, h)
+    rec, fin, src = hb.Frame(ctx, w, h), hb.Frame(ctx, w, h), hb.Frame(ctx, w, h)
+    src.upload_u8(*org)
+
+    def step():
+        rec.upload_u8(*planes)                                   # stands for the reconstruction the T/Q kernels left on the device
+        ctx.deblock_units(rec, units, 2, 2)
+        st = ctx.sao_stats(src, rec)
+        ctx.sao_apply(rec, fin, types, offs)                     # the host's SAO decision would sit between the two calls
+        return st
+    for _ in range(max(3, args.warmup)):
+        step()
+    steps = min(args.steps, 50)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        st = step()
+    secs = time.perf_counter() - t0
+    line = {"metric": "reference-frame finalisation frames/s", "value": steps / secs, "unit": "frames/s", "n_gpus": 1, "steps": steps, "warmup": max(3, args.warmup),
+            "ms_per_step": secs / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 samples, int32 accumulate", "data": "synthetic",
+            "config": {"workload": f"{w}x{h}: deblocking (random CU/TU trees, modes, cbf, QPs, vectors) + SAO statistics + SAO offset pass + border",
+                       "timing": "wall clock around the blocking API calls, host buffers in and out (the picture upload included)"},
+            "e2e": {"value": steps / secs, "unit": "frames/s", "h2d_bytes_per_step": int(sum(p.nbytes for p in planes) + units.nbytes + types.nbytes + 2 * offs.nbytes // 4),
+                    "d2h_bytes_per_step": int(st.nbytes + 2 * units.size)},
+            "gpu_launches": int(steps * 9)}
+    if have_ref() and not args.no_cpu_baseline:
+        try:
+            t0 = time.perf_counter()
+            dexp, bsv, bsh, _ = ref_deblock(planes, w, h, m)
+            rst = ref_sao_stats(dexp, org, w, h)
+            rfin = ref_sao_apply(dexp, w, h, types, offs)
+            ref_secs = time.perf_counter() - t0
+            got = fin.download()
+            line["cpu_baseline"] = {"value": 1.0 / ref_secs, "unit": "frames/s", "cores": 1, "kind": "reference",
+                                    "sample": "1 frame: hmr_deblock_filter_cu per CTU and direction, get_sao_stats, sao_offset_ctu (oracle/_ref), one thread, int16 conversions included",
+                                    "identical_to_gpu": bool(all((a == b).all() for a, b in zip(got, rfin)) and all((st[f] == rst[f]).all() for f in st.dtype.names))}
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+    print(json.dumps(line))
+
+
 def run_bands(args, w, h, rank, world, local, torch, dist, hb, synth, barrier):
     """strong scaling of ONE stream of frames: every GPU owns a CTU-row band; per frame the reference rows a band needs from
     its neighbours (68 luma / 36 chroma rows per side) are exchanged over NCCL, then the band's pre-pass runs"""
@@ -268,7 +322,7 @@ def main():
     ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=16, help="independent GOP streams in flight per GPU")
-    ap.add_argument("--mode", default="gops", choices=["gops", "bands", "intra"],
+    ap.add_argument("--mode", default="gops", choices=["gops", "bands", "intra", "finalise"],
                     help="gops: independent GOP streams per GPU (default, weak scaling); bands: one frame split into CTU-row bands "
                          "across the GPUs with an NCCL halo exchange of the reference (BASELINE.json configs[3], strong scaling)")
     args = ap.parse_args()
@@ -298,6 +352,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.mode == "finalise":
+        run_finalise(args, w, h, rank, world, local, hb, synth)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.mode == "intra":
         run_intra(args, w, h, rank, world, local, hb, synth)
         if world > 1:
