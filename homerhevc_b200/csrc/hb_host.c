@@ -584,6 +584,90 @@ done:
     return rc;
 }
 
+/* merge / skip candidates: hb_mc_predict + hb_tq_encode over the candidates' transform units, reduced per candidate */
+int hb_merge_eval(hb_ctx *ctx, const hb_frame *cur, const hb_frame *ref, hb_frame *pred, hb_frame *recon, const hb_mc_job *cands, int n_cands,
+                  int qp, int chroma_qp_offset, const hb_tq_params *params, hb_merge_result *out)
+{
+    int rc;
+    if (!ctx || !cur || !ref || !pred || !recon || !cands || !params || !out || n_cands < 0) return hbi_fail(HB_ERR_ARG, "hb_merge_eval: bad argument");
+    if (qp < 0 || qp > 51) return hbi_fail(HB_ERR_ARG, "hb_merge_eval: qp %d", qp);
+    if (n_cands == 0) return HB_OK;
+    if ((rc = hb_mc_predict(ctx, ref, pred, cands, n_cands)) != HB_OK) return rc;          /* validates the candidates as well */
+    const int qp_c = hbi_chroma_qp(qp, chroma_qp_offset);
+    hb_tq_params prm = *params;
+    prm.chroma_weight = pow(2.0, (qp - qp_c) / 3.0);                                        /* hmr_motion_inter.c:3525 */
+    /* no-residual distortion: ssd16b(orig, pred) of the whole block per plane, exact, before anything is reduced per unit */
+    uint32_t *ssd3 = (uint32_t *)malloc(sizeof(uint32_t) * 3 * (size_t)n_cands);
+    if (!ssd3) return hbi_fail(HB_ERR_NOMEM, "hb_merge_eval: out of memory");
+    {
+        static const int sizes[4] = { 64, 32, 16, 8 };
+        void *d_pus, *h_pus, *d_out, *h_out;
+        int crc = 0, n = 0, start_of[5], *order = (int *)malloc(sizeof(int) * (size_t)n_cands);
+        if (!order) { free(ssd3); return hbi_fail(HB_ERR_NOMEM, "hb_merge_eval: out of memory"); }
+        pthread_mutex_lock(&ctx->lock);
+        rc = hbi_scratch(ctx, 0, sizeof(hbd_mc_pu) * (size_t)n_cands, &d_pus, &h_pus);
+        if (rc == HB_OK) rc = hbi_scratch(ctx, 1, sizeof(uint32_t) * 3 * (size_t)n_cands, &d_out, &h_out);
+        if (rc == HB_OK) {
+            hbd_mc_pu *hp = (hbd_mc_pu *)h_pus;
+            for (int s = 0; s < 4; s++) {
+                start_of[s] = n;
+                for (int i = 0; i < n_cands; i++) if (cands[i].size == sizes[s]) { hp[n].x = cands[i].x; hp[n].y = cands[i].y; hp[n].mv_idx = i; order[n] = i; n++; }
+            }
+            start_of[4] = n;
+            crc = hbc_h2d_async(d_pus, h_pus, sizeof(hbd_mc_pu) * (size_t)n_cands, ctx->stream);
+            for (int s = 0; s < 4 && !crc; s++)
+                if (start_of[s + 1] > start_of[s]) {
+                    crc = hbk_block_ssd(&cur->d, &pred->d, (const hbd_mc_pu *)d_pus + start_of[s], start_of[s + 1] - start_of[s], sizes[s],
+                                        (uint32_t *)d_out + 3 * start_of[s], ctx->stream);
+                    ctx->launches++;
+                }
+            if (!crc) crc = hbc_d2h_async(h_out, d_out, sizeof(uint32_t) * 3 * (size_t)n_cands, ctx->stream);
+            if (!crc) crc = hbc_stream_sync(ctx->stream);
+            if (!crc) for (int k = 0; k < n_cands; k++) memcpy(ssd3 + 3 * order[k], (uint32_t *)h_out + 3 * k, sizeof(uint32_t) * 3);
+        }
+        pthread_mutex_unlock(&ctx->lock);
+        free(order);
+        if (rc != HB_OK) { free(ssd3); return rc; }
+        if (crc) { free(ssd3); return hbi_cuda_fail(crc, "hb_merge_eval"); }
+    }
+    /* transform units: luma size (64x64: four 32x32), chroma half of that (encode_inter walks a 64x64 unit as four 32x32 ones, :3094) */
+    size_t n_tu = 0, n_co = 0;
+    for (int i = 0; i < n_cands; i++) {
+        const int s = cands[i].size, nl = s == 64 ? 4 : 1, ls = s == 64 ? 32 : s;
+        n_tu += 3 * (size_t)nl; n_co += (size_t)nl * (ls * ls + 2 * (ls / 2) * (ls / 2));
+    }
+    hb_tu_job *tj = (hb_tu_job *)malloc(sizeof *tj * n_tu);
+    hb_tu_result *tr = (hb_tu_result *)malloc(sizeof *tr * n_tu);
+    int16_t *co = (int16_t *)malloc(sizeof *co * n_co);
+    if (!tj || !tr || !co) { free(tj); free(tr); free(co); free(ssd3); return hbi_fail(HB_ERR_NOMEM, "hb_merge_eval: out of memory"); }
+    size_t k = 0;
+    for (int i = 0; i < n_cands; i++) {
+        const int s = cands[i].size, ls = s == 64 ? 32 : s;
+        for (int c = 0; c < 3; c++) {
+            const int ts = c ? ls / 2 : ls, bx = c ? cands[i].x / 2 : cands[i].x, by = c ? cands[i].y / 2 : cands[i].y, bs = c ? s / 2 : s;
+            for (int yy = 0; yy < bs; yy += ts)
+                for (int xx = 0; xx < bs; xx += ts) { tj[k].comp = c; tj[k].x = bx + xx; tj[k].y = by + yy; tj[k].size = ts; tj[k].qp = c ? qp_c : qp; k++; }
+        }
+    }
+    rc = hb_tq_encode(ctx, cur, pred, recon, tj, (int)n_tu, &prm, co, tr);
+    if (rc == HB_OK) {
+        k = 0;
+        for (int i = 0; i < n_cands; i++) {
+            const int n = 3 * (cands[i].size == 64 ? 4 : 1);
+            hb_merge_result r = { 0, 0, 0, 0 };
+            for (int t = 0; t < n; t++, k++) {
+                r.dist_coded += tr[k].ssd; r.sum += tr[k].sum;
+                if (tr[k].sum > 0) r.cbf |= 1 << tj[k].comp;
+            }
+            r.dist_skip = ssd3[3 * i] + (uint32_t)(prm.chroma_weight * ssd3[3 * i + 1]) + (uint32_t)(prm.chroma_weight * ssd3[3 * i + 2]);
+            out[i] = r;
+        }
+    }
+    free(ssd3);
+    free(tj); free(tr); free(co);
+    return rc;
+}
+
 /* deblocking of a whole picture in place (pixel stage; strengths and QPs from the host) */
 int hb_deblock_frame(hb_ctx *ctx, hb_frame *frame, const uint8_t *bs_ver, const uint8_t *bs_hor, const uint8_t *qp, int units_w,
                      const hb_deblock_params *params)

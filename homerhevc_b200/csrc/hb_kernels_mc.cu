@@ -161,6 +161,27 @@ __global__ void __launch_bounds__(128) k_mc_luma(const McLArgs a)
     }
 }
 
+// ---- SSD between the current picture and a prediction over square blocks of the three planes (ssd16b of the "no residual" branch of
+// the merge check, hmr_motion_inter.c:3686-3688): one warp per (block, plane), out[block * 3 + plane]
+__global__ void __launch_bounds__(256) k_block_ssd(hbd_frame cur, hbd_frame pred, const hbd_mc_pu *pus, int n_pus, int size, uint32_t *out)
+{
+    const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= n_pus * 3) return;
+    const int plane = w % 3;
+    const hbd_mc_pu pu = pus[w / 3];
+    const int n = plane ? size >> 1 : size, x = plane ? pu.x >> 1 : pu.x, y = plane ? pu.y >> 1 : pu.y;
+    const hbd_plane &pc = cur.p[plane], &pp = pred.p[plane];
+    uint32_t acc = 0;
+    for (int i = lane; i < (n >> 2) * n; i += 32) {
+        const int r = i / (n >> 2), c = (i % (n >> 2)) * 4;
+        const uint32_t a = *reinterpret_cast<const uint32_t *>(pc.org + (y + r) * pc.pitch + x + c), b = *reinterpret_cast<const uint32_t *>(pp.org + (y + r) * pp.pitch + x + c);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int d = static_cast<int>((a >> (8 * k)) & 255u) - static_cast<int>((b >> (8 * k)) & 255u); acc += d * d; }
+    }
+    acc = __reduce_add_sync(HB_FULL_MASK, acc);
+    if (lane == 0) out[w] = acc;
+}
+
 // ---- border replication of one plane (reference_picture_border_padding_ctu, hmr_encoder_lib.c:1723): every sample
 // outside the picture takes the nearest picture sample.
 __global__ void k_pad_frame(hbd_frame f)
@@ -278,6 +299,13 @@ extern "C" int hbk_mc_predict_bi(const hbd_frame *ref0, const hbd_frame *ref1, c
         if (rs == 4) k_mc_chroma<4, true><<<grid, 256, 0, s>>>(c);
         else k_mc_chroma<8, true><<<grid, 256, 0, s>>>(c);
     }
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int hbk_block_ssd(const hbd_frame *cur, const hbd_frame *pred, const hbd_mc_pu *pus, int n_pus, int size, uint32_t *out, void *stream)
+{
+    if (n_pus <= 0) return 0;
+    k_block_ssd<<<(n_pus * 3 + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(*cur, *pred, pus, n_pus, size, out);
     return static_cast<int>(cudaGetLastError());
 }
 

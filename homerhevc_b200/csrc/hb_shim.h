@@ -96,6 +96,8 @@ int hbk_me_search(const hbd_frame *cur, const hbd_frame *ref, int size, const hb
 typedef struct hbd_mc_pu { int32_t x, y; int32_t mv_idx; } hbd_mc_pu;   /* luma position; mv = mvsrc[mv_idx].mv */
 int hbk_mc_predict(const hbd_frame *ref, const hbd_frame *pred, int size, const hbd_mc_pu *pus, int n_pus,
                    const hb_me_result *mvsrc, int planes /* bit 0 luma, bit 1 chroma */, void *stream);
+/* SSD(cur, pred) of square blocks of `size` (chroma size/2) at pus[i], all three planes: out[i * 3 + plane] */
+int hbk_block_ssd(const hbd_frame *cur, const hbd_frame *pred, const hbd_mc_pu *pus, int n_pus, int size, uint32_t *out, void *stream);
 /* bi-prediction: the average of the two lists' 14-bit predictions (one luma + one chroma kernel) */
 int hbk_mc_predict_bi(const hbd_frame *ref0, const hbd_frame *ref1, const hbd_frame *pred, int size, const hbd_mc_pu *pus, int n_pus,
                       const hb_me_result *mvsrc0, const hb_me_result *mvsrc1, void *stream);

@@ -171,6 +171,7 @@ def load_library():
     L.hb_deblock_frame_units.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb_sao_stats_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb_sao_apply_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hb_merge_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(McJob), C.c_int, C.c_int, C.c_int, C.POINTER(TqParams), C.c_void_p]
     L.hb_tq_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TuJob), C.c_int,
                                C.POINTER(TqParams), i16p, C.POINTER(TuResult)]
     L.hb_tq_encode_intra.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(IntraTuJob), C.c_int, C.c_int, C.c_int, C.c_double,
@@ -331,6 +332,14 @@ class Context:
         n = len(jobs)
         arr = (McBiJob * n)(*jobs)
         _check(self.L.hb_mc_predict_bi(self.h, ref0.h, ref1.h, pred.h, arr, n), "hb_mc_predict_bi")
+
+    def merge_eval(self, cur, ref, pred, recon, cands, qp, chroma_qp_offset, params):
+        """merge / skip candidates (non-overlapping blocks): returns an (n,) array {dist_coded, sum, dist_skip, cbf}"""
+        n = len(cands)
+        arr = (McJob * n)(*cands)
+        out = np.zeros(n, np.dtype([("dist_coded", "<u4"), ("sum", "<i4"), ("dist_skip", "<u4"), ("cbf", "<i4")]))
+        _check(self.L.hb_merge_eval(self.h, cur.h, ref.h, pred.h, recon.h, arr, n, qp, chroma_qp_offset, C.byref(params), out.ctypes.data), "hb_merge_eval")
+        return out
 
     def tq_encode(self, cur, pred, recon, jobs, params):
         n = len(jobs)

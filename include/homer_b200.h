@@ -214,6 +214,16 @@ int hb_intra_run(hb_ctx *ctx, const hb_frame *cur, hb_frame *pred, const hb_intr
 void hb_create_intra_planar_prediction(int16_t *prediction, int pred_stride, int16_t *adi_pred_buff, int adi_size, int cu_size, int cu_size_shift);
 void hb_create_intra_angular_prediction(int16_t *prediction, int pred_stride, int16_t *adi_pred_buff, int adi_size, int cu_size, int cu_mode, int is_luma);
 
+/* Merge / skip candidate evaluation (the compute of check_rd_cost_merge_2nx2n, hmr_motion_inter.c:3493, with
+ * one transform depth): for every candidate {CU, list-0 vector} motion compensation (luma + chroma) into `pred`, then the inter
+ * T/Q chain of its transform units (luma: the block, a 64x64 one as four 32x32; chroma: half the luma unit) into `recon`.  Per candidate: dist_coded = sum of the
+ * units' ssd (what encode_inter returns, :3071), sum = sum of their level sums, dist_skip = ssd16b(orig, pred) of the whole luma block plus
+ * the truncated weighted ones of the two chroma blocks (:3686-3688, the "no residual" branch), cbf bit c set when component c keeps coefficients.  The blocks
+ * of ONE call must not overlap (one call per candidate index of the merge list). */
+typedef struct hb_merge_result { uint32_t dist_coded; int32_t sum; uint32_t dist_skip; int32_t cbf; } hb_merge_result;
+int hb_merge_eval(hb_ctx *ctx, const hb_frame *cur, const hb_frame *ref, hb_frame *pred, hb_frame *recon, const hb_mc_job *cands, int n_cands,
+                  int qp, int chroma_qp_offset, const hb_tq_params *params, hb_merge_result *out);
+
 /* Deblocking of a whole picture, pixel stage, in place (deblock_filter_luma / _chroma hmr_deblocking_filter.c:351/:504 with
  * filter_luma :287, filter_chroma :478, use_strong_filter :275, in the picture order of hmr_deblock_filter :827: every vertical
  * edge, then every horizontal one).  The boundary strengths are INPUTS: bs_ver / bs_hor hold, per 4x4 luma unit in picture

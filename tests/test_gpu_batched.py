@@ -328,3 +328,50 @@ def test_deblocking_against_reference_pictures(ctx):
         for c in range(3):
             assert np.array_equal(got[c], exp[c]), ("units", w, h, c)
         f.close()
+
+
+def test_merge_candidates(ctx):
+    """merge / skip candidate evaluation: per candidate the coded distortion and level sum of its units (oracle MC + oracle T/Q
+    chain) and the no-residual distortion exactly as check_rd_cost_merge_2nx2n adds it up (ssd luma + truncated weighted chroma)"""
+    from homerhevc_b200.lib import Mv
+    rng = np.random.default_rng(45)
+    qp, off, avg = 30, 2, 420.0
+    cur, ref = clip_pair(W, H, n=3, noise=5.0, seed=29)
+    fc, fr = upload(ctx, cur, W, H), upload(ctx, ref, W, H)
+    pred, rec = hb.Frame(ctx, W, H), hb.Frame(ctx, W, H)
+    cands = []
+    for cy in range(0, H - 63, 64):
+        for cx in range(0, W - 63, 64):
+            size = int(rng.choice([64, 32, 16, 8]))
+            for oy in range(0, 64, size):
+                for ox in range(0, 64, size):
+                    if rng.random() < 0.5:
+                        cands.append(hb.McJob(cx + ox, cy + oy, size, Mv(int(rng.integers(-30, 31)), int(rng.integers(-30, 31)))))
+    prm = hb.TqParams(0, 1, avg, 1.0)
+    got = ctx.merge_eval(fc, fr, pred, rec, cands, qp, off, prm)
+    qp_c = chroma_qp(qp, off)
+    weight = 2.0 ** ((qp - qp_c) / 3.0)
+    n_coded = 0
+    for j, g in zip(cands, got):
+        dist = ssum = 0
+        skip = 0
+        ls = 32 if j.size == 64 else j.size
+        p_y = oracle_mc(ref, 0, j.x, j.y, j.size, j.mv.x, j.mv.y)
+        for yy in range(0, j.size, ls):
+            for xx in range(0, j.size, ls):
+                _, _, eo = oracle_tu(cur.block(0, j.x + xx, j.y + yy, ls), p_y[yy:yy + ls, xx:xx + ls], ls, 0, qp, 0, 1, avg, 1.0)
+                dist += eo.ssd; ssum += eo.sum
+        skip += int(((cur.block(0, j.x, j.y, j.size).astype(np.int64) - p_y) ** 2).sum())
+        c = j.size // 2
+        cs = ls // 2
+        for comp in (1, 2):
+            p_c = oracle_mc(ref, comp, j.x // 2, j.y // 2, c, j.mv.x, j.mv.y)
+            for yy in range(0, c, cs):
+                for xx in range(0, c, cs):
+                    _, _, eo = oracle_tu(cur.block(comp, j.x // 2 + xx, j.y // 2 + yy, cs), p_c[yy:yy + cs, xx:xx + cs], cs, comp, qp_c, 0, 1, avg, weight)
+                    dist += eo.ssd; ssum += eo.sum
+            skip += int(weight * float(((cur.block(comp, j.x // 2, j.y // 2, c).astype(np.int64) - p_c) ** 2).sum()))
+        assert (int(g["dist_coded"]), int(g["sum"]), int(g["dist_skip"])) == (dist, ssum, skip), (j.x, j.y, j.size, j.mv.x, j.mv.y)
+        n_coded += ssum > 0
+    assert n_coded > 5 and len(cands) > 30
+    fc.close(); fr.close(); pred.close(); rec.close()
