@@ -79,25 +79,6 @@ __device__ __forceinline__ void intra_filter_adi(const int16_t *adi, int16_t *fl
     }
 }
 
-// the same with LJ lanes per block and a compile-time size
-template <int N, int LJ> __device__ __forceinline__ void intra_filter_adi_n(const int16_t *adi, int16_t *flt, int sl)
-{
-    constexpr int size = 4 * N + 1;
-    constexpr int lg = (N == 4) ? 2 : (N == 8) ? 3 : (N == 16) ? 4 : 5;
-    const int lb = adi[0], lt = adi[2 * N], tr = adi[size - 1];
-    const bool strong = N >= 32 && abs(lb + lt - 2 * adi[N]) < 8 && abs(lt + tr - 2 * adi[3 * N]) < 8;
-    for (int i = sl; i < size; i += LJ) {
-        int v;
-        if (i == 0 || i == size - 1) v = adi[i];
-        else if (strong) {
-            if (i == 2 * N) v = adi[i];
-            else if (i < 2 * N) v = ((2 * N - i) * lb + i * lt + N) >> (lg + 1);
-            else v = ((4 * N - i) * lt + (i - 2 * N) * tr + N) >> (lg + 1);
-        } else v = (adi[i - 1] + 2 * adi[i] + adi[i + 1] + 2) >> 2;
-        flt[i] = static_cast<int16_t>(v);
-    }
-}
-
 __device__ __forceinline__ bool intra_uses_filtered(int lg, int mode)
 {
     const int d = min(abs(mode - 10), abs(mode - 26));
@@ -150,57 +131,158 @@ __global__ void __launch_bounds__(kIntraWarps * 32) k_intra(const hbd_intra_args
 
 // ---- SAD form, one launch per block size: the SADs of all 35 luma modes against the current block (what the mode search of
 // homer_loop1_motion_intra, hmr_motion_intra.c:1084, probes one call at a time).  `idx` lists the jobs of this size; a 4x4
-// block takes 16 lanes, so two of them share a warp.  A lane keeps its current samples in registers for all modes; the mode is
-// uniform per iteration, so the kind switch does not diverge.
+// block takes 16 lanes, so two of them share a warp.
+// The reference samples are laid out once per job as four arrays indexed -N..2N+1 from the corner: {top, left} x {raw, smoothed}.
+// A mode's main array is the top one (vertical modes) or the left one (horizontal modes, evaluated on the transposed block, which
+// turns them into the vertical formula); for negative angles its slots -1..(N*angle)>>5 are refilled per mode with the projected
+// samples of the other array, so the inner loop is two neighbouring loads and one interpolation per sample with no branches.
+template <int N> struct IntraSadCfg {
+    static constexpr int LJ = (N * N < 32) ? N * N : 32;      // lanes per job
+    static constexpr int JPW = 32 / LJ;                       // jobs per warp
+    static constexpr int SPL = N * N / LJ;                    // samples per lane
+    static constexpr int LG = (N == 4) ? 2 : (N == 8) ? 3 : (N == 16) ? 4 : 5;
+    static constexpr int EXT = 3 * N + 4;                     // -N .. 2N+1, padded to an even count
+};
+
+// modes of one orientation on the lane's samples `cur` (block transposed when HOR); main/side arrays point at their corner element
+template <int N, bool HOR>
+__device__ __forceinline__ void intra_sads_pass(int16_t (*arr)[IntraSadCfg<N>::EXT], const int (&cur)[IntraSadCfg<N>::SPL], int sl, int sub, bool valid,
+                                                uint32_t *out)
+{
+    using C = IntraSadCfg<N>;
+    const int first = HOR ? 2 : 18, last = HOR ? 17 : 34;
+    for (int mode = first; mode <= last; mode++) {
+        const int a = HOR ? 10 - mode : mode - 26;
+        const bool flt = intra_uses_filtered(C::LG, mode);
+        int16_t *mainp = arr[(HOR ? 2 : 0) + flt] + N;
+        const int16_t *side = arr[(HOR ? 0 : 2) + flt] + N;
+        uint32_t acc = 0;
+        if (a == 0) {                                          // pure vertical / horizontal with the first line smoothed on small blocks
+            const int corner = mainp[0];
+#pragma unroll
+            for (int q = 0; q < C::SPL; q++) {
+                const int e = sl + q * C::LJ, i = e % N, j = e / N;
+                int v = mainp[i + 1];
+                if (N <= 16 && i == 0) v = hb_clip255(v + ((side[j + 1] - corner) >> 1));
+                acc = __sad(v, cur[q], acc);
+            }
+        } else {
+            const int aa = abs(a);
+            const int angle = a < 0 ? -c_ang[aa] : c_ang[aa];
+            if (a < 0) {
+                const int inv = c_inv_ang[aa], kmin = (N * angle) >> 5;
+                __syncwarp();
+                for (int kk = -1 - sl; kk >= kmin; kk -= C::LJ) mainp[kk] = side[(128 - kk * inv) >> 8];
+                __syncwarp();
+            }
+#pragma unroll
+            for (int q = 0; q < C::SPL; q++) {
+                const int e = sl + q * C::LJ, i = e % N, j = e / N;
+                const int pos = (j + 1) * angle, f = pos & 31;
+                const int16_t *p = mainp + i + (pos >> 5) + 1;
+                const int r0 = p[0], r1 = p[1];
+                acc = __sad((32 * r0 + f * (r1 - r0) + 16) >> 5, cur[q], acc);
+            }
+        }
+        if constexpr (C::JPW == 1) {
+            acc = __reduce_add_sync(HB_FULL_MASK, acc);
+            if (sl == 0) out[mode] = acc;
+        } else {
+            const uint32_t t0 = __reduce_add_sync(HB_FULL_MASK, sub == 0 ? acc : 0u), t1 = __reduce_add_sync(HB_FULL_MASK, sub == 1 ? acc : 0u);
+            if (sl == 0 && valid) out[mode] = sub ? t1 : t0;
+        }
+    }
+}
+
 template <int N>
 __global__ void __launch_bounds__(kIntraWarps * 32) k_intra_sads(const hbd_intra_args a, const int32_t *idx, int n_idx)
 {
-    constexpr int LJ = (N * N < 32) ? N * N : 32;      // lanes per job
-    constexpr int JPW = 32 / LJ;                       // jobs per warp
-    constexpr int SPL = N * N / LJ;                    // samples per lane
-    constexpr int LG = (N == 4) ? 2 : (N == 8) ? 3 : (N == 16) ? 4 : 5;
-    __shared__ int16_t s_adi[kIntraWarps][JPW][2][4 * N + 4];
+    using C = IntraSadCfg<N>;
+    constexpr int LJ = C::LJ, JPW = C::JPW, SPL = C::SPL, LG = C::LG;
+    __shared__ int16_t s_lin[kIntraWarps][JPW][4 * N + 4];
+    __shared__ int16_t s_arr[kIntraWarps][JPW][4][C::EXT];              // top raw, top smoothed, left raw, left smoothed
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane / LJ, sl = lane % LJ;
     const int k = (blockIdx.x * kIntraWarps + warp) * JPW + sub;
     if ((blockIdx.x * kIntraWarps + warp) * JPW >= n_idx) return;          // whole warp
     const bool valid = k < n_idx;
     const int ji = idx[min(k, n_idx - 1)];
     const hbd_intra_job job = a.jobs[ji];
-    int16_t *raw = s_adi[warp][sub][0], *flt = s_adi[warp][sub][1];
+    int16_t *raw = s_lin[warp][sub];
+    int16_t (*arr)[C::EXT] = s_arr[warp][sub];
     for (int i = sl; i < 4 * N + 1; i += LJ) raw[i] = a.adi[job.adi_off + i];
     __syncwarp();
-    intra_filter_adi_n<N, LJ>(raw, flt, sl);
+    {   // smoothing (as intra_filter_adi) fused with the split into the four corner-relative arrays
+        constexpr int size = 4 * N + 1;
+        const int lb = raw[0], lt = raw[2 * N], tr = raw[size - 1];
+        const bool strong = N >= 32 && abs(lb + lt - 2 * raw[N]) < 8 && abs(lt + tr - 2 * raw[3 * N]) < 8;
+        for (int i = sl; i < size; i += LJ) {
+            int v;
+            if (i == 0 || i == size - 1) v = raw[i];
+            else if (strong) {
+                if (i == 2 * N) v = raw[i];
+                else if (i < 2 * N) v = ((2 * N - i) * lb + i * lt + N) >> (LG + 1);
+                else v = ((4 * N - i) * lt + (i - 2 * N) * tr + N) >> (LG + 1);
+            } else v = (raw[i - 1] + 2 * raw[i] + raw[i + 1] + 2) >> 2;
+            const int kk = i - 2 * N;
+            if (kk >= 0) { arr[0][N + kk] = raw[i]; arr[1][N + kk] = static_cast<int16_t>(v); }
+            if (kk <= 0) { arr[2][N - kk] = raw[i]; arr[3][N - kk] = static_cast<int16_t>(v); }
+        }
+        if (sl < 4) arr[sl][3 * N + 1] = 0;                    // read with a zero weight only
+    }
     __syncwarp();
+    uint32_t *out = a.sads + static_cast<size_t>(ji) * 35;
     int cur[SPL];
 #pragma unroll
     for (int q = 0; q < SPL; q++) {
         const int e = sl + q * LJ;
         cur[q] = a.cur.org[(job.y + e / N) * a.cur.pitch + job.x + e % N];
     }
-    // DC value (mode 1 always reads the raw samples)
-    int dcs = 0;
-    for (int i = 1 + sl; i <= N; i += LJ) dcs += raw[2 * N + i] + raw[2 * N - i];
-#pragma unroll
-    for (int d = LJ / 2; d > 0; d >>= 1) dcs += __shfl_xor_sync(HB_FULL_MASK, dcs, d);
-    const int dc = (dcs + N) >> (LG + 1);
-    const bool edge = N <= 16;
-    for (int mode = 0; mode < 35; mode++) {
-        const int16_t *mid = (intra_uses_filtered(LG, mode) ? flt : raw) + 2 * N;
-        const IntraMode m = intra_mode_info(mode);
-        uint32_t acc = 0;
+    {   // planar and DC (symmetric in the two reference arrays): x = i, y = j
+        const bool pf = intra_uses_filtered(LG, 0);
+        const int16_t *top = arr[pf] + N, *left = arr[2 + pf] + N;
+        const int lbv = left[N + 1], trv = top[N + 1];
+        uint32_t acc0 = 0;
 #pragma unroll
         for (int q = 0; q < SPL; q++) {
-            const int e = sl + q * LJ;
-            acc = __sad(intra_sample(mid, N, LG, m, dc, edge, e % N, e / N), cur[q], acc);
+            const int e = sl + q * LJ, x = e % N, y = e / N;
+            const int l = left[y + 1], t = top[x + 1];
+            acc0 = __sad(((l << LG) + N + (x + 1) * (trv - l) + (t << LG) + (y + 1) * (lbv - t)) >> (LG + 1), cur[q], acc0);
+        }
+        const int16_t *rt = arr[0] + N, *rl = arr[2] + N;       // DC always reads the raw samples
+        int dcs = 0;
+        for (int i = 1 + sl; i <= N; i += LJ) dcs += rt[i] + rl[i];
+#pragma unroll
+        for (int d = LJ / 2; d > 0; d >>= 1) dcs += __shfl_xor_sync(HB_FULL_MASK, dcs, d);
+        const int dc = (dcs + N) >> (LG + 1);
+        uint32_t acc1 = 0;
+#pragma unroll
+        for (int q = 0; q < SPL; q++) {
+            const int e = sl + q * LJ, x = e % N, y = e / N;
+            int v = dc;
+            if (N <= 16) {
+                if (x == 0 && y == 0) v = (rl[1] + rt[1] + 2 * dc + 2) >> 2;
+                else if (y == 0) v = (rt[1 + x] + 3 * dc + 2) >> 2;
+                else if (x == 0) v = (rl[1 + y] + 3 * dc + 2) >> 2;
+            }
+            acc1 = __sad(v, cur[q], acc1);
         }
         if constexpr (JPW == 1) {
-            acc = __reduce_add_sync(HB_FULL_MASK, acc);
-            if (lane == 0) a.sads[static_cast<size_t>(ji) * 35 + mode] = acc;
+            acc0 = __reduce_add_sync(HB_FULL_MASK, acc0); acc1 = __reduce_add_sync(HB_FULL_MASK, acc1);
+            if (sl == 0) { out[0] = acc0; out[1] = acc1; }
         } else {
-            const uint32_t t0 = __reduce_add_sync(HB_FULL_MASK, sub == 0 ? acc : 0u), t1 = __reduce_add_sync(HB_FULL_MASK, sub == 1 ? acc : 0u);
-            if (sl == 0 && valid) a.sads[static_cast<size_t>(ji) * 35 + mode] = sub ? t1 : t0;
+            const uint32_t p0 = __reduce_add_sync(HB_FULL_MASK, sub == 0 ? acc0 : 0u), p1 = __reduce_add_sync(HB_FULL_MASK, sub == 1 ? acc0 : 0u);
+            const uint32_t d0 = __reduce_add_sync(HB_FULL_MASK, sub == 0 ? acc1 : 0u), d1 = __reduce_add_sync(HB_FULL_MASK, sub == 1 ? acc1 : 0u);
+            if (sl == 0 && valid) { out[0] = sub ? p1 : p0; out[1] = sub ? d1 : d0; }
         }
     }
+    intra_sads_pass<N, false>(arr, cur, sl, sub, valid, out);
+    // horizontal modes: the same formula on the transposed block with the left array as the main one
+#pragma unroll
+    for (int q = 0; q < SPL; q++) {
+        const int e = sl + q * LJ;
+        cur[q] = a.cur.org[(job.y + e % N) * a.cur.pitch + job.x + e / N];
+    }
+    intra_sads_pass<N, true>(arr, cur, sl, sub, valid, out);
 }
 
 // per-call form: prediction of one block as int16 into a caller buffer (the table members create_intra_*_prediction)

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import homerhevc_b200 as hb
+from homerhevc_b200.lib import UNIT_INFO_DT
 from _oracle import aligned_i16, oracle, ptr
 
 pytestmark = pytest.mark.gpu
@@ -233,3 +234,38 @@ def test_batched_api_rejects_bad_arguments(ctx):
     f.upload_i16(ok, c16, c16)
     assert int(f.download()[0][5, 7]) == 200
     f.close()
+
+
+@pytest.mark.gpu
+def test_finalisation_api_rejects_bad_arguments(ctx):
+    """the deblocking, SAO, bi-prediction and merge entry points refuse inconsistent input before any launch"""
+    w, h = 128, 64
+    a, b, small = hb.Frame(ctx, w, h), hb.Frame(ctx, w, h), hb.Frame(ctx, 64, 64)
+    z = np.zeros((h, w), np.uint8); zc = np.zeros((h // 2, w // 2), np.uint8)
+    for f in (a, b):
+        f.upload_u8(z, zc, zc)
+    n_ctus = 2
+    types = np.zeros((n_ctus, 3), np.int8); offs = np.zeros((n_ctus, 3, 32), np.int16)
+    with pytest.raises(hb.HbError):
+        ctx.sao_apply(a, a, types, offs)                                               # classes come from the untouched picture
+    with pytest.raises(hb.HbError):
+        ctx.sao_apply(a, small, types, offs)
+    bad_types = types.copy(); bad_types[1, 2] = 7
+    with pytest.raises(hb.HbError):
+        ctx.sao_apply(a, b, bad_types, offs)
+    with pytest.raises(hb.HbError):
+        ctx.sao_stats(a, small)
+    narrow = np.zeros((h // 4, w // 4 - 1), np.uint8)
+    with pytest.raises(hb.HbError):
+        ctx.deblock(a, narrow, narrow, narrow)                                         # maps narrower than the picture
+    with pytest.raises(hb.HbError):
+        ctx.deblock_units(a, np.zeros((h // 4, w // 4 - 1), UNIT_INFO_DT))
+    far = hb.McBiJob(); far.x, far.y, far.size = 0, 0, 16
+    far.mv0.x = -4 * 200                                                               # further outside than the padding reaches
+    with pytest.raises(hb.HbError):
+        ctx.mc_predict_bi(a, b, a, [far])
+    cand = hb.McJob(); cand.x, cand.y, cand.size = 0, 0, 16
+    with pytest.raises(hb.HbError):
+        ctx.merge_eval(a, b, a, b, [cand], 60, 0, hb.TqParams(0, 1, 0.0, 1.0))          # qp out of range
+    for f in (a, b, small):
+        f.close()
