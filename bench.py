@@ -343,6 +343,15 @@ def main():
     import homerhevc_b200 as hb
     from homerhevc_b200 import synth
 
+    if os.environ.get("HB_PIN_CPUS") == "1" and world > 1:
+        cpus = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cpus) // world)
+        os.sched_setaffinity(0, set(cpus[local * per:(local + 1) * per]))
+    if os.environ.get("HB_BLOCKING") == "1":
+        import ctypes
+        cu = ctypes.CDLL("libcuda.so.1")
+        cu.cuInit(0)
+        print("blocking flags rc", cu.cuDevicePrimaryCtxSetFlags_v2(local, 4), file=sys.stderr)
     if world > 1:
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -444,7 +453,7 @@ def main():
     def finish_frame(sl):
         sl["d2h"] += sl["pp"].frame_finish(LAMBDA, sl["tables"], sl["sel"], sl["off"], sl["out"]) + sl["tables"].nbytes
 
-    E2E_THREADS = max(1, N_SLOTS // 2)
+    E2E_THREADS = int(os.environ.get("HB_E2E_THREADS", max(1, N_SLOTS // 2)))
 
     def run_e2e(n):
         # one host thread per TWO in-flight streams (the reference runs one pthread per encoder engine, hmr_encoder_lib.c:1647):

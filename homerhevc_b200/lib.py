@@ -171,6 +171,8 @@ def load_library():
     L.hb_deblock_frame_units.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb_sao_stats_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb_sao_apply_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hb_sao_derive_offsets.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+    L.hb_sao_decide_standin.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_void_p]
     L.hb_merge_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(McJob), C.c_int, C.c_int, C.c_int, C.POINTER(TqParams), C.c_void_p]
     L.hb_tq_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TuJob), C.c_int,
                                C.POINTER(TqParams), i16p, C.POINTER(TuResult)]
@@ -425,6 +427,25 @@ def _sao_apply(self, src, dst, types, offsets):
 
 
 Context.sao_apply = _sao_apply
+
+
+def sao_derive_offsets(stats, sao_type, lam):
+    """host arithmetic of the SAO decision on one (CTU, component) record of SAO_DT: (offsets[32] int16, band, dist)"""
+    L = load_library()
+    rec = np.ascontiguousarray(stats, SAO_DT).reshape(1)
+    off = np.zeros(32, np.int16); band = C.c_int32(0); dist = C.c_int64(0)
+    _check(L.hb_sao_derive_offsets(rec.ctypes.data, sao_type, float(lam), off.ctypes.data, C.byref(band), C.byref(dist)), "hb_sao_derive_offsets")
+    return off, band.value, dist.value
+
+
+def sao_decide_standin(stats, lambdas):
+    """stand-in SAO decision over hb_sao_stats_frame's output (n_ctus, 3): returns the SAO_PARAM_DT array hb_sao_apply_frame takes"""
+    L = load_library()
+    stats = np.ascontiguousarray(stats, SAO_DT)
+    prm = np.zeros(stats.shape[0], SAO_PARAM_DT)
+    lam = (C.c_double * 3)(*[float(x) for x in lambdas])
+    _check(L.hb_sao_decide_standin(stats.ctypes.data, stats.shape[0], lam, prm.ctypes.data), "hb_sao_decide_standin")
+    return prm
 
 
 def presearch_records(jobs_xyn):

@@ -254,6 +254,15 @@ int hb_sao_stats_frame(hb_ctx *ctx, const hb_frame *orig, const hb_frame *rec, h
  * types -2..2), 4 band offset (offset[band], 32 entries) -- the values of sao_offset_t.offset.  dst must be another frame. */
 typedef struct hb_sao_param { int8_t type[3]; int8_t reserved; int16_t offset[3][32]; } hb_sao_param;   /* 196 bytes */
 int hb_sao_apply_frame(hb_ctx *ctx, const hb_frame *src, hb_frame *dst, const hb_sao_param *params);
+/* The arithmetic half of the SAO decision (host code, no device work): sao_derive_offsets hmr_sao.c:480 (with est_iter_offset
+ * :445), sao_invert_quant_offsets :592 and sao_get_distortion :620 for 8-bit video, on one CTU component's statistics.
+ * type 0..3 EO_0/90/135/45, 4 band offset; lambda = enc_engine->sao_lambdas[component].  offset[]: the 32 entries of
+ * sao_offset_t.offset (what hb_sao_param carries), *band: typeAuxInfo, *dist: the estimated distortion change. */
+int hb_sao_derive_offsets(const hb_sao_stats *stats, int type, double lambda, int16_t offset[32], int32_t *band, int64_t *dist);
+/* A stand-in for sao_decide_blk_params (hmr_sao.c:1295), whose real form prices the syntax with the CABAC state and stays with
+ * the encoder: per CTU, luma alone and both chroma planes jointly, the type minimising dist + lambda * bits against "off", with
+ * the constant prices of the reference's COMPUTE_AS_HM branch (8 / 11 bits, off = 2.5 lambda) and no merge candidates. */
+int hb_sao_decide_standin(const hb_sao_stats *stats, int n_ctus, const double lambda[3], hb_sao_param *params);
 
 /* ------------------------------------------------------------------ D. frame-level pre-pass ----------------
  * For every CTU and every inter PU size 64/32/16/8 at once: motion search chained parent -> child exactly as

@@ -851,3 +851,30 @@ int refdrv_deblock(refdrv *d, const uint8_t *const in[3], int w, int h, const ui
     return cols * rows;
 }
 void refdrv_pps_qp_offsets(refdrv *d, int *cb, int *cr) { *cb = d->enc->pps.cb_qp_offset; *cr = d->enc->pps.cr_qp_offset; }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * The arithmetic half of the SAO decision through the reference's own sao_derive_offsets (hmr_sao.c:480),
+ * sao_invert_quant_offsets (:592) and sao_get_distortion (:620) on one component's statistics of one type.
+ * diff / count: 32 entries each (EO: classes 0..4).  offsets: 32 reconstructed offsets; *band: typeAuxInfo.  Returns the distortion.
+ * ------------------------------------------------------------------------------------------------------------ */
+void sao_init(int bit_depth);
+void sao_derive_offsets(henc_thread_t *wpp_thread, int component, int type_idc, sao_stat_data_t *stats, int *quant_offsets, int *type_aux_info);
+void sao_invert_quant_offsets(int component, int type_idc, int typeAuxInfo, int *dstOffsets, int *srcOffsets);
+int64_t sao_get_distortion(int typeIdc, int typeAuxInfo, int *invQuantOffset, sao_stat_data_t *stats, int bit_depth);
+int64_t refdrv_sao_derive(refdrv *d, const int64_t *diff, const int64_t *count, int comp, int type, double lambda, int32_t *offsets, int32_t *band)
+{
+    henc_thread_t *et = d->et;
+    sao_stat_data_t st;
+    int q[MAX_NUM_SAO_CLASSES], inv[MAX_NUM_SAO_CLASSES], aux = 0;
+    const double save = et->enc_engine->sao_lambdas[comp];
+    memcpy(st.diff, diff, sizeof st.diff); memcpy(st.count, count, sizeof st.count);
+    sao_init(et->bit_depth);
+    et->enc_engine->sao_lambdas[comp] = lambda;
+    sao_derive_offsets(et, comp, type, &st, q, &aux);
+    sao_invert_quant_offsets(comp, type, aux, inv, q);
+    const int64_t dist = sao_get_distortion(type, aux, inv, &st, et->bit_depth);
+    et->enc_engine->sao_lambdas[comp] = save;
+    for (int k = 0; k < MAX_NUM_SAO_CLASSES; k++) offsets[k] = inv[k];
+    *band = aux;
+    return dist;
+}

@@ -357,6 +357,32 @@ def ref_sao_stats(rec, org, w, h):
     return out
 
 
+def ref_sao_derive(rec, comp, sao_type, lam):
+    """sao_derive_offsets + sao_invert_quant_offsets + sao_get_distortion of the reference on one SAO_DT record: (offsets[32], band, dist)"""
+    _, D = ref()
+    hnd = refdrv()
+    D.refdrv_sao_derive.restype = C.c_int64
+    D.refdrv_sao_derive.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.POINTER(C.c_int32)]
+    diff = np.zeros(32, np.int64); count = np.zeros(32, np.int64)
+    if sao_type < 4:
+        diff[:5] = rec["eo_diff"][sao_type]; count[:5] = rec["eo_count"][sao_type]
+    else:
+        diff[:] = rec["bo_diff"]; count[:] = rec["bo_count"]
+    off = np.zeros(32, np.int32); band = C.c_int32(0)
+    dist = D.refdrv_sao_derive(hnd, diff.ctypes.data, count.ctypes.data, comp, sao_type, float(lam), off.ctypes.data, C.byref(band))
+    return off, band.value, dist
+
+
+def random_sao_stats(rng, n):
+    """plausible statistics records: counts of a 64x64 CTU spread over the classes, differences of either sign, some empty classes"""
+    st = np.zeros(n, SAO_DT)
+    st["eo_count"] = rng.integers(0, 1500, (n, 4, 5)) * (rng.random((n, 4, 5)) > 0.15)
+    st["eo_diff"] = (st["eo_count"] * rng.normal(0, 2.5, (n, 4, 5))).astype(np.int32)
+    st["bo_count"] = rng.integers(0, 700, (n, 32)) * (rng.random((n, 32)) > 0.4)
+    st["bo_diff"] = (st["bo_count"] * rng.normal(0, 3.0, (n, 32))).astype(np.int32)
+    return st
+
+
 def ref_intra_presearch(luma, jobs, adi, adi_off, n_threads=1):
     """35-mode SADs of every job through the reference's own functions; returns (seconds, sads (n,35) uint32)"""
     _, D = ref()

@@ -193,6 +193,18 @@ def main():
     g["dbk_in"] = np.concatenate([p_.reshape(-1) for p_ in dplanes]); g["dbk_out"] = np.concatenate([p_.reshape(-1) for p_ in dexp])
     g["dbk_bsv"], g["dbk_bsh"], g["dbk_qp"], g["dbk_offs"] = dbsv, dbsh, dm["qp"], np.array(doffs, np.int32)
 
+    # ---- 8f item 4: the arithmetic half of the SAO decision (sao_derive_offsets + sao_get_distortion) on random statistics
+    from _oracle import random_sao_stats, ref_sao_derive
+    sd = random_sao_stats(rng, 24)
+    sd_lam = rng.choice([0.5, 7.0, 33.3, 120.0, 900.0, 1e4], len(sd))
+    sd_off, sd_band, sd_dist = [], [], []
+    for i_, rec_ in enumerate(sd):
+        for t_ in range(5):
+            o_, b_, d_ = ref_sao_derive(rec_, i_ % 3, t_, sd_lam[i_])
+            sd_off.append(o_.astype(np.int16)); sd_band.append(b_ if t_ == 4 else 0); sd_dist.append(d_)
+    g["saod_stats"] = np.frombuffer(sd.tobytes(), np.int32).copy(); g["saod_lambda"] = sd_lam
+    g["saod_off"], g["saod_band"], g["saod_dist"] = np.array(sd_off), np.array(sd_band, np.int32), np.array(sd_dist, np.int64)
+
     out = os.path.join(HERE, "ref_vectors.npz")
     np.savez_compressed(out, **g)
     print("wrote", out, os.path.getsize(out), "bytes")

@@ -92,3 +92,37 @@ def test_band_halo_exchange_gloo(tmp_path):
         assert all(o[0] == 1 for o in oks), line
         assert all(o[2] == 9 for o in oks), line
         assert oks[0][1] == 3 * 2 and (world == 2 or oks[1][1] == 3 * 4), line          # edge ranks: send+recv per plane; inner: both sides
+
+
+def test_sao_offset_derivation_matches_reference_vectors():
+    """hb_sao_derive_offsets (host code of the library, no device work) against results of the reference's sao_derive_offsets +
+    sao_get_distortion stored by tests/golden/make_golden.py; then the stand-in decision on the same statistics: it may only
+    pick offsets the derivation produced, and "off" where nothing pays for its syntax"""
+    from homerhevc_b200.lib import SAO_DT, sao_decide_standin, sao_derive_offsets
+    G = np.load(os.path.join(ROOT, "tests", "golden", "ref_vectors.npz"))
+    st = np.frombuffer(G["saod_stats"].tobytes(), SAO_DT)
+    k = 0
+    for i, rec in enumerate(st):
+        for t in range(5):
+            off, band, dist = sao_derive_offsets(rec, t, G["saod_lambda"][i])
+            assert np.array_equal(off, G["saod_off"][k]) and dist == G["saod_dist"][k], (i, t)
+            if t == 4:
+                assert band == G["saod_band"][k]
+            k += 1
+    n = len(st) // 3
+    lam = (33.3, 40.0, 40.0)
+    prm = sao_decide_standin(st[:n * 3].reshape(n, 3), lam)
+    picked = 0
+    for i in range(n):
+        assert prm["type"][i, 1] == prm["type"][i, 2]                      # the chroma planes share their type
+        for c in range(3):
+            t = int(prm["type"][i, c])
+            if t < 0:
+                assert not prm["offset"][i, c].any()
+                continue
+            off, _, dist = sao_derive_offsets(st[i * 3 + c], t, lam[c])
+            assert np.array_equal(prm["offset"][i, c], off)
+            picked += 1
+            if c == 0:
+                assert dist + lam[0] * (11 if t == 4 else 8) < 2.5 * lam[0]
+    assert picked > 0

@@ -284,6 +284,27 @@ def test_sao_offset_pass_against_reference():
         assert any((a[c] != src[c]).any() for c in range(3))
 
 
+def test_sao_offset_derivation_against_reference():
+    """the library's host half of the SAO decision (hb_sao_derive_offsets: initial offsets, sign rules, the rate-distortion walk,
+    the band position, the distortion estimate) against the reference's sao_derive_offsets / sao_get_distortion, every type,
+    luma and chroma lambdas from tiny to huge"""
+    from _oracle import random_sao_stats, ref_sao_derive
+    from homerhevc_b200.lib import sao_derive_offsets
+    rng = np.random.default_rng(111)
+    st = random_sao_stats(rng, 60)
+    n_nonzero = 0
+    for i, rec in enumerate(st):
+        lam = float(rng.choice([0.5, 7.0, 33.3, 120.0, 900.0, 1e4]))
+        for t in range(5):
+            off, band, dist = sao_derive_offsets(rec, t, lam)
+            roff, rband, rdist = ref_sao_derive(rec, i % 3, t, lam)
+            assert np.array_equal(off.astype(np.int32), roff) and dist == rdist, (i, t, lam, off, roff, dist, rdist)
+            if t == 4:
+                assert band == rband, (i, lam, band, rband)
+            n_nonzero += int((off != 0).any())
+    assert n_nonzero > 100
+
+
 def test_deblocking_pixel_stage_against_reference():
     """the reference's own deblocking (its per-CTU function, vertical edges of the whole picture first) on random CU/TU trees,
     modes, cbf, QPs and vectors; the restatement gets the boundary strengths the reference derived and must produce the same
