@@ -490,6 +490,51 @@ def main():
     e2e_ms = (time.perf_counter() - t0) * 1e3          # the host is in this loop: wall clock around fully synchronised ends
     d2h_per_step = sum(sl["d2h"] for sl in slots) // e2e_steps
     barrier()
+
+    # ---- e2e, reference picture kept on the device (SURVEY.md 8f item 4 closed into a loop): per frame only the source goes up;
+    # the cost tables, the level streams of the chosen units and the SAO statistics come down; gather -> deblocking -> SAO
+    # statistics -> stand-in SAO decision (host) -> SAO offset pass -> border produce the next reference picture in HBM.
+    # Every in-flight stream is a real IPPP chain here (frame n+1 searches in the finished frame n).
+    from homerhevc_b200.lib import SAO_DT, SAO_PARAM_DT
+    SAO_LAMBDA, DBK = (float(LAMBDA), LAMBDA / 1.26, LAMBDA / 1.26), (2, 2, 0, 0)
+    for sl in slots:
+        c = sl["ctx"]
+        sl["refs"] = [sl["ref"], hb.Frame(c, w, h)]; sl["rec"] = hb.Frame(c, w, h); sl["which"] = 0; sl["count"] = 0
+        sl["levels"] = c.pinned(4 * w * h); sl["stats"] = np.zeros((n_ctus, 3), SAO_DT); sl["prm"] = np.zeros(n_ctus, SAO_PARAM_DT)
+        sl["refs"][0].upload_u8(*pinned[0])
+
+    def begin_frame_res(sl, i):
+        j = 1 + sl["count"] % N_RESIDENT
+        sl["count"] += 1
+        sl["pp"].frame_begin_resident(sl["cur"], sl["refs"][sl["which"]], pinned[j], AVG_DIST, sl["tables"])
+
+    def finish_frame_res(sl):
+        nlev = sl["pp"].frame_finish_resident(sl["cur"], LAMBDA, sl["tables"], sl["sel"], sl["off"], sl["rec"], sl["refs"][1 - sl["which"]], DBK, SAO_LAMBDA,
+                                              sl["levels"], sl["stats"], sl["prm"])
+        sl["which"] = 1 - sl["which"]
+        sl["d2h"] += nlev + sl["tables"].nbytes + sl["stats"].nbytes
+        sl["h2d"] = sl.get("h2d", 0) + frame_bytes + sl["prm"].nbytes + sl["sel"].nbytes + sl["off"].nbytes
+
+    res_ms, res_d2h, res_h2d = None, 0, 0
+    try:
+        begin_frame, finish_frame = begin_frame_res, finish_frame_res          # run_e2e picks them up by name
+        run_e2e(2 * N_SLOTS)
+        barrier()
+        for sl in slots:
+            sl["d2h"] = 0; sl["h2d"] = 0
+        l_res0 = sum(sl["ctx"].launch_count() for sl in slots)
+        t0 = time.perf_counter()
+        run_e2e(e2e_steps)
+        torch.cuda.synchronize()
+        res_ms = (time.perf_counter() - t0) * 1e3
+        res_launches = sum(sl["ctx"].launch_count() for sl in slots) - l_res0
+        res_d2h = sum(sl["d2h"] for sl in slots) // e2e_steps
+        res_h2d = sum(sl["h2d"] for sl in slots) // e2e_steps
+        sao_on = float(np.mean([(sl["prm"]["type"] >= 0).mean() for sl in slots]))
+    except hb.HbError as e:
+        print(f"[bench] device-resident e2e variant failed: {e}", file=sys.stderr)
+        res_ms = None
+    barrier()
     # the unfiltered variant for reference: one stream, every table / level / reconstruction of all five passes fetched
     e2e_cur, e2e_ref = hb.Frame(ctx, w, h), hb.Frame(ctx, w, h)
     def step_full(i):
@@ -513,9 +558,10 @@ def main():
     prof = {k: statistics.mean(v[1:]) for k, v in prof.items()}
 
     if world > 1:
-        t = torch.tensor([ms, e2e_ms, full_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, e2e_ms, full_ms, res_ms if res_ms is not None else 1e12], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms, full_ms = t.tolist()
+        ms, e2e_ms, full_ms, res_all = t.tolist()
+        res_ms = None if res_all >= 1e12 else res_all
     if rank == 0:
         peaks, peak_src = measured_peaks()
         abytes = algorithmic_bytes(pp, w, h)
@@ -558,7 +604,12 @@ def main():
             "e2e": {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 2 * frame_bytes,
                     "d2h_bytes_per_step": int(d2h_per_step), "steps": e2e_steps, "streams_in_flight": N_SLOTS, "host_threads": E2E_THREADS,
                     "flow": "upload cur+ref -> pre-pass -> fetch cost tables (compact 12-byte records) -> host depth choice per CTU -> gather + fetch recon and coded levels of that choice",
-                    "fetch_everything_variant": {"value": world * 20 / (full_ms * 1e-3), "unit": "frames/s", "d2h_bytes_per_step": out_bytes}},
+                    "fetch_everything_variant": {"value": world * 20 / (full_ms * 1e-3), "unit": "frames/s", "d2h_bytes_per_step": out_bytes},
+                    "device_resident_reference_variant": None if res_ms is None else {
+                        "value": world * e2e_steps / (res_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(res_h2d), "d2h_bytes_per_step": int(res_d2h),
+                        "gpu_launches": int(res_launches), "ctus_with_sao": round(sao_on, 3),
+                        "flow": "upload cur only -> pre-pass against the finished previous frame in HBM -> fetch cost tables -> host choice per CTU -> gather into a frame + "
+                                "deblocking (strengths from the plan's tables) + fetch coded levels -> SAO statistics -> host SAO decision (stand-in) -> SAO offset pass + border"}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) k_gather(const hbd_gather_args a)
         for (int e = tid; e < cs * cs / 4; e += 256) {
             const int r = e / (cs / 4), q = (e % (cs / 4)) * 4;
             if (y0 + r < h && x0 + q < w)
-                *reinterpret_cast<uint32_t *>(dst + static_cast<size_t>(y0 + r) * w + x0 + q) =
+                *reinterpret_cast<uint32_t *>(dst + static_cast<size_t>(y0 + r) * a.out_pitch[c] + x0 + q) =
                     *reinterpret_cast<const uint32_t *>(src.org + (y0 + r) * src.pitch + x0 + q);
         }
     }
@@ -82,6 +82,27 @@ __global__ void __launch_bounds__(256) k_gather(const hbd_gather_args a)
         if (tid == 0) s_base = base + total;
         __syncthreads();
     }
+}
+
+// ---- what deblocking needs to know per 4x4 unit about the host's choice, straight from the pre-pass tables in HBM (no host
+// round trip): pass p of a CTU means CUs of 64 >> min(p, 3) with one luma TU each (four for p = 0 and p = 4)
+__global__ void __launch_bounds__(256) k_units_from_selection(const hbd_units_args a)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= a.uw * a.uh) return;
+    const int ux = i % a.uw, uy = i / a.uw;
+    const int pass = a.sel[(uy >> 4) * a.ctu_cols + (ux >> 4)];
+    const int d = min(pass, 3), cu = 64 >> d;
+    const hb_me_result m = a.me[d][((uy * 4) / cu) * a.me_grid_w[d] + (ux * 4) / cu];
+    const hbd_gather_pc pc = a.luma[pass];
+    const int idx = pc.tu_index[((uy * 4) / pc.tu) * pc.grid_w + (ux * 4) / pc.tu];
+    const int tu_depth = (pass == 0 || pass == 4) ? 1 : 0;
+    hb_unit_info u;
+    u.cu_depth = static_cast<uint8_t>(d); u.tu_depth = static_cast<uint8_t>(tu_depth); u.intra = 0;
+    u.cbf_luma = static_cast<uint8_t>((idx >= 0 && pc.res[idx].sum > 0) ? (1 << tu_depth) : 0);
+    u.ref_idx = 0; u.qp = static_cast<uint8_t>(a.qp);
+    u.mvx = static_cast<int16_t>(m.mv.x); u.mvy = static_cast<int16_t>(m.mv.y);
+    a.units[uy * a.units_w + ux] = u;
 }
 
 }  // namespace
@@ -397,6 +418,14 @@ extern "C" int hbk_pack_tables(const void *full, void *compact, int n_me, int n_
     hb_me_result_c *me_c = static_cast<hb_me_result_c *>(compact);
     k_pack_tables<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(me, reinterpret_cast<const hb_tu_result *>(me + n_me), me_c,
                                                                                  reinterpret_cast<hb_tu_result_c *>(me_c + n_me), n_me, n_tu);
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int hbk_units_from_selection(const hbd_units_args *a, void *stream)
+{
+    const int n = a->uw * a->uh;
+    if (n <= 0) return 0;
+    k_units_from_selection<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
     return static_cast<int>(cudaGetLastError());
 }
 

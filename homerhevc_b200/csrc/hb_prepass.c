@@ -59,6 +59,7 @@ struct hb_prepass {
     int launches_per_frame;
     /* gather of the host's selection */
     uint8_t *d_sel; int32_t *d_ctu_off; uint8_t *d_sel_recon; int16_t *d_sel_levels; size_t sel_levels_cap;
+    hb_unit_info *d_units; uint8_t *d_dbk_maps;     /* hb_prepass_finalise: unit data, then strengths (2 planes) + QP map */
     /* side streams per depth: [0] MC then luma T/Q, [1] chroma T/Q, [2] the 4x4 luma pass of depth 3.  They overlap the search of depth d+1 */
     void *side[N_DEPTH][3];
     void *ev_fork[N_DEPTH], *ev_mc[N_DEPTH], *ev_join[N_DEPTH][3];
@@ -245,6 +246,8 @@ void hb_prepass_destroy(hb_prepass *pp)
     if (pp->d_ctu_off) hbc_free(pp->d_ctu_off);
     if (pp->d_sel_recon) hbc_free(pp->d_sel_recon);
     if (pp->d_sel_levels) hbc_free(pp->d_sel_levels);
+    if (pp->d_units) hbc_free(pp->d_units);
+    if (pp->d_dbk_maps) hbc_free(pp->d_dbk_maps);
     for (int d = 0; d < N_DEPTH; d++) {
         for (int k = 0; k < 3; k++) {
             if (pp->side[d][k]) { hbc_stream_sync(pp->side[d][k]); hbc_stream_destroy(pp->side[d][k]); }
@@ -591,8 +594,12 @@ int hb_prepass_select(const hb_prepass *pp, const void *tables, int lambda, uint
         }
     int32_t off = 0;
     for (int i = 0; i < n_ctus; i++) {
-        uint64_t best = ~(uint64_t)0; int bp = 0;
+        uint64_t best = ~(uint64_t)0; int bp = N_DEPTH - 1;
+        /* the part of the CTU inside the picture must be tiled by the pass's units (the reference forces the split at the border) */
+        const int ew = pp->w - (i % pp->ctu_cols) * 64, eh = pp->h - (i / pp->ctu_cols) * 64;
         for (int p = 0; p < N_PASS; p++) {
+            const int cu = 64 >> pass_depth(p);
+            if ((ew < 64 && ew % cu) || (eh < 64 && eh % cu)) continue;
             uint64_t v = cost[i * 8 + (p == 4 ? 4 : p)];
             if (p >= 3) v += cost[i * 8 + 5];
             if (v < best) { best = v; bp = p; }
@@ -612,28 +619,24 @@ size_t hb_prepass_gather_bytes(const hb_prepass *pp, const int32_t *ctu_off)
     return (size_t)pp->w * pp->h * 3 / 2 + sizeof(int16_t) * (size_t)ctu_off[hb_prepass_num_ctus(pp)];
 }
 
-/* Queue the gather of the host's choice and its copy to pinned_dst: reconstruction Y,U,V (tight planes) followed by the level
- * streams of all CTUs (layout in hb_kernels_gather.cu).  Asynchronous: hb_ctx_sync before reading. */
-int hb_prepass_gather(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_off, void *pinned_dst, size_t cap, size_t *bytes_out)
+/* queue the gather kernel of the host's choice: reconstruction into out_recon (NULL: the tight fetch buffer), levels into d_sel_levels */
+static int gather_queue(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_off, uint8_t *const out_recon[3], const int out_pitch[3], const char *what)
 {
-    if (!pp || !sel || !ctu_off || !pinned_dst) return hbi_fail(HB_ERR_ARG, "hb_prepass_gather: NULL argument");
     hb_ctx *ctx = pp->ctx;
     const int n_ctus = hb_prepass_num_ctus(pp);
     const size_t recon_bytes = (size_t)pp->w * pp->h * 3 / 2, lev = (size_t)ctu_off[n_ctus];
-    const size_t need = recon_bytes + sizeof(int16_t) * lev;
     int crc = 0;
-    if (cap < need) return hbi_fail(HB_ERR_ARG, "hb_prepass_gather: need %zu bytes, got %zu", need, cap);
-    for (int i = 0; i < n_ctus; i++) if (sel[i] > 4) return hbi_fail(HB_ERR_ARG, "hb_prepass_gather: sel[%d] = %d", i, sel[i]);
+    for (int i = 0; i < n_ctus; i++) if (sel[i] > 4) return hbi_fail(HB_ERR_ARG, "%s: sel[%d] = %d", what, i, sel[i]);
     hbc_set_device(ctx->device);
     if (!pp->d_sel) {
         if ((crc = hbc_malloc((void **)&pp->d_sel, (size_t)n_ctus)) || (crc = hbc_malloc((void **)&pp->d_ctu_off, sizeof(int32_t) * ((size_t)n_ctus + 1))) ||
-            (crc = hbc_malloc((void **)&pp->d_sel_recon, recon_bytes))) return hbi_cuda_fail(crc, "hb_prepass_gather: cudaMalloc");
+            (crc = hbc_malloc((void **)&pp->d_sel_recon, recon_bytes))) return hbi_cuda_fail(crc, what);
     }
     if (pp->sel_levels_cap < lev + 8) {
-        if ((crc = hbc_stream_sync(ctx->stream))) return hbi_cuda_fail(crc, "hb_prepass_gather: sync");
+        if ((crc = hbc_stream_sync(ctx->stream))) return hbi_cuda_fail(crc, what);
         if (pp->d_sel_levels) hbc_free(pp->d_sel_levels);
         pp->sel_levels_cap = (lev + 8) * 2;
-        if ((crc = hbc_malloc((void **)&pp->d_sel_levels, sizeof(int16_t) * pp->sel_levels_cap))) { pp->sel_levels_cap = 0; pp->d_sel_levels = NULL; return hbi_cuda_fail(crc, "hb_prepass_gather: cudaMalloc"); }
+        if ((crc = hbc_malloc((void **)&pp->d_sel_levels, sizeof(int16_t) * pp->sel_levels_cap))) { pp->sel_levels_cap = 0; pp->d_sel_levels = NULL; return hbi_cuda_fail(crc, what); }
     }
     /* sel / ctu_off are pageable: staged by the runtime before the call returns */
     crc = hbc_h2d_async(pp->d_sel, sel, (size_t)n_ctus, ctx->stream);
@@ -649,14 +652,94 @@ int hb_prepass_gather(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_off
             a.pc[p][c].res = pc->d_res; a.pc[p][c].coeff = pc->d_coeff;
         }
     }
-    a.out_recon[0] = pp->d_sel_recon; a.out_recon[1] = pp->d_sel_recon + (size_t)pp->w * pp->h; a.out_recon[2] = a.out_recon[1] + (size_t)pp->w * pp->h / 4;
+    if (out_recon) for (int c = 0; c < 3; c++) { a.out_recon[c] = out_recon[c]; a.out_pitch[c] = out_pitch[c]; }
+    else {
+        a.out_recon[0] = pp->d_sel_recon; a.out_recon[1] = pp->d_sel_recon + (size_t)pp->w * pp->h; a.out_recon[2] = a.out_recon[1] + (size_t)pp->w * pp->h / 4;
+        a.out_pitch[0] = pp->w; a.out_pitch[1] = a.out_pitch[2] = pp->w / 2;
+    }
     a.out_levels = pp->d_sel_levels;
     if (!crc) { crc = hbk_gather(&a, n_ctus, ctx->stream); ctx->launches++; }
-    if (!crc) crc = hbc_d2h_async(pinned_dst, pp->d_sel_recon, recon_bytes, ctx->stream);
+    return crc ? hbi_cuda_fail(crc, what) : HB_OK;
+}
+
+/* Queue the gather of the host's choice and its copy to pinned_dst: reconstruction Y,U,V (tight planes) followed by the level
+ * streams of all CTUs (layout in hb_kernels_gather.cu).  Asynchronous: hb_ctx_sync before reading. */
+int hb_prepass_gather(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_off, void *pinned_dst, size_t cap, size_t *bytes_out)
+{
+    if (!pp || !sel || !ctu_off || !pinned_dst) return hbi_fail(HB_ERR_ARG, "hb_prepass_gather: NULL argument");
+    hb_ctx *ctx = pp->ctx;
+    const int n_ctus = hb_prepass_num_ctus(pp);
+    const size_t recon_bytes = (size_t)pp->w * pp->h * 3 / 2, lev = (size_t)ctu_off[n_ctus];
+    const size_t need = recon_bytes + sizeof(int16_t) * lev;
+    int rc, crc;
+    if (cap < need) return hbi_fail(HB_ERR_ARG, "hb_prepass_gather: need %zu bytes, got %zu", need, cap);
+    if ((rc = gather_queue(pp, sel, ctu_off, NULL, NULL, "hb_prepass_gather")) != HB_OK) return rc;
+    crc = hbc_d2h_async(pinned_dst, pp->d_sel_recon, recon_bytes, ctx->stream);
     if (!crc && lev) crc = hbc_d2h_async((char *)pinned_dst + recon_bytes, pp->d_sel_levels, sizeof(int16_t) * lev, ctx->stream);
     if (crc) return hbi_cuda_fail(crc, "hb_prepass_gather");
     if (bytes_out) *bytes_out = need;
     return HB_OK;
+}
+
+/* The device-resident continuation of the host's choice: the reconstruction of the chosen passes goes
+ * straight into `rec` (no trip to the host), the level streams of the coded TUs go to pinned_levels as in hb_prepass_gather, and
+ * `rec` is deblocked in place with strengths derived on the device from the pre-pass's own tables (CU / TU sizes of the pass,
+ * vectors, coded flags), then border-padded.  Asynchronous: hb_ctx_sync before reading pinned_levels.  What remains for the next
+ * reference picture is SAO: hb_sao_stats_frame(cur, rec) -> the host's decision -> hb_sao_apply_frame(rec, next reference). */
+int hb_prepass_finalise(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_off, hb_frame *rec, const hb_deblock_params *dbk,
+                        void *pinned_levels, size_t cap, size_t *bytes_out)
+{
+    if (!pp || !sel || !ctu_off || !rec || !dbk || !pinned_levels) return hbi_fail(HB_ERR_ARG, "hb_prepass_finalise: NULL argument");
+    if (rec->w != pp->w || rec->h != pp->h) return hbi_fail(HB_ERR_ARG, "hb_prepass_finalise: frame size differs from the plan's");
+    if (pp->rows != pp->ctu_rows) return hbi_fail(HB_ERR_ARG, "hb_prepass_finalise: not available for a CTU-row band");
+    hb_ctx *ctx = pp->ctx;
+    const int n_ctus = hb_prepass_num_ctus(pp);
+    const size_t lev = (size_t)ctu_off[n_ctus], need = sizeof(int16_t) * lev;
+    const int uw = pp->w / 4, uh = pp->h / 4;
+    const size_t plane = (size_t)uw * uh;
+    int rc, crc = 0;
+    if (cap < need) return hbi_fail(HB_ERR_ARG, "hb_prepass_finalise: need %zu bytes, got %zu", need, cap);
+    hbc_set_device(ctx->device);
+    if (!pp->d_units) {
+        if ((crc = hbc_malloc((void **)&pp->d_units, sizeof(hb_unit_info) * plane)) || (crc = hbc_malloc((void **)&pp->d_dbk_maps, 3 * plane)))
+            return hbi_cuda_fail(crc, "hb_prepass_finalise: cudaMalloc");
+    }
+    uint8_t *planes[3] = { rec->d.p[0].org, rec->d.p[1].org, rec->d.p[2].org };
+    const int pitch[3] = { rec->d.p[0].pitch, rec->d.p[1].pitch, rec->d.p[2].pitch };
+    if ((rc = gather_queue(pp, sel, ctu_off, planes, pitch, "hb_prepass_finalise")) != HB_OK) return rc;
+    if (lev) crc = hbc_d2h_async(pinned_levels, pp->d_sel_levels, need, ctx->stream);
+    hbd_units_args u;
+    memset(&u, 0, sizeof u);
+    u.sel = pp->d_sel; u.ctu_cols = pp->ctu_cols; u.uw = uw; u.uh = uh; u.units_w = uw; u.qp = pp->cfg.qp;
+    for (int d = 0; d < N_DEPTH; d++) { u.me[d] = pp->d_me[d]; u.me_grid_w[d] = pp->grid_w[d]; }
+    for (int p = 0; p < N_PASS; p++) {
+        const pass_comp *pc = &pp->pc[p][0];
+        u.luma[p].tu_index = pc->d_index; u.luma[p].grid_w = pc->grid_w; u.luma[p].grid_h = pc->grid_h; u.luma[p].tu = pc->tu; u.luma[p].res = pc->d_res;
+    }
+    u.units = pp->d_units;
+    uint8_t *bv = pp->d_dbk_maps, *bh = bv + plane, *qp = bh + plane;
+    if (!crc) { crc = hbk_units_from_selection(&u, ctx->stream); ctx->launches++; }
+    if (!crc) { crc = hbk_deblock_strengths(pp->d_units, uw, pp->w, pp->h, bv, bh, qp, ctx->stream); ctx->launches++; }
+    if (!crc) { crc = hbk_deblock(&rec->d, bv, bh, qp, uw, dbk->cb_qp_offset, dbk->cr_qp_offset, dbk->beta_offset_div2, dbk->tc_offset_div2, ctx->stream); ctx->launches += 2; }
+    if (!crc) { crc = hbk_pad_frame(&rec->d, ctx->stream); ctx->launches++; }
+    if (crc) return hbi_cuda_fail(crc, "hb_prepass_finalise");
+    if (bytes_out) *bytes_out = need;
+    return HB_OK;
+}
+
+/* debugging / testing aid: the unit data and strengths the last hb_prepass_finalise used (each may be NULL).  Blocking. */
+int hb_prepass_fetch_units(hb_prepass *pp, hb_unit_info *units, uint8_t *bs_ver, uint8_t *bs_hor)
+{
+    if (!pp || !pp->d_units) return hbi_fail(HB_ERR_ARG, "hb_prepass_fetch_units: hb_prepass_finalise has not run");
+    hb_ctx *ctx = pp->ctx;
+    const size_t plane = (size_t)(pp->w / 4) * (pp->h / 4);
+    int crc = 0;
+    hbc_set_device(ctx->device);
+    if (units) crc = hbc_d2h_async(units, pp->d_units, sizeof(hb_unit_info) * plane, ctx->stream);
+    if (!crc && bs_ver) crc = hbc_d2h_async(bs_ver, pp->d_dbk_maps, plane, ctx->stream);
+    if (!crc && bs_hor) crc = hbc_d2h_async(bs_hor, pp->d_dbk_maps + plane, plane, ctx->stream);
+    if (!crc) crc = hbc_stream_sync(ctx->stream);
+    return crc ? hbi_cuda_fail(crc, "hb_prepass_fetch_units") : HB_OK;
 }
 
 /* The whole per-frame host flow in one blocking call (what one encoder thread does per frame): upload cur and ref from
@@ -697,4 +780,37 @@ int hb_prepass_process_frame(hb_prepass *pp, hb_frame *cur, hb_frame *ref, const
     const int rc = hb_prepass_frame_begin(pp, cur, ref, cur_planes, ref_planes, avg_dist, tables, tables_cap);
     if (rc != HB_OK) return rc;
     return hb_prepass_frame_finish(pp, lambda, tables, sel, ctu_off, out, out_cap, out_bytes);
+}
+
+/* The per-frame flow with the reference picture kept on the device (SURVEY.md 8f item 4 closed into a loop): only the source
+ * picture goes up and only the cost tables, the level streams and the SAO statistics come down.  begin queues the upload of
+ * `cur`, the pre-pass against `ref` (a frame a previous finish produced, or an uploaded one) and the table fetch, and returns. */
+int hb_prepass_frame_begin_resident(hb_prepass *pp, hb_frame *cur, hb_frame *ref, const uint8_t *const cur_planes[3], double avg_dist,
+                                    void *tables, size_t tables_cap)
+{
+    int rc;
+    if (!pp || !cur || !ref || !cur_planes) return hbi_fail(HB_ERR_ARG, "hb_prepass_frame_begin_resident: NULL argument");
+    hb_ctx *ctx = pp->ctx;
+    const int w = pp->w;
+    if ((rc = hb_frame_upload_u8_ex(ctx, cur, cur_planes[0], w, cur_planes[1], w / 2, cur_planes[2], w / 2, HB_UPLOAD_NO_BORDER)) != HB_OK) return rc;
+    if ((rc = hb_prepass_run(pp, cur, ref, avg_dist)) != HB_OK) return rc;
+    return hb_prepass_fetch_tables(pp, tables, tables_cap);
+}
+
+/* finish waits for the tables, lets the stand-in decision pick a pass per CTU, gathers that choice into `rec` and deblocks it
+ * (hb_prepass_finalise), fetches the SAO statistics of `rec` against `cur`, runs the stand-in SAO decision and writes the
+ * finished picture into `next_ref`, border included.  levels must be pinned; stats / params hold num_ctus * 3 / num_ctus records. */
+int hb_prepass_frame_finish_resident(hb_prepass *pp, const hb_frame *cur, int lambda, const void *tables, uint8_t *sel, int32_t *ctu_off,
+                                     hb_frame *rec, hb_frame *next_ref, const hb_deblock_params *dbk, const double sao_lambda[3],
+                                     void *levels, size_t levels_cap, size_t *levels_bytes, hb_sao_stats *stats, hb_sao_param *params)
+{
+    int rc;
+    if (!pp || !cur || !stats || !params || !sao_lambda) return hbi_fail(HB_ERR_ARG, "hb_prepass_frame_finish_resident: NULL argument");
+    hb_ctx *ctx = pp->ctx;
+    if ((rc = hb_ctx_sync(ctx)) != HB_OK) return rc;
+    if ((rc = hb_prepass_select(pp, tables, lambda, sel, ctu_off)) != HB_OK) return rc;
+    if ((rc = hb_prepass_finalise(pp, sel, ctu_off, rec, dbk, levels, levels_cap, levels_bytes)) != HB_OK) return rc;
+    if ((rc = hb_sao_stats_frame(ctx, cur, rec, stats)) != HB_OK) return rc;             /* waits for the queue above as well */
+    if ((rc = hb_sao_decide_standin(stats, hb_prepass_num_ctus(pp), sao_lambda, params)) != HB_OK) return rc;
+    return hb_sao_apply_frame(ctx, rec, next_ref, params);
 }

@@ -155,10 +155,22 @@ typedef struct hbd_gather_args {
     int32_t ctu_cols;
     hbd_frame recon[5];
     hbd_gather_pc pc[5][3];
-    uint8_t *out_recon[3];        /* tight planes w*h, (w/2)*(h/2) x2 */
+    uint8_t *out_recon[3];        /* destination planes: the tight fetch buffer (pitch = plane width) or a frame's planes */
+    int32_t out_pitch[3];
     int16_t *out_levels;
 } hbd_gather_args;
 int hbk_gather(const hbd_gather_args *a, int n_ctus, void *stream);
+/* deblocking unit data of the chosen passes, from what the pre-pass left on the device: per 4x4 unit the CU / TU depth of the CTU's
+ * pass, the vector of the PU and the coded flag of the luma TU that cover it */
+typedef struct hbd_units_args {
+    const uint8_t *sel;
+    int32_t ctu_cols, uw, uh, units_w, qp;
+    const hb_me_result *me[4];
+    int32_t me_grid_w[4];
+    hbd_gather_pc luma[5];
+    hb_unit_info *units;
+} hbd_units_args;
+int hbk_units_from_selection(const hbd_units_args *a, void *stream);
 /* SAO statistics of every CTU and component of a frame: out[ctu * 3 + comp] */
 int hbk_sao_stats(const hbd_frame *org, const hbd_frame *rec, int ctu_cols, int n_ctus, hb_sao_stats *out, void *stream);
 /* boundary strengths + QP map of a P picture from per-unit mode data (device pointers) */

@@ -208,6 +208,11 @@ def load_library():
     L.hb_prepass_select.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.hb_prepass_gather_bytes.restype = C.c_size_t
     L.hb_prepass_gather_bytes.argtypes = [C.c_void_p, C.c_void_p]
+    L.hb_prepass_finalise.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.hb_prepass_fetch_units.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hb_prepass_frame_begin_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_double, C.c_void_p, C.c_size_t]
+    L.hb_prepass_frame_finish_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   C.POINTER(C.c_double), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p]
     L.hb_prepass_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.hb_prepass_process_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_double, C.c_int,
                                            C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -633,6 +638,36 @@ class Prepass:
         n = C.c_size_t(0)
         _check(self.ctx.L.hb_prepass_frame_finish(self.h, lam, tables.ctypes.data, sel.ctypes.data, ctu_off.ctypes.data, out.ctypes.data, out.nbytes,
                                                   C.byref(n)), "hb_prepass_frame_finish")
+        return n.value
+
+    # ---- the same flow with the reference picture kept on the device
+    def finalise(self, sel, ctu_off, rec, pinned_levels, cb_qp_offset=0, cr_qp_offset=0, beta_offset_div2=0, tc_offset_div2=0):
+        """gather the choice into `rec`, deblock it there, queue the level streams to pinned memory; returns their byte count (async)"""
+        prm = (C.c_int32 * 4)(cb_qp_offset, cr_qp_offset, beta_offset_div2, tc_offset_div2)
+        n = C.c_size_t(0)
+        _check(self.ctx.L.hb_prepass_finalise(self.h, sel.ctypes.data, ctu_off.ctypes.data, rec.h, prm, pinned_levels.ctypes.data, pinned_levels.nbytes,
+                                              C.byref(n)), "hb_prepass_finalise")
+        return n.value
+
+    def fetch_units(self):
+        """(units, bs_ver, bs_hor) of the last finalise, each (height/4, width/4)"""
+        shape = (self.h_px // 4, self.w // 4)
+        units = np.zeros(shape, UNIT_INFO_DT); bsv = np.zeros(shape, np.uint8); bsh = np.zeros(shape, np.uint8)
+        _check(self.ctx.L.hb_prepass_fetch_units(self.h, units.ctypes.data, bsv.ctypes.data, bsh.ctypes.data), "hb_prepass_fetch_units")
+        return units, bsv, bsh
+
+    def frame_begin_resident(self, cur, ref, cur_planes, avg_dist, tables):
+        cp = (C.c_void_p * 3)(*[p.ctypes.data for p in cur_planes])
+        _check(self.ctx.L.hb_prepass_frame_begin_resident(self.h, cur.h, ref.h, cp, avg_dist, tables.ctypes.data, tables.nbytes), "hb_prepass_frame_begin_resident")
+
+    def frame_finish_resident(self, cur, lam, tables, sel, ctu_off, rec, next_ref, dbk, sao_lambda, levels, stats, params):
+        """dbk: four ints (cb, cr qp offsets, beta / tc offsets div 2); stats: (n_ctus, 3) SAO_DT; params: (n_ctus,) SAO_PARAM_DT.  Returns the level bytes"""
+        prm = (C.c_int32 * 4)(*dbk)
+        lamv = (C.c_double * 3)(*[float(x) for x in sao_lambda])
+        n = C.c_size_t(0)
+        _check(self.ctx.L.hb_prepass_frame_finish_resident(self.h, cur.h, lam, tables.ctypes.data, sel.ctypes.data, ctu_off.ctypes.data, rec.h, next_ref.h, prm, lamv,
+                                                           levels.ctypes.data, levels.nbytes, C.byref(n), stats.ctypes.data, params.ctypes.data),
+               "hb_prepass_frame_finish_resident")
         return n.value
 
     def output_bytes(self):

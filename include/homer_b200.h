@@ -318,6 +318,15 @@ size_t hb_prepass_gather_bytes(const hb_prepass *pp, const int32_t *ctu_off);
 /* out: recon Y,U,V tight planes, then per CTU (from ctu_off[i], int16 units) for Y,U,V the coded TUs in raster order:
  * { hdr_lo, hdr_hi, N*N levels }, hdr = plane << 28 | N << 16 | TU raster position inside the CTU */
 int  hb_prepass_gather(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_off, void *pinned_dst, size_t cap, size_t *bytes_out);
+/* The device-resident continuation of the choice: the reconstruction of the chosen passes goes straight
+ * into `rec`, which is then deblocked in place (hmr_deblocking_filter.c, strengths derived on the device from the plan's own
+ * tables: CU / TU sizes of the pass, vectors, coded flags; fixed QP) and border-padded; the level streams go to pinned_levels
+ * as in hb_prepass_gather (without the reconstruction in front).  Asynchronous.  SAO follows through hb_sao_stats_frame(cur, rec),
+ * the host's decision and hb_sao_apply_frame(rec, next reference). */
+int  hb_prepass_finalise(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_off, hb_frame *rec, const hb_deblock_params *dbk,
+                         void *pinned_levels, size_t cap, size_t *bytes_out);
+/* the unit data and strengths the last hb_prepass_finalise used (width/4 x height/4 each; any may be NULL).  Blocking. */
+int  hb_prepass_fetch_units(hb_prepass *pp, hb_unit_info *units, uint8_t *bs_ver, uint8_t *bs_hor);
 /* the whole per-frame host flow as one blocking call: upload cur + ref (tight, pinned host planes) -> pre-pass -> cost tables ->
  * hb_prepass_select -> gather -> results in `out` (pinned).  One encoder thread per in-flight stream calls this per frame. */
 int  hb_prepass_process_frame(hb_prepass *pp, hb_frame *cur, hb_frame *ref, const uint8_t *const cur_planes[3], const uint8_t *const ref_planes[3],
@@ -329,6 +338,14 @@ int  hb_prepass_process_frame(hb_prepass *pp, hb_frame *cur, hb_frame *ref, cons
 int  hb_prepass_frame_begin(hb_prepass *pp, hb_frame *cur, hb_frame *ref, const uint8_t *const cur_planes[3], const uint8_t *const ref_planes[3],
                             double avg_dist, void *tables, size_t tables_cap);
 int  hb_prepass_frame_finish(hb_prepass *pp, int lambda, const void *tables, uint8_t *sel, int32_t *ctu_off, void *out, size_t out_cap, size_t *out_bytes);
+/* The same per-frame flow with the reference picture kept on the device: only the source goes up; the cost tables, the level
+ * streams and the SAO statistics come down; the finished picture (deblocked, SAO applied with hb_sao_decide_standin, border
+ * padded) lands in `next_ref` for the following frame.  `rec` is a scratch frame; levels pinned; stats num_ctus*3, params num_ctus. */
+int  hb_prepass_frame_begin_resident(hb_prepass *pp, hb_frame *cur, hb_frame *ref, const uint8_t *const cur_planes[3], double avg_dist,
+                                     void *tables, size_t tables_cap);
+int  hb_prepass_frame_finish_resident(hb_prepass *pp, const hb_frame *cur, int lambda, const void *tables, uint8_t *sel, int32_t *ctu_off,
+                                      hb_frame *rec, hb_frame *next_ref, const hb_deblock_params *dbk, const double sao_lambda[3],
+                                      void *levels, size_t levels_cap, size_t *levels_bytes, hb_sao_stats *stats, hb_sao_param *params);
 const hb_frame *hb_prepass_pred(const hb_prepass *pp, int depth);     /* resident prediction of that depth */
 const hb_frame *hb_prepass_recon(const hb_prepass *pp, int pass);
 

@@ -429,3 +429,103 @@ def test_bands_across_gpus_with_nccl_halo_exchange(ctx):
                          capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
     assert "mismatches=0" in out.stdout
+
+
+def _host_units(pp, sel, w, h, qp):
+    """deblocking unit data of a selection, rebuilt on the host from the individually fetched tables"""
+    from homerhevc_b200.lib import UNIT_INFO_DT
+    cols = (w + 63) // 64
+    units = np.zeros((h // 4, w // 4), UNIT_INFO_DT)
+    me = [pp.fetch_me(d) for d in range(4)]
+    coded = []
+    for p in range(5):
+        t = pp.tu_size(p, 0)
+        xy, res = pp.tu_xy(p, 0), pp.fetch_tu(p, 0)
+        coded.append((t, {(int(x), int(y)): int(r["sum"]) > 0 for (x, y), r in zip(xy, res)}))
+    for uy in range(h // 4):
+        for ux in range(w // 4):
+            x, y = ux * 4, uy * 4
+            p = int(sel[(y // 64) * cols + x // 64])
+            d = min(p, 3); cu = 64 >> d
+            m = me[d][(y // cu) * (cols * (64 // cu)) + x // cu]
+            t, tab = coded[p]
+            td = 1 if p in (0, 4) else 0
+            u = units[uy, ux]
+            u["cu_depth"], u["tu_depth"], u["qp"], u["mvx"], u["mvy"] = d, td, qp, m["mvx"], m["mvy"]
+            u["cbf_luma"] = (1 << td) if tab.get((x // t * t, y // t * t), False) else 0
+    return units
+
+
+def test_device_resident_finalisation(ctx):
+    """the choice gathered into a frame and deblocked without leaving the device equals the host-composed chain (gather to the host,
+    unit data rebuilt from the fetched tables, upload, hb_deblock_frame_units); then the whole resident per-frame flow -- SAO
+    statistics, stand-in decision, offset pass, border -- equals the same calls made one by one, and its output serves as a
+    reference picture exactly like an uploaded copy of it"""
+    from homerhevc_b200.lib import SAO_DT, SAO_PARAM_DT, sao_decide_standin
+    w, h, qp, avg = 320, 200, 30, 300.0
+    cur, ref = clip_pair(w, h, n=4, noise=5.0, seed=21)
+    fc, fr = upload(ctx, cur, w, h), upload(ctx, ref, w, h)
+    pp = hb.Prepass(ctx, w, h, qp=qp)
+    pp.run(fc, fr, avg)
+    tables = ctx.pinned(pp.tables_bytes())
+    pp.fetch_tables(tables); ctx.sync()
+    n_ctus = pp.num_ctus()
+    sel = np.zeros(n_ctus, np.uint8); off = np.zeros(n_ctus + 1, np.int32)
+    pp.select(tables, 40, sel, off)
+    assert set(int(v) for v in sel[15:]) <= {3, 4}                  # 8 picture rows in the last CTU row: only 8x8 units tile them
+    assert len(set(int(v) for v in sel)) >= 2
+    out = ctx.pinned(w * h * 3 // 2 + 2 * int(off[-1]) + 64)
+    nbytes = pp.gather(sel, off, out); ctx.sync()
+    ry = out[:w * h].reshape(h, w); ru = out[w * h:w * h * 5 // 4].reshape(h // 2, w // 2); rv = out[w * h * 5 // 4:w * h * 3 // 2].reshape(h // 2, w // 2)
+    lev = out[w * h * 3 // 2:nbytes].copy()
+    units = _host_units(pp, sel, w, h, qp)
+    fa = hb.Frame(ctx, w, h); fa.upload_u8(ry.copy(), ru.copy(), rv.copy())
+    bsv, bsh = ctx.deblock_units(fa, units, 2, 2)
+    exp = fa.download()
+    assert any((a != b).any() for a, b in zip(exp, (ry, ru, rv)))   # the filter did something
+
+    rec = hb.Frame(ctx, w, h)
+    levels = ctx.pinned(2 * int(off[-1]) + 64)
+    nlev = pp.finalise(sel, off, rec, levels, 2, 2); ctx.sync()
+    assert nlev == 2 * int(off[-1]) and bytes(levels[:nlev]) == bytes(lev)
+    got_units, gv, gh = pp.fetch_units()
+    for f in units.dtype.names:
+        assert np.array_equal(got_units[f], units[f]), f
+    assert np.array_equal(gv, bsv) and np.array_equal(gh, bsh)
+    got = rec.download()
+    for c in range(3):
+        assert np.array_equal(got[c], exp[c]), ("deblocked", c, np.argwhere(got[c] != exp[c])[:4])
+
+    # ---- the resident flow in two halves, against the same calls made one by one
+    lam_sao = (30.0, 36.0, 36.0)
+    st = ctx.sao_stats(fc, rec)
+    prm = sao_decide_standin(st, lam_sao)
+    assert (prm["type"] >= 0).any()
+    fin_exp = hb.Frame(ctx, w, h)
+    ctx.sao_apply(rec, fin_exp, prm["type"], prm["offset"])
+    exp_fin = fin_exp.download()
+
+    cur_pin = ctx.pinned(w * h * 3 // 2)
+    py = cur_pin[:w * h].reshape(h, w); pu = cur_pin[w * h:w * h * 5 // 4].reshape(h // 2, w // 2); pv = cur_pin[w * h * 5 // 4:].reshape(h // 2, w // 2)
+    py[:], pu[:], pv[:] = cur
+    fc2, rec2, nxt = hb.Frame(ctx, w, h), hb.Frame(ctx, w, h), hb.Frame(ctx, w, h)
+    sel2 = np.zeros(n_ctus, np.uint8); off2 = np.zeros(n_ctus + 1, np.int32)
+    st2 = np.zeros((n_ctus, 3), SAO_DT); prm2 = np.zeros(n_ctus, SAO_PARAM_DT)
+    levels2 = ctx.pinned(w * h * 4)
+    pp.frame_begin_resident(fc2, fr, (py, pu, pv), avg, tables)
+    nlev2 = pp.frame_finish_resident(fc2, 40, tables, sel2, off2, rec2, nxt, (2, 2, 0, 0), lam_sao, levels2, st2, prm2)
+    assert np.array_equal(sel2, sel) and np.array_equal(off2, off) and nlev2 == nlev and bytes(levels2[:nlev2]) == bytes(lev)
+    assert st2.tobytes() == st.tobytes() and prm2.tobytes() == prm.tobytes()
+    got_fin = nxt.download()
+    for c in range(3):
+        assert np.array_equal(got_fin[c], exp_fin[c]), ("finished", c)
+    assert any((a != b).any() for a, b in zip(got_fin, got))        # SAO changed samples
+
+    # ---- the finished frame as the next reference: identical search results to an uploaded copy of it (border included)
+    nxt_copy = upload(ctx, got_fin, w, h)
+    pp.run(fc, nxt, avg); a = [pp.fetch_me(d).tobytes() for d in range(4)]
+    pp.run(fc, nxt_copy, avg); b = [pp.fetch_me(d).tobytes() for d in range(4)]
+    assert a == b
+    for f in (fa, rec, fin_exp, fc2, rec2, nxt, nxt_copy, fc, fr):
+        f.close()
+    pp.close()
