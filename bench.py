@@ -495,12 +495,12 @@ def main():
     # the cost tables, the level streams of the chosen units and the SAO statistics come down; gather -> deblocking -> SAO
     # statistics -> stand-in SAO decision (host) -> SAO offset pass -> border produce the next reference picture in HBM.
     # Every in-flight stream is a real IPPP chain here (frame n+1 searches in the finished frame n).
-    from homerhevc_b200.lib import SAO_DT, SAO_PARAM_DT
+    from homerhevc_b200.lib import SAO_PARAM_DT
     SAO_LAMBDA, DBK = (float(LAMBDA), LAMBDA / 1.26, LAMBDA / 1.26), (2, 2, 0, 0)
     for sl in slots:
         c = sl["ctx"]
         sl["refs"] = [sl["ref"], hb.Frame(c, w, h)]; sl["rec"] = hb.Frame(c, w, h); sl["which"] = 0; sl["count"] = 0
-        sl["levels"] = c.pinned(4 * w * h); sl["stats"] = np.zeros((n_ctus, 3), SAO_DT); sl["prm"] = np.zeros(n_ctus, SAO_PARAM_DT)
+        sl["levels"] = c.pinned(4 * w * h); sl["prm"] = np.zeros(n_ctus, SAO_PARAM_DT)
         sl["refs"][0].upload_u8(*pinned[0])
 
     def begin_frame_res(sl, i):
@@ -510,9 +510,9 @@ def main():
 
     def finish_frame_res(sl):
         nlev = sl["pp"].frame_finish_resident(sl["cur"], LAMBDA, sl["tables"], sl["sel"], sl["off"], sl["rec"], sl["refs"][1 - sl["which"]], DBK, SAO_LAMBDA,
-                                              sl["levels"], sl["stats"], sl["prm"])
+                                              sl["levels"], sl["prm"])
         sl["which"] = 1 - sl["which"]
-        sl["d2h"] += nlev + sl["tables"].nbytes + sl["stats"].nbytes
+        sl["d2h"] += nlev + sl["tables"].nbytes + n_ctus * 15 * 16
         sl["h2d"] = sl.get("h2d", 0) + frame_bytes + sl["prm"].nbytes + sl["sel"].nbytes + sl["off"].nbytes
 
     res_ms, res_d2h, res_h2d = None, 0, 0
@@ -609,7 +609,7 @@ def main():
                         "value": world * e2e_steps / (res_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(res_h2d), "d2h_bytes_per_step": int(res_d2h),
                         "gpu_launches": int(res_launches), "ctus_with_sao": round(sao_on, 3),
                         "flow": "upload cur only -> pre-pass against the finished previous frame in HBM -> fetch cost tables -> host choice per CTU -> gather into a frame + "
-                                "deblocking (strengths from the plan's tables) + fetch coded levels -> SAO statistics -> host SAO decision (stand-in) -> SAO offset pass + border"}},
+                                "deblocking (strengths from the plan's tables) + fetch coded levels -> SAO statistics + per-type offsets/distortions on the device -> fetch those -> host SAO type choice (stand-in) -> SAO offset pass + border"}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",

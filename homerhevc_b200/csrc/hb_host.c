@@ -751,6 +751,33 @@ done:
     return rc;
 }
 
+/* SAO statistics + the per-type offsets / band positions / distortion estimates derived from them on the device */
+int hb_sao_candidates_frame(hb_ctx *ctx, const hb_frame *orig, const hb_frame *rec, const double lambda[3], hb_sao_candidate *cand, hb_sao_stats *stats)
+{
+    int rc = HB_OK, crc = 0;
+    void *d_st, *h_st, *d_cand, *h_cand;
+    if (!ctx || !orig || !rec || !lambda || !cand) return hbi_fail(HB_ERR_ARG, "hb_sao_candidates_frame: NULL argument");
+    if (orig->w != rec->w || orig->h != rec->h) return hbi_fail(HB_ERR_ARG, "hb_sao_candidates_frame: frame sizes differ");
+    const int cols = (rec->w + 63) / 64, n_ctus = cols * ((rec->h + 63) / 64);
+    const size_t st_bytes = sizeof(hb_sao_stats) * 3 * (size_t)n_ctus, cand_bytes = sizeof(hb_sao_candidate) * 15 * (size_t)n_ctus;
+    hbc_set_device(ctx->device);
+    pthread_mutex_lock(&ctx->lock);
+    if ((rc = hbi_scratch(ctx, 0, st_bytes, &d_st, &h_st)) != HB_OK) goto done;
+    if ((rc = hbi_scratch(ctx, 1, cand_bytes, &d_cand, &h_cand)) != HB_OK) goto done;
+    crc = hbk_sao_stats(&orig->d, &rec->d, cols, n_ctus, (hb_sao_stats *)d_st, ctx->stream);
+    ctx->launches++;
+    if (!crc) { crc = hbk_sao_derive((const hb_sao_stats *)d_st, 3 * n_ctus, lambda, (hb_sao_candidate *)d_cand, ctx->stream); ctx->launches++; }
+    if (!crc) crc = hbc_d2h_async(h_cand, d_cand, cand_bytes, ctx->stream);
+    if (!crc && stats) crc = hbc_d2h_async(h_st, d_st, st_bytes, ctx->stream);
+    if (!crc) crc = hbc_stream_sync(ctx->stream);
+    if (!crc) memcpy(cand, h_cand, cand_bytes);
+    if (!crc && stats) memcpy(stats, h_st, st_bytes);
+done:
+    pthread_mutex_unlock(&ctx->lock);
+    if (crc) return hbi_cuda_fail(crc, "hb_sao_candidates_frame");
+    return rc;
+}
+
 /* SAO offset pass of a whole picture; refreshes dst's replicated border afterwards (dst is the next reference picture) */
 int hb_sao_apply_frame(hb_ctx *ctx, const hb_frame *src, hb_frame *dst, const hb_sao_param *params)
 {

@@ -111,58 +111,64 @@ __global__ void __launch_bounds__(256) k_units_from_selection(const hbd_units_ar
 // per CTU and component, for the four edge directions the count and the sum of (source - reconstruction) of every sample by
 // edge class sign(c - a) + sign(c - b), and the same by band (c >> 3).  The reference walks rows with running sign buffers;
 // per sample this is a closed form inside a rectangle that depends on the neighbouring CTUs and on the columns / rows the
-// deblocking filter has not finished (5/3 columns, 4/2 rows).  One CTA per (CTU, component): edge classes accumulate in
-// registers and are reduced once, bands go through shared atomics.
+// deblocking filter has not finished (5/3 columns, 4/2 rows).  One CTA per (CTU, component).
 namespace {
 __device__ __forceinline__ int sgn3(int v) { return (v > 0) - (v < 0); }
 
-__global__ void __launch_bounds__(256) k_sao_stats(hbd_frame org, hbd_frame rec, int ctu_cols, hb_sao_stats *out)
+// Accumulation: every lane owns a private column of 52 bins (20 edge-class bins, 32 bands) in shared memory -- address
+// (warp, bin, lane), so bank = lane and plain load / add / store never conflicts and needs no atomics.  A bin word packs the
+// sample count (bits 16..) and the sum of the biased differences d + 256 (bits 0..15): a lane sees at most 32 samples per bin.
+constexpr int kSaoWarps = 4, kSaoBins = 52;
+
+__global__ void __launch_bounds__(kSaoWarps * 32) k_sao_stats(hbd_frame org, hbd_frame rec, int ctu_cols, hb_sao_stats *out)
 {
-    __shared__ int s_acc[104];                           // eo_diff[4][5], eo_count[4][5], bo_diff[32], bo_count[32]
+    __shared__ uint32_t s_bin[kSaoWarps][kSaoBins][32];
     const int comp = blockIdx.y, ctu = blockIdx.x;
-    const hbd_plane &pr = rec.p[comp], &po = org.p[comp];
-    const int cs = comp ? 32 : 64;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const hbd_plane pr = hbd_pick_plane(rec, comp), po = hbd_pick_plane(org, comp);
+    const int cs = comp ? 32 : 64, lcs = comp ? 5 : 6;
     const int x0 = (ctu % ctu_cols) * cs, y0 = (ctu / ctu_cols) * cs;
     const int w = min(cs, pr.w - x0), h = min(cs, pr.h - y0);
     const bool l = x0 > 0, t = y0 > 0, r = x0 + cs < pr.w, b = y0 + cs < pr.h;
     const int skr = comp ? 3 : 5, skb = comp ? 2 : 4;
-    for (int i = threadIdx.x; i < 104; i += 256) s_acc[i] = 0;
+    for (int i = threadIdx.x; i < kSaoWarps * kSaoBins * 32; i += kSaoWarps * 32) (&s_bin[0][0][0])[i] = 0;
     __syncthreads();
     // the rectangles of the five types (hmr_sao.c:123-127, :154-157, :201-205, :262-264, :312-314)
     const int ex_e = r ? w - skr : w - 1, ex_f = r ? w - skr : w;          // EO_0/135/45 stop one short of a picture edge; EO_90 and BO do not
     const int sx_e = l ? 0 : 1, sy_v = t ? 0 : 1;
     const int ey_all = b ? h - skb : h, ey_v = b ? h - skb : h - 1;
-    int cnt[4][5], dif[4][5];
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-#pragma unroll
-        for (int c = 0; c < 5; c++) { cnt[k][c] = 0; dif[k][c] = 0; }
-    for (int i = threadIdx.x; i < w * h; i += 256) {
-        const int x = i % w, y = i / w;
-        const uint8_t *p = pr.org + (y0 + y) * pr.pitch + x0 + x;
-        const int c = p[0], d = static_cast<int>(po.org[(y0 + y) * po.pitch + x0 + x]) - c;
+    uint32_t *mine = &s_bin[warp][0][lane];
+    const int pitch = pr.pitch;
+    for (int i = threadIdx.x; i < cs * h; i += kSaoWarps * 32) {
+        const int x = i & (cs - 1), y = i >> lcs;
+        if (x >= w) continue;
+        const uint8_t *p = pr.org + (y0 + y) * pitch + x0 + x;
+        const int c = p[0];
+        const uint32_t inc = 0x10000u + 256u + static_cast<uint32_t>(static_cast<int>(po.org[(y0 + y) * po.pitch + x0 + x]) - c);
         const bool in_e = x >= sx_e && x < ex_e, in_f = x < ex_f;
-        const bool v0 = in_e && y < ey_all, v1 = in_f && y >= sy_v && y < ey_v, v23 = in_e && y >= sy_v && y < ey_v, vb = in_f && y < ey_all;
+        const bool row_all = y < ey_all, row_v = y >= sy_v && y < ey_v;
         // samples outside the picture are never classified (the rectangles exclude them); the border keeps the loads legal
-        const int cls[4] = { 2 + sgn3(c - p[-1]) + sgn3(c - p[1]), 2 + sgn3(c - p[-pr.pitch]) + sgn3(c - p[pr.pitch]),
-                             2 + sgn3(c - p[-pr.pitch - 1]) + sgn3(c - p[pr.pitch + 1]), 2 + sgn3(c - p[-pr.pitch + 1]) + sgn3(c - p[pr.pitch - 1]) };
-        const bool val[4] = { v0, v1, v23, v23 };
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-#pragma unroll
-            for (int q = 0; q < 5; q++) { const bool hit = val[k] && cls[k] == q; cnt[k][q] += hit; dif[k][q] += hit ? d : 0; }
-        if (vb) { atomicAdd(&s_acc[40 + (c >> 3)], d); atomicAdd(&s_acc[72 + (c >> 3)], 1); }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-#pragma unroll
-        for (int q = 0; q < 5; q++) {
-            const int sd = __reduce_add_sync(HB_FULL_MASK, dif[k][q]), sc = __reduce_add_sync(HB_FULL_MASK, cnt[k][q]);
-            if ((threadIdx.x & 31) == 0 && sc) { atomicAdd(&s_acc[k * 5 + q], sd); atomicAdd(&s_acc[20 + k * 5 + q], sc); }
+        if (in_e && row_all) mine[(0 + 2 + sgn3(c - p[-1]) + sgn3(c - p[1])) * 32] += inc;
+        if (in_f && row_v) mine[(5 + 2 + sgn3(c - p[-pitch]) + sgn3(c - p[pitch])) * 32] += inc;
+        if (in_e && row_v) {
+            mine[(10 + 2 + sgn3(c - p[-pitch - 1]) + sgn3(c - p[pitch + 1])) * 32] += inc;
+            mine[(15 + 2 + sgn3(c - p[-pitch + 1]) + sgn3(c - p[pitch - 1])) * 32] += inc;
         }
+        if (in_f && row_all) mine[(20 + (c >> 3)) * 32] += inc;
+    }
     __syncthreads();
-    int *o = reinterpret_cast<int *>(out + (static_cast<size_t>(ctu) * 3 + comp));
-    for (int i = threadIdx.x; i < 104; i += 256) o[i] = s_acc[i];
+    int *o = reinterpret_cast<int *>(out + (static_cast<size_t>(ctu) * 3 + comp));     // eo_diff[4][5], eo_count[4][5], bo_diff[32], bo_count[32]
+    for (int bin = warp; bin < kSaoBins; bin += kSaoWarps) {
+        int cnt = 0, sum = 0;
+#pragma unroll
+        for (int ww = 0; ww < kSaoWarps; ww++) { const uint32_t v = s_bin[ww][bin][lane]; cnt += v >> 16; sum += v & 0xffffu; }
+        cnt = __reduce_add_sync(HB_FULL_MASK, cnt); sum = __reduce_add_sync(HB_FULL_MASK, sum);
+        if (lane == 0) {
+            const int dif = sum - 256 * cnt;
+            if (bin < 20) { o[bin] = dif; o[20 + bin] = cnt; }
+            else { o[40 + bin - 20] = dif; o[72 + bin - 20] = cnt; }
+        }
+    }
 }
 }  // namespace
 
@@ -339,7 +345,7 @@ __global__ void __launch_bounds__(256) k_sao_apply(hbd_frame src, hbd_frame dst,
 {
     __shared__ int s_off[32];
     const int comp = blockIdx.y, ctu = blockIdx.x;
-    const hbd_plane &ps = src.p[comp], &pd = dst.p[comp];
+    const hbd_plane ps = hbd_pick_plane(src, comp), pd = hbd_pick_plane(dst, comp);
     const int cs = comp ? 32 : 64;
     const int x0 = (ctu % ctu_cols) * cs, y0 = (ctu / ctu_cols) * cs;
     const int w = min(cs, ps.w - x0), h = min(cs, ps.h - y0);
@@ -383,10 +389,106 @@ extern "C" int hbk_sao_apply(const hbd_frame *src, const hbd_frame *dst, int ctu
     return static_cast<int>(cudaGetLastError());
 }
 
+namespace {
+// ---- the arithmetic half of the SAO decision on the device (sao_derive_offsets hmr_sao.c:480 with est_iter_offset :445,
+// sao_get_distortion :620, 8-bit video): one warp per (CTU, component).  Lanes 0..19 own an (edge type, class) pair, every lane
+// owns a band; the costs are IEEE doubles combined in the reference's order with explicit round-to-nearest operations (no fused
+// multiply-add), so the choices are the host function's bit for bit.
+struct SaoIter { int off; long long dist; double cost; };
+
+__device__ __forceinline__ SaoIter sao_class_offset(int cnt, int dif, double lambda, bool is_bo, int sign_rule)
+{
+    SaoIter r; r.off = 0; r.dist = 0; r.cost = lambda;
+    if (cnt == 0) return r;
+    const double x = __ddiv_rn(static_cast<double>(dif), static_cast<double>(cnt));
+    int o = x >= 0 ? static_cast<int>(__dadd_rn(x, 0.5)) : static_cast<int>(__dadd_rn(x, -0.5));
+    o = min(max(o, -7), 7);
+    if (sign_rule > 0 && o < 0) o = 0;                   // valleys are only raised
+    if (sign_rule < 0 && o > 0) o = 0;                   // peaks only lowered
+    double best = lambda;
+    for (int it = o; it != 0; it += (it > 0) ? -1 : 1) {
+        int bits = abs(it) + (is_bo ? 2 : 1);
+        if (abs(it) == 7) bits--;
+        const long long d = static_cast<long long>(cnt) * it * it - 2ll * dif * it;
+        const double c = __dadd_rn(static_cast<double>(d), __dmul_rn(lambda, static_cast<double>(bits)));
+        if (c < best) { best = c; r.off = it; r.dist = d; r.cost = c; }
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(128) k_sao_derive(const hb_sao_stats *stats, int n_units, double lam_y, double lam_u, double lam_v, hb_sao_candidate *out)
+{
+    const int unit = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (unit >= n_units) return;
+    const hb_sao_stats &st = stats[unit];
+    const int comp = unit % 3;
+    const double lambda = comp == 0 ? lam_y : (comp == 1 ? lam_u : lam_v);
+    hb_sao_candidate *o = out + static_cast<size_t>(unit) * 5;
+    // ---- edge types: lane = type * 5 + class
+    {
+        const int type = min(lane / 5, 3), cls = lane % 5;
+        const bool act = lane < 20 && cls != 2;
+        const int cnt = act ? st.eo_count[type][cls] : 0, dif = act ? st.eo_diff[type][cls] : 0;
+        const SaoIter r = sao_class_offset(cnt, dif, lambda, false, cls < 2 ? 1 : -1);
+        const long long cd = static_cast<long long>(cnt) * r.off * r.off - 2ll * dif * r.off;
+        long long sum = cd;
+        int offs[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) offs[k] = __shfl_sync(HB_FULL_MASK, r.off, (lane / 5) * 5 + k);
+#pragma unroll
+        for (int k = 1; k < 5; k++) sum += __shfl_down_sync(HB_FULL_MASK, cd, k);
+        if (lane < 20 && cls == 0) {
+            hb_sao_candidate c;
+            c.dist = sum; c.offset[0] = static_cast<int8_t>(offs[0]); c.offset[1] = static_cast<int8_t>(offs[1]);
+            c.offset[2] = static_cast<int8_t>(offs[3]); c.offset[3] = static_cast<int8_t>(offs[4]);
+            c.band = 0; c.reserved[0] = c.reserved[1] = c.reserved[2] = 0;
+            o[type] = c;
+        }
+    }
+    // ---- band type: lane = band
+    {
+        const int cnt = st.bo_count[lane], dif = st.bo_diff[lane];
+        const SaoIter r = sao_class_offset(cnt, dif, lambda, true, 0);
+        double c = r.cost;                               // the cost of four consecutive bands, summed in the reference's order
+        c = __dadd_rn(c, __shfl_down_sync(HB_FULL_MASK, r.cost, 1));
+        c = __dadd_rn(c, __shfl_down_sync(HB_FULL_MASK, r.cost, 2));
+        c = __dadd_rn(c, __shfl_down_sync(HB_FULL_MASK, r.cost, 3));
+        if (lane > 28) c = 1.0e300;
+        int band = lane;                                 // first minimum wins
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const double oc = __shfl_xor_sync(HB_FULL_MASK, c, d);
+            const int ob = __shfl_xor_sync(HB_FULL_MASK, band, d);
+            if (oc < c || (oc == c && ob < band)) { c = oc; band = ob; }
+        }
+        const long long cd = static_cast<long long>(cnt) * r.off * r.off - 2ll * dif * r.off;
+        long long sum = 0;
+        int offs[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { sum += __shfl_sync(HB_FULL_MASK, cd, band + k); offs[k] = __shfl_sync(HB_FULL_MASK, r.off, band + k); }
+        if (lane == 0) {
+            hb_sao_candidate cnd;
+            cnd.dist = sum;
+#pragma unroll
+            for (int k = 0; k < 4; k++) cnd.offset[k] = static_cast<int8_t>(offs[k]);
+            cnd.band = static_cast<int8_t>(band); cnd.reserved[0] = cnd.reserved[1] = cnd.reserved[2] = 0;
+            o[4] = cnd;
+        }
+    }
+}
+}  // namespace
+
+extern "C" int hbk_sao_derive(const hb_sao_stats *stats, int n_units, const double lambda[3], hb_sao_candidate *out, void *stream)
+{
+    if (n_units <= 0) return 0;
+    k_sao_derive<<<(n_units + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(stats, n_units, lambda[0], lambda[1], lambda[2], out);
+    return static_cast<int>(cudaGetLastError());
+}
+
 extern "C" int hbk_sao_stats(const hbd_frame *org, const hbd_frame *rec, int ctu_cols, int n_ctus, hb_sao_stats *out, void *stream)
 {
     if (n_ctus <= 0) return 0;
-    k_sao_stats<<<dim3(n_ctus, 3), 256, 0, static_cast<cudaStream_t>(stream)>>>(*org, *rec, ctu_cols, out);
+    k_sao_stats<<<dim3(n_ctus, 3), kSaoWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(*org, *rec, ctu_cols, out);
     return static_cast<int>(cudaGetLastError());
 }
 

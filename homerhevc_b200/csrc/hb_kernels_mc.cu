@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) k_block_ssd(hbd_frame cur, hbd_frame pred
     const int plane = w % 3;
     const hbd_mc_pu pu = pus[w / 3];
     const int n = plane ? size >> 1 : size, x = plane ? pu.x >> 1 : pu.x, y = plane ? pu.y >> 1 : pu.y;
-    const hbd_plane &pc = cur.p[plane], &pp = pred.p[plane];
+    const hbd_plane pc = hbd_pick_plane(cur, plane), pp = hbd_pick_plane(pred, plane);
     uint32_t acc = 0;
     for (int i = lane; i < (n >> 2) * n; i += 32) {
         const int r = i / (n >> 2), c = (i % (n >> 2)) * 4;
@@ -186,23 +186,27 @@ __global__ void __launch_bounds__(256) k_block_ssd(hbd_frame cur, hbd_frame pred
 // outside the picture takes the nearest picture sample.
 __global__ void k_pad_frame(hbd_frame f)
 {
-    const hbd_plane p = f.p[blockIdx.y];                // one grid row per plane: a single launch pads Y, U and V
-    const int W = p.w + 2 * p.pad;
-    const int n_side = 2 * p.pad * p.h;                 // left+right strips of the picture rows
-    const int n_tb = 2 * p.pad * W;                     // top+bottom bands, full padded width
+    const hbd_plane p = hbd_pick_plane(f, blockIdx.y);  // one grid row per plane: a single launch pads Y, U and V
+    const int pw = p.pad >> 2, Ww = (p.w + 2 * p.pad) >> 2;     // widths and borders are multiples of 4, rows 4-byte aligned: words
+    const int n_side = 2 * pw * p.h;                    // left+right strips of the picture rows
+    const int n_tb = 2 * p.pad * Ww;                    // top+bottom bands, full padded width
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_side + n_tb; i += gridDim.x * blockDim.x) {
-        int px, py;                                     // padded coordinates
+        int px, py;                                     // padded coordinates of the word's first sample
         if (i < n_side) {
-            const int r = i / (2 * p.pad), c = i % (2 * p.pad);
+            const int r = i / (2 * pw), c = i % (2 * pw);
             py = p.pad + r;
-            px = c < p.pad ? c : p.w + c;
+            px = c < pw ? 4 * c : p.w + 4 * c;
         } else {
-            const int j = i - n_side, r = j / W;
-            px = j % W;
+            const int j = i - n_side, r = j / Ww;
+            px = 4 * (j % Ww);
             py = r < p.pad ? r : p.h + r;
         }
-        const int sx = min(max(px - p.pad, 0), p.w - 1), sy = min(max(py - p.pad, 0), p.h - 1);
-        p.org[(py - p.pad) * p.pitch + (px - p.pad)] = p.org[sy * p.pitch + sx];
+        const int x = px - p.pad, sy = min(max(py - p.pad, 0), p.h - 1);
+        const uint8_t *row = p.org + sy * p.pitch;
+        uint32_t v;
+        if (x >= 0 && x < p.w) v = *reinterpret_cast<const uint32_t *>(row + x);
+        else v = static_cast<uint32_t>(x < 0 ? row[0] : row[p.w - 1]) * 0x01010101u;
+        *reinterpret_cast<uint32_t *>(p.org + (py - p.pad) * p.pitch + x) = v;
     }
 }
 
@@ -211,7 +215,7 @@ __global__ void k_pad_frame(hbd_frame f)
 // picture or a replicated edge sample (widths and borders are multiples of 4).  border = 0 writes the picture only.
 __global__ void k_ingest_frame(hbd_frame f, const uint8_t *stage, int border)
 {
-    const hbd_plane p = f.p[blockIdx.y];
+    const hbd_plane p = hbd_pick_plane(f, blockIdx.y);
     const uint8_t *src = stage + (blockIdx.y == 0 ? 0 : f.p[0].w * f.p[0].h + (blockIdx.y == 2 ? f.p[1].w * f.p[1].h : 0));
     const int pad = border ? p.pad : 0;
     const int ww = (p.w + 2 * pad) >> 2, rows = p.h + 2 * pad;
@@ -313,7 +317,7 @@ extern "C" int hbk_pad_frame(const hbd_frame *f, void *stream)
 {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const hbd_plane &p = f->p[0];
-    const int n = 2 * p.pad * p.h + 2 * p.pad * (p.w + 2 * p.pad);
+    const int n = (2 * p.pad * p.h + 2 * p.pad * (p.w + 2 * p.pad)) / 4;
     k_pad_frame<<<dim3((n + 255) / 256, 3), 256, 0, s>>>(*f);
     return static_cast<int>(cudaGetLastError());
 }

@@ -60,6 +60,7 @@ struct hb_prepass {
     /* gather of the host's selection */
     uint8_t *d_sel; int32_t *d_ctu_off; uint8_t *d_sel_recon; int16_t *d_sel_levels; size_t sel_levels_cap;
     hb_unit_info *d_units; uint8_t *d_dbk_maps;     /* hb_prepass_finalise: unit data, then strengths (2 planes) + QP map */
+    char *d_sao, *h_sao;                            /* resident flow: statistics | candidates | parameters (device); candidates | parameters (pinned) */
     /* side streams per depth: [0] MC then luma T/Q, [1] chroma T/Q, [2] the 4x4 luma pass of depth 3.  They overlap the search of depth d+1 */
     void *side[N_DEPTH][3];
     void *ev_fork[N_DEPTH], *ev_mc[N_DEPTH], *ev_join[N_DEPTH][3];
@@ -248,6 +249,8 @@ void hb_prepass_destroy(hb_prepass *pp)
     if (pp->d_sel_levels) hbc_free(pp->d_sel_levels);
     if (pp->d_units) hbc_free(pp->d_units);
     if (pp->d_dbk_maps) hbc_free(pp->d_dbk_maps);
+    if (pp->d_sao) hbc_free(pp->d_sao);
+    if (pp->h_sao) hbc_host_free(pp->h_sao);
     for (int d = 0; d < N_DEPTH; d++) {
         for (int k = 0; k < 3; k++) {
             if (pp->side[d][k]) { hbc_stream_sync(pp->side[d][k]); hbc_stream_destroy(pp->side[d][k]); }
@@ -798,19 +801,43 @@ int hb_prepass_frame_begin_resident(hb_prepass *pp, hb_frame *cur, hb_frame *ref
 }
 
 /* finish waits for the tables, lets the stand-in decision pick a pass per CTU, gathers that choice into `rec` and deblocks it
- * (hb_prepass_finalise), fetches the SAO statistics of `rec` against `cur`, runs the stand-in SAO decision and writes the
- * finished picture into `next_ref`, border included.  levels must be pinned; stats / params hold num_ctus * 3 / num_ctus records. */
+ * (hb_prepass_finalise), derives the SAO candidates of `rec` against `cur` on the device, fetches them (one wait), runs the
+ * stand-in SAO decision and QUEUES the offset pass into `next_ref`, border included -- it does not wait for it: work queued on
+ * the same context afterwards (the next frame's begin) is ordered behind it; hb_ctx_sync before reading next_ref from elsewhere.
+ * levels must be pinned and are complete on return; params_out (optional, num_ctus records) receives the SAO decision. */
 int hb_prepass_frame_finish_resident(hb_prepass *pp, const hb_frame *cur, int lambda, const void *tables, uint8_t *sel, int32_t *ctu_off,
                                      hb_frame *rec, hb_frame *next_ref, const hb_deblock_params *dbk, const double sao_lambda[3],
-                                     void *levels, size_t levels_cap, size_t *levels_bytes, hb_sao_stats *stats, hb_sao_param *params)
+                                     void *levels, size_t levels_cap, size_t *levels_bytes, hb_sao_param *params_out)
 {
-    int rc;
-    if (!pp || !cur || !stats || !params || !sao_lambda) return hbi_fail(HB_ERR_ARG, "hb_prepass_frame_finish_resident: NULL argument");
+    int rc, crc = 0;
+    if (!pp || !cur || !rec || !next_ref || !sao_lambda) return hbi_fail(HB_ERR_ARG, "hb_prepass_frame_finish_resident: NULL argument");
+    if (next_ref == rec || next_ref->w != pp->w || next_ref->h != pp->h || cur->w != pp->w || cur->h != pp->h)
+        return hbi_fail(HB_ERR_ARG, "hb_prepass_frame_finish_resident: next_ref must be another frame of the plan's size");
     hb_ctx *ctx = pp->ctx;
+    const int n_ctus = hb_prepass_num_ctus(pp);
+    const size_t st_bytes = sizeof(hb_sao_stats) * 3 * (size_t)n_ctus, cand_bytes = sizeof(hb_sao_candidate) * 15 * (size_t)n_ctus;
+    const size_t prm_bytes = sizeof(hb_sao_param) * (size_t)n_ctus;
+    hbc_set_device(ctx->device);
+    if (!pp->d_sao) {
+        if ((crc = hbc_malloc((void **)&pp->d_sao, st_bytes + cand_bytes + prm_bytes)) || (crc = hbc_host_alloc((void **)&pp->h_sao, cand_bytes + prm_bytes)))
+            return hbi_cuda_fail(crc, "hb_prepass_frame_finish_resident: allocation");
+    }
+    hb_sao_stats *d_st = (hb_sao_stats *)pp->d_sao;
+    hb_sao_candidate *d_cand = (hb_sao_candidate *)(pp->d_sao + st_bytes), *h_cand = (hb_sao_candidate *)pp->h_sao;
+    hb_sao_param *d_prm = (hb_sao_param *)(pp->d_sao + st_bytes + cand_bytes), *h_prm = (hb_sao_param *)(pp->h_sao + cand_bytes);
     if ((rc = hb_ctx_sync(ctx)) != HB_OK) return rc;
     if ((rc = hb_prepass_select(pp, tables, lambda, sel, ctu_off)) != HB_OK) return rc;
     if ((rc = hb_prepass_finalise(pp, sel, ctu_off, rec, dbk, levels, levels_cap, levels_bytes)) != HB_OK) return rc;
-    if ((rc = hb_sao_stats_frame(ctx, cur, rec, stats)) != HB_OK) return rc;             /* waits for the queue above as well */
-    if ((rc = hb_sao_decide_standin(stats, hb_prepass_num_ctus(pp), sao_lambda, params)) != HB_OK) return rc;
-    return hb_sao_apply_frame(ctx, rec, next_ref, params);
+    crc = hbk_sao_stats(&cur->d, &rec->d, pp->ctu_cols, n_ctus, d_st, ctx->stream); ctx->launches++;
+    if (!crc) { crc = hbk_sao_derive(d_st, 3 * n_ctus, sao_lambda, d_cand, ctx->stream); ctx->launches++; }
+    if (!crc) crc = hbc_d2h_async(h_cand, d_cand, cand_bytes, ctx->stream);
+    if (!crc) crc = hbc_stream_sync(ctx->stream);
+    if (crc) return hbi_cuda_fail(crc, "hb_prepass_frame_finish_resident");
+    if ((rc = hb_sao_decide_from_candidates(h_cand, n_ctus, sao_lambda, h_prm)) != HB_OK) return rc;
+    crc = hbc_h2d_async(d_prm, h_prm, prm_bytes, ctx->stream);
+    if (!crc) { crc = hbk_sao_apply(&rec->d, &next_ref->d, pp->ctu_cols, n_ctus, d_prm, ctx->stream); ctx->launches++; }
+    if (!crc) { crc = hbk_pad_frame(&next_ref->d, ctx->stream); ctx->launches++; }
+    if (crc) return hbi_cuda_fail(crc, "hb_prepass_frame_finish_resident");
+    if (params_out) memcpy(params_out, h_prm, prm_bytes);
+    return HB_OK;
 }

@@ -115,3 +115,37 @@ int hb_sao_decide_standin(const hb_sao_stats *stats, int n_ctus, const double la
     }
     return HB_OK;
 }
+
+static void sao_candidate_to_param(const hb_sao_candidate *c, int type, int16_t offset[32])
+{
+    memset(offset, 0, 32 * sizeof offset[0]);
+    if (type < 4) { offset[0] = c->offset[0]; offset[1] = c->offset[1]; offset[3] = c->offset[2]; offset[4] = c->offset[3]; }
+    else for (int k = 0; k < 4; k++) offset[c->band + k] = c->offset[k];
+}
+
+/* the same stand-in from the candidates the device derived (hb_sao_candidates_frame): only the comparison of the five types is left */
+int hb_sao_decide_from_candidates(const hb_sao_candidate *cand, int n_ctus, const double lambda[3], hb_sao_param *params)
+{
+    if (!cand || !lambda || !params || n_ctus < 0) return hbi_fail(HB_ERR_ARG, "hb_sao_decide_from_candidates: bad argument");
+    for (int i = 0; i < n_ctus; i++) {
+        hb_sao_param *p = &params[i];
+        const hb_sao_candidate *c = cand + (size_t)i * 15;
+        memset(p, 0, sizeof *p);
+        p->type[0] = p->type[1] = p->type[2] = -1;
+        double best = 2.5 * lambda[0];
+        for (int t = 0; t < 5; t++) {
+            const double v = (double)c[t].dist + lambda[0] * (t == 4 ? 11 : 8);
+            if (v < best) { best = v; p->type[0] = (int8_t)t; }
+        }
+        if (p->type[0] >= 0) sao_candidate_to_param(&c[p->type[0]], p->type[0], p->offset[0]);
+        best = 2.5 * lambda[1];
+        int bt = -1;
+        for (int t = 0; t < 5; t++) {
+            double v = 0;
+            for (int k = 0; k < 2; k++) { v += (double)c[5 * (1 + k) + t].dist; v += lambda[1 + k] * (t == 4 ? 11 : 8); }
+            if (v < best) { best = v; bt = t; }
+        }
+        for (int k = 0; k < 2 && bt >= 0; k++) { p->type[1 + k] = (int8_t)bt; sao_candidate_to_param(&c[5 * (1 + k) + bt], bt, p->offset[1 + k]); }
+    }
+    return HB_OK;
+}

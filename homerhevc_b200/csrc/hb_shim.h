@@ -23,6 +23,10 @@ typedef struct hbd_plane {
     int32_t pad;        /* border on each side */
 } hbd_plane;
 typedef struct hbd_frame { hbd_plane p[3]; } hbd_frame;
+#ifdef __CUDACC__
+/* plane c of a by-value kernel argument through selects (indexing the parameter with a run-time value makes a local copy) */
+__device__ __forceinline__ hbd_plane hbd_pick_plane(const hbd_frame &f, int c) { return c == 0 ? f.p[0] : (c == 1 ? f.p[1] : f.p[2]); }
+#endif
 
 /* ---- CUDA runtime wrappers */
 int  hbc_device_count(void);
@@ -173,6 +177,8 @@ typedef struct hbd_units_args {
 int hbk_units_from_selection(const hbd_units_args *a, void *stream);
 /* SAO statistics of every CTU and component of a frame: out[ctu * 3 + comp] */
 int hbk_sao_stats(const hbd_frame *org, const hbd_frame *rec, int ctu_cols, int n_ctus, hb_sao_stats *out, void *stream);
+/* offsets, band position and distortion estimate of all five types per (CTU, component): out[unit * 5 + type], device memory */
+int hbk_sao_derive(const hb_sao_stats *stats, int n_units, const double lambda[3], hb_sao_candidate *out, void *stream);
 /* boundary strengths + QP map of a P picture from per-unit mode data (device pointers) */
 int hbk_deblock_strengths(const hb_unit_info *units, int units_w, int w, int h, uint8_t *bs_ver, uint8_t *bs_hor, uint8_t *qp, void *stream);
 /* deblocking, pixel stage, in place: all vertical edges, then all horizontal ones (two launches); maps in device memory */

@@ -212,7 +212,9 @@ def load_library():
     L.hb_prepass_fetch_units.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb_prepass_frame_begin_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_double, C.c_void_p, C.c_size_t]
     L.hb_prepass_frame_finish_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                                   C.POINTER(C.c_double), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p]
+                                                   C.POINTER(C.c_double), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]
+    L.hb_sao_candidates_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
+    L.hb_sao_decide_from_candidates.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_void_p]
     L.hb_prepass_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.hb_prepass_process_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_double, C.c_int,
                                            C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -453,6 +455,32 @@ def sao_decide_standin(stats, lambdas):
     return prm
 
 
+SAO_CAND_DT = np.dtype([("dist", "<i8"), ("offset", "i1", (4,)), ("band", "i1"), ("reserved", "i1", (3,))])
+
+
+def _sao_candidates(self, orig, rec, lambdas, want_stats=False):
+    """SAO statistics + the offsets / band position / distortion estimate of all five types derived on the device: (n_ctus, 3, 5) SAO_CAND_DT
+    (and the (n_ctus, 3) statistics when asked)"""
+    n = ((rec.w + 63) // 64) * ((rec.h_px + 63) // 64)
+    cand = np.zeros((n, 3, 5), SAO_CAND_DT)
+    st = np.zeros((n, 3), SAO_DT) if want_stats else None
+    lam = (C.c_double * 3)(*[float(x) for x in lambdas])
+    _check(self.L.hb_sao_candidates_frame(self.h, orig.h, rec.h, lam, cand.ctypes.data, st.ctypes.data if want_stats else None), "hb_sao_candidates_frame")
+    return (cand, st) if want_stats else cand
+
+
+Context.sao_candidates = _sao_candidates
+
+
+def sao_decide_from_candidates(cand, lambdas):
+    L = load_library()
+    cand = np.ascontiguousarray(cand, SAO_CAND_DT)
+    prm = np.zeros(cand.shape[0], SAO_PARAM_DT)
+    lam = (C.c_double * 3)(*[float(x) for x in lambdas])
+    _check(L.hb_sao_decide_from_candidates(cand.ctypes.data, cand.shape[0], lam, prm.ctypes.data), "hb_sao_decide_from_candidates")
+    return prm
+
+
 def presearch_records(jobs_xyn):
     """int32 (n, 3) {x, y, size} -> the hb_intra_job records of an all-mode search (build once, reuse every frame of that size)"""
     rec = np.zeros((len(jobs_xyn), 6), np.int32)
@@ -660,13 +688,14 @@ class Prepass:
         cp = (C.c_void_p * 3)(*[p.ctypes.data for p in cur_planes])
         _check(self.ctx.L.hb_prepass_frame_begin_resident(self.h, cur.h, ref.h, cp, avg_dist, tables.ctypes.data, tables.nbytes), "hb_prepass_frame_begin_resident")
 
-    def frame_finish_resident(self, cur, lam, tables, sel, ctu_off, rec, next_ref, dbk, sao_lambda, levels, stats, params):
-        """dbk: four ints (cb, cr qp offsets, beta / tc offsets div 2); stats: (n_ctus, 3) SAO_DT; params: (n_ctus,) SAO_PARAM_DT.  Returns the level bytes"""
+    def frame_finish_resident(self, cur, lam, tables, sel, ctu_off, rec, next_ref, dbk, sao_lambda, levels, params=None):
+        """dbk: four ints (cb, cr qp offsets, beta / tc offsets div 2); params (optional): (n_ctus,) SAO_PARAM_DT receiving the SAO decision.
+        Returns the level bytes; next_ref is complete after ctx.sync() (or for anything queued on the same context)"""
         prm = (C.c_int32 * 4)(*dbk)
         lamv = (C.c_double * 3)(*[float(x) for x in sao_lambda])
         n = C.c_size_t(0)
         _check(self.ctx.L.hb_prepass_frame_finish_resident(self.h, cur.h, lam, tables.ctypes.data, sel.ctypes.data, ctu_off.ctypes.data, rec.h, next_ref.h, prm, lamv,
-                                                           levels.ctypes.data, levels.nbytes, C.byref(n), stats.ctypes.data, params.ctypes.data),
+                                                           levels.ctypes.data, levels.nbytes, C.byref(n), params.ctypes.data if params is not None else None),
                "hb_prepass_frame_finish_resident")
         return n.value
 

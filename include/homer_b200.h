@@ -259,10 +259,16 @@ int hb_sao_apply_frame(hb_ctx *ctx, const hb_frame *src, hb_frame *dst, const hb
  * type 0..3 EO_0/90/135/45, 4 band offset; lambda = enc_engine->sao_lambdas[component].  offset[]: the 32 entries of
  * sao_offset_t.offset (what hb_sao_param carries), *band: typeAuxInfo, *dist: the estimated distortion change. */
 int hb_sao_derive_offsets(const hb_sao_stats *stats, int type, double lambda, int16_t offset[32], int32_t *band, int64_t *dist);
+/* The same arithmetic on the device, for every CTU, component and type of a picture, right after the statistics (one more launch):
+ * cand[(ctu * 3 + comp) * 5 + type].  offset[]: edge types -- classes 0, 1, 3, 4 (the plain class never has one); band type -- bands
+ * band .. band + 3.  stats (optional) also receives the statistics.  Identical to hb_sao_derive_offsets on those statistics. */
+typedef struct hb_sao_candidate { int64_t dist; int8_t offset[4]; int8_t band; int8_t reserved[3]; } hb_sao_candidate;   /* 16 bytes */
+int hb_sao_candidates_frame(hb_ctx *ctx, const hb_frame *orig, const hb_frame *rec, const double lambda[3], hb_sao_candidate *cand, hb_sao_stats *stats);
 /* A stand-in for sao_decide_blk_params (hmr_sao.c:1295), whose real form prices the syntax with the CABAC state and stays with
  * the encoder: per CTU, luma alone and both chroma planes jointly, the type minimising dist + lambda * bits against "off", with
  * the constant prices of the reference's COMPUTE_AS_HM branch (8 / 11 bits, off = 2.5 lambda) and no merge candidates. */
 int hb_sao_decide_standin(const hb_sao_stats *stats, int n_ctus, const double lambda[3], hb_sao_param *params);
+int hb_sao_decide_from_candidates(const hb_sao_candidate *cand, int n_ctus, const double lambda[3], hb_sao_param *params);   /* the same from hb_sao_candidates_frame's output */
 
 /* ------------------------------------------------------------------ D. frame-level pre-pass ----------------
  * For every CTU and every inter PU size 64/32/16/8 at once: motion search chained parent -> child exactly as
@@ -339,13 +345,15 @@ int  hb_prepass_frame_begin(hb_prepass *pp, hb_frame *cur, hb_frame *ref, const 
                             double avg_dist, void *tables, size_t tables_cap);
 int  hb_prepass_frame_finish(hb_prepass *pp, int lambda, const void *tables, uint8_t *sel, int32_t *ctu_off, void *out, size_t out_cap, size_t *out_bytes);
 /* The same per-frame flow with the reference picture kept on the device: only the source goes up; the cost tables, the level
- * streams and the SAO statistics come down; the finished picture (deblocked, SAO applied with hb_sao_decide_standin, border
- * padded) lands in `next_ref` for the following frame.  `rec` is a scratch frame; levels pinned; stats num_ctus*3, params num_ctus. */
+ * streams and the SAO candidates (hb_sao_candidates_frame's records) come down; the finished picture (deblocked, SAO applied
+ * with hb_sao_decide_from_candidates, border padded) is queued into `next_ref` for the following frame -- finish does not wait
+ * for that last step (work queued on the same context afterwards is ordered behind it; hb_ctx_sync otherwise).
+ * `rec` is a scratch frame; levels pinned, complete on return; params_out (optional): the SAO decision, num_ctus records. */
 int  hb_prepass_frame_begin_resident(hb_prepass *pp, hb_frame *cur, hb_frame *ref, const uint8_t *const cur_planes[3], double avg_dist,
                                      void *tables, size_t tables_cap);
 int  hb_prepass_frame_finish_resident(hb_prepass *pp, const hb_frame *cur, int lambda, const void *tables, uint8_t *sel, int32_t *ctu_off,
                                       hb_frame *rec, hb_frame *next_ref, const hb_deblock_params *dbk, const double sao_lambda[3],
-                                      void *levels, size_t levels_cap, size_t *levels_bytes, hb_sao_stats *stats, hb_sao_param *params);
+                                      void *levels, size_t levels_cap, size_t *levels_bytes, hb_sao_param *params_out);
 const hb_frame *hb_prepass_pred(const hb_prepass *pp, int depth);     /* resident prediction of that depth */
 const hb_frame *hb_prepass_recon(const hb_prepass *pp, int pass);
 

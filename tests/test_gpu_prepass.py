@@ -461,7 +461,7 @@ def test_device_resident_finalisation(ctx):
     unit data rebuilt from the fetched tables, upload, hb_deblock_frame_units); then the whole resident per-frame flow -- SAO
     statistics, stand-in decision, offset pass, border -- equals the same calls made one by one, and its output serves as a
     reference picture exactly like an uploaded copy of it"""
-    from homerhevc_b200.lib import SAO_DT, SAO_PARAM_DT, sao_decide_standin
+    from homerhevc_b200.lib import SAO_PARAM_DT, sao_decide_from_candidates, sao_decide_standin, sao_derive_offsets
     w, h, qp, avg = 320, 200, 30, 300.0
     cur, ref = clip_pair(w, h, n=4, noise=5.0, seed=21)
     fc, fr = upload(ctx, cur, w, h), upload(ctx, ref, w, h)
@@ -501,31 +501,44 @@ def test_device_resident_finalisation(ctx):
     st = ctx.sao_stats(fc, rec)
     prm = sao_decide_standin(st, lam_sao)
     assert (prm["type"] >= 0).any()
+    # the candidates derived on the device are the host function's (which is pinned to the reference), for every CTU, component, type
+    cand, st_again = ctx.sao_candidates(fc, rec, lam_sao, want_stats=True)
+    assert st_again.tobytes() == st.tobytes()
+    for i in range(n_ctus):
+        for c in range(3):
+            for t in range(5):
+                o32, band, dist = sao_derive_offsets(st[i, c], t, lam_sao[c])
+                k = cand[i, c, t]
+                exp_off = o32[[0, 1, 3, 4]] if t < 4 else o32[band:band + 4]
+                assert int(k["dist"]) == dist and np.array_equal(k["offset"], exp_off) and int(k["band"]) == band, (i, c, t, k, o32, band, dist)
+    assert sao_decide_from_candidates(cand, lam_sao).tobytes() == prm.tobytes()
     fin_exp = hb.Frame(ctx, w, h)
     ctx.sao_apply(rec, fin_exp, prm["type"], prm["offset"])
     exp_fin = fin_exp.download()
 
     cur_pin = ctx.pinned(w * h * 3 // 2)
     py = cur_pin[:w * h].reshape(h, w); pu = cur_pin[w * h:w * h * 5 // 4].reshape(h // 2, w // 2); pv = cur_pin[w * h * 5 // 4:].reshape(h // 2, w // 2)
-    py[:], pu[:], pv[:] = cur
+    py[:], pu[:], pv[:] = cur.y, cur.u, cur.v
     fc2, rec2, nxt = hb.Frame(ctx, w, h), hb.Frame(ctx, w, h), hb.Frame(ctx, w, h)
     sel2 = np.zeros(n_ctus, np.uint8); off2 = np.zeros(n_ctus + 1, np.int32)
-    st2 = np.zeros((n_ctus, 3), SAO_DT); prm2 = np.zeros(n_ctus, SAO_PARAM_DT)
+    prm2 = np.zeros(n_ctus, SAO_PARAM_DT)
     levels2 = ctx.pinned(w * h * 4)
     pp.frame_begin_resident(fc2, fr, (py, pu, pv), avg, tables)
-    nlev2 = pp.frame_finish_resident(fc2, 40, tables, sel2, off2, rec2, nxt, (2, 2, 0, 0), lam_sao, levels2, st2, prm2)
+    nlev2 = pp.frame_finish_resident(fc2, 40, tables, sel2, off2, rec2, nxt, (2, 2, 0, 0), lam_sao, levels2, prm2)
     assert np.array_equal(sel2, sel) and np.array_equal(off2, off) and nlev2 == nlev and bytes(levels2[:nlev2]) == bytes(lev)
-    assert st2.tobytes() == st.tobytes() and prm2.tobytes() == prm.tobytes()
+    assert prm2.tobytes() == prm.tobytes()
+    # the offset pass is only queued: a second pre-pass on the same context must see the finished frame without an explicit wait
+    pp.run(fc, nxt, avg); me_unsynced = [pp.fetch_me(d).tobytes() for d in range(4)]
     got_fin = nxt.download()
     for c in range(3):
         assert np.array_equal(got_fin[c], exp_fin[c]), ("finished", c)
     assert any((a != b).any() for a, b in zip(got_fin, got))        # SAO changed samples
 
     # ---- the finished frame as the next reference: identical search results to an uploaded copy of it (border included)
-    nxt_copy = upload(ctx, got_fin, w, h)
+    nxt_copy = hb.Frame(ctx, w, h); nxt_copy.upload_u8(*[np.ascontiguousarray(p) for p in got_fin])
     pp.run(fc, nxt, avg); a = [pp.fetch_me(d).tobytes() for d in range(4)]
     pp.run(fc, nxt_copy, avg); b = [pp.fetch_me(d).tobytes() for d in range(4)]
-    assert a == b
+    assert a == b == me_unsynced
     for f in (fa, rec, fin_exp, fc2, rec2, nxt, nxt_copy, fc, fr):
         f.close()
     pp.close()

@@ -126,3 +126,13 @@ def test_sao_offset_derivation_matches_reference_vectors():
             if c == 0:
                 assert dist + lam[0] * (11 if t == 4 else 8) < 2.5 * lam[0]
     assert picked > 0
+    # the same decision from candidate records (what hb_sao_candidates_frame delivers), built here with the host derivation
+    from homerhevc_b200.lib import SAO_CAND_DT, sao_decide_from_candidates
+    cand = np.zeros((n, 3, 5), SAO_CAND_DT)
+    for i in range(n):
+        for c in range(3):
+            for t in range(5):
+                off, band, dist = sao_derive_offsets(st[i * 3 + c], t, lam[c])
+                cand[i, c, t]["dist"], cand[i, c, t]["band"] = dist, band
+                cand[i, c, t]["offset"] = off[[0, 1, 3, 4]] if t < 4 else off[band:band + 4]
+    assert sao_decide_from_candidates(cand, lam).tobytes() == prm.tobytes()
