@@ -13,74 +13,72 @@ namespace {
 
 __global__ void __launch_bounds__(256) k_gather(const hbd_gather_args a)
 {
-    __shared__ int s_scan[256];
-    __shared__ int s_base;
-    const int ctu = blockIdx.x, tid = threadIdx.x;
+    __shared__ int s_warp[8];                            // coded TUs per warp (scan)
+    __shared__ int s_list[256];                          // compacted coded TUs of the plane: index among the plane's coded TUs
+    __shared__ int s_pos[256];                           // ... and raster position inside the CTU
+    const int ctu = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cx = ctu % a.ctu_cols, cy = ctu / a.ctu_cols;
     const int sel = a.sel[ctu];
-    if (tid == 0) s_base = 0;
 
-    // ---- reconstruction of the chosen depth
+    // ---- reconstruction of the chosen pass: all loads of a thread are issued before its stores
     for (int c = 0; c < 3; c++) {
         const int pass = c ? min(sel, 3) : sel;
         const hbd_plane src = a.recon[pass].p[c];
         const int cs = c ? 32 : 64, x0 = cx * cs, y0 = cy * cs;
-        uint8_t *dst = a.out_recon[c];
-        const int w = src.w, h = src.h;
-        for (int e = tid; e < cs * cs / 4; e += 256) {
-            const int r = e / (cs / 4), q = (e % (cs / 4)) * 4;
-            if (y0 + r < h && x0 + q < w)
-                *reinterpret_cast<uint32_t *>(dst + static_cast<size_t>(y0 + r) * a.out_pitch[c] + x0 + q) =
-                    *reinterpret_cast<const uint32_t *>(src.org + (y0 + r) * src.pitch + x0 + q);
+        uint8_t *__restrict__ dst = a.out_recon[c];
+        const int pitch = a.out_pitch[c], wq = cs / 4, per = cs * cs / 4 / 256;     // 4 words per thread for luma, 1 for chroma
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int e = tid + k * 256, r = e / wq, q = (e % wq) * 4;
+            const bool ok = k < per && y0 + r < src.h && x0 + q < src.w;
+            v[k] = ok ? __ldg(reinterpret_cast<const uint32_t *>(src.org + (y0 + r) * src.pitch + x0 + q)) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int e = tid + k * 256, r = e / wq, q = (e % wq) * 4;
+            if (k < per && y0 + r < src.h && x0 + q < src.w) *reinterpret_cast<uint32_t *>(dst + static_cast<size_t>(y0 + r) * pitch + x0 + q) = v[k];
         }
     }
-    __syncthreads();
 
-    // ---- levels of the coded TUs
+    // ---- levels of the coded TUs: { hdr_lo, hdr_hi, N*N levels } per TU in raster order.  Every coded TU of a plane has the same
+    // length, so a ballot scan yields its rank and the copy runs over (TU, 16-byte chunk) pairs with independent loads
     int16_t *out = a.out_levels + a.ctu_off[ctu];
+    int base = 0;
     for (int c = 0; c < 3; c++) {
         const int pass = c ? min(sel, 3) : sel;
         const hbd_gather_pc pc = a.pc[pass][c];
         const int cs = c ? 32 : 64, tpr = cs / pc.tu, n = tpr * tpr, nn = pc.tu * pc.tu;
-        int idx = -1, len = 0;
+        int idx = -1;
         if (tid < n) {
             const int tx = cx * tpr + tid % tpr, ty = cy * tpr + tid / tpr;
             if (tx < pc.grid_w && ty < pc.grid_h) idx = pc.tu_index[ty * pc.grid_w + tx];
-            if (idx >= 0 && pc.res[idx].sum > 0) len = 2 + nn; else idx = -1;
+            if (idx >= 0 && pc.res[idx].sum <= 0) idx = -1;
         }
-        // exclusive scan of len over the 256 threads
-        s_scan[tid] = len;
+        const uint32_t m = __ballot_sync(HB_FULL_MASK, idx >= 0);
+        if (lane == 0) s_warp[warp] = __popc(m);
         __syncthreads();
-        for (int d = 1; d < 256; d <<= 1) {
-            const int v = tid >= d ? s_scan[tid - d] : 0;
-            __syncthreads();
-            s_scan[tid] += v;
-            __syncthreads();
-        }
-        const int base = s_base;
-        const int my_off = base + s_scan[tid] - len;
+        int before = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const int v = s_warp[k]; before += k < warp ? v : 0; total += v; }
         if (idx >= 0) {
-            const uint32_t hdr = (static_cast<uint32_t>(c) << 28) | (static_cast<uint32_t>(pc.tu) << 16) | static_cast<uint32_t>(tid);
-            out[my_off] = static_cast<int16_t>(hdr & 0xffffu);
-            out[my_off + 1] = static_cast<int16_t>(hdr >> 16);
-        }
-        // publish (offset, idx) so that warps can copy cooperatively
-        const int total = s_scan[255];
-        __syncthreads();                                   // everyone has read the scan before it is overwritten
-        s_scan[tid] = idx >= 0 ? my_off : -1;
-        __shared__ int s_idx[256];
-        s_idx[tid] = idx;
-        __syncthreads();
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int t = warp; t < n; t += 8) {
-            const int o = s_scan[t];
-            if (o < 0) continue;
-            const int16_t *src = pc.coeff + static_cast<size_t>(s_idx[t]) * nn;
-            for (int e = lane; e < nn; e += 32) out[o + 2 + e] = src[e];
+            const int rank = before + __popc(m & ((1u << lane) - 1u));
+            s_list[rank] = idx; s_pos[rank] = tid;
         }
         __syncthreads();
-        if (tid == 0) s_base = base + total;
-        __syncthreads();
+        const int rec_len = 2 + nn, cpt = nn / 8;         // int16 per record, 16-byte chunks per TU
+        for (int k = tid; k < total; k += 256) {
+            const uint32_t hdr = (static_cast<uint32_t>(c) << 28) | (static_cast<uint32_t>(pc.tu) << 16) | static_cast<uint32_t>(s_pos[k]);
+            *reinterpret_cast<uint32_t *>(out + base + k * rec_len) = hdr;              // low half first: hdr_lo, hdr_hi (the stream is 4-byte aligned)
+        }
+        for (int q = tid; q < total * cpt; q += 256) {
+            const int k = q / cpt, j = q % cpt;
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(pc.coeff + static_cast<size_t>(s_list[k]) * nn) + j);
+            uint32_t *o = reinterpret_cast<uint32_t *>(out + base + k * rec_len + 2 + j * 8);
+            o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+        }
+        base += total * rec_len;
+        __syncthreads();                                   // the lists are rewritten by the next plane
     }
 }
 
