@@ -230,6 +230,32 @@ __global__ void k_ingest_frame(hbd_frame f, const uint8_t *stage, int border)
     }
 }
 
+// the same, 16 bytes per thread in padded coordinates (rows start 128-byte aligned): every 8-byte half of a chunk is either inside
+// the picture (one 8-byte load from the dense plane; needs width % 16 == 0 so that chroma rows stay 8-byte aligned) or a
+// replicated edge sample.  border = 0 visits only the chunks that touch the picture.
+__global__ void k_ingest_frame16(hbd_frame f, const uint8_t *stage, int border)
+{
+    const hbd_plane p = hbd_pick_plane(f, blockIdx.y);
+    const uint8_t *src = stage + (blockIdx.y == 0 ? 0 : f.p[0].w * f.p[0].h + (blockIdx.y == 2 ? f.p[1].w * f.p[1].h : 0));
+    const int W = p.w + 2 * p.pad;
+    const int j0 = border ? 0 : p.pad >> 4, j1 = border ? (W + 15) >> 4 : (p.pad + p.w + 15) >> 4;
+    const int r0 = border ? 0 : p.pad, rows = border ? p.h + 2 * p.pad : p.h, cols = j1 - j0;
+    uint8_t *row0 = p.org - p.pad * p.pitch - p.pad;                    // first padded row, 128-byte aligned
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cols * rows; i += gridDim.x * blockDim.x) {
+        const int r = r0 + i / cols, j = j0 + i % cols;
+        const int y = min(max(r - p.pad, 0), p.h - 1);
+        const uint8_t *srow = src + y * p.w;
+        uint2 h[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int x = 16 * j + 8 * k - p.pad;
+            if (x >= 0 && x < p.w) h[k] = *reinterpret_cast<const uint2 *>(srow + x);
+            else { const uint32_t v = static_cast<uint32_t>(x < 0 ? srow[0] : srow[p.w - 1]) * 0x01010101u; h[k] = make_uint2(v, v); }
+        }
+        *reinterpret_cast<uint4 *>(row0 + static_cast<size_t>(r) * p.pitch + 16 * j) = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y);
+    }
+}
+
 __global__ void k_narrow_plane(const int16_t *src, int src_stride, hbd_plane dst, uint32_t *range_flag)
 {
     bool bad = false;
@@ -327,6 +353,11 @@ extern "C" int hbk_ingest_frame(const hbd_frame *f, const uint8_t *stage, int bo
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const hbd_plane &p = f->p[0];
     const int pad = border ? p.pad : 0;
+    if (p.w % 16 == 0 && p.pad % 16 == 0 && f->p[1].pad % 8 == 0 && p.pitch % 16 == 0 && f->p[1].pitch % 16 == 0) {
+        const int n16 = ((p.w + 2 * p.pad) / 16 + 1) * (p.h + 2 * pad);
+        k_ingest_frame16<<<dim3(min((n16 + 255) / 256, 148 * 8), 3), 256, 0, s>>>(*f, stage, border);
+        return static_cast<int>(cudaGetLastError());
+    }
     const int n = ((p.w + 2 * pad) / 4) * (p.h + 2 * pad);
     k_ingest_frame<<<dim3(min((n + 255) / 256, 148 * 8), 3), 256, 0, s>>>(*f, stage, border);
     return static_cast<int>(cudaGetLastError());
