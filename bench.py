@@ -403,7 +403,7 @@ def main():
     slots = []
     for k in range(N_SLOTS):
         c = hb.Context(local)
-        spp = hb.Prepass(c, w, h, qp=QP, use_graph=1, compact_tables=1)    # 12-byte cost records on the wire (e2e); `value` never fetches
+        spp = hb.Prepass(c, w, h, qp=QP, use_graph=1, compact_tables=2)    # compact ME records + one cost record per coding unit on the wire (e2e); `value` never fetches
         n_ctus = spp.num_ctus()
         slots.append({"ctx": c, "cur": hb.Frame(c, w, h), "ref": hb.Frame(c, w, h), "pp": spp, "tables": c.pinned(spp.tables_bytes()),
                       "out": c.pinned(frame_bytes + 4 * w * h), "sel": np.zeros(n_ctus, np.uint8), "off": np.zeros(n_ctus + 1, np.int32), "d2h": 0})
@@ -603,7 +603,7 @@ def main():
                        "cuda_graph": True},
             "e2e": {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 2 * frame_bytes,
                     "d2h_bytes_per_step": int(d2h_per_step), "steps": e2e_steps, "streams_in_flight": N_SLOTS, "host_threads": E2E_THREADS,
-                    "flow": "upload cur+ref -> pre-pass -> fetch cost tables (compact 12-byte records) -> host depth choice per CTU -> gather + fetch recon and coded levels of that choice",
+                    "flow": "upload cur+ref -> pre-pass -> fetch cost tables (compact ME records + one 12-byte cost record per coding unit and pass) -> host depth choice per CTU -> gather + fetch recon and coded levels of that choice",
                     "fetch_everything_variant": {"value": world * 20 / (full_ms * 1e-3), "unit": "frames/s", "d2h_bytes_per_step": out_bytes},
                     "device_resident_reference_variant": None if res_ms is None else {
                         "value": world * e2e_steps / (res_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(res_h2d), "d2h_bytes_per_step": int(res_d2h),

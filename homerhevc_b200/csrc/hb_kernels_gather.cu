@@ -521,6 +521,43 @@ extern "C" int hbk_pack_tables(const void *full, void *compact, int n_me, int n_
     return static_cast<int>(cudaGetLastError());
 }
 
+namespace {
+// ---- one cost record per coding unit and pass (hb_cu_cost): the sums a choice between partition depths needs, so that the
+// per-TU tables need not cross the link
+__global__ void __launch_bounds__(256) k_pack_cu_costs(const hbd_cu_pack_args a)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= a.first[5]) return;
+    int p = 0;
+    while (i >= a.first[p + 1]) p++;
+    const int d = min(p, 3), cu = 64 >> d, k = i - a.first[p];
+    const int cx = k % a.grid_w[d], cy = k / a.grid_w[d];
+    uint32_t ssd = 0, sum = 0, cbf = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const hbd_gather_pc pc = a.pc[c ? d : p][c];
+        const int per = (c ? cu / 2 : cu) / pc.tu;                      // 1 or 2 TUs per CU side
+        for (int t = 0; t < per * per; t++) {
+            const int idx = pc.tu_index[(cy * per + t / per) * pc.grid_w + cx * per + t % per];
+            if (idx < 0) continue;
+            const hb_tu_result r = pc.res[idx];
+            ssd += r.ssd; sum += static_cast<uint32_t>(r.sum);
+            if (r.sum > 0) cbf |= 1u << (4 * c + t);
+        }
+    }
+    hb_cu_cost o;
+    o.ssd = ssd; o.sum = sum; o.cbf = static_cast<uint16_t>(cbf); o.reserved = 0;
+    a.out[i] = o;
+}
+}  // namespace
+
+extern "C" int hbk_pack_cu_costs(const hbd_cu_pack_args *a, void *stream)
+{
+    if (a->first[5] <= 0) return 0;
+    k_pack_cu_costs<<<(a->first[5] + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+    return static_cast<int>(cudaGetLastError());
+}
+
 extern "C" int hbk_units_from_selection(const hbd_units_args *a, void *stream)
 {
     const int n = a->uw * a->uh;

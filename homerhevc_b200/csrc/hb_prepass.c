@@ -46,7 +46,7 @@ struct hb_prepass {
                                                      * exactly the layout hb_prepass_fetch_tables delivers, so the fetch is ONE copy */
     size_t tables_bytes;
     char *d_tables_c;                               /* compact copy (cfg.compact_tables), packed right before each fetch */
-    int n_me_total, n_tu_total;
+    int n_me_total, n_tu_total, n_cu_total;
     hb_frame *pred[N_DEPTH];
     /* T/Q */
     pass_comp pc[N_PASS][3];
@@ -193,6 +193,8 @@ int hb_prepass_create(hb_ctx *ctx, int width, int height, const hb_prepass_cfg *
                 pp->tables_bytes = total;
                 pp->n_me_total = (int)(me_bytes / sizeof(hb_me_result));
                 pp->n_tu_total = (int)((total - me_bytes) / sizeof(hb_tu_result));
+                pp->n_cu_total = 0;
+                for (int p = 0; p < N_PASS; p++) pp->n_cu_total += pp->grid_w[pass_depth(p)] * pp->grid_h[pass_depth(p)];
                 if (cfg->compact_tables) {
                     const int c2 = hbc_malloc((void **)&pp->d_tables_c, sizeof(hb_me_result_c) * (size_t)pp->n_me_total + sizeof(hb_tu_result_c) * (size_t)pp->n_tu_total + 16);
                     if (c2) rc = hbi_cuda_fail(c2, "prepass: compact tables");
@@ -532,6 +534,7 @@ int hb_prepass_fetch_all(hb_prepass *pp, void *pinned_dst, size_t cap, size_t *b
 size_t hb_prepass_tables_bytes(const hb_prepass *pp)
 {
     if (!pp) return 0;
+    if (pp->cfg.compact_tables == 2) return sizeof(hb_me_result_c) * (size_t)pp->n_me_total + sizeof(hb_cu_cost) * (size_t)pp->n_cu_total;
     if (pp->cfg.compact_tables) return sizeof(hb_me_result_c) * (size_t)pp->n_me_total + sizeof(hb_tu_result_c) * (size_t)pp->n_tu_total;
     return pp->tables_bytes;
 }
@@ -545,7 +548,23 @@ int hb_prepass_fetch_tables(hb_prepass *pp, void *pinned_dst, size_t cap)
     hb_ctx *ctx = pp->ctx;
     hbc_set_device(ctx->device);
     int crc;
-    if (pp->cfg.compact_tables) {
+    if (pp->cfg.compact_tables == 2) {
+        hbd_cu_pack_args a;
+        memset(&a, 0, sizeof a);
+        for (int p = 0; p < N_PASS; p++) {
+            for (int c = 0; c < 3; c++) {
+                const pass_comp *pc = &pp->pc[p][c];
+                a.pc[p][c].tu_index = pc->d_index; a.pc[p][c].grid_w = pc->grid_w; a.pc[p][c].grid_h = pc->grid_h; a.pc[p][c].tu = pc->tu; a.pc[p][c].res = pc->d_res;
+            }
+            a.first[p + 1] = a.first[p] + pp->grid_w[pass_depth(p)] * pp->grid_h[pass_depth(p)];
+        }
+        for (int d = 0; d < N_DEPTH; d++) a.grid_w[d] = pp->grid_w[d];
+        a.out = (hb_cu_cost *)(pp->d_tables_c + sizeof(hb_me_result_c) * (size_t)pp->n_me_total);
+        crc = hbk_pack_tables(pp->d_tables, pp->d_tables_c, pp->n_me_total, 0, ctx->stream);
+        if (!crc) crc = hbk_pack_cu_costs(&a, ctx->stream);
+        ctx->launches += 2;
+        if (!crc) crc = hbc_d2h_async(pinned_dst, pp->d_tables_c, hb_prepass_tables_bytes(pp), ctx->stream);
+    } else if (pp->cfg.compact_tables) {
         crc = hbk_pack_tables(pp->d_tables, pp->d_tables_c, pp->n_me_total, pp->n_tu_total, ctx->stream);
         ctx->launches++;
         if (!crc) crc = hbc_d2h_async(pinned_dst, pp->d_tables_c, hb_prepass_tables_bytes(pp), ctx->stream);
@@ -560,10 +579,55 @@ int hb_prepass_num_ctus(const hb_prepass *pp) { return pp ? pp->ctu_cols * pp->c
  * (PU 64/32/16/8, and 8 with 4x4 luma TUs) that minimises sum(ssd) + lambda * sum(|levels|) over its luma TUs and the chroma
  * TUs of pass min(p,3).  Also lays out the gather stream: ctu_off[i] = start of CTU i's levels (int16 units), ctu_off[n] = total.
  * `tables` is what hb_prepass_fetch_tables delivered.  Pure host code. */
+static int popc4(unsigned v) { v &= 15u; return (int)((v & 1u) + ((v >> 1) & 1u) + ((v >> 2) & 1u) + (v >> 3)); }
+
+/* the same choice from the per-CU records (compact_tables = 2): identical costs, the stream lengths come from the coded flags */
+static int select_from_cu_costs(const hb_prepass *pp, const void *tables, int lambda, uint8_t *sel, int32_t *ctu_off)
+{
+    const int n_ctus = hb_prepass_num_ctus(pp);
+    const hb_cu_cost *rec = (const hb_cu_cost *)((const char *)tables + sizeof(hb_me_result_c) * (size_t)pp->n_me_total);
+    const hb_cu_cost *first[N_PASS];
+    for (int p = 0; p < N_PASS; p++) { first[p] = rec; rec += (size_t)pp->grid_w[pass_depth(p)] * pp->grid_h[pass_depth(p)]; }
+    int32_t off = 0;
+    for (int i = 0; i < n_ctus; i++) {
+        uint64_t best = ~(uint64_t)0; int bp = N_DEPTH - 1; int32_t best_len = 0;
+        const int cx = i % pp->ctu_cols, cy = i / pp->ctu_cols;
+        const int ew = pp->w - cx * 64, eh = pp->h - cy * 64;
+        for (int p = 0; p < N_PASS; p++) {
+            const int d = pass_depth(p), cu = 64 >> d, per = 64 / cu, gw = pp->grid_w[d];
+            const int len_y = 2 + pass_luma_tu(p) * pass_luma_tu(p), tc = pp->pc[d][1].tu, len_c = 2 + tc * tc;
+            uint64_t v = 0; int32_t len = 0;
+            for (int y = 0; y < per; y++) {
+                const hb_cu_cost *row = first[p] + (size_t)(cy * per + y) * gw + cx * per;
+                for (int x = 0; x < per; x++) {
+                    v += (uint64_t)row[x].ssd + (uint64_t)((int64_t)lambda * (int64_t)row[x].sum);
+                    len += popc4(row[x].cbf) * len_y + (popc4(row[x].cbf >> 4) + popc4(row[x].cbf >> 8)) * len_c;
+                }
+            }
+            if ((ew < 64 && ew % cu) || (eh < 64 && eh % cu)) continue;
+            if (v < best) { best = v; bp = p; best_len = len; }
+        }
+        if (best == ~(uint64_t)0) {                      /* cannot happen (8x8 units always tile), keep the layout consistent anyway */
+            const int d = N_DEPTH - 1, gw = pp->grid_w[d];
+            best_len = 0;
+            for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) {
+                const hb_cu_cost *r = first[d] + (size_t)(cy * 8 + y) * gw + cx * 8 + x;
+                best_len += popc4(r->cbf) * (2 + 64) + (popc4(r->cbf >> 4) + popc4(r->cbf >> 8)) * (2 + 16);
+            }
+        }
+        sel[i] = (uint8_t)bp;
+        ctu_off[i] = off;
+        off += best_len;
+    }
+    ctu_off[n_ctus] = off;
+    return HB_OK;
+}
+
 int hb_prepass_select(const hb_prepass *pp, const void *tables, int lambda, uint8_t *sel, int32_t *ctu_off)
 {
     if (!pp || !tables || !sel || !ctu_off) return hbi_fail(HB_ERR_ARG, "hb_prepass_select: NULL argument");
     const int n_ctus = hb_prepass_num_ctus(pp);
+    if (pp->cfg.compact_tables == 2) return select_from_cu_costs(pp, tables, lambda, sel, ctu_off);
     const int compact = pp->cfg.compact_tables != 0;
     const char *t = (const char *)tables + (compact ? sizeof(hb_me_result_c) : sizeof(hb_me_result)) * (size_t)pp->n_me_total;
     const size_t rec = compact ? sizeof(hb_tu_result_c) : sizeof(hb_tu_result);
@@ -635,12 +699,13 @@ static int gather_queue(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_o
         if ((crc = hbc_malloc((void **)&pp->d_sel, (size_t)n_ctus)) || (crc = hbc_malloc((void **)&pp->d_ctu_off, sizeof(int32_t) * ((size_t)n_ctus + 1))) ||
             (crc = hbc_malloc((void **)&pp->d_sel_recon, recon_bytes))) return hbi_cuda_fail(crc, what);
     }
-    if (pp->sel_levels_cap < lev + 8) {
-        if ((crc = hbc_stream_sync(ctx->stream))) return hbi_cuda_fail(crc, what);
-        if (pp->d_sel_levels) hbc_free(pp->d_sel_levels);
-        pp->sel_levels_cap = (lev + 8) * 2;
+    if (!pp->d_sel_levels) {
+        /* worst case once (every unit coded with the smallest transform: 18 int16 per 16 samples): growing the buffer later would
+         * mean cudaFree / cudaMalloc, which wait for every stream of the device and drain the frames in flight on other contexts */
+        pp->sel_levels_cap = (size_t)pp->ctu_cols * pp->ctu_rows * (64 * 64 * 3 / 2) * 18 / 16 + 64;
         if ((crc = hbc_malloc((void **)&pp->d_sel_levels, sizeof(int16_t) * pp->sel_levels_cap))) { pp->sel_levels_cap = 0; pp->d_sel_levels = NULL; return hbi_cuda_fail(crc, what); }
     }
+    if (lev > pp->sel_levels_cap) return hbi_fail(HB_ERR_ARG, "%s: ctu_off claims %zu levels, more than the frame can hold", what, lev);
     /* sel / ctu_off are pageable: staged by the runtime before the call returns */
     crc = hbc_h2d_async(pp->d_sel, sel, (size_t)n_ctus, ctx->stream);
     if (!crc) crc = hbc_h2d_async(pp->d_ctu_off, ctu_off, sizeof(int32_t) * ((size_t)n_ctus + 1), ctx->stream);

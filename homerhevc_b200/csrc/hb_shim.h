@@ -175,6 +175,14 @@ typedef struct hbd_units_args {
     hb_unit_info *units;
 } hbd_units_args;
 int hbk_units_from_selection(const hbd_units_args *a, void *stream);
+/* per-CU cost records of every pass (hb_cu_cost, compact_tables = 2) */
+typedef struct hbd_cu_pack_args {
+    hbd_gather_pc pc[5][3];
+    int32_t grid_w[4];
+    int32_t first[6];             /* first record of pass p; first[5] = total */
+    hb_cu_cost *out;
+} hbd_cu_pack_args;
+int hbk_pack_cu_costs(const hbd_cu_pack_args *a, void *stream);
 /* SAO statistics of every CTU and component of a frame: out[ctu * 3 + comp] */
 int hbk_sao_stats(const hbd_frame *org, const hbd_frame *rec, int ctu_cols, int n_ctus, hb_sao_stats *out, void *stream);
 /* offsets, band position and distortion estimate of all five types per (CTU, component): out[unit * 5 + type], device memory */

@@ -76,6 +76,7 @@ class PrepassCfg(C.Structure):
 # numpy views of the compact wire records (hb_me_result_c / hb_tu_result_c, 12 bytes each)
 ME_COMPACT_DT = np.dtype([("mvx", "<i2"), ("mvy", "<i2"), ("sad", "<u4"), ("n_probes", "<u2"), ("subx", "i1"), ("suby", "i1")])
 TU_COMPACT_DT = np.dtype([("ssd", "<u4"), ("ssd_zero", "<u4"), ("sum_zeroed", "<u4")])
+CU_COST_DT = np.dtype([("ssd", "<u4"), ("sum", "<u4"), ("cbf", "<u2"), ("reserved", "<u2")])      # hb_cu_cost, compact_tables = 2
 
 
 class LowLevelFuncs(C.Structure):

@@ -286,11 +286,16 @@ typedef struct hb_prepass_cfg {
     int32_t band_ctu_row0, band_ctu_rows;
     /* != 0: hb_prepass_fetch_tables delivers (and hb_prepass_select expects) 12-byte records -- hb_me_result_c, hb_tu_result_c --
      * instead of the 24 / 16-byte hb_me_result / hb_tu_result: 30 % fewer bytes on the way to the host's decision */
-    int32_t compact_tables;
+    int32_t compact_tables;     /* 0 full records, 1 compact ME + TU records, 2 compact ME + per-CU records (hb_cu_cost) */
 } hb_prepass_cfg;
 /* the compact wire records (same order and counts as the full tables) */
 typedef struct hb_me_result_c { int16_t mvx, mvy; uint32_t sad; uint16_t n_probes; int8_t subx, suby; } hb_me_result_c;   /* 12 bytes */
 typedef struct hb_tu_result_c { uint32_t ssd, ssd_zero, sum_zeroed; } hb_tu_result_c;   /* sum in bits 0..30, zeroed in bit 31 */
+/* compact_tables = 2: after the compact ME records, ONE record per coding unit and pass instead of one per transform unit -- what a
+ * choice between partition depths needs.  Pass p = 0..4 in turn, the CUs of 64 >> min(p, 3) in raster order over whole CTUs (the
+ * order of the ME table of that depth).  ssd / sum: totals over the CU's luma TUs of pass p and chroma TUs of pass min(p, 3);
+ * cbf: coded flags of those TUs in raster order inside the CU, bits 0..3 luma, 4..7 U, 8..11 V. */
+typedef struct hb_cu_cost { uint32_t ssd, sum; uint16_t cbf, reserved; } hb_cu_cost;   /* 12 bytes */
 #define HB_PREPASS_DEPTHS 4     /* PU 64,32,16,8 */
 #define HB_PREPASS_TQ_PASSES 5  /* luma TU 32(d0),32(d1),16(d2),8(d3),4(d3) */
 int  hb_prepass_create(hb_ctx *ctx, int width, int height, const hb_prepass_cfg *cfg, hb_prepass **out);

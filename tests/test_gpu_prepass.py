@@ -412,6 +412,44 @@ def test_compact_tables(ctx):
     assert np.array_equal(uf["sum"], (uc["sum_zeroed"] & 0x7fffffff).astype(np.int32)) and np.array_equal(uf["zeroed"] != 0, (uc["sum_zeroed"] >> 31) != 0)
     assert (uf["zeroed"] != 0).any() and (uf["sum"] > 0).any()
     assert np.array_equal(self_, selc) and np.array_equal(offf, offc) and outf == outc
+
+    # ---- compact_tables = 2: one record per coding unit and pass; the sums and coded flags of the CU's transform units
+    from homerhevc_b200.lib import CU_COST_DT
+    pp = hb.Prepass(ctx, w, h, qp=qp, compact_tables=2)
+    pp.run(fc, fr, avg)
+    tables = ctx.pinned(pp.tables_bytes()); pp.fetch_tables(tables); ctx.sync()
+    cols, rows = (w + 63) // 64, (h + 63) // 64
+    n_cu = sum(cols * rows * (64 // (64 >> min(p, 3))) ** 2 for p in range(5))
+    assert pp.tables_bytes() == 12 * (n_me + n_cu) and bytes(tables[:12 * n_me]) == tc[:12 * n_me]
+    cu = np.frombuffer(bytes(tables[12 * n_me:]), CU_COST_DT)
+    tus = {(p, c): (pp.tu_size(p, c), {(int(x), int(y)): r for (x, y), r in zip(pp.tu_xy(p, c), pp.fetch_tu(p, c))}) for p in range(5) for c in range(3)}
+    k = 0
+    coded_any = False
+    for p in range(5):
+        d = min(p, 3); s_cu = 64 >> d
+        for cy in range(rows * (64 // s_cu)):
+            for cx in range(cols * (64 // s_cu)):
+                ssd = tot = cbf = 0
+                for c in range(3):
+                    t, tab = tus[(p if c == 0 else d, c)]
+                    side = s_cu if c == 0 else s_cu // 2
+                    per = side // t
+                    for q in range(per * per):
+                        r = tab.get((cx * side + (q % per) * t, cy * side + (q // per) * t))
+                        if r is None:
+                            continue
+                        ssd += int(r["ssd"]); tot += int(r["sum"])
+                        if r["sum"] > 0:
+                            cbf |= 1 << (4 * c + q)
+                assert (int(cu[k]["ssd"]), int(cu[k]["sum"]), int(cu[k]["cbf"])) == (ssd, tot, cbf), (p, cx, cy)
+                coded_any |= cbf != 0
+                k += 1
+    assert k == n_cu and coded_any
+    sel2 = np.zeros(n_ctus, np.uint8); off2 = np.zeros(n_ctus + 1, np.int32)
+    pp.select(tables, lam, sel2, off2)
+    out2 = ctx.pinned(w * h * 3 // 2 + 4 * w * h); n2 = pp.gather(sel2, off2, out2); ctx.sync()
+    assert np.array_equal(sel2, self_) and np.array_equal(off2, offf) and bytes(out2[:n2]) == outf
+    pp.close()
     fc.close(); fr.close()
 
 

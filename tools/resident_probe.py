@@ -16,7 +16,7 @@ for i in range(6):
     py = b[:w * h].reshape(h, w); pu = b[w * h:w * h * 5 // 4].reshape(h // 2, w // 2); pv = b[w * h * 5 // 4:].reshape(h // 2, w // 2)
     py[:], pu[:], pv[:] = y, u, v
     planes.append((py, pu, pv))
-pp = hb.Prepass(ctx, w, h, qp=32, use_graph=1, compact_tables=1)
+pp = hb.Prepass(ctx, w, h, qp=32, use_graph=1, compact_tables=2)
 n = pp.num_ctus()
 cur, rec, refs = hb.Frame(ctx, w, h), hb.Frame(ctx, w, h), [hb.Frame(ctx, w, h), hb.Frame(ctx, w, h)]
 refs[0].upload_u8(*planes[0]); ctx.sync()
