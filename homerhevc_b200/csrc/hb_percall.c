@@ -47,13 +47,17 @@ hb_ctx *hb_default_ctx(void)
 
 static pc_slot *slot(void)
 {
+    static int poison = -1;                              /* $HB_POISON_STAGING: fill the staging with a pattern before every call (tests) */
+    if (poison < 0) { const char *e = getenv("HB_POISON_STAGING"); poison = e && *e == '1'; }
     if (!t_slot.stream) {
         hb_ctx *ctx = hb_default_ctx();
         int rc;
         hbc_set_device(ctx->device);
         if ((rc = hbc_stream_create(&t_slot.stream)) || (rc = hbc_host_alloc((void **)&t_slot.host, STAGE_BYTES)) ||
             (rc = hbc_host_devptr(t_slot.host, (void **)&t_slot.dev))) { hbi_cuda_fail(rc, "per-thread slot"); die("per-call setup"); }
+        memset(t_slot.host, 0, STAGE_BYTES);             /* pinned pages may be recycled ones */
     }
+    if (poison) memset(t_slot.host, 0xA5, STAGE_BYTES);
     return &t_slot;
 }
 

@@ -285,7 +285,7 @@ long refdrv_encode_lockstep(int width, int height, int n_frames, const uint8_t *
                 }
                 got++;
             } else {
-                usleep(50);
+                usleep(400);          /* poll gently: the encoder thread owns the output queue */
             }
         }
     }

@@ -43,8 +43,15 @@ def test_bitstream_identical_with_gpu_table(ctx, which, nf, force_intra):
     hook = C.c_void_p(D.refdrv_install_gpu_table_addr())
     gpu_bs, gpu_rec, t_gpu = _encode(D, w, h, yuv, nf, hook=hook, user=C.cast(C.pointer(user), C.c_void_p), force_intra=force_intra)
     assert len(gold_bs) > 200
-    assert gpu_bs == gold_bs, f"bitstreams differ: {len(gpu_bs)} vs {len(gold_bs)} bytes"
-    assert np.array_equal(gpu_rec, gold_rec)
+    if gpu_bs != gold_bs or not np.array_equal(gpu_rec, gold_rec):
+        # say as much as possible about a mismatch: where it starts, and whether a second run of either side repeats it
+        first = next((i for i, (a, b) in enumerate(zip(gpu_bs, gold_bs)) if a != b), min(len(gpu_bs), len(gold_bs)))
+        bad = np.flatnonzero(gpu_rec != gold_rec)
+        frame = int(bad[0]) // (w * h * 3 // 2) if bad.size else -1
+        gpu2, _, _ = _encode(D, w, h, yuv, nf, hook=hook, user=C.cast(C.pointer(user), C.c_void_p), force_intra=force_intra)
+        gold2, _, _ = _encode(D, w, h, yuv, nf, force_intra=force_intra)
+        pytest.fail(f"bitstreams differ from byte {first} ({len(gpu_bs)} vs {len(gold_bs)} bytes), {bad.size} reconstructed samples differ, first in frame {frame}; "
+                    f"second GPU run {'equals' if gpu2 == gold_bs else 'differs from'} the CPU stream, second CPU run {'equals' if gold2 == gold_bs else 'differs from'} the first")
     D.refdrv_gpu_quant_calls.restype = C.c_long
     assert D.refdrv_gpu_quant_calls() > 100          # the GPU table really was on the path
     print(f"\nwhole encode {w}x{h}x{nf}: {len(gold_bs)} bytes identical; cpu {t_cpu:.2f}s, per-call gpu table {t_gpu:.2f}s")
