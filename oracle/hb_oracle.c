@@ -813,7 +813,8 @@ void orc_intra_predict(const int16_t *adi, int n, int mode, int is_luma, int16_t
     const int a = abs(angle), sgn = angle < 0 ? -1 : 1;
     const int inv = k_inv_ang[a];
     angle = sgn * k_ang[a];
-    int16_t above[3 * 64 + 2], left[3 * 64 + 2];
+    int16_t above_buf[3 * 64 + 4], left_buf[3 * 64 + 4];
+    int16_t *const above = above_buf + 2, *const left = left_buf + 2;     /* two spare samples in front keep gcc's bounds analysis quiet */
     int16_t *ref_main, *ref_side;
     if (angle < 0) {
         for (int i = 0; i < n + 1; i++) { above[i + n - 1] = mid[i]; left[i + n - 1] = mid[-i]; }
