@@ -532,19 +532,30 @@ __global__ void __launch_bounds__(256) k_pack_cu_costs(const hbd_cu_pack_args a)
     while (i >= a.first[p + 1]) p++;
     const int d = min(p, 3), cu = 64 >> d, k = i - a.first[p];
     const int cx = k % a.grid_w[d], cy = k / a.grid_w[d];
-    uint32_t ssd = 0, sum = 0, cbf = 0;
+    // two rounds of independent loads (all TU indices, then all records) instead of a dependent chain per TU
+    int idx[3][4];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        const hbd_gather_pc pc = a.pc[c ? d : p][c];
+        const hbd_gather_pc &pc = a.pc[c ? d : p][c];
         const int per = (c ? cu / 2 : cu) / pc.tu;                      // 1 or 2 TUs per CU side
-        for (int t = 0; t < per * per; t++) {
-            const int idx = pc.tu_index[(cy * per + t / per) * pc.grid_w + cx * per + t % per];
-            if (idx < 0) continue;
-            const hb_tu_result r = pc.res[idx];
-            ssd += r.ssd; sum += static_cast<uint32_t>(r.sum);
-            if (r.sum > 0) cbf |= 1u << (4 * c + t);
-        }
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+            idx[c][t] = t < per * per ? __ldg(pc.tu_index + (cy * per + t / per) * pc.grid_w + cx * per + t % per) : -1;
     }
+    int2 rec[3][4];                                      // {sum, ssd}: the first half of hb_tu_result (the table block guarantees 8-byte alignment only)
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+            rec[c][t] = idx[c][t] >= 0 ? __ldg(reinterpret_cast<const int2 *>(a.pc[c ? d : p][c].res + idx[c][t])) : make_int2(0, 0);
+    uint32_t ssd = 0, sum = 0, cbf = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            ssd += static_cast<uint32_t>(rec[c][t].y); sum += static_cast<uint32_t>(rec[c][t].x);
+            if (rec[c][t].x > 0) cbf |= 1u << (4 * c + t);
+        }
     hb_cu_cost o;
     o.ssd = ssd; o.sum = sum; o.cbf = static_cast<uint16_t>(cbf); o.reserved = 0;
     a.out[i] = o;
