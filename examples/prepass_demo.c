@@ -78,6 +78,33 @@ int main(int argc, char **argv)
                n, ms, out_bytes, hist[0], hist[1], hist[2], hist[3], hist[4], me[0].mvx, me[0].mvy, me[0].sad);
         if (me[0].sad == 0xffffffffu || out_bytes < fb) { fprintf(stderr, "unexpected result\n"); return 1; }
     }
+    /* ---- the same stream of frames with the reference picture kept on the device: only the source goes up; the finished
+     * picture of frame n (chosen units gathered, deblocked, SAO applied) is the reference of frame n + 1 */
+    {
+        hb_frame *rec, *refs[2] = { ref, NULL };
+        hb_sao_param *sao = (hb_sao_param *)malloc(sizeof(hb_sao_param) * (size_t)n_ctus);
+        const hb_deblock_params dbk = { 2, 2, 0, 0 };
+        const double sao_lambda[3] = { 60.0, 48.0, 48.0 };
+        CHECK(hb_frame_create(ctx, w, h, &rec));
+        CHECK(hb_frame_create(ctx, w, h, &refs[1]));
+        if (!sao) { fprintf(stderr, "out of memory\n"); return 1; }
+        make_frame(in, in + luma, in + luma + luma / 4, w, h, 0);
+        CHECK(hb_frame_upload_u8(ctx, refs[0], in, w, in + luma, w / 2, in + luma + luma / 4, w / 2));     /* frame 0 stands for an intra picture */
+        for (int n = 1; n <= frames; n++) {
+            uint8_t *now = in + (n & 1) * fb;
+            make_frame(now, now + luma, now + luma + luma / 4, w, h, n);
+            const uint8_t *cp[3] = { now, now + luma, now + luma + luma / 4 };
+            size_t level_bytes = 0;
+            CHECK(hb_prepass_frame_begin_resident(pp, cur, refs[(n - 1) & 1], cp, avg_dist, tables, hb_prepass_tables_bytes(pp)));
+            CHECK(hb_prepass_frame_finish_resident(pp, cur, 60, tables, sel, off, rec, refs[n & 1], &dbk, sao_lambda, out, out_cap, &level_bytes, sao));
+            int with_sao = 0;
+            for (int i = 0; i < n_ctus; i++) with_sao += sao[i].type[0] >= 0;
+            printf("resident frame %d: %zu bytes of levels back, SAO on in %d of %d CTUs (luma)\n", n, level_bytes, with_sao, n_ctus);
+        }
+        CHECK(hb_ctx_sync(ctx));
+        free(sao);
+        hb_frame_destroy(rec); hb_frame_destroy(refs[1]);
+    }
     printf("%llu kernel launches\n", (unsigned long long)hb_ctx_launch_count(ctx));
     free(sel); free(off);
     hb_pinned_free(in); hb_pinned_free(tables); hb_pinned_free(out);

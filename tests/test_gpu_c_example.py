@@ -16,4 +16,4 @@ def test_prepass_demo_in_c(ctx):
                            "-lhomer_b200", "-Wl,-rpath," + os.path.join(ROOT, "homerhevc_b200"), "-lm"])
     out = subprocess.run([exe, "320", "192", "3"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "prepass_demo ok" in out.stdout and out.stdout.count("frame ") == 3, out.stdout
+    assert "prepass_demo ok" in out.stdout and out.stdout.count("frame ") == 6 and "resident frame 3:" in out.stdout, out.stdout
