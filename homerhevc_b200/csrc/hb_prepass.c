@@ -695,10 +695,9 @@ static int gather_queue(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_o
     int crc = 0;
     for (int i = 0; i < n_ctus; i++) if (sel[i] > 4) return hbi_fail(HB_ERR_ARG, "%s: sel[%d] = %d", what, i, sel[i]);
     hbc_set_device(ctx->device);
-    if (!pp->d_sel) {
-        if ((crc = hbc_malloc((void **)&pp->d_sel, (size_t)n_ctus)) || (crc = hbc_malloc((void **)&pp->d_ctu_off, sizeof(int32_t) * ((size_t)n_ctus + 1))) ||
-            (crc = hbc_malloc((void **)&pp->d_sel_recon, recon_bytes))) return hbi_cuda_fail(crc, what);
-    }
+    if (!pp->d_sel && (crc = hbc_malloc((void **)&pp->d_sel, (size_t)n_ctus))) { pp->d_sel = NULL; return hbi_cuda_fail(crc, what); }
+    if (!pp->d_ctu_off && (crc = hbc_malloc((void **)&pp->d_ctu_off, sizeof(int32_t) * ((size_t)n_ctus + 1)))) { pp->d_ctu_off = NULL; return hbi_cuda_fail(crc, what); }
+    if (!pp->d_sel_recon && (crc = hbc_malloc((void **)&pp->d_sel_recon, recon_bytes))) { pp->d_sel_recon = NULL; return hbi_cuda_fail(crc, what); }
     if (!pp->d_sel_levels) {
         /* worst case once (every unit coded with the smallest transform: 18 int16 per 16 samples): growing the buffer later would
          * mean cudaFree / cudaMalloc, which wait for every stream of the device and drain the frames in flight on other contexts */
@@ -768,10 +767,8 @@ int hb_prepass_finalise(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_o
     int rc, crc = 0;
     if (cap < need) return hbi_fail(HB_ERR_ARG, "hb_prepass_finalise: need %zu bytes, got %zu", need, cap);
     hbc_set_device(ctx->device);
-    if (!pp->d_units) {
-        if ((crc = hbc_malloc((void **)&pp->d_units, sizeof(hb_unit_info) * plane)) || (crc = hbc_malloc((void **)&pp->d_dbk_maps, 3 * plane)))
-            return hbi_cuda_fail(crc, "hb_prepass_finalise: cudaMalloc");
-    }
+    if (!pp->d_units && (crc = hbc_malloc((void **)&pp->d_units, sizeof(hb_unit_info) * plane))) { pp->d_units = NULL; return hbi_cuda_fail(crc, "hb_prepass_finalise: cudaMalloc"); }
+    if (!pp->d_dbk_maps && (crc = hbc_malloc((void **)&pp->d_dbk_maps, 3 * plane))) { pp->d_dbk_maps = NULL; return hbi_cuda_fail(crc, "hb_prepass_finalise: cudaMalloc"); }
     uint8_t *planes[3] = { rec->d.p[0].org, rec->d.p[1].org, rec->d.p[2].org };
     const int pitch[3] = { rec->d.p[0].pitch, rec->d.p[1].pitch, rec->d.p[2].pitch };
     if ((rc = gather_queue(pp, sel, ctu_off, planes, pitch, "hb_prepass_finalise")) != HB_OK) return rc;
@@ -883,10 +880,8 @@ int hb_prepass_frame_finish_resident(hb_prepass *pp, const hb_frame *cur, int la
     const size_t st_bytes = sizeof(hb_sao_stats) * 3 * (size_t)n_ctus, cand_bytes = sizeof(hb_sao_candidate) * 15 * (size_t)n_ctus;
     const size_t prm_bytes = sizeof(hb_sao_param) * (size_t)n_ctus;
     hbc_set_device(ctx->device);
-    if (!pp->d_sao) {
-        if ((crc = hbc_malloc((void **)&pp->d_sao, st_bytes + cand_bytes + prm_bytes)) || (crc = hbc_host_alloc((void **)&pp->h_sao, cand_bytes + prm_bytes)))
-            return hbi_cuda_fail(crc, "hb_prepass_frame_finish_resident: allocation");
-    }
+    if (!pp->d_sao && (crc = hbc_malloc((void **)&pp->d_sao, st_bytes + cand_bytes + prm_bytes))) { pp->d_sao = NULL; return hbi_cuda_fail(crc, "hb_prepass_frame_finish_resident: cudaMalloc"); }
+    if (!pp->h_sao && (crc = hbc_host_alloc((void **)&pp->h_sao, cand_bytes + prm_bytes))) { pp->h_sao = NULL; return hbi_cuda_fail(crc, "hb_prepass_frame_finish_resident: cudaHostAlloc"); }
     hb_sao_stats *d_st = (hb_sao_stats *)pp->d_sao;
     hb_sao_candidate *d_cand = (hb_sao_candidate *)(pp->d_sao + st_bytes), *h_cand = (hb_sao_candidate *)pp->h_sao;
     hb_sao_param *d_prm = (hb_sao_param *)(pp->d_sao + st_bytes + cand_bytes), *h_prm = (hb_sao_param *)(pp->h_sao + cand_bytes);
