@@ -753,8 +753,8 @@ int hb_prepass_gather(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_off
  * `rec` is deblocked in place with strengths derived on the device from the pre-pass's own tables (CU / TU sizes of the pass,
  * vectors, coded flags), then border-padded.  Asynchronous: hb_ctx_sync before reading pinned_levels.  What remains for the next
  * reference picture is SAO: hb_sao_stats_frame(cur, rec) -> the host's decision -> hb_sao_apply_frame(rec, next reference). */
-int hb_prepass_finalise(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_off, hb_frame *rec, const hb_deblock_params *dbk,
-                        void *pinned_levels, size_t cap, size_t *bytes_out)
+static int finalise_queue(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_off, hb_frame *rec, const hb_deblock_params *dbk,
+                          void *pinned_levels, size_t cap, size_t *bytes_out, int pad)
 {
     if (!pp || !sel || !ctu_off || !rec || !dbk || !pinned_levels) return hbi_fail(HB_ERR_ARG, "hb_prepass_finalise: NULL argument");
     if (rec->w != pp->w || rec->h != pp->h) return hbi_fail(HB_ERR_ARG, "hb_prepass_finalise: frame size differs from the plan's");
@@ -786,10 +786,16 @@ int hb_prepass_finalise(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_o
     if (!crc) { crc = hbk_units_from_selection(&u, ctx->stream); ctx->launches++; }
     if (!crc) { crc = hbk_deblock_strengths(pp->d_units, uw, pp->w, pp->h, bv, bh, qp, ctx->stream); ctx->launches++; }
     if (!crc) { crc = hbk_deblock(&rec->d, bv, bh, qp, uw, dbk->cb_qp_offset, dbk->cr_qp_offset, dbk->beta_offset_div2, dbk->tc_offset_div2, ctx->stream); ctx->launches += 2; }
-    if (!crc) { crc = hbk_pad_frame(&rec->d, ctx->stream); ctx->launches++; }
+    if (!crc && pad) { crc = hbk_pad_frame(&rec->d, ctx->stream); ctx->launches++; }
     if (crc) return hbi_cuda_fail(crc, "hb_prepass_finalise");
     if (bytes_out) *bytes_out = need;
     return HB_OK;
+}
+
+int hb_prepass_finalise(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_off, hb_frame *rec, const hb_deblock_params *dbk,
+                        void *pinned_levels, size_t cap, size_t *bytes_out)
+{
+    return finalise_queue(pp, sel, ctu_off, rec, dbk, pinned_levels, cap, bytes_out, 1);
 }
 
 /* debugging / testing aid: the unit data and strengths the last hb_prepass_finalise used (each may be NULL).  Blocking. */
@@ -887,7 +893,8 @@ int hb_prepass_frame_finish_resident(hb_prepass *pp, const hb_frame *cur, int la
     hb_sao_param *d_prm = (hb_sao_param *)(pp->d_sao + st_bytes + cand_bytes), *h_prm = (hb_sao_param *)(pp->h_sao + cand_bytes);
     if ((rc = hb_ctx_sync(ctx)) != HB_OK) return rc;
     if ((rc = hb_prepass_select(pp, tables, lambda, sel, ctu_off)) != HB_OK) return rc;
-    if ((rc = hb_prepass_finalise(pp, sel, ctu_off, rec, dbk, levels, levels_cap, levels_bytes)) != HB_OK) return rc;
+    /* no border for `rec`: the SAO kernels never classify a sample whose neighbours lie outside the picture */
+    if ((rc = finalise_queue(pp, sel, ctu_off, rec, dbk, levels, levels_cap, levels_bytes, 0)) != HB_OK) return rc;
     crc = hbk_sao_stats(&cur->d, &rec->d, pp->ctu_cols, n_ctus, d_st, ctx->stream); ctx->launches++;
     if (!crc) { crc = hbk_sao_derive(d_st, 3 * n_ctus, sao_lambda, d_cand, ctx->stream); ctx->launches++; }
     if (!crc) crc = hbc_d2h_async(h_cand, d_cand, cand_bytes, ctx->stream);
