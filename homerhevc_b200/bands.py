@@ -1,8 +1,11 @@
 """CTU-row bands across the GPUs of one box (BASELINE.json configs[3]).
 
-Host-side plan + the neighbour halo exchange, written against torch.distributed so that the same code runs over NCCL on
-GPUs and over gloo on CPUs (tests).  Each rank owns a contiguous band of CTU rows of the picture and holds the rows of the
-reference frame it reconstructed itself; before searching it needs HALO more rows from the band above and below."""
+Host-side plan + the halo exchange, written against torch.distributed so that the same code runs over NCCL on GPUs and
+over gloo on CPUs (tests).  Each rank owns a contiguous band of CTU rows of the picture and holds the rows of the
+reference frame it reconstructed itself; before searching it needs HALO more rows above and below its band.  Those rows
+belong to the neighbouring bands -- to rank +-1 as a rule, and to rank +-2, ... as well when a band is lower than the halo
+(a one-CTU-row band has 64 luma rows, the halo is 68: 720p on 8 GPUs) -- so the plan is the intersection of every rank's
+halo interval with every other rank's band."""
 HALO_LUMA, HALO_CHROMA = 68, 36       # 64 search + 4 (8-tap) luma; 32 + 1 + 2 (4-tap) + rounding slack chroma
 
 
@@ -22,23 +25,35 @@ def band_sample_rows(height, ctu_rows, world, rank, chroma=False):
     return min(r0 * unit, h), min((r0 + n) * unit, h)
 
 
-def halo_plan(height, ctu_rows, world, rank, chroma=False):
-    """rows to send / receive: dict with 'send_up', 'send_down', 'recv_up', 'recv_down' = (row0, n_rows) or None.
-    'up' is the neighbour with the smaller rank."""
+def _halo_intervals(height, ctu_rows, world, rank, chroma):
+    """the two row intervals outside its band that `rank` reads: [y0 - halo, y0) and [y1, y1 + halo), clipped to the plane"""
     halo = HALO_CHROMA if chroma else HALO_LUMA
+    h = height // 2 if chroma else height
     y0, y1 = band_sample_rows(height, ctu_rows, world, rank, chroma)
-    plan = {"send_up": None, "send_down": None, "recv_up": None, "recv_down": None}
-    if rank > 0 and y1 > y0:
-        py0, py1 = band_sample_rows(height, ctu_rows, world, rank - 1, chroma)
-        if py1 > py0:
-            plan["send_up"] = (y0, min(halo, y1 - y0))
-            plan["recv_up"] = (max(py1 - halo, py0), min(halo, py1 - py0))
-    if rank < world - 1 and y1 > y0:
-        ny0, ny1 = band_sample_rows(height, ctu_rows, world, rank + 1, chroma)
-        if ny1 > ny0:
-            plan["send_down"] = (max(y1 - halo, y0), min(halo, y1 - y0))
-            plan["recv_down"] = (ny0, min(halo, ny1 - ny0))
-    return plan
+    if y1 <= y0:
+        return []
+    return [(max(0, y0 - halo), y0), (y1, min(h, y1 + halo))]
+
+
+def halo_transfers(height, ctu_rows, world, rank, chroma=False):
+    """{'send': [(peer, row0, n_rows)], 'recv': [(peer, row0, n_rows)]} for `rank`, both sorted by (peer, row0) so that the two
+    sides of every transfer enumerate it in the same order.  A transfer is the overlap of the receiver's halo interval with the
+    sender's own band."""
+    def overlaps(needy, owner):
+        o0, o1 = band_sample_rows(height, ctu_rows, world, owner, chroma)
+        out = []
+        for a, b in _halo_intervals(height, ctu_rows, world, needy, chroma):
+            lo, hi = max(a, o0), min(b, o1)
+            if hi > lo:
+                out.append((lo, hi - lo))
+        return out
+    send, recv = [], []
+    for peer in range(world):
+        if peer == rank:
+            continue
+        recv += [(peer, r0, n) for (r0, n) in overlaps(rank, peer)]
+        send += [(peer, r0, n) for (r0, n) in overlaps(peer, rank)]
+    return {"send": sorted(send), "recv": sorted(recv)}
 
 
 def exchange_halos(dist, planes, height, ctu_rows, world, rank):
@@ -46,17 +61,13 @@ def exchange_halos(dist, planes, height, ctu_rows, world, rank):
     After the call the halo rows above and below the band are valid too.  One batch of point-to-point operations."""
     ops, keep = [], []
     for c, t in enumerate(planes):
-        p = halo_plan(height, ctu_rows, world, rank, chroma=c > 0)
-        for key, peer in (("send_up", rank - 1), ("send_down", rank + 1)):
-            if p[key]:
-                r0, n = p[key]
-                buf = t[r0:r0 + n].contiguous()
-                keep.append(buf)
-                ops.append(dist.P2POp(dist.isend, buf, peer))
-        for key, peer in (("recv_up", rank - 1), ("recv_down", rank + 1)):
-            if p[key]:
-                r0, n = p[key]
-                ops.append(dist.P2POp(dist.irecv, t[r0:r0 + n], peer))
+        p = halo_transfers(height, ctu_rows, world, rank, chroma=c > 0)
+        for peer, r0, n in p["send"]:
+            buf = t[r0:r0 + n].contiguous()
+            keep.append(buf)
+            ops.append(dist.P2POp(dist.isend, buf, peer))
+        for peer, r0, n in p["recv"]:
+            ops.append(dist.P2POp(dist.irecv, t[r0:r0 + n], peer))
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
@@ -64,9 +75,11 @@ def exchange_halos(dist, planes, height, ctu_rows, world, rank):
 
 
 class FrameHaloExchanger:
-    """Halo exchange for an hb.Frame resident on this rank's GPU: the band's boundary rows are exported into tight torch
-    tensors, swapped with the neighbours over NCCL (NVLink / NVSwitch), imported on the other side, and the replicated
-    border is refreshed.  Buffers are allocated once."""
+    """Halo exchange for an hb.Frame resident on this rank's GPU, entirely on the device timeline: the band's boundary rows
+    are exported into tight torch tensors on the library context's stream, swapped with the other bands by one grouped NCCL
+    send/recv (NVLink / NVSwitch) that torch orders after that stream with events, imported on the other side and the
+    replicated border is refreshed -- the host queues all of it and never waits.  Whatever is queued on the context
+    afterwards (the next frame's search) runs behind the exchange.  Buffers are allocated once."""
 
     def __init__(self, torch, dist, ctx, width, height, world, rank, device):
         self.torch, self.dist, self.ctx = torch, dist, ctx
@@ -75,25 +88,26 @@ class FrameHaloExchanger:
         self.items = []                       # (plane, kind, row0, n_rows, peer, tensor)
         for c in range(3):
             w = width // 2 if c else width
-            p = halo_plan(height, self.ctu_rows, world, rank, chroma=c > 0)
-            for key, peer in (("send_up", rank - 1), ("send_down", rank + 1), ("recv_up", rank - 1), ("recv_down", rank + 1)):
-                if p[key]:
-                    r0, n = p[key]
-                    self.items.append((c, key[:4], r0, n, peer, torch.empty((n, w), dtype=torch.uint8, device=device)))
+            p = halo_transfers(height, self.ctu_rows, world, rank, chroma=c > 0)
+            for kind in ("send", "recv"):
+                for peer, r0, n in p[kind]:
+                    self.items.append((c, kind, r0, n, peer, torch.empty((n, w), dtype=torch.uint8, device=device)))
         self.bytes_per_exchange = sum(t.numel() for (_, kind, _, _, _, t) in self.items if kind == "send")
+        # the library's stream as a torch stream: collectives issued under it are ordered against it by events on the device
+        self.stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=device)
 
     def exchange(self, frame):
+        """queue export -> send/recv -> import -> border on the context's stream; returns without waiting"""
         dist = self.dist
-        for c, kind, r0, n, _, t in self.items:
-            if kind == "send":
-                frame.export_rows(c, r0, n, t.data_ptr())
-        self.ctx.sync()                       # exported rows are complete before NCCL reads them on torch's stream
-        ops = [dist.P2POp(dist.isend if kind == "send" else dist.irecv, t, peer) for (_, kind, _, _, peer, t) in self.items]
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-        self.torch.cuda.synchronize()
-        for c, kind, r0, n, _, t in self.items:
-            if kind == "recv":
-                frame.import_rows(c, r0, n, t.data_ptr())
-        frame.pad()
+        with self.torch.cuda.stream(self.stream):
+            for c, kind, r0, n, _, t in self.items:
+                if kind == "send":
+                    frame.export_rows(c, r0, n, t.data_ptr())
+            ops = [dist.P2POp(dist.isend if kind == "send" else dist.irecv, t, peer) for (_, kind, _, _, peer, t) in self.items]
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()                # stream-ordered for NCCL: makes the current (= the context's) stream wait, not the host
+            for c, kind, r0, n, _, t in self.items:
+                if kind == "recv":
+                    frame.import_rows(c, r0, n, t.data_ptr())
+            frame.pad()

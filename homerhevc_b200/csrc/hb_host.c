@@ -216,11 +216,13 @@ uint64_t hb_ctx_launch_count(hb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int hb_timer_begin(hb_ctx *ctx)
 {
+    if (!ctx) return hbi_fail(HB_ERR_ARG, "hb_timer_begin: NULL context");
     const int rc = hbc_event_record(ctx->ev[0], ctx->stream);
     return rc ? hbi_cuda_fail(rc, "hb_timer_begin") : HB_OK;
 }
 int hb_timer_end(hb_ctx *ctx, float *ms_out)
 {
+    if (!ctx || !ms_out) return hbi_fail(HB_ERR_ARG, "hb_timer_end: NULL argument");
     int rc = hbc_event_record(ctx->ev[1], ctx->stream);
     if (!rc) rc = hbc_event_elapsed(ctx->ev[0], ctx->ev[1], ms_out);
     return rc ? hbi_cuda_fail(rc, "hb_timer_end") : HB_OK;
@@ -592,7 +594,10 @@ int hb_merge_eval(hb_ctx *ctx, const hb_frame *cur, const hb_frame *ref, hb_fram
     if (!ctx || !cur || !ref || !pred || !recon || !cands || !params || !out || n_cands < 0) return hbi_fail(HB_ERR_ARG, "hb_merge_eval: bad argument");
     if (qp < 0 || qp > 51) return hbi_fail(HB_ERR_ARG, "hb_merge_eval: qp %d", qp);
     if (n_cands == 0) return HB_OK;
-    if ((rc = hb_mc_predict(ctx, ref, pred, cands, n_cands)) != HB_OK) return rc;          /* validates the candidates as well */
+    for (int i = 0; i < n_cands; i++)        /* coding units sit on their own grid; their transform units inherit the alignment the T/Q kernels need */
+        if (cands[i].size > 0 && ((cands[i].x | cands[i].y) & (cands[i].size - 1)))
+            return hbi_fail(HB_ERR_ARG, "hb_merge_eval: candidate %d is not aligned to its size", i);
+    if ((rc = hb_mc_predict(ctx, ref, pred, cands, n_cands)) != HB_OK) return rc;          /* validates the rest */
     const int qp_c = hbi_chroma_qp(qp, chroma_qp_offset);
     hb_tq_params prm = *params;
     prm.chroma_weight = pow(2.0, (qp - qp_c) / 3.0);                                        /* hmr_motion_inter.c:3525 */
@@ -822,6 +827,10 @@ void hbi_tq_setup(hb_ctx *ctx, hbd_tq_args *a, int comp, int n, int qp, int is_i
     a->is_luma = comp == 0;
 }
 
+/* the T/Q kernels read and write a unit's rows with one vector access per lane: 4 bytes (4x4), 8 (8x8) or 16 (16x16, 32x32),
+ * so a unit's x must be a multiple of min(size, 16) -- which every transform unit of the quadtree is */
+static int tq_row_align(int size) { return size < 16 ? size : 16; }
+
 int hb_tq_encode(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_frame *recon, const hb_tu_job *jobs, int n_jobs,
                  const hb_tq_params *params, int16_t *coeffs, hb_tu_result *results)
 {
@@ -832,9 +841,9 @@ int hb_tq_encode(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_fram
     for (int i = 0; i < n_jobs; i++) {
         const hb_tu_job *j = &jobs[i];
         if (j->comp < 0 || j->comp > 2 || (j->size != 4 && j->size != 8 && j->size != 16 && j->size != 32) || j->qp < 0 || j->qp > 51 ||
-            j->x < 0 || j->y < 0 || (j->x & 3) || j->x + j->size > cur->d.p[j->comp].w || j->y + j->size > cur->d.p[j->comp].h ||
+            j->x < 0 || j->y < 0 || (j->x & (tq_row_align(j->size) - 1)) || j->x + j->size > cur->d.p[j->comp].w || j->y + j->size > cur->d.p[j->comp].h ||
             (j->comp && j->size == 32))
-            return hbi_fail(HB_ERR_ARG, "hb_tq_encode: job %d is invalid", i);
+            return hbi_fail(HB_ERR_ARG, "hb_tq_encode: job %d is invalid (x must be a multiple of min(size, 16))", i);
         total += (size_t)j->size * j->size;
     }
     hbc_set_device(ctx->device);
@@ -912,7 +921,7 @@ int hb_tq_encode_intra(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, h
     for (int i = 0; i < n_jobs; i++) {
         const hb_intra_tu_job *j = &jobs[i];
         if (j->comp < 0 || j->comp > 2 || (j->size != 4 && j->size != 8 && j->size != 16 && j->size != 32) || j->qp < 0 || j->qp > 51 ||
-            j->x < 0 || j->y < 0 || (j->x & 3) || j->x + j->size > cur->d.p[j->comp].w || j->y + j->size > cur->d.p[j->comp].h ||
+            j->x < 0 || j->y < 0 || (j->x & (tq_row_align(j->size) - 1)) || j->x + j->size > cur->d.p[j->comp].w || j->y + j->size > cur->d.p[j->comp].h ||
             (j->comp && j->size == 32) || j->scan_mode < HB_SCAN_HOR || j->scan_mode > HB_SCAN_DIAG || (j->size > 8 && j->scan_mode != HB_SCAN_DIAG))
             return hbi_fail(HB_ERR_ARG, "hb_tq_encode_intra: job %d is invalid", i);
         total += (size_t)j->size * j->size;

@@ -26,6 +26,17 @@ typedef struct pc_slot {
 static hb_ctx *g_ctx;
 static pthread_once_t g_once = PTHREAD_ONCE_INIT;
 static __thread pc_slot t_slot;
+static pthread_key_t g_slot_key;          /* its destructor releases a thread's stream and staging area when the thread exits */
+
+static void slot_release(void *p)
+{
+    pc_slot *s = (pc_slot *)p;
+    if (!s) return;
+    if (g_ctx) hbc_set_device(g_ctx->device);
+    if (s->stream) { hbc_stream_sync(s->stream); hbc_stream_destroy(s->stream); }
+    if (s->host) hbc_host_free(s->host);
+    free(s);
+}
 
 static void die(const char *what)
 {
@@ -37,6 +48,7 @@ static void default_ctx_init(void)
 {
     const char *e = getenv("HB_DEVICE");
     if (hb_ctx_create(&g_ctx, e ? atoi(e) : 0) != HB_OK) die("default context");
+    if (pthread_key_create(&g_slot_key, slot_release)) die("per-thread key");
 }
 
 hb_ctx *hb_default_ctx(void)
@@ -56,6 +68,12 @@ static pc_slot *slot(void)
         if ((rc = hbc_stream_create(&t_slot.stream)) || (rc = hbc_host_alloc((void **)&t_slot.host, STAGE_BYTES)) ||
             (rc = hbc_host_devptr(t_slot.host, (void **)&t_slot.dev))) { hbi_cuda_fail(rc, "per-thread slot"); die("per-call setup"); }
         memset(t_slot.host, 0, STAGE_BYTES);             /* pinned pages may be recycled ones */
+        /* an encoder that spawns its workers per frame or GOP must not leak a stream and 256 KiB of pinned memory per thread:
+         * a heap copy of the handles rides on the thread-specific key and is released by its destructor at thread exit */
+        pc_slot *own = (pc_slot *)malloc(sizeof *own);
+        if (!own) die("per-call setup: out of memory");
+        *own = t_slot;
+        if (pthread_setspecific(g_slot_key, own)) die("per-call setup: pthread_setspecific");
     }
     if (poison) memset(t_slot.host, 0xA5, STAGE_BYTES);
     return &t_slot;

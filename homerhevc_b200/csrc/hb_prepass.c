@@ -54,7 +54,9 @@ struct hb_prepass {
     /* per-frame scalars */
     hbd_dyn_params *d_dyn;
     /* captured replays */
-    struct { const hb_frame *cur, *ref; void *exec; } graphs[MAX_GRAPHS];
+    /* keyed on the DEVICE addresses the captured kernels hold (the six planes of cur and ref), not on the host hb_frame
+     * structs: a destroyed frame's struct address is readily handed out again by calloc for a frame with other planes */
+    struct { const uint8_t *plane[6]; void *exec; } graphs[MAX_GRAPHS];
     int n_graphs;
     int launches_per_frame;
     /* gather of the host's selection */
@@ -374,14 +376,16 @@ int hb_prepass_run(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, dou
         crc = enqueue(pp, cur, ref, &n, 0);
     } else {
         void *exec = NULL;
-        for (int i = 0; i < pp->n_graphs; i++) if (pp->graphs[i].cur == cur && pp->graphs[i].ref == ref) exec = pp->graphs[i].exec;
+        const uint8_t *key[6];
+        for (int c = 0; c < 3; c++) { key[c] = cur->d.p[c].base; key[3 + c] = ref->d.p[c].base; }
+        for (int i = 0; i < pp->n_graphs; i++) if (!memcmp(pp->graphs[i].plane, key, sizeof key)) exec = pp->graphs[i].exec;
         if (!exec) {
             if (pp->n_graphs == MAX_GRAPHS) { hbc_graph_destroy(pp->graphs[0].exec); memmove(&pp->graphs[0], &pp->graphs[1], sizeof pp->graphs[0] * (MAX_GRAPHS - 1)); pp->n_graphs--; }
             if ((crc = hbc_graph_begin(ctx->stream))) return hbi_cuda_fail(crc, "hb_prepass_run: begin capture");
             crc = enqueue(pp, cur, ref, &n, 0);
             const int erc = hbc_graph_end(ctx->stream, &exec);
             if (crc || erc) return hbi_cuda_fail(crc ? crc : erc, "hb_prepass_run: capture");
-            pp->graphs[pp->n_graphs].cur = cur; pp->graphs[pp->n_graphs].ref = ref; pp->graphs[pp->n_graphs].exec = exec;
+            memcpy(pp->graphs[pp->n_graphs].plane, key, sizeof key); pp->graphs[pp->n_graphs].exec = exec;
             pp->n_graphs++;
             pp->launches_per_frame = n;
         }
@@ -693,7 +697,15 @@ static int gather_queue(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_o
     const int n_ctus = hb_prepass_num_ctus(pp);
     const size_t recon_bytes = (size_t)pp->w * pp->h * 3 / 2, lev = (size_t)ctu_off[n_ctus];
     int crc = 0;
-    for (int i = 0; i < n_ctus; i++) if (sel[i] > 4) return hbi_fail(HB_ERR_ARG, "%s: sel[%d] = %d", what, i, sel[i]);
+    for (int i = 0; i < n_ctus; i++) {
+        if (sel[i] > 4) return hbi_fail(HB_ERR_ARG, "%s: sel[%d] = %d", what, i, sel[i]);
+        /* the in-picture part of a partial CTU must be tiled by the chosen pass's coding units (hb_prepass_select's rule): anything
+         * else would gather samples no transform unit wrote and search records of units that were never searched */
+        const int ew = pp->w - (i % pp->ctu_cols) * 64, eh = pp->h - (i / pp->ctu_cols) * 64, cu = 64 >> pass_depth(sel[i]);
+        if ((ew < 64 && ew % cu) || (eh < 64 && eh % cu))
+            return hbi_fail(HB_ERR_ARG, "%s: sel[%d] = %d, but %dx%d units do not tile the %dx%d picture part of that CTU", what, i, sel[i], cu, cu,
+                            ew < 64 ? ew : 64, eh < 64 ? eh : 64);
+    }
     hbc_set_device(ctx->device);
     if (!pp->d_sel && (crc = hbc_malloc((void **)&pp->d_sel, (size_t)n_ctus))) { pp->d_sel = NULL; return hbi_cuda_fail(crc, what); }
     if (!pp->d_ctu_off && (crc = hbc_malloc((void **)&pp->d_ctu_off, sizeof(int32_t) * ((size_t)n_ctus + 1)))) { pp->d_ctu_off = NULL; return hbi_cuda_fail(crc, what); }

@@ -308,6 +308,10 @@ class Context:
     def launch_count(self):
         return int(self.L.hb_ctx_launch_count(self.h))
 
+    def stream_ptr(self):
+        """the cudaStream_t the context queues its work on (for torch.cuda.ExternalStream)"""
+        return int(self.L.hb_ctx_stream(self.h) or 0)
+
     def timer_begin(self):
         _check(self.L.hb_timer_begin(self.h), "hb_timer_begin")
 

@@ -223,6 +223,12 @@ def test_batched_api_rejects_bad_arguments(ctx):
         ctx.me_search(f, f, [odd], 100.0)
     with pytest.raises(hb.HbError):
         ctx.tq_encode(f, f, f, [hb.TuJob(1, 0, 0, 32, 30)], hb.TqParams(0, 1, 0.0, 1.0))                       # no 32x32 chroma TU
+    # the T/Q kernels move a unit's rows with 8- / 16-byte accesses: x must be a multiple of min(size, 16)
+    for comp, x, size in ((0, 4, 8), (0, 8, 16), (0, 16 + 8, 32), (1, 4, 8), (2, 8, 16)):
+        with pytest.raises(hb.HbError):
+            ctx.tq_encode(f, f, f, [hb.TuJob(comp, x, 0, size, 30)], hb.TqParams(0, 1, 0.0, 1.0))
+        with pytest.raises(hb.HbError):
+            ctx.tq_encode_intra(f, f, f, [hb.IntraTuJob(comp, x, 0, size, 30, 3)], 1, 1, 1.0)
     with pytest.raises(hb.HbError):
         hb.Frame(ctx, 100, 60)                                                                                 # not a multiple of 8
     with pytest.raises(hb.HbError):
@@ -267,5 +273,8 @@ def test_finalisation_api_rejects_bad_arguments(ctx):
     cand = hb.McJob(); cand.x, cand.y, cand.size = 0, 0, 16
     with pytest.raises(hb.HbError):
         ctx.merge_eval(a, b, a, b, [cand], 60, 0, hb.TqParams(0, 1, 0.0, 1.0))          # qp out of range
+    off_grid = hb.McJob(); off_grid.x, off_grid.y, off_grid.size = 8, 0, 16            # a 16x16 unit off its own grid
+    with pytest.raises(hb.HbError):
+        ctx.merge_eval(a, b, a, b, [off_grid], 30, 0, hb.TqParams(0, 1, 0.0, 1.0))
     for f in (a, b, small):
         f.close()

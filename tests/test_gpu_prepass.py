@@ -270,6 +270,10 @@ def test_host_decision_flow_gather(ctx):
         pp.select(tables, lam, sel, off)
         if lam == 0:
             sel[:] = np.arange(n_ctus) % 5          # force every choice to appear, offsets must follow
+            sel[15:] = 3 + np.arange(5) % 2         # the last CTU row is 8 samples high: only 8x8 units tile it
+            bad = sel.copy(); bad[17] = 1           # 32x32 units in an 8-row CTU: refused, nothing is gathered from unwritten samples
+            with pytest.raises(hb.HbError):
+                pp.gather(bad, off, ctx.pinned(w * h * 3 // 2 + 64))
             # recompute the layout for the forced selection
             off[:] = 0
             for i in range(n_ctus):
@@ -580,3 +584,26 @@ def test_device_resident_finalisation(ctx):
     for f in (fa, rec, fin_exp, fc2, rec2, nxt, nxt_copy, fc, fr):
         f.close()
     pp.close()
+
+
+def test_graph_cache_follows_the_device_planes(ctx):
+    """the captured replay is keyed on the frames' device planes: a frame that is destroyed and re-created (same size, quite
+    possibly the same host struct address) must be searched with ITS samples, not with a stale graph's"""
+    w, h, qp, avg = 128, 64, 32, 500.0
+    cur, ref = clip_pair(w, h, n=2, noise=3.0, seed=21)
+    cur2, ref2 = clip_pair(w, h, n=2, noise=3.0, seed=22)
+    pp = hb.Prepass(ctx, w, h, qp=qp, use_graph=1)
+    plain = hb.Prepass(ctx, w, h, qp=qp, use_graph=0)
+    keep = []
+    for rep in range(6):
+        c, r = (cur, ref) if rep % 2 == 0 else (cur2, ref2)
+        fc, fr = upload(ctx, c, w, h), upload(ctx, r, w, h)
+        pp.run(fc, fr, avg); ctx.sync()
+        got = pp.fetch_me(3).copy()
+        plain.run(fc, fr, avg); ctx.sync()
+        assert got.tobytes() == plain.fetch_me(3).tobytes(), rep
+        fc.close(); fr.close()
+        keep.append(hb.Frame(ctx, w, h)) if rep == 2 else None       # perturb the allocator between generations
+    for f in keep:
+        f.close()
+    pp.close(); plain.close()

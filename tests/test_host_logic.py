@@ -94,6 +94,39 @@ def test_band_halo_exchange_gloo(tmp_path):
         assert oks[0][1] == 3 * 2 and (world == 2 or oks[1][1] == 3 * 4), line          # edge ranks: send+recv per plane; inner: both sides
 
 
+def test_band_plan_reaches_past_a_band_lower_than_the_halo():
+    """a one-CTU-row band has 64 luma rows, the halo is 68: its neighbour's halo reaches into the band after it (720p on 8 GPUs).
+    Every rank must receive exactly its halo rows, each from the rank that owns them, and the two sides of a transfer must agree."""
+    from homerhevc_b200 import bands
+    for (h, world) in ((720, 8), (720, 12), (1080, 8), (2160, 8), (128, 2), (552, 3)):
+        ctu_rows = (h + 63) // 64
+        for chroma in (False, True):
+            ph, halo = (h // 2, bands.HALO_CHROMA) if chroma else (h, bands.HALO_LUMA)
+            owner = np.full(ph, -1)
+            for r in range(world):
+                y0, y1 = bands.band_sample_rows(h, ctu_rows, world, r, chroma)
+                owner[y0:y1] = r
+            assert (owner >= 0).all()
+            plans = [bands.halo_transfers(h, ctu_rows, world, r, chroma) for r in range(world)]
+            for r in range(world):
+                y0, y1 = bands.band_sample_rows(h, ctu_rows, world, r, chroma)
+                got = np.zeros(ph, bool)
+                for peer, r0, n in plans[r]["recv"]:
+                    assert (owner[r0:r0 + n] == peer).all() and not got[r0:r0 + n].any()
+                    got[r0:r0 + n] = True
+                    assert (r, r0, n) in plans[peer]["send"]                               # the owner sends exactly these rows
+                want = np.zeros(ph, bool)
+                if y1 > y0:
+                    want[max(0, y0 - halo):y0] = True; want[y1:min(ph, y1 + halo)] = True
+                assert np.array_equal(got, want), (h, world, chroma, r)
+                for peer, r0, n in plans[r]["send"]:
+                    assert (peer, r0, n) not in plans[r]["recv"] and (r, r0, n) in plans[peer]["recv"]
+    # the case the single-hop plan missed: 720p on 8 GPUs, rank 5 owns CTU row 9 (rows 576..640) and needs rows 508..576:
+    # 64 from rank 4's one-row band and 4 from rank 3
+    p = bands.halo_transfers(720, 12, 8, 5)
+    assert (3, 508, 4) in p["recv"] and (4, 512, 64) in p["recv"]
+
+
 def test_sao_offset_derivation_matches_reference_vectors():
     """hb_sao_derive_offsets (host code of the library, no device work) against results of the reference's sao_derive_offsets +
     sao_get_distortion stored by tests/golden/make_golden.py; then the stand-in decision on the same statistics: it may only
