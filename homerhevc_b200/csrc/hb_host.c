@@ -481,26 +481,22 @@ done:
     return rc;
 }
 
-int hb_mc_predict(hb_ctx *ctx, const hb_frame *ref, hb_frame *pred, const hb_mc_job *jobs, int n_jobs)
+/* validate, pack and launch the motion compensation of `jobs`; the caller holds ctx->lock and waits for the stream */
+int hbi_mc_predict_queue(hb_ctx *ctx, const hb_frame *ref, hb_frame *pred, const hb_mc_job *jobs, int n_jobs, const char *what)
 {
     static const int sizes[4] = { 64, 32, 16, 8 };
     int rc = HB_OK, crc = 0;
     void *d_pus, *h_pus, *d_mv, *h_mv;
-    if (!ctx || !ref || !pred || !jobs || n_jobs < 0) return hbi_fail(HB_ERR_ARG, "hb_mc_predict: bad argument");
-    if (pred->w != ref->w || pred->h != ref->h) return hbi_fail(HB_ERR_ARG, "hb_mc_predict: frame sizes differ");
-    if (n_jobs == 0) return HB_OK;
     const int reach = HB_PAD_LUMA - 16;                    /* how far outside the picture a predicted block may reach */
     for (int i = 0; i < n_jobs; i++) {
         const hb_mc_job *j = &jobs[i];
         const int x0 = j->x + (j->mv.x >> 2), y0 = j->y + (j->mv.y >> 2);
         if ((j->size != 8 && j->size != 16 && j->size != 32 && j->size != 64) || j->x < 0 || j->y < 0 || ((j->x | j->y) & 7) || j->x + j->size > ref->w ||
             j->y + j->size > ref->h || x0 < -reach || y0 < -reach || x0 + j->size > ref->w + reach || y0 + j->size > ref->h + reach)
-            return hbi_fail(HB_ERR_ARG, "hb_mc_predict: job %d is invalid or points further than %d samples outside the picture", i, reach);
+            return hbi_fail(HB_ERR_ARG, "%s: job %d is invalid or points further than %d samples outside the picture", what, i, reach);
     }
-    hbc_set_device(ctx->device);
-    pthread_mutex_lock(&ctx->lock);
-    if ((rc = hbi_scratch(ctx, 0, sizeof(hbd_mc_pu) * (size_t)n_jobs, &d_pus, &h_pus)) != HB_OK) goto done;
-    if ((rc = hbi_scratch(ctx, 1, sizeof(hb_me_result) * (size_t)n_jobs, &d_mv, &h_mv)) != HB_OK) goto done;
+    if ((rc = hbi_scratch(ctx, 0, sizeof(hbd_mc_pu) * (size_t)n_jobs, &d_pus, &h_pus)) != HB_OK) return rc;
+    if ((rc = hbi_scratch(ctx, 1, sizeof(hb_me_result) * (size_t)n_jobs, &d_mv, &h_mv)) != HB_OK) return rc;
     hbd_mc_pu *hp = (hbd_mc_pu *)h_pus;
     hb_me_result *hm = (hb_me_result *)h_mv;
     int n = 0, start_of[5];
@@ -523,8 +519,19 @@ int hb_mc_predict(hb_ctx *ctx, const hb_frame *ref, hb_frame *pred, const hb_mc_
         crc = hbk_mc_predict(&ref->d, &pred->d, sizes[s], (const hbd_mc_pu *)d_pus + start_of[s], cnt, (const hb_me_result *)d_mv, 3, ctx->stream);
         ctx->launches += 2;                                /* one luma, one chroma kernel */
     }
-    if (!crc) crc = hbc_stream_sync(ctx->stream);
-done:
+    return crc ? hbi_cuda_fail(crc, what) : HB_OK;
+}
+
+int hb_mc_predict(hb_ctx *ctx, const hb_frame *ref, hb_frame *pred, const hb_mc_job *jobs, int n_jobs)
+{
+    int rc, crc;
+    if (!ctx || !ref || !pred || !jobs || n_jobs < 0) return hbi_fail(HB_ERR_ARG, "hb_mc_predict: bad argument");
+    if (pred->w != ref->w || pred->h != ref->h) return hbi_fail(HB_ERR_ARG, "hb_mc_predict: frame sizes differ");
+    if (n_jobs == 0) return HB_OK;
+    hbc_set_device(ctx->device);
+    pthread_mutex_lock(&ctx->lock);
+    rc = hbi_mc_predict_queue(ctx, ref, pred, jobs, n_jobs, "hb_mc_predict");
+    crc = rc == HB_OK ? hbc_stream_sync(ctx->stream) : 0;
     pthread_mutex_unlock(&ctx->lock);
     if (crc) return hbi_cuda_fail(crc, "hb_mc_predict");
     return rc;
@@ -831,32 +838,35 @@ void hbi_tq_setup(hb_ctx *ctx, hbd_tq_args *a, int comp, int n, int qp, int is_i
  * so a unit's x must be a multiple of min(size, 16) -- which every transform unit of the quadtree is */
 static int tq_row_align(int size) { return size < 16 ? size : 16; }
 
-int hb_tq_encode(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_frame *recon, const hb_tu_job *jobs, int n_jobs,
-                 const hb_tq_params *params, int16_t *coeffs, hb_tu_result *results)
+void hbi_tq_pack_free(hbi_tq_pack *pk) { free(pk->order); free(pk->coeff_off); pk->order = NULL; pk->coeff_off = NULL; }
+
+/* validate, group by (component, size, qp), launch, and queue the copies of levels and records into the pinned twins; the caller
+ * holds ctx->lock, waits for the stream and calls hbi_tq_collect + hbi_tq_pack_free */
+int hbi_tq_encode_queue(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_frame *recon, const hb_tu_job *jobs, int n_jobs,
+                        const hb_tq_params *params, hbi_tq_pack *pk, const char *what)
 {
     int rc = HB_OK, crc = 0;
-    if (!ctx || !cur || !pred || !recon || !jobs || !params || !coeffs || !results || n_jobs < 0) return hbi_fail(HB_ERR_ARG, "hb_tq_encode: bad argument");
-    if (n_jobs == 0) return HB_OK;
     size_t total = 0;
+    memset(pk, 0, sizeof *pk);
     for (int i = 0; i < n_jobs; i++) {
         const hb_tu_job *j = &jobs[i];
         if (j->comp < 0 || j->comp > 2 || (j->size != 4 && j->size != 8 && j->size != 16 && j->size != 32) || j->qp < 0 || j->qp > 51 ||
             j->x < 0 || j->y < 0 || (j->x & (tq_row_align(j->size) - 1)) || j->x + j->size > cur->d.p[j->comp].w || j->y + j->size > cur->d.p[j->comp].h ||
             (j->comp && j->size == 32))
-            return hbi_fail(HB_ERR_ARG, "hb_tq_encode: job %d is invalid (x must be a multiple of min(size, 16))", i);
+            return hbi_fail(HB_ERR_ARG, "%s: job %d is invalid (x must be a multiple of min(size, 16))", what, i);
         total += (size_t)j->size * j->size;
     }
-    hbc_set_device(ctx->device);
-    pthread_mutex_lock(&ctx->lock);
     void *d_xy, *h_xy, *d_co, *h_co, *d_rs, *h_rs;
-    int *order = (int *)malloc(sizeof(int) * (size_t)n_jobs);
     char *done_flag = (char *)calloc((size_t)n_jobs, 1);
-    size_t *coeff_off = (size_t *)malloc(sizeof(size_t) * (size_t)n_jobs);
-    if (!order || !done_flag || !coeff_off) { rc = hbi_fail(HB_ERR_NOMEM, "hb_tq_encode: out of memory"); goto done; }
+    pk->order = (int *)malloc(sizeof(int) * (size_t)n_jobs);
+    pk->coeff_off = (size_t *)malloc(sizeof(size_t) * (size_t)n_jobs);
+    pk->total = total;
+    if (!pk->order || !done_flag || !pk->coeff_off) { rc = hbi_fail(HB_ERR_NOMEM, "%s: out of memory", what); goto done; }
     if ((rc = hbi_scratch(ctx, 0, sizeof(int32_t) * 2 * (size_t)n_jobs, &d_xy, &h_xy)) != HB_OK) goto done;
     if ((rc = hbi_scratch(ctx, 1, sizeof(int16_t) * total, &d_co, &h_co)) != HB_OK) goto done;
     if ((rc = hbi_scratch(ctx, 2, sizeof(hb_tu_result) * (size_t)n_jobs, &d_rs, &h_rs)) != HB_OK) goto done;
-    { size_t o = 0; for (int i = 0; i < n_jobs; i++) { coeff_off[i] = o; o += (size_t)jobs[i].size * jobs[i].size; } }
+    pk->h_co = h_co; pk->h_rs = h_rs;
+    { size_t o = 0; for (int i = 0; i < n_jobs; i++) { pk->coeff_off[i] = o; o += (size_t)jobs[i].size * jobs[i].size; } }
     /* launch one group per distinct (comp, size, qp); jobs of a group are packed in caller order */
     int packed = 0;
     size_t packed_coeff = 0;
@@ -868,7 +878,7 @@ int hb_tq_encode(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_fram
         int32_t *xy = (int32_t *)h_xy;
         for (int k = i; k < n_jobs; k++) {
             if (done_flag[k] || jobs[k].comp != key.comp || jobs[k].size != key.size || jobs[k].qp != key.qp) continue;
-            done_flag[k] = 1; order[packed] = k;
+            done_flag[k] = 1; pk->order[packed] = k;
             xy[2 * packed] = jobs[k].x; xy[2 * packed + 1] = jobs[k].y;
             packed++; packed_coeff += (size_t)key.size * key.size;
         }
@@ -890,19 +900,41 @@ int hb_tq_encode(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_fram
     }
     if (!crc) crc = hbc_d2h_async(h_co, d_co, sizeof(int16_t) * total, ctx->stream);
     if (!crc) crc = hbc_d2h_async(h_rs, d_rs, sizeof(hb_tu_result) * (size_t)n_jobs, ctx->stream);
-    if (!crc) crc = hbc_stream_sync(ctx->stream);
-    if (!crc) {
-        size_t o = 0;
-        for (int p = 0; p < n_jobs; p++) {
-            const int k = order[p];
-            const size_t nn = (size_t)jobs[k].size * jobs[k].size;
-            memcpy(coeffs + coeff_off[k], (int16_t *)h_co + o, sizeof(int16_t) * nn);
-            results[k] = ((hb_tu_result *)h_rs)[p];
-            o += nn;
-        }
-    }
+    if (crc) rc = hbi_cuda_fail(crc, what);
 done:
-    free(order); free(done_flag); free(coeff_off);
+    free(done_flag);
+    if (rc != HB_OK) hbi_tq_pack_free(pk);
+    return rc;
+}
+
+/* after the stream has been waited for: packed launch order -> the caller's job order */
+void hbi_tq_collect(const hbi_tq_pack *pk, const hb_tu_job *jobs, int n_jobs, int16_t *coeffs, hb_tu_result *results)
+{
+    size_t o = 0;
+    for (int p = 0; p < n_jobs; p++) {
+        const int k = pk->order[p];
+        const size_t nn = (size_t)jobs[k].size * jobs[k].size;
+        memcpy(coeffs + pk->coeff_off[k], (int16_t *)pk->h_co + o, sizeof(int16_t) * nn);
+        results[k] = ((hb_tu_result *)pk->h_rs)[p];
+        o += nn;
+    }
+}
+
+int hb_tq_encode(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_frame *recon, const hb_tu_job *jobs, int n_jobs,
+                 const hb_tq_params *params, int16_t *coeffs, hb_tu_result *results)
+{
+    int rc, crc = 0;
+    hbi_tq_pack pk;
+    if (!ctx || !cur || !pred || !recon || !jobs || !params || !coeffs || !results || n_jobs < 0) return hbi_fail(HB_ERR_ARG, "hb_tq_encode: bad argument");
+    if (n_jobs == 0) return HB_OK;
+    hbc_set_device(ctx->device);
+    pthread_mutex_lock(&ctx->lock);
+    rc = hbi_tq_encode_queue(ctx, cur, pred, recon, jobs, n_jobs, params, &pk, "hb_tq_encode");
+    if (rc == HB_OK) {
+        crc = hbc_stream_sync(ctx->stream);
+        if (!crc) hbi_tq_collect(&pk, jobs, n_jobs, coeffs, results);
+        hbi_tq_pack_free(&pk);
+    }
     pthread_mutex_unlock(&ctx->lock);
     if (crc) return hbi_cuda_fail(crc, "hb_tq_encode");
     return rc;

@@ -8,7 +8,7 @@
 #define HB_SCAN_HOR  1      /* hmr_private.h:92-96 */
 #define HB_SCAN_VER  2
 #define HB_SCAN_DIAG 3
-#define HB_N_SCRATCH 4
+#define HB_N_SCRATCH 6
 
 struct hb_ctx {
     int device;
@@ -40,5 +40,13 @@ size_t hbi_tab_q_off(int lg, int list, int rem);
 int hbi_chroma_qp(int qp, int offset);
 double hbi_zero_out_k(double avg_dist);
 void hbi_tq_setup(hb_ctx *ctx, hbd_tq_args *a, int comp, int n, int qp, int is_islice, int sign_hiding);
+/* the queueing halves of hb_mc_predict / hb_tq_encode: validate, pack, launch; the caller holds ctx->lock, synchronises and
+ * (hbi_tq_collect) spreads the packed results.  hb_encode.c appends its block read-back before the one wait. */
+int hbi_mc_predict_queue(hb_ctx *ctx, const hb_frame *ref, hb_frame *pred, const hb_mc_job *jobs, int n_jobs, const char *what);
+typedef struct hbi_tq_pack { int *order; size_t *coeff_off; size_t total; void *h_co, *h_rs; } hbi_tq_pack;
+int hbi_tq_encode_queue(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_frame *recon, const hb_tu_job *jobs, int n_jobs,
+                        const hb_tq_params *params, hbi_tq_pack *pk, const char *what);
+void hbi_tq_collect(const hbi_tq_pack *pk, const hb_tu_job *jobs, int n_jobs, int16_t *coeffs, hb_tu_result *results);
+void hbi_tq_pack_free(hbi_tq_pack *pk);
 
 #endif

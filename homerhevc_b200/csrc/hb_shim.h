@@ -125,6 +125,11 @@ typedef struct hbd_tq_args {
 } hbd_tq_args;
 int hbk_tq_encode(const hbd_tq_args *a, void *stream);
 
+/* ---- block read-back (hb_kernels_enc.cu): size x size samples of plane `comp` at (x, y), x a multiple of 4, widened to int16 at
+ * out + off (off in int16 units, a multiple of 4) */
+typedef struct hbd_fetch_job { int32_t comp, x, y, size, off, pad_; } hbd_fetch_job;
+int hbk_fetch_blocks(const hbd_frame *f, const hbd_fetch_job *jobs, int n_jobs, int16_t *out, void *stream);
+
 /* ---- intra prediction (hb_kernels_intra.cu) */
 typedef struct hbd_intra_job {
     int32_t comp, x, y, size;     /* plane, position and size (4..32) in samples of that plane */

@@ -362,6 +362,35 @@ int  hb_prepass_frame_finish_resident(hb_prepass *pp, const hb_frame *cur, int l
 const hb_frame *hb_prepass_pred(const hb_prepass *pp, int depth);     /* resident prediction of that depth */
 const hb_frame *hb_prepass_recon(const hb_prepass *pp, int pass);
 
+/* ------------------------------------------------------------------ E. CU-granularity calls inside the encoder's own loop ------
+ * The batched jobs of section C at the granularity of the reference's call sites, for a host loop that keeps every decision
+ * (AMVP / merge candidates, TU tree, mode choice, CABAC): one round trip per call -- jobs up, kernels, the blocks the loop goes
+ * on reading down, one wait.  A session owns four resident pictures; the prediction a T/Q job subtracts is whatever
+ * hb_enc_predict last left at that place, as encode_inter_cu reads what hmr_motion_compensation_* last left in
+ * et->prediction_wnd[0].  INTEGRATION.md section 2 shows the reference-side binding; tests/test_gpu_encode_hooks.py encodes whole
+ * streams through it (oracle/ref_hooks.c) and compares them byte for byte with the unmodified reference.
+ *   per picture (hook after hmr_rd_init, hmr_encoder_lib.c:3201): hb_frame_upload_i16(hb_enc_frame(e, HB_ENC_CUR), source wnd_t),
+ *                                                            hb_frame_upload_i16(hb_enc_frame(e, HB_ENC_REF), reference wnd_t)
+ *   hmr_motion_estimation, hmr_motion_inter.c:2625         -> hb_enc_me (the real AMVP list and start points in the jobs)
+ *   hmr_motion_compensation_luma/_chroma, :3047-3049, :3655 -> hb_enc_predict
+ *   encode_inter_cu / encode_inter_cu_chroma, :3165-3170    -> hb_enc_tq */
+typedef struct hb_enc hb_enc;
+#define HB_ENC_CUR 0
+#define HB_ENC_REF 1
+#define HB_ENC_PRED 2
+#define HB_ENC_RECON 3
+int       hb_enc_create(hb_ctx *ctx, int width, int height, hb_enc **out);
+void      hb_enc_destroy(hb_enc *e);
+hb_frame *hb_enc_frame(hb_enc *e, int which);
+/* = hb_me_search on the session's source and reference pictures (no parent table: the caller's start list carries the parent's vector) */
+int hb_enc_me(hb_enc *e, const hb_me_job *jobs, int n_jobs, double avg_dist, int action, hb_me_result *results);
+/* uni-prediction of every job into the session's prediction picture; blocks: per job size^2 luma, (size/2)^2 U, (size/2)^2 V samples as
+ * int16 (the sample type of the reference's CTU windows), jobs back to back */
+int hb_enc_predict(hb_enc *e, const hb_mc_job *jobs, int n_jobs, int16_t *blocks);
+/* the inter T/Q chain of every job (hb_tq_encode) on the session's source / prediction pictures into its reconstruction picture;
+ * coeffs and decoded: size^2 int16 per job, jobs back to back; results[i].ssd is what encode_inter_cu returns, .sum its *curr_sum */
+int hb_enc_tq(hb_enc *e, const hb_tu_job *jobs, int n_jobs, const hb_tq_params *params, int16_t *coeffs, int16_t *decoded, hb_tu_result *results);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,155 @@
+/*
+ * ref_shadow.c -- TEST INFRASTRUCTURE: a function table for the reference encoder in which every member runs TWICE, once as the
+ * reference's own SSE4.2 function (whose result the encoder goes on with) and once as libhomer_b200's per-call drop-in on
+ * private copies of the same operands; the two results are compared on the spot.  A whole encode through this table pins the first
+ * call -- function, arguments, operands -- on which the GPU path and the CPU path ever disagree, which a comparison of finished
+ * bitstreams cannot (tools/flake_hunt.py loops it to look for rare, timing-dependent differences).
+ */
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "hmr_private.h"
+#include "hmr_common.h"
+#include "hmr_sse42_functions.h"
+
+typedef struct gpu_quant_env { int32_t is_islice, sign_hiding, max_cu_size_shift, bit_depth; int16_t *delta_u; } gpu_quant_env;
+
+static struct {
+    uint32_t (*sad)(int16_t *, uint32_t, int16_t *, uint32_t, int);
+    uint32_t (*ssd16b)(int16_t *, uint32_t, int16_t *, uint32_t, int);
+    void (*predict)(int16_t *, int, int16_t *, int, int16_t *, int, int);
+    void (*reconst)(int16_t *, int, int16_t *, int, int16_t *, int, int);
+    void (*interp_luma)(int16_t *, int, int16_t *, int, int, int, int, int, int, int);
+    void (*interp_chroma)(int16_t *, int, int16_t *, int, int, int, int, int, int, int);
+    void (*transform)(int, int16_t *, int16_t *, int, int, int, int, int, uint16_t, int16_t *);
+    void (*itransform)(int, int16_t *, int16_t *, int, int, int, unsigned int, int16_t *);
+    void (*quant)(const gpu_quant_env *, int16_t *, int16_t *, int, int, int, int, int, int *, int, int, int);
+    void (*inv_quant)(const gpu_quant_env *, int16_t *, int16_t *, int, int, int, int, int, int);
+} GPU;
+
+#define SH_MAX_DUMP (80 * 80)
+typedef struct shadow_report {
+    long calls, mismatches;
+    int first_fn;                 /* 1 sad 2 ssd16b 3 predict 4 reconst 5 interp luma 6 interp chroma 7 transform 8 itransform 9 quant 10 inv_quant */
+    int args[12];
+    long first_call;              /* ordinal of the first mismatching call */
+    int first_at;                 /* index of the first differing output element */
+    int32_t cpu_val, gpu_val;
+} shadow_report;
+static shadow_report S;
+static __thread int16_t t_a[SH_MAX_DUMP], t_b[SH_MAX_DUMP];
+
+static void report(int fn, const int *args, int n_args, int at, int cpu, int gpu)
+{
+    if (__atomic_add_fetch(&S.mismatches, 1, __ATOMIC_RELAXED) != 1) return;
+    S.first_fn = fn; S.first_call = S.calls; S.first_at = at; S.cpu_val = cpu; S.gpu_val = gpu;
+    memset(S.args, 0, sizeof S.args);
+    for (int i = 0; i < n_args && i < 12; i++) S.args[i] = args[i];
+}
+#define CALL() __atomic_add_fetch(&S.calls, 1, __ATOMIC_RELAXED)
+
+static int cmp_block(const int16_t *a, int as, const int16_t *b, int bs, int w, int h, int *cv, int *gv)
+{
+    for (int r = 0; r < h; r++) for (int c = 0; c < w; c++)
+        if (a[r * as + c] != b[r * bs + c]) { *cv = a[r * as + c]; *gv = b[r * bs + c]; return r * w + c; }
+    return -1;
+}
+
+static uint32_t sh_sad(int16_t *src, uint32_t ss, int16_t *pred, uint32_t ps, int size)
+{
+    CALL();
+    const uint32_t c = sse_aligned_sad(src, ss, pred, ps, size), g = GPU.sad(src, ss, pred, ps, size);
+    if (c != g) { const int a[3] = { (int)ss, (int)ps, size }; report(1, a, 3, 0, (int)c, (int)g); }
+    return c;
+}
+static uint32_t sh_ssd(int16_t *src, uint32_t ss, int16_t *pred, uint32_t ps, int size)
+{
+    CALL();
+    const uint32_t c = sse_aligned_ssd16b(src, ss, pred, ps, size), g = GPU.ssd16b(src, ss, pred, ps, size);
+    if (c != g) { const int a[3] = { (int)ss, (int)ps, size }; report(2, a, 3, 0, (int)c, (int)g); }
+    return c;
+}
+static void sh_predict(int16_t *o, int os, int16_t *p, int ps, int16_t *r, int rs, int size)
+{
+    int cv, gv, at;
+    CALL();
+    GPU.predict(o, os, p, ps, t_a, size, size);
+    sse_aligned_predict(o, os, p, ps, r, rs, size);
+    if ((at = cmp_block(r, rs, t_a, size, size, size, &cv, &gv)) >= 0) { const int a[4] = { os, ps, rs, size }; report(3, a, 4, at, cv, gv); }
+}
+static void sh_reconst(int16_t *p, int ps, int16_t *r, int rs, int16_t *d, int ds, int size)
+{
+    int cv, gv, at;
+    CALL();
+    GPU.reconst(p, ps, r, rs, t_a, size, size);
+    sse_aligned_reconst(p, ps, r, rs, d, ds, size);
+    if ((at = cmp_block(d, ds, t_a, size, size, size, &cv, &gv)) >= 0) { const int a[4] = { ps, rs, ds, size }; report(4, a, 4, at, cv, gv); }
+}
+static void sh_interp(int chroma, int16_t *ref, int rs, int16_t *dst, int ds, int frac, int w, int h, int vert, int first, int last)
+{
+    int cv, gv, at;
+    CALL();
+    if (w * h <= SH_MAX_DUMP) (chroma ? GPU.interp_chroma : GPU.interp_luma)(ref, rs, t_a, w, frac, w, h, vert, first, last);
+    (chroma ? sse_interpolate_chroma : sse_interpolate_luma)(ref, rs, dst, ds, frac, w, h, vert, first, last);
+    if (w * h <= SH_MAX_DUMP && (at = cmp_block(dst, ds, t_a, w, w, h, &cv, &gv)) >= 0) {
+        const int a[8] = { rs, ds, frac, w, h, vert, first, last };
+        report(chroma ? 6 : 5, a, 8, at, cv, gv);
+    }
+}
+static void sh_interp_luma(int16_t *ref, int rs, int16_t *dst, int ds, int frac, int w, int h, int vert, int first, int last) { sh_interp(0, ref, rs, dst, ds, frac, w, h, vert, first, last); }
+static void sh_interp_chroma(int16_t *ref, int rs, int16_t *dst, int ds, int frac, int w, int h, int vert, int first, int last) { sh_interp(1, ref, rs, dst, ds, frac, w, h, vert, first, last); }
+static void sh_transform(int bd, int16_t *block, int16_t *coeff, int bs, int w, int h, int wsh, int hsh, uint16_t mode, int16_t *aux)
+{
+    int cv, gv, at;
+    CALL();
+    GPU.transform(bd, block, t_a, bs, w, h, wsh, hsh, mode, t_b);
+    sse_transform(bd, block, coeff, bs, w, h, wsh, hsh, mode, aux);
+    if ((at = cmp_block(coeff, w, t_a, w, w, h, &cv, &gv)) >= 0) { const int a[4] = { bs, w, h, mode }; report(7, a, 4, at, cv, gv); }
+}
+static void sh_itransform(int bd, int16_t *block, int16_t *coeff, int bs, int w, int h, unsigned int mode, int16_t *aux)
+{
+    int cv, gv, at;
+    CALL();
+    GPU.itransform(bd, t_a, coeff, w, w, h, mode, t_b);
+    sse_itransform(bd, block, coeff, bs, w, h, mode, aux);
+    if ((at = cmp_block(block, bs, t_a, w, w, h, &cv, &gv)) >= 0) { const int a[4] = { bs, w, h, (int)mode }; report(8, a, 4, at, cv, gv); }
+}
+static void sh_quant(henc_thread_t *et, int16_t *src, int16_t *dst, int scan_mode, int depth, int comp, int cu_mode, int is_intra, int *ac_sum, int cu_size, int per, int rem)
+{
+    int cv, gv, at, gsum = 0;
+    gpu_quant_env env = { et->enc_engine->current_pict.slice.slice_type == I_SLICE, (int32_t)et->pps->sign_data_hiding_flag, et->max_cu_size_shift, et->bit_depth, t_b };
+    CALL();
+    GPU.quant(&env, src, t_a, scan_mode, depth, comp, cu_mode, is_intra, &gsum, cu_size, per, rem);
+    sse_aligned_quant(et, src, dst, scan_mode, depth, comp, cu_mode, is_intra, ac_sum, cu_size, per, rem);
+    at = cmp_block(dst, cu_size, t_a, cu_size, cu_size, cu_size, &cv, &gv);
+    if (at < 0 && gsum != *ac_sum) { at = cu_size * cu_size; cv = *ac_sum; gv = gsum; }
+    if (at >= 0) { const int a[9] = { scan_mode, depth, comp, cu_mode, is_intra, cu_size, per, rem, env.is_islice }; report(9, a, 9, at, cv, gv); }
+}
+static void sh_inv_quant(henc_thread_t *et, short *src, short *dst, int depth, int comp, int is_intra, int cu_size, int per, int rem)
+{
+    int cv, gv, at;
+    gpu_quant_env env = { 0, 0, et->max_cu_size_shift, et->bit_depth, NULL };
+    CALL();
+    GPU.inv_quant(&env, src, t_a, depth, comp, is_intra, cu_size, per, rem);
+    sse_aligned_inv_quant(et, src, dst, depth, comp, is_intra, cu_size, per, rem);
+    if ((at = cmp_block(dst, cu_size, t_a, cu_size, cu_size, cu_size, &cv, &gv)) >= 0) { const int a[6] = { depth, comp, is_intra, cu_size, per, rem }; report(10, a, 6, at, cv, gv); }
+}
+
+/* a refdrv_table_hook: user = { lib (dlopen handle of libhomer_b200.so), which (ignored) } */
+void refdrv_install_shadow_table(void *funcs_table, void *user)
+{
+    struct { void *lib; int which; } *u = user;
+    low_level_funcs_t *f = (low_level_funcs_t *)funcs_table;
+    void *lib = u->lib;
+    memset(&S, 0, sizeof S);
+    GPU.sad = dlsym(lib, "hb_sad"); GPU.ssd16b = dlsym(lib, "hb_ssd16b"); GPU.predict = dlsym(lib, "hb_predict"); GPU.reconst = dlsym(lib, "hb_reconst");
+    GPU.interp_luma = dlsym(lib, "hb_interpolate_luma"); GPU.interp_chroma = dlsym(lib, "hb_interpolate_chroma");
+    GPU.transform = dlsym(lib, "hb_transform"); GPU.itransform = dlsym(lib, "hb_itransform"); GPU.quant = dlsym(lib, "hb_quant"); GPU.inv_quant = dlsym(lib, "hb_inv_quant");
+    f->sad = sh_sad; f->ssd16b = sh_ssd; f->predict = sh_predict; f->reconst = sh_reconst;
+    f->interpolate_luma_m_compensation = sh_interp_luma; f->interpolate_luma_m_estimation = sh_interp_luma; f->interpolate_chroma_m_compensation = sh_interp_chroma;
+    f->transform = sh_transform; f->itransform = sh_itransform; f->quant = sh_quant; f->inv_quant = sh_inv_quant;
+}
+void *refdrv_install_shadow_table_addr(void) { return (void *)refdrv_install_shadow_table; }
+void refdrv_shadow_report(shadow_report *out) { *out = S; }

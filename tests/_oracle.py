@@ -108,8 +108,10 @@ def ref():
     """(libhomer_ref, librefdrv) -- the compiled reference.  Only call when have_ref()."""
     global _ref
     if _ref is None:
+        # librefdrv.so FIRST and global: oracle/ref_hooks.c interposes hmr_motion_estimation & co., which only works when the
+        # harness precedes libhomer_ref.so (its dependency) in the lookup order of the calls made inside the reference
+        D = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "librefdrv.so"), mode=C.RTLD_GLOBAL)
         R = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libhomer_ref.so"), mode=C.RTLD_GLOBAL)
-        D = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "librefdrv.so"))
         R.sse_aligned_sad.restype = C.c_uint32
         R.sse_aligned_ssd16b.restype = C.c_uint32
         R.sad.restype = C.c_uint32
