@@ -94,21 +94,70 @@ extern "C" const char *hbc_error_string(int code) { return cudaGetErrorString(st
 // ------------------------------------------------------------------ per-call pixel kernels
 namespace {
 
+// sad / ssd16b of the function table with the EXACT lane arithmetic of the reference's SSE4.2 functions (hmr_sse42_functions_pixel.c:
+// sad :330-460, ssd16b :619-745).  On 8-bit video they are the plain sums of hmr_motion_intra.c:51 / :128; the encoder, however, also
+// calls them on operands that are not video -- its 64x64 intra mode search predicts with 16-bit arithmetic that wraps
+// (homer_loop1_motion_intra, hmr_motion_intra.c:1084 -> :1130) -- and there the SIMD lanes decide the value the mode decision sees:
+//   difference: 16-bit wrapping subtraction, |.| with |-32768| = 32768 (psubw, pabsw);
+//   sad 4/8/16: the eight 16-bit lanes wrap while they accumulate and while they are folded 8 -> 4 -> 2, the last two add in 32 bits;
+//   sad 32    : sixteen lanes (two accumulators) add with unsigned saturation over all rows, then widen;
+//   sad 64    : per row, eight lanes add their eight column groups with unsigned saturation, then widen;
+//   ssd16b    : squares of the wrapped difference, everything modulo 2^32 (pmaddwd, paddd).
+__device__ __forceinline__ uint32_t pc_absdiff16(int a, int b)
+{
+    const int t = static_cast<int16_t>(a - b);
+    return static_cast<uint32_t>(t < 0 ? -t : t);        // 32768 for t = -32768, as pabsw leaves 0x8000
+}
+
 __global__ void __launch_bounds__(256) k_pc_sad(const int16_t *a, int as, const int16_t *b, int bs, int n, int squared, uint32_t *out)
 {
-    __shared__ uint32_t red[8];
-    uint32_t acc = 0;
-    for (int e = threadIdx.x; e < n * n; e += 256) {
-        const int d = static_cast<int>(a[(e / n) * as + e % n]) - static_cast<int>(b[(e / n) * bs + e % n]);
-        acc += squared ? static_cast<uint32_t>(d) * static_cast<uint32_t>(d) : static_cast<uint32_t>(abs(d));
+    __shared__ uint32_t lane[16], total;
+    if (threadIdx.x < 16) lane[threadIdx.x] = 0;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    if (squared) {
+        uint32_t acc = 0;
+        for (int e = threadIdx.x; e < n * n; e += 256) {
+            const int t = static_cast<int16_t>(a[(e / n) * as + e % n] - b[(e / n) * bs + e % n]);
+            acc += static_cast<uint32_t>(t * t);
+        }
+        acc = __reduce_add_sync(HB_FULL_MASK, acc);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&total, acc);
+        __syncthreads();
+        if (threadIdx.x == 0) *out = total;
+        return;
     }
-    acc = __reduce_add_sync(HB_FULL_MASK, acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    if (n == 64) {                                            // 64 rows x 8 lanes: saturate per row, then exact
+        uint32_t acc = 0;
+        for (int u = threadIdx.x; u < 64 * 8; u += 256) {
+            const int r = u >> 3, j = u & 7;
+            uint32_t s = 0;
+            for (int g = 0; g < 8; g++) s += pc_absdiff16(a[r * as + 8 * g + j], b[r * bs + 8 * g + j]);
+            acc += min(s, 65535u);
+        }
+        acc = __reduce_add_sync(HB_FULL_MASK, acc);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&total, acc);
+        __syncthreads();
+        if (threadIdx.x == 0) *out = total;
+        return;
+    }
+    for (int e = threadIdx.x; e < n * n; e += 256) {
+        const int r = e / n, c = e % n;
+        const uint32_t d = pc_absdiff16(a[r * as + c], b[r * bs + c]);
+        // lane of the element: 4x4 packs two rows per vector; 32x32 keeps columns 0..15 and 16..31 in two accumulators
+        const int l = n == 4 ? ((r & 1) * 4 + c) : n == 32 ? ((c >> 4) * 8 + (c & 7)) : (c & 7);
+        atomicAdd(&lane[l], d);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t s = 0;
-        for (int i = 0; i < 8; i++) s += red[i];
-        *out = s;
+        uint32_t r;
+        if (n == 32) {
+            r = 0;
+            for (int l = 0; l < 16; l++) r += min(lane[l], 65535u);
+        } else {
+            r = ((lane[0] + lane[4] + lane[2] + lane[6]) & 0xffffu) + ((lane[1] + lane[5] + lane[3] + lane[7]) & 0xffffu);
+        }
+        *out = r;
     }
 }
 

@@ -36,6 +36,44 @@ uint32_t orc_ssd16b(const int16_t *src, int src_stride, const int16_t *pred, int
     return acc;
 }
 
+/* The table members as the SSE4.2 build computes them on ANY int16 operands (hmr_sse42_functions_pixel.c:330-460 sad, :619-745
+ * ssd16b): equal to the plain sums above on 8-bit video, but the encoder also calls them on the wrapped 16-bit predictions of its
+ * 64x64 intra mode search (hmr_motion_intra.c:1130), where the SIMD lane arithmetic decides the value.  Differences wrap at 16 bits
+ * (psubw) and |-32768| stays 32768 (pabsw); 4/8/16: eight wrapping 16-bit lanes folded 8 -> 4 -> 2, the last two added in 32 bits
+ * (sse_128_hacc_i16_ :42); 32: sixteen lanes with unsigned saturation over all rows (:374-410); 64: eight lanes saturating over the
+ * eight column groups of each row (:413-449); ssd16b: squares of the wrapped difference modulo 2^32 (pmaddwd / paddd). */
+static uint32_t absdiff16(int a, int b)
+{
+    const int t = (int16_t)(a - b);
+    return (uint32_t)(t < 0 ? -t : t);
+}
+uint32_t orc_sad_sse(const int16_t *src, int src_stride, const int16_t *pred, int pred_stride, int size)
+{
+    uint32_t lane[16] = { 0 }, total = 0;
+    for (int y = 0; y < size; y++) {
+        uint32_t row[8] = { 0 };
+        for (int x = 0; x < size; x++) {
+            const uint32_t d = absdiff16(src[y * src_stride + x], pred[y * pred_stride + x]);
+            if (size == 64) row[x & 7] += d;
+            else lane[size == 4 ? ((y & 1) * 4 + x) : size == 32 ? ((x >> 4) * 8 + (x & 7)) : (x & 7)] += d;
+        }
+        if (size == 64) for (int j = 0; j < 8; j++) total += row[j] > 65535u ? 65535u : row[j];
+    }
+    if (size == 64) return total;
+    if (size == 32) { for (int l = 0; l < 16; l++) total += lane[l] > 65535u ? 65535u : lane[l]; return total; }
+    return ((lane[0] + lane[4] + lane[2] + lane[6]) & 0xffffu) + ((lane[1] + lane[5] + lane[3] + lane[7]) & 0xffffu);
+}
+uint32_t orc_ssd16b_sse(const int16_t *src, int src_stride, const int16_t *pred, int pred_stride, int size)
+{
+    uint32_t acc = 0;
+    for (int y = 0; y < size; y++)
+        for (int x = 0; x < size; x++) {
+            const int t = (int16_t)(src[y * src_stride + x] - pred[y * pred_stride + x]);
+            acc += (uint32_t)(t * t);
+        }
+    return acc;
+}
+
 void orc_predict(const int16_t *orig, int orig_stride, const int16_t *pred, int pred_stride,
                  int16_t *resid, int resid_stride, int size)
 {

@@ -8,6 +8,7 @@
  *
  * Build: see oracle/Makefile (outputs only into oracle/_ref/).
  */
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -323,6 +324,8 @@ typedef struct rp_shared {
     double avg_dist;
     int16_t *cur[3], *ref[3];           /* padded int16 planes (origin pointers) */
     int stride[3];
+    const uint8_t *cur8[3], *ref8[3];   /* the caller's 8-bit planes */
+    pthread_barrier_t planes_ready;
     int *tu_index[5][3];                /* raster position -> index among coded TUs, or -1 */
     int tu_grid_w[5][3];
     refdrv_prepass_out *out;
@@ -337,17 +340,27 @@ static int rp_pu_valid(const rp_shared *sh, int x, int y, int s)
     return x + s <= sh->w && y + s <= sh->h && row >= sh->row0 && row < sh->row0 + sh->rows;
 }
 
-static int16_t *rp_make_plane(const uint8_t *src, int w, int h, int pad, int *stride_out, int16_t **alloc_out)
+/* the reference's frames are int16 planes with a replicated border (put_frame_to_encode widens the 8-bit input, hmr_encoder_lib.c:293-305);
+ * the workers fill disjoint row slices of the six planes before the CTU loop starts (rp_fill_rows), so that the conversion does
+ * not serialise the multi-threaded run */
+static int16_t *rp_alloc_plane(int w, int h, int pad, int *stride_out, int16_t **alloc_out)
 {
     const int stride = w + 2 * pad;
     int16_t *a = (int16_t *)malloc(sizeof(int16_t) * (size_t)stride * (h + 2 * pad));
-    for (int y = -pad; y < h + pad; y++) {
-        const int sy = y < 0 ? 0 : (y >= h ? h - 1 : y);
-        int16_t *row = a + (size_t)(y + pad) * stride + pad;
-        for (int x = -pad; x < w + pad; x++) row[x] = src[(size_t)sy * w + (x < 0 ? 0 : (x >= w ? w - 1 : x))];
-    }
     *stride_out = stride; *alloc_out = a;
     return a + (size_t)pad * stride + pad;
+}
+static void rp_fill_rows(int16_t *org, int stride, const uint8_t *src, int w, int h, int pad, int part, int parts)
+{
+    const int rows = h + 2 * pad, lo = (int)((long)rows * part / parts) - pad, hi = (int)((long)rows * (part + 1) / parts) - pad;
+    for (int y = lo; y < hi; y++) {
+        const int sy = y < 0 ? 0 : (y >= h ? h - 1 : y);
+        const uint8_t *s = src + (size_t)sy * w;
+        int16_t *row = org + (ptrdiff_t)y * stride;
+        for (int x = -pad; x < 0; x++) row[x] = s[0];
+        for (int x = 0; x < w; x++) row[x] = s[x];
+        for (int x = w; x < w + pad; x++) row[x] = s[w - 1];
+    }
 }
 
 static cu_partition_info_t *rp_find_cu(henc_thread_t *et, ctu_info_t *ctu, int depth, int x, int y)
@@ -369,6 +382,13 @@ static void *rp_thread(void *arg)
     d->eng->avg_dist = sh->avg_dist;
     d->eng->current_pict.slice.slice_type = P_SLICE;
     d->eng->current_pict.slice.qp = sh->qp;
+
+    for (int c = 0; c < 3; c++) {
+        const int pw = c ? sh->w / 2 : sh->w, ph = c ? sh->h / 2 : sh->h, pad = c ? 72 : 144;
+        rp_fill_rows(sh->cur[c], sh->stride[c], sh->cur8[c], pw, ph, pad, wk->tid, sh->n_threads);
+        rp_fill_rows(sh->ref[c], sh->stride[c], sh->ref8[c], pw, ph, pad, wk->tid, sh->n_threads);
+    }
+    pthread_barrier_wait(&sh->planes_ready);
 
     for (int ci = sh->row0 * sh->ctu_cols + wk->tid; ci < (sh->row0 + sh->rows) * sh->ctu_cols; ci += sh->n_threads) {
         const int x0 = (ci % sh->ctu_cols) * 64, y0 = (ci / sh->ctu_cols) * 64;
@@ -489,7 +509,7 @@ int refdrv_prepass_num_tus(int w, int h, int ctu_row0, int ctu_rows, int pass, i
     return n;
 }
 
-/* returns the seconds spent (conversion of the 8-bit planes to the reference's int16 frames included) or < 0 */
+/* returns the seconds spent (conversion of the 8-bit planes to the reference's int16 frames included, done by the workers) or < 0 */
 double refdrv_prepass(refdrv **drv, int n_threads, const uint8_t *const cur[3], const uint8_t *const ref[3], int w, int h, int qp,
                       double avg_dist, int ctu_row0, int ctu_rows, refdrv_prepass_out *out)
 {
@@ -504,9 +524,12 @@ double refdrv_prepass(refdrv **drv, int n_threads, const uint8_t *const cur[3], 
     sh.row0 = ctu_rows > 0 ? ctu_row0 : 0; sh.rows = ctu_rows > 0 ? ctu_rows : sh.ctu_rows;
     for (int c = 0; c < 3; c++) {
         const int pw = c ? w / 2 : w, ph = c ? h / 2 : h, pad = c ? 72 : 144;      /* room for partial CTUs at the bottom/right edge */
-        sh.cur[c] = rp_make_plane(cur[c], pw, ph, pad, &sh.stride[c], &alloc[c]);
-        sh.ref[c] = rp_make_plane(ref[c], pw, ph, pad, &sh.stride[c], &alloc[3 + c]);
+        (void)ph;
+        sh.cur[c] = rp_alloc_plane(pw, c ? h / 2 : h, pad, &sh.stride[c], &alloc[c]);
+        sh.ref[c] = rp_alloc_plane(pw, c ? h / 2 : h, pad, &sh.stride[c], &alloc[3 + c]);
+        sh.cur8[c] = cur[c]; sh.ref8[c] = ref[c];
     }
+    pthread_barrier_init(&sh.planes_ready, NULL, (unsigned)n_threads);
     for (int p = 0; p < 5; p++) for (int c = 0; c < 3; c++) {
         if (c > 0 && p == 4) continue;
         const int s = 64 >> rp_pass_depth(p), tu = c ? rp_pass_tu[p] / 2 : rp_pass_tu[p], sc = c ? s / 2 : s;
@@ -523,6 +546,7 @@ double refdrv_prepass(refdrv **drv, int n_threads, const uint8_t *const cur[3], 
     }
     for (int t = 0; t < n_threads; t++) { wk[t].sh = &sh; wk[t].drv = drv[t]; wk[t].tid = t; pthread_create(&wk[t].th, NULL, rp_thread, &wk[t]); }
     for (int t = 0; t < n_threads; t++) pthread_join(wk[t].th, NULL);
+    pthread_barrier_destroy(&sh.planes_ready);
     for (int i = 0; i < 6; i++) free(alloc[i]);
     for (int p = 0; p < 5; p++) for (int c = 0; c < 3; c++) free(sh.tu_index[p][c]);
     free(wk);

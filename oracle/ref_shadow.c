@@ -5,6 +5,7 @@
  * call -- function, arguments, operands -- on which the GPU path and the CPU path ever disagree, which a comparison of finished
  * bitstreams cannot (tools/flake_hunt.py loops it to look for rare, timing-dependent differences).
  */
+#define _GNU_SOURCE
 #include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -37,12 +38,14 @@ typedef struct shadow_report {
     long first_call;              /* ordinal of the first mismatching call */
     int first_at;                 /* index of the first differing output element */
     int32_t cpu_val, gpu_val;
+    long per_fn[12];              /* mismatching calls per function (index = fn) */
 } shadow_report;
 static shadow_report S;
 static __thread int16_t t_a[SH_MAX_DUMP], t_b[SH_MAX_DUMP];
 
 static void report(int fn, const int *args, int n_args, int at, int cpu, int gpu)
 {
+    __atomic_add_fetch(&S.per_fn[fn], 1, __ATOMIC_RELAXED);
     if (__atomic_add_fetch(&S.mismatches, 1, __ATOMIC_RELAXED) != 1) return;
     S.first_fn = fn; S.first_call = S.calls; S.first_at = at; S.cpu_val = cpu; S.gpu_val = gpu;
     memset(S.args, 0, sizeof S.args);
@@ -153,3 +156,60 @@ void refdrv_install_shadow_table(void *funcs_table, void *user)
 }
 void *refdrv_install_shadow_table_addr(void) { return (void *)refdrv_install_shadow_table; }
 void refdrv_shadow_report(shadow_report *out) { *out = S; }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Range audit (CPU only): which of the reference's own table calls hand sad / ssd16b operands that are NOT 8-bit video?  There
+ * the SSE4.2 functions (16-bit lanes, saturating adds, hmr_sse42_functions_pixel.c:353-435) and the arithmetic definition
+ * (hmr_motion_intra.c:51) give different numbers, so a bit-exact replacement is only defined on video-range operands
+ * (SURVEY.md 8a a1).  The audit forwards every call to the SSE4.2 function, counts the calls with an operand outside
+ * [-255, 510] (the widest range real data reaches: bi-prediction's 2*orig - pred) and keeps the call stack of the first one.
+ * ------------------------------------------------------------------------------------------------------------ */
+#include <execinfo.h>
+typedef struct audit_report { long sad_calls, sad_out_of_range, ssd_calls, ssd_out_of_range; int first_size, first_min, first_max; long first_call; char first_stack[1024]; } audit_report;
+static audit_report A;
+
+static int block_range(const int16_t *p, int stride, int n, int *mn, int *mx)
+{
+    int lo = 32767, hi = -32768;
+    for (int r = 0; r < n; r++) for (int c = 0; c < n; c++) { const int v = p[r * stride + c]; if (v < lo) lo = v; if (v > hi) hi = v; }
+    if (lo < *mn) *mn = lo;
+    if (hi > *mx) *mx = hi;
+    return lo < -255 || hi > 510;
+}
+static void audit_note(int size, int mn, int mx, long ordinal)
+{
+    void *bt[16];
+    if (A.first_stack[0]) return;
+    A.first_size = size; A.first_min = mn; A.first_max = mx; A.first_call = ordinal;
+    const int n = backtrace(bt, 16);
+    size_t used = 0;
+    for (int i = 1; i < n && used + 64 < sizeof A.first_stack; i++) {
+        Dl_info info;
+        const char *name = (dladdr(bt[i], &info) && info.dli_sname) ? info.dli_sname : "?";
+        used += (size_t)snprintf(A.first_stack + used, sizeof A.first_stack - used, "%s%s", i > 1 ? " < " : "", name);
+    }
+}
+static uint32_t au_sad(int16_t *src, uint32_t ss, int16_t *pred, uint32_t ps, int size)
+{
+    int mn = 32767, mx = -32768;
+    A.sad_calls++;
+    if (A.sad_calls == 1 && getenv("HB_AUDIT_FIRST_CALL")) { block_range(src, (int)ss, size, &mn, &mx); block_range(pred, (int)ps, size, &mn, &mx); audit_note(size, mn, mx, 1); }
+    if (block_range(src, (int)ss, size, &mn, &mx) | block_range(pred, (int)ps, size, &mn, &mx)) { A.sad_out_of_range++; audit_note(size, mn, mx, A.sad_calls); }
+    return sse_aligned_sad(src, ss, pred, ps, size);
+}
+static uint32_t au_ssd(int16_t *src, uint32_t ss, int16_t *pred, uint32_t ps, int size)
+{
+    int mn = 32767, mx = -32768;
+    A.ssd_calls++;
+    if (block_range(src, (int)ss, size, &mn, &mx) | (ps ? block_range(pred, (int)ps, size, &mn, &mx) : 0)) A.ssd_out_of_range++;
+    return sse_aligned_ssd16b(src, ss, pred, ps, size);
+}
+void refdrv_install_audit_table(void *funcs_table, void *user)
+{
+    low_level_funcs_t *f = (low_level_funcs_t *)funcs_table;
+    (void)user;
+    memset(&A, 0, sizeof A);
+    f->sad = au_sad; f->ssd16b = au_ssd;
+}
+void *refdrv_install_audit_table_addr(void) { return (void *)refdrv_install_audit_table; }
+void refdrv_audit_report(audit_report *out) { *out = A; }

@@ -20,7 +20,7 @@ class CuHookCfg(C.Structure):            # user data of refdrv_install_cu_hooks 
 
 class ShadowReport(C.Structure):         # shadow_report, oracle/ref_shadow.c
     _fields_ = [("calls", C.c_long), ("mismatches", C.c_long), ("first_fn", C.c_int), ("args", C.c_int * 12), ("first_call", C.c_long),
-                ("first_at", C.c_int), ("cpu_val", C.c_int32), ("gpu_val", C.c_int32)]
+                ("first_at", C.c_int), ("cpu_val", C.c_int32), ("gpu_val", C.c_int32), ("per_fn", C.c_long * 12)]
 
 
 def make_yuv(w, h, nf, seed=21):

@@ -404,7 +404,10 @@ def ref_intra_presearch(luma, jobs, adi, adi_off, n_threads=1):
     return secs, sads
 
 
-def ref_prepass(cur, ref_planes, w, h, qp=32, avg_dist=650.0, n_threads=1, band=(0, 0), sign_hiding=1, want_pred=True):
+_rp_out_cache = {}
+
+
+def ref_prepass(cur, ref_planes, w, h, qp=32, avg_dist=650.0, n_threads=1, band=(0, 0), sign_hiding=1, want_pred=True, reuse_outputs=False):
     """cur / ref_planes: (y, u, v) uint8 planes.  Returns (seconds, dict) with the GPU library's output layouts."""
     _, D = ref()
     D.refdrv_prepass.restype = C.c_double
@@ -422,6 +425,15 @@ def ref_prepass(cur, ref_planes, w, h, qp=32, avg_dist=650.0, n_threads=1, band=
     ref_planes = [np.ascontiguousarray(p) for p in ref_planes]
     cp = (C.c_void_p * 3)(*[p.ctypes.data for p in cur])
     rp = (C.c_void_p * 3)(*[p.ctypes.data for p in ref_planes])
+    # output arrays are allocated once per shape and reused (bench.py times this call in a loop: ~80 MB of np.zeros per frame
+    # would be timed as the reference's work otherwise); results of a previous call with the same shape are overwritten
+    ck = (w, h, tuple(band), bool(want_pred))
+    if reuse_outputs and ck in _rp_out_cache:
+        out, res = _rp_out_cache[ck]
+        for a in res["me"]:
+            a["sad"] = 0xFFFFFFFF
+        secs = D.refdrv_prepass(handles, n_threads, cp, rp, w, h, qp, avg_dist, band[0], band[1], C.byref(out))
+        return secs, res
     out = _RpOut()
     res = {"me": [], "tu": {}, "coeff": {}, "recon": [], "pred": []}
     cc, cr = (w + 63) // 64, (h + 63) // 64
@@ -448,5 +460,7 @@ def ref_prepass(cur, ref_planes, w, h, qp=32, avg_dist=650.0, n_threads=1, band=
             if n:
                 out.tu[p][c] = res["tu"][(p, c)].ctypes.data
                 out.coeff[p][c] = res["coeff"][(p, c)].ctypes.data
+    if reuse_outputs:
+        _rp_out_cache[ck] = (out, res)
     secs = D.refdrv_prepass(handles, n_threads, cp, rp, w, h, qp, avg_dist, band[0], band[1], C.byref(out))
     return secs, res

@@ -27,6 +27,20 @@ def test_sad_ssd(ctx):
         off = int(rng.integers(0, 900))
         assert ll.sad(a, 64, b, 160, n, pred_off=off) == O.orc_sad(ptr(a), 64, ptr(b, off), 160, n)
         assert ll.ssd16b(a, 64, b, 160, n, pred_off=off) == O.orc_ssd16b(ptr(a), 64, ptr(b, off), 160, n)
+    # operands that are not video: the reference's 64x64 intra mode search hands sad() wrapped 16-bit predictions
+    # (hmr_motion_intra.c:1130), where the SSE4.2 lane arithmetic decides the value -- the drop-ins reproduce it exactly
+    O.orc_sad_sse.restype = C.c_uint32; O.orc_ssd16b_sse.restype = C.c_uint32
+    for it in range(100):
+        n = int(rng.choice([4, 8, 16, 32, 64]))
+        a = aligned_i16(64 * 64); b = aligned_i16(160 * 100)
+        if it % 2:
+            a[:] = rng.integers(-32768, 32768, a.size); b[:] = rng.integers(-32768, 32768, b.size)
+            a[::97] = -32768; b[::89] = 32767
+        else:
+            a[:] = rng.integers(0, 256, a.size); b[:] = rng.integers(-30000, 30000, b.size)
+        off = int(rng.integers(0, 900))
+        assert ll.sad(a, 64, b, 160, n, pred_off=off) == O.orc_sad_sse(ptr(a), 64, ptr(b, off), 160, n), (it, n)
+        assert ll.ssd16b(a, 64, b, 160, n, pred_off=off) == O.orc_ssd16b_sse(ptr(a), 64, ptr(b, off), 160, n), (it, n)
     # pred_stride = 0 against a zero row (hmr_motion_inter.c:94)
     z = np.zeros(256, np.int16)
     a = aligned_i16(64 * 64); a[:] = rng.integers(-255, 256, a.size)

@@ -15,6 +15,38 @@ def test_reference_selects_sse42_table():
     assert D.refdrv_sse_selected(refdrv()) == 1
 
 
+def test_sad_ssd_sse_lane_arithmetic_on_the_full_int16_range():
+    """the encoder also calls sad / ssd16b on operands that are not 8-bit video (the wrapped 16-bit predictions of its 64x64 intra mode
+    search, hmr_motion_intra.c:1130): there the SSE4.2 lanes -- wrapping differences, wrapping or saturating 16-bit accumulation -- decide
+    the value.  orc_sad_sse / orc_ssd16b_sse restate exactly that; on video-range data they equal the plain sums."""
+    O = oracle(); R, _ = ref()
+    O.orc_sad_sse.restype = C.c_uint32; O.orc_ssd16b_sse.restype = C.c_uint32
+    rng = np.random.default_rng(321)
+    differs = 0
+    for it in range(600):
+        n = int(rng.choice([4, 8, 16, 32, 64]))
+        a = aligned_i16(64 * 64); b = aligned_i16(80 * 80)
+        kind = it % 4
+        if kind == 0:        # anything an int16 can hold, extremes included
+            a[:] = rng.integers(-32768, 32768, a.size); b[:] = rng.integers(-32768, 32768, b.size)
+            a[::97] = -32768; b[::89] = 32767
+        elif kind == 1:      # video against a wrapped prediction (what the 64x64 intra search produces)
+            a[:] = rng.integers(0, 256, a.size); b[:] = rng.integers(-30000, 30000, b.size)
+        elif kind == 2:      # moderate overflow: lanes wrap / saturate only partly
+            a[:] = rng.integers(0, 256, a.size); b[:] = rng.integers(-3000, 3000, b.size)
+        else:                # video
+            a[:] = rng.integers(0, 256, a.size); b[:] = rng.integers(0, 256, b.size)
+        off = int(rng.integers(0, 8))
+        sse = R.sse_aligned_sad(ptr(a), 64, ptr(b, off), 80, n)
+        assert sse == O.orc_sad_sse(ptr(a), 64, ptr(b, off), 80, n), (kind, n)
+        assert R.sse_aligned_ssd16b(ptr(a), 64, ptr(b, off), 80, n) == O.orc_ssd16b_sse(ptr(a), 64, ptr(b, off), 80, n), (kind, n)
+        if kind == 3:
+            assert sse == O.orc_sad(ptr(a), 64, ptr(b, off), 80, n)
+        else:
+            differs += sse != O.orc_sad(ptr(a), 64, ptr(b, off), 80, n)
+    assert differs > 100          # the lane arithmetic really matters off the video range
+
+
 def test_pixel_interp_transform_random():
     O = oracle(); R, _ = ref()
     rng = np.random.default_rng(100)

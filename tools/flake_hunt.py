@@ -20,41 +20,50 @@ import numpy as np
 import homerhevc_b200 as hb
 from _encode import CuHookCfg, TableHook, cu_hooks_off, describe_mismatch, encode, hook_addr, make_yuv, shadow_report
 
+FN_NAMES = ["-", "sad", "ssd16b", "predict", "reconst", "interpolate_luma", "interpolate_chroma", "transform", "itransform", "quant", "inv_quant", "-"]
 n_iter = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 max_seconds = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-w, h, nf = 192, 128, 3
+w, h, nf = (int(v) for v in os.environ.get("HB_FLAKE_CLIP", "192x128x3").split("x"))
 L = hb.load_library()
 yuv = make_yuv(w, h, nf)
 gold_bs, gold_rec, _ = encode(w, h, yuv, nf)
-out = {"clip": f"{w}x{h}x{nf} IPP", "iterations": n_iter, "poison": os.environ.get("HB_POISON_STAGING", "0"), "shadow": {"calls": 0, "mismatches": 0, "first": None},
+INSTRUMENTS = os.environ.get("HB_FLAKE_INSTRUMENTS", "cpu,shadow,table,hooks").split(",")
+out = {"clip": f"{w}x{h}x{nf} IPP", "iterations": n_iter, "instruments": INSTRUMENTS, "poison": os.environ.get("HB_POISON_STAGING", "0"), "shadow": {"calls": 0, "mismatches": 0, "first": None},
        "table": {"mismatches": 0, "detail": []}, "hooks": {"mismatches": 0, "detail": []}, "cpu_repeat_mismatches": 0}
 t0 = time.time()
 for it in range(n_iter):
     # the CPU side alone must stay deterministic under the same polling pattern
-    b, r, _ = encode(w, h, yuv, nf)
-    out["cpu_repeat_mismatches"] += int(b != gold_bs or not np.array_equal(r, gold_rec))
-    bs, rec, _ = encode(w, h, yuv, nf, hook=hook_addr("refdrv_install_shadow_table"), user=TableHook(L._handle, 31))
+    if "cpu" in INSTRUMENTS:
+        b, r, _ = encode(w, h, yuv, nf)
+        out["cpu_repeat_mismatches"] += int(b != gold_bs or not np.array_equal(r, gold_rec))
+    if "shadow" in INSTRUMENTS:
+        bs, rec, _ = encode(w, h, yuv, nf, hook=hook_addr("refdrv_install_shadow_table"), user=TableHook(L._handle, 31))
+        assert bs == gold_bs, "the shadow table feeds the CPU results back: its stream must be the reference's"
     rep = shadow_report()
     out["shadow"]["calls"] += int(rep.calls); out["shadow"]["mismatches"] += int(rep.mismatches)
+    for k, name in enumerate(FN_NAMES):
+        if rep.per_fn[k]:
+            out["shadow"].setdefault("per_fn", {})[name] = out["shadow"].get("per_fn", {}).get(name, 0) + int(rep.per_fn[k])
     if rep.mismatches and out["shadow"]["first"] is None:
         out["shadow"]["first"] = {"iteration": it, "fn": int(rep.first_fn), "args": list(rep.args), "call": int(rep.first_call), "at": int(rep.first_at),
                                   "cpu": int(rep.cpu_val), "gpu": int(rep.gpu_val)}
-    assert bs == gold_bs, "the shadow table feeds the CPU results back: its stream must be the reference's"
-    bs, rec, _ = encode(w, h, yuv, nf, hook=hook_addr("refdrv_install_gpu_table"), user=TableHook(L._handle, 31))
-    if bs != gold_bs or not np.array_equal(rec, gold_rec):
-        out["table"]["mismatches"] += 1
-        out["table"]["detail"].append({"iteration": it, "what": describe_mismatch(w, h, bs, rec, gold_bs, gold_rec)})
-    try:
-        bs, rec, _ = encode(w, h, yuv, nf, hook=hook_addr("refdrv_install_cu_hooks"), user=CuHookCfg(L._handle, 31, 1))
-    finally:
-        cu_hooks_off()
-    if bs != gold_bs or not np.array_equal(rec, gold_rec):
-        out["hooks"]["mismatches"] += 1
-        out["hooks"]["detail"].append({"iteration": it, "what": describe_mismatch(w, h, bs, rec, gold_bs, gold_rec)})
+    if "table" in INSTRUMENTS:
+        bs, rec, _ = encode(w, h, yuv, nf, hook=hook_addr("refdrv_install_gpu_table"), user=TableHook(L._handle, 31))
+        if bs != gold_bs or not np.array_equal(rec, gold_rec):
+            out["table"]["mismatches"] += 1
+            out["table"]["detail"].append({"iteration": it, "what": describe_mismatch(w, h, bs, rec, gold_bs, gold_rec)})
+    if "hooks" in INSTRUMENTS:
+        try:
+            bs, rec, _ = encode(w, h, yuv, nf, hook=hook_addr("refdrv_install_cu_hooks"), user=CuHookCfg(L._handle, 31, 1))
+        finally:
+            cu_hooks_off()
+        if bs != gold_bs or not np.array_equal(rec, gold_rec):
+            out["hooks"]["mismatches"] += 1
+            out["hooks"]["detail"].append({"iteration": it, "what": describe_mismatch(w, h, bs, rec, gold_bs, gold_rec)})
     out["done"] = it + 1
     out["seconds"] = round(time.time() - t0, 1)
-    with open(os.path.join(ROOT, "gpurun_out", "flake_hunt.json"), "w") as f:        # after every iteration: a time-out keeps what was done
+    with open(os.path.join(ROOT, "gpurun_out", os.environ.get("HB_FLAKE_OUT", "flake_hunt.json")), "w") as f:        # after every iteration: a time-out keeps what was done
         f.write(json.dumps(out) + "\n")
     if max_seconds and time.time() - t0 > max_seconds:
         break
