@@ -1,23 +1,37 @@
 #!/usr/bin/env python
 """bench.py -- ME+TQ frames/s of the frame-level pre-pass (BASELINE.json metric) on N B200s.
 
-A step = one pass of the hot path over one frame pair: motion search of every PU 64/32/16/8 (parent -> child chain,
-integer walk + half + quarter pel), motion compensation luma + chroma at each size, and the inter T/Q chain over TU
+A step = one pass of the hot path over one frame pair per in-flight stream: motion search of every PU 64/32/16/8 (parent -> child
+chain, integer walk + half + quarter pel), motion compensation luma + chroma at each size, and the inter T/Q chain over TU
 32/32/16/8/4 (+ chroma) with reconstruction.  Workload: synthetic YUV 4:2:0 of SURVEY.md 8(d), IPPP quarter-pel, fixed QP 32.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 720p|1080p|2160p] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 720p|1080p|2160p] [--impl ours|reference] [--mode ...]
 
-N > 1 is launched by torchrun (one rank per GPU); every rank processes its own independent stream of frames
-(GOP-per-GPU batching, BASELINE.json configs[4]; no data-path collective), value = frames of all ranks / max time.
-`--impl reference` times the reference's own CPU functions (oracle/_ref, compiled from /root/reference) over the same
-pre-pass on the host cores of the box; rank 0 only.
+One JSON line (rank 0).  What it carries:
+  value        frames/s of the pre-pass with inputs resident in HBM, independent GOP streams per GPU (weak scaling over N);
+  e2e          the same through the C ABI with HOST buffers, reference picture kept on the device (source up, cost tables / level
+               streams / SAO candidates down, the finished picture becomes the next reference in HBM); the flow that also moves the
+               reference picture over the link is `e2e.host_reference_variant`;
+  roofline     the dominant kernel's ALGORITHMIC integer work (pixel-abs-diffs of the reference's own search pattern +
+               interpolation / transform MACs) / its device time, against the measured integer-op ceiling (tools/int_peak.cu); the HBM
+               view of the same launch under `roofline.hbm`; executed-instruction issue utilisation under `issue_roofline` (only from an
+               ncu profile taken on exactly these kernel sources);
+  bands_2160p  BASELINE.json configs[3]: ONE 3840x2160 frame split into CTU-row bands over the N GPUs, reference halos exchanged
+               over NCCL on the device timeline (strong scaling), with the band tables checked against a whole-frame run in-process;
+  extra_workloads (N = 1)  value / e2e of the other two picture sizes;
+  cpu_baseline (N = 1)  the reference's own functions on the host cores, and its console encoder homer_app in both thread settings.
+`--impl reference` times the reference's CPU implementation of the same path (oracle/_ref, compiled from /root/reference); rank 0 only.
+`--mode encode` times the reference's whole encoder with the batched API in its loop (oracle/ref_hooks.c) next to homer_app.
 """
 import argparse
+import hashlib
 import json
+import math
 import os
 import statistics
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -32,6 +46,9 @@ WORKLOADS = {"720p": (1280, 720), "1080p": (1920, 1080), "2160p": (3840, 2160)}
 QP, AVG_DIST = 32, 650.0
 N_RESIDENT = 16           # distinct frames cycled through so that no step finds its inputs in L2
 L2_BYTES = 126 * 2 ** 20
+N_SM = 148
+# measured on a B200 (tools/int_peak.cu, profiles/int_peak_r01.txt): warp instructions per clock and SM
+PEAK_BOTH_PIPES, PEAK_ONE_PIPE = 3.80, 1.96
 
 
 def measured_peaks():
@@ -40,6 +57,17 @@ def measured_peaks():
             return json.load(f), "measured"
     except Exception:
         return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def kernel_source_sha():
+    """identity of the kernel sources: an ncu profile is only quoted when it was taken on exactly these"""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "homerhevc_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh")):
+            with open(os.path.join(d, name), "rb") as f:
+                h.update(name.encode()); h.update(f.read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -85,16 +113,31 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_name(w, h):
+    return f"{w}x{h} IPPP quarter-pel ME (PU 64/32/16/8) + MC + inter T/Q (TU 32/32/16/8/4), fixed QP {QP}, synthetic YUV420"
+
+
+def bench_config(args, w, h, world, streams):
+    """the SAME dictionary in both arms (ours / --impl reference): the workload, not the implementation"""
+    return {"workload": workload_name(w, h), "qp": QP, "avg_dist": AVG_DIST,
+            "parallelism": f"gop-per-gpu x{world}" if world > 1 else "single gpu",
+            "streams_in_flight_per_gpu": streams,
+            "l2": f"inputs rotate over {N_RESIDENT} resident frame pairs (a 1080p step touches ~114 MiB per stream): no step finds its inputs in the {L2_BYTES // 2**20} MiB L2"}
+
+
+# ---------------------------------------------------------------------------------------------------------------- algorithmic work
 def algorithmic_bytes(pp, w, h):
-    """per-launch algorithmic HBM bytes of every pre-pass kernel (DESIGN.md section 5): each input plane read once,
+    """per-launch algorithmic HBM bytes of every pre-pass kernel (DESIGN.md section 3): each input plane read once,
     each output written once, for the PUs / TUs that launch covers."""
     out = {}
     luma = w * h
+    out["sp"] = luma + 15 * luma                                  # reference luma in, fifteen quarter-pel planes out
     for d in range(4):
         s = 64 >> d
         n_pu = (w // s) * (h // s)
-        out[f"me{s}"] = 2 * luma + 24 * n_pu                    # cur + ref luma (u8) in, one result record per PU out
-        out[f"mc{s}"] = int(1.5 * n_pu * s * s) * 2 + 8 * n_pu  # ref in, pred out (luma + chroma), mv in
+        # cur + ref luma (u8) in, the 16 sub-pel candidate blocks of every PU from the planes, one result record and the luma prediction out
+        out[f"me{s}"] = 2 * luma + 16 * n_pu * s * s + 24 * n_pu + n_pu * s * s
+        out[f"mc{s}"] = int(0.5 * n_pu * s * s) * 2 + 8 * n_pu     # chroma: ref in, pred out, mv in
     for p in range(5):
         for c in range(3):
             t = pp.tu_size(p, c)
@@ -105,8 +148,79 @@ def algorithmic_bytes(pp, w, h):
     return out
 
 
+def algorithmic_ops(pp, w, h):
+    """per-launch algorithmic INTEGER work, independent of how a kernel is written:
+      search   pixel-abs-diffs of the reference's own pattern = (integer probes the walk makes, counted by the kernel itself, + 18
+               sub-pel probes) x N^2 per PU, plus the interpolation MACs of the reference's per-PU plane builders: 13 passes x 8 taps
+               over (N+1) x (N+8) samples (hmr_motion_inter.c:395-562) -- charged to the search launches as SURVEY.md 8(d) defines the
+               work, although this implementation builds the planes once per picture (`sp`: 15 x 8 MAC per sample);
+      T/Q      forward 2-D transform as matrix products 2N MAC per sample, the same again for the inverse of the units that keep
+               levels, + 2 multiplies per sample for quantisation / dequantisation;
+      chroma MC  two 4-tap passes per sample, both planes.
+    -> {kernel: {"pad": .., "mac": .., "packing": ..}}; packing = how many of these operations one lane instruction can carry at best
+    (4 for 8-bit samples: VABSDIFF4 / dp4a; 2 for the 16-bit operands of the transforms: dp2a) and on how many of the two integer pipes."""
+    out = {"sp": {"pad": 0, "mac": 15 * 8 * w * h, "lanes_per_inst": 4, "pipes": PEAK_ONE_PIPE}}     # 3 H + 12 V passes x 8 taps per sample
+    for d in range(4):
+        s = 64 >> d
+        me = pp.fetch_me(d)
+        ok = me["sad"] != 0xFFFFFFFF
+        n_pu = int(ok.sum())
+        probes = int(me["n_probes"][ok].astype(np.int64).sum())
+        out[f"me{s}"] = {"pad": (probes + 18 * n_pu) * s * s, "mac": n_pu * 13 * 8 * (s + 1) * (s + 8), "lanes_per_inst": 4, "pipes": PEAK_BOTH_PIPES}
+        out[f"mc{s}"] = {"pad": 0, "mac": n_pu * 2 * (s // 2) * (s // 2) * 8, "lanes_per_inst": 4, "pipes": PEAK_ONE_PIPE}
+    for p in range(5):
+        for c in range(3):
+            t = pp.tu_size(p, c)
+            if not t:
+                continue
+            res = pp.fetch_tu(p, c)
+            n, coded = len(res), int((res["sum"] > 0).sum() + (res["zeroed"] != 0).sum())
+            out[f"tq{p}{'yuv'[c]}{t}"] = {"pad": 0, "mac": (n + coded) * 2 * t * t * t + 2 * n * t * t, "lanes_per_inst": 2, "pipes": PEAK_ONE_PIPE}
+    return out
+
+
+def int_peak_ops(entry, sm_hz):
+    """operations per second the CUDA cores can retire for this kind of work: SMs x warp-inst/clk x 32 lanes x packed ops per lane"""
+    return N_SM * entry["pipes"] * 32 * entry["lanes_per_inst"] * sm_hz
+
+
+# ---------------------------------------------------------------------------------------------------------------- reference arm
+def homer_app_fps(w, h, n_frames, wpp, engines, seed=5):
+    """the reference's own console encoder (oracle/_ref/homer_app, compiled unmodified) on a synthetic clip: its own fps print"""
+    from homerhevc_b200 import synth
+    exe = os.path.join(ROOT, "oracle", "_ref", "homer_app")
+    if not os.path.exists(exe):
+        return None
+    clip = synth.make_clip(w, h, n_frames, seed=seed)
+    with tempfile.TemporaryDirectory() as td:
+        src, dst = os.path.join(td, "in.yuv"), os.path.join(td, "out.265")
+        with open(src, "wb") as f:
+            for fr in clip:
+                for p in fr:
+                    f.write(p.tobytes())
+        cmd = [exe, "-i", src, "-o", dst, "-widthxheight", f"{w}x{h}", "-gop_size", "1", "-b_frames", "0", "-bitrate_mode", "0", "-qp", str(QP),
+               "-n_frames", str(n_frames), "-n_wpp_threads", str(wpp), "-n_enc_engines", str(engines)]
+        try:
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+            tail = out.stdout.replace("\r", "\n").strip().splitlines()[-1]
+            fps = float(tail.split(":")[-1].split("fps")[0])
+            return {"value": fps, "unit": "frames/s", "frames": n_frames, "n_wpp_threads": wpp, "n_enc_engines": engines,
+                    "stream_bytes": os.path.getsize(dst) if os.path.exists(dst) else None}
+        except Exception as e:
+            return {"value": None, "what": f"failed: {e}"}
+
+
+def homer_app_baseline(w, h, cores):
+    """parity setting (1 engine, WPP off) and throughput setting (WPP threads = CTU rows or cores, 3 engines)"""
+    nf = 12 if (w, h) == WORKLOADS["720p"] else (8 if (w, h) == WORKLOADS["1080p"] else 4)
+    rows = (h + 63) // 64
+    return {"nproc": cores, "cmd": "oracle/_ref/homer_app -gop_size 1 -b_frames 0 -bitrate_mode 0 -qp 32 (fixed QP, IPPP, quarter-pel, all stages incl. CABAC)",
+            "parity": homer_app_fps(w, h, nf, 0, 1), "throughput": homer_app_fps(w, h, 3 * nf, min(rows, max(cores, 1)), 3)}
+
+
 def run_reference(args, w, h, rank, world):
-    """the reference's own CPU functions over the same pre-pass, all host threads; a step = `sample` frames"""
+    """the reference's own CPU functions over the same pre-pass, all host threads; a step = `sample` frames; seconds are the C
+    driver's own clock around its worker threads (output arrays are allocated once, outside)"""
     from homerhevc_b200 import synth
     from _oracle import have_ref, ref_prepass
     if rank != 0:
@@ -118,48 +232,31 @@ def run_reference(args, w, h, rank, world):
     tex = synth.make_texture(w, h)
     frames = [synth.make_frame(tex, w, h, n) for n in range(5)]
     sample = 1 if (w, h) == WORKLOADS["2160p"] else (2 if (w, h) == WORKLOADS["1080p"] else 4)
+
     def step(i):
         t = 0.0
         for k in range(sample):
             j = (i * sample + k) % 4
-            s, _ = ref_prepass(frames[j + 1], frames[j], w, h, QP, AVG_DIST, n_threads=cores, want_pred=False)
+            s, _ = ref_prepass(frames[j + 1], frames[j], w, h, QP, AVG_DIST, n_threads=cores, want_pred=False, reuse_outputs=True)
             t += s
         return t
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, 1)):
         step(i)
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step(i)
-    secs = time.perf_counter() - t0
+    secs = sum(step(i) for i in range(args.steps))
     fps = args.steps * sample / secs
     line = {"impl": "reference", "metric": "ME+TQ frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8/int16/int32", "data": "synthetic",
-            "config": {"workload": workload_name(args, w, h), "frames_per_step": sample, "qp": QP, "avg_dist": AVG_DIST},
+            "vs_baseline": None, "dtype": "u8 samples, int16 residual/levels, int32 accumulate", "data": "synthetic",
+            "config": bench_config(args, w, h, world, max(1, args.streams)),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference",
-                             "sample": f"{sample} frame(s) per step, reference functions via oracle/_ref, {cores} threads, CTUs dealt round-robin"},
+                             "sample": f"{sample} frame(s) per step, the reference's own functions (oracle/_ref: hmr_motion_estimation, hmr_motion_compensation_*, "
+                                       f"predict, encode_inter_cu*), {cores} threads, CTUs dealt round-robin, timed inside the C driver"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    # for context (not the metric): the WHOLE unmodified reference encoder -- mode decision, CABAC, in-loop filters included -- on
-    # the same kind of input, one engine, WPP off, fixed QP (the configuration whose output the parity tests pin)
-    try:
-        import ctypes as C
-        import numpy as np
-        from _oracle import ref
-        _, D = ref()
-        nf = 3
-        clip = synth.make_clip(w, h, nf, seed=5)
-        yuv = np.concatenate([np.concatenate([p.reshape(-1) for p in f]) for f in clip])
-        bs = np.zeros(16 << 20, np.uint8); enc_secs = C.c_double(0)
-        n = D.refdrv_encode_lockstep(w, h, nf, yuv.ctypes.data_as(C.POINTER(C.c_uint8)), QP, 1, 0, -1, bs.ctypes.data_as(C.POINTER(C.c_uint8)), bs.size,
-                                     None, None, None, C.byref(enc_secs))
-        if n > 0 and enc_secs.value > 0:
-            line["whole_encoder"] = {"value": nf / enc_secs.value, "unit": "frames/s", "frames": nf, "bytes": int(n),
-                                     "what": "unmodified reference encoder (homer_lib), IPP, 1 engine, WPP off, fixed QP, all stages"}
-    except Exception as e:
-        line["whole_encoder"] = {"value": None, "what": f"failed: {e}"}
+    line["homer_app"] = homer_app_baseline(w, h, cores)
     print(json.dumps(line))
 
 
+# ---------------------------------------------------------------------------------------------------------------- side modes
 def run_intra(args, w, h, rank, world, local, hb, synth):
     """the intra mode pre-search of one picture -- SADs of all 35 modes for every 32/16/8/4 luma block, reference
     samples from the original picture -- through hb_intra_run (host job list and samples in, host SAD table out, copies inside
@@ -173,7 +270,6 @@ def run_intra(args, w, h, rank, world, local, hb, synth):
     from homerhevc_b200.lib import presearch_records
     prep = [presearch_jobs(f[0]) for f in frames]
     rec = presearch_records(prep[0][0])                     # the block list is the same for every frame of this size
-    # samples and SAD table in pinned host memory, as an encoder would keep them
     adi_pin = [ctx.pinned(p[1].nbytes).view(np.int16) for p in prep]
     for a, p in zip(adi_pin, prep):
         a[:] = p[1]
@@ -192,7 +288,7 @@ def run_intra(args, w, h, rank, world, local, hb, synth):
     jobs, adi, off = prep[(steps - 1) % 4]
     line = {"metric": "intra 35-mode pre-search frames/s", "value": steps / secs, "unit": "frames/s", "n_gpus": 1, "steps": steps, "warmup": max(3, args.warmup),
             "ms_per_step": secs / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 samples, int32 accumulate",
-            "data": "synthetic", "config": {"workload": workload_name(args, w, h) + ", every 32/16/8/4 luma block, reference samples from the original picture",
+            "data": "synthetic", "config": {"workload": workload_name(w, h) + ", every 32/16/8/4 luma block, reference samples from the original picture",
                                             "blocks": int(len(jobs)), "modes": 35, "timing": "wall clock around the blocking API call, host buffers in and out"},
             "e2e": {"value": steps / secs, "unit": "frames/s", "h2d_bytes_per_step": int(jobs.nbytes * 2 + adi.nbytes), "d2h_bytes_per_step": int(sads.nbytes)},
             "gpu_launches": steps}
@@ -263,120 +359,156 @@ def run_finalise(args, w, h, rank, world, local, hb, synth):
     print(json.dumps(line))
 
 
-def run_bands(args, w, h, rank, world, local, torch, dist, hb, synth, barrier):
-    """strong scaling of ONE stream of frames: every GPU owns a CTU-row band; per frame the reference rows a band needs from
-    its neighbours (68 luma / 36 chroma rows per side) are exchanged over NCCL, then the band's pre-pass runs"""
+def run_encode(args, w, h, rank):
+    """the reference's WHOLE encoder (host mode decision, CABAC, in-loop filters: unmodified) with the batched GPU API in its loop
+    (oracle/ref_hooks.c: hb_enc_me / hb_enc_predict / hb_enc_tq per coding unit, per-call table for the rest) in lock step, its
+    output compared byte for byte with the unmodified encoder's, next to homer_app in both thread settings.  Rank 0 only."""
+    if rank != 0:
+        return
+    import homerhevc_b200 as hb
+    from _encode import CuHookCfg, cu_hooks_off, encode, hook_addr, make_yuv
+    from _oracle import have_ref
+    if not have_ref():
+        print(json.dumps({"metric": "encoder frames/s", "unavailable": "oracle/_ref (compiled reference) is not in this tree"}))
+        return
+    nf = max(3, min(args.steps, 10))
+    L = hb.load_library()
+    yuv = make_yuv(w, h, nf)
+    gold_bs, gold_rec, t_cpu = encode(w, h, yuv, nf)
+    cfg = CuHookCfg(L._handle, 31, 1)
+    try:
+        bs, rec, t_gpu = encode(w, h, yuv, nf, hook=hook_addr("refdrv_install_cu_hooks"), user=cfg)
+    finally:
+        cnt = cu_hooks_off()
+    cores = len(os.sched_getaffinity(0))
+    line = {"metric": "encoder frames/s (whole encode, host decisions + CABAC on the CPU, ME / MC / inter T/Q through the batched GPU API per coding unit)",
+            "value": nf / t_gpu, "unit": "frames/s", "n_gpus": 1, "steps": nf, "warmup": 0, "ms_per_step": 1e3 * t_gpu / nf, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8 samples, int16 residual/levels", "data": "synthetic",
+            "config": {"workload": f"{w}x{h} IPPP quarter-pel, fixed QP {QP}, {nf} frames, 1 engine, WPP off, lock step", "hook_calls": cnt},
+            "identical_stream": bool(bs == gold_bs and np.array_equal(rec, gold_rec)), "stream_bytes": len(gold_bs),
+            "e2e": {"value": nf / t_gpu, "unit": "frames/s", "h2d_bytes_per_step": int(2 * w * h * 3), "d2h_bytes_per_step": 0,
+                    "note": "one blocking GPU round trip per hmr_motion_estimation / motion compensation / transform unit call: launch latency, not throughput, sets this number"},
+            "gpu_launches": int(cnt["me"] + 3 * cnt["mc"] + 2 * cnt["tq"]),
+            "cpu_baseline": {"value": nf / t_cpu, "unit": "frames/s", "cores": 1, "kind": "reference",
+                             "sample": f"the same {nf} frames through the unmodified reference library in lock step, 1 engine, WPP off"},
+            "homer_app": homer_app_baseline(w, h, cores)}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------- bands (configs[3])
+def measure_bands(args, rank, world, local, torch, dist, hb, synth, barrier, steps):
+    """BASELINE.json configs[3]: 3840x2160 frames split into CTU-row bands over the GPUs, the reference rows a band needs from the
+    other bands (68 luma / 36 chroma rows per side) exchanged over NCCL on the device timeline before every frame's search.
+    Strong scaling: the job (S streams x K frames of 2160p) is fixed, every GPU does its band of every frame.  Also checks, in this
+    process, that the band tables equal the rows of a whole-frame run on the exchanged reference."""
     from homerhevc_b200 import bands
-    ctx = hb.Context(local)
-    tex = synth.make_texture(w, h)
-    n_pairs = 4
-    host = [synth.make_frame(tex, w, h, n) for n in range(n_pairs + 1)]
-    frames = [hb.Frame(ctx, w, h) for _ in range(n_pairs + 1)]
-    for f, p in zip(frames, host):
-        f.upload_u8(*p)
+    w, h = WORKLOADS["2160p"]
     ctu_rows = (h + 63) // 64
     row0, nrows = bands.band_ctu_rows(ctu_rows, world, rank)
-    pp = hb.Prepass(ctx, w, h, qp=QP, use_graph=1, band=(row0, nrows))
-    ex = bands.FrameHaloExchanger(torch, dist, ctx, w, h, world, rank, torch.device("cuda", local)) if world > 1 else None
+    dev = torch.device("cuda", local)
+    tex = synth.make_texture(w, h)
+    n_pairs = 3
+    host = [synth.make_frame(tex, w, h, n) for n in range(n_pairs + 1)]
+    out = {}
+    for S in (1, 8):
+        slots = []
+        for k in range(S):
+            c = hb.Context(local)
+            frames = [hb.Frame(c, w, h) for _ in range(n_pairs + 1)]
+            for f, p in zip(frames, host):
+                # every rank holds only ITS rows of a reference picture (it reconstructed them); the rest arrives over NVLink
+                y0, y1 = bands.band_sample_rows(h, ctu_rows, world, rank)
+                own = [np.zeros_like(p[0]), np.zeros_like(p[1]), np.zeros_like(p[2])]
+                own[0][y0:y1] = p[0][y0:y1]; own[1][y0 // 2:y1 // 2] = p[1][y0 // 2:y1 // 2]; own[2][y0 // 2:y1 // 2] = p[2][y0 // 2:y1 // 2]
+                f.upload_u8(*own)
+            pp = hb.Prepass(c, w, h, qp=QP, use_graph=1, band=(row0, nrows))
+            ex = bands.FrameHaloExchanger(torch, dist, c, w, h, world, rank, dev) if world > 1 else None
+            # the current picture is read inside the band only, so the banded upload above is all a rank needs of it
+            slots.append({"ctx": c, "frames": frames, "pp": pp, "ex": ex})
 
-    def step(i):
-        j = i % n_pairs
-        if ex:
-            ex.exchange(frames[j])            # the reference of this frame: halos from the neighbours over NVLink
-        pp.run(frames[j + 1], frames[j], AVG_DIST)
+        def step(i):
+            for sl in slots:
+                j = i % n_pairs
+                if sl["ex"]:
+                    sl["ex"].exchange(sl["frames"][j])        # queued on the context's stream: export -> NCCL send/recv -> import -> border
+                sl["pp"].run(sl["frames"][j + 1], sl["frames"][j], AVG_DIST)
 
-    for i in range(max(args.warmup, n_pairs)):
-        step(i)
-    ctx.sync()
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step(i)
-    ctx.sync()
-    barrier()
-    ms = (time.perf_counter() - t0) * 1e3
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
-    if rank == 0:
-        print(json.dumps({"metric": "ME+TQ frames/s", "value": args.steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-                          "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                          "dtype": "u8 samples, int16 residual/levels, int32 accumulate", "data": "synthetic",
-                          "config": {"workload": workload_name(args, w, h), "parallelism": f"ctu-row bands x{world}, NCCL halo exchange",
-                                     "halo_rows": {"luma": bands.HALO_LUMA, "chroma": bands.HALO_CHROMA},
-                                     "halo_bytes_sent_per_frame_rank0": ex.bytes_per_exchange if ex else 0,
-                                     "timing": "wall clock between device-synchronised barriers (host drives the NCCL exchange)"}}))
+        def sync_all():
+            for sl in slots:
+                sl["ctx"].sync()
+            torch.cuda.synchronize()
 
-
-def workload_name(args, w, h):
-    return f"{w}x{h} IPPP quarter-pel ME (PU 64/32/16/8) + MC + inter T/Q (TU 32/32/16/8/4), fixed QP {QP}, synthetic YUV420"
-
-
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=16, help="independent GOP streams in flight per GPU")
-    ap.add_argument("--mode", default="gops", choices=["gops", "bands", "intra", "finalise"],
-                    help="gops: independent GOP streams per GPU (default, weak scaling); bands: one frame split into CTU-row bands "
-                         "across the GPUs with an NCCL halo exchange of the reference (BASELINE.json configs[3], strong scaling)")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    w, h = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-
-    if args.impl == "reference":
-        if args.steps > 20:
-            args.steps, args.warmup = 5, 1
-        run_reference(args, w, h, rank, world)
-        return
-
-    import torch
-    import torch.distributed as dist
-    import homerhevc_b200 as hb
-    from homerhevc_b200 import synth
-
-    if os.environ.get("HB_PIN_CPUS") == "1" and world > 1:
-        cpus = sorted(os.sched_getaffinity(0))
-        per = max(1, len(cpus) // world)
-        os.sched_setaffinity(0, set(cpus[local * per:(local + 1) * per]))
-    if os.environ.get("HB_BLOCKING") == "1":
-        import ctypes
-        cu = ctypes.CDLL("libcuda.so.1")
-        cu.cuInit(0)
-        print("blocking flags rc", cu.cuDevicePrimaryCtxSetFlags_v2(local, 4), file=sys.stderr)
-    if world > 1:
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
+        for i in range(max(3, n_pairs)):
+            step(i)
+        sync_all()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            step(i)
+        sync_all()
+        ms = (time.perf_counter() - t0) * 1e3
+        barrier()
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        out[f"streams_{S}"] = {"value": S * steps / (ms * 1e-3), "unit": "frames/s", "ms_per_frame": ms / (S * steps), "frames": S * steps}
+        if S == 1:
+            # parity inside the run: this rank's band tables against the same rows of a whole-frame pre-pass on a complete reference
+            sl = slots[0]
+            whole_ref, whole_cur = hb.Frame(sl["ctx"], w, h), hb.Frame(sl["ctx"], w, h)
+            whole_ref.upload_u8(*host[0]); whole_cur.upload_u8(*host[1])
+            if sl["ex"]:
+                sl["ex"].exchange(sl["frames"][0])
+            sl["pp"].run(sl["frames"][1], sl["frames"][0], AVG_DIST)
+            sl["ctx"].sync()
+            band_me = [sl["pp"].fetch_me(d) for d in range(4)]
+            band_tu = {(p, c): sl["pp"].fetch_tu(p, c) for p in range(5) for c in range(3) if sl["pp"].tu_size(p, c)}
+            band_xy = {k: sl["pp"].tu_xy(*k) for k in band_tu}
+            full = hb.Prepass(sl["ctx"], w, h, qp=QP, use_graph=0)
+            full.run(whole_cur, whole_ref, AVG_DIST)
+            sl["ctx"].sync()
+            mism = 0
+            for d in range(4):
+                s = 64 >> d
+                fm = full.fetch_me(d)
+                gw = ((w + 63) // 64) * (64 // s)
+                rows_lo, rows_hi = row0 * (64 // s), (row0 + nrows) * (64 // s)
+                a = band_me[d].reshape(-1, gw)[rows_lo:rows_hi]; b = fm.reshape(-1, gw)[rows_lo:rows_hi]
+                mism += int((a.tobytes() != b.tobytes()))
+            for k, res in band_tu.items():
+                if not len(res):
+                    continue
+                fxy = np.asarray(full.tu_xy(*k), dtype=np.int64).reshape(-1, 2); fres = full.fetch_tu(*k)
+                bxy = np.asarray(band_xy[k], dtype=np.int64).reshape(-1, 2)
+                fkey, bkey = fxy[:, 1] * 65536 + fxy[:, 0], bxy[:, 1] * 65536 + bxy[:, 0]
+                order = np.argsort(fkey)
+                idx = order[np.searchsorted(fkey[order], bkey)]
+                mism += int(not np.array_equal(fkey[idx], bkey) or res.tobytes() != fres[idx].tobytes())
+            if world > 1:
+                t = torch.tensor([mism], dtype=torch.int64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                mism = int(t.item())
+            out["mismatches"] = mism
+            out["parity"] = "every rank: ME tables of its band rows (4 depths) and TU records (13 passes x planes) of a band run on the exchanged reference == the same rows of a whole-frame run on the complete reference"
+            out["halo_bytes_sent_per_frame_rank0"] = sl["ex"].bytes_per_exchange if sl["ex"] else 0
+            full.close(); whole_ref.close(); whole_cur.close()
+        for sl in slots:
+            sl["pp"].close()
+            for f in sl["frames"]:
+                f.close()
+            sl["ctx"].close()
+    out.update({"n_gpus": world, "scaling": "strong", "workload": workload_name(w, h),
+                "parallelism": f"ctu-row bands x{world}: rank r owns CTU rows [{row0}, {row0 + nrows}) of {ctu_rows}; halo exchange by grouped NCCL send/recv ordered on the library's stream (no host wait)",
+                "halo_rows": {"luma": bands.HALO_LUMA, "chroma": bands.HALO_CHROMA},
+                "timing": "wall clock between device-synchronised barriers, MAX over ranks"})
+    return out
 
-    if args.mode == "finalise":
-        run_finalise(args, w, h, rank, world, local, hb, synth)
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    if args.mode == "intra":
-        run_intra(args, w, h, rank, world, local, hb, synth)
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    if args.mode == "bands":
-        run_bands(args, w, h, rank, world, local, torch, dist, hb, synth, barrier)
-        if world > 1:
-            dist.destroy_process_group()
-        return
 
+# ---------------------------------------------------------------------------------------------------------------- the main measurement
+def measure_workload(args, w, h, rank, world, local, torch, dist, hb, synth, barrier, steps, warmup, n_slots, full):
+    """value (resident inputs, device-timed), e2e (host buffers, device-resident reference picture) and -- full only -- the other
+    e2e variants and the per-kernel profile of one picture size"""
     ctx = hb.Context(local)
     tex = synth.make_texture(w, h)
     # every rank works on its own stream of frames (its own GOP): same texture, different pan phase
@@ -393,15 +525,13 @@ def main():
     for f, p in zip(resident, pinned):
         f.upload_u8(*p)
     pp = hb.Prepass(ctx, w, h, qp=QP, use_graph=1)
-    out_bytes = pp.output_bytes()
-    out_pin = ctx.pinned(out_bytes)
     ctx.sync()
 
-    # N_SLOTS independent streams of frames (GOPs, BASELINE.json configs[4]) are in flight per GPU: each has its own context
+    # n_slots independent streams of frames (GOPs, BASELINE.json configs[4]) are in flight per GPU: each has its own context
     # (CUDA stream), pre-pass plan and output buffers, so the search chain of one frame overlaps the T/Q tail of another
-    N_SLOTS, LAMBDA = max(1, args.streams), 60
+    LAMBDA = 60
     slots = []
-    for k in range(N_SLOTS):
+    for k in range(n_slots):
         c = hb.Context(local)
         spp = hb.Prepass(c, w, h, qp=QP, use_graph=1, compact_tables=2)    # compact ME records + one cost record per coding unit on the wire (e2e); `value` never fetches
         n_ctus = spp.num_ctus()
@@ -423,7 +553,7 @@ def main():
     # in-flight streams are ordered after the start event and before the stop event on the device)
     for i in range(N_RESIDENT):          # one-time CUDA graph capture per (stream, cur, ref), outside warm-up and timing
         step_resident(i)
-    for i in range(args.warmup):
+    for i in range(warmup):
         step_resident(i)
     sync_all()
     barrier()
@@ -433,7 +563,7 @@ def main():
     ctx.timer_begin()
     for sl in slots:
         sl["ctx"].wait(ctx)
-    for i in range(args.steps):
+    for i in range(steps):
         step_resident(i)
     for sl in slots:
         ctx.wait(sl["ctx"])
@@ -441,60 +571,63 @@ def main():
     launches = sum(sl["ctx"].launch_count() for sl in slots) - l0
     barrier()
     clocks = sampler.stop()
+    # ---- one dependent IPPP chain (a single stream, each frame queued behind the previous one): what one encoder instance sees
+    one = slots[0]
+    one["ctx"].timer_begin()
+    n_chain = max(8, min(steps, 64))
+    for i in range(n_chain):
+        one["pp"].run(resident[i % N_RESIDENT + 1], resident[i % N_RESIDENT], AVG_DIST)
+    chain_ms = one["ctx"].timer_end()
+    barrier()
 
-    # ---- e2e: the call sequence a host encoder makes, with HOST buffers, per frame:
-    #   upload cur + ref (pinned, async) -> pre-pass -> fetch the cost tables -> host picks a depth per CTU (hb_prepass_select,
-    #   the stand-in for the host's mode decision) -> gather + fetch the reconstruction and coded levels of that choice.
-    # N_SLOTS independent streams of frames (GOPs) are in flight per GPU so that copies, kernels and the host step overlap.
-    def begin_frame(sl, i):
-        j = i % N_RESIDENT
-        sl["pp"].frame_begin(sl["cur"], sl["ref"], pinned[j + 1], pinned[j], AVG_DIST, sl["tables"])
-
-    def finish_frame(sl):
-        sl["d2h"] += sl["pp"].frame_finish(LAMBDA, sl["tables"], sl["sel"], sl["off"], sl["out"]) + sl["tables"].nbytes
-
-    E2E_THREADS = int(os.environ.get("HB_E2E_THREADS", max(1, N_SLOTS // 2)))
+    # ---- e2e: the call sequence a host encoder makes, with HOST buffers, per frame.  One host thread per TWO in-flight streams
+    # (the reference runs one pthread per encoder engine, hmr_encoder_lib.c:1647): a thread queues frame n+1 on its second stream
+    # (the begin call returns at once) before it blocks in the finish call of frame n.  The C calls release the GIL.
+    E2E_THREADS = int(os.environ.get("HB_E2E_THREADS", max(1, n_slots // 2)))
+    flow = {}
 
     def run_e2e(n):
-        # one host thread per TWO in-flight streams (the reference runs one pthread per encoder engine, hmr_encoder_lib.c:1647):
-        # a thread queues frame n+1 on its second stream (hb_prepass_frame_begin returns at once) before it blocks in
-        # hb_prepass_frame_finish of frame n.  The C calls release the GIL, so the threads overlap as well.
         def worker(k):
-            mine = [slots[k], slots[k + E2E_THREADS]] if k + E2E_THREADS < N_SLOTS else [slots[k]]
+            mine = [slots[k], slots[k + E2E_THREADS]] if k + E2E_THREADS < n_slots else [slots[k]]
             pending = None
             for c, i in enumerate(range(k, n, E2E_THREADS)):
                 sl = mine[c % len(mine)]
                 if pending is sl:                       # single-stream fallback: finish before reusing the stream
-                    finish_frame(pending); pending = None
-                begin_frame(sl, i)
+                    flow["finish"](pending); pending = None
+                flow["begin"](sl, i)
                 if pending is not None:
-                    finish_frame(pending)
+                    flow["finish"](pending)
                 pending = sl
             if pending is not None:
-                finish_frame(pending)
+                flow["finish"](pending)
         ths = [threading.Thread(target=worker, args=(k,)) for k in range(E2E_THREADS)]
         for t in ths:
             t.start()
         for t in ths:
             t.join()
 
-    # long enough for a stable wall-clock figure (>= 0.1 s), the same number of frames on every in-flight stream
-    e2e_steps = max(4 * N_SLOTS, min(4 * args.steps, 960)) // N_SLOTS * N_SLOTS
-    run_e2e(2 * N_SLOTS)
-    barrier()
-    for sl in slots:
-        sl["d2h"] = 0
-    t0 = time.perf_counter()
-    run_e2e(e2e_steps)
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3          # the host is in this loop: wall clock around fully synchronised ends
-    d2h_per_step = sum(sl["d2h"] for sl in slots) // e2e_steps
-    barrier()
+    def timed_e2e():
+        """warm run (also calibrates the length), then a window of at least 0.6 s whatever --steps says"""
+        t0 = time.perf_counter()
+        run_e2e(2 * n_slots)
+        torch.cuda.synchronize()
+        rate = 2 * n_slots / max(time.perf_counter() - t0, 1e-6)
+        n = int(min(20000, max(4 * n_slots, math.ceil(0.6 * rate)))) // n_slots * n_slots
+        barrier()
+        for sl in slots:
+            sl["d2h"] = 0; sl["h2d"] = 0
+        l_0 = sum(sl["ctx"].launch_count() for sl in slots)
+        t0 = time.perf_counter()
+        run_e2e(n)
+        torch.cuda.synchronize()
+        e_ms = (time.perf_counter() - t0) * 1e3          # the host is in this loop: wall clock around fully synchronised ends
+        barrier()
+        return n, e_ms, sum(sl["d2h"] for sl in slots) // n, sum(sl["h2d"] for sl in slots) // n, sum(sl["ctx"].launch_count() for sl in slots) - l_0
 
-    # ---- e2e, reference picture kept on the device (SURVEY.md 8f item 4 closed into a loop): per frame only the source goes up;
-    # the cost tables, the level streams of the chosen units and the SAO statistics come down; gather -> deblocking -> SAO
-    # statistics -> stand-in SAO decision (host) -> SAO offset pass -> border produce the next reference picture in HBM.
-    # Every in-flight stream is a real IPPP chain here (frame n+1 searches in the finished frame n).
+    # (1) headline: the reference picture stays on the device (SURVEY.md 8f item 4 closed into a loop): per frame only the source goes
+    # up; the cost tables, the level streams of the chosen units and the SAO candidates come down; gather -> deblocking -> SAO
+    # statistics -> stand-in SAO decision (host) -> SAO offset pass -> border produce the next reference picture in HBM.  Every
+    # in-flight stream is a real IPPP chain here (frame n+1 searches in the finished frame n).
     from homerhevc_b200.lib import SAO_PARAM_DT
     SAO_LAMBDA, DBK = (float(LAMBDA), LAMBDA / 1.26, LAMBDA / 1.26), (2, 2, 0, 0)
     for sl in slots:
@@ -515,130 +648,257 @@ def main():
         sl["d2h"] += nlev + sl["tables"].nbytes + n_ctus * 15 * 16
         sl["h2d"] = sl.get("h2d", 0) + frame_bytes + sl["prm"].nbytes + sl["sel"].nbytes + sl["off"].nbytes
 
-    res_ms, res_d2h, res_h2d = None, 0, 0
+    res = None
     try:
-        begin_frame, finish_frame = begin_frame_res, finish_frame_res          # run_e2e picks them up by name
-        run_e2e(2 * N_SLOTS)
-        barrier()
-        for sl in slots:
-            sl["d2h"] = 0; sl["h2d"] = 0
-        l_res0 = sum(sl["ctx"].launch_count() for sl in slots)
-        t0 = time.perf_counter()
-        run_e2e(e2e_steps)
-        torch.cuda.synchronize()
-        res_ms = (time.perf_counter() - t0) * 1e3
-        res_launches = sum(sl["ctx"].launch_count() for sl in slots) - l_res0
-        res_d2h = sum(sl["d2h"] for sl in slots) // e2e_steps
-        res_h2d = sum(sl["h2d"] for sl in slots) // e2e_steps
-        sao_on = float(np.mean([(sl["prm"]["type"] >= 0).mean() for sl in slots]))
+        flow["begin"], flow["finish"] = begin_frame_res, finish_frame_res
+        n, e_ms, d2h, h2d, nl = timed_e2e()
+        res = {"steps": n, "ms": e_ms, "d2h": d2h, "h2d": h2d, "launches": nl, "sao_on": float(np.mean([(sl["prm"]["type"] >= 0).mean() for sl in slots]))}
     except hb.HbError as e:
-        print(f"[bench] device-resident e2e variant failed: {e}", file=sys.stderr)
-        res_ms = None
-    barrier()
-    # the unfiltered variant for reference: one stream, every table / level / reconstruction of all five passes fetched
-    e2e_cur, e2e_ref = hb.Frame(ctx, w, h), hb.Frame(ctx, w, h)
-    def step_full(i):
+        print(f"[bench] device-resident e2e flow failed: {e}", file=sys.stderr)
+
+    # (2) the reference picture crosses the link as well: upload cur + ref -> pre-pass -> cost tables -> host choice -> gather + fetch
+    # the reconstruction and coded levels of that choice
+    def begin_frame(sl, i):
         j = i % N_RESIDENT
-        e2e_cur.upload_u8(*pinned[j + 1]); e2e_ref.upload_u8(*pinned[j])
-        pp.run(e2e_cur, e2e_ref, AVG_DIST)
-        pp.fetch_all(out_pin)
-    for i in range(3):
-        step_full(i)
-    t0 = time.perf_counter()
-    for i in range(20):
-        step_full(i)
-    full_ms = (time.perf_counter() - t0) * 1e3
-    barrier()
+        sl["pp"].frame_begin(sl["cur"], sl["ref"], pinned[j + 1], pinned[j], AVG_DIST, sl["tables"])
 
-    # ---- per-kernel device times (CUDA events between launches, same stream) for the roofline
-    prof = {}
-    for rep in range(5):
-        for name, t in pp.run_profiled(resident[rep + 1], resident[rep], AVG_DIST):
-            prof.setdefault(name, []).append(t)
-    prof = {k: statistics.mean(v[1:]) for k, v in prof.items()}
+    def finish_frame(sl):
+        sl["d2h"] += sl["pp"].frame_finish(LAMBDA, sl["tables"], sl["sel"], sl["off"], sl["out"]) + sl["tables"].nbytes
+        sl["h2d"] = sl.get("h2d", 0) + 2 * frame_bytes
 
+    hostref = None
+    if full:
+        flow["begin"], flow["finish"] = begin_frame, finish_frame
+        n, e_ms, d2h, h2d, nl = timed_e2e()
+        hostref = {"steps": n, "ms": e_ms, "d2h": d2h, "h2d": h2d}
+
+    # ---- per-kernel device times (CUDA events between launches, same stream) and the algorithmic work of each launch
+    prof, abytes, aops = {}, None, None
+    if full:
+        for rep in range(5):
+            for name, t in pp.run_profiled(resident[rep + 1], resident[rep], AVG_DIST):
+                prof.setdefault(name, []).append(t)
+        prof = {k: statistics.mean(v[1:]) for k, v in prof.items()}
+        abytes = algorithmic_bytes(pp, w, h)
+        aops = algorithmic_ops(pp, w, h)          # from the tables the last profiled run left (probe counts, coded flags)
+    t = [ms, chain_ms, res["ms"] if res else 1e12, hostref["ms"] if hostref else 1e12]
     if world > 1:
-        t = torch.tensor([ms, e2e_ms, full_ms, res_ms if res_ms is not None else 1e12], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms, full_ms, res_all = t.tolist()
-        res_ms = None if res_all >= 1e12 else res_all
+        tt = torch.tensor(t, dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = tt.tolist()
+    ms, chain_ms = t[0], t[1]
+    if res:
+        res["ms"] = t[2]
+    if hostref:
+        hostref["ms"] = t[3]
+    r = {"w": w, "h": h, "ms": ms, "steps": steps, "n_slots": n_slots, "launches": launches, "clocks": clocks, "chain_fps": n_chain / (chain_ms * 1e-3),
+         "resident": res, "hostref": hostref, "prof": prof, "abytes": abytes, "aops": aops, "frame_bytes": frame_bytes, "e2e_threads": E2E_THREADS,
+         "host_frames": host}
+    # release the device memory of this picture size before the next one is set up
+    for sl in slots:
+        sl["pp"].close()
+        for f in [sl["cur"], sl["rec"]] + sl["refs"]:
+            f.close()
+        sl["ctx"].close()
+    pp.close()
+    for f in resident:
+        f.close()
+    ctx.close()
+    return r
+
+
+def e2e_object(r, world):
+    res, hostref = r["resident"], r["hostref"]
+    if res is None:
+        return {"value": None, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "what": "device-resident flow failed, see stderr"}
+    e = {"value": world * res["steps"] / (res["ms"] * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(res["h2d"]), "d2h_bytes_per_step": int(res["d2h"]),
+         "steps": res["steps"], "window_s": round(res["ms"] * 1e-3, 3), "streams_in_flight": r["n_slots"], "host_threads": r["e2e_threads"],
+         "gpu_launches": int(res["launches"]), "ctus_with_sao": round(res["sao_on"], 3),
+         "flow": "per frame and stream: upload the source (pinned host planes) -> pre-pass against the finished previous picture in HBM -> fetch cost tables (compact ME "
+                 "records + one 12-byte record per coding unit and pass) -> host depth choice per CTU -> gather into a frame + deblocking + fetch the coded level streams -> "
+                 "SAO statistics + per-type offsets on the device -> fetch those -> host SAO type choice (stand-in) -> SAO offset pass + border = the next reference picture"}
+    if hostref:
+        e["host_reference_variant"] = {"value": world * hostref["steps"] / (hostref["ms"] * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(hostref["h2d"]),
+                                       "d2h_bytes_per_step": int(hostref["d2h"]), "steps": hostref["steps"],
+                                       "flow": "upload cur + ref -> pre-pass -> cost tables -> host choice -> gather + fetch reconstruction and coded levels (the round-1 headline)"}
+    return e
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip extra_workloads and bands_2160p (kernel work, profiling)")
+    ap.add_argument("--streams", type=int, default=16, help="independent GOP streams in flight per GPU")
+    ap.add_argument("--mode", default="gops", choices=["gops", "bands", "intra", "finalise", "encode"],
+                    help="gops: the headline line (independent GOP streams per GPU + the 2160p band line); bands: only the 2160p CTU-row-band "
+                         "measurement; intra / finalise / encode: side measurements (rank 0)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    w, h = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if args.steps > 20:
+            args.steps, args.warmup = 5, 1
+        run_reference(args, w, h, rank, world)
+        return
+    if args.mode == "encode":
+        run_encode(args, w, h, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import homerhevc_b200 as hb
+    from homerhevc_b200 import synth
+
+    if os.environ.get("HB_PIN_CPUS") == "1" and world > 1:
+        cpus = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cpus) // world)
+        os.sched_setaffinity(0, set(cpus[local * per:(local + 1) * per]))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def finish():
+        if world > 1:
+            dist.destroy_process_group()
+
+    if args.mode == "finalise":
+        run_finalise(args, w, h, rank, world, local, hb, synth); finish(); return
+    if args.mode == "intra":
+        run_intra(args, w, h, rank, world, local, hb, synth); finish(); return
+    if args.mode == "bands":
+        torch.cuda.set_device(local)
+        b = measure_bands(args, rank, world, local, torch, dist, hb, synth, barrier, max(8, min(args.steps, 40)))
+        if rank == 0:
+            print(json.dumps({"metric": "ME+TQ frames/s", "value": b["streams_8"]["value"], "unit": "frames/s", "n_gpus": world, "steps": b["streams_8"]["frames"],
+                              "warmup": 3, "ms_per_step": b["streams_8"]["ms_per_frame"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                              "dtype": "u8 samples, int16 residual/levels, int32 accumulate", "data": "synthetic",
+                              "config": {"workload": b["workload"], "parallelism": b["parallelism"]}, "bands_2160p": b}))
+        finish(); return
+
+    torch.cuda.set_device(local)
+    n_slots = max(1, args.streams)
+    r = measure_workload(args, w, h, rank, world, local, torch, dist, hb, synth, barrier, args.steps, args.warmup, n_slots, True)
+    extras = {}
+    if world == 1 and not args.no_extras:
+        for name, (ew, eh) in WORKLOADS.items():
+            if (ew, eh) == (w, h):
+                continue
+            try:
+                x = measure_workload(args, ew, eh, rank, world, local, torch, dist, hb, synth, barrier, max(8, min(args.steps, 40)), 3, n_slots, False)
+                extras[name] = {"value": n_slots * x["steps"] / (x["ms"] * 1e-3), "unit": "frames/s", "e2e": e2e_object(x, world)["value"],
+                                "one_stream_chain": x["chain_fps"], "steps": x["steps"]}
+            except Exception as e:
+                extras[name] = {"value": None, "what": f"failed: {e}"}
+    bands = None
+    if not args.no_extras:
+        try:
+            bands = measure_bands(args, rank, world, local, torch, dist, hb, synth, barrier, max(8, min(args.steps, 24)))
+        except Exception as e:
+            bands = {"value": None, "what": f"failed: {type(e).__name__}: {e}"}
+
     if rank == 0:
         peaks, peak_src = measured_peaks()
-        abytes = algorithmic_bytes(pp, w, h)
+        prof, abytes, aops, ms, clocks = r["prof"], r["abytes"], r["aops"], r["ms"], r["clocks"]
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
         top = max(prof, key=prof.get)
-        achieved = abytes[top] / (prof[top] * 1e-3) / 1e9
-        step_bytes = sum(abytes.values())
         total_prof = sum(prof.values())
-        # instruction-issue roofline (the governing one): warp instructions per frame counted by ncu
-        # (profiles/inst_r01_v26.json, 1080p; scaled by the pixel count for the other sizes) against SMs x 4 schedulers x clock
-        issue, traffic = None, None
+        ops_top = aops[top]["pad"] + aops[top]["mac"]
+        peak_top = int_peak_ops(aops[top], sm_hz)
+        achieved = ops_top / (prof[top] * 1e-3)
+        # the whole step: time the integer pipes need at best for every launch's algorithmic work / the measured step time per frame
+        ideal_s = sum((aops[k]["pad"] + aops[k]["mac"]) / int_peak_ops(aops[k], sm_hz) for k in prof if k in aops)
+        frame_s = ms * 1e-3 / (args.steps * n_slots)
+        step_bytes = sum(abytes.values())
+        # executed-instruction view and DRAM traffic: only from an ncu profile taken on exactly these kernel sources
+        issue, traffic, sha = None, None, kernel_source_sha()
         try:
-            with open(os.path.join(ROOT, "profiles", "inst_r01_v26.json")) as f:
-                prof_counts = json.load(f)
-            scale = (w * h) / (1920 * 1080)
-            inst_per_frame = prof_counts["total_warp_inst"] * scale
-            sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
-            peak_issue = 148 * 3.8 * sm_hz        # measured: 3.80 warp-inst/clk/SM when both integer pipes are fed (tools/int_peak.cu, profiles/int_peak_r01.txt)
-            fps_gpu = N_SLOTS * args.steps / (ms * 1e-3)
-            issue = {"bound": "warp-instruction issue (int-op roofline)", "achieved": inst_per_frame * fps_gpu, "peak": peak_issue, "unit": "warp-inst/s",
-                     "frac": inst_per_frame * fps_gpu / peak_issue, "warp_inst_per_frame": inst_per_frame,
-                     "source": "ncu smsp__inst_executed.sum per kernel, profiles/inst_r01_v26.json" + ("" if scale == 1 else " (scaled by pixel count)")}
-            if scale == 1:
-                want = {"me": "k_me<", "mc": "k_mc", "tq": "k_tq<"}[top[:2]] + (top[2:] + ">" if top[:2] == "me" else "")
-                for kk in prof_counts["kernels"]:
-                    if kk["kernel"].startswith(want):
-                        traffic = kk["dram_read_bytes"] + kk["dram_write_bytes"]
+            with open(os.path.join(ROOT, "profiles", "inst_r02.json")) as f:
+                pc = json.load(f)
+            if pc.get("kernel_source_sha") != sha:
+                issue = {"stale_profile": True, "profile_sha": pc.get("kernel_source_sha"), "kernel_source_sha": sha}
+            elif (w, h) == WORKLOADS["1080p"]:
+                inst = pc["total_warp_inst"]
+                fps_gpu = n_slots * args.steps / (ms * 1e-3)
+                issue = {"what": "executed warp instructions (ncu smsp__inst_executed.sum, profiles/inst_r02.json) x frames/s against the measured issue ceiling; utilisation, not a roofline",
+                         "warp_inst_per_frame": inst, "achieved": inst * fps_gpu, "peak": N_SM * PEAK_BOTH_PIPES * sm_hz, "unit": "warp-inst/s",
+                         "frac": inst * fps_gpu / (N_SM * PEAK_BOTH_PIPES * sm_hz), "kernel_source_sha": sha}
+                want = {"me": "k_me<", "mc": "k_mc", "tq": "k_tq"}[top[:2]]
+                for kk in pc["kernels"]:
+                    if kk["kernel"].startswith(want) and (top[:2] != "me" or kk["kernel"].startswith(f"k_me<{top[2:]}>")):
+                        traffic = (kk.get("dram_read_bytes") or 0) + (kk.get("dram_write_bytes") or 0)
                         break
-        except Exception:
-            pass
+        except FileNotFoundError:
+            issue = {"stale_profile": True, "what": "no profiles/inst_r02.json for these kernel sources", "kernel_source_sha": sha}
+        except Exception as e:
+            issue = {"stale_profile": True, "what": f"{type(e).__name__}: {e}"}
+        e2e = e2e_object(r, world)
         line = {
-            "metric": "ME+TQ frames/s", "value": world * N_SLOTS * args.steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+            "metric": "ME+TQ frames/s", "value": world * n_slots * args.steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8 samples, int16 residual/levels, int32 accumulate",
             "data": "synthetic",
-            "config": {"workload": workload_name(args, w, h), "frames_per_step_per_gpu": N_SLOTS, "streams_in_flight_per_gpu": N_SLOTS, "qp": QP, "avg_dist": AVG_DIST,
-                       "parallelism": f"gop-per-gpu x{world}" if world > 1 else "single gpu",
-                       "l2": f"inputs rotate over {N_RESIDENT} resident frame pairs; a step touches ~{step_bytes / 2**20:.0f} MiB, "
-                             f"{N_RESIDENT} steps > {L2_BYTES / 2**20:.0f} MiB L2 before any input is reused",
-                       "cuda_graph": True},
-            "e2e": {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 2 * frame_bytes,
-                    "d2h_bytes_per_step": int(d2h_per_step), "steps": e2e_steps, "streams_in_flight": N_SLOTS, "host_threads": E2E_THREADS,
-                    "flow": "upload cur+ref -> pre-pass -> fetch cost tables (compact ME records + one 12-byte cost record per coding unit and pass) -> host depth choice per CTU -> gather + fetch recon and coded levels of that choice",
-                    "fetch_everything_variant": {"value": world * 20 / (full_ms * 1e-3), "unit": "frames/s", "d2h_bytes_per_step": out_bytes},
-                    "device_resident_reference_variant": None if res_ms is None else {
-                        "value": world * e2e_steps / (res_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(res_h2d), "d2h_bytes_per_step": int(res_d2h),
-                        "gpu_launches": int(res_launches), "ctus_with_sao": round(sao_on, 3),
-                        "flow": "upload cur only -> pre-pass against the finished previous frame in HBM -> fetch cost tables -> host choice per CTU -> gather into a frame + "
-                                "deblocking (strengths from the plan's tables) + fetch coded levels -> SAO statistics + per-type offsets/distortions on the device -> fetch those -> host SAO type choice (stand-in) -> SAO offset pass + border"}},
-            "gpu_launches": int(launches),
+            "config": bench_config(args, w, h, world, n_slots),
+            "gpu_launches": int(r["launches"]),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
-                         "kernel_ms": prof[top], "kernel_share_of_step": prof[top] / total_prof,
-                         "step_algorithmic_bytes": step_bytes,
-                         "step_frac": N_SLOTS * step_bytes / (ms / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"]},
-            "issue_roofline": issue,
             "kernels_ms": {k: round(v, 5) for k, v in prof.items()},
+            "issue_roofline": issue,
+            "roofline": {"bound": "int-op", "kernel": top, "achieved": achieved / 1e9, "peak": peak_top / 1e9, "unit": "Gop/s", "frac": achieved / peak_top,
+                         "traffic": traffic,
+                         "what": "algorithmic integer operations of the launch (pixel-abs-diffs of the reference's own search pattern, probe counts from the kernel's own "
+                                 "result table, + interpolation MACs of the reference's per-PU plane builders; SURVEY.md 8d) / its device time (CUDA events around the launch, "
+                                 "same stream), against SMs x measured warp-inst/clk (tools/int_peak.cu: both integer pipes 3.80, one 1.96) x 32 lanes x 4 packed 8-bit operations",
+                         "algorithmic_ops": {"pad": aops[top]["pad"], "mac": aops[top]["mac"]}, "kernel_ms": prof[top], "kernel_share_of_step": prof[top] / total_prof,
+                         "step_frac": ideal_s / frame_s, "peak_source": "profiles/int_peak_r01.txt (measured on a B200)",
+                         "hbm": {"achieved": abytes[top] / (prof[top] * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                 "frac": abytes[top] / (prof[top] * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": abytes[top], "peak_source": peak_src,
+                                 "step_algorithmic_bytes": step_bytes, "step_frac": step_bytes / frame_s / 1e9 / peaks["hbm_gbs"]}},
+            "e2e": e2e,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
                 from _oracle import have_ref, ref_prepass
                 if have_ref():
                     cores = len(os.sched_getaffinity(0))
-                    ref_prepass(host[1], host[0], w, h, QP, AVG_DIST, n_threads=cores, want_pred=False)     # warm
+                    host = r["host_frames"]
+                    ref_prepass(host[1], host[0], w, h, QP, AVG_DIST, n_threads=cores, want_pred=False, reuse_outputs=True)     # warm
                     n_cpu, secs = 0, 0.0
                     while secs < 8.0 and n_cpu < 64:
-                        s, _ = ref_prepass(host[n_cpu % N_RESIDENT + 1], host[n_cpu % N_RESIDENT], w, h, QP, AVG_DIST, n_threads=cores, want_pred=False)
+                        s, _ = ref_prepass(host[n_cpu % N_RESIDENT + 1], host[n_cpu % N_RESIDENT], w, h, QP, AVG_DIST, n_threads=cores, want_pred=False, reuse_outputs=True)
                         secs += s; n_cpu += 1
                     line["cpu_baseline"] = {"value": n_cpu / secs, "unit": "frames/s", "cores": cores, "kind": "reference",
-                                            "sample": f"{n_cpu} frames of the same workload through the reference's own functions (oracle/_ref), {cores} threads"}
+                                            "sample": f"{n_cpu} frames of the same workload through the reference's own functions (oracle/_ref), {cores} threads, timed inside the C driver",
+                                            "homer_app": homer_app_baseline(w, h, cores)}
                 else:
                     line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
             except Exception as e:  # the baseline is a reported figure; never lose the GPU line over it
                 line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+        if extras:
+            line["extra_workloads"] = extras
+        line["bands_2160p"] = bands
+        # short figures at the very end of the line (a truncated tail still carries them)
+        line["summary"] = {"n_gpus": world, "value_fps": round(line["value"], 1), "e2e_fps": None if e2e["value"] is None else round(e2e["value"], 1),
+                           "e2e_host_ref_fps": round(e2e["host_reference_variant"]["value"], 1) if "host_reference_variant" in e2e else None,
+                           "one_stream_chain_fps": round(r["chain_fps"], 1), "roofline_frac": round(line["roofline"]["frac"], 4),
+                           "roofline_step_frac": round(line["roofline"]["step_frac"], 4),
+                           "bands_2160p_fps_1stream": None if not bands or "streams_1" not in bands else round(bands["streams_1"]["value"], 1),
+                           "bands_2160p_fps_8streams": None if not bands or "streams_8" not in bands else round(bands["streams_8"]["value"], 1),
+                           "bands_mismatches": None if not bands else bands.get("mismatches")}
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":

@@ -290,7 +290,23 @@ void hb_frame_destroy(hb_frame *f)
     hbc_stream_sync(f->ctx->stream);
     for (int c = 0; c < 3; c++) if (f->d.p[c].base) hbc_free(f->d.p[c].base);
     if (f->stage) hbc_free(f->stage);
+    if (f->sp.base) hbc_free(f->sp.base);
     free(f);
+}
+
+int hbi_frame_subpel_alloc(hb_frame *f)
+{
+    if (f->sp.base) return HB_OK;
+    hbd_subpel sp;
+    memset(&sp, 0, sizeof sp);
+    sp.w = f->w + 2 * HB_SUBPEL_OFF; sp.h = f->h + 2 * HB_SUBPEL_OFF;
+    sp.pitch = (int32_t)align_up((size_t)sp.w, 128);
+    sp.plane_bytes = (uint64_t)sp.pitch * (uint64_t)sp.h;
+    hbc_set_device(f->ctx->device);
+    const int rc = hbc_malloc((void **)&sp.base, (size_t)(15 * sp.plane_bytes) + 256);
+    if (rc) return hbi_cuda_fail(rc, "sub-pel planes: cudaMalloc");
+    f->sp = sp;
+    return HB_OK;
 }
 int hb_frame_width(const hb_frame *f) { return f ? f->w : 0; }
 int hb_frame_height(const hb_frame *f) { return f ? f->h : 0; }
@@ -469,7 +485,7 @@ int hb_me_search(hb_ctx *ctx, const hb_frame *cur, const hb_frame *ref, const hb
         const int cnt = start_of[s + 1] - start_of[s];
         if (!cnt) continue;
         crc = hbk_me_search(&cur->d, &ref->d, sizes[s], (const hbd_me_job *)d_jobs + start_of[s], cnt, (const hb_me_result *)d_par,
-                            (hb_me_result *)d_res, action, NULL, NULL, ctx->stream);
+                            (hb_me_result *)d_res, action, NULL, NULL, NULL, ctx->stream);
         ctx->launches++;
     }
     if (!crc) crc = hbc_d2h_async(h_res, d_res, sizeof(hb_me_result) * (size_t)n_jobs, ctx->stream);

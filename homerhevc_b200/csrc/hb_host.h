@@ -29,6 +29,7 @@ struct hb_frame {
     int w, h;
     hbd_frame d;
     uint8_t *stage;            /* dense device copy of the last uploaded planes (allocated on first upload) */
+    hbd_subpel sp;             /* quarter-pel planes of the luma (allocated the first time the frame is a pre-pass reference) */
 };
 
 hb_ctx *hb_default_ctx(void);
@@ -48,5 +49,7 @@ int hbi_tq_encode_queue(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, 
                         const hb_tq_params *params, hbi_tq_pack *pk, const char *what);
 void hbi_tq_collect(const hbi_tq_pack *pk, const hb_tu_job *jobs, int n_jobs, int16_t *coeffs, hb_tu_result *results);
 void hbi_tq_pack_free(hbi_tq_pack *pk);
+/* storage for the quarter-pel planes of a frame (never inside a stream capture: it allocates) */
+int hbi_frame_subpel_alloc(hb_frame *f);
 
 #endif

@@ -47,6 +47,7 @@ struct MeArgs {
     int action;
     const hbd_dyn_params *dyn;
     hbd_plane pred;             // luma plane receiving the prediction of the winning vector (org == nullptr: not wanted)
+    hbd_subpel sp;              // PL kernels: the reference picture's quarter-pel planes (hb_kernels_subpel.cu)
 };
 
 template <int N> struct MeCfg {
@@ -179,8 +180,10 @@ template <int K> __device__ __forceinline__ uint32_t visited(uint32_t vmask, int
     return __popc(vmask & ((m << next_start) | (m >> (K - next_start))) & ((1u << K) - 1u));
 }
 
-template <int N>
-__global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(const MeArgs a)
+// PL = false: the sub-pel stage builds its planes per PU in shared memory (the reference's own scheme); PL = true: it reads the
+// reference picture's fifteen quarter-pel planes, built once per picture, and needs no shared memory beyond the exchange slots
+template <int N, bool PL>
+__global__ void __launch_bounds__(256, PL ? 4 : ((N <= 16) ? 3 : (N == 64) ? 4 : 3)) k_me(const MeArgs a)
 {
     using Cfg = MeCfg<N>;
     constexpr int G = Cfg::G, L = Cfg::L, SEG = Cfg::SEG, NSEG = Cfg::NSEG, SPS = Cfg::SEG_PER_SLOT, PUS = Cfg::PUS;
@@ -446,6 +449,91 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
         mvx = bx << 2; mvy = by << 2;
     }
 
+    if constexpr (PL) {
+      if (a.action & HB_ME_HALF) {
+        // ---- sub-pel refinement against the picture's quarter-pel planes: a candidate at quarter-pel offset (cx, cy) from the integer
+        // winner is the block of plane (cx & 3, cy & 3) at (ix + (cx >> 2), iy + (cy >> 2)); its SAD is taken exactly like an integer
+        // probe's (same lanes, same words).  Half-pel: the eight neighbours in the reference's order (s_acMvRefineH_HM, :1035), two
+        // rounds of four; quarter-pel: the eight neighbours of the half-pel winner (s_acMvRefineQ, :1062); plain SAD, strict '<'.
+        const int ix = mvx >> 2, iy = mvy >> 2;
+        uint32_t cur_best = bsad;
+        if (!(a.action & HB_ME_PEL)) {
+            const int cx[4] = { ix, 0, 0, 0 }, cy[4] = { iy, 0, 0, 0 };
+            const bool cv[4] = { true, false, false, false };
+            uint32_t sad[4], rd[4];
+            round4(cx, cy, cv, sad, rd);
+            cur_best = sad[0];
+        }
+        const uint32_t sp_pitch = static_cast<uint32_t>(a.sp.pitch);
+        const uint32_t sp_lane = static_cast<uint32_t>(jy + HB_SUBPEL_OFF + prow0) * sp_pitch + static_cast<uint32_t>(jx + HB_SUBPEL_OFF + pcol);
+        const uint32_t sp_step = (L / PPR) * sp_pitch;
+        auto plane_of = [&](int cx, int cy) -> const uint8_t * {
+            return a.sp.base + static_cast<size_t>(((cy & 3) * 4 + (cx & 3)) - 1) * a.sp.plane_bytes;       // never (0, 0): that is the integer position
+        };
+        auto plane_off = [&](int cx, int cy) -> uint32_t {
+            return sp_lane + static_cast<uint32_t>((iy + (cy >> 2)) * static_cast<int>(sp_pitch) + ix + (cx >> 2));
+        };
+        auto sad_plane = [&](int cx, int cy) -> uint32_t {
+            const uint8_t *pl = plane_of(cx, cy);
+            uint32_t off = plane_off(cx, cy);
+            const uint32_t sh = (off & 3u) * 8u;
+            off &= ~3u;
+            uint32_t acc = 0, acc1 = 0;
+#pragma unroll
+            for (int k = 0; k < PPL; k++) {
+                const uint32_t *q = reinterpret_cast<const uint32_t *>(pl + off);
+                const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+                acc = hb_sad4_acc(cur[2 * k], __funnelshift_r(w0, w1, sh), acc);
+                acc1 = hb_sad4_acc(cur[2 * k + 1], __funnelshift_r(w1, w2, sh), acc1);
+                off += sp_step;
+            }
+            return acc + acc1;
+        };
+        int bidx = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint32_t sad[4], cst[4];
+            exchange(sad_plane(2 * c_half[1 + 4 * h + slot][0], 2 * c_half[1 + 4 * h + slot][1]), 0u, sad, cst);
+#pragma unroll
+            for (int s = 0; s < 4; s++)
+                if (sad[s] < cur_best) { cur_best = sad[s]; bidx = 1 + 4 * h + s; }
+        }
+        const int hx = c_half[bidx][0], hy = c_half[bidx][1];
+        int sbx = hx * 2, sby = hy * 2;
+        if (a.action & HB_ME_QUARTER) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint32_t sad[4], cst[4];
+                exchange(sad_plane(hx * 2 + c_quarter[1 + 4 * h + slot][0], hy * 2 + c_quarter[1 + 4 * h + slot][1]), 0u, sad, cst);
+#pragma unroll
+                for (int s = 0; s < 4; s++)
+                    if (sad[s] < cur_best) { cur_best = sad[s]; sbx = hx * 2 + quarter_off(1 + 4 * h + s, 0); sby = hy * 2 + quarter_off(1 + 4 * h + s, 1); }
+            }
+        }
+        best_sad = cur_best;
+        mvx = (ix << 2) + sbx; mvy = (iy << 2) + sby;
+        subx = sbx; suby = sby;
+        // ---- the luma prediction of the winner is its block of the plane (of the reference picture itself for an integer vector):
+        // the samples hmr_motion_compensation_luma (:1779) produces for this vector.  Slot 0's lanes cover the block.
+        if (a.pred.org != nullptr && slot == 0) {
+            const bool integer = (sbx | sby) == 0;
+            const uint8_t *src = integer ? a.ref.base : plane_of(sbx, sby);
+            uint32_t off = integer ? ref_lane + static_cast<uint32_t>(iy * static_cast<int>(rpitch) + ix) : plane_off(sbx, sby);
+            const uint32_t step = integer ? ref_step : sp_step;
+            const uint32_t sh = (off & 3u) * 8u;
+            off &= ~3u;
+            uint8_t *dst = a.pred.org + (jy + prow0) * a.pred.pitch + jx + pcol;
+#pragma unroll
+            for (int k = 0; k < PPL; k++) {
+                const uint32_t *q = reinterpret_cast<const uint32_t *>(src + off);
+                const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+                *reinterpret_cast<uint2 *>(dst) = make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+                off += step;
+                dst += (L / PPR) * a.pred.pitch;
+            }
+        }
+      }
+    } else
     if (a.action & HB_ME_HALF) {
         const int ix = mvx >> 2, iy = mvy >> 2;
         uint32_t cur_best = bsad;
@@ -667,13 +755,14 @@ __global__ void __launch_bounds__(256, (N <= 16) ? 3 : (N == 64) ? 4 : 3) k_me(c
 
 template <int N> int configure_me()
 {
-    return static_cast<int>(cudaFuncSetAttribute(k_me<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, MeCfg<N>::SMEM_TOTAL));
+    return static_cast<int>(cudaFuncSetAttribute(k_me<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MeCfg<N>::SMEM_TOTAL));
 }
 
 template <int N> int launch_me(const MeArgs &a, cudaStream_t s)
 {
     const int grid = (a.n_jobs + MeCfg<N>::PUS - 1) / MeCfg<N>::PUS;
-    k_me<N><<<grid, 256, MeCfg<N>::SMEM_TOTAL, s>>>(a);
+    if (a.sp.base) k_me<N, true><<<grid, 256, 0, s>>>(a);
+    else k_me<N, false><<<grid, 256, MeCfg<N>::SMEM_TOTAL, s>>>(a);
     return static_cast<int>(cudaGetLastError());
 }
 
@@ -690,11 +779,14 @@ extern "C" int hbk_me_configure(void)
 }
 
 extern "C" int hbk_me_search(const hbd_frame *cur, const hbd_frame *ref, int size, const hbd_me_job *jobs, int n_jobs,
-                             const hb_me_result *parent, hb_me_result *out, int action, const hbd_dyn_params *dyn, const hbd_frame *pred_out, void *stream)
+                             const hb_me_result *parent, hb_me_result *out, int action, const hbd_dyn_params *dyn, const hbd_frame *pred_out,
+                             const hbd_subpel *sp, void *stream)
 {
     if (n_jobs <= 0) return 0;
     MeArgs a;
     memset(&a.pred, 0, sizeof a.pred);
+    memset(&a.sp, 0, sizeof a.sp);
+    if (sp && (action & HB_ME_HALF)) a.sp = *sp;
     if (pred_out && (action & HB_ME_HALF)) a.pred = pred_out->p[0];
     a.cur = cur->p[0]; a.ref = ref->p[0]; a.jobs = jobs; a.n_jobs = n_jobs; a.parent = parent; a.out = out; a.action = action; a.dyn = dyn;
     cudaStream_t s = static_cast<cudaStream_t>(stream);

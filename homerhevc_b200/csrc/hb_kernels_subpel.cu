@@ -1,0 +1,189 @@
+// hb_kernels_subpel.cu -- the fifteen quarter-pel planes of a reference picture's luma, built ONCE per picture.
+//
+// The reference rebuilds its sub-pel planes per PU around that PU's integer winner (hmr_half_pixel_estimation_luma_hm
+// hmr_motion_inter.c:395, hmr_quarter_pixel_estimation_luma_hm :442: 13 interpolation passes per PU and depth).  Every sample it
+// compares, though, is a function of the reference picture and of the absolute quarter-pel position alone:
+//     T_fx[y][x]      = sum_k h_fx[k] * ref[y][x - 3 + k] - 8192                                  (first pass, 14 bit; h_0 = 64 at k = 3)
+//     Q_fy,fx[y][x]   = clip255((sum_k v_fy[k] * T_fx[y - 3 + k][x] + 2048 + (8192 << 6)) >> 12)  (second pass)
+// -- the two-stage arithmetic of its interpolation functions (:312), which also is what hmr_motion_compensation_luma (:1779)
+// produces for a vector with fractions (fx, fy) (one-pass cases included: sum v = 64 makes them the same expression).  So the
+// planes Q_fy,fx, (fx, fy) != (0, 0), are computed here for the whole picture and the search kernels only take SADs against them
+// (and copy the winner's block out as the luma prediction): 120 MAC per sample and picture instead of ~416.
+//
+// One CTA = a 64 x 32 tile of all fifteen planes.  The (64+16) x 40 patch of the padded reference it needs arrives in shared memory
+// as ONE TMA tile copy (cp.async.bulk.tensor.2d, completion on an mbarrier); the four horizontal planes go to shared memory
+// pair-interleaved (one word = rows 2q, 2q+1 of a column) through dp4a, and a thread then walks one column of one horizontal plane
+// down the tile, feeding every window of five words to the three vertical filters through dp2a: two output rows of three planes per
+// fifteen multiply instructions, the fourth (fy = 0) is a shift.
+#include <cuda.h>
+#include <cstdlib>
+#include "hb_shim.h"
+#include "hb_dev_common.cuh"
+
+namespace {
+
+constexpr int TW = 64, TH = 32;                    // output tile
+constexpr int BOX_W = 80, BOX_H = 40;              // patch: columns x0-3 .. x0+76, rows y0-3 .. y0+36 (71 x 39 needed)
+constexpr int QR = BOX_H / 2;                      // pair rows of a horizontal plane
+constexpr int kVRound = 2048 + (8192 << 6);
+
+__host__ __device__ constexpr int tap0(int f, int k) { return (k < 0 || k > 7) ? 0 : luma_tap(f, k); }
+// word i of the five-word window holds rows 2m+2i, 2m+2i+1: output row 2m takes taps (2i, 2i+1), output row 2m+1 taps (2i-1, 2i)
+__host__ __device__ constexpr uint32_t vpair(int f, int i) { return pack_s8(tap0(f, 2 * i), tap0(f, 2 * i + 1), tap0(f, 2 * i - 1), tap0(f, 2 * i)); }
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
+                 ::"r"(bar), "r"(parity) : "memory");
+}
+
+template <int FY> __device__ __forceinline__ void vfilter2(const uint32_t (&win)[5], int m, int &a, int &b)
+{
+    int sa = kVRound, sb = kVRound;
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        const int w = static_cast<int>(win[(m + i) % 5]);
+        if (i < 4) sa = __dp2a_lo(w, static_cast<int>(vpair(FY, i)), sa);       // row 2m: taps 0..7 sit in words 0..3
+        sb = __dp2a_hi(w, static_cast<int>(vpair(FY, i)), sb);
+    }
+    a = __vimin_s32_relu(sa >> 12, 255); b = __vimin_s32_relu(sb >> 12, 255);
+}
+
+template <bool TMA>
+__global__ void __launch_bounds__(256) k_subpel_planes(const __grid_constant__ CUtensorMap tmap, const hbd_plane ref, const hbd_subpel sp)
+{
+    __shared__ __align__(128) uint8_t s_patch[BOX_H * BOX_W];
+    __shared__ __align__(16) uint32_t s_t[4][QR][TW];
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW - HB_SUBPEL_OFF, y0 = blockIdx.y * TH - HB_SUBPEL_OFF;      // picture position of the tile's first sample
+
+    if (TMA) {
+        const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&s_bar));
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(s_patch));
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(BOX_W * BOX_H) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(x0 - 3 + ref.pad), "r"(y0 - 3 + ref.pad), "r"(bar) : "memory");
+        }
+        mbar_wait(bar, 0);
+    } else {
+        for (int wi = tid; wi < BOX_H * (BOX_W / 4); wi += 256) {
+            const int r = wi / (BOX_W / 4), c4 = (wi % (BOX_W / 4)) * 4;
+            *reinterpret_cast<uint32_t *>(s_patch + r * BOX_W + c4) = hb_ld_u8x4(ref.org + (y0 - 3 + r) * ref.pitch + x0 - 3 + c4);
+        }
+        __syncthreads();
+    }
+
+    // ---- horizontal planes T_0..T_3, pair-interleaved: one item = two rows x four columns x four fractions
+    for (int wi = tid; wi < QR * (TW / 4); wi += 256) {
+        const int q = wi / (TW / 4), j0 = (wi % (TW / 4)) * 4;
+        int o[2][4][4];
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const uint32_t *pw = reinterpret_cast<const uint32_t *>(s_patch + (2 * q + rr) * BOX_W + j0);
+            const uint32_t w0 = pw[0], w1 = pw[1], w2 = pw[2];
+            uint32_t win[8];                                       // win[c] = samples j0+c .. j0+c+3
+            win[0] = w0; win[4] = w1;
+#pragma unroll
+            for (int c = 1; c < 4; c++) { win[c] = __funnelshift_r(w0, w1, 8 * c); win[4 + c] = __funnelshift_r(w1, w2, 8 * c); }
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                o[rr][0][c] = hb_dp4a_us(win[c], htap4(0, 0), -8192);
+#pragma unroll
+                for (int f = 1; f < 4; f++) o[rr][f][c] = hb_dp4a_us(win[c + 4], htap4(f, 1), hb_dp4a_us(win[c], htap4(f, 0), -8192));
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < 4; f++) {
+            uint4 v;
+            v.x = __byte_perm(o[0][f][0], o[1][f][0], 0x5410); v.y = __byte_perm(o[0][f][1], o[1][f][1], 0x5410);
+            v.z = __byte_perm(o[0][f][2], o[1][f][2], 0x5410); v.w = __byte_perm(o[0][f][3], o[1][f][3], 0x5410);
+            *reinterpret_cast<uint4 *>(&s_t[f][q][j0]) = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- vertical pass: thread = (horizontal fraction fx, column c); a warp holds one fx, so its byte stores of a row are contiguous
+    const int fx = tid >> 6, c = tid & 63;
+    const int px = blockIdx.x * TW + c;                            // plane coordinates of this column
+    if (px >= sp.w) return;
+    const uint32_t *col = &s_t[fx][0][c];
+    uint8_t *dst = sp.base + static_cast<size_t>(blockIdx.y * TH) * sp.pitch + px;
+    const int rows = min(TH, sp.h - blockIdx.y * TH);
+    uint32_t win[5];
+#pragma unroll
+    for (int k = 0; k < 4; k++) win[k] = col[k * TW];
+#pragma unroll 4
+    for (int m = 0; m < TH / 2; m++) {
+        win[(m + 4) % 5] = col[(m + 4) * TW];
+        int v[4][2];
+        // fy = 0: the first-pass sample itself, rounded: rows 2m+3 (high half of word m+1) and 2m+4 (low half of word m+2)
+        v[0][0] = __vimin_s32_relu(__dp2a_lo(static_cast<int>(win[(m + 1) % 5]), 0x0100, 8192 + 32) >> 6, 255);
+        v[0][1] = __vimin_s32_relu(__dp2a_lo(static_cast<int>(win[(m + 2) % 5]), 0x0001, 8192 + 32) >> 6, 255);
+        vfilter2<1>(win, m, v[1][0], v[1][1]);
+        vfilter2<2>(win, m, v[2][0], v[2][1]);
+        vfilter2<3>(win, m, v[3][0], v[3][1]);
+#pragma unroll
+        for (int fy = 0; fy < 4; fy++) {
+            if (fy == 0 && fx == 0) continue;                      // (0, 0) is the reference picture itself
+            uint8_t *p = dst + static_cast<size_t>(fy * 4 + fx - 1) * sp.plane_bytes + static_cast<size_t>(2 * m) * sp.pitch;
+            if (2 * m < rows) p[0] = static_cast<uint8_t>(v[fy][0]);
+            if (2 * m + 1 < rows) p[sp.pitch] = static_cast<uint8_t>(v[fy][1]);
+        }
+    }
+}
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+encode_tiled_fn tensor_map_encoder()
+{
+    static encode_tiled_fn fn = nullptr;
+    static int tried = 0;
+    if (!tried) {
+        tried = 1;
+        const char *e = getenv("HB_NO_TMA");
+        if (!(e && *e == '1')) {
+            void *p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+                fn = reinterpret_cast<encode_tiled_fn>(p);
+        }
+    }
+    return fn;
+}
+
+}  // namespace
+
+// 1 when the plane kernel stages its patch with TMA (the default), 0 with plain loads ($HB_NO_TMA=1 or no driver entry point)
+extern "C" int hbk_subpel_uses_tma(void) { return tensor_map_encoder() != nullptr; }
+
+extern "C" int hbk_subpel_planes(const hbd_frame *ref, const hbd_subpel *sp, void *stream)
+{
+    const hbd_plane &p = ref->p[0];
+    const dim3 grid((sp->w + TW - 1) / TW, (sp->h + TH - 1) / TH);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    encode_tiled_fn enc = tensor_map_encoder();
+    if (enc) {
+        // the padded luma plane as a 2-D tensor of bytes: {pitch, rows}; tiles may hang over its right / bottom end (zero filled,
+        // never inside the samples a tile's outputs depend on)
+        const cuuint64_t dims[2] = { static_cast<cuuint64_t>(p.pitch), static_cast<cuuint64_t>(p.h + 2 * p.pad) };
+        const cuuint64_t strides[1] = { static_cast<cuuint64_t>(p.pitch) };
+        const cuuint32_t box[2] = { BOX_W, BOX_H }, estr[2] = { 1, 1 };
+        const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, p.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return static_cast<int>(cudaErrorInvalidValue);
+        k_subpel_planes<true><<<grid, 256, 0, s>>>(tmap, p, *sp);
+    } else {
+        k_subpel_planes<false><<<grid, 256, 0, s>>>(tmap, p, *sp);
+    }
+    return static_cast<int>(cudaGetLastError());
+}

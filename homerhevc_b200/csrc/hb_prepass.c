@@ -56,7 +56,7 @@ struct hb_prepass {
     /* captured replays */
     /* keyed on the DEVICE addresses the captured kernels hold (the six planes of cur and ref), not on the host hb_frame
      * structs: a destroyed frame's struct address is readily handed out again by calloc for a frame with other planes */
-    struct { const uint8_t *plane[6]; void *exec; } graphs[MAX_GRAPHS];
+    struct { const uint8_t *plane[7]; void *exec; } graphs[MAX_GRAPHS];
     int n_graphs;
     int launches_per_frame;
     /* gather of the host's selection */
@@ -310,12 +310,20 @@ static int enqueue(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, int
     int crc = 0, n = 0;
     /* with sub-pel refinement on, the search kernel leaves the luma prediction of its winner itself; MC then does chroma only */
     const int fused = (pp->cfg.me_action & HB_ME_HALF) != 0;
+    /* the reference picture's quarter-pel planes, once per picture: every depth's sub-pel probes and luma predictions read them */
+    const hbd_subpel *sp = (fused && ref->sp.base && !pp->cfg.subpel_per_pu) ? &ref->sp : NULL;
+    if (sp) {
+        void *st = main_st;
+        PROF_MARK("sp");
+        if (!crc) crc = hbk_subpel_planes(&ref->d, sp, main_st);
+        n++;
+    }
     for (int d = 0; d < N_DEPTH && !crc; d++) {
         if (!pp->n_valid[d]) continue;
         void *st = main_st;                      /* name used by PROF_MARK */
         PROF_MARK("me%d", 64 >> d);
         if (!crc) crc = hbk_me_search(&cur->d, &ref->d, 64 >> d, pp->d_jobs[d], pp->n_valid[d], d ? pp->d_me[d - 1] : NULL, pp->d_me[d],
-                                      pp->cfg.me_action, pp->d_dyn, fused ? &pp->pred[d]->d : NULL, main_st);
+                                      pp->cfg.me_action, pp->d_dyn, fused ? &pp->pred[d]->d : NULL, sp, main_st);
         n++;
         if (prof) {
             PROF_MARK("mc%d", 64 >> d);
@@ -360,6 +368,7 @@ int hb_prepass_run(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, dou
     int crc = 0, n = 0;
     if (!pp || !cur || !ref) return hbi_fail(HB_ERR_ARG, "hb_prepass_run: NULL argument");
     if (cur->w != pp->w || cur->h != pp->h || ref->w != pp->w || ref->h != pp->h) return hbi_fail(HB_ERR_ARG, "hb_prepass_run: frame size differs from the plan");
+    if ((pp->cfg.me_action & HB_ME_HALF) && !pp->cfg.subpel_per_pu && (crc = hbi_frame_subpel_alloc((hb_frame *)ref)) != HB_OK) return crc;   /* a cache inside the frame, outside any capture */
     hb_ctx *ctx = pp->ctx;
     hbc_set_device(ctx->device);
     /* per-frame scalars: same expressions, same host libm as the reference (hmr_common.h:53, hmr_motion_inter.c:106) */
@@ -376,8 +385,9 @@ int hb_prepass_run(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, dou
         crc = enqueue(pp, cur, ref, &n, 0);
     } else {
         void *exec = NULL;
-        const uint8_t *key[6];
+        const uint8_t *key[7];
         for (int c = 0; c < 3; c++) { key[c] = cur->d.p[c].base; key[3 + c] = ref->d.p[c].base; }
+        key[6] = ref->sp.base;
         for (int i = 0; i < pp->n_graphs; i++) if (!memcmp(pp->graphs[i].plane, key, sizeof key)) exec = pp->graphs[i].exec;
         if (!exec) {
             if (pp->n_graphs == MAX_GRAPHS) { hbc_graph_destroy(pp->graphs[0].exec); memmove(&pp->graphs[0], &pp->graphs[1], sizeof pp->graphs[0] * (MAX_GRAPHS - 1)); pp->n_graphs--; }
@@ -408,6 +418,7 @@ int hb_prepass_run_profiled(hb_prepass *pp, const hb_frame *cur, const hb_frame 
     hbc_set_device(ctx->device);
     for (int i = 0; i <= HB_PREPASS_MAX_KERNELS && !crc; i++) if (!pp->prof_ev[i]) crc = hbc_event_create(&pp->prof_ev[i]);
     if (crc) return hbi_cuda_fail(crc, "hb_prepass_run_profiled: events");
+    if ((pp->cfg.me_action & HB_ME_HALF) && !pp->cfg.subpel_per_pu && (crc = hbi_frame_subpel_alloc((hb_frame *)ref)) != HB_OK) return crc;
     double w = avg_dist / 2000.;
     w = w < .15 ? .15 : (w > 1.4 ? 1.4 : w);
     hbd_dyn_params dyn;

@@ -92,10 +92,18 @@ typedef struct hbd_me_job {       /* one PU, device layout */
     int32_t pad_;
     double  corr;                 /* qp * clip(avg_dist/2000, .15, 1.4), hmr_common.h:53 */
 } hbd_me_job;
+/* the fifteen quarter-pel planes of a reference picture's luma (hb_kernels_subpel.cu): plane q = fy * 4 + fx (1..15) starts at
+ * base + (q - 1) * plane_bytes; the sample at picture position (X + fx/4, Y + fy/4) sits at row Y + HB_SUBPEL_OFF, column X + HB_SUBPEL_OFF;
+ * w, h = picture size + 2 * HB_SUBPEL_OFF */
+#define HB_SUBPEL_OFF 4
+typedef struct hbd_subpel { uint8_t *base; int32_t pitch; int32_t w, h; int32_t pad_; uint64_t plane_bytes; } hbd_subpel;
+int hbk_subpel_planes(const hbd_frame *ref, const hbd_subpel *sp, void *stream);
+int hbk_subpel_uses_tma(void);
 int hbk_me_configure(void);   /* once per device, before the first search launch */
 int hbk_me_search(const hbd_frame *cur, const hbd_frame *ref, int size, const hbd_me_job *jobs, int n_jobs,
                   const hb_me_result *parent, hb_me_result *out, int action, const hbd_dyn_params *dyn,
-                  const hbd_frame *pred_out /* NULL, or receives the luma prediction of every winner (needs HB_ME_HALF) */, void *stream);
+                  const hbd_frame *pred_out /* NULL, or receives the luma prediction of every winner (needs HB_ME_HALF) */,
+                  const hbd_subpel *sp /* NULL: sub-pel planes are built per PU in shared memory; else the picture's planes are read */, void *stream);
 
 typedef struct hbd_mc_pu { int32_t x, y; int32_t mv_idx; } hbd_mc_pu;   /* luma position; mv = mvsrc[mv_idx].mv */
 int hbk_mc_predict(const hbd_frame *ref, const hbd_frame *pred, int size, const hbd_mc_pu *pus, int n_pus,

@@ -287,6 +287,10 @@ typedef struct hb_prepass_cfg {
     /* != 0: hb_prepass_fetch_tables delivers (and hb_prepass_select expects) 12-byte records -- hb_me_result_c, hb_tu_result_c --
      * instead of the 24 / 16-byte hb_me_result / hb_tu_result: 30 % fewer bytes on the way to the host's decision */
     int32_t compact_tables;     /* 0 full records, 1 compact ME + TU records, 2 compact ME + per-CU records (hb_cu_cost) */
+    /* 0 (default): the fifteen quarter-pel planes of the reference picture are built once per picture (one launch, TMA-staged tiles)
+     * and every depth's sub-pel probes and luma predictions read them; != 0: each PU builds its own planes in shared memory around
+     * its integer winner, as the reference does (hmr_motion_inter.c:395 / :442) -- same results, kept for comparison */
+    int32_t subpel_per_pu;
 } hb_prepass_cfg;
 /* the compact wire records (same order and counts as the full tables) */
 typedef struct hb_me_result_c { int16_t mvx, mvy; uint32_t sad; uint16_t n_probes; int8_t subx, suby; } hb_me_result_c;   /* 12 bytes */

@@ -110,8 +110,9 @@ def ref():
     if _ref is None:
         # librefdrv.so FIRST and global: oracle/ref_hooks.c interposes hmr_motion_estimation & co., which only works when the
         # harness precedes libhomer_ref.so (its dependency) in the lookup order of the calls made inside the reference
-        D = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "librefdrv.so"), mode=C.RTLD_GLOBAL)
-        R = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libhomer_ref.so"), mode=C.RTLD_GLOBAL)
+        ref_dir = os.environ.get("HB_REF_DIR", os.path.join(ORACLE_DIR, "_ref"))      # diagnostic builds of the reference (tools/ref_uninit_probe.sh)
+        D = C.CDLL(os.path.join(ref_dir, "librefdrv.so"), mode=C.RTLD_GLOBAL)
+        R = C.CDLL(os.path.join(ref_dir, "libhomer_ref.so"), mode=C.RTLD_GLOBAL)
         R.sse_aligned_sad.restype = C.c_uint32
         R.sse_aligned_ssd16b.restype = C.c_uint32
         R.sad.restype = C.c_uint32

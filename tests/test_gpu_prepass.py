@@ -607,3 +607,42 @@ def test_graph_cache_follows_the_device_planes(ctx):
     for f in keep:
         f.close()
     pp.close(); plain.close()
+
+
+def test_subpel_planes_per_picture_equal_per_pu(ctx):
+    """the quarter-pel planes built once per reference picture (default; TMA-staged tiles) give the same vectors, SADs and luma
+    predictions as planes built per PU in shared memory (subpel_per_pu = 1, the reference's own scheme), partial CTUs included"""
+    w, h, qp, avg = 328, 200, 30, 420.0
+    cur, ref = clip_pair(w, h, n=3, noise=4.0, seed=31)
+    fc, fr = upload(ctx, cur, w, h), upload(ctx, ref, w, h)
+    a, b = hb.Prepass(ctx, w, h, qp=qp), hb.Prepass(ctx, w, h, qp=qp, subpel_per_pu=1)
+    for rep in range(2):
+        a.run(fc, fr, avg); b.run(fc, fr, avg)
+    ctx.sync()
+    moved = 0
+    for d in range(4):
+        ma, mb = a.fetch_me(d), b.fetch_me(d)
+        assert ma.tobytes() == mb.tobytes(), d
+        ok = ma["sad"] != 0xFFFFFFFF
+        moved += int(((ma["subx"][ok] != 0) | (ma["suby"][ok] != 0)).sum())
+        pa, pb = a.pred(d).download(), b.pred(d).download()
+        s = 64 >> d
+        for c in range(3):
+            sc = s // 2 if c else s
+            hh, ww = (h // 2 if c else h) // sc * sc, (w // 2 if c else w) // sc * sc
+            assert np.array_equal(pa[c][:hh, :ww], pb[c][:hh, :ww]), (d, c)
+    assert moved > 50, "the clip never produced sub-pel vectors"
+    for p in range(5):
+        for c in range(3):
+            if a.tu_size(p, c):
+                assert a.fetch_tu(p, c).tobytes() == b.fetch_tu(p, c).tobytes() and np.array_equal(a.fetch_coeffs(p, c), b.fetch_coeffs(p, c)), (p, c)
+    a.close(); b.close(); fc.close(); fr.close()
+
+
+def test_subpel_planes_without_tma():
+    """the same kernels with the plane tiles staged by plain loads ($HB_NO_TMA=1 is read once per process)"""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_prepass.py"), "-q", "-x", "-m", "gpu", "-k",
+                          "matches_oracle or per_picture_equal"], capture_output=True, text=True, timeout=900, cwd=root, env=dict(os.environ, HB_NO_TMA="1"))
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-1000:]

@@ -40,3 +40,19 @@ def test_inactive_hooks_forward_to_the_reference():
     assert a == b and np.array_equal(ra, rb) and len(a) > 100
     cnt = cu_hooks_off()
     assert cnt["frames"] == 0 and cnt["me"] == 0
+
+
+def test_cu_hooks_emulated_on_the_zero_initialised_build_at_720p():
+    """the same check at BASELINE.json's 1280x720 (partial last CTU row), both arms on oracle/_ref/zinit (see tests/test_gpu_encode_hooks.py
+    for why), in its own process"""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    zinit = os.path.join(root, "oracle", "_ref", "zinit")
+    if not os.path.exists(os.path.join(zinit, "librefdrv.so")):
+        pytest.skip("oracle/_ref/zinit was not built")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "encode_check.py"), "1280x720x3", "-1", "emu", "1"], capture_output=True, text=True,
+                         timeout=900, cwd=root, env=dict(os.environ, HB_REF_DIR=zinit))
+    assert out.returncode == 0, out.stderr[-2000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["identical"], r
+    assert r["hook_calls"]["me"] > 1000 and r["hook_calls"]["tq_fwd"] == 0 and r["hook_calls"]["errors"] == 0

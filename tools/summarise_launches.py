@@ -1,7 +1,9 @@
 """ncu launch list (csv written by `ncu --metrics ... --csv --log-file X`) -> per-kernel summary of ONE pre-pass frame.
 usage: python tools/summarise_launches.py launches.csv out.json [first_kernel_substring]
 The frame taken is the LAST complete run of consecutive pre-pass kernels (k_me<64> ... k_tq<4>) in the list."""
-import csv, json, sys, collections, re
+import csv, json, sys, collections, re, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import kernel_source_sha
 src, dst = sys.argv[1], sys.argv[2]
 rows = list(csv.reader(l for l in open(src) if l.startswith('"')))
 hdr = rows[0]; ix = {h: i for i, h in enumerate(hdr)}
@@ -30,7 +32,7 @@ tot_t = sum(k["time_us"] for k in out)
 for k in out: k["share_of_frame_time"] = round(k["time_us"] / tot_t, 4)
 fam = collections.Counter()
 for k in out: fam[k["kernel"].split("<")[0]] += k["time_us"] / tot_t
-json.dump({"workload": "1920x1080, one frame of the pre-pass (%d kernels), per-launch ncu metrics, --clock-control none (cold cache, serialised)" % len(out),
+json.dump({"kernel_source_sha": kernel_source_sha(), "workload": "1920x1080, one frame of the pre-pass (%d kernels), per-launch ncu metrics, --clock-control none (cold cache, serialised)" % len(out),
            "source": src.split("/")[-1], "total_warp_inst": sum(k["warp_inst"] for k in out), "total_time_us": tot_t,
            "family_share_of_time": {k: round(v, 4) for k, v in fam.items()}, "kernels": out}, open(dst, "w"), indent=1)
 print(len(out), "kernels", round(tot_t, 1), "us", round(sum(k["warp_inst"] for k in out) / 1e6, 1), "M warp inst", dict(fam))
