@@ -23,7 +23,10 @@
 namespace {
 
 constexpr int TW = 64, TH = 32;                    // output tile
-constexpr int BOX_W = 80, BOX_H = 40;              // patch: columns x0-3 .. x0+76, rows y0-3 .. y0+36 (71 x 39 needed)
+// patch: the 71 x 39 samples a tile depends on (columns x0-3 .. x0+67, rows y0-3 .. y0+35) sit at column PATCH_X of a 96 x 40 box whose
+// first column is x0 - 12: that is a multiple of 16 samples from the start of the padded plane (64 bx - 16 + pad, pad = 96), so the
+// box starts on a 16-byte boundary of global memory
+constexpr int BOX_W = 96, BOX_H = 40, PATCH_X = 9;
 constexpr int QR = BOX_H / 2;                      // pair rows of a horizontal plane
 constexpr int kVRound = 2048 + (8192 << 6);
 
@@ -69,13 +72,13 @@ __global__ void __launch_bounds__(256) k_subpel_planes(const __grid_constant__ C
             const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(s_patch));
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(BOX_W * BOX_H) : "memory");
             asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(x0 - 3 + ref.pad), "r"(y0 - 3 + ref.pad), "r"(bar) : "memory");
+                         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(x0 - 3 - PATCH_X + ref.pad), "r"(y0 - 3 + ref.pad), "r"(bar) : "memory");
         }
         mbar_wait(bar, 0);
     } else {
         for (int wi = tid; wi < BOX_H * (BOX_W / 4); wi += 256) {
             const int r = wi / (BOX_W / 4), c4 = (wi % (BOX_W / 4)) * 4;
-            *reinterpret_cast<uint32_t *>(s_patch + r * BOX_W + c4) = hb_ld_u8x4(ref.org + (y0 - 3 + r) * ref.pitch + x0 - 3 + c4);
+            *reinterpret_cast<uint32_t *>(s_patch + r * BOX_W + c4) = __ldg(reinterpret_cast<const uint32_t *>(ref.org + (y0 - 3 + r) * ref.pitch + x0 - 3 - PATCH_X + c4));
         }
         __syncthreads();
     }
@@ -86,12 +89,13 @@ __global__ void __launch_bounds__(256) k_subpel_planes(const __grid_constant__ C
         int o[2][4][4];
 #pragma unroll
         for (int rr = 0; rr < 2; rr++) {
-            const uint32_t *pw = reinterpret_cast<const uint32_t *>(s_patch + (2 * q + rr) * BOX_W + j0);
+            // patch column j0 sits one byte into the aligned word at box column PATCH_X - 1 + j0
+            const uint32_t *pw = reinterpret_cast<const uint32_t *>(s_patch + (2 * q + rr) * BOX_W + PATCH_X - 1 + j0);
             const uint32_t w0 = pw[0], w1 = pw[1], w2 = pw[2];
-            uint32_t win[8];                                       // win[c] = samples j0+c .. j0+c+3
-            win[0] = w0; win[4] = w1;
+            uint32_t win[8];                                       // win[c] = patch samples j0+c .. j0+c+3
+            win[3] = w1; win[7] = w2;
 #pragma unroll
-            for (int c = 1; c < 4; c++) { win[c] = __funnelshift_r(w0, w1, 8 * c); win[4 + c] = __funnelshift_r(w1, w2, 8 * c); }
+            for (int c = 0; c < 3; c++) { win[c] = __funnelshift_r(w0, w1, 8 * (c + 1)); win[4 + c] = __funnelshift_r(w1, w2, 8 * (c + 1)); }
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 o[rr][0][c] = hb_dp4a_us(win[c], htap4(0, 0), -8192);
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(256) k_subpel_planes(const __grid_constant__ C
     uint32_t win[5];
 #pragma unroll
     for (int k = 0; k < 4; k++) win[k] = col[k * TW];
-#pragma unroll 4
+#pragma unroll
     for (int m = 0; m < TH / 2; m++) {
         win[(m + 4) % 5] = col[(m + 4) * TW];
         int v[4][2];
