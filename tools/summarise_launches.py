@@ -15,12 +15,14 @@ for r in rows[1:]:
     e[r[ix['Metric Name']]] = float(r[ix['Metric Value']].replace(',', ''))
 ks = list(agg.values())
 # last index of k_me<64>, then everything up to the next k_me<64> / non pre-pass kernel
-starts = [i for i, k in enumerate(ks) if k["kernel"].startswith("k_me<64>")]
-pre = ("k_me<", "k_mc", "k_tq")
+# a frame starts with the plane kernel (k_subpel_planes) when the plan builds the planes per picture, else with k_me<64
+first = "k_subpel_planes" if any(k["kernel"].startswith("k_subpel_planes") for k in ks) else "k_me<64"
+starts = [i for i, k in enumerate(ks) if k["kernel"].startswith(first)]
+pre = ("k_me<", "k_mc", "k_tq", "k_subpel")
 frames = []
 for s in starts:
     e = s + 1
-    while e < len(ks) and ks[e]["kernel"].startswith(pre) and not ks[e]["kernel"].startswith("k_me<64>"): e += 1
+    while e < len(ks) and ks[e]["kernel"].startswith(pre) and not ks[e]["kernel"].startswith(first): e += 1
     frames.append((s, e))
 s, e = max(frames, key=lambda f: (f[1] - f[0], f[0]))
 out = []
