@@ -485,7 +485,7 @@ int hb_me_search(hb_ctx *ctx, const hb_frame *cur, const hb_frame *ref, const hb
         const int cnt = start_of[s + 1] - start_of[s];
         if (!cnt) continue;
         crc = hbk_me_search(&cur->d, &ref->d, sizes[s], (const hbd_me_job *)d_jobs + start_of[s], cnt, (const hb_me_result *)d_par,
-                            (hb_me_result *)d_res, action, NULL, NULL, NULL, ctx->stream);
+                            (hb_me_result *)d_res, action, NULL, NULL, NULL, 0, ctx->stream);
         ctx->launches++;
     }
     if (!crc) crc = hbc_d2h_async(h_res, d_res, sizeof(hb_me_result) * (size_t)n_jobs, ctx->stream);

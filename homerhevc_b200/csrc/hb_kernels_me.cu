@@ -71,6 +71,11 @@ template <int N> struct MeCfg {
     static constexpr int CS = N + 4;                   // column stride (bytes) of the transposed current block
     static constexpr int SMEM_PER_PU = PATCH_BYTES + 4 * PLANE_ELEMS * 2;
     static constexpr int SMEM_TOTAL = PUS * SMEM_PER_PU;
+    // WIN kernels: the CTA's PUs are PUS neighbours of one PU row (a strip of PUS * N samples); every position their walks can probe
+    // lies in the strip widened by the search range, +-128 x +-64 (hmr_private.h:76-77), clipped to the picture
+    static constexpr int WIN_ROWS = N + 128;
+    static constexpr int WIN_P = PUS * N + 256 + 16;       // bytes per window row: a multiple of 16, 4 or 20 words mod 32 (row-to-row bank shift)
+    static constexpr int WIN_BYTES = WIN_ROWS * WIN_P;
 };
 
 // Vertical: the planes hold two rows per word, so an 8-tap column sum over rows rho0..rho0+7 is four dp2a when rho0 is even
@@ -182,8 +187,12 @@ template <int K> __device__ __forceinline__ uint32_t visited(uint32_t vmask, int
 
 // PL = false: the sub-pel stage builds its planes per PU in shared memory (the reference's own scheme); PL = true: it reads the
 // reference picture's fifteen quarter-pel planes, built once per picture, and needs no shared memory beyond the exchange slots
-template <int N, bool PL>
-__global__ void __launch_bounds__(256, PL ? 4 : ((N <= 16) ? 3 : (N == 64) ? 4 : 3)) k_me(const MeArgs a)
+// WIN = true (pre-pass, PL only): the reference area the integer walk can reach is staged in shared memory first -- one bulk
+// asynchronous copy (cp.async.bulk, the TMA engine) per window row, all completing on one mbarrier -- and every probe of the walk
+// reads it from there instead of gathering 32-bit words through L1 (which was the limiter: l1tex 80-86 % of peak, ~8-10 sectors
+// per request).  The CTA's jobs then are PUS neighbours of one PU row; entries with x < 0 pad the last strip of a row.
+template <int N, bool PL, bool WIN>
+__global__ void __launch_bounds__(256, WIN ? 3 : PL ? 4 : ((N <= 16) ? 3 : (N == 64) ? 4 : 3)) k_me(const MeArgs a)
 {
     using Cfg = MeCfg<N>;
     constexpr int G = Cfg::G, L = Cfg::L, SEG = Cfg::SEG, NSEG = Cfg::NSEG, SPS = Cfg::SEG_PER_SLOT, PUS = Cfg::PUS;
@@ -197,9 +206,35 @@ __global__ void __launch_bounds__(256, PL ? 4 : ((N <= 16) ? 3 : (N == 64) ? 4 :
     const int group = threadIdx.x / G, gl = threadIdx.x % G, lane = threadIdx.x & 31;
     const int slot = gl / L, l = gl % L, seg = gl / SEG;
     const int job_idx = blockIdx.x * PUS + group;
+    // ---- WIN: stage the strip's search window.  Row r of the window = picture row wy0 + r, columns wx0 .. (both clipped to the
+    // picture: a probed block never leaves it, :1424-1427); every thread issues the copies of its rows, thread 0 arms the barrier.
+    int wx0 = 0, wy0 = 0;
+    if constexpr (WIN) {
+        __shared__ __align__(8) uint64_t s_bar;
+        const hbd_me_job *j0 = a.jobs + blockIdx.x * PUS;              // the first entry of a strip is always a real PU
+        const int xa = j0->x, ya = j0->y;
+        wx0 = max(xa - 128, 0); wy0 = max(ya - 64, 0);
+        const int x_hi = min(xa + PUS * N + 128, a.cur.w), y_hi = min(ya + N + 64, a.cur.h);
+        const int wbytes = (x_hi - wx0 + 3 + 15) & ~15, rows = y_hi - wy0;     // + 3: a probe's last word may start up to 3 bytes past its block
+        const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&s_bar));
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(rows * wbytes) : "memory");
+        for (int r = threadIdx.x; r < rows; r += 256) {
+            const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(s_raw + r * Cfg::WIN_P));
+            const uint8_t *src = a.ref.org + (wy0 + r) * a.ref.pitch + wx0;          // 16-byte aligned: pad, pitch and wx0 are multiples of 16
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(src), "r"(wbytes), "r"(bar) : "memory");
+        }
+        asm volatile("{\n .reg .pred p;\n WAITW_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n @p bra DONEW_%=;\n bra WAITW_%=;\n DONEW_%=:\n}\n" ::"r"(bar) : "memory");
+    }
     if (job_idx >= a.n_jobs) return;                   // the whole group leaves together
     const hbd_me_job *jp = a.jobs + job_idx;
     const int jx = jp->x, jy = jp->y;
+    if (WIN && jx < 0) return;                         // padding entry of a strip
     const double corr = a.dyn ? a.dyn->corr : jp->corr;
     const int n_amvp = jp->n_amvp;
     const int a0x = jp->amvp[0], a0y = jp->amvp[1], a1x = jp->amvp[2], a1y = jp->amvp[3];
@@ -282,8 +317,24 @@ __global__ void __launch_bounds__(256, PL ? 4 : ((N <= 16) ? 3 : (N == 64) ? 4 :
         }
     };
     // SAD of this lane's words at integer displacement (mx, my)
+    // this lane's first pair inside the staged window (WIN)
+    const uint32_t win_lane = static_cast<uint32_t>((jy - wy0 + prow0) * Cfg::WIN_P + (jx - wx0 + pcol));
     auto sad_at = [&](int mx, int my) -> uint32_t {
         uint32_t acc = 0, acc1 = 0;
+        if constexpr (WIN) {
+            uint32_t off = win_lane + static_cast<uint32_t>(my * Cfg::WIN_P + mx);
+            const uint32_t sh = (off & 3u) * 8u;
+            off &= ~3u;
+#pragma unroll
+            for (int k = 0; k < PPL; k++) {
+                const uint32_t *q = reinterpret_cast<const uint32_t *>(s_raw + off);
+                const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+                acc = hb_sad4_acc(cur[2 * k], __funnelshift_r(w0, w1, sh), acc);
+                acc1 = hb_sad4_acc(cur[2 * k + 1], __funnelshift_r(w1, w2, sh), acc1);
+                off += (L / PPR) * Cfg::WIN_P;
+            }
+            return acc + acc1;
+        }
         // the pitch is a multiple of 4, so every word of this candidate has the same misalignment: shift once
         uint32_t off = ref_lane + static_cast<uint32_t>(my * static_cast<int>(rpitch) + mx);
         const uint32_t sh = (off & 3u) * 8u;
@@ -755,20 +806,26 @@ __global__ void __launch_bounds__(256, PL ? 4 : ((N <= 16) ? 3 : (N == 64) ? 4 :
 
 template <int N> int configure_me()
 {
-    return static_cast<int>(cudaFuncSetAttribute(k_me<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MeCfg<N>::SMEM_TOTAL));
+    int e = static_cast<int>(cudaFuncSetAttribute(k_me<N, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MeCfg<N>::SMEM_TOTAL));
+    if (!e) e = static_cast<int>(cudaFuncSetAttribute(k_me<N, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MeCfg<N>::WIN_BYTES));
+    return e;
 }
 
-template <int N> int launch_me(const MeArgs &a, cudaStream_t s)
+template <int N> int launch_me(const MeArgs &a, bool window, cudaStream_t s)
 {
     const int grid = (a.n_jobs + MeCfg<N>::PUS - 1) / MeCfg<N>::PUS;
-    if (a.sp.base) k_me<N, true><<<grid, 256, 0, s>>>(a);
-    else k_me<N, false><<<grid, 256, MeCfg<N>::SMEM_TOTAL, s>>>(a);
+    if (a.sp.base && window) k_me<N, true, true><<<grid, 256, MeCfg<N>::WIN_BYTES, s>>>(a);
+    else if (a.sp.base) k_me<N, true, false><<<grid, 256, 0, s>>>(a);
+    else k_me<N, false, false><<<grid, 256, MeCfg<N>::SMEM_TOTAL, s>>>(a);
     return static_cast<int>(cudaGetLastError());
 }
 
 }  // namespace
 
 // opt in to the dynamic shared memory the search kernels need; once per device, outside any stream capture
+// PUs of one window strip (= PUs per CTA) for a PU size: the strip-ordered job lists of the pre-pass are built around it
+extern "C" int hbk_me_strip_pus(int size) { return size == 64 ? MeCfg<64>::PUS : size == 32 ? MeCfg<32>::PUS : size == 16 ? MeCfg<16>::PUS : MeCfg<8>::PUS; }
+
 extern "C" int hbk_me_configure(void)
 {
     int e = configure_me<64>();
@@ -780,7 +837,7 @@ extern "C" int hbk_me_configure(void)
 
 extern "C" int hbk_me_search(const hbd_frame *cur, const hbd_frame *ref, int size, const hbd_me_job *jobs, int n_jobs,
                              const hb_me_result *parent, hb_me_result *out, int action, const hbd_dyn_params *dyn, const hbd_frame *pred_out,
-                             const hbd_subpel *sp, void *stream)
+                             const hbd_subpel *sp, int window, void *stream)
 {
     if (n_jobs <= 0) return 0;
     MeArgs a;
@@ -790,11 +847,12 @@ extern "C" int hbk_me_search(const hbd_frame *cur, const hbd_frame *ref, int siz
     if (pred_out && (action & HB_ME_HALF)) a.pred = pred_out->p[0];
     a.cur = cur->p[0]; a.ref = ref->p[0]; a.jobs = jobs; a.n_jobs = n_jobs; a.parent = parent; a.out = out; a.action = action; a.dyn = dyn;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool win = window != 0 && a.sp.base != nullptr;        // strip-ordered job list (hbk_me_strip_pus) + the picture's sub-pel planes
     switch (size) {
-    case 64: return launch_me<64>(a, s);
-    case 32: return launch_me<32>(a, s);
-    case 16: return launch_me<16>(a, s);
-    case 8: return launch_me<8>(a, s);
+    case 64: return launch_me<64>(a, win, s);
+    case 32: return launch_me<32>(a, win, s);
+    case 16: return launch_me<16>(a, win, s);
+    case 8: return launch_me<8>(a, win, s);
     default: return static_cast<int>(cudaErrorInvalidValue);
     }
 }

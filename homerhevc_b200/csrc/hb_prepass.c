@@ -40,6 +40,7 @@ struct hb_prepass {
     int grid_w[N_DEPTH], grid_h[N_DEPTH];      /* PU raster grid per depth (covers whole CTUs) */
     int n_valid[N_DEPTH];
     hbd_me_job *d_jobs[N_DEPTH];
+    hbd_me_job *d_jobs_strip[N_DEPTH]; int n_strip[N_DEPTH];     /* the same jobs in strip order for the windowed search kernels */
     hbd_mc_pu *d_pus[N_DEPTH];
     hb_me_result *d_me[N_DEPTH];
     char *d_tables;                                 /* one block: ME results of every depth, then TU results of every (pass, comp) --
@@ -133,6 +134,27 @@ int hb_prepass_create(hb_ctx *ctx, int width, int height, const hb_prepass_cfg *
                 n++;
             }
         pp->n_valid[d] = n;
+        /* strip order: per PU row, runs of hbk_me_strip_pus(s) neighbours starting at a multiple of that count; runs without a valid PU are
+         * dropped, the rest of a partly valid run is padding (x = -1).  A run is what one CTA of the windowed search kernel works on. */
+        {
+            const int run = hbk_me_strip_pus(s);
+            hbd_me_job *strip = (hbd_me_job *)calloc((size_t)gh * ((size_t)(gw + run - 1) / run) * run, sizeof *strip);
+            if (!strip) { free(jobs); free(pus); rc = hbi_fail(HB_ERR_NOMEM, "hb_prepass_create: out of memory"); break; }
+            int ns = 0, k = 0;
+            for (int py = 0; py < gh; py++)
+                for (int px0 = 0; px0 < gw; px0 += run) {
+                    if (!pu_valid(pp, px0 * s, py * s, s)) continue;
+                    for (int px = px0; px < px0 + run; px++) {
+                        if (px < gw && pu_valid(pp, px * s, py * s, s)) strip[ns++] = jobs[k++];       /* `jobs` is in raster order of the valid PUs */
+                        else { memset(&strip[ns], 0, sizeof strip[ns]); strip[ns].x = -1; strip[ns].y = -1; strip[ns].parent = -1; ns++; }
+                    }
+                }
+            pp->n_strip[d] = ns;
+            if (k != n) rc = hbi_fail(HB_ERR_ARG, "hb_prepass_create: strip order lost PUs (%d of %d)", k, n);
+            if (rc == HB_OK) rc = upload(ctx, (void **)&pp->d_jobs_strip[d], strip, sizeof *strip * (size_t)(ns ? ns : 1));
+            free(strip);
+            if (rc != HB_OK) { free(jobs); free(pus); break; }
+        }
         rc = upload(ctx, (void **)&pp->d_jobs[d], jobs, sizeof *jobs * (size_t)n);
         if (rc == HB_OK) rc = upload(ctx, (void **)&pp->d_pus[d], pus, sizeof *pus * (size_t)n);
         free(jobs); free(pus);
@@ -232,6 +254,7 @@ void hb_prepass_destroy(hb_prepass *pp)
     for (int i = 0; i < pp->n_graphs; i++) hbc_graph_destroy(pp->graphs[i].exec);
     for (int d = 0; d < N_DEPTH; d++) {
         if (pp->d_jobs[d]) hbc_free(pp->d_jobs[d]);
+        if (pp->d_jobs_strip[d]) hbc_free(pp->d_jobs_strip[d]);
         if (pp->d_pus[d]) hbc_free(pp->d_pus[d]);
         hb_frame_destroy(pp->pred[d]);
     }
@@ -322,8 +345,9 @@ static int enqueue(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, int
         if (!pp->n_valid[d]) continue;
         void *st = main_st;                      /* name used by PROF_MARK */
         PROF_MARK("me%d", 64 >> d);
-        if (!crc) crc = hbk_me_search(&cur->d, &ref->d, 64 >> d, pp->d_jobs[d], pp->n_valid[d], d ? pp->d_me[d - 1] : NULL, pp->d_me[d],
-                                      pp->cfg.me_action, pp->d_dyn, fused ? &pp->pred[d]->d : NULL, sp, main_st);
+        const int win = sp && !pp->cfg.me_global_window;      /* windowed kernels read the strip-ordered list */
+        if (!crc) crc = hbk_me_search(&cur->d, &ref->d, 64 >> d, win ? pp->d_jobs_strip[d] : pp->d_jobs[d], win ? pp->n_strip[d] : pp->n_valid[d],
+                                      d ? pp->d_me[d - 1] : NULL, pp->d_me[d], pp->cfg.me_action, pp->d_dyn, fused ? &pp->pred[d]->d : NULL, sp, win, main_st);
         n++;
         if (prof) {
             PROF_MARK("mc%d", 64 >> d);

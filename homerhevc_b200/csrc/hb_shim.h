@@ -103,7 +103,11 @@ int hbk_me_configure(void);   /* once per device, before the first search launch
 int hbk_me_search(const hbd_frame *cur, const hbd_frame *ref, int size, const hbd_me_job *jobs, int n_jobs,
                   const hb_me_result *parent, hb_me_result *out, int action, const hbd_dyn_params *dyn,
                   const hbd_frame *pred_out /* NULL, or receives the luma prediction of every winner (needs HB_ME_HALF) */,
-                  const hbd_subpel *sp /* NULL: sub-pel planes are built per PU in shared memory; else the picture's planes are read */, void *stream);
+                  const hbd_subpel *sp /* NULL: sub-pel planes are built per PU in shared memory; else the picture's planes are read */,
+                  int window /* != 0 (needs sp): `jobs` is strip ordered -- every hbk_me_strip_pus(size) consecutive entries are neighbours of one PU
+                                row, the first one real, x < 0 marks padding -- and each CTA stages its strip's search window in shared memory */,
+                  void *stream);
+int hbk_me_strip_pus(int size);
 
 typedef struct hbd_mc_pu { int32_t x, y; int32_t mv_idx; } hbd_mc_pu;   /* luma position; mv = mvsrc[mv_idx].mv */
 int hbk_mc_predict(const hbd_frame *ref, const hbd_frame *pred, int size, const hbd_mc_pu *pus, int n_pus,

@@ -616,13 +616,15 @@ def test_subpel_planes_per_picture_equal_per_pu(ctx):
     cur, ref = clip_pair(w, h, n=3, noise=4.0, seed=31)
     fc, fr = upload(ctx, cur, w, h), upload(ctx, ref, w, h)
     a, b = hb.Prepass(ctx, w, h, qp=qp), hb.Prepass(ctx, w, h, qp=qp, subpel_per_pu=1)
+    g = hb.Prepass(ctx, w, h, qp=qp, me_global_window=1)          # planes per picture, but every probe gathered from global memory
     for rep in range(2):
-        a.run(fc, fr, avg); b.run(fc, fr, avg)
+        a.run(fc, fr, avg); b.run(fc, fr, avg); g.run(fc, fr, avg)
     ctx.sync()
     moved = 0
     for d in range(4):
         ma, mb = a.fetch_me(d), b.fetch_me(d)
         assert ma.tobytes() == mb.tobytes(), d
+        assert ma.tobytes() == g.fetch_me(d).tobytes(), ("staged window vs global window", d)
         ok = ma["sad"] != 0xFFFFFFFF
         moved += int(((ma["subx"][ok] != 0) | (ma["suby"][ok] != 0)).sum())
         pa, pb = a.pred(d).download(), b.pred(d).download()
@@ -636,7 +638,7 @@ def test_subpel_planes_per_picture_equal_per_pu(ctx):
         for c in range(3):
             if a.tu_size(p, c):
                 assert a.fetch_tu(p, c).tobytes() == b.fetch_tu(p, c).tobytes() and np.array_equal(a.fetch_coeffs(p, c), b.fetch_coeffs(p, c)), (p, c)
-    a.close(); b.close(); fc.close(); fr.close()
+    a.close(); b.close(); g.close(); fc.close(); fr.close()
 
 
 def test_subpel_planes_without_tma():
