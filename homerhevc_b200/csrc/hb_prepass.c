@@ -345,7 +345,7 @@ static int enqueue(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, int
         if (!pp->n_valid[d]) continue;
         void *st = main_st;                      /* name used by PROF_MARK */
         PROF_MARK("me%d", 64 >> d);
-        const int win = sp && !pp->cfg.me_global_window;      /* windowed kernels read the strip-ordered list */
+        const int win = sp && pp->cfg.me_staged_window;       /* windowed kernels read the strip-ordered list */
         if (!crc) crc = hbk_me_search(&cur->d, &ref->d, 64 >> d, win ? pp->d_jobs_strip[d] : pp->d_jobs[d], win ? pp->n_strip[d] : pp->n_valid[d],
                                       d ? pp->d_me[d - 1] : NULL, pp->d_me[d], pp->cfg.me_action, pp->d_dyn, fused ? &pp->pred[d]->d : NULL, sp, win, main_st);
         n++;

@@ -291,10 +291,12 @@ typedef struct hb_prepass_cfg {
      * and every depth's sub-pel probes and luma predictions read them; != 0: each PU builds its own planes in shared memory around
      * its integer winner, as the reference does (hmr_motion_inter.c:395 / :442) -- same results, kept for comparison */
     int32_t subpel_per_pu;
-    /* 0 (default, with the per-picture planes): a search CTA stages the reference area its PUs' walks can reach (their strip of the
-     * picture widened by +-128 x +-64) in shared memory with bulk asynchronous copies and probes it there; != 0: every probe gathers
-     * its words from global memory through L1 -- same results, kept for comparison */
-    int32_t me_global_window;
+    /* != 0 (needs the per-picture planes): a search CTA first stages the reference area its PUs' walks can reach (their strip of the
+     * picture widened by +-128 x +-64) in shared memory -- one bulk asynchronous copy per window row on an mbarrier -- and probes it
+     * there; 0 (default): every probe gathers its words from global memory through L1.  Same results.  Measured on a B200 at 1080p
+     * (profiles/ncu_r02.txt): shared memory shares the L1TEX data pipe with the gathers it replaces (l1tex 79-86 % of peak -> 62-74 %) and the
+     * staging latency is paid once per CTA at three CTAs per SM: 146 us of search per frame against 142 us, 6 170 frames/s against 6 430 */
+    int32_t me_staged_window;
 } hb_prepass_cfg;
 /* the compact wire records (same order and counts as the full tables) */
 typedef struct hb_me_result_c { int16_t mvx, mvy; uint32_t sad; uint16_t n_probes; int8_t subx, suby; } hb_me_result_c;   /* 12 bytes */

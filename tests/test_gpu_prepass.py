@@ -616,7 +616,7 @@ def test_subpel_planes_per_picture_equal_per_pu(ctx):
     cur, ref = clip_pair(w, h, n=3, noise=4.0, seed=31)
     fc, fr = upload(ctx, cur, w, h), upload(ctx, ref, w, h)
     a, b = hb.Prepass(ctx, w, h, qp=qp), hb.Prepass(ctx, w, h, qp=qp, subpel_per_pu=1)
-    g = hb.Prepass(ctx, w, h, qp=qp, me_global_window=1)          # planes per picture, but every probe gathered from global memory
+    g = hb.Prepass(ctx, w, h, qp=qp, me_staged_window=1)          # planes per picture + the search window staged in shared memory (bulk async copies)
     for rep in range(2):
         a.run(fc, fr, avg); b.run(fc, fr, avg); g.run(fc, fr, avg)
     ctx.sync()
@@ -624,7 +624,7 @@ def test_subpel_planes_per_picture_equal_per_pu(ctx):
     for d in range(4):
         ma, mb = a.fetch_me(d), b.fetch_me(d)
         assert ma.tobytes() == mb.tobytes(), d
-        assert ma.tobytes() == g.fetch_me(d).tobytes(), ("staged window vs global window", d)
+        assert ma.tobytes() == g.fetch_me(d).tobytes(), ("search window staged in shared memory vs gathered from global memory", d)
         ok = ma["sad"] != 0xFFFFFFFF
         moved += int(((ma["subx"][ok] != 0) | (ma["suby"][ok] != 0)).sum())
         pa, pb = a.pred(d).download(), b.pred(d).download()
