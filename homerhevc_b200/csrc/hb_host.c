@@ -609,34 +609,58 @@ done:
     return rc;
 }
 
-/* merge / skip candidates: hb_mc_predict + hb_tq_encode over the candidates' transform units, reduced per candidate */
+/* merge / skip candidates: motion compensation, the no-residual block SSDs and the inter T/Q chain of every candidate's transform units
+ * are QUEUED back to back on the context's stream (the same kernels hb_mc_predict / hb_tq_encode launch) and waited for ONCE (round 1:
+ * three blocking calls); the reduction per candidate runs on the host afterwards */
 int hb_merge_eval(hb_ctx *ctx, const hb_frame *cur, const hb_frame *ref, hb_frame *pred, hb_frame *recon, const hb_mc_job *cands, int n_cands,
                   int qp, int chroma_qp_offset, const hb_tq_params *params, hb_merge_result *out)
 {
-    int rc;
+    static const int sizes[4] = { 64, 32, 16, 8 };
+    int rc = HB_OK, crc = 0;
     if (!ctx || !cur || !ref || !pred || !recon || !cands || !params || !out || n_cands < 0) return hbi_fail(HB_ERR_ARG, "hb_merge_eval: bad argument");
     if (qp < 0 || qp > 51) return hbi_fail(HB_ERR_ARG, "hb_merge_eval: qp %d", qp);
+    if (pred->w != ref->w || pred->h != ref->h || cur->w != ref->w || cur->h != ref->h) return hbi_fail(HB_ERR_ARG, "hb_merge_eval: frame sizes differ");
     if (n_cands == 0) return HB_OK;
     for (int i = 0; i < n_cands; i++)        /* coding units sit on their own grid; their transform units inherit the alignment the T/Q kernels need */
         if (cands[i].size > 0 && ((cands[i].x | cands[i].y) & (cands[i].size - 1)))
             return hbi_fail(HB_ERR_ARG, "hb_merge_eval: candidate %d is not aligned to its size", i);
-    if ((rc = hb_mc_predict(ctx, ref, pred, cands, n_cands)) != HB_OK) return rc;          /* validates the rest */
     const int qp_c = hbi_chroma_qp(qp, chroma_qp_offset);
     hb_tq_params prm = *params;
     prm.chroma_weight = pow(2.0, (qp - qp_c) / 3.0);                                        /* hmr_motion_inter.c:3525 */
-    /* no-residual distortion: ssd16b(orig, pred) of the whole block per plane, exact, before anything is reduced per unit */
+    /* transform units: luma size (64x64: four 32x32), chroma half of that (encode_inter walks a 64x64 unit as four 32x32 ones, :3094) */
+    size_t n_tu = 0, n_co = 0;
+    for (int i = 0; i < n_cands; i++) {
+        const int s = cands[i].size, nl = s == 64 ? 4 : 1, ls = s == 64 ? 32 : s;
+        n_tu += 3 * (size_t)nl; n_co += (size_t)nl * (ls * ls + 2 * (ls / 2) * (ls / 2));
+    }
+    hb_tu_job *tj = (hb_tu_job *)malloc(sizeof *tj * (n_tu ? n_tu : 1));
+    hb_tu_result *tr = (hb_tu_result *)malloc(sizeof *tr * (n_tu ? n_tu : 1));
+    int16_t *co = (int16_t *)malloc(sizeof *co * (n_co ? n_co : 1));
+    int *order = (int *)malloc(sizeof(int) * (size_t)n_cands);
     uint32_t *ssd3 = (uint32_t *)malloc(sizeof(uint32_t) * 3 * (size_t)n_cands);
-    if (!ssd3) return hbi_fail(HB_ERR_NOMEM, "hb_merge_eval: out of memory");
+    if (!tj || !tr || !co || !order || !ssd3) { rc = hbi_fail(HB_ERR_NOMEM, "hb_merge_eval: out of memory"); goto out; }
+    size_t k = 0;
+    for (int i = 0; i < n_cands; i++) {
+        const int s = cands[i].size, ls = s == 64 ? 32 : s;
+        for (int c = 0; c < 3; c++) {
+            const int ts = c ? ls / 2 : ls, bx = c ? cands[i].x / 2 : cands[i].x, by = c ? cands[i].y / 2 : cands[i].y, bs = c ? s / 2 : s;
+            for (int yy = 0; yy < bs; yy += ts)
+                for (int xx = 0; xx < bs; xx += ts) { tj[k].comp = c; tj[k].x = bx + xx; tj[k].y = by + yy; tj[k].size = ts; tj[k].qp = c ? qp_c : qp; k++; }
+        }
+    }
+    hbc_set_device(ctx->device);
+    pthread_mutex_lock(&ctx->lock);
     {
-        static const int sizes[4] = { 64, 32, 16, 8 };
+        hbi_tq_pack pk;
         void *d_pus, *h_pus, *d_out, *h_out;
-        int crc = 0, n = 0, start_of[5], *order = (int *)malloc(sizeof(int) * (size_t)n_cands);
-        if (!order) { free(ssd3); return hbi_fail(HB_ERR_NOMEM, "hb_merge_eval: out of memory"); }
-        pthread_mutex_lock(&ctx->lock);
-        rc = hbi_scratch(ctx, 0, sizeof(hbd_mc_pu) * (size_t)n_cands, &d_pus, &h_pus);
-        if (rc == HB_OK) rc = hbi_scratch(ctx, 1, sizeof(uint32_t) * 3 * (size_t)n_cands, &d_out, &h_out);
+        int have_pk = 0;
+        rc = hbi_mc_predict_queue(ctx, ref, pred, cands, n_cands, "hb_merge_eval");          /* validates the candidates; scratch 0, 1 */
+        /* no-residual distortion: ssd16b(orig, pred) of the whole block per plane (scratch 3, 4: the T/Q queue below takes 0..2) */
+        if (rc == HB_OK) rc = hbi_scratch(ctx, 3, sizeof(hbd_mc_pu) * (size_t)n_cands, &d_pus, &h_pus);
+        if (rc == HB_OK) rc = hbi_scratch(ctx, 4, sizeof(uint32_t) * 3 * (size_t)n_cands, &d_out, &h_out);
         if (rc == HB_OK) {
             hbd_mc_pu *hp = (hbd_mc_pu *)h_pus;
+            int n = 0, start_of[5];
             for (int s = 0; s < 4; s++) {
                 start_of[s] = n;
                 for (int i = 0; i < n_cands; i++) if (cands[i].size == sizes[s]) { hp[n].x = cands[i].x; hp[n].y = cands[i].y; hp[n].mv_idx = i; order[n] = i; n++; }
@@ -650,34 +674,21 @@ int hb_merge_eval(hb_ctx *ctx, const hb_frame *cur, const hb_frame *ref, hb_fram
                     ctx->launches++;
                 }
             if (!crc) crc = hbc_d2h_async(h_out, d_out, sizeof(uint32_t) * 3 * (size_t)n_cands, ctx->stream);
-            if (!crc) crc = hbc_stream_sync(ctx->stream);
-            if (!crc) for (int k = 0; k < n_cands; k++) memcpy(ssd3 + 3 * order[k], (uint32_t *)h_out + 3 * k, sizeof(uint32_t) * 3);
+            if (crc) rc = hbi_cuda_fail(crc, "hb_merge_eval");
         }
-        pthread_mutex_unlock(&ctx->lock);
-        free(order);
-        if (rc != HB_OK) { free(ssd3); return rc; }
-        if (crc) { free(ssd3); return hbi_cuda_fail(crc, "hb_merge_eval"); }
-    }
-    /* transform units: luma size (64x64: four 32x32), chroma half of that (encode_inter walks a 64x64 unit as four 32x32 ones, :3094) */
-    size_t n_tu = 0, n_co = 0;
-    for (int i = 0; i < n_cands; i++) {
-        const int s = cands[i].size, nl = s == 64 ? 4 : 1, ls = s == 64 ? 32 : s;
-        n_tu += 3 * (size_t)nl; n_co += (size_t)nl * (ls * ls + 2 * (ls / 2) * (ls / 2));
-    }
-    hb_tu_job *tj = (hb_tu_job *)malloc(sizeof *tj * n_tu);
-    hb_tu_result *tr = (hb_tu_result *)malloc(sizeof *tr * n_tu);
-    int16_t *co = (int16_t *)malloc(sizeof *co * n_co);
-    if (!tj || !tr || !co) { free(tj); free(tr); free(co); free(ssd3); return hbi_fail(HB_ERR_NOMEM, "hb_merge_eval: out of memory"); }
-    size_t k = 0;
-    for (int i = 0; i < n_cands; i++) {
-        const int s = cands[i].size, ls = s == 64 ? 32 : s;
-        for (int c = 0; c < 3; c++) {
-            const int ts = c ? ls / 2 : ls, bx = c ? cands[i].x / 2 : cands[i].x, by = c ? cands[i].y / 2 : cands[i].y, bs = c ? s / 2 : s;
-            for (int yy = 0; yy < bs; yy += ts)
-                for (int xx = 0; xx < bs; xx += ts) { tj[k].comp = c; tj[k].x = bx + xx; tj[k].y = by + yy; tj[k].size = ts; tj[k].qp = c ? qp_c : qp; k++; }
+        /* the kernels queued so far still read scratch 0, 1, 3, 4: the T/Q queue takes 5..7, and ONE wait ends the call */
+        if (rc == HB_OK) { rc = hbi_tq_encode_queue_at(ctx, cur, pred, recon, tj, (int)n_tu, &prm, &pk, "hb_merge_eval", 5); have_pk = rc == HB_OK; }
+        if (rc == HB_OK) {
+            crc = hbc_stream_sync(ctx->stream);
+            if (crc) rc = hbi_cuda_fail(crc, "hb_merge_eval");
+            else {
+                hbi_tq_collect(&pk, tj, (int)n_tu, co, tr);
+                for (int q = 0; q < n_cands; q++) memcpy(ssd3 + 3 * order[q], (uint32_t *)h_out + 3 * q, sizeof(uint32_t) * 3);
+            }
         }
+        if (have_pk) hbi_tq_pack_free(&pk);
     }
-    rc = hb_tq_encode(ctx, cur, pred, recon, tj, (int)n_tu, &prm, co, tr);
+    pthread_mutex_unlock(&ctx->lock);
     if (rc == HB_OK) {
         k = 0;
         for (int i = 0; i < n_cands; i++) {
@@ -691,8 +702,8 @@ int hb_merge_eval(hb_ctx *ctx, const hb_frame *cur, const hb_frame *ref, hb_fram
             out[i] = r;
         }
     }
-    free(ssd3);
-    free(tj); free(tr); free(co);
+out:
+    free(ssd3); free(order); free(tj); free(tr); free(co);
     return rc;
 }
 
@@ -861,6 +872,13 @@ void hbi_tq_pack_free(hbi_tq_pack *pk) { free(pk->order); free(pk->coeff_off); p
 int hbi_tq_encode_queue(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_frame *recon, const hb_tu_job *jobs, int n_jobs,
                         const hb_tq_params *params, hbi_tq_pack *pk, const char *what)
 {
+    return hbi_tq_encode_queue_at(ctx, cur, pred, recon, jobs, n_jobs, params, pk, what, 0);
+}
+
+/* sb: first of the three scratch buffers to use (a caller that still has work queued on buffers 0.. picks others) */
+int hbi_tq_encode_queue_at(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_frame *recon, const hb_tu_job *jobs, int n_jobs,
+                           const hb_tq_params *params, hbi_tq_pack *pk, const char *what, int sb)
+{
     int rc = HB_OK, crc = 0;
     size_t total = 0;
     memset(pk, 0, sizeof *pk);
@@ -878,9 +896,9 @@ int hbi_tq_encode_queue(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, 
     pk->coeff_off = (size_t *)malloc(sizeof(size_t) * (size_t)n_jobs);
     pk->total = total;
     if (!pk->order || !done_flag || !pk->coeff_off) { rc = hbi_fail(HB_ERR_NOMEM, "%s: out of memory", what); goto done; }
-    if ((rc = hbi_scratch(ctx, 0, sizeof(int32_t) * 2 * (size_t)n_jobs, &d_xy, &h_xy)) != HB_OK) goto done;
-    if ((rc = hbi_scratch(ctx, 1, sizeof(int16_t) * total, &d_co, &h_co)) != HB_OK) goto done;
-    if ((rc = hbi_scratch(ctx, 2, sizeof(hb_tu_result) * (size_t)n_jobs, &d_rs, &h_rs)) != HB_OK) goto done;
+    if ((rc = hbi_scratch(ctx, sb, sizeof(int32_t) * 2 * (size_t)n_jobs, &d_xy, &h_xy)) != HB_OK) goto done;
+    if ((rc = hbi_scratch(ctx, sb + 1, sizeof(int16_t) * total, &d_co, &h_co)) != HB_OK) goto done;
+    if ((rc = hbi_scratch(ctx, sb + 2, sizeof(hb_tu_result) * (size_t)n_jobs, &d_rs, &h_rs)) != HB_OK) goto done;
     pk->h_co = h_co; pk->h_rs = h_rs;
     { size_t o = 0; for (int i = 0; i < n_jobs; i++) { pk->coeff_off[i] = o; o += (size_t)jobs[i].size * jobs[i].size; } }
     /* launch one group per distinct (comp, size, qp); jobs of a group are packed in caller order */

@@ -8,7 +8,7 @@
 #define HB_SCAN_HOR  1      /* hmr_private.h:92-96 */
 #define HB_SCAN_VER  2
 #define HB_SCAN_DIAG 3
-#define HB_N_SCRATCH 6
+#define HB_N_SCRATCH 8
 
 struct hb_ctx {
     int device;
@@ -47,6 +47,8 @@ int hbi_mc_predict_queue(hb_ctx *ctx, const hb_frame *ref, hb_frame *pred, const
 typedef struct hbi_tq_pack { int *order; size_t *coeff_off; size_t total; void *h_co, *h_rs; } hbi_tq_pack;
 int hbi_tq_encode_queue(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_frame *recon, const hb_tu_job *jobs, int n_jobs,
                         const hb_tq_params *params, hbi_tq_pack *pk, const char *what);
+int hbi_tq_encode_queue_at(hb_ctx *ctx, const hb_frame *cur, const hb_frame *pred, hb_frame *recon, const hb_tu_job *jobs, int n_jobs,
+                           const hb_tq_params *params, hbi_tq_pack *pk, const char *what, int scratch_base);
 void hbi_tq_collect(const hbi_tq_pack *pk, const hb_tu_job *jobs, int n_jobs, int16_t *coeffs, hb_tu_result *results);
 void hbi_tq_pack_free(hbi_tq_pack *pk);
 /* storage for the quarter-pel planes of a frame (never inside a stream capture: it allocates) */
