@@ -138,6 +138,8 @@ def algorithmic_bytes(pp, w, h):
         # cur + ref luma (u8) in, the 16 sub-pel candidate blocks of every PU from the planes, one result record and the luma prediction out
         out[f"me{s}"] = 2 * luma + 16 * n_pu * s * s + 24 * n_pu + n_pu * s * s
         out[f"mc{s}"] = int(0.5 * n_pu * s * s) * 2 + 8 * n_pu     # chroma: ref in, pred out, mv in
+    # the single-launch search reads cur + ref once for all four PU sizes
+    out["me"] = 2 * luma + sum(out[f"me{64 >> d}"] - 2 * luma for d in range(4))
     for p in range(5):
         for c in range(3):
             t = pp.tu_size(p, c)
@@ -168,6 +170,9 @@ def algorithmic_ops(pp, w, h):
         probes = int(me["n_probes"][ok].astype(np.int64).sum())
         out[f"me{s}"] = {"pad": (probes + 18 * n_pu) * s * s, "mac": n_pu * 13 * 8 * (s + 1) * (s + 8), "lanes_per_inst": 4, "pipes": PEAK_BOTH_PIPES}
         out[f"mc{s}"] = {"pad": 0, "mac": n_pu * 2 * (s // 2) * (s // 2) * 8, "lanes_per_inst": 4, "pipes": PEAK_ONE_PIPE}
+    # the single-launch search (a CTA per CTU, all four PU sizes): the work of the four per-size launches
+    out["me"] = {"pad": sum(out[f"me{64 >> d}"]["pad"] for d in range(4)), "mac": sum(out[f"me{64 >> d}"]["mac"] for d in range(4)),
+                 "lanes_per_inst": 4, "pipes": PEAK_BOTH_PIPES}
     for p in range(5):
         for c in range(3):
             t = pp.tu_size(p, c)
@@ -829,7 +834,7 @@ def main():
         # the whole step: time the integer pipes need at best for every launch's algorithmic work / the measured step time per frame
         ideal_s = sum((aops[k]["pad"] + aops[k]["mac"]) / int_peak_ops(aops[k], sm_hz) for k in prof if k in aops)
         frame_s = ms * 1e-3 / (args.steps * n_slots)
-        step_bytes = sum(abytes.values())
+        step_bytes = sum(abytes[k] for k in prof if k in abytes)
         # executed-instruction view and DRAM traffic: only from an ncu profile taken on exactly these kernel sources
         issue, traffic, sha = None, None, kernel_source_sha()
         try:
@@ -843,9 +848,9 @@ def main():
                 issue = {"what": "executed warp instructions (ncu smsp__inst_executed.sum, profiles/inst_r02.json) x frames/s against the measured issue ceiling; utilisation, not a roofline",
                          "warp_inst_per_frame": inst, "achieved": inst * fps_gpu, "peak": N_SM * PEAK_BOTH_PIPES * sm_hz, "unit": "warp-inst/s",
                          "frac": inst * fps_gpu / (N_SM * PEAK_BOTH_PIPES * sm_hz), "kernel_source_sha": sha}
-                want = {"me": "k_me<", "mc": "k_mc", "tq": "k_tq"}[top[:2]]
+                want = "k_me_ctu" if top == "me" else {"me": "k_me<", "mc": "k_mc", "tq": "k_tq", "sp": "k_subpel"}[top[:2]]
                 for kk in pc["kernels"]:
-                    if kk["kernel"].startswith(want) and (top[:2] != "me" or kk["kernel"].startswith(f"k_me<{top[2:]}>")):
+                    if kk["kernel"].startswith(want) and (top[:2] != "me" or top == "me" or kk["kernel"].startswith(f"k_me<{top[2:]},")):
                         traffic = (kk.get("dram_read_bytes") or 0) + (kk.get("dram_write_bytes") or 0)
                         break
         except FileNotFoundError:

@@ -6,6 +6,17 @@
 #define HB_FULL_MASK 0xffffffffu
 
 // unaligned 4-byte read of 8-bit samples: two aligned words + funnel shift (read-only path)
+// three consecutive 32-bit words from the 4-byte aligned byte offset `off` of `base` (8-byte aligned), as TWO 64-bit loads: one L1
+// request less than three word loads -- the search kernels are bound by L1 wavefronts (l1tex 70-90 % of peak), not by ALU work.
+// Reads up to 4 bytes past the third word (inside the padded planes).
+__device__ __forceinline__ void hb_ld_words3(const uint8_t *base, uint32_t off, uint32_t &w0, uint32_t &w1, uint32_t &w2)
+{
+    const uint2 a = __ldg(reinterpret_cast<const uint2 *>(base + (off & ~7u)));
+    const uint2 b = __ldg(reinterpret_cast<const uint2 *>(base + (off & ~7u) + 8));
+    const bool odd = (off & 4u) != 0;
+    w0 = odd ? a.y : a.x; w1 = odd ? b.x : a.y; w2 = odd ? b.y : b.x;
+}
+
 __device__ __forceinline__ uint32_t hb_ld_u8x4(const uint8_t *p)
 {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);

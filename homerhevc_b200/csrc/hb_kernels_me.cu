@@ -185,60 +185,48 @@ template <int K> __device__ __forceinline__ uint32_t visited(uint32_t vmask, int
     return __popc(vmask & ((m << next_start) | (m >> (K - next_start))) & ((1u << K) - 1u));
 }
 
+// one PU's inputs, in registers.  out < 0: a lock-step filler (the PU is searched, nothing is written)
+struct MePu {
+    int x, y;
+    int n_amvp, a0x, a0y, a1x, a1y;
+    int n_start, start[6];
+    bool has_parent; int pmvx, pmvy;     // the parent PU's winning vector (quarter-pel)
+    int out;
+    double corr;
+};
+
 // PL = false: the sub-pel stage builds its planes per PU in shared memory (the reference's own scheme); PL = true: it reads the
 // reference picture's fifteen quarter-pel planes, built once per picture, and needs no shared memory beyond the exchange slots
 // WIN = true (pre-pass, PL only): the reference area the integer walk can reach is staged in shared memory first -- one bulk
 // asynchronous copy (cp.async.bulk, the TMA engine) per window row, all completing on one mbarrier -- and every probe of the walk
 // reads it from there instead of gathering 32-bit words through L1 (which was the limiter: l1tex 80-86 % of peak, ~8-10 sectors
 // per request).  The CTA's jobs then are PUS neighbours of one PU row; entries with x < 0 pad the last strip of a row.
-template <int N, bool PL, bool WIN>
-__global__ void __launch_bounds__(256, WIN ? 3 : PL ? 4 : ((N <= 16) ? 3 : (N == 64) ? 4 : 3)) k_me(const MeArgs a)
+// PRE = true: the pre-pass form known at compile time -- two zero AMVP predictors, no caller start points.
+// s_x: exchange slots of the groups wider than a warp, [group][phase][segment]{partial SAD, cost}; s_half: [group][8] (PL = false only)
+template <int N, bool PL, bool WIN, bool PRE>
+__device__ __forceinline__ void me_pu(const MeArgs &a, const MePu &j, const int group, const int gl, uint8_t *s_raw, uint32_t *s_x, uint32_t *s_half,
+                                      const int wx0, const int wy0, int &win_mvx, int &win_mvy)
 {
     using Cfg = MeCfg<N>;
-    constexpr int G = Cfg::G, L = Cfg::L, SEG = Cfg::SEG, NSEG = Cfg::NSEG, SPS = Cfg::SEG_PER_SLOT, PUS = Cfg::PUS;
+    constexpr int G = Cfg::G, L = Cfg::L, SEG = Cfg::SEG, NSEG = Cfg::NSEG, SPS = Cfg::SEG_PER_SLOT;
     constexpr int WPR = Cfg::WPR, WPL = Cfg::WPL, CPL = Cfg::CPL, PS = Cfg::PS, TS = Cfg::TS, PROWS = Cfg::PROWS;
     constexpr int QROWS = Cfg::QROWS, PLANE_WORDS = Cfg::PLANE_WORDS, CS = Cfg::CS;
 
-    extern __shared__ __align__(16) uint8_t s_raw[];
-    __shared__ uint32_t s_x[(G > 32) ? PUS : 1][2][NSEG][2];   // G > 32: [phase][segment]{partial SAD, cost of the segment's slot}
-    __shared__ __align__(16) uint32_t s_half[PUS][8];                        // SADs of the eight half-pel candidates (c_half order 1..8)
-
-    const int group = threadIdx.x / G, gl = threadIdx.x % G, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     const int slot = gl / L, l = gl % L, seg = gl / SEG;
-    const int job_idx = blockIdx.x * PUS + group;
-    // ---- WIN: stage the strip's search window.  Row r of the window = picture row wy0 + r, columns wx0 .. (both clipped to the
-    // picture: a probed block never leaves it, :1424-1427); every thread issues the copies of its rows, thread 0 arms the barrier.
-    int wx0 = 0, wy0 = 0;
-    if constexpr (WIN) {
-        __shared__ __align__(8) uint64_t s_bar;
-        const hbd_me_job *j0 = a.jobs + blockIdx.x * PUS;              // the first entry of a strip is always a real PU
-        const int xa = j0->x, ya = j0->y;
-        wx0 = max(xa - 128, 0); wy0 = max(ya - 64, 0);
-        const int x_hi = min(xa + PUS * N + 128, a.cur.w), y_hi = min(ya + N + 64, a.cur.h);
-        const int wbytes = (x_hi - wx0 + 3 + 15) & ~15, rows = y_hi - wy0;     // + 3: a probe's last word may start up to 3 bytes past its block
-        const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&s_bar));
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(rows * wbytes) : "memory");
-        for (int r = threadIdx.x; r < rows; r += 256) {
-            const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(s_raw + r * Cfg::WIN_P));
-            const uint8_t *src = a.ref.org + (wy0 + r) * a.ref.pitch + wx0;          // 16-byte aligned: pad, pitch and wx0 are multiples of 16
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst), "l"(src), "r"(wbytes), "r"(bar) : "memory");
-        }
-        asm volatile("{\n .reg .pred p;\n WAITW_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n @p bra DONEW_%=;\n bra WAITW_%=;\n DONEW_%=:\n}\n" ::"r"(bar) : "memory");
-    }
-    if (job_idx >= a.n_jobs) return;                   // the whole group leaves together
-    const hbd_me_job *jp = a.jobs + job_idx;
-    const int jx = jp->x, jy = jp->y;
-    if (WIN && jx < 0) return;                         // padding entry of a strip
-    const double corr = a.dyn ? a.dyn->corr : jp->corr;
-    const int n_amvp = jp->n_amvp;
-    const int a0x = jp->amvp[0], a0y = jp->amvp[1], a1x = jp->amvp[2], a1y = jp->amvp[3];
-    const bool two_costs = n_amvp > 1 && (a0x != a1x || a0y != a1y);
+    const int jx = j.x, jy = j.y;
+    const double corr = a.dyn ? a.dyn->corr : j.corr;
+    const int n_amvp = PRE ? 2 : j.n_amvp;
+    const int a0x = PRE ? 0 : j.a0x, a0y = PRE ? 0 : j.a0y, a1x = PRE ? 0 : j.a1x, a1y = PRE ? 0 : j.a1y;
+    const bool two_costs = !PRE && n_amvp > 1 && (a0x != a1x || a0y != a1y);
+    auto sx_at = [&](int ph, int sg, int k) -> uint32_t & { return s_x[((group * 2 + ph) * NSEG + sg) * 2 + k]; };
+    // three consecutive words of a reference / plane row.  64x64 PUs (eight lanes side by side on a row) take them as two 64-bit loads,
+    // 10 % faster there; for the smaller PUs, whose lanes scatter over rows, the wider requests cost more than the saved one
+    // (measured: 16x16 34.8 -> 42.9 us, 8x8 36.9 -> 41.9 us per launch)
+    auto ld3 = [&](const uint8_t *base, uint32_t off, uint32_t &w0, uint32_t &w1, uint32_t &w2) {
+        if constexpr (N == 64) hb_ld_words3(base, off, w0, w1, w2);
+        else { const uint32_t *q = reinterpret_cast<const uint32_t *>(base + off); w0 = __ldg(q); w1 = __ldg(q + 1); w2 = __ldg(q + 2); }
+    };
 
     uint8_t *s_patch = s_raw + group * Cfg::SMEM_PER_PU;
     uint32_t *s_plane = reinterpret_cast<uint32_t *>(s_patch + Cfg::PATCH_BYTES);  // [4][QROWS][TS] by x fraction, rows in pairs
@@ -303,15 +291,15 @@ __global__ void __launch_bounds__(256, WIN ? 3 : PL ? 4 : ((N <= 16) ? 3 : (N ==
                 cst[s] = __shfl_sync(HB_FULL_MASK, cost, s * L, G);
             }
         } else {
-            if ((gl & (SEG - 1)) == 0) { s_x[group][phase][seg][0] = part; s_x[group][phase][seg][1] = cost; }
+            if ((gl & (SEG - 1)) == 0) { sx_at(phase, seg, 0) = part; sx_at(phase, seg, 1) = cost; }
             group_barrier<G>(group, gmask);
 #pragma unroll
             for (int s = 0; s < 4; s++) {
                 uint32_t t = 0;
 #pragma unroll
-                for (int q = 0; q < SPS; q++) t += s_x[group][phase][s * SPS + q][0];
+                for (int q = 0; q < SPS; q++) t += sx_at(phase, s * SPS + q, 0);
                 tot[s] = t;
-                cst[s] = s_x[group][phase][s * SPS][1];
+                cst[s] = sx_at(phase, s * SPS, 1);
             }
             phase ^= 1;
         }
@@ -341,8 +329,8 @@ __global__ void __launch_bounds__(256, WIN ? 3 : PL ? 4 : ((N <= 16) ? 3 : (N ==
         off &= ~3u;
 #pragma unroll
         for (int k = 0; k < PPL; k++) {
-            const uint32_t *q = reinterpret_cast<const uint32_t *>(a.ref.base + off);
-            const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+            uint32_t w0, w1, w2;
+            ld3(a.ref.base, off, w0, w1, w2);
             acc = hb_sad4_acc(cur[2 * k], __funnelshift_r(w0, w1, sh), acc);
             acc1 = hb_sad4_acc(cur[2 * k + 1], __funnelshift_r(w1, w2, sh), acc1);       // two chains for ILP
             off += ref_step;
@@ -383,19 +371,18 @@ __global__ void __launch_bounds__(256, WIN ? 3 : PL ? 4 : ((N <= 16) ? 3 : (N ==
         // ---- origin + extra start points (caller's list, then the parent PU's vector when both components are non-zero)
         int sx[5], sy[5]; bool sv[5];
         sx[0] = min(max(0, xlo), xhi); sy[0] = min(max(0, ylo), yhi); sv[0] = true;
-        const int n_start = jp->n_start;
+        const int n_start = PRE ? 0 : j.n_start;
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-            const int x = jp->start[2 * i] >> 2, y = jp->start[2 * i + 1] >> 2;
+            const int x = PRE ? 0 : j.start[2 * i] >> 2, y = PRE ? 0 : j.start[2 * i + 1] >> 2;
             sx[1 + i] = x; sy[1 + i] = y;
             sv[1 + i] = i < n_start && !(x == 0 && y == 0) && inside(x, y);
         }
         sx[4] = 0; sy[4] = 0; sv[4] = false;
-        if (jp->parent >= 0) {
-            const hb_mv pmv = a.parent[jp->parent].mv;
-            const int x = pmv.x >> 2, y = pmv.y >> 2;
+        if (j.has_parent) {
+            const int x = j.pmvx >> 2, y = j.pmvy >> 2;
             sx[4] = x; sy[4] = y;
-            sv[4] = pmv.x != 0 && pmv.y != 0 && !(x == 0 && y == 0) && inside(x, y);
+            sv[4] = j.pmvx != 0 && j.pmvy != 0 && !(x == 0 && y == 0) && inside(x, y);
         }
         uint32_t ssad[5], srd[5];
         // the parent's vector rides in the fourth slot of the first round when the caller's list leaves it free (always in the
@@ -532,8 +519,8 @@ __global__ void __launch_bounds__(256, WIN ? 3 : PL ? 4 : ((N <= 16) ? 3 : (N ==
             uint32_t acc = 0, acc1 = 0;
 #pragma unroll
             for (int k = 0; k < PPL; k++) {
-                const uint32_t *q = reinterpret_cast<const uint32_t *>(pl + off);
-                const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+                uint32_t w0, w1, w2;
+                ld3(pl, off, w0, w1, w2);
                 acc = hb_sad4_acc(cur[2 * k], __funnelshift_r(w0, w1, sh), acc);
                 acc1 = hb_sad4_acc(cur[2 * k + 1], __funnelshift_r(w1, w2, sh), acc1);
                 off += sp_step;
@@ -566,7 +553,7 @@ __global__ void __launch_bounds__(256, WIN ? 3 : PL ? 4 : ((N <= 16) ? 3 : (N ==
         subx = sbx; suby = sby;
         // ---- the luma prediction of the winner is its block of the plane (of the reference picture itself for an integer vector):
         // the samples hmr_motion_compensation_luma (:1779) produces for this vector.  Slot 0's lanes cover the block.
-        if (a.pred.org != nullptr && slot == 0) {
+        if (a.pred.org != nullptr && slot == 0 && j.out >= 0) {
             const bool integer = (sbx | sby) == 0;
             const uint8_t *src = integer ? a.ref.base : plane_of(sbx, sby);
             uint32_t off = integer ? ref_lane + static_cast<uint32_t>(iy * static_cast<int>(rpitch) + ix) : plane_off(sbx, sby);
@@ -576,8 +563,8 @@ __global__ void __launch_bounds__(256, WIN ? 3 : PL ? 4 : ((N <= 16) ? 3 : (N ==
             uint8_t *dst = a.pred.org + (jy + prow0) * a.pred.pitch + jx + pcol;
 #pragma unroll
             for (int k = 0; k < PPL; k++) {
-                const uint32_t *q = reinterpret_cast<const uint32_t *>(src + off);
-                const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+                uint32_t w0, w1, w2;
+                ld3(src, off, w0, w1, w2);
                 *reinterpret_cast<uint2 *>(dst) = make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
                 off += step;
                 dst += (L / PPR) * a.pred.pitch;
@@ -660,7 +647,7 @@ __global__ void __launch_bounds__(256, WIN ? 3 : PL ? 4 : ((N <= 16) ? 3 : (N ==
             const int row = prow0 + (k / 2) * (L / PPR), col = pcol + (k & 1) * 4 + slot;     // slot s stores byte s of every word
             s_cur[col * CS + row] = static_cast<uint8_t>(cur[k] >> (8 * slot));
         }
-        if (gl < 8) s_half[group][gl] = 0;
+        if (gl < 8) s_half[group * 8 + gl] = 0;
         group_barrier<G>(group, gmask);
 
         // one round: SADs of four sub-pel candidates at quarter-pel offsets (qx[s], qy[s]) in [-3,3]^2 from (ix,iy).  A lane filters
@@ -708,13 +695,13 @@ __global__ void __launch_bounds__(256, WIN ? 3 : PL ? 4 : ((N <= 16) ? 3 : (N ==
         auto t0_strip = [&](int j) {                                  // plane column j: x = ix - 1 + j, block column j - 1
             uint32_t acc[6] = { 0, 0, 0, 0, 0, 0 };                   // {minus,L} {minus,R} {plus,L} {plus,R} {u,L} {u,R}
             half_strip<N, TS, false>(s_plane + j, s_cur + (j - 1) * CS, s_cur, acc);
-            atomicAdd(&s_half[group][0], acc[0]); atomicAdd(&s_half[group][1], acc[2]);
+            atomicAdd(&s_half[group * 8 + 0], acc[0]); atomicAdd(&s_half[group * 8 + 1], acc[2]);
         };
         auto t2_strip = [&](int j) {                                  // x = ix - 1/2 + j: block columns j - 1 (L) and j (R)
             uint32_t acc[6] = { 0, 0, 0, 0, 0, 0 };
             half_strip<N, TS, true>(s_plane + 2 * PLANE_WORDS + j, s_cur + max(j - 1, 0) * CS, s_cur + j * CS, acc);
-            if (j >= 1) { atomicAdd(&s_half[group][5], acc[0]); atomicAdd(&s_half[group][7], acc[2]); atomicAdd(&s_half[group][3], acc[4]); }
-            atomicAdd(&s_half[group][4], acc[1]); atomicAdd(&s_half[group][6], acc[3]); atomicAdd(&s_half[group][2], acc[5]);
+            if (j >= 1) { atomicAdd(&s_half[group * 8 + 5], acc[0]); atomicAdd(&s_half[group * 8 + 7], acc[2]); atomicAdd(&s_half[group * 8 + 3], acc[4]); }
+            atomicAdd(&s_half[group * 8 + 4], acc[1]); atomicAdd(&s_half[group * 8 + 6], acc[3]); atomicAdd(&s_half[group * 8 + 2], acc[5]);
         };
         if constexpr (G == N) {                                       // small PUs: every lane takes one column of each plane
             t0_strip(gl + 1);
@@ -741,15 +728,15 @@ __global__ void __launch_bounds__(256, WIN ? 3 : PL ? 4 : ((N <= 16) ? 3 : (N ==
             }
             if constexpr (G >= 32) {
                 am = __reduce_add_sync(HB_FULL_MASK, am); ap = __reduce_add_sync(HB_FULL_MASK, ap); au = __reduce_add_sync(HB_FULL_MASK, au);
-                if (lane == 0 && (am | ap | au)) { atomicAdd(&s_half[group][5], am); atomicAdd(&s_half[group][7], ap); atomicAdd(&s_half[group][3], au); }
+                if (lane == 0 && (am | ap | au)) { atomicAdd(&s_half[group * 8 + 5], am); atomicAdd(&s_half[group * 8 + 7], ap); atomicAdd(&s_half[group * 8 + 3], au); }
             } else if (rho <= N) {
-                atomicAdd(&s_half[group][5], am); atomicAdd(&s_half[group][7], ap); atomicAdd(&s_half[group][3], au);
+                atomicAdd(&s_half[group * 8 + 5], am); atomicAdd(&s_half[group * 8 + 7], ap); atomicAdd(&s_half[group * 8 + 3], au);
             }
         }
         group_barrier<G>(group, gmask);
         int bidx = 0;
         {
-            const uint4 h0 = *reinterpret_cast<const uint4 *>(&s_half[group][0]), h1 = *reinterpret_cast<const uint4 *>(&s_half[group][4]);
+            const uint4 h0 = *reinterpret_cast<const uint4 *>(&s_half[group * 8 + 0]), h1 = *reinterpret_cast<const uint4 *>(&s_half[group * 8 + 4]);
             const uint32_t hv[8] = { h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w };
 #pragma unroll
             for (int i = 1; i < 9; i++)                    // candidate 0 is the integer position itself: never smaller
@@ -797,11 +784,138 @@ __global__ void __launch_bounds__(256, WIN ? 3 : PL ? 4 : ((N <= 16) ? 3 : (N ==
         }
     }
 
-    if (gl == 0) {
+    if (gl == 0 && j.out >= 0) {
         hb_me_result r;
         r.mv.x = mvx; r.mv.y = mvy; r.subpix.x = subx; r.subpix.y = suby; r.sad = best_sad; r.n_probes = n_probes;
-        a.out[jp->out] = r;
+        a.out[j.out] = r;
     }
+    win_mvx = mvx; win_mvy = mvy;
+}
+
+// ---- one launch per PU size, PUs from a job list (hb_me_search; the pre-pass with per-PU planes or the staged window)
+template <int N, bool PL, bool WIN>
+__global__ void __launch_bounds__(256, WIN ? 3 : PL ? 4 : ((N <= 16) ? 3 : (N == 64) ? 4 : 3)) k_me(const MeArgs a)
+{
+    using Cfg = MeCfg<N>;
+    constexpr int G = Cfg::G, PUS = Cfg::PUS, NSEG = Cfg::NSEG;
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    __shared__ uint32_t s_x[((G > 32) ? PUS : 1) * 2 * NSEG * 2];
+    __shared__ __align__(16) uint32_t s_half[PUS * 8];                      // SADs of the eight half-pel candidates (c_half order 1..8)
+
+    const int group = threadIdx.x / G, gl = threadIdx.x % G;
+    const int job_idx = blockIdx.x * PUS + group;
+    // ---- WIN: stage the strip's search window.  Row r of the window = picture row wy0 + r, columns wx0 .. (both clipped to the
+    // picture: a probed block never leaves it, :1424-1427); every thread issues the copies of its rows, thread 0 arms the barrier.
+    int wx0 = 0, wy0 = 0;
+    if constexpr (WIN) {
+        __shared__ __align__(8) uint64_t s_bar;
+        const hbd_me_job *j0 = a.jobs + blockIdx.x * PUS;              // the first entry of a strip is always a real PU
+        const int xa = j0->x, ya = j0->y;
+        wx0 = max(xa - 128, 0); wy0 = max(ya - 64, 0);
+        const int x_hi = min(xa + PUS * N + 128, a.cur.w), y_hi = min(ya + N + 64, a.cur.h);
+        const int wbytes = (x_hi - wx0 + 3 + 15) & ~15, rows = y_hi - wy0;     // + 3: a probe's last word may start up to 3 bytes past its block
+        const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&s_bar));
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(rows * wbytes) : "memory");
+        for (int r = threadIdx.x; r < rows; r += 256) {
+            const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(s_raw + r * Cfg::WIN_P));
+            const uint8_t *src = a.ref.org + (wy0 + r) * a.ref.pitch + wx0;          // 16-byte aligned: pad, pitch and wx0 are multiples of 16
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(src), "r"(wbytes), "r"(bar) : "memory");
+        }
+        asm volatile("{\n .reg .pred p;\n WAITW_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n @p bra DONEW_%=;\n bra WAITW_%=;\n DONEW_%=:\n}\n" ::"r"(bar) : "memory");
+    }
+    if (job_idx >= a.n_jobs) return;                   // the whole group leaves together
+    const hbd_me_job *jp = a.jobs + job_idx;
+    if (WIN && jp->x < 0) return;                      // padding entry of a strip
+    MePu j;
+    j.x = jp->x; j.y = jp->y; j.n_amvp = jp->n_amvp;
+    j.a0x = jp->amvp[0]; j.a0y = jp->amvp[1]; j.a1x = jp->amvp[2]; j.a1y = jp->amvp[3];
+    j.n_start = jp->n_start;
+#pragma unroll
+    for (int i = 0; i < 6; i++) j.start[i] = jp->start[i];
+    j.has_parent = jp->parent >= 0; j.pmvx = 0; j.pmvy = 0;
+    if (j.has_parent) { const hb_mv pmv = a.parent[jp->parent].mv; j.pmvx = pmv.x; j.pmvy = pmv.y; }
+    j.out = jp->out; j.corr = jp->corr;
+    int mvx, mvy;
+    me_pu<N, PL, WIN, false>(a, j, group, gl, s_raw, s_x, s_half, wx0, wy0, mvx, mvy);
+}
+
+// ---- the pre-pass search as ONE launch: a CTA owns a CTU and searches its 64x64 PU, then its four 32x32, sixteen 16x16 and
+// sixty-four 8x8 PUs (two rounds of 32) -- the thread-group shapes of the per-size kernels tile a CTU exactly.  A child's extra start
+// point (the parent's winning vector, hmr_motion_inter.c:2613) travels through shared memory; the reference picture's quarter-pel
+// planes serve every depth.  PUs outside the picture do not exist; where they share a warp with existing ones (lock-step groups)
+// they re-run a neighbour's search without writing anything.
+struct MeCtuArgs {
+    hbd_plane cur, ref;
+    hbd_subpel sp;
+    hb_me_result *out[4];
+    hbd_plane pred[4];
+    const hbd_dyn_params *dyn;
+    int action, ctu_cols, ctu_row0;
+    int grid_w[4];
+};
+
+template <int N, int D>
+__device__ __forceinline__ void me_ctu_depth(const MeCtuArgs &c, const int X0, const int Y0, const int round, uint32_t *s_x, int2 *s_mv)
+{
+    using Cfg = MeCfg<N>;
+    constexpr int G = Cfg::G, PUS = Cfg::PUS, SIDE = 64 / N;                   // SIDE x SIDE PUs per CTU
+    constexpr int BASE = (D == 0) ? 0 : (D == 1) ? 1 : (D == 2) ? 5 : 21;       // slot of this depth's first PU in s_mv (breadth first)
+    constexpr int PBASE = (D <= 1) ? 0 : (D == 2) ? 1 : 5;
+    const int group = threadIdx.x / G, gl = threadIdx.x % G;
+    int pu = round * PUS + group;                                               // raster index inside the CTU
+    const int fw = c.cur.w, fh = c.cur.h;
+    auto exists = [&](int p) { return X0 + (p % SIDE) * N + N <= fw && Y0 + (p / SIDE) * N + N <= fh; };
+    bool mine = exists(pu);
+    if constexpr (G < 32) {
+        // lock-step groups: a warp runs as long as one of its PUs exists, the others repeat the first existing one
+        const uint32_t vm = __ballot_sync(HB_FULL_MASK, mine);
+        if (vm == 0) return;
+        if (!mine) pu = round * PUS + (threadIdx.x & ~31) / G + (__ffs(vm) - 1) / G;
+    } else {
+        if (!mine) return;                                                      // whole warps (a named-barrier group or the CTA) leave together
+    }
+    const int lx = pu % SIDE, ly = pu / SIDE;
+    MePu j;
+    j.x = X0 + lx * N; j.y = Y0 + ly * N;
+    j.n_amvp = 2; j.a0x = j.a0y = j.a1x = j.a1y = 0; j.n_start = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) j.start[i] = 0;
+    j.has_parent = false; j.pmvx = 0; j.pmvy = 0;
+    if constexpr (D > 0) {
+        const int plx = lx / 2, ply = ly / 2;
+        j.has_parent = X0 + plx * 2 * N + 2 * N <= fw && Y0 + ply * 2 * N + 2 * N <= fh;
+        if (j.has_parent) { const int2 m = s_mv[PBASE + ply * (SIDE / 2) + plx]; j.pmvx = m.x; j.pmvy = m.y; }
+    }
+    j.out = mine ? ((Y0 / N) + ly) * c.grid_w[D] + (X0 / N) + lx : -1;
+    j.corr = 0.;
+    MeArgs a;
+    a.cur = c.cur; a.ref = c.ref; a.jobs = nullptr; a.n_jobs = 0; a.parent = nullptr; a.out = c.out[D]; a.action = c.action; a.dyn = c.dyn;
+    a.pred = c.pred[D]; a.sp = c.sp;
+    int mvx, mvy;
+    me_pu<N, true, false, true>(a, j, group, gl, nullptr, s_x, nullptr, 0, 0, mvx, mvy);
+    if (D < 3 && gl == 0 && mine) s_mv[BASE + pu] = make_int2(mvx, mvy);
+}
+
+__global__ void __launch_bounds__(256, 4) k_me_ctu(const MeCtuArgs c)
+{
+    constexpr int SX64 = 2 * MeCfg<64>::NSEG * 2, SX32 = MeCfg<32>::PUS * 2 * MeCfg<32>::NSEG * 2;
+    __shared__ uint32_t s_x[SX64 > SX32 ? SX64 : SX32];
+    __shared__ int2 s_mv[1 + 4 + 16];
+    const int X0 = (blockIdx.x % c.ctu_cols) * 64, Y0 = (c.ctu_row0 + blockIdx.x / c.ctu_cols) * 64;
+    me_ctu_depth<64, 0>(c, X0, Y0, 0, s_x, s_mv);
+    __syncthreads();
+    me_ctu_depth<32, 1>(c, X0, Y0, 0, s_x, s_mv);
+    __syncthreads();
+    me_ctu_depth<16, 2>(c, X0, Y0, 0, s_x, s_mv);
+    __syncthreads();
+    me_ctu_depth<8, 3>(c, X0, Y0, 0, s_x, s_mv);
+    me_ctu_depth<8, 3>(c, X0, Y0, 1, s_x, s_mv);
 }
 
 template <int N> int configure_me()
@@ -855,4 +969,19 @@ extern "C" int hbk_me_search(const hbd_frame *cur, const hbd_frame *ref, int siz
     case 8: return launch_me<8>(a, win, s);
     default: return static_cast<int>(cudaErrorInvalidValue);
     }
+}
+
+// the whole search of a picture (or of a band of CTU rows) in one launch: every CTU's PUs of all four sizes, zero predictors, the
+// parent's vector as extra start point.  out[d] / pred_out[d]: result table (PU raster of the picture) and prediction picture of depth d.
+extern "C" int hbk_me_search_ctus(const hbd_frame *cur, const hbd_frame *ref, const hbd_subpel *sp, hb_me_result *const out[4], const hbd_frame *const pred_out[4],
+                                  int action, const hbd_dyn_params *dyn, int ctu_cols, int ctu_row0, int ctu_rows, const int grid_w[4], void *stream)
+{
+    if (!sp || !sp->base || !(action & HB_ME_HALF) || !dyn) return static_cast<int>(cudaErrorInvalidValue);
+    if (ctu_cols <= 0 || ctu_rows <= 0) return 0;
+    MeCtuArgs c;
+    memset(&c, 0, sizeof c);
+    c.cur = cur->p[0]; c.ref = ref->p[0]; c.sp = *sp; c.dyn = dyn; c.action = action; c.ctu_cols = ctu_cols; c.ctu_row0 = ctu_row0;
+    for (int d = 0; d < 4; d++) { c.out[d] = out[d]; c.grid_w[d] = grid_w[d]; if (pred_out && pred_out[d]) c.pred[d] = pred_out[d]->p[0]; }
+    k_me_ctu<<<ctu_cols * ctu_rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(c);
+    return static_cast<int>(cudaGetLastError());
 }

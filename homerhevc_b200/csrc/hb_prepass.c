@@ -341,14 +341,27 @@ static int enqueue(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, int
         if (!crc) crc = hbk_subpel_planes(&ref->d, sp, main_st);
         n++;
     }
+    /* the search: one launch for the whole picture (a CTA per CTU, PU sizes 64 -> 8 in turn), or one launch per PU size */
+    const int merged = sp && !pp->cfg.me_staged_window && !pp->cfg.me_per_depth;
+    if (merged) {
+        void *st = main_st;
+        hb_me_result *outs[N_DEPTH];
+        const hbd_frame *preds[N_DEPTH];
+        for (int d = 0; d < N_DEPTH; d++) { outs[d] = pp->d_me[d]; preds[d] = &pp->pred[d]->d; }
+        PROF_MARK("me");
+        if (!crc) crc = hbk_me_search_ctus(&cur->d, &ref->d, sp, outs, preds, pp->cfg.me_action, pp->d_dyn, pp->ctu_cols, pp->row0, pp->rows, pp->grid_w, main_st);
+        n++;
+    }
     for (int d = 0; d < N_DEPTH && !crc; d++) {
         if (!pp->n_valid[d]) continue;
         void *st = main_st;                      /* name used by PROF_MARK */
-        PROF_MARK("me%d", 64 >> d);
-        const int win = sp && pp->cfg.me_staged_window;       /* windowed kernels read the strip-ordered list */
-        if (!crc) crc = hbk_me_search(&cur->d, &ref->d, 64 >> d, win ? pp->d_jobs_strip[d] : pp->d_jobs[d], win ? pp->n_strip[d] : pp->n_valid[d],
-                                      d ? pp->d_me[d - 1] : NULL, pp->d_me[d], pp->cfg.me_action, pp->d_dyn, fused ? &pp->pred[d]->d : NULL, sp, win, main_st);
-        n++;
+        if (!merged) {
+            PROF_MARK("me%d", 64 >> d);
+            const int win = sp && pp->cfg.me_staged_window;       /* windowed kernels read the strip-ordered list */
+            if (!crc) crc = hbk_me_search(&cur->d, &ref->d, 64 >> d, win ? pp->d_jobs_strip[d] : pp->d_jobs[d], win ? pp->n_strip[d] : pp->n_valid[d],
+                                          d ? pp->d_me[d - 1] : NULL, pp->d_me[d], pp->cfg.me_action, pp->d_dyn, fused ? &pp->pred[d]->d : NULL, sp, win, main_st);
+            n++;
+        }
         if (prof) {
             PROF_MARK("mc%d", 64 >> d);
             if (!crc) { crc = enqueue_mc(pp, ref, d, fused, st); n++; }

@@ -108,6 +108,10 @@ int hbk_me_search(const hbd_frame *cur, const hbd_frame *ref, int size, const hb
                                 row, the first one real, x < 0 marks padding -- and each CTA stages its strip's search window in shared memory */,
                   void *stream);
 int hbk_me_strip_pus(int size);
+/* the whole search of a picture (or a band of CTU rows) in one launch: a CTA per CTU, PU sizes 64 -> 8 in turn, zero predictors, the parent's
+ * vector as extra start point; out[d] / pred_out[d] = result table (PU raster of the picture) and prediction picture of depth d */
+int hbk_me_search_ctus(const hbd_frame *cur, const hbd_frame *ref, const hbd_subpel *sp, hb_me_result *const out[4], const hbd_frame *const pred_out[4],
+                       int action, const hbd_dyn_params *dyn, int ctu_cols, int ctu_row0, int ctu_rows, const int grid_w[4], void *stream);
 
 typedef struct hbd_mc_pu { int32_t x, y; int32_t mv_idx; } hbd_mc_pu;   /* luma position; mv = mvsrc[mv_idx].mv */
 int hbk_mc_predict(const hbd_frame *ref, const hbd_frame *pred, int size, const hbd_mc_pu *pus, int n_pus,

@@ -70,7 +70,7 @@ class QuantEnv(C.Structure):
 class PrepassCfg(C.Structure):
     _fields_ = [("qp", C.c_int32), ("chroma_qp_offset", C.c_int32), ("sign_hiding", C.c_int32),
                 ("is_islice", C.c_int32), ("me_action", C.c_int32), ("use_graph", C.c_int32),
-                ("band_ctu_row0", C.c_int32), ("band_ctu_rows", C.c_int32), ("compact_tables", C.c_int32), ("subpel_per_pu", C.c_int32), ("me_staged_window", C.c_int32)]
+                ("band_ctu_row0", C.c_int32), ("band_ctu_rows", C.c_int32), ("compact_tables", C.c_int32), ("subpel_per_pu", C.c_int32), ("me_staged_window", C.c_int32), ("me_per_depth", C.c_int32)]
 
 
 # numpy views of the compact wire records (hb_me_result_c / hb_tu_result_c, 12 bytes each)
@@ -564,9 +564,9 @@ class Prepass:
     DEPTHS, PASSES = 4, 5
 
     def __init__(self, ctx, width, height, qp=32, chroma_qp_offset=2, sign_hiding=1, is_islice=0, me_action=7,
-                 use_graph=1, band=(0, 0), compact_tables=0, subpel_per_pu=0, me_staged_window=0):
+                 use_graph=1, band=(0, 0), compact_tables=0, subpel_per_pu=0, me_staged_window=0, me_per_depth=0):
         self.ctx, self.w, self.h_px = ctx, width, height
-        self.cfg = PrepassCfg(qp, chroma_qp_offset, sign_hiding, is_islice, me_action, use_graph, band[0], band[1], compact_tables, subpel_per_pu, me_staged_window)
+        self.cfg = PrepassCfg(qp, chroma_qp_offset, sign_hiding, is_islice, me_action, use_graph, band[0], band[1], compact_tables, subpel_per_pu, me_staged_window, me_per_depth)
         h = C.c_void_p()
         _check(ctx.L.hb_prepass_create(ctx.h, width, height, C.byref(self.cfg), C.byref(h)), "hb_prepass_create")
         self.h = h

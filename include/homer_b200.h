@@ -297,6 +297,11 @@ typedef struct hb_prepass_cfg {
      * (profiles/ncu_r02.txt): shared memory shares the L1TEX data pipe with the gathers it replaces (l1tex 79-86 % of peak -> 62-74 %) and the
      * staging latency is paid once per CTA at three CTAs per SM: 146 us of search per frame against 142 us, 6 170 frames/s against 6 430 */
     int32_t me_staged_window;
+    /* 0 (default, needs the per-picture planes and no staged window): the search of a picture is ONE launch -- a CTA owns a CTU and walks
+     * its 64x64, 32x32, 16x16 and 8x8 PUs in turn, the parent's vector handed down in shared memory; != 0: one launch per PU size, each
+     * reading the previous size's result table (the round-1 structure; same results).  One dependent frame costs 4 x ~35 us of search
+     * launches in the latter form (each an under-filled wave of a latency-bound chain) against one launch of all four chains */
+    int32_t me_per_depth;
 } hb_prepass_cfg;
 /* the compact wire records (same order and counts as the full tables) */
 typedef struct hb_me_result_c { int16_t mvx, mvy; uint32_t sad; uint16_t n_probes; int8_t subx, suby; } hb_me_result_c;   /* 12 bytes */

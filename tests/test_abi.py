@@ -37,7 +37,7 @@ def test_struct_layouts_match_header():
     # sizes the C side relies on (hb_me_job 17 int32, hb_me_result 6, hb_tu_result 4, 19 function pointers)
     assert C.sizeof(hb.MeJob) == 68 and C.sizeof(hb.MeResult) == 24 and C.sizeof(hb.TuResult) == 16
     assert C.sizeof(hb.McJob) == 20 and C.sizeof(hb.TuJob) == 20 and C.sizeof(hb.LowLevelFuncs) == 19 * C.sizeof(C.c_void_p)
-    assert C.sizeof(hb.PrepassCfg) == 44 and C.sizeof(hb.TqParams) == 24
+    assert C.sizeof(hb.PrepassCfg) == 48 and C.sizeof(hb.TqParams) == 24
     assert hb.lib.ME_COMPACT_DT.itemsize == 12 and hb.lib.TU_COMPACT_DT.itemsize == 12
     assert hb.lib.SAO_DT.itemsize == 416 and hb.lib.SAO_PARAM_DT.itemsize == 196 and hb.lib.UNIT_INFO_DT.itemsize == 10
 

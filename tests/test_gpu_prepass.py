@@ -617,13 +617,16 @@ def test_subpel_planes_per_picture_equal_per_pu(ctx):
     fc, fr = upload(ctx, cur, w, h), upload(ctx, ref, w, h)
     a, b = hb.Prepass(ctx, w, h, qp=qp), hb.Prepass(ctx, w, h, qp=qp, subpel_per_pu=1)
     g = hb.Prepass(ctx, w, h, qp=qp, me_staged_window=1)          # planes per picture + the search window staged in shared memory (bulk async copies)
+    e = hb.Prepass(ctx, w, h, qp=qp, me_per_depth=1)              # one search launch per PU size instead of one per picture (a CTA per CTU)
     for rep in range(2):
-        a.run(fc, fr, avg); b.run(fc, fr, avg); g.run(fc, fr, avg)
+        a.run(fc, fr, avg); b.run(fc, fr, avg); g.run(fc, fr, avg); e.run(fc, fr, avg)
     ctx.sync()
     moved = 0
     for d in range(4):
         ma, mb = a.fetch_me(d), b.fetch_me(d)
         assert ma.tobytes() == mb.tobytes(), d
+        assert ma.tobytes() == e.fetch_me(d).tobytes(), ("one launch per picture vs one per PU size", d)
+        assert all(np.array_equal(x, y) for x, y in zip(a.pred(d).download(), e.pred(d).download())), d
         assert ma.tobytes() == g.fetch_me(d).tobytes(), ("search window staged in shared memory vs gathered from global memory", d)
         ok = ma["sad"] != 0xFFFFFFFF
         moved += int(((ma["subx"][ok] != 0) | (ma["suby"][ok] != 0)).sum())

@@ -13,7 +13,7 @@ ctx = hb.Context(0)
 res = []
 for n in range(frames + 1):
     f = hb.Frame(ctx, w, h); f.upload_u8(*synth.make_frame(tex, w, h, n)); res.append(f)
-pp = hb.Prepass(ctx, w, h, qp=32, use_graph=0, subpel_per_pu=int(os.environ.get("HB_SUBPEL_PER_PU", "0")), me_staged_window=int(os.environ.get("HB_STAGED_WINDOW", "0")))      # 1: the round-1 per-PU plane kernels
+pp = hb.Prepass(ctx, w, h, qp=32, use_graph=0, subpel_per_pu=int(os.environ.get("HB_SUBPEL_PER_PU", "0")), me_staged_window=int(os.environ.get("HB_STAGED_WINDOW", "0")), me_per_depth=int(os.environ.get("HB_ME_PER_DEPTH", "0")))      # 1: the round-1 per-PU plane kernels
 for n in range(frames):
     pp.run(res[n + 1], res[n], 650.0)
 ctx.sync()

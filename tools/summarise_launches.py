@@ -18,7 +18,7 @@ ks = list(agg.values())
 # a frame starts with the plane kernel (k_subpel_planes) when the plan builds the planes per picture, else with k_me<64
 first = "k_subpel_planes" if any(k["kernel"].startswith("k_subpel_planes") for k in ks) else "k_me<64"
 starts = [i for i, k in enumerate(ks) if k["kernel"].startswith(first)]
-pre = ("k_me<", "k_mc", "k_tq", "k_subpel")
+pre = ("k_me<", "k_me_ctu", "k_mc", "k_tq", "k_subpel")
 frames = []
 for s in starts:
     e = s + 1
