@@ -203,10 +203,25 @@ struct MePu {
 // per request).  The CTA's jobs then are PUS neighbours of one PU row; entries with x < 0 pad the last strip of a row.
 // PRE = true: the pre-pass form known at compile time -- two zero AMVP predictors, no caller start points.
 // s_x: exchange slots of the groups wider than a warp, [group][phase][segment]{partial SAD, cost}; s_half: [group][8] (PL = false only)
-template <int N, bool PL, bool WIN, bool PRE>
+// ---- SAD pyramid of a CTU (single-launch search).  Every position the 64x64 PU probes -- integer or sub-pel, keyed by its quarter-pel
+// displacement -- leaves the SADs of the CTU's sixty-four 8x8 blocks at that displacement (the partial sums its own SAD is made of) in
+// shared memory; a smaller PU that probes the same displacement later (it mostly does: same origin, parent's vector, same small
+// patterns -- tools/me_reuse_study.py: 80-99 % of the probes of the children on the benchmark clip, 60-70 % under sigma-30 noise)
+// adds up its blocks instead of reading the reference again.  Same samples, same sums: results cannot differ.
+struct MeMemo {
+    static constexpr int ENTRIES = 64, SLOTS = 256;
+    uint32_t sum[ENTRIES][32];      // word (j, bx) = blocks (by = 2j, bx) | (by = 2j + 1, bx) << 16, j = 0..3... see block()
+    uint32_t tag[ENTRIES];          // quarter-pel displacement: (x & 0xffff) | y << 16
+    uint8_t idx[SLOTS];             // hash slot -> entry, 0xff = empty
+    static __device__ __forceinline__ uint32_t key(int qx, int qy) { return (static_cast<uint32_t>(qx) & 0xffffu) | (static_cast<uint32_t>(qy) << 16); }
+    static __device__ __forceinline__ uint32_t hash(uint32_t k) { return (k * 2654435761u) >> 24; }
+};
+// MEMO: 0 no pyramid, 1 this PU is the CTU (N = 64) and fills it, 2 this PU looks its probes up (blk = its raster index inside the CTU)
+template <int N, bool PL, bool WIN, bool PRE, int MEMO = 0>
 __device__ __forceinline__ void me_pu(const MeArgs &a, const MePu &j, const int group, const int gl, uint8_t *s_raw, uint32_t *s_x, uint32_t *s_half,
-                                      const int wx0, const int wy0, int &win_mvx, int &win_mvy)
+                                      const int wx0, const int wy0, int &win_mvx, int &win_mvy, MeMemo *memo = nullptr, const int blk = 0)
 {
+    static_assert(MEMO != 1 || N == 64, "the pyramid is filled by the 64x64 PU");
     using Cfg = MeCfg<N>;
     constexpr int G = Cfg::G, L = Cfg::L, SEG = Cfg::SEG, NSEG = Cfg::NSEG, SPS = Cfg::SEG_PER_SLOT;
     constexpr int WPR = Cfg::WPR, WPL = Cfg::WPL, CPL = Cfg::CPL, PS = Cfg::PS, TS = Cfg::TS, PROWS = Cfg::PROWS;
@@ -226,6 +241,57 @@ __device__ __forceinline__ void me_pu(const MeArgs &a, const MePu &j, const int 
     auto ld3 = [&](const uint8_t *base, uint32_t off, uint32_t &w0, uint32_t &w1, uint32_t &w2) {
         if constexpr (N == 64) hb_ld_words3(base, off, w0, w1, w2);
         else { const uint32_t *q = reinterpret_cast<const uint32_t *>(base + off); w0 = __ldg(q); w1 = __ldg(q + 1); w2 = __ldg(q + 2); }
+    };
+
+    // MEMO == 2: the SAD of this PU at quarter-pel displacement (qx, qy) from the pyramid, if the CTU probed it
+    auto memo_get = [&](int qx, int qy, uint32_t &val) -> bool {
+        const uint32_t k = MeMemo::key(qx, qy), h = MeMemo::hash(k);
+        uint32_t id = memo->idx[h];
+        if (id == 0xffu) return false;
+        if (memo->tag[id] != k) {                      // second home of a key: the neighbouring slot
+            id = memo->idx[h ^ 1u];
+            if (id == 0xffu || memo->tag[id] != k) return false;
+        }
+        const uint32_t *e = memo->sum[id];
+        constexpr int SIDE = 64 / N;
+        const int bx = blk % SIDE, by = blk / SIDE;
+        if constexpr (N == 8) {
+            const uint32_t w = e[(by >> 1) * 8 + bx];
+            val = (by & 1) ? (w >> 16) : (w & 0xffffu);
+        } else if constexpr (N == 16) {
+            const uint32_t w0 = e[by * 8 + 2 * bx], w1 = e[by * 8 + 2 * bx + 1];
+            val = (w0 & 0xffffu) + (w0 >> 16) + (w1 & 0xffffu) + (w1 >> 16);
+        } else {
+            uint32_t t = 0;
+#pragma unroll
+            for (int jj = 0; jj < 2; jj++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) { const uint32_t w = e[(2 * by + jj) * 8 + 4 * bx + c]; t += (w & 0xffffu) + (w >> 16); }
+            val = t;
+        }
+        return true;
+    };
+    // MEMO == 1: lane l of a slot holds, per pair k, the 8 samples of row (l / 8) + 8k in block column l % 8, i.e. one row of block
+    // (by = k, bx = l % 8).  p[k] = its SAD over them; the eight lanes l % 8 == bx (rows 0..7 of the blocks) add up by a reduce-scatter
+    // (xor 8, xor 16: three shuffles) and the two warps of the slot by shared-memory atomics into entry `id`.
+    int memo_n = 0;                                    // entries handed out so far (four per round, one per slot)
+    auto memo_put = [&](const uint32_t (&pk)[4], int qx, int qy, bool valid) {
+        const int id = memo_n + slot;
+        if (id < MeMemo::ENTRIES && valid) {           // uniform per slot (two warps)
+            const bool b3 = (l & 8) != 0, b4 = (l & 16) != 0;
+            const uint32_t s0 = __shfl_xor_sync(HB_FULL_MASK, b3 ? pk[0] : pk[2], 8), s1 = __shfl_xor_sync(HB_FULL_MASK, b3 ? pk[1] : pk[3], 8);
+            const uint32_t k0 = (b3 ? pk[2] : pk[0]) + s0, k1 = (b3 ? pk[3] : pk[1]) + s1;       // words j = 2 b3, 2 b3 + 1
+            const uint32_t s2 = __shfl_xor_sync(HB_FULL_MASK, b4 ? k0 : k1, 16);
+            const uint32_t kk = (b4 ? k1 : k0) + s2;                                              // word j = 2 b3 + b4
+            atomicAdd(&memo->sum[id][((b3 ? 2 : 0) + (b4 ? 1 : 0)) * 8 + (l & 7)], kk);
+            if (l == 0) {
+                const uint32_t k = MeMemo::key(qx, qy), h = MeMemo::hash(k);
+                memo->tag[id] = k;
+                // first come (a lost race between two slots of a round only loses reuse); a displacement probed twice keeps its first entry
+                if (memo->idx[h] == 0xffu) memo->idx[h] = static_cast<uint8_t>(id);
+                else if (memo->tag[memo->idx[h]] != k && memo->idx[h ^ 1u] == 0xffu) memo->idx[h ^ 1u] = static_cast<uint8_t>(id);
+            }
+        }
     };
 
     uint8_t *s_patch = s_raw + group * Cfg::SMEM_PER_PU;
@@ -307,9 +373,39 @@ __device__ __forceinline__ void me_pu(const MeArgs &a, const MePu &j, const int 
     // SAD of this lane's words at integer displacement (mx, my)
     // this lane's first pair inside the staged window (WIN)
     const uint32_t win_lane = static_cast<uint32_t>((jy - wy0 + prow0) * Cfg::WIN_P + (jx - wx0 + pcol));
-    auto sad_at = [&](int mx, int my) -> uint32_t {
-        uint32_t acc = 0, acc1 = 0;
+    // SAD of this lane's pairs against the rows at base + off (row step `step`); MEMO == 1: the per-pair sums packed two to a word in pk
+    auto sad_rows = [&](const uint8_t *base, uint32_t off, const uint32_t step, uint32_t (&pk)[4]) -> uint32_t {
+        // the pitch is a multiple of 4, so every word of this candidate has the same misalignment: shift once
+        const uint32_t sh = (off & 3u) * 8u;
+        off &= ~3u;
+        if constexpr (MEMO == 1) {
+            uint32_t tot = 0;
+#pragma unroll
+            for (int k = 0; k < PPL; k++) {
+                uint32_t w0, w1, w2;
+                ld3(base, off, w0, w1, w2);
+                const uint32_t pr = hb_sad4_acc(cur[2 * k + 1], __funnelshift_r(w1, w2, sh), hb_sad4_acc(cur[2 * k], __funnelshift_r(w0, w1, sh), 0u));
+                if (k & 1) pk[k / 2] |= pr << 16; else pk[k / 2] = pr;
+                tot += pr;
+                off += step;
+            }
+            return tot;
+        } else {
+            uint32_t acc = 0, acc1 = 0;
+#pragma unroll
+            for (int k = 0; k < PPL; k++) {
+                uint32_t w0, w1, w2;
+                ld3(base, off, w0, w1, w2);
+                acc = hb_sad4_acc(cur[2 * k], __funnelshift_r(w0, w1, sh), acc);
+                acc1 = hb_sad4_acc(cur[2 * k + 1], __funnelshift_r(w1, w2, sh), acc1);       // two chains for ILP
+                off += step;
+            }
+            return acc + acc1;
+        }
+    };
+    auto sad_at = [&](int mx, int my, uint32_t (&pk)[4]) -> uint32_t {
         if constexpr (WIN) {
+            uint32_t acc = 0, acc1 = 0;
             uint32_t off = win_lane + static_cast<uint32_t>(my * Cfg::WIN_P + mx);
             const uint32_t sh = (off & 3u) * 8u;
             off &= ~3u;
@@ -323,26 +419,28 @@ __device__ __forceinline__ void me_pu(const MeArgs &a, const MePu &j, const int 
             }
             return acc + acc1;
         }
-        // the pitch is a multiple of 4, so every word of this candidate has the same misalignment: shift once
-        uint32_t off = ref_lane + static_cast<uint32_t>(my * static_cast<int>(rpitch) + mx);
-        const uint32_t sh = (off & 3u) * 8u;
-        off &= ~3u;
-#pragma unroll
-        for (int k = 0; k < PPL; k++) {
-            uint32_t w0, w1, w2;
-            ld3(a.ref.base, off, w0, w1, w2);
-            acc = hb_sad4_acc(cur[2 * k], __funnelshift_r(w0, w1, sh), acc);
-            acc1 = hb_sad4_acc(cur[2 * k + 1], __funnelshift_r(w1, w2, sh), acc1);       // two chains for ILP
-            off += ref_step;
+        return sad_rows(a.ref.base, ref_lane + static_cast<uint32_t>(my * static_cast<int>(rpitch) + mx), ref_step, pk);
+    };
+    // one probe of this lane's slot at integer (mx, my): from the CTU's pyramid when it is there (MEMO == 2: lane 0 of the slot carries
+    // the sum), else from the reference picture; MEMO == 1 leaves the block sums in the pyramid
+    auto probe_int = [&](int mx, int my, bool mv) -> uint32_t {
+        uint32_t pk[4] = { 0, 0, 0, 0 }, acc = 0;
+        if (mv) {
+            if constexpr (MEMO == 2) {
+                uint32_t v;
+                if (memo_get(mx << 2, my << 2, v)) acc = (l == 0) ? v : 0u;
+                else acc = sad_at(mx, my, pk);
+            } else acc = sad_at(mx, my, pk);
         }
-        return acc + acc1;
+        if constexpr (MEMO == 1) { memo_put(pk, mx << 2, my << 2, mv); memo_n += 4; }
+        return acc;
     };
     // one round: SAD + cost of up to four integer positions (cx[s], cy[s]); invalid slots give garbage that is never read
     auto round4 = [&](const int (&cx)[4], const int (&cy)[4], const bool (&cv)[4], uint32_t (&sad)[4], uint32_t (&rd)[4]) {
         int mx = cx[0], my = cy[0]; bool mv = cv[0];
 #pragma unroll
         for (int s = 1; s < 4; s++) if (slot == s) { mx = cx[s]; my = cy[s]; mv = cv[s]; }
-        const uint32_t acc = mv ? sad_at(mx, my) : 0u;
+        const uint32_t acc = probe_int(mx, my, mv);
         uint32_t cst[4];
         exchange(acc, mv_cost(mx << 2, my << 2), sad, cst);
 #pragma unroll
@@ -351,7 +449,7 @@ __device__ __forceinline__ void me_pu(const MeArgs &a, const MePu &j, const int 
     // the same for the pattern stages: every lane derives ITS slot's position (mx, my) itself and tests it alone; whether the
     // other three slots were inside the search area comes back with their cost (no cost is ever 0xffffffff)
     auto round_own = [&](int mx, int my, bool mv, uint32_t (&sad)[4], uint32_t (&rd)[4], uint32_t &vmask) {
-        const uint32_t acc = mv ? sad_at(mx, my) : 0u;
+        const uint32_t acc = probe_int(mx, my, mv);
         uint32_t cst[4];
         exchange(acc, mv ? mv_cost(mx << 2, my << 2) : 0xffffffffu, sad, cst);
         vmask = 0;
@@ -512,20 +610,15 @@ __device__ __forceinline__ void me_pu(const MeArgs &a, const MePu &j, const int 
             return sp_lane + static_cast<uint32_t>((iy + (cy >> 2)) * static_cast<int>(sp_pitch) + ix + (cx >> 2));
         };
         auto sad_plane = [&](int cx, int cy) -> uint32_t {
-            const uint8_t *pl = plane_of(cx, cy);
-            uint32_t off = plane_off(cx, cy);
-            const uint32_t sh = (off & 3u) * 8u;
-            off &= ~3u;
-            uint32_t acc = 0, acc1 = 0;
-#pragma unroll
-            for (int k = 0; k < PPL; k++) {
-                uint32_t w0, w1, w2;
-                ld3(pl, off, w0, w1, w2);
-                acc = hb_sad4_acc(cur[2 * k], __funnelshift_r(w0, w1, sh), acc);
-                acc1 = hb_sad4_acc(cur[2 * k + 1], __funnelshift_r(w1, w2, sh), acc1);
-                off += sp_step;
-            }
-            return acc + acc1;
+            uint32_t pk[4] = { 0, 0, 0, 0 }, acc;
+            const int qx = (ix << 2) + cx, qy = (iy << 2) + cy;
+            if constexpr (MEMO == 2) {
+                uint32_t v;
+                if (memo_get(qx, qy, v)) acc = (l == 0) ? v : 0u;
+                else acc = sad_rows(plane_of(cx, cy), plane_off(cx, cy), sp_step, pk);
+            } else acc = sad_rows(plane_of(cx, cy), plane_off(cx, cy), sp_step, pk);
+            if constexpr (MEMO == 1) { memo_put(pk, qx, qy, true); memo_n += 4; }
+            return acc;
         };
         int bidx = 0;
 #pragma unroll
@@ -861,7 +954,7 @@ struct MeCtuArgs {
 };
 
 template <int N, int D>
-__device__ __forceinline__ void me_ctu_depth(const MeCtuArgs &c, const int X0, const int Y0, const int round, uint32_t *s_x, int2 *s_mv)
+__device__ __forceinline__ void me_ctu_depth(const MeCtuArgs &c, const int X0, const int Y0, const int round, uint32_t *s_x, int2 *s_mv, MeMemo *memo)
 {
     using Cfg = MeCfg<N>;
     constexpr int G = Cfg::G, PUS = Cfg::PUS, SIDE = 64 / N;                   // SIDE x SIDE PUs per CTU
@@ -898,7 +991,7 @@ __device__ __forceinline__ void me_ctu_depth(const MeCtuArgs &c, const int X0, c
     a.cur = c.cur; a.ref = c.ref; a.jobs = nullptr; a.n_jobs = 0; a.parent = nullptr; a.out = c.out[D]; a.action = c.action; a.dyn = c.dyn;
     a.pred = c.pred[D]; a.sp = c.sp;
     int mvx, mvy;
-    me_pu<N, true, false, true>(a, j, group, gl, nullptr, s_x, nullptr, 0, 0, mvx, mvy);
+    me_pu<N, true, false, true, (D == 0) ? 1 : 2>(a, j, group, gl, nullptr, s_x, nullptr, 0, 0, mvx, mvy, memo, pu);
     if (D < 3 && gl == 0 && mine) s_mv[BASE + pu] = make_int2(mvx, mvy);
 }
 
@@ -907,15 +1000,19 @@ __global__ void __launch_bounds__(256, 4) k_me_ctu(const MeCtuArgs c)
     constexpr int SX64 = 2 * MeCfg<64>::NSEG * 2, SX32 = MeCfg<32>::PUS * 2 * MeCfg<32>::NSEG * 2;
     __shared__ uint32_t s_x[SX64 > SX32 ? SX64 : SX32];
     __shared__ int2 s_mv[1 + 4 + 16];
+    __shared__ MeMemo s_memo;
     const int X0 = (blockIdx.x % c.ctu_cols) * 64, Y0 = (c.ctu_row0 + blockIdx.x / c.ctu_cols) * 64;
-    me_ctu_depth<64, 0>(c, X0, Y0, 0, s_x, s_mv);
+    for (int i = threadIdx.x; i < MeMemo::ENTRIES * 32; i += 256) (&s_memo.sum[0][0])[i] = 0;
+    if (threadIdx.x < MeMemo::SLOTS / 4) reinterpret_cast<uint32_t *>(s_memo.idx)[threadIdx.x] = 0xffffffffu;
     __syncthreads();
-    me_ctu_depth<32, 1>(c, X0, Y0, 0, s_x, s_mv);
+    me_ctu_depth<64, 0>(c, X0, Y0, 0, s_x, s_mv, &s_memo);
     __syncthreads();
-    me_ctu_depth<16, 2>(c, X0, Y0, 0, s_x, s_mv);
+    me_ctu_depth<32, 1>(c, X0, Y0, 0, s_x, s_mv, &s_memo);
     __syncthreads();
-    me_ctu_depth<8, 3>(c, X0, Y0, 0, s_x, s_mv);
-    me_ctu_depth<8, 3>(c, X0, Y0, 1, s_x, s_mv);
+    me_ctu_depth<16, 2>(c, X0, Y0, 0, s_x, s_mv, &s_memo);
+    __syncthreads();
+    me_ctu_depth<8, 3>(c, X0, Y0, 0, s_x, s_mv, &s_memo);
+    me_ctu_depth<8, 3>(c, X0, Y0, 1, s_x, s_mv, &s_memo);
 }
 
 template <int N> int configure_me()

@@ -481,10 +481,18 @@ typedef struct me_state {
 
 static int me_inside(const me_state *s, int x, int y) { return x >= s->xlo && x <= s->xhi && y >= s->ylo && y <= s->yhi; }
 
+/* test aid (tools/me_reuse_study.py): when a buffer is set, every integer probe is appended as (x, y), then (0x7fff, 0x7fff) and the
+ * half-pel winner (hx, hy) */
+static __thread int16_t *g_trace; static __thread int g_trace_cap, g_trace_n;
+void orc_me_trace(int16_t *buf, int cap) { g_trace = buf; g_trace_cap = cap; g_trace_n = 0; }
+int orc_me_trace_count(void) { return g_trace_n; }
+static void trace_put(int x, int y) { if (g_trace && g_trace_n + 2 <= g_trace_cap) { g_trace[g_trace_n++] = (int16_t)x; g_trace[g_trace_n++] = (int16_t)y; } }
+
 static uint32_t me_sad_at(me_state *s, int x, int y)
 {
     const orc_me_in *in = s->in;
     s->n_sads++;
+    trace_put(x, y);
     return orc_sad(in->orig, in->orig_stride, in->ref + y * in->ref_stride + x, in->ref_stride, in->size);
 }
 
@@ -655,6 +663,7 @@ refine:                                                              /* :1601-16
         best_sad = cur;
         if (in->action & 4) {
             const int hx = k_half_order[bidx][0], hy = k_half_order[bidx][1];
+            trace_put(0x7fff, 0x7fff); trace_put(hx, hy);
             build_quarter_planes(p, ref, in->ref_stride, n, hx, hy);
             bx = hx * 2; by = hy * 2;
             for (int i = 0; i < 9; i++) {
