@@ -414,6 +414,7 @@ def measure_bands(args, rank, world, local, torch, dist, hb, synth, barrier, ste
     tex = synth.make_texture(w, h)
     n_pairs = 3
     host = [synth.make_frame(tex, w, h, n) for n in range(n_pairs + 1)]
+    exchange = os.environ.get("HB_BANDS_EXCHANGE", "peer")       # peer: CUDA IPC pulls out of the neighbours' HBM; nccl: staged send / recv
     out = {}
     for S in (1, 8):
         slots = []
@@ -427,14 +428,23 @@ def measure_bands(args, rank, world, local, torch, dist, hb, synth, barrier, ste
                 own[0][y0:y1] = p[0][y0:y1]; own[1][y0 // 2:y1 // 2] = p[1][y0 // 2:y1 // 2]; own[2][y0 // 2:y1 // 2] = p[2][y0 // 2:y1 // 2]
                 f.upload_u8(*own)
             pp = hb.Prepass(c, w, h, qp=QP, use_graph=1, band=(row0, nrows))
-            ex = bands.FrameHaloExchanger(torch, dist, c, w, h, world, rank, dev) if world > 1 else None
+            ex = None
+            if world > 1 and exchange == "peer":
+                c.sync()
+                ex = bands.PeerHaloPuller(hb, dist, c, frames, w, h, world, rank)
+                for j in range(len(frames)):
+                    ex.mark_ready(j)
+            elif world > 1:
+                ex = bands.FrameHaloExchanger(torch, dist, c, w, h, world, rank, dev)
             # the current picture is read inside the band only, so the banded upload above is all a rank needs of it
             slots.append({"ctx": c, "frames": frames, "pp": pp, "ex": ex})
 
         def step(i):
             for sl in slots:
                 j = i % n_pairs
-                if sl["ex"]:
+                if sl["ex"] and exchange == "peer":
+                    sl["ex"].pull(j)                          # wait for the owners' events, one copy kernel out of their HBM, border: all on the stream
+                elif sl["ex"]:
                     sl["ex"].exchange(sl["frames"][j])        # queued on the context's stream: export -> NCCL send/recv -> import -> border
                 sl["pp"].run(sl["frames"][j + 1], sl["frames"][j], AVG_DIST)
 
@@ -463,7 +473,9 @@ def measure_bands(args, rank, world, local, torch, dist, hb, synth, barrier, ste
             sl = slots[0]
             whole_ref, whole_cur = hb.Frame(sl["ctx"], w, h), hb.Frame(sl["ctx"], w, h)
             whole_ref.upload_u8(*host[0]); whole_cur.upload_u8(*host[1])
-            if sl["ex"]:
+            if sl["ex"] and exchange == "peer":
+                sl["ex"].pull(0)
+            elif sl["ex"]:
                 sl["ex"].exchange(sl["frames"][0])
             sl["pp"].run(sl["frames"][1], sl["frames"][0], AVG_DIST)
             sl["ctx"].sync()
@@ -499,12 +511,17 @@ def measure_bands(args, rank, world, local, torch, dist, hb, synth, barrier, ste
             out["halo_bytes_sent_per_frame_rank0"] = sl["ex"].bytes_per_exchange if sl["ex"] else 0
             full.close(); whole_ref.close(); whole_cur.close()
         for sl in slots:
+            sl["ctx"].sync()
+            if sl["ex"] and exchange == "peer":
+                sl["ex"].close()                  # views of the neighbours' pictures go before anybody frees a picture
+        barrier()
+        for sl in slots:
             sl["pp"].close()
             for f in sl["frames"]:
                 f.close()
             sl["ctx"].close()
     out.update({"n_gpus": world, "scaling": "strong", "workload": workload_name(w, h),
-                "parallelism": f"ctu-row bands x{world}: rank r owns CTU rows [{row0}, {row0 + nrows}) of {ctu_rows}; halo exchange by grouped NCCL send/recv ordered on the library's stream (no host wait)",
+                "parallelism": f"ctu-row bands x{world}: rank r owns CTU rows [{row0}, {row0 + nrows}) of {ctu_rows}; " + ("halo rows pulled out of the neighbours' HBM over NVLink (CUDA IPC views, one copy kernel per picture on the library's stream, inter-process events; no host wait)" if exchange == "peer" else "halo exchange by grouped NCCL send/recv ordered on the library's stream (no host wait)"),
                 "halo_rows": {"luma": bands.HALO_LUMA, "chroma": bands.HALO_CHROMA},
                 "timing": "wall clock between device-synchronised barriers, MAX over ranks"})
     return out

@@ -9,9 +9,9 @@ There is no CPU fallback: importing works anywhere (so the build and symbol chec
 compute call needs the CUDA library and a visible device and raises otherwise.
 """
 from .lib import (HbError, Context, Frame, Prepass, MeJob, MeResult, McJob, McBiJob, TuJob, IntraTuJob, IntraJob, TuResult, TqParams, QuantEnv,
-                  PrepassCfg, LowLevelFuncs, load_library, library_path, build_library, lowlevel,
+                  PrepassCfg, LowLevelFuncs, FrameIpc, RowSpan, IpcEvent, load_library, library_path, build_library, lowlevel,
                   ME_PEL, ME_HALF, ME_QUARTER, REG_DCT)
 
 __all__ = ["HbError", "Context", "Frame", "Prepass", "MeJob", "MeResult", "McJob", "McBiJob", "TuJob", "IntraTuJob", "IntraJob", "TuResult", "TqParams",
-           "QuantEnv", "PrepassCfg", "LowLevelFuncs", "load_library", "library_path", "build_library", "lowlevel",
+           "QuantEnv", "PrepassCfg", "LowLevelFuncs", "FrameIpc", "RowSpan", "IpcEvent", "load_library", "library_path", "build_library", "lowlevel",
            "ME_PEL", "ME_HALF", "ME_QUARTER", "REG_DCT"]

@@ -111,3 +111,47 @@ class FrameHaloExchanger:
                 if kind == "recv":
                     frame.import_rows(c, r0, n, t.data_ptr())
             frame.pad()
+
+
+class PeerHaloPuller:
+    """The halo exchange of a SET of pictures resident on this rank's GPU through peer memory (NVLink / NVSwitch, one process per
+    GPU): at set-up every rank exports its pictures and one "finished" event per picture (CUDA IPC) and opens those of the ranks whose
+    bands its halos reach into (all_gather_object, once).  Per picture and frame the exchange then is: make the stream wait for the
+    owners' events, ONE copy kernel that reads the halo rows straight out of the owners' HBM, the border refresh -- two launches queued
+    by one library call, no staging buffers, no collective, no host wait.  `mark_ready(j)` records this rank's event of picture j."""
+
+    def __init__(self, hb, dist, ctx, frames, width, height, world, rank):
+        self.ctx, self.frames, self.rank = ctx, frames, rank
+        ctu_rows = (height + 63) // 64
+        self.events = [hb.IpcEvent(ctx) for _ in frames]
+        mine = [(f.ipc_export(), e.handle) for f, e in zip(frames, self.events)]
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        need = {}                                      # peer -> [(plane, row0, n_rows)]
+        for c in range(3):
+            for peer, r0, n in halo_transfers(height, ctu_rows, world, rank, chroma=c > 0)["recv"]:
+                need.setdefault(peer, []).append((c, r0, n))
+        self.peers = sorted(need)
+        self.views = [[hb.Frame.ipc_open(ctx, everyone[p][j][0]) for p in self.peers] for j in range(len(frames))]
+        self.peer_events = [[hb.IpcEvent(ctx, everyone[p][j][1]) for p in self.peers] for j in range(len(frames))]
+        self.spans = [(i, c, r0, n) for i, p in enumerate(self.peers) for (c, r0, n) in need[p]]
+        width_of = lambda c: width // 2 if c else width
+        self.bytes_per_exchange = sum(n * width_of(c) for (_, c, _, n) in self.spans)      # pulled, per picture
+
+    def mark_ready(self, j):
+        self.events[j].record()
+
+    def pull(self, j):
+        for e in self.peer_events[j]:
+            e.wait()
+        self.frames[j].pull_rows(self.views[j], self.spans, refresh_border=True)
+
+    def close(self):
+        for row in self.views:
+            for v in row:
+                v.close()
+        for row in self.peer_events:
+            for e in row:
+                e.close()
+        for e in self.events:
+            e.close()

@@ -260,6 +260,13 @@ int hbi_scratch(hb_ctx *ctx, int i, size_t bytes, void **dev, void **host)
 /* ------------------------------------------------------------------ resident frames */
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+/* layout of plane c of a width x height picture (also what a view of another process's picture assumes) */
+static void plane_geometry(hbd_plane *p, int c, int width, int height)
+{
+    p->w = c ? width / 2 : width; p->h = c ? height / 2 : height;
+    p->pad = c ? HB_PAD_LUMA / 2 : HB_PAD_LUMA;
+    p->pitch = (int32_t)align_up((size_t)p->w + 2 * (size_t)p->pad, 128);
+}
 int hb_frame_create(hb_ctx *ctx, int width, int height, hb_frame **out)
 {
     if (!ctx || !out) return hbi_fail(HB_ERR_ARG, "hb_frame_create: NULL argument");
@@ -270,9 +277,7 @@ int hb_frame_create(hb_ctx *ctx, int width, int height, hb_frame **out)
     hbc_set_device(ctx->device);
     for (int c = 0; c < 3; c++) {
         hbd_plane *p = &f->d.p[c];
-        p->w = c ? width / 2 : width; p->h = c ? height / 2 : height;
-        p->pad = c ? HB_PAD_LUMA / 2 : HB_PAD_LUMA;
-        p->pitch = (int32_t)align_up((size_t)p->w + 2 * (size_t)p->pad, 128);
+        plane_geometry(p, c, width, height);
         const size_t bytes = (size_t)p->pitch * ((size_t)p->h + 2 * (size_t)p->pad) + 256;
         const int rc = hbc_malloc((void **)&p->base, bytes);
         if (rc) { hb_frame_destroy(f); return hbi_cuda_fail(rc, "hb_frame_create: cudaMalloc"); }
@@ -288,7 +293,7 @@ void hb_frame_destroy(hb_frame *f)
     if (!f) return;
     hbc_set_device(f->ctx->device);
     hbc_stream_sync(f->ctx->stream);
-    for (int c = 0; c < 3; c++) if (f->d.p[c].base) hbc_free(f->d.p[c].base);
+    for (int c = 0; c < 3; c++) if (f->d.p[c].base) { if (f->ipc_view) hbc_ipc_close_mem(f->d.p[c].base); else hbc_free(f->d.p[c].base); }
     if (f->stage) hbc_free(f->stage);
     if (f->sp.base) hbc_free(f->sp.base);
     free(f);
@@ -422,6 +427,107 @@ int hb_frame_pad(hb_ctx *ctx, hb_frame *f)
     const int rc = hbk_pad_frame(&f->d, ctx->stream);
     ctx->launches += 1;
     return rc ? hbi_cuda_fail(rc, "hb_frame_pad") : HB_OK;
+}
+
+/* ---- peer pictures: CUDA IPC views and the halo pull (include/homer_b200.h) */
+int hb_frame_ipc_export(const hb_frame *f, hb_frame_ipc *out)
+{
+    if (!f || !out) return hbi_fail(HB_ERR_ARG, "hb_frame_ipc_export: NULL argument");
+    if (f->ipc_view) return hbi_fail(HB_ERR_ARG, "hb_frame_ipc_export: a view cannot be exported again");
+    memset(out, 0, sizeof *out);
+    hbc_set_device(f->ctx->device);
+    for (int c = 0; c < 3; c++) {
+        const int rc = hbc_ipc_get_mem(f->d.p[c].base, out->mem[c]);
+        if (rc) return hbi_cuda_fail(rc, "hb_frame_ipc_export: cudaIpcGetMemHandle");
+    }
+    out->width = f->w; out->height = f->h;
+    return HB_OK;
+}
+int hb_frame_ipc_open(hb_ctx *ctx, const hb_frame_ipc *in, hb_frame **view)
+{
+    if (!ctx || !in || !view) return hbi_fail(HB_ERR_ARG, "hb_frame_ipc_open: NULL argument");
+    *view = NULL;
+    if (in->width < 16 || in->height < 16 || (in->width & 7) || (in->height & 7)) return hbi_fail(HB_ERR_ARG, "hb_frame_ipc_open: bad geometry %dx%d", in->width, in->height);
+    hb_frame *f = (hb_frame *)calloc(1, sizeof *f);
+    if (!f) return hbi_fail(HB_ERR_NOMEM, "hb_frame_ipc_open: out of memory");
+    f->ctx = ctx; f->w = in->width; f->h = in->height; f->ipc_view = 1;
+    hbc_set_device(ctx->device);
+    for (int c = 0; c < 3; c++) {
+        hbd_plane *p = &f->d.p[c];
+        plane_geometry(p, c, in->width, in->height);          /* the owner laid its planes out with the same rule (hb_frame_create) */
+        const int rc = hbc_ipc_open_mem(in->mem[c], (void **)&p->base);
+        if (rc) { p->base = NULL; hb_frame_destroy(f); return hbi_cuda_fail(rc, "hb_frame_ipc_open: cudaIpcOpenMemHandle"); }
+        p->org = p->base + (size_t)p->pad * p->pitch + p->pad;
+    }
+    *view = f;
+    return HB_OK;
+}
+int hb_frame_pull_rows(hb_ctx *ctx, hb_frame *dst, const hb_frame *const *srcs, int n_srcs, const hb_row_span *spans, int n_spans, int refresh_border)
+{
+    hbd_pull_span ps[HB_MAX_ROW_SPANS];
+    if (!ctx || !dst || (n_spans > 0 && (!srcs || !spans)) || n_spans < 0 || n_spans > HB_MAX_ROW_SPANS) return hbi_fail(HB_ERR_ARG, "hb_frame_pull_rows: bad argument");
+    if (dst->ipc_view) return hbi_fail(HB_ERR_ARG, "hb_frame_pull_rows: the destination is a view of another process's picture");
+    for (int i = 0; i < n_spans; i++) {
+        const hb_row_span *s = &spans[i];
+        if (s->src < 0 || s->src >= n_srcs || !srcs[s->src] || s->plane < 0 || s->plane > 2) return hbi_fail(HB_ERR_ARG, "hb_frame_pull_rows: span %d: bad source or plane", i);
+        const hb_frame *sf = srcs[s->src];
+        if (sf->w != dst->w || sf->h != dst->h) return hbi_fail(HB_ERR_ARG, "hb_frame_pull_rows: span %d: picture sizes differ", i);
+        const hbd_plane *sp = &sf->d.p[s->plane], *dp = &dst->d.p[s->plane];
+        if (s->row0 < 0 || s->n_rows < 0 || s->row0 + s->n_rows > dp->h) return hbi_fail(HB_ERR_ARG, "hb_frame_pull_rows: span %d: rows %d..%d outside the plane", i, s->row0, s->row0 + s->n_rows);
+        ps[i].src = sp->org + (size_t)s->row0 * sp->pitch; ps[i].dst = dp->org + (size_t)s->row0 * dp->pitch;
+        ps[i].src_pitch = sp->pitch; ps[i].dst_pitch = dp->pitch; ps[i].width = dp->w; ps[i].rows = s->n_rows;
+    }
+    hbc_set_device(ctx->device);
+    int rc = hbk_pull_rows(ps, n_spans, ctx->stream);
+    if (!rc && n_spans) ctx->launches += 1;
+    if (!rc && refresh_border) { rc = hbk_pad_frame(&dst->d, ctx->stream); ctx->launches += 1; }
+    return rc ? hbi_cuda_fail(rc, "hb_frame_pull_rows") : HB_OK;
+}
+struct hb_ipc_event { void *ev; int device; };
+int hb_ipc_event_create(hb_ctx *ctx, hb_ipc_event **ev, uint8_t handle[HB_IPC_HANDLE_BYTES])
+{
+    if (!ctx || !ev || !handle) return hbi_fail(HB_ERR_ARG, "hb_ipc_event_create: NULL argument");
+    hb_ipc_event *e = (hb_ipc_event *)calloc(1, sizeof *e);
+    if (!e) return hbi_fail(HB_ERR_NOMEM, "hb_ipc_event_create: out of memory");
+    hbc_set_device(ctx->device);
+    const int rc = hbc_ipc_event_create(&e->ev, handle);
+    if (rc) { free(e); return hbi_cuda_fail(rc, "hb_ipc_event_create"); }
+    e->device = ctx->device;
+    *ev = e;
+    return HB_OK;
+}
+int hb_ipc_event_open(hb_ctx *ctx, const uint8_t handle[HB_IPC_HANDLE_BYTES], hb_ipc_event **ev)
+{
+    if (!ctx || !ev || !handle) return hbi_fail(HB_ERR_ARG, "hb_ipc_event_open: NULL argument");
+    hb_ipc_event *e = (hb_ipc_event *)calloc(1, sizeof *e);
+    if (!e) return hbi_fail(HB_ERR_NOMEM, "hb_ipc_event_open: out of memory");
+    hbc_set_device(ctx->device);
+    const int rc = hbc_ipc_event_open(handle, &e->ev);
+    if (rc) { free(e); return hbi_cuda_fail(rc, "hb_ipc_event_open"); }
+    e->device = ctx->device;
+    *ev = e;
+    return HB_OK;
+}
+int hb_ipc_event_record(hb_ctx *ctx, hb_ipc_event *ev)
+{
+    if (!ctx || !ev) return hbi_fail(HB_ERR_ARG, "hb_ipc_event_record: NULL argument");
+    hbc_set_device(ctx->device);
+    const int rc = hbc_event_record(ev->ev, ctx->stream);
+    return rc ? hbi_cuda_fail(rc, "hb_ipc_event_record") : HB_OK;
+}
+int hb_ipc_event_wait(hb_ctx *ctx, hb_ipc_event *ev)
+{
+    if (!ctx || !ev) return hbi_fail(HB_ERR_ARG, "hb_ipc_event_wait: NULL argument");
+    hbc_set_device(ctx->device);
+    const int rc = hbc_stream_wait_event(ctx->stream, ev->ev);
+    return rc ? hbi_cuda_fail(rc, "hb_ipc_event_wait") : HB_OK;
+}
+void hb_ipc_event_destroy(hb_ipc_event *ev)
+{
+    if (!ev) return;
+    hbc_set_device(ev->device);
+    hbc_event_destroy(ev->ev);
+    free(ev);
 }
 
 /* ------------------------------------------------------------------ batched jobs (host arrays in, host arrays out) */

@@ -30,6 +30,7 @@ struct hb_frame {
     hbd_frame d;
     uint8_t *stage;            /* dense device copy of the last uploaded planes (allocated on first upload) */
     hbd_subpel sp;             /* quarter-pel planes of the luma (allocated the first time the frame is a pre-pass reference) */
+    int ipc_view;              /* the planes belong to another process (hb_frame_ipc_open): closed, not freed */
 };
 
 hb_ctx *hb_default_ctx(void);

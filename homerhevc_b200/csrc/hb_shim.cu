@@ -235,3 +235,70 @@ extern "C" int hbk_pc_interp(const int16_t *src, int ss, int org_off, int16_t *d
     k_pc_interp<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, ss, org_off, dst, ds, chroma, fraction, w, h, vertical, first, last);
     return static_cast<int>(cudaGetLastError());
 }
+
+// ---- CUDA IPC: another process's device allocations and events (CTU-row bands, one process per GPU)
+static_assert(sizeof(cudaIpcMemHandle_t) == 64 && sizeof(cudaIpcEventHandle_t) == 64, "HB_IPC_HANDLE_BYTES");
+extern "C" int hbc_ipc_get_mem(void *dev, unsigned char out[64])
+{
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, dev);
+    if (e == cudaSuccess) memcpy(out, &h, 64);
+    return static_cast<int>(e);
+}
+extern "C" int hbc_ipc_open_mem(const unsigned char in[64], void **dev)
+{
+    cudaIpcMemHandle_t h;
+    memcpy(&h, in, 64);
+    return static_cast<int>(cudaIpcOpenMemHandle(dev, h, cudaIpcMemLazyEnablePeerAccess));
+}
+extern "C" int hbc_ipc_close_mem(void *dev) { return static_cast<int>(cudaIpcCloseMemHandle(dev)); }
+extern "C" int hbc_ipc_event_create(void **ev, unsigned char out[64])
+{
+    cudaEvent_t e;
+    cudaError_t rc = cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventInterprocess);
+    if (rc != cudaSuccess) return static_cast<int>(rc);
+    cudaIpcEventHandle_t h;
+    rc = cudaIpcGetEventHandle(&h, e);
+    if (rc != cudaSuccess) { cudaEventDestroy(e); return static_cast<int>(rc); }
+    memcpy(out, &h, 64);
+    *ev = e;
+    return 0;
+}
+extern "C" int hbc_ipc_event_open(const unsigned char in[64], void **ev)
+{
+    cudaIpcEventHandle_t h;
+    memcpy(&h, in, 64);
+    cudaEvent_t e;
+    const cudaError_t rc = cudaIpcOpenEventHandle(&e, h);
+    if (rc == cudaSuccess) *ev = e;
+    return static_cast<int>(rc);
+}
+
+// rows of up to twelve plane pieces, each from its own source (peer memory over NVLink or local) into this GPU's picture: one CTA per
+// row, 16 bytes per thread where the row allows it
+struct PullArgs { hbd_pull_span s[12]; };
+__global__ void __launch_bounds__(256) k_pull_rows(const PullArgs a)
+{
+    const hbd_pull_span sp = a.s[blockIdx.y];
+    const int row = blockIdx.x;
+    if (row >= sp.rows) return;
+    const uint8_t *src = sp.src + static_cast<size_t>(row) * sp.src_pitch;
+    uint8_t *dst = sp.dst + static_cast<size_t>(row) * sp.dst_pitch;
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | static_cast<uintptr_t>(sp.width)) & 15) == 0) {
+        for (int i = threadIdx.x; i < sp.width / 16; i += 256) reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
+    } else {
+        for (int i = threadIdx.x; i < sp.width / 4; i += 256) reinterpret_cast<uint32_t *>(dst)[i] = reinterpret_cast<const uint32_t *>(src)[i];
+    }
+}
+extern "C" int hbk_pull_rows(const hbd_pull_span *spans, int n_spans, void *stream)
+{
+    if (n_spans <= 0) return 0;
+    if (n_spans > 12) return static_cast<int>(cudaErrorInvalidValue);
+    PullArgs a;
+    memset(&a, 0, sizeof a);
+    int rows = 0;
+    for (int i = 0; i < n_spans; i++) { a.s[i] = spans[i]; rows = spans[i].rows > rows ? spans[i].rows : rows; }
+    if (rows <= 0) return 0;
+    k_pull_rows<<<dim3(rows, n_spans), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return static_cast<int>(cudaGetLastError());
+}

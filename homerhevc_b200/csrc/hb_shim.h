@@ -99,6 +99,14 @@ typedef struct hbd_me_job {       /* one PU, device layout */
 typedef struct hbd_subpel { uint8_t *base; int32_t pitch; int32_t w, h; int32_t pad_; uint64_t plane_bytes; } hbd_subpel;
 int hbk_subpel_planes(const hbd_frame *ref, const hbd_subpel *sp, void *stream);
 int hbk_subpel_uses_tma(void);
+/* CUDA IPC (peer pictures of the CTU-row bands) */
+int hbc_ipc_get_mem(void *dev, unsigned char out[64]);
+int hbc_ipc_open_mem(const unsigned char in[64], void **dev);
+int hbc_ipc_close_mem(void *dev);
+int hbc_ipc_event_create(void **ev, unsigned char out[64]);
+int hbc_ipc_event_open(const unsigned char in[64], void **ev);
+typedef struct hbd_pull_span { const uint8_t *src; uint8_t *dst; int32_t src_pitch, dst_pitch, width, rows; } hbd_pull_span;
+int hbk_pull_rows(const hbd_pull_span *spans, int n_spans, void *stream);       /* n_spans <= 12, widths multiples of 4 */
 int hbk_me_configure(void);   /* once per device, before the first search launch */
 int hbk_me_search(const hbd_frame *cur, const hbd_frame *ref, int size, const hbd_me_job *jobs, int n_jobs,
                   const hb_me_result *parent, hb_me_result *out, int action, const hbd_dyn_params *dyn,

@@ -163,6 +163,15 @@ def load_library():
     L.hb_frame_export_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.hb_frame_import_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.hb_frame_pad.argtypes = [C.c_void_p, C.c_void_p]
+    L.hb_frame_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.hb_frame_ipc_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.hb_frame_pull_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    L.hb_ipc_event_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
+    L.hb_ipc_event_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.hb_ipc_event_record.argtypes = [C.c_void_p, C.c_void_p]
+    L.hb_ipc_event_wait.argtypes = [C.c_void_p, C.c_void_p]
+    L.hb_ipc_event_destroy.argtypes = [C.c_void_p]
+    L.hb_ipc_event_destroy.restype = None
     # section C
     L.hb_me_search.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(MeJob), C.c_int, C.POINTER(MeResult), C.c_int,
                                C.c_double, C.c_int, C.POINTER(MeResult)]
@@ -509,6 +518,42 @@ def _intra_presearch(self, cur, jobs, adi, out=None):
 Context.intra_presearch = _intra_presearch
 
 
+class FrameIpc(C.Structure):
+    _fields_ = [("mem", (C.c_uint8 * 64) * 3), ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class RowSpan(C.Structure):
+    _fields_ = [("src", C.c_int32), ("plane", C.c_int32), ("row0", C.c_int32), ("n_rows", C.c_int32)]
+
+
+class IpcEvent:
+    """inter-process event on a context's stream: the owner records, another process's stream waits (no host wait)"""
+
+    def __init__(self, ctx, handle=None):
+        self.ctx = ctx
+        ev = C.c_void_p()
+        if handle is None:
+            buf = (C.c_uint8 * 64)()
+            _check(ctx.L.hb_ipc_event_create(ctx.h, C.byref(ev), buf), "hb_ipc_event_create")
+            self.handle = bytes(buf)
+        else:
+            buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+            _check(ctx.L.hb_ipc_event_open(ctx.h, buf, C.byref(ev)), "hb_ipc_event_open")
+            self.handle = bytes(handle)
+        self.h = ev
+
+    def record(self):
+        _check(self.ctx.L.hb_ipc_event_record(self.ctx.h, self.h), "hb_ipc_event_record")
+
+    def wait(self):
+        _check(self.ctx.L.hb_ipc_event_wait(self.ctx.h, self.h), "hb_ipc_event_wait")
+
+    def close(self):
+        if self.h:
+            self.ctx.L.hb_ipc_event_destroy(self.h)
+            self.h = None
+
+
 class Frame:
     def __init__(self, ctx, width, height):
         self.ctx, self.w, self.h_px = ctx, width, height
@@ -541,6 +586,28 @@ class Frame:
 
     def pad(self):
         _check(self.ctx.L.hb_frame_pad(self.ctx.h, self.h), "hb_frame_pad")
+
+    # ---- peer pictures (CUDA IPC): bytes another process opens with Frame.ipc_open; rows pulled straight out of the owner's HBM
+    def ipc_export(self):
+        d = FrameIpc()
+        _check(self.ctx.L.hb_frame_ipc_export(self.h, C.byref(d)), "hb_frame_ipc_export")
+        return bytes(d)
+
+    @classmethod
+    def ipc_open(cls, ctx, blob):
+        d = FrameIpc.from_buffer_copy(blob)
+        f = cls.__new__(cls)
+        f.ctx, f.w, f.h_px = ctx, d.width, d.height
+        h = C.c_void_p()
+        _check(ctx.L.hb_frame_ipc_open(ctx.h, C.byref(d), C.byref(h)), "hb_frame_ipc_open")
+        f.h = h
+        return f
+
+    def pull_rows(self, srcs, spans, refresh_border=True):
+        """spans: [(index into srcs, plane, row0, n_rows)]: one copy kernel on the context's stream, nothing waits"""
+        arr = (C.c_void_p * max(1, len(srcs)))(*[s.h for s in srcs])
+        sp = (RowSpan * max(1, len(spans)))(*[RowSpan(*s) for s in spans])
+        _check(self.ctx.L.hb_frame_pull_rows(self.ctx.h, self.h, arr, len(srcs), sp, len(spans), 1 if refresh_border else 0), "hb_frame_pull_rows")
 
     def download(self):
         y = np.zeros((self.h_px, self.w), np.uint8)

@@ -143,6 +143,25 @@ int  hb_frame_export_rows(hb_ctx *ctx, const hb_frame *f, int plane, int row0, i
 int  hb_frame_import_rows(hb_ctx *ctx, hb_frame *f, int plane, int row0, int n_rows, const void *dev_src);
 int  hb_frame_pad(hb_ctx *ctx, hb_frame *f);
 
+/* The same exchange without staging buffers or a collective (one process per GPU, NVLink / NVSwitch peer memory): the owner of a
+ * picture exports its three device allocations once (CUDA IPC), a neighbour opens them as a read-only VIEW and pulls the halo rows
+ * it needs straight out of the owner's HBM with ONE copy kernel per picture on its own stream (+ the border refresh); nothing for the
+ * host to wait on.  Ordering across the two processes is an inter-process event: the owner records it on its stream when the picture
+ * is finished, the neighbour makes its stream wait for it before it pulls. */
+#define HB_IPC_HANDLE_BYTES 64
+typedef struct hb_frame_ipc { uint8_t mem[3][HB_IPC_HANDLE_BYTES]; int32_t width, height; } hb_frame_ipc;
+int  hb_frame_ipc_export(const hb_frame *f, hb_frame_ipc *out);
+int  hb_frame_ipc_open(hb_ctx *ctx, const hb_frame_ipc *in, hb_frame **view);      /* another process's picture; hb_frame_destroy closes the view */
+typedef struct hb_row_span { int32_t src, plane, row0, n_rows; } hb_row_span;      /* rows [row0, row0 + n_rows) of `plane` from srcs[src] */
+#define HB_MAX_ROW_SPANS 12
+int  hb_frame_pull_rows(hb_ctx *ctx, hb_frame *dst, const hb_frame *const *srcs, int n_srcs, const hb_row_span *spans, int n_spans, int refresh_border);
+typedef struct hb_ipc_event hb_ipc_event;
+int  hb_ipc_event_create(hb_ctx *ctx, hb_ipc_event **ev, uint8_t handle[HB_IPC_HANDLE_BYTES]);
+int  hb_ipc_event_open(hb_ctx *ctx, const uint8_t handle[HB_IPC_HANDLE_BYTES], hb_ipc_event **ev);
+int  hb_ipc_event_record(hb_ctx *ctx, hb_ipc_event *ev);     /* on the context's stream */
+int  hb_ipc_event_wait(hb_ctx *ctx, hb_ipc_event *ev);       /* the context's stream waits; the host does not */
+void hb_ipc_event_destroy(hb_ipc_event *ev);
+
 /* ------------------------------------------------------------------ C. batched jobs on resident frames ----- */
 typedef struct hb_mv { int32_t x, y; } hb_mv;                 /* quarter-pel units (motion_vector_t, hmr_private.h:712) */
 

@@ -457,8 +457,10 @@ def test_compact_tables(ctx):
     fc.close(); fr.close()
 
 
-def test_bands_across_gpus_with_nccl_halo_exchange(ctx):
-    """configs[3]: CTU-row bands on two GPUs, reference halos swapped over NCCL; needs >= 2 devices (skipped on one)"""
+@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+def test_bands_across_gpus_with_nccl_halo_exchange(ctx, exchange):
+    """configs[3]: CTU-row bands on two GPUs, reference halos swapped over NCCL (staged send / recv) or pulled out of the neighbour's
+    HBM through CUDA IPC peer memory; needs >= 2 devices (skipped on one)"""
     import os
     import subprocess
     import sys
@@ -467,7 +469,7 @@ def test_bands_across_gpus_with_nccl_halo_exchange(ctx):
         pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                          "--master-port", "29641", os.path.join(root, "tools", "band_check.py"), "1280", "720"],
+                          "--master-port", "29641" if exchange == "nccl" else "29642", os.path.join(root, "tools", "band_check.py"), "1280", "720", exchange],
                          capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
     assert "mismatches=0" in out.stdout

@@ -169,3 +169,50 @@ def test_sao_offset_derivation_matches_reference_vectors():
                 cand[i, c, t]["dist"], cand[i, c, t]["band"] = dist, band
                 cand[i, c, t]["offset"] = off[[0, 1, 3, 4]] if t < 4 else off[band:band + 4]
     assert sao_decide_from_candidates(cand, lam).tobytes() == prm.tobytes()
+
+
+def test_peer_halo_puller_plan_covers_every_halo_row():
+    """PeerHaloPuller (CUDA IPC pulls): with stubbed device objects, the spans it would pull are exactly the halo rows outside the rank's own
+    band, each from the rank that owns it -- including the thin-band case where a halo reaches past the direct neighbour (720p on 8 ranks)"""
+    from homerhevc_b200 import bands
+
+    class _Ev:
+        def __init__(self, ctx, handle=None): self.handle = handle or b"e"
+        def record(self): pass
+        def wait(self): pass
+        def close(self): pass
+
+    class _Frame:
+        opened = []
+        def ipc_export(self): return b"f"
+        @classmethod
+        def ipc_open(cls, ctx, blob): cls.opened.append(blob); return cls()
+        def close(self): pass
+
+    class _Hb:
+        IpcEvent, Frame = _Ev, _Frame
+
+    class _Dist:
+        def __init__(self, world): self.world = world
+        def all_gather_object(self, out, mine):
+            for r in range(self.world): out[r] = mine
+
+    for (w, h, world) in ((1280, 720, 8), (3840, 2160, 8), (1920, 1080, 2)):
+        ctu_rows = (h + 63) // 64
+        for rank in range(world):
+            p = bands.PeerHaloPuller(_Hb, _Dist(world), None, [_Frame(), _Frame()], w, h, world, rank)
+            for c in range(3):
+                chroma = c > 0
+                want = set()
+                for a, b in bands._halo_intervals(h, ctu_rows, world, rank, chroma):
+                    want |= set(range(a, b))
+                got = set()
+                for (i, pc, r0, n) in p.spans:
+                    if pc != c:
+                        continue
+                    o0, o1 = bands.band_sample_rows(h, ctu_rows, world, p.peers[i], chroma)
+                    assert o0 <= r0 and r0 + n <= o1, "pulled from a rank that does not own the rows"
+                    assert not (got & set(range(r0, r0 + n)))
+                    got |= set(range(r0, r0 + n))
+                assert got == want, (w, h, world, rank, c)
+            assert len(p.spans) <= 12 and rank not in p.peers

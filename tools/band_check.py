@@ -15,6 +15,7 @@ import homerhevc_b200 as hb
 from homerhevc_b200 import bands, synth
 
 w, h = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (1280, 720)
+mode = sys.argv[3] if len(sys.argv) > 3 else "nccl"         # nccl: staged send/recv; peer: rows pulled out of the neighbours' HBM (CUDA IPC)
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -39,8 +40,14 @@ for c, pl in enumerate(ref_h):
     masked.append(m)
 ref_band = hb.Frame(ctx, w, h)
 ref_band.upload_u8(*masked)
-ex = bands.FrameHaloExchanger(torch, dist, ctx, w, h, world, rank, torch.device("cuda", local))
-ex.exchange(ref_band)
+if mode == "peer":
+    ctx.sync()
+    ex = bands.PeerHaloPuller(hb, dist, ctx, [ref_band], w, h, world, rank)
+    ex.mark_ready(0)
+    ex.pull(0)
+else:
+    ex = bands.FrameHaloExchanger(torch, dist, ctx, w, h, world, rank, torch.device("cuda", local))
+    ex.exchange(ref_band)
 band = hb.Prepass(ctx, w, h, use_graph=0, band=(row0, nrows))
 band.run(cur, ref_band, 650.0)
 ctx.sync()
@@ -72,6 +79,7 @@ for p in range(5):
 t = torch.tensor([bad, n_tu, ex.bytes_per_exchange], device="cuda")
 dist.all_reduce(t)
 if rank == 0:
-    print(f"BANDS world={world} {w}x{h}: mismatches={int(t[0])} tus_checked={int(t[1])} halo_bytes_sent_total={int(t[2])}")
+    print(f"BANDS world={world} {w}x{h} exchange={mode}: mismatches={int(t[0])} tus_checked={int(t[1])} halo_bytes_sent_total={int(t[2])}")
+dist.barrier()                 # nobody closes a picture a neighbour may still be reading
 dist.destroy_process_group()
 sys.exit(1 if int(t[0]) else 0)
