@@ -262,7 +262,7 @@ def run_reference(args, w, h, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------------------------- side modes
-def run_intra(args, w, h, rank, world, local, hb, synth):
+def run_intra(args, w, h, rank, world, local, hb, synth, quiet=False, max_steps=40):
     """the intra mode pre-search of one picture -- SADs of all 35 modes for every 32/16/8/4 luma block, reference
     samples from the original picture -- through hb_intra_run (host job list and samples in, host SAD table out, copies inside
     the timed call), next to the reference's own predictors + sad on all host cores.  Rank 0 only; not the headline metric."""
@@ -285,7 +285,7 @@ def run_intra(args, w, h, rank, world, local, hb, synth):
     ctx.sync()
     for i in range(max(3, args.warmup)):
         ctx.intra_presearch(dev[i % 4], rec, adi_pin[i % 4], sad_pin)
-    steps = min(args.steps, 40)
+    steps = min(args.steps, max_steps)
     t0 = time.perf_counter()
     for i in range(steps):
         sads = ctx.intra_presearch(dev[i % 4], rec, adi_pin[i % 4], sad_pin)
@@ -307,7 +307,12 @@ def run_intra(args, w, h, rank, world, local, hb, synth):
                                     "identical_to_gpu": bool((ref_sads == sads).all())}
     except Exception as e:
         line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
-    print(json.dumps(line))
+    for d in dev:
+        d.close()
+    ctx.close()
+    if not quiet:
+        print(json.dumps(line))
+    return line
 
 
 def run_finalise(args, w, h, rank, world, local, hb, synth):
@@ -416,16 +421,19 @@ def measure_bands(args, rank, world, local, torch, dist, hb, synth, barrier, ste
     host = [synth.make_frame(tex, w, h, n) for n in range(n_pairs + 1)]
     exchange = os.environ.get("HB_BANDS_EXCHANGE", "peer")       # peer: CUDA IPC pulls out of the neighbours' HBM; nccl: staged send / recv
     out = {}
-    for S in (1, 8):
+    # every rank holds only ITS rows of a reference picture (it reconstructed them); the rest arrives over NVLink
+    own_frames = []
+    for p in host:
+        y0, y1 = bands.band_sample_rows(h, ctu_rows, world, rank)
+        own = [np.zeros_like(p[0]), np.zeros_like(p[1]), np.zeros_like(p[2])]
+        own[0][y0:y1] = p[0][y0:y1]; own[1][y0 // 2:y1 // 2] = p[1][y0 // 2:y1 // 2]; own[2][y0 // 2:y1 // 2] = p[2][y0 // 2:y1 // 2]
+        own_frames.append(own)
+    for S in (1, 8, 32):          # frame streams in flight: a band's launches are small, several streams fill the SMs they leave idle
         slots = []
         for k in range(S):
             c = hb.Context(local)
             frames = [hb.Frame(c, w, h) for _ in range(n_pairs + 1)]
-            for f, p in zip(frames, host):
-                # every rank holds only ITS rows of a reference picture (it reconstructed them); the rest arrives over NVLink
-                y0, y1 = bands.band_sample_rows(h, ctu_rows, world, rank)
-                own = [np.zeros_like(p[0]), np.zeros_like(p[1]), np.zeros_like(p[2])]
-                own[0][y0:y1] = p[0][y0:y1]; own[1][y0 // 2:y1 // 2] = p[1][y0 // 2:y1 // 2]; own[2][y0 // 2:y1 // 2] = p[2][y0 // 2:y1 // 2]
+            for f, own in zip(frames, own_frames):
                 f.upload_u8(*own)
             pp = hb.Prepass(c, w, h, qp=QP, use_graph=1, band=(row0, nrows))
             ex = None
@@ -832,6 +840,15 @@ def main():
                                 "one_stream_chain": x["chain_fps"], "steps": x["steps"]}
             except Exception as e:
                 extras[name] = {"value": None, "what": f"failed: {e}"}
+    if world == 1 and rank == 0 and not args.no_extras:
+        # BASELINE.json configs[0] / [4] are intra: the 35-mode pre-search of every 32/16/8/4 luma block of a 1080p picture
+        try:
+            il = run_intra(args, 1920, 1080, rank, world, local, hb, synth, quiet=True, max_steps=12)
+            extras["intra_presearch_1080p"] = {"value": il["value"], "unit": "frames/s", "blocks": il["config"]["blocks"], "modes": 35,
+                                               "cpu_reference": (il.get("cpu_baseline") or {}).get("value"), "cpu_cores": (il.get("cpu_baseline") or {}).get("cores"),
+                                               "identical_to_reference": (il.get("cpu_baseline") or {}).get("identical_to_gpu")}
+        except Exception as e:
+            extras["intra_presearch_1080p"] = {"value": None, "what": f"failed: {type(e).__name__}: {e}"}
     bands = None
     if not args.no_extras:
         try:
@@ -925,6 +942,7 @@ def main():
                            "roofline_step_frac": round(line["roofline"]["step_frac"], 4),
                            "bands_2160p_fps_1stream": None if not bands or "streams_1" not in bands else round(bands["streams_1"]["value"], 1),
                            "bands_2160p_fps_8streams": None if not bands or "streams_8" not in bands else round(bands["streams_8"]["value"], 1),
+                           "bands_2160p_fps_32streams": None if not bands or "streams_32" not in bands else round(bands["streams_32"]["value"], 1),
                            "bands_mismatches": None if not bands else bands.get("mismatches")}
         print(json.dumps(line))
     finish()

@@ -137,6 +137,7 @@ class PeerHaloPuller:
         self.spans = [(i, c, r0, n) for i, p in enumerate(self.peers) for (c, r0, n) in need[p]]
         width_of = lambda c: width // 2 if c else width
         self.bytes_per_exchange = sum(n * width_of(c) for (_, c, _, n) in self.spans)      # pulled, per picture
+        self._prepared = None
 
     def mark_ready(self, j):
         self.events[j].record()
@@ -144,7 +145,9 @@ class PeerHaloPuller:
     def pull(self, j):
         for e in self.peer_events[j]:
             e.wait()
-        self.frames[j].pull_rows(self.views[j], self.spans, refresh_border=True)
+        if self._prepared is None:           # the ctypes argument arrays of every picture, built once (the per-frame path is two library calls)
+            self._prepared = [self.frames[k].pull_rows_prepare(self.views[k], self.spans) for k in range(len(self.frames))]
+        self.frames[j].pull_rows_prepared(self._prepared[j], refresh_border=True)
 
     def close(self):
         for row in self.views:

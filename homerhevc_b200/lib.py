@@ -603,6 +603,12 @@ class Frame:
         f.h = h
         return f
 
+    def pull_rows_prepare(self, srcs, spans):
+        return ((C.c_void_p * max(1, len(srcs)))(*[s.h for s in srcs]), len(srcs), (RowSpan * max(1, len(spans)))(*[RowSpan(*s) for s in spans]), len(spans))
+
+    def pull_rows_prepared(self, prep, refresh_border=True):
+        _check(self.ctx.L.hb_frame_pull_rows(self.ctx.h, self.h, prep[0], prep[1], prep[2], prep[3], 1 if refresh_border else 0), "hb_frame_pull_rows")
+
     def pull_rows(self, srcs, spans, refresh_border=True):
         """spans: [(index into srcs, plane, row0, n_rows)]: one copy kernel on the context's stream, nothing waits"""
         arr = (C.c_void_p * max(1, len(srcs)))(*[s.h for s in srcs])
