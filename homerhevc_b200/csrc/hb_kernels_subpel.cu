@@ -53,13 +53,14 @@ template <int FY> __device__ __forceinline__ void vfilter2(const uint32_t (&win)
 }
 
 template <bool TMA>
-__global__ void __launch_bounds__(256) k_subpel_planes(const __grid_constant__ CUtensorMap tmap, const hbd_plane ref, const hbd_subpel sp)
+__global__ void __launch_bounds__(256) k_subpel_planes(const __grid_constant__ CUtensorMap tmap, const hbd_plane ref, const hbd_subpel sp, const int tile_row0)
 {
+    const int tile_y = blockIdx.y + tile_row0;                       // a band of the picture: tile rows tile_row0 .. (the grid's height)
     __shared__ __align__(128) uint8_t s_patch[BOX_H * BOX_W];
     __shared__ __align__(16) uint32_t s_t[4][QR][TW];
     __shared__ __align__(8) uint64_t s_bar;
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TW - HB_SUBPEL_OFF, y0 = blockIdx.y * TH - HB_SUBPEL_OFF;      // picture position of the tile's first sample
+    const int x0 = blockIdx.x * TW - HB_SUBPEL_OFF, y0 = tile_y * TH - HB_SUBPEL_OFF;      // picture position of the tile's first sample
 
     if (TMA) {
         const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&s_bar));
@@ -118,8 +119,8 @@ __global__ void __launch_bounds__(256) k_subpel_planes(const __grid_constant__ C
     const int px = blockIdx.x * TW + c;                            // plane coordinates of this column
     if (px >= sp.w) return;
     const uint32_t *col = &s_t[fx][0][c];
-    uint8_t *dst = sp.base + static_cast<size_t>(blockIdx.y * TH) * sp.pitch + px;
-    const int rows = min(TH, sp.h - blockIdx.y * TH);
+    uint8_t *dst = sp.base + static_cast<size_t>(tile_y * TH) * sp.pitch + px;
+    const int rows = min(TH, sp.h - tile_y * TH);
     uint32_t win[5];
 #pragma unroll
     for (int k = 0; k < 4; k++) win[k] = col[k * TW];
@@ -168,10 +169,18 @@ encode_tiled_fn tensor_map_encoder()
 // 1 when the plane kernel stages its patch with TMA (the default), 0 with plain loads ($HB_NO_TMA=1 or no driver entry point)
 extern "C" int hbk_subpel_uses_tma(void) { return tensor_map_encoder() != nullptr; }
 
-extern "C" int hbk_subpel_planes(const hbd_frame *ref, const hbd_subpel *sp, void *stream)
+// y_lo, y_hi: picture rows [y_lo, y_hi) whose plane samples are wanted (a CTU-row band + the rows its searches can reach); the tile rows
+// that hold them are built, the rest of the planes is left as it is
+extern "C" int hbk_subpel_planes(const hbd_frame *ref, const hbd_subpel *sp, int y_lo, int y_hi, void *stream)
 {
     const hbd_plane &p = ref->p[0];
-    const dim3 grid((sp->w + TW - 1) / TW, (sp->h + TH - 1) / TH);
+    const int tiles_y = (sp->h + TH - 1) / TH;
+    int t0 = (y_lo + HB_SUBPEL_OFF) / TH, t1 = (y_hi + HB_SUBPEL_OFF + TH - 1) / TH;
+    if (y_lo <= 0) t0 = 0;
+    t0 = t0 < 0 ? 0 : t0; t1 = t1 > tiles_y ? tiles_y : t1;
+    if (y_hi >= p.h) t1 = tiles_y;
+    if (t1 <= t0) return 0;
+    const dim3 grid((sp->w + TW - 1) / TW, t1 - t0);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
@@ -185,9 +194,9 @@ extern "C" int hbk_subpel_planes(const hbd_frame *ref, const hbd_subpel *sp, voi
         const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, p.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return static_cast<int>(cudaErrorInvalidValue);
-        k_subpel_planes<true><<<grid, 256, 0, s>>>(tmap, p, *sp);
+        k_subpel_planes<true><<<grid, 256, 0, s>>>(tmap, p, *sp, t0);
     } else {
-        k_subpel_planes<false><<<grid, 256, 0, s>>>(tmap, p, *sp);
+        k_subpel_planes<false><<<grid, 256, 0, s>>>(tmap, p, *sp, t0);
     }
     return static_cast<int>(cudaGetLastError());
 }

@@ -338,7 +338,9 @@ static int enqueue(hb_prepass *pp, const hb_frame *cur, const hb_frame *ref, int
     if (sp) {
         void *st = main_st;
         PROF_MARK("sp");
-        if (!crc) crc = hbk_subpel_planes(&ref->d, sp, main_st);
+        /* a band needs the planes of its own rows and of the rows its searches reach: +-64 integer, one more above for the negative
+         * quarter offsets, the block height below (72 rows on either side cover it) */
+        if (!crc) crc = hbk_subpel_planes(&ref->d, sp, pp->row0 * 64 - 72, (pp->row0 + pp->rows) * 64 + 72, main_st);
         n++;
     }
     /* the search: one launch for the whole picture (a CTA per CTU, PU sizes 64 -> 8 in turn), or one launch per PU size */
