@@ -1097,3 +1097,86 @@ void orc_deblock_strengths(const uint8_t *cu_depth, const uint8_t *tu_depth, con
             }
         }
 }
+
+
+/* ------------------------------------------------------------------------------------------
+ * AMVP candidates (P picture, one reference picture).  hmr_motion_inter.c:2342-2460.
+ * ------------------------------------------------------------------------------------------ */
+static int zscan16(int ux, int uy)                       /* raster2abs_table of a 16 x 16 unit CTU: x bits even, y bits odd */
+{
+    int a = 0;
+    for (int b = 0; b < 4; b++) a |= ((ux >> b) & 1) << (2 * b) | ((uy >> b) & 1) << (2 * b + 1);
+    return a;
+}
+/* left_bottom_neighbour / top_right_neighbour of the partition of `size` at (px, py) inside the CTU at (ctu_x, ctu_y): the CTU's
+ * own flags (hmr_motion_intra.c:676-683; ctu_left_bottom is never set) handed down the quadtree by cu_partition_get_neighbours (:625-657) */
+static void amvp_flags(int ctu_x, int ctu_y, int w, int h, int px, int py, int size, int *left_bottom, int *top_right)
+{
+    const int cols = (w + 63) / 64;
+    int l = ctu_x > 0, t = ctu_y > 0, lb = 0, tr = ctu_y > 0 && ctu_x / 64 + 1 < cols;
+    const int valid_lines = h - ctu_y < 64 ? h - ctu_y : 64, valid_cols = w - ctu_x < 64 ? w - ctu_x : 64;
+    int par_x = 0, par_y = 0;
+    for (int s = 32; s >= size; s >>= 1) {
+        const int cx = par_x + ((px - par_x) >= s ? s : 0), cy = par_y + ((py - par_y) >= s ? s : 0);
+        const int nlb = (lb && cx == par_x) || (l && cx == par_x && cy == par_y && valid_lines > cy + s);
+        const int ntr = (tr && cy == par_y) || (t && cx == par_x && cy == par_y && valid_cols > cx + s) || (cx == par_x && cy != par_y && valid_cols > cx + s);
+        l = l || cx; t = t || cy; lb = nlb; tr = ntr; par_x = cx; par_y = cy;
+    }
+    *left_bottom = lb; *top_right = tr;
+}
+void orc_amvp_candidates(const uint8_t *inter, const int16_t *mv, int units_w, int w, int h, int x, int y, int size, int32_t out[4])
+{
+    const int ctu_x = x & ~63, ctu_y = y & ~63, px = x - ctu_x, py = y - ctu_y;
+    const int cols = (w + 63) / 64;
+    const int has_left = ctu_x > 0, has_top = ctu_y > 0, has_top_right = ctu_y > 0 && ctu_x / 64 + 1 < cols, has_top_left = ctu_x > 0 && ctu_y > 0;
+    int lb_flag, tr_flag;
+    amvp_flags(ctu_x, ctu_y, w, h, px, py, size, &lb_flag, &tr_flag);
+    const int gx0 = ctu_x / 4, gy0 = ctu_y / 4;                           /* the CTU's first unit, picture unit coordinates */
+    int cand[5][2], ok[5];                                                 /* A0, A1, B0, B1, B2: unit coordinates, usable */
+    {   /* bottom-left 4x4 unit of the PU */
+        const int ux = px / 4, uy = (py + size) / 4 - 1;
+        /* get_pu_left_bottom :245 */
+        cand[0][0] = gx0 + ux - 1; cand[0][1] = gy0 + uy + 1;
+        if (!lb_flag) ok[0] = 0;
+        else if (ux == 0 && uy == 15) ok[0] = 0;                           /* ctu_left_bottom: NULL */
+        else if (ux == 0) ok[0] = has_left;
+        else if (uy == 15) ok[0] = 0;
+        else ok[0] = zscan16(ux, uy) > zscan16(ux - 1, uy + 1);
+        /* get_pu_left :229 */
+        cand[1][0] = gx0 + ux - 1; cand[1][1] = gy0 + uy;
+        ok[1] = ux == 0 ? has_left : 1;
+    }
+    {   /* top-right unit */
+        const int ux = (px + size) / 4 - 1, uy = py / 4;
+        /* get_pu_top_right :301 */
+        cand[2][0] = gx0 + ux + 1; cand[2][1] = gy0 + uy - 1;
+        if (!tr_flag) ok[2] = 0;
+        else if (ux == 15 && uy == 0) ok[2] = has_top_right;
+        else if (uy == 0) ok[2] = has_top;
+        else if (ux == 15) ok[2] = 0;
+        else ok[2] = zscan16(ux, uy) > zscan16(ux + 1, uy - 1);
+        /* get_pu_top :282 */
+        cand[3][0] = gx0 + ux; cand[3][1] = gy0 + uy - 1;
+        ok[3] = uy == 0 ? has_top : 1;
+    }
+    {   /* top-left unit: get_pu_top_left :335 */
+        const int ux = px / 4, uy = py / 4;
+        cand[4][0] = gx0 + ux - 1; cand[4][1] = gy0 + uy - 1;
+        ok[4] = (ux == 0 && uy == 0) ? has_top_left : uy == 0 ? has_top : ux == 0 ? has_left : 1;
+    }
+    int32_t list[3][2];
+    int n = 0;
+    for (int k = 0; k < 5; k++) ok[k] = ok[k] && inter[cand[k][1] * units_w + cand[k][0]];      /* add_amvp_cand :2198: mv_ref_idx >= 0, same picture */
+    const int smvp = ok[0] || ok[1];
+    const int a = ok[0] ? 0 : ok[1] ? 1 : -1;
+    if (a >= 0) { const int u = cand[a][1] * units_w + cand[a][0]; list[n][0] = mv[2 * u]; list[n][1] = mv[2 * u + 1]; n++; }
+    const int b = ok[2] ? 2 : ok[3] ? 3 : ok[4] ? 4 : -1;
+    if (b >= 0) { const int u = cand[b][1] * units_w + cand[b][0]; list[n][0] = mv[2 * u]; list[n][1] = mv[2 * u + 1]; n++; }
+    /* no left candidate: the above group is walked a second time with add_amvp_cand_order (:2405-2420), which takes the same neighbour's
+     * vector again (same picture distance: no scaling) */
+    if (!smvp && b >= 0) { list[n][0] = list[n - 1][0]; list[n][1] = list[n - 1][1]; n++; }
+    if (n == 2 && list[0][0] == list[1][0] && list[0][1] == list[1][1]) n = 1;
+    if (n > 2) n = 2;
+    for (; n < 2; n++) { list[n][0] = 0; list[n][1] = 0; }
+    out[0] = list[0][0]; out[1] = list[0][1]; out[2] = list[1][0]; out[3] = list[1][1];
+}

@@ -902,3 +902,64 @@ int64_t refdrv_sao_derive(refdrv *d, const int64_t *diff, const int64_t *count, 
     *band = aux;
     return dist;
 }
+
+
+/* ------------------------------------------------------------------------------------------------------------
+ * The reference's own get_amvp_candidates (hmr_motion_inter.c:2342) on CTU descriptions filled in from per-4x4-unit maps
+ * (picture raster over whole CTUs, as refdrv_deblock): inter flag and list-0 vector.  jobs: n x { x, y, size } of 2Nx2N PUs
+ * inside the picture; out: n x { mv0.x, mv0.y, mv1.x, mv1.y }.  `d` must have been opened with the picture size.
+ * ------------------------------------------------------------------------------------------------------------ */
+void get_amvp_candidates(henc_thread_t *et, slice_t *currslice, ctu_info_t *ctu, cu_partition_info_t *curr_cu_info, mv_candiate_list_t *search_candidate_list,
+                         int ref_pic_list, int ref_idx, PartSize part_size_type);
+int refdrv_amvp(refdrv *d, int w, int h, const uint8_t *inter, const int16_t *mv, const int32_t *jobs, int n_jobs, int32_t *out)
+{
+    henc_thread_t *et = d->et;
+    hvenc_engine_t *eng = et->enc_engine;
+    slice_t *slice = &eng->current_pict.slice;
+    static video_frame_t ref_frame;
+    const int cols = (w + 63) / 64, rows = (h + 63) / 64, units_w = cols * 16;
+    if (eng->pict_total_ctu != cols * rows || et->pict_width[0] != w || et->pict_height[0] != h) return -1;
+    memset(&ref_frame, 0, sizeof ref_frame);
+    ref_frame.temp_info.poc = 7;
+    slice->slice_type = P_SLICE; slice->poc = 8;
+    slice->ref_pic_list[REF_PIC_LIST_0][0] = &ref_frame; slice->ref_poc_list[REF_PIC_LIST_0][0] = 7;
+    for (int n = 0; n < cols * rows; n++) {
+        ctu_info_t *ctu = &eng->ctu_info[n];
+        const int cx = n % cols, cy = n / cols;
+        ctu->ctu_number = n; ctu->size = 64;
+        ctu->x[0] = cx * 64; ctu->y[0] = cy * 64; ctu->x[1] = ctu->x[2] = cx * 32; ctu->y[1] = ctu->y[2] = cy * 32;
+        ctu->ctu_left = cx ? &eng->ctu_info[n - 1] : NULL;
+        ctu->ctu_top = cy ? &eng->ctu_info[n - cols] : NULL;
+        ctu->ctu_top_left = (cx && cy) ? &eng->ctu_info[n - cols - 1] : NULL;
+        ctu->ctu_top_right = (cy && cx + 1 < cols) ? &eng->ctu_info[n - cols + 1] : NULL;
+        ctu->ctu_left_bottom = NULL;
+        for (int r = 0; r < 256; r++) {
+            const int a = eng->raster2abs_table[r];
+            const int u = (cy * 16 + r / 16) * units_w + cx * 16 + r % 16;
+            ctu->pred_mode[a] = inter[u] ? INTER_MODE : INTRA_MODE;
+            ctu->mv_ref[REF_PIC_LIST_0][a].hor_vector = mv[2 * u]; ctu->mv_ref[REF_PIC_LIST_0][a].ver_vector = mv[2 * u + 1];
+            ctu->mv_ref_idx[REF_PIC_LIST_0][a] = inter[u] ? 0 : -1;
+            ctu->mv_ref[REF_PIC_LIST_1][a].hor_vector = 0; ctu->mv_ref[REF_PIC_LIST_1][a].ver_vector = 0;
+            ctu->mv_ref_idx[REF_PIC_LIST_1][a] = -1;
+        }
+        create_partition_ctu_neighbours(et, ctu, ctu->partition_list);
+    }
+    for (int i = 0; i < n_jobs; i++) {
+        const int x = jobs[3 * i], y = jobs[3 * i + 1], size = jobs[3 * i + 2];
+        ctu_info_t *ctu = &eng->ctu_info[(y / 64) * cols + x / 64];
+        int depth = 0;
+        for (int s = 64; s > size; s >>= 1) depth++;
+        /* the partition of that size at that place: abs_index = z-order of its first unit, position inside its depth = abs_index / units per partition */
+        const int ux = (x & 63) / 4, uy = (y & 63) / 4;
+        const int abs_index = eng->raster2abs_table[uy * 16 + ux];
+        cu_partition_info_t *cu = &ctu->partition_list[et->partition_depth_start[depth]] + abs_index / ((size / 4) * (size / 4));
+        if (cu->size != size || cu->x_position != (x & 63) || cu->y_position != (y & 63)) return -2 - i;
+        create_partition_ctu_neighbours(et, ctu, ctu->partition_list);       /* the function overwrites flags of the corner units: start clean */
+        mv_candiate_list_t list;
+        memset(&list, 0, sizeof list);
+        get_amvp_candidates(et, slice, ctu, cu, &list, REF_PIC_LIST_0, 0, SIZE_2Nx2N);
+        if (list.num_mv_candidates != 2) return -100000 - i;
+        for (int k = 0; k < 2; k++) { out[4 * i + 2 * k] = list.mv_candidates[k].mv.hor_vector; out[4 * i + 2 * k + 1] = list.mv_candidates[k].mv.ver_vector; }
+    }
+    return n_jobs;
+}

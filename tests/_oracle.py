@@ -465,3 +465,33 @@ def ref_prepass(cur, ref_planes, w, h, qp=32, avg_dist=650.0, n_threads=1, band=
         _rp_out_cache[ck] = (out, res)
     secs = D.refdrv_prepass(handles, n_threads, cp, rp, w, h, qp, avg_dist, band[0], band[1], C.byref(out))
     return secs, res
+
+
+def amvp_jobs(w, h):
+    """every 2Nx2N PU of every size inside the picture: (x, y, size)"""
+    return np.array([(x, y, s) for s in (64, 32, 16, 8) for y in range(0, h - s + 1, s) for x in range(0, w - s + 1, s)], np.int32)
+
+
+def ref_amvp(w, h, m, jobs):
+    """the reference's own get_amvp_candidates on CTU descriptions built from the unit maps: (n, 4) int32"""
+    _, D = ref()
+    D.refdrv_open.restype = C.c_void_p
+    D.refdrv_open.argtypes = [C.c_int] * 4
+    if (w, h) not in _dbk_handles:
+        _dbk_handles[(w, h)] = D.refdrv_open(w, h, 32, 1)
+    D.refdrv_amvp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    inter = np.ascontiguousarray(1 - m["intra"].astype(np.uint8)); mv = np.ascontiguousarray(m["mv"]); jobs = np.ascontiguousarray(jobs, np.int32)
+    out = np.zeros((len(jobs), 4), np.int32)
+    n = D.refdrv_amvp(_dbk_handles[(w, h)], w, h, inter.ctypes.data, mv.ctypes.data, jobs.ctypes.data, len(jobs), out.ctypes.data)
+    assert n == len(jobs), n
+    return out
+
+
+def oracle_amvp(w, h, m, jobs):
+    O = oracle()
+    O.orc_amvp_candidates.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]
+    inter = np.ascontiguousarray(1 - m["intra"].astype(np.uint8)); mv = np.ascontiguousarray(m["mv"])
+    out = np.zeros((len(jobs), 4), np.int32)
+    for i, (x, y, s) in enumerate(jobs):
+        O.orc_amvp_candidates(inter.ctypes.data, mv.ctypes.data, inter.shape[1], w, h, int(x), int(y), int(s), out[i].ctypes.data)
+    return out

@@ -355,3 +355,23 @@ def test_deblocking_pixel_stage_against_reference():
             for c in range(3):
                 assert np.array_equal(got[c], exp[c]), (w, h, rep, c, np.argwhere(got[c] != exp[c])[:4])
             assert (exp[0] != planes[0]).sum() > 500 and (exp[1] != planes[1]).sum() > 20
+
+
+def test_amvp_candidates_against_reference():
+    """get_amvp_candidates (hmr_motion_inter.c:2342) of every 2Nx2N PU of every size on random CU trees with intra / inter units and
+    random vectors: left-bottom / left, top-right / top / top-left look-ups across CTU borders, z-order availability, the
+    quadtree's neighbour flags, partial CTUs on both picture edges, duplicate removal and zero fill"""
+    from _oracle import amvp_jobs, oracle_amvp, random_deblock_case, ref_amvp
+    rng = np.random.default_rng(2342)
+    seen = set()
+    for (w, h) in ((192, 136), (128, 128), (200, 72), (72, 200), (320, 192)):
+        for rep in range(3):
+            m, _ = random_deblock_case(rng, w, h)
+            m["mv"] = rng.integers(-40, 41, m["mv"].shape).astype(np.int16) if rep == 2 else m["mv"]     # per-unit vectors: nothing may depend on CU-constant fields
+            jobs = amvp_jobs(w, h)
+            exp, got = ref_amvp(w, h, m, jobs), oracle_amvp(w, h, m, jobs)
+            bad = np.argwhere((exp != got).any(1))
+            assert not len(bad), (w, h, rep, jobs[bad[0, 0]], exp[bad[0, 0]], got[bad[0, 0]])
+            for e in exp:
+                seen.add((bool(e[0] or e[1]), bool(e[2] or e[3])))
+    assert seen == {(False, False), (True, False), (True, True)} or seen == {(False, False), (True, False), (True, True), (False, True)}
