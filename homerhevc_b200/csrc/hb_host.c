@@ -873,6 +873,57 @@ done:
     return rc;
 }
 
+/* AMVP / merge candidates of a batch of PUs from the per-unit motion field: one launch, one copy back.  max_cands = 0: AMVP */
+static int neighbour_candidates(hb_ctx *ctx, const hb_unit_info *units, int units_w, int width, int height, const hb_amvp_job *jobs, int n_jobs, int max_cands,
+                                void *out, const char *what)
+{
+    int rc = HB_OK, crc = 0;
+    void *d_units, *h_units, *d_jobs, *h_jobs, *d_out, *h_out;
+    if (!ctx || !units || !jobs || !out || n_jobs < 0) return hbi_fail(HB_ERR_ARG, "%s: bad argument", what);
+    if (width < 16 || height < 16 || (width & 7) || (height & 7)) return hbi_fail(HB_ERR_ARG, "%s: %dx%d", what, width, height);
+    const int cols = (width + 63) / 64, rows = (height + 63) / 64;
+    if (units_w < cols * 16) return hbi_fail(HB_ERR_ARG, "%s: units_w %d does not cover %d whole CTUs", what, units_w, cols);
+    for (int i = 0; i < n_jobs; i++) {
+        const hb_amvp_job *j = &jobs[i];
+        if ((j->size != 64 && j->size != 32 && j->size != 16 && j->size != 8) || j->x < 0 || j->y < 0 || (j->x % j->size) || (j->y % j->size) ||
+            j->x + j->size > width || j->y + j->size > height)
+            return hbi_fail(HB_ERR_ARG, "%s: job %d: %dx%d at (%d,%d)", what, i, j->size, j->size, j->x, j->y);
+    }
+    if (n_jobs == 0) return HB_OK;
+    const size_t plane = (size_t)units_w * (size_t)rows * 16;
+    const size_t out_bytes = (max_cands ? sizeof(hb_mv) * (size_t)max_cands : sizeof(hb_amvp_list)) * (size_t)n_jobs;
+    hbc_set_device(ctx->device);
+    pthread_mutex_lock(&ctx->lock);
+    if ((rc = hbi_scratch(ctx, 0, sizeof(hb_unit_info) * plane, &d_units, &h_units)) != HB_OK) goto done;
+    if ((rc = hbi_scratch(ctx, 1, sizeof(hb_amvp_job) * (size_t)n_jobs, &d_jobs, &h_jobs)) != HB_OK) goto done;
+    if ((rc = hbi_scratch(ctx, 2, out_bytes, &d_out, &h_out)) != HB_OK) goto done;
+    memcpy(h_units, units, sizeof(hb_unit_info) * plane);
+    memcpy(h_jobs, jobs, sizeof(hb_amvp_job) * (size_t)n_jobs);
+    crc = hbc_h2d_async(d_units, h_units, sizeof(hb_unit_info) * plane, ctx->stream);
+    if (!crc) crc = hbc_h2d_async(d_jobs, h_jobs, sizeof(hb_amvp_job) * (size_t)n_jobs, ctx->stream);
+    if (!crc) {
+        if (max_cands) crc = hbk_merge_cands((const hb_unit_info *)d_units, units_w, width, height, (const hb_amvp_job *)d_jobs, n_jobs, max_cands, (hb_mv *)d_out, ctx->stream);
+        else crc = hbk_amvp((const hb_unit_info *)d_units, units_w, width, height, (const hb_amvp_job *)d_jobs, n_jobs, (hb_amvp_list *)d_out, ctx->stream);
+        ctx->launches++;
+    }
+    if (!crc) crc = hbc_d2h_async(h_out, d_out, out_bytes, ctx->stream);
+    if (!crc) crc = hbc_stream_sync(ctx->stream);
+    if (!crc) memcpy(out, h_out, out_bytes);
+done:
+    pthread_mutex_unlock(&ctx->lock);
+    if (crc) return hbi_cuda_fail(crc, what);
+    return rc;
+}
+int hb_amvp_candidates(hb_ctx *ctx, const hb_unit_info *units, int units_w, int width, int height, const hb_amvp_job *jobs, int n_jobs, hb_amvp_list *out)
+{
+    return neighbour_candidates(ctx, units, units_w, width, height, jobs, n_jobs, 0, out, "hb_amvp_candidates");
+}
+int hb_merge_candidates(hb_ctx *ctx, const hb_unit_info *units, int units_w, int width, int height, const hb_amvp_job *jobs, int n_jobs, int max_cands, hb_mv *out)
+{
+    if (max_cands < 1 || max_cands > 5) return hbi_fail(HB_ERR_ARG, "hb_merge_candidates: max_cands %d", max_cands);
+    return neighbour_candidates(ctx, units, units_w, width, height, jobs, n_jobs, max_cands, out, "hb_merge_candidates");
+}
+
 /* SAO statistics of a whole picture: one launch, one copy back */
 int hb_sao_stats_frame(hb_ctx *ctx, const hb_frame *orig, const hb_frame *rec, hb_sao_stats *out)
 {

@@ -331,6 +331,133 @@ __global__ void __launch_bounds__(256) k_deblock_strengths(const hb_unit_info *u
 }
 }  // namespace
 
+namespace {
+// ---- AMVP candidates of 2Nx2N PUs from the per-unit motion field (get_amvp_candidates hmr_motion_inter.c:2342; neighbour look-ups
+// hmr_arithmetic_encoding.c:229-354; neighbour flags of the quadtree hmr_motion_intra.c:625-657, CTU level :676-683): one thread per PU
+__device__ __forceinline__ int zscan16(int ux, int uy)
+{
+    int a = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) a |= ((ux >> b) & 1) << (2 * b) | ((uy >> b) & 1) << (2 * b + 1);
+    return a;
+}
+// the five spatial neighbours of a PU (A0 left-bottom, A1 left, B0 top-right, B1 top, B2 top-left): unit index in the maps, vector,
+// and the bit mask of those that exist, were coded before the PU and are inter predicted
+__device__ __forceinline__ int pu_neighbours(const hb_unit_info *units, int units_w, int w, int h, int x, int y, int size, hb_mv (&cand)[5])
+{
+    const int ctu_x = x & ~63, ctu_y = y & ~63, px = x - ctu_x, py = y - ctu_y;
+    const int cols = (w + 63) / 64;
+    const bool has_left = ctu_x > 0, has_top = ctu_y > 0, has_top_right = ctu_y > 0 && ctu_x / 64 + 1 < cols, has_top_left = ctu_x > 0 && ctu_y > 0;
+    // the partition's left_bottom / top_right flags, handed down from the CTU (whose left-bottom neighbour never exists)
+    bool l = has_left, t = has_top, lb = false, tr = has_top_right;
+    {
+        const int valid_lines = min(64, h - ctu_y), valid_cols = min(64, w - ctu_x);
+        int par_x = 0, par_y = 0;
+        for (int s = 32; s >= size; s >>= 1) {
+            const int cx = par_x + ((px - par_x) >= s ? s : 0), cy = par_y + ((py - par_y) >= s ? s : 0);
+            const bool nlb = (lb && cx == par_x) || (l && cx == par_x && cy == par_y && valid_lines > cy + s);
+            const bool ntr = (tr && cy == par_y) || (t && cx == par_x && cy == par_y && valid_cols > cx + s) || (cx == par_x && cy != par_y && valid_cols > cx + s);
+            l = l || cx; t = t || cy; lb = nlb; tr = ntr; par_x = cx; par_y = cy;
+        }
+    }
+    const int gx0 = ctu_x / 4, gy0 = ctu_y / 4;
+    int cu[5], okm = 0;
+    {
+        const int ux = px / 4, uy = (py + size) / 4 - 1;   // bottom-left unit of the PU
+        bool a0;
+        if (!lb) a0 = false;
+        else if (ux == 0 && uy == 15) a0 = false;
+        else if (ux == 0) a0 = has_left;
+        else if (uy == 15) a0 = false;
+        else a0 = zscan16(ux, uy) > zscan16(ux - 1, uy + 1);
+        cu[0] = (gy0 + uy + 1) * units_w + gx0 + ux - 1;
+        cu[1] = (gy0 + uy) * units_w + gx0 + ux - 1;
+        okm |= (a0 ? 1 : 0) | ((ux == 0 ? has_left : true) ? 2 : 0);
+    }
+    {
+        const int ux = (px + size) / 4 - 1, uy = py / 4;   // top-right unit
+        bool b0;
+        if (!tr) b0 = false;
+        else if (ux == 15 && uy == 0) b0 = has_top_right;
+        else if (uy == 0) b0 = has_top;
+        else if (ux == 15) b0 = false;
+        else b0 = zscan16(ux, uy) > zscan16(ux + 1, uy - 1);
+        cu[2] = (gy0 + uy - 1) * units_w + gx0 + ux + 1;
+        cu[3] = (gy0 + uy - 1) * units_w + gx0 + ux;
+        okm |= (b0 ? 4 : 0) | ((uy == 0 ? has_top : true) ? 8 : 0);
+    }
+    {
+        const int ux = px / 4, uy = py / 4;                // top-left unit
+        cu[4] = (gy0 + uy - 1) * units_w + gx0 + ux - 1;
+        okm |= ((ux == 0 && uy == 0) ? has_top_left : uy == 0 ? has_top : ux == 0 ? has_left : true) ? 16 : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        cand[k].x = 0; cand[k].y = 0;
+        if ((okm >> k) & 1) {
+            const hb_unit_info u = units[cu[k]];
+            if (u.intra || u.ref_idx < 0) okm &= ~(1 << k);
+            else { cand[k].x = u.mvx; cand[k].y = u.mvy; }
+        }
+    }
+    return okm;
+}
+
+__global__ void __launch_bounds__(128) k_amvp(const hb_unit_info *units, int units_w, int w, int h, const hb_amvp_job *jobs, int n_jobs, hb_amvp_list *out)
+{
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n_jobs) return;
+    hb_mv cand[5];
+    const int okm = pu_neighbours(units, units_w, w, h, jobs[i].x, jobs[i].y, jobs[i].size, cand);
+    hb_mv list[3];
+    int n = 0;
+    const bool smvp = (okm & 3) != 0;
+    if (okm & 1) list[n++] = cand[0]; else if (okm & 2) list[n++] = cand[1];
+    const int b = (okm & 4) ? 2 : (okm & 8) ? 3 : (okm & 16) ? 4 : -1;
+    if (b >= 0) { list[n] = b == 2 ? cand[2] : b == 3 ? cand[3] : cand[4]; n++; }
+    if (!smvp && b >= 0) { list[n] = list[n - 1]; n++; }           // the above group walked a second time (:2405-2420): the same vector again
+    if (n == 2 && list[0].x == list[1].x && list[0].y == list[1].y) n = 1;
+    if (n > 2) n = 2;
+    hb_amvp_list r;
+    r.mv[0].x = n > 0 ? list[0].x : 0; r.mv[0].y = n > 0 ? list[0].y : 0;
+    r.mv[1].x = n > 1 ? list[1].x : 0; r.mv[1].y = n > 1 ? list[1].y : 0;
+    out[i] = r;
+}
+
+// merge candidates (get_merge_mvp_candidates hmr_motion_inter.c:1937, P picture, one reference picture): A1, B1, B0, A0, then B2 while fewer
+// than four, each pruned against the neighbours the reference compares it with (equal_motion :1915); closed at max_cands, zero filled
+__global__ void __launch_bounds__(128) k_merge_cands(const hb_unit_info *units, int units_w, int w, int h, const hb_amvp_job *jobs, int n_jobs, int max_cands, hb_mv *out)
+{
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n_jobs) return;
+    hb_mv c[5];
+    const int okm = pu_neighbours(units, units_w, w, h, jobs[i].x, jobs[i].y, jobs[i].size, c);
+    const bool a0 = okm & 1, a1 = okm & 2, b0 = okm & 4, b1 = okm & 8, b2 = okm & 16;
+    auto same = [&](int p, int q) { return c[p].x == c[q].x && c[p].y == c[q].y; };
+    hb_mv *o = out + static_cast<size_t>(i) * max_cands;
+    int n = 0;
+    if (a1) o[n++] = c[1];
+    if (n < max_cands && b1 && (!a1 || !same(1, 3))) o[n++] = c[3];
+    if (n < max_cands && b0 && (!b1 || !same(3, 2))) o[n++] = c[2];
+    if (n < max_cands && a0 && (!a1 || !same(1, 0))) o[n++] = c[0];
+    if (n < max_cands && n < 4 && b2 && (!a1 || !same(1, 4)) && (!b1 || !same(3, 4))) o[n++] = c[4];
+    for (; n < max_cands; n++) { o[n].x = 0; o[n].y = 0; }
+}
+}  // namespace
+
+extern "C" int hbk_amvp(const hb_unit_info *units, int units_w, int w, int h, const hb_amvp_job *jobs, int n_jobs, hb_amvp_list *out, void *stream)
+{
+    if (n_jobs <= 0) return 0;
+    k_amvp<<<(n_jobs + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(units, units_w, w, h, jobs, n_jobs, out);
+    return static_cast<int>(cudaGetLastError());
+}
+extern "C" int hbk_merge_cands(const hb_unit_info *units, int units_w, int w, int h, const hb_amvp_job *jobs, int n_jobs, int max_cands, hb_mv *out, void *stream)
+{
+    if (n_jobs <= 0) return 0;
+    k_merge_cands<<<(n_jobs + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(units, units_w, w, h, jobs, n_jobs, max_cands, out);
+    return static_cast<int>(cudaGetLastError());
+}
+
 extern "C" int hbk_deblock_strengths(const hb_unit_info *units, int units_w, int w, int h, uint8_t *bs_ver, uint8_t *bs_hor, uint8_t *qp, void *stream)
 {
     const int uw = w >> 2, uh = h >> 2;

@@ -164,6 +164,8 @@ def load_library():
     L.hb_frame_import_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.hb_frame_pad.argtypes = [C.c_void_p, C.c_void_p]
     L.hb_frame_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.hb_amvp_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    L.hb_merge_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.hb_frame_ipc_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
     L.hb_frame_pull_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
     L.hb_ipc_event_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
@@ -436,6 +438,31 @@ def _deblock_units(self, frame, units, cb_qp_offset=0, cr_qp_offset=0, beta_offs
 
 
 Context.deblock_units = _deblock_units
+
+
+def _amvp_candidates(self, units, width, height, jobs):
+    """AMVP predictors of 2Nx2N PUs from the per-unit motion field; units: (16 * CTU rows, units_w) UNIT_INFO_DT, jobs: (n, 3) int32
+    (x, y, size).  Returns (n, 2, 2) int32: the two predictors (x, y) of every PU."""
+    units = np.ascontiguousarray(units, UNIT_INFO_DT)
+    jobs = np.ascontiguousarray(jobs, np.int32).reshape(-1, 3)
+    out = np.zeros((len(jobs), 2, 2), np.int32)
+    _check(self.L.hb_amvp_candidates(self.h, units.ctypes.data, units.shape[1], width, height, jobs.ctypes.data, len(jobs), out.ctypes.data), "hb_amvp_candidates")
+    return out
+
+
+Context.amvp_candidates = _amvp_candidates
+
+
+def _merge_candidates(self, units, width, height, jobs, max_cands=5):
+    """merge candidates of 2Nx2N PUs from the per-unit motion field: (n, max_cands, 2) int32"""
+    units = np.ascontiguousarray(units, UNIT_INFO_DT)
+    jobs = np.ascontiguousarray(jobs, np.int32).reshape(-1, 3)
+    out = np.zeros((len(jobs), max_cands, 2), np.int32)
+    _check(self.L.hb_merge_candidates(self.h, units.ctypes.data, units.shape[1], width, height, jobs.ctypes.data, len(jobs), max_cands, out.ctypes.data), "hb_merge_candidates")
+    return out
+
+
+Context.merge_candidates = _merge_candidates
 
 SAO_PARAM_DT = np.dtype([("type", "i1", (3,)), ("reserved", "i1"), ("offset", "<i2", (3, 32))])
 

@@ -262,6 +262,20 @@ typedef struct hb_unit_info { uint8_t cu_depth, tu_depth, intra, cbf_luma; int8_
 int hb_deblock_frame_units(hb_ctx *ctx, hb_frame *frame, const hb_unit_info *units, int units_w, const hb_deblock_params *params,
                            uint8_t *bs_ver_out, uint8_t *bs_hor_out);
 
+/* AMVP candidates (get_amvp_candidates, hmr_motion_inter.c:2342, P pictures with one reference picture) of a
+ * batch of 2Nx2N PUs from the motion field the host's decisions left per 4x4 unit (the same hb_unit_info maps the deblocking reads;
+ * on the device they can come straight from hb_prepass_finalise): left-bottom / left, top-right / top / top-left neighbours with the
+ * reference's availability rules (z-order inside the CTU, neighbour CTUs, the quadtree's left_bottom / top_right flags :625), the
+ * above group taken twice when there is no left candidate, duplicate removal, zero fill.  out[i] = the two predictors of jobs[i]
+ * (what hb_me_job.amvp takes).  units must cover whole CTUs: units_w >= 16 * CTU columns, 16 * CTU rows rows. */
+typedef struct hb_amvp_job { int32_t x, y, size; } hb_amvp_job;              /* size 64 / 32 / 16 / 8, inside the picture */
+typedef struct hb_amvp_list { hb_mv mv[2]; } hb_amvp_list;
+int hb_amvp_candidates(hb_ctx *ctx, const hb_unit_info *units, int units_w, int width, int height, const hb_amvp_job *jobs, int n_jobs, hb_amvp_list *out);
+/* Merge candidates of the same PUs (get_merge_mvp_candidates, hmr_motion_inter.c:1937; P pictures, one reference picture): the neighbours in
+ * the order A1, B1, B0, A0, then B2 while fewer than four, pruned pairwise as equal_motion :1915 does, closed at max_cands (1..5, the
+ * slice's max_num_merge_candidates) and filled with zero vectors.  out[i * max_cands + k] = candidate k of jobs[i]; what hb_merge_eval takes. */
+int hb_merge_candidates(hb_ctx *ctx, const hb_unit_info *units, int units_w, int width, int height, const hb_amvp_job *jobs, int n_jobs, int max_cands, hb_mv *out);
+
 /* SAO statistics (get_sao_stats of the function table, hmr_private.h:1091; sao_get_ctu_stats hmr_sao.c:75 /
  * sse_sao_get_ctu_stats hmr_sse42_sao.c:35, calculate_preblock_stats = 0) for every CTU and component of a picture in one
  * launch: `rec` is the deblocked reconstruction (before SAO), `orig` the source.  out[ctu * 3 + comp], CTUs in raster order.

@@ -1124,7 +1124,9 @@ static void amvp_flags(int ctu_x, int ctu_y, int w, int h, int px, int py, int s
     }
     *left_bottom = lb; *top_right = tr;
 }
-void orc_amvp_candidates(const uint8_t *inter, const int16_t *mv, int units_w, int w, int h, int x, int y, int size, int32_t out[4])
+/* the five spatial neighbours of the PU, as unit indices into the maps, and whether the reference would look at them at all
+ * (A0 left-bottom, A1 left, B0 top-right, B1 top, B2 top-left) */
+static void pu_neighbours(int units_w, int w, int h, int x, int y, int size, int cand[5], int ok[5])
 {
     const int ctu_x = x & ~63, ctu_y = y & ~63, px = x - ctu_x, py = y - ctu_y;
     const int cols = (w + 63) / 64;
@@ -1132,46 +1134,50 @@ void orc_amvp_candidates(const uint8_t *inter, const int16_t *mv, int units_w, i
     int lb_flag, tr_flag;
     amvp_flags(ctu_x, ctu_y, w, h, px, py, size, &lb_flag, &tr_flag);
     const int gx0 = ctu_x / 4, gy0 = ctu_y / 4;                           /* the CTU's first unit, picture unit coordinates */
-    int cand[5][2], ok[5];                                                 /* A0, A1, B0, B1, B2: unit coordinates, usable */
     {   /* bottom-left 4x4 unit of the PU */
         const int ux = px / 4, uy = (py + size) / 4 - 1;
         /* get_pu_left_bottom :245 */
-        cand[0][0] = gx0 + ux - 1; cand[0][1] = gy0 + uy + 1;
+        cand[0] = (gy0 + uy + 1) * units_w + gx0 + ux - 1;
         if (!lb_flag) ok[0] = 0;
         else if (ux == 0 && uy == 15) ok[0] = 0;                           /* ctu_left_bottom: NULL */
         else if (ux == 0) ok[0] = has_left;
         else if (uy == 15) ok[0] = 0;
         else ok[0] = zscan16(ux, uy) > zscan16(ux - 1, uy + 1);
         /* get_pu_left :229 */
-        cand[1][0] = gx0 + ux - 1; cand[1][1] = gy0 + uy;
+        cand[1] = (gy0 + uy) * units_w + gx0 + ux - 1;
         ok[1] = ux == 0 ? has_left : 1;
     }
     {   /* top-right unit */
         const int ux = (px + size) / 4 - 1, uy = py / 4;
         /* get_pu_top_right :301 */
-        cand[2][0] = gx0 + ux + 1; cand[2][1] = gy0 + uy - 1;
+        cand[2] = (gy0 + uy - 1) * units_w + gx0 + ux + 1;
         if (!tr_flag) ok[2] = 0;
         else if (ux == 15 && uy == 0) ok[2] = has_top_right;
         else if (uy == 0) ok[2] = has_top;
         else if (ux == 15) ok[2] = 0;
         else ok[2] = zscan16(ux, uy) > zscan16(ux + 1, uy - 1);
         /* get_pu_top :282 */
-        cand[3][0] = gx0 + ux; cand[3][1] = gy0 + uy - 1;
+        cand[3] = (gy0 + uy - 1) * units_w + gx0 + ux;
         ok[3] = uy == 0 ? has_top : 1;
     }
     {   /* top-left unit: get_pu_top_left :335 */
         const int ux = px / 4, uy = py / 4;
-        cand[4][0] = gx0 + ux - 1; cand[4][1] = gy0 + uy - 1;
+        cand[4] = (gy0 + uy - 1) * units_w + gx0 + ux - 1;
         ok[4] = (ux == 0 && uy == 0) ? has_top_left : uy == 0 ? has_top : ux == 0 ? has_left : 1;
     }
+}
+void orc_amvp_candidates(const uint8_t *inter, const int16_t *mv, int units_w, int w, int h, int x, int y, int size, int32_t out[4])
+{
+    int cand[5], ok[5];                                                    /* A0, A1, B0, B1, B2 */
+    pu_neighbours(units_w, w, h, x, y, size, cand, ok);
     int32_t list[3][2];
     int n = 0;
-    for (int k = 0; k < 5; k++) ok[k] = ok[k] && inter[cand[k][1] * units_w + cand[k][0]];      /* add_amvp_cand :2198: mv_ref_idx >= 0, same picture */
+    for (int k = 0; k < 5; k++) ok[k] = ok[k] && inter[cand[k]];          /* add_amvp_cand :2198: mv_ref_idx >= 0, same picture */
     const int smvp = ok[0] || ok[1];
     const int a = ok[0] ? 0 : ok[1] ? 1 : -1;
-    if (a >= 0) { const int u = cand[a][1] * units_w + cand[a][0]; list[n][0] = mv[2 * u]; list[n][1] = mv[2 * u + 1]; n++; }
+    if (a >= 0) { list[n][0] = mv[2 * cand[a]]; list[n][1] = mv[2 * cand[a] + 1]; n++; }
     const int b = ok[2] ? 2 : ok[3] ? 3 : ok[4] ? 4 : -1;
-    if (b >= 0) { const int u = cand[b][1] * units_w + cand[b][0]; list[n][0] = mv[2 * u]; list[n][1] = mv[2 * u + 1]; n++; }
+    if (b >= 0) { list[n][0] = mv[2 * cand[b]]; list[n][1] = mv[2 * cand[b] + 1]; n++; }
     /* no left candidate: the above group is walked a second time with add_amvp_cand_order (:2405-2420), which takes the same neighbour's
      * vector again (same picture distance: no scaling) */
     if (!smvp && b >= 0) { list[n][0] = list[n - 1][0]; list[n][1] = list[n - 1][1]; n++; }
@@ -1179,4 +1185,27 @@ void orc_amvp_candidates(const uint8_t *inter, const int16_t *mv, int units_w, i
     if (n > 2) n = 2;
     for (; n < 2; n++) { list[n][0] = 0; list[n][1] = 0; }
     out[0] = list[0][0]; out[1] = list[0][1]; out[2] = list[1][0]; out[3] = list[1][1];
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Merge candidates (P picture, one reference picture).  hmr_motion_inter.c:1937-2196: A1, B1, B0, A0, then B2 while fewer than four,
+ * each pruned against the neighbours the reference compares it with (equal_motion :1915), the list closed at max_cands and filled
+ * up with zero vectors (:2163-2192).  out = max_cands x { x, y }; every candidate refers to picture 0 of list 0.
+ * ------------------------------------------------------------------------------------------ */
+void orc_merge_candidates(const uint8_t *inter, const int16_t *mv, int units_w, int w, int h, int x, int y, int size, int max_cands, int32_t *out)
+{
+    int cand[5], ok[5];
+    pu_neighbours(units_w, w, h, x, y, size, cand, ok);
+    for (int k = 0; k < 5; k++) ok[k] = ok[k] && inter[cand[k]];
+    #define SAME(a, b) (mv[2 * cand[a]] == mv[2 * cand[b]] && mv[2 * cand[a] + 1] == mv[2 * cand[b] + 1])
+    int n = 0;
+    #define TAKE(k) do { out[2 * n] = mv[2 * cand[k]]; out[2 * n + 1] = mv[2 * cand[k] + 1]; n++; } while (0)
+    if (ok[1]) TAKE(1);                                                    /* A1 */
+    if (n < max_cands && ok[3] && (!ok[1] || !SAME(1, 3))) TAKE(3);        /* B1 vs A1 */
+    if (n < max_cands && ok[2] && (!ok[3] || !SAME(3, 2))) TAKE(2);        /* B0 vs B1 */
+    if (n < max_cands && ok[0] && (!ok[1] || !SAME(1, 0))) TAKE(0);        /* A0 vs A1 */
+    if (n < max_cands && n < 4 && ok[4] && (!ok[1] || !SAME(1, 4)) && (!ok[3] || !SAME(3, 4))) TAKE(4);   /* B2 vs A1 and B1 */
+    for (; n < max_cands; n++) { out[2 * n] = 0; out[2 * n + 1] = 0; }
+    #undef TAKE
+    #undef SAME
 }

@@ -911,7 +911,14 @@ int64_t refdrv_sao_derive(refdrv *d, const int64_t *diff, const int64_t *count, 
  * ------------------------------------------------------------------------------------------------------------ */
 void get_amvp_candidates(henc_thread_t *et, slice_t *currslice, ctu_info_t *ctu, cu_partition_info_t *curr_cu_info, mv_candiate_list_t *search_candidate_list,
                          int ref_pic_list, int ref_idx, PartSize part_size_type);
+void get_merge_mvp_candidates(henc_thread_t *et, slice_t *currslice, ctu_info_t *ctu, cu_partition_info_t *curr_cu_info, PartSize part_size_type, uint8_t *inter_mode_neighbours);
+/* merge_max > 0: out receives merge_max x { x, y } per job from get_merge_mvp_candidates (:1937) instead of the two AMVP predictors */
+int refdrv_amvp_or_merge(refdrv *d, int w, int h, const uint8_t *inter, const int16_t *mv, const int32_t *jobs, int n_jobs, int merge_max, int32_t *out);
 int refdrv_amvp(refdrv *d, int w, int h, const uint8_t *inter, const int16_t *mv, const int32_t *jobs, int n_jobs, int32_t *out)
+{
+    return refdrv_amvp_or_merge(d, w, h, inter, mv, jobs, n_jobs, 0, out);
+}
+int refdrv_amvp_or_merge(refdrv *d, int w, int h, const uint8_t *inter, const int16_t *mv, const int32_t *jobs, int n_jobs, int merge_max, int32_t *out)
 {
     henc_thread_t *et = d->et;
     hvenc_engine_t *eng = et->enc_engine;
@@ -939,6 +946,7 @@ int refdrv_amvp(refdrv *d, int w, int h, const uint8_t *inter, const int16_t *mv
             ctu->pred_mode[a] = inter[u] ? INTER_MODE : INTRA_MODE;
             ctu->mv_ref[REF_PIC_LIST_0][a].hor_vector = mv[2 * u]; ctu->mv_ref[REF_PIC_LIST_0][a].ver_vector = mv[2 * u + 1];
             ctu->mv_ref_idx[REF_PIC_LIST_0][a] = inter[u] ? 0 : -1;
+            ctu->inter_mode[a] = inter[u] ? 1 : 0;
             ctu->mv_ref[REF_PIC_LIST_1][a].hor_vector = 0; ctu->mv_ref[REF_PIC_LIST_1][a].ver_vector = 0;
             ctu->mv_ref_idx[REF_PIC_LIST_1][a] = -1;
         }
@@ -955,6 +963,18 @@ int refdrv_amvp(refdrv *d, int w, int h, const uint8_t *inter, const int16_t *mv
         cu_partition_info_t *cu = &ctu->partition_list[et->partition_depth_start[depth]] + abs_index / ((size / 4) * (size / 4));
         if (cu->size != size || cu->x_position != (x & 63) || cu->y_position != (y & 63)) return -2 - i;
         create_partition_ctu_neighbours(et, ctu, ctu->partition_list);       /* the function overwrites flags of the corner units: start clean */
+        if (merge_max > 0) {
+            uint8_t modes[MERGE_MVP_MAX_NUM_CANDS];
+            slice->max_num_merge_candidates = merge_max; slice->num_ref_idx[REF_PIC_LIST_0] = 1;
+            get_merge_mvp_candidates(et, slice, ctu, cu, SIZE_2Nx2N, modes);
+            const mv_candiate_list_t *l0 = &et->merge_mvp_candidates[REF_PIC_LIST_0];
+            if (l0->num_mv_candidates != merge_max) return -200000 - i;
+            for (int k = 0; k < merge_max; k++) {
+                if (l0->mv_candidates[k].ref_idx != 0) return -300000 - i;
+                out[2 * merge_max * i + 2 * k] = l0->mv_candidates[k].mv.hor_vector; out[2 * merge_max * i + 2 * k + 1] = l0->mv_candidates[k].mv.ver_vector;
+            }
+            continue;
+        }
         mv_candiate_list_t list;
         memset(&list, 0, sizeof list);
         get_amvp_candidates(et, slice, ctu, cu, &list, REF_PIC_LIST_0, 0, SIZE_2Nx2N);

@@ -495,3 +495,28 @@ def oracle_amvp(w, h, m, jobs):
     for i, (x, y, s) in enumerate(jobs):
         O.orc_amvp_candidates(inter.ctypes.data, mv.ctypes.data, inter.shape[1], w, h, int(x), int(y), int(s), out[i].ctypes.data)
     return out
+
+
+def ref_merge(w, h, m, jobs, max_cands):
+    """the reference's own get_merge_mvp_candidates: (n, max_cands, 2) int32"""
+    _, D = ref()
+    D.refdrv_open.restype = C.c_void_p
+    D.refdrv_open.argtypes = [C.c_int] * 4
+    if (w, h) not in _dbk_handles:
+        _dbk_handles[(w, h)] = D.refdrv_open(w, h, 32, 1)
+    D.refdrv_amvp_or_merge.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    inter = np.ascontiguousarray(1 - m["intra"].astype(np.uint8)); mv = np.ascontiguousarray(m["mv"]); jobs = np.ascontiguousarray(jobs, np.int32)
+    out = np.zeros((len(jobs), max_cands, 2), np.int32)
+    n = D.refdrv_amvp_or_merge(_dbk_handles[(w, h)], w, h, inter.ctypes.data, mv.ctypes.data, jobs.ctypes.data, len(jobs), max_cands, out.ctypes.data)
+    assert n == len(jobs), n
+    return out
+
+
+def oracle_merge(w, h, m, jobs, max_cands):
+    O = oracle()
+    O.orc_merge_candidates.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]
+    inter = np.ascontiguousarray(1 - m["intra"].astype(np.uint8)); mv = np.ascontiguousarray(m["mv"])
+    out = np.zeros((len(jobs), max_cands, 2), np.int32)
+    for i, (x, y, s) in enumerate(jobs):
+        O.orc_merge_candidates(inter.ctypes.data, mv.ctypes.data, inter.shape[1], w, h, int(x), int(y), int(s), max_cands, out[i].ctypes.data)
+    return out

@@ -375,3 +375,36 @@ def test_merge_candidates(ctx):
         n_coded += ssum > 0
     assert n_coded > 5 and len(cands) > 30
     fc.close(); fr.close(); pred.close(); rec.close()
+
+
+@pytest.mark.gpu
+def test_amvp_candidates_from_unit_field(ctx):
+    """hb_amvp_candidates == the restatement of get_amvp_candidates (itself pinned against the reference, tests/test_oracle_vs_ref.py) for every
+    2Nx2N PU of every size on random CU trees, intra / inter units, per-unit vectors, partial CTUs on both edges; argument checks"""
+    from homerhevc_b200.lib import UNIT_INFO_DT, HbError
+    from _oracle import amvp_jobs, oracle_amvp, oracle_merge, random_deblock_case
+    rng = np.random.default_rng(77)
+    two = 0
+    for (w, h) in ((192, 136), (200, 72), (72, 200), (1280, 720)):
+        m, _ = random_deblock_case(rng, w, h)
+        m["mv"] = rng.integers(-300, 301, m["mv"].shape).astype(np.int16)
+        units = np.zeros(m["cu"].shape, UNIT_INFO_DT)
+        units["cu_depth"], units["tu_depth"], units["intra"], units["cbf_luma"], units["qp"] = m["cu"], m["tu"], m["intra"], m["cbf"], m["qp"]
+        units["ref_idx"] = np.where(m["intra"] != 0, -1, 0); units["mvx"], units["mvy"] = m["mv"][..., 0], m["mv"][..., 1]
+        jobs = amvp_jobs(w, h)
+        got = ctx.amvp_candidates(units, w, h, jobs).reshape(-1, 4)
+        exp = oracle_amvp(w, h, m, jobs)
+        bad = np.argwhere((got != exp).any(1))
+        assert not len(bad), (w, h, jobs[bad[0, 0]], got[bad[0, 0]], exp[bad[0, 0]])
+        two += int(((exp[:, 2] != 0) | (exp[:, 3] != 0)).sum())
+        m["mv"] = (m["mv"] // 150).astype(np.int16)                         # few distinct vectors: the merge pruning has work to do
+        units["mvx"], units["mvy"] = m["mv"][..., 0], m["mv"][..., 1]
+        for mx in (5, 2):
+            gm, em = ctx.merge_candidates(units, w, h, jobs, mx), oracle_merge(w, h, m, jobs, mx)
+            bad = np.argwhere((gm != em).any((1, 2)))
+            assert not len(bad), ("merge", w, h, mx, jobs[bad[0, 0]], gm[bad[0, 0]].tolist(), em[bad[0, 0]].tolist())
+    assert two > 1000
+    with pytest.raises(HbError):
+        ctx.amvp_candidates(units, w, h, np.array([[4, 0, 8]], np.int32))        # not on the size grid
+    with pytest.raises(HbError):
+        ctx.amvp_candidates(units, w, h, np.array([[w - 8, 0, 16]], np.int32))   # leaves the picture

@@ -375,3 +375,24 @@ def test_amvp_candidates_against_reference():
             for e in exp:
                 seen.add((bool(e[0] or e[1]), bool(e[2] or e[3])))
     assert seen == {(False, False), (True, False), (True, True)} or seen == {(False, False), (True, False), (True, True), (False, True)}
+
+
+def test_merge_candidates_against_reference():
+    """get_merge_mvp_candidates (hmr_motion_inter.c:1937) for every 2Nx2N PU: order A1, B1, B0, A0, B2, the pairwise pruning, the
+    fifth neighbour only while fewer than four were found, list lengths 1..5 and the zero fill"""
+    from _oracle import amvp_jobs, oracle_merge, random_deblock_case, ref_merge
+    rng = np.random.default_rng(1937)
+    full = 0
+    for (w, h) in ((192, 136), (200, 72), (72, 200), (320, 192)):
+        for rep in range(3):
+            m, _ = random_deblock_case(rng, w, h)
+            if rep == 2:
+                m["mv"] = rng.integers(-2, 3, m["mv"].shape).astype(np.int16)       # few distinct vectors: the pruning has work to do
+            jobs = amvp_jobs(w, h)
+            for mx in (5, 3, 1, 2, 4):
+                exp, got = ref_merge(w, h, m, jobs, mx), oracle_merge(w, h, m, jobs, mx)
+                bad = np.argwhere((exp != got).any((1, 2)))
+                assert not len(bad), (w, h, rep, mx, jobs[bad[0, 0]], exp[bad[0, 0]].tolist(), got[bad[0, 0]].tolist())
+                if mx == 5:
+                    full += int((exp[:, 3] != 0).any(1).sum())
+    assert full > 50
