@@ -543,12 +543,30 @@ double hbi_zero_out_k(double avg_dist)                     /* hmr_motion_inter.c
     return k < 1. ? 1. : (k > 20000. ? 20000. : k);
 }
 
+static int me_search(hb_ctx *ctx, const hb_frame *cur, const hb_frame *ref, const hb_me_job *jobs, int n_jobs, const hb_me_result *parent_results, int n_parent,
+                     double avg_dist, int action, hb_me_result *results, const hb_unit_info *units, int units_w);
 int hb_me_search(hb_ctx *ctx, const hb_frame *cur, const hb_frame *ref, const hb_me_job *jobs, int n_jobs,
                  const hb_me_result *parent_results, int n_parent, double avg_dist, int action, hb_me_result *results)
 {
+    return me_search(ctx, cur, ref, jobs, n_jobs, parent_results, n_parent, avg_dist, action, results, NULL, 0);
+}
+/* the same with the AMVP predictors of every job derived ON THE DEVICE from the per-unit motion field (hb_amvp_candidates) right before its
+ * search: jobs[i].amvp / n_amvp are ignored, the PUs must sit on their size grid */
+int hb_me_search_field(hb_ctx *ctx, const hb_frame *cur, const hb_frame *ref, const hb_unit_info *units, int units_w, const hb_me_job *jobs, int n_jobs,
+                       const hb_me_result *parent_results, int n_parent, double avg_dist, int action, hb_me_result *results)
+{
+    if (!units) return hbi_fail(HB_ERR_ARG, "hb_me_search_field: NULL unit field");
+    if (cur && units_w < ((cur->w + 63) / 64) * 16) return hbi_fail(HB_ERR_ARG, "hb_me_search_field: units_w %d does not cover whole CTUs", units_w);
+    for (int i = 0; jobs && i < n_jobs; i++)
+        if (jobs[i].size > 0 && ((jobs[i].x % jobs[i].size) || (jobs[i].y % jobs[i].size))) return hbi_fail(HB_ERR_ARG, "hb_me_search_field: job %d is off its size grid", i);
+    return me_search(ctx, cur, ref, jobs, n_jobs, parent_results, n_parent, avg_dist, action, results, units, units_w);
+}
+static int me_search(hb_ctx *ctx, const hb_frame *cur, const hb_frame *ref, const hb_me_job *jobs, int n_jobs, const hb_me_result *parent_results, int n_parent,
+                     double avg_dist, int action, hb_me_result *results, const hb_unit_info *units, int units_w)
+{
     static const int sizes[4] = { 64, 32, 16, 8 };
     int rc = HB_OK, crc = 0;
-    void *d_jobs, *h_jobs, *d_res, *h_res, *d_par = NULL, *h_par = NULL;
+    void *d_jobs, *h_jobs, *d_res, *h_res, *d_par = NULL, *h_par = NULL, *d_units = NULL, *h_units = NULL;
     if (!ctx || !cur || !ref || !jobs || !results || n_jobs < 0) return hbi_fail(HB_ERR_ARG, "hb_me_search: bad argument");
     if (cur->w != ref->w || cur->h != ref->h) return hbi_fail(HB_ERR_ARG, "hb_me_search: frame sizes differ");
     if (n_jobs == 0) return HB_OK;
@@ -587,9 +605,20 @@ int hb_me_search(hb_ctx *ctx, const hb_frame *cur, const hb_frame *ref, const hb
     }
     start_of[4] = n;
     if ((crc = hbc_h2d_async(d_jobs, h_jobs, sizeof(hbd_me_job) * (size_t)n_jobs, ctx->stream))) goto done;
+    if (units) {
+        const size_t plane = (size_t)units_w * (size_t)((cur->h + 63) / 64) * 16;
+        if ((rc = hbi_scratch(ctx, 3, sizeof(hb_unit_info) * plane, &d_units, &h_units)) != HB_OK) goto done;
+        memcpy(h_units, units, sizeof(hb_unit_info) * plane);
+        if ((crc = hbc_h2d_async(d_units, h_units, sizeof(hb_unit_info) * plane, ctx->stream))) goto done;
+    }
     for (int s = 0; s < 4 && !crc; s++) {
         const int cnt = start_of[s + 1] - start_of[s];
         if (!cnt) continue;
+        if (units) {
+            crc = hbk_amvp_fill((const hb_unit_info *)d_units, units_w, cur->w, cur->h, (hbd_me_job *)d_jobs + start_of[s], cnt, sizes[s], ctx->stream);
+            ctx->launches++;
+            if (crc) break;
+        }
         crc = hbk_me_search(&cur->d, &ref->d, sizes[s], (const hbd_me_job *)d_jobs + start_of[s], cnt, (const hb_me_result *)d_par,
                             (hb_me_result *)d_res, action, NULL, NULL, NULL, 0, ctx->stream);
         ctx->launches++;

@@ -403,12 +403,10 @@ __device__ __forceinline__ int pu_neighbours(const hb_unit_info *units, int unit
     return okm;
 }
 
-__global__ void __launch_bounds__(128) k_amvp(const hb_unit_info *units, int units_w, int w, int h, const hb_amvp_job *jobs, int n_jobs, hb_amvp_list *out)
+__device__ __forceinline__ hb_amvp_list amvp_of(const hb_unit_info *units, int units_w, int w, int h, int x, int y, int size)
 {
-    const int i = blockIdx.x * 128 + threadIdx.x;
-    if (i >= n_jobs) return;
     hb_mv cand[5];
-    const int okm = pu_neighbours(units, units_w, w, h, jobs[i].x, jobs[i].y, jobs[i].size, cand);
+    const int okm = pu_neighbours(units, units_w, w, h, x, y, size, cand);
     hb_mv list[3];
     int n = 0;
     const bool smvp = (okm & 3) != 0;
@@ -421,7 +419,22 @@ __global__ void __launch_bounds__(128) k_amvp(const hb_unit_info *units, int uni
     hb_amvp_list r;
     r.mv[0].x = n > 0 ? list[0].x : 0; r.mv[0].y = n > 0 ? list[0].y : 0;
     r.mv[1].x = n > 1 ? list[1].x : 0; r.mv[1].y = n > 1 ? list[1].y : 0;
-    out[i] = r;
+    return r;
+}
+__global__ void __launch_bounds__(128) k_amvp(const hb_unit_info *units, int units_w, int w, int h, const hb_amvp_job *jobs, int n_jobs, hb_amvp_list *out)
+{
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n_jobs) return;
+    out[i] = amvp_of(units, units_w, w, h, jobs[i].x, jobs[i].y, jobs[i].size);
+}
+// the same, written straight into the predictor fields of queued search jobs (hb_me_search_field: no trip to the host in between)
+__global__ void __launch_bounds__(128) k_amvp_fill(const hb_unit_info *units, int units_w, int w, int h, hbd_me_job *jobs, int n_jobs, int size)
+{
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n_jobs) return;
+    const hb_amvp_list r = amvp_of(units, units_w, w, h, jobs[i].x, jobs[i].y, size);
+    jobs[i].n_amvp = 2;
+    jobs[i].amvp[0] = r.mv[0].x; jobs[i].amvp[1] = r.mv[0].y; jobs[i].amvp[2] = r.mv[1].x; jobs[i].amvp[3] = r.mv[1].y;
 }
 
 // merge candidates (get_merge_mvp_candidates hmr_motion_inter.c:1937, P picture, one reference picture): A1, B1, B0, A0, then B2 while fewer
@@ -449,6 +462,12 @@ extern "C" int hbk_amvp(const hb_unit_info *units, int units_w, int w, int h, co
 {
     if (n_jobs <= 0) return 0;
     k_amvp<<<(n_jobs + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(units, units_w, w, h, jobs, n_jobs, out);
+    return static_cast<int>(cudaGetLastError());
+}
+extern "C" int hbk_amvp_fill(const hb_unit_info *units, int units_w, int w, int h, hbd_me_job *jobs, int n_jobs, int size, void *stream)
+{
+    if (n_jobs <= 0) return 0;
+    k_amvp_fill<<<(n_jobs + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(units, units_w, w, h, jobs, n_jobs, size);
     return static_cast<int>(cudaGetLastError());
 }
 extern "C" int hbk_merge_cands(const hb_unit_info *units, int units_w, int w, int h, const hb_amvp_job *jobs, int n_jobs, int max_cands, hb_mv *out, void *stream)

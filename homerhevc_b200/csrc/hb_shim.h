@@ -218,6 +218,7 @@ int hbk_sao_stats(const hbd_frame *org, const hbd_frame *rec, int ctu_cols, int 
 int hbk_sao_derive(const hb_sao_stats *stats, int n_units, const double lambda[3], hb_sao_candidate *out, void *stream);
 /* boundary strengths + QP map of a P picture from per-unit mode data (device pointers) */
 int hbk_amvp(const hb_unit_info *units, int units_w, int w, int h, const hb_amvp_job *jobs, int n_jobs, hb_amvp_list *out, void *stream);
+int hbk_amvp_fill(const hb_unit_info *units, int units_w, int w, int h, hbd_me_job *jobs, int n_jobs, int size, void *stream);
 int hbk_merge_cands(const hb_unit_info *units, int units_w, int w, int h, const hb_amvp_job *jobs, int n_jobs, int max_cands, hb_mv *out, void *stream);
 int hbk_deblock_strengths(const hb_unit_info *units, int units_w, int w, int h, uint8_t *bs_ver, uint8_t *bs_hor, uint8_t *qp, void *stream);
 /* deblocking, pixel stage, in place: all vertical edges, then all horizontal ones (two launches); maps in device memory */

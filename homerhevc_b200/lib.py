@@ -348,6 +348,17 @@ class Context:
         _check(self.L.hb_me_search(self.h, cur.h, ref.h, arr, n, par, npar, avg_dist, action, out), "hb_me_search")
         return list(out)
 
+    def me_search_field(self, cur, ref, units, jobs, avg_dist, action=7):
+        """hb_me_search with the AMVP predictors of every job taken on the device from the per-unit motion field"""
+        units = np.ascontiguousarray(units, UNIT_INFO_DT)
+        n = len(jobs)
+        arr = (MeJob * n)(*jobs)
+        out = (MeResult * n)()
+        self.L.hb_me_search_field.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(MeJob), C.c_int, C.POINTER(MeResult), C.c_int,
+                                              C.c_double, C.c_int, C.POINTER(MeResult)]
+        _check(self.L.hb_me_search_field(self.h, cur.h, ref.h, units.ctypes.data, units.shape[1], arr, n, None, 0, avg_dist, action, out), "hb_me_search_field")
+        return list(out)
+
     def mc_predict(self, ref, pred, jobs):
         n = len(jobs)
         arr = (McJob * n)(*jobs)

@@ -271,6 +271,10 @@ int hb_deblock_frame_units(hb_ctx *ctx, hb_frame *frame, const hb_unit_info *uni
 typedef struct hb_amvp_job { int32_t x, y, size; } hb_amvp_job;              /* size 64 / 32 / 16 / 8, inside the picture */
 typedef struct hb_amvp_list { hb_mv mv[2]; } hb_amvp_list;
 int hb_amvp_candidates(hb_ctx *ctx, const hb_unit_info *units, int units_w, int width, int height, const hb_amvp_job *jobs, int n_jobs, hb_amvp_list *out);
+/* hb_me_search with the predictors of every job derived on the device from the unit field right before its search (k_amvp_fill -> k_me, no
+ * host round trip in between): jobs[i].amvp / n_amvp are ignored.  == hb_amvp_candidates followed by hb_me_search. */
+int hb_me_search_field(hb_ctx *ctx, const hb_frame *cur, const hb_frame *ref, const hb_unit_info *units, int units_w, const hb_me_job *jobs, int n_jobs,
+                       const hb_me_result *parent_results, int n_parent, double avg_dist, int action, hb_me_result *results);
 /* Merge candidates of the same PUs (get_merge_mvp_candidates, hmr_motion_inter.c:1937; P pictures, one reference picture): the neighbours in
  * the order A1, B1, B0, A0, then B2 while fewer than four, pruned pairwise as equal_motion :1915 does, closed at max_cands (1..5, the
  * slice's max_num_merge_candidates) and filled with zero vectors.  out[i * max_cands + k] = candidate k of jobs[i]; what hb_merge_eval takes. */

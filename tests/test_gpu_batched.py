@@ -408,3 +408,30 @@ def test_amvp_candidates_from_unit_field(ctx):
         ctx.amvp_candidates(units, w, h, np.array([[4, 0, 8]], np.int32))        # not on the size grid
     with pytest.raises(HbError):
         ctx.amvp_candidates(units, w, h, np.array([[w - 8, 0, 16]], np.int32))   # leaves the picture
+
+
+def test_search_with_predictors_from_the_unit_field(ctx):
+    """hb_me_search_field (AMVP lists derived on the device right before the search) == hb_amvp_candidates + hb_me_search, and the
+    predictors do change vectors / costs against the zero-predictor search"""
+    from homerhevc_b200.lib import UNIT_INFO_DT
+    from _oracle import amvp_jobs, random_deblock_case
+    w, h, qp, avg = 192, 136, 30, 500.0
+    cur, ref = clip_pair(w, h, n=2, noise=6.0, seed=5)
+    fc, fr = upload(ctx, cur, w, h), upload(ctx, ref, w, h)
+    rng = np.random.default_rng(8)
+    m, _ = random_deblock_case(rng, w, h)
+    m["mv"] = rng.integers(-24, 25, m["mv"].shape).astype(np.int16)
+    units = np.zeros(m["cu"].shape, UNIT_INFO_DT)
+    units["intra"] = m["intra"]; units["ref_idx"] = np.where(m["intra"] != 0, -1, 0); units["mvx"], units["mvy"] = m["mv"][..., 0], m["mv"][..., 1]
+    pus = amvp_jobs(w, h)
+    lists = ctx.amvp_candidates(units, w, h, pus)
+    jobs_zero = [hb.MeJob(int(x), int(y), int(s), qp, 2, (Mv * 2)(Mv(0, 0), Mv(0, 0)), 0, (Mv * 3)(), -1) for (x, y, s) in pus]
+    jobs_amvp = [hb.MeJob(int(x), int(y), int(s), qp, 2, (Mv * 2)(Mv(int(l[0][0]), int(l[0][1])), Mv(int(l[1][0]), int(l[1][1]))), 0, (Mv * 3)(), -1)
+                 for (x, y, s), l in zip(pus, lists)]
+    a = ctx.me_search(fc, fr, jobs_amvp, avg)
+    b = ctx.me_search_field(fc, fr, units, jobs_zero, avg)
+    z = ctx.me_search(fc, fr, jobs_zero, avg)
+    key = lambda r: (r.mv.x, r.mv.y, r.subpix.x, r.subpix.y, r.sad, r.n_probes)
+    assert [key(r) for r in a] == [key(r) for r in b]
+    assert sum(key(p) != key(q) for p, q in zip(a, z)) > 10
+    fc.close(); fr.close()
