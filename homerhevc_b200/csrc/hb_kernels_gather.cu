@@ -739,6 +739,53 @@ extern "C" int hbk_units_from_selection(const hbd_units_args *a, void *stream)
     return static_cast<int>(cudaGetLastError());
 }
 
+namespace {
+// ---- the levels of the chosen passes in the layout the reference's entropy coder reads (ctu->coeff_wnd, hmr_encoder_lib.c:2945,
+// encode_residual hmr_arithmetic_encoding.c:1087): per CTU three 1-D windows (64*64 luma, 32*32 U, 32*32 V int16); a transform unit's
+// N*N levels lie row-major at offset abs_index << 4 (luma) / (abs_index << 4) >> 2 (chroma), abs_index = z-order number of the
+// unit's first 4x4 luma block inside the CTU (hmr_motion_inter.c:73, :174).  Units without levels are zero.  One CTA per CTU.
+__device__ __forceinline__ int zorder4(int ux, int uy)
+{
+    int a = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) a |= ((ux >> b) & 1) << (2 * b) | ((uy >> b) & 1) << (2 * b + 1);
+    return a;
+}
+__global__ void __launch_bounds__(256) k_coeff_wnd(const hbd_gather_args a, int16_t *out)
+{
+    const int ctu = blockIdx.x, tid = threadIdx.x;
+    const int cx = ctu % a.ctu_cols, cy = ctu / a.ctu_cols;
+    const int sel = a.sel[ctu];
+    int16_t *dst_ctu = out + static_cast<size_t>(ctu) * (64 * 64 + 2 * 32 * 32);
+    for (int c = 0; c < 3; c++) {
+        const int pass = c ? min(sel, 3) : sel;
+        const hbd_gather_pc pc = a.pc[pass][c];
+        const int cs = c ? 32 : 64, tpr = cs / pc.tu, nn = pc.tu * pc.tu, lum = c ? pc.tu * 2 : pc.tu;      // lum: the unit's side in luma samples
+        int16_t *dst = dst_ctu + (c == 0 ? 0 : c == 1 ? 64 * 64 : 64 * 64 + 32 * 32);
+        // (unit, 8-level chunk) pairs over the whole window: every level of the window is written, coded or zero
+        for (int q = tid; q < cs * cs / 8; q += 256) {
+            const int unit = q / (nn / 8), chunk = q % (nn / 8);
+            const int tx = cx * tpr + unit % tpr, ty = cy * tpr + unit / tpr;
+            int idx = -1;
+            if (tx < pc.grid_w && ty < pc.grid_h) idx = pc.tu_index[ty * pc.grid_w + tx];
+            if (idx >= 0 && pc.res[idx].sum <= 0) idx = -1;
+            const int abs_index = zorder4((unit % tpr) * lum / 4, (unit / tpr) * lum / 4);
+            const int off = c ? (abs_index << 4) >> 2 : abs_index << 4;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (idx >= 0) v = __ldg(reinterpret_cast<const uint4 *>(pc.coeff + static_cast<size_t>(idx) * nn) + chunk);
+            reinterpret_cast<uint4 *>(dst + off)[chunk] = v;
+        }
+    }
+}
+}  // namespace
+
+extern "C" int hbk_coeff_wnd(const hbd_gather_args *a, int n_ctus, int16_t *out, void *stream)
+{
+    if (n_ctus <= 0) return 0;
+    k_coeff_wnd<<<n_ctus, 256, 0, static_cast<cudaStream_t>(stream)>>>(*a, out);
+    return static_cast<int>(cudaGetLastError());
+}
+
 extern "C" int hbk_gather(const hbd_gather_args *a, int n_ctus, void *stream)
 {
     if (n_ctus <= 0) return 0;

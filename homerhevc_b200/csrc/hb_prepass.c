@@ -791,6 +791,39 @@ static int gather_queue(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_o
     return crc ? hbi_cuda_fail(crc, what) : HB_OK;
 }
 
+/* The levels of the host's choice in the reference's own hand-off layout (ctu->coeff_wnd): per CTU 64*64 luma, 32*32 U, 32*32 V int16,
+ * a transform unit's levels row-major at abs_index << 4 (chroma >> 2).  Blocking. */
+int hb_prepass_fetch_coeff_wnd(hb_prepass *pp, const uint8_t *sel, int16_t *out)
+{
+    if (!pp || !sel || !out) return hbi_fail(HB_ERR_ARG, "hb_prepass_fetch_coeff_wnd: NULL argument");
+    hb_ctx *ctx = pp->ctx;
+    const int n_ctus = hb_prepass_num_ctus(pp);
+    const size_t bytes = sizeof(int16_t) * HB_COEFF_WND_PER_CTU * (size_t)n_ctus;
+    int crc = 0, rc;
+    void *d_out, *h_out;
+    for (int i = 0; i < n_ctus; i++) if (sel[i] > 4) return hbi_fail(HB_ERR_ARG, "hb_prepass_fetch_coeff_wnd: sel[%d] = %d", i, sel[i]);
+    hbc_set_device(ctx->device);
+    if (!pp->d_sel && (crc = hbc_malloc((void **)&pp->d_sel, (size_t)n_ctus))) { pp->d_sel = NULL; return hbi_cuda_fail(crc, "hb_prepass_fetch_coeff_wnd"); }
+    pthread_mutex_lock(&ctx->lock);
+    if ((rc = hbi_scratch(ctx, 3, bytes, &d_out, &h_out)) != HB_OK) { pthread_mutex_unlock(&ctx->lock); return rc; }
+    crc = hbc_h2d_async(pp->d_sel, sel, (size_t)n_ctus, ctx->stream);
+    hbd_gather_args a;
+    memset(&a, 0, sizeof a);
+    a.sel = pp->d_sel; a.ctu_cols = pp->ctu_cols;
+    for (int p = 0; p < N_PASS; p++)
+        for (int c = 0; c < 3; c++) {
+            const pass_comp *pc = &pp->pc[p][c];
+            a.pc[p][c].tu_index = pc->d_index; a.pc[p][c].grid_w = pc->grid_w; a.pc[p][c].grid_h = pc->grid_h; a.pc[p][c].tu = pc->tu;
+            a.pc[p][c].res = pc->d_res; a.pc[p][c].coeff = pc->d_coeff;
+        }
+    if (!crc) { crc = hbk_coeff_wnd(&a, n_ctus, (int16_t *)d_out, ctx->stream); ctx->launches++; }
+    if (!crc) crc = hbc_d2h_async(h_out, d_out, bytes, ctx->stream);
+    if (!crc) crc = hbc_stream_sync(ctx->stream);
+    if (!crc) memcpy(out, h_out, bytes);
+    pthread_mutex_unlock(&ctx->lock);
+    return crc ? hbi_cuda_fail(crc, "hb_prepass_fetch_coeff_wnd") : HB_OK;
+}
+
 /* Queue the gather of the host's choice and its copy to pinned_dst: reconstruction Y,U,V (tight planes) followed by the level
  * streams of all CTUs (layout in hb_kernels_gather.cu).  Asynchronous: hb_ctx_sync before reading. */
 int hb_prepass_gather(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_off, void *pinned_dst, size_t cap, size_t *bytes_out)

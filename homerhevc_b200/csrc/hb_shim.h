@@ -193,6 +193,7 @@ typedef struct hbd_gather_args {
     int16_t *out_levels;
 } hbd_gather_args;
 int hbk_gather(const hbd_gather_args *a, int n_ctus, void *stream);
+int hbk_coeff_wnd(const hbd_gather_args *a, int n_ctus, int16_t *out /* n_ctus x 6144 */, void *stream);
 /* deblocking unit data of the chosen passes, from what the pre-pass left on the device: per 4x4 unit the CU / TU depth of the CTU's
  * pass, the vector of the PU and the coded flag of the luma TU that cover it */
 typedef struct hbd_units_args {

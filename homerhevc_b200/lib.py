@@ -755,6 +755,14 @@ class Prepass:
     def select(self, tables, lam, sel, ctu_off):
         _check(self.ctx.L.hb_prepass_select(self.h, tables.ctypes.data, lam, sel.ctypes.data, ctu_off.ctypes.data), "hb_prepass_select")
 
+    def fetch_coeff_wnd(self, sel):
+        """levels of the chosen passes in the reference's ctu->coeff_wnd layout: (n_ctus, 6144) int16 = 64*64 Y | 32*32 U | 32*32 V per CTU"""
+        sel = np.ascontiguousarray(sel, np.uint8)
+        out = np.zeros((self.num_ctus(), 64 * 64 + 2 * 32 * 32), np.int16)
+        self.ctx.L.hb_prepass_fetch_coeff_wnd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _check(self.ctx.L.hb_prepass_fetch_coeff_wnd(self.h, sel.ctypes.data, out.ctypes.data), "hb_prepass_fetch_coeff_wnd")
+        return out
+
     def gather(self, sel, ctu_off, pinned):
         n = C.c_size_t(0)
         _check(self.ctx.L.hb_prepass_gather(self.h, sel.ctypes.data, ctu_off.ctypes.data, pinned.ctypes.data, pinned.nbytes, C.byref(n)),

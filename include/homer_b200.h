@@ -378,6 +378,14 @@ int  hb_prepass_num_ctus(const hb_prepass *pp);
 /* stand-in for the host's decision: per CTU the pass (0..4) minimising sum(ssd) + lambda*sum(|level|); also lays out the stream */
 int  hb_prepass_select(const hb_prepass *pp, const void *tables, int lambda, uint8_t *sel, int32_t *ctu_off /* num_ctus + 1 */);
 size_t hb_prepass_gather_bytes(const hb_prepass *pp, const int32_t *ctu_off);
+/* The levels of the chosen passes in the reference's OWN hand-off layout to its entropy coder (ctu->coeff_wnd, hmr_encoder_lib.c:2945; read by
+ * encode_residual, hmr_arithmetic_encoding.c:1087): per CTU HB_COEFF_WND_PER_CTU int16 = 64*64 luma, then 32*32 U, then 32*32 V; the N*N
+ * levels of a transform unit lie row-major at offset abs_index << 4 in the luma window and (abs_index << 4) >> 2 in a chroma window,
+ * abs_index = z-order number of the unit's first 4x4 luma block inside the CTU (hmr_motion_inter.c:73, :174); units without levels are
+ * zero.  sel: chosen pass per CTU as for hb_prepass_gather.  Blocking; out: hb_prepass_num_ctus(pp) * HB_COEFF_WND_PER_CTU int16. */
+#define HB_COEFF_WND_PER_CTU (64 * 64 + 2 * 32 * 32)
+int hb_prepass_fetch_coeff_wnd(hb_prepass *pp, const uint8_t *sel, int16_t *out);
+
 /* out: recon Y,U,V tight planes, then per CTU (from ctu_off[i], int16 units) for Y,U,V the coded TUs in raster order:
  * { hdr_lo, hdr_hi, N*N levels }, hdr = plane << 28 | N << 16 | TU raster position inside the CTU */
 int  hb_prepass_gather(hb_prepass *pp, const uint8_t *sel, const int32_t *ctu_off, void *pinned_dst, size_t cap, size_t *bytes_out);

@@ -653,3 +653,40 @@ def test_subpel_planes_without_tma():
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_prepass.py"), "-q", "-x", "-m", "gpu", "-k",
                           "matches_oracle or per_picture_equal"], capture_output=True, text=True, timeout=900, cwd=root, env=dict(os.environ, HB_NO_TMA="1"))
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-1000:]
+
+
+def test_levels_in_the_reference_coeff_wnd_layout(ctx):
+    """hb_prepass_fetch_coeff_wnd: the chosen passes' levels where the reference's entropy coder looks for them (ctu->coeff_wnd: a unit's
+    levels row-major at abs_index << 4, chroma >> 2, abs_index = z-order number of its first 4x4 luma block), rebuilt on the host from the
+    per-pass tables; every pass chosen somewhere, partial CTUs on both edges"""
+    w, h, qp, avg = 328, 200, 26, 300.0
+    cur, ref = clip_pair(w, h, n=3, noise=5.0, seed=12)
+    fc, fr = upload(ctx, cur, w, h), upload(ctx, ref, w, h)
+    pp = hb.Prepass(ctx, w, h, qp=qp)
+    pp.run(fc, fr, avg); ctx.sync()
+    cols, rows = (w + 63) // 64, (h + 63) // 64
+    sel = np.array([(3 + (i % 2)) if (i % cols == cols - 1 or i // cols == rows - 1) else i % 5 for i in range(cols * rows)], np.uint8)   # partial CTUs: 8x8 units
+    got = pp.fetch_coeff_wnd(sel)
+
+    def zorder(ux, uy):
+        return sum((((ux >> b) & 1) << (2 * b)) | (((uy >> b) & 1) << (2 * b + 1)) for b in range(4))
+    exp = np.zeros_like(got)
+    coded = 0
+    for ctu in range(cols * rows):
+        for c in range(3):
+            p = min(int(sel[ctu]), 3) if c else int(sel[ctu])
+            t = pp.tu_size(p, c)
+            xy, res, co = pp.tu_xy(p, c), pp.fetch_tu(p, c), pp.fetch_coeffs(p, c)
+            cs = 32 if c else 64
+            x0, y0 = (ctu % cols) * cs, (ctu // cols) * cs
+            base = 0 if c == 0 else (4096 if c == 1 else 4096 + 1024)
+            for i in np.nonzero((xy[:, 0] >= x0) & (xy[:, 0] < x0 + cs) & (xy[:, 1] >= y0) & (xy[:, 1] < y0 + cs))[0]:
+                if res[i]["sum"] <= 0:
+                    continue
+                lx, ly = (int(xy[i, 0]) - x0) * (2 if c else 1), (int(xy[i, 1]) - y0) * (2 if c else 1)     # luma position inside the CTU
+                a = zorder(lx // 4, ly // 4)
+                off = (a << 4) >> 2 if c else a << 4
+                exp[ctu, base + off:base + off + t * t] = co[i].reshape(-1)
+                coded += 1
+    assert coded > 200 and np.array_equal(got, exp), np.argwhere(got != exp)[:5]
+    pp.close(); fc.close(); fr.close()
