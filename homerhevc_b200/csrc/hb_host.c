@@ -870,23 +870,30 @@ done:
 }
 
 /* deblocking of a whole picture in place, strengths derived on the device from per-unit mode data */
-int hb_deblock_frame_units(hb_ctx *ctx, hb_frame *frame, const hb_unit_info *units, int units_w, const hb_deblock_params *params,
-                           uint8_t *bs_ver_out, uint8_t *bs_hor_out)
+static int deblock_units(hb_ctx *ctx, hb_frame *frame, const hb_unit_info *units, const hb_unit_l1 *units1, int units_w, const int32_t *pic_l0, int n_l0,
+                         const int32_t *pic_l1, int n_l1, const hb_deblock_params *params, uint8_t *bs_ver_out, uint8_t *bs_hor_out, const char *what)
 {
     int rc = HB_OK, crc = 0;
-    void *d_units, *h_units, *d_maps, *h_maps;
-    if (!ctx || !frame || !units || !params) return hbi_fail(HB_ERR_ARG, "hb_deblock_frame_units: NULL argument");
-    if (units_w < frame->w / 4) return hbi_fail(HB_ERR_ARG, "hb_deblock_frame_units: units_w %d is smaller than width/4", units_w);
+    void *d_units, *h_units, *d_maps, *h_maps, *d_u1 = NULL, *h_u1 = NULL;
+    if (!ctx || !frame || !units || !params) return hbi_fail(HB_ERR_ARG, "%s: NULL argument", what);
+    if (units_w < frame->w / 4) return hbi_fail(HB_ERR_ARG, "%s: units_w %d is smaller than width/4", what, units_w);
+    if (units1 && (!pic_l0 || !pic_l1 || n_l0 < 0 || n_l0 > 16 || n_l1 < 0 || n_l1 > 16)) return hbi_fail(HB_ERR_ARG, "%s: bad reference picture lists", what);
     const size_t plane = (size_t)units_w * (size_t)(frame->h / 4);
     hbc_set_device(ctx->device);
     pthread_mutex_lock(&ctx->lock);
     if ((rc = hbi_scratch(ctx, 0, sizeof(hb_unit_info) * plane, &d_units, &h_units)) != HB_OK) goto done;
     if ((rc = hbi_scratch(ctx, 1, 3 * plane, &d_maps, &h_maps)) != HB_OK) goto done;
+    if (units1 && (rc = hbi_scratch(ctx, 2, sizeof(hb_unit_l1) * plane, &d_u1, &h_u1)) != HB_OK) goto done;
     memcpy(h_units, units, sizeof(hb_unit_info) * plane);
     crc = hbc_h2d_async(d_units, h_units, sizeof(hb_unit_info) * plane, ctx->stream);
+    if (!crc && units1) { memcpy(h_u1, units1, sizeof(hb_unit_l1) * plane); crc = hbc_h2d_async(d_u1, h_u1, sizeof(hb_unit_l1) * plane, ctx->stream); }
     if (!crc) crc = hbc_memset_async(d_maps, 0, 3 * plane, ctx->stream);
     uint8_t *bv = (uint8_t *)d_maps, *bh = bv + plane, *qp = bh + plane;
-    if (!crc) { crc = hbk_deblock_strengths((const hb_unit_info *)d_units, units_w, frame->w, frame->h, bv, bh, qp, ctx->stream); ctx->launches++; }
+    if (!crc) {
+        if (units1) crc = hbk_deblock_strengths_b((const hb_unit_info *)d_units, (const hb_unit_l1 *)d_u1, pic_l0, n_l0, pic_l1, n_l1, units_w, frame->w, frame->h, bv, bh, qp, ctx->stream);
+        else crc = hbk_deblock_strengths((const hb_unit_info *)d_units, units_w, frame->w, frame->h, bv, bh, qp, ctx->stream);
+        ctx->launches++;
+    }
     if (!crc) {
         crc = hbk_deblock(&frame->d, bv, bh, qp, units_w, params->cb_qp_offset, params->cr_qp_offset, params->beta_offset_div2, params->tc_offset_div2, ctx->stream);
         ctx->launches += 2;
@@ -898,8 +905,20 @@ int hb_deblock_frame_units(hb_ctx *ctx, hb_frame *frame, const hb_unit_info *uni
     if (!crc && bs_hor_out) memcpy(bs_hor_out, (char *)h_maps + plane, plane);
 done:
     pthread_mutex_unlock(&ctx->lock);
-    if (crc) return hbi_cuda_fail(crc, "hb_deblock_frame_units");
+    if (crc) return hbi_cuda_fail(crc, what);
     return rc;
+}
+int hb_deblock_frame_units(hb_ctx *ctx, hb_frame *frame, const hb_unit_info *units, int units_w, const hb_deblock_params *params,
+                           uint8_t *bs_ver_out, uint8_t *bs_hor_out)
+{
+    return deblock_units(ctx, frame, units, NULL, units_w, NULL, 0, NULL, 0, params, bs_ver_out, bs_hor_out, "hb_deblock_frame_units");
+}
+int hb_deblock_frame_units_b(hb_ctx *ctx, hb_frame *frame, const hb_unit_info *units, const hb_unit_l1 *units_l1, int units_w,
+                             const int32_t *pic_l0, int n_l0, const int32_t *pic_l1, int n_l1, const hb_deblock_params *params,
+                             uint8_t *bs_ver_out, uint8_t *bs_hor_out)
+{
+    if (!units_l1) return hbi_fail(HB_ERR_ARG, "hb_deblock_frame_units_b: NULL list-1 units");
+    return deblock_units(ctx, frame, units, units_l1, units_w, pic_l0, n_l0, pic_l1, n_l1, params, bs_ver_out, bs_hor_out, "hb_deblock_frame_units_b");
 }
 
 /* AMVP / merge candidates of a batch of PUs from the per-unit motion field: one launch, one copy back.  max_cands = 0: AMVP */

@@ -308,7 +308,9 @@ __global__ void __launch_bounds__(256) k_deblock(const DbkArgs a)
 namespace {
 // ---- boundary strengths of a P picture from per-unit mode data (hmr_deblock_filter_cu :737 edge marking, set_edge_filter_pu :692,
 // get_boundary_strength_single :138): one thread per 4x4 unit writes the strength of its left and top side and its QP
-__global__ void __launch_bounds__(256) k_deblock_strengths(const hb_unit_info *units, int units_w, int uw, int uh, uint8_t *bs_ver, uint8_t *bs_hor, uint8_t *qp)
+struct DbkPics { int32_t l0[16], l1[16]; };               // the pictures the reference indices of the two lists name (B pictures)
+__global__ void __launch_bounds__(256) k_deblock_strengths(const hb_unit_info *units, const hb_unit_l1 *units1, const DbkPics pics, int units_w, int uw, int uh,
+                                                           uint8_t *bs_ver, uint8_t *bs_hor, uint8_t *qp)
 {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= uw * uh) return;
@@ -324,7 +326,20 @@ __global__ void __launch_bounds__(256) k_deblock_strengths(const hb_unit_info *u
             const hb_unit_info p = units[dir ? qi - units_w : qi - 1];
             if (p.intra || q.intra) bs = 2;
             else if (((q.cbf_luma >> q.tu_depth) & 1) || ((p.cbf_luma >> p.tu_depth) & 1)) bs = 1;
-            else bs = (p.ref_idx != q.ref_idx) || abs(q.mvx - p.mvx) >= 4 || abs(q.mvy - p.mvy) >= 4;
+            else if (units1 == nullptr) bs = (p.ref_idx != q.ref_idx) || abs(q.mvx - p.mvx) >= 4 || abs(q.mvy - p.mvy) >= 4;
+            else {
+                // B picture (hmr_deblocking_filter.c:173-229): two (picture, vector) pairs a side; an unused list has no picture and a zero vector
+                const hb_unit_l1 p1 = units1[dir ? qi - units_w : qi - 1], q1 = units1[qi];
+                auto pic = [&](int r, bool list1) { return r < 0 ? -1 : (list1 ? pics.l1[r & 15] : pics.l0[r & 15]); };
+                const int r0 = pic(p.ref_idx, false), r1 = pic(p1.ref_idx, true), c0 = pic(q.ref_idx, false), c1 = pic(q1.ref_idx, true);
+                const int p0x = r0 < 0 ? 0 : p.mvx, p0y = r0 < 0 ? 0 : p.mvy, p1x = r1 < 0 ? 0 : p1.mvx, p1y = r1 < 0 ? 0 : p1.mvy;
+                const int q0x = c0 < 0 ? 0 : q.mvx, q0y = c0 < 0 ? 0 : q.mvy, q1x = c1 < 0 ? 0 : q1.mvx, q1y = c1 < 0 ? 0 : q1.mvy;
+                auto far = [](int ax, int ay, int bx, int by) { return abs(ax - bx) >= 4 || abs(ay - by) >= 4; };
+                if ((r0 == c0 && r1 == c1) || (r0 == c1 && r1 == c0)) {
+                    if (r0 != r1) bs = (r0 == c0) ? (far(q0x, q0y, p0x, p0y) || far(q1x, q1y, p1x, p1y)) : (far(q1x, q1y, p0x, p0y) || far(q0x, q0y, p1x, p1y));
+                    else bs = (far(q0x, q0y, p0x, p0y) || far(q1x, q1y, p1x, p1y)) && (far(q1x, q1y, p0x, p0y) || far(q0x, q0y, p1x, p1y));
+                } else bs = 1;
+            }
         }
         (dir ? bs_hor : bs_ver)[qi] = static_cast<uint8_t>(bs);
     }
@@ -480,7 +495,18 @@ extern "C" int hbk_merge_cands(const hb_unit_info *units, int units_w, int w, in
 extern "C" int hbk_deblock_strengths(const hb_unit_info *units, int units_w, int w, int h, uint8_t *bs_ver, uint8_t *bs_hor, uint8_t *qp, void *stream)
 {
     const int uw = w >> 2, uh = h >> 2;
-    k_deblock_strengths<<<(uw * uh + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(units, units_w, uw, uh, bs_ver, bs_hor, qp);
+    DbkPics pics;
+    memset(&pics, 0, sizeof pics);
+    k_deblock_strengths<<<(uw * uh + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(units, nullptr, pics, units_w, uw, uh, bs_ver, bs_hor, qp);
+    return static_cast<int>(cudaGetLastError());
+}
+extern "C" int hbk_deblock_strengths_b(const hb_unit_info *units, const hb_unit_l1 *units1, const int32_t *pic_l0, int n_l0, const int32_t *pic_l1, int n_l1,
+                                       int units_w, int w, int h, uint8_t *bs_ver, uint8_t *bs_hor, uint8_t *qp, void *stream)
+{
+    const int uw = w >> 2, uh = h >> 2;
+    DbkPics pics;
+    for (int i = 0; i < 16; i++) { pics.l0[i] = i < n_l0 ? pic_l0[i] : -1; pics.l1[i] = i < n_l1 ? pic_l1[i] : -1; }
+    k_deblock_strengths<<<(uw * uh + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(units, units1, pics, units_w, uw, uh, bs_ver, bs_hor, qp);
     return static_cast<int>(cudaGetLastError());
 }
 

@@ -221,6 +221,8 @@ int hbk_sao_derive(const hb_sao_stats *stats, int n_units, const double lambda[3
 int hbk_amvp(const hb_unit_info *units, int units_w, int w, int h, const hb_amvp_job *jobs, int n_jobs, hb_amvp_list *out, void *stream);
 int hbk_amvp_fill(const hb_unit_info *units, int units_w, int w, int h, hbd_me_job *jobs, int n_jobs, int size, void *stream);
 int hbk_merge_cands(const hb_unit_info *units, int units_w, int w, int h, const hb_amvp_job *jobs, int n_jobs, int max_cands, hb_mv *out, void *stream);
+int hbk_deblock_strengths_b(const hb_unit_info *units, const hb_unit_l1 *units1, const int32_t *pic_l0, int n_l0, const int32_t *pic_l1, int n_l1,
+                            int units_w, int w, int h, uint8_t *bs_ver, uint8_t *bs_hor, uint8_t *qp, void *stream);
 int hbk_deblock_strengths(const hb_unit_info *units, int units_w, int w, int h, uint8_t *bs_ver, uint8_t *bs_hor, uint8_t *qp, void *stream);
 /* deblocking, pixel stage, in place: all vertical edges, then all horizontal ones (two launches); maps in device memory */
 int hbk_deblock(const hbd_frame *f, const uint8_t *bs_ver, const uint8_t *bs_hor, const uint8_t *qp, int units_w,

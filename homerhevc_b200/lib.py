@@ -450,6 +450,23 @@ def _deblock_units(self, frame, units, cb_qp_offset=0, cr_qp_offset=0, beta_offs
 
 Context.deblock_units = _deblock_units
 
+UNIT_L1_DT = np.dtype([("ref_idx", "i1"), ("reserved", "i1"), ("mvx", "<i2"), ("mvy", "<i2")])
+
+
+def _deblock_units_b(self, frame, units, units_l1, pic_l0, pic_l1, cb_qp_offset=0, cr_qp_offset=0, beta_offset_div2=0, tc_offset_div2=0):
+    """B pictures: units = list 0 (UNIT_INFO_DT), units_l1 = list 1 (UNIT_L1_DT), pic_l0 / pic_l1 = picture behind every reference index"""
+    units = np.ascontiguousarray(units, UNIT_INFO_DT); units_l1 = np.ascontiguousarray(units_l1, UNIT_L1_DT)
+    p0 = np.ascontiguousarray(pic_l0, np.int32); p1 = np.ascontiguousarray(pic_l1, np.int32)
+    bsv = np.zeros(units.shape, np.uint8); bsh = np.zeros(units.shape, np.uint8)
+    prm = (C.c_int32 * 4)(cb_qp_offset, cr_qp_offset, beta_offset_div2, tc_offset_div2)
+    self.L.hb_deblock_frame_units_b.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    _check(self.L.hb_deblock_frame_units_b(self.h, frame.h, units.ctypes.data, units_l1.ctypes.data, units.shape[1], p0.ctypes.data, len(p0), p1.ctypes.data, len(p1),
+                                           prm, bsv.ctypes.data, bsh.ctypes.data), "hb_deblock_frame_units_b")
+    return bsv, bsh
+
+
+Context.deblock_units_b = _deblock_units_b
+
 
 def _amvp_candidates(self, units, width, height, jobs):
     """AMVP predictors of 2Nx2N PUs from the per-unit motion field; units: (16 * CTU rows, units_w) UNIT_INFO_DT, jobs: (n, 3) int32

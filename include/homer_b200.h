@@ -261,6 +261,14 @@ int hb_deblock_frame(hb_ctx *ctx, hb_frame *frame, const uint8_t *bs_ver, const 
 typedef struct hb_unit_info { uint8_t cu_depth, tu_depth, intra, cbf_luma; int8_t ref_idx; uint8_t qp; int16_t mvx, mvy; } hb_unit_info;   /* 10 bytes */
 int hb_deblock_frame_units(hb_ctx *ctx, hb_frame *frame, const hb_unit_info *units, int units_w, const hb_deblock_params *params,
                            uint8_t *bs_ver_out, uint8_t *bs_hor_out);
+/* B pictures (the two-list branch of get_boundary_strength_single, hmr_deblocking_filter.c:173-229): units carries list 0, units_l1 list 1
+ * (ref_idx < 0 = list not used by that unit); pic_l0 / pic_l1 name the picture behind every reference index (any numbering; equal numbers
+ * = the same picture -- the reference compares picture pointers).  Prediction units smaller than their CU (NxN) need nothing special: the
+ * motion is per 4x4 unit and only the 8x8 edge grid is filtered. */
+typedef struct hb_unit_l1 { int8_t ref_idx, reserved; int16_t mvx, mvy; } hb_unit_l1;   /* 6 bytes */
+int hb_deblock_frame_units_b(hb_ctx *ctx, hb_frame *frame, const hb_unit_info *units, const hb_unit_l1 *units_l1, int units_w,
+                             const int32_t *pic_l0, int n_l0, const int32_t *pic_l1, int n_l1, const hb_deblock_params *params,
+                             uint8_t *bs_ver_out, uint8_t *bs_hor_out);
 
 /* AMVP candidates (get_amvp_candidates, hmr_motion_inter.c:2342, P pictures with one reference picture) of a
  * batch of 2Nx2N PUs from the motion field the host's decisions left per 4x4 unit (the same hb_unit_info maps the deblocking reads;

@@ -1099,6 +1099,51 @@ void orc_deblock_strengths(const uint8_t *cu_depth, const uint8_t *tu_depth, con
 }
 
 
+/* the same for a B picture (:173-229): the motion of either side is two (picture, vector) pairs -- list 0 and list 1, a list that is not
+ * used has no picture and a zero vector; pic_l0 / pic_l1 map a reference index to the picture it names (the reference compares picture
+ * pointers).  Same set of pictures on both sides: no edge only if the vectors of matching pictures differ by less than 4 (both pairings
+ * count when the two lists name one picture); different sets: strength 1. */
+void orc_deblock_strengths_b(const uint8_t *cu_depth, const uint8_t *tu_depth, const uint8_t *intra, const uint8_t *cbf, const int8_t *ref0, const int16_t *mv0,
+                             const int8_t *ref1, const int16_t *mv1, const int32_t *pic_l0, const int32_t *pic_l1, int units_w, int w, int h,
+                             uint8_t *bs_ver, uint8_t *bs_hor)
+{
+    for (int uy = 0; uy < h / 4; uy++)
+        for (int ux = 0; ux < w / 4; ux++) {
+            const int q = uy * units_w + ux;
+            int ts = 64 >> (cu_depth[q] + tu_depth[q]);
+            if (ts < 8) ts = 8;
+            for (int dir = 0; dir < 2; dir++) {
+                const int pos = 4 * (dir ? uy : ux);
+                uint8_t *out = (dir ? bs_hor : bs_ver) + q;
+                *out = 0;
+                if (pos == 0 || pos % ts) continue;
+                const int p = dir ? q - units_w : q - 1;
+                int bs;
+                if (intra[p] || intra[q]) bs = 2;
+                else if (((cbf[q] >> tu_depth[q]) & 1) || ((cbf[p] >> tu_depth[p]) & 1)) bs = 1;
+                else {
+                    #define PIC(r, tab) ((r) < 0 ? -1 : (tab)[r])
+                    const int r0 = PIC(ref0[p], pic_l0), r1 = PIC(ref1[p], pic_l1), c0 = PIC(ref0[q], pic_l0), c1 = PIC(ref1[q], pic_l1);
+                    #undef PIC
+                    const int p0x = r0 < 0 ? 0 : mv0[2 * p], p0y = r0 < 0 ? 0 : mv0[2 * p + 1], p1x = r1 < 0 ? 0 : mv1[2 * p], p1y = r1 < 0 ? 0 : mv1[2 * p + 1];
+                    const int q0x = c0 < 0 ? 0 : mv0[2 * q], q0y = c0 < 0 ? 0 : mv0[2 * q + 1], q1x = c1 < 0 ? 0 : mv1[2 * q], q1y = c1 < 0 ? 0 : mv1[2 * q + 1];
+                    #define FAR(ax, ay, bx, by) (abs((ax) - (bx)) >= 4 || abs((ay) - (by)) >= 4)
+                    if ((r0 == c0 && r1 == c1) || (r0 == c1 && r1 == c0)) {
+                        if (r0 != r1) {
+                            if (r0 == c0) bs = FAR(q0x, q0y, p0x, p0y) || FAR(q1x, q1y, p1x, p1y);
+                            else bs = FAR(q1x, q1y, p0x, p0y) || FAR(q0x, q0y, p1x, p1y);
+                        } else {
+                            bs = (FAR(q0x, q0y, p0x, p0y) || FAR(q1x, q1y, p1x, p1y)) && (FAR(q1x, q1y, p0x, p0y) || FAR(q0x, q0y, p1x, p1y));
+                        }
+                    } else bs = 1;
+                    #undef FAR
+                }
+                *out = (uint8_t)bs;
+            }
+        }
+}
+
+
 /* ------------------------------------------------------------------------------------------
  * AMVP candidates (P picture, one reference picture).  hmr_motion_inter.c:2342-2460.
  * ------------------------------------------------------------------------------------------ */

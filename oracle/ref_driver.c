@@ -983,3 +983,77 @@ int refdrv_amvp_or_merge(refdrv *d, int w, int h, const uint8_t *inter, const in
     }
     return n_jobs;
 }
+
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Boundary strengths of a B picture through the reference's own hmr_deblock_filter_cu (its get_boundary_strength_single, two-list
+ * branch :173-229): as refdrv_deblock, with per-unit reference indices and vectors of both lists and the pictures the indices name
+ * (pic_l0 / pic_l1: small non-negative picture numbers; equal numbers = the same picture).  Only the strengths are handed back.
+ * ------------------------------------------------------------------------------------------------------------ */
+int refdrv_deblock_strengths_b(refdrv *d, int w, int h, const uint8_t *cu_depth, const uint8_t *tu_depth, const uint8_t *intra, const uint8_t *cbf,
+                               const int8_t *ref0, const int16_t *mv0, const int8_t *ref1, const int16_t *mv1, const int32_t *pic_l0, int n_l0,
+                               const int32_t *pic_l1, int n_l1, uint8_t *bs_ver, uint8_t *bs_hor)
+{
+    henc_thread_t *et = d->et;
+    hvenc_engine_t *eng = et->enc_engine;
+    slice_t *slice = &eng->current_pict.slice;
+    static video_frame_t pics[32];
+    video_frame_t fr;
+    video_frame_t *save_ref = eng->curr_reference_frame;
+    const int cols = (w + 63) / 64, rows = (h + 63) / 64, units_w = cols * 16;
+    if (eng->pict_total_ctu != cols * rows || et->pict_width[0] != w || et->pict_height[0] != h) return -1;
+    memset(&fr, 0, sizeof fr);
+    wnd_alloc(&fr.img, w, h, 80, 80, sizeof(int16_t));
+    for (int c = 0; c < 3; c++) {
+        const int pw = c ? w / 2 : w, ph = c ? h / 2 : h;
+        int16_t *p = (int16_t *)fr.img.pwnd[c];
+        for (int y = 0; y < ph; y++) for (int x = 0; x < pw; x++) p[y * fr.img.window_size_x[c] + x] = 128;
+    }
+    eng->curr_reference_frame = &fr;
+    slice->slice_type = B_SLICE; slice->sps = &d->enc->sps; slice->pps = &d->enc->pps;
+    slice->deblocking_filter_disabled_flag = 0; slice->slice_beta_offset_div2 = 0; slice->slice_tc_offset_div2 = 0;
+    for (int i = 0; i < n_l0; i++) slice->ref_pic_list[REF_PIC_LIST_0][i] = &pics[pic_l0[i] & 31];
+    for (int i = 0; i < n_l1; i++) slice->ref_pic_list[REF_PIC_LIST_1][i] = &pics[pic_l1[i] & 31];
+    for (int n = 0; n < cols * rows; n++) {
+        ctu_info_t *ctu = &eng->ctu_info[n];
+        const int cx = n % cols, cy = n / cols;
+        ctu->ctu_number = n; ctu->size = 64;
+        ctu->x[0] = cx * 64; ctu->y[0] = cy * 64; ctu->x[1] = ctu->x[2] = cx * 32; ctu->y[1] = ctu->y[2] = cy * 32;
+        ctu->ctu_left = cx ? &eng->ctu_info[n - 1] : NULL;
+        ctu->ctu_top = cy ? &eng->ctu_info[n - cols] : NULL;
+        ctu->ctu_top_left = (cx && cy) ? &eng->ctu_info[n - cols - 1] : NULL;
+        ctu->ctu_top_right = (cy && cx + 1 < cols) ? &eng->ctu_info[n - cols + 1] : NULL;
+        ctu->ctu_left_bottom = NULL;
+        for (int r = 0; r < 256; r++) {
+            const int a = eng->raster2abs_table[r];
+            const int u = (cy * 16 + r / 16) * units_w + cx * 16 + r % 16;
+            ctu->pred_depth[a] = cu_depth[u]; ctu->tr_idx[a] = tu_depth[u];
+            ctu->pred_mode[a] = intra[u] ? INTRA_MODE : INTER_MODE;
+            ctu->cbf[Y_COMP][a] = cbf[u]; ctu->cbf[U_COMP][a] = 0; ctu->cbf[V_COMP][a] = 0;
+            ctu->qp[a] = 30;
+            ctu->part_size_type[a] = SIZE_2Nx2N;
+            ctu->mv_ref[REF_PIC_LIST_0][a].hor_vector = mv0[2 * u]; ctu->mv_ref[REF_PIC_LIST_0][a].ver_vector = mv0[2 * u + 1];
+            ctu->mv_ref[REF_PIC_LIST_1][a].hor_vector = mv1[2 * u]; ctu->mv_ref[REF_PIC_LIST_1][a].ver_vector = mv1[2 * u + 1];
+            ctu->mv_ref_idx[REF_PIC_LIST_0][a] = intra[u] ? -1 : ref0[u];
+            ctu->mv_ref_idx[REF_PIC_LIST_1][a] = intra[u] ? -1 : ref1[u];
+        }
+    }
+    memset(bs_ver, 0, (size_t)units_w * rows * 16); memset(bs_hor, 0, (size_t)units_w * rows * 16);
+    hush();
+    for (int dir = EDGE_VER; dir <= EDGE_HOR; dir++)
+        for (int n = 0; n < cols * rows; n++) {
+            ctu_info_t *ctu = &eng->ctu_info[n];
+            const int cx = n % cols, cy = n / cols;
+            create_partition_ctu_neighbours(et, ctu, ctu->partition_list);
+            hmr_deblock_filter_cu(et, slice, ctu, dir);
+            for (int r = 0; r < 256; r++) {
+                const int u = (cy * 16 + r / 16) * units_w + cx * 16 + r % 16;
+                (dir == EDGE_VER ? bs_ver : bs_hor)[u] = et->deblock_filter_strength_bs[dir][eng->raster2abs_table[r]];
+            }
+        }
+    unhush();
+    slice->slice_type = P_SLICE;
+    eng->curr_reference_frame = save_ref;
+    wnd_delete(&fr.img);
+    return cols * rows;
+}

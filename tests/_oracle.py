@@ -520,3 +520,53 @@ def oracle_merge(w, h, m, jobs, max_cands):
     for i, (x, y, s) in enumerate(jobs):
         O.orc_merge_candidates(inter.ctypes.data, mv.ctypes.data, inter.shape[1], w, h, int(x), int(y), int(s), max_cands, out[i].ctypes.data)
     return out
+
+
+def random_b_motion(rng, m, n_l0=2, n_l1=2):
+    """two-list motion for the units of a random_deblock_case: per CU a prediction direction (list 0, list 1 or both), reference indices
+    and vectors, few distinct values so that equal / swapped / nearly equal motion on the two sides of an edge all occur; the pictures
+    the indices name overlap between the lists"""
+    uh, uw = m["cu"].shape
+    ref0 = np.full((uh, uw), -1, np.int8); ref1 = np.full((uh, uw), -1, np.int8)
+    mv0 = np.zeros((uh, uw, 2), np.int16); mv1 = np.zeros((uh, uw, 2), np.int16)
+    for uy in range(0, uh, 2):
+        for ux in range(0, uw, 2):
+            size = max(64 >> int(m["cu"][uy, ux]), 8) // 4
+            if (uy % size) or (ux % size):
+                continue
+            d = int(rng.integers(1, 4))
+            if d & 1:
+                ref0[uy:uy + size, ux:ux + size] = rng.integers(0, n_l0); mv0[uy:uy + size, ux:ux + size] = rng.integers(-1, 2, 2) * 5
+            if d & 2:
+                ref1[uy:uy + size, ux:ux + size] = rng.integers(0, n_l1); mv1[uy:uy + size, ux:ux + size] = rng.integers(-1, 2, 2) * 5
+    ref0[m["intra"] != 0] = -1; ref1[m["intra"] != 0] = -1
+    pic_l0 = np.array([3, 5][:n_l0], np.int32); pic_l1 = np.array([5, 3][:n_l1], np.int32)       # the lists name the same two pictures, in opposite order
+    return ref0, mv0, ref1, mv1, pic_l0, pic_l1
+
+
+def ref_deblock_strengths_b(w, h, m, ref0, mv0, ref1, mv1, pic_l0, pic_l1):
+    _, D = ref()
+    D.refdrv_open.restype = C.c_void_p
+    D.refdrv_open.argtypes = [C.c_int] * 4
+    if (w, h) not in _dbk_handles:
+        _dbk_handles[(w, h)] = D.refdrv_open(w, h, 32, 1)
+    D.refdrv_deblock_strengths_b.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 9 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    a = {k: np.ascontiguousarray(v) for k, v in m.items()}
+    arrs = [np.ascontiguousarray(x) for x in (ref0, mv0, ref1, mv1, pic_l0, pic_l1)]
+    bsv = np.zeros_like(a["cu"]); bsh = np.zeros_like(a["cu"])
+    n = D.refdrv_deblock_strengths_b(_dbk_handles[(w, h)], w, h, a["cu"].ctypes.data, a["tu"].ctypes.data, a["intra"].ctypes.data, a["cbf"].ctypes.data,
+                                     arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data, arrs[3].ctypes.data, arrs[4].ctypes.data, len(pic_l0),
+                                     arrs[5].ctypes.data, len(pic_l1), bsv.ctypes.data, bsh.ctypes.data)
+    assert n > 0, n
+    return bsv, bsh
+
+
+def oracle_deblock_strengths_b(w, h, m, ref0, mv0, ref1, mv1, pic_l0, pic_l1):
+    O = oracle()
+    O.orc_deblock_strengths_b.argtypes = [C.c_void_p] * 10 + [C.c_int] * 3 + [C.c_void_p] * 2
+    a = {k: np.ascontiguousarray(v) for k, v in m.items()}
+    arrs = [np.ascontiguousarray(x) for x in (ref0, mv0, ref1, mv1, pic_l0, pic_l1)]
+    bsv = np.zeros_like(a["cu"]); bsh = np.zeros_like(a["cu"])
+    O.orc_deblock_strengths_b(a["cu"].ctypes.data, a["tu"].ctypes.data, a["intra"].ctypes.data, a["cbf"].ctypes.data, arrs[0].ctypes.data, arrs[1].ctypes.data,
+                              arrs[2].ctypes.data, arrs[3].ctypes.data, arrs[4].ctypes.data, arrs[5].ctypes.data, bsv.shape[1], w, h, bsv.ctypes.data, bsh.ctypes.data)
+    return bsv, bsh

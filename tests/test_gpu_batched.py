@@ -435,3 +435,29 @@ def test_search_with_predictors_from_the_unit_field(ctx):
     assert [key(r) for r in a] == [key(r) for r in b]
     assert sum(key(p) != key(q) for p, q in zip(a, z)) > 10
     fc.close(); fr.close()
+
+
+def test_boundary_strengths_of_b_pictures(ctx):
+    """hb_deblock_frame_units_b: strengths of a B picture derived on the device == the restatement of the reference's two-list rule (pinned
+    against hmr_deblock_filter_cu in tests/test_oracle_vs_ref.py), and the picture filtered with them == the oracle's pixel stage"""
+    from homerhevc_b200.lib import UNIT_INFO_DT, UNIT_L1_DT
+    from _oracle import oracle_deblock, oracle_deblock_strengths_b, random_b_motion, random_deblock_case
+    rng = np.random.default_rng(229)
+    for (w, h) in ((192, 136), (200, 72)):
+        m, planes = random_deblock_case(rng, w, h)
+        m["cbf"] = (m["cbf"] * (rng.random(m["cbf"].shape) < 0.25)).astype(np.uint8)
+        ref0, mv0, ref1, mv1, p0, p1 = random_b_motion(rng, m)
+        units = np.zeros(m["cu"].shape, UNIT_INFO_DT); u1 = np.zeros(m["cu"].shape, UNIT_L1_DT)
+        units["cu_depth"], units["tu_depth"], units["intra"], units["cbf_luma"], units["qp"] = m["cu"], m["tu"], m["intra"], m["cbf"], m["qp"]
+        units["ref_idx"], units["mvx"], units["mvy"] = ref0, mv0[..., 0], mv0[..., 1]
+        u1["ref_idx"], u1["mvx"], u1["mvy"] = ref1, mv1[..., 0], mv1[..., 1]
+        f = hb.Frame(ctx, w, h); f.upload_u8(*planes)
+        bsv, bsh = ctx.deblock_units_b(f, units, u1, p0, p1, 1, -1)
+        ev, eh = oracle_deblock_strengths_b(w, h, m, ref0, mv0, ref1, mv1, p0, p1)
+        assert np.array_equal(bsv[:h // 4, :w // 4], ev[:h // 4, :w // 4]) and np.array_equal(bsh[:h // 4, :w // 4], eh[:h // 4, :w // 4]), (w, h)
+        assert {0, 1, 2} <= set(np.unique(ev[:h // 4, 2:w // 4:2]))
+        exp = oracle_deblock(planes, w, h, ev, eh, m["qp"], (1, -1))
+        got = f.download()
+        for c in range(3):
+            assert np.array_equal(got[c], exp[c]), (w, h, c)
+        f.close()

@@ -396,3 +396,23 @@ def test_merge_candidates_against_reference():
                 if mx == 5:
                     full += int((exp[:, 3] != 0).any(1).sum())
     assert full > 50
+
+
+def test_boundary_strengths_of_b_pictures_against_reference():
+    """the two-list branch of get_boundary_strength_single (hmr_deblocking_filter.c:173-229): uni- and bi-predicted units, lists that name
+    the same pictures in opposite order (so equal motion can sit in swapped lists), same-picture pairs, coded / intra neighbours"""
+    from _oracle import oracle_deblock_strengths_b, random_b_motion, random_deblock_case, ref_deblock_strengths_b
+    rng = np.random.default_rng(173)
+    seen = {0: 0, 1: 0, 2: 0}
+    for (w, h) in ((192, 136), (128, 128), (200, 72)):
+        for rep in range(4):
+            m, _ = random_deblock_case(rng, w, h)
+            m["cbf"] = (m["cbf"] * (rng.random(m["cbf"].shape) < 0.25)).astype(np.uint8)          # mostly uncoded: the motion rule decides
+            n1 = 1 if rep == 3 else 2
+            mot = random_b_motion(rng, m, 2, n1)
+            ev, eh = ref_deblock_strengths_b(w, h, m, *mot)
+            gv, gh = oracle_deblock_strengths_b(w, h, m, *mot)
+            assert np.array_equal(gv[:h // 4, :w // 4], ev[:h // 4, :w // 4]) and np.array_equal(gh[:h // 4, :w // 4], eh[:h // 4, :w // 4]), (w, h, rep)
+            for v in (0, 1, 2):
+                seen[v] += int((ev[:h // 4, 2:w // 4:2] == v).sum())
+    assert min(seen.values()) > 50, seen
