@@ -1254,3 +1254,97 @@ void orc_merge_candidates(const uint8_t *inter, const int16_t *mv, int units_w, 
     #undef TAKE
     #undef SAME
 }
+
+
+/* ------------------------------------------------------------------------------------------
+ * Reconstruction of intra transform units from the reconstructed picture around them.
+ * fill_reference_samples hmr_motion_intra.c:246-406, the neighbour flags of the quadtree :625-657 / :676-683, then the chain of
+ * encode_intra_cu :1017-1069 (luma) / hmr_motion_intra_chroma.c:325-365 (chroma).
+ * ------------------------------------------------------------------------------------------ */
+/* the four neighbour flags of the quadtree node of `size` luma samples at luma position (x, y), and how many samples of its left-bottom /
+ * top-right runs lie inside the picture, in samples of the plane the unit is coded in (n = size for luma, size / 2 for chroma; :291, :339) */
+void orc_intra_neighbours(int w, int h, int x, int y, int size, int chroma, int32_t out[6])
+{
+    const int ctu_x = x & ~63, ctu_y = y & ~63, px = x - ctu_x, py = y - ctu_y;
+    const int cols = (w + 63) / 64;
+    int l = ctu_x > 0, t = ctu_y > 0, lb = 0, tr = ctu_y > 0 && ctu_x / 64 + 1 < cols;
+    const int valid_lines = h - ctu_y < 64 ? h - ctu_y : 64, valid_cols = w - ctu_x < 64 ? w - ctu_x : 64;
+    int par_x = 0, par_y = 0;
+    for (int s = 32; s >= size; s >>= 1) {
+        const int cx = par_x + ((px - par_x) >= s ? s : 0), cy = par_y + ((py - par_y) >= s ? s : 0);
+        const int nlb = (lb && cx == par_x) || (l && cx == par_x && cy == par_y && valid_lines > cy + s);
+        const int ntr = (tr && cy == par_y) || (t && cx == par_x && cy == par_y && valid_cols > cx + s) || (cx == par_x && cy != par_y && valid_cols > cx + s);
+        l = l || cx; t = t || cy; lb = nlb; tr = ntr; par_x = cx; par_y = cy;
+    }
+    const int n = chroma ? size / 2 : size, ph = chroma ? h / 2 : h, pw = chroma ? w / 2 : w, gx = chroma ? x / 2 : x, gy = chroma ? y / 2 : y;
+    int lbs = ph - (gy + n), trs = pw - (gx + n);
+    if (lbs > n) lbs = n;
+    if (trs > n) trs = n;
+    out[0] = l; out[1] = t; out[2] = lb; out[3] = tr; out[4] = lbs; out[5] = trs;
+}
+
+/* rec: the plane's sample (0, 0); the unit's n x n block sits at (x, y).  adi: 4n + 1 samples, index 2n = corner, 2n + 1 + i above,
+ * 2n - 1 - r the left column at row y + r.  A restatement of :246-406 statement for statement: the copies, then the two padding runs. */
+void orc_intra_fill_reference(const int16_t *rec, int stride, int x, int y, int n, const int32_t nb[6], int16_t *adi)
+{
+    const int left = nb[0], top = nb[1], left_bottom = nb[2], top_right = nb[3], lbs = nb[4], trs = nb[5];
+    if (!left && !top) { for (int i = 0; i < 4 * n + 1; i++) adi[i] = 128; return; }
+    const int16_t *corner = rec + (y - 1) * stride + (x - 1);          /* decoded_buff - stride - 1 */
+    int16_t first = 0, last = 0;
+    int16_t *pad_left = NULL, *pad_top = NULL;
+    int pad_left_n = 0, pad_top_n = 0;
+    int16_t *ptr = adi + n;
+    if (left) {
+        for (int i = 0; i < n; i++) *ptr++ = corner[(n - i) * stride];
+        first = ptr[-n]; last = ptr[-1];
+    } else { pad_left = ptr; pad_left_n = n; }
+    ptr = adi + n - 1;
+    if (left_bottom) {
+        for (int i = 0; i < lbs; i++) *ptr-- = corner[(n + 1 + i) * stride];
+        first = ptr[1];
+        if (lbs != n) { pad_left = adi; pad_left_n = n - lbs; }
+    } else {
+        pad_left = adi;
+        if (left) pad_left_n = n; else pad_left_n += n;
+    }
+    ptr = adi + 2 * n + 1;
+    const int16_t *rp = corner + 1;
+    if (top) {
+        for (int i = 0; i < n; i++) *ptr++ = *rp++;
+        if (!left) first = ptr[-n];
+        last = ptr[-1];
+    } else { pad_top = ptr; pad_top_n = n; }
+    if (top_right) {
+        for (int i = 0; i < trs; i++) *ptr++ = *rp++;
+        last = ptr[-1];
+        if (trs != n) { pad_top = ptr; pad_top_n = n - trs; }
+    } else {
+        if (top) { pad_top = ptr; pad_top_n = n; } else pad_top_n += n;
+    }
+    if (left && top) adi[2 * n] = corner[0];
+    else if (left) { pad_top--; pad_top_n++; }
+    else pad_left_n++;
+    for (int i = 0; i < pad_left_n; i++) *pad_left++ = first;
+    for (int i = 0; i < pad_top_n; i++) *pad_top++ = last;
+}
+
+/* the units in coding order; every unit predicts from what the earlier ones left in rec.  tu: n x { comp, x, y, size, mode, qp (of the
+ * component), scan_mode, luma x, luma y, luma size of the quadtree node whose neighbour flags apply }.  coeff: the levels back to back. */
+void orc_intra_recon_tus(const orc_tables *tab, const int16_t *const orig[3], const int orig_stride[3], int16_t *const rec[3], const int rec_stride[3],
+                         int w, int h, const int32_t *tu, int n_tus, int is_islice, int sign_hiding, double chroma_weight, int16_t *coeff, orc_tu_out *res)
+{
+    int16_t adi[4 * 32 + 1], flt[4 * 32 + 1], pred[32 * 32];
+    for (int i = 0; i < n_tus; i++) {
+        const int32_t *u = tu + 10 * i;
+        const int comp = u[0], x = u[1], y = u[2], n = u[3], mode = u[4], qp = u[5], scan = u[6];
+        int32_t nb[6];
+        orc_intra_neighbours(w, h, u[7], u[8], u[9], comp != 0, nb);
+        orc_intra_fill_reference(rec[comp], rec_stride[comp], x, y, n, nb, adi);
+        const int16_t *use = adi;
+        if (comp == 0 && orc_intra_uses_filtered(n, mode)) { orc_adi_filter(adi, flt, n, 1); use = flt; }
+        orc_intra_predict(use, n, mode, comp == 0, pred, n);
+        orc_encode_intra_tu(tab, orig[comp] + y * orig_stride[comp] + x, orig_stride[comp], pred, n, coeff, rec[comp] + y * rec_stride[comp] + x, rec_stride[comp],
+                            n, comp, qp, scan, is_islice, sign_hiding, comp ? chroma_weight : 1.0, &res[i]);
+        coeff += n * n;
+    }
+}

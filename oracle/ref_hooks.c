@@ -551,3 +551,57 @@ int refdrv_cu_hooks_off(long *counters)
     H.eng = NULL;
     return C_N;
 }
+
+
+/* ------------------------------------------------------------------ capture of a picture's decisions, CTU by CTU
+ * hmr_deblock_sao_pad_sync_ctu (hmr_encoder_lib.c:2386) is called right after a CTU's reconstruction went into the picture
+ * (mem_transfer_decoded_blocks :2942) and its levels into ctu->coeff_wnd (:2945), before any in-loop filter touches them: the hook
+ * copies the CTU's part of the UNFILTERED reconstruction, its levels and the per-4x4-unit decision arrays, then forwards.  This is what
+ * tests/test_intra_recon*.py rebuild an intra picture from. */
+typedef void (*fn_sync_ctu)(henc_thread_t *, slice_t *, ctu_info_t *);
+typedef struct refdrv_capture {
+    int32_t width, height, frame, n_seen;      /* capture the picture with num_encoded_frames == frame; n_seen counts its CTUs */
+    uint8_t *recon[3];                         /* tight planes, unfiltered reconstruction */
+    uint8_t *pred_depth, *part_size, *mode_y, *mode_c, *tr_idx, *qp, *pred_mode, *cbf[3];   /* per 4x4 unit, picture raster over whole CTUs */
+    int16_t *coeff;                            /* per CTU 64*64 + 2*32*32 levels in the reference's own layout */
+    int32_t slice_type, slice_qp;
+} refdrv_capture;
+static refdrv_capture *g_cap;
+void refdrv_capture_set(refdrv_capture *c) { g_cap = c; if (c) c->n_seen = 0; }
+
+void hmr_deblock_sao_pad_sync_ctu(henc_thread_t *et, slice_t *currslice, ctu_info_t *ctu)
+{
+    static fn_sync_ctu real;
+    if (!real) {
+        void *ref = dlopen("libhomer_ref.so", RTLD_LAZY | RTLD_NOLOAD);
+        real = (fn_sync_ctu)(ref ? dlsym(ref, "hmr_deblock_sao_pad_sync_ctu") : NULL);
+        if (!real) real = (fn_sync_ctu)dlsym(RTLD_NEXT, "hmr_deblock_sao_pad_sync_ctu");
+        if (!real) { fprintf(stderr, "ref_hooks: cannot find the reference's hmr_deblock_sao_pad_sync_ctu\n"); abort(); }
+    }
+    refdrv_capture *c = g_cap;
+    if (c && et->enc_engine->num_encoded_frames == c->frame && c->width == et->pict_width[Y_COMP] && c->height == et->pict_height[Y_COMP]) {
+        const wnd_t *img = &et->enc_engine->curr_reference_frame->img;
+        const int cols = (c->width + 63) / 64, units_w = cols * 16;
+        const int cx = ctu->x[Y_COMP] / 64, cy = ctu->y[Y_COMP] / 64;
+        for (int comp = 0; comp < 3; comp++) {
+            const int pw = comp ? c->width / 2 : c->width, ph = comp ? c->height / 2 : c->height, cs = comp ? 32 : 64;
+            const int16_t *src = (const int16_t *)img->pwnd[comp];
+            for (int y = cy * cs; y < cy * cs + cs && y < ph; y++)
+                for (int x = cx * cs; x < cx * cs + cs && x < pw; x++) c->recon[comp][(size_t)y * pw + x] = (uint8_t)src[(size_t)y * img->window_size_x[comp] + x];
+        }
+        for (int r = 0; r < 256; r++) {
+            const int a = et->enc_engine->raster2abs_table[r];
+            const size_t u = (size_t)(cy * 16 + r / 16) * units_w + cx * 16 + r % 16;
+            c->pred_depth[u] = ctu->pred_depth[a]; c->part_size[u] = ctu->part_size_type[a]; c->mode_y[u] = ctu->intra_mode[Y_COMP][a];
+            c->mode_c[u] = ctu->intra_mode[CHR_COMP][a]; c->tr_idx[u] = ctu->tr_idx[a]; c->qp[u] = ctu->qp[a]; c->pred_mode[u] = ctu->pred_mode[a];
+            for (int comp = 0; comp < 3; comp++) c->cbf[comp][u] = ctu->cbf[comp][a];
+        }
+        int16_t *dst = c->coeff + (size_t)(cy * cols + cx) * (64 * 64 + 2 * 32 * 32);
+        memcpy(dst, ctu->coeff_wnd->pwnd[Y_COMP], sizeof(int16_t) * 64 * 64);
+        memcpy(dst + 64 * 64, ctu->coeff_wnd->pwnd[U_COMP], sizeof(int16_t) * 32 * 32);
+        memcpy(dst + 64 * 64 + 32 * 32, ctu->coeff_wnd->pwnd[V_COMP], sizeof(int16_t) * 32 * 32);
+        c->slice_type = currslice->slice_type; c->slice_qp = currslice->qp;
+        c->n_seen++;
+    }
+    real(et, currslice, ctu);
+}

@@ -66,3 +66,35 @@ def describe_mismatch(w, h, a_bs, a_rec, b_bs, b_rec):
     bad = np.flatnonzero(a_rec != b_rec)
     frame = int(bad[0]) // (w * h * 3 // 2) if bad.size else -1
     return f"bitstreams differ from byte {first} ({len(a_bs)} vs {len(b_bs)} bytes), {bad.size} reconstructed samples differ, first in frame {frame}"
+
+
+class Capture(C.Structure):              # refdrv_capture, oracle/ref_hooks.c
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("frame", C.c_int32), ("n_seen", C.c_int32), ("recon", C.c_void_p * 3),
+                ("pred_depth", C.c_void_p), ("part_size", C.c_void_p), ("mode_y", C.c_void_p), ("mode_c", C.c_void_p), ("tr_idx", C.c_void_p),
+                ("qp", C.c_void_p), ("pred_mode", C.c_void_p), ("cbf", C.c_void_p * 3), ("coeff", C.c_void_p), ("slice_type", C.c_int32), ("slice_qp", C.c_int32)]
+
+
+def encode_and_capture(w, h, yuv, nf, frame=0, force_intra=0, qp=32, sign_hiding=1):
+    """the reference's own encode of `nf` frames; of picture `frame`: its decisions per 4x4 unit, its levels and its reconstruction BEFORE
+    the in-loop filters, taken CTU by CTU as the encoder finishes them.  -> dict of numpy arrays"""
+    _, D = ref()
+    cols, rows = (w + 63) // 64, (h + 63) // 64
+    a = {k: np.zeros((rows * 16, cols * 16), np.uint8) for k in ("pred_depth", "part_size", "mode_y", "mode_c", "tr_idx", "qp", "pred_mode", "cbf_y", "cbf_u", "cbf_v")}
+    rec = [np.zeros((h, w), np.uint8), np.zeros((h // 2, w // 2), np.uint8), np.zeros((h // 2, w // 2), np.uint8)]
+    coeff = np.zeros((cols * rows, 64 * 64 + 2 * 32 * 32), np.int16)
+    c = Capture()
+    c.width, c.height, c.frame = w, h, frame
+    for i in range(3):
+        c.recon[i] = rec[i].ctypes.data; c.cbf[i] = a["cbf_" + "yuv"[i]].ctypes.data
+    for k in ("pred_depth", "part_size", "mode_y", "mode_c", "tr_idx", "qp", "pred_mode"):
+        setattr(c, k, a[k].ctypes.data)
+    c.coeff = coeff.ctypes.data
+    D.refdrv_capture_set.argtypes = [C.c_void_p]
+    D.refdrv_capture_set(C.byref(c))
+    try:
+        bs, out, _ = encode(w, h, yuv, nf, force_intra=force_intra, qp=qp, sign_hiding=sign_hiding)
+    finally:
+        D.refdrv_capture_set(None)
+    assert c.n_seen == cols * rows, (c.n_seen, cols * rows)
+    a.update(recon=rec, coeff=coeff, slice_type=int(c.slice_type), slice_qp=int(c.slice_qp), filtered=out)
+    return a

@@ -416,3 +416,30 @@ def test_boundary_strengths_of_b_pictures_against_reference():
             for v in (0, 1, 2):
                 seen[v] += int((ev[:h // 4, 2:w // 4:2] == v).sum())
     assert min(seen.values()) > 50, seen
+
+
+def test_intra_picture_reconstruction_against_the_reference_encoder():
+    """a whole I picture rebuilt by the restatement from the decisions the reference's own encoder made (captured CTU by CTU through
+    oracle/ref_hooks.c: CU / TU trees, luma and chroma modes incl. the derived mode, QPs) == the encoder's reconstruction BEFORE its in-loop
+    filters, sample for sample in all three planes, and the same levels where the encoder's coeff_wnd holds a unit: reference samples from
+    the reconstructed neighbours with the encoder's own availability and padding rules (fill_reference_samples hmr_motion_intra.c:246),
+    smoothing rule, 35 predictors, DST / DCT, mode-dependent scans, sign hiding; partial CTUs on both picture edges"""
+    from homerhevc_b200 import synth
+    from _encode import encode_and_capture, make_yuv
+    from _intra import coeff_wnd_of, intra_tus, oracle_intra_recon
+    seen_sizes, seen_modes, n_dm = set(), set(), 0
+    for (w, h, qp, sh, seed) in ((192, 136, 32, 1, 21), (200, 72, 24, 1, 5), (328, 200, 38, 0, 9), (320, 192, 30, 1, 3)):
+        clip = synth.make_clip(w, h, 1, seed=seed)
+        a = encode_and_capture(w, h, make_yuv(w, h, 1, seed=seed), 1, qp=qp, sign_hiding=sh)
+        assert a["slice_type"] == 2 and (a["pred_mode"][:h // 4, :w // 4] == 1).all()          # I_SLICE, every unit intra
+        tus = intra_tus(a, w, h)
+        rec, coeff, res = oracle_intra_recon(clip[0], w, h, tus, is_islice=1, sign_hiding=sh)
+        for c in range(3):
+            bad = np.argwhere(rec[c] != a["recon"][c])
+            assert not len(bad), (w, h, qp, c, len(bad), bad[:3].tolist())
+        mine = coeff_wnd_of(tus, coeff, w, h)
+        covered = coeff_wnd_of(tus, np.ones_like(coeff), w, h) != 0
+        assert np.array_equal(mine[covered], a["coeff"][covered]), (w, h, qp)
+        seen_sizes |= set(int(s) for s in tus[tus[:, 0] == 0][:, 3]); seen_modes |= set(int(m) for m in tus[:, 4])
+        n_dm += int((a["mode_c"][:h // 4, :w // 4] == 36).sum())
+    assert seen_sizes == {4, 8, 16, 32} and len(seen_modes) > 15 and n_dm > 0, (seen_sizes, seen_modes, n_dm)
