@@ -921,6 +921,191 @@ int hb_deblock_frame_units_b(hb_ctx *ctx, hb_frame *frame, const hb_unit_info *u
     return deblock_units(ctx, frame, units, units_l1, units_w, pic_l0, n_l0, pic_l1, n_l1, params, bs_ver_out, bs_hor_out, "hb_deblock_frame_units_b");
 }
 
+/* ---- wavefront-batched reconstruction of intra transform units (include/homer_b200.h: hb_intra_reconstruct) */
+static int tq_row_align(int size);
+/* neighbour flags of the quadtree node of `size` luma samples at luma (x, y) -- the CTU's own (hmr_motion_intra.c:676-683; its left-bottom
+ * neighbour never exists) handed down by cu_partition_get_neighbours (:625-657) -- and the lengths of its left-bottom / top-right runs inside
+ * the picture, in samples of the plane the unit is coded in (:291, :339).  flags: bit 0 left, 1 top, 2 left-bottom, 3 top-right */
+static void intra_neighbours(int w, int h, int x, int y, int size, int chroma, int *flags, int *lbs_out, int *trs_out)
+{
+    const int ctu_x = x & ~63, ctu_y = y & ~63, px = x - ctu_x, py = y - ctu_y;
+    const int cols = (w + 63) / 64;
+    int l = ctu_x > 0, t = ctu_y > 0, lb = 0, tr = ctu_y > 0 && ctu_x / 64 + 1 < cols;
+    const int valid_lines = h - ctu_y < 64 ? h - ctu_y : 64, valid_cols = w - ctu_x < 64 ? w - ctu_x : 64;
+    int par_x = 0, par_y = 0;
+    for (int s = 32; s >= size; s >>= 1) {
+        const int cx = par_x + ((px - par_x) >= s ? s : 0), cy = par_y + ((py - par_y) >= s ? s : 0);
+        const int nlb = (lb && cx == par_x) || (l && cx == par_x && cy == par_y && valid_lines > cy + s);
+        const int ntr = (tr && cy == par_y) || (t && cx == par_x && cy == par_y && valid_cols > cx + s) || (cx == par_x && cy != par_y && valid_cols > cx + s);
+        l = l || cx; t = t || cy; lb = nlb; tr = ntr; par_x = cx; par_y = cy;
+    }
+    const int n = chroma ? size / 2 : size, ph = chroma ? h / 2 : h, pw = chroma ? w / 2 : w, gx = chroma ? x / 2 : x, gy = chroma ? y / 2 : y;
+    int lbs = ph - (gy + n), trs = pw - (gx + n);
+    if (lbs > n) lbs = n;
+    if (trs > n) trs = n;
+    if (lbs < 0) lbs = 0;
+    if (trs < 0) trs = 0;
+    *flags = (l ? 1 : 0) | (t ? 2 : 0) | (lb ? 4 : 0) | (tr ? 8 : 0); *lbs_out = lbs; *trs_out = trs;
+}
+
+typedef struct intra_sorted { int level, comp, size, qp, scan, idx; } intra_sorted;
+static int intra_sorted_cmp(const void *pa, const void *pb)
+{
+    const intra_sorted *a = (const intra_sorted *)pa, *b = (const intra_sorted *)pb;
+    if (a->level != b->level) return a->level - b->level;
+    if (a->comp != b->comp) return a->comp - b->comp;
+    if (a->size != b->size) return a->size - b->size;
+    if (a->qp != b->qp) return a->qp - b->qp;
+    if (a->scan != b->scan) return a->scan - b->scan;
+    return a->idx - b->idx;
+}
+
+int hb_intra_reconstruct(hb_ctx *ctx, const hb_frame *cur, hb_frame *pred, hb_frame *recon, const hb_intra_unit *units, int n_units,
+                         int is_islice, int sign_hiding, double chroma_weight, int16_t *coeffs, hb_tu_result *results, int32_t *n_levels_out)
+{
+    int rc = HB_OK, crc = 0;
+    if (!ctx || !cur || !pred || !recon || !units || !coeffs || !results || n_units < 0) return hbi_fail(HB_ERR_ARG, "hb_intra_reconstruct: bad argument");
+    if (cur->w != recon->w || cur->h != recon->h || pred->w != cur->w || pred->h != cur->h) return hbi_fail(HB_ERR_ARG, "hb_intra_reconstruct: picture sizes differ");
+    if (n_levels_out) *n_levels_out = 0;
+    if (n_units == 0) return HB_OK;
+    const int w = cur->w, h = cur->h;
+    size_t total = 0, n_adi = 0;
+    for (int i = 0; i < n_units; i++) {
+        const hb_intra_unit *u = &units[i];
+        const int lum = u->comp ? 2 : 1;
+        if (u->comp < 0 || u->comp > 2 || (u->size != 4 && u->size != 8 && u->size != 16 && u->size != 32) || (u->comp && u->size == 32) || u->qp < 0 || u->qp > 51 ||
+            u->mode < 0 || u->mode > 34 || u->x < 0 || u->y < 0 || (u->x & (tq_row_align(u->size) - 1)) || (u->y & 3) ||
+            u->x + u->size > cur->d.p[u->comp].w || u->y + u->size > cur->d.p[u->comp].h ||
+            u->scan_mode < HB_SCAN_HOR || u->scan_mode > HB_SCAN_DIAG || (u->size > 8 && u->scan_mode != HB_SCAN_DIAG) ||
+            (u->node_size != 4 && u->node_size != 8 && u->node_size != 16 && u->node_size != 32 && u->node_size != 64) ||
+            u->node_x < 0 || u->node_y < 0 || (u->node_x % u->node_size) || (u->node_y % u->node_size) || u->node_x >= w || u->node_y >= h ||
+            u->node_x != u->x * lum || u->node_y != u->y * lum || u->node_size < u->size * lum)
+            return hbi_fail(HB_ERR_ARG, "hb_intra_reconstruct: unit %d is invalid", i);
+        total += (size_t)u->size * u->size; n_adi += 4 * (size_t)u->size + 1;
+    }
+    /* ---- levels of the dependency: per plane a map of the level that produced every 4x4 block of samples */
+    intra_sorted *srt = (intra_sorted *)malloc(sizeof *srt * (size_t)n_units);
+    hbd_adi_job *aj = (hbd_adi_job *)malloc(sizeof *aj * (size_t)n_units);
+    size_t *coeff_off = (size_t *)malloc(sizeof(size_t) * (size_t)n_units);
+    int32_t *map[3] = { NULL, NULL, NULL };
+    int mw[3], mh[3], n_levels = 0;
+    for (int c = 0; c < 3; c++) {
+        mw[c] = (c ? w / 2 : w) / 4; mh[c] = (c ? h / 2 : h) / 4;
+        map[c] = (int32_t *)calloc((size_t)mw[c] * mh[c], sizeof(int32_t));       /* 0: nothing of this call wrote here */
+    }
+    if (!srt || !aj || !coeff_off || !map[0] || !map[1] || !map[2]) { rc = hbi_fail(HB_ERR_NOMEM, "hb_intra_reconstruct: out of memory"); goto cleanup; }
+    {
+        size_t co = 0, ao = 0;
+        for (int i = 0; i < n_units; i++) {
+            const hb_intra_unit *u = &units[i];
+            const int c = u->comp, n = u->size, bx = u->x / 4, by = u->y / 4, nb = n / 4;
+            int flags, lbs, trs, level = 0;
+            intra_neighbours(w, h, u->node_x, u->node_y, u->node_size, c != 0, &flags, &lbs, &trs);
+            #define AT(xx, yy) (((xx) >= 0 && (yy) >= 0 && (xx) < mw[c] && (yy) < mh[c]) ? map[c][(size_t)(yy) * mw[c] + (xx)] : 0)
+            #define UP(v) do { const int v_ = (v); if (v_ > level) level = v_; } while (0)
+            if (flags & 1) for (int k = 0; k < nb; k++) UP(AT(bx - 1, by + k));
+            if (flags & 4) for (int k = 0; k < (lbs + 3) / 4; k++) UP(AT(bx - 1, by + nb + k));
+            if (flags & 2) for (int k = 0; k < nb; k++) UP(AT(bx + k, by - 1));
+            if (flags & 8) for (int k = 0; k < (trs + 3) / 4; k++) UP(AT(bx + nb + k, by - 1));
+            if ((flags & 3) == 3) UP(AT(bx - 1, by - 1));
+            #undef UP
+            #undef AT
+            level += 1;
+            for (int yy = by; yy < by + nb; yy++) for (int xx = bx; xx < bx + nb; xx++) map[c][(size_t)yy * mw[c] + xx] = level;
+            if (level > n_levels) n_levels = level;
+            srt[i].level = level; srt[i].comp = c; srt[i].size = n; srt[i].qp = u->qp; srt[i].scan = u->scan_mode; srt[i].idx = i;
+            coeff_off[i] = co; co += (size_t)n * n;
+            aj[i].comp = c; aj[i].x = u->x; aj[i].y = u->y; aj[i].n = n; aj[i].flags = flags; aj[i].lbs = lbs; aj[i].trs = trs; aj[i].adi_off = (int32_t)ao;
+            ao += 4 * (size_t)n + 1;
+        }
+    }
+    qsort(srt, (size_t)n_units, sizeof *srt, intra_sorted_cmp);
+    hbc_set_device(ctx->device);
+    pthread_mutex_lock(&ctx->lock);
+    {
+        void *d_a, *h_a, *d_j, *h_j, *d_xy, *h_xy, *d_adi, *h_adi, *d_co, *h_co, *d_rs, *h_rs;
+        if ((rc = hbi_scratch(ctx, 0, sizeof(hbd_adi_job) * (size_t)n_units, &d_a, &h_a)) != HB_OK) goto unlock;
+        if ((rc = hbi_scratch(ctx, 1, sizeof(hbd_intra_job) * (size_t)n_units, &d_j, &h_j)) != HB_OK) goto unlock;
+        if ((rc = hbi_scratch(ctx, 2, sizeof(int32_t) * 2 * (size_t)n_units, &d_xy, &h_xy)) != HB_OK) goto unlock;
+        if ((rc = hbi_scratch(ctx, 3, sizeof(int16_t) * n_adi, &d_adi, &h_adi)) != HB_OK) goto unlock;
+        if ((rc = hbi_scratch(ctx, 4, sizeof(int16_t) * total, &d_co, &h_co)) != HB_OK) goto unlock;
+        if ((rc = hbi_scratch(ctx, 5, sizeof(hb_tu_result) * (size_t)n_units, &d_rs, &h_rs)) != HB_OK) goto unlock;
+        /* records in launch order (level, plane, size, qp, scan) */
+        size_t packed_coeff = 0;
+        size_t *launch_coeff = (size_t *)malloc(sizeof(size_t) * (size_t)n_units);
+        if (!launch_coeff) { rc = hbi_fail(HB_ERR_NOMEM, "hb_intra_reconstruct: out of memory"); goto unlock; }
+        for (int k = 0; k < n_units; k++) {
+            const int i = srt[k].idx;
+            const hb_intra_unit *u = &units[i];
+            ((hbd_adi_job *)h_a)[k] = aj[i];
+            hbd_intra_job *pj = &((hbd_intra_job *)h_j)[k];
+            pj->comp = u->comp; pj->x = u->x; pj->y = u->y; pj->size = u->size; pj->mode = u->mode;
+            pj->filtered = u->comp ? 0 : -1;             /* luma: the reference's rule (:1011); chroma: never (hmr_motion_intra_chroma.c:337) */
+            pj->adi_off = aj[i].adi_off; pj->pad_ = 0;
+            ((int32_t *)h_xy)[2 * k] = u->x; ((int32_t *)h_xy)[2 * k + 1] = u->y;
+            launch_coeff[k] = packed_coeff; packed_coeff += (size_t)u->size * u->size;
+        }
+        crc = hbc_h2d_async(d_a, h_a, sizeof(hbd_adi_job) * (size_t)n_units, ctx->stream);
+        if (!crc) crc = hbc_h2d_async(d_j, h_j, sizeof(hbd_intra_job) * (size_t)n_units, ctx->stream);
+        if (!crc) crc = hbc_h2d_async(d_xy, h_xy, sizeof(int32_t) * 2 * (size_t)n_units, ctx->stream);
+        /* ---- level by level: reference samples from `recon`, predictions into `pred`, the T/Q chain of every (plane, size, qp, scan) group */
+        for (int k0 = 0; k0 < n_units && !crc; ) {
+            int k1 = k0;
+            while (k1 < n_units && srt[k1].level == srt[k0].level) k1++;
+            crc = hbk_intra_adi(&recon->d, (const hbd_adi_job *)d_a + k0, k1 - k0, (int16_t *)d_adi, ctx->stream);
+            ctx->launches++;
+            if (crc) break;
+            hbd_intra_args ia;
+            memset(&ia, 0, sizeof ia);
+            ia.pred = pred->d; ia.jobs = (const hbd_intra_job *)d_j + k0; ia.n_jobs = k1 - k0; ia.adi = (const int16_t *)d_adi;
+            crc = hbk_intra(&ia, ctx->stream);
+            ctx->launches++;
+            for (int g0 = k0; g0 < k1 && !crc; ) {
+                int g1 = g0;
+                while (g1 < k1 && srt[g1].comp == srt[g0].comp && srt[g1].size == srt[g0].size && srt[g1].qp == srt[g0].qp && srt[g1].scan == srt[g0].scan) g1++;
+                const int comp = srt[g0].comp, size = srt[g0].size, qp = srt[g0].qp;
+                hbd_tq_args a;
+                memset(&a, 0, sizeof a);
+                hbi_tq_setup(ctx, &a, comp, size, qp, is_islice, sign_hiding);
+                int lg = 2;
+                while ((1 << lg) < size) lg++;
+                a.qtab = ctx->d_q + hbi_tab_q_off(lg, comp, qp % 6);          /* intra lists: (is_intra ? 0 : 3) + comp */
+                a.dqtab = ctx->d_dq + hbi_tab_q_off(lg, 0, qp % 6);           /* SSE4.2 inv_quant: is_intra -> list 0 (hmr_sse42_functions_quant.c:138) */
+                a.scan = ctx->d_scan + hbi_tab_scan_off(srt[g0].scan, lg);
+                a.intra = 1;
+                a.cur = cur->d.p[comp]; a.pred = pred->d.p[comp]; a.rec = recon->d.p[comp];
+                a.jobs_xy = (const int32_t *)d_xy + 2 * g0; a.n_jobs = g1 - g0;
+                a.weight = comp ? chroma_weight : 1.0;
+                a.coeff_out = (int16_t *)d_co + launch_coeff[g0];
+                a.res_out = (hb_tu_result *)d_rs + g0;
+                crc = hbk_tq_encode(&a, ctx->stream);
+                ctx->launches++;
+                g0 = g1;
+            }
+            k0 = k1;
+        }
+        if (!crc) { crc = hbk_pad_frame(&recon->d, ctx->stream); ctx->launches++; }
+        if (!crc) crc = hbc_d2h_async(h_co, d_co, sizeof(int16_t) * total, ctx->stream);
+        if (!crc) crc = hbc_d2h_async(h_rs, d_rs, sizeof(hb_tu_result) * (size_t)n_units, ctx->stream);
+        if (!crc) crc = hbc_stream_sync(ctx->stream);
+        if (!crc)
+            for (int k = 0; k < n_units; k++) {
+                const int i = srt[k].idx;
+                memcpy(coeffs + coeff_off[i], (int16_t *)h_co + launch_coeff[k], sizeof(int16_t) * (size_t)units[i].size * units[i].size);
+                results[i] = ((hb_tu_result *)h_rs)[k];
+            }
+        free(launch_coeff);
+    }
+unlock:
+    pthread_mutex_unlock(&ctx->lock);
+    if (n_levels_out) *n_levels_out = n_levels;
+cleanup:
+    free(srt); free(aj); free(coeff_off);
+    for (int c = 0; c < 3; c++) free(map[c]);
+    if (crc) return hbi_cuda_fail(crc, "hb_intra_reconstruct");
+    return rc;
+}
+
 /* AMVP / merge candidates of a batch of PUs from the per-unit motion field: one launch, one copy back.  max_cands = 0: AMVP */
 static int neighbour_candidates(hb_ctx *ctx, const hb_unit_info *units, int units_w, int width, int height, const hb_amvp_job *jobs, int n_jobs, int max_cands,
                                 void *out, const char *what)

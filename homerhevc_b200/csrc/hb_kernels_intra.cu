@@ -328,3 +328,65 @@ extern "C" int hbk_pc_intra(const int16_t *adi, int n, int mode, int is_luma, in
     k_pc_intra<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(adi, n, mode, is_luma, pred, stride);
     return static_cast<int>(cudaGetLastError());
 }
+
+
+// ---- reference samples of a batch of intra units from the reconstructed picture: fill_reference_samples (hmr_motion_intra.c:246-406), one
+// thread per unit, statement for statement: the left column bottom-up, the left-bottom run as far as it lies inside the picture, the row
+// above and the top-right run, the corner, then the reference's two padding runs (first copied sample downwards / to the left, last copied
+// sample to the right).  adi: index 2n = corner, 2n + 1 + i above, 2n - 1 - r the left column at row y + r.
+namespace {
+__global__ void __launch_bounds__(64) k_intra_adi(const hbd_frame rec, const hbd_adi_job *jobs, int n_jobs, int16_t *adi_all)
+{
+    const int i = blockIdx.x * 64 + threadIdx.x;
+    if (i >= n_jobs) return;
+    const hbd_adi_job j = jobs[i];
+    const hbd_plane p = hbd_pick_plane(rec, j.comp);
+    int16_t *adi = adi_all + j.adi_off;
+    const int n = j.n;
+    const bool left = j.flags & 1, top = j.flags & 2, left_bottom = j.flags & 4, top_right = j.flags & 8;
+    if (!left && !top) { for (int k = 0; k < 4 * n + 1; k++) adi[k] = 128; return; }
+    const uint8_t *corner = p.org + (j.y - 1) * p.pitch + (j.x - 1);
+    int16_t first = 0, last = 0;
+    int pad_left = -1, pad_top = -1, pad_left_n = 0, pad_top_n = 0;        // start indices into adi
+    int ptr = n;
+    if (left) {
+        for (int k = 0; k < n; k++) adi[ptr++] = corner[(n - k) * p.pitch];
+        first = adi[ptr - n]; last = adi[ptr - 1];
+    } else { pad_left = ptr; pad_left_n = n; }
+    ptr = n - 1;
+    if (left_bottom) {
+        for (int k = 0; k < j.lbs; k++) adi[ptr--] = corner[(n + 1 + k) * p.pitch];
+        first = adi[ptr + 1];
+        if (j.lbs != n) { pad_left = 0; pad_left_n = n - j.lbs; }
+    } else {
+        pad_left = 0;
+        if (left) pad_left_n = n; else pad_left_n += n;
+    }
+    ptr = 2 * n + 1;
+    const uint8_t *rp = corner + 1;
+    if (top) {
+        for (int k = 0; k < n; k++) adi[ptr++] = *rp++;
+        if (!left) first = adi[ptr - n];
+        last = adi[ptr - 1];
+    } else { pad_top = ptr; pad_top_n = n; }
+    if (top_right) {
+        for (int k = 0; k < j.trs; k++) adi[ptr++] = *rp++;
+        last = adi[ptr - 1];
+        if (j.trs != n) { pad_top = ptr; pad_top_n = n - j.trs; }
+    } else {
+        if (top) { pad_top = ptr; pad_top_n = n; } else pad_top_n += n;
+    }
+    if (left && top) adi[2 * n] = corner[0];
+    else if (left) { pad_top--; pad_top_n++; }
+    else pad_left_n++;
+    for (int k = 0; k < pad_left_n; k++) adi[pad_left++] = first;
+    for (int k = 0; k < pad_top_n; k++) adi[pad_top++] = last;
+}
+}  // namespace
+
+extern "C" int hbk_intra_adi(const hbd_frame *rec, const hbd_adi_job *jobs, int n_jobs, int16_t *adi, void *stream)
+{
+    if (n_jobs <= 0) return 0;
+    k_intra_adi<<<(n_jobs + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(*rec, jobs, n_jobs, adi);
+    return static_cast<int>(cudaGetLastError());
+}

@@ -172,6 +172,9 @@ typedef struct hbd_intra_args {
 } hbd_intra_args;
 int hbk_intra(const hbd_intra_args *a, void *stream);                                  /* prediction-form jobs (mode >= 0) */
 int hbk_intra_sads(const hbd_intra_args *a, int size, const int32_t *idx, int n_idx, void *stream);   /* SAD-form jobs of one size */
+/* reference samples of intra units from the reconstructed picture (fill_reference_samples hmr_motion_intra.c:246): 4n+1 int16 per job at adi + adi_off */
+typedef struct hbd_adi_job { int32_t comp, x, y, n; int32_t flags /* bit 0 left, 1 top, 2 left-bottom, 3 top-right */, lbs, trs, adi_off; } hbd_adi_job;
+int hbk_intra_adi(const hbd_frame *rec, const hbd_adi_job *jobs, int n_jobs, int16_t *adi, void *stream);
 int hbk_pc_intra(const int16_t *adi, int n, int mode, int is_luma, int16_t *pred, int stride, void *stream);
 
 /* ---- gather of the host's selection (hb_kernels_gather.cu) */

@@ -233,6 +233,21 @@ int hb_intra_run(hb_ctx *ctx, const hb_frame *cur, hb_frame *pred, const hb_intr
 void hb_create_intra_planar_prediction(int16_t *prediction, int pred_stride, int16_t *adi_pred_buff, int adi_size, int cu_size, int cu_size_shift);
 void hb_create_intra_angular_prediction(int16_t *prediction, int pred_stride, int16_t *adi_pred_buff, int adi_size, int cu_size, int cu_mode, int is_luma);
 
+/* Reconstruction of the intra transform units of a picture (BASELINE.json configs[0] / [4]; encode_intra_cu hmr_motion_intra.c:973-1069, chroma
+ * hmr_motion_intra_chroma.c:293-365) from the host's decisions, WAVEFRONT-batched: a unit predicts from reconstructed samples of its
+ * neighbours (fill_reference_samples :246 with the reference's own availability flags :625 / :676 and padding), so the units of a picture are
+ * levelled by that dependency -- level k holds the units all of whose neighbours lie in levels < k -- and every level runs as a batch:
+ * reference samples gathered from the reconstructed picture on the device, smoothing rule (:1011) and predictor of the unit's mode, residual,
+ * DST / DCT, quantisation with sign hiding, dequantisation, inverse transform, reconstruction into `recon`, which the next level reads.
+ * units: in coding order (any order in which a unit comes after the units it predicts from).  comp / x / y / size: plane and block in samples
+ * of that plane; mode 0..34 (the derived chroma mode resolved by the host); qp of the component; scan_mode as find_scan_mode gives it
+ * (hmr_tables.c:376); node_x / node_y / node_size: the quadtree node, in luma samples, whose neighbour flags apply (the unit itself; for the
+ * 4x4 chroma unit of an 8x8 coding unit that node).  `pred` receives the predictions (scratch picture of the same size).
+ * coeffs: size^2 levels per unit, back to back in unit order; results[i].sum / ssd as for hb_tq_encode_intra. */
+typedef struct hb_intra_unit { int32_t comp, x, y, size, mode, qp, scan_mode, node_x, node_y, node_size; } hb_intra_unit;
+int hb_intra_reconstruct(hb_ctx *ctx, const hb_frame *cur, hb_frame *pred, hb_frame *recon, const hb_intra_unit *units, int n_units,
+                         int is_islice, int sign_hiding, double chroma_weight, int16_t *coeffs, hb_tu_result *results, int32_t *n_levels_out);
+
 /* Merge / skip candidate evaluation (the compute of check_rd_cost_merge_2nx2n, hmr_motion_inter.c:3493, with
  * one transform depth): for every candidate {CU, list-0 vector} motion compensation (luma + chroma) into `pred`, then the inter
  * T/Q chain of its transform units (luma: the block, a 64x64 one as four 32x32; chroma: half the luma unit) into `recon`.  Per candidate: dist_coded = sum of the

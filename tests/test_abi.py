@@ -65,14 +65,14 @@ def test_struct_sizes_match_the_c_header(tmp_path):
     """the ctypes / numpy mirrors have the sizes a C compiler gives the structs of include/homer_b200.h"""
     import subprocess
     names = ["hb_me_job", "hb_me_result", "hb_mc_job", "hb_mc_bi_job", "hb_tu_job", "hb_tu_result", "hb_tq_params", "hb_prepass_cfg", "hb_me_result_c",
-             "hb_tu_result_c", "hb_sao_stats", "hb_sao_param", "hb_sao_candidate", "hb_unit_info", "hb_deblock_params", "hb_low_level_funcs", "hb_frame_ipc", "hb_row_span", "hb_amvp_job", "hb_amvp_list", "hb_unit_l1"]
+             "hb_tu_result_c", "hb_sao_stats", "hb_sao_param", "hb_sao_candidate", "hb_unit_info", "hb_deblock_params", "hb_low_level_funcs", "hb_frame_ipc", "hb_row_span", "hb_amvp_job", "hb_amvp_list", "hb_unit_l1", "hb_intra_unit"]
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include "homer_b200.h"\nint main(void) {\n' +
                    "".join(f'    printf("{n} %zu\\n", sizeof({n}));\n' for n in names) + "    return 0;\n}\n")
     exe = tmp_path / "sizes"
     subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
-    mirror = {"hb_frame_ipc": C.sizeof(hb.FrameIpc), "hb_row_span": C.sizeof(hb.RowSpan), "hb_amvp_job": 12, "hb_amvp_list": 16, "hb_unit_l1": 6, "hb_me_job": C.sizeof(hb.MeJob), "hb_me_result": C.sizeof(hb.MeResult), "hb_mc_job": C.sizeof(hb.McJob), "hb_mc_bi_job": C.sizeof(hb.McBiJob),
+    mirror = {"hb_frame_ipc": C.sizeof(hb.FrameIpc), "hb_row_span": C.sizeof(hb.RowSpan), "hb_amvp_job": 12, "hb_amvp_list": 16, "hb_unit_l1": 6, "hb_intra_unit": 40, "hb_me_job": C.sizeof(hb.MeJob), "hb_me_result": C.sizeof(hb.MeResult), "hb_mc_job": C.sizeof(hb.McJob), "hb_mc_bi_job": C.sizeof(hb.McBiJob),
               "hb_tu_job": C.sizeof(hb.TuJob), "hb_tu_result": C.sizeof(hb.TuResult), "hb_tq_params": C.sizeof(hb.TqParams), "hb_prepass_cfg": C.sizeof(hb.PrepassCfg),
               "hb_me_result_c": hb.lib.ME_COMPACT_DT.itemsize, "hb_tu_result_c": hb.lib.TU_COMPACT_DT.itemsize, "hb_sao_stats": hb.lib.SAO_DT.itemsize,
               "hb_sao_param": hb.lib.SAO_PARAM_DT.itemsize, "hb_sao_candidate": hb.lib.SAO_CAND_DT.itemsize, "hb_unit_info": hb.lib.UNIT_INFO_DT.itemsize,

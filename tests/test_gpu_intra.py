@@ -123,3 +123,40 @@ def test_presearch_against_reference_functions(ctx):
     bad = np.argwhere(got != exp)
     assert len(bad) == 0, (len(bad), bad[:4], jobs[bad[0][0]])
     fc.close()
+
+
+def test_intra_picture_reconstruction_wavefront(ctx):
+    """hb_intra_reconstruct: whole I pictures rebuilt on the device, dependency level by dependency level, from the decisions the reference's own
+    encoder made == the encoder's unfiltered reconstruction (all three planes) and the oracle's levels / sums / distortions unit by unit.
+    Partial CTUs on both picture edges, several QPs, sign hiding on and off; the argument checks"""
+    from homerhevc_b200 import synth
+    from homerhevc_b200.lib import HbError
+    from _encode import encode_and_capture, make_yuv
+    from _intra import intra_tus, oracle_intra_recon
+    from _oracle import have_ref
+    if not have_ref():
+        pytest.skip("needs the compiled reference (oracle/_ref)")
+    for (w, h, qp, sh, seed) in ((192, 136, 32, 1, 21), (328, 200, 38, 0, 9), (1280, 720, 30, 1, 1234)):
+        clip = synth.make_clip(w, h, 1, seed=seed)
+        a = encode_and_capture(w, h, make_yuv(w, h, 1, seed=seed), 1, qp=qp, sign_hiding=sh)
+        tus = intra_tus(a, w, h)
+        cur, pred, rec = hb.Frame(ctx, w, h), hb.Frame(ctx, w, h), hb.Frame(ctx, w, h)
+        cur.upload_u8(*clip[0])
+        coeffs, res, levels = ctx.intra_reconstruct(cur, pred, rec, tus, 1, sh, 1.0)
+        got = rec.download()
+        for c in range(3):
+            bad = np.argwhere(got[c] != a["recon"][c])
+            assert not len(bad), (w, h, c, len(bad), bad[:3].tolist())
+        orec, ocoeff, ores = oracle_intra_recon(clip[0], w, h, tus, 1, sh, 1.0)
+        assert np.array_equal(coeffs, ocoeff)
+        assert [int(r["sum"]) for r in res] == [r.sum for r in ores] and [int(r["ssd"]) for r in res] == [r.ssd for r in ores]
+        assert 2 < levels < len(tus), levels
+        print(f"\nintra reconstruction {w}x{h}: {len(tus)} units in {levels} dependency levels")
+        for f in (cur, pred, rec):
+            f.close()
+    cur, pred, rec = hb.Frame(ctx, 64, 64), hb.Frame(ctx, 64, 64), hb.Frame(ctx, 64, 64)
+    for bad_unit in ([0, 4, 0, 8, 1, 30, 3, 4, 0, 8], [1, 0, 0, 32, 1, 30, 3, 0, 0, 64], [0, 0, 0, 8, 35, 30, 3, 0, 0, 8], [0, 0, 0, 16, 1, 30, 1, 0, 0, 16]):
+        with pytest.raises(HbError):
+            ctx.intra_reconstruct(cur, pred, rec, np.array([bad_unit], np.int32))
+    for f in (cur, pred, rec):
+        f.close()
