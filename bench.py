@@ -315,6 +315,88 @@ def run_intra(args, w, h, rank, world, local, hb, synth, quiet=False, max_steps=
     return line
 
 
+def run_intra_recon(args, w, h, rank, world, local, torch, dist, hb, synth, barrier, quiet=False, n_streams=None, max_steps=24):
+    """BASELINE.json configs[4] / [0]: reconstruction of I pictures on the device, wavefront-batched (hb_intra_reconstruct), from the decisions the
+    reference's own encoder made for the picture (one reference encode on the CPU, outside the timed region); every GPU runs its own independent
+    intra GOPs (streams), one host thread per stream: per picture the source goes up, the units' levels / sums / distortions come down and the
+    reconstruction stays on the device.  Weak scaling over N.  Next to it: the oracle's restatement of the same reconstruction on one host core
+    and the reference's whole all-intra encode (decisions + entropy coding included)."""
+    from _intra import capture_intra_picture, intra_tus, oracle_intra_recon
+    from _oracle import have_ref
+    if not have_ref():
+        if rank == 0 and not quiet:
+            print(json.dumps({"metric": "intra reconstruction frames/s", "unavailable": "oracle/_ref (compiled reference) is not in this tree: no decisions to rebuild"}))
+        return None
+    seed = synth.SEEDS.get((w, h), 7)
+    clip = synth.make_clip(w, h, 1, seed=seed)
+    cap = capture_intra_picture(w, h, QP, 1, seed)      # own process, zero-initialised build of the reference (its as-is build depends on stack garbage)
+    t_ref_encode = cap["seconds"]
+    tus = intra_tus(cap, w, h)
+    S = n_streams or max(1, min(args.streams, 8))
+    slots = []
+    for k in range(S):
+        c = hb.Context(local)
+        slots.append({"ctx": c, "f": [hb.Frame(c, w, h) for _ in range(3)], "pin": [c.pinned(p.nbytes).view(np.uint8).reshape(p.shape) for p in clip[0]]})
+        for dst, src in zip(slots[-1]["pin"], clip[0]):
+            dst[:] = src
+    steps = max(3, min(args.steps, max_steps))
+    state = {"levels": 0, "ok": True}
+
+    def work(sl, n):
+        try:
+            for _ in range(n):
+                sl["f"][0].upload_u8(*sl["pin"])
+                _, _, lv = sl["ctx"].intra_reconstruct(sl["f"][0], sl["f"][1], sl["f"][2], tus, 1, 1, 1.0)
+                state["levels"] = lv
+        except Exception as e:          # a dead worker must not turn into a fast, wrong number
+            state["error"] = e
+
+    def run(n):
+        th = [threading.Thread(target=work, args=(sl, n)) for sl in slots]
+        for t in th: t.start()
+        for t in th: t.join()
+        if state.get("error"):
+            raise state["error"]
+    run(2)
+    got = slots[0]["f"][2].download()
+    identical = all(np.array_equal(got[c], cap["recon"][c]) for c in range(3))
+    barrier()
+    t0 = time.perf_counter()
+    run(steps)
+    secs = time.perf_counter() - t0
+    barrier()
+    if world > 1:
+        t = torch.tensor([secs], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = t.item()
+    launches = sum(int(sl["ctx"].launch_count()) for sl in slots)
+    line = None
+    if rank == 0:
+        fps = world * S * steps / secs
+        line = {"metric": "intra reconstruction frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": 2, "ms_per_step": 1e3 * secs / steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 samples, int16 residual/levels", "data": "synthetic",
+                "config": {"workload": workload_name(w, h).split(" IPPP")[0] + f" I picture, fixed QP {QP}: {len(tus)} transform units of the reference encoder's own decisions in {state['levels']} dependency levels",
+                           "parallelism": f"{S} independent intra GOPs per GPU, one host thread each" + (f", x{world} GPUs" if world > 1 else ""),
+                           "timing": "wall clock around the blocking calls, source upload and level download inside"},
+                "identical_to_reference_reconstruction": bool(identical),
+                "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": int(w * h * 3 // 2 + tus.nbytes), "d2h_bytes_per_step": int(2 * (tus[:, 3].astype(np.int64) ** 2).sum() + 16 * len(tus))},
+                "gpu_launches": launches}
+        if not args.no_cpu_baseline:
+            t0 = time.perf_counter()
+            oracle_intra_recon(clip[0], w, h, tus)
+            t_port = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": 1.0 / t_port, "unit": "frames/s", "cores": 1, "kind": "port", "sample": "1 picture through the oracle's restatement of the same reconstruction (oracle/hb_oracle.c: orc_intra_recon_tus)",
+                                    "reference_whole_intra_encode_fps": 1.0 / t_ref_encode,
+                                    "reference_whole_intra_encode": "the reference's encoder on that picture, decisions and entropy coding included, 1 engine, WPP off (where the decisions come from)"}
+        if not quiet:
+            print(json.dumps(line))
+    for sl in slots:
+        for f in sl["f"]:
+            f.close()
+        sl["ctx"].close()
+    return line
+
+
 def run_finalise(args, w, h, rank, world, local, hb, synth):
     """reference-frame finalisation of one picture -- deblocking (strengths derived on the device from per-unit mode
     data), SAO statistics, SAO offset pass, border -- through the blocking C API with host buffers, next to the reference's own
@@ -771,7 +853,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip extra_workloads and bands_2160p (kernel work, profiling)")
     ap.add_argument("--streams", type=int, default=16, help="independent GOP streams in flight per GPU")
-    ap.add_argument("--mode", default="gops", choices=["gops", "bands", "intra", "finalise", "encode"],
+    ap.add_argument("--mode", default="gops", choices=["gops", "bands", "intra", "intra_recon", "finalise", "encode"],
                     help="gops: the headline line (independent GOP streams per GPU + the 2160p band line); bands: only the 2160p CTU-row-band "
                          "measurement; intra / finalise / encode: side measurements (rank 0)")
     args = ap.parse_args()
@@ -816,6 +898,9 @@ def main():
         run_finalise(args, w, h, rank, world, local, hb, synth); finish(); return
     if args.mode == "intra":
         run_intra(args, w, h, rank, world, local, hb, synth); finish(); return
+    if args.mode == "intra_recon":
+        torch.cuda.set_device(local)
+        run_intra_recon(args, w, h, rank, world, local, torch, dist, hb, synth, barrier); finish(); return
     if args.mode == "bands":
         torch.cuda.set_device(local)
         b = measure_bands(args, rank, world, local, torch, dist, hb, synth, barrier, max(8, min(args.steps, 40)))
@@ -849,6 +934,14 @@ def main():
                                                "identical_to_reference": (il.get("cpu_baseline") or {}).get("identical_to_gpu")}
         except Exception as e:
             extras["intra_presearch_1080p"] = {"value": None, "what": f"failed: {type(e).__name__}: {e}"}
+        # ... and the wavefront-batched reconstruction of an I picture from the reference encoder's decisions (configs[0]: 720p)
+        try:
+            rl = run_intra_recon(args, 1280, 720, rank, world, local, torch, dist, hb, synth, barrier, quiet=True, max_steps=10)
+            if rl:
+                extras["intra_reconstruction_720p"] = {"value": rl["value"], "unit": "frames/s", "config": rl["config"], "identical_to_reference_reconstruction": rl["identical_to_reference_reconstruction"],
+                                                       "cpu_port_1core": (rl.get("cpu_baseline") or {}).get("value"), "reference_whole_intra_encode_fps": (rl.get("cpu_baseline") or {}).get("reference_whole_intra_encode_fps")}
+        except Exception as e:
+            extras["intra_reconstruction_720p"] = {"value": None, "what": f"failed: {type(e).__name__}: {e}"}
     bands = None
     if not args.no_extras:
         try:

@@ -336,9 +336,14 @@ int hb_frame_upload_u8_ex(hb_ctx *ctx, hb_frame *f, const uint8_t *y, int ys, co
      * replicates the borders in the same pass. */
     const size_t luma = (size_t)f->w * f->h;
     if (!f->stage && (rc = hbc_malloc((void **)&f->stage, luma + luma / 2 + 16))) return hbi_cuda_fail(rc, "hb_frame_upload_u8: cudaMalloc");
-    if (ys == f->w && us == f->w / 2 && vs == f->w / 2 && u == y + luma && v == u + luma / 4)
+    int one_copy = ys == f->w && us == f->w / 2 && vs == f->w / 2 && u == y + luma && v == u + luma / 4;
+    if (one_copy) {
         rc = hbc_h2d_async(f->stage, y, luma + luma / 2, ctx->stream);
-    else {
+        /* adjacent addresses are not one allocation: three separately pinned planes that happen to touch make the runtime refuse a copy
+         * across them (cudaErrorInvalidValue = 1, not sticky) -- take them plane by plane then */
+        if (rc == 1) { hbc_clear_error(); rc = 0; one_copy = 0; }
+    }
+    if (!one_copy) {
         size_t off = 0;
         for (int c = 0; c < 3 && !rc; c++) {
             const hbd_plane *p = &f->d.p[c];

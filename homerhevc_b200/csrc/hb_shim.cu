@@ -302,3 +302,5 @@ extern "C" int hbk_pull_rows(const hbd_pull_span *spans, int n_spans, void *stre
     k_pull_rows<<<dim3(rows, n_spans), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return static_cast<int>(cudaGetLastError());
 }
+
+extern "C" int hbc_clear_error(void) { return static_cast<int>(cudaGetLastError()); }

@@ -10,6 +10,27 @@ HOR, VER, DM = 10, 26, 36
 SCAN_HOR, SCAN_VER, SCAN_DIAG = 1, 2, 3        # scan_pyramid index (hmr_private.h:92-94: HOR_SCAN, VER_SCAN, DIAG_SCAN)
 
 
+def capture_intra_picture(w, h, qp=32, sign_hiding=1, seed=21):
+    """the reference encoder's decisions, levels and unfiltered reconstruction of one synthetic I picture (tools/intra_capture.py in its own
+    process, on the zero-initialised build of the reference when it exists: the as-is build's pictures depend on stack garbage)"""
+    import os, subprocess, sys, tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    zinit = os.path.join(root, "oracle", "_ref", "zinit")
+    env = dict(os.environ)
+    if "HB_REF_DIR" not in env and os.path.exists(os.path.join(zinit, "librefdrv.so")):
+        env["HB_REF_DIR"] = zinit
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "cap.npz")
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "intra_capture.py"), str(w), str(h), str(qp), str(sign_hiding), str(seed), out],
+                           capture_output=True, text=True, timeout=900, cwd=root, env=env)
+        assert r.returncode == 0, r.stderr[-2000:]
+        z = np.load(out)
+        a = {k: z[k] for k in z.files}
+    a["recon"] = [a.pop("recon_y"), a.pop("recon_u"), a.pop("recon_v")]
+    a["slice_type"], a["slice_qp"], a["seconds"] = int(a["slice_type"]), int(a["slice_qp"]), float(a["seconds"])
+    return a
+
+
 def scan_mode(is_luma, size, mode):
     """find_scan_mode(TRUE, is_luma, size, mode, 0), hmr_tables.c:376: mode dependent for luma 4 / 8 and chroma 4 (and the 2x2 case)"""
     if (is_luma and size in (4, 8)) or (not is_luma and size in (2, 4)):

@@ -131,14 +131,13 @@ def test_intra_picture_reconstruction_wavefront(ctx):
     Partial CTUs on both picture edges, several QPs, sign hiding on and off; the argument checks"""
     from homerhevc_b200 import synth
     from homerhevc_b200.lib import HbError
-    from _encode import encode_and_capture, make_yuv
-    from _intra import intra_tus, oracle_intra_recon
+    from _intra import capture_intra_picture, intra_tus, oracle_intra_recon
     from _oracle import have_ref
     if not have_ref():
         pytest.skip("needs the compiled reference (oracle/_ref)")
     for (w, h, qp, sh, seed) in ((192, 136, 32, 1, 21), (328, 200, 38, 0, 9), (1280, 720, 30, 1, 1234)):
         clip = synth.make_clip(w, h, 1, seed=seed)
-        a = encode_and_capture(w, h, make_yuv(w, h, 1, seed=seed), 1, qp=qp, sign_hiding=sh)
+        a = capture_intra_picture(w, h, qp, sh, seed)
         tus = intra_tus(a, w, h)
         cur, pred, rec = hb.Frame(ctx, w, h), hb.Frame(ctx, w, h), hb.Frame(ctx, w, h)
         cur.upload_u8(*clip[0])

@@ -690,3 +690,18 @@ def test_levels_in_the_reference_coeff_wnd_layout(ctx):
                 coded += 1
     assert coded > 200 and np.array_equal(got, exp), np.argwhere(got != exp)[:5]
     pp.close(); fc.close(); fr.close()
+
+
+def test_upload_of_separately_pinned_planes_that_touch(ctx):
+    """three pinned allocations that happen to be adjacent look like one contiguous picture to hb_frame_upload_u8, but the runtime refuses a
+    copy that spans allocations: the one-copy shortcut must fall back to plane copies (found by bench.py --mode intra_recon at 1280x704)"""
+    rng = np.random.default_rng(3)
+    for (w, h) in ((1280, 704), (1280, 720), (256, 128)):
+        planes = [rng.integers(0, 256, s, dtype=np.uint8) for s in ((h, w), (h // 2, w // 2), (h // 2, w // 2))]
+        pin = [ctx.pinned(p.nbytes).view(np.uint8).reshape(p.shape) for p in planes]
+        for d, s in zip(pin, planes):
+            d[:] = s
+        f = hb.Frame(ctx, w, h)
+        f.upload_u8(*pin); ctx.sync()
+        assert all(np.array_equal(a, b) for a, b in zip(f.download(), planes)), (w, h)
+        f.close()

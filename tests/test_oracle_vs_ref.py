@@ -425,12 +425,11 @@ def test_intra_picture_reconstruction_against_the_reference_encoder():
     the reconstructed neighbours with the encoder's own availability and padding rules (fill_reference_samples hmr_motion_intra.c:246),
     smoothing rule, 35 predictors, DST / DCT, mode-dependent scans, sign hiding; partial CTUs on both picture edges"""
     from homerhevc_b200 import synth
-    from _encode import encode_and_capture, make_yuv
-    from _intra import coeff_wnd_of, intra_tus, oracle_intra_recon
+    from _intra import capture_intra_picture, coeff_wnd_of, intra_tus, oracle_intra_recon
     seen_sizes, seen_modes, n_dm = set(), set(), 0
     for (w, h, qp, sh, seed) in ((192, 136, 32, 1, 21), (200, 72, 24, 1, 5), (328, 200, 38, 0, 9), (320, 192, 30, 1, 3)):
         clip = synth.make_clip(w, h, 1, seed=seed)
-        a = encode_and_capture(w, h, make_yuv(w, h, 1, seed=seed), 1, qp=qp, sign_hiding=sh)
+        a = capture_intra_picture(w, h, qp, sh, seed)
         assert a["slice_type"] == 2 and (a["pred_mode"][:h // 4, :w // 4] == 1).all()          # I_SLICE, every unit intra
         tus = intra_tus(a, w, h)
         rec, coeff, res = oracle_intra_recon(clip[0], w, h, tus, is_islice=1, sign_hiding=sh)
