@@ -9,89 +9,9 @@
 // mode < 0: the SADs of all 35 luma modes against the current block (what the host's mode search probes).
 #include "hb_shim.h"
 #include "hb_dev_common.cuh"
+#include "hb_intra_core.cuh"
 
 namespace {
-
-__constant__ int c_ang[9] = { 0, 2, 5, 9, 13, 17, 21, 26, 32 };
-__constant__ int c_inv_ang[9] = { 0, 4096, 1638, 910, 630, 482, 390, 315, 256 };
-__constant__ int c_flt_thr[4] = { 10, 7, 1, 0 };
-
-struct IntraMode { int kind; int hor; int angle; int inv; };      // kind 0 planar, 1 DC, 2 pure H/V, 3 angular
-
-__device__ __forceinline__ IntraMode intra_mode_info(int mode)
-{
-    IntraMode m;
-    m.hor = mode < 18; m.angle = 0; m.inv = 0;
-    if (mode == 0) { m.kind = 0; return m; }
-    if (mode == 1) { m.kind = 1; return m; }
-    const int a = m.hor ? -(mode - 10) : mode - 26;
-    const int aa = abs(a);
-    m.angle = (a < 0 ? -1 : 1) * c_ang[aa];
-    m.inv = c_inv_ang[aa];
-    m.kind = a == 0 ? 2 : 3;
-    return m;
-}
-
-// mid points at the top-left corner sample of the 4n+1 array
-__device__ __forceinline__ int intra_sample(const int16_t *mid, int n, int lg, const IntraMode &m, int dc, bool edge, int x, int y)
-{
-    if (m.kind == 0) {
-        const int l = mid[-(y + 1)], t = mid[x + 1], lb = mid[-(n + 1)], tr = mid[n + 1];
-        return ((l << lg) + n + (x + 1) * (tr - l) + (t << lg) + (y + 1) * (lb - t)) >> (lg + 1);
-    }
-    if (m.kind == 1) {
-        if (edge) {
-            if (x == 0 && y == 0) return (mid[-1] + mid[1] + 2 * dc + 2) >> 2;
-            if (y == 0) return (mid[1 + x] + 3 * dc + 2) >> 2;
-            if (x == 0) return (mid[-1 - y] + 3 * dc + 2) >> 2;
-        }
-        return dc;
-    }
-    const int j = m.hor ? x : y, i = m.hor ? y : x;
-    const int sm = m.hor ? -1 : 1;                          // main[k] = mid[sm*k], side[k] = mid[-sm*k]
-    if (m.kind == 2) {
-        int v = mid[sm * (i + 1)];
-        if (edge && i == 0) v = hb_clip255(v + ((mid[-sm * (j + 1)] - mid[0]) >> 1));   // first sample of every line along the direction
-        return v;
-    }
-    const int pos = (j + 1) * m.angle, d = pos >> 5, f = pos & 31;
-    const int k = i + d + 1;
-    auto ref = [&](int kk) -> int { return kk >= 0 ? mid[sm * kk] : mid[-sm * ((128 - kk * m.inv) >> 8)]; };
-    if (!f) return ref(k);
-    return ((32 - f) * ref(k) + f * ref(k + 1) + 16) >> 5;
-}
-
-// [1,2,1] or strong bilinear smoothing of the 4n+1 reference samples (hmr_motion_intra.c:189, strong_intra_smooth on)
-__device__ __forceinline__ void intra_filter_adi(const int16_t *adi, int16_t *flt, int n, int lg, int lane)
-{
-    const int size = 4 * n + 1;
-    const int lb = adi[0], lt = adi[2 * n], tr = adi[size - 1];
-    const bool strong = n >= 32 && abs(lb + lt - 2 * adi[n]) < 8 && abs(lt + tr - 2 * adi[3 * n]) < 8;
-    for (int i = lane; i < size; i += 32) {
-        int v;
-        if (i == 0 || i == size - 1) v = adi[i];
-        else if (strong) {
-            if (i == 2 * n) v = adi[i];
-            else if (i < 2 * n) v = ((2 * n - i) * lb + i * lt + n) >> (lg + 1);
-            else v = ((4 * n - i) * lt + (i - 2 * n) * tr + n) >> (lg + 1);
-        } else v = (adi[i - 1] + 2 * adi[i] + adi[i + 1] + 2) >> 2;
-        flt[i] = static_cast<int16_t>(v);
-    }
-}
-
-__device__ __forceinline__ bool intra_uses_filtered(int lg, int mode)
-{
-    const int d = min(abs(mode - 10), abs(mode - 26));
-    return mode != 1 && d > c_flt_thr[lg - 2];
-}
-
-__device__ __forceinline__ int intra_dc(const int16_t *mid, int n, int lane)
-{
-    int s = 0;
-    for (int i = 1 + lane; i <= n; i += 32) s += mid[i] + mid[-i];
-    s = __reduce_add_sync(HB_FULL_MASK, s);
-    return (s + n) / (2 * n);
-}
 
 constexpr int kIntraWarps = 4;
 
@@ -330,63 +250,21 @@ extern "C" int hbk_pc_intra(const int16_t *adi, int n, int mode, int is_luma, in
 }
 
 
-// ---- reference samples of a batch of intra units from the reconstructed picture: fill_reference_samples (hmr_motion_intra.c:246-406), one
-// thread per unit, statement for statement: the left column bottom-up, the left-bottom run as far as it lies inside the picture, the row
-// above and the top-right run, the corner, then the reference's two padding runs (first copied sample downwards / to the left, last copied
-// sample to the right).  adi: index 2n = corner, 2n + 1 + i above, 2n - 1 - r the left column at row y + r.
+// ---- reference samples of a batch of intra units from the reconstructed picture (fill_reference_samples, hmr_motion_intra.c:246-406, in the
+// closed form of hb_intra_core.cuh): one warp per unit.  adi: index 2n = corner, 2n + 1 + i above, 2n - 1 - r the left column at row y + r.
 namespace {
-__global__ void __launch_bounds__(64) k_intra_adi(const hbd_frame rec, const hbd_adi_job *jobs, int n_jobs, int16_t *adi_all)
+__global__ void __launch_bounds__(128) k_intra_adi(const hbd_frame rec, const hbd_adi_job *jobs, int n_jobs, int16_t *adi_all)
 {
-    const int i = blockIdx.x * 64 + threadIdx.x;
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (i >= n_jobs) return;
     const hbd_adi_job j = jobs[i];
-    const hbd_plane p = hbd_pick_plane(rec, j.comp);
-    int16_t *adi = adi_all + j.adi_off;
-    const int n = j.n;
-    const bool left = j.flags & 1, top = j.flags & 2, left_bottom = j.flags & 4, top_right = j.flags & 8;
-    if (!left && !top) { for (int k = 0; k < 4 * n + 1; k++) adi[k] = 128; return; }
-    const uint8_t *corner = p.org + (j.y - 1) * p.pitch + (j.x - 1);
-    int16_t first = 0, last = 0;
-    int pad_left = -1, pad_top = -1, pad_left_n = 0, pad_top_n = 0;        // start indices into adi
-    int ptr = n;
-    if (left) {
-        for (int k = 0; k < n; k++) adi[ptr++] = corner[(n - k) * p.pitch];
-        first = adi[ptr - n]; last = adi[ptr - 1];
-    } else { pad_left = ptr; pad_left_n = n; }
-    ptr = n - 1;
-    if (left_bottom) {
-        for (int k = 0; k < j.lbs; k++) adi[ptr--] = corner[(n + 1 + k) * p.pitch];
-        first = adi[ptr + 1];
-        if (j.lbs != n) { pad_left = 0; pad_left_n = n - j.lbs; }
-    } else {
-        pad_left = 0;
-        if (left) pad_left_n = n; else pad_left_n += n;
-    }
-    ptr = 2 * n + 1;
-    const uint8_t *rp = corner + 1;
-    if (top) {
-        for (int k = 0; k < n; k++) adi[ptr++] = *rp++;
-        if (!left) first = adi[ptr - n];
-        last = adi[ptr - 1];
-    } else { pad_top = ptr; pad_top_n = n; }
-    if (top_right) {
-        for (int k = 0; k < j.trs; k++) adi[ptr++] = *rp++;
-        last = adi[ptr - 1];
-        if (j.trs != n) { pad_top = ptr; pad_top_n = n - j.trs; }
-    } else {
-        if (top) { pad_top = ptr; pad_top_n = n; } else pad_top_n += n;
-    }
-    if (left && top) adi[2 * n] = corner[0];
-    else if (left) { pad_top--; pad_top_n++; }
-    else pad_left_n++;
-    for (int k = 0; k < pad_left_n; k++) adi[pad_left++] = first;
-    for (int k = 0; k < pad_top_n; k++) adi[pad_top++] = last;
+    intra_gather_adi(hbd_pick_plane(rec, j.comp), j.x, j.y, j.n, j.flags, j.lbs, j.trs, adi_all + j.adi_off, threadIdx.x & 31);
 }
 }  // namespace
 
 extern "C" int hbk_intra_adi(const hbd_frame *rec, const hbd_adi_job *jobs, int n_jobs, int16_t *adi, void *stream)
 {
     if (n_jobs <= 0) return 0;
-    k_intra_adi<<<(n_jobs + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(*rec, jobs, n_jobs, adi);
+    k_intra_adi<<<(n_jobs + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(*rec, jobs, n_jobs, adi);
     return static_cast<int>(cudaGetLastError());
 }
