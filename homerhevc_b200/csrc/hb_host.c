@@ -968,6 +968,11 @@ static int intra_sorted_cmp(const void *pa, const void *pb)
 int hb_intra_reconstruct(hb_ctx *ctx, const hb_frame *cur, hb_frame *pred, hb_frame *recon, const hb_intra_unit *units, int n_units,
                          int is_islice, int sign_hiding, double chroma_weight, int16_t *coeffs, hb_tu_result *results, int32_t *n_levels_out)
 {
+    return hb_intra_reconstruct_ex(ctx, cur, pred, recon, units, n_units, is_islice, sign_hiding, chroma_weight, 0, coeffs, results, n_levels_out);
+}
+int hb_intra_reconstruct_ex(hb_ctx *ctx, const hb_frame *cur, hb_frame *pred, hb_frame *recon, const hb_intra_unit *units, int n_units,
+                            int is_islice, int sign_hiding, double chroma_weight, int flags, int16_t *coeffs, hb_tu_result *results, int32_t *n_levels_out)
+{
     int rc = HB_OK, crc = 0;
     if (!ctx || !cur || !pred || !recon || !units || !coeffs || !results || n_units < 0) return hbi_fail(HB_ERR_ARG, "hb_intra_reconstruct: bad argument");
     if (cur->w != recon->w || cur->h != recon->h || pred->w != cur->w || pred->h != cur->h) return hbi_fail(HB_ERR_ARG, "hb_intra_reconstruct: picture sizes differ");
@@ -1050,6 +1055,69 @@ int hb_intra_reconstruct(hb_ctx *ctx, const hb_frame *cur, hb_frame *pred, hb_fr
             ((int32_t *)h_xy)[2 * k] = u->x; ((int32_t *)h_xy)[2 * k + 1] = u->y;
             launch_coeff[k] = packed_coeff; packed_coeff += (size_t)u->size * u->size;
         }
+        if (!(flags & HB_INTRA_PER_LEVEL_LAUNCHES)) {
+            /* ---- one persistent launch: units, tasks (32 / size consecutive units of one group and level) and groups */
+            void *d_w, *h_w, *d_t, *h_t;
+            const size_t units_bytes = (sizeof(hbd_wave_unit) * (size_t)n_units + 15) & ~(size_t)15;
+            const size_t tasks_cap = (size_t)n_units, groups_cap = (size_t)n_units;
+            const size_t tasks_bytes = (sizeof(hbd_wave_task) * tasks_cap + 15) & ~(size_t)15;
+            if ((rc = hbi_scratch(ctx, 0, units_bytes + 64, &d_w, &h_w)) != HB_OK) { free(launch_coeff); goto unlock; }
+            if ((rc = hbi_scratch(ctx, 1, tasks_bytes + sizeof(hbd_wave_group) * groups_cap, &d_t, &h_t)) != HB_OK) { free(launch_coeff); goto unlock; }
+            hbd_wave_unit *wu = (hbd_wave_unit *)h_w;
+            hbd_wave_task *wt = (hbd_wave_task *)h_t;
+            hbd_wave_group *wg = (hbd_wave_group *)((char *)h_t + tasks_bytes);
+            const hbd_wave_group *d_groups = (const hbd_wave_group *)((char *)d_t + tasks_bytes);
+            int n_tasks = 0, n_groups = 0, level_first = 0;
+            for (int k = 0; k < n_units; k++) {
+                const int i = srt[k].idx;
+                wu[k].x = units[i].x; wu[k].y = units[i].y; wu[k].mode = units[i].mode; wu[k].flags = aj[i].flags; wu[k].lbs = aj[i].lbs; wu[k].trs = aj[i].trs;
+            }
+            for (int k0 = 0; k0 < n_units; ) {
+                if (k0 == 0 || srt[k0].level != srt[k0 - 1].level) level_first = k0;
+                int k1 = k0;
+                while (k1 < n_units && srt[k1].level == srt[k0].level && srt[k1].comp == srt[k0].comp && srt[k1].size == srt[k0].size && srt[k1].qp == srt[k0].qp &&
+                       srt[k1].scan == srt[k0].scan) k1++;
+                /* the group's tables (one record per distinct plane / size / qp / scan) */
+                const int comp = srt[k0].comp, size = srt[k0].size, qp = srt[k0].qp, scan = srt[k0].scan;
+                hbd_tq_args a;
+                memset(&a, 0, sizeof a);
+                hbi_tq_setup(ctx, &a, comp, size, qp, is_islice, sign_hiding);
+                int lg = 2;
+                while ((1 << lg) < size) lg++;
+                hbd_wave_group g;
+                memset(&g, 0, sizeof g);
+                g.comp = comp; g.qbits = a.qbits; g.add = a.add; g.per = a.per;
+                g.qtab = ctx->d_q + hbi_tab_q_off(lg, comp, qp % 6);           /* intra lists: (is_intra ? 0 : 3) + comp */
+                g.dqtab = ctx->d_dq + hbi_tab_q_off(lg, 0, qp % 6);            /* SSE4.2 inv_quant: is_intra -> list 0 (hmr_sse42_functions_quant.c:138) */
+                g.scan = ctx->d_scan + hbi_tab_scan_off(scan, lg);
+                g.weight = comp ? chroma_weight : 1.0;
+                int gi = -1;
+                for (int q = 0; q < n_groups; q++) if (!memcmp(&wg[q], &g, sizeof g)) { gi = q; break; }
+                if (gi < 0) { gi = n_groups; wg[n_groups++] = g; }
+                const int tpw = 32 / size;
+                for (int f = k0; f < k1; f += tpw) {
+                    hbd_wave_task *t = &wt[n_tasks++];
+                    t->first_unit = f; t->n_units = k1 - f < tpw ? k1 - f : tpw; t->group = gi; t->size = size;
+                    t->units_before = level_first; t->pad_ = 0; t->coeff_off = (int64_t)launch_coeff[f];
+                }
+                k0 = k1;
+            }
+            unsigned *d_cnt = (unsigned *)((char *)d_w + units_bytes);
+            crc = hbc_h2d_async(d_w, h_w, units_bytes, ctx->stream);
+            if (!crc) crc = hbc_memset_async(d_cnt, 0, 64, ctx->stream);
+            if (!crc) crc = hbc_h2d_async(d_t, h_t, tasks_bytes + sizeof(hbd_wave_group) * (size_t)n_groups, ctx->stream);
+            if (!crc) crc = hbc_h2d_async(d_xy, h_xy, sizeof(int32_t) * 2 * (size_t)n_units, ctx->stream);
+            hbd_wave_args wa;
+            memset(&wa, 0, sizeof wa);
+            wa.cur = cur->d; wa.pred = pred->d; wa.rec = recon->d;
+            wa.units = (const hbd_wave_unit *)d_w; wa.xy = (const int32_t *)d_xy; wa.tasks = (const hbd_wave_task *)d_t; wa.groups = d_groups;
+            wa.n_tasks = n_tasks; wa.sign_hiding = sign_hiding; wa.coeff = (int16_t *)d_co; wa.res = (hb_tu_result *)d_rs; wa.counters = d_cnt;
+            /* enough warps for the widest levels, few enough to leave SMs to the other pictures in flight */
+            int ctas = (n_tasks + 15) / 16;
+            ctas = ctas < 8 ? 8 : (ctas > 48 ? 48 : ctas);
+            if (!crc) { crc = hbk_intra_wave(&wa, ctas, ctx->stream); ctx->launches++; }
+            goto collect;
+        }
         crc = hbc_h2d_async(d_a, h_a, sizeof(hbd_adi_job) * (size_t)n_units, ctx->stream);
         if (!crc) crc = hbc_h2d_async(d_j, h_j, sizeof(hbd_intra_job) * (size_t)n_units, ctx->stream);
         if (!crc) crc = hbc_h2d_async(d_xy, h_xy, sizeof(int32_t) * 2 * (size_t)n_units, ctx->stream);
@@ -1089,6 +1157,7 @@ int hb_intra_reconstruct(hb_ctx *ctx, const hb_frame *cur, hb_frame *pred, hb_fr
             }
             k0 = k1;
         }
+collect:
         if (!crc) { crc = hbk_pad_frame(&recon->d, ctx->stream); ctx->launches++; }
         if (!crc) crc = hbc_d2h_async(h_co, d_co, sizeof(int16_t) * total, ctx->stream);
         if (!crc) crc = hbc_d2h_async(h_rs, d_rs, sizeof(hb_tu_result) * (size_t)n_units, ctx->stream);

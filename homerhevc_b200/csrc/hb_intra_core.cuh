@@ -100,10 +100,11 @@ __device__ __forceinline__ void intra_gather_adi(const hbd_plane &p, int x, int 
     const int pitch = p.pitch;
     for (int k = lane; k < 4 * n + 1; k += 32) {
         int v;
+        // ld.global.cg: inside the persistent kernel the samples were written by other SMs moments ago and L1 is not coherent
         if (!l && !t) v = 128;
-        else if (k < 2 * n) v = l ? org[(y + min(2 * n - 1 - k, rows - 1)) * pitch + x - 1] : org[(y - 1) * pitch + x];
-        else if (k == 2 * n) v = (l && t) ? org[(y - 1) * pitch + x - 1] : l ? org[y * pitch + x - 1] : org[(y - 1) * pitch + x];
-        else v = t ? org[(y - 1) * pitch + x + min(k - 2 * n - 1, cols - 1)] : org[y * pitch + x - 1];
+        else if (k < 2 * n) v = l ? __ldcg(org + (y + min(2 * n - 1 - k, rows - 1)) * pitch + x - 1) : __ldcg(org + (y - 1) * pitch + x);
+        else if (k == 2 * n) v = (l && t) ? __ldcg(org + (y - 1) * pitch + x - 1) : l ? __ldcg(org + y * pitch + x - 1) : __ldcg(org + (y - 1) * pitch + x);
+        else v = t ? __ldcg(org + (y - 1) * pitch + x + min(k - 2 * n - 1, cols - 1)) : __ldcg(org + y * pitch + x - 1);
         adi[k] = static_cast<int16_t>(v);
     }
 }

@@ -11,6 +11,7 @@
 // HBM traffic per sample: 2 B read (cur, pred) + 1 B recon + 2 B levels; everything else stays on chip.
 #include "hb_shim.h"
 #include "hb_tq_core.cuh"
+#include "hb_intra_core.cuh"
 
 namespace {
 
@@ -336,16 +337,13 @@ __global__ void __launch_bounds__(kTq4Threads) k_tq4(const hbd_tq_args a)
 // encode_intra_cu (hmr_motion_intra.c:1023-1069) and the chroma loop of hmr_motion_intra_chroma.c:340-365: residual ->
 // DST-VII (4x4 luma) or DCT -> quant (intra lists, scan from the intra mode, sign hiding) -> if any level: dequant -> inverse
 // -> reconstruction; distortion = SSD(original, reconstruction) (chroma weighted).  No zero-out heuristic on this path.
+// one warp's stack of 32 / N units starting at job `first_job`; sm: 5 * HbTq<N>::ELEMS int16 of the warp's shared memory
 template <int N>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) k_tq_intra(const hbd_tq_args a)
+__device__ __forceinline__ void tq_intra_warp(const hbd_tq_args &a, const int first_job, int16_t *sm, const int lane)
 {
     using Q = HbTq<N>;
     constexpr int TPW = Q::TPW;
-    __shared__ __align__(16) int16_t smem[kWarpsPerCta][5][Q::ELEMS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int first_job = (blockIdx.x * kWarpsPerCta + warp) * TPW;
-    if (first_job >= a.n_jobs) return;
-    int16_t *X = smem[warp][0], *T = smem[warp][1], *C = smem[warp][2], *L = smem[warp][3], *U = smem[warp][4];
+    int16_t *X = sm, *T = sm + Q::ELEMS, *C = sm + 2 * Q::ELEMS, *L = sm + 3 * Q::ELEMS, *U = sm + 4 * Q::ELEMS;
     const bool dst = (N == 4) && a.is_luma;
     int jx[TPW], jy[TPW];
 #pragma unroll
@@ -430,6 +428,76 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_tq_intra(const hbd_tq_arg
     }
 }
 
+template <int N>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) k_tq_intra(const hbd_tq_args a)
+{
+    using Q = HbTq<N>;
+    __shared__ __align__(16) int16_t smem[kWarpsPerCta][5 * Q::ELEMS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int first_job = (blockIdx.x * kWarpsPerCta + warp) * Q::TPW;
+    if (first_job >= a.n_jobs) return;
+    tq_intra_warp<N>(a, first_job, smem[warp], lane);
+}
+
+// ------------------------------------------------------------------ a whole intra picture in ONE launch
+// hb_intra_reconstruct: the units of a picture sorted by dependency level and, inside a level, by (plane, size, QP, scan); a TASK is up to
+// 32 / N consecutive units of one such group -- what one warp stacks into a T/Q pass.  The kernel is persistent: every warp draws the next
+// task from a global counter (tasks are numbered level by level), waits until all units of the earlier levels are finished (one global
+// count of finished units against the task's prefix; the units it waits for belong to tasks drawn before its own, i.e. to warps that are
+// running, so nobody waits for work that is not in flight), gathers the reference samples of its units from the reconstructed picture,
+// writes their predictions, runs the intra T/Q chain on them, and adds its units to the count.  One launch instead of ~7 per level.
+template <int N>
+__device__ __forceinline__ void intra_wave_task(const hbd_wave_args &w, const hbd_wave_task &t, int16_t *sm, int16_t *adi, const int lane)
+{
+    const hbd_wave_group g = w.groups[t.group];
+    for (int u = 0; u < t.n_units; u++) {
+        const hbd_wave_unit un = w.units[t.first_unit + u];
+        int16_t *raw = adi, *flt = adi + 132;
+        intra_gather_adi(hbd_pick_plane(w.rec, g.comp), un.x, un.y, N, un.flags, un.lbs, un.trs, raw, lane);
+        __syncwarp();
+        intra_predict_block(hbd_pick_plane(w.pred, g.comp), g.comp, un.x, un.y, N, un.mode, g.comp ? 0 : -1, raw, flt, lane);
+        __syncwarp();
+    }
+    __threadfence_block();
+    __syncwarp();                                            // the warp's own predictions are visible to all its lanes
+    hbd_tq_args a;
+    a.cur = hbd_pick_plane(w.cur, g.comp); a.pred = hbd_pick_plane(w.pred, g.comp); a.rec = hbd_pick_plane(w.rec, g.comp);
+    a.jobs_xy = w.xy + 2 * t.first_unit; a.n_jobs = t.n_units; a.n = N;
+    a.qtab = g.qtab; a.dqtab = g.dqtab; a.scan = g.scan; a.qbits = g.qbits; a.add = g.add; a.per = g.per;
+    a.sign_hiding = w.sign_hiding; a.is_luma = g.comp == 0; a.intra = 1; a.thr_k = 0.; a.weight = g.weight; a.dyn = nullptr;
+    a.coeff_out = w.coeff + t.coeff_off; a.res_out = w.res + t.first_unit;
+    tq_intra_warp<N>(a, 0, sm, lane);
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32) k_intra_wave(const hbd_wave_args w)
+{
+    __shared__ __align__(16) int16_t smem[kWarpsPerCta][5 * HbTq<32>::ELEMS];
+    __shared__ int16_t s_adi[kWarpsPerCta][2 * 132];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned ti = 0;
+        if (lane == 0) ti = atomicAdd(&w.counters[0], 1u);
+        ti = __shfl_sync(HB_FULL_MASK, ti, 0);
+        if (ti >= static_cast<unsigned>(w.n_tasks)) return;
+        const hbd_wave_task t = w.tasks[ti];
+        if (lane == 0) {
+            const volatile unsigned *done = w.counters + 1;
+            while (*done < static_cast<unsigned>(t.units_before)) __nanosleep(64);
+        }
+        __syncwarp();
+        __threadfence();                                     // what the earlier levels wrote is read after this point
+        switch (t.size) {
+        case 4: intra_wave_task<4>(w, t, smem[warp], s_adi[warp], lane); break;
+        case 8: intra_wave_task<8>(w, t, smem[warp], s_adi[warp], lane); break;
+        case 16: intra_wave_task<16>(w, t, smem[warp], s_adi[warp], lane); break;
+        default: intra_wave_task<32>(w, t, smem[warp], s_adi[warp], lane); break;
+        }
+        __threadfence();                                     // reconstruction, levels and records before the count moves
+        __syncwarp();
+        if (lane == 0) atomicAdd(&w.counters[1], static_cast<unsigned>(t.n_units));
+    }
+}
+
 // ------------------------------------------------------------------ per-call kernels (one warp, one unit)
 template <int N, bool DST>
 __global__ void __launch_bounds__(32) k_pc_transform(const int16_t *block, int bs, int16_t *coeff)
@@ -505,6 +573,13 @@ template <int N> int launch_tq(const hbd_tq_args *a, cudaStream_t s)
 }
 
 }  // namespace
+
+extern "C" int hbk_intra_wave(const hbd_wave_args *w, int ctas, void *stream)
+{
+    if (w->n_tasks <= 0) return 0;
+    k_intra_wave<<<ctas, kWarpsPerCta * 32, 0, static_cast<cudaStream_t>(stream)>>>(*w);
+    return static_cast<int>(cudaGetLastError());
+}
 
 extern "C" int hbk_tq_encode(const hbd_tq_args *a, void *stream)
 {

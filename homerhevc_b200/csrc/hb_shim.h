@@ -150,6 +150,19 @@ typedef struct hbd_tq_args {
 } hbd_tq_args;
 int hbk_tq_encode(const hbd_tq_args *a, void *stream);
 
+/* ---- a whole intra picture in one persistent launch (k_intra_wave, hb_kernels_tq.cu): units sorted by (dependency level, plane, size, qp, scan) */
+typedef struct hbd_wave_unit { int32_t x, y, mode; int32_t flags, lbs, trs; } hbd_wave_unit;          /* flags: bit 0 left, 1 top, 2 left-bottom, 3 top-right */
+typedef struct hbd_wave_group { int32_t comp, qbits, add, per; const int32_t *qtab, *dqtab; const uint16_t *scan; double weight; } hbd_wave_group;
+typedef struct hbd_wave_task { int32_t first_unit, n_units, group, size; int32_t units_before /* units of all earlier levels */, pad_; int64_t coeff_off; } hbd_wave_task;
+typedef struct hbd_wave_args {
+    hbd_frame cur, pred, rec;
+    const hbd_wave_unit *units; const int32_t *xy; const hbd_wave_task *tasks; const hbd_wave_group *groups;
+    int32_t n_tasks, sign_hiding;
+    int16_t *coeff; hb_tu_result *res;
+    unsigned *counters;           /* [0] next task, [1] finished units; zeroed before the launch */
+} hbd_wave_args;
+int hbk_intra_wave(const hbd_wave_args *w, int ctas, void *stream);
+
 /* ---- block read-back (hb_kernels_enc.cu): size x size samples of plane `comp` at (x, y), x a multiple of 4, widened to int16 at
  * out + off (off in int16 units, a multiple of 4) */
 typedef struct hbd_fetch_job { int32_t comp, x, y, size, off, pad_; } hbd_fetch_job;

@@ -483,7 +483,7 @@ Context.amvp_candidates = _amvp_candidates
 INTRA_UNIT_DT = np.dtype([(k, "<i4") for k in ("comp", "x", "y", "size", "mode", "qp", "scan_mode", "node_x", "node_y", "node_size")])
 
 
-def _intra_reconstruct(self, cur, pred, recon, units, is_islice=1, sign_hiding=1, chroma_weight=1.0):
+def _intra_reconstruct(self, cur, pred, recon, units, is_islice=1, sign_hiding=1, chroma_weight=1.0, per_level_launches=0):
     """wavefront-batched reconstruction of intra transform units; units: (n, 10) int32 or INTRA_UNIT_DT in coding order.
     Returns (levels back to back in unit order, results array {sum, ssd, ssd_zero, zeroed}, number of dependency levels)"""
     u = np.ascontiguousarray(units, np.int32).reshape(-1, 10)
@@ -491,9 +491,9 @@ def _intra_reconstruct(self, cur, pred, recon, units, is_islice=1, sign_hiding=1
     coeffs = np.zeros(int((u[:, 3].astype(np.int64) ** 2).sum()), np.int16)
     res = np.zeros(n, np.dtype([("sum", "<i4"), ("ssd", "<u4"), ("ssd_zero", "<u4"), ("zeroed", "<i4")]))
     levels = C.c_int32(0)
-    self.L.hb_intra_reconstruct.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
-    _check(self.L.hb_intra_reconstruct(self.h, cur.h, pred.h, recon.h, u.ctypes.data, n, is_islice, sign_hiding, chroma_weight, coeffs.ctypes.data, res.ctypes.data,
-                                       C.byref(levels)), "hb_intra_reconstruct")
+    self.L.hb_intra_reconstruct_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    _check(self.L.hb_intra_reconstruct_ex(self.h, cur.h, pred.h, recon.h, u.ctypes.data, n, is_islice, sign_hiding, chroma_weight, 1 if per_level_launches else 0,
+                                          coeffs.ctypes.data, res.ctypes.data, C.byref(levels)), "hb_intra_reconstruct")
     return coeffs, res, levels.value
 
 

@@ -247,6 +247,12 @@ void hb_create_intra_angular_prediction(int16_t *prediction, int pred_stride, in
 typedef struct hb_intra_unit { int32_t comp, x, y, size, mode, qp, scan_mode, node_x, node_y, node_size; } hb_intra_unit;
 int hb_intra_reconstruct(hb_ctx *ctx, const hb_frame *cur, hb_frame *pred, hb_frame *recon, const hb_intra_unit *units, int n_units,
                          int is_islice, int sign_hiding, double chroma_weight, int16_t *coeffs, hb_tu_result *results, int32_t *n_levels_out);
+/* flags = 0: ONE persistent launch per picture -- warps draw tasks (32 / size units of one level and group) from a global counter and wait on
+ * a global count of finished units for the earlier levels; HB_INTRA_PER_LEVEL_LAUNCHES: a batch of launches per level (gather, predict, one
+ * T/Q launch per plane / size / QP / scan group), the first form, kept for comparison.  Same results. */
+#define HB_INTRA_PER_LEVEL_LAUNCHES 1
+int hb_intra_reconstruct_ex(hb_ctx *ctx, const hb_frame *cur, hb_frame *pred, hb_frame *recon, const hb_intra_unit *units, int n_units,
+                            int is_islice, int sign_hiding, double chroma_weight, int flags, int16_t *coeffs, hb_tu_result *results, int32_t *n_levels_out);
 
 /* Merge / skip candidate evaluation (the compute of check_rd_cost_merge_2nx2n, hmr_motion_inter.c:3493, with
  * one transform depth): for every candidate {CU, list-0 vector} motion compensation (luma + chroma) into `pred`, then the inter

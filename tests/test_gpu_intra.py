@@ -141,11 +141,17 @@ def test_intra_picture_reconstruction_wavefront(ctx):
         tus = intra_tus(a, w, h)
         cur, pred, rec = hb.Frame(ctx, w, h), hb.Frame(ctx, w, h), hb.Frame(ctx, w, h)
         cur.upload_u8(*clip[0])
-        coeffs, res, levels = ctx.intra_reconstruct(cur, pred, rec, tus, 1, sh, 1.0)
-        got = rec.download()
-        for c in range(3):
-            bad = np.argwhere(got[c] != a["recon"][c])
-            assert not len(bad), (w, h, c, len(bad), bad[:3].tolist())
+        for per_level in (1, 0, 0):          # a batch of launches per dependency level; one persistent launch (twice: it must leave no state behind)
+            coeffs, res, levels = ctx.intra_reconstruct(cur, pred, rec, tus, 1, sh, 1.0, per_level_launches=per_level)
+            got = rec.download()
+            for c in range(3):
+                bad = np.argwhere(got[c] != a["recon"][c])
+                assert not len(bad), (w, h, c, per_level, len(bad), bad[:3].tolist())
+            if per_level:
+                first = (coeffs.copy(), res.copy())
+                rec.upload_u8(*[np.full_like(p, 77) for p in clip[0]])      # the persistent form must not find the answer already there
+            else:
+                assert np.array_equal(coeffs, first[0]) and res.tobytes() == first[1].tobytes(), per_level
         orec, ocoeff, ores = oracle_intra_recon(clip[0], w, h, tus, 1, sh, 1.0)
         assert np.array_equal(coeffs, ocoeff)
         assert [int(r["sum"]) for r in res] == [r.sum for r in ores] and [int(r["ssd"]) for r in res] == [r.ssd for r in ores]
