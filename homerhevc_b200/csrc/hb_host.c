@@ -331,19 +331,16 @@ int hb_frame_upload_u8_ex(hb_ctx *ctx, hb_frame *f, const uint8_t *y, int ys, co
     int rc = 0;
     if (!ctx || !f || !y || !u || !v) return hbi_fail(HB_ERR_ARG, "hb_frame_upload_u8: NULL argument");
     hbc_set_device(ctx->device);
-    /* One plain copy per plane (a single one when the caller's planes are contiguous) into a dense staging buffer -- 1-D copies
+    /* One plain copy per plane (a single one when the caller's planes are one buffer) into a dense staging buffer -- 1-D copies
      * run at link speed, pitched ones at about half of it -- then one kernel spreads the samples into the padded planes and
      * replicates the borders in the same pass. */
     const size_t luma = (size_t)f->w * f->h;
     if (!f->stage && (rc = hbc_malloc((void **)&f->stage, luma + luma / 2 + 16))) return hbi_cuda_fail(rc, "hb_frame_upload_u8: cudaMalloc");
-    int one_copy = ys == f->w && us == f->w / 2 && vs == f->w / 2 && u == y + luma && v == u + luma / 4;
-    if (one_copy) {
+    /* one copy when the three planes are one tight buffer -- which adjacent addresses alone do not prove: three separately pinned planes
+     * may touch, and the runtime refuses a copy that spans allocations (hbc_host_span_one_copy asks the driver) -- else plane by plane */
+    if (ys == f->w && us == f->w / 2 && vs == f->w / 2 && u == y + luma && v == u + luma / 4 && hbc_host_span_one_copy(y, luma + luma / 2))
         rc = hbc_h2d_async(f->stage, y, luma + luma / 2, ctx->stream);
-        /* adjacent addresses are not one allocation: three separately pinned planes that happen to touch make the runtime refuse a copy
-         * across them (cudaErrorInvalidValue = 1, not sticky) -- take them plane by plane then */
-        if (rc == 1) { hbc_clear_error(); rc = 0; one_copy = 0; }
-    }
-    if (!one_copy) {
+    else {
         size_t off = 0;
         for (int c = 0; c < 3 && !rc; c++) {
             const hbd_plane *p = &f->d.p[c];

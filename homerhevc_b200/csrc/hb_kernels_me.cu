@@ -212,7 +212,7 @@ struct MeMemo {
     static constexpr int ENTRIES = 64, SLOTS = 256;
     uint32_t sum[ENTRIES][32];      // word (j, bx) = blocks (by = 2j, bx) | (by = 2j + 1, bx) << 16, j = 0..3... see block()
     uint32_t tag[ENTRIES];          // quarter-pel displacement: (x & 0xffff) | y << 16
-    uint8_t idx[SLOTS];             // hash slot -> entry, 0xff = empty
+    uint32_t idx[SLOTS / 4];        // hash slot -> entry, one byte each, 0xff = empty; claimed by compare-and-swap on the word
     static __device__ __forceinline__ uint32_t key(int qx, int qy) { return (static_cast<uint32_t>(qx) & 0xffffu) | (static_cast<uint32_t>(qy) << 16); }
     static __device__ __forceinline__ uint32_t hash(uint32_t k) { return (k * 2654435761u) >> 24; }
 };
@@ -246,10 +246,10 @@ __device__ __forceinline__ void me_pu(const MeArgs &a, const MePu &j, const int 
     // MEMO == 2: the SAD of this PU at quarter-pel displacement (qx, qy) from the pyramid, if the CTU probed it
     auto memo_get = [&](int qx, int qy, uint32_t &val) -> bool {
         const uint32_t k = MeMemo::key(qx, qy), h = MeMemo::hash(k);
-        uint32_t id = memo->idx[h];
+        uint32_t id = (memo->idx[h >> 2] >> ((h & 3u) * 8u)) & 0xffu;
         if (id == 0xffu) return false;
         if (memo->tag[id] != k) {                      // second home of a key: the neighbouring slot
-            id = memo->idx[h ^ 1u];
+            id = (memo->idx[(h ^ 1u) >> 2] >> (((h ^ 1u) & 3u) * 8u)) & 0xffu;
             if (id == 0xffu || memo->tag[id] != k) return false;
         }
         const uint32_t *e = memo->sum[id];
@@ -275,6 +275,7 @@ __device__ __forceinline__ void me_pu(const MeArgs &a, const MePu &j, const int 
     // (by = k, bx = l % 8).  p[k] = its SAD over them; the eight lanes l % 8 == bx (rows 0..7 of the blocks) add up by a reduce-scatter
     // (xor 8, xor 16: three shuffles) and the two warps of the slot by shared-memory atomics into entry `id`.
     int memo_n = 0;                                    // entries handed out so far (four per round, one per slot)
+    int phase = 0;                                     // double buffer of the exchange slots (and of the pyramid's pending entries)
     auto memo_put = [&](const uint32_t (&pk)[4], int qx, int qy, bool valid) {
         const int id = memo_n + slot;
         if (id < MeMemo::ENTRIES && valid) {           // uniform per slot (two warps)
@@ -284,19 +285,32 @@ __device__ __forceinline__ void me_pu(const MeArgs &a, const MePu &j, const int 
             const uint32_t s2 = __shfl_xor_sync(HB_FULL_MASK, b4 ? k0 : k1, 16);
             const uint32_t kk = (b4 ? k1 : k0) + s2;                                              // word j = 2 b3 + b4
             atomicAdd(&memo->sum[id][((b3 ? 2 : 0) + (b4 ? 1 : 0)) * 8 + (l & 7)], kk);
-            if (l == 0) {
-                const uint32_t k = MeMemo::key(qx, qy), h = MeMemo::hash(k);
-                memo->tag[id] = k;
-                // first come (a lost race between two slots of a round only loses reuse); a displacement probed twice keeps its first entry
-                if (memo->idx[h] == 0xffu) memo->idx[h] = static_cast<uint8_t>(id);
-                else if (memo->tag[memo->idx[h]] != k && memo->idx[h ^ 1u] == 0xffu) memo->idx[h ^ 1u] = static_cast<uint8_t>(id);
+        }
+        // the slot's first lane files the entry: its tag, then one of the key's two hash slots claimed by compare-and-swap (the four slots of a
+        // round file concurrently).  A displacement probed again in a later round finds its first entry (filed before an earlier barrier) and
+        // keeps it; two slots of ONE round never probe the same position.
+        if (l == 0 && id < MeMemo::ENTRIES && valid) {
+            const uint32_t k = MeMemo::key(qx, qy), h = MeMemo::hash(k);
+            memo->tag[id] = k;
+            bool filed = false;
+#pragma unroll
+            for (int alt = 0; alt < 2 && !filed; alt++) {
+                const uint32_t hh = h ^ static_cast<uint32_t>(alt), sh = (hh & 3u) * 8u;
+                uint32_t *wp = &memo->idx[hh >> 2];
+                uint32_t cur = atomicOr(wp, 0u);
+                for (;;) {
+                    const uint32_t e = (cur >> sh) & 0xffu;
+                    if (e != 0xffu) { filed = static_cast<int>(e) < memo_n && memo->tag[e] == k; break; }      // taken: by this displacement's earlier entry?
+                    const uint32_t prev = atomicCAS(wp, cur, (cur & ~(0xffu << sh)) | (static_cast<uint32_t>(id) << sh));
+                    if (prev == cur) { filed = true; break; }
+                    cur = prev;
+                }
             }
         }
     };
 
     uint8_t *s_patch = s_raw + group * Cfg::SMEM_PER_PU;
     uint32_t *s_plane = reinterpret_cast<uint32_t *>(s_patch + Cfg::PATCH_BYTES);  // [4][QROWS][TS] by x fraction, rows in pairs
-    int phase = 0;
     // G < 32: several PUs share a warp.  Their data-dependent loops are run in LOCK STEP (a PU that is finished idles through the
     // rounds the others still need -- the hardware would serialise them anyway), so every warp primitive names the full warp
     // and compiles to a single instruction; groups are addressed through the width argument of the shuffles.
@@ -1003,7 +1017,7 @@ __global__ void __launch_bounds__(256, 4) k_me_ctu(const MeCtuArgs c)
     __shared__ MeMemo s_memo;
     const int X0 = (blockIdx.x % c.ctu_cols) * 64, Y0 = (c.ctu_row0 + blockIdx.x / c.ctu_cols) * 64;
     for (int i = threadIdx.x; i < MeMemo::ENTRIES * 32; i += 256) (&s_memo.sum[0][0])[i] = 0;
-    if (threadIdx.x < MeMemo::SLOTS / 4) reinterpret_cast<uint32_t *>(s_memo.idx)[threadIdx.x] = 0xffffffffu;
+    if (threadIdx.x < MeMemo::SLOTS / 4) s_memo.idx[threadIdx.x] = 0xffffffffu;
     __syncthreads();
     me_ctu_depth<64, 0>(c, X0, Y0, 0, s_x, s_mv, &s_memo);
     __syncthreads();

@@ -304,3 +304,29 @@ extern "C" int hbk_pull_rows(const hbd_pull_span *spans, int n_spans, void *stre
 }
 
 extern "C" int hbc_clear_error(void) { return static_cast<int>(cudaGetLastError()); }
+
+// Can [p, p + bytes) of host memory go up as ONE copy?  Pageable memory: yes, the runtime stages it.  Pinned memory: only when the span lies
+// inside one allocation -- adjacent addresses need not be (three separately pinned planes that happen to touch), and a copy across
+// allocations is refused.  The allocation's range comes from the driver (cuMemGetAddressRange on the pointer's unified address).
+extern "C" int hbc_host_span_one_copy(const void *p, size_t bytes)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return 1; }
+    if (at.type == cudaMemoryTypeUnregistered) return 1;
+    typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);
+    static range_fn fn = nullptr;
+    static int tried = 0;
+    if (!tried) {
+        tried = 1;
+        void *q = nullptr;
+        cudaDriverEntryPointQueryResult r;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &q, cudaEnableDefault, &r) == cudaSuccess && r == cudaDriverEntryPointSuccess) fn = reinterpret_cast<range_fn>(q);
+        else cudaGetLastError();
+    }
+    if (!fn || !at.devicePointer) return 0;
+    unsigned long long base = 0;
+    size_t size = 0;
+    const unsigned long long d = reinterpret_cast<unsigned long long>(at.devicePointer);
+    if (fn(&base, &size, d) != 0) return 0;
+    return d + bytes <= base + size;
+}

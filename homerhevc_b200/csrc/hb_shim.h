@@ -99,7 +99,8 @@ typedef struct hbd_me_job {       /* one PU, device layout */
 typedef struct hbd_subpel { uint8_t *base; int32_t pitch; int32_t w, h; int32_t pad_; uint64_t plane_bytes; } hbd_subpel;
 int hbk_subpel_planes(const hbd_frame *ref, const hbd_subpel *sp, int y_lo, int y_hi /* picture rows wanted */, void *stream);
 int hbk_subpel_uses_tma(void);
-int hbc_clear_error(void);     /* cudaGetLastError: returns and resets the last (non-sticky) error */
+int hbc_clear_error(void);
+int hbc_host_span_one_copy(const void *p, size_t bytes);   /* 1: [p, p + bytes) of host memory may be copied in one piece */     /* cudaGetLastError: returns and resets the last (non-sticky) error */
 /* CUDA IPC (peer pictures of the CTU-row bands) */
 int hbc_ipc_get_mem(void *dev, unsigned char out[64]);
 int hbc_ipc_open_mem(const unsigned char in[64], void **dev);

@@ -1,7 +1,5 @@
-for wl in 720p 1080p; do
-timeout 600 python bench.py --mode intra_recon --workload $wl --steps 24 > gpurun_out/q1_ir_$wl.json 2> gpurun_out/q1_ir_$wl.err; echo "rc=$?"
-python -c "
-import json;d=json.loads(open('gpurun_out/q1_ir_$wl.json').read().strip().splitlines()[-1]);print({k:d[k] for k in ('value','ms_per_step','identical_to_reference_reconstruction','gpu_launches')}, d['config']['workload'])" || tail -5 gpurun_out/q1_ir_$wl.err
-done
-timeout 300 python bench.py --mode intra_recon --workload 720p --steps 24 --streams 1 --no-cpu-baseline | python -c "
-import json,sys;d=json.loads(sys.stdin.read().strip().splitlines()[-1]);print('1 stream', d['value'], d['ms_per_step'])"
+cd /root/repo
+timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_prepass.py -m gpu -x -q -k "matches_oracle or subpel_planes" > gpurun_out/san_racecheck_b.log 2>&1; echo "racecheck b rc=$?"; tail -3 gpurun_out/san_racecheck_b.log | cut -c1-200
+timeout 600 python -m pytest tests/test_gpu_prepass.py -m gpu -x -q > gpurun_out/q1_tests.log 2>&1; tail -2 gpurun_out/q1_tests.log
+for i in 1 2; do timeout 300 python bench.py --no-extras --no-cpu-baseline > gpurun_out/q1_bench.json 2> gpurun_out/q1_bench.err; python -c "
+import json;d=json.loads(open('gpurun_out/q1_bench.json').read().strip().splitlines()[-1]);print(d['summary']['value_fps'], d['summary']['e2e_fps'], d['kernels_ms']['me'])"; done
