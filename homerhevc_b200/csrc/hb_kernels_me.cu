@@ -1025,8 +1025,9 @@ __global__ void __launch_bounds__(256, 4) k_me_ctu(const MeCtuArgs c)
     __syncthreads();
     me_ctu_depth<16, 2>(c, X0, Y0, 0, s_x, s_mv, &s_memo);
     __syncthreads();
-    me_ctu_depth<8, 3>(c, X0, Y0, 0, s_x, s_mv, &s_memo);
-    me_ctu_depth<8, 3>(c, X0, Y0, 1, s_x, s_mv, &s_memo);
+    // the sixty-four 8x8 PUs in two rounds through ONE copy of the code (the kernel's instructions are its largest cache footprint)
+#pragma unroll 1
+    for (int round = 0; round < 2; round++) me_ctu_depth<8, 3>(c, X0, Y0, round, s_x, s_mv, &s_memo);
 }
 
 template <int N> int configure_me()
