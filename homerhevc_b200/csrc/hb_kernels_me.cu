@@ -635,7 +635,8 @@ __device__ __forceinline__ void me_pu(const MeArgs &a, const MePu &j, const int 
             return acc;
         };
         int bidx = 0;
-#pragma unroll
+        // the two rounds of a stage run through one copy of the probe (instruction footprint, see k_me_ctu)
+#pragma unroll 1
         for (int h = 0; h < 2; h++) {
             uint32_t sad[4], cst[4];
             exchange(sad_plane(2 * c_half[1 + 4 * h + slot][0], 2 * c_half[1 + 4 * h + slot][1]), 0u, sad, cst);
@@ -646,13 +647,13 @@ __device__ __forceinline__ void me_pu(const MeArgs &a, const MePu &j, const int 
         const int hx = c_half[bidx][0], hy = c_half[bidx][1];
         int sbx = hx * 2, sby = hy * 2;
         if (a.action & HB_ME_QUARTER) {
-#pragma unroll
+#pragma unroll 1
             for (int h = 0; h < 2; h++) {
                 uint32_t sad[4], cst[4];
                 exchange(sad_plane(hx * 2 + c_quarter[1 + 4 * h + slot][0], hy * 2 + c_quarter[1 + 4 * h + slot][1]), 0u, sad, cst);
 #pragma unroll
                 for (int s = 0; s < 4; s++)
-                    if (sad[s] < cur_best) { cur_best = sad[s]; sbx = hx * 2 + quarter_off(1 + 4 * h + s, 0); sby = hy * 2 + quarter_off(1 + 4 * h + s, 1); }
+                    if (sad[s] < cur_best) { cur_best = sad[s]; sbx = hx * 2 + c_quarter[1 + 4 * h + s][0]; sby = hy * 2 + c_quarter[1 + 4 * h + s][1]; }
             }
         }
         best_sad = cur_best;
