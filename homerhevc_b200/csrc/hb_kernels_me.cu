@@ -653,7 +653,7 @@ __device__ __forceinline__ void me_pu(const MeArgs &a, const MePu &j, const int 
                 exchange(sad_plane(hx * 2 + c_quarter[1 + 4 * h + slot][0], hy * 2 + c_quarter[1 + 4 * h + slot][1]), 0u, sad, cst);
 #pragma unroll
                 for (int s = 0; s < 4; s++)
-                    if (sad[s] < cur_best) { cur_best = sad[s]; sbx = hx * 2 + c_quarter[1 + 4 * h + s][0]; sby = hy * 2 + c_quarter[1 + 4 * h + s][1]; }
+                    if (sad[s] < cur_best) { cur_best = sad[s]; sbx = hx * 2 + (h ? quarter_off(5 + s, 0) : quarter_off(1 + s, 0)); sby = hy * 2 + (h ? quarter_off(5 + s, 1) : quarter_off(1 + s, 1)); }
             }
         }
         best_sad = cur_best;
