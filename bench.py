@@ -252,7 +252,7 @@ def run_reference(args, w, h, rank, world):
     line = {"impl": "reference", "metric": "ME+TQ frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8 samples, int16 residual/levels, int32 accumulate", "data": "synthetic",
-            "config": bench_config(args, w, h, world, max(1, args.streams)),
+            "config": bench_config(args, w, h, world, max(1, min(args.value_streams, args.streams))),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference",
                              "sample": f"{sample} frame(s) per step, the reference's own functions (oracle/_ref: hmr_motion_estimation, hmr_motion_compensation_*, "
                                        f"predict, encode_inter_cu*), {cores} threads, CTUs dealt round-robin, timed inside the C driver"},
@@ -618,7 +618,7 @@ def measure_bands(args, rank, world, local, torch, dist, hb, synth, barrier, ste
 
 
 # ---------------------------------------------------------------------------------------------------------------- the main measurement
-def measure_workload(args, w, h, rank, world, local, torch, dist, hb, synth, barrier, steps, warmup, n_slots, full):
+def measure_workload(args, w, h, rank, world, local, torch, dist, hb, synth, barrier, steps, warmup, n_slots, full, n_value=None):
     """value (resident inputs, device-timed), e2e (host buffers, device-resident reference picture) and -- full only -- the other
     e2e variants and the per-kernel profile of one picture size"""
     ctx = hb.Context(local)
@@ -650,9 +650,15 @@ def measure_workload(args, w, h, rank, world, local, torch, dist, hb, synth, bar
         slots.append({"ctx": c, "cur": hb.Frame(c, w, h), "ref": hb.Frame(c, w, h), "pp": spp, "tables": c.pinned(spp.tables_bytes()),
                       "out": c.pinned(frame_bytes + 4 * w * h), "sel": np.zeros(n_ctus, np.uint8), "off": np.zeros(n_ctus + 1, np.int32), "d2h": 0})
 
+    # `value` keeps n_value of the streams in flight (default 4: the device is full from four frames on; with more, the kernels of more frames
+    # evict each other's instructions and lines -- measured 7 196 / 7 021 / 6 909 frames/s at 4 / 8 / 16 streams); the e2e flows use all of them,
+    # they need the depth to cover the host's share of a frame
+    n_value = max(1, min(n_value or n_slots, n_slots))
+    vslots = slots[:n_value]
+
     def step_resident(i):
         """one step = one frame on every in-flight stream, inputs resident in HBM"""
-        for k, sl in enumerate(slots):
+        for k, sl in enumerate(vslots):
             j = (i + 4 * k) % N_RESIDENT
             sl["pp"].run(resident[j + 1], resident[j], AVG_DIST)
 
@@ -673,11 +679,11 @@ def measure_workload(args, w, h, rank, world, local, torch, dist, hb, synth, bar
     sampler.start()
     l0 = sum(sl["ctx"].launch_count() for sl in slots)
     ctx.timer_begin()
-    for sl in slots:
+    for sl in vslots:
         sl["ctx"].wait(ctx)
     for i in range(steps):
         step_resident(i)
-    for sl in slots:
+    for sl in vslots:
         ctx.wait(sl["ctx"])
     ms = ctx.timer_end()
     launches = sum(sl["ctx"].launch_count() for sl in slots) - l0
@@ -810,7 +816,7 @@ def measure_workload(args, w, h, rank, world, local, torch, dist, hb, synth, bar
         res["ms"] = t[2]
     if hostref:
         hostref["ms"] = t[3]
-    r = {"w": w, "h": h, "ms": ms, "steps": steps, "n_slots": n_slots, "launches": launches, "clocks": clocks, "chain_fps": n_chain / (chain_ms * 1e-3),
+    r = {"w": w, "h": h, "ms": ms, "steps": steps, "n_slots": n_slots, "n_value": n_value, "launches": launches, "clocks": clocks, "chain_fps": n_chain / (chain_ms * 1e-3),
          "resident": res, "hostref": hostref, "prof": prof, "abytes": abytes, "aops": aops, "frame_bytes": frame_bytes, "e2e_threads": E2E_THREADS,
          "host_frames": host}
     # release the device memory of this picture size before the next one is set up
@@ -852,7 +858,8 @@ def main():
     ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip extra_workloads and bands_2160p (kernel work, profiling)")
-    ap.add_argument("--streams", type=int, default=16, help="independent GOP streams in flight per GPU")
+    ap.add_argument("--streams", type=int, default=16, help="independent GOP streams in flight per GPU (e2e flows)")
+    ap.add_argument("--value-streams", type=int, default=4, help="of those, the streams the device-timed `value` keeps in flight")
     ap.add_argument("--mode", default="gops", choices=["gops", "bands", "intra", "intra_recon", "finalise", "encode"],
                     help="gops: the headline line (independent GOP streams per GPU + the 2160p band line); bands: only the 2160p CTU-row-band "
                          "measurement; intra / finalise / encode: side measurements (rank 0)")
@@ -913,15 +920,16 @@ def main():
 
     torch.cuda.set_device(local)
     n_slots = max(1, args.streams)
-    r = measure_workload(args, w, h, rank, world, local, torch, dist, hb, synth, barrier, args.steps, args.warmup, n_slots, True)
+    n_value = max(1, min(args.value_streams, n_slots))
+    r = measure_workload(args, w, h, rank, world, local, torch, dist, hb, synth, barrier, args.steps, args.warmup, n_slots, True, n_value)
     extras = {}
     if world == 1 and not args.no_extras:
         for name, (ew, eh) in WORKLOADS.items():
             if (ew, eh) == (w, h):
                 continue
             try:
-                x = measure_workload(args, ew, eh, rank, world, local, torch, dist, hb, synth, barrier, max(8, min(args.steps, 40)), 3, n_slots, False)
-                extras[name] = {"value": n_slots * x["steps"] / (x["ms"] * 1e-3), "unit": "frames/s", "e2e": e2e_object(x, world)["value"],
+                x = measure_workload(args, ew, eh, rank, world, local, torch, dist, hb, synth, barrier, max(8, min(args.steps, 40)), 3, n_slots, False, n_value)
+                extras[name] = {"value": n_value * x["steps"] / (x["ms"] * 1e-3), "unit": "frames/s", "e2e": e2e_object(x, world)["value"],
                                 "one_stream_chain": x["chain_fps"], "steps": x["steps"]}
             except Exception as e:
                 extras[name] = {"value": None, "what": f"failed: {e}"}
@@ -960,7 +968,7 @@ def main():
         achieved = ops_top / (prof[top] * 1e-3)
         # the whole step: time the integer pipes need at best for every launch's algorithmic work / the measured step time per frame
         ideal_s = sum((aops[k]["pad"] + aops[k]["mac"]) / int_peak_ops(aops[k], sm_hz) for k in prof if k in aops)
-        frame_s = ms * 1e-3 / (args.steps * n_slots)
+        frame_s = ms * 1e-3 / (args.steps * n_value)
         step_bytes = sum(abytes[k] for k in prof if k in abytes)
         # executed-instruction view and DRAM traffic: only from an ncu profile taken on exactly these kernel sources
         issue, traffic, sha = None, None, kernel_source_sha()
@@ -971,7 +979,7 @@ def main():
                 issue = {"stale_profile": True, "profile_sha": pc.get("kernel_source_sha"), "kernel_source_sha": sha}
             elif (w, h) == WORKLOADS["1080p"]:
                 inst = pc["total_warp_inst"]
-                fps_gpu = n_slots * args.steps / (ms * 1e-3)
+                fps_gpu = n_value * args.steps / (ms * 1e-3)
                 issue = {"what": "executed warp instructions (ncu smsp__inst_executed.sum, profiles/inst_r02.json) x frames/s against the measured issue ceiling; utilisation, not a roofline",
                          "warp_inst_per_frame": inst, "achieved": inst * fps_gpu, "peak": N_SM * PEAK_BOTH_PIPES * sm_hz, "unit": "warp-inst/s",
                          "frac": inst * fps_gpu / (N_SM * PEAK_BOTH_PIPES * sm_hz), "kernel_source_sha": sha}
@@ -986,11 +994,11 @@ def main():
             issue = {"stale_profile": True, "what": f"{type(e).__name__}: {e}"}
         e2e = e2e_object(r, world)
         line = {
-            "metric": "ME+TQ frames/s", "value": world * n_slots * args.steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+            "metric": "ME+TQ frames/s", "value": world * n_value * args.steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8 samples, int16 residual/levels, int32 accumulate",
             "data": "synthetic",
-            "config": bench_config(args, w, h, world, n_slots),
+            "config": bench_config(args, w, h, world, n_value),
             "gpu_launches": int(r["launches"]),
             "clocks": clocks,
             "kernels_ms": {k: round(v, 5) for k, v in prof.items()},
