@@ -49,7 +49,7 @@ template <int FY> __device__ __forceinline__ void vfilter2(const uint32_t (&win)
         if (i < 4) sa = __dp2a_lo(w, static_cast<int>(vpair(FY, i)), sa);       // row 2m: taps 0..7 sit in words 0..3
         sb = __dp2a_hi(w, static_cast<int>(vpair(FY, i)), sb);
     }
-    a = __vimin_s32_relu(sa >> 12, 255); b = __vimin_s32_relu(sb >> 12, 255);
+    a = sa >> 12; b = sb >> 12;                        // the caller's pack clips to 0..255
 }
 
 template <bool TMA>
@@ -114,13 +114,22 @@ __global__ void __launch_bounds__(256) k_subpel_planes(const __grid_constant__ C
     }
     __syncthreads();
 
-    // ---- vertical pass: thread = (horizontal fraction fx, column c); a warp holds one fx, so its byte stores of a row are contiguous
-    const int fx = tid >> 6, c = tid & 63;
-    const int px = blockIdx.x * TW + c;                            // plane coordinates of this column
-    if (px >= sp.w) return;
+    // ---- vertical pass: thread = (horizontal fraction fx, column c).  A lane ends up with the four vertical fractions of its column (one
+    // saturating pack per row: the clip of the second pass); the four lanes of a column quad then swap bytes (4x4 transpose in two shuffle
+    // + byte-permute steps) so that lane j holds four neighbouring samples of the plane with vertical fraction j: one 32-bit store per lane
+    // and row instead of four byte stores
+    const int fx = tid >> 6, c = tid & 63, lane = tid & 31, j = lane & 3;
+    const int px = blockIdx.x * TW + (c & ~3);                     // plane column of the quad's first sample
+    const bool col_ok = px < sp.w;                                 // whole warps beyond the plane still take part in the shuffles
     const uint32_t *col = &s_t[fx][0][c];
-    uint8_t *dst = sp.base + static_cast<size_t>(tile_y * TH) * sp.pitch + px;
     const int rows = min(TH, sp.h - tile_y * TH);
+    const bool plane_ok = col_ok && !(j == 0 && fx == 0);          // (0, 0) is the reference picture itself
+    uint8_t *p0 = sp.base + static_cast<size_t>(max(j * 4 + fx - 1, 0)) * sp.plane_bytes + static_cast<size_t>(tile_y * TH) * sp.pitch + px;
+    const uint32_t sel0 = (lane & 1) ? 0x3715u : 0x6240u, sel1 = (lane & 2) ? 0x3276u : 0x5410u;
+    auto transpose4 = [&](uint32_t w) -> uint32_t {
+        const uint32_t a = __byte_perm(w, __shfl_xor_sync(HB_FULL_MASK, w, 1), sel0);
+        return __byte_perm(a, __shfl_xor_sync(HB_FULL_MASK, a, 2), sel1);
+    };
     uint32_t win[5];
 #pragma unroll
     for (int k = 0; k < 4; k++) win[k] = col[k * TW];
@@ -129,18 +138,16 @@ __global__ void __launch_bounds__(256) k_subpel_planes(const __grid_constant__ C
         win[(m + 4) % 5] = col[(m + 4) * TW];
         int v[4][2];
         // fy = 0: the first-pass sample itself, rounded: rows 2m+3 (high half of word m+1) and 2m+4 (low half of word m+2)
-        v[0][0] = __vimin_s32_relu(__dp2a_lo(static_cast<int>(win[(m + 1) % 5]), 0x0100, 8192 + 32) >> 6, 255);
-        v[0][1] = __vimin_s32_relu(__dp2a_lo(static_cast<int>(win[(m + 2) % 5]), 0x0001, 8192 + 32) >> 6, 255);
+        v[0][0] = __dp2a_lo(static_cast<int>(win[(m + 1) % 5]), 0x0100, 8192 + 32) >> 6;
+        v[0][1] = __dp2a_lo(static_cast<int>(win[(m + 2) % 5]), 0x0001, 8192 + 32) >> 6;
         vfilter2<1>(win, m, v[1][0], v[1][1]);
         vfilter2<2>(win, m, v[2][0], v[2][1]);
         vfilter2<3>(win, m, v[3][0], v[3][1]);
-#pragma unroll
-        for (int fy = 0; fy < 4; fy++) {
-            if (fy == 0 && fx == 0) continue;                      // (0, 0) is the reference picture itself
-            uint8_t *p = dst + static_cast<size_t>(fy * 4 + fx - 1) * sp.plane_bytes + static_cast<size_t>(2 * m) * sp.pitch;
-            if (2 * m < rows) p[0] = static_cast<uint8_t>(v[fy][0]);
-            if (2 * m + 1 < rows) p[sp.pitch] = static_cast<uint8_t>(v[fy][1]);
-        }
+        const uint32_t w0 = transpose4(hb_pack_sat_u8x4(v[0][0], v[1][0], v[2][0], v[3][0]));
+        const uint32_t w1 = transpose4(hb_pack_sat_u8x4(v[0][1], v[1][1], v[2][1], v[3][1]));
+        if (plane_ok && 2 * m < rows) *reinterpret_cast<uint32_t *>(p0) = w0;
+        if (plane_ok && 2 * m + 1 < rows) *reinterpret_cast<uint32_t *>(p0 + sp.pitch) = w1;
+        p0 += 2 * static_cast<size_t>(sp.pitch);
     }
 }
 
