@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 import subprocess
+import sys
 
 import pytest
 
@@ -79,3 +80,21 @@ def test_struct_sizes_match_the_c_header(tmp_path):
               "hb_deblock_params": 16, "hb_low_level_funcs": C.sizeof(hb.LowLevelFuncs)}
     for n in names:
         assert int(got[n]) == mirror[n], (n, got[n], mirror[n])
+
+
+def test_committed_ncu_profile_belongs_to_the_committed_kernels():
+    """bench.py quotes executed instructions and DRAM traffic from profiles/inst_r02.json only when that profile was taken on exactly the
+    kernel sources in the tree (a sha over csrc/*.cu, *.cuh): a kernel edit without a fresh launch list must not go unnoticed"""
+    import importlib.util
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("hb_bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(bench)
+    finally:
+        sys.argv = argv
+    with open(os.path.join(root, "profiles", "inst_r02.json")) as f:
+        prof = json.load(f)
+    assert prof["kernel_source_sha"] == bench.kernel_source_sha(), "profiles/inst_r02.json is stale: re-run tools/gpu_round.sh and commit its launch list"
