@@ -457,27 +457,31 @@ def run_encode(args, w, h, rank):
     output compared byte for byte with the unmodified encoder's, next to homer_app in both thread settings.  Rank 0 only."""
     if rank != 0:
         return
-    import homerhevc_b200 as hb
-    from _encode import CuHookCfg, cu_hooks_off, encode, hook_addr, make_yuv
+    import subprocess
     from _oracle import have_ref
     if not have_ref():
         print(json.dumps({"metric": "encoder frames/s", "unavailable": "oracle/_ref (compiled reference) is not in this tree"}))
         return
     nf = max(3, min(args.steps, 10))
-    L = hb.load_library()
-    yuv = make_yuv(w, h, nf)
-    gold_bs, gold_rec, t_cpu = encode(w, h, yuv, nf)
-    cfg = CuHookCfg(L._handle, 31, 1)
-    try:
-        bs, rec, t_gpu = encode(w, h, yuv, nf, hook=hook_addr("refdrv_install_cu_hooks"), user=cfg)
-    finally:
-        cnt = cu_hooks_off()
+    # both arms on oracle/_ref/zinit (the unmodified sources compiled with -ftrivial-auto-var-init=zero), in a process of their own: the as-is
+    # build's stream depends on what earlier calls left on the stack (its SSE4.2 intra predictors read automatic variables they never wrote;
+    # DESIGN.md section 7, tests/test_gpu_encode_hooks.py), which no replacement can reproduce
+    zinit = os.path.join(ROOT, "oracle", "_ref", "zinit")
+    ref_dir = zinit if os.path.exists(os.path.join(zinit, "librefdrv.so")) else os.path.join(ROOT, "oracle", "_ref")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "encode_check.py"), f"{w}x{h}x{nf}", "-1", "hooks", "1"], capture_output=True, text=True,
+                         timeout=3000, cwd=ROOT, env=dict(os.environ, HB_REF_DIR=ref_dir))
+    if out.returncode != 0:
+        print(json.dumps({"metric": "encoder frames/s", "unavailable": "tools/encode_check.py failed: " + out.stderr[-300:]}))
+        return
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    cnt, t_gpu, t_cpu = r["hook_calls"], r["seconds_replaced"], r["seconds_reference"]
+    identical, stream_bytes = bool(r["identical"]), int(r["bytes"])
     cores = len(os.sched_getaffinity(0))
     line = {"metric": "encoder frames/s (whole encode, host decisions + CABAC on the CPU, ME / MC / inter T/Q through the batched GPU API per coding unit)",
             "value": nf / t_gpu, "unit": "frames/s", "n_gpus": 1, "steps": nf, "warmup": 0, "ms_per_step": 1e3 * t_gpu / nf, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8 samples, int16 residual/levels", "data": "synthetic",
             "config": {"workload": f"{w}x{h} IPPP quarter-pel, fixed QP {QP}, {nf} frames, 1 engine, WPP off, lock step", "hook_calls": cnt},
-            "identical_stream": bool(bs == gold_bs and np.array_equal(rec, gold_rec)), "stream_bytes": len(gold_bs),
+            "identical_stream": identical, "stream_bytes": stream_bytes, "reference_build": os.path.relpath(ref_dir, ROOT),
             "e2e": {"value": nf / t_gpu, "unit": "frames/s", "h2d_bytes_per_step": int(2 * w * h * 3), "d2h_bytes_per_step": 0,
                     "note": "one blocking GPU round trip per hmr_motion_estimation / motion compensation / transform unit call: launch latency, not throughput, sets this number"},
             "gpu_launches": int(cnt["me"] + 3 * cnt["mc"] + 2 * cnt["tq"]),
