@@ -187,3 +187,59 @@ def test_deblocking():
     for c in range(3):
         assert np.array_equal(got[c], exp[c]), c
     assert (exp[0] != planes(G["dbk_in"])[0]).sum() > 1000
+
+
+# ---- round 2: tests/golden/ref_vectors_r02.npz (tests/golden/make_golden_r02.py)
+G2 = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_vectors_r02.npz"))
+
+
+def _units(prefix):
+    return {k: G2[f"{prefix}_{k}"] for k in ("cu", "tu", "intra", "cbf", "qp", "mv")}
+
+
+def _planes(a, w, h):
+    return [a[:w * h].reshape(h, w), a[w * h:w * h * 5 // 4].reshape(h // 2, w // 2), a[w * h * 5 // 4:].reshape(h // 2, w // 2)]
+
+
+def test_amvp_and_merge_candidates():
+    from _oracle import oracle_amvp, oracle_merge
+    w, h = 200, 136
+    m, jobs = _units("cand"), G2["cand_jobs"]
+    assert np.array_equal(oracle_amvp(w, h, m, jobs), G2["cand_amvp"])
+    assert np.array_equal(oracle_merge(w, h, m, jobs, 5), G2["cand_merge5"])
+    assert np.array_equal(oracle_merge(w, h, m, jobs, 2), G2["cand_merge2"])
+    assert (G2["cand_amvp"] != 0).any() and (G2["cand_merge5"][:, 3] != 0).any()
+
+
+def test_boundary_strengths_of_a_b_picture():
+    from _oracle import oracle_deblock_strengths_b
+    w, h = 192, 136
+    mot = [G2["bsb_" + k] for k in ("ref0", "mv0", "ref1", "mv1", "pic_l0", "pic_l1")]
+    gv, gh = oracle_deblock_strengths_b(w, h, _units("bsb"), *mot)
+    assert np.array_equal(gv[:h // 4, :w // 4], G2["bsb_ver"][:h // 4, :w // 4]) and np.array_equal(gh[:h // 4, :w // 4], G2["bsb_hor"][:h // 4, :w // 4])
+    assert all((G2["bsb_ver"][:h // 4, 2:w // 4:2] == v).sum() > 20 for v in (0, 1, 2))
+
+
+def test_sao_offset_pass():
+    from _oracle import oracle_sao_apply
+    w, h = 200, 136
+    got = oracle_sao_apply(_planes(G2["saoa_in"], w, h), w, h, G2["saoa_types"], G2["saoa_offs"])
+    exp = _planes(G2["saoa_out"], w, h)
+    for c in range(3):
+        assert np.array_equal(got[c], exp[c]), c
+    assert (exp[0] != _planes(G2["saoa_in"], w, h)[0]).sum() > 500
+
+
+def test_intra_picture_of_the_reference_encoder():
+    """the I picture the reference's encoder made of a 192x136 source: from its decisions per transform unit the restatement rebuilds its
+    unfiltered reconstruction sample for sample and its levels"""
+    from _intra import coeff_wnd_of, oracle_intra_recon
+    w, h, qp, sh, seed = (int(v) for v in G2["ipic_cfg"])
+    tus = G2["ipic_tus"]
+    rec, coeff, _ = oracle_intra_recon(_planes(G2["ipic_src"], w, h), w, h, tus, is_islice=1, sign_hiding=sh)
+    exp = _planes(G2["ipic_recon"], w, h)
+    for c in range(3):
+        assert np.array_equal(rec[c], exp[c]), (c, np.argwhere(rec[c] != exp[c])[:3].tolist())
+    covered = coeff_wnd_of(tus, np.ones_like(coeff), w, h) != 0
+    assert np.array_equal(coeff_wnd_of(tus, coeff, w, h)[covered], G2["ipic_coeff"][covered])
+    assert set(int(s) for s in tus[tus[:, 0] == 0][:, 3]) >= {4, 8, 16}
