@@ -1006,15 +1006,15 @@ int hb_intra_reconstruct_ex(hb_ctx *ctx, const hb_frame *cur, hb_frame *pred, hb
         for (int i = 0; i < n_units; i++) {
             const hb_intra_unit *u = &units[i];
             const int c = u->comp, n = u->size, bx = u->x / 4, by = u->y / 4, nb = n / 4;
-            int flags, lbs, trs, level = 0;
-            intra_neighbours(w, h, u->node_x, u->node_y, u->node_size, c != 0, &flags, &lbs, &trs);
+            int nflags, lbs, trs, level = 0;
+            intra_neighbours(w, h, u->node_x, u->node_y, u->node_size, c != 0, &nflags, &lbs, &trs);
             #define AT(xx, yy) (((xx) >= 0 && (yy) >= 0 && (xx) < mw[c] && (yy) < mh[c]) ? map[c][(size_t)(yy) * mw[c] + (xx)] : 0)
             #define UP(v) do { const int v_ = (v); if (v_ > level) level = v_; } while (0)
-            if (flags & 1) for (int k = 0; k < nb; k++) UP(AT(bx - 1, by + k));
-            if (flags & 4) for (int k = 0; k < (lbs + 3) / 4; k++) UP(AT(bx - 1, by + nb + k));
-            if (flags & 2) for (int k = 0; k < nb; k++) UP(AT(bx + k, by - 1));
-            if (flags & 8) for (int k = 0; k < (trs + 3) / 4; k++) UP(AT(bx + nb + k, by - 1));
-            if ((flags & 3) == 3) UP(AT(bx - 1, by - 1));
+            if (nflags & 1) for (int k = 0; k < nb; k++) UP(AT(bx - 1, by + k));
+            if (nflags & 4) for (int k = 0; k < (lbs + 3) / 4; k++) UP(AT(bx - 1, by + nb + k));
+            if (nflags & 2) for (int k = 0; k < nb; k++) UP(AT(bx + k, by - 1));
+            if (nflags & 8) for (int k = 0; k < (trs + 3) / 4; k++) UP(AT(bx + nb + k, by - 1));
+            if ((nflags & 3) == 3) UP(AT(bx - 1, by - 1));
             #undef UP
             #undef AT
             level += 1;
@@ -1022,7 +1022,7 @@ int hb_intra_reconstruct_ex(hb_ctx *ctx, const hb_frame *cur, hb_frame *pred, hb
             if (level > n_levels) n_levels = level;
             srt[i].level = level; srt[i].comp = c; srt[i].size = n; srt[i].qp = u->qp; srt[i].scan = u->scan_mode; srt[i].idx = i;
             coeff_off[i] = co; co += (size_t)n * n;
-            aj[i].comp = c; aj[i].x = u->x; aj[i].y = u->y; aj[i].n = n; aj[i].flags = flags; aj[i].lbs = lbs; aj[i].trs = trs; aj[i].adi_off = (int32_t)ao;
+            aj[i].comp = c; aj[i].x = u->x; aj[i].y = u->y; aj[i].n = n; aj[i].flags = nflags; aj[i].lbs = lbs; aj[i].trs = trs; aj[i].adi_off = (int32_t)ao;
             ao += 4 * (size_t)n + 1;
         }
     }
